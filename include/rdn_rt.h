@@ -1,0 +1,206 @@
+/* rdn_rt.h — C ABI of the B200-native BVH closest-hit path (drop-in boundary).
+ *
+ * What a thin Rust `-sys` crate (or any FFI) binds in place of rendiation's software ray-tracing
+ * geometry backend and its space-query helpers.  Every entry point cites the reference interface
+ * it replaces (paths relative to the rendiation repo root).
+ *
+ * Conventions (following the reference's own C API style,
+ * application/viewer-content-api/src/c_api/viewer.rs:295-336, but with status codes instead of
+ * panics — the reference aborts on error, Cargo.toml:161-162):
+ *   - every function returns 0 on success, a negative rdn_status on error; never throws/aborts;
+ *   - rdn_rt_last_error() returns a thread-local message for the last failure;
+ *   - the caller owns every array passed in or out; build inputs are copied by the callee
+ *     (`source.to_vec()`, geometry/naive/mod.rs:98-119); the scene object owns all device memory;
+ *   - create/delete/bind take a write lock, trace a read lock (the Arc<RwLock<..>> discipline of
+ *     geometry/naive/mod.rs:497-536), so a scene may be shared between threads.
+ */
+#ifndef RDN_RT_H
+#define RDN_RT_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum rdn_status {
+  RDN_OK = 0,
+  RDN_ERR_INVALID_ARGUMENT = -1,
+  RDN_ERR_CUDA = -2,
+  RDN_ERR_INVALID_HANDLE = -3,   /* the reference panics: unwrap() on a deleted BLAS, naive/mod.rs:273-275 */
+  RDN_ERR_BUILD = -4,            /* the reference panics inside the builder (index out of bounds) */
+  RDN_ERR_NOT_COMMITTED = -5,
+  RDN_ERR_CAPACITY = -6          /* scene exceeds the 32-bit reference encoding of the flattened layout */
+} rdn_status;
+
+/* ---- ray flags: RayFlagConfigRaw, shader/ray-tracing/src/api/ty.rs:102-114 ---- */
+#define RDN_RAY_FLAG_NONE 0x00u
+#define RDN_RAY_FLAG_FORCE_OPAQUE 0x01u
+#define RDN_RAY_FLAG_FORCE_NON_OPAQUE 0x02u
+#define RDN_RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH 0x04u
+#define RDN_RAY_FLAG_SKIP_CLOSEST_HIT_SHADER 0x08u
+#define RDN_RAY_FLAG_CULL_BACK_FACING_TRIANGLES 0x10u
+#define RDN_RAY_FLAG_CULL_FRONT_FACING_TRIANGLES 0x20u
+#define RDN_RAY_FLAG_CULL_OPAQUE 0x40u
+#define RDN_RAY_FLAG_CULL_NON_OPAQUE 0x80u
+#define RDN_RAY_FLAG_SKIP_TRIANGLES 0x100u
+#define RDN_RAY_FLAG_SKIP_PROCEDURAL_PRIMITIVES 0x200u
+/* ---- GeometryInstanceFlags, api/ty.rs:143-151 ---- */
+#define RDN_GEOMETRY_INSTANCE_TRIANGLE_FACING_CULL_DISABLE 0x1u
+#define RDN_GEOMETRY_INSTANCE_TRIANGLE_FLIP_FACING 0x2u
+#define RDN_GEOMETRY_INSTANCE_FORCE_OPAQUE 0x4u
+#define RDN_GEOMETRY_INSTANCE_FORCE_NO_OPAQUE 0x8u
+/* ---- GeometryFlags, api/ty.rs:155-159 ---- */
+#define RDN_GEOMETRY_FLAG_OPAQUE 0x1u
+#define RDN_GEOMETRY_FLAG_NO_DUPLICATE_ANYHIT_INVOCATION 0x2u
+/* ---- RayHitKind, api/ty.rs:138-140 ---- */
+#define RDN_HIT_KIND_FRONT_FACING_TRIANGLE 0xFEu
+#define RDN_HIT_KIND_BACK_FACING_TRIANGLE 0xFFu
+#define RDN_INVALID_ID 0xFFFFFFFFu
+
+/* One ray: the reference's `Ray` (geometry/mod.rs:33-42: origin, flags, direction, mask) with the two
+ * u32 slots carrying the per-ray range of ShaderRayTraceCallStoragePayload.range
+ * (wavefront_compute/ctx.rs:15-29).  32 B = 2 x float4. */
+typedef struct rdn_ray { float ox, oy, oz, tmin, dx, dy, dz, tmax; } rdn_ray;
+
+/* Launch-uniform part of ShaderRayTraceCallStoragePayload (ctx.rs:15-29): tlas_idx, ray_flags, cull_mask.
+ * grid_width: optional hint — rays form a row-major 2D launch of this width (launch_size.x); 0 = plain list.
+ * The result is identical either way; the hint only lets the kernel walk rays in 8x4 pixel tiles. */
+typedef struct rdn_launch { uint32_t ray_flags, cull_mask, tlas_idx, grid_width; } rdn_launch;
+
+/* Closest-hit record = the fields of RayClosestHitCtx a consumer reads (api/ctx.rs:13-55;
+ * storage forms wavefront_compute/ctx.rs:34-57): hit_distance (world), bary_coord (u,v) with
+ * p = v0 + u*e1 + v*e2, primitive_id (original triangle index of the geometry), geometry_id,
+ * instance_id (slot in BVH-sorted tlas_data), instance_custom_id, hit_kind.
+ * Miss: instance_id == primitive_id == RDN_INVALID_ID, t == ray.tmax, hit_kind == 0. */
+typedef struct rdn_hit {
+  float t, u, v;
+  uint32_t primitive_id, geometry_id, instance_id, instance_custom_id, hit_kind;
+} rdn_hit;
+
+/* BottomLevelAccelerationStructureBuildSource, api/backend.rs:104-118.
+ * kind 0 = Triangles{positions, indices (NULL => non-indexed)}, kind 1 = AABBs (accepted and ignored,
+ * exactly as the reference's naive builder does, geometry/naive/mod.rs:201-237). */
+typedef struct rdn_blas_geometry {
+  const float *positions;   /* 3 floats per vertex (or 6 per AABB) */
+  uint64_t n_positions;     /* vertex (or AABB) count */
+  const uint32_t *indices;  /* may be NULL */
+  uint64_t n_indices;
+  uint32_t flags;           /* RDN_GEOMETRY_FLAG_* */
+  uint32_t kind;
+} rdn_blas_geometry;
+
+/* TopLevelAccelerationStructureSourceInstance, api/backend.rs:160-167.  transform is the reference's
+ * column-major Mat4 (a1..d4, math/algebra/src/mat/mat4.rs:9-14). */
+typedef struct rdn_instance {
+  float transform[16];
+  uint32_t instance_custom_index, mask, instance_shader_binding_table_record_offset, flags, blas_handle;
+} rdn_instance;
+
+/* The reference's traversal counters (naive/traverse_cpu.rs:37-41) + instances entered + candidates the
+ * reference's RayRange::update_far asserts would have aborted on (traverse_cpu.rs:272-276). */
+typedef struct rdn_counters { uint64_t bvh_visit, bvh_hit, tri_visit, tri_hit, inst_visit, ref_abort; } rdn_counters;
+
+/* traversal order selection for rdn_rt_trace_closest_device */
+typedef enum rdn_trace_mode {
+  RDN_TRACE_AUTO = 0,            /* ordered traversal + exact tie resolution (default) */
+  RDN_TRACE_REFERENCE_ORDER = 1  /* the reference's threaded pre-order walk, one ray per thread */
+} rdn_trace_mode;
+
+typedef struct rdn_trace_stats {
+  uint64_t rays, tie_rays;       /* rays re-walked in reference order to resolve a near-tie */
+  uint32_t kernel_launches;      /* kernels this call launched */
+  float kernel_ms;               /* device time of the traversal kernels (CUDA events on the call's stream) */
+} rdn_trace_stats;
+
+typedef struct rdn_rt_scene rdn_rt_scene;   /* opaque: NaiveSahBVHSystem (geometry/naive/mod.rs:495-610) */
+
+/* ---- scene lifetime ----
+ * n_devices CUDA devices; the flattened scene is replicated to each on commit and host-buffer traces
+ * are sharded across them by ray tile.  (One process per GPU uses n_devices = 1.) */
+int rdn_rt_scene_create(int n_devices, const int *device_ids, rdn_rt_scene **out);
+void rdn_rt_scene_destroy(rdn_rt_scene *scene);
+
+/* ---- GPUAccelerationStructureSystemProvider (api/backend.rs:120-142) ---- */
+int rdn_rt_blas_create(rdn_rt_scene *scene, const rdn_blas_geometry *geometries, uint32_t n, uint32_t *out_handle);
+                                                            /* create_bottom_level_acceleration_structure */
+int rdn_rt_blas_destroy(rdn_rt_scene *scene, uint32_t handle); /* delete_bottom_level_acceleration_structure */
+int rdn_rt_tlas_create(rdn_rt_scene *scene, const rdn_instance *instances, uint32_t n, uint32_t *out_handle);
+                                                            /* create_top_level_acceleration_structure */
+int rdn_rt_tlas_destroy(rdn_rt_scene *scene, uint32_t handle); /* delete_top_level_acceleration_structure */
+int rdn_rt_bind_tlas(rdn_rt_scene *scene, const uint32_t *handles, uint32_t n);   /* bind_tlas */
+uint32_t rdn_rt_bind_tlas_max_len(const rdn_rt_scene *scene);                     /* bind_tlas_max_len */
+
+/* Lazy build -> flatten -> upload -> replicate; what create_comp_instance triggers through
+ * get_or_build_gpu_data (geometry/naive/mod.rs:521-536,561-567).  Idempotent; traces call it implicitly. */
+int rdn_rt_commit(rdn_rt_scene *scene);
+
+/* ---- ...InvocationTraversable::traverse, batched (geometry/mod.rs:16-25; CPU twin
+ *      NaiveSahBvhCpu::traverse, naive/traverse_cpu.rs:52-245) ---- */
+/* host buffers: H2D, traversal, D2H pipelined inside the call; sharded over the scene's devices */
+int rdn_rt_trace_closest(rdn_rt_scene *scene, const rdn_launch *launch, const rdn_ray *rays, uint64_t n,
+                         rdn_hit *out_hits);
+/* device-resident buffers on device `device_index` (index into the scene's device list); asynchronous on
+ * `cuda_stream` (a cudaStream_t, 0 = default stream) unless `stats` is non-NULL (then it synchronises). */
+int rdn_rt_trace_closest_device(rdn_rt_scene *scene, int device_index, const rdn_launch *launch,
+                                const rdn_ray *d_rays, uint64_t n, rdn_hit *d_hits, void *cuda_stream,
+                                int mode, rdn_trace_stats *stats);
+/* reference-order walk with the reference's visit counters (host buffers; for parity / bytes model) */
+int rdn_rt_trace_counted(rdn_rt_scene *scene, const rdn_launch *launch, const rdn_ray *rays, uint64_t n,
+                         rdn_hit *out_hits, rdn_counters *out_counters);
+
+/* ---- wavefront active-list compaction: use_stream_compaction
+ *      (shader/parallel-compute/src/stream_compaction.rs:3-45) as used by use_compact_alive_tasks
+ *      (shader/task-graph/src/runtime/task_group.rs:220-278).  Stable; out has n slots, zero past *out_n. ---- */
+int rdn_rt_compact_u32(rdn_rt_scene *scene, const uint32_t *in, const uint8_t *keep, uint64_t n,
+                       uint32_t *out, uint64_t *out_n);
+int rdn_rt_compact_u32_device(rdn_rt_scene *scene, int device_index, const uint32_t *d_in, const uint8_t *d_keep,
+                              uint64_t n, uint32_t *d_out, uint64_t *d_out_n, void *cuda_stream);
+
+/* ---- replication of the flattened scene (one contiguous device blob) for one-process-per-GPU drivers:
+ *      rank 0 commits, broadcasts the blob (NCCL over NVLink), the other ranks adopt it. ---- */
+int rdn_rt_scene_blob(rdn_rt_scene *scene, int device_index, void **out_device_ptr, uint64_t *out_bytes);
+int rdn_rt_scene_adopt_blob(rdn_rt_scene *scene, int device_index, const void *d_blob, uint64_t bytes);
+
+/* ---- flattened reference-layout arrays, copied to host, for cross-checking the flattener ---- */
+typedef enum rdn_array_id {
+  RDN_ARRAY_TLAS_BINDING = 0, RDN_ARRAY_TLAS_BVH_ROOT, RDN_ARRAY_TLAS_BVH_FOREST, RDN_ARRAY_TLAS_BOUNDING,
+  RDN_ARRAY_INSTANCES, RDN_ARRAY_BLAS_META, RDN_ARRAY_GEOMETRY_META, RDN_ARRAY_TRI_BVH_FOREST,
+  RDN_ARRAY_TRIANGLES, RDN_ARRAY_SLOT_INFO, RDN_ARRAY_WIDE_NODES, RDN_ARRAY_COUNT
+} rdn_array_id;
+int rdn_rt_scene_array(rdn_rt_scene *scene, int array_id, void *out, uint64_t capacity_bytes, uint64_t *out_bytes);
+
+/* ---- space-query surface: FlattenBVH::new (content/space/src/bvh/mod.rs:55-79) and
+ *      intersect_nearest_bvh (content/mesh/core/src/feature/bvh.rs:57-86) ---- */
+typedef struct rdn_flat_bvh rdn_flat_bvh;
+typedef struct rdn_tree_build_option { uint64_t max_tree_depth, bin_size; } rdn_tree_build_option; /* utils.rs:20-32 */
+typedef enum rdn_bvh_strategy { RDN_BVH_SAH = 0, RDN_BVH_BALANCE_TREE = 1 } rdn_bvh_strategy;
+typedef struct rdn_flat_bvh_node {          /* FlattenBVHNode, content/space/src/bvh/node.rs:5-27 */
+  float bounding_min[3], bounding_max[3];
+  uint64_t primitive_start, primitive_end, self_index, left_count;
+  int32_t has_child, split_axis;
+} rdn_flat_bvh_node;
+typedef enum rdn_face_side { RDN_FACE_FRONT = 0, RDN_FACE_BACK = 1, RDN_FACE_DOUBLE = 2 } rdn_face_side;
+typedef struct rdn_mesh_view { const float *positions; uint64_t n_positions; const uint32_t *indices; uint64_t n_indices; } rdn_mesh_view;
+/* MeshBufferHitPoint (content/mesh/core/src/feature/intersection.rs:42-45): hit == 0 => OptionalNearest::none */
+typedef struct rdn_mesh_hit { float px, py, pz, distance; uint32_t primitive_index, hit, pad0, pad1; } rdn_mesh_hit;
+
+int rdn_bvh_build(const float *boxes_min_max6, uint64_t n, int strategy, uint32_t sah_buckets,
+                  const rdn_tree_build_option *option, rdn_flat_bvh **out);
+void rdn_bvh_destroy(rdn_flat_bvh *bvh);
+int rdn_bvh_nodes(const rdn_flat_bvh *bvh, const rdn_flat_bvh_node **out_nodes, uint64_t *out_n);
+int rdn_bvh_sorted_primitive_index(const rdn_flat_bvh *bvh, const uint64_t **out_index, uint64_t *out_n);
+/* build_bvh_for_abstract_mesh over an indexed triangle list (feature/bvh.rs:5-21) */
+int rdn_bvh_build_for_mesh(const rdn_mesh_view *mesh, int strategy, uint32_t sah_buckets,
+                           const rdn_tree_build_option *option, rdn_flat_bvh **out);
+/* intersect_nearest_bvh for a batch of rays on CUDA device `device` (host buffers) */
+int rdn_bvh_query_nearest(const rdn_flat_bvh *bvh, const rdn_mesh_view *mesh, const rdn_ray *rays, uint64_t n,
+                          uint32_t face_side, int device, rdn_mesh_hit *out);
+
+const char *rdn_rt_last_error(void);
+const char *rdn_rt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RDN_RT_H */

@@ -1,0 +1,495 @@
+/* ORACLE — TEST INFRASTRUCTURE ONLY.  BLAS/TLAS assembly + CPU traversal (path B).
+ *
+ * Follows /root/reference/shader/ray-tracing/src/backend/wavefront_compute/geometry:
+ *   naive/mod.rs:98-119    create/delete blas/tlas (handles = push index, never recycled)
+ *   naive/mod.rs:122-260   build_blas  (SAH::new(4), depth 50, bin 2; blas_box pushed PER GEOMETRY — kept as is)
+ *   naive/mod.rs:262-320   build_tlas  (SAH::new(4), depth 50, bin 10; FLIP_FACING xor when det(mat3) < 0)
+ *   naive/mod.rs:322-493   build (flatten_bvh_to_gpu_node, forest offsets)
+ *   naive/traverse_cpu.rs:52-319  NaiveSahBvhCpu::traverse, RayRange, TraverseBvhIteratorCpu
+ *   naive/flag.rs:6-117    TraverseFlags
+ *   mod.rs:44-64           intersect_ray_aabb_cpu
+ *   mod.rs:105-155         intersect_ray_triangle_cpu
+ *
+ * Deliberate, documented deviations (the reference has no defined result there):
+ *   - RayRange::update_far asserts (traverse_cpu.rs:272-276) abort the reference process; here the
+ *     candidate is rejected and counted in counters.ref_abort (NaN distance from zero-area triangles,
+ *     or distance rounding outside [near, far]).
+ *   - out-of-range handles / deleted BLAS referenced by an instance panic in the reference
+ *     (naive/mod.rs:273-275 unwrap); orc_scene_build returns a negative code instead.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include "oracle.h"
+
+/* ---- flag constants (api/ty.rs:102-159, naive/flag.rs:6-25) ---- */
+#define F_FORCE_OPAQUE 0x01u
+#define F_FORCE_NON_OPAQUE 0x02u
+#define F_ACCEPT_FIRST_HIT_AND_END_SEARCH 0x04u
+#define F_CULL_BACK_FACING_TRIANGLES 0x10u
+#define F_CULL_FRONT_FACING_TRIANGLES 0x20u
+#define F_CULL_OPAQUE 0x40u
+#define F_CULL_NON_OPAQUE 0x80u
+#define F_SKIP_TRIANGLES 0x100u
+#define F_TRIANGLE_FLIP_FACING 0x400u
+#define GI_TRIANGLE_FACING_CULL_DISABLE 0x1u
+#define GI_TRIANGLE_FLIP_FACING 0x2u
+#define GI_FORCE_OPAQUE 0x4u
+#define GI_FORCE_NO_OPAQUE 0x8u
+#define G_OPAQUE 0x1u
+#define HIT_KIND_FRONT 0xFEu
+#define HIT_KIND_BACK 0xFFu
+
+typedef struct { float *positions; uint64_t n_pos; uint32_t *indices; uint64_t n_idx; int has_indices; uint32_t flags; uint8_t is_aabb; } geom_src;
+typedef struct { geom_src *geoms; uint32_t n_geoms; int alive; } blas_src;
+typedef struct { orc_instance_src *inst; uint32_t n; int alive; } tlas_src;
+
+#define VEC(T) struct { T *p; uint64_t n, cap; }
+#define VEC_PUSH(v, val) do { if ((v).n == (v).cap) { (v).cap = (v).cap ? (v).cap * 2 : 16; (v).p = realloc((v).p, (v).cap * sizeof(*(v).p)); } (v).p[(v).n++] = (val); } while (0)
+#define VEC_FREE(v) do { free((v).p); (v).p = NULL; (v).n = (v).cap = 0; } while (0)
+
+struct orc_scene {
+  VEC(blas_src) blas;
+  VEC(tlas_src) tlas;
+  VEC(uint32_t) binding;
+  /* NaiveSahBvhCpu */
+  VEC(uint32_t) tlas_bvh_root;
+  VEC(orc_dev_node) tlas_bvh_forest;
+  VEC(orc_dev_instance) tlas_data;
+  VEC(orc_tlas_bounding) tlas_bounding;
+  VEC(orc_blas_meta) blas_meta_info;
+  VEC(orc_geom_meta) tri_bvh_root;
+  VEC(orc_dev_node) tri_bvh_forest;
+  VEC(uint32_t) indices_redirect;
+  VEC(uint32_t) indices;
+  VEC(ov3) vertices;
+  uint64_t balance_fallbacks, balance_fallbacks_gt10;
+  int built;
+};
+
+orc_scene *orc_scene_new(void) { return (orc_scene *)calloc(1, sizeof(orc_scene)); }
+
+static void free_built(orc_scene *s) {
+  VEC_FREE(s->tlas_bvh_root); VEC_FREE(s->tlas_bvh_forest); VEC_FREE(s->tlas_data); VEC_FREE(s->tlas_bounding);
+  VEC_FREE(s->blas_meta_info); VEC_FREE(s->tri_bvh_root); VEC_FREE(s->tri_bvh_forest);
+  VEC_FREE(s->indices_redirect); VEC_FREE(s->indices); VEC_FREE(s->vertices);
+  s->built = 0;
+}
+static void free_blas(blas_src *b) {
+  for (uint32_t g = 0; g < b->n_geoms; g++) { free(b->geoms[g].positions); free(b->geoms[g].indices); }
+  free(b->geoms); b->geoms = NULL; b->n_geoms = 0; b->alive = 0;
+}
+void orc_scene_free(orc_scene *s) {
+  if (!s) return;
+  free_built(s);
+  for (uint64_t i = 0; i < s->blas.n; i++) free_blas(&s->blas.p[i]);
+  for (uint64_t i = 0; i < s->tlas.n; i++) free(s->tlas.p[i].inst);
+  VEC_FREE(s->blas); VEC_FREE(s->tlas); VEC_FREE(s->binding);
+  free(s);
+}
+
+uint32_t orc_scene_create_blas(orc_scene *s, uint32_t n_geoms, const float *const *positions, const uint64_t *n_pos,
+                               const uint32_t *const *indices, const uint64_t *n_idx, const uint32_t *flags,
+                               const uint8_t *is_aabb) {
+  blas_src b;
+  b.n_geoms = n_geoms; b.alive = 1;
+  b.geoms = (geom_src *)calloc(n_geoms ? n_geoms : 1, sizeof(geom_src));
+  for (uint32_t g = 0; g < n_geoms; g++) {
+    geom_src *q = &b.geoms[g];
+    q->n_pos = n_pos[g];
+    q->positions = (float *)malloc((q->n_pos ? q->n_pos : 1) * 3 * sizeof(float));
+    memcpy(q->positions, positions[g], q->n_pos * 3 * sizeof(float));
+    q->has_indices = indices && indices[g] != NULL;
+    q->n_idx = q->has_indices ? n_idx[g] : 0;
+    q->indices = NULL;
+    if (q->has_indices) {
+      q->indices = (uint32_t *)malloc((q->n_idx ? q->n_idx : 1) * sizeof(uint32_t));
+      memcpy(q->indices, indices[g], q->n_idx * sizeof(uint32_t));
+    }
+    q->flags = flags[g];
+    q->is_aabb = is_aabb ? is_aabb[g] : 0;
+  }
+  s->built = 0;
+  VEC_PUSH(s->blas, b);
+  return (uint32_t)(s->blas.n - 1);
+}
+void orc_scene_delete_blas(orc_scene *s, uint32_t h) { if (h < s->blas.n) { free_blas(&s->blas.p[h]); s->built = 0; } }
+uint32_t orc_scene_create_tlas(orc_scene *s, const orc_instance_src *inst, uint32_t n) {
+  tlas_src t; t.n = n; t.alive = 1;
+  t.inst = (orc_instance_src *)malloc((n ? n : 1) * sizeof(orc_instance_src));
+  memcpy(t.inst, inst, n * sizeof(orc_instance_src));
+  s->built = 0;
+  VEC_PUSH(s->tlas, t);
+  return (uint32_t)(s->tlas.n - 1);
+}
+void orc_scene_delete_tlas(orc_scene *s, uint32_t h) {
+  if (h < s->tlas.n) { free(s->tlas.p[h].inst); s->tlas.p[h].inst = NULL; s->tlas.p[h].n = 0; s->tlas.p[h].alive = 0; s->built = 0; }
+}
+void orc_scene_bind_tlas(orc_scene *s, const uint32_t *handles, uint32_t n) {
+  s->binding.n = 0;
+  for (uint32_t i = 0; i < n; i++) VEC_PUSH(s->binding, handles[i]);
+  s->built = 0;
+}
+
+static orc_dev_node flatten_node(const orc_bvh_node *n, uint32_t hit, uint32_t miss, uint32_t next_offset, uint32_t primitive_offset) {
+  orc_dev_node d;
+  memset(&d, 0, sizeof(d));
+  d.aabb_min = n->bounding.min;
+  d.aabb_max = n->bounding.max;
+  d.hit_next = hit != ORC_INVALID_NEXT ? hit + next_offset : ORC_INVALID_NEXT;
+  d.miss_next = miss != ORC_INVALID_NEXT ? miss + next_offset : ORC_INVALID_NEXT;
+  d.range_x = (uint32_t)n->start + primitive_offset;
+  d.range_y = (uint32_t)n->end + primitive_offset;
+  return d;
+}
+
+typedef struct { int some; obox box; } opt_box;
+
+int orc_scene_build(orc_scene *s) {
+  free_built(s);
+  s->balance_fallbacks = s->balance_fallbacks_gt10 = 0;
+  VEC(opt_box) blas_box; memset(&blas_box, 0, sizeof(blas_box));
+  int rc = 0;
+
+  /* ---- build_blas + the tri_bvh_forest part of build ---- */
+  for (uint64_t bi = 0; bi < s->blas.n; bi++) {
+    blas_src *blas = &s->blas.p[bi];
+    if (!blas->alive) {
+      orc_blas_meta z = {0, 0};
+      VEC_PUSH(s->blas_meta_info, z);
+      opt_box none; memset(&none, 0, sizeof(none));
+      VEC_PUSH(blas_box, none);
+      continue;
+    }
+    uint32_t tri_start = (uint32_t)s->tri_bvh_root.n;
+    for (uint32_t g = 0; g < blas->n_geoms; g++) {
+      geom_src *src = &blas->geoms[g];
+      obox root_box = obox_empty();
+      if (!src->is_aabb) {
+        uint32_t primitive_start = (uint32_t)(s->indices.n / 3);
+        uint32_t vertex_start = (uint32_t)s->vertices.n;
+        uint64_t n_idx = src->has_indices ? src->n_idx : src->n_pos;
+        uint64_t n_tri = n_idx / 3;
+        for (uint64_t v = 0; v < src->n_pos; v++)
+          VEC_PUSH(s->vertices, ov3_new(src->positions[3 * v], src->positions[3 * v + 1], src->positions[3 * v + 2]));
+        obox *boxes = (obox *)malloc((n_tri ? n_tri : 1) * sizeof(obox));
+        for (uint64_t t = 0; t < n_tri; t++) {
+          obox b = obox_empty();
+          for (int k = 0; k < 3; k++) {
+            uint64_t idx = src->has_indices ? src->indices[3 * t + k] : (3 * t + k);
+            if (idx >= src->n_pos) { rc = -2; idx = 0; } /* reference: index out of bounds panic */
+            obox_expand_point(&b, ov3_new(src->positions[3 * idx], src->positions[3 * idx + 1], src->positions[3 * idx + 2]));
+          }
+          boxes[t] = b;
+        }
+        orc_bvh *bvh = orc_bvh_build(boxes, n_tri, ORC_STRATEGY_SAH, 4, 50, 2);
+        free(boxes);
+        if (bvh->error) rc = -3;
+        s->balance_fallbacks += bvh->balance_fallbacks;
+        s->balance_fallbacks_gt10 += bvh->balance_fallbacks_gt10;
+        obox_expand_box(&root_box, bvh->nodes[0].bounding);
+        uint32_t *next = (uint32_t *)malloc(bvh->n_nodes * 2 * sizeof(uint32_t));
+        orc_bvh_compute_next(bvh, next);
+        uint32_t raw_primitive_start = (uint32_t)(s->indices.n / 3);
+        for (uint64_t i = 0; i < bvh->n_prims; i++)
+          VEC_PUSH(s->indices_redirect, raw_primitive_start + (uint32_t)bvh->sorted_primitive_index[i]);
+        for (uint64_t t = 0; t < n_tri; t++)
+          for (int k = 0; k < 3; k++) {
+            uint32_t idx = src->has_indices ? src->indices[3 * t + k] : (uint32_t)(3 * t + k);
+            VEC_PUSH(s->indices, vertex_start + idx);
+          }
+        /* forest append (naive/mod.rs:368-384) */
+        uint32_t bvh_start = (uint32_t)s->tri_bvh_forest.n;
+        orc_geom_meta gm = {bvh_start, g, primitive_start, src->flags};
+        VEC_PUSH(s->tri_bvh_root, gm);
+        for (uint64_t i = 0; i < bvh->n_nodes; i++)
+          VEC_PUSH(s->tri_bvh_forest, flatten_node(&bvh->nodes[i], next[2 * i], next[2 * i + 1], bvh_start, primitive_start));
+        free(next);
+        orc_bvh_free(bvh);
+      }
+      opt_box ob; ob.some = 1; ob.box = root_box;
+      VEC_PUSH(blas_box, ob); /* per geometry, exactly as naive/mod.rs:239 */
+    }
+    orc_blas_meta m = {tri_start, (uint32_t)s->tri_bvh_root.n};
+    VEC_PUSH(s->blas_meta_info, m);
+  }
+
+  /* ---- build_tlas per TLAS ---- */
+  for (uint64_t ti = 0; ti < s->tlas.n; ti++) {
+    tlas_src *tlas = &s->tlas.p[ti];
+    if (!tlas->alive) { VEC_PUSH(s->tlas_bvh_root, ORC_INVALID_NEXT); continue; }
+    uint32_t bvh_start = (uint32_t)s->tlas_bvh_forest.n;
+    uint32_t primitive_start = (uint32_t)s->tlas_data.n;
+    obox *aabbs = (obox *)malloc((tlas->n ? tlas->n : 1) * sizeof(obox));
+    for (uint32_t i = 0; i < tlas->n; i++) {
+      const orc_instance_src *src = &tlas->inst[i];
+      om4 m; memcpy(&m, src->transform, sizeof(m));
+      if (src->blas_handle >= blas_box.n || !blas_box.p[src->blas_handle].some) {
+        rc = -4; aabbs[i] = obox_empty(); continue; /* reference: unwrap() on None / OOB panic */
+      }
+      aabbs[i] = obox_apply_matrix(blas_box.p[src->blas_handle].box, m);
+    }
+    orc_bvh *bvh = orc_bvh_build(aabbs, tlas->n, ORC_STRATEGY_SAH, 4, 50, 10);
+    if (bvh->error) rc = -3;
+    s->balance_fallbacks += bvh->balance_fallbacks;
+    s->balance_fallbacks_gt10 += bvh->balance_fallbacks_gt10;
+    uint32_t *next = (uint32_t *)malloc(bvh->n_nodes * 2 * sizeof(uint32_t));
+    orc_bvh_compute_next(bvh, next);
+    for (uint64_t k = 0; k < bvh->n_prims; k++) {
+      uint64_t box_idx = bvh->sorted_primitive_index[k];
+      const orc_instance_src *src = &tlas->inst[box_idx];
+      om4 m; memcpy(&m, src->transform, sizeof(m));
+      uint32_t flags = src->flags;
+      if (om3_det(om4_to_mat3(m)) < 0.0f) flags ^= GI_TRIANGLE_FLIP_FACING;
+      orc_dev_instance di;
+      memset(&di, 0, sizeof(di));
+      di.transform = m;
+      di.transform_inv = om4_inverse_or_identity(m);
+      di.instance_custom_index = src->instance_custom_index;
+      di.sbt_offset = src->sbt_offset;
+      di.flags = flags;
+      di.blas = src->blas_handle;
+      orc_tlas_bounding tb;
+      tb.world_min = aabbs[box_idx].min; tb.world_max = aabbs[box_idx].max;
+      tb.mask = src->mask; tb.flags = flags;
+      VEC_PUSH(s->tlas_data, di);
+      VEC_PUSH(s->tlas_bounding, tb);
+    }
+    VEC_PUSH(s->tlas_bvh_root, bvh_start);
+    for (uint64_t i = 0; i < bvh->n_nodes; i++)
+      VEC_PUSH(s->tlas_bvh_forest, flatten_node(&bvh->nodes[i], next[2 * i], next[2 * i + 1], bvh_start, primitive_start));
+    free(next); free(aabbs);
+    orc_bvh_free(bvh);
+  }
+  VEC_FREE(blas_box);
+  s->built = (rc == 0);
+  return rc;
+}
+
+void orc_scene_get_view(const orc_scene *s, orc_scene_view *o) {
+  o->tlas_binding = s->binding.p; o->n_tlas_binding = s->binding.n;
+  o->tlas_bvh_root = s->tlas_bvh_root.p; o->n_tlas_bvh_root = s->tlas_bvh_root.n;
+  o->tlas_bvh_forest = s->tlas_bvh_forest.p; o->n_tlas_bvh_forest = s->tlas_bvh_forest.n;
+  o->tlas_data = s->tlas_data.p; o->n_tlas_data = s->tlas_data.n;
+  o->tlas_bounding = s->tlas_bounding.p; o->n_tlas_bounding = s->tlas_bounding.n;
+  o->blas_meta_info = s->blas_meta_info.p; o->n_blas_meta_info = s->blas_meta_info.n;
+  o->tri_bvh_root = s->tri_bvh_root.p; o->n_tri_bvh_root = s->tri_bvh_root.n;
+  o->tri_bvh_forest = s->tri_bvh_forest.p; o->n_tri_bvh_forest = s->tri_bvh_forest.n;
+  o->indices_redirect = s->indices_redirect.p; o->n_indices_redirect = s->indices_redirect.n;
+  o->indices = s->indices.p; o->n_indices = s->indices.n;
+  o->vertices = (const float *)s->vertices.p; o->n_vertices = s->vertices.n;
+  o->balance_fallbacks = s->balance_fallbacks; o->balance_fallbacks_gt10 = s->balance_fallbacks_gt10;
+}
+
+/* ---------------- traversal ---------------- */
+
+static inline int intersect_ray_aabb(ov3 o, ov3 d, float t_min, float t_max, ov3 bmin, ov3 bmax) {
+  ov3 inv_d = ov3_div(ov3_new(1.0f, 1.0f, 1.0f), d);
+  ov3 t0 = ov3_mul(ov3_sub(bmin, o), inv_d);
+  ov3 t1 = ov3_mul(ov3_sub(bmax, o), inv_d);
+  ov3 t_near = ov3_min(t0, t1);
+  ov3 t_far = ov3_max(t0, t1);
+  float t_near_max = ov3_max_channel(t_near);
+  float t_far_min = ov3_min_channel(t_far);
+  return t_near_max <= t_far_min && t_min < t_far_min && t_near_max < t_max;
+}
+
+/* returns (sign, t, u, v); sign == 0 -> miss */
+static inline ov4 intersect_ray_triangle(ov3 origin, ov3 direction, float rx, float ry, ov3 v0, ov3 v1, ov3 v2,
+                                         int cull_enable, int cull_back) {
+  ov4 zero = {0, 0, 0, 0};
+  ov3 e1 = ov3_sub(v1, v0);
+  ov3 e2 = ov3_sub(v2, v0);
+  ov3 normal = ov3_normalize(ov3_cross(e1, e2));
+  float b = ov3_dot(normal, direction);
+  float sign = of_signum(b);
+  if (cull_enable) {
+    int pass = cull_back != (b < 0.0f);
+    if (!pass) return zero;
+  }
+  ov3 w0 = ov3_sub(origin, v0);
+  float a = -ov3_dot(normal, w0);
+  float t = a / b;
+  if (t < rx || t > ry) return zero;
+  ov3 p = ov3_add(origin, ov3_scale(direction, t));
+  float uu = ov3_dot(e1, e1);
+  float uv = ov3_dot(e1, e2);
+  float vv = ov3_dot(e2, e2);
+  ov3 w = ov3_sub(p, v0);
+  float wu = ov3_dot(w, e1);
+  float wv = ov3_dot(w, e2);
+  float inverse_d = 1.0f / (uv * uv - uu * vv);
+  float u = (uv * wv - vv * wu) * inverse_d;
+  if (u < 0.0f || u > 1.0f) return zero;
+  float v = (uv * wu - uu * wv) * inverse_d;
+  if (v < 0.0f || (u + v) > 1.0f) return zero;
+  ov4 r = {sign, t, u, v};
+  return r;
+}
+
+static inline uint32_t merge_geometry_instance_flag(uint32_t f, uint32_t gi) {
+  if (gi & GI_TRIANGLE_FACING_CULL_DISABLE) f &= ~(F_CULL_BACK_FACING_TRIANGLES | F_CULL_FRONT_FACING_TRIANGLES);
+  if (gi & GI_TRIANGLE_FLIP_FACING) f ^= F_TRIANGLE_FLIP_FACING;
+  if (gi & GI_FORCE_OPAQUE) f |= F_FORCE_OPAQUE;
+  if (gi & GI_FORCE_NO_OPAQUE) f |= F_FORCE_NON_OPAQUE;
+  return f;
+}
+
+/* threaded walk: returns next leaf index or INVALID */
+static inline uint32_t bvh_iter_next(const orc_dev_node *bvh, uint32_t *curr_idx, ov3 o, ov3 d, float near, const float *far,
+                                     float scaling, orc_counters *c) {
+  while (*curr_idx != ORC_INVALID_NEXT) {
+    c->bvh_visit++;
+    const orc_dev_node *node = &bvh[*curr_idx];
+    if (intersect_ray_aabb(o, d, near * scaling, *far * scaling, node->aabb_min, node->aabb_max)) {
+      uint32_t curr = *curr_idx;
+      *curr_idx = node->hit_next;
+      if (node->hit_next == node->miss_next) { c->bvh_hit++; return curr; }
+    } else {
+      *curr_idx = node->miss_next;
+    }
+  }
+  return ORC_INVALID_NEXT;
+}
+
+static void traverse_one(const orc_scene *s, const orc_launch *L, const orc_ray *ray, orc_hit *out, orc_counters *c) {
+  out->t = ray->tmax; out->u = 0; out->v = 0;
+  out->primitive_id = out->geometry_id = out->instance_id = out->instance_custom_id = 0xFFFFFFFFu;
+  out->hit_kind = 0;
+
+  const uint32_t flags0 = L->ray_flags;
+  const float near = ray->tmin;
+  float far = ray->tmax;             /* the shared Rc<Cell<f32>> */
+  const ov3 ro = ov3_new(ray->ox, ray->oy, ray->oz);
+  const ov3 rd = ov3_new(ray->dx, ray->dy, ray->dz);
+
+  if (L->tlas_idx >= s->binding.n) return;
+  uint32_t handle = s->binding.p[L->tlas_idx];
+  if (handle >= s->tlas_bvh_root.n) return;
+  uint32_t tlas_cursor = s->tlas_bvh_root.p[handle];
+
+  for (;;) {
+    uint32_t leaf = bvh_iter_next(s->tlas_bvh_forest.p, &tlas_cursor, ro, rd, near, &far, 1.0f, c);
+    if (leaf == ORC_INVALID_NEXT) break;
+    const orc_dev_node *node = &s->tlas_bvh_forest.p[leaf];
+    for (uint32_t tlas_idx = node->range_x; tlas_idx < node->range_y; tlas_idx++) {
+      const orc_tlas_bounding *tb = &s->tlas_bounding.p[tlas_idx];
+      /* ORIGINAL ray.range, not the shrunken far (traverse_cpu.rs:80-86) */
+      if (!intersect_ray_aabb(ro, rd, ray->tmin, ray->tmax, tb->world_min, tb->world_max)) continue;
+      if ((L->cull_mask & tb->mask) == 0) continue;
+      c->inst_visit++;
+      const orc_dev_instance *td = &s->tlas_data.p[tlas_idx];
+      uint32_t blas_idx = td->blas;
+      uint32_t flags = merge_geometry_instance_flag(flags0, td->flags);
+
+      ov4 o4 = {ro.x, ro.y, ro.z, 1.0f};
+      o4 = om4_mul_v4(td->transform_inv, o4);
+      ov3 bo = ov3_divs(ov3_new(o4.x, o4.y, o4.z), o4.w);
+      ov3 bd = om3_mul_v3(om4_to_mat3(td->transform_inv), rd);
+      float scaling = ov3_length(bd);
+      bd = ov3_normalize(bd);
+
+      if (blas_idx >= s->blas_meta_info.n) continue;
+      const orc_blas_meta *bm = &s->blas_meta_info.p[blas_idx];
+      if (flags & F_SKIP_TRIANGLES) continue;
+
+      for (uint32_t tri_root_index = bm->tri_root_x; tri_root_index < bm->tri_root_y; tri_root_index++) {
+        orc_geom_meta geometry = s->tri_bvh_root.p[tri_root_index];
+        /* cull_geometry */
+        int geometry_opaque = (geometry.geometry_flags & G_OPAQUE) != 0;
+        int force_opaque = (flags & F_FORCE_OPAQUE) != 0, force_non_opaque = (flags & F_FORCE_NON_OPAQUE) != 0;
+        int cull_opaque = (flags & F_CULL_OPAQUE) != 0, cull_non_opaque = (flags & F_CULL_NON_OPAQUE) != 0;
+        int is_opaque = (geometry_opaque || force_opaque) && !force_non_opaque;
+        int pass = (is_opaque && !cull_opaque) || (!is_opaque && !cull_non_opaque);
+        if (!pass) continue;
+        /* cull_triangle */
+        int flip = (flags & F_TRIANGLE_FLIP_FACING) != 0;
+        int cull_front = (flags & F_CULL_FRONT_FACING_TRIANGLES) != 0, cull_back_f = (flags & F_CULL_BACK_FACING_TRIANGLES) != 0;
+        int cull_enable = cull_front || cull_back_f;
+        int cull_back = (flip && cull_back_f) || (!flip && cull_front);
+
+        uint32_t cursor = geometry.bvh_root_idx;
+        for (;;) {
+          uint32_t bl = bvh_iter_next(s->tri_bvh_forest.p, &cursor, bo, bd, near, &far, scaling, c);
+          if (bl == ORC_INVALID_NEXT) break;
+          const orc_dev_node *bn = &s->tri_bvh_forest.p[bl];
+          for (uint32_t slot = bn->range_x; slot < bn->range_y; slot++) {
+            uint32_t tri_idx = s->indices_redirect.p[slot];
+            uint32_t i0 = s->indices.p[(uint64_t)tri_idx * 3], i1 = s->indices.p[(uint64_t)tri_idx * 3 + 1], i2 = s->indices.p[(uint64_t)tri_idx * 3 + 2];
+            ov3 v0 = s->vertices.p[i0], v1 = s->vertices.p[i1], v2 = s->vertices.p[i2];
+            c->tri_visit++;
+            ov4 isect = intersect_ray_triangle(bo, bd, near * scaling, far * scaling, v0, v1, v2, cull_enable, cull_back);
+            if (isect.x != 0.0f) {
+              float distance = isect.y / scaling;
+              uint32_t primitive_idx = tri_idx - geometry.primitive_start;
+              c->tri_hit++;
+              /* opaque -> ACCEPT; non-opaque -> any_hit(), fixed to ACCEPT here */
+              (void)is_opaque;
+              /* RayRange::update_far: assert!(near <= far); assert!(far <= self.far) */
+              if (!(near <= distance) || !(distance <= far)) { c->ref_abort++; continue; }
+              far = distance;
+              out->t = distance; out->u = isect.z; out->v = isect.w;
+              out->primitive_id = primitive_idx; out->geometry_id = geometry.geometry_idx;
+              out->instance_id = tlas_idx; out->instance_custom_id = td->instance_custom_index;
+              out->hit_kind = isect.x < 0.0f ? HIT_KIND_BACK : HIT_KIND_FRONT;
+              if (flags & F_ACCEPT_FIRST_HIT_AND_END_SEARCH) return;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+typedef struct { const orc_scene *s; const orc_launch *L; const orc_ray *rays; orc_hit *hits; uint64_t begin, end; orc_counters c; } trace_job;
+static void *trace_worker(void *p) {
+  trace_job *j = (trace_job *)p;
+  for (uint64_t i = j->begin; i < j->end; i++) traverse_one(j->s, j->L, &j->rays[i], &j->hits[i], &j->c);
+  return NULL;
+}
+
+int orc_scene_trace(const orc_scene *s, const orc_launch *launch, const orc_ray *rays, uint64_t n_rays,
+                    orc_hit *out_hits, orc_counters *counters, int n_threads) {
+  if (!s->built) return -1;
+  if (n_threads < 1) n_threads = 1;
+  if ((uint64_t)n_threads > n_rays) n_threads = n_rays ? (int)n_rays : 1;
+  trace_job *jobs = (trace_job *)calloc(n_threads, sizeof(trace_job));
+  pthread_t *th = (pthread_t *)calloc(n_threads, sizeof(pthread_t));
+  uint64_t chunk = (n_rays + n_threads - 1) / n_threads;
+  for (int t = 0; t < n_threads; t++) {
+    jobs[t].s = s; jobs[t].L = launch; jobs[t].rays = rays; jobs[t].hits = out_hits;
+    jobs[t].begin = (uint64_t)t * chunk < n_rays ? (uint64_t)t * chunk : n_rays;
+    jobs[t].end = jobs[t].begin + chunk < n_rays ? jobs[t].begin + chunk : n_rays;
+  }
+  if (n_threads == 1) trace_worker(&jobs[0]);
+  else {
+    for (int t = 0; t < n_threads; t++) pthread_create(&th[t], NULL, trace_worker, &jobs[t]);
+    for (int t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
+  }
+  if (counters) {
+    memset(counters, 0, sizeof(*counters));
+    for (int t = 0; t < n_threads; t++) {
+      counters->bvh_visit += jobs[t].c.bvh_visit; counters->bvh_hit += jobs[t].c.bvh_hit;
+      counters->tri_visit += jobs[t].c.tri_visit; counters->tri_hit += jobs[t].c.tri_hit;
+      counters->inst_visit += jobs[t].c.inst_visit; counters->ref_abort += jobs[t].c.ref_abort;
+    }
+  }
+  free(jobs); free(th);
+  return 0;
+}
+
+/* ---- Mat4 helpers for KATs / scene builders ---- */
+void orc_mat4_compose(const float *a16, const float *b16, float *out16) {
+  om4 a, b; memcpy(&a, a16, sizeof(a)); memcpy(&b, b16, sizeof(b));
+  om4 r = om4_mul(a, b); memcpy(out16, &r, sizeof(r));
+}
+void orc_mat4_inverse_or_identity(const float *m16, float *out16) {
+  om4 m; memcpy(&m, m16, sizeof(m));
+  om4 r = om4_inverse_or_identity(m); memcpy(out16, &r, sizeof(r));
+}
+void orc_mat4_mul_vec4(const float *m16, const float *v4, float *out4) {
+  om4 m; memcpy(&m, m16, sizeof(m));
+  ov4 v = {v4[0], v4[1], v4[2], v4[3]};
+  ov4 r = om4_mul_v4(m, v);
+  out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = r.w;
+}

@@ -1,0 +1,427 @@
+"""Host-side mirror of the reference interface over the C ABI (``include/rdn_rt.h``).
+
+Names, argument meaning and error behaviour follow rendiation:
+
+* :class:`NaiveSahBVHSystem` — ``GPUAccelerationStructureSystemProvider`` (shader/ray-tracing/src/api/backend.rs:120-142)
+  as implemented by ``NaiveSahBVHSystem`` (…/geometry/naive/mod.rs:495-610): ``create_bottom_level_acceleration_structure``,
+  ``delete_…``, ``create_top_level_acceleration_structure``, ``delete_…``, ``bind_tlas``, ``bind_tlas_max_len``; plus the
+  batched replacement of ``…InvocationTraversable::traverse`` (geometry/mod.rs:16-25): ``trace_closest_batch``.
+* :class:`FlattenBVH`, :class:`TreeBuildOption`, ``SAH`` / ``BalanceTree`` — content/space/src/bvh, utils.rs:20-37;
+  :func:`build_bvh_for_abstract_mesh`, :func:`intersect_nearest_bvh` — content/mesh/core/src/feature/bvh.rs:5-86.
+* where the reference panics (= aborts, Cargo.toml:161-162) a :class:`RdnError` is raised instead.
+
+No CPU fallback exists: loading fails loudly when ``librdn_rt.so`` is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from .scenes import INSTANCE_DTYPE, RAY_DTYPE
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librdn_rt.so")
+
+HIT_DTYPE = np.dtype([("t", "f4"), ("u", "f4"), ("v", "f4"), ("primitive_id", "u4"), ("geometry_id", "u4"),
+                      ("instance_id", "u4"), ("instance_custom_id", "u4"), ("hit_kind", "u4")])
+MESH_HIT_DTYPE = np.dtype([("px", "f4"), ("py", "f4"), ("pz", "f4"), ("distance", "f4"),
+                           ("primitive_index", "u4"), ("hit", "u4"), ("pad0", "u4"), ("pad1", "u4")])
+FLAT_BVH_NODE_DTYPE = np.dtype([("bmin", "f4", (3,)), ("bmax", "f4", (3,)), ("start", "u8"), ("end", "u8"), ("self_index", "u8"),
+                                ("left_count", "u8"), ("has_child", "i4"), ("split_axis", "i4")])
+DEV_NODE_DTYPE = np.dtype([("aabb_min", "f4", (3,)), ("hit_next", "u4"), ("aabb_max", "f4", (3,)), ("miss_next", "u4"),
+                           ("range", "u4", (2,)), ("tail", "u4", (2,))])
+TLAS_BOUNDING_DTYPE = np.dtype([("world_min", "f4", (3,)), ("mask", "u4"), ("world_max", "f4", (3,)), ("flags", "u4")])
+INSTANCE_RECORD_DTYPE = np.dtype([("transform_inv", "f4", (16,)), ("instance_custom_index", "u4"), ("sbt_offset", "u4"),
+                                  ("flags", "u4"), ("blas", "u4")])
+GEOMETRY_META_DTYPE = np.dtype([("bvh_root_idx", "u4"), ("geometry_idx", "u4"), ("primitive_start", "u4"), ("geometry_flags", "u4"),
+                                ("wide_root", "u4"), ("pad", "u4", (3,))])
+TRI_RECORD_DTYPE = np.dtype([("n", "f4", (3,)), ("inv_d", "f4"), ("v0", "f4", (3,)), ("uu", "f4"),
+                             ("e1", "f4", (3,)), ("uv", "f4"), ("e2", "f4", (3,)), ("vv", "f4")])
+WIDE_NODE_DTYPE = np.dtype([("c0_min", "f4", (3,)), ("ref0", "u4"), ("c0_max", "f4", (3,)), ("ref1", "u4"),
+                            ("c1_min", "f4", (3,)), ("pad0", "u4"), ("c1_max", "f4", (3,)), ("pad1", "u4")])
+
+ARRAYS = {  # rdn_array_id -> (name, dtype)
+    0: ("tlas_binding", np.dtype("u4")), 1: ("tlas_root", np.dtype(("u4", (2,)))), 2: ("tlas_bvh_forest", DEV_NODE_DTYPE),
+    3: ("tlas_bounding", TLAS_BOUNDING_DTYPE), 4: ("instances", INSTANCE_RECORD_DTYPE), 5: ("blas_meta", np.dtype(("u4", (2,)))),
+    6: ("geometry_meta", GEOMETRY_META_DTYPE), 7: ("tri_bvh_forest", DEV_NODE_DTYPE), 8: ("triangles", TRI_RECORD_DTYPE),
+    9: ("slot_info", np.dtype(("u4", (2,)))), 10: ("wide_nodes", WIDE_NODE_DTYPE),
+}
+
+# RayFlagConfigRaw (api/ty.rs:102-114)
+RAY_FLAG_NONE = 0x00
+RAY_FLAG_FORCE_OPAQUE = 0x01
+RAY_FLAG_FORCE_NON_OPAQUE = 0x02
+RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH = 0x04
+RAY_FLAG_SKIP_CLOSEST_HIT_SHADER = 0x08
+RAY_FLAG_CULL_BACK_FACING_TRIANGLES = 0x10
+RAY_FLAG_CULL_FRONT_FACING_TRIANGLES = 0x20
+RAY_FLAG_CULL_OPAQUE = 0x40
+RAY_FLAG_CULL_NON_OPAQUE = 0x80
+RAY_FLAG_SKIP_TRIANGLES = 0x100
+RAY_FLAG_SKIP_PROCEDURAL_PRIMITIVES = 0x200
+# GeometryInstanceFlags / GeometryFlags / hit kinds (api/ty.rs:138-159)
+GEOMETRY_INSTANCE_TRIANGLE_FACING_CULL_DISABLE = 0x1
+GEOMETRY_INSTANCE_TRIANGLE_FLIP_FACING = 0x2
+GEOMETRY_INSTANCE_FORCE_OPAQUE = 0x4
+GEOMETRY_INSTANCE_FORCE_NO_OPAQUE = 0x8
+GEOMETRY_FLAG_OPAQUE = 0x1
+GEOMETRY_FLAG_NO_DUPLICATE_ANYHIT_INVOCATION = 0x2
+HIT_KIND_FRONT_FACING_TRIANGLE = 0xFE
+HIT_KIND_BACK_FACING_TRIANGLE = 0xFF
+INVALID_ID = 0xFFFFFFFF
+
+TRACE_AUTO, TRACE_REFERENCE_ORDER = 0, 1
+FACE_FRONT, FACE_BACK, FACE_DOUBLE = 0, 1, 2
+
+
+class RdnError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"rdn_rt error {code}: {message}")
+        self.code = code
+
+
+class _Launch(C.Structure):
+    _fields_ = [("ray_flags", C.c_uint32), ("cull_mask", C.c_uint32), ("tlas_idx", C.c_uint32), ("grid_width", C.c_uint32)]
+
+
+class _Geometry(C.Structure):
+    _fields_ = [("positions", C.c_void_p), ("n_positions", C.c_uint64), ("indices", C.c_void_p), ("n_indices", C.c_uint64),
+                ("flags", C.c_uint32), ("kind", C.c_uint32)]
+
+
+class _Counters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("bvh_visit", "bvh_hit", "tri_visit", "tri_hit", "inst_visit", "ref_abort")]
+
+
+class _TraceStats(C.Structure):
+    _fields_ = [("rays", C.c_uint64), ("tie_rays", C.c_uint64), ("kernel_launches", C.c_uint32), ("kernel_ms", C.c_float)]
+
+
+class _Option(C.Structure):
+    _fields_ = [("max_tree_depth", C.c_uint64), ("bin_size", C.c_uint64)]
+
+
+class _MeshView(C.Structure):
+    _fields_ = [("positions", C.c_void_p), ("n_positions", C.c_uint64), ("indices", C.c_void_p), ("n_indices", C.c_uint64)]
+
+
+EXPORTED_SYMBOLS = [
+    "rdn_rt_scene_create", "rdn_rt_scene_destroy", "rdn_rt_blas_create", "rdn_rt_blas_destroy", "rdn_rt_tlas_create",
+    "rdn_rt_tlas_destroy", "rdn_rt_bind_tlas", "rdn_rt_bind_tlas_max_len", "rdn_rt_commit", "rdn_rt_trace_closest",
+    "rdn_rt_trace_closest_device", "rdn_rt_trace_counted", "rdn_rt_compact_u32", "rdn_rt_compact_u32_device",
+    "rdn_rt_scene_blob", "rdn_rt_scene_adopt_blob", "rdn_rt_scene_array", "rdn_bvh_build", "rdn_bvh_destroy", "rdn_bvh_nodes",
+    "rdn_bvh_sorted_primitive_index", "rdn_bvh_build_for_mesh", "rdn_bvh_query_nearest", "rdn_rt_last_error", "rdn_rt_version",
+]
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load ``librdn_rt.so``; raises (no fallback) when the CUDA library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing — build it with `python -m rendiation_b200.build` "
+                          "(rendiation_b200 has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+    P = C.POINTER
+    L.rdn_rt_last_error.restype = C.c_char_p
+    L.rdn_rt_version.restype = C.c_char_p
+    L.rdn_rt_scene_create.argtypes = [i32, P(C.c_int), P(vp)]
+    L.rdn_rt_scene_destroy.argtypes = [vp]
+    L.rdn_rt_scene_destroy.restype = None
+    L.rdn_rt_blas_create.argtypes = [vp, P(_Geometry), u32, P(u32)]
+    L.rdn_rt_blas_destroy.argtypes = [vp, u32]
+    L.rdn_rt_tlas_create.argtypes = [vp, vp, u32, P(u32)]
+    L.rdn_rt_tlas_destroy.argtypes = [vp, u32]
+    L.rdn_rt_bind_tlas.argtypes = [vp, vp, u32]
+    L.rdn_rt_bind_tlas_max_len.argtypes = [vp]
+    L.rdn_rt_bind_tlas_max_len.restype = u32
+    L.rdn_rt_commit.argtypes = [vp]
+    L.rdn_rt_trace_closest.argtypes = [vp, P(_Launch), vp, u64, vp]
+    L.rdn_rt_trace_closest_device.argtypes = [vp, i32, P(_Launch), vp, u64, vp, vp, i32, P(_TraceStats)]
+    L.rdn_rt_trace_counted.argtypes = [vp, P(_Launch), vp, u64, vp, P(_Counters)]
+    L.rdn_rt_compact_u32.argtypes = [vp, vp, vp, u64, vp, P(u64)]
+    L.rdn_rt_compact_u32_device.argtypes = [vp, i32, vp, vp, u64, vp, vp, vp]
+    L.rdn_rt_scene_blob.argtypes = [vp, i32, P(vp), P(u64)]
+    L.rdn_rt_scene_adopt_blob.argtypes = [vp, i32, vp, u64]
+    L.rdn_rt_scene_array.argtypes = [vp, i32, vp, u64, P(u64)]
+    L.rdn_bvh_build.argtypes = [vp, u64, i32, u32, P(_Option), P(vp)]
+    L.rdn_bvh_build_for_mesh.argtypes = [P(_MeshView), i32, u32, P(_Option), P(vp)]
+    L.rdn_bvh_destroy.argtypes = [vp]
+    L.rdn_bvh_destroy.restype = None
+    L.rdn_bvh_nodes.argtypes = [vp, P(vp), P(u64)]
+    L.rdn_bvh_sorted_primitive_index.argtypes = [vp, P(vp), P(u64)]
+    L.rdn_bvh_query_nearest.argtypes = [vp, P(_MeshView), vp, u64, u32, i32, vp]
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise RdnError(rc, lib().rdn_rt_last_error().decode("utf-8", "replace"))
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dtype) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+# ------------------------------------------------------------------------------------------------ ray tracing API
+@dataclass
+class BlasHandle:
+    id: int
+
+
+@dataclass
+class TlasHandle:
+    id: int
+
+
+@dataclass
+class BottomLevelAccelerationStructureBuildSource:
+    """api/backend.rs:104-118.  ``positions`` [n,3] f32; ``indices`` u32 or None; ``aabbs`` marks the AABBs variant."""
+    positions: np.ndarray
+    indices: np.ndarray | None = None
+    flags: int = GEOMETRY_FLAG_OPAQUE
+    aabbs: bool = False
+
+
+class NaiveSahBVHSystem:
+    """The software TLAS/BLAS system with the traversal running on B200.
+
+    ``devices``: CUDA device ordinals; the flattened scene is replicated to each and host-buffer traces are
+    sharded across them (one process per GPU passes a single ordinal)."""
+
+    def __init__(self, devices=(0,)):
+        self._L = lib()
+        ids = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        _check(self._L.rdn_rt_scene_create(len(devices), ids, C.byref(h)))
+        self._h = h
+        self.devices = tuple(devices)
+
+    # --- GPUAccelerationStructureSystemProvider ---
+    def create_bottom_level_acceleration_structure(self, source) -> BlasHandle:
+        geoms = (_Geometry * max(len(source), 1))()
+        keep = []
+        for g, src in zip(geoms, source):
+            pos = _c(src.positions, np.float32).reshape(-1, 6 if src.aabbs else 3)
+            idx = None if src.indices is None else _c(src.indices, np.uint32).reshape(-1)
+            keep += [pos, idx]
+            g.positions = pos.ctypes.data
+            g.n_positions = pos.shape[0]
+            g.indices = None if idx is None else idx.ctypes.data
+            g.n_indices = 0 if idx is None else idx.size
+            g.flags = src.flags
+            g.kind = 1 if src.aabbs else 0
+        out = C.c_uint32()
+        _check(self._L.rdn_rt_blas_create(self._h, geoms, len(source), C.byref(out)))
+        return BlasHandle(out.value)
+
+    def delete_bottom_level_acceleration_structure(self, handle: BlasHandle):
+        _check(self._L.rdn_rt_blas_destroy(self._h, handle.id))
+
+    def create_top_level_acceleration_structure(self, source: np.ndarray) -> TlasHandle:
+        inst = _c(source, INSTANCE_DTYPE)
+        out = C.c_uint32()
+        _check(self._L.rdn_rt_tlas_create(self._h, _p(inst), inst.shape[0], C.byref(out)))
+        return TlasHandle(out.value)
+
+    def delete_top_level_acceleration_structure(self, handle: TlasHandle):
+        _check(self._L.rdn_rt_tlas_destroy(self._h, handle.id))
+
+    def bind_tlas(self, tlas):
+        ids = _c([t.id if isinstance(t, TlasHandle) else int(t) for t in tlas], np.uint32)
+        _check(self._L.rdn_rt_bind_tlas(self._h, _p(ids), ids.size))
+
+    def bind_tlas_max_len(self) -> int:
+        return int(self._L.rdn_rt_bind_tlas_max_len(self._h))
+
+    def commit(self):
+        """get_or_build_gpu_data: build + flatten + upload + replicate if anything changed."""
+        _check(self._L.rdn_rt_commit(self._h))
+
+    # --- traversal ---
+    def trace_closest_batch(self, rays: np.ndarray, ray_flags: int = 0, cull_mask: int = 0xFFFFFFFF, tlas_idx: int = 0,
+                            grid_width: int = 0, out: np.ndarray | None = None) -> np.ndarray:
+        """Host buffers in, host buffers out (H2D + traversal + D2H inside the call)."""
+        rays = _c(rays, RAY_DTYPE)
+        hits = np.empty(rays.shape[0], HIT_DTYPE) if out is None else out
+        launch = _Launch(ray_flags, cull_mask, tlas_idx, grid_width)
+        _check(self._L.rdn_rt_trace_closest(self._h, C.byref(launch), _p(rays), rays.shape[0], _p(hits)))
+        return hits
+
+    def trace_closest_host_ptr(self, rays_ptr: int, n: int, hits_ptr: int, ray_flags=0, cull_mask=0xFFFFFFFF, tlas_idx=0, grid_width=0):
+        """Same as :meth:`trace_closest_batch` on raw host pointers (e.g. pinned torch tensors)."""
+        launch = _Launch(ray_flags, cull_mask, tlas_idx, grid_width)
+        _check(self._L.rdn_rt_trace_closest(self._h, C.byref(launch), C.c_void_p(rays_ptr), n, C.c_void_p(hits_ptr)))
+
+    def trace_closest_device(self, d_rays_ptr: int, n: int, d_hits_ptr: int, ray_flags=0, cull_mask=0xFFFFFFFF, tlas_idx=0,
+                             grid_width=0, stream: int = 0, mode: int = TRACE_AUTO, device_index: int = 0, want_stats: bool = False):
+        """Device-resident rays/hits; asynchronous on ``stream`` unless ``want_stats``."""
+        launch = _Launch(ray_flags, cull_mask, tlas_idx, grid_width)
+        st = _TraceStats()
+        _check(self._L.rdn_rt_trace_closest_device(self._h, device_index, C.byref(launch), C.c_void_p(d_rays_ptr), n,
+                                                   C.c_void_p(d_hits_ptr), C.c_void_p(stream), mode,
+                                                   C.byref(st) if want_stats else None))
+        if want_stats:
+            return {"rays": int(st.rays), "tie_rays": int(st.tie_rays), "kernel_launches": int(st.kernel_launches),
+                    "kernel_ms": float(st.kernel_ms)}
+        return None
+
+    def trace_counted(self, rays: np.ndarray, ray_flags=0, cull_mask=0xFFFFFFFF, tlas_idx=0):
+        """Reference-order walk returning hits and the reference's visit counters."""
+        rays = _c(rays, RAY_DTYPE)
+        hits = np.empty(rays.shape[0], HIT_DTYPE)
+        launch = _Launch(ray_flags, cull_mask, tlas_idx, 0)
+        ctr = _Counters()
+        _check(self._L.rdn_rt_trace_counted(self._h, C.byref(launch), _p(rays), rays.shape[0], _p(hits), C.byref(ctr)))
+        return hits, {n: int(getattr(ctr, n)) for n, _ in _Counters._fields_}
+
+    # --- wavefront queue compaction ---
+    def compact_u32(self, values, keep):
+        values = _c(values, np.uint32); keep = _c(keep, np.uint8)
+        out = np.empty_like(values)
+        n = C.c_uint64()
+        _check(self._L.rdn_rt_compact_u32(self._h, _p(values), _p(keep), values.size, _p(out), C.byref(n)))
+        return out, int(n.value)
+
+    def compact_u32_device(self, d_in: int, d_keep: int, n: int, d_out: int, d_out_n: int, stream: int = 0, device_index: int = 0):
+        _check(self._L.rdn_rt_compact_u32_device(self._h, device_index, C.c_void_p(d_in), C.c_void_p(d_keep), n, C.c_void_p(d_out),
+                                                 C.c_void_p(d_out_n), C.c_void_p(stream)))
+
+    # --- replication ---
+    def blob(self, device_index: int = 0):
+        ptr = C.c_void_p(); nbytes = C.c_uint64()
+        _check(self._L.rdn_rt_scene_blob(self._h, device_index, C.byref(ptr), C.byref(nbytes)))
+        return int(ptr.value), int(nbytes.value)
+
+    def adopt_blob(self, d_blob_ptr: int, nbytes: int, device_index: int = 0):
+        _check(self._L.rdn_rt_scene_adopt_blob(self._h, device_index, C.c_void_p(d_blob_ptr), nbytes))
+
+    def array(self, array_id: int) -> np.ndarray:
+        name, dt = ARRAYS[array_id]
+        nb = C.c_uint64()
+        _check(self._L.rdn_rt_scene_array(self._h, array_id, None, 0, C.byref(nb)))
+        out = np.zeros(int(nb.value) // dt.itemsize, dt)
+        if nb.value:
+            _check(self._L.rdn_rt_scene_array(self._h, array_id, _p(out), nb.value, C.byref(nb)))
+        return out
+
+    def arrays(self) -> dict:
+        return {ARRAYS[i][0]: self.array(i) for i in ARRAYS}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.rdn_rt_scene_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------------ space query API
+@dataclass
+class TreeBuildOption:
+    """content/space/src/utils.rs:20-32 (defaults 10 / 50)."""
+    max_tree_depth: int = 10
+    bin_size: int = 50
+
+
+@dataclass
+class SAH:
+    """content/space/src/bvh/strategy.rs:99-117: ``SAH::new(pre_partition_check_count)``."""
+    pre_partition_check_count: int = 4
+
+
+class BalanceTree:
+    """content/space/src/bvh/strategy.rs:65."""
+
+
+class FlattenBVH:
+    """content/space/src/bvh/mod.rs:26-79: ``FlattenBVH::new(boxes, &mut strategy, &option)``; boxes = [n,6] (min,max)."""
+
+    def __init__(self, boxes=None, strategy=None, option: TreeBuildOption | None = None, _handle=None):
+        self._L = lib()
+        if _handle is not None:
+            self._h = _handle
+            return
+        boxes = _c(boxes, np.float32).reshape(-1, 6)
+        strategy = strategy if strategy is not None else SAH(4)
+        option = option or TreeBuildOption()
+        opt = _Option(option.max_tree_depth, option.bin_size)
+        h = C.c_void_p()
+        if isinstance(strategy, SAH):
+            rc = self._L.rdn_bvh_build(_p(boxes), boxes.shape[0], 0, strategy.pre_partition_check_count, C.byref(opt), C.byref(h))
+        else:
+            rc = self._L.rdn_bvh_build(_p(boxes), boxes.shape[0], 1, 0, C.byref(opt), C.byref(h))
+        _check(rc)
+        self._h = h
+
+    @property
+    def nodes(self) -> np.ndarray:
+        ptr = C.c_void_p(); n = C.c_uint64()
+        _check(self._L.rdn_bvh_nodes(self._h, C.byref(ptr), C.byref(n)))
+        buf = (C.c_char * (n.value * FLAT_BVH_NODE_DTYPE.itemsize)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=FLAT_BVH_NODE_DTYPE).copy()
+
+    @property
+    def sorted_primitive_index(self) -> np.ndarray:
+        ptr = C.c_void_p(); n = C.c_uint64()
+        _check(self._L.rdn_bvh_sorted_primitive_index(self._h, C.byref(ptr), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0, np.uint64)
+        buf = (C.c_char * (n.value * 8)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=np.uint64).copy()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._L.rdn_bvh_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def _mesh_view(positions, indices):
+    pos = _c(positions, np.float32).reshape(-1, 3)
+    idx = _c(indices, np.uint32).reshape(-1)
+    return _MeshView(pos.ctypes.data, pos.shape[0], idx.ctypes.data, idx.size), (pos, idx)
+
+
+def build_bvh_for_abstract_mesh(positions, indices, strategy=None, option: TreeBuildOption | None = None) -> FlattenBVH:
+    """content/mesh/core/src/feature/bvh.rs:5-21 over an indexed triangle list."""
+    L = lib()
+    mv, _keep = _mesh_view(positions, indices)
+    strategy = strategy if strategy is not None else SAH(4)
+    option = option or TreeBuildOption()
+    opt = _Option(option.max_tree_depth, option.bin_size)
+    h = C.c_void_p()
+    if isinstance(strategy, SAH):
+        rc = L.rdn_bvh_build_for_mesh(C.byref(mv), 0, strategy.pre_partition_check_count, C.byref(opt), C.byref(h))
+    else:
+        rc = L.rdn_bvh_build_for_mesh(C.byref(mv), 1, 0, C.byref(opt), C.byref(h))
+    _check(rc)
+    return FlattenBVH(_handle=h)
+
+
+def intersect_nearest_bvh(positions, indices, rays, bvh: FlattenBVH, face_side: int = FACE_DOUBLE, device: int = 0) -> np.ndarray:
+    """content/mesh/core/src/feature/bvh.rs:57-86 for a batch of rays; ``hit == 0`` is ``OptionalNearest::none()``."""
+    L = lib()
+    mv, _keep = _mesh_view(positions, indices)
+    rays = _c(rays, RAY_DTYPE)
+    out = np.zeros(rays.shape[0], MESH_HIT_DTYPE)
+    _check(L.rdn_bvh_query_nearest(bvh._h, C.byref(mv), _p(rays), rays.shape[0], face_side, device, _p(out)))
+    return out

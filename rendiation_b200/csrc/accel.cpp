@@ -1,0 +1,372 @@
+// accel.cpp — BLAS/TLAS assembly and flattening.  Compiled with -ffp-contract=off.
+#include "accel.h"
+
+#include <cstring>
+
+#include "../../include/rdn_rt.h"
+
+namespace rdn {
+
+// ------------------------------------------------------------------------------------------------ matrices
+// three-term cofactor row: x*(p*q - r*s) + y*(...) + z*(...), the shape of every entry of mat4.rs:82-100
+static inline float cof3(float x, float p0, float q0, float r0, float s0, float y, float p1, float q1, float r1, float s1,
+                         float z, float p2, float q2, float r2, float s2) {
+  return x * (p0 * q0 - r0 * s0) + y * (p1 * q1 - r1 * s1) + z * (p2 * q2 - r2 * s2);
+}
+
+static float mat4_det(const Mat4 &m) {
+  // 24-term expansion in the order of mat4.rs:40-70
+  return m.a1 * m.b2 * m.c3 * m.d4 - m.a1 * m.b2 * m.c4 * m.d3 + m.a1 * m.b3 * m.c4 * m.d2 - m.a1 * m.b3 * m.c2 * m.d4 +
+         m.a1 * m.b4 * m.c2 * m.d3 - m.a1 * m.b4 * m.c3 * m.d2 - m.a2 * m.b3 * m.c4 * m.d1 + m.a2 * m.b3 * m.c1 * m.d4 -
+         m.a2 * m.b4 * m.c1 * m.d3 + m.a2 * m.b4 * m.c3 * m.d1 - m.a2 * m.b1 * m.c3 * m.d4 + m.a2 * m.b1 * m.c4 * m.d3 +
+         m.a3 * m.b4 * m.c1 * m.d2 - m.a3 * m.b4 * m.c2 * m.d1 + m.a3 * m.b1 * m.c2 * m.d4 - m.a3 * m.b1 * m.c4 * m.d2 +
+         m.a3 * m.b2 * m.c4 * m.d1 - m.a3 * m.b2 * m.c1 * m.d4 - m.a4 * m.b1 * m.c2 * m.d3 + m.a4 * m.b1 * m.c3 * m.d2 -
+         m.a4 * m.b2 * m.c3 * m.d1 + m.a4 * m.b2 * m.c1 * m.d3 - m.a4 * m.b3 * m.c1 * m.d2 + m.a4 * m.b3 * m.c2 * m.d1;
+}
+
+Mat4 mat4_inverse_or_identity(const Mat4 &m) {
+  const float det = mat4_det(m);
+  if (det == 0.0f) return Mat4{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  const float p = 1.0f / det;  // inv_det
+  const float q = -p;          // `-inv_det * (...)`
+  Mat4 r;
+  r.a1 = p * cof3(m.b2, m.c3, m.d4, m.c4, m.d3, m.b3, m.c4, m.d2, m.c2, m.d4, m.b4, m.c2, m.d3, m.c3, m.d2);
+  r.a2 = q * cof3(m.a2, m.c3, m.d4, m.c4, m.d3, m.a3, m.c4, m.d2, m.c2, m.d4, m.a4, m.c2, m.d3, m.c3, m.d2);
+  r.a3 = p * cof3(m.a2, m.b3, m.d4, m.b4, m.d3, m.a3, m.b4, m.d2, m.b2, m.d4, m.a4, m.b2, m.d3, m.b3, m.d2);
+  r.a4 = q * cof3(m.a2, m.b3, m.c4, m.b4, m.c3, m.a3, m.b4, m.c2, m.b2, m.c4, m.a4, m.b2, m.c3, m.b3, m.c2);
+  r.b1 = q * cof3(m.b1, m.c3, m.d4, m.c4, m.d3, m.b3, m.c4, m.d1, m.c1, m.d4, m.b4, m.c1, m.d3, m.c3, m.d1);
+  r.b2 = p * cof3(m.a1, m.c3, m.d4, m.c4, m.d3, m.a3, m.c4, m.d1, m.c1, m.d4, m.a4, m.c1, m.d3, m.c3, m.d1);
+  r.b3 = q * cof3(m.a1, m.b3, m.d4, m.b4, m.d3, m.a3, m.b4, m.d1, m.b1, m.d4, m.a4, m.b1, m.d3, m.b3, m.d1);
+  r.b4 = p * cof3(m.a1, m.b3, m.c4, m.b4, m.c3, m.a3, m.b4, m.c1, m.b1, m.c4, m.a4, m.b1, m.c3, m.b3, m.c1);
+  r.c1 = p * cof3(m.b1, m.c2, m.d4, m.c4, m.d2, m.b2, m.c4, m.d1, m.c1, m.d4, m.b4, m.c1, m.d2, m.c2, m.d1);
+  r.c2 = q * cof3(m.a1, m.c2, m.d4, m.c4, m.d2, m.a2, m.c4, m.d1, m.c1, m.d4, m.a4, m.c1, m.d2, m.c2, m.d1);
+  r.c3 = p * cof3(m.a1, m.b2, m.d4, m.b4, m.d2, m.a2, m.b4, m.d1, m.b1, m.d4, m.a4, m.b1, m.d2, m.b2, m.d1);
+  r.c4 = q * cof3(m.a1, m.b2, m.c4, m.b4, m.c2, m.a2, m.b4, m.c1, m.b1, m.c4, m.a4, m.b1, m.c2, m.b2, m.c1);
+  r.d1 = q * cof3(m.b1, m.c2, m.d3, m.c3, m.d2, m.b2, m.c3, m.d1, m.c1, m.d3, m.b3, m.c1, m.d2, m.c2, m.d1);
+  r.d2 = p * cof3(m.a1, m.c2, m.d3, m.c3, m.d2, m.a2, m.c3, m.d1, m.c1, m.d3, m.a3, m.c1, m.d2, m.c2, m.d1);
+  r.d3 = q * cof3(m.a1, m.b2, m.d3, m.b3, m.d2, m.a2, m.b3, m.d1, m.b1, m.d3, m.a3, m.b1, m.d2, m.b2, m.d1);
+  r.d4 = p * cof3(m.a1, m.b2, m.c3, m.b3, m.c2, m.a2, m.b3, m.c1, m.b1, m.c3, m.a3, m.b1, m.c2, m.b2, m.c1);
+  return r;
+}
+
+float mat4_upper3_det(const Mat4 &m) {
+  // Mat4::to_mat3().det(), mat3.rs:37-42
+  const float t11 = m.c3 * m.b2 - m.b3 * m.c2;
+  const float t12 = m.b3 * m.c1 - m.c3 * m.b1;
+  const float t13 = m.c2 * m.b1 - m.b2 * m.c1;
+  return m.a1 * t11 + m.a2 * t12 + m.a3 * t13;
+}
+
+static inline Vec3 transform_point(const Mat4 &m, float x, float y, float z) {
+  // Mat4 * Vec3: expand with w = 1, divide by the resulting w (mat4.rs:140-168)
+  const float rx = x * m.a1 + y * m.b1 + z * m.c1 + 1.0f * m.d1;
+  const float ry = x * m.a2 + y * m.b2 + z * m.c2 + 1.0f * m.d2;
+  const float rz = x * m.a3 + y * m.b3 + z * m.c3 + 1.0f * m.d3;
+  const float rw = x * m.a4 + y * m.b4 + z * m.c4 + 1.0f * m.d4;
+  return Vec3{rx / rw, ry / rw, rz / rw};
+}
+
+Box3 box_apply_matrix(const Box3 &b, const Mat4 &m) {
+  // box3.rs:22-38: untouched when empty, else the bound of the 8 transformed corners (000,001,...,111)
+  if ((b.max.x < b.min.x) || (b.max.y < b.min.y) || (b.max.z < b.min.z)) return b;
+  Box3 r = box_empty();
+  for (int corner = 0; corner < 8; ++corner) {
+    const float x = (corner & 4) ? b.max.x : b.min.x;
+    const float y = (corner & 2) ? b.max.y : b.min.y;
+    const float z = (corner & 1) ? b.max.z : b.min.z;
+    expand(r, transform_point(m, x, y, z));
+  }
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------ sources
+uint32_t NaiveSahBvhSource::create_blas(std::vector<GeometrySource> source) {
+  blas_data_.push_back(Blas{true, std::move(source)});
+  return static_cast<uint32_t>(blas_data_.size() - 1);
+}
+uint32_t NaiveSahBvhSource::create_tlas(std::vector<InstanceSource> source) {
+  tlas_data_.push_back(Tlas{true, std::move(source)});
+  return static_cast<uint32_t>(tlas_data_.size() - 1);
+}
+bool NaiveSahBvhSource::delete_blas(uint32_t h) {
+  if (h >= blas_data_.size()) return false;
+  blas_data_[h] = Blas{};
+  return true;
+}
+bool NaiveSahBvhSource::delete_tlas(uint32_t h) {
+  if (h >= tlas_data_.size()) return false;
+  tlas_data_[h] = Tlas{};
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------ flatten
+static DeviceBVHNode to_device_node(const FlattenBVHNode &n, uint32_t hit, uint32_t miss, uint32_t next_offset,
+                                    uint32_t primitive_offset) {
+  // flatten_bvh_to_gpu_node, mod.rs:338-367
+  DeviceBVHNode d;
+  std::memset(&d, 0, sizeof(d));
+  d.aabb_min[0] = n.bounding.min.x; d.aabb_min[1] = n.bounding.min.y; d.aabb_min[2] = n.bounding.min.z;
+  d.aabb_max[0] = n.bounding.max.x; d.aabb_max[1] = n.bounding.max.y; d.aabb_max[2] = n.bounding.max.z;
+  d.hit_next = hit == INVALID_NEXT ? INVALID_NEXT : hit + next_offset;
+  d.miss_next = miss == INVALID_NEXT ? INVALID_NEXT : miss + next_offset;
+  d.content_range[0] = static_cast<uint32_t>(n.primitive_start) + primitive_offset;
+  d.content_range[1] = static_cast<uint32_t>(n.primitive_end) + primitive_offset;
+  return d;
+}
+
+static void set_child(WideNode &w, int which, const Box3 *box, uint32_t ref) {
+  const float nan = NAN;  // a NaN box fails every comparison of the slab test: never entered
+  float *mn = which == 0 ? w.c0_min : w.c1_min;
+  float *mx = which == 0 ? w.c0_max : w.c1_max;
+  mn[0] = box ? box->min.x : nan; mn[1] = box ? box->min.y : nan; mn[2] = box ? box->min.z : nan;
+  mx[0] = box ? box->max.x : nan; mx[1] = box ? box->max.y : nan; mx[2] = box ? box->max.z : nan;
+  (which == 0 ? w.ref0 : w.ref1) = ref;
+}
+
+uint32_t emit_wide_nodes(const std::vector<FlattenBVHNode> &nodes, uint64_t slot_offset, std::vector<WideNode> &out,
+                         bool &capacity_error) {
+  if (nodes.empty() || nodes[0].primitive_end == nodes[0].primitive_start) return REF_EMPTY;
+  // wide index of every inner reference node (pre-order), after the pseudo root
+  const uint64_t base = out.size();
+  std::vector<uint32_t> wide_of(nodes.size(), 0);
+  uint64_t n_inner = 0;
+  for (size_t i = 0; i < nodes.size(); ++i)
+    if (nodes[i].has_child) wide_of[i] = static_cast<uint32_t>(base + 1 + n_inner++);
+  out.resize(base + 1 + n_inner);
+
+  // a leaf reference; leaves longer than REF_LEAF_MAX_COUNT become a chain of nodes that repeat the leaf's box
+  auto leaf_ref = [&](const FlattenBVHNode &leaf) -> uint32_t {
+    uint64_t start = slot_offset + leaf.primitive_start;
+    uint64_t count = leaf.primitive_end - leaf.primitive_start;
+    if (count == 0) return REF_EMPTY;
+    if (start + count > REF_LEAF_START_MASK) { capacity_error = true; return REF_EMPTY; }
+    auto enc = [](uint64_t s, uint64_t c) { return REF_LEAF_BIT | (static_cast<uint32_t>(c - 1) << REF_LEAF_COUNT_SHIFT) | static_cast<uint32_t>(s); };
+    if (count <= REF_LEAF_MAX_COUNT) return enc(start, count);
+    // chain: node k = {first 16 slots, rest}
+    uint32_t head = static_cast<uint32_t>(out.size());
+    while (count > REF_LEAF_MAX_COUNT) {
+      WideNode w;
+      std::memset(&w, 0, sizeof(w));
+      const uint64_t rest = count - REF_LEAF_MAX_COUNT;
+      const uint32_t next = rest > REF_LEAF_MAX_COUNT ? static_cast<uint32_t>(out.size() + 1) : enc(start + REF_LEAF_MAX_COUNT, rest);
+      set_child(w, 0, &leaf.bounding, enc(start, REF_LEAF_MAX_COUNT));
+      set_child(w, 1, &leaf.bounding, next);
+      out.push_back(w);
+      start += REF_LEAF_MAX_COUNT;
+      count = rest;
+    }
+    return head;
+  };
+  auto child_ref = [&](size_t idx) -> uint32_t { return nodes[idx].has_child ? wide_of[idx] : leaf_ref(nodes[idx]); };
+
+  // pseudo root: the reference tests the root's own box before anything else
+  {
+    WideNode w;
+    std::memset(&w, 0, sizeof(w));
+    const uint32_t r = child_ref(0);
+    set_child(w, 0, &nodes[0].bounding, r);
+    set_child(w, 1, nullptr, REF_EMPTY);
+    out[base] = w;
+  }
+  for (size_t i = 0; i < nodes.size(); ++i) {
+    if (!nodes[i].has_child) continue;
+    const size_t l = nodes[i].left_child_offset(), r = nodes[i].right_child_offset();
+    WideNode w;
+    std::memset(&w, 0, sizeof(w));
+    const uint32_t lr = child_ref(l), rr = child_ref(r);
+    set_child(w, 0, &nodes[l].bounding, lr);
+    set_child(w, 1, &nodes[r].bounding, rr);
+    out[wide_of[i]] = w;
+  }
+  if (out.size() >= REF_SPECIAL) capacity_error = true;
+  return static_cast<uint32_t>(base);
+}
+
+static TriRecord make_tri_record(Vec3 v0, Vec3 v1, Vec3 v2) {
+  // the ray-independent part of intersect_ray_triangle_cpu (geometry/mod.rs:115-148), same operation order
+  const Vec3 e1 = v1 - v0;
+  const Vec3 e2 = v2 - v0;
+  const Vec3 normal = normalize(cross(e1, e2));
+  const float uu = dot(e1, e1);
+  const float uv = dot(e1, e2);
+  const float vv = dot(e2, e2);
+  const float inverse_d = 1.0f / (uv * uv - uu * vv);
+  TriRecord t;
+  t.n[0] = normal.x; t.n[1] = normal.y; t.n[2] = normal.z; t.inv_d = inverse_d;
+  t.v0[0] = v0.x; t.v0[1] = v0.y; t.v0[2] = v0.z; t.uu = uu;
+  t.e1[0] = e1.x; t.e1[1] = e1.y; t.e1[2] = e1.z; t.uv = uv;
+  t.e2[0] = e2.x; t.e2[1] = e2.y; t.e2[2] = e2.z; t.vv = vv;
+  return t;
+}
+
+int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScene &out, std::string &err) const {
+  out = FlatScene{};
+  out.tlas_binding = tlas_binding;
+  bool capacity_error = false;
+
+  // ---- build_blas (mod.rs:122-260).  NOTE blas_box gets one entry PER GEOMETRY of a live BLAS but one per
+  // deleted BLAS, and build_tlas indexes it by BLAS handle (mod.rs:239,273) — reproduced as is.
+  struct OptBox { bool some; Box3 box; };
+  std::vector<OptBox> blas_box;
+  uint64_t n_indices_total = 0;  // geometry_indices.len()
+  const TreeBuildOption blas_option{50, 2};
+
+  for (const Blas &blas : blas_data_) {
+    if (!blas.alive) {
+      out.blas_meta.push_back(BlasMeta{{0, 0}});
+      blas_box.push_back(OptBox{false, box_empty()});
+      continue;
+    }
+    const uint32_t tri_start = static_cast<uint32_t>(out.geometry_meta.size());
+    for (size_t g = 0; g < blas.geometries.size(); ++g) {
+      const GeometrySource &src = blas.geometries[g];
+      Box3 root_box = box_empty();
+      if (!src.is_aabbs) {
+        const uint32_t primitive_start = static_cast<uint32_t>(n_indices_total / 3);
+        const uint64_t n_idx = src.has_indices ? src.indices.size() : src.positions.size();
+        const uint64_t n_tri = n_idx / 3;  // as_chunks::<3>().0 drops the remainder
+        auto vertex_of = [&](uint64_t tri, int k) -> uint64_t { return src.has_indices ? src.indices[3 * tri + k] : 3 * tri + k; };
+        std::vector<Box3> boxes(n_tri);
+        for (uint64_t t = 0; t < n_tri; ++t) {
+          Box3 b = box_empty();
+          for (int k = 0; k < 3; ++k) {
+            const uint64_t vi = vertex_of(t, k);
+            if (vi >= src.positions.size()) { err = "triangle index out of bounds (the reference panics here)"; return RDN_ERR_BUILD; }
+            expand(b, src.positions[vi]);
+          }
+          boxes[t] = b;
+        }
+        SAH sah(4);
+        FlattenBVH bvh = FlattenBVH::build(boxes.data(), n_tri, sah, blas_option);
+        if (bvh.stats.bucket_out_of_range) { err = "SAH bucket index out of range (the reference panics here)"; return RDN_ERR_BUILD; }
+        out.stats.balance_fallbacks += bvh.stats.balance_fallbacks;
+        out.stats.balance_fallbacks_gt10 += bvh.stats.balance_fallbacks_gt10;
+        expand(root_box, bvh.nodes[0].bounding);
+        const auto next = compute_bvh_next(bvh.nodes);
+
+        // slots of this geometry start at primitive_start (indices_redirect and indices grow in lock step)
+        const uint64_t slot_base = out.triangles.size();
+        if (slot_base != primitive_start) { err = "internal: slot/primitive offset mismatch"; return RDN_ERR_BUILD; }
+        for (uint64_t k = 0; k < n_tri; ++k) {
+          const uint64_t tri = bvh.sorted_primitive_index[k];  // indices_redirect[slot] - raw_primitive_start
+          out.triangles.push_back(make_tri_record(src.positions[vertex_of(tri, 0)], src.positions[vertex_of(tri, 1)],
+                                                  src.positions[vertex_of(tri, 2)]));
+          out.slot_info.push_back(SlotInfo{static_cast<uint32_t>(tri), static_cast<uint32_t>(g)});
+        }
+        n_indices_total += n_tri * 3;
+
+        const uint32_t bvh_start = static_cast<uint32_t>(out.tri_bvh_forest.size());
+        GeometryMeta gm;
+        std::memset(&gm, 0, sizeof(gm));
+        gm.bvh_root_idx = bvh_start;
+        gm.geometry_idx = static_cast<uint32_t>(g);
+        gm.primitive_start = primitive_start;
+        gm.geometry_flags = src.flags;
+        gm.wide_root = emit_wide_nodes(bvh.nodes, primitive_start, out.wide_nodes, capacity_error);
+        out.geometry_meta.push_back(gm);
+        for (size_t i = 0; i < bvh.nodes.size(); ++i)
+          out.tri_bvh_forest.push_back(to_device_node(bvh.nodes[i], next[i].first, next[i].second, bvh_start, primitive_start));
+      }
+      blas_box.push_back(OptBox{true, root_box});
+    }
+    out.blas_meta.push_back(BlasMeta{{tri_start, static_cast<uint32_t>(out.geometry_meta.size())}});
+  }
+
+  // ---- build_tlas per TLAS (mod.rs:262-320, 428-448)
+  const TreeBuildOption tlas_option{50, 10};
+  for (const Tlas &tlas : tlas_data_) {
+    if (!tlas.alive) {
+      out.tlas_root.push_back(TlasRoot{INVALID_NEXT, REF_EMPTY});
+      continue;
+    }
+    const uint32_t bvh_start = static_cast<uint32_t>(out.tlas_bvh_forest.size());
+    const uint32_t primitive_start = static_cast<uint32_t>(out.instances.size());
+    std::vector<Box3> aabbs(tlas.instances.size());
+    for (size_t i = 0; i < tlas.instances.size(); ++i) {
+      const InstanceSource &src = tlas.instances[i];
+      if (src.blas_handle >= blas_box.size() || !blas_box[src.blas_handle].some) {
+        err = "instance references a deleted or unknown BLAS (the reference panics here)";
+        return RDN_ERR_INVALID_HANDLE;
+      }
+      aabbs[i] = box_apply_matrix(blas_box[src.blas_handle].box, src.transform);
+    }
+    SAH sah(4);
+    FlattenBVH bvh = FlattenBVH::build(aabbs.data(), aabbs.size(), sah, tlas_option);
+    if (bvh.stats.bucket_out_of_range) { err = "SAH bucket index out of range (the reference panics here)"; return RDN_ERR_BUILD; }
+    out.stats.balance_fallbacks += bvh.stats.balance_fallbacks;
+    out.stats.balance_fallbacks_gt10 += bvh.stats.balance_fallbacks_gt10;
+    const auto next = compute_bvh_next(bvh.nodes);
+
+    for (uint64_t box_idx : bvh.sorted_primitive_index) {
+      const InstanceSource &src = tlas.instances[box_idx];
+      uint32_t flags = src.flags;
+      if (mat4_upper3_det(src.transform) < 0.0f) flags ^= RDN_GEOMETRY_INSTANCE_TRIANGLE_FLIP_FACING;
+      InstanceRecord rec;
+      const Mat4 inv = mat4_inverse_or_identity(src.transform);
+      std::memcpy(rec.transform_inv, &inv, sizeof(inv));
+      rec.instance_custom_index = src.instance_custom_index;
+      rec.sbt_offset = src.sbt_offset;
+      rec.flags = flags;
+      rec.blas = src.blas_handle;
+      out.instances.push_back(rec);
+      TlasBounding tb;
+      tb.world_min[0] = aabbs[box_idx].min.x; tb.world_min[1] = aabbs[box_idx].min.y; tb.world_min[2] = aabbs[box_idx].min.z;
+      tb.world_max[0] = aabbs[box_idx].max.x; tb.world_max[1] = aabbs[box_idx].max.y; tb.world_max[2] = aabbs[box_idx].max.z;
+      tb.mask = src.mask;
+      tb.flags = flags;
+      out.tlas_bounding.push_back(tb);
+    }
+    TlasRoot root;
+    root.bvh_root_idx = bvh_start;
+    root.wide_root = emit_wide_nodes(bvh.nodes, primitive_start, out.wide_nodes, capacity_error);
+    out.tlas_root.push_back(root);
+    for (size_t i = 0; i < bvh.nodes.size(); ++i)
+      out.tlas_bvh_forest.push_back(to_device_node(bvh.nodes[i], next[i].first, next[i].second, bvh_start, primitive_start));
+  }
+
+  if (out.geometry_meta.size() > REF_GEOM_ITER_MAX) capacity_error = true;
+  if (capacity_error) {
+    err = "scene exceeds the 32-bit child-reference encoding (2^27 slots / 0x7F000000 nodes / 2^24 geometries)";
+    return RDN_ERR_CAPACITY;
+  }
+  return RDN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ blob
+template <typename T>
+static void place(std::vector<uint8_t> &blob, BlobHeader &h, int id, const std::vector<T> &v) {
+  uint64_t off = (blob.size() + BLOB_ALIGN - 1) / BLOB_ALIGN * BLOB_ALIGN;
+  // every array keeps at least one zeroed element so kernels never see a null base (create_gpu_buffer, mod.rs:386-400)
+  const uint64_t bytes = (v.empty() ? 1 : v.size()) * sizeof(T);
+  blob.resize(off + bytes, 0);
+  if (!v.empty()) std::memcpy(blob.data() + off, v.data(), v.size() * sizeof(T));
+  h.offset[id] = off;
+  h.count[id] = v.size();
+  h.elem_size[id] = sizeof(T);
+}
+
+std::vector<uint8_t> FlatScene::serialize() const {
+  BlobHeader h;
+  std::memset(&h, 0, sizeof(h));
+  h.magic = BLOB_MAGIC;
+  h.version = BLOB_VERSION;
+  h.header_bytes = sizeof(BlobHeader);
+  std::vector<uint8_t> blob(sizeof(BlobHeader), 0);
+  place(blob, h, ARR_TLAS_BINDING, tlas_binding);
+  place(blob, h, ARR_TLAS_ROOT, tlas_root);
+  place(blob, h, ARR_TLAS_BVH_FOREST, tlas_bvh_forest);
+  place(blob, h, ARR_TLAS_BOUNDING, tlas_bounding);
+  place(blob, h, ARR_INSTANCES, instances);
+  place(blob, h, ARR_BLAS_META, blas_meta);
+  place(blob, h, ARR_GEOMETRY_META, geometry_meta);
+  place(blob, h, ARR_TRI_BVH_FOREST, tri_bvh_forest);
+  place(blob, h, ARR_TRIANGLES, triangles);
+  place(blob, h, ARR_SLOT_INFO, slot_info);
+  place(blob, h, ARR_WIDE_NODES, wide_nodes);
+  blob.resize((blob.size() + BLOB_ALIGN - 1) / BLOB_ALIGN * BLOB_ALIGN, 0);
+  h.total_bytes = blob.size();
+  std::memcpy(blob.data(), &h, sizeof(h));
+  return blob;
+}
+
+}  // namespace rdn

@@ -1,0 +1,76 @@
+// accel.h — host side of the software acceleration-structure system (build + flatten).
+//
+// Mirrors NaiveSahBVHSystem / NaiveSahBvhSource (shader/ray-tracing/src/backend/wavefront_compute/geometry/
+// naive/mod.rs:73-119,122-493): create/delete BLAS & TLAS only store sources and invalidate; the actual build
+// is lazy (mod.rs:521-536) and always from scratch (mod.rs:121 `todo incremental change`).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "bvh_builder.h"
+#include "layout.h"
+
+namespace rdn {
+
+struct GeometrySource {  // BottomLevelAccelerationStructureBuildSource (api/backend.rs:104-118)
+  std::vector<Vec3> positions;
+  std::vector<uint32_t> indices;
+  bool has_indices = false;
+  bool is_aabbs = false;  // accepted, ignored by the naive builder (mod.rs:201-237)
+  uint32_t flags = 0;
+};
+
+struct InstanceSource {  // TopLevelAccelerationStructureSourceInstance (api/backend.rs:160-167)
+  Mat4 transform;
+  uint32_t instance_custom_index, mask, sbt_offset, flags, blas_handle;
+};
+
+// The flattened scene on the host, one vector per blob array.
+struct FlatScene {
+  std::vector<uint32_t> tlas_binding;
+  std::vector<TlasRoot> tlas_root;
+  std::vector<DeviceBVHNode> tlas_bvh_forest;
+  std::vector<TlasBounding> tlas_bounding;
+  std::vector<InstanceRecord> instances;
+  std::vector<BlasMeta> blas_meta;
+  std::vector<GeometryMeta> geometry_meta;
+  std::vector<DeviceBVHNode> tri_bvh_forest;
+  std::vector<TriRecord> triangles;
+  std::vector<SlotInfo> slot_info;
+  std::vector<WideNode> wide_nodes;
+  BuildStats stats;
+
+  // pack into one contiguous, BLOB_ALIGN-aligned byte image starting with a BlobHeader
+  std::vector<uint8_t> serialize() const;
+};
+
+class NaiveSahBvhSource {
+ public:
+  uint32_t create_blas(std::vector<GeometrySource> source);
+  uint32_t create_tlas(std::vector<InstanceSource> source);
+  bool delete_blas(uint32_t handle);
+  bool delete_tlas(uint32_t handle);
+
+  // NaiveSahBvhSource::build: returns 0 or a negative rdn_status; `err` gets a message on failure
+  int build(const std::vector<uint32_t> &tlas_binding, FlatScene &out, std::string &err) const;
+
+ private:
+  struct Blas { bool alive = false; std::vector<GeometrySource> geometries; };
+  struct Tlas { bool alive = false; std::vector<InstanceSource> instances; };
+  std::vector<Blas> blas_data_;
+  std::vector<Tlas> tlas_data_;
+};
+
+// Mat4 helpers (math/algebra/src/mat/mat4.rs:40-104, mat3.rs:37-42) used by the TLAS assembly
+Mat4 mat4_inverse_or_identity(const Mat4 &m);
+float mat4_upper3_det(const Mat4 &m);
+Box3 box_apply_matrix(const Box3 &b, const Mat4 &m);
+
+// Emit the wide (two-boxes-per-node) view of one reference tree into `out`; leaf references address
+// `slot_offset + primitive_range`.  Returns the pseudo-root reference (REF_EMPTY for an empty tree) or
+// sets `capacity_error`.
+uint32_t emit_wide_nodes(const std::vector<FlattenBVHNode> &nodes, uint64_t slot_offset, std::vector<WideNode> &out,
+                         bool &capacity_error);
+
+}  // namespace rdn

@@ -1,0 +1,185 @@
+// bvh_builder.cpp — see bvh_builder.h.  Compiled with -ffp-contract=off.
+#include "bvh_builder.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace rdn {
+
+int longest_axis(const Box3 &b) {
+  // the exact `>` cascade of math/geometry/src/dimension3/box3.rs:117-133
+  const float x_length = b.max.x - b.min.x;
+  const float y_length = b.max.y - b.min.y;
+  const float z_length = b.max.z - b.min.z;
+  if (x_length > y_length) return x_length > z_length ? 0 : 2;
+  if (y_length > z_length) return 1;
+  return 2;
+}
+
+float surface_area(const Box3 &b) {
+  // LebesgueMeasurable<2> for Box3, box3.rs:5-11
+  const float w = b.max.x - b.min.x, h = b.max.y - b.min.y, d = b.max.z - b.min.z;
+  return 2.0f * (w * h + w * d + h * d);
+}
+
+Vec3 box_center(const Box3 &b) { return (b.min + b.max) * 0.5f; }
+
+static inline float component(const Vec3 &v, int axis) { return axis == 0 ? v.x : (axis == 1 ? v.y : v.z); }
+
+static Box3 bounding_of_range(const std::vector<BuildPrimitive> &src, const std::vector<uint64_t> &index, uint64_t begin,
+                              uint64_t end) {
+  Box3 r = box_empty();
+  for (uint64_t i = begin; i < end; ++i) expand(r, src[index[i]].bounding);
+  return r;
+}
+
+SplitResult BalanceTree::split(const FlattenBVHNode &parent, const std::vector<BuildPrimitive> &src,
+                               std::vector<uint64_t> &index, BuildStats &) {
+  SplitResult r;
+  r.axis = longest_axis(parent.bounding);
+  const uint64_t begin = parent.primitive_start, end = parent.primitive_end;
+  const uint64_t middle = (end + begin) / 2;
+  if ((end - begin) / 2 != 0) {
+    // median_partition_at_axis (apply.rs:19-49).  Rust's select_nth_unstable_by leaves an unspecified
+    // permutation; a stable sort by centre is a valid one and equals std's insertion-sort path (<= 10 items).
+    const int axis = r.axis;
+    std::stable_sort(index.begin() + begin, index.begin() + end, [&](uint64_t a, uint64_t b) {
+      return component(src[a].center, axis) < component(src[b].center, axis);
+    });
+  }
+  r.left_start = begin; r.left_end = middle; r.right_start = middle; r.right_end = end;
+  r.left_box = bounding_of_range(src, index, begin, middle);
+  r.right_box = bounding_of_range(src, index, middle, end);
+  return r;
+}
+
+SAH::SAH(uint32_t n) : pre_partition_(std::max<uint32_t>(n, 2u)) {}
+
+// Rust `as usize` on f32: saturating, NaN -> 0
+static inline uint64_t saturating_usize(float v) {
+  if (!(v == v) || v <= 0.0f) return 0;
+  if (v >= 18446744073709551616.0f) return UINT64_MAX;
+  return static_cast<uint64_t>(v);
+}
+
+SplitResult SAH::split(const FlattenBVHNode &parent, const std::vector<BuildPrimitive> &src, std::vector<uint64_t> &index,
+                       BuildStats &stats) {
+  const uint64_t begin = parent.primitive_start, end = parent.primitive_end;
+  const size_t n_part = pre_partition_.size();
+  for (auto &p : pre_partition_) { p.primitive_bucket.clear(); p.bounding = box_empty(); }
+
+  // step 1: bucket every primitive by its centre along the longest axis of the NODE box
+  const int axis = longest_axis(parent.bounding);
+  const float range_start = component(parent.bounding.min, axis);
+  const float range_end = component(parent.bounding.max, axis);
+  const float step = (range_end - range_start) / static_cast<float>(n_part);
+  for (uint64_t i = begin; i < end; ++i) {
+    const uint64_t prim = index[i];
+    const float axis_value = component(src[prim].center, axis);
+    uint64_t which = saturating_usize(floorf((axis_value - range_start) / step));
+    if (which == n_part) which -= 1;
+    if (which >= n_part) { stats.bucket_out_of_range = true; which = n_part - 1; }
+    expand(pre_partition_[which].bounding, src[prim].bounding);
+    pre_partition_[which].primitive_bucket.push_back(prim);
+  }
+
+  size_t empty_buckets = 0;
+  for (const auto &p : pre_partition_) empty_buckets += p.primitive_bucket.empty();
+  if (empty_buckets == n_part - 1) {
+    stats.balance_fallbacks++;
+    if (end - begin > 10) stats.balance_fallbacks_gt10++;
+    BalanceTree fallback;
+    return fallback.split(parent, src, index, stats);
+  }
+
+  // step 2: cost of each of the n_part-1 prefix partitions; first strict minimum wins
+  struct Group { Box3 box; uint64_t count; };
+  auto group_of = [&](size_t from, size_t to) {
+    Group g{box_empty(), 0};
+    for (size_t k = from; k < to; ++k) { expand(g.box, pre_partition_[k].bounding); g.count += pre_partition_[k].primitive_bucket.size(); }
+    return g;
+  };
+  Group best_left = group_of(0, 1), best_right = group_of(1, n_part);
+  float best_cost = INFINITY;
+  for (size_t i = 0; i + 1 < n_part; ++i) {
+    const Group l = group_of(0, i + 1), r = group_of(i + 1, n_part);
+    const float cost = surface_area(l.box) * static_cast<float>(l.count) + surface_area(r.box) * static_cast<float>(r.count);
+    if (cost < best_cost) { best_cost = cost; best_left = l; best_right = r; }
+  }
+
+  // step 3: rewrite the index range bucket by bucket (stable)
+  uint64_t ptr = begin;
+  for (const auto &p : pre_partition_)
+    for (uint64_t prim : p.primitive_bucket) index[ptr++] = prim;
+
+  SplitResult r;
+  r.axis = axis;
+  r.left_box = best_left.box; r.left_start = begin; r.left_end = begin + best_left.count;
+  r.right_box = best_right.box; r.right_start = begin + best_left.count; r.right_end = end;
+  return r;
+}
+
+FlattenBVH FlattenBVH::build(const Box3 *boxes, uint64_t n, BVHBuildStrategy &strategy, const TreeBuildOption &option) {
+  FlattenBVH out;
+  std::vector<BuildPrimitive> primitives(n);
+  out.sorted_primitive_index.resize(n);
+  for (uint64_t i = 0; i < n; ++i) {
+    primitives[i].bounding = boxes[i];
+    primitives[i].center = box_center(boxes[i]);
+    out.sorted_primitive_index[i] = i;
+  }
+  auto make_node = [&](const Box3 &b, uint64_t s, uint64_t e) {
+    FlattenBVHNode nd;
+    std::memset(&nd, 0, sizeof(nd));
+    nd.bounding = b; nd.primitive_start = s; nd.primitive_end = e; nd.self_index = out.nodes.size();
+    out.nodes.push_back(nd);
+  };
+  make_node(bounding_of_range(primitives, out.sorted_primitive_index, 0, n), 0, n);
+
+  // Pre-order construction without recursion: descend left, park the right sibling; when a leaf is
+  // reached the most recent parked sibling is emitted next, which fixes its parent's left_count.
+  struct Parked { uint64_t parent; Box3 box; uint64_t start, end; uint64_t depth; int32_t axis; };
+  std::vector<Parked> parked;
+  uint64_t cur = 0, depth = 0;
+  for (;;) {
+    const FlattenBVHNode node = out.nodes[cur];
+    if (option.should_continue(node.primitive_end - node.primitive_start, depth)) {
+      const SplitResult s = strategy.split(node, primitives, out.sorted_primitive_index, out.stats);
+      parked.push_back(Parked{cur, s.right_box, s.right_start, s.right_end, depth + 1, s.axis});
+      make_node(s.left_box, s.left_start, s.left_end);
+      cur = out.nodes.size() - 1;
+      depth += 1;
+      continue;
+    }
+    if (parked.empty()) break;
+    const Parked p = parked.back();
+    parked.pop_back();
+    FlattenBVHNode &parent = out.nodes[p.parent];
+    parent.has_child = 1;
+    parent.split_axis = p.axis;
+    parent.left_count = out.nodes.size() - (p.parent + 1);
+    make_node(p.box, p.start, p.end);
+    cur = out.nodes.size() - 1;
+    depth = p.depth;
+  }
+  return out;
+}
+
+std::vector<std::pair<uint32_t, uint32_t>> compute_bvh_next(const std::vector<FlattenBVHNode> &nodes) {
+  std::vector<std::pair<uint32_t, uint32_t>> result;
+  result.reserve(nodes.size());
+  std::vector<uint32_t> pending_right;
+  for (const FlattenBVHNode &node : nodes) {
+    if (!pending_right.empty() && pending_right.back() == static_cast<uint32_t>(node.self_index)) pending_right.pop_back();
+    const uint32_t miss = pending_right.empty() ? INVALID_NEXT : pending_right.back();
+    if (node.has_child) {
+      pending_right.push_back(static_cast<uint32_t>(node.right_child_offset()));
+      result.emplace_back(static_cast<uint32_t>(node.left_child_offset()), miss);
+    } else {
+      result.emplace_back(miss, miss);
+    }
+  }
+  return result;
+}
+
+}  // namespace rdn

@@ -1,0 +1,99 @@
+// bvh_builder.h — host-side FlattenBVH builder (the flattener's input).
+//
+// Mirrors the reference's space-query surface, same names and argument meaning:
+//   FlattenBVH::new / FlattenBVHNode      content/space/src/bvh/mod.rs:26-79, bvh/node.rs:5-53
+//   BVHBuildStrategy / BalanceTree / SAH  content/space/src/bvh/strategy.rs:11-284
+//   TreeBuildOption                       content/space/src/utils.rs:20-37
+//   compute_bvh_next                      shader/ray-tracing/.../geometry/naive/mod.rs:612-632
+// The tree must be the reference's tree node for node (pre-order, left = self+1,
+// right = self+left_count+1): visit order decides which of two equal-distance hits is reported.
+#pragma once
+#include <cstdint>
+#include <utility>
+#include <vector>
+
+#include "rdn_math.h"
+
+namespace rdn {
+
+struct TreeBuildOption {
+  uint64_t max_tree_depth = 10;
+  uint64_t bin_size = 50;
+  bool should_continue(uint64_t item_count, uint64_t depth) const { return depth < max_tree_depth && item_count > bin_size; }
+};
+
+// layout-compatible with rdn_flat_bvh_node (include/rdn_rt.h)
+struct FlattenBVHNode {
+  Box3 bounding;
+  uint64_t primitive_start, primitive_end;  // range into sorted_primitive_index
+  uint64_t self_index;
+  uint64_t left_count;                      // nodes in the left subtree, valid iff has_child
+  int32_t has_child;
+  int32_t split_axis;                       // 0 X, 1 Y, 2 Z
+  bool is_leaf() const { return !has_child; }
+  uint64_t left_child_offset() const { return self_index + 1; }
+  uint64_t right_child_offset() const { return self_index + left_count + 1; }
+};
+
+struct BuildPrimitive {
+  Box3 bounding;
+  Vec3 center;
+};
+
+struct SplitResult {
+  Box3 left_box, right_box;
+  uint64_t left_start, left_end, right_start, right_end;
+  int32_t axis;
+};
+
+struct BuildStats {
+  uint64_t balance_fallbacks = 0;       // SAH -> BalanceTree fallbacks (all primitives in one bucket)
+  uint64_t balance_fallbacks_gt10 = 0;  // ... over more than 10 primitives (Rust's select_nth order is unspecified there)
+  bool bucket_out_of_range = false;     // the reference would have panicked
+};
+
+class BVHBuildStrategy {
+ public:
+  virtual ~BVHBuildStrategy() = default;
+  virtual SplitResult split(const FlattenBVHNode &parent, const std::vector<BuildPrimitive> &build_source,
+                            std::vector<uint64_t> &index_source, BuildStats &stats) = 0;
+};
+
+class BalanceTree : public BVHBuildStrategy {
+ public:
+  SplitResult split(const FlattenBVHNode &parent, const std::vector<BuildPrimitive> &build_source,
+                    std::vector<uint64_t> &index_source, BuildStats &stats) override;
+};
+
+class SAH : public BVHBuildStrategy {
+ public:
+  explicit SAH(uint32_t pre_partition_check_count);
+  SplitResult split(const FlattenBVHNode &parent, const std::vector<BuildPrimitive> &build_source,
+                    std::vector<uint64_t> &index_source, BuildStats &stats) override;
+
+ private:
+  struct Bucket {
+    Box3 bounding;
+    std::vector<uint64_t> primitive_bucket;
+  };
+  std::vector<Bucket> pre_partition_;
+};
+
+struct FlattenBVH {
+  std::vector<FlattenBVHNode> nodes;
+  std::vector<uint64_t> sorted_primitive_index;
+  BuildStats stats;
+
+  static FlattenBVH build(const Box3 *boxes, uint64_t n, BVHBuildStrategy &strategy, const TreeBuildOption &option);
+};
+
+constexpr uint32_t INVALID_NEXT = 0xFFFFFFFFu;
+// (hit_next, miss_next) per node for the stackless threaded walk
+std::vector<std::pair<uint32_t, uint32_t>> compute_bvh_next(const std::vector<FlattenBVHNode> &nodes);
+
+// box3.rs helpers the builder and the TLAS assembly need
+int longest_axis(const Box3 &b);
+float surface_area(const Box3 &b);
+Vec3 box_center(const Box3 &b);
+
+}  // namespace rdn

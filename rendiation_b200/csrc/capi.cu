@@ -1,0 +1,715 @@
+// capi.cu — the extern "C" boundary (include/rdn_rt.h): scene object, lazy commit, replication, trace drivers.
+//
+// Host-side mirror of NaiveSahBVHSystem (shader/ray-tracing/src/backend/wavefront_compute/geometry/naive/mod.rs:
+// 495-610): mutations store + invalidate under a write lock, the first use after a mutation rebuilds everything
+// (get_or_build_gpu_data, mod.rs:521-536).  Errors are status codes + a thread-local message, never an abort.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <shared_mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/rdn_rt.h"
+#include "accel.h"
+#include "kernels.h"
+
+using namespace rdn;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define RDN_CUDA(expr)                                                                                      \
+  do {                                                                                                      \
+    cudaError_t e__ = (expr);                                                                               \
+    if (e__ != cudaSuccess) return fail(RDN_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+constexpr uint64_t HOST_CHUNK_RAYS = 1u << 20;  // rays per pipelined H2D/trace/D2H chunk (32 MiB in, 32 MiB out)
+constexpr uint64_t MAX_LAUNCH_RAYS = 1ull << 31;
+constexpr int N_SLOTS = 3;
+
+struct Scratch {
+  void *base = nullptr;        // small block: work_counter | tie_count | tie_unresolved | stack_overflow | counters[6]
+  uint32_t *tie_queue = nullptr;
+  float *tie_clamp = nullptr;
+  uint64_t capacity = 0;       // rays
+  TraceScratch view() const {
+    TraceScratch s;
+    char *b = static_cast<char *>(base);
+    s.work_counter = reinterpret_cast<unsigned long long *>(b);
+    s.tie_count = reinterpret_cast<uint32_t *>(b + 8);
+    s.tie_unresolved = reinterpret_cast<uint32_t *>(b + 12);
+    s.stack_overflow = reinterpret_cast<uint32_t *>(b + 16);
+    s.counters = reinterpret_cast<unsigned long long *>(b + 32);
+    s.tie_queue = tie_queue;
+    s.tie_clamp = tie_clamp;
+    return s;
+  }
+};
+constexpr size_t SCRATCH_BASE_BYTES = 32 + 6 * 8;
+
+struct Slot {  // one pipeline lane of the host-buffer path
+  cudaStream_t stream = nullptr;
+  rdn_ray *d_rays = nullptr;
+  rdn_hit *d_hits = nullptr;
+  uint64_t capacity = 0;
+  Scratch scratch;
+};
+
+struct DeviceCtx {
+  int device = 0;
+  int sm_count = 148;
+  void *d_blob = nullptr;
+  uint64_t blob_bytes = 0;
+  SceneDev dev{};
+  Slot slots[N_SLOTS];
+  Scratch ext_scratch;            // for caller-stream (device-resident) traces
+  cudaEvent_t ext_done = nullptr; // orders successive device-resident traces that share ext_scratch
+  bool ext_pending = false;
+  unsigned long long *d_compact_status = nullptr;
+  uint64_t compact_status_cap = 0;
+};
+
+}  // namespace
+
+struct rdn_rt_scene {
+  std::shared_mutex lock;
+  std::mutex launch_lock;          // serialises use of the per-device scratch / slots
+  NaiveSahBvhSource source;
+  std::vector<uint32_t> tlas_binding;
+  bool dirty = true;               // invalidate(): cpu_data = gpu_data = None
+  bool adopted = false;            // blob came from another rank; local sources are not authoritative
+  FlatScene flat;                  // host copy (empty when adopted)
+  std::vector<uint8_t> host_blob;  // kept only by host-only scenes (n_devices == 0)
+  std::vector<uint32_t> h_tlas_binding;  // host copies used to resolve the wide root of a launch
+  std::vector<TlasRoot> h_tlas_root;
+  std::vector<DeviceCtx> devices;
+};
+
+namespace {
+
+int ensure_scratch(Scratch &s, uint64_t n) {
+  if (!s.base) {
+    RDN_CUDA(cudaMalloc(&s.base, SCRATCH_BASE_BYTES));
+    RDN_CUDA(cudaMemset(s.base, 0, SCRATCH_BASE_BYTES));
+  }
+  if (s.capacity < n) {
+    if (s.tie_queue) cudaFree(s.tie_queue);
+    if (s.tie_clamp) cudaFree(s.tie_clamp);
+    s.tie_queue = nullptr; s.tie_clamp = nullptr; s.capacity = 0;
+    RDN_CUDA(cudaMalloc(&s.tie_queue, std::max<uint64_t>(n, 1) * sizeof(uint32_t)));
+    RDN_CUDA(cudaMalloc(&s.tie_clamp, std::max<uint64_t>(n, 1) * sizeof(float)));
+    s.capacity = n;
+  }
+  return RDN_OK;
+}
+
+void free_scratch(Scratch &s) {
+  if (s.base) cudaFree(s.base);
+  if (s.tie_queue) cudaFree(s.tie_queue);
+  if (s.tie_clamp) cudaFree(s.tie_clamp);
+  s = Scratch{};
+}
+
+void bind_blob(DeviceCtx &dc, const BlobHeader &h) {
+  const char *b = static_cast<const char *>(dc.d_blob);
+  SceneDev &d = dc.dev;
+  d.tlas_binding = reinterpret_cast<const uint32_t *>(b + h.offset[ARR_TLAS_BINDING]);
+  d.tlas_root = reinterpret_cast<const TlasRoot *>(b + h.offset[ARR_TLAS_ROOT]);
+  d.tlas_bvh_forest = reinterpret_cast<const DeviceBVHNode *>(b + h.offset[ARR_TLAS_BVH_FOREST]);
+  d.tlas_bounding = reinterpret_cast<const TlasBounding *>(b + h.offset[ARR_TLAS_BOUNDING]);
+  d.instances = reinterpret_cast<const InstanceRecord *>(b + h.offset[ARR_INSTANCES]);
+  d.blas_meta = reinterpret_cast<const BlasMeta *>(b + h.offset[ARR_BLAS_META]);
+  d.geometry_meta = reinterpret_cast<const GeometryMeta *>(b + h.offset[ARR_GEOMETRY_META]);
+  d.tri_bvh_forest = reinterpret_cast<const DeviceBVHNode *>(b + h.offset[ARR_TRI_BVH_FOREST]);
+  d.triangles = reinterpret_cast<const TriRecord *>(b + h.offset[ARR_TRIANGLES]);
+  d.slot_info = reinterpret_cast<const SlotInfo *>(b + h.offset[ARR_SLOT_INFO]);
+  d.wide_nodes = reinterpret_cast<const WideNode *>(b + h.offset[ARR_WIDE_NODES]);
+  d.n_tlas_binding = static_cast<uint32_t>(h.count[ARR_TLAS_BINDING]);
+  d.n_tlas_root = static_cast<uint32_t>(h.count[ARR_TLAS_ROOT]);
+  d.n_blas_meta = static_cast<uint32_t>(h.count[ARR_BLAS_META]);
+  d.n_instances = static_cast<uint32_t>(h.count[ARR_INSTANCES]);
+}
+
+bool header_ok(const BlobHeader &h, uint64_t bytes) {
+  if (h.magic != BLOB_MAGIC || h.version != BLOB_VERSION || h.header_bytes != sizeof(BlobHeader) || h.total_bytes != bytes) return false;
+  for (int i = 0; i < ARR_COUNT; ++i)
+    if (h.offset[i] % 16 != 0 || h.offset[i] + std::max<uint64_t>(h.count[i], 1) * h.elem_size[i] > bytes) return false;
+  return true;
+}
+
+// build -> flatten -> upload to device 0 -> replicate to the other devices (peer copy: NVLink when available)
+int commit_locked(rdn_rt_scene *s) {
+  if (!s->dirty) return RDN_OK;
+  if (s->adopted && !s->devices.empty() && s->devices[0].d_blob) { s->dirty = false; return RDN_OK; }
+  std::string err;
+  FlatScene flat;
+  const int rc = s->source.build(s->tlas_binding, flat, err);
+  if (rc != RDN_OK) return fail(rc, err);
+  const std::vector<uint8_t> blob = flat.serialize();
+  BlobHeader h;
+  std::memcpy(&h, blob.data(), sizeof(h));
+  for (size_t i = 0; i < s->devices.size(); ++i) {
+    DeviceCtx &dc = s->devices[i];
+    RDN_CUDA(cudaSetDevice(dc.device));
+    if (dc.d_blob) { cudaFree(dc.d_blob); dc.d_blob = nullptr; }
+    RDN_CUDA(cudaMalloc(&dc.d_blob, blob.size()));
+    dc.blob_bytes = blob.size();
+    if (i == 0) {
+      RDN_CUDA(cudaMemcpy(dc.d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    } else {
+      RDN_CUDA(cudaMemcpyPeer(dc.d_blob, dc.device, s->devices[0].d_blob, s->devices[0].device, blob.size()));
+    }
+    bind_blob(dc, h);
+  }
+  s->h_tlas_binding = flat.tlas_binding;
+  s->h_tlas_root = flat.tlas_root;
+  s->flat = std::move(flat);
+  if (s->devices.empty()) s->host_blob = blob;
+  s->dirty = false;
+  return RDN_OK;
+}
+
+int ensure_committed(rdn_rt_scene *s) {
+  {
+    std::shared_lock<std::shared_mutex> rd(s->lock);
+    if (!s->dirty) return RDN_OK;
+  }
+  std::unique_lock<std::shared_mutex> wr(s->lock);
+  return commit_locked(s);
+}
+
+uint32_t resolve_world_root(const rdn_rt_scene *s, uint32_t tlas_idx) {
+  if (tlas_idx >= s->h_tlas_binding.size()) return REF_EMPTY;
+  const uint32_t handle = s->h_tlas_binding[tlas_idx];
+  if (handle >= s->h_tlas_root.size()) return REF_EMPTY;
+  return s->h_tlas_root[handle].wide_root;
+}
+
+// enqueue the kernels of one trace on `stream`; returns the number of kernels launched
+int enqueue_trace(rdn_rt_scene *s, DeviceCtx &dc, const Scratch &scratch, const rdn_launch &launch, const rdn_ray *d_rays, uint64_t n,
+                  rdn_hit *d_hits, int mode, cudaStream_t stream, uint32_t *launches) {
+  const TraceScratch ts = scratch.view();
+  RDN_CUDA(cudaMemsetAsync(scratch.base, 0, 12, stream));  // work_counter + tie_count; the two error flags accumulate until read
+  const bool end_search = (launch.ray_flags & RDN_RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH) != 0;
+  if (mode == RDN_TRACE_REFERENCE_ORDER || end_search) {
+    launch_trace_reference(dc.dev, launch, d_rays, n, d_hits, ts, false, false, dc.sm_count, stream);
+    if (launches) *launches += 1;
+  } else {
+    launch_trace_ordered(dc.dev, launch, resolve_world_root(s, launch.tlas_idx), d_rays, n, d_hits, ts, dc.sm_count, stream);
+    launch_trace_reference(dc.dev, launch, d_rays, n, d_hits, ts, true, false, dc.sm_count, stream);
+    if (launches) *launches += 2;
+  }
+  RDN_CUDA(cudaGetLastError());
+  return RDN_OK;
+}
+
+int ensure_slot(Slot &slot, uint64_t rays) {
+  if (!slot.stream) RDN_CUDA(cudaStreamCreateWithFlags(&slot.stream, cudaStreamNonBlocking));
+  if (slot.capacity < rays) {
+    if (slot.d_rays) cudaFree(slot.d_rays);
+    if (slot.d_hits) cudaFree(slot.d_hits);
+    slot.d_rays = nullptr; slot.d_hits = nullptr; slot.capacity = 0;
+    RDN_CUDA(cudaMalloc(&slot.d_rays, rays * sizeof(rdn_ray)));
+    RDN_CUDA(cudaMalloc(&slot.d_hits, rays * sizeof(rdn_hit)));
+    slot.capacity = rays;
+  }
+  return ensure_scratch(slot.scratch, rays);
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char *rdn_rt_last_error(void) { return g_last_error.c_str(); }
+const char *rdn_rt_version(void) { return "rendiation_b200 0.1 (sm_100a)"; }
+
+int rdn_rt_scene_create(int n_devices, const int *device_ids, rdn_rt_scene **out) {
+  if (!out || n_devices < 0) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_scene_create: need out and n_devices >= 0");
+  int available = 0;
+  if (n_devices > 0) RDN_CUDA(cudaGetDeviceCount(&available));  // n_devices == 0: host-only scene (build/flatten inspection, no tracing)
+  auto *s = new rdn_rt_scene();
+  s->devices.resize(n_devices);
+  for (int i = 0; i < n_devices; ++i) {
+    const int dev = device_ids ? device_ids[i] : i;
+    if (dev < 0 || dev >= available) { delete s; return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_scene_create: no such CUDA device"); }
+    s->devices[i].device = dev;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) s->devices[i].sm_count = prop.multiProcessorCount;
+  }
+  // let device 0 push the blob to its peers over NVLink
+  for (int i = 1; i < n_devices; ++i) {
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, s->devices[i].device, s->devices[0].device) == cudaSuccess && can) {
+      cudaSetDevice(s->devices[i].device);
+      cudaDeviceEnablePeerAccess(s->devices[0].device, 0);
+      cudaGetLastError();
+    }
+  }
+  *out = s;
+  return RDN_OK;
+}
+
+void rdn_rt_scene_destroy(rdn_rt_scene *s) {
+  if (!s) return;
+  for (DeviceCtx &dc : s->devices) {
+    cudaSetDevice(dc.device);
+    cudaDeviceSynchronize();
+    if (dc.d_blob) cudaFree(dc.d_blob);
+    for (Slot &slot : dc.slots) {
+      if (slot.d_rays) cudaFree(slot.d_rays);
+      if (slot.d_hits) cudaFree(slot.d_hits);
+      free_scratch(slot.scratch);
+      if (slot.stream) cudaStreamDestroy(slot.stream);
+    }
+    free_scratch(dc.ext_scratch);
+    if (dc.ext_done) cudaEventDestroy(dc.ext_done);
+    if (dc.d_compact_status) cudaFree(dc.d_compact_status);
+  }
+  delete s;
+}
+
+int rdn_rt_blas_create(rdn_rt_scene *s, const rdn_blas_geometry *geoms, uint32_t n, uint32_t *out_handle) {
+  if (!s || !out_handle || (n && !geoms)) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_blas_create: null argument");
+  std::vector<GeometrySource> src(n);
+  for (uint32_t g = 0; g < n; ++g) {
+    const rdn_blas_geometry &in = geoms[g];
+    src[g].flags = in.flags;
+    src[g].is_aabbs = in.kind != 0;
+    if (src[g].is_aabbs) continue;
+    if (in.n_positions && !in.positions) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_blas_create: null positions");
+    src[g].positions.resize(in.n_positions);
+    if (in.n_positions) std::memcpy(src[g].positions.data(), in.positions, in.n_positions * sizeof(Vec3));
+    src[g].has_indices = in.indices != nullptr;
+    if (in.indices) src[g].indices.assign(in.indices, in.indices + in.n_indices);
+  }
+  std::unique_lock<std::shared_mutex> wr(s->lock);
+  s->dirty = true; s->adopted = false;
+  *out_handle = s->source.create_blas(std::move(src));
+  return RDN_OK;
+}
+
+int rdn_rt_blas_destroy(rdn_rt_scene *s, uint32_t handle) {
+  if (!s) return fail(RDN_ERR_INVALID_ARGUMENT, "null scene");
+  std::unique_lock<std::shared_mutex> wr(s->lock);
+  s->dirty = true; s->adopted = false;
+  return s->source.delete_blas(handle) ? RDN_OK : fail(RDN_ERR_INVALID_HANDLE, "rdn_rt_blas_destroy: unknown handle");
+}
+
+int rdn_rt_tlas_create(rdn_rt_scene *s, const rdn_instance *inst, uint32_t n, uint32_t *out_handle) {
+  if (!s || !out_handle || (n && !inst)) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_tlas_create: null argument");
+  std::vector<InstanceSource> src(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    std::memcpy(&src[i].transform, inst[i].transform, sizeof(Mat4));
+    src[i].instance_custom_index = inst[i].instance_custom_index;
+    src[i].mask = inst[i].mask;
+    src[i].sbt_offset = inst[i].instance_shader_binding_table_record_offset;
+    src[i].flags = inst[i].flags;
+    src[i].blas_handle = inst[i].blas_handle;
+  }
+  std::unique_lock<std::shared_mutex> wr(s->lock);
+  s->dirty = true; s->adopted = false;
+  *out_handle = s->source.create_tlas(std::move(src));
+  return RDN_OK;
+}
+
+int rdn_rt_tlas_destroy(rdn_rt_scene *s, uint32_t handle) {
+  if (!s) return fail(RDN_ERR_INVALID_ARGUMENT, "null scene");
+  std::unique_lock<std::shared_mutex> wr(s->lock);
+  s->dirty = true; s->adopted = false;
+  return s->source.delete_tlas(handle) ? RDN_OK : fail(RDN_ERR_INVALID_HANDLE, "rdn_rt_tlas_destroy: unknown handle");
+}
+
+int rdn_rt_bind_tlas(rdn_rt_scene *s, const uint32_t *handles, uint32_t n) {
+  if (!s || (n && !handles)) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_bind_tlas: null argument");
+  std::vector<uint32_t> nb(handles, handles + n);
+  std::unique_lock<std::shared_mutex> wr(s->lock);
+  if (nb != s->tlas_binding) {  // set_binding, mod.rs:539-545
+    s->tlas_binding = std::move(nb);
+    s->dirty = true; s->adopted = false;
+  }
+  return RDN_OK;
+}
+
+uint32_t rdn_rt_bind_tlas_max_len(const rdn_rt_scene *) { return 0xFFFFFFFFu; }  // mod.rs:569-571
+
+int rdn_rt_commit(rdn_rt_scene *s) {
+  if (!s) return fail(RDN_ERR_INVALID_ARGUMENT, "null scene");
+  std::unique_lock<std::shared_mutex> wr(s->lock);
+  return commit_locked(s);
+}
+
+int rdn_rt_trace_closest_device(rdn_rt_scene *s, int device_index, const rdn_launch *launch, const rdn_ray *d_rays, uint64_t n,
+                                rdn_hit *d_hits, void *cuda_stream, int mode, rdn_trace_stats *stats) {
+  if (!s || !launch || (n && (!d_rays || !d_hits))) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_trace_closest_device: null argument");
+  if (device_index < 0 || device_index >= static_cast<int>(s->devices.size())) return fail(RDN_ERR_INVALID_ARGUMENT, "bad device_index (host-only scene?)");
+  int rc = ensure_committed(s);
+  if (rc != RDN_OK) return rc;
+  std::shared_lock<std::shared_mutex> rd(s->lock);
+  std::lock_guard<std::mutex> lg(s->launch_lock);
+  DeviceCtx &dc = s->devices[device_index];
+  RDN_CUDA(cudaSetDevice(dc.device));
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  if (!dc.ext_done) RDN_CUDA(cudaEventCreateWithFlags(&dc.ext_done, cudaEventDisableTiming));
+  if (dc.ext_pending) RDN_CUDA(cudaStreamWaitEvent(stream, dc.ext_done, 0));  // the scratch is shared between calls
+  const uint64_t chunk = std::min<uint64_t>(std::max<uint64_t>(n, 1), MAX_LAUNCH_RAYS);
+  rc = ensure_scratch(dc.ext_scratch, chunk);
+  if (rc != RDN_OK) return rc;
+
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (stats) { RDN_CUDA(cudaEventCreate(&e0)); RDN_CUDA(cudaEventCreate(&e1)); }
+  uint64_t ties = 0;
+  float ms_total = 0.f;
+  for (uint64_t off = 0; off < n; off += chunk) {
+    const uint64_t m = std::min(chunk, n - off);
+    rdn_launch l = *launch;
+    if (off != 0 || m != n) l.grid_width = (l.grid_width && m % l.grid_width == 0 && off % l.grid_width == 0) ? l.grid_width : 0;
+    if (stats) RDN_CUDA(cudaEventRecord(e0, stream));
+    rc = enqueue_trace(s, dc, dc.ext_scratch, l, d_rays + off, m, d_hits + off, mode, stream, stats ? &stats->kernel_launches : nullptr);
+    if (rc != RDN_OK) return rc;
+    if (stats) {
+      RDN_CUDA(cudaEventRecord(e1, stream));
+      RDN_CUDA(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      RDN_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      ms_total += ms;
+      uint32_t small[3] = {0, 0, 0};
+      RDN_CUDA(cudaMemcpy(small, static_cast<char *>(dc.ext_scratch.base) + 8, sizeof(small), cudaMemcpyDeviceToHost));
+      ties += small[0];
+      if (small[1]) return fail(RDN_ERR_CUDA, "tie re-walk found no hit (internal invariant broken)");
+      if (small[2]) return fail(RDN_ERR_CAPACITY, "traversal stack overflow");
+    }
+  }
+  RDN_CUDA(cudaEventRecord(dc.ext_done, stream));
+  dc.ext_pending = true;
+  if (stats) {
+    stats->rays = n; stats->tie_rays = ties; stats->kernel_ms = ms_total;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
+  return RDN_OK;
+}
+
+int rdn_rt_trace_closest(rdn_rt_scene *s, const rdn_launch *launch, const rdn_ray *rays, uint64_t n, rdn_hit *out_hits) {
+  if (!s || !launch || (n && (!rays || !out_hits))) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_trace_closest: null argument");
+  if (s->devices.empty()) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_trace_closest: host-only scene has no CUDA device (there is no CPU fallback)");
+  int rc = ensure_committed(s);
+  if (rc != RDN_OK) return rc;
+  if (n == 0) return RDN_OK;
+  std::shared_lock<std::shared_mutex> rd(s->lock);
+  std::lock_guard<std::mutex> lg(s->launch_lock);
+
+  // chunk = whole rows of the launch grid (multiple of 4 rows) when a grid hint is given, so every chunk keeps the hint
+  uint64_t chunk = HOST_CHUNK_RAYS;
+  const uint32_t gw = launch->grid_width;
+  const bool grid = gw != 0 && n % gw == 0;
+  if (grid) {
+    uint64_t rows = std::max<uint64_t>(4, (HOST_CHUNK_RAYS / gw) / 4 * 4);
+    chunk = rows * gw;
+  }
+  const uint64_t n_chunks = (n + chunk - 1) / chunk;
+  const size_t n_dev = s->devices.size();
+
+  // tiles (chunks) are dealt round-robin to devices; each device pipelines its chunks over N_SLOTS streams:
+  // H2D(k+1) || kernels(k) || D2H(k-1)
+  for (size_t di = 0; di < n_dev; ++di) {
+    DeviceCtx &dc = s->devices[di];
+    RDN_CUDA(cudaSetDevice(dc.device));
+    for (Slot &slot : dc.slots) {
+      rc = ensure_slot(slot, std::min<uint64_t>(chunk, n));
+      if (rc != RDN_OK) return rc;
+    }
+  }
+  std::vector<uint64_t> per_dev_seq(n_dev, 0);
+  for (uint64_t c = 0; c < n_chunks; ++c) {
+    const size_t di = c % n_dev;
+    DeviceCtx &dc = s->devices[di];
+    RDN_CUDA(cudaSetDevice(dc.device));
+    Slot &slot = dc.slots[per_dev_seq[di]++ % N_SLOTS];
+    const uint64_t off = c * chunk, m = std::min(chunk, n - off);
+    rdn_launch l = *launch;
+    l.grid_width = grid ? gw : 0;
+    RDN_CUDA(cudaMemcpyAsync(slot.d_rays, rays + off, m * sizeof(rdn_ray), cudaMemcpyHostToDevice, slot.stream));
+    rc = enqueue_trace(s, dc, slot.scratch, l, slot.d_rays, m, slot.d_hits, RDN_TRACE_AUTO, slot.stream, nullptr);
+    if (rc != RDN_OK) return rc;
+    RDN_CUDA(cudaMemcpyAsync(out_hits + off, slot.d_hits, m * sizeof(rdn_hit), cudaMemcpyDeviceToHost, slot.stream));
+  }
+  for (size_t di = 0; di < n_dev; ++di) {
+    DeviceCtx &dc = s->devices[di];
+    RDN_CUDA(cudaSetDevice(dc.device));
+    for (Slot &slot : dc.slots) {
+      RDN_CUDA(cudaStreamSynchronize(slot.stream));
+      uint32_t small[3] = {0, 0, 0};
+      RDN_CUDA(cudaMemcpy(small, static_cast<char *>(slot.scratch.base) + 8, sizeof(small), cudaMemcpyDeviceToHost));
+      if (small[1]) return fail(RDN_ERR_CUDA, "tie re-walk found no hit (internal invariant broken)");
+      if (small[2]) return fail(RDN_ERR_CAPACITY, "traversal stack overflow");
+    }
+  }
+  return RDN_OK;
+}
+
+int rdn_rt_trace_counted(rdn_rt_scene *s, const rdn_launch *launch, const rdn_ray *rays, uint64_t n, rdn_hit *out_hits,
+                         rdn_counters *out_counters) {
+  if (!s || !launch || (n && (!rays || !out_hits))) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_trace_counted: null argument");
+  if (s->devices.empty()) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_trace_counted: host-only scene has no CUDA device (there is no CPU fallback)");
+  int rc = ensure_committed(s);
+  if (rc != RDN_OK) return rc;
+  std::shared_lock<std::shared_mutex> rd(s->lock);
+  std::lock_guard<std::mutex> lg(s->launch_lock);
+  DeviceCtx &dc = s->devices[0];
+  RDN_CUDA(cudaSetDevice(dc.device));
+  if (out_counters) std::memset(out_counters, 0, sizeof(*out_counters));
+  const uint64_t chunk = 1u << 22;
+  Slot &slot = dc.slots[0];
+  rc = ensure_slot(slot, std::min<uint64_t>(chunk, std::max<uint64_t>(n, 1)));
+  if (rc != RDN_OK) return rc;
+  for (uint64_t off = 0; off < n; off += chunk) {
+    const uint64_t m = std::min(chunk, n - off);
+    RDN_CUDA(cudaMemcpyAsync(slot.d_rays, rays + off, m * sizeof(rdn_ray), cudaMemcpyHostToDevice, slot.stream));
+    RDN_CUDA(cudaMemsetAsync(slot.scratch.base, 0, SCRATCH_BASE_BYTES, slot.stream));
+    launch_trace_reference(dc.dev, *launch, slot.d_rays, m, slot.d_hits, slot.scratch.view(), false, true, dc.sm_count, slot.stream);
+    RDN_CUDA(cudaGetLastError());
+    RDN_CUDA(cudaMemcpyAsync(out_hits + off, slot.d_hits, m * sizeof(rdn_hit), cudaMemcpyDeviceToHost, slot.stream));
+    unsigned long long c[6];
+    RDN_CUDA(cudaMemcpyAsync(c, static_cast<char *>(slot.scratch.base) + 32, sizeof(c), cudaMemcpyDeviceToHost, slot.stream));
+    RDN_CUDA(cudaStreamSynchronize(slot.stream));
+    if (out_counters) {
+      out_counters->bvh_visit += c[0]; out_counters->bvh_hit += c[1]; out_counters->tri_visit += c[2];
+      out_counters->tri_hit += c[3]; out_counters->inst_visit += c[4]; out_counters->ref_abort += c[5];
+    }
+  }
+  return RDN_OK;
+}
+
+int rdn_rt_compact_u32_device(rdn_rt_scene *s, int device_index, const uint32_t *d_in, const uint8_t *d_keep, uint64_t n,
+                              uint32_t *d_out, uint64_t *d_out_n, void *cuda_stream) {
+  if (!s || !d_out_n || (n && (!d_in || !d_keep || !d_out))) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_compact_u32_device: null argument");
+  if (device_index < 0 || device_index >= static_cast<int>(s->devices.size())) return fail(RDN_ERR_INVALID_ARGUMENT, "bad device_index");
+  std::lock_guard<std::mutex> lg(s->launch_lock);
+  DeviceCtx &dc = s->devices[device_index];
+  RDN_CUDA(cudaSetDevice(dc.device));
+  const uint64_t words = compact_status_words(n);
+  if (dc.compact_status_cap < words) {
+    if (dc.d_compact_status) cudaFree(dc.d_compact_status);
+    dc.d_compact_status = nullptr; dc.compact_status_cap = 0;
+    RDN_CUDA(cudaMalloc(&dc.d_compact_status, words * sizeof(unsigned long long)));
+    dc.compact_status_cap = words;
+  }
+  launch_compact_u32(d_in, d_keep, n, d_out, d_out_n, dc.d_compact_status, static_cast<cudaStream_t>(cuda_stream));
+  RDN_CUDA(cudaGetLastError());
+  return RDN_OK;
+}
+
+int rdn_rt_compact_u32(rdn_rt_scene *s, const uint32_t *in, const uint8_t *keep, uint64_t n, uint32_t *out, uint64_t *out_n) {
+  if (!s || !out_n || (n && (!in || !keep || !out))) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_compact_u32: null argument");
+  if (s->devices.empty()) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_compact_u32: host-only scene has no CUDA device (there is no CPU fallback)");
+  DeviceCtx &dc = s->devices[0];
+  RDN_CUDA(cudaSetDevice(dc.device));
+  uint32_t *d_in = nullptr, *d_out = nullptr;
+  uint8_t *d_keep = nullptr;
+  uint64_t *d_n = nullptr;
+  const uint64_t m = std::max<uint64_t>(n, 1);
+  RDN_CUDA(cudaMalloc(&d_in, m * 4)); RDN_CUDA(cudaMalloc(&d_out, m * 4)); RDN_CUDA(cudaMalloc(&d_keep, m)); RDN_CUDA(cudaMalloc(&d_n, 8));
+  RDN_CUDA(cudaMemcpy(d_in, in, n * 4, cudaMemcpyHostToDevice));
+  RDN_CUDA(cudaMemcpy(d_keep, keep, n, cudaMemcpyHostToDevice));
+  int rc = rdn_rt_compact_u32_device(s, 0, d_in, d_keep, n, d_out, d_n, nullptr);
+  if (rc == RDN_OK) {
+    RDN_CUDA(cudaDeviceSynchronize());
+    RDN_CUDA(cudaMemcpy(out, d_out, n * 4, cudaMemcpyDeviceToHost));
+    RDN_CUDA(cudaMemcpy(out_n, d_n, 8, cudaMemcpyDeviceToHost));
+  }
+  cudaFree(d_in); cudaFree(d_out); cudaFree(d_keep); cudaFree(d_n);
+  return rc;
+}
+
+int rdn_rt_scene_blob(rdn_rt_scene *s, int device_index, void **out_ptr, uint64_t *out_bytes) {
+  if (!s || !out_ptr || !out_bytes) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_scene_blob: null argument");
+  if (device_index < 0 || device_index >= static_cast<int>(s->devices.size())) return fail(RDN_ERR_INVALID_ARGUMENT, "bad device_index");
+  int rc = ensure_committed(s);
+  if (rc != RDN_OK) return rc;
+  *out_ptr = s->devices[device_index].d_blob;
+  *out_bytes = s->devices[device_index].blob_bytes;
+  return RDN_OK;
+}
+
+int rdn_rt_scene_adopt_blob(rdn_rt_scene *s, int device_index, const void *d_blob, uint64_t bytes) {
+  if (!s || !d_blob || bytes < sizeof(BlobHeader)) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_scene_adopt_blob: null/short blob");
+  if (device_index < 0 || device_index >= static_cast<int>(s->devices.size())) return fail(RDN_ERR_INVALID_ARGUMENT, "bad device_index");
+  std::unique_lock<std::shared_mutex> wr(s->lock);
+  DeviceCtx &dc = s->devices[device_index];
+  RDN_CUDA(cudaSetDevice(dc.device));
+  BlobHeader h;
+  RDN_CUDA(cudaMemcpy(&h, d_blob, sizeof(h), cudaMemcpyDeviceToHost));
+  if (!header_ok(h, bytes)) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_scene_adopt_blob: bad header");
+  if (dc.d_blob) { cudaFree(dc.d_blob); dc.d_blob = nullptr; }
+  RDN_CUDA(cudaMalloc(&dc.d_blob, bytes));
+  RDN_CUDA(cudaMemcpy(dc.d_blob, d_blob, bytes, cudaMemcpyDeviceToDevice));
+  dc.blob_bytes = bytes;
+  bind_blob(dc, h);
+  s->h_tlas_binding.assign(h.count[ARR_TLAS_BINDING], 0);
+  s->h_tlas_root.assign(h.count[ARR_TLAS_ROOT], TlasRoot{INVALID_NEXT, REF_EMPTY});
+  if (!s->h_tlas_binding.empty())
+    RDN_CUDA(cudaMemcpy(s->h_tlas_binding.data(), dc.dev.tlas_binding, s->h_tlas_binding.size() * 4, cudaMemcpyDeviceToHost));
+  if (!s->h_tlas_root.empty())
+    RDN_CUDA(cudaMemcpy(s->h_tlas_root.data(), dc.dev.tlas_root, s->h_tlas_root.size() * sizeof(TlasRoot), cudaMemcpyDeviceToHost));
+  s->flat = FlatScene{};
+  s->adopted = true;
+  s->dirty = false;
+  return RDN_OK;
+}
+
+int rdn_rt_scene_array(rdn_rt_scene *s, int array_id, void *out, uint64_t capacity, uint64_t *out_bytes) {
+  if (!s || !out_bytes || array_id < 0 || array_id >= ARR_COUNT) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_scene_array: bad argument");
+  int rc = ensure_committed(s);
+  if (rc != RDN_OK) return rc;
+  std::shared_lock<std::shared_mutex> rd(s->lock);
+  BlobHeader h;
+  if (s->devices.empty()) {
+    std::memcpy(&h, s->host_blob.data(), sizeof(h));
+  } else {
+    RDN_CUDA(cudaSetDevice(s->devices[0].device));
+    RDN_CUDA(cudaMemcpy(&h, s->devices[0].d_blob, sizeof(h), cudaMemcpyDeviceToHost));
+  }
+  const uint64_t bytes = h.count[array_id] * h.elem_size[array_id];
+  *out_bytes = bytes;
+  if (!out) return RDN_OK;
+  if (capacity < bytes) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_scene_array: buffer too small");
+  if (bytes) {
+    if (s->devices.empty()) std::memcpy(out, s->host_blob.data() + h.offset[array_id], bytes);
+    else RDN_CUDA(cudaMemcpy(out, static_cast<const char *>(s->devices[0].d_blob) + h.offset[array_id], bytes, cudaMemcpyDeviceToHost));
+  }
+  return RDN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ space query (path A)
+struct rdn_flat_bvh {
+  FlattenBVH bvh;
+  uint64_t depth = 0;
+};
+
+static uint64_t tree_depth(const std::vector<FlattenBVHNode> &nodes) {
+  // pre-order walk with an explicit stack of (node, depth)
+  uint64_t best = 0;
+  std::vector<std::pair<uint64_t, uint64_t>> st;
+  if (!nodes.empty()) st.emplace_back(0, 1);
+  while (!st.empty()) {
+    auto [i, d] = st.back();
+    st.pop_back();
+    best = std::max(best, d);
+    if (nodes[i].has_child) { st.emplace_back(nodes[i].left_child_offset(), d + 1); st.emplace_back(nodes[i].right_child_offset(), d + 1); }
+  }
+  return best;
+}
+
+static int build_bvh_common(const Box3 *boxes, uint64_t n, int strategy, uint32_t buckets, const rdn_tree_build_option *option,
+                            rdn_flat_bvh **out) {
+  TreeBuildOption opt;
+  if (option) { opt.max_tree_depth = option->max_tree_depth; opt.bin_size = option->bin_size; }
+  auto *r = new rdn_flat_bvh();
+  if (strategy == RDN_BVH_SAH) {
+    SAH sah(buckets ? buckets : 4);
+    r->bvh = FlattenBVH::build(boxes, n, sah, opt);
+  } else if (strategy == RDN_BVH_BALANCE_TREE) {
+    BalanceTree bt;
+    r->bvh = FlattenBVH::build(boxes, n, bt, opt);
+  } else {
+    delete r;
+    return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_bvh_build: unknown strategy");
+  }
+  if (r->bvh.stats.bucket_out_of_range) { delete r; return fail(RDN_ERR_BUILD, "SAH bucket index out of range (the reference panics here)"); }
+  r->depth = tree_depth(r->bvh.nodes);
+  *out = r;
+  return RDN_OK;
+}
+
+int rdn_bvh_build(const float *boxes6, uint64_t n, int strategy, uint32_t sah_buckets, const rdn_tree_build_option *option, rdn_flat_bvh **out) {
+  if (!out || (n && !boxes6)) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_bvh_build: null argument");
+  static_assert(sizeof(Box3) == 24, "Box3 layout");
+  return build_bvh_common(reinterpret_cast<const Box3 *>(boxes6), n, strategy, sah_buckets, option, out);
+}
+
+int rdn_bvh_build_for_mesh(const rdn_mesh_view *mesh, int strategy, uint32_t sah_buckets, const rdn_tree_build_option *option, rdn_flat_bvh **out) {
+  if (!out || !mesh || !mesh->positions || !mesh->indices) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_bvh_build_for_mesh: null argument");
+  const uint64_t n_tri = mesh->n_indices / 3;
+  std::vector<Box3> boxes(n_tri);
+  for (uint64_t t = 0; t < n_tri; ++t) {
+    Box3 b = box_empty();  // Triangle::to_bounding, bounding_impl.rs:3-12
+    for (int k = 0; k < 3; ++k) {
+      const uint64_t vi = mesh->indices[3 * t + k];
+      if (vi >= mesh->n_positions) return fail(RDN_ERR_BUILD, "triangle index out of bounds");
+      expand(b, Vec3{mesh->positions[3 * vi], mesh->positions[3 * vi + 1], mesh->positions[3 * vi + 2]});
+    }
+    boxes[t] = b;
+  }
+  return build_bvh_common(boxes.data(), n_tri, strategy, sah_buckets, option, out);
+}
+
+void rdn_bvh_destroy(rdn_flat_bvh *b) { delete b; }
+
+int rdn_bvh_nodes(const rdn_flat_bvh *b, const rdn_flat_bvh_node **out_nodes, uint64_t *out_n) {
+  if (!b || !out_nodes || !out_n) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_bvh_nodes: null argument");
+  static_assert(sizeof(FlattenBVHNode) == sizeof(rdn_flat_bvh_node), "FlattenBVHNode layout");
+  *out_nodes = reinterpret_cast<const rdn_flat_bvh_node *>(b->bvh.nodes.data());
+  *out_n = b->bvh.nodes.size();
+  return RDN_OK;
+}
+
+int rdn_bvh_sorted_primitive_index(const rdn_flat_bvh *b, const uint64_t **out_index, uint64_t *out_n) {
+  if (!b || !out_index || !out_n) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_bvh_sorted_primitive_index: null argument");
+  *out_index = b->bvh.sorted_primitive_index.data();
+  *out_n = b->bvh.sorted_primitive_index.size();
+  return RDN_OK;
+}
+
+int rdn_bvh_query_nearest(const rdn_flat_bvh *b, const rdn_mesh_view *mesh, const rdn_ray *rays, uint64_t n, uint32_t face_side,
+                          int device, rdn_mesh_hit *out) {
+  if (!b || !mesh || !mesh->positions || !mesh->indices || (n && (!rays || !out))) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_bvh_query_nearest: null argument");
+  if (face_side > RDN_FACE_DOUBLE) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_bvh_query_nearest: bad face_side");
+  if (b->depth > static_cast<uint64_t>(PATHA_MAX_DEPTH)) return fail(RDN_ERR_CAPACITY, "rdn_bvh_query_nearest: tree deeper than 128 levels");
+  if (b->bvh.sorted_primitive_index.size() * 3 > mesh->n_indices) return fail(RDN_ERR_INVALID_ARGUMENT, "mesh smaller than the BVH it was built for");
+  RDN_CUDA(cudaSetDevice(device));
+  const auto &nodes = b->bvh.nodes;
+  std::vector<PathANode> pn(nodes.size());
+  for (size_t i = 0; i < nodes.size(); ++i) {
+    const FlattenBVHNode &nd = nodes[i];
+    PathANode &p = pn[i];
+    p.bmin[0] = nd.bounding.min.x; p.bmin[1] = nd.bounding.min.y; p.bmin[2] = nd.bounding.min.z;
+    p.bmax[0] = nd.bounding.max.x; p.bmax[1] = nd.bounding.max.y; p.bmax[2] = nd.bounding.max.z;
+    if (nd.has_child) { p.a = static_cast<uint32_t>(nd.right_child_offset()); p.b = 0xFFFFFFFFu; }
+    else { p.a = static_cast<uint32_t>(nd.primitive_start); p.b = static_cast<uint32_t>(nd.primitive_end); }
+  }
+  std::vector<uint32_t> sorted(b->bvh.sorted_primitive_index.begin(), b->bvh.sorted_primitive_index.end());
+  PathANode *d_nodes = nullptr; uint32_t *d_sorted = nullptr, *d_idx = nullptr; float *d_pos = nullptr;
+  rdn_ray *d_rays = nullptr; rdn_mesh_hit *d_out = nullptr;
+  auto cleanup = [&]() { cudaFree(d_nodes); cudaFree(d_sorted); cudaFree(d_idx); cudaFree(d_pos); cudaFree(d_rays); cudaFree(d_out); };
+#define RDN_CUDA_C(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); return fail(RDN_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
+  RDN_CUDA_C(cudaMalloc(&d_nodes, std::max<size_t>(pn.size(), 1) * sizeof(PathANode)));
+  RDN_CUDA_C(cudaMalloc(&d_sorted, std::max<size_t>(sorted.size(), 1) * 4));
+  RDN_CUDA_C(cudaMalloc(&d_idx, std::max<uint64_t>(mesh->n_indices, 1) * 4));
+  RDN_CUDA_C(cudaMalloc(&d_pos, std::max<uint64_t>(mesh->n_positions, 1) * 12));
+  RDN_CUDA_C(cudaMalloc(&d_rays, std::max<uint64_t>(n, 1) * sizeof(rdn_ray)));
+  RDN_CUDA_C(cudaMalloc(&d_out, std::max<uint64_t>(n, 1) * sizeof(rdn_mesh_hit)));
+  RDN_CUDA_C(cudaMemcpy(d_nodes, pn.data(), pn.size() * sizeof(PathANode), cudaMemcpyHostToDevice));
+  RDN_CUDA_C(cudaMemcpy(d_sorted, sorted.data(), sorted.size() * 4, cudaMemcpyHostToDevice));
+  RDN_CUDA_C(cudaMemcpy(d_idx, mesh->indices, mesh->n_indices * 4, cudaMemcpyHostToDevice));
+  RDN_CUDA_C(cudaMemcpy(d_pos, mesh->positions, mesh->n_positions * 12, cudaMemcpyHostToDevice));
+  RDN_CUDA_C(cudaMemcpy(d_rays, rays, n * sizeof(rdn_ray), cudaMemcpyHostToDevice));
+  launch_patha_nearest(d_nodes, d_sorted, d_pos, d_idx, d_rays, n, face_side, d_out, nullptr);
+  RDN_CUDA_C(cudaGetLastError());
+  RDN_CUDA_C(cudaDeviceSynchronize());
+  RDN_CUDA_C(cudaMemcpy(out, d_out, n * sizeof(rdn_mesh_hit), cudaMemcpyDeviceToHost));
+  cleanup();
+  return RDN_OK;
+}
+
+}  // extern "C"

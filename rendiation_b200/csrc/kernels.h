@@ -1,0 +1,69 @@
+// kernels.h — launch wrappers of the CUDA kernels (traverse.cu, compact.cu) used by the C ABI (capi.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/rdn_rt.h"
+#include "layout.h"
+
+namespace rdn {
+
+// device pointers into one blob
+struct SceneDev {
+  const uint32_t *tlas_binding;
+  const TlasRoot *tlas_root;
+  const DeviceBVHNode *tlas_bvh_forest;
+  const TlasBounding *tlas_bounding;
+  const InstanceRecord *instances;
+  const BlasMeta *blas_meta;
+  const GeometryMeta *geometry_meta;
+  const DeviceBVHNode *tri_bvh_forest;
+  const TriRecord *triangles;
+  const SlotInfo *slot_info;
+  const WideNode *wide_nodes;
+  uint32_t n_tlas_binding, n_tlas_root, n_blas_meta, n_instances;
+};
+
+// per-device scratch owned by the scene
+struct TraceScratch {
+  unsigned long long *work_counter;  // next ray fetch index (persistent kernel)
+  uint32_t *tie_count;               // rays queued for exact tie resolution
+  uint32_t *tie_unresolved;          // safety net: clamped re-walk found nothing (must stay 0)
+  uint32_t *stack_overflow;          // safety net: traversal stack overflow (must stay 0)
+  uint32_t *tie_queue;               // ray indices, capacity >= n
+  float *tie_clamp;                  // per queued ray: initial far for the reference-order re-walk
+  unsigned long long *counters;      // 6 x u64 (rdn_counters)
+};
+
+// relative slack of the ordered kernel's pruning bound and near-tie detection (see DESIGN.md "Exactness")
+constexpr float TIE_EPS = 1e-5f;
+
+// The reference's threaded pre-order walk, one ray per thread (NaiveSahBvhCpu::traverse on the device).
+// queue == nullptr: rays [0, n).  queue != nullptr: rays queue[0 .. *queue_count) with initial far = clamp[k];
+// a re-walk that finds nothing leaves the existing hit record untouched and bumps tie_unresolved.
+void launch_trace_reference(const SceneDev &scene, const rdn_launch &launch, const rdn_ray *d_rays, uint64_t n, rdn_hit *d_hits,
+                            const TraceScratch &scratch, bool use_tie_queue, bool count_visits, int sm_count, cudaStream_t stream);
+
+// Ordered (near child first) persistent-thread traversal with tie detection; queues near-tie rays in scratch.
+// world_root = TlasRoot::wide_root of tlas_binding[launch.tlas_idx] (resolved by the caller from its host copy).
+void launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, uint32_t world_root, const rdn_ray *d_rays, uint64_t n,
+                          rdn_hit *d_hits, const TraceScratch &scratch, int sm_count, cudaStream_t stream);
+
+// Stable stream compaction of u32 (single pass, decoupled look-back); d_status needs compact_status_words(n) u64.
+uint64_t compact_status_words(uint64_t n);
+void launch_compact_u32(const uint32_t *d_in, const uint8_t *d_keep, uint64_t n, uint32_t *d_out, uint64_t *d_out_n,
+                        unsigned long long *d_status, cudaStream_t stream);
+
+// path A: intersect_nearest_bvh over a FlattenBVH (content/mesh/core/src/feature/bvh.rs:57-86); the kernel walks
+// the tree in the reference's order (right child first, no distance pruning) so equal-distance ties resolve identically.
+constexpr int PATHA_MAX_DEPTH = 128;
+struct PathANode {  // 32 B: box + (left_count | leaf range)
+  float bmin[3]; uint32_t a;   // inner: right child index; leaf: primitive_start
+  float bmax[3]; uint32_t b;   // inner: 0xFFFFFFFF;        leaf: primitive_end (leaf iff b != 0xFFFFFFFF)
+};
+void launch_patha_nearest(const PathANode *d_nodes, const uint32_t *d_sorted_prims,
+                          const float *d_positions, const uint32_t *d_indices, const rdn_ray *d_rays, uint64_t n,
+                          uint32_t face_side, rdn_mesh_hit *d_out, cudaStream_t stream);
+
+}  // namespace rdn

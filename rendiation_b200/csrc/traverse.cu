@@ -1,0 +1,488 @@
+// traverse.cu — BVH closest-hit traversal kernels for sm_100a.
+//
+// Compiled with -fmad=false (no FMA contraction) and IEEE div/sqrt: every ray/box and ray/triangle value is
+// bit-identical to the reference's CPU arithmetic
+//   intersect_ray_aabb_cpu      shader/ray-tracing/src/backend/wavefront_compute/geometry/mod.rs:44-64
+//   intersect_ray_triangle_cpu  .../geometry/mod.rs:105-155
+//   NaiveSahBvhCpu::traverse    .../geometry/naive/traverse_cpu.rs:52-319
+//   TraverseFlags               .../geometry/naive/flag.rs:6-117
+//
+// Two kernels:
+//   k_trace_reference  the reference's stackless threaded pre-order walk, one ray per thread.  Identical to the
+//                      CPU query by construction (same visit order, same live-range pruning, "last accepted of
+//                      equal t wins").  Used for ACCEPT_FIRST_HIT rays, for visit counters, and to resolve ties.
+//   k_trace_ordered    persistent-thread, near-child-first walk over the 64 B two-box nodes with a per-thread
+//                      stack, float4 node/triangle fetches through the read-only path, warp-level ray refill
+//                      (ballot + one atomic per warp).  Box decisions use the reference's arithmetic on the
+//                      reference's boxes; the pruning bound is inflated by TIE_EPS and any ray that saw a second
+//                      candidate within TIE_EPS of the closest is queued (warp-aggregated append) and re-walked by
+//                      k_trace_reference with its range clamped — so ids come out exactly as the CPU query's.
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+#include "rdn_math.h"
+
+namespace rdn {
+
+namespace {
+
+constexpr uint32_t FULL_MASK = 0xFFFFFFFFu;
+constexpr int STACK_MAX = 120;       // TLAS depth 50 + BLAS depth 50 (TreeBuildOption of naive/mod.rs:173-176,280-283) + bookkeeping
+constexpr int ORDERED_BLOCK = 128;
+constexpr int ORDERED_STEPS = 24;    // traversal steps between warp re-convergence / ray refill points
+
+// TraverseFlags bits (flag.rs:6-25)
+constexpr uint32_t TF_FORCE_OPAQUE = 0x01, TF_FORCE_NON_OPAQUE = 0x02, TF_END_SEARCH = 0x04, TF_CULL_BACK = 0x10,
+                   TF_CULL_FRONT = 0x20, TF_CULL_OPAQUE = 0x40, TF_CULL_NON_OPAQUE = 0x80, TF_SKIP_TRIANGLES = 0x100,
+                   TF_FLIP_FACING = 0x400;
+
+__device__ __forceinline__ uint32_t merge_geometry_instance_flag(uint32_t f, uint32_t gi) {
+  if (gi & RDN_GEOMETRY_INSTANCE_TRIANGLE_FACING_CULL_DISABLE) f &= ~(TF_CULL_BACK | TF_CULL_FRONT);
+  if (gi & RDN_GEOMETRY_INSTANCE_TRIANGLE_FLIP_FACING) f ^= TF_FLIP_FACING;
+  if (gi & RDN_GEOMETRY_INSTANCE_FORCE_OPAQUE) f |= TF_FORCE_OPAQUE;
+  if (gi & RDN_GEOMETRY_INSTANCE_FORCE_NO_OPAQUE) f |= TF_FORCE_NON_OPAQUE;
+  return f;
+}
+// cull_geometry -> pass (is_opaque only selects the any-hit path, which is fixed to ACCEPT here)
+__device__ __forceinline__ bool cull_geometry_pass(uint32_t f, uint32_t geometry_flags) {
+  const bool geometry_opaque = (geometry_flags & RDN_GEOMETRY_FLAG_OPAQUE) != 0;
+  const bool is_opaque = (geometry_opaque || (f & TF_FORCE_OPAQUE)) && !(f & TF_FORCE_NON_OPAQUE);
+  return (is_opaque && !(f & TF_CULL_OPAQUE)) || (!is_opaque && !(f & TF_CULL_NON_OPAQUE));
+}
+// cull_triangle -> bit0 cull_enable, bit1 cull_back
+__device__ __forceinline__ uint32_t cull_triangle_bits(uint32_t f) {
+  const bool flip = (f & TF_FLIP_FACING) != 0, cull_front = (f & TF_CULL_FRONT) != 0, cull_back = (f & TF_CULL_BACK) != 0;
+  const bool enable = cull_front || cull_back;
+  const bool back = (flip && cull_back) || (!flip && cull_front);
+  return (enable ? 1u : 0u) | (back ? 2u : 0u);
+}
+
+__device__ __forceinline__ Vec3 xyz(const float4 &q) { return Vec3{q.x, q.y, q.z}; }
+__device__ __forceinline__ Vec3 recip3(Vec3 d) { return Vec3{1.0f / d.x, 1.0f / d.y, 1.0f / d.z}; }
+
+// intersect_ray_aabb_cpu with inv_d = 1/d hoisted (same value every call)
+__device__ __forceinline__ bool slab_test(Vec3 o, Vec3 inv_d, float t_min, float t_max, Vec3 bmin, Vec3 bmax, float &t_near_max) {
+  const Vec3 t0 = (bmin - o) * inv_d;
+  const Vec3 t1 = (bmax - o) * inv_d;
+  const Vec3 t_near = vmin(t0, t1);
+  const Vec3 t_far = vmax(t0, t1);
+  t_near_max = fmaxf(fmaxf(t_near.x, t_near.y), t_near.z);
+  const float t_far_min = fminf(fminf(t_far.x, t_far.y), t_far.z);
+  return t_near_max <= t_far_min && t_min < t_far_min && t_near_max < t_max;
+}
+
+// intersect_ray_triangle_cpu with the ray-independent terms read from the TriRecord
+__device__ __forceinline__ bool triangle_test(const float4 qn, const float4 qv0, const float4 qe1, const float4 qe2, Vec3 origin,
+                                              Vec3 direction, float range_x, float range_y, uint32_t cull_bits, float &sign,
+                                              float &t, float &u, float &v) {
+  const Vec3 normal = xyz(qn), v0 = xyz(qv0), e1 = xyz(qe1), e2 = xyz(qe2);
+  const float b = dot(normal, direction);
+  sign = copysignf(1.0f, b);
+  if (cull_bits & 1u) {
+    const bool cull_back = (cull_bits & 2u) != 0;
+    if (!(cull_back != (b < 0.0f))) return false;
+  }
+  const Vec3 w0 = origin - v0;
+  const float a = -dot(normal, w0);
+  t = a / b;
+  if (t < range_x || t > range_y) return false;
+  const Vec3 p = origin + direction * t;
+  const float uu = qv0.w, uv = qe1.w, vv = qe2.w, inverse_d = qn.w;
+  const Vec3 w = p - v0;
+  const float wu = dot(w, e1);
+  const float wv = dot(w, e2);
+  u = (uv * wv - vv * wu) * inverse_d;
+  if (u < 0.0f || u > 1.0f) return false;
+  v = (uv * wu - uu * wv) * inverse_d;
+  if (v < 0.0f || (u + v) > 1.0f) return false;
+  return true;
+}
+
+// world -> object ray (traverse_cpu.rs:99-104)
+__device__ __forceinline__ void to_object_space(const InstanceRecord *rec, Vec3 ro, Vec3 rd, Vec3 &bo, Vec3 &bd, float &scaling) {
+  const float4 *m = reinterpret_cast<const float4 *>(rec->transform_inv);
+  const float4 ca = __ldg(m), cb = __ldg(m + 1), cc = __ldg(m + 2), cd = __ldg(m + 3);  // columns a,b,c,d
+  const float x = ro.x * ca.x + ro.y * cb.x + ro.z * cc.x + 1.0f * cd.x;
+  const float y = ro.x * ca.y + ro.y * cb.y + ro.z * cc.y + 1.0f * cd.y;
+  const float z = ro.x * ca.z + ro.y * cb.z + ro.z * cc.z + 1.0f * cd.z;
+  const float w = ro.x * ca.w + ro.y * cb.w + ro.z * cc.w + 1.0f * cd.w;
+  bo = Vec3{x / w, y / w, z / w};
+  const Vec3 d0 = Vec3{rd.x * ca.x + rd.y * cb.x + rd.z * cc.x, rd.x * ca.y + rd.y * cb.y + rd.z * cc.y,
+                       rd.x * ca.z + rd.y * cb.z + rd.z * cc.z};
+  scaling = length(d0);
+  bd = normalize(d0);
+}
+
+__device__ __forceinline__ void store_hit(rdn_hit *dst, float t, float u, float v, uint32_t prim, uint32_t geom, uint32_t inst,
+                                          uint32_t custom, uint32_t kind) {
+  float4 *p = reinterpret_cast<float4 *>(dst);
+  p[0] = make_float4(t, u, v, __uint_as_float(prim));
+  p[1] = make_float4(__uint_as_float(geom), __uint_as_float(inst), __uint_as_float(custom), __uint_as_float(kind));
+}
+
+// ================================================================================================ reference order
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_trace_reference(const SceneDev S, const rdn_launch L, const rdn_ray *__restrict__ rays,
+                                                         uint64_t n, rdn_hit *__restrict__ hits, const TraceScratch scratch,
+                                                         const bool use_queue) {
+  const uint64_t limit = use_queue ? static_cast<uint64_t>(*scratch.tie_count) : n;
+  unsigned long long c_bvh_visit = 0, c_bvh_hit = 0, c_tri_visit = 0, c_tri_hit = 0, c_inst = 0, c_abort = 0;
+
+  for (uint64_t k = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; k < limit;
+       k += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t ri = use_queue ? scratch.tie_queue[k] : k;
+    const float4 r0 = __ldg(reinterpret_cast<const float4 *>(rays + ri));
+    const float4 r1 = __ldg(reinterpret_cast<const float4 *>(rays + ri) + 1);
+    const Vec3 ro = xyz(r0), rd = xyz(r1);
+    const float near = r0.w, far0 = r1.w;
+    float far = use_queue ? fminf(far0, scratch.tie_clamp[k]) : far0;  // the shared Rc<Cell<f32>> of RayRange
+
+    float best_t = far0, best_u = 0.f, best_v = 0.f;
+    uint32_t best_slot = RDN_INVALID_ID, best_inst = RDN_INVALID_ID, best_kind = 0;
+
+    uint32_t tlas_cursor = 0xFFFFFFFFu;
+    if (L.tlas_idx < S.n_tlas_binding) {
+      const uint32_t handle = S.tlas_binding[L.tlas_idx];
+      if (handle < S.n_tlas_root) tlas_cursor = S.tlas_root[handle].bvh_root_idx;
+    }
+    const Vec3 inv_rd = recip3(rd);
+    bool end_search = false;
+
+    while (tlas_cursor != 0xFFFFFFFFu && !end_search) {
+      // ---- TraverseBvhIteratorCpu over the TLAS
+      const float4 *np = reinterpret_cast<const float4 *>(S.tlas_bvh_forest + tlas_cursor);
+      const float4 n0 = __ldg(np), n1 = __ldg(np + 1);
+      if (COUNT) c_bvh_visit++;
+      float tn;
+      const uint32_t hit_next = __float_as_uint(n0.w), miss_next = __float_as_uint(n1.w);
+      if (!slab_test(ro, inv_rd, near * 1.0f, far * 1.0f, xyz(n0), xyz(n1), tn)) { tlas_cursor = miss_next; continue; }
+      const uint32_t leaf_node = tlas_cursor;
+      tlas_cursor = hit_next;
+      if (hit_next != miss_next) continue;
+      if (COUNT) c_bvh_hit++;
+      const uint2 irange = *reinterpret_cast<const uint2 *>(S.tlas_bvh_forest[leaf_node].content_range);
+
+      for (uint32_t tlas_idx = irange.x; tlas_idx < irange.y && !end_search; ++tlas_idx) {
+        const float4 *tb = reinterpret_cast<const float4 *>(S.tlas_bounding + tlas_idx);
+        const float4 b0 = __ldg(tb), b1 = __ldg(tb + 1);
+        // ORIGINAL ray.range for the instance box (traverse_cpu.rs:80-86)
+        if (!slab_test(ro, inv_rd, near, far0, xyz(b0), xyz(b1), tn)) continue;
+        if ((L.cull_mask & __float_as_uint(b0.w)) == 0) continue;
+        if (COUNT) c_inst++;
+        const InstanceRecord *rec = S.instances + tlas_idx;
+        const uint32_t flags = merge_geometry_instance_flag(L.ray_flags, rec->flags);
+        Vec3 bo, bd;
+        float scaling;
+        to_object_space(rec, ro, rd, bo, bd, scaling);
+        const Vec3 inv_bd = recip3(bd);
+        const uint32_t blas_idx = rec->blas;
+        if (blas_idx >= S.n_blas_meta) continue;
+        if (flags & TF_SKIP_TRIANGLES) continue;
+        const uint32_t g0 = S.blas_meta[blas_idx].tri_root_range[0], g1 = S.blas_meta[blas_idx].tri_root_range[1];
+        const uint32_t cull_bits = cull_triangle_bits(flags);
+
+        for (uint32_t g = g0; g < g1 && !end_search; ++g) {
+          const GeometryMeta gm = S.geometry_meta[g];
+          if (!cull_geometry_pass(flags, gm.geometry_flags)) continue;
+          uint32_t cursor = gm.bvh_root_idx;
+          while (cursor != 0xFFFFFFFFu && !end_search) {
+            const float4 *bp = reinterpret_cast<const float4 *>(S.tri_bvh_forest + cursor);
+            const float4 m0 = __ldg(bp), m1 = __ldg(bp + 1);
+            if (COUNT) c_bvh_visit++;
+            const uint32_t bh = __float_as_uint(m0.w), bm = __float_as_uint(m1.w);
+            if (!slab_test(bo, inv_bd, near * scaling, far * scaling, xyz(m0), xyz(m1), tn)) { cursor = bm; continue; }
+            const uint32_t leaf = cursor;
+            cursor = bh;
+            if (bh != bm) continue;
+            if (COUNT) c_bvh_hit++;
+            const uint2 trange = *reinterpret_cast<const uint2 *>(S.tri_bvh_forest[leaf].content_range);
+            for (uint32_t slot = trange.x; slot < trange.y; ++slot) {
+              const float4 *tp = reinterpret_cast<const float4 *>(S.triangles + slot);
+              const float4 qn = __ldg(tp), qv0 = __ldg(tp + 1), qe1 = __ldg(tp + 2), qe2 = __ldg(tp + 3);
+              if (COUNT) c_tri_visit++;
+              float sign, t, u, v;
+              if (!triangle_test(qn, qv0, qe1, qe2, bo, bd, near * scaling, far * scaling, cull_bits, sign, t, u, v)) continue;
+              const float distance = t / scaling;
+              if (COUNT) c_tri_hit++;
+              // RayRange::update_far asserts: the reference aborts; the candidate is rejected here
+              if (!(near <= distance) || !(distance <= far)) { if (COUNT) c_abort++; continue; }
+              far = distance;
+              best_t = distance; best_u = u; best_v = v;
+              best_slot = slot; best_inst = tlas_idx;
+              best_kind = sign < 0.0f ? RDN_HIT_KIND_BACK_FACING_TRIANGLE : RDN_HIT_KIND_FRONT_FACING_TRIANGLE;
+              if (flags & TF_END_SEARCH) { end_search = true; break; }
+            }
+          }
+        }
+      }
+    }
+
+    if (best_slot != RDN_INVALID_ID) {
+      const SlotInfo si = S.slot_info[best_slot];
+      store_hit(hits + ri, best_t, best_u, best_v, si.primitive_id, si.geometry_idx, best_inst,
+                S.instances[best_inst].instance_custom_index, best_kind);
+    } else if (!use_queue) {
+      store_hit(hits + ri, far0, 0.f, 0.f, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, 0);
+    } else {
+      atomicAdd(scratch.tie_unresolved, 1u);
+    }
+  }
+
+  if (COUNT) {
+    // warp-reduce, one atomic per warp per counter
+    unsigned long long vals[6] = {c_bvh_visit, c_bvh_hit, c_tri_visit, c_tri_hit, c_inst, c_abort};
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      unsigned long long x = vals[i];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(FULL_MASK, x, off);
+      if ((threadIdx.x & 31) == 0 && x) atomicAdd(scratch.counters + i, x);
+    }
+  }
+}
+
+// ================================================================================================ ordered
+struct OrderedParams {
+  SceneDev S;
+  rdn_launch L;
+  const rdn_ray *rays;
+  rdn_hit *hits;
+  uint64_t n;        // rays
+  uint64_t n_fetch;  // fetch indices (= n, or 32 * tiles when walking 8x4 pixel tiles)
+  uint32_t tiles_x;  // 0: linear
+  uint32_t width, height;
+  uint32_t world_root;  // wide reference of the bound TLAS (REF_EMPTY: every ray misses)
+  TraceScratch scratch;
+};
+
+__global__ void __launch_bounds__(ORDERED_BLOCK) k_trace_ordered(const OrderedParams P) {
+  const SceneDev &S = P.S;
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t stack[STACK_MAX];
+  int sp = 0;
+
+  // per-lane ray state
+  bool alive = false;
+  uint64_t ri = 0;
+  Vec3 o = {0, 0, 0}, d = {0, 0, 1}, inv = {0, 0, 0};
+  float t_near_world = 0.f, far0 = 0.f;  // ray.range
+  float scaling = 1.f, near_s = 0.f, far_s = 0.f;
+  float bound = 0.f;                     // world-space pruning / acceptance bound: min(far0, best*(1+eps))
+  float best = 0.f, second = 0.f, best_u = 0.f, best_v = 0.f;
+  uint32_t best_slot = RDN_INVALID_ID, best_inst = RDN_INVALID_ID, best_back = 0;
+  uint32_t cur = REF_EMPTY, cur_inst = 0, cur_flags = 0, cull_bits = 0, geom_end = 0;
+  bool in_object = false;
+  bool warp_exhausted = false;
+
+  for (;;) {
+    // ---------------- warp-converged refill point: lanes without a ray grab the next fetch indices
+    const uint32_t want = __ballot_sync(FULL_MASK, !alive);
+    if (want && !warp_exhausted) {
+      const int cnt = __popc(want);
+      const int leader = __ffs(want) - 1;
+      unsigned long long base = 0;
+      if (static_cast<int>(lane) == leader) base = atomicAdd(P.scratch.work_counter, static_cast<unsigned long long>(cnt));
+      base = __shfl_sync(FULL_MASK, base, leader);
+      if (base + cnt >= P.n_fetch) warp_exhausted = true;
+      if (!alive) {
+        const uint64_t f = base + __popc(want & ((1u << lane) - 1u));
+        bool valid = f < P.n_fetch;
+        uint64_t idx = f;
+        if (valid && P.tiles_x) {  // 8x4 pixel tiles, row-major tile order
+          const uint64_t tile = f >> 5;
+          const uint32_t in_tile = static_cast<uint32_t>(f & 31u);
+          const uint32_t tx = static_cast<uint32_t>(tile % P.tiles_x), ty = static_cast<uint32_t>(tile / P.tiles_x);
+          const uint32_t x = tx * 8u + (in_tile & 7u), y = ty * 4u + (in_tile >> 3);
+          valid = x < P.width && y < P.height;
+          idx = static_cast<uint64_t>(y) * P.width + x;
+        }
+        if (valid) {
+          ri = idx;
+          const float4 r0 = __ldg(reinterpret_cast<const float4 *>(P.rays + ri));
+          const float4 r1 = __ldg(reinterpret_cast<const float4 *>(P.rays + ri) + 1);
+          o = xyz(r0); d = xyz(r1); inv = recip3(d);
+          t_near_world = r0.w; far0 = r1.w;
+          scaling = 1.f; near_s = t_near_world; bound = far0; far_s = far0;
+          best = INFINITY; second = INFINITY; best_slot = RDN_INVALID_ID; best_inst = RDN_INVALID_ID;
+          in_object = false; sp = 0;
+          cur = P.world_root;
+          alive = true;
+        }
+      }
+    }
+    if (__ballot_sync(FULL_MASK, alive) == 0) break;
+
+    if (alive) {
+      int steps = ORDERED_STEPS;
+      bool done = false;
+      while (steps-- > 0) {
+        bool need_pop = false;
+        if (cur < REF_SPECIAL) {
+          // ---------------- inner node: both child boxes in one 64 B fetch
+          const float4 *np = reinterpret_cast<const float4 *>(S.wide_nodes + cur);
+          const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
+          float n0, n1;
+          const bool h0 = slab_test(o, inv, near_s, far_s, xyz(q0), xyz(q1), n0);
+          const bool h1 = slab_test(o, inv, near_s, far_s, xyz(q2), xyz(q3), n1);
+          const uint32_t r0 = __float_as_uint(q0.w), r1 = __float_as_uint(q1.w);
+          if (h0 && h1) {
+            const bool first0 = n0 <= n1;
+            if (sp < STACK_MAX) stack[sp++] = first0 ? r1 : r0; else atomicAdd(P.scratch.stack_overflow, 1u);
+            cur = first0 ? r0 : r1;
+          } else if (h0) {
+            cur = r0;
+          } else if (h1) {
+            cur = r1;
+          } else {
+            need_pop = true;
+          }
+        } else if (cur & REF_LEAF_BIT) {
+          const uint32_t start = cur & REF_LEAF_START_MASK;
+          const uint32_t count = ((cur >> REF_LEAF_COUNT_SHIFT) & 15u) + 1u;
+          if (in_object) {
+            // ---------------- triangle leaf
+            for (uint32_t k = 0; k < count; ++k) {
+              const uint32_t slot = start + k;
+              const float4 *tp = reinterpret_cast<const float4 *>(S.triangles + slot);
+              const float4 qn = __ldg(tp), qv0 = __ldg(tp + 1), qe1 = __ldg(tp + 2), qe2 = __ldg(tp + 3);
+              float sign, t, u, v;
+              if (!triangle_test(qn, qv0, qe1, qe2, o, d, near_s, far_s, cull_bits, sign, t, u, v)) continue;
+              const float distance = t / scaling;
+              if (!(t_near_world <= distance) || !(distance <= far0)) continue;  // the reference's update_far asserts
+              if (distance < best) {
+                second = fminf(second, best);
+                best = distance; best_u = u; best_v = v; best_slot = slot; best_inst = cur_inst;
+                best_back = sign < 0.0f ? 1u : 0u;
+                bound = fminf(far0, best * (1.0f + TIE_EPS));
+                far_s = bound * scaling;
+              } else {
+                second = fminf(second, distance);
+              }
+            }
+            need_pop = true;
+          } else {
+            // ---------------- instance leaf (world space): take the first slot, park the rest
+            if (count > 1) {
+              const uint32_t rest = REF_LEAF_BIT | ((count - 2u) << REF_LEAF_COUNT_SHIFT) | (start + 1u);
+              if (sp < STACK_MAX) stack[sp++] = rest; else atomicAdd(P.scratch.stack_overflow, 1u);
+            }
+            const float4 *tb = reinterpret_cast<const float4 *>(S.tlas_bounding + start);
+            const float4 b0 = __ldg(tb), b1 = __ldg(tb + 1);
+            float tn;
+            need_pop = true;
+            if (slab_test(o, inv, t_near_world, bound, xyz(b0), xyz(b1), tn) && (P.L.cull_mask & __float_as_uint(b0.w)) != 0) {
+              const InstanceRecord *rec = S.instances + start;
+              const uint4 tail = __ldg(reinterpret_cast<const uint4 *>(&rec->instance_custom_index));
+              const uint32_t flags = merge_geometry_instance_flag(P.L.ray_flags, tail.z);
+              if (!(flags & TF_SKIP_TRIANGLES) && tail.w < S.n_blas_meta) {
+                const uint2 groots = __ldg(reinterpret_cast<const uint2 *>(S.blas_meta[tail.w].tri_root_range));
+                if (groots.x < groots.y) {
+                  Vec3 bo, bd;
+                  float s;
+                  to_object_space(rec, o, d, bo, bd, s);
+                  o = bo; d = bd; inv = recip3(bd);
+                  scaling = s; near_s = t_near_world * s; far_s = bound * s;
+                  cur_inst = start; cur_flags = flags; cull_bits = cull_triangle_bits(flags); geom_end = groots.y;
+                  in_object = true;
+                  if (sp < STACK_MAX) stack[sp++] = REF_EXIT_INSTANCE; else atomicAdd(P.scratch.stack_overflow, 1u);
+                  cur = REF_SPECIAL | groots.x;
+                  need_pop = false;
+                }
+              }
+            }
+          }
+        } else if (cur == REF_EXIT_INSTANCE) {
+          // ---------------- back to world space: the world ray is re-read instead of kept in registers
+          const float4 r0 = __ldg(reinterpret_cast<const float4 *>(P.rays + ri));
+          const float4 r1 = __ldg(reinterpret_cast<const float4 *>(P.rays + ri) + 1);
+          o = xyz(r0); d = xyz(r1); inv = recip3(d);
+          scaling = 1.f; near_s = t_near_world; far_s = bound;
+          in_object = false;
+          need_pop = true;
+        } else if (cur == REF_EMPTY) {
+          need_pop = true;
+        } else {
+          // ---------------- geometry iterator of the current instance's BLAS
+          const uint32_t g = cur & 0x00FFFFFFu;
+          if (g + 1u < geom_end) {
+            if (sp < STACK_MAX) stack[sp++] = REF_SPECIAL | (g + 1u); else atomicAdd(P.scratch.stack_overflow, 1u);
+          }
+          const uint4 gm0 = __ldg(reinterpret_cast<const uint4 *>(S.geometry_meta + g));       // root, geometry_idx, primitive_start, flags
+          const uint32_t wide_root = __ldg(&S.geometry_meta[g].wide_root);
+          if (cull_geometry_pass(cur_flags, gm0.w) && wide_root != REF_EMPTY) cur = wide_root; else need_pop = true;
+        }
+        if (need_pop) {
+          if (sp == 0) { done = true; break; }
+          cur = stack[--sp];
+        }
+      }
+
+      if (done) {
+        rdn_hit *dst = P.hits + ri;
+        if (best_slot != RDN_INVALID_ID) {
+          const SlotInfo si = S.slot_info[best_slot];
+          store_hit(dst, best, best_u, best_v, si.primitive_id, si.geometry_idx, best_inst,
+                    S.instances[best_inst].instance_custom_index,
+                    best_back ? RDN_HIT_KIND_BACK_FACING_TRIANGLE : RDN_HIT_KIND_FRONT_FACING_TRIANGLE);
+          if (second <= best * (1.0f + TIE_EPS)) {
+            // near-tie: queue for the exact reference-order re-walk (warp-aggregated append)
+            const uint32_t peers = __activemask();
+            const int pl = __ffs(peers) - 1;
+            uint32_t qbase = 0;
+            if (static_cast<int>(lane) == pl) qbase = atomicAdd(P.scratch.tie_count, static_cast<uint32_t>(__popc(peers)));
+            qbase = __shfl_sync(peers, qbase, pl);
+            const uint32_t q = qbase + __popc(peers & ((1u << lane) - 1u));
+            P.scratch.tie_queue[q] = static_cast<uint32_t>(ri);
+            P.scratch.tie_clamp[q] = fminf(far0, best * (1.0f + 3.0f * TIE_EPS));
+          }
+        } else {
+          store_hit(dst, far0, 0.f, 0.f, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, 0);
+        }
+        alive = false;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ launchers
+void launch_trace_reference(const SceneDev &scene, const rdn_launch &launch, const rdn_ray *d_rays, uint64_t n, rdn_hit *d_hits,
+                            const TraceScratch &scratch, bool use_tie_queue, bool count_visits, int sm_count, cudaStream_t stream) {
+  if (n == 0) return;
+  const int block = 128;
+  uint64_t blocks = (n + block - 1) / block;
+  const uint64_t cap = static_cast<uint64_t>(sm_count) * 16;
+  if (use_tie_queue) blocks = static_cast<uint64_t>(sm_count) * 2;  // queue length is device-side; grid-stride over it
+  else if (blocks > cap * 64) blocks = cap * 64;
+  if (count_visits)
+    k_trace_reference<true><<<static_cast<unsigned>(blocks), block, 0, stream>>>(scene, launch, d_rays, n, d_hits, scratch, use_tie_queue);
+  else
+    k_trace_reference<false><<<static_cast<unsigned>(blocks), block, 0, stream>>>(scene, launch, d_rays, n, d_hits, scratch, use_tie_queue);
+}
+
+void launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, uint32_t world_root, const rdn_ray *d_rays, uint64_t n,
+                          rdn_hit *d_hits, const TraceScratch &scratch, int sm_count, cudaStream_t stream) {
+  if (n == 0) return;
+  OrderedParams P;
+  P.S = scene; P.L = launch; P.rays = d_rays; P.hits = d_hits; P.n = n; P.scratch = scratch;
+  P.tiles_x = 0; P.width = 0; P.height = 0; P.n_fetch = n;
+  if (launch.grid_width != 0 && n % launch.grid_width == 0) {
+    P.width = launch.grid_width;
+    P.height = static_cast<uint32_t>(n / launch.grid_width);
+    P.tiles_x = (P.width + 7u) / 8u;
+    P.n_fetch = static_cast<uint64_t>(P.tiles_x) * ((P.height + 3u) / 4u) * 32u;
+  }
+  P.world_root = world_root;
+
+  int blocks_per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace_ordered, ORDERED_BLOCK, 0);
+  if (blocks_per_sm < 1) blocks_per_sm = 1;
+  uint64_t blocks = static_cast<uint64_t>(sm_count) * blocks_per_sm;
+  const uint64_t needed = (P.n_fetch + ORDERED_BLOCK - 1) / ORDERED_BLOCK;
+  if (blocks > needed) blocks = needed;
+  k_trace_ordered<<<static_cast<unsigned>(blocks), ORDERED_BLOCK, 0, stream>>>(P);
+}
+
+}  // namespace rdn

@@ -1,0 +1,179 @@
+"""CPU-side checks of the product: the C-ABI library loads and exports what include/rdn_rt.h declares, the host
+builder/flattener reproduce the oracle's (= the reference's) trees and arrays, and errors come back as codes."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+from rendiation_b200 import api, scenes as S
+
+import helpers
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "rdn_rt.h")).read()
+    declared = set(re.findall(r"\b(rdn_(?:rt|bvh)_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(api.EXPORTED_SYMBOLS), declared ^ set(api.EXPORTED_SYMBOLS)
+    L = ctypes.CDLL(api.LIB_PATH)
+    for sym in declared:
+        assert hasattr(L, sym), sym
+    assert b"sm_100a" in api.lib().rdn_rt_version()
+
+
+def test_record_sizes_match_header():
+    assert api.HIT_DTYPE.itemsize == 32 and S.RAY_DTYPE.itemsize == 32 and api.MESH_HIT_DTYPE.itemsize == 32
+    assert S.INSTANCE_DTYPE.itemsize == 84 and api.FLAT_BVH_NODE_DTYPE.itemsize == 64
+    assert api.DEV_NODE_DTYPE.itemsize == 48 and api.TRI_RECORD_DTYPE.itemsize == 64 and api.WIDE_NODE_DTYPE.itemsize == 64
+    assert oracle.HIT_DTYPE == api.HIT_DTYPE
+
+
+def _eq(a, b):
+    """numeric equality field by field (+0 == -0: f32::min/max leave the sign of zero unspecified)"""
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if a.dtype.names:
+        return all(_eq(a[f], b[f]) for f in a.dtype.names)
+    return bool(np.array_equal(a, b))
+
+
+@pytest.mark.parametrize("opt", [(50, 2), (10, 50), (15, 10), (3, 1)])
+@pytest.mark.parametrize("strategy", ["sah", "balance"])
+def test_flatten_bvh_builder_matches_oracle(strategy, opt):
+    pos, idx = S.torus_mesh(40, 24)
+    tri = idx.reshape(-1, 3)
+    boxes = np.concatenate([pos[tri].min(1), pos[tri].max(1)], 1)
+    ob = oracle.FlattenBVH(boxes, oracle.STRATEGY_SAH if strategy == "sah" else oracle.STRATEGY_BALANCE, 4, *opt)
+    pb = api.FlattenBVH(boxes, api.SAH(4) if strategy == "sah" else api.BalanceTree(), api.TreeBuildOption(*opt))
+    on, pn = ob.nodes, pb.nodes
+    assert _eq(on, pn)
+    assert np.array_equal(ob.sorted_primitive_index, pb.sorted_primitive_index)
+
+
+def test_builder_edge_cases():
+    for n in (0, 1, 2, 3):
+        boxes = np.tile(np.array([[0, 0, 0, 1, 1, 1]], np.float32), (n, 1))
+        ob = oracle.FlattenBVH(boxes, oracle.STRATEGY_SAH, 4, 50, 2)
+        pb = api.FlattenBVH(boxes, api.SAH(4), api.TreeBuildOption(50, 2))
+        assert _eq(ob.nodes, pb.nodes) and np.array_equal(ob.sorted_primitive_index, pb.sorted_primitive_index)
+    # identical centres -> SAH degenerate -> BalanceTree fallback
+    boxes = np.tile(np.array([[0, 0, 0, 1, 1, 1]], np.float32), (9, 1))
+    ob = oracle.FlattenBVH(boxes, oracle.STRATEGY_SAH, 4, 50, 2)
+    assert ob.balance_fallbacks > 0
+    pb = api.FlattenBVH(boxes, api.SAH(4), api.TreeBuildOption(50, 2))
+    assert _eq(ob.nodes, pb.nodes)
+
+
+def test_build_bvh_for_abstract_mesh_matches_box_build():
+    pos, idx = S.uv_sphere_mesh(12, 10)
+    tri = idx.reshape(-1, 3)
+    boxes = np.concatenate([pos[tri].min(1), pos[tri].max(1)], 1)
+    a = api.build_bvh_for_abstract_mesh(pos, idx, api.SAH(4), api.TreeBuildOption(50, 2))
+    b = api.FlattenBVH(boxes, api.SAH(4), api.TreeBuildOption(50, 2))
+    assert _eq(a.nodes, b.nodes)
+
+
+def _flat_pair(builder):
+    sp = builder(devices=(), product=True)
+    sp = sp[0] if isinstance(sp, tuple) else sp
+    return sp.o.view(), sp.p.arrays(), sp
+
+
+def test_flattened_scene_matches_oracle_reference_fixture():
+    ov, pa, sp = _flat_pair(helpers.reference_fixture)
+    assert np.array_equal(pa["tlas_binding"], ov["tlas_binding"])
+    assert np.array_equal(pa["tlas_root"][:, 0], ov["tlas_bvh_root"])
+    assert _eq(pa["tlas_bvh_forest"], ov["tlas_bvh_forest"])
+    assert _eq(pa["tlas_bounding"], ov["tlas_bounding"])
+    assert _eq(pa["tri_bvh_forest"], ov["tri_bvh_forest"])
+    assert np.array_equal(pa["blas_meta"], ov["blas_meta_info"])
+    for f in ("bvh_root_idx", "geometry_idx", "primitive_start", "geometry_flags"):
+        assert np.array_equal(pa["geometry_meta"][f], ov["tri_bvh_root"][f])
+    for f, g in (("transform_inv", "transform_inv"), ("instance_custom_index", "instance_custom_index"), ("sbt_offset", "sbt_offset"),
+                 ("flags", "flags"), ("blas", "blas")):
+        assert np.array_equal(pa["instances"][f], ov["tlas_data"][g])
+    # slot_info = indices_redirect - primitive_start of the owning geometry
+    starts = ov["tri_bvh_root"]["primitive_start"]
+    owner = np.searchsorted(starts, ov["indices_redirect"], side="right") - 1
+    assert np.array_equal(pa["slot_info"][:, 0], ov["indices_redirect"] - starts[owner])
+    # pre-gathered triangle records carry the reference's vertices in slot order
+    tri = ov["indices"].reshape(-1, 3)[ov["indices_redirect"]]
+    v0, v1, v2 = ov["vertices"][tri[:, 0]], ov["vertices"][tri[:, 1]], ov["vertices"][tri[:, 2]]
+    assert np.array_equal(pa["triangles"]["v0"], v0)
+    assert np.array_equal(pa["triangles"]["e1"], v1 - v0) and np.array_equal(pa["triangles"]["e2"], v2 - v0)
+
+
+def test_wide_nodes_cover_the_reference_tree():
+    """every inner reference node appears once with its children's exact boxes; leaves decode to the same slot ranges"""
+    ov, pa, sp = _flat_pair(helpers.sphere_c1)
+    wide, forest, gm = pa["wide_nodes"], pa["tri_bvh_forest"], pa["geometry_meta"][0]
+    LEAF = 0x80000000
+    seen_slots = []
+
+    def walk(ref, ref_node):
+        rn = forest[ref_node]
+        if ref & LEAF:
+            start, cnt = ref & ((1 << 27) - 1), ((ref >> 27) & 15) + 1
+            assert rn["hit_next"] == rn["miss_next"] and start == rn["range"][0] and start + cnt == rn["range"][1]
+            seen_slots.extend(range(start, start + cnt))
+            return
+        w = wide[ref]
+        left, right = ref_node + 1, None
+        assert rn["hit_next"] == left
+        # right child = the miss link of the left child
+        right = int(forest[left]["miss_next"])
+        for cmin, cmax, child in ((w["c0_min"], w["c0_max"], left), (w["c1_min"], w["c1_max"], right)):
+            assert np.array_equal(cmin, forest[child]["aabb_min"]) and np.array_equal(cmax, forest[child]["aabb_max"])
+        walk(int(w["ref0"]), left)
+        walk(int(w["ref1"]), right)
+
+    import sys
+    sys.setrecursionlimit(10000)
+    root = wide[gm["wide_root"]]
+    assert np.array_equal(root["c0_min"], forest[0]["aabb_min"]) and np.isnan(root["c1_min"]).all() and root["ref1"] == 0x7FFFFFFE
+    walk(int(root["ref0"]), 0)
+    assert sorted(seen_slots) == list(range(len(pa["triangles"])))
+
+
+def test_errors_are_status_codes_not_aborts():
+    s = api.NaiveSahBVHSystem(devices=())
+    b = s.create_bottom_level_acceleration_structure([api.BottomLevelAccelerationStructureBuildSource(S.CUBE_POSITION, S.CUBE_INDEX)])
+    t = s.create_top_level_acceleration_structure(S.make_instance(S.mat4_identity(), b.id))
+    s.bind_tlas([t])
+    s.commit()
+    assert s.bind_tlas_max_len() == 0xFFFFFFFF
+    s.delete_bottom_level_acceleration_structure(b)
+    with pytest.raises(api.RdnError) as e:  # the reference panics on unwrap() (naive/mod.rs:273-275)
+        s.commit()
+    assert e.value.code == -3
+    with pytest.raises(api.RdnError):
+        s.delete_top_level_acceleration_structure(api.TlasHandle(99))
+    bad = api.BottomLevelAccelerationStructureBuildSource(S.CUBE_POSITION, np.array([0, 1, 999], np.uint32))
+    s2 = api.NaiveSahBVHSystem(devices=())
+    s2.create_bottom_level_acceleration_structure([bad])
+    with pytest.raises(api.RdnError) as e:
+        s2.commit()
+    assert e.value.code == -4
+
+
+def test_no_cpu_fallback():
+    """a host-only scene can build and flatten but must refuse to trace: the product has no CPU path"""
+    s = api.NaiveSahBVHSystem(devices=())
+    b = s.create_bottom_level_acceleration_structure([api.BottomLevelAccelerationStructureBuildSource(S.CUBE_POSITION, S.CUBE_INDEX)])
+    t = s.create_top_level_acceleration_structure(S.make_instance(S.mat4_translate(0, 0, -3), b.id))
+    s.bind_tlas([t])
+    with pytest.raises(api.RdnError):
+        s.trace_closest_batch(S.pinhole_rays(4, 4))
+    with pytest.raises(api.RdnError):
+        s.compact_u32(np.arange(4, dtype=np.uint32), np.ones(4, np.uint8))
+    # and the package never imports the oracle
+    import rendiation_b200
+    src_dir = os.path.dirname(rendiation_b200.__file__)
+    for dirpath, _, files in os.walk(src_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "import oracle" not in txt and "oracle/" not in txt and "liboracle" not in txt, f
