@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py — closest-hit Mrays/s of the BVH traversal hot path (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU traversal (oracle port) on host cores
+
+Workload (config.workload): BASELINE.json configs[1] — 1920x1080 primary rays vs a 1,002,528-triangle generated
+parametric-surface mesh (708x708 torus, x5 at z=-10, rotate_x(-0.5)), RAY_FLAG_CULL_BACK_FACING_TRIANGLES, range
+(0.01, 100), one TLAS with one instance.  One "step" = one closest-hit pass over one frame of rays on every GPU.
+For N > 1 the flattened BVH is built on rank 0, replicated with one NCCL broadcast, and every rank traces its own
+(differently jittered) frame: rays are sharded by frame tile, no collective on the data path -> "weak" scaling.
+
+value   = whole-job Mrays/s with rays/hits resident in HBM, device-timed (CUDA events), max over ranks.
+e2e     = same metric through the host-buffer C-ABI call (pinned host rays -> H2D -> traversal -> D2H hits).
+roofline= algorithmic bytes (64 + 48*V_node + 52*V_tri + 176*V_inst per ray, V counted by the oracle
+          under the reference traversal order) / ordered-kernel time, against the measured HBM copy peak.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 1920, 1080
+SEG = 708
+RAY_FLAGS = 0x10  # RAY_FLAG_CULL_BACK_FACING_TRIANGLES
+TMIN, TMAX = 0.01, 100.0
+WORKLOAD = "1920x1080 primary rays vs 1,002,528-triangle generated torus mesh (BASELINE configs[1])"
+
+
+def scene_inputs():
+    from rendiation_b200 import scenes as S
+    pos, idx = S.torus_mesh(SEG, SEG, 1.0, 0.35)
+    m = S.mat4_mul(S.mat4_mul(S.mat4_translate(0, 0, -10), S.mat4_scale(5, 5, 5)), S.mat4_rotate_x(-0.5))
+    return pos, idx, m
+
+
+def frame_rays(sample_index: int):
+    """frame `sample_index`: pixel-centre rays for 0, (van der Corput, Sobol) sub-pixel jitter otherwise"""
+    from rendiation_b200 import scenes as S
+    jitter = None
+    if sample_index:
+        j = S.sample_2d(np.full(1, sample_index, np.uint32))
+        jitter = np.repeat(j, W * H, axis=0)
+    return S.pinhole_rays(W, H, TMIN, TMAX, aspect_correct=True, jitter=jitter)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)"""
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.stop = threading.Event()
+        self.gpu = gpu_index
+        self.th = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes_per_ray(osc, rays, n_threads):
+    """SURVEY.md §8(d) bytes model from the oracle's reference-order counters on a 1/8 row-strided sample of the frame"""
+    sample = rays.reshape(H, W)[::8].reshape(-1)
+    _, c = osc.trace(sample, ray_flags=RAY_FLAGS, n_threads=n_threads)
+    n = sample.shape[0]
+    per_ray = 64 + (48 * c["bvh_visit"] + 52 * c["tri_visit"] + 176 * c["inst_visit"]) / n
+    return per_ray, {k: v / n for k, v in c.items()}, n
+
+
+def build_oracle_scene():
+    import oracle
+    from rendiation_b200 import scenes as S
+    pos, idx, m = scene_inputs()
+    osc = oracle.Scene()
+    b = osc.create_blas([(pos, idx.reshape(-1), 1)])
+    osc.bind_tlas([osc.create_tlas(S.make_instance(m, b))])
+    assert osc.build() == 0
+    return osc
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU traversal (NaiveSahBvhCpu::traverse restated in C, oracle/) on all host
+    cores; each step = a bounded 1/4-frame sample (every 4th row) of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    osc = build_oracle_scene()
+    rays = frame_rays(0).reshape(H, W)[::4].reshape(-1).copy()
+    for _ in range(args.warmup):
+        osc.trace(rays, ray_flags=RAY_FLAGS, n_threads=cores, want_counters=False)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        osc.trace(rays, ray_flags=RAY_FLAGS, n_threads=cores, want_counters=False)
+    dt = time.perf_counter() - t0
+    v = rays.shape[0] * args.steps / dt / 1e6
+    sample = f"every 4th row of the 1920x1080 frame ({rays.shape[0]} rays) per step"
+    print(json.dumps({
+        "impl": "reference", "metric": "closest-hit Mrays/s", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "rays_per_step": int(rays.shape[0]), "host_threads": cores},
+        "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from rendiation_b200 import api, scenes as S
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- scene: build + flatten on rank 0, one NCCL broadcast of the blob, every other rank adopts it
+    sysm = api.NaiveSahBVHSystem(devices=(local_rank,))
+    t_build = 0.0
+    if rank == 0:
+        pos, idx, m = scene_inputs()
+        t0 = time.perf_counter()
+        b = sysm.create_bottom_level_acceleration_structure([api.BottomLevelAccelerationStructureBuildSource(pos, idx.reshape(-1))])
+        t = sysm.create_top_level_acceleration_structure(S.make_instance(m, b.id))
+        sysm.bind_tlas([t])
+        sysm.commit()
+        t_build = time.perf_counter() - t0
+    t_repl_ms = 0.0
+    if world > 1:
+        from cuda.bindings import runtime as cudart
+        nbytes = torch.zeros(1, dtype=torch.int64, device=dev)
+        if rank == 0:
+            ptr, nb = sysm.blob()
+            nbytes[0] = nb
+        dist.broadcast(nbytes, 0)
+        nb = int(nbytes.item())
+        buf = torch.empty(nb, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            (err,) = cudart.cudaMemcpy(buf.data_ptr(), ptr, nb, cudart.cudaMemcpyKind.cudaMemcpyDeviceToDevice)
+            assert int(err) == 0
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.broadcast(buf, 0)  # BVH replication over NVLink / NVSwitch
+        e1.record()
+        torch.cuda.synchronize()
+        t_repl_ms = e0.elapsed_time(e1)
+        if rank != 0:
+            sysm.adopt_blob(buf.data_ptr(), nb)
+        del buf
+    blob_bytes = sysm.blob()[1]
+
+    # ---- rays: this rank's frame (tile shard of the N-frame job), resident in HBM
+    rays_np = frame_rays(rank)
+    n = rays_np.shape[0]
+    d_rays = torch.from_numpy(rays_np.view(np.uint8).reshape(-1, 32)).to(dev)
+    d_hits = torch.zeros((n, 32), dtype=torch.uint8, device=dev)
+    h_rays = torch.from_numpy(rays_np.view(np.uint8).reshape(-1, 32).copy()).pin_memory()
+    h_hits = torch.zeros((n, 32), dtype=torch.uint8).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_device(stats=False):
+        return sysm.trace_closest_device(d_rays.data_ptr(), n, d_hits.data_ptr(), ray_flags=RAY_FLAGS, grid_width=W, stream=stream,
+                                         want_stats=stats)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    st = step_device(stats=True)
+    launches_per_step = st["kernel_launches"]
+    tie_rays = st["tie_rays"]
+
+    # ---- timed region: exactly K steps, CUDA events on the launching stream, L2 flushed between steps (untimed)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        t_wall0 = time.perf_counter()
+        for k in range(args.steps):
+            flush.zero_()
+            ev[k][0].record()
+            step_device()
+            ev[k][1].record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    ms_per_step = total_ms / args.steps
+    value = world * n / (ms_per_step * 1e-3) / 1e6
+
+    # ---- e2e: host-buffer C-ABI call (pinned host memory; H2D + traversal + D2H inside the timed region)
+    def step_host():
+        sysm.trace_closest_host_ptr(h_rays.data_ptr(), n, h_hits.data_ptr(), ray_flags=RAY_FLAGS, grid_width=W)
+
+    for _ in range(2):
+        step_host()
+    e2e_steps = max(3, min(args.steps, 10))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * e2e_steps / float(t_e2e.item()) / 1e6
+    # device-resident and host-path results must be the same bits
+    same = bool((torch.from_numpy(h_hits.numpy()) == d_hits.cpu()).all().item())
+
+    if rank == 0:
+        # ---- roofline + cpu baseline + parity spot check (oracle = checker / baseline only)
+        cores = os.cpu_count() or 1
+        osc = build_oracle_scene()
+        bytes_per_ray, visits, n_sample = algorithmic_bytes_per_ray(osc, rays_np, cores)
+        sample = rays_np.reshape(H, W)[::4].reshape(-1).copy()
+        t0 = time.perf_counter()
+        ohits = osc.trace(sample, ray_flags=RAY_FLAGS, n_threads=cores, want_counters=False)
+        t_cpu = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        osc.trace(sample[::8].copy(), ray_flags=RAY_FLAGS, n_threads=1, want_counters=False)
+        t_cpu1 = time.perf_counter() - t0
+        ghits = d_hits.cpu().numpy().view(api.HIT_DTYPE).reshape(H, W)[::4].reshape(-1)
+        parity_bits = bool(ghits.tobytes() == ohits.tobytes())
+
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        kernel_ms = min(step_ms)  # the traversal kernels are the whole device step; best step = least interference
+        achieved = bytes_per_ray * n / (ms_per_step * 1e-3) / 1e9
+        compulsory = (64.0 * n + blob_bytes) / (ms_per_step * 1e-3) / 1e9
+        out = {
+            "metric": "closest-hit Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rays_per_gpu_per_step": n, "triangles": int(SEG * SEG * 2), "ray_flags": RAY_FLAGS,
+                       "l2": "256 MiB buffer written between timed steps (L2 flush, untimed); scene+rays+hits = %.0f MB" %
+                             ((blob_bytes + 64 * n) / 1e6),
+                       "parallelism": f"rays sharded by frame x{world}, BVH replicated ({blob_bytes / 1e6:.0f} MB blob, "
+                                      f"NCCL broadcast {t_repl_ms:.2f} ms)", "build_s": round(t_build, 3)},
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 32 * n,
+                    "steps": e2e_steps, "matches_device_path": same},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_ray": bytes_per_ray, "visits_per_ray": visits,
+                         "bytes_model_sample_rays": n_sample, "compulsory_hbm_gbs": compulsory, "best_step_ms": kernel_ms,
+                         "kernel": "k_trace_ordered (+ tie re-walk k_trace_reference)", "tie_rays_per_step": tie_rays},
+            "cpu_baseline": {"value": sample.shape[0] / t_cpu / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                             "sample": f"every 4th row of the frame ({sample.shape[0]} rays), {t_cpu:.2f} s",
+                             "single_thread_mrays": sample[::8].shape[0] / t_cpu1 / 1e6, "parity_bit_identical_on_sample": parity_bits},
+            "clocks": clocks.summary(), "wall_s_timed_region": t_wall,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

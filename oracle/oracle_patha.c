@@ -18,6 +18,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <pthread.h>
+#include <stdatomic.h>
 #include "oracle.h"
 
 int orc_ray_box_a(const float *r, const obox *box3) {
@@ -129,19 +130,29 @@ static void patha_one(const orc_bvh *bvh, const float *positions, const uint32_t
 
 typedef struct {
   const orc_bvh *bvh; const float *positions; const uint32_t *indices; uint64_t n_tris;
-  const orc_ray *rays; orc_mesh_hit *out; int face_side; uint64_t begin, end;
+  const orc_ray *rays; orc_mesh_hit *out; int face_side; uint64_t n; atomic_ullong *cursor;
 } qa_job;
+#define ORC_QA_CHUNK 1024u
 
 static void *patha_worker(void *p) {
   qa_job *j = (qa_job *)p;
   uint64_t *stack = (uint64_t *)malloc((j->bvh->n_nodes + 2) * sizeof(uint64_t));
-  for (uint64_t i = j->begin; i < j->end; i++) patha_one(j->bvh, j->positions, j->indices, &j->rays[i], j->face_side, &j->out[i], stack);
+  for (;;) {
+    uint64_t begin = atomic_fetch_add(j->cursor, ORC_QA_CHUNK);
+    if (begin >= j->n) break;
+    uint64_t end = begin + ORC_QA_CHUNK < j->n ? begin + ORC_QA_CHUNK : j->n;
+    for (uint64_t i = begin; i < end; i++) patha_one(j->bvh, j->positions, j->indices, &j->rays[i], j->face_side, &j->out[i], stack);
+  }
   free(stack);
   return NULL;
 }
 static void *brute_worker(void *p) {
   qa_job *j = (qa_job *)p;
-  for (uint64_t i = j->begin; i < j->end; i++) {
+  for (;;) {
+  uint64_t begin = atomic_fetch_add(j->cursor, ORC_QA_CHUNK);
+  if (begin >= j->n) break;
+  uint64_t end = begin + ORC_QA_CHUNK < j->n ? begin + ORC_QA_CHUNK : j->n;
+  for (uint64_t i = begin; i < end; i++) {
     const orc_ray *ray = &j->rays[i];
     float r[6] = {ray->ox, ray->oy, ray->oz, ray->dx, ray->dy, ray->dz};
     orc_mesh_hit *out = &j->out[i];
@@ -152,20 +163,17 @@ static void *brute_worker(void *p) {
       if (orc_ray_triangle_a(r, a, b, c, j->face_side, pd)) refresh_nearest(out, pd, prim);
     }
   }
+  }
   return NULL;
 }
 
 static void run_jobs(qa_job proto, uint64_t n_rays, int n_threads, void *(*fn)(void *)) {
   if (n_threads < 1) n_threads = 1;
-  if ((uint64_t)n_threads > n_rays) n_threads = n_rays ? (int)n_rays : 1;
   qa_job *jobs = (qa_job *)calloc(n_threads, sizeof(qa_job));
   pthread_t *th = (pthread_t *)calloc(n_threads, sizeof(pthread_t));
-  uint64_t chunk = (n_rays + n_threads - 1) / n_threads;
-  for (int t = 0; t < n_threads; t++) {
-    jobs[t] = proto;
-    jobs[t].begin = (uint64_t)t * chunk < n_rays ? (uint64_t)t * chunk : n_rays;
-    jobs[t].end = jobs[t].begin + chunk < n_rays ? jobs[t].begin + chunk : n_rays;
-  }
+  atomic_ullong cursor;
+  atomic_init(&cursor, 0);
+  for (int t = 0; t < n_threads; t++) { jobs[t] = proto; jobs[t].n = n_rays; jobs[t].cursor = &cursor; }
   if (n_threads == 1) fn(&jobs[0]);
   else {
     for (int t = 0; t < n_threads; t++) pthread_create(&th[t], NULL, fn, &jobs[t]);

@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <pthread.h>
+#include <stdatomic.h>
 #include "oracle.h"
 
 /* ---- flag constants (api/ty.rs:102-159, naive/flag.rs:6-25) ---- */
@@ -441,10 +442,18 @@ static void traverse_one(const orc_scene *s, const orc_launch *L, const orc_ray 
   }
 }
 
-typedef struct { const orc_scene *s; const orc_launch *L; const orc_ray *rays; orc_hit *hits; uint64_t begin, end; orc_counters c; } trace_job;
+/* multi-thread driver: rays are handed out in chunks from an atomic cursor (hit rays cluster in image space, so static
+ * ranges would leave most threads idle) */
+#define ORC_CHUNK 2048u
+typedef struct { const orc_scene *s; const orc_launch *L; const orc_ray *rays; orc_hit *hits; uint64_t n; atomic_ullong *cursor; orc_counters c; } trace_job;
 static void *trace_worker(void *p) {
   trace_job *j = (trace_job *)p;
-  for (uint64_t i = j->begin; i < j->end; i++) traverse_one(j->s, j->L, &j->rays[i], &j->hits[i], &j->c);
+  for (;;) {
+    uint64_t begin = atomic_fetch_add(j->cursor, ORC_CHUNK);
+    if (begin >= j->n) break;
+    uint64_t end = begin + ORC_CHUNK < j->n ? begin + ORC_CHUNK : j->n;
+    for (uint64_t i = begin; i < end; i++) traverse_one(j->s, j->L, &j->rays[i], &j->hits[i], &j->c);
+  }
   return NULL;
 }
 
@@ -452,14 +461,12 @@ int orc_scene_trace(const orc_scene *s, const orc_launch *launch, const orc_ray 
                     orc_hit *out_hits, orc_counters *counters, int n_threads) {
   if (!s->built) return -1;
   if (n_threads < 1) n_threads = 1;
-  if ((uint64_t)n_threads > n_rays) n_threads = n_rays ? (int)n_rays : 1;
   trace_job *jobs = (trace_job *)calloc(n_threads, sizeof(trace_job));
   pthread_t *th = (pthread_t *)calloc(n_threads, sizeof(pthread_t));
-  uint64_t chunk = (n_rays + n_threads - 1) / n_threads;
+  atomic_ullong cursor;
+  atomic_init(&cursor, 0);
   for (int t = 0; t < n_threads; t++) {
-    jobs[t].s = s; jobs[t].L = launch; jobs[t].rays = rays; jobs[t].hits = out_hits;
-    jobs[t].begin = (uint64_t)t * chunk < n_rays ? (uint64_t)t * chunk : n_rays;
-    jobs[t].end = jobs[t].begin + chunk < n_rays ? jobs[t].begin + chunk : n_rays;
+    jobs[t].s = s; jobs[t].L = launch; jobs[t].rays = rays; jobs[t].hits = out_hits; jobs[t].n = n_rays; jobs[t].cursor = &cursor;
   }
   if (n_threads == 1) trace_worker(&jobs[0]);
   else {

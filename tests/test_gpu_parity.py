@@ -1,0 +1,277 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the committed goldens.
+
+Bar (BASELINE.json north_star): hit primitive/instance ids bit-exact, t/u/v within 1e-6 relative, near-ties counted
+separately.  Because the kernels use the reference's arithmetic un-fused and resolve near-ties in reference order, the
+expectation here is stronger: whole hit records bit-identical.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from rendiation_b200 import api, scenes as S
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+CTR = ("bvh_visit", "bvh_hit", "tri_visit", "tri_hit", "inst_visit", "ref_abort")
+REL_TOL = 1e-6  # north star tolerance for t / barycentrics
+
+
+def _report(name, rep):
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/parity.jsonl", "a") as f:
+        f.write(json.dumps({"case": name, **rep}) + "\n")
+
+
+def _assert_parity(name, got, want, require_bits=True):
+    rep = helpers.compare_hits(got, want, REL_TOL)
+    _report(name, rep)
+    assert rep["hard_mismatch"] == 0, rep
+    assert rep["max_rel_t"] <= REL_TOL and rep["max_abs_uv"] <= REL_TOL, rep
+    if require_bits:
+        assert rep["near_ties"] == 0 and rep["bit_identical"], rep
+    return rep
+
+
+def _device_trace(sysm, rays, mode, **kw):
+    import torch
+    r = torch.from_numpy(rays.view(np.uint8).reshape(-1, 32).copy()).cuda()
+    h = torch.zeros((rays.shape[0], 32), dtype=torch.uint8, device="cuda")
+    stats = sysm.trace_closest_device(r.data_ptr(), rays.shape[0], h.data_ptr(), stream=torch.cuda.current_stream().cuda_stream,
+                                      mode=mode, want_stats=True, **kw)
+    torch.cuda.synchronize()
+    return h.cpu().numpy().view(api.HIT_DTYPE).reshape(-1), stats
+
+
+# ---- goldens (no oracle needed at run time) -----------------------------------------------------------
+@pytest.mark.parametrize("k", range(5))
+def test_reference_fixture_goldens(k):
+    g = np.load(os.path.join(GOLD, "reference_fixture_64.npz"))
+    sp, _ = helpers.reference_fixture()
+    rays = g["rays"]
+    for name, flags in (("cull_back", 0x10), ("none", 0x00), ("first_hit", 0x14)):
+        want = g[f"hits_tlas{k}_{name}"]
+        got = sp.p.trace_closest_batch(rays, ray_flags=flags, tlas_idx=k)
+        _assert_parity(f"fixture_tlas{k}_{name}_auto", got, want)
+        got_ref, ctr = sp.p.trace_counted(rays, ray_flags=flags, tlas_idx=k)
+        _assert_parity(f"fixture_tlas{k}_{name}_reforder", got_ref, want)
+        assert [ctr[c] for c in CTR] == g[f"ctr_tlas{k}_{name}"].tolist(), (name, ctr)
+
+
+def test_c1_golden_path_b_and_a():
+    g = np.load(os.path.join(GOLD, "c1_sphere_96.npz"))
+    sp, (pos, idx, m) = helpers.sphere_c1()
+    got = sp.p.trace_closest_batch(g["rays"], ray_flags=0x10, grid_width=96)
+    _assert_parity("c1_golden_b", got, g["hits_b"])
+    wpos = S.mat4_apply_point(m, pos)
+    bvh = api.build_bvh_for_abstract_mesh(wpos, idx, api.SAH(4), api.TreeBuildOption(50, 2))
+    got_a = api.intersect_nearest_bvh(wpos, idx, g["rays"], bvh, api.FACE_DOUBLE)
+    assert got_a.tobytes() == g["hits_a"].tobytes()
+
+
+# ---- oracle comparisons on seeded inputs -------------------------------------------------------------
+@pytest.mark.parametrize("mode", [api.TRACE_AUTO, api.TRACE_REFERENCE_ORDER])
+def test_c1_sphere_full_size(mode):
+    """BASELINE config 1: 1024x1024 coherent primary rays vs the 64x64-segment sphere"""
+    sp, _ = helpers.sphere_c1()
+    rays = S.pinhole_rays(1024, 1024, 0.0, 100.0)
+    want, ctr = sp.o.trace(rays, ray_flags=0x10, n_threads=os.cpu_count() or 4)
+    assert ctr["ref_abort"] == 0
+    got, stats = _device_trace(sp.p, rays, mode, ray_flags=0x10, grid_width=1024)
+    rep = _assert_parity(f"c1_full_mode{mode}", got, want)
+    assert rep["hits"] > 200000
+    if mode == api.TRACE_REFERENCE_ORDER:
+        _, gctr = sp.p.trace_counted(rays[:65536], ray_flags=0x10)
+        _, octr = sp.o.trace(rays[:65536], ray_flags=0x10, n_threads=4)
+        assert gctr == octr
+
+
+def test_torus_medium_primary_and_bounce():
+    """configs 2/3 at a size the oracle finishes in seconds: 256x256-segment torus (131k tris), 640x360 primary rays +
+    one incoherent cosine-weighted bounce per hit (no culling)"""
+    sp, (pos, idx, m) = helpers.torus_scene(256)
+    rays = S.pinhole_rays(640, 360, 0.01, 100.0, aspect_correct=True)
+    nt = os.cpu_count() or 4
+    want, ctr = sp.o.trace(rays, ray_flags=0x10, n_threads=nt)
+    got = sp.p.trace_closest_batch(rays, ray_flags=0x10, grid_width=640)
+    rep = _assert_parity("torus256_primary", got, want)
+    assert rep["hits"] > 20000 and ctr["ref_abort"] == 0
+    d = np.stack([rays["dx"], rays["dy"], rays["dz"]], -1)
+    hit = want["instance_id"] != 0xFFFFFFFF
+    normals = np.zeros((rays.shape[0], 3), np.float32)
+    normals[hit] = S.geometric_normals(pos, idx, want["primitive_id"][hit], m, d[hit])
+    brays, _ = S.bounce_rays(rays, want, normals)
+    bwant, bctr = sp.o.trace(brays, ray_flags=0, n_threads=nt)
+    bgot = sp.p.trace_closest_batch(brays, ray_flags=0)
+    brep = _assert_parity("torus256_bounce", bgot, bwant)
+    assert brep["hits"] > 1000 and bctr["ref_abort"] == 0
+
+
+def test_instanced_scene_ids_exact():
+    """config 4 shape at reduced size: 20x20 transform-instanced copies of a 64x64 sphere, instance ids exact"""
+    pos, idx = S.uv_sphere_mesh(64, 64)
+    sp = helpers.ScenePair()
+    b = sp.blas([(pos, idx.reshape(-1), 1)])
+    t = sp.tlas(S.instance_grid(20, 20, b, spacing=3.5, z=-60.0))
+    sp.bind([t])
+    sp.build()
+    rays = S.pinhole_rays(512, 512, 0.0, 1000.0)
+    want, ctr = sp.o.trace(rays, ray_flags=0x10, n_threads=os.cpu_count() or 4)
+    got = sp.p.trace_closest_batch(rays, ray_flags=0x10, grid_width=512)
+    rep = _assert_parity("instanced_20x20", got, want)
+    assert rep["hits"] > 10000 and len(np.unique(want["instance_custom_id"])) > 50
+
+
+def test_flags_masks_multi_geometry_and_edge_cases():
+    cube = (S.CUBE_POSITION, S.CUBE_INDEX, 1)
+    non_opaque = (S.CUBE_POSITION + np.array([2.0, 0, 0], np.float32), S.CUBE_INDEX, 0)
+    nonindexed = (S.CUBE_POSITION[S.CUBE_INDEX] + np.array([-2.0, 0, 0], np.float32), None, 1)
+    aabb = (np.array([[0, 0, 0, 1, 1, 1]], np.float32), None, 1, True)
+    sp = helpers.ScenePair()
+    b = sp.blas([cube, non_opaque, nonindexed, aabb])
+    empty = sp.blas([(np.zeros((0, 3), np.float32), np.zeros(0, np.uint32), 1)])
+    T, Sc, mul = S.mat4_translate, S.mat4_scale, S.mat4_mul
+    inst = np.concatenate([
+        S.make_instance(T(0, 0, -6), b, custom_index=7, mask=0x1),
+        S.make_instance(mul(T(0, 2.5, -6), Sc(-1, 1, 1)), b, custom_index=8, mask=0x2),           # det < 0 -> FLIP_FACING
+        S.make_instance(T(0, -2.5, -6), b, custom_index=9, mask=0x4, flags=api.GEOMETRY_INSTANCE_TRIANGLE_FACING_CULL_DISABLE),
+        S.make_instance(T(0, 0, -9), b, custom_index=10, mask=0x8, flags=api.GEOMETRY_INSTANCE_FORCE_NO_OPAQUE),
+        S.make_instance(T(0, 0, -3), empty, custom_index=11, mask=0xFF),
+    ])
+    t_main = sp.tlas(inst)
+    t_deleted = sp.tlas(S.make_instance(T(0, 0, -4), b))
+    sp.o.delete_tlas(t_deleted)
+    sp.p.delete_top_level_acceleration_structure(api.TlasHandle(t_deleted))
+    sp.bind([t_main, t_deleted])
+    sp.build()
+    rays = S.pinhole_rays(160, 160, 0.0, 100.0)
+    for flags in (0x00, 0x10, 0x20, 0x40, 0x80, 0x01 | 0x40, 0x02 | 0x80, 0x100, 0x04, 0x14):
+        for mask in (0xFFFFFFFF, 0x1, 0x6, 0x0):
+            want, _ = sp.o.trace(rays, ray_flags=flags, cull_mask=mask, tlas_idx=0, n_threads=4)
+            got = sp.p.trace_closest_batch(rays, ray_flags=flags, cull_mask=mask, tlas_idx=0)
+            _assert_parity(f"flags{flags:#x}_mask{mask:#x}", got, want)
+    # a deleted TLAS and an out-of-range tlas_idx both miss everywhere
+    for tl in (1, 5):
+        got = sp.p.trace_closest_batch(rays[:256], tlas_idx=tl)
+        assert (got["instance_id"] == 0xFFFFFFFF).all() and (got["t"] == 100.0).all()
+    # empty and ragged launches
+    assert sp.p.trace_closest_batch(rays[:0]).shape == (0,)
+    for n in (1, 31, 33, 1000):
+        want, _ = sp.o.trace(rays[:n], ray_flags=0x10)
+        assert sp.p.trace_closest_batch(rays[:n], ray_flags=0x10).tobytes() == want.tobytes()
+    # rays starting inside geometry / tight ranges
+    tight = rays.copy()
+    tight["tmin"], tight["tmax"] = 5.4, 5.6
+    want, _ = sp.o.trace(tight, ray_flags=0)
+    _assert_parity("tight_range", sp.p.trace_closest_batch(tight, ray_flags=0), want)
+
+
+def test_exact_ties_resolve_like_the_reference():
+    """coplanar duplicated geometry: every hit is an exact tie; the reference keeps the LAST accepted in its visit order"""
+    pos, idx = S.uv_sphere_mesh(24, 24)
+    sp = helpers.ScenePair()
+    b1 = sp.blas([(pos, idx.reshape(-1), 1)])
+    b2 = sp.blas([(pos, idx.reshape(-1), 1), (pos, idx.reshape(-1), 1)])  # duplicated geometry inside one BLAS
+    m = S.mat4_mul(S.mat4_translate(0, 0, -6), S.mat4_scale(2, 2, 2))
+    t = sp.tlas(np.concatenate([S.make_instance(m, b1, custom_index=1), S.make_instance(m, b1, custom_index=2),
+                                S.make_instance(m, b2, custom_index=3)]))
+    sp.bind([t])
+    sp.build()
+    rays = S.pinhole_rays(256, 256, 0.0, 100.0)
+    want, ctr = sp.o.trace(rays, ray_flags=0x10, n_threads=4)
+    got, stats = _device_trace(sp.p, rays, api.TRACE_AUTO, ray_flags=0x10, grid_width=256)
+    rep = _assert_parity("exact_ties", got, want)
+    assert stats["tie_rays"] >= rep["hits"] > 1000  # every hit went through the exact tie resolution
+
+
+def test_degenerate_triangles_are_ignored():
+    """zero-area pole triangles without culling: NaN t is never reported (the reference's CPU path aborts there)"""
+    pos, idx = S.uv_sphere_mesh(16, 16)
+    m = S.mat4_mul(S.mat4_translate(0, 0, -10), S.mat4_scale(5, 5, 5))
+    sp = helpers.single_mesh_scene(pos, idx, m)
+    rays = S.pinhole_rays(128, 128, 0.0, 100.0)
+    want, ctr = sp.o.trace(rays, ray_flags=0)
+    got = sp.p.trace_closest_batch(rays, ray_flags=0)
+    assert not np.isnan(got["t"]).any()
+    _assert_parity("degenerate_no_cull", got, want)
+
+
+def test_path_a_space_query_matches_oracle():
+    pos, idx = S.torus_mesh(96, 64)
+    m = S.mat4_mul(S.mat4_mul(S.mat4_translate(0, 0, -10), S.mat4_scale(5, 5, 5)), S.mat4_rotate_x(-0.5))
+    wpos = S.mat4_apply_point(m, pos)
+    tri = idx.reshape(-1, 3)
+    boxes = np.concatenate([wpos[tri].min(1), wpos[tri].max(1)], 1)
+    rays = S.pinhole_rays(200, 200, 0.0, 100.0)
+    for strat_o, strat_p, opt in ((oracle.STRATEGY_SAH, api.SAH(4), (50, 2)), (oracle.STRATEGY_SAH, api.SAH(4), (10, 50)),
+                                  (oracle.STRATEGY_BALANCE, api.BalanceTree(), (15, 10))):
+        ob = oracle.FlattenBVH(boxes, strat_o, 4, *opt)
+        pb = api.build_bvh_for_abstract_mesh(wpos, idx, strat_p, api.TreeBuildOption(*opt))
+        for side in (api.FACE_FRONT, api.FACE_BACK, api.FACE_DOUBLE):
+            want = ob.query_nearest(wpos, idx, rays, side, 4)
+            got = api.intersect_nearest_bvh(wpos, idx, rays, pb, side)
+            assert got.tobytes() == want.tobytes(), (opt, side)
+            assert want["hit"].sum() > 1000
+
+
+# ---- wavefront queue compaction ---------------------------------------------------------------------
+def test_compaction_known_answers_and_random():
+    s = api.NaiveSahBVHSystem()
+    x = np.array([1, 0, 1, 0, 1, 1, 0], np.uint32)  # stream_compaction.rs:100-125
+    out, n = s.compact_u32(x, x == 1)
+    assert out.tolist() == [1, 1, 1, 1, 0, 0, 0] and n == 4
+    rng = np.random.default_rng(3)
+    for size in (0, 1, 7, 2047, 2048, 2049, 70, 100003, 5_000_000):
+        for p in (0.0, 0.3, 1.0):
+            vals = rng.integers(0, 2 ** 32, size, dtype=np.uint32)
+            keep = (rng.random(size) < p).astype(np.uint8) * rng.integers(1, 255, size, dtype=np.uint8)
+            want, wn = oracle.stream_compaction(vals, keep)
+            got, gn = s.compact_u32(vals, keep)
+            assert gn == wn == int((keep != 0).sum()) and np.array_equal(got, want), (size, p)
+
+
+def test_compaction_feeds_a_bounce_wave():
+    """wavefront step: trace primaries, compact the indices of rays that hit (device side), gather those rays, trace again"""
+    import torch
+    sp, (pos, idx, m) = helpers.torus_scene(128)
+    rays = S.pinhole_rays(256, 256, 0.01, 100.0)
+    d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1, 32).copy()).cuda()
+    d_hits = torch.zeros_like(d_rays)
+    n = rays.shape[0]
+    st = torch.cuda.current_stream().cuda_stream
+    sp.p.trace_closest_device(d_rays.data_ptr(), n, d_hits.data_ptr(), ray_flags=0x10, stream=st)
+    inst = d_hits.view(torch.int32)[:, 5]
+    keep = (inst != -1).to(torch.uint8)
+    ids = torch.arange(n, dtype=torch.int32, device="cuda")
+    out = torch.empty_like(ids)
+    out_n = torch.zeros(1, dtype=torch.int64, device="cuda")
+    sp.p.compact_u32_device(ids.data_ptr(), keep.data_ptr(), n, out.data_ptr(), out_n.data_ptr(), stream=st)
+    torch.cuda.synchronize()
+    want_hits, _ = sp.o.trace(rays, ray_flags=0x10, n_threads=4)
+    want_ids = np.nonzero(want_hits["instance_id"] != 0xFFFFFFFF)[0]
+    k = int(out_n.item())
+    assert k == want_ids.size and np.array_equal(out[:k].cpu().numpy(), want_ids) and (out[k:] == 0).all()
+
+
+# ---- replication ---------------------------------------------------------------------------------------
+def test_blob_adoption_gives_identical_results():
+    import torch
+    sp, _ = helpers.reference_fixture()
+    ptr, nbytes = sp.p.blob()
+    # copy the blob like an NCCL broadcast would deliver it, then adopt it in a second scene object
+    src = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    from cuda.bindings import runtime as cudart
+    (err,) = cudart.cudaMemcpy(src.data_ptr(), ptr, nbytes, cudart.cudaMemcpyKind.cudaMemcpyDeviceToDevice)
+    assert int(err) == 0
+    other = api.NaiveSahBVHSystem()
+    other.adopt_blob(src.data_ptr(), nbytes)
+    del src
+    rays = S.pinhole_rays(96, 96, 0.0, 100.0)
+    for k in range(5):
+        a = sp.p.trace_closest_batch(rays, ray_flags=0x10, tlas_idx=k)
+        b = other.trace_closest_batch(rays, ray_flags=0x10, tlas_idx=k)
+        assert a.tobytes() == b.tobytes()
