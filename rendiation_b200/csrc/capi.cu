@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <shared_mutex>
@@ -40,7 +41,7 @@ constexpr int N_SLOTS = 3;
 struct Scratch {
   void *base = nullptr;        // small block: work_counter | tie_count | tie_unresolved | stack_overflow | counters[6]
   uint32_t *tie_queue = nullptr;
-  float *tie_clamp = nullptr;
+  float *tie_best = nullptr;
   uint64_t capacity = 0;       // rays
   TraceScratch view() const {
     TraceScratch s;
@@ -51,7 +52,7 @@ struct Scratch {
     s.stack_overflow = reinterpret_cast<uint32_t *>(b + 16);
     s.counters = reinterpret_cast<unsigned long long *>(b + 32);
     s.tie_queue = tie_queue;
-    s.tie_clamp = tie_clamp;
+    s.tie_best = tie_best;
     return s;
   }
 };
@@ -104,10 +105,10 @@ int ensure_scratch(Scratch &s, uint64_t n) {
   }
   if (s.capacity < n) {
     if (s.tie_queue) cudaFree(s.tie_queue);
-    if (s.tie_clamp) cudaFree(s.tie_clamp);
-    s.tie_queue = nullptr; s.tie_clamp = nullptr; s.capacity = 0;
+    if (s.tie_best) cudaFree(s.tie_best);
+    s.tie_queue = nullptr; s.tie_best = nullptr; s.capacity = 0;
     RDN_CUDA(cudaMalloc(&s.tie_queue, std::max<uint64_t>(n, 1) * sizeof(uint32_t)));
-    RDN_CUDA(cudaMalloc(&s.tie_clamp, std::max<uint64_t>(n, 1) * sizeof(float)));
+    RDN_CUDA(cudaMalloc(&s.tie_best, std::max<uint64_t>(n, 1) * sizeof(float)));
     s.capacity = n;
   }
   return RDN_OK;
@@ -116,7 +117,7 @@ int ensure_scratch(Scratch &s, uint64_t n) {
 void free_scratch(Scratch &s) {
   if (s.base) cudaFree(s.base);
   if (s.tie_queue) cudaFree(s.tie_queue);
-  if (s.tie_clamp) cudaFree(s.tie_clamp);
+  if (s.tie_best) cudaFree(s.tie_best);
   s = Scratch{};
 }
 
@@ -201,14 +202,14 @@ int enqueue_trace(rdn_rt_scene *s, DeviceCtx &dc, const Scratch &scratch, const 
   const TraceScratch ts = scratch.view();
   RDN_CUDA(cudaMemsetAsync(scratch.base, 0, 12, stream));  // work_counter + tie_count; the two error flags accumulate until read
   const bool end_search = (launch.ray_flags & RDN_RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH) != 0;
-  if (mode == RDN_TRACE_REFERENCE_ORDER || end_search) {
-    launch_trace_reference(dc.dev, launch, d_rays, n, d_hits, ts, false, false, dc.sm_count, stream);
-    if (launches) *launches += 1;
-  } else {
+  if (mode == RDN_TRACE_REFERENCE_ORDER || end_search)
+    launch_trace_reference(dc.dev, launch, d_rays, n, d_hits, ts, false, dc.sm_count, stream);
+  else {
     launch_trace_ordered(dc.dev, launch, resolve_world_root(s, launch.tlas_idx), d_rays, n, d_hits, ts, dc.sm_count, stream);
-    launch_trace_reference(dc.dev, launch, d_rays, n, d_hits, ts, true, false, dc.sm_count, stream);
-    if (launches) *launches += 2;
+    launch_resolve_ties(dc.dev, launch, d_rays, d_hits, ts, dc.sm_count, stream);
+    if (launches) *launches += 1;
   }
+  if (launches) *launches += 1;
   RDN_CUDA(cudaGetLastError());
   return RDN_OK;
 }
@@ -477,7 +478,7 @@ int rdn_rt_trace_counted(rdn_rt_scene *s, const rdn_launch *launch, const rdn_ra
     const uint64_t m = std::min(chunk, n - off);
     RDN_CUDA(cudaMemcpyAsync(slot.d_rays, rays + off, m * sizeof(rdn_ray), cudaMemcpyHostToDevice, slot.stream));
     RDN_CUDA(cudaMemsetAsync(slot.scratch.base, 0, SCRATCH_BASE_BYTES, slot.stream));
-    launch_trace_reference(dc.dev, *launch, slot.d_rays, m, slot.d_hits, slot.scratch.view(), false, true, dc.sm_count, slot.stream);
+    launch_trace_reference(dc.dev, *launch, slot.d_rays, m, slot.d_hits, slot.scratch.view(), true, dc.sm_count, slot.stream);
     RDN_CUDA(cudaGetLastError());
     RDN_CUDA(cudaMemcpyAsync(out_hits + off, slot.d_hits, m * sizeof(rdn_hit), cudaMemcpyDeviceToHost, slot.stream));
     unsigned long long c[6];

@@ -31,8 +31,8 @@ struct TraceScratch {
   uint32_t *tie_count;               // rays queued for exact tie resolution
   uint32_t *tie_unresolved;          // safety net: clamped re-walk found nothing (must stay 0)
   uint32_t *stack_overflow;          // safety net: traversal stack overflow (must stay 0)
-  uint32_t *tie_queue;               // ray indices, capacity >= n
-  float *tie_clamp;                  // per queued ray: initial far for the reference-order re-walk
+  uint32_t *tie_queue;               // ray indices, capacity >= rays of the launch
+  float *tie_best;                   // closest distance found by the ordered kernel, per queued ray
   unsigned long long *counters;      // 6 x u64 (rdn_counters)
 };
 
@@ -40,10 +40,12 @@ struct TraceScratch {
 constexpr float TIE_EPS = 1e-5f;
 
 // The reference's threaded pre-order walk, one ray per thread (NaiveSahBvhCpu::traverse on the device).
-// queue == nullptr: rays [0, n).  queue != nullptr: rays queue[0 .. *queue_count) with initial far = clamp[k];
-// a re-walk that finds nothing leaves the existing hit record untouched and bumps tie_unresolved.
 void launch_trace_reference(const SceneDev &scene, const rdn_launch &launch, const rdn_ray *d_rays, uint64_t n, rdn_hit *d_hits,
-                            const TraceScratch &scratch, bool use_tie_queue, bool count_visits, int sm_count, cudaStream_t stream);
+                            const TraceScratch &scratch, bool count_visits, int sm_count, cudaStream_t stream);
+
+// Re-walk of the rays queued by the ordered kernel (grid-stride over the device-side queue, no host sync in between).
+void launch_resolve_ties(const SceneDev &scene, const rdn_launch &launch, const rdn_ray *d_rays, rdn_hit *d_hits,
+                         const TraceScratch &scratch, int sm_count, cudaStream_t stream);
 
 // Ordered (near child first) persistent-thread traversal with tie detection; queues near-tie rays in scratch.
 // world_root = TlasRoot::wide_root of tlas_binding[launch.tlas_idx] (resolved by the caller from its host copy).

@@ -93,9 +93,10 @@ constexpr uint32_t REF_LEAF_COUNT_SHIFT = 27;
 constexpr uint32_t REF_LEAF_START_MASK = (1u << 27) - 1u;
 constexpr uint32_t REF_LEAF_MAX_COUNT = 16;
 constexpr uint32_t REF_SPECIAL = 0x7F000000u;
+constexpr uint32_t REF_DONE = 0x7FFFFFFDu;           // traversal stack exhausted (kernel-internal)
 constexpr uint32_t REF_EMPTY = 0x7FFFFFFEu;
 constexpr uint32_t REF_EXIT_INSTANCE = 0x7FFFFFFFu;
-constexpr uint32_t REF_GEOM_ITER_MAX = 0x00FFFFFDu;
+constexpr uint32_t REF_GEOM_ITER_MAX = 0x00FFFFFCu;
 
 enum ArrayId : int {
   ARR_TLAS_BINDING = 0,   // u32

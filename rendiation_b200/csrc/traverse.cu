@@ -16,8 +16,11 @@
 //                      (ballot + one atomic per warp).  Box decisions use the reference's arithmetic on the
 //                      reference's boxes; the pruning bound is inflated by TIE_EPS and any ray that saw a second
 //                      candidate within TIE_EPS of the closest is queued (warp-aggregated append) and re-walked by
-//                      k_trace_reference with its range clamped — so ids come out exactly as the CPU query's.
+//                      k_resolve_ties in the reference's order with its range clamped around the closest distance —
+//                      so ids come out exactly as the CPU query's.
 #include <cuda_runtime.h>
+
+#include <cstdlib>
 
 #include "kernels.h"
 #include "rdn_math.h"
@@ -121,116 +124,127 @@ __device__ __forceinline__ void store_hit(rdn_hit *dst, float t, float u, float 
 }
 
 // ================================================================================================ reference order
+struct WalkResult {
+  float t, u, v;
+  uint32_t slot, inst, kind;
+};
+struct WalkCounters {
+  unsigned long long bvh_visit = 0, bvh_hit = 0, tri_visit = 0, tri_hit = 0, inst = 0, abort = 0;
+};
+
+// NaiveSahBvhCpu::traverse for one ray: stackless threaded pre-order walk over the reference-layout forests.
+// Plain query: near_walk = near, far_init = far0.  Tie re-walk: the range used for box / triangle range tests is clamped to
+// [near_walk, far_init] just around the closest distance (subtrees that end before it hold no hit at all, candidates
+// beyond it cannot win), while the update_far asserts keep using the ray's own near.
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_trace_reference(const SceneDev S, const rdn_launch L, const rdn_ray *__restrict__ rays,
-                                                         uint64_t n, rdn_hit *__restrict__ hits, const TraceScratch scratch,
-                                                         const bool use_queue) {
-  const uint64_t limit = use_queue ? static_cast<uint64_t>(*scratch.tie_count) : n;
-  unsigned long long c_bvh_visit = 0, c_bvh_hit = 0, c_tri_visit = 0, c_tri_hit = 0, c_inst = 0, c_abort = 0;
+__device__ __forceinline__ void reference_walk(const SceneDev &S, const rdn_launch &L, Vec3 ro, Vec3 rd, float near, float far0,
+                                               float near_walk, float far_init, WalkResult &res, WalkCounters &ctr) {
+  float far = far_init;  // the shared Rc<Cell<f32>> of RayRange
+  res.t = far0; res.u = 0.f; res.v = 0.f;
+  res.slot = RDN_INVALID_ID; res.inst = RDN_INVALID_ID; res.kind = 0;
 
-  for (uint64_t k = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; k < limit;
-       k += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
-    const uint64_t ri = use_queue ? scratch.tie_queue[k] : k;
-    const float4 r0 = __ldg(reinterpret_cast<const float4 *>(rays + ri));
-    const float4 r1 = __ldg(reinterpret_cast<const float4 *>(rays + ri) + 1);
-    const Vec3 ro = xyz(r0), rd = xyz(r1);
-    const float near = r0.w, far0 = r1.w;
-    float far = use_queue ? fminf(far0, scratch.tie_clamp[k]) : far0;  // the shared Rc<Cell<f32>> of RayRange
+  uint32_t tlas_cursor = 0xFFFFFFFFu;
+  if (L.tlas_idx < S.n_tlas_binding) {
+    const uint32_t handle = S.tlas_binding[L.tlas_idx];
+    if (handle < S.n_tlas_root) tlas_cursor = S.tlas_root[handle].bvh_root_idx;
+  }
+  const Vec3 inv_rd = recip3(rd);
+  bool end_search = false;
 
-    float best_t = far0, best_u = 0.f, best_v = 0.f;
-    uint32_t best_slot = RDN_INVALID_ID, best_inst = RDN_INVALID_ID, best_kind = 0;
+  while (tlas_cursor != 0xFFFFFFFFu && !end_search) {
+    // ---- TraverseBvhIteratorCpu over the TLAS
+    const float4 *np = reinterpret_cast<const float4 *>(S.tlas_bvh_forest + tlas_cursor);
+    const float4 n0 = __ldg(np), n1 = __ldg(np + 1);
+    if (COUNT) ctr.bvh_visit++;
+    float tn;
+    const uint32_t hit_next = __float_as_uint(n0.w), miss_next = __float_as_uint(n1.w);
+    if (!slab_test(ro, inv_rd, near_walk * 1.0f, far * 1.0f, xyz(n0), xyz(n1), tn)) { tlas_cursor = miss_next; continue; }
+    const uint32_t leaf_node = tlas_cursor;
+    tlas_cursor = hit_next;
+    if (hit_next != miss_next) continue;
+    if (COUNT) ctr.bvh_hit++;
+    const uint2 irange = *reinterpret_cast<const uint2 *>(S.tlas_bvh_forest[leaf_node].content_range);
 
-    uint32_t tlas_cursor = 0xFFFFFFFFu;
-    if (L.tlas_idx < S.n_tlas_binding) {
-      const uint32_t handle = S.tlas_binding[L.tlas_idx];
-      if (handle < S.n_tlas_root) tlas_cursor = S.tlas_root[handle].bvh_root_idx;
-    }
-    const Vec3 inv_rd = recip3(rd);
-    bool end_search = false;
+    for (uint32_t tlas_idx = irange.x; tlas_idx < irange.y && !end_search; ++tlas_idx) {
+      const float4 *tb = reinterpret_cast<const float4 *>(S.tlas_bounding + tlas_idx);
+      const float4 b0 = __ldg(tb), b1 = __ldg(tb + 1);
+      // ORIGINAL ray.range for the instance box (traverse_cpu.rs:80-86)
+      if (!slab_test(ro, inv_rd, near, far0, xyz(b0), xyz(b1), tn)) continue;
+      if ((L.cull_mask & __float_as_uint(b0.w)) == 0) continue;
+      if (COUNT) ctr.inst++;
+      const InstanceRecord *rec = S.instances + tlas_idx;
+      const uint32_t flags = merge_geometry_instance_flag(L.ray_flags, rec->flags);
+      Vec3 bo, bd;
+      float scaling;
+      to_object_space(rec, ro, rd, bo, bd, scaling);
+      const Vec3 inv_bd = recip3(bd);
+      const uint32_t blas_idx = rec->blas;
+      if (blas_idx >= S.n_blas_meta) continue;
+      if (flags & TF_SKIP_TRIANGLES) continue;
+      const uint32_t g0 = S.blas_meta[blas_idx].tri_root_range[0], g1 = S.blas_meta[blas_idx].tri_root_range[1];
+      const uint32_t cull_bits = cull_triangle_bits(flags);
 
-    while (tlas_cursor != 0xFFFFFFFFu && !end_search) {
-      // ---- TraverseBvhIteratorCpu over the TLAS
-      const float4 *np = reinterpret_cast<const float4 *>(S.tlas_bvh_forest + tlas_cursor);
-      const float4 n0 = __ldg(np), n1 = __ldg(np + 1);
-      if (COUNT) c_bvh_visit++;
-      float tn;
-      const uint32_t hit_next = __float_as_uint(n0.w), miss_next = __float_as_uint(n1.w);
-      if (!slab_test(ro, inv_rd, near * 1.0f, far * 1.0f, xyz(n0), xyz(n1), tn)) { tlas_cursor = miss_next; continue; }
-      const uint32_t leaf_node = tlas_cursor;
-      tlas_cursor = hit_next;
-      if (hit_next != miss_next) continue;
-      if (COUNT) c_bvh_hit++;
-      const uint2 irange = *reinterpret_cast<const uint2 *>(S.tlas_bvh_forest[leaf_node].content_range);
-
-      for (uint32_t tlas_idx = irange.x; tlas_idx < irange.y && !end_search; ++tlas_idx) {
-        const float4 *tb = reinterpret_cast<const float4 *>(S.tlas_bounding + tlas_idx);
-        const float4 b0 = __ldg(tb), b1 = __ldg(tb + 1);
-        // ORIGINAL ray.range for the instance box (traverse_cpu.rs:80-86)
-        if (!slab_test(ro, inv_rd, near, far0, xyz(b0), xyz(b1), tn)) continue;
-        if ((L.cull_mask & __float_as_uint(b0.w)) == 0) continue;
-        if (COUNT) c_inst++;
-        const InstanceRecord *rec = S.instances + tlas_idx;
-        const uint32_t flags = merge_geometry_instance_flag(L.ray_flags, rec->flags);
-        Vec3 bo, bd;
-        float scaling;
-        to_object_space(rec, ro, rd, bo, bd, scaling);
-        const Vec3 inv_bd = recip3(bd);
-        const uint32_t blas_idx = rec->blas;
-        if (blas_idx >= S.n_blas_meta) continue;
-        if (flags & TF_SKIP_TRIANGLES) continue;
-        const uint32_t g0 = S.blas_meta[blas_idx].tri_root_range[0], g1 = S.blas_meta[blas_idx].tri_root_range[1];
-        const uint32_t cull_bits = cull_triangle_bits(flags);
-
-        for (uint32_t g = g0; g < g1 && !end_search; ++g) {
-          const GeometryMeta gm = S.geometry_meta[g];
-          if (!cull_geometry_pass(flags, gm.geometry_flags)) continue;
-          uint32_t cursor = gm.bvh_root_idx;
-          while (cursor != 0xFFFFFFFFu && !end_search) {
-            const float4 *bp = reinterpret_cast<const float4 *>(S.tri_bvh_forest + cursor);
-            const float4 m0 = __ldg(bp), m1 = __ldg(bp + 1);
-            if (COUNT) c_bvh_visit++;
-            const uint32_t bh = __float_as_uint(m0.w), bm = __float_as_uint(m1.w);
-            if (!slab_test(bo, inv_bd, near * scaling, far * scaling, xyz(m0), xyz(m1), tn)) { cursor = bm; continue; }
-            const uint32_t leaf = cursor;
-            cursor = bh;
-            if (bh != bm) continue;
-            if (COUNT) c_bvh_hit++;
-            const uint2 trange = *reinterpret_cast<const uint2 *>(S.tri_bvh_forest[leaf].content_range);
-            for (uint32_t slot = trange.x; slot < trange.y; ++slot) {
-              const float4 *tp = reinterpret_cast<const float4 *>(S.triangles + slot);
-              const float4 qn = __ldg(tp), qv0 = __ldg(tp + 1), qe1 = __ldg(tp + 2), qe2 = __ldg(tp + 3);
-              if (COUNT) c_tri_visit++;
-              float sign, t, u, v;
-              if (!triangle_test(qn, qv0, qe1, qe2, bo, bd, near * scaling, far * scaling, cull_bits, sign, t, u, v)) continue;
-              const float distance = t / scaling;
-              if (COUNT) c_tri_hit++;
-              // RayRange::update_far asserts: the reference aborts; the candidate is rejected here
-              if (!(near <= distance) || !(distance <= far)) { if (COUNT) c_abort++; continue; }
-              far = distance;
-              best_t = distance; best_u = u; best_v = v;
-              best_slot = slot; best_inst = tlas_idx;
-              best_kind = sign < 0.0f ? RDN_HIT_KIND_BACK_FACING_TRIANGLE : RDN_HIT_KIND_FRONT_FACING_TRIANGLE;
-              if (flags & TF_END_SEARCH) { end_search = true; break; }
-            }
+      for (uint32_t g = g0; g < g1 && !end_search; ++g) {
+        const GeometryMeta gm = S.geometry_meta[g];
+        if (!cull_geometry_pass(flags, gm.geometry_flags)) continue;
+        uint32_t cursor = gm.bvh_root_idx;
+        while (cursor != 0xFFFFFFFFu && !end_search) {
+          const float4 *bp = reinterpret_cast<const float4 *>(S.tri_bvh_forest + cursor);
+          const float4 m0 = __ldg(bp), m1 = __ldg(bp + 1);
+          if (COUNT) ctr.bvh_visit++;
+          const uint32_t bh = __float_as_uint(m0.w), bm = __float_as_uint(m1.w);
+          if (!slab_test(bo, inv_bd, near_walk * scaling, far * scaling, xyz(m0), xyz(m1), tn)) { cursor = bm; continue; }
+          const uint32_t leaf = cursor;
+          cursor = bh;
+          if (bh != bm) continue;
+          if (COUNT) ctr.bvh_hit++;
+          const uint2 trange = *reinterpret_cast<const uint2 *>(S.tri_bvh_forest[leaf].content_range);
+          for (uint32_t slot = trange.x; slot < trange.y; ++slot) {
+            const float4 *tp = reinterpret_cast<const float4 *>(S.triangles + slot);
+            const float4 qn = __ldg(tp), qv0 = __ldg(tp + 1), qe1 = __ldg(tp + 2), qe2 = __ldg(tp + 3);
+            if (COUNT) ctr.tri_visit++;
+            float sign, t, u, v;
+            if (!triangle_test(qn, qv0, qe1, qe2, bo, bd, near_walk * scaling, far * scaling, cull_bits, sign, t, u, v)) continue;
+            const float distance = t / scaling;
+            if (COUNT) ctr.tri_hit++;
+            // RayRange::update_far asserts: the reference aborts; the candidate is rejected here
+            if (!(near <= distance) || !(distance <= far)) { if (COUNT) ctr.abort++; continue; }
+            far = distance;
+            res.t = distance; res.u = u; res.v = v;
+            res.slot = slot; res.inst = tlas_idx;
+            res.kind = sign < 0.0f ? RDN_HIT_KIND_BACK_FACING_TRIANGLE : RDN_HIT_KIND_FRONT_FACING_TRIANGLE;
+            if (flags & TF_END_SEARCH) { end_search = true; break; }
           }
         }
       }
     }
-
-    if (best_slot != RDN_INVALID_ID) {
-      const SlotInfo si = S.slot_info[best_slot];
-      store_hit(hits + ri, best_t, best_u, best_v, si.primitive_id, si.geometry_idx, best_inst,
-                S.instances[best_inst].instance_custom_index, best_kind);
-    } else if (!use_queue) {
-      store_hit(hits + ri, far0, 0.f, 0.f, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, 0);
-    } else {
-      atomicAdd(scratch.tie_unresolved, 1u);
-    }
   }
+}
 
+__device__ __forceinline__ void store_walk_result(const SceneDev &S, rdn_hit *dst, const WalkResult &r, float far0) {
+  if (r.slot != RDN_INVALID_ID) {
+    const SlotInfo si = S.slot_info[r.slot];
+    store_hit(dst, r.t, r.u, r.v, si.primitive_id, si.geometry_idx, r.inst, S.instances[r.inst].instance_custom_index, r.kind);
+  } else {
+    store_hit(dst, far0, 0.f, 0.f, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, 0);
+  }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_trace_reference(const SceneDev S, const rdn_launch L, const rdn_ray *__restrict__ rays,
+                                                         uint64_t n, rdn_hit *__restrict__ hits, const TraceScratch scratch) {
+  WalkCounters ctr;
+  for (uint64_t ri = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; ri < n;
+       ri += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const float4 r0 = __ldg(reinterpret_cast<const float4 *>(rays + ri));
+    const float4 r1 = __ldg(reinterpret_cast<const float4 *>(rays + ri) + 1);
+    WalkResult res;
+    reference_walk<COUNT>(S, L, xyz(r0), xyz(r1), r0.w, r1.w, r0.w, r1.w, res, ctr);
+    store_walk_result(S, hits + ri, res, r1.w);
+  }
   if (COUNT) {
     // warp-reduce, one atomic per warp per counter
-    unsigned long long vals[6] = {c_bvh_visit, c_bvh_hit, c_tri_visit, c_tri_hit, c_inst, c_abort};
+    unsigned long long vals[6] = {ctr.bvh_visit, ctr.bvh_hit, ctr.tri_visit, ctr.tri_hit, ctr.inst, ctr.abort};
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       unsigned long long x = vals[i];
@@ -238,6 +252,29 @@ __global__ void __launch_bounds__(128) k_trace_reference(const SceneDev S, const
       for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(FULL_MASK, x, off);
       if ((threadIdx.x & 31) == 0 && x) atomicAdd(scratch.counters + i, x);
     }
+  }
+}
+
+// Exact tie resolution: every ray the ordered kernel queued (a second candidate within TIE_EPS of its closest hit) is
+// re-walked in the reference's order with its range clamped to [best*(1-3eps), best*(1+3eps)].  Subtrees that end before
+// the clamp hold no hit at all and candidates beyond it cannot win, so from the first shared accept on the clamped walk is
+// in the same state as the reference's unclamped one and ends on the reference's answer.  Grid-stride over the
+// device-side queue: no host round trip between the two kernels.
+__global__ void __launch_bounds__(128) k_resolve_ties(const SceneDev S, const rdn_launch L, const rdn_ray *__restrict__ rays,
+                                                      rdn_hit *__restrict__ hits, const TraceScratch scratch) {
+  const uint32_t count = *scratch.tie_count;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+    const uint64_t ri = scratch.tie_queue[k];
+    const float best = scratch.tie_best[k];
+    const float4 r0 = __ldg(reinterpret_cast<const float4 *>(rays + ri));
+    const float4 r1 = __ldg(reinterpret_cast<const float4 *>(rays + ri) + 1);
+    WalkResult res;
+    WalkCounters ctr;
+    const float near_walk = fmaxf(r0.w, best * (1.0f - 3.0f * TIE_EPS));
+    const float far_init = fminf(r1.w, best * (1.0f + 3.0f * TIE_EPS));
+    reference_walk<false>(S, L, xyz(r0), xyz(r1), r0.w, r1.w, near_walk, far_init, res, ctr);
+    if (res.slot != RDN_INVALID_ID) store_walk_result(S, hits + ri, res, r1.w);
+    else atomicAdd(scratch.tie_unresolved, 1u);  // cannot happen: the closest candidate itself lies inside the clamp
   }
 }
 
@@ -425,7 +462,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK) k_trace_ordered(const OrderedPa
                     S.instances[best_inst].instance_custom_index,
                     best_back ? RDN_HIT_KIND_BACK_FACING_TRIANGLE : RDN_HIT_KIND_FRONT_FACING_TRIANGLE);
           if (second <= best * (1.0f + TIE_EPS)) {
-            // near-tie: queue for the exact reference-order re-walk (warp-aggregated append)
+            // near-tie: queue the ray for the exact reference-order re-walk (warp-aggregated append)
             const uint32_t peers = __activemask();
             const int pl = __ffs(peers) - 1;
             uint32_t qbase = 0;
@@ -433,7 +470,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK) k_trace_ordered(const OrderedPa
             qbase = __shfl_sync(peers, qbase, pl);
             const uint32_t q = qbase + __popc(peers & ((1u << lane) - 1u));
             P.scratch.tie_queue[q] = static_cast<uint32_t>(ri);
-            P.scratch.tie_clamp[q] = fminf(far0, best * (1.0f + 3.0f * TIE_EPS));
+            P.scratch.tie_best[q] = best;
           }
         } else {
           store_hit(dst, far0, 0.f, 0.f, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, 0);
@@ -445,21 +482,249 @@ __global__ void __launch_bounds__(ORDERED_BLOCK) k_trace_ordered(const OrderedPa
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-synchronous rounds: every round the alive lanes (1) descend up to K inner nodes each, (2) re-converge
+// (__syncwarp) and handle their leaf / instance / bookkeeping item TOGETHER — on Volta+ lanes do not re-converge at a
+// loop exit by themselves, and a triangle test executed by 3 lanes costs the warp as much as one executed by 32 —
+// (3) vote: when fewer than THRESH lanes still hold a ray (and rays remain) the warp goes back to the refill point.
+// Refill culls rays against the TLAS root box on the spot (the reference's first test), so rays that miss the scene
+// never occupy a traversal lane.
+template <int K, int MINB, int THRESH>
+__global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(const OrderedParams P) {
+  const SceneDev &S = P.S;
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t stack[STACK_MAX];
+  int sp = 0;
+
+  // the world pseudo-root (TLAS root box + its reference) is launch-uniform: keep it in registers
+  Vec3 root_min = {0, 0, 0}, root_max = {0, 0, 0};
+  uint32_t world_entry = REF_EMPTY;
+  if (P.world_root != REF_EMPTY) {
+    const float4 *np = reinterpret_cast<const float4 *>(S.wide_nodes + P.world_root);
+    const float4 q0 = __ldg(np), q1 = __ldg(np + 1);
+    root_min = xyz(q0); root_max = xyz(q1);
+    world_entry = __float_as_uint(q0.w);
+  }
+
+  bool alive = false;
+  uint64_t ri = 0;
+  Vec3 o = {0, 0, 0}, d = {0, 0, 1}, inv = {0, 0, 0};
+  float t_near_world = 0.f, far0 = 0.f;
+  float scaling = 1.f, near_s = 0.f, far_s = 0.f;
+  float bound = 0.f;
+  float best = 0.f, second = 0.f, best_u = 0.f, best_v = 0.f;
+  uint32_t best_slot = RDN_INVALID_ID, best_inst = RDN_INVALID_ID, best_back = 0;
+  uint32_t cur = REF_DONE, cur_inst = 0, cur_flags = 0, cull_bits = 0, geom_end = 0;
+  bool in_object = false;
+  bool warp_exhausted = false;
+
+#define RDN_PUSH(v) do { if (sp < STACK_MAX) stack[sp++] = (v); else atomicAdd(P.scratch.stack_overflow, 1u); } while (0)
+#define RDN_POP() (sp > 0 ? stack[--sp] : REF_DONE)
+
+  for (;;) {
+    // ---------------- warp-converged refill (a few rounds, so scene-missing rays are retired here)
+#pragma unroll 1
+    for (int attempt = 0; attempt < 4; ++attempt) {
+      const uint32_t want = __ballot_sync(FULL_MASK, !alive);
+      if (!want || warp_exhausted) break;
+      const int cnt = __popc(want);
+      const int leader = __ffs(want) - 1;
+      unsigned long long base = 0;
+      if (static_cast<int>(lane) == leader) base = atomicAdd(P.scratch.work_counter, static_cast<unsigned long long>(cnt));
+      base = __shfl_sync(FULL_MASK, base, leader);
+      if (base + cnt >= P.n_fetch) warp_exhausted = true;
+      if (!alive) {
+        const uint64_t f = base + __popc(want & ((1u << lane) - 1u));
+        bool valid = f < P.n_fetch;
+        uint64_t idx = f;
+        if (valid && P.tiles_x) {
+          const uint64_t tile = f >> 5;
+          const uint32_t in_tile = static_cast<uint32_t>(f & 31u);
+          const uint32_t tx = static_cast<uint32_t>(tile % P.tiles_x), ty = static_cast<uint32_t>(tile / P.tiles_x);
+          const uint32_t x = tx * 8u + (in_tile & 7u), y = ty * 4u + (in_tile >> 3);
+          valid = x < P.width && y < P.height;
+          idx = static_cast<uint64_t>(y) * P.width + x;
+        }
+        if (valid) {
+          const float4 r0 = __ldg(reinterpret_cast<const float4 *>(P.rays + idx));
+          const float4 r1 = __ldg(reinterpret_cast<const float4 *>(P.rays + idx) + 1);
+          const Vec3 ro = xyz(r0), rd = xyz(r1), rinv = recip3(rd);
+          float tn;
+          if (world_entry != REF_EMPTY && slab_test(ro, rinv, r0.w, r1.w, root_min, root_max, tn)) {
+            ri = idx; o = ro; d = rd; inv = rinv;
+            t_near_world = r0.w; far0 = r1.w;
+            scaling = 1.f; near_s = t_near_world; bound = far0; far_s = far0;
+            best = INFINITY; second = INFINITY; best_slot = RDN_INVALID_ID; best_inst = RDN_INVALID_ID;
+            in_object = false; sp = 0;
+            cur = world_entry;
+            alive = true;
+          } else {
+            store_hit(P.hits + idx, r1.w, 0.f, 0.f, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, 0);
+          }
+        }
+      }
+    }
+    const uint32_t amask = __ballot_sync(FULL_MASK, alive);
+    if (amask == 0) {
+      if (warp_exhausted) break;
+      continue;
+    }
+
+    if (alive) {
+#pragma unroll 1
+      for (;;) {
+        // ---------------- phase 1: up to K inner nodes (both child boxes in one 64 B fetch)
+#pragma unroll 1
+        for (int k = 0; k < K && cur < REF_SPECIAL; ++k) {
+          const float4 *np = reinterpret_cast<const float4 *>(S.wide_nodes + cur);
+          const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
+          float n0, n1;
+          const bool h0 = slab_test(o, inv, near_s, far_s, xyz(q0), xyz(q1), n0);
+          const bool h1 = slab_test(o, inv, near_s, far_s, xyz(q2), xyz(q3), n1);
+          const uint32_t r0 = __float_as_uint(q0.w), r1 = __float_as_uint(q1.w);
+          if (h0 && h1) {
+            const bool first0 = n0 <= n1;
+            RDN_PUSH(first0 ? r1 : r0);
+            cur = first0 ? r0 : r1;
+          } else if (h0) {
+            cur = r0;
+          } else if (h1) {
+            cur = r1;
+          } else {
+            cur = RDN_POP();
+          }
+        }
+        __syncwarp(amask);
+
+        // ---------------- phase 2: one leaf / instance / bookkeeping item, all lanes that have one at the same time
+        if (cur >= REF_SPECIAL && cur != REF_DONE) {
+          if (cur & REF_LEAF_BIT) {
+            const uint32_t start = cur & REF_LEAF_START_MASK;
+            const uint32_t count = ((cur >> REF_LEAF_COUNT_SHIFT) & 15u) + 1u;
+            if (in_object) {
+              for (uint32_t k = 0; k < count; ++k) {
+                const uint32_t slot = start + k;
+                const float4 *tp = reinterpret_cast<const float4 *>(S.triangles + slot);
+                const float4 qn = __ldg(tp), qv0 = __ldg(tp + 1), qe1 = __ldg(tp + 2), qe2 = __ldg(tp + 3);
+                float sign, t, u, v;
+                if (!triangle_test(qn, qv0, qe1, qe2, o, d, near_s, far_s, cull_bits, sign, t, u, v)) continue;
+                const float distance = t / scaling;
+                if (!(t_near_world <= distance) || !(distance <= far0)) continue;  // the reference's update_far asserts
+                if (distance < best) {
+                  second = fminf(second, best);
+                  best = distance; best_u = u; best_v = v; best_slot = slot; best_inst = cur_inst;
+                  best_back = sign < 0.0f ? 1u : 0u;
+                  bound = fminf(far0, best * (1.0f + TIE_EPS));
+                  far_s = bound * scaling;
+                } else {
+                  second = fminf(second, distance);
+                }
+              }
+              cur = RDN_POP();
+            } else {
+              // instance leaf (world space): take the first slot, park the rest
+              if (count > 1) RDN_PUSH(REF_LEAF_BIT | ((count - 2u) << REF_LEAF_COUNT_SHIFT) | (start + 1u));
+              const float4 *tb = reinterpret_cast<const float4 *>(S.tlas_bounding + start);
+              const float4 b0 = __ldg(tb), b1 = __ldg(tb + 1);
+              float tn;
+              bool entered = false;
+              if (slab_test(o, inv, t_near_world, bound, xyz(b0), xyz(b1), tn) && (P.L.cull_mask & __float_as_uint(b0.w)) != 0) {
+                const InstanceRecord *rec = S.instances + start;
+                const uint4 tail = __ldg(reinterpret_cast<const uint4 *>(&rec->instance_custom_index));
+                const uint32_t flags = merge_geometry_instance_flag(P.L.ray_flags, tail.z);
+                if (!(flags & TF_SKIP_TRIANGLES) && tail.w < S.n_blas_meta) {
+                  const uint2 groots = __ldg(reinterpret_cast<const uint2 *>(S.blas_meta[tail.w].tri_root_range));
+                  if (groots.x < groots.y) {
+                    Vec3 bo, bd;
+                    float s;
+                    to_object_space(rec, o, d, bo, bd, s);
+                    o = bo; d = bd; inv = recip3(bd);
+                    scaling = s; near_s = t_near_world * s; far_s = bound * s;
+                    cur_inst = start; cur_flags = flags; cull_bits = cull_triangle_bits(flags); geom_end = groots.y;
+                    in_object = true;
+                    RDN_PUSH(REF_EXIT_INSTANCE);
+                    cur = REF_SPECIAL | groots.x;
+                    entered = true;
+                  }
+                }
+              }
+              if (!entered) cur = RDN_POP();
+            }
+          } else if (cur == REF_EXIT_INSTANCE) {
+            // back to world space: the world ray is re-read instead of being held in registers
+            const float4 r0 = __ldg(reinterpret_cast<const float4 *>(P.rays + ri));
+            const float4 r1 = __ldg(reinterpret_cast<const float4 *>(P.rays + ri) + 1);
+            o = xyz(r0); d = xyz(r1); inv = recip3(d);
+            scaling = 1.f; near_s = t_near_world; far_s = bound;
+            in_object = false;
+            cur = RDN_POP();
+          } else if (cur == REF_EMPTY) {
+            cur = RDN_POP();
+          } else {
+            // geometry iterator of the current instance's BLAS
+            const uint32_t g = cur & 0x00FFFFFFu;
+            if (g + 1u < geom_end) RDN_PUSH(REF_SPECIAL | (g + 1u));
+            const uint4 gm0 = __ldg(reinterpret_cast<const uint4 *>(S.geometry_meta + g));
+            const uint32_t wide_root = __ldg(&S.geometry_meta[g].wide_root);
+            cur = (cull_geometry_pass(cur_flags, gm0.w) && wide_root != REF_EMPTY) ? wide_root : RDN_POP();
+          }
+        }
+
+        // ---------------- vote (also the re-convergence point of phase 2)
+        const int active = __popc(__ballot_sync(amask, cur != REF_DONE));
+        if (active == 0 || (active < THRESH && !warp_exhausted)) break;
+      }
+
+      if (cur == REF_DONE) {
+        rdn_hit *dst = P.hits + ri;
+        if (best_slot != RDN_INVALID_ID) {
+          const SlotInfo si = S.slot_info[best_slot];
+          store_hit(dst, best, best_u, best_v, si.primitive_id, si.geometry_idx, best_inst,
+                    S.instances[best_inst].instance_custom_index,
+                    best_back ? RDN_HIT_KIND_BACK_FACING_TRIANGLE : RDN_HIT_KIND_FRONT_FACING_TRIANGLE);
+          if (second <= best * (1.0f + TIE_EPS)) {
+            // near-tie: queue the ray for the exact reference-order re-walk (warp-aggregated append)
+            const uint32_t peers = __activemask();
+            const int pl = __ffs(peers) - 1;
+            uint32_t qbase = 0;
+            if (static_cast<int>(lane) == pl) qbase = atomicAdd(P.scratch.tie_count, static_cast<uint32_t>(__popc(peers)));
+            qbase = __shfl_sync(peers, qbase, pl);
+            const uint32_t q = qbase + __popc(peers & ((1u << lane) - 1u));
+            P.scratch.tie_queue[q] = static_cast<uint32_t>(ri);
+            P.scratch.tie_best[q] = best;
+          }
+        } else {
+          store_hit(dst, far0, 0.f, 0.f, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, 0);
+        }
+        alive = false;
+      }
+    }
+    __syncwarp();
+  }
+#undef RDN_PUSH
+#undef RDN_POP
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ launchers
 void launch_trace_reference(const SceneDev &scene, const rdn_launch &launch, const rdn_ray *d_rays, uint64_t n, rdn_hit *d_hits,
-                            const TraceScratch &scratch, bool use_tie_queue, bool count_visits, int sm_count, cudaStream_t stream) {
+                            const TraceScratch &scratch, bool count_visits, int sm_count, cudaStream_t stream) {
   if (n == 0) return;
   const int block = 128;
   uint64_t blocks = (n + block - 1) / block;
-  const uint64_t cap = static_cast<uint64_t>(sm_count) * 16;
-  if (use_tie_queue) blocks = static_cast<uint64_t>(sm_count) * 2;  // queue length is device-side; grid-stride over it
-  else if (blocks > cap * 64) blocks = cap * 64;
+  const uint64_t cap = static_cast<uint64_t>(sm_count) * 1024;
+  if (blocks > cap) blocks = cap;
   if (count_visits)
-    k_trace_reference<true><<<static_cast<unsigned>(blocks), block, 0, stream>>>(scene, launch, d_rays, n, d_hits, scratch, use_tie_queue);
+    k_trace_reference<true><<<static_cast<unsigned>(blocks), block, 0, stream>>>(scene, launch, d_rays, n, d_hits, scratch);
   else
-    k_trace_reference<false><<<static_cast<unsigned>(blocks), block, 0, stream>>>(scene, launch, d_rays, n, d_hits, scratch, use_tie_queue);
+    k_trace_reference<false><<<static_cast<unsigned>(blocks), block, 0, stream>>>(scene, launch, d_rays, n, d_hits, scratch);
+}
+
+void launch_resolve_ties(const SceneDev &scene, const rdn_launch &launch, const rdn_ray *d_rays, rdn_hit *d_hits,
+                         const TraceScratch &scratch, int sm_count, cudaStream_t stream) {
+  k_resolve_ties<<<static_cast<unsigned>(sm_count), 128, 0, stream>>>(scene, launch, d_rays, d_hits, scratch);
 }
 
 void launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, uint32_t world_root, const rdn_ray *d_rays, uint64_t n,
@@ -476,13 +741,28 @@ void launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, uint3
   }
   P.world_root = world_root;
 
+  // RDN_ORDERED_VARIANT: experimentation knob (kernel structure / refill window / register cap)
+  static const int variant = []() { const char *e = getenv("RDN_ORDERED_VARIANT"); return e ? atoi(e) : 1; }();
+  using KernelFn = void (*)(const OrderedParams);
+  KernelFn fn;
+  switch (variant) {
+    case 0: fn = k_trace_ordered; break;
+    case 2: fn = k_trace_ordered_rounds<4, 8, 20>; break;
+    case 3: fn = k_trace_ordered_rounds<8, 8, 20>; break;
+    case 4: fn = k_trace_ordered_rounds<4, 8, 28>; break;
+    case 5: fn = k_trace_ordered_rounds<4, 8, 12>; break;
+    case 6: fn = k_trace_ordered_rounds<2, 8, 20>; break;
+    case 7: fn = k_trace_ordered_rounds<16, 8, 20>; break;
+    case 8: fn = k_trace_ordered_rounds<4, 7, 20>; break;
+    default: fn = k_trace_ordered_rounds<4, 8, 20>; break;
+  }
   int blocks_per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace_ordered, ORDERED_BLOCK, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, ORDERED_BLOCK, 0);
   if (blocks_per_sm < 1) blocks_per_sm = 1;
   uint64_t blocks = static_cast<uint64_t>(sm_count) * blocks_per_sm;
   const uint64_t needed = (P.n_fetch + ORDERED_BLOCK - 1) / ORDERED_BLOCK;
   if (blocks > needed) blocks = needed;
-  k_trace_ordered<<<static_cast<unsigned>(blocks), ORDERED_BLOCK, 0, stream>>>(P);
+  fn<<<static_cast<unsigned>(blocks), ORDERED_BLOCK, 0, stream>>>(P);
 }
 
 }  // namespace rdn

@@ -1,0 +1,82 @@
+"""Kernel experiment harness (not part of the product): times the device-resident trace on a BASELINE config and
+checks a row-strided sample against the oracle.  Usage: [RDN_ORDERED_VARIANT=k] python tools/kbench.py [c1|c2|c3|c4] [iters]"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import oracle  # noqa: E402
+from rendiation_b200 import api, scenes as S  # noqa: E402
+
+cfg = sys.argv[1] if len(sys.argv) > 1 else "c2"
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+check = os.environ.get("KBENCH_CHECK", "1") == "1"
+
+T, Sc, Rx, mul = S.mat4_translate, S.mat4_scale, S.mat4_rotate_x, S.mat4_mul
+sysm = api.NaiveSahBVHSystem()
+osc = oracle.Scene()
+flags = 0x10
+if cfg in ("c2", "c3"):
+    pos, idx = S.torus_mesh(708, 708, 1.0, 0.35)
+    m = mul(mul(T(0, 0, -10), Sc(5, 5, 5)), Rx(-0.5))
+    inst_o = inst_p = None
+    W, H = 1920, 1080
+    rays = S.pinhole_rays(W, H, 0.01, 100.0, aspect_correct=True)
+    insts = lambda b: S.make_instance(m, b)
+elif cfg == "c1":
+    pos, idx = S.uv_sphere_mesh(64, 64)
+    m = mul(T(0, 0, -10), Sc(5, 5, 5))
+    W, H = 1024, 1024
+    rays = S.pinhole_rays(W, H, 0.0, 100.0)
+    insts = lambda b: S.make_instance(m, b)
+elif cfg == "c4":
+    pos, idx = S.uv_sphere_mesh(224, 224)
+    W, H = 1920, 1080
+    rays = S.pinhole_rays(W, H, 0.0, 1000.0, aspect_correct=True)
+    insts = lambda b: S.instance_grid(100, 100, b, 3.5, -200.0)
+t0 = time.time()
+b = sysm.create_bottom_level_acceleration_structure([api.BottomLevelAccelerationStructureBuildSource(pos, idx.reshape(-1))])
+t = sysm.create_top_level_acceleration_structure(insts(b.id))
+sysm.bind_tlas([t]); sysm.commit()
+t_build = time.time() - t0
+ob = osc.create_blas([(pos, idx.reshape(-1), 1)])
+osc.bind_tlas([osc.create_tlas(insts(ob))]); assert osc.build() == 0
+nt = os.cpu_count() or 4
+grid = W
+if cfg == "c3":  # incoherent cosine-weighted bounce rays off the primary hits, no culling
+    ph = osc.trace(rays, ray_flags=0x10, n_threads=nt, want_counters=False)
+    d = np.stack([rays["dx"], rays["dy"], rays["dz"]], -1)
+    hit = ph["instance_id"] != 0xFFFFFFFF
+    normals = np.zeros((rays.shape[0], 3), np.float32)
+    normals[hit] = S.geometric_normals(pos, idx, ph["primitive_id"][hit], m, d[hit])
+    rays, _ = S.bounce_rays(rays, ph, normals)
+    flags, grid = 0, 0
+n = rays.shape[0]
+d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1, 32).copy()).cuda()
+d_hits = torch.zeros((n, 32), dtype=torch.uint8, device="cuda")
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+st = torch.cuda.current_stream().cuda_stream
+for _ in range(3):
+    sysm.trace_closest_device(d_rays.data_ptr(), n, d_hits.data_ptr(), ray_flags=flags, grid_width=grid, stream=st)
+stats = sysm.trace_closest_device(d_rays.data_ptr(), n, d_hits.data_ptr(), ray_flags=flags, grid_width=grid, stream=st, want_stats=True)
+ms = []
+for _ in range(iters):
+    flush.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sysm.trace_closest_device(d_rays.data_ptr(), n, d_hits.data_ptr(), ray_flags=flags, grid_width=grid, stream=st)
+    e1.record(); torch.cuda.synchronize()
+    ms.append(e0.elapsed_time(e1))
+ms = np.array(ms)
+ok = None
+if check:
+    sel = np.arange(0, n, 7)
+    want = osc.trace(rays[sel], ray_flags=flags, n_threads=nt, want_counters=False)
+    got = d_hits.cpu().numpy().view(api.HIT_DTYPE).reshape(-1)[sel]
+    ok = got.tobytes() == want.tobytes()
+print(f"cfg={cfg} variant={os.environ.get('RDN_ORDERED_VARIANT','default')} skip_tie={'RDN_DEBUG_SKIP_TIE' in os.environ} rays={n} "
+      f"mean_ms={ms.mean():.4f} min_ms={ms.min():.4f} Mrays/s(mean)={n/ms.mean()/1e3:.1f} best={n/ms.min()/1e3:.1f} ties={stats['tie_rays']} "
+      f"bit_identical_sample={ok} build_s={t_build:.2f}")
