@@ -44,6 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h")] + [os.path.join(INCLUDE, "rdn_rt.h"), __file__]
     nvcc = _nvcc()
+    extra = os.environ.get("RDN_EXTRA_NVCC_FLAGS", "").split()  # experiments only (e.g. -DRDN_DEBUG_STEPS)
     jobs = []
     objs = []
     for src in SOURCES:
@@ -51,7 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         op = os.path.join(OBJ, src.rsplit(".", 1)[0] + ".o")
         objs.append(op)
         if force or _stale(op, [sp] + headers):
-            cmd = [nvcc, *NVCC_FLAGS, "-Xptxas", "-v", "-c", sp, "-o", op]
+            cmd = [nvcc, *NVCC_FLAGS, *extra, "-Xptxas", "-v", "-c", sp, "-o", op]
             jobs.append(cmd)
 
     def run(cmd):

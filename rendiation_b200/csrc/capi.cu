@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -390,6 +391,12 @@ int rdn_rt_trace_closest_device(rdn_rt_scene *s, int device_index, const rdn_lau
       ties += small[0];
       if (small[1]) return fail(RDN_ERR_CUDA, "tie re-walk found no hit (internal invariant broken)");
       if (small[2]) return fail(RDN_ERR_CAPACITY, "traversal stack overflow");
+#ifdef RDN_DEBUG_STEPS
+      unsigned long long c[6];
+      RDN_CUDA(cudaMemcpy(c, static_cast<char *>(dc.ext_scratch.base) + 32, sizeof(c), cudaMemcpyDeviceToHost));
+      fprintf(stderr, "[dbg steps] max=%llu sum=%llu rays=%llu >200:%llu >500:%llu >1000:%llu\n", c[0], c[1], c[2], c[3], c[4], c[5]);
+      RDN_CUDA(cudaMemset(static_cast<char *>(dc.ext_scratch.base) + 32, 0, sizeof(c)));
+#endif
     }
   }
   RDN_CUDA(cudaEventRecord(dc.ext_done, stream));

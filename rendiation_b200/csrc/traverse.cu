@@ -11,9 +11,9 @@
 //   k_trace_reference  the reference's stackless threaded pre-order walk, one ray per thread.  Identical to the
 //                      CPU query by construction (same visit order, same live-range pruning, "last accepted of
 //                      equal t wins").  Used for ACCEPT_FIRST_HIT rays, for visit counters, and to resolve ties.
-//   k_trace_ordered    persistent-thread, near-child-first walk over the 64 B two-box nodes with a per-thread
-//                      stack, float4 node/triangle fetches through the read-only path, warp-level ray refill
-//                      (ballot + one atomic per warp).  Box decisions use the reference's arithmetic on the
+//   k_trace_ordered_rounds  persistent-thread, near-child-first walk over the 64 B two-box nodes with a per-thread
+//                      stack, float4 node/triangle fetches through the read-only path, warp-synchronous rounds and
+//                      warp-level ray refill (ballot + one atomic per warp).  Box decisions use the reference's arithmetic on the
 //                      reference's boxes; the pruning bound is inflated by TIE_EPS and any ray that saw a second
 //                      candidate within TIE_EPS of the closest is queued (warp-aggregated append) and re-walked by
 //                      k_resolve_ties in the reference's order with its range clamped around the closest distance —
@@ -32,7 +32,6 @@ namespace {
 constexpr uint32_t FULL_MASK = 0xFFFFFFFFu;
 constexpr int STACK_MAX = 120;       // TLAS depth 50 + BLAS depth 50 (TreeBuildOption of naive/mod.rs:173-176,280-283) + bookkeeping
 constexpr int ORDERED_BLOCK = 128;
-constexpr int ORDERED_STEPS = 24;    // traversal steps between warp re-convergence / ray refill points
 
 // TraverseFlags bits (flag.rs:6-25)
 constexpr uint32_t TF_FORCE_OPAQUE = 0x01, TF_FORCE_NON_OPAQUE = 0x02, TF_END_SEARCH = 0x04, TF_CULL_BACK = 0x10,
@@ -292,197 +291,6 @@ struct OrderedParams {
   TraceScratch scratch;
 };
 
-__global__ void __launch_bounds__(ORDERED_BLOCK) k_trace_ordered(const OrderedParams P) {
-  const SceneDev &S = P.S;
-  const uint32_t lane = threadIdx.x & 31u;
-  uint32_t stack[STACK_MAX];
-  int sp = 0;
-
-  // per-lane ray state
-  bool alive = false;
-  uint64_t ri = 0;
-  Vec3 o = {0, 0, 0}, d = {0, 0, 1}, inv = {0, 0, 0};
-  float t_near_world = 0.f, far0 = 0.f;  // ray.range
-  float scaling = 1.f, near_s = 0.f, far_s = 0.f;
-  float bound = 0.f;                     // world-space pruning / acceptance bound: min(far0, best*(1+eps))
-  float best = 0.f, second = 0.f, best_u = 0.f, best_v = 0.f;
-  uint32_t best_slot = RDN_INVALID_ID, best_inst = RDN_INVALID_ID, best_back = 0;
-  uint32_t cur = REF_EMPTY, cur_inst = 0, cur_flags = 0, cull_bits = 0, geom_end = 0;
-  bool in_object = false;
-  bool warp_exhausted = false;
-
-  for (;;) {
-    // ---------------- warp-converged refill point: lanes without a ray grab the next fetch indices
-    const uint32_t want = __ballot_sync(FULL_MASK, !alive);
-    if (want && !warp_exhausted) {
-      const int cnt = __popc(want);
-      const int leader = __ffs(want) - 1;
-      unsigned long long base = 0;
-      if (static_cast<int>(lane) == leader) base = atomicAdd(P.scratch.work_counter, static_cast<unsigned long long>(cnt));
-      base = __shfl_sync(FULL_MASK, base, leader);
-      if (base + cnt >= P.n_fetch) warp_exhausted = true;
-      if (!alive) {
-        const uint64_t f = base + __popc(want & ((1u << lane) - 1u));
-        bool valid = f < P.n_fetch;
-        uint64_t idx = f;
-        if (valid && P.tiles_x) {  // 8x4 pixel tiles, row-major tile order
-          const uint64_t tile = f >> 5;
-          const uint32_t in_tile = static_cast<uint32_t>(f & 31u);
-          const uint32_t tx = static_cast<uint32_t>(tile % P.tiles_x), ty = static_cast<uint32_t>(tile / P.tiles_x);
-          const uint32_t x = tx * 8u + (in_tile & 7u), y = ty * 4u + (in_tile >> 3);
-          valid = x < P.width && y < P.height;
-          idx = static_cast<uint64_t>(y) * P.width + x;
-        }
-        if (valid) {
-          ri = idx;
-          const float4 r0 = __ldg(reinterpret_cast<const float4 *>(P.rays + ri));
-          const float4 r1 = __ldg(reinterpret_cast<const float4 *>(P.rays + ri) + 1);
-          o = xyz(r0); d = xyz(r1); inv = recip3(d);
-          t_near_world = r0.w; far0 = r1.w;
-          scaling = 1.f; near_s = t_near_world; bound = far0; far_s = far0;
-          best = INFINITY; second = INFINITY; best_slot = RDN_INVALID_ID; best_inst = RDN_INVALID_ID;
-          in_object = false; sp = 0;
-          cur = P.world_root;
-          alive = true;
-        }
-      }
-    }
-    if (__ballot_sync(FULL_MASK, alive) == 0) break;
-
-    if (alive) {
-      int steps = ORDERED_STEPS;
-      bool done = false;
-      while (steps-- > 0) {
-        bool need_pop = false;
-        if (cur < REF_SPECIAL) {
-          // ---------------- inner node: both child boxes in one 64 B fetch
-          const float4 *np = reinterpret_cast<const float4 *>(S.wide_nodes + cur);
-          const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
-          float n0, n1;
-          const bool h0 = slab_test(o, inv, near_s, far_s, xyz(q0), xyz(q1), n0);
-          const bool h1 = slab_test(o, inv, near_s, far_s, xyz(q2), xyz(q3), n1);
-          const uint32_t r0 = __float_as_uint(q0.w), r1 = __float_as_uint(q1.w);
-          if (h0 && h1) {
-            const bool first0 = n0 <= n1;
-            if (sp < STACK_MAX) stack[sp++] = first0 ? r1 : r0; else atomicAdd(P.scratch.stack_overflow, 1u);
-            cur = first0 ? r0 : r1;
-          } else if (h0) {
-            cur = r0;
-          } else if (h1) {
-            cur = r1;
-          } else {
-            need_pop = true;
-          }
-        } else if (cur & REF_LEAF_BIT) {
-          const uint32_t start = cur & REF_LEAF_START_MASK;
-          const uint32_t count = ((cur >> REF_LEAF_COUNT_SHIFT) & 15u) + 1u;
-          if (in_object) {
-            // ---------------- triangle leaf
-            for (uint32_t k = 0; k < count; ++k) {
-              const uint32_t slot = start + k;
-              const float4 *tp = reinterpret_cast<const float4 *>(S.triangles + slot);
-              const float4 qn = __ldg(tp), qv0 = __ldg(tp + 1), qe1 = __ldg(tp + 2), qe2 = __ldg(tp + 3);
-              float sign, t, u, v;
-              if (!triangle_test(qn, qv0, qe1, qe2, o, d, near_s, far_s, cull_bits, sign, t, u, v)) continue;
-              const float distance = t / scaling;
-              if (!(t_near_world <= distance) || !(distance <= far0)) continue;  // the reference's update_far asserts
-              if (distance < best) {
-                second = fminf(second, best);
-                best = distance; best_u = u; best_v = v; best_slot = slot; best_inst = cur_inst;
-                best_back = sign < 0.0f ? 1u : 0u;
-                bound = fminf(far0, best * (1.0f + TIE_EPS));
-                far_s = bound * scaling;
-              } else {
-                second = fminf(second, distance);
-              }
-            }
-            need_pop = true;
-          } else {
-            // ---------------- instance leaf (world space): take the first slot, park the rest
-            if (count > 1) {
-              const uint32_t rest = REF_LEAF_BIT | ((count - 2u) << REF_LEAF_COUNT_SHIFT) | (start + 1u);
-              if (sp < STACK_MAX) stack[sp++] = rest; else atomicAdd(P.scratch.stack_overflow, 1u);
-            }
-            const float4 *tb = reinterpret_cast<const float4 *>(S.tlas_bounding + start);
-            const float4 b0 = __ldg(tb), b1 = __ldg(tb + 1);
-            float tn;
-            need_pop = true;
-            if (slab_test(o, inv, t_near_world, bound, xyz(b0), xyz(b1), tn) && (P.L.cull_mask & __float_as_uint(b0.w)) != 0) {
-              const InstanceRecord *rec = S.instances + start;
-              const uint4 tail = __ldg(reinterpret_cast<const uint4 *>(&rec->instance_custom_index));
-              const uint32_t flags = merge_geometry_instance_flag(P.L.ray_flags, tail.z);
-              if (!(flags & TF_SKIP_TRIANGLES) && tail.w < S.n_blas_meta) {
-                const uint2 groots = __ldg(reinterpret_cast<const uint2 *>(S.blas_meta[tail.w].tri_root_range));
-                if (groots.x < groots.y) {
-                  Vec3 bo, bd;
-                  float s;
-                  to_object_space(rec, o, d, bo, bd, s);
-                  o = bo; d = bd; inv = recip3(bd);
-                  scaling = s; near_s = t_near_world * s; far_s = bound * s;
-                  cur_inst = start; cur_flags = flags; cull_bits = cull_triangle_bits(flags); geom_end = groots.y;
-                  in_object = true;
-                  if (sp < STACK_MAX) stack[sp++] = REF_EXIT_INSTANCE; else atomicAdd(P.scratch.stack_overflow, 1u);
-                  cur = REF_SPECIAL | groots.x;
-                  need_pop = false;
-                }
-              }
-            }
-          }
-        } else if (cur == REF_EXIT_INSTANCE) {
-          // ---------------- back to world space: the world ray is re-read instead of kept in registers
-          const float4 r0 = __ldg(reinterpret_cast<const float4 *>(P.rays + ri));
-          const float4 r1 = __ldg(reinterpret_cast<const float4 *>(P.rays + ri) + 1);
-          o = xyz(r0); d = xyz(r1); inv = recip3(d);
-          scaling = 1.f; near_s = t_near_world; far_s = bound;
-          in_object = false;
-          need_pop = true;
-        } else if (cur == REF_EMPTY) {
-          need_pop = true;
-        } else {
-          // ---------------- geometry iterator of the current instance's BLAS
-          const uint32_t g = cur & 0x00FFFFFFu;
-          if (g + 1u < geom_end) {
-            if (sp < STACK_MAX) stack[sp++] = REF_SPECIAL | (g + 1u); else atomicAdd(P.scratch.stack_overflow, 1u);
-          }
-          const uint4 gm0 = __ldg(reinterpret_cast<const uint4 *>(S.geometry_meta + g));       // root, geometry_idx, primitive_start, flags
-          const uint32_t wide_root = __ldg(&S.geometry_meta[g].wide_root);
-          if (cull_geometry_pass(cur_flags, gm0.w) && wide_root != REF_EMPTY) cur = wide_root; else need_pop = true;
-        }
-        if (need_pop) {
-          if (sp == 0) { done = true; break; }
-          cur = stack[--sp];
-        }
-      }
-
-      if (done) {
-        rdn_hit *dst = P.hits + ri;
-        if (best_slot != RDN_INVALID_ID) {
-          const SlotInfo si = S.slot_info[best_slot];
-          store_hit(dst, best, best_u, best_v, si.primitive_id, si.geometry_idx, best_inst,
-                    S.instances[best_inst].instance_custom_index,
-                    best_back ? RDN_HIT_KIND_BACK_FACING_TRIANGLE : RDN_HIT_KIND_FRONT_FACING_TRIANGLE);
-          if (second <= best * (1.0f + TIE_EPS)) {
-            // near-tie: queue the ray for the exact reference-order re-walk (warp-aggregated append)
-            const uint32_t peers = __activemask();
-            const int pl = __ffs(peers) - 1;
-            uint32_t qbase = 0;
-            if (static_cast<int>(lane) == pl) qbase = atomicAdd(P.scratch.tie_count, static_cast<uint32_t>(__popc(peers)));
-            qbase = __shfl_sync(peers, qbase, pl);
-            const uint32_t q = qbase + __popc(peers & ((1u << lane) - 1u));
-            P.scratch.tie_queue[q] = static_cast<uint32_t>(ri);
-            P.scratch.tie_best[q] = best;
-          }
-        } else {
-          store_hit(dst, far0, 0.f, 0.f, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, 0);
-        }
-        alive = false;
-      }
-    }
-    __syncwarp();
-  }
-}
-
-
 // ---------------------------------------------------------------------------------------------------------------
 // Warp-synchronous rounds: every round the alive lanes (1) descend up to K inner nodes each, (2) re-converge
 // (__syncwarp) and handle their leaf / instance / bookkeeping item TOGETHER — on Volta+ lanes do not re-converge at a
@@ -518,6 +326,9 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
   uint32_t cur = REF_DONE, cur_inst = 0, cur_flags = 0, cull_bits = 0, geom_end = 0;
   bool in_object = false;
   bool warp_exhausted = false;
+#ifdef RDN_DEBUG_STEPS
+  unsigned long long dbg_steps = 0;
+#endif
 
 #define RDN_PUSH(v) do { if (sp < STACK_MAX) stack[sp++] = (v); else atomicAdd(P.scratch.stack_overflow, 1u); } while (0)
 #define RDN_POP() (sp > 0 ? stack[--sp] : REF_DONE)
@@ -577,6 +388,9 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
         // ---------------- phase 1: up to K inner nodes (both child boxes in one 64 B fetch)
 #pragma unroll 1
         for (int k = 0; k < K && cur < REF_SPECIAL; ++k) {
+#ifdef RDN_DEBUG_STEPS
+          ++dbg_steps;
+#endif
           const float4 *np = reinterpret_cast<const float4 *>(S.wide_nodes + cur);
           const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
           float n0, n1;
@@ -677,6 +491,15 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
       }
 
       if (cur == REF_DONE) {
+#ifdef RDN_DEBUG_STEPS
+        atomicMax(P.scratch.counters + 0, dbg_steps);   // longest ray, inner-node steps
+        atomicAdd(P.scratch.counters + 1, dbg_steps);   // all inner-node steps
+        atomicAdd(P.scratch.counters + 2, 1ull);        // rays that entered the traversal loop
+        if (dbg_steps > 200) atomicAdd(P.scratch.counters + 3, 1ull);
+        if (dbg_steps > 500) atomicAdd(P.scratch.counters + 4, 1ull);
+        if (dbg_steps > 1000) atomicAdd(P.scratch.counters + 5, 1ull);
+        dbg_steps = 0;
+#endif
         rdn_hit *dst = P.hits + ri;
         if (best_slot != RDN_INVALID_ID) {
           const SlotInfo si = S.slot_info[best_slot];
@@ -742,19 +565,14 @@ void launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, uint3
   P.world_root = world_root;
 
   // RDN_ORDERED_VARIANT: experimentation knob (kernel structure / refill window / register cap)
-  static const int variant = []() { const char *e = getenv("RDN_ORDERED_VARIANT"); return e ? atoi(e) : 1; }();
+  static const int variant = []() { const char *e = getenv("RDN_ORDERED_VARIANT"); return e ? atoi(e) : 0; }();
   using KernelFn = void (*)(const OrderedParams);
   KernelFn fn;
   switch (variant) {
-    case 0: fn = k_trace_ordered; break;
-    case 2: fn = k_trace_ordered_rounds<4, 8, 20>; break;
-    case 3: fn = k_trace_ordered_rounds<8, 8, 20>; break;
-    case 4: fn = k_trace_ordered_rounds<4, 8, 28>; break;
-    case 5: fn = k_trace_ordered_rounds<4, 8, 12>; break;
-    case 6: fn = k_trace_ordered_rounds<2, 8, 20>; break;
-    case 7: fn = k_trace_ordered_rounds<16, 8, 20>; break;
-    case 8: fn = k_trace_ordered_rounds<4, 7, 20>; break;
-    default: fn = k_trace_ordered_rounds<4, 8, 20>; break;
+    case 1: fn = k_trace_ordered_rounds<4, 8, 1>; break;
+    case 2: fn = k_trace_ordered_rounds<4, 8, 16>; break;
+    case 3: fn = k_trace_ordered_rounds<3, 8, 8>; break;
+    default: fn = k_trace_ordered_rounds<4, 8, 8>; break;
   }
   int blocks_per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, ORDERED_BLOCK, 0);

@@ -54,6 +54,14 @@ if cfg == "c3":  # incoherent cosine-weighted bounce rays off the primary hits, 
     normals[hit] = S.geometric_normals(pos, idx, ph["primitive_id"][hit], m, d[hit])
     rays, _ = S.bounce_rays(rays, ph, normals)
     flags, grid = 0, 0
+rows = os.environ.get("KBENCH_ROWS")
+if rows:
+    r0, r1 = (int(x) for x in rows.split(":"))
+    rays = rays.reshape(H, W)[r0:r1].reshape(-1).copy()
+rep = int(os.environ.get("KBENCH_REPEAT", "1"))
+if rep > 1:
+    rays = np.tile(rays, rep)
+    grid = grid  # rows simply repeat: still a multiple of the width
 n = rays.shape[0]
 d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1, 32).copy()).cuda()
 d_hits = torch.zeros((n, 32), dtype=torch.uint8, device="cuda")
