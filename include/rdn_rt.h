@@ -149,6 +149,16 @@ int rdn_rt_trace_closest_device(rdn_rt_scene *scene, int device_index, const rdn
 int rdn_rt_trace_counted(rdn_rt_scene *scene, const rdn_launch *launch, const rdn_ray *rays, uint64_t n,
                          rdn_hit *out_hits, rdn_counters *out_counters);
 
+/* ---- measurement hook (no reference counterpart): between _begin and _end every traversal kernel launched on the
+ *      device is bracketed by CUDA events on its launching stream; _end waits for them and returns the summed device
+ *      time per kernel (k_trace_ordered_rounds / k_resolve_ties / k_trace_reference). ---- */
+typedef struct rdn_kernel_times {
+  uint64_t ordered_launches, tie_launches, reference_launches;
+  double ordered_ms, tie_ms, reference_ms;
+} rdn_kernel_times;
+int rdn_rt_kernel_timing_begin(rdn_rt_scene *scene, int device_index);
+int rdn_rt_kernel_timing_end(rdn_rt_scene *scene, int device_index, rdn_kernel_times *out);
+
 /* ---- wavefront active-list compaction: use_stream_compaction
  *      (shader/parallel-compute/src/stream_compaction.rs:3-45) as used by use_compact_alive_tasks
  *      (shader/task-graph/src/runtime/task_group.rs:220-278).  Stable; out has n slots, zero past *out_n. ---- */

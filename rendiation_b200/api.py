@@ -100,6 +100,11 @@ class _TraceStats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("tie_rays", C.c_uint64), ("kernel_launches", C.c_uint32), ("kernel_ms", C.c_float)]
 
 
+class _KernelTimes(C.Structure):
+    _fields_ = [("ordered_launches", C.c_uint64), ("tie_launches", C.c_uint64), ("reference_launches", C.c_uint64),
+                ("ordered_ms", C.c_double), ("tie_ms", C.c_double), ("reference_ms", C.c_double)]
+
+
 class _Option(C.Structure):
     _fields_ = [("max_tree_depth", C.c_uint64), ("bin_size", C.c_uint64)]
 
@@ -111,7 +116,7 @@ class _MeshView(C.Structure):
 EXPORTED_SYMBOLS = [
     "rdn_rt_scene_create", "rdn_rt_scene_destroy", "rdn_rt_blas_create", "rdn_rt_blas_destroy", "rdn_rt_tlas_create",
     "rdn_rt_tlas_destroy", "rdn_rt_bind_tlas", "rdn_rt_bind_tlas_max_len", "rdn_rt_commit", "rdn_rt_trace_closest",
-    "rdn_rt_trace_closest_device", "rdn_rt_trace_counted", "rdn_rt_compact_u32", "rdn_rt_compact_u32_device",
+    "rdn_rt_trace_closest_device", "rdn_rt_trace_counted", "rdn_rt_kernel_timing_begin", "rdn_rt_kernel_timing_end", "rdn_rt_compact_u32", "rdn_rt_compact_u32_device",
     "rdn_rt_scene_blob", "rdn_rt_scene_adopt_blob", "rdn_rt_scene_array", "rdn_bvh_build", "rdn_bvh_destroy", "rdn_bvh_nodes",
     "rdn_bvh_sorted_primitive_index", "rdn_bvh_build_for_mesh", "rdn_bvh_query_nearest", "rdn_rt_last_error", "rdn_rt_version",
 ]
@@ -146,6 +151,8 @@ def lib() -> C.CDLL:
     L.rdn_rt_trace_closest.argtypes = [vp, P(_Launch), vp, u64, vp]
     L.rdn_rt_trace_closest_device.argtypes = [vp, i32, P(_Launch), vp, u64, vp, vp, i32, P(_TraceStats)]
     L.rdn_rt_trace_counted.argtypes = [vp, P(_Launch), vp, u64, vp, P(_Counters)]
+    L.rdn_rt_kernel_timing_begin.argtypes = [vp, i32]
+    L.rdn_rt_kernel_timing_end.argtypes = [vp, i32, P(_KernelTimes)]
     L.rdn_rt_compact_u32.argtypes = [vp, vp, vp, u64, vp, P(u64)]
     L.rdn_rt_compact_u32_device.argtypes = [vp, i32, vp, vp, u64, vp, vp, vp]
     L.rdn_rt_scene_blob.argtypes = [vp, i32, P(vp), P(u64)]
@@ -286,6 +293,16 @@ class NaiveSahBVHSystem:
         ctr = _Counters()
         _check(self._L.rdn_rt_trace_counted(self._h, C.byref(launch), _p(rays), rays.shape[0], _p(hits), C.byref(ctr)))
         return hits, {n: int(getattr(ctr, n)) for n, _ in _Counters._fields_}
+
+    def kernel_timing_begin(self, device_index: int = 0):
+        """Bracket every traversal kernel launched from now on with CUDA events (measurement hook)."""
+        _check(self._L.rdn_rt_kernel_timing_begin(self._h, device_index))
+
+    def kernel_timing_end(self, device_index: int = 0) -> dict:
+        """Wait for the bracketed launches; summed device milliseconds and launch counts per kernel."""
+        kt = _KernelTimes()
+        _check(self._L.rdn_rt_kernel_timing_end(self._h, device_index, C.byref(kt)))
+        return {n: (int(getattr(kt, n)) if n.endswith("launches") else float(getattr(kt, n))) for n, _ in _KernelTimes._fields_}
 
     # --- wavefront queue compaction ---
     def compact_u32(self, values, keep):

@@ -35,9 +35,12 @@ int fail(int code, const std::string &msg) {
     if (e__ != cudaSuccess) return fail(RDN_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
   } while (0)
 
-constexpr uint64_t HOST_CHUNK_RAYS = 1u << 20;  // rays per pipelined H2D/trace/D2H chunk (32 MiB in, 32 MiB out)
+// rays per pipelined H2D/trace/D2H chunk of the host-buffer path (8 MiB in, 8 MiB out): small enough that the un-overlapped
+// head (first H2D) and tail (last D2H) of the pipeline are a few percent of a 2 M-ray frame, large enough for PCIe efficiency
+// and to fill the 148 SMs (8 Ki warps per chunk)
+constexpr uint64_t HOST_CHUNK_RAYS = 1u << 18;
 constexpr uint64_t MAX_LAUNCH_RAYS = 1ull << 31;
-constexpr int N_SLOTS = 3;
+constexpr int N_SLOTS = 4;
 
 struct Scratch {
   void *base = nullptr;        // small block: work_counter | tie_count | tie_unresolved | stack_overflow | counters[6]
@@ -65,6 +68,13 @@ struct Slot {  // one pipeline lane of the host-buffer path
   rdn_hit *d_hits = nullptr;
   uint64_t capacity = 0;
   Scratch scratch;
+  uint32_t *h_flags = nullptr;  // pinned: tie_count | tie_unresolved | stack_overflow read back after the last chunk
+};
+
+enum KernelKind : int { KERNEL_ORDERED = 0, KERNEL_TIES = 1, KERNEL_REFERENCE = 2, KERNEL_KIND_COUNT = 3 };
+struct TimedLaunch {
+  int kind;
+  cudaEvent_t begin, end;
 };
 
 struct DeviceCtx {
@@ -79,6 +89,8 @@ struct DeviceCtx {
   bool ext_pending = false;
   unsigned long long *d_compact_status = nullptr;
   uint64_t compact_status_cap = 0;
+  bool timing = false;                 // rdn_rt_kernel_timing_begin .. _end: events around every traversal kernel
+  std::vector<TimedLaunch> timed;
 };
 
 }  // namespace
@@ -197,17 +209,43 @@ uint32_t resolve_world_root(const rdn_rt_scene *s, uint32_t tlas_idx) {
   return s->h_tlas_root[handle].wide_root;
 }
 
+// CUDA events around one kernel launch while kernel timing is enabled (recorded on the launching stream)
+struct ScopedKernelTimer {
+  DeviceCtx &dc;
+  cudaStream_t stream;
+  TimedLaunch t{};
+  bool on;
+  ScopedKernelTimer(DeviceCtx &d, int kind, cudaStream_t s) : dc(d), stream(s), on(d.timing) {
+    if (!on) return;
+    t.kind = kind;
+    if (cudaEventCreate(&t.begin) != cudaSuccess || cudaEventCreate(&t.end) != cudaSuccess) { on = false; return; }
+    cudaEventRecord(t.begin, stream);
+  }
+  ~ScopedKernelTimer() {
+    if (!on) return;
+    cudaEventRecord(t.end, stream);
+    dc.timed.push_back(t);
+  }
+};
+
 // enqueue the kernels of one trace on `stream`; returns the number of kernels launched
 int enqueue_trace(rdn_rt_scene *s, DeviceCtx &dc, const Scratch &scratch, const rdn_launch &launch, const rdn_ray *d_rays, uint64_t n,
                   rdn_hit *d_hits, int mode, cudaStream_t stream, uint32_t *launches) {
   const TraceScratch ts = scratch.view();
   RDN_CUDA(cudaMemsetAsync(scratch.base, 0, 12, stream));  // work_counter + tie_count; the two error flags accumulate until read
   const bool end_search = (launch.ray_flags & RDN_RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH) != 0;
-  if (mode == RDN_TRACE_REFERENCE_ORDER || end_search)
+  if (mode == RDN_TRACE_REFERENCE_ORDER || end_search) {
+    ScopedKernelTimer tm(dc, KERNEL_REFERENCE, stream);
     launch_trace_reference(dc.dev, launch, d_rays, n, d_hits, ts, false, dc.sm_count, stream);
-  else {
-    launch_trace_ordered(dc.dev, launch, resolve_world_root(s, launch.tlas_idx), d_rays, n, d_hits, ts, dc.sm_count, stream);
-    launch_resolve_ties(dc.dev, launch, d_rays, d_hits, ts, dc.sm_count, stream);
+  } else {
+    {
+      ScopedKernelTimer tm(dc, KERNEL_ORDERED, stream);
+      launch_trace_ordered(dc.dev, launch, resolve_world_root(s, launch.tlas_idx), d_rays, n, d_hits, ts, dc.sm_count, stream);
+    }
+    {
+      ScopedKernelTimer tm(dc, KERNEL_TIES, stream);
+      launch_resolve_ties(dc.dev, launch, d_rays, d_hits, ts, dc.sm_count, stream);
+    }
     if (launches) *launches += 1;
   }
   if (launches) *launches += 1;
@@ -225,6 +263,7 @@ int ensure_slot(Slot &slot, uint64_t rays) {
     RDN_CUDA(cudaMalloc(&slot.d_hits, rays * sizeof(rdn_hit)));
     slot.capacity = rays;
   }
+  if (!slot.h_flags) RDN_CUDA(cudaMallocHost(&slot.h_flags, 4 * sizeof(uint32_t)));
   return ensure_scratch(slot.scratch, rays);
 }
 
@@ -272,9 +311,11 @@ void rdn_rt_scene_destroy(rdn_rt_scene *s) {
       if (slot.d_rays) cudaFree(slot.d_rays);
       if (slot.d_hits) cudaFree(slot.d_hits);
       free_scratch(slot.scratch);
+      if (slot.h_flags) cudaFreeHost(slot.h_flags);
       if (slot.stream) cudaStreamDestroy(slot.stream);
     }
     free_scratch(dc.ext_scratch);
+    for (TimedLaunch &t : dc.timed) { cudaEventDestroy(t.begin); cudaEventDestroy(t.end); }
     if (dc.ext_done) cudaEventDestroy(dc.ext_done);
     if (dc.d_compact_status) cudaFree(dc.d_compact_status);
   }
@@ -452,15 +493,25 @@ int rdn_rt_trace_closest(rdn_rt_scene *s, const rdn_launch *launch, const rdn_ra
     if (rc != RDN_OK) return rc;
     RDN_CUDA(cudaMemcpyAsync(out_hits + off, slot.d_hits, m * sizeof(rdn_hit), cudaMemcpyDeviceToHost, slot.stream));
   }
+  // error flags of every used slot come back through pinned memory behind the slot's last chunk: one wait per stream
   for (size_t di = 0; di < n_dev; ++di) {
     DeviceCtx &dc = s->devices[di];
     RDN_CUDA(cudaSetDevice(dc.device));
-    for (Slot &slot : dc.slots) {
+    const uint64_t used = std::min<uint64_t>(per_dev_seq[di], N_SLOTS);
+    for (uint64_t k = 0; k < used; ++k) {
+      Slot &slot = dc.slots[k];
+      RDN_CUDA(cudaMemcpyAsync(slot.h_flags, static_cast<char *>(slot.scratch.base) + 8, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, slot.stream));
+    }
+  }
+  for (size_t di = 0; di < n_dev; ++di) {
+    DeviceCtx &dc = s->devices[di];
+    RDN_CUDA(cudaSetDevice(dc.device));
+    const uint64_t used = std::min<uint64_t>(per_dev_seq[di], N_SLOTS);
+    for (uint64_t k = 0; k < used; ++k) {
+      Slot &slot = dc.slots[k];
       RDN_CUDA(cudaStreamSynchronize(slot.stream));
-      uint32_t small[3] = {0, 0, 0};
-      RDN_CUDA(cudaMemcpy(small, static_cast<char *>(slot.scratch.base) + 8, sizeof(small), cudaMemcpyDeviceToHost));
-      if (small[1]) return fail(RDN_ERR_CUDA, "tie re-walk found no hit (internal invariant broken)");
-      if (small[2]) return fail(RDN_ERR_CAPACITY, "traversal stack overflow");
+      if (slot.h_flags[1]) return fail(RDN_ERR_CUDA, "tie re-walk found no hit (internal invariant broken)");
+      if (slot.h_flags[2]) return fail(RDN_ERR_CAPACITY, "traversal stack overflow");
     }
   }
   return RDN_OK;
@@ -496,6 +547,36 @@ int rdn_rt_trace_counted(rdn_rt_scene *s, const rdn_launch *launch, const rdn_ra
       out_counters->tri_hit += c[3]; out_counters->inst_visit += c[4]; out_counters->ref_abort += c[5];
     }
   }
+  return RDN_OK;
+}
+
+int rdn_rt_kernel_timing_begin(rdn_rt_scene *s, int device_index) {
+  if (!s || device_index < 0 || device_index >= static_cast<int>(s->devices.size())) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_kernel_timing_begin: bad argument");
+  std::lock_guard<std::mutex> lg(s->launch_lock);
+  DeviceCtx &dc = s->devices[device_index];
+  for (TimedLaunch &t : dc.timed) { cudaEventDestroy(t.begin); cudaEventDestroy(t.end); }
+  dc.timed.clear();
+  dc.timing = true;
+  return RDN_OK;
+}
+
+int rdn_rt_kernel_timing_end(rdn_rt_scene *s, int device_index, rdn_kernel_times *out) {
+  if (!s || !out || device_index < 0 || device_index >= static_cast<int>(s->devices.size())) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_kernel_timing_end: bad argument");
+  std::lock_guard<std::mutex> lg(s->launch_lock);
+  DeviceCtx &dc = s->devices[device_index];
+  RDN_CUDA(cudaSetDevice(dc.device));
+  std::memset(out, 0, sizeof(*out));
+  dc.timing = false;
+  for (TimedLaunch &t : dc.timed) {
+    RDN_CUDA(cudaEventSynchronize(t.end));
+    float ms = 0.f;
+    RDN_CUDA(cudaEventElapsedTime(&ms, t.begin, t.end));
+    if (t.kind == KERNEL_ORDERED) { out->ordered_launches++; out->ordered_ms += ms; }
+    else if (t.kind == KERNEL_TIES) { out->tie_launches++; out->tie_ms += ms; }
+    else { out->reference_launches++; out->reference_ms += ms; }
+    cudaEventDestroy(t.begin); cudaEventDestroy(t.end);
+  }
+  dc.timed.clear();
   return RDN_OK;
 }
 
