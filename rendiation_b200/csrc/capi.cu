@@ -43,7 +43,7 @@ constexpr uint64_t MAX_LAUNCH_RAYS = 1ull << 31;
 constexpr int N_SLOTS = 4;
 
 struct Scratch {
-  void *base = nullptr;        // small block: work_counter | tie_count | tie_unresolved | stack_overflow | counters[6]
+  void *base = nullptr;        // small block: work_counter u64 | tie_count | tie_unresolved | stack_overflow | blocks_done | tie_cursor | tie_total | counters[10]
   uint32_t *tie_queue = nullptr;
   float *tie_best = nullptr;
   uint64_t capacity = 0;       // rays
@@ -54,13 +54,16 @@ struct Scratch {
     s.tie_count = reinterpret_cast<uint32_t *>(b + 8);
     s.tie_unresolved = reinterpret_cast<uint32_t *>(b + 12);
     s.stack_overflow = reinterpret_cast<uint32_t *>(b + 16);
+    s.blocks_done = reinterpret_cast<uint32_t *>(b + 20);
+    s.tie_cursor = reinterpret_cast<uint32_t *>(b + 24);
+    s.tie_total = reinterpret_cast<uint32_t *>(b + 28);
     s.counters = reinterpret_cast<unsigned long long *>(b + 32);
     s.tie_queue = tie_queue;
     s.tie_best = tie_best;
     return s;
   }
 };
-constexpr size_t SCRATCH_BASE_BYTES = 32 + 6 * 8;
+constexpr size_t SCRATCH_BASE_BYTES = 32 + 10 * 8;  // + 6 visit counters (rdn_counters) + 3 debug timestamps + 1 spare
 
 struct Slot {  // one pipeline lane of the host-buffer path
   cudaStream_t stream = nullptr;
@@ -122,6 +125,7 @@ int ensure_scratch(Scratch &s, uint64_t n) {
     s.tie_queue = nullptr; s.tie_best = nullptr; s.capacity = 0;
     RDN_CUDA(cudaMalloc(&s.tie_queue, std::max<uint64_t>(n, 1) * sizeof(uint32_t)));
     RDN_CUDA(cudaMalloc(&s.tie_best, std::max<uint64_t>(n, 1) * sizeof(float)));
+    RDN_CUDA(cudaMemset(s.tie_queue, 0xFF, std::max<uint64_t>(n, 1) * sizeof(uint32_t)));  // RDN_INVALID_ID = slot not published
     s.capacity = n;
   }
   return RDN_OK;
@@ -230,23 +234,28 @@ struct ScopedKernelTimer {
 
 // enqueue the kernels of one trace on `stream`; returns the number of kernels launched
 int enqueue_trace(rdn_rt_scene *s, DeviceCtx &dc, const Scratch &scratch, const rdn_launch &launch, const rdn_ray *d_rays, uint64_t n,
-                  rdn_hit *d_hits, int mode, cudaStream_t stream, uint32_t *launches) {
+                  rdn_hit *d_hits, int mode, cudaStream_t stream, uint32_t *launches, bool count_ties = false) {
   const TraceScratch ts = scratch.view();
-  RDN_CUDA(cudaMemsetAsync(scratch.base, 0, 12, stream));  // work_counter + tie_count; the two error flags accumulate until read
+  // work_counter is zero here: zeroed at allocation and re-armed by the last CTA of every ordered launch.  tie_count and
+  // the two error flags accumulate until read (the stats path clears tie_count first).
+  const int tie_mode = ordered_tie_mode();
+  if (tie_mode == 0 || (count_ties && tie_mode != 3)) RDN_CUDA(cudaMemsetAsync(static_cast<char *>(scratch.base) + 8, 0, 4, stream));
+  if (count_ties && tie_mode == 3) RDN_CUDA(cudaMemsetAsync(static_cast<char *>(scratch.base) + 28, 0, 4, stream));
   const bool end_search = (launch.ray_flags & RDN_RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH) != 0;
   if (mode == RDN_TRACE_REFERENCE_ORDER || end_search) {
     ScopedKernelTimer tm(dc, KERNEL_REFERENCE, stream);
     launch_trace_reference(dc.dev, launch, d_rays, n, d_hits, ts, false, dc.sm_count, stream);
   } else {
+    bool ties_done;
     {
       ScopedKernelTimer tm(dc, KERNEL_ORDERED, stream);
-      launch_trace_ordered(dc.dev, launch, resolve_world_root(s, launch.tlas_idx), d_rays, n, d_hits, ts, dc.sm_count, stream);
+      ties_done = launch_trace_ordered(dc.dev, launch, resolve_world_root(s, launch.tlas_idx), d_rays, n, d_hits, ts, dc.sm_count, stream);
     }
-    {
+    if (!ties_done) {
       ScopedKernelTimer tm(dc, KERNEL_TIES, stream);
       launch_resolve_ties(dc.dev, launch, d_rays, d_hits, ts, dc.sm_count, stream);
+      if (launches) *launches += 1;
     }
-    if (launches) *launches += 1;
   }
   if (launches) *launches += 1;
   RDN_CUDA(cudaGetLastError());
@@ -418,8 +427,15 @@ int rdn_rt_trace_closest_device(rdn_rt_scene *s, int device_index, const rdn_lau
     const uint64_t m = std::min(chunk, n - off);
     rdn_launch l = *launch;
     if (off != 0 || m != n) l.grid_width = (l.grid_width && m % l.grid_width == 0 && off % l.grid_width == 0) ? l.grid_width : 0;
+#ifdef RDN_DEBUG_STEPS
+    if (stats) {
+      RDN_CUDA(cudaMemsetAsync(static_cast<char *>(dc.ext_scratch.base) + 32, 0, 6 * 8, stream));
+      RDN_CUDA(cudaMemsetAsync(static_cast<char *>(dc.ext_scratch.base) + 32 + 6 * 8, 0xFF, 2 * 8, stream));
+      RDN_CUDA(cudaMemsetAsync(static_cast<char *>(dc.ext_scratch.base) + 32 + 8 * 8, 0, 8, stream));
+    }
+#endif
     if (stats) RDN_CUDA(cudaEventRecord(e0, stream));
-    rc = enqueue_trace(s, dc, dc.ext_scratch, l, d_rays + off, m, d_hits + off, mode, stream, stats ? &stats->kernel_launches : nullptr);
+    rc = enqueue_trace(s, dc, dc.ext_scratch, l, d_rays + off, m, d_hits + off, mode, stream, stats ? &stats->kernel_launches : nullptr, stats != nullptr);
     if (rc != RDN_OK) return rc;
     if (stats) {
       RDN_CUDA(cudaEventRecord(e1, stream));
@@ -427,16 +443,19 @@ int rdn_rt_trace_closest_device(rdn_rt_scene *s, int device_index, const rdn_lau
       float ms = 0.f;
       RDN_CUDA(cudaEventElapsedTime(&ms, e0, e1));
       ms_total += ms;
-      uint32_t small[3] = {0, 0, 0};
+      uint32_t small[6] = {0, 0, 0, 0, 0, 0};  // tie_count | tie_unresolved | stack_overflow | blocks_done | tie_cursor | tie_total
       RDN_CUDA(cudaMemcpy(small, static_cast<char *>(dc.ext_scratch.base) + 8, sizeof(small), cudaMemcpyDeviceToHost));
-      ties += small[0];
+      ties += ordered_tie_mode() == 3 ? small[5] : small[0];
       if (small[1]) return fail(RDN_ERR_CUDA, "tie re-walk found no hit (internal invariant broken)");
       if (small[2]) return fail(RDN_ERR_CAPACITY, "traversal stack overflow");
 #ifdef RDN_DEBUG_STEPS
-      unsigned long long c[6];
+      unsigned long long c[9];
       RDN_CUDA(cudaMemcpy(c, static_cast<char *>(dc.ext_scratch.base) + 32, sizeof(c), cudaMemcpyDeviceToHost));
-      fprintf(stderr, "[dbg steps] max=%llu sum=%llu rays=%llu >200:%llu >500:%llu >1000:%llu\n", c[0], c[1], c[2], c[3], c[4], c[5]);
-      RDN_CUDA(cudaMemset(static_cast<char *>(dc.ext_scratch.base) + 32, 0, sizeof(c)));
+      const double r = double(c[2] ? c[2] : 1);
+      fprintf(stderr, "[dbg steps] max=%llu steps=%llu rays_entered=%llu tri_tests=%llu pushes=%llu rays>200steps=%llu | per entered ray: %.2f steps "
+              "%.2f tris %.2f pushes | timeline: list dry after %.1f us, kernel end after %.1f us (tail %.1f us)\n",
+              c[0], c[1], c[2], c[3], c[4], c[5], double(c[1]) / r, double(c[3]) / r, double(c[4]) / r,
+              (double(c[7]) - double(c[6])) * 1e-3, (double(c[8]) - double(c[6])) * 1e-3, (double(c[8]) - double(c[7])) * 1e-3);
 #endif
     }
   }

@@ -31,6 +31,9 @@ struct TraceScratch {
   uint32_t *tie_count;               // rays queued for exact tie resolution
   uint32_t *tie_unresolved;          // safety net: clamped re-walk found nothing (must stay 0)
   uint32_t *stack_overflow;          // safety net: traversal stack overflow (must stay 0)
+  uint32_t *tie_cursor;              // next queued tie to resolve (in-kernel drain)
+  uint32_t *tie_total;               // ties of completed launches since the host last cleared it (in-kernel drain resets tie_count)
+  uint32_t *blocks_done;             // CTAs of the running ordered kernel that have left; the last one re-arms work_counter
   uint32_t *tie_queue;               // ray indices, capacity >= rays of the launch
   float *tie_best;                   // closest distance found by the ordered kernel, per queued ray
   unsigned long long *counters;      // 6 x u64 (rdn_counters)
@@ -47,9 +50,12 @@ void launch_trace_reference(const SceneDev &scene, const rdn_launch &launch, con
 void launch_resolve_ties(const SceneDev &scene, const rdn_launch &launch, const rdn_ray *d_rays, rdn_hit *d_hits,
                          const TraceScratch &scratch, int sm_count, cudaStream_t stream);
 
-// Ordered (near child first) persistent-thread traversal with tie detection; queues near-tie rays in scratch.
+// Ordered (near child first) persistent-thread traversal with tie detection.  Near-tie rays are re-walked in the
+// reference's order by the finishing lane itself (returns true), or — RDN_ORDERED_VARIANT=9 — queued in scratch for
+// launch_resolve_ties (returns false).  Needs *work_counter == 0 at launch; its last CTA resets it on the way out.
 // world_root = TlasRoot::wide_root of tlas_binding[launch.tlas_idx] (resolved by the caller from its host copy).
-void launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, uint32_t world_root, const rdn_ray *d_rays, uint64_t n,
+int ordered_tie_mode();  // 0: queue + launch_resolve_ties; 1/2: re-walk by the finishing lane; 3: queue drained inside the kernel
+bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, uint32_t world_root, const rdn_ray *d_rays, uint64_t n,
                           rdn_hit *d_hits, const TraceScratch &scratch, int sm_count, cudaStream_t stream);
 
 // Stable stream compaction of u32 (single pass, decoupled look-back); d_status needs compact_status_words(n) u64.

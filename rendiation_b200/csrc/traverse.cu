@@ -59,6 +59,11 @@ __device__ __forceinline__ uint32_t cull_triangle_bits(uint32_t f) {
   return (enable ? 1u : 0u) | (back ? 2u : 0u);
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ Vec3 xyz(const float4 &q) { return Vec3{q.x, q.y, q.z}; }
 __device__ __forceinline__ Vec3 recip3(Vec3 d) { return Vec3{1.0f / d.x, 1.0f / d.y, 1.0f / d.z}; }
 
@@ -291,6 +296,60 @@ struct OrderedParams {
   TraceScratch scratch;
 };
 
+// Exact tie resolution inside the ordered kernel: the lane that finished a ray with a second candidate within TIE_EPS of
+// its closest hit re-walks it on the spot in the reference's order, range clamped around the closest distance (same
+// argument as k_resolve_ties).  Near-ties are a handful of rays per frame, so the cost is one lane for a few tens of
+// microseconds — far less than a second kernel launch whose whole duration is this one serial walk.
+__device__ __forceinline__ bool resolve_tie_body(const OrderedParams &P, uint64_t ri, float best) {
+  const float4 r0 = __ldg(reinterpret_cast<const float4 *>(P.rays + ri));
+  const float4 r1 = __ldg(reinterpret_cast<const float4 *>(P.rays + ri) + 1);
+  WalkResult res;
+  WalkCounters ctr;
+  const float near_walk = fmaxf(r0.w, best * (1.0f - 3.0f * TIE_EPS));
+  const float far_init = fminf(r1.w, best * (1.0f + 3.0f * TIE_EPS));
+  reference_walk<false>(P.S, P.L, xyz(r0), xyz(r1), r0.w, r1.w, near_walk, far_init, res, ctr);
+  if (res.slot == RDN_INVALID_ID) return false;
+  store_walk_result(P.S, P.hits + ri, res, r1.w);
+  return true;
+}
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+
+// Drain of the device-side tie queue by threads that have left the traversal loop (DRAIN_TIES).  Entries are
+// claimed one at a time with a CAS on the cursor; a claimed slot is awaited until its ray index is published (the
+// appender bumps tie_count first, writes the closest distance, fences, then publishes the index) and handed back as
+// RDN_INVALID_ID so the queue is clean for the next launch.  Warps that run dry early resolve the ties found so far
+// while the stragglers finish; the last CTA sweeps whatever was appended after that.
+__device__ __forceinline__ void drain_tie_queue(const OrderedParams &P) {
+  const uint32_t lane = threadIdx.x & 31u;
+  for (;;) {
+    // lane 0 claims up to 8 entries for the warp (so a burst of ties spreads over many warps); the claimed lanes re-walk together
+    uint32_t base = 0, take = 0;
+    if (lane == 0) {
+      for (;;) {
+        const uint32_t cur = ld_volatile_u32(P.scratch.tie_cursor);
+        const uint32_t cnt = ld_volatile_u32(P.scratch.tie_count);
+        if (cur >= cnt) break;
+        const uint32_t want = cnt - cur < 8u ? cnt - cur : 8u;
+        if (atomicCAS(P.scratch.tie_cursor, cur, cur + want) == cur) { base = cur; take = want; break; }
+      }
+    }
+    base = __shfl_sync(FULL_MASK, base, 0);
+    take = __shfl_sync(FULL_MASK, take, 0);
+    if (take == 0) break;
+    if (lane < take) {
+      const uint32_t q = base + lane;
+      uint32_t ri;
+      while ((ri = ld_volatile_u32(P.scratch.tie_queue + q)) == RDN_INVALID_ID) {}
+      __threadfence();
+      const float best = __ldcg(P.scratch.tie_best + q);
+      P.scratch.tie_queue[q] = RDN_INVALID_ID;
+      if (!resolve_tie_body(P, ri, best)) atomicAdd(P.scratch.tie_unresolved, 1u);  // cannot happen: the closest candidate lies inside the clamp
+    }
+    __syncwarp();
+  }
+}
+
+
 // ---------------------------------------------------------------------------------------------------------------
 // Warp-synchronous rounds: every round the alive lanes (1) descend up to K inner nodes each, (2) re-converge
 // (__syncwarp) and handle their leaf / instance / bookkeeping item TOGETHER — on Volta+ lanes do not re-converge at a
@@ -298,10 +357,11 @@ struct OrderedParams {
 // (3) vote: when fewer than THRESH lanes still hold a ray (and rays remain) the warp goes back to the refill point.
 // Refill culls rays against the TLAS root box on the spot (the reference's first test), so rays that miss the scene
 // never occupy a traversal lane.
-template <int K, int MINB, int THRESH>
-__global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(const OrderedParams P) {
+template <int K, int MINB, int THRESH, bool DRAIN_TIES>  // DRAIN_TIES: near-tie queue drained inside the kernel (else by k_resolve_ties)
+__global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(const __grid_constant__ OrderedParams P) {
   const SceneDev &S = P.S;
   const uint32_t lane = threadIdx.x & 31u;
+
   uint32_t stack[STACK_MAX];
   int sp = 0;
 
@@ -327,7 +387,9 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
   bool in_object = false;
   bool warp_exhausted = false;
 #ifdef RDN_DEBUG_STEPS
-  unsigned long long dbg_steps = 0;
+  // per-thread totals, reduced once per warp at kernel exit so the counters do not perturb the timeline
+  unsigned long long dbg_steps = 0, dbg_tris = 0, dbg_pushes = 0, dbg_ray_steps = 0, dbg_max = 0, dbg_rays = 0, dbg_long = 0;
+  if (lane == 0) atomicMin(P.scratch.counters + 6, globaltimer_ns());  // first warp in
 #endif
 
 #define RDN_PUSH(v) do { if (sp < STACK_MAX) stack[sp++] = (v); else atomicAdd(P.scratch.stack_overflow, 1u); } while (0)
@@ -344,15 +406,20 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
       unsigned long long base = 0;
       if (static_cast<int>(lane) == leader) base = atomicAdd(P.scratch.work_counter, static_cast<unsigned long long>(cnt));
       base = __shfl_sync(FULL_MASK, base, leader);
-      if (base + cnt >= P.n_fetch) warp_exhausted = true;
+      if (base + cnt >= P.n_fetch) {
+#ifdef RDN_DEBUG_STEPS
+        if (!warp_exhausted && static_cast<int>(lane) == leader) atomicMin(P.scratch.counters + 7, globaltimer_ns());  // ray list ran dry
+#endif
+        warp_exhausted = true;
+      }
       if (!alive) {
         const uint64_t f = base + __popc(want & ((1u << lane) - 1u));
         bool valid = f < P.n_fetch;
         uint64_t idx = f;
         if (valid && P.tiles_x) {
-          const uint64_t tile = f >> 5;
-          const uint32_t in_tile = static_cast<uint32_t>(f & 31u);
-          const uint32_t tx = static_cast<uint32_t>(tile % P.tiles_x), ty = static_cast<uint32_t>(tile / P.tiles_x);
+          const uint32_t tile = static_cast<uint32_t>(f >> 5);  // launches hold < 2^31 rays: 32-bit tile arithmetic
+          const uint32_t in_tile = static_cast<uint32_t>(f) & 31u;
+          const uint32_t ty = tile / P.tiles_x, tx = tile - ty * P.tiles_x;
           const uint32_t x = tx * 8u + (in_tile & 7u), y = ty * 4u + (in_tile >> 3);
           valid = x < P.width && y < P.height;
           idx = static_cast<uint64_t>(y) * P.width + x;
@@ -389,7 +456,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
 #pragma unroll 1
         for (int k = 0; k < K && cur < REF_SPECIAL; ++k) {
 #ifdef RDN_DEBUG_STEPS
-          ++dbg_steps;
+          ++dbg_steps; ++dbg_ray_steps;
 #endif
           const float4 *np = reinterpret_cast<const float4 *>(S.wide_nodes + cur);
           const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
@@ -400,6 +467,9 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
           if (h0 && h1) {
             const bool first0 = n0 <= n1;
             RDN_PUSH(first0 ? r1 : r0);
+#ifdef RDN_DEBUG_STEPS
+            ++dbg_pushes;
+#endif
             cur = first0 ? r0 : r1;
           } else if (h0) {
             cur = r0;
@@ -422,6 +492,9 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
                 const float4 *tp = reinterpret_cast<const float4 *>(S.triangles + slot);
                 const float4 qn = __ldg(tp), qv0 = __ldg(tp + 1), qe1 = __ldg(tp + 2), qe2 = __ldg(tp + 3);
                 float sign, t, u, v;
+#ifdef RDN_DEBUG_STEPS
+                ++dbg_tris;
+#endif
                 if (!triangle_test(qn, qv0, qe1, qe2, o, d, near_s, far_s, cull_bits, sign, t, u, v)) continue;
                 const float distance = t / scaling;
                 if (!(t_near_world <= distance) || !(distance <= far0)) continue;  // the reference's update_far asserts
@@ -465,6 +538,8 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
               }
               if (!entered) cur = RDN_POP();
             }
+          } else if (cur == REF_EXIT_INSTANCE && sp == 0) {
+            cur = REF_DONE;  // nothing deferred in world space: the ray is finished, no need to restore the world ray
           } else if (cur == REF_EXIT_INSTANCE) {
             // back to world space: the world ray is re-read instead of being held in registers
             const float4 r0 = __ldg(reinterpret_cast<const float4 *>(P.rays + ri));
@@ -492,30 +567,30 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
 
       if (cur == REF_DONE) {
 #ifdef RDN_DEBUG_STEPS
-        atomicMax(P.scratch.counters + 0, dbg_steps);   // longest ray, inner-node steps
-        atomicAdd(P.scratch.counters + 1, dbg_steps);   // all inner-node steps
-        atomicAdd(P.scratch.counters + 2, 1ull);        // rays that entered the traversal loop
-        if (dbg_steps > 200) atomicAdd(P.scratch.counters + 3, 1ull);
-        if (dbg_steps > 500) atomicAdd(P.scratch.counters + 4, 1ull);
-        if (dbg_steps > 1000) atomicAdd(P.scratch.counters + 5, 1ull);
-        dbg_steps = 0;
+        dbg_max = dbg_ray_steps > dbg_max ? dbg_ray_steps : dbg_max;
+        dbg_long += dbg_ray_steps > 200 ? 1 : 0;
+        ++dbg_rays;
+        dbg_ray_steps = 0;
 #endif
         rdn_hit *dst = P.hits + ri;
         if (best_slot != RDN_INVALID_ID) {
+          // the ordered result is stored first; a near-tie ray is also queued (warp-aggregated append) for the exact
+          // reference-order re-walk, which overwrites the record
           const SlotInfo si = S.slot_info[best_slot];
           store_hit(dst, best, best_u, best_v, si.primitive_id, si.geometry_idx, best_inst,
                     S.instances[best_inst].instance_custom_index,
                     best_back ? RDN_HIT_KIND_BACK_FACING_TRIANGLE : RDN_HIT_KIND_FRONT_FACING_TRIANGLE);
           if (second <= best * (1.0f + TIE_EPS)) {
-            // near-tie: queue the ray for the exact reference-order re-walk (warp-aggregated append)
+            __threadfence();  // the ordered record lands before whoever drains the queue writes the exact one
             const uint32_t peers = __activemask();
             const int pl = __ffs(peers) - 1;
             uint32_t qbase = 0;
             if (static_cast<int>(lane) == pl) qbase = atomicAdd(P.scratch.tie_count, static_cast<uint32_t>(__popc(peers)));
             qbase = __shfl_sync(peers, qbase, pl);
             const uint32_t q = qbase + __popc(peers & ((1u << lane) - 1u));
-            P.scratch.tie_queue[q] = static_cast<uint32_t>(ri);
             P.scratch.tie_best[q] = best;
+            if (DRAIN_TIES) __threadfence();  // the distance is visible before the index publishes the slot
+            *reinterpret_cast<volatile uint32_t *>(P.scratch.tie_queue + q) = static_cast<uint32_t>(ri);
           }
         } else {
           store_hit(dst, far0, 0.f, 0.f, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, 0);
@@ -527,6 +602,47 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
   }
 #undef RDN_PUSH
 #undef RDN_POP
+#ifdef RDN_DEBUG_STEPS
+  {
+    unsigned long long vals[5] = {dbg_steps, dbg_rays, dbg_tris, dbg_pushes, dbg_long};
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      unsigned long long x = vals[i];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(FULL_MASK, x, off);
+      if (lane == 0 && x) atomicAdd(P.scratch.counters + 1 + i, x);  // steps, rays entered, triangle tests, pushes, rays > 200 steps
+    }
+    atomicMax(P.scratch.counters + 0, dbg_max);                           // longest ray, inner-node steps
+    if (lane == 0) atomicMax(P.scratch.counters + 8, globaltimer_ns());  // last warp out
+  }
+#endif
+  if (DRAIN_TIES) drain_tie_queue(P);
+  // the last CTA to leave sweeps the ties appended after everyone else looked, then re-arms the counters for the next
+  // launch on this scratch (no memset node between launches)
+  __shared__ uint32_t s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(P.scratch.blocks_done, 1u) == gridDim.x - 1u ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last) {
+    if (DRAIN_TIES) {
+      __threadfence();
+      drain_tie_queue(P);
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      *P.scratch.work_counter = 0ull;
+      *P.scratch.blocks_done = 0u;
+      if (DRAIN_TIES) {
+        atomicAdd(P.scratch.tie_total, ld_volatile_u32(P.scratch.tie_count));
+        *P.scratch.tie_count = 0u;
+        *P.scratch.tie_cursor = 0u;
+      }
+      __threadfence();
+    }
+  }
 }
 
 }  // namespace
@@ -550,9 +666,15 @@ void launch_resolve_ties(const SceneDev &scene, const rdn_launch &launch, const 
   k_resolve_ties<<<static_cast<unsigned>(sm_count), 128, 0, stream>>>(scene, launch, d_rays, d_hits, scratch);
 }
 
-void launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, uint32_t world_root, const rdn_ray *d_rays, uint64_t n,
+static int ordered_variant() {
+  static const int variant = []() { const char *e = getenv("RDN_ORDERED_VARIANT"); return e ? atoi(e) : 0; }();
+  return variant;
+}
+int ordered_tie_mode() { return ordered_variant() == 9 ? 0 : 3; }
+
+bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, uint32_t world_root, const rdn_ray *d_rays, uint64_t n,
                           rdn_hit *d_hits, const TraceScratch &scratch, int sm_count, cudaStream_t stream) {
-  if (n == 0) return;
+  if (n == 0) return true;
   OrderedParams P;
   P.S = scene; P.L = launch; P.rays = d_rays; P.hits = d_hits; P.n = n; P.scratch = scratch;
   P.tiles_x = 0; P.width = 0; P.height = 0; P.n_fetch = n;
@@ -564,15 +686,17 @@ void launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, uint3
   }
   P.world_root = world_root;
 
-  // RDN_ORDERED_VARIANT: experimentation knob (kernel structure / refill window / register cap)
-  static const int variant = []() { const char *e = getenv("RDN_ORDERED_VARIANT"); return e ? atoi(e) : 0; }();
+  // RDN_ORDERED_VARIANT: experimentation knob (rounds per vote / refill threshold / tie handling / register cap)
+  const int variant = ordered_variant();
   using KernelFn = void (*)(const OrderedParams);
   KernelFn fn;
+  bool inline_ties = true;
   switch (variant) {
-    case 1: fn = k_trace_ordered_rounds<4, 8, 1>; break;
-    case 2: fn = k_trace_ordered_rounds<4, 8, 16>; break;
-    case 3: fn = k_trace_ordered_rounds<3, 8, 8>; break;
-    default: fn = k_trace_ordered_rounds<4, 8, 8>; break;
+    case 1: fn = k_trace_ordered_rounds<4, 8, 1, true>; break;
+    case 2: fn = k_trace_ordered_rounds<3, 8, 4, true>; break;
+    case 3: fn = k_trace_ordered_rounds<4, 8, 8, true>; break;
+    case 9: fn = k_trace_ordered_rounds<2, 8, 1, false>; inline_ties = false; break;  // queue drained by k_resolve_ties
+    default: fn = k_trace_ordered_rounds<2, 8, 1, true>; break;
   }
   int blocks_per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, ORDERED_BLOCK, 0);
@@ -581,6 +705,7 @@ void launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, uint3
   const uint64_t needed = (P.n_fetch + ORDERED_BLOCK - 1) / ORDERED_BLOCK;
   if (blocks > needed) blocks = needed;
   fn<<<static_cast<unsigned>(blocks), ORDERED_BLOCK, 0, stream>>>(P);
+  return inline_ties;
 }
 
 }  // namespace rdn
