@@ -211,28 +211,9 @@ def run_ours(args):
         sysm.commit()
         t_build = time.perf_counter() - t0
     t_repl_ms = 0.0
-    if world > 1:
-        from cuda.bindings import runtime as cudart
-        nbytes = torch.zeros(1, dtype=torch.int64, device=dev)
-        if rank == 0:
-            ptr, nb = sysm.blob()
-            nbytes[0] = nb
-        dist.broadcast(nbytes, 0)
-        nb = int(nbytes.item())
-        buf = torch.empty(nb, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            (err,) = cudart.cudaMemcpy(buf.data_ptr(), ptr, nb, cudart.cudaMemcpyKind.cudaMemcpyDeviceToDevice)
-            assert int(err) == 0
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        dist.broadcast(buf, 0)  # BVH replication over NVLink / NVSwitch
-        e1.record()
-        torch.cuda.synchronize()
-        t_repl_ms = e0.elapsed_time(e1)
-        if rank != 0:
-            sysm.adopt_blob(buf.data_ptr(), nb)
-        del buf
+    if world > 1:  # the one collective of the path: BVH replication (NCCL broadcast over NVLink), then the other ranks adopt the blob
+        from rendiation_b200 import multi_gpu
+        t_repl_ms = multi_gpu.replicate_scene(sysm, src=0, device=dev)
     blob_bytes = sysm.blob()[1]
 
     # ---- rays: this rank's frames (tile shard of the job), resident in HBM; steps cycle through N_FRAMES buffers

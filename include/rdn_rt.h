@@ -169,6 +169,7 @@ int rdn_rt_compact_u32_device(rdn_rt_scene *scene, int device_index, const uint3
 
 /* ---- replication of the flattened scene (one contiguous device blob) for one-process-per-GPU drivers:
  *      rank 0 commits, broadcasts the blob (NCCL over NVLink), the other ranks adopt it. ---- */
+/* device_index == -1 on a host-only scene (n_devices == 0): the blob is host memory (used to test replication without a GPU) */
 int rdn_rt_scene_blob(rdn_rt_scene *scene, int device_index, void **out_device_ptr, uint64_t *out_bytes);
 int rdn_rt_scene_adopt_blob(rdn_rt_scene *scene, int device_index, const void *d_blob, uint64_t bytes);
 

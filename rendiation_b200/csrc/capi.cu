@@ -168,7 +168,7 @@ bool header_ok(const BlobHeader &h, uint64_t bytes) {
 // build -> flatten -> upload to device 0 -> replicate to the other devices (peer copy: NVLink when available)
 int commit_locked(rdn_rt_scene *s) {
   if (!s->dirty) return RDN_OK;
-  if (s->adopted && !s->devices.empty() && s->devices[0].d_blob) { s->dirty = false; return RDN_OK; }
+  if (s->adopted && ((!s->devices.empty() && s->devices[0].d_blob) || (s->devices.empty() && !s->host_blob.empty()))) { s->dirty = false; return RDN_OK; }
   std::string err;
   FlatScene flat;
   const int rc = s->source.build(s->tlas_binding, flat, err);
@@ -478,11 +478,16 @@ int rdn_rt_trace_closest(rdn_rt_scene *s, const rdn_launch *launch, const rdn_ra
   std::lock_guard<std::mutex> lg(s->launch_lock);
 
   // chunk = whole rows of the launch grid (multiple of 4 rows) when a grid hint is given, so every chunk keeps the hint
-  uint64_t chunk = HOST_CHUNK_RAYS;
+  static const uint64_t chunk_rays = []() {  // RDN_HOST_CHUNK_RAYS: experimentation knob
+    const char *e = getenv("RDN_HOST_CHUNK_RAYS");
+    const long long v = e ? atoll(e) : 0;
+    return v > 0 ? static_cast<uint64_t>(v) : HOST_CHUNK_RAYS;
+  }();
+  uint64_t chunk = chunk_rays;
   const uint32_t gw = launch->grid_width;
   const bool grid = gw != 0 && n % gw == 0;
   if (grid) {
-    uint64_t rows = std::max<uint64_t>(4, (HOST_CHUNK_RAYS / gw) / 4 * 4);
+    uint64_t rows = std::max<uint64_t>(4, (chunk_rays / gw) / 4 * 4);
     chunk = rows * gw;
   }
   const uint64_t n_chunks = (n + chunk - 1) / chunk;
@@ -642,9 +647,15 @@ int rdn_rt_compact_u32(rdn_rt_scene *s, const uint32_t *in, const uint8_t *keep,
 
 int rdn_rt_scene_blob(rdn_rt_scene *s, int device_index, void **out_ptr, uint64_t *out_bytes) {
   if (!s || !out_ptr || !out_bytes) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_scene_blob: null argument");
-  if (device_index < 0 || device_index >= static_cast<int>(s->devices.size())) return fail(RDN_ERR_INVALID_ARGUMENT, "bad device_index");
+  const bool host_only = s->devices.empty() && device_index == -1;
+  if (!host_only && (device_index < 0 || device_index >= static_cast<int>(s->devices.size()))) return fail(RDN_ERR_INVALID_ARGUMENT, "bad device_index");
   int rc = ensure_committed(s);
   if (rc != RDN_OK) return rc;
+  if (host_only) {  // host-only scene (n_devices == 0): the blob lives in host memory
+    *out_ptr = s->host_blob.data();
+    *out_bytes = s->host_blob.size();
+    return RDN_OK;
+  }
   *out_ptr = s->devices[device_index].d_blob;
   *out_bytes = s->devices[device_index].blob_bytes;
   return RDN_OK;
@@ -652,6 +663,22 @@ int rdn_rt_scene_blob(rdn_rt_scene *s, int device_index, void **out_ptr, uint64_
 
 int rdn_rt_scene_adopt_blob(rdn_rt_scene *s, int device_index, const void *d_blob, uint64_t bytes) {
   if (!s || !d_blob || bytes < sizeof(BlobHeader)) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_scene_adopt_blob: null/short blob");
+  if (s->devices.empty() && device_index == -1) {  // host-only scene adopting a host blob (replication logic without a GPU)
+    BlobHeader hh;
+    std::memcpy(&hh, d_blob, sizeof(hh));
+    if (!header_ok(hh, bytes)) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_scene_adopt_blob: bad header");
+    std::unique_lock<std::shared_mutex> wr(s->lock);
+    s->host_blob.assign(static_cast<const uint8_t *>(d_blob), static_cast<const uint8_t *>(d_blob) + bytes);
+    const uint8_t *b = s->host_blob.data();
+    s->h_tlas_binding.assign(reinterpret_cast<const uint32_t *>(b + hh.offset[ARR_TLAS_BINDING]),
+                             reinterpret_cast<const uint32_t *>(b + hh.offset[ARR_TLAS_BINDING]) + hh.count[ARR_TLAS_BINDING]);
+    s->h_tlas_root.assign(reinterpret_cast<const TlasRoot *>(b + hh.offset[ARR_TLAS_ROOT]),
+                          reinterpret_cast<const TlasRoot *>(b + hh.offset[ARR_TLAS_ROOT]) + hh.count[ARR_TLAS_ROOT]);
+    s->flat = FlatScene{};
+    s->adopted = true;
+    s->dirty = false;
+    return RDN_OK;
+  }
   if (device_index < 0 || device_index >= static_cast<int>(s->devices.size())) return fail(RDN_ERR_INVALID_ARGUMENT, "bad device_index");
   std::unique_lock<std::shared_mutex> wr(s->lock);
   DeviceCtx &dc = s->devices[device_index];

@@ -1,0 +1,161 @@
+"""Multi-GPU driver of the traversal path: one process per GPU, BVH replicated, rays sharded by tile.
+
+The reference renders through a single wgpu queue; its only sharding notion is the 512 x 512 launch tile of
+``GPUWaveFrontComputeRaytracingEncoder::trace_ray`` (shader/ray-tracing/src/backend/wavefront_compute/mod.rs:134) cut
+by ``rect_split_iter`` (mod.rs:234-244), which silently drops the remainder columns when the width is not a multiple
+of the split (``sub_width = w / split_count``).  Here the same tile quantum is the unit dealt to ranks, but the cut is
+exact: edge tiles are simply narrower.
+
+Rays never interact and the scene is read-only during a launch, so the data path has NO collective.  The only
+exchanges are (1) one broadcast of the flattened-scene blob after ``commit`` (NCCL over NVLink between GPUs, gloo
+between host-only scenes in the CPU tests) and (2) an optional gather of the hit records onto one rank.
+
+``torch.distributed`` is plumbing here: process groups, the broadcast and the gather.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+TILE = 512  # the reference's launch tile (wavefront_compute/mod.rs:134)
+
+Tile = Tuple[int, int, int, int]  # x0, y0, w, h
+
+
+def launch_tiles(width: int, height: int, tile: int = TILE) -> List[Tile]:
+    """Row-major list of tiles covering a ``width x height`` launch exactly (edge tiles are narrower; nothing dropped)."""
+    if width < 0 or height < 0 or tile <= 0:
+        raise ValueError("launch_tiles: bad extent")
+    out = []
+    for y0 in range(0, height, tile):
+        for x0 in range(0, width, tile):
+            out.append((x0, y0, min(tile, width - x0), min(tile, height - y0)))
+    return out
+
+
+def shard_tiles(n_tiles: int, world: int, rank: int) -> List[int]:
+    """Tiles dealt round-robin: rank r owns tiles r, r + world, r + 2 world, ..."""
+    if not 0 <= rank < world:
+        raise ValueError("shard_tiles: rank outside the world")
+    return list(range(rank, n_tiles, world))
+
+
+def tile_ray_indices(width: int, tile: Tile) -> np.ndarray:
+    """Linear (row-major) launch indices of one tile's rays, in the tile's own row-major order."""
+    x0, y0, w, h = tile
+    return ((np.arange(y0, y0 + h, dtype=np.int64)[:, None] * width) + np.arange(x0, x0 + w, dtype=np.int64)[None, :]).reshape(-1)
+
+
+class TileShard:
+    """This rank's slice of a 2-D launch: which tiles it owns, how to pull its rays out of the full launch and how to
+    put its hits back.  Rays of a tile are stored contiguously in the tile's row-major order, so each tile is traced
+    as its own small 2-D launch (``grid_width`` = tile width keeps the kernel's 8 x 4 pixel-tile walk)."""
+
+    def __init__(self, width: int, height: int, world: int, rank: int, tile: int = TILE):
+        self.width, self.height, self.world, self.rank, self.tile = width, height, world, rank, tile
+        self.tiles_all = launch_tiles(width, height, tile)
+        self.tile_ids = shard_tiles(len(self.tiles_all), world, rank)
+        self.tiles = [self.tiles_all[i] for i in self.tile_ids]
+        counts = [w * h for (_, _, w, h) in self.tiles]
+        self.offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        self.n_rays = int(self.offsets[-1])
+
+    def indices(self) -> np.ndarray:
+        """launch indices of this rank's rays, tile after tile"""
+        if not self.tiles:
+            return np.zeros(0, np.int64)
+        return np.concatenate([tile_ray_indices(self.width, t) for t in self.tiles])
+
+    def gather_rays(self, launch_rays: np.ndarray) -> np.ndarray:
+        return np.ascontiguousarray(launch_rays.reshape(-1)[self.indices()])
+
+    def launches(self):
+        """(offset, count, grid_width) of each owned tile inside the shard buffer"""
+        for k, (_, _, w, h) in enumerate(self.tiles):
+            yield int(self.offsets[k]), w * h, w
+
+    def scatter_hits(self, shard_hits: np.ndarray, launch_hits: np.ndarray) -> None:
+        launch_hits.reshape(-1)[self.indices()] = shard_hits
+
+
+def trace_shard(system, shard: TileShard, shard_rays: np.ndarray, **launch_kw) -> np.ndarray:
+    """Trace this rank's tiles through the host-buffer C-ABI call, one 2-D launch per tile."""
+    from . import api
+    hits = np.empty(shard.n_rays, api.HIT_DTYPE)
+    for off, cnt, gw in shard.launches():
+        system.trace_closest_batch(shard_rays[off:off + cnt], grid_width=gw, out=hits[off:off + cnt], **launch_kw)
+    return hits
+
+
+# ----------------------------------------------------------------------------------------------- replication
+def replicate_scene(system, src: int = 0, group=None, device=None) -> float:
+    """Broadcast the flattened scene of rank ``src`` to every rank of ``group`` and adopt it there.
+
+    GPU scenes (``system.devices`` non-empty) broadcast the device blob in place with the group's backend (NCCL: NVLink /
+    NVSwitch); host-only scenes (``devices == ()``, CPU tests) broadcast the host blob (gloo).  Returns the broadcast time in
+    milliseconds (CUDA events for the device path, wall clock for the host path)."""
+    import time
+
+    import torch
+    import torch.distributed as dist
+
+    rank = dist.get_rank(group)
+    host_only = len(system.devices) == 0
+    if host_only:
+        nbytes = torch.zeros(1, dtype=torch.int64)
+        if rank == src:
+            ptr, nb = system.blob(device_index=-1)
+            nbytes[0] = nb
+        dist.broadcast(nbytes, src, group=group)
+        nb = int(nbytes.item())
+        buf = torch.empty(nb, dtype=torch.uint8)
+        if rank == src:
+            import ctypes
+            buf.copy_(torch.from_numpy(np.ctypeslib.as_array((ctypes.c_uint8 * nb).from_address(ptr)).copy()))
+        t0 = time.perf_counter()
+        dist.broadcast(buf, src, group=group)
+        ms = (time.perf_counter() - t0) * 1e3
+        if rank != src:
+            system.adopt_blob(buf.data_ptr(), nb, device_index=-1)
+        return ms
+
+    from cuda.bindings import runtime as cudart
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    nbytes = torch.zeros(1, dtype=torch.int64, device=dev)
+    ptr = 0
+    if rank == src:
+        ptr, nb = system.blob()
+        nbytes[0] = nb
+    dist.broadcast(nbytes, src, group=group)
+    nb = int(nbytes.item())
+    buf = torch.empty(nb, dtype=torch.uint8, device=dev)
+    if rank == src:
+        (err,) = cudart.cudaMemcpy(buf.data_ptr(), ptr, nb, cudart.cudaMemcpyKind.cudaMemcpyDeviceToDevice)
+        if int(err) != 0:
+            raise RuntimeError(f"cudaMemcpy of the scene blob failed: {err}")
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    dist.broadcast(buf, src, group=group)  # the one collective of the path: BVH replication
+    e1.record()
+    torch.cuda.synchronize()
+    if rank != src:
+        system.adopt_blob(buf.data_ptr(), nb)
+    return float(e0.elapsed_time(e1))
+
+
+def gather_launch_hits(shard: TileShard, shard_hits: np.ndarray, dst: int = 0, group=None):
+    """Assemble the full launch on rank ``dst`` from every rank's shard (host records; returns None elsewhere)."""
+    import torch.distributed as dist
+
+    from . import api
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    parts: Sequence = [None] * world if rank == dst else None
+    dist.gather_object(shard_hits, parts, dst=dst, group=group)
+    if rank != dst:
+        return None
+    full = np.empty(shard.width * shard.height, api.HIT_DTYPE)
+    for r, part in enumerate(parts):
+        TileShard(shard.width, shard.height, world, r, tile=shard.tile).scatter_hits(part, full)
+    return full
