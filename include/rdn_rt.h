@@ -159,6 +159,45 @@ typedef struct rdn_kernel_times {
 int rdn_rt_kernel_timing_begin(rdn_rt_scene *scene, int device_index);
 int rdn_rt_kernel_timing_end(rdn_rt_scene *scene, int device_index, rdn_kernel_times *out);
 
+/* ---- the step on either side of the traversal, on the device: primary-ray generation and the
+ *      closest-hit -> bounce-ray step, so a frame never moves rays or hits through the host.
+ * All buffers are device pointers on device `device_index`; calls are asynchronous on `cuda_stream`. ---- */
+/* Pinhole grid of the reference's own trace tests (geometry/naive/test.rs:259-264): for pixel (i, j) of a width x height
+ * launch  x = (i + jitter_x) / width * 2 - 1 [* aspect],  y = 1 - (j + jitter_y) / height * 2,  d = normalize((x, y, -1) - origin).
+ * Rays of the sub-rectangle (rect_x, rect_y, rect_w, rect_h) are written row-major (a launch tile, rdn multi-GPU sharding). */
+typedef struct rdn_pinhole {
+  uint32_t width, height, rect_x, rect_y, rect_w, rect_h;
+  float origin[3], tmin, tmax, aspect, jitter_x, jitter_y;   /* aspect 1 = none; jitter 0.5 = pixel centre */
+} rdn_pinhole;
+int rdn_rt_gen_pinhole_rays_device(rdn_rt_scene *scene, int device_index, const rdn_pinhole *params, rdn_ray *d_rays,
+                                   void *cuda_stream);
+/* DefaultRtxCameraInvocation::generate_ray (scene/rendering/gpu-ray-tracing/src/camera.rs:66-98):
+ * uv = pixel / size + sampler.next_2d() / size with PCGRandomSampler seeded by xxhash32(pixel.x, pixel.y, sample_index)
+ * (sampler.rs:11-72); target = unproject(view_projection_inv, uv, ndc_depth) (shader/library/src/lib.rs:18-28);
+ * d = normalize(target - world_position).  view_projection_inv is the reference's column-major Mat4. */
+typedef struct rdn_camera {
+  float view_projection_inv[16], world_position[3], ndc_depth, tmin, tmax;
+  uint32_t width, height, rect_x, rect_y, rect_w, rect_h, sample_index, pad;
+} rdn_camera;
+int rdn_rt_gen_camera_rays_device(rdn_rt_scene *scene, int device_index, const rdn_camera *params, rdn_ray *d_rays,
+                                  void *cuda_stream);
+/* One bounce ray per primary hit, stably compacted (misses produce no ray): origin = hit_world_position
+ * (api/ctx.rs:209-211), normal = geometric normal turned towards the ray origin (bindless_mesh_bridge.rs:103-114),
+ * direction by `mode`:
+ *   0  cosine_sample_hemisphere_in_dir(normal, (van_der_corput, sobol)(index_base + source ray index)) with the given
+ *      scrambles (math/statistics/src/distribution_map.rs:10-58, sampling/sobol.rs:40-68)
+ *   1  tbn(normal) * sample_hemisphere_cos(hammersley_2d(sample_index, max_sample)), the AO secondary ray
+ *      (feature/ao.rs:249-284, shader/library/src/sampling.rs:33-83)
+ * d_rays_out and d_src_index need n slots; d_src_index[k] = index of the primary ray behind bounce ray k;
+ * *d_out_n (device) = number of bounce rays.  Uses the scene's compaction scratch (rdn_rt_compact_u32_device). */
+typedef struct rdn_bounce {
+  uint32_t mode, index_base, scramble0, scramble1, sample_index, max_sample;
+  float tmin, tmax;
+} rdn_bounce;
+int rdn_rt_gen_bounce_rays_device(rdn_rt_scene *scene, int device_index, const rdn_bounce *params, const rdn_ray *d_rays_in,
+                                  const rdn_hit *d_hits, uint64_t n, rdn_ray *d_rays_out, uint32_t *d_src_index,
+                                  uint64_t *d_out_n, void *cuda_stream);
+
 /* ---- wavefront active-list compaction: use_stream_compaction
  *      (shader/parallel-compute/src/stream_compaction.rs:3-45) as used by use_compact_alive_tasks
  *      (shader/task-graph/src/runtime/task_group.rs:220-278).  Stable; out has n slots, zero past *out_n. ---- */
@@ -177,7 +216,7 @@ int rdn_rt_scene_adopt_blob(rdn_rt_scene *scene, int device_index, const void *d
 typedef enum rdn_array_id {
   RDN_ARRAY_TLAS_BINDING = 0, RDN_ARRAY_TLAS_BVH_ROOT, RDN_ARRAY_TLAS_BVH_FOREST, RDN_ARRAY_TLAS_BOUNDING,
   RDN_ARRAY_INSTANCES, RDN_ARRAY_BLAS_META, RDN_ARRAY_GEOMETRY_META, RDN_ARRAY_TRI_BVH_FOREST,
-  RDN_ARRAY_TRIANGLES, RDN_ARRAY_SLOT_INFO, RDN_ARRAY_WIDE_NODES, RDN_ARRAY_COUNT
+  RDN_ARRAY_TRIANGLES, RDN_ARRAY_SLOT_INFO, RDN_ARRAY_WIDE_NODES, RDN_ARRAY_PRIM_TO_SLOT, RDN_ARRAY_COUNT
 } rdn_array_id;
 int rdn_rt_scene_array(rdn_rt_scene *scene, int array_id, void *out, uint64_t capacity_bytes, uint64_t *out_bytes);
 

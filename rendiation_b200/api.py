@@ -47,7 +47,7 @@ ARRAYS = {  # rdn_array_id -> (name, dtype)
     0: ("tlas_binding", np.dtype("u4")), 1: ("tlas_root", np.dtype(("u4", (2,)))), 2: ("tlas_bvh_forest", DEV_NODE_DTYPE),
     3: ("tlas_bounding", TLAS_BOUNDING_DTYPE), 4: ("instances", INSTANCE_RECORD_DTYPE), 5: ("blas_meta", np.dtype(("u4", (2,)))),
     6: ("geometry_meta", GEOMETRY_META_DTYPE), 7: ("tri_bvh_forest", DEV_NODE_DTYPE), 8: ("triangles", TRI_RECORD_DTYPE),
-    9: ("slot_info", np.dtype(("u4", (2,)))), 10: ("wide_nodes", WIDE_NODE_DTYPE),
+    9: ("slot_info", np.dtype(("u4", (2,)))), 10: ("wide_nodes", WIDE_NODE_DTYPE), 11: ("prim_to_slot", np.dtype("u4")),
 }
 
 # RayFlagConfigRaw (api/ty.rs:102-114)
@@ -105,6 +105,23 @@ class _KernelTimes(C.Structure):
                 ("ordered_ms", C.c_double), ("tie_ms", C.c_double), ("reference_ms", C.c_double)]
 
 
+class _Pinhole(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("rect_x", C.c_uint32), ("rect_y", C.c_uint32), ("rect_w", C.c_uint32),
+                ("rect_h", C.c_uint32), ("origin", C.c_float * 3), ("tmin", C.c_float), ("tmax", C.c_float), ("aspect", C.c_float),
+                ("jitter_x", C.c_float), ("jitter_y", C.c_float)]
+
+
+class _Camera(C.Structure):
+    _fields_ = [("view_projection_inv", C.c_float * 16), ("world_position", C.c_float * 3), ("ndc_depth", C.c_float), ("tmin", C.c_float),
+                ("tmax", C.c_float), ("width", C.c_uint32), ("height", C.c_uint32), ("rect_x", C.c_uint32), ("rect_y", C.c_uint32),
+                ("rect_w", C.c_uint32), ("rect_h", C.c_uint32), ("sample_index", C.c_uint32), ("pad", C.c_uint32)]
+
+
+class _Bounce(C.Structure):
+    _fields_ = [("mode", C.c_uint32), ("index_base", C.c_uint32), ("scramble0", C.c_uint32), ("scramble1", C.c_uint32),
+                ("sample_index", C.c_uint32), ("max_sample", C.c_uint32), ("tmin", C.c_float), ("tmax", C.c_float)]
+
+
 class _Option(C.Structure):
     _fields_ = [("max_tree_depth", C.c_uint64), ("bin_size", C.c_uint64)]
 
@@ -116,7 +133,8 @@ class _MeshView(C.Structure):
 EXPORTED_SYMBOLS = [
     "rdn_rt_scene_create", "rdn_rt_scene_destroy", "rdn_rt_blas_create", "rdn_rt_blas_destroy", "rdn_rt_tlas_create",
     "rdn_rt_tlas_destroy", "rdn_rt_bind_tlas", "rdn_rt_bind_tlas_max_len", "rdn_rt_commit", "rdn_rt_trace_closest",
-    "rdn_rt_trace_closest_device", "rdn_rt_trace_counted", "rdn_rt_kernel_timing_begin", "rdn_rt_kernel_timing_end", "rdn_rt_compact_u32", "rdn_rt_compact_u32_device",
+    "rdn_rt_trace_closest_device", "rdn_rt_trace_counted", "rdn_rt_kernel_timing_begin", "rdn_rt_kernel_timing_end",
+    "rdn_rt_gen_pinhole_rays_device", "rdn_rt_gen_camera_rays_device", "rdn_rt_gen_bounce_rays_device", "rdn_rt_compact_u32", "rdn_rt_compact_u32_device",
     "rdn_rt_scene_blob", "rdn_rt_scene_adopt_blob", "rdn_rt_scene_array", "rdn_bvh_build", "rdn_bvh_destroy", "rdn_bvh_nodes",
     "rdn_bvh_sorted_primitive_index", "rdn_bvh_build_for_mesh", "rdn_bvh_query_nearest", "rdn_rt_last_error", "rdn_rt_version",
 ]
@@ -153,6 +171,9 @@ def lib() -> C.CDLL:
     L.rdn_rt_trace_counted.argtypes = [vp, P(_Launch), vp, u64, vp, P(_Counters)]
     L.rdn_rt_kernel_timing_begin.argtypes = [vp, i32]
     L.rdn_rt_kernel_timing_end.argtypes = [vp, i32, P(_KernelTimes)]
+    L.rdn_rt_gen_pinhole_rays_device.argtypes = [vp, i32, P(_Pinhole), vp, vp]
+    L.rdn_rt_gen_camera_rays_device.argtypes = [vp, i32, P(_Camera), vp, vp]
+    L.rdn_rt_gen_bounce_rays_device.argtypes = [vp, i32, P(_Bounce), vp, vp, u64, vp, vp, vp, vp]
     L.rdn_rt_compact_u32.argtypes = [vp, vp, vp, u64, vp, P(u64)]
     L.rdn_rt_compact_u32_device.argtypes = [vp, i32, vp, vp, u64, vp, vp, vp]
     L.rdn_rt_scene_blob.argtypes = [vp, i32, P(vp), P(u64)]
@@ -303,6 +324,32 @@ class NaiveSahBVHSystem:
         kt = _KernelTimes()
         _check(self._L.rdn_rt_kernel_timing_end(self._h, device_index, C.byref(kt)))
         return {n: (int(getattr(kt, n)) if n.endswith("launches") else float(getattr(kt, n))) for n, _ in _KernelTimes._fields_}
+
+    # --- ray generation / bounce on the device ---
+    def gen_pinhole_rays_device(self, d_rays: int, width: int, height: int, rect=None, origin=(0.0, 0.0, 0.0), tmin=0.0, tmax=100.0,
+                                aspect=1.0, jitter=(0.5, 0.5), stream: int = 0, device_index: int = 0) -> int:
+        """naive/test.rs:259-264 pinhole grid (optionally a sub-rectangle, row-major) written to device rays; returns the ray count."""
+        x0, y0, w, h = rect if rect is not None else (0, 0, width, height)
+        p = _Pinhole(width, height, x0, y0, w, h, (C.c_float * 3)(*origin), tmin, tmax, aspect, jitter[0], jitter[1])
+        _check(self._L.rdn_rt_gen_pinhole_rays_device(self._h, device_index, C.byref(p), C.c_void_p(d_rays), C.c_void_p(stream)))
+        return w * h
+
+    def gen_camera_rays_device(self, d_rays: int, view_projection_inv, world_position, width: int, height: int, sample_index: int = 0,
+                               rect=None, ndc_depth=1.0, tmin=0.0, tmax=3.4028235e38, stream: int = 0, device_index: int = 0) -> int:
+        """DefaultRtxCameraInvocation::generate_ray (camera.rs:66-98) with the PCG sampler; returns the ray count."""
+        x0, y0, w, h = rect if rect is not None else (0, 0, width, height)
+        m = np.asarray(view_projection_inv, np.float32).reshape(-1)
+        p = _Camera((C.c_float * 16)(*m), (C.c_float * 3)(*world_position), ndc_depth, tmin, tmax, width, height, x0, y0, w, h, sample_index, 0)
+        _check(self._L.rdn_rt_gen_camera_rays_device(self._h, device_index, C.byref(p), C.c_void_p(d_rays), C.c_void_p(stream)))
+        return w * h
+
+    def gen_bounce_rays_device(self, d_rays_in: int, d_hits: int, n: int, d_rays_out: int, d_src_index: int, d_out_n: int, mode: int = 0,
+                               index_base: int = 0, scrambles=(0x9E3779B9, 0x85EBCA6B), sample_index: int = 0, max_sample: int = 256,
+                               tmin=0.01, tmax=100.0, stream: int = 0, device_index: int = 0):
+        """One compacted bounce ray per primary hit (mode 0: SURVEY config-3 cosine bounce, mode 1: the AO secondary ray of ao.rs:249-284)."""
+        p = _Bounce(mode, index_base, scrambles[0], scrambles[1], sample_index, max_sample, tmin, tmax)
+        _check(self._L.rdn_rt_gen_bounce_rays_device(self._h, device_index, C.byref(p), C.c_void_p(d_rays_in), C.c_void_p(d_hits), n,
+                                                     C.c_void_p(d_rays_out), C.c_void_p(d_src_index), C.c_void_p(d_out_n), C.c_void_p(stream)))
 
     # --- wavefront queue compaction ---
     def compact_u32(self, values, keep):

@@ -247,8 +247,10 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
         // slots of this geometry start at primitive_start (indices_redirect and indices grow in lock step)
         const uint64_t slot_base = out.triangles.size();
         if (slot_base != primitive_start) { err = "internal: slot/primitive offset mismatch"; return RDN_ERR_BUILD; }
+        out.prim_to_slot.resize(slot_base + n_tri, 0u);
         for (uint64_t k = 0; k < n_tri; ++k) {
           const uint64_t tri = bvh.sorted_primitive_index[k];  // indices_redirect[slot] - raw_primitive_start
+          out.prim_to_slot[slot_base + tri] = static_cast<uint32_t>(slot_base + k);
           out.triangles.push_back(make_tri_record(src.positions[vertex_of(tri, 0)], src.positions[vertex_of(tri, 1)],
                                                   src.positions[vertex_of(tri, 2)]));
           out.slot_info.push_back(SlotInfo{static_cast<uint32_t>(tri), static_cast<uint32_t>(g)});
@@ -363,6 +365,7 @@ std::vector<uint8_t> FlatScene::serialize() const {
   place(blob, h, ARR_TRIANGLES, triangles);
   place(blob, h, ARR_SLOT_INFO, slot_info);
   place(blob, h, ARR_WIDE_NODES, wide_nodes);
+  place(blob, h, ARR_PRIM_TO_SLOT, prim_to_slot);
   blob.resize((blob.size() + BLOB_ALIGN - 1) / BLOB_ALIGN * BLOB_ALIGN, 0);
   h.total_bytes = blob.size();
   std::memcpy(blob.data(), &h, sizeof(h));

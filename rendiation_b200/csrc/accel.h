@@ -39,6 +39,7 @@ struct FlatScene {
   std::vector<TriRecord> triangles;
   std::vector<SlotInfo> slot_info;
   std::vector<WideNode> wide_nodes;
+  std::vector<uint32_t> prim_to_slot;
   BuildStats stats;
 
   // pack into one contiguous, BLOB_ALIGN-aligned byte image starting with a BlobHeader

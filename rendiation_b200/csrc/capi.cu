@@ -92,6 +92,9 @@ struct DeviceCtx {
   bool ext_pending = false;
   unsigned long long *d_compact_status = nullptr;
   uint64_t compact_status_cap = 0;
+  uint8_t *d_keep = nullptr;       // bounce step: keep flags + identity indices feeding the compaction
+  uint32_t *d_iota = nullptr;
+  uint64_t bounce_cap = 0;
   bool timing = false;                 // rdn_rt_kernel_timing_begin .. _end: events around every traversal kernel
   std::vector<TimedLaunch> timed;
 };
@@ -152,6 +155,7 @@ void bind_blob(DeviceCtx &dc, const BlobHeader &h) {
   d.triangles = reinterpret_cast<const TriRecord *>(b + h.offset[ARR_TRIANGLES]);
   d.slot_info = reinterpret_cast<const SlotInfo *>(b + h.offset[ARR_SLOT_INFO]);
   d.wide_nodes = reinterpret_cast<const WideNode *>(b + h.offset[ARR_WIDE_NODES]);
+  d.prim_to_slot = reinterpret_cast<const uint32_t *>(b + h.offset[ARR_PRIM_TO_SLOT]);
   d.n_tlas_binding = static_cast<uint32_t>(h.count[ARR_TLAS_BINDING]);
   d.n_tlas_root = static_cast<uint32_t>(h.count[ARR_TLAS_ROOT]);
   d.n_blas_meta = static_cast<uint32_t>(h.count[ARR_BLAS_META]);
@@ -327,6 +331,8 @@ void rdn_rt_scene_destroy(rdn_rt_scene *s) {
     for (TimedLaunch &t : dc.timed) { cudaEventDestroy(t.begin); cudaEventDestroy(t.end); }
     if (dc.ext_done) cudaEventDestroy(dc.ext_done);
     if (dc.d_compact_status) cudaFree(dc.d_compact_status);
+    if (dc.d_keep) cudaFree(dc.d_keep);
+    if (dc.d_iota) cudaFree(dc.d_iota);
   }
   delete s;
 }
@@ -571,6 +577,63 @@ int rdn_rt_trace_counted(rdn_rt_scene *s, const rdn_launch *launch, const rdn_ra
       out_counters->tri_hit += c[3]; out_counters->inst_visit += c[4]; out_counters->ref_abort += c[5];
     }
   }
+  return RDN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ ray generation / bounce (f1)
+int rdn_rt_gen_pinhole_rays_device(rdn_rt_scene *s, int device_index, const rdn_pinhole *p, rdn_ray *d_rays, void *cuda_stream) {
+  if (!s || !p || !d_rays) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_gen_pinhole_rays_device: null argument");
+  if (device_index < 0 || device_index >= static_cast<int>(s->devices.size())) return fail(RDN_ERR_INVALID_ARGUMENT, "bad device_index");
+  if (p->width == 0 || p->height == 0 || p->rect_x + static_cast<uint64_t>(p->rect_w) > p->width || p->rect_y + static_cast<uint64_t>(p->rect_h) > p->height)
+    return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_gen_pinhole_rays_device: rectangle outside the launch");
+  RDN_CUDA(cudaSetDevice(s->devices[device_index].device));
+  launch_gen_pinhole_rays(*p, d_rays, static_cast<cudaStream_t>(cuda_stream));
+  RDN_CUDA(cudaGetLastError());
+  return RDN_OK;
+}
+
+int rdn_rt_gen_camera_rays_device(rdn_rt_scene *s, int device_index, const rdn_camera *p, rdn_ray *d_rays, void *cuda_stream) {
+  if (!s || !p || !d_rays) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_gen_camera_rays_device: null argument");
+  if (device_index < 0 || device_index >= static_cast<int>(s->devices.size())) return fail(RDN_ERR_INVALID_ARGUMENT, "bad device_index");
+  if (p->width == 0 || p->height == 0 || p->rect_x + static_cast<uint64_t>(p->rect_w) > p->width || p->rect_y + static_cast<uint64_t>(p->rect_h) > p->height)
+    return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_gen_camera_rays_device: rectangle outside the launch");
+  RDN_CUDA(cudaSetDevice(s->devices[device_index].device));
+  launch_gen_camera_rays(*p, d_rays, static_cast<cudaStream_t>(cuda_stream));
+  RDN_CUDA(cudaGetLastError());
+  return RDN_OK;
+}
+
+int rdn_rt_gen_bounce_rays_device(rdn_rt_scene *s, int device_index, const rdn_bounce *p, const rdn_ray *d_rays_in, const rdn_hit *d_hits,
+                                  uint64_t n, rdn_ray *d_rays_out, uint32_t *d_src_index, uint64_t *d_out_n, void *cuda_stream) {
+  if (!s || !p || !d_out_n || (n && (!d_rays_in || !d_hits || !d_rays_out || !d_src_index)))
+    return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_gen_bounce_rays_device: null argument");
+  if (device_index < 0 || device_index >= static_cast<int>(s->devices.size())) return fail(RDN_ERR_INVALID_ARGUMENT, "bad device_index");
+  if (p->mode > 1 || (p->mode == 1 && p->max_sample == 0)) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_gen_bounce_rays_device: bad mode");
+  if (n > MAX_LAUNCH_RAYS) return fail(RDN_ERR_CAPACITY, "rdn_rt_gen_bounce_rays_device: more than 2^31 rays in one call");
+  int rc = ensure_committed(s);
+  if (rc != RDN_OK) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  {
+    std::shared_lock<std::shared_mutex> rd(s->lock);
+    std::lock_guard<std::mutex> lg(s->launch_lock);
+    DeviceCtx &dc = s->devices[device_index];
+    RDN_CUDA(cudaSetDevice(dc.device));
+    if (dc.bounce_cap < n) {
+      if (dc.d_keep) cudaFree(dc.d_keep);
+      if (dc.d_iota) cudaFree(dc.d_iota);
+      dc.d_keep = nullptr; dc.d_iota = nullptr; dc.bounce_cap = 0;
+      RDN_CUDA(cudaMalloc(&dc.d_keep, std::max<uint64_t>(n, 1)));
+      RDN_CUDA(cudaMalloc(&dc.d_iota, std::max<uint64_t>(n, 1) * sizeof(uint32_t)));
+      dc.bounce_cap = n;
+    }
+    launch_mark_hits(d_hits, n, dc.d_keep, dc.d_iota, stream);
+  }
+  DeviceCtx &dc = s->devices[device_index];
+  rc = rdn_rt_compact_u32_device(s, device_index, dc.d_iota, dc.d_keep, n, d_src_index, d_out_n, cuda_stream);
+  if (rc != RDN_OK) return rc;
+  std::shared_lock<std::shared_mutex> rd(s->lock);
+  launch_gen_bounce_rays(dc.dev, *p, d_rays_in, d_hits, d_src_index, d_out_n, n, d_rays_out, stream);
+  RDN_CUDA(cudaGetLastError());
   return RDN_OK;
 }
 

@@ -22,6 +22,7 @@ struct SceneDev {
   const TriRecord *triangles;
   const SlotInfo *slot_info;
   const WideNode *wide_nodes;
+  const uint32_t *prim_to_slot;
   uint32_t n_tlas_binding, n_tlas_root, n_blas_meta, n_instances;
 };
 
@@ -62,6 +63,14 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, uint3
 uint64_t compact_status_words(uint64_t n);
 void launch_compact_u32(const uint32_t *d_in, const uint8_t *d_keep, uint64_t n, uint32_t *d_out, uint64_t *d_out_n,
                         unsigned long long *d_status, cudaStream_t stream);
+
+// ray generation and the closest-hit -> bounce step on the device (raygen.cu)
+void launch_gen_pinhole_rays(const rdn_pinhole &p, rdn_ray *d_rays, cudaStream_t stream);
+void launch_gen_camera_rays(const rdn_camera &p, rdn_ray *d_rays, cudaStream_t stream);
+void launch_mark_hits(const rdn_hit *d_hits, uint64_t n, uint8_t *d_keep, uint32_t *d_iota, cudaStream_t stream);
+// d_src_index[0 .. *d_n_src) = indices of the source rays (stable compaction of the hits); n_max bounds the grid
+void launch_gen_bounce_rays(const SceneDev &scene, const rdn_bounce &p, const rdn_ray *d_rays_in, const rdn_hit *d_hits,
+                            const uint32_t *d_src_index, const uint64_t *d_n_src, uint64_t n_max, rdn_ray *d_rays_out, cudaStream_t stream);
 
 // path A: intersect_nearest_bvh over a FlattenBVH (content/mesh/core/src/feature/bvh.rs:57-86); the kernel walks
 // the tree in the reference's order (right child first, no distance pruning) so equal-distance ties resolve identically.

@@ -110,11 +110,12 @@ enum ArrayId : int {
   ARR_TRIANGLES,          // TriRecord
   ARR_SLOT_INFO,          // SlotInfo
   ARR_WIDE_NODES,         // WideNode
+  ARR_PRIM_TO_SLOT,       // u32: (primitive_start + original triangle index) -> slot; inverse of the reference's indices_redirect
   ARR_COUNT
 };
 
 constexpr uint64_t BLOB_MAGIC = 0x52444E5F424C4F42ull;  // "RDN_BLOB"
-constexpr uint32_t BLOB_VERSION = 1;
+constexpr uint32_t BLOB_VERSION = 2;
 constexpr uint64_t BLOB_ALIGN = 128;
 
 struct BlobHeader {
