@@ -61,46 +61,50 @@ def main():
     groups = {}
     for t in shard.tiles:
         groups.setdefault(t[2], []).append(t)
+    # all spp samples of a group form ONE wave (sample after sample, tiles stacked vertically): one traversal launch, one
+    # compaction + bounce generation, one wave-size read-back and one bounce launch per group instead of one of each per sample
+    spp = args.spp
     bufs = {}
     for gw, tiles in groups.items():
-        n = sum(t[2] * t[3] for t in tiles)
-        bufs[gw] = dict(n=n, tiles=tiles, rays=torch.empty((n, 32), dtype=torch.uint8, device=dev), hits=torch.empty((n, 32), dtype=torch.uint8, device=dev),
+        n1 = sum(t[2] * t[3] for t in tiles)
+        n = n1 * spp
+        bufs[gw] = dict(n=n, n1=n1, tiles=tiles, rays=torch.empty((n, 32), dtype=torch.uint8, device=dev), hits=torch.empty((n, 32), dtype=torch.uint8, device=dev),
                         brays=torch.empty((n, 32), dtype=torch.uint8, device=dev), bhits=torch.empty((n, 32), dtype=torch.uint8, device=dev),
                         src=torch.empty(n, dtype=torch.int32, device=dev), cnt=torch.zeros(1, dtype=torch.int64, device=dev))
     st = torch.cuda.current_stream().cuda_stream
     aspect = float(np.float32(W / H))
+    jitters = [S.sample_2d(np.full(1, s, np.uint32))[0] if s else np.array([0.5, 0.5], np.float32) for s in range(spp)]
 
-    def one_sample(s: int):
-        jit = S.sample_2d(np.full(1, s, np.uint32))[0] if s else np.array([0.5, 0.5], np.float32)
+    def frame():
         n_bounce = 0
         for gw, B in bufs.items():
             off = 0
-            for t in B["tiles"]:
-                sysm.gen_pinhole_rays_device(B["rays"].data_ptr() + off * 32, W, H, rect=t, tmin=TMIN, tmax=TMAX, aspect=aspect,
-                                             jitter=(float(jit[0]), float(jit[1])), stream=st)
-                off += t[2] * t[3]
+            for s in range(spp):
+                for t in B["tiles"]:
+                    sysm.gen_pinhole_rays_device(B["rays"].data_ptr() + off * 32, W, H, rect=t, tmin=TMIN, tmax=TMAX, aspect=aspect,
+                                                 jitter=(float(jitters[s][0]), float(jitters[s][1])), stream=st)
+                    off += t[2] * t[3]
             sysm.trace_closest_device(B["rays"].data_ptr(), B["n"], B["hits"].data_ptr(), ray_flags=CULL_BACK, grid_width=gw, stream=st)
             sysm.gen_bounce_rays_device(B["rays"].data_ptr(), B["hits"].data_ptr(), B["n"], B["brays"].data_ptr(), B["src"].data_ptr(),
-                                        B["cnt"].data_ptr(), mode=0, index_base=(s * B["n"]) & 0x7FFFFFFF, tmin=TMIN, tmax=TMAX, stream=st)
+                                        B["cnt"].data_ptr(), mode=0, index_base=0, tmin=TMIN, tmax=TMAX, stream=st)
+        for gw, B in bufs.items():
             k = int(B["cnt"].item())  # wave size read back, as the reference does after its compaction (task_group.rs:259-277)
             sysm.trace_closest_device(B["brays"].data_ptr(), k, B["bhits"].data_ptr(), ray_flags=0, stream=st)
             B["k"] = k
             n_bounce += k
         return n_bounce
 
-    one_sample(0)  # warm-up (allocates scratch)
+    frame()  # warm-up (allocates scratch)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    n_bounce = 0
-    for s in range(args.spp):
-        n_bounce += one_sample(s)
+    n_bounce = frame()
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    counts = torch.tensor([shard.n_rays * args.spp, n_bounce], dtype=torch.float64, device=dev)
+    counts = torch.tensor([shard.n_rays * spp, n_bounce], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
@@ -113,7 +117,7 @@ def main():
         osc.bind_tlas([osc.create_tlas(S.make_instance(m, ob))])
         assert osc.build() == 0
         gw, B = next(iter(bufs.items()))
-        n1 = B["tiles"][0][2] * B["tiles"][0][3]
+        n1 = B["tiles"][0][2] * B["tiles"][0][3]  # first owned tile of sample 0
         cores = os.cpu_count() or 1
         r1 = B["rays"][:n1].cpu().numpy().view(S.RAY_DTYPE).reshape(-1)
         h1 = B["hits"][:n1].cpu().numpy().view(api.HIT_DTYPE).reshape(-1)
