@@ -247,6 +247,12 @@ int rdn_bvh_build_for_mesh(const rdn_mesh_view *mesh, int strategy, uint32_t sah
 int rdn_bvh_query_nearest(const rdn_flat_bvh *bvh, const rdn_mesh_view *mesh, const rdn_ray *rays, uint64_t n,
                           uint32_t face_side, int device, rdn_mesh_hit *out);
 
+/* device-resident form: gather the mesh through the BVH's sorted_primitive_index and upload it with the nodes once, then
+ * query any number of device ray batches (asynchronous on cuda_stream) */
+int rdn_bvh_upload(rdn_flat_bvh *bvh, const rdn_mesh_view *mesh, int device);
+int rdn_bvh_query_nearest_device(const rdn_flat_bvh *bvh, const rdn_ray *d_rays, uint64_t n, uint32_t face_side,
+                                 rdn_mesh_hit *d_out, void *cuda_stream);
+
 const char *rdn_rt_last_error(void);
 const char *rdn_rt_version(void);
 

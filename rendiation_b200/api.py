@@ -136,7 +136,7 @@ EXPORTED_SYMBOLS = [
     "rdn_rt_trace_closest_device", "rdn_rt_trace_counted", "rdn_rt_kernel_timing_begin", "rdn_rt_kernel_timing_end",
     "rdn_rt_gen_pinhole_rays_device", "rdn_rt_gen_camera_rays_device", "rdn_rt_gen_bounce_rays_device", "rdn_rt_compact_u32", "rdn_rt_compact_u32_device",
     "rdn_rt_scene_blob", "rdn_rt_scene_adopt_blob", "rdn_rt_scene_array", "rdn_bvh_build", "rdn_bvh_destroy", "rdn_bvh_nodes",
-    "rdn_bvh_sorted_primitive_index", "rdn_bvh_build_for_mesh", "rdn_bvh_query_nearest", "rdn_rt_last_error", "rdn_rt_version",
+    "rdn_bvh_sorted_primitive_index", "rdn_bvh_build_for_mesh", "rdn_bvh_query_nearest", "rdn_bvh_upload", "rdn_bvh_query_nearest_device", "rdn_rt_last_error", "rdn_rt_version",
 ]
 
 _lib = None
@@ -186,6 +186,8 @@ def lib() -> C.CDLL:
     L.rdn_bvh_nodes.argtypes = [vp, P(vp), P(u64)]
     L.rdn_bvh_sorted_primitive_index.argtypes = [vp, P(vp), P(u64)]
     L.rdn_bvh_query_nearest.argtypes = [vp, P(_MeshView), vp, u64, u32, i32, vp]
+    L.rdn_bvh_upload.argtypes = [vp, P(_MeshView), i32]
+    L.rdn_bvh_query_nearest_device.argtypes = [vp, vp, u64, u32, vp, vp]
     _lib = L
     return L
 
@@ -479,6 +481,17 @@ def build_bvh_for_abstract_mesh(positions, indices, strategy=None, option: TreeB
         rc = L.rdn_bvh_build_for_mesh(C.byref(mv), 1, 0, C.byref(opt), C.byref(h))
     _check(rc)
     return FlattenBVH(_handle=h)
+
+
+def upload_bvh(bvh: FlattenBVH, positions, indices, device: int = 0) -> None:
+    """Make the space query device-resident: nodes + the mesh gathered in BVH order are uploaded once."""
+    mv, _keep = _mesh_view(positions, indices)
+    _check(lib().rdn_bvh_upload(bvh._h, C.byref(mv), device))
+
+
+def intersect_nearest_bvh_device(bvh: FlattenBVH, d_rays: int, n: int, d_out: int, face_side: int = FACE_DOUBLE, stream: int = 0) -> None:
+    """intersect_nearest_bvh on device buffers (after :func:`upload_bvh`); asynchronous on ``stream``."""
+    _check(lib().rdn_bvh_query_nearest_device(bvh._h, C.c_void_p(d_rays), n, face_side, C.c_void_p(d_out), C.c_void_p(stream)))
 
 
 def intersect_nearest_bvh(positions, indices, rays, bvh: FlattenBVH, face_side: int = FACE_DOUBLE, device: int = 0) -> np.ndarray:

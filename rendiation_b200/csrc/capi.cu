@@ -793,6 +793,11 @@ int rdn_rt_scene_array(rdn_rt_scene *s, int array_id, void *out, uint64_t capaci
 struct rdn_flat_bvh {
   FlattenBVH bvh;
   uint64_t depth = 0;
+  // device-resident copy made by rdn_bvh_upload: nodes + triangles pre-gathered in sorted_primitive_index order
+  int device = -1;
+  PathANode *d_nodes = nullptr;
+  PathATri *d_tris = nullptr;
+  std::mutex lock;
 };
 
 static uint64_t tree_depth(const std::vector<FlattenBVHNode> &nodes) {
@@ -852,7 +857,75 @@ int rdn_bvh_build_for_mesh(const rdn_mesh_view *mesh, int strategy, uint32_t sah
   return build_bvh_common(boxes.data(), n_tri, strategy, sah_buckets, option, out);
 }
 
-void rdn_bvh_destroy(rdn_flat_bvh *b) { delete b; }
+static void free_bvh_device(rdn_flat_bvh *b) {
+  if (b->device >= 0) {
+    cudaSetDevice(b->device);
+    if (b->d_nodes) cudaFree(b->d_nodes);
+    if (b->d_tris) cudaFree(b->d_tris);
+  }
+  b->d_nodes = nullptr; b->d_tris = nullptr; b->device = -1;
+}
+
+void rdn_bvh_destroy(rdn_flat_bvh *b) {
+  if (!b) return;
+  free_bvh_device(b);
+  delete b;
+}
+
+int rdn_bvh_upload(rdn_flat_bvh *b, const rdn_mesh_view *mesh, int device) {
+  if (!b || !mesh || !mesh->positions || !mesh->indices) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_bvh_upload: null argument");
+  if (b->depth > static_cast<uint64_t>(PATHA_MAX_DEPTH)) return fail(RDN_ERR_CAPACITY, "rdn_bvh_upload: tree deeper than 128 levels");
+  const auto &nodes = b->bvh.nodes;
+  const auto &sorted = b->bvh.sorted_primitive_index;
+  if (sorted.size() * 3 > mesh->n_indices) return fail(RDN_ERR_INVALID_ARGUMENT, "mesh smaller than the BVH it was built for");
+  if (nodes.size() >= 0xFFFFFFFFull || sorted.size() >= 0xFFFFFFFFull) return fail(RDN_ERR_CAPACITY, "rdn_bvh_upload: more than 2^32 nodes / primitives");
+  std::vector<PathANode> pn(nodes.size());
+  for (size_t i = 0; i < nodes.size(); ++i) {
+    const FlattenBVHNode &nd = nodes[i];
+    PathANode &p = pn[i];
+    p.bmin[0] = nd.bounding.min.x; p.bmin[1] = nd.bounding.min.y; p.bmin[2] = nd.bounding.min.z;
+    p.bmax[0] = nd.bounding.max.x; p.bmax[1] = nd.bounding.max.y; p.bmax[2] = nd.bounding.max.z;
+    if (nd.has_child) { p.a = static_cast<uint32_t>(nd.right_child_offset()); p.b = 0xFFFFFFFFu; }
+    else { p.a = static_cast<uint32_t>(nd.primitive_start); p.b = static_cast<uint32_t>(nd.primitive_end); }
+  }
+  std::vector<PathATri> pt(sorted.size());
+  for (size_t k = 0; k < sorted.size(); ++k) {
+    const uint64_t prim = sorted[k];
+    PathATri &t = pt[k];
+    std::memset(&t, 0, sizeof(t));
+    float *dst[3] = {t.a, t.b, t.c};
+    for (int v = 0; v < 3; ++v) {
+      const uint64_t vi = mesh->indices[3 * prim + v];
+      if (vi >= mesh->n_positions) return fail(RDN_ERR_BUILD, "triangle index out of bounds");
+      std::memcpy(dst[v], mesh->positions + 3 * vi, 3 * sizeof(float));
+    }
+    t.prim = static_cast<uint32_t>(prim);
+  }
+  std::lock_guard<std::mutex> lg(b->lock);
+  free_bvh_device(b);
+  RDN_CUDA(cudaSetDevice(device));
+  b->device = device;
+  RDN_CUDA(cudaMalloc(&b->d_nodes, std::max<size_t>(pn.size(), 1) * sizeof(PathANode)));
+  RDN_CUDA(cudaMalloc(&b->d_tris, std::max<size_t>(pt.size(), 1) * sizeof(PathATri)));
+  RDN_CUDA(cudaMemcpy(b->d_nodes, pn.data(), pn.size() * sizeof(PathANode), cudaMemcpyHostToDevice));
+  RDN_CUDA(cudaMemcpy(b->d_tris, pt.data(), pt.size() * sizeof(PathATri), cudaMemcpyHostToDevice));
+  return RDN_OK;
+}
+
+int rdn_bvh_query_nearest_device(const rdn_flat_bvh *b, const rdn_ray *d_rays, uint64_t n, uint32_t face_side, rdn_mesh_hit *d_out,
+                                 void *cuda_stream) {
+  if (!b || (n && (!d_rays || !d_out))) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_bvh_query_nearest_device: null argument");
+  if (face_side > RDN_FACE_DOUBLE) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_bvh_query_nearest_device: bad face_side");
+  if (b->device < 0 || !b->d_nodes) return fail(RDN_ERR_NOT_COMMITTED, "rdn_bvh_query_nearest_device: call rdn_bvh_upload first");
+  RDN_CUDA(cudaSetDevice(b->device));
+  if (b->bvh.nodes.empty()) {  // empty tree: every query is OptionalNearest::none()
+    RDN_CUDA(cudaMemsetAsync(d_out, 0, n * sizeof(rdn_mesh_hit), static_cast<cudaStream_t>(cuda_stream)));
+    return RDN_OK;
+  }
+  launch_patha_nearest(b->d_nodes, b->d_tris, d_rays, n, face_side, d_out, static_cast<cudaStream_t>(cuda_stream));
+  RDN_CUDA(cudaGetLastError());
+  return RDN_OK;
+}
 
 int rdn_bvh_nodes(const rdn_flat_bvh *b, const rdn_flat_bvh_node **out_nodes, uint64_t *out_n) {
   if (!b || !out_nodes || !out_n) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_bvh_nodes: null argument");
@@ -873,37 +946,17 @@ int rdn_bvh_query_nearest(const rdn_flat_bvh *b, const rdn_mesh_view *mesh, cons
                           int device, rdn_mesh_hit *out) {
   if (!b || !mesh || !mesh->positions || !mesh->indices || (n && (!rays || !out))) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_bvh_query_nearest: null argument");
   if (face_side > RDN_FACE_DOUBLE) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_bvh_query_nearest: bad face_side");
-  if (b->depth > static_cast<uint64_t>(PATHA_MAX_DEPTH)) return fail(RDN_ERR_CAPACITY, "rdn_bvh_query_nearest: tree deeper than 128 levels");
-  if (b->bvh.sorted_primitive_index.size() * 3 > mesh->n_indices) return fail(RDN_ERR_INVALID_ARGUMENT, "mesh smaller than the BVH it was built for");
-  RDN_CUDA(cudaSetDevice(device));
-  const auto &nodes = b->bvh.nodes;
-  std::vector<PathANode> pn(nodes.size());
-  for (size_t i = 0; i < nodes.size(); ++i) {
-    const FlattenBVHNode &nd = nodes[i];
-    PathANode &p = pn[i];
-    p.bmin[0] = nd.bounding.min.x; p.bmin[1] = nd.bounding.min.y; p.bmin[2] = nd.bounding.min.z;
-    p.bmax[0] = nd.bounding.max.x; p.bmax[1] = nd.bounding.max.y; p.bmax[2] = nd.bounding.max.z;
-    if (nd.has_child) { p.a = static_cast<uint32_t>(nd.right_child_offset()); p.b = 0xFFFFFFFFu; }
-    else { p.a = static_cast<uint32_t>(nd.primitive_start); p.b = static_cast<uint32_t>(nd.primitive_end); }
-  }
-  std::vector<uint32_t> sorted(b->bvh.sorted_primitive_index.begin(), b->bvh.sorted_primitive_index.end());
-  PathANode *d_nodes = nullptr; uint32_t *d_sorted = nullptr, *d_idx = nullptr; float *d_pos = nullptr;
+  // the mesh is borrowed per call (as in intersect_nearest_bvh(mesh, ray, bvh, conf)): gather + upload it, then run the resident query
+  int rc = rdn_bvh_upload(const_cast<rdn_flat_bvh *>(b), mesh, device);
+  if (rc != RDN_OK) return rc;
   rdn_ray *d_rays = nullptr; rdn_mesh_hit *d_out = nullptr;
-  auto cleanup = [&]() { cudaFree(d_nodes); cudaFree(d_sorted); cudaFree(d_idx); cudaFree(d_pos); cudaFree(d_rays); cudaFree(d_out); };
+  auto cleanup = [&]() { cudaFree(d_rays); cudaFree(d_out); };
 #define RDN_CUDA_C(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); return fail(RDN_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
-  RDN_CUDA_C(cudaMalloc(&d_nodes, std::max<size_t>(pn.size(), 1) * sizeof(PathANode)));
-  RDN_CUDA_C(cudaMalloc(&d_sorted, std::max<size_t>(sorted.size(), 1) * 4));
-  RDN_CUDA_C(cudaMalloc(&d_idx, std::max<uint64_t>(mesh->n_indices, 1) * 4));
-  RDN_CUDA_C(cudaMalloc(&d_pos, std::max<uint64_t>(mesh->n_positions, 1) * 12));
   RDN_CUDA_C(cudaMalloc(&d_rays, std::max<uint64_t>(n, 1) * sizeof(rdn_ray)));
   RDN_CUDA_C(cudaMalloc(&d_out, std::max<uint64_t>(n, 1) * sizeof(rdn_mesh_hit)));
-  RDN_CUDA_C(cudaMemcpy(d_nodes, pn.data(), pn.size() * sizeof(PathANode), cudaMemcpyHostToDevice));
-  RDN_CUDA_C(cudaMemcpy(d_sorted, sorted.data(), sorted.size() * 4, cudaMemcpyHostToDevice));
-  RDN_CUDA_C(cudaMemcpy(d_idx, mesh->indices, mesh->n_indices * 4, cudaMemcpyHostToDevice));
-  RDN_CUDA_C(cudaMemcpy(d_pos, mesh->positions, mesh->n_positions * 12, cudaMemcpyHostToDevice));
   RDN_CUDA_C(cudaMemcpy(d_rays, rays, n * sizeof(rdn_ray), cudaMemcpyHostToDevice));
-  launch_patha_nearest(d_nodes, d_sorted, d_pos, d_idx, d_rays, n, face_side, d_out, nullptr);
-  RDN_CUDA_C(cudaGetLastError());
+  rc = rdn_bvh_query_nearest_device(b, d_rays, n, face_side, d_out, nullptr);
+  if (rc != RDN_OK) { cleanup(); return rc; }
   RDN_CUDA_C(cudaDeviceSynchronize());
   RDN_CUDA_C(cudaMemcpy(out, d_out, n * sizeof(rdn_mesh_hit), cudaMemcpyDeviceToHost));
   cleanup();

@@ -186,8 +186,7 @@ __device__ __forceinline__ bool ray_triangle_a(Vec3 origin, Vec3 dir, Vec3 a, Ve
   return true;
 }
 
-__global__ void __launch_bounds__(128) k_patha_nearest(const PathANode *__restrict__ nodes, const uint32_t *__restrict__ sorted_prims,
-                                                       const float *__restrict__ positions, const uint32_t *__restrict__ indices,
+__global__ void __launch_bounds__(128) k_patha_nearest(const PathANode *__restrict__ nodes, const PathATri *__restrict__ tris,
                                                        const rdn_ray *__restrict__ rays, uint64_t n, uint32_t face_side,
                                                        rdn_mesh_hit *__restrict__ out) {
   uint32_t stack[PATHA_MAX_DEPTH + 2];
@@ -206,14 +205,12 @@ __global__ void __launch_bounds__(128) k_patha_nearest(const PathANode *__restri
       const float4 n0 = __ldg(np), n1 = __ldg(np + 1);
       const uint32_t a = __float_as_uint(n0.w), b = __float_as_uint(n1.w);
       if (b != 0xFFFFFFFFu) {
-        for (uint32_t k = a; k < b; ++k) {
-          const uint32_t prim = sorted_prims[k];
-          const uint32_t i0 = indices[3ull * prim], i1 = indices[3ull * prim + 1], i2 = indices[3ull * prim + 2];
-          const Vec3 va = {positions[3ull * i0], positions[3ull * i0 + 1], positions[3ull * i0 + 2]};
-          const Vec3 vb = {positions[3ull * i1], positions[3ull * i1 + 1], positions[3ull * i1 + 2]};
-          const Vec3 vc = {positions[3ull * i2], positions[3ull * i2 + 1], positions[3ull * i2 + 2]};
+        for (uint32_t k = a; k < b; ++k) {  // slots in sorted_primitive_index order: one contiguous 48 B record each
+          const float4 *tp = reinterpret_cast<const float4 *>(tris + k);
+          const float4 qa = __ldg(tp), qb = __ldg(tp + 1), qc = __ldg(tp + 2);
           float t;
-          if (ray_triangle_a(origin, dir, va, vb, vc, face_side, t) && (!have || t < best_t)) { best_t = t; best_prim = prim; have = 1; }
+          if (ray_triangle_a(origin, dir, Vec3{qa.x, qa.y, qa.z}, Vec3{qb.x, qb.y, qb.z}, Vec3{qc.x, qc.y, qc.z}, face_side, t) &&
+              (!have || t < best_t)) { best_t = t; best_prim = __float_as_uint(qa.w); have = 1; }
         }
       } else if (ray_box_a(origin, dir, Vec3{n0.x, n0.y, n0.z}, Vec3{n1.x, n1.y, n1.z})) {
         if (sp + 2 <= PATHA_MAX_DEPTH + 2) {
@@ -250,13 +247,12 @@ void launch_compact_u32(const uint32_t *d_in, const uint8_t *d_keep, uint64_t n,
   k_zero_tail_u32<<<zb, 256, 0, stream>>>(d_out, d_out_n, n);
 }
 
-void launch_patha_nearest(const PathANode *d_nodes, const uint32_t *d_sorted_prims, const float *d_positions,
-                          const uint32_t *d_indices, const rdn_ray *d_rays, uint64_t n, uint32_t face_side, rdn_mesh_hit *d_out,
-                          cudaStream_t stream) {
+void launch_patha_nearest(const PathANode *d_nodes, const PathATri *d_tris, const rdn_ray *d_rays, uint64_t n, uint32_t face_side,
+                          rdn_mesh_hit *d_out, cudaStream_t stream) {
   if (n == 0) return;
   uint64_t blocks = (n + 127) / 128;
   if (blocks > 148ull * 64) blocks = 148ull * 64;
-  k_patha_nearest<<<static_cast<unsigned>(blocks), 128, 0, stream>>>(d_nodes, d_sorted_prims, d_positions, d_indices, d_rays, n, face_side, d_out);
+  k_patha_nearest<<<static_cast<unsigned>(blocks), 128, 0, stream>>>(d_nodes, d_tris, d_rays, n, face_side, d_out);
 }
 
 }  // namespace rdn

@@ -76,11 +76,15 @@ void launch_gen_bounce_rays(const SceneDev &scene, const rdn_bounce &p, const rd
 // the tree in the reference's order (right child first, no distance pruning) so equal-distance ties resolve identically.
 constexpr int PATHA_MAX_DEPTH = 128;
 struct PathANode {  // 32 B: box + (left_count | leaf range)
-  float bmin[3]; uint32_t a;   // inner: right child index; leaf: primitive_start
-  float bmax[3]; uint32_t b;   // inner: 0xFFFFFFFF;        leaf: primitive_end (leaf iff b != 0xFFFFFFFF)
+  float bmin[3]; uint32_t a;   // inner: right child index; leaf: first slot
+  float bmax[3]; uint32_t b;   // inner: 0xFFFFFFFF;        leaf: one past the last slot (leaf iff b != 0xFFFFFFFF)
 };
-void launch_patha_nearest(const PathANode *d_nodes, const uint32_t *d_sorted_prims,
-                          const float *d_positions, const uint32_t *d_indices, const rdn_ray *d_rays, uint64_t n,
-                          uint32_t face_side, rdn_mesh_hit *d_out, cudaStream_t stream);
+struct PathATri {  // 48 B: the triangle of a slot (sorted_primitive_index order), pre-gathered through indices -> positions
+  float a[3]; uint32_t prim;   // original primitive index (MeshBufferHitPoint::primitive_index)
+  float b[3]; uint32_t pad0;
+  float c[3]; uint32_t pad1;
+};
+void launch_patha_nearest(const PathANode *d_nodes, const PathATri *d_tris, const rdn_ray *d_rays, uint64_t n, uint32_t face_side,
+                          rdn_mesh_hit *d_out, cudaStream_t stream);
 
 }  // namespace rdn

@@ -218,6 +218,40 @@ def test_path_a_space_query_matches_oracle():
             assert want["hit"].sum() > 1000
 
 
+def test_path_a_device_resident_query_and_edge_cases():
+    """upload once / query device buffers; n = 0; a query before upload is an error code; empty tree answers none"""
+    import torch
+    pos, idx = S.uv_sphere_mesh(24, 24)  # has zero-area pole triangles: DdN == 0 -> none, as in the reference
+    wpos = S.mat4_apply_point(S.mat4_mul(S.mat4_translate(0, 0, -10), S.mat4_scale(5, 5, 5)), pos)
+    tri = idx.reshape(-1, 3)
+    boxes = np.concatenate([wpos[tri].min(1), wpos[tri].max(1)], 1)
+    rays = S.pinhole_rays(160, 120, 0.0, 100.0)
+    ob = oracle.FlattenBVH(boxes, oracle.STRATEGY_SAH, 4, 50, 2)
+    pb = api.build_bvh_for_abstract_mesh(wpos, idx, api.SAH(4), api.TreeBuildOption(50, 2))
+    d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1, 32).copy()).cuda()
+    d_out = torch.full((rays.shape[0], 32), 0xAB, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    with pytest.raises(api.RdnError):
+        api.intersect_nearest_bvh_device(pb, d_rays.data_ptr(), rays.shape[0], d_out.data_ptr(), api.FACE_DOUBLE, st)
+    api.upload_bvh(pb, wpos, idx, 0)
+    api.intersect_nearest_bvh_device(pb, d_rays.data_ptr(), 0, d_out.data_ptr(), api.FACE_DOUBLE, st)  # nothing to do
+    for side in (api.FACE_FRONT, api.FACE_BACK, api.FACE_DOUBLE):
+        api.intersect_nearest_bvh_device(pb, d_rays.data_ptr(), rays.shape[0], d_out.data_ptr(), side, st)
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy().view(api.MESH_HIT_DTYPE).reshape(-1)
+        want = ob.query_nearest(wpos, idx, rays, side, 4)
+        assert got.tobytes() == want.tobytes(), side
+    # brute force over the same mesh agrees (the BVH only prunes)
+    brute = oracle.brute_query_nearest(wpos, idx, rays, api.FACE_DOUBLE, 4)
+    assert np.array_equal(brute["hit"], want["hit"]) and np.array_equal(brute["distance"][want["hit"] == 1], want["distance"][want["hit"] == 1])
+    # empty mesh -> empty tree -> every ray is OptionalNearest::none()
+    eb = api.build_bvh_for_abstract_mesh(wpos[:3], np.zeros(0, np.uint32), api.SAH(4), api.TreeBuildOption(50, 2))
+    api.upload_bvh(eb, wpos[:3], np.zeros(0, np.uint32), 0)
+    api.intersect_nearest_bvh_device(eb, d_rays.data_ptr(), rays.shape[0], d_out.data_ptr(), api.FACE_DOUBLE, st)
+    torch.cuda.synchronize()
+    assert not d_out.any().item()
+
+
 # ---- wavefront queue compaction ---------------------------------------------------------------------
 def test_compaction_known_answers_and_random():
     s = api.NaiveSahBVHSystem()
