@@ -171,6 +171,9 @@ typedef struct rdn_pinhole {
 } rdn_pinhole;
 int rdn_rt_gen_pinhole_rays_device(rdn_rt_scene *scene, int device_index, const rdn_pinhole *params, rdn_ray *d_rays,
                                    void *cuda_stream);
+/* n_params rectangles (launch tiles x samples) in ONE kernel launch: the rays of params[k] follow those of params[k-1] in d_rays */
+int rdn_rt_gen_pinhole_rays_batch_device(rdn_rt_scene *scene, int device_index, const rdn_pinhole *params, uint32_t n_params,
+                                         rdn_ray *d_rays, void *cuda_stream);
 /* DefaultRtxCameraInvocation::generate_ray (scene/rendering/gpu-ray-tracing/src/camera.rs:66-98):
  * uv = pixel / size + sampler.next_2d() / size with PCGRandomSampler seeded by xxhash32(pixel.x, pixel.y, sample_index)
  * (sampler.rs:11-72); target = unproject(view_projection_inv, uv, ndc_depth) (shader/library/src/lib.rs:18-28);
@@ -247,6 +250,12 @@ int rdn_bvh_build_for_mesh(const rdn_mesh_view *mesh, int strategy, uint32_t sah
 int rdn_bvh_query_nearest(const rdn_flat_bvh *bvh, const rdn_mesh_view *mesh, const rdn_ray *rays, uint64_t n,
                           uint32_t face_side, int device, rdn_mesh_hit *out);
 
+/* intersect_list_bvh (content/mesh/core/src/feature/bvh.rs:23-55) for a batch of rays: EVERY intersected primitive, as a CSR
+ * list — the hits of ray i are out_hits[out_offsets[i] .. out_offsets[i+1]) in the reference's Vec order (right-first DFS, leaf
+ * primitives in sorted_primitive_index order).  out_offsets has n + 1 slots; *out_total = number of hits.  Two-call protocol:
+ * with out_hits == NULL (or capacity < total) only offsets and total are produced. */
+int rdn_bvh_query_list(const rdn_flat_bvh *bvh, const rdn_mesh_view *mesh, const rdn_ray *rays, uint64_t n, uint32_t face_side,
+                       int device, uint64_t *out_offsets, rdn_mesh_hit *out_hits, uint64_t capacity, uint64_t *out_total);
 /* device-resident form: gather the mesh through the BVH's sorted_primitive_index and upload it with the nodes once, then
  * query any number of device ray batches (asynchronous on cuda_stream) */
 int rdn_bvh_upload(rdn_flat_bvh *bvh, const rdn_mesh_view *mesh, int device);

@@ -91,6 +91,8 @@ def lib() -> C.CDLL:
     L.orc_ray_box_a.restype = i32
     L.orc_ray_box_a.argtypes = [vp, vp]
     L.orc_patha_query_nearest.argtypes = [C.POINTER(_Bvh), vp, vp, vp, u64, i32, vp, i32]
+    L.orc_patha_query_list.argtypes = [C.POINTER(_Bvh), vp, vp, vp, u64, i32, vp, vp, u64]
+    L.orc_patha_query_list.restype = u64
     L.orc_brute_query_nearest.argtypes = [vp, vp, u64, vp, u64, i32, vp, i32]
     L.orc_scene_new.restype = vp
     L.orc_scene_free.argtypes = [vp]
@@ -162,6 +164,17 @@ class FlattenBVH:
         out = np.zeros(rays.shape[0], MESH_HIT_DTYPE)
         lib().orc_patha_query_nearest(self._h, _p(positions), _p(indices), _p(rays), rays.shape[0], face_side, _p(out), n_threads)
         return out
+
+    def query_list(self, positions, indices, rays, face_side=FACE_DOUBLE):
+        """intersect_list_bvh for every ray: (offsets[n+1], hits[total]) in the reference's visiting order"""
+        positions = _c(positions, np.float32); indices = _c(indices, np.uint32)
+        rays = _c(rays, RAY_DTYPE)
+        offsets = np.zeros(rays.shape[0] + 1, np.uint64)
+        L = lib()
+        total = L.orc_patha_query_list(self._h, _p(positions), _p(indices), _p(rays), rays.shape[0], face_side, _p(offsets), None, 0)
+        out = np.zeros(int(total), MESH_HIT_DTYPE)
+        L.orc_patha_query_list(self._h, _p(positions), _p(indices), _p(rays), rays.shape[0], face_side, _p(offsets), _p(out), int(total))
+        return offsets, out
 
     def __del__(self):
         if getattr(self, "_h", None) is not None and _lib is not None:

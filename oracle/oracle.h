@@ -74,6 +74,9 @@ int orc_ray_triangle_a(const float *ray_od6, ov3 a, ov3 b, ov3 c, int face_side,
 void orc_patha_query_nearest(const orc_bvh *bvh, const float *positions, const uint32_t *indices,
                              const orc_ray *rays, uint64_t n_rays, int face_side, orc_mesh_hit *out,
                              int n_threads);
+/* intersect_list_bvh (feature/bvh.rs:23-55): CSR list of every intersection per ray, in visiting order; returns the total */
+uint64_t orc_patha_query_list(const orc_bvh *bvh, const float *positions, const uint32_t *indices, const orc_ray *rays,
+                              uint64_t n_rays, int face_side, uint64_t *offsets, orc_mesh_hit *out, uint64_t capacity);
 /* brute force ray_intersect_nearest (content/mesh/core/src/feature/intersection.rs:11-37) */
 void orc_brute_query_nearest(const float *positions, const uint32_t *indices, uint64_t n_tris,
                              const orc_ray *rays, uint64_t n_rays, int face_side, orc_mesh_hit *out,

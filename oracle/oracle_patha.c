@@ -196,6 +196,46 @@ void orc_brute_query_nearest(const float *positions, const uint32_t *indices, ui
   run_jobs(j, n_rays, n_threads, brute_worker);
 }
 
+/* intersect_list_bvh (content/mesh/core/src/feature/bvh.rs:23-55): every intersected primitive in visiting order (same
+ * right-first DFS, primitives of a leaf in sorted_primitive_index order).  Pass out == NULL to count only.  Single thread:
+ * the list of one ray is appended after the previous ray's (CSR: offsets[i] .. offsets[i+1]). */
+uint64_t orc_patha_query_list(const orc_bvh *bvh, const float *positions, const uint32_t *indices, const orc_ray *rays,
+                              uint64_t n_rays, int face_side, uint64_t *offsets, orc_mesh_hit *out, uint64_t capacity) {
+  uint64_t *stack = (uint64_t *)malloc((bvh->n_nodes + 2) * sizeof(uint64_t));
+  uint64_t total = 0;
+  for (uint64_t i = 0; i < n_rays; i++) {
+    const orc_ray *ray = &rays[i];
+    float r[6] = {ray->ox, ray->oy, ray->oz, ray->dx, ray->dy, ray->dz};
+    offsets[i] = total;
+    uint64_t sp = 0;
+    stack[sp++] = 0;
+    while (sp > 0) {
+      const orc_bvh_node *node = &bvh->nodes[stack[--sp]];
+      if (!node->has_child) {
+        for (uint64_t k = node->start; k < node->end; k++) {
+          uint64_t prim = bvh->sorted_primitive_index[k];
+          ov3 a, b, c; tri_of(positions, indices, prim, &a, &b, &c);
+          float pd[4];
+          if (orc_ray_triangle_a(r, a, b, c, face_side, pd)) {
+            if (out && total < capacity) {
+              orc_mesh_hit *h = &out[total];
+              memset(h, 0, sizeof(*h));
+              h->px = pd[0]; h->py = pd[1]; h->pz = pd[2]; h->distance = pd[3]; h->primitive_index = (uint32_t)prim; h->hit = 1;
+            }
+            total++;
+          }
+        }
+      } else if (orc_ray_box_a(r, &node->bounding)) {
+        stack[sp++] = node->self_index + 1;
+        stack[sp++] = node->self_index + node->left_count + 1;
+      }
+    }
+  }
+  offsets[n_rays] = total;
+  free(stack);
+  return total;
+}
+
 /* ---- parallel-compute restatements ---- */
 
 /* Kogge-Stone per workgroup: after log2(W) steps value[i] = sum of its workgroup prefix (prefix_scan.rs:64-101) */

@@ -134,9 +134,9 @@ EXPORTED_SYMBOLS = [
     "rdn_rt_scene_create", "rdn_rt_scene_destroy", "rdn_rt_blas_create", "rdn_rt_blas_destroy", "rdn_rt_tlas_create",
     "rdn_rt_tlas_destroy", "rdn_rt_bind_tlas", "rdn_rt_bind_tlas_max_len", "rdn_rt_commit", "rdn_rt_trace_closest",
     "rdn_rt_trace_closest_device", "rdn_rt_trace_counted", "rdn_rt_kernel_timing_begin", "rdn_rt_kernel_timing_end",
-    "rdn_rt_gen_pinhole_rays_device", "rdn_rt_gen_camera_rays_device", "rdn_rt_gen_bounce_rays_device", "rdn_rt_compact_u32", "rdn_rt_compact_u32_device",
+    "rdn_rt_gen_pinhole_rays_device", "rdn_rt_gen_pinhole_rays_batch_device", "rdn_rt_gen_camera_rays_device", "rdn_rt_gen_bounce_rays_device", "rdn_rt_compact_u32", "rdn_rt_compact_u32_device",
     "rdn_rt_scene_blob", "rdn_rt_scene_adopt_blob", "rdn_rt_scene_array", "rdn_bvh_build", "rdn_bvh_destroy", "rdn_bvh_nodes",
-    "rdn_bvh_sorted_primitive_index", "rdn_bvh_build_for_mesh", "rdn_bvh_query_nearest", "rdn_bvh_upload", "rdn_bvh_query_nearest_device", "rdn_rt_last_error", "rdn_rt_version",
+    "rdn_bvh_sorted_primitive_index", "rdn_bvh_build_for_mesh", "rdn_bvh_query_nearest", "rdn_bvh_upload", "rdn_bvh_query_nearest_device", "rdn_bvh_query_list", "rdn_rt_last_error", "rdn_rt_version",
 ]
 
 _lib = None
@@ -172,6 +172,7 @@ def lib() -> C.CDLL:
     L.rdn_rt_kernel_timing_begin.argtypes = [vp, i32]
     L.rdn_rt_kernel_timing_end.argtypes = [vp, i32, P(_KernelTimes)]
     L.rdn_rt_gen_pinhole_rays_device.argtypes = [vp, i32, P(_Pinhole), vp, vp]
+    L.rdn_rt_gen_pinhole_rays_batch_device.argtypes = [vp, i32, P(_Pinhole), u32, vp, vp]
     L.rdn_rt_gen_camera_rays_device.argtypes = [vp, i32, P(_Camera), vp, vp]
     L.rdn_rt_gen_bounce_rays_device.argtypes = [vp, i32, P(_Bounce), vp, vp, u64, vp, vp, vp, vp]
     L.rdn_rt_compact_u32.argtypes = [vp, vp, vp, u64, vp, P(u64)]
@@ -187,6 +188,7 @@ def lib() -> C.CDLL:
     L.rdn_bvh_sorted_primitive_index.argtypes = [vp, P(vp), P(u64)]
     L.rdn_bvh_query_nearest.argtypes = [vp, P(_MeshView), vp, u64, u32, i32, vp]
     L.rdn_bvh_upload.argtypes = [vp, P(_MeshView), i32]
+    L.rdn_bvh_query_list.argtypes = [vp, P(_MeshView), vp, u64, u32, i32, vp, vp, u64, P(u64)]
     L.rdn_bvh_query_nearest_device.argtypes = [vp, vp, u64, u32, vp, vp]
     _lib = L
     return L
@@ -336,6 +338,18 @@ class NaiveSahBVHSystem:
         _check(self._L.rdn_rt_gen_pinhole_rays_device(self._h, device_index, C.byref(p), C.c_void_p(d_rays), C.c_void_p(stream)))
         return w * h
 
+    def gen_pinhole_rays_batch_device(self, d_rays: int, width: int, height: int, rects, jitters, origin=(0.0, 0.0, 0.0), tmin=0.0,
+                                      tmax=100.0, aspect=1.0, stream: int = 0, device_index: int = 0) -> int:
+        """Many rectangles (launch tiles x samples) in one launch: ``rects[k]`` with sub-pixel offset ``jitters[k]``, written
+        back to back.  Returns the total ray count."""
+        arr = (_Pinhole * max(len(rects), 1))()
+        total = 0
+        for k, ((x0, y0, w, h), (jx, jy)) in enumerate(zip(rects, jitters)):
+            arr[k] = _Pinhole(width, height, x0, y0, w, h, (C.c_float * 3)(*origin), tmin, tmax, aspect, jx, jy)
+            total += w * h
+        _check(self._L.rdn_rt_gen_pinhole_rays_batch_device(self._h, device_index, arr, len(rects), C.c_void_p(d_rays), C.c_void_p(stream)))
+        return total
+
     def gen_camera_rays_device(self, d_rays: int, view_projection_inv, world_position, width: int, height: int, sample_index: int = 0,
                                rect=None, ndc_depth=1.0, tmin=0.0, tmax=3.4028235e38, stream: int = 0, device_index: int = 0) -> int:
         """DefaultRtxCameraInvocation::generate_ray (camera.rs:66-98) with the PCG sampler; returns the ray count."""
@@ -481,6 +495,21 @@ def build_bvh_for_abstract_mesh(positions, indices, strategy=None, option: TreeB
         rc = L.rdn_bvh_build_for_mesh(C.byref(mv), 1, 0, C.byref(opt), C.byref(h))
     _check(rc)
     return FlattenBVH(_handle=h)
+
+
+def intersect_list_bvh(positions, indices, rays, bvh: FlattenBVH, face_side: int = FACE_DOUBLE, device: int = 0):
+    """content/mesh/core/src/feature/bvh.rs:23-55 for a batch of rays: ``(offsets[n+1], hits[total])`` — the hits of ray ``i`` are
+    ``hits[offsets[i]:offsets[i+1]]`` in the reference's visiting order."""
+    L = lib()
+    mv, _keep = _mesh_view(positions, indices)
+    rays = _c(rays, RAY_DTYPE)
+    offsets = np.zeros(rays.shape[0] + 1, np.uint64)
+    total = C.c_uint64()
+    _check(L.rdn_bvh_query_list(bvh._h, C.byref(mv), _p(rays), rays.shape[0], face_side, device, _p(offsets), None, 0, C.byref(total)))
+    out = np.zeros(int(total.value), MESH_HIT_DTYPE)
+    if total.value:
+        _check(L.rdn_bvh_query_list(bvh._h, C.byref(mv), _p(rays), rays.shape[0], face_side, device, _p(offsets), _p(out), int(total.value), C.byref(total)))
+    return offsets, out
 
 
 def upload_bvh(bvh: FlattenBVH, positions, indices, device: int = 0) -> None:

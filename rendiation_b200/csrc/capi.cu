@@ -592,6 +592,41 @@ int rdn_rt_gen_pinhole_rays_device(rdn_rt_scene *s, int device_index, const rdn_
   return RDN_OK;
 }
 
+int rdn_rt_gen_pinhole_rays_batch_device(rdn_rt_scene *s, int device_index, const rdn_pinhole *params, uint32_t n_params, rdn_ray *d_rays,
+                                         void *cuda_stream) {
+  if (!s || (n_params && (!params || !d_rays))) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_gen_pinhole_rays_batch_device: null argument");
+  if (device_index < 0 || device_index >= static_cast<int>(s->devices.size())) return fail(RDN_ERR_INVALID_ARGUMENT, "bad device_index");
+  if (n_params == 0) return RDN_OK;
+  std::vector<uint64_t> offsets(n_params);
+  uint64_t total = 0, biggest = 0;
+  for (uint32_t k = 0; k < n_params; ++k) {
+    const rdn_pinhole &p = params[k];
+    if (p.width == 0 || p.height == 0 || p.rect_x + static_cast<uint64_t>(p.rect_w) > p.width || p.rect_y + static_cast<uint64_t>(p.rect_h) > p.height)
+      return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_gen_pinhole_rays_batch_device: rectangle outside the launch");
+    offsets[k] = total;
+    const uint64_t m = static_cast<uint64_t>(p.rect_w) * p.rect_h;
+    total += m;
+    biggest = std::max(biggest, m);
+  }
+  RDN_CUDA(cudaSetDevice(s->devices[device_index].device));
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  // descriptors travel through a stream-ordered allocation, so calls on different streams never share them
+  rdn_pinhole *d_params = nullptr;
+  uint64_t *d_offsets = nullptr;
+  RDN_CUDA(cudaMallocAsync(&d_params, n_params * sizeof(rdn_pinhole), stream));
+  RDN_CUDA(cudaMallocAsync(&d_offsets, n_params * sizeof(uint64_t), stream));
+  RDN_CUDA(cudaMemcpyAsync(d_params, params, n_params * sizeof(rdn_pinhole), cudaMemcpyHostToDevice, stream));
+  RDN_CUDA(cudaMemcpyAsync(d_offsets, offsets.data(), n_params * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+  for (uint32_t first = 0; first < n_params; first += 65535u) {
+    const uint32_t m = std::min<uint32_t>(65535u, n_params - first);
+    launch_gen_pinhole_rays_batch(d_params + first, d_offsets + first, m, biggest, d_rays, stream);
+  }
+  RDN_CUDA(cudaGetLastError());
+  RDN_CUDA(cudaFreeAsync(d_params, stream));
+  RDN_CUDA(cudaFreeAsync(d_offsets, stream));
+  return RDN_OK;
+}
+
 int rdn_rt_gen_camera_rays_device(rdn_rt_scene *s, int device_index, const rdn_camera *p, rdn_ray *d_rays, void *cuda_stream) {
   if (!s || !p || !d_rays) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_gen_camera_rays_device: null argument");
   if (device_index < 0 || device_index >= static_cast<int>(s->devices.size())) return fail(RDN_ERR_INVALID_ARGUMENT, "bad device_index");
@@ -959,6 +994,38 @@ int rdn_bvh_query_nearest(const rdn_flat_bvh *b, const rdn_mesh_view *mesh, cons
   if (rc != RDN_OK) { cleanup(); return rc; }
   RDN_CUDA_C(cudaDeviceSynchronize());
   RDN_CUDA_C(cudaMemcpy(out, d_out, n * sizeof(rdn_mesh_hit), cudaMemcpyDeviceToHost));
+  cleanup();
+  return RDN_OK;
+}
+
+int rdn_bvh_query_list(const rdn_flat_bvh *b, const rdn_mesh_view *mesh, const rdn_ray *rays, uint64_t n, uint32_t face_side, int device,
+                       uint64_t *out_offsets, rdn_mesh_hit *out_hits, uint64_t capacity, uint64_t *out_total) {
+  if (!b || !mesh || !mesh->positions || !mesh->indices || !out_offsets || !out_total || (n && !rays))
+    return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_bvh_query_list: null argument");
+  if (face_side > RDN_FACE_DOUBLE) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_bvh_query_list: bad face_side");
+  int rc = rdn_bvh_upload(const_cast<rdn_flat_bvh *>(b), mesh, device);
+  if (rc != RDN_OK) return rc;
+  rdn_ray *d_rays = nullptr; uint32_t *d_counts = nullptr; uint64_t *d_offsets = nullptr; rdn_mesh_hit *d_out = nullptr;
+  auto cleanup = [&]() { cudaFree(d_rays); cudaFree(d_counts); cudaFree(d_offsets); cudaFree(d_out); };
+  RDN_CUDA_C(cudaMalloc(&d_rays, std::max<uint64_t>(n, 1) * sizeof(rdn_ray)));
+  RDN_CUDA_C(cudaMalloc(&d_counts, std::max<uint64_t>(n, 1) * sizeof(uint32_t)));
+  RDN_CUDA_C(cudaMemcpy(d_rays, rays, n * sizeof(rdn_ray), cudaMemcpyHostToDevice));
+  launch_patha_list(b->d_nodes, b->d_tris, d_rays, n, face_side, d_counts, nullptr, nullptr, nullptr);
+  RDN_CUDA_C(cudaGetLastError());
+  std::vector<uint32_t> counts(n);
+  RDN_CUDA_C(cudaMemcpy(counts.data(), d_counts, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  uint64_t total = 0;  // exclusive scan on the host: the call is host-buffer bound anyway
+  for (uint64_t i = 0; i < n; ++i) { out_offsets[i] = total; total += counts[i]; }
+  out_offsets[n] = total;
+  *out_total = total;
+  if (!out_hits || capacity < total || total == 0) { cleanup(); return RDN_OK; }  // size query, or nothing to write
+  RDN_CUDA_C(cudaMalloc(&d_offsets, (n + 1) * sizeof(uint64_t)));
+  RDN_CUDA_C(cudaMalloc(&d_out, total * sizeof(rdn_mesh_hit)));
+  RDN_CUDA_C(cudaMemcpy(d_offsets, out_offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  launch_patha_list(b->d_nodes, b->d_tris, d_rays, n, face_side, nullptr, d_offsets, d_out, nullptr);
+  RDN_CUDA_C(cudaGetLastError());
+  RDN_CUDA_C(cudaDeviceSynchronize());
+  RDN_CUDA_C(cudaMemcpy(out_hits, d_out, total * sizeof(rdn_mesh_hit), cudaMemcpyDeviceToHost));
   cleanup();
   return RDN_OK;
 }

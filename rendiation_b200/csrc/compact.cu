@@ -226,6 +226,55 @@ __global__ void __launch_bounds__(128) k_patha_nearest(const PathANode *__restri
   }
 }
 
+// intersect_list_bvh (content/mesh/core/src/feature/bvh.rs:23-55): the same right-first DFS, but EVERY intersected primitive
+// is reported, in visiting order.  FILL = false counts the hits of each ray; FILL = true writes them at offsets[ray] (exclusive
+// scan of the counts), so the ragged result is a CSR list whose per-ray order is the reference's Vec order.
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_patha_list(const PathANode *__restrict__ nodes, const PathATri *__restrict__ tris,
+                                                    const rdn_ray *__restrict__ rays, uint64_t n, uint32_t face_side,
+                                                    uint32_t *__restrict__ counts, const uint64_t *__restrict__ offsets,
+                                                    rdn_mesh_hit *__restrict__ out) {
+  uint32_t stack[PATHA_MAX_DEPTH + 2];
+  for (uint64_t ri = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; ri < n;
+       ri += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const float4 r0 = __ldg(reinterpret_cast<const float4 *>(rays + ri));
+    const float4 r1 = __ldg(reinterpret_cast<const float4 *>(rays + ri) + 1);
+    const Vec3 origin = {r0.x, r0.y, r0.z}, dir = {r1.x, r1.y, r1.z};
+    uint32_t found = 0;
+    uint64_t dst = FILL ? offsets[ri] : 0;
+    int sp = 0;
+    stack[sp++] = 0;
+    while (sp > 0) {
+      const uint32_t ni = stack[--sp];
+      const float4 *np = reinterpret_cast<const float4 *>(nodes + ni);
+      const float4 n0 = __ldg(np), n1 = __ldg(np + 1);
+      const uint32_t a = __float_as_uint(n0.w), b = __float_as_uint(n1.w);
+      if (b != 0xFFFFFFFFu) {
+        for (uint32_t k = a; k < b; ++k) {
+          const float4 *tp = reinterpret_cast<const float4 *>(tris + k);
+          const float4 qa = __ldg(tp), qb = __ldg(tp + 1), qc = __ldg(tp + 2);
+          float t;
+          if (!ray_triangle_a(origin, dir, Vec3{qa.x, qa.y, qa.z}, Vec3{qb.x, qb.y, qb.z}, Vec3{qc.x, qc.y, qc.z}, face_side, t)) continue;
+          if (FILL) {
+            const Vec3 p = origin + dir * t;
+            float4 *o = reinterpret_cast<float4 *>(out + dst);
+            o[0] = make_float4(p.x, p.y, p.z, t);
+            o[1] = make_float4(qa.w, __uint_as_float(1u), 0.f, 0.f);
+            ++dst;
+          }
+          ++found;
+        }
+      } else if (ray_box_a(origin, dir, Vec3{n0.x, n0.y, n0.z}, Vec3{n1.x, n1.y, n1.z})) {
+        if (sp + 2 <= PATHA_MAX_DEPTH + 2) {
+          stack[sp++] = ni + 1;
+          stack[sp++] = a;
+        }
+      }
+    }
+    if (!FILL) counts[ri] = found;
+  }
+}
+
 }  // namespace
 
 uint64_t compact_status_words(uint64_t n) { return 2 + (n + TILE - 1) / TILE; }
@@ -253,6 +302,15 @@ void launch_patha_nearest(const PathANode *d_nodes, const PathATri *d_tris, cons
   uint64_t blocks = (n + 127) / 128;
   if (blocks > 148ull * 64) blocks = 148ull * 64;
   k_patha_nearest<<<static_cast<unsigned>(blocks), 128, 0, stream>>>(d_nodes, d_tris, d_rays, n, face_side, d_out);
+}
+
+void launch_patha_list(const PathANode *d_nodes, const PathATri *d_tris, const rdn_ray *d_rays, uint64_t n, uint32_t face_side,
+                       uint32_t *d_counts, const uint64_t *d_offsets, rdn_mesh_hit *d_out, cudaStream_t stream) {
+  if (n == 0) return;
+  uint64_t blocks = (n + 127) / 128;
+  if (blocks > 148ull * 64) blocks = 148ull * 64;
+  if (d_out) k_patha_list<true><<<static_cast<unsigned>(blocks), 128, 0, stream>>>(d_nodes, d_tris, d_rays, n, face_side, nullptr, d_offsets, d_out);
+  else k_patha_list<false><<<static_cast<unsigned>(blocks), 128, 0, stream>>>(d_nodes, d_tris, d_rays, n, face_side, d_counts, nullptr, nullptr);
 }
 
 }  // namespace rdn

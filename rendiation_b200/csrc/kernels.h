@@ -66,6 +66,8 @@ void launch_compact_u32(const uint32_t *d_in, const uint8_t *d_keep, uint64_t n,
 
 // ray generation and the closest-hit -> bounce step on the device (raygen.cu)
 void launch_gen_pinhole_rays(const rdn_pinhole &p, rdn_ray *d_rays, cudaStream_t stream);
+void launch_gen_pinhole_rays_batch(const rdn_pinhole *d_params, const uint64_t *d_offsets, uint32_t n_params, uint64_t max_rays_per_param,
+                                   rdn_ray *d_rays, cudaStream_t stream);  // n_params <= 65535 per call
 void launch_gen_camera_rays(const rdn_camera &p, rdn_ray *d_rays, cudaStream_t stream);
 void launch_mark_hits(const rdn_hit *d_hits, uint64_t n, uint8_t *d_keep, uint32_t *d_iota, cudaStream_t stream);
 // d_src_index[0 .. *d_n_src) = indices of the source rays (stable compaction of the hits); n_max bounds the grid
@@ -86,5 +88,9 @@ struct PathATri {  // 48 B: the triangle of a slot (sorted_primitive_index order
 };
 void launch_patha_nearest(const PathANode *d_nodes, const PathATri *d_tris, const rdn_ray *d_rays, uint64_t n, uint32_t face_side,
                           rdn_mesh_hit *d_out, cudaStream_t stream);
+
+// intersect_list_bvh: d_out == nullptr -> per-ray hit counts into d_counts; else hits written at d_offsets[ray] in visiting order
+void launch_patha_list(const PathANode *d_nodes, const PathATri *d_tris, const rdn_ray *d_rays, uint64_t n, uint32_t face_side,
+                       uint32_t *d_counts, const uint64_t *d_offsets, rdn_mesh_hit *d_out, cudaStream_t stream);
 
 }  // namespace rdn

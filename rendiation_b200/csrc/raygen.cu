@@ -49,6 +49,24 @@ __global__ void __launch_bounds__(256) k_gen_pinhole_rays(const rdn_pinhole P, r
   }
 }
 
+// many rectangles in one launch: blockIdx.y = descriptor, rays of descriptor k start at offsets[k]
+__global__ void __launch_bounds__(256) k_gen_pinhole_rays_batch(const rdn_pinhole *__restrict__ params, const uint64_t *__restrict__ offsets,
+                                                                rdn_ray *__restrict__ rays) {
+  const rdn_pinhole P = params[blockIdx.y];
+  rdn_ray *dst = rays + offsets[blockIdx.y];
+  const uint64_t n = static_cast<uint64_t>(P.rect_w) * P.rect_h;
+  for (uint64_t k = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; k < n; k += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint32_t ry = static_cast<uint32_t>(k / P.rect_w), rx = static_cast<uint32_t>(k - static_cast<uint64_t>(ry) * P.rect_w);
+    const float i = static_cast<float>(P.rect_x + rx), j = static_cast<float>(P.rect_y + ry);
+    float x = (i + P.jitter_x) / static_cast<float>(P.width) * 2.0f - 1.0f;
+    const float y = 1.0f - (j + P.jitter_y) / static_cast<float>(P.height) * 2.0f;
+    if (P.aspect != 1.0f) x = x * P.aspect;
+    const Vec3 o = {P.origin[0], P.origin[1], P.origin[2]};
+    const Vec3 target = {x, y, -1.0f};
+    store_ray(dst + k, o, P.tmin, normalize(target - o), P.tmax);
+  }
+}
+
 // ---- sampler.rs:11-72
 __device__ __forceinline__ uint32_t xxhash32(uint32_t px, uint32_t py, uint32_t pz) {
   const uint32_t p0 = 2246822519u, p1 = 3266489917u, p2 = 668265263u, p3 = 374761393u;
@@ -214,6 +232,13 @@ int grid_for(uint64_t n, int block) {
 void launch_gen_pinhole_rays(const rdn_pinhole &p, rdn_ray *d_rays, cudaStream_t stream) {
   const uint64_t n = static_cast<uint64_t>(p.rect_w) * p.rect_h;
   if (n) k_gen_pinhole_rays<<<grid_for(n, 256), 256, 0, stream>>>(p, d_rays);
+}
+void launch_gen_pinhole_rays_batch(const rdn_pinhole *d_params, const uint64_t *d_offsets, uint32_t n_params, uint64_t max_rays_per_param,
+                                   rdn_ray *d_rays, cudaStream_t stream) {
+  if (n_params == 0 || max_rays_per_param == 0) return;
+  const uint64_t bx = (max_rays_per_param + 255) / 256;
+  const dim3 grid(static_cast<unsigned>(bx < 64 ? bx : 64), n_params);  // a few CTAs per rectangle, grid-stride inside
+  k_gen_pinhole_rays_batch<<<grid, 256, 0, stream>>>(d_params, d_offsets, d_rays);
 }
 void launch_gen_camera_rays(const rdn_camera &p, rdn_ray *d_rays, cudaStream_t stream) {
   const uint64_t n = static_cast<uint64_t>(p.rect_w) * p.rect_h;

@@ -252,6 +252,28 @@ def test_path_a_device_resident_query_and_edge_cases():
     assert not d_out.any().item()
 
 
+def test_path_a_list_query_matches_oracle():
+    """intersect_list_bvh: ragged CSR result, per-ray order = the reference's visiting order; sizes via the two-call protocol"""
+    pos, idx = S.torus_mesh(64, 48)
+    wpos = S.mat4_apply_point(S.mat4_mul(S.mat4_mul(S.mat4_translate(0, 0, -10), S.mat4_scale(5, 5, 5)), S.mat4_rotate_x(-0.5)), pos)
+    tri = idx.reshape(-1, 3)
+    boxes = np.concatenate([wpos[tri].min(1), wpos[tri].max(1)], 1)
+    rays = S.pinhole_rays(150, 130, 0.0, 100.0)
+    for opt in ((50, 2), (10, 50)):
+        ob = oracle.FlattenBVH(boxes, oracle.STRATEGY_SAH, 4, *opt)
+        pb = api.build_bvh_for_abstract_mesh(wpos, idx, api.SAH(4), api.TreeBuildOption(*opt))
+        for side in (api.FACE_FRONT, api.FACE_DOUBLE):
+            woff, whits = ob.query_list(wpos, idx, rays, side)
+            goff, ghits = api.intersect_list_bvh(wpos, idx, rays, pb, side)
+            assert np.array_equal(goff, woff) and ghits.tobytes() == whits.tobytes(), (opt, side)
+            assert whits.size > 2000
+    goff, ghits = api.intersect_list_bvh(wpos, idx, rays[:0], pb)  # no rays
+    assert goff.tolist() == [0] and ghits.size == 0
+    away = S.pinhole_rays(8, 8, 0.0, 100.0, origin=(0.0, 0.0, -40.0))  # looking away from the mesh: empty lists
+    goff, ghits = api.intersect_list_bvh(wpos, idx, away, pb)
+    assert not goff.any() and ghits.size == 0
+
+
 # ---- wavefront queue compaction ---------------------------------------------------------------------
 def test_compaction_known_answers_and_random():
     s = api.NaiveSahBVHSystem()
@@ -309,3 +331,27 @@ def test_blob_adoption_gives_identical_results():
         a = sp.p.trace_closest_batch(rays, ray_flags=0x10, tlas_idx=k)
         b = other.trace_closest_batch(rays, ray_flags=0x10, tlas_idx=k)
         assert a.tobytes() == b.tobytes()
+
+
+def test_in_process_multi_device_scene_shards_host_rays():
+    """rdn_rt_scene_create(n_devices = 2): the blob is replicated by peer copy on commit and the host-buffer trace deals ray chunks
+    round-robin to the devices; the assembled result is the single-device result (= the oracle's), and each device answers
+    device-resident traces from its own replica."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    pos, idx = S.torus_mesh(128, 96, 1.0, 0.35)
+    m = S.mat4_mul(S.mat4_mul(S.mat4_translate(0, 0, -10), S.mat4_scale(5, 5, 5)), S.mat4_rotate_x(-0.5))
+    sp = helpers.single_mesh_scene(pos, idx, m, devices=(0, 1))
+    rays = S.pinhole_rays(1024, 640, 0.01, 100.0)  # 655,360 rays: three 256 Ki chunks -> both devices work
+    want = sp.o.trace(rays, ray_flags=helpers.CULL_BACK, n_threads=8, want_counters=False)
+    got = sp.p.trace_closest_batch(rays, ray_flags=helpers.CULL_BACK, grid_width=1024)
+    _assert_parity("two_devices_host_path", got, want)
+    for di in (0, 1):
+        with torch.cuda.device(di):
+            r = torch.from_numpy(rays.view(np.uint8).reshape(-1, 32).copy()).to(f"cuda:{di}")
+            h = torch.zeros_like(r)
+            sp.p.trace_closest_device(r.data_ptr(), rays.shape[0], h.data_ptr(), ray_flags=helpers.CULL_BACK, grid_width=1024,
+                                      stream=torch.cuda.current_stream(di).cuda_stream, device_index=di)
+            torch.cuda.synchronize(di)
+            assert h.cpu().numpy().view(api.HIT_DTYPE).reshape(-1).tobytes() == want.tobytes(), di

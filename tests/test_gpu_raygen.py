@@ -49,6 +49,20 @@ def test_pinhole_rays_equal_the_host_recipe_bit_for_bit():
         assert n == w * h and _np_rays(d).tobytes() == want.tobytes(), (W, H, rect)
     with pytest.raises(api.RdnError):
         sp.p.gen_pinhole_rays_device(_dev_rays(4).data_ptr(), 4, 4, rect=(2, 2, 3, 1))
+    # many rectangles (tiles x samples) in one launch == the same rectangles one by one
+    W, H = 300, 170
+    rects = [(0, 0, 128, 128), (128, 0, 128, 128), (256, 0, 44, 128), (0, 128, 128, 42), (256, 128, 44, 42)] * 2
+    jits = [(0.5, 0.5)] * 5 + [(0.125, 0.875)] * 5
+    total = sum(w * h for (_, _, w, h) in rects)
+    d = _dev_rays(total)
+    assert sp.p.gen_pinhole_rays_batch_device(d.data_ptr(), W, H, rects, jits, tmin=0.01, tmax=100.0, aspect=float(f32(W / H)), stream=st) == total
+    torch.cuda.synchronize()
+    got, off = _np_rays(d), 0
+    for (x0, y0, w, h), jit in zip(rects, jits):
+        full = S.pinhole_rays(W, H, 0.01, 100.0, aspect_correct=True, jitter=np.tile(np.array([jit], f32), (W * H, 1)))
+        want = full.reshape(H, W)[y0:y0 + h, x0:x0 + w].reshape(-1)
+        assert got[off:off + w * h].tobytes() == want.tobytes(), (x0, y0)
+        off += w * h
 
 
 def test_camera_rays_equal_the_restated_ray_gen_shader():

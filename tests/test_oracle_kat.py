@@ -215,3 +215,26 @@ def test_multi_geometry_blas_box_quirk_and_deleted_blas():
     sc2.bind_tlas([t2])
     sc2.delete_blas(c)
     assert sc2.build() < 0
+
+
+def test_list_query_contains_the_nearest_and_every_brute_force_hit():
+    """intersect_list_bvh (feature/bvh.rs:23-55): per ray, the list is every brute-force intersection (the BVH only prunes
+    boxes the ray misses), and intersect_nearest_bvh is its first minimum"""
+    pos, idx = S.torus_mesh(24, 16)
+    tri = idx.reshape(-1, 3)
+    boxes = np.concatenate([pos[tri].min(1), pos[tri].max(1)], 1)
+    ob = oracle.FlattenBVH(boxes, oracle.STRATEGY_SAH, 4, 50, 2)
+    rays = S.pinhole_rays(40, 40, 0.0, 100.0, origin=(0.0, 0.0, 4.0))
+    off, hits = ob.query_list(pos, idx, rays)
+    near = ob.query_nearest(pos, idx, rays)
+    assert off[0] == 0 and off[-1] == hits.size and np.all(np.diff(off.astype(np.int64)) >= 0) and hits.size > near["hit"].sum()
+    for i in range(rays.shape[0]):
+        lst = hits[int(off[i]):int(off[i + 1])]
+        if near["hit"][i]:
+            j = int(np.argmin(lst["distance"]))  # argmin = first of equal distances = strict `<` in visiting order
+            assert lst[j].tobytes() == near[i].tobytes()
+        else:
+            assert lst.size == 0
+    # a torus is closed: a ray from outside crosses an even number of faces (2 or 4) unless it grazes an edge
+    n_per_ray = np.diff(off.astype(np.int64))
+    assert set(np.unique(n_per_ray)) <= {0, 1, 2, 3, 4, 5, 6} and np.count_nonzero(n_per_ray % 2) < 0.05 * rays.shape[0]

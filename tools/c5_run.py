@@ -78,12 +78,9 @@ def main():
     def frame():
         n_bounce = 0
         for gw, B in bufs.items():
-            off = 0
-            for s in range(spp):
-                for t in B["tiles"]:
-                    sysm.gen_pinhole_rays_device(B["rays"].data_ptr() + off * 32, W, H, rect=t, tmin=TMIN, tmax=TMAX, aspect=aspect,
-                                                 jitter=(float(jitters[s][0]), float(jitters[s][1])), stream=st)
-                    off += t[2] * t[3]
+            rects = [t for s in range(spp) for t in B["tiles"]]
+            jits = [(float(jitters[s][0]), float(jitters[s][1])) for s in range(spp) for _ in B["tiles"]]
+            sysm.gen_pinhole_rays_batch_device(B["rays"].data_ptr(), W, H, rects, jits, tmin=TMIN, tmax=TMAX, aspect=aspect, stream=st)
             sysm.trace_closest_device(B["rays"].data_ptr(), B["n"], B["hits"].data_ptr(), ray_flags=CULL_BACK, grid_width=gw, stream=st)
             sysm.gen_bounce_rays_device(B["rays"].data_ptr(), B["hits"].data_ptr(), B["n"], B["brays"].data_ptr(), B["src"].data_ptr(),
                                         B["cnt"].data_ptr(), mode=0, index_base=0, tmin=TMIN, tmax=TMAX, stream=st)
