@@ -87,8 +87,11 @@ struct DeviceCtx {
   uint64_t blob_bytes = 0;
   SceneDev dev{};
   Slot slots[N_SLOTS];
-  Scratch ext_scratch;            // for caller-stream (device-resident) traces
-  cudaEvent_t ext_done = nullptr; // orders successive device-resident traces that share ext_scratch
+  Scratch ext_scratch[2];         // for caller-stream (device-resident) traces; launches alternate so that consecutive ordered
+                                  // launches on one stream may overlap their tails (programmatic dependent launch, traverse.cu)
+  int ext_next = 0;
+  cudaEvent_t ext_done = nullptr; // orders device-resident traces issued on DIFFERENT streams (they share the scratch sets)
+  cudaStream_t ext_last_stream = nullptr;
   bool ext_pending = false;
   unsigned long long *d_compact_status = nullptr;
   uint64_t compact_status_cap = 0;
@@ -238,7 +241,7 @@ struct ScopedKernelTimer {
 
 // enqueue the kernels of one trace on `stream`; returns the number of kernels launched
 int enqueue_trace(rdn_rt_scene *s, DeviceCtx &dc, const Scratch &scratch, const rdn_launch &launch, const rdn_ray *d_rays, uint64_t n,
-                  rdn_hit *d_hits, int mode, cudaStream_t stream, uint32_t *launches, bool count_ties = false) {
+                  rdn_hit *d_hits, int mode, cudaStream_t stream, uint32_t *launches, bool count_ties = false, bool allow_overlap = false) {
   const TraceScratch ts = scratch.view();
   // work_counter is zero here: zeroed at allocation and re-armed by the last CTA of every ordered launch.  tie_count and
   // the two error flags accumulate until read (the stats path clears tie_count first).
@@ -253,7 +256,8 @@ int enqueue_trace(rdn_rt_scene *s, DeviceCtx &dc, const Scratch &scratch, const 
     bool ties_done;
     {
       ScopedKernelTimer tm(dc, KERNEL_ORDERED, stream);
-      ties_done = launch_trace_ordered(dc.dev, launch, resolve_world_root(s, launch.tlas_idx), d_rays, n, d_hits, ts, dc.sm_count, stream);
+      ties_done = launch_trace_ordered(dc.dev, launch, resolve_world_root(s, launch.tlas_idx), d_rays, n, d_hits, ts, dc.sm_count, stream,
+                                       allow_overlap && !dc.timing && !count_ties);
     }
     if (!ties_done) {
       ScopedKernelTimer tm(dc, KERNEL_TIES, stream);
@@ -327,7 +331,8 @@ void rdn_rt_scene_destroy(rdn_rt_scene *s) {
       if (slot.h_flags) cudaFreeHost(slot.h_flags);
       if (slot.stream) cudaStreamDestroy(slot.stream);
     }
-    free_scratch(dc.ext_scratch);
+    free_scratch(dc.ext_scratch[0]);
+    free_scratch(dc.ext_scratch[1]);
     for (TimedLaunch &t : dc.timed) { cudaEventDestroy(t.begin); cudaEventDestroy(t.end); }
     if (dc.ext_done) cudaEventDestroy(dc.ext_done);
     if (dc.d_compact_status) cudaFree(dc.d_compact_status);
@@ -419,10 +424,18 @@ int rdn_rt_trace_closest_device(rdn_rt_scene *s, int device_index, const rdn_lau
   RDN_CUDA(cudaSetDevice(dc.device));
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   if (stats) std::memset(stats, 0, sizeof(*stats));
+  // The scratch sets are shared by every caller stream: a call on another stream than the previous one first waits for that
+  // stream's work (event recorded there now).  Calls on the same stream need nothing — and get nothing between their kernels.
   if (!dc.ext_done) RDN_CUDA(cudaEventCreateWithFlags(&dc.ext_done, cudaEventDisableTiming));
-  if (dc.ext_pending) RDN_CUDA(cudaStreamWaitEvent(stream, dc.ext_done, 0));  // the scratch is shared between calls
+  if (dc.ext_pending && dc.ext_last_stream != stream) {
+    if (cudaEventRecord(dc.ext_done, dc.ext_last_stream) == cudaSuccess) RDN_CUDA(cudaStreamWaitEvent(stream, dc.ext_done, 0));
+    else { cudaGetLastError(); RDN_CUDA(cudaDeviceSynchronize()); }  // the previous stream no longer exists
+  }
+  dc.ext_last_stream = stream;
+  dc.ext_pending = true;
   const uint64_t chunk = std::min<uint64_t>(std::max<uint64_t>(n, 1), MAX_LAUNCH_RAYS);
-  rc = ensure_scratch(dc.ext_scratch, chunk);
+  rc = ensure_scratch(dc.ext_scratch[0], chunk);
+  if (rc == RDN_OK) rc = ensure_scratch(dc.ext_scratch[1], chunk);
   if (rc != RDN_OK) return rc;
 
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -433,15 +446,17 @@ int rdn_rt_trace_closest_device(rdn_rt_scene *s, int device_index, const rdn_lau
     const uint64_t m = std::min(chunk, n - off);
     rdn_launch l = *launch;
     if (off != 0 || m != n) l.grid_width = (l.grid_width && m % l.grid_width == 0 && off % l.grid_width == 0) ? l.grid_width : 0;
-#ifdef RDN_DEBUG_STEPS
+    Scratch &scratch = dc.ext_scratch[dc.ext_next];
+    dc.ext_next ^= 1;
+#if defined(RDN_DEBUG_STEPS) || defined(RDN_DEBUG_TIMELINE)
     if (stats) {
-      RDN_CUDA(cudaMemsetAsync(static_cast<char *>(dc.ext_scratch.base) + 32, 0, 6 * 8, stream));
-      RDN_CUDA(cudaMemsetAsync(static_cast<char *>(dc.ext_scratch.base) + 32 + 6 * 8, 0xFF, 2 * 8, stream));
-      RDN_CUDA(cudaMemsetAsync(static_cast<char *>(dc.ext_scratch.base) + 32 + 8 * 8, 0, 8, stream));
+      RDN_CUDA(cudaMemsetAsync(static_cast<char *>(scratch.base) + 32, 0, 6 * 8, stream));
+      RDN_CUDA(cudaMemsetAsync(static_cast<char *>(scratch.base) + 32 + 6 * 8, 0xFF, 2 * 8, stream));
+      RDN_CUDA(cudaMemsetAsync(static_cast<char *>(scratch.base) + 32 + 8 * 8, 0, 16, stream));
     }
 #endif
     if (stats) RDN_CUDA(cudaEventRecord(e0, stream));
-    rc = enqueue_trace(s, dc, dc.ext_scratch, l, d_rays + off, m, d_hits + off, mode, stream, stats ? &stats->kernel_launches : nullptr, stats != nullptr);
+    rc = enqueue_trace(s, dc, scratch, l, d_rays + off, m, d_hits + off, mode, stream, stats ? &stats->kernel_launches : nullptr, stats != nullptr, true);
     if (rc != RDN_OK) return rc;
     if (stats) {
       RDN_CUDA(cudaEventRecord(e1, stream));
@@ -450,23 +465,24 @@ int rdn_rt_trace_closest_device(rdn_rt_scene *s, int device_index, const rdn_lau
       RDN_CUDA(cudaEventElapsedTime(&ms, e0, e1));
       ms_total += ms;
       uint32_t small[6] = {0, 0, 0, 0, 0, 0};  // tie_count | tie_unresolved | stack_overflow | blocks_done | tie_cursor | tie_total
-      RDN_CUDA(cudaMemcpy(small, static_cast<char *>(dc.ext_scratch.base) + 8, sizeof(small), cudaMemcpyDeviceToHost));
+      RDN_CUDA(cudaMemcpy(small, static_cast<char *>(scratch.base) + 8, sizeof(small), cudaMemcpyDeviceToHost));
       ties += ordered_tie_mode() == 3 ? small[5] : small[0];
       if (small[1]) return fail(RDN_ERR_CUDA, "tie re-walk found no hit (internal invariant broken)");
       if (small[2]) return fail(RDN_ERR_CAPACITY, "traversal stack overflow");
-#ifdef RDN_DEBUG_STEPS
-      unsigned long long c[9];
-      RDN_CUDA(cudaMemcpy(c, static_cast<char *>(dc.ext_scratch.base) + 32, sizeof(c), cudaMemcpyDeviceToHost));
+#if defined(RDN_DEBUG_STEPS) || defined(RDN_DEBUG_TIMELINE)
+      unsigned long long c[10];
+      RDN_CUDA(cudaMemcpy(c, static_cast<char *>(scratch.base) + 32, sizeof(c), cudaMemcpyDeviceToHost));
       const double r = double(c[2] ? c[2] : 1);
+      const double span_us = (double(c[8]) - double(c[6])) * 1e-3;
+      const double warps = double((m + 31) / 32 < 148ull * 32 ? (m + 31) / 32 : 148ull * 32);
       fprintf(stderr, "[dbg steps] max=%llu steps=%llu rays_entered=%llu tri_tests=%llu pushes=%llu rays>200steps=%llu | per entered ray: %.2f steps "
-              "%.2f tris %.2f pushes | timeline: list dry after %.1f us, kernel end after %.1f us (tail %.1f us)\n",
+              "%.2f tris %.2f pushes | timeline: list dry after %.1f us, last warp out after %.1f us (tail %.1f us), mean warp busy %.1f us = %.0f%% of the span\n",
               c[0], c[1], c[2], c[3], c[4], c[5], double(c[1]) / r, double(c[3]) / r, double(c[4]) / r,
-              (double(c[7]) - double(c[6])) * 1e-3, (double(c[8]) - double(c[6])) * 1e-3, (double(c[8]) - double(c[7])) * 1e-3);
+              (double(c[7]) - double(c[6])) * 1e-3, span_us, (double(c[8]) - double(c[7])) * 1e-3, double(c[9]) * 1e-3 / warps,
+              100.0 * double(c[9]) * 1e-3 / warps / (span_us > 0 ? span_us : 1));
 #endif
     }
   }
-  RDN_CUDA(cudaEventRecord(dc.ext_done, stream));
-  dc.ext_pending = true;
   if (stats) {
     stats->rays = n; stats->tie_rays = ties; stats->kernel_ms = ms_total;
     cudaEventDestroy(e0); cudaEventDestroy(e1);

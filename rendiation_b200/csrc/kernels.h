@@ -57,7 +57,7 @@ void launch_resolve_ties(const SceneDev &scene, const rdn_launch &launch, const 
 // world_root = TlasRoot::wide_root of tlas_binding[launch.tlas_idx] (resolved by the caller from its host copy).
 int ordered_tie_mode();  // 0: queue + launch_resolve_ties; 1/2: re-walk by the finishing lane; 3: queue drained inside the kernel
 bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, uint32_t world_root, const rdn_ray *d_rays, uint64_t n,
-                          rdn_hit *d_hits, const TraceScratch &scratch, int sm_count, cudaStream_t stream);
+                          rdn_hit *d_hits, const TraceScratch &scratch, int sm_count, cudaStream_t stream, bool allow_overlap = false);
 
 // Stable stream compaction of u32 (single pass, decoupled look-back); d_status needs compact_status_words(n) u64.
 uint64_t compact_status_words(uint64_t n);

@@ -361,9 +361,12 @@ template <int K, int MINB, int THRESH, bool DRAIN_TIES>  // DRAIN_TIES: near-tie
 __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(const __grid_constant__ OrderedParams P) {
   const SceneDev &S = P.S;
   const uint32_t lane = threadIdx.x & 31u;
-
   uint32_t stack[STACK_MAX];
   int sp = 0;
+  // Programmatic dependent launch: the NEXT ordered launch on this stream may start filling SM slots as soon as CTAs of this one
+  // leave, i.e. while the last long rays of this launch are still being walked (a no-op when launched without the attribute).
+  // The next launch reads nothing this one writes (its own rays, the read-only scene, the other scratch set).
+  asm volatile("griddepcontrol.launch_dependents;");
 
   // the world pseudo-root (TLAS root box + its reference) is launch-uniform: keep it in registers
   Vec3 root_min = {0, 0, 0}, root_max = {0, 0, 0};
@@ -389,7 +392,10 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
 #ifdef RDN_DEBUG_STEPS
   // per-thread totals, reduced once per warp at kernel exit so the counters do not perturb the timeline
   unsigned long long dbg_steps = 0, dbg_tris = 0, dbg_pushes = 0, dbg_ray_steps = 0, dbg_max = 0, dbg_rays = 0, dbg_long = 0;
-  if (lane == 0) atomicMin(P.scratch.counters + 6, globaltimer_ns());  // first warp in
+#endif
+#if defined(RDN_DEBUG_STEPS) || defined(RDN_DEBUG_TIMELINE)
+  const unsigned long long dbg_t_in = globaltimer_ns();
+  if (lane == 0) atomicMin(P.scratch.counters + 6, dbg_t_in);  // first warp in
 #endif
 
 #define RDN_PUSH(v) do { if (sp < STACK_MAX) stack[sp++] = (v); else atomicAdd(P.scratch.stack_overflow, 1u); } while (0)
@@ -407,7 +413,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
       if (static_cast<int>(lane) == leader) base = atomicAdd(P.scratch.work_counter, static_cast<unsigned long long>(cnt));
       base = __shfl_sync(FULL_MASK, base, leader);
       if (base + cnt >= P.n_fetch) {
-#ifdef RDN_DEBUG_STEPS
+#if defined(RDN_DEBUG_STEPS) || defined(RDN_DEBUG_TIMELINE)
         if (!warp_exhausted && static_cast<int>(lane) == leader) atomicMin(P.scratch.counters + 7, globaltimer_ns());  // ray list ran dry
 #endif
         warp_exhausted = true;
@@ -613,7 +619,13 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
       if (lane == 0 && x) atomicAdd(P.scratch.counters + 1 + i, x);  // steps, rays entered, triangle tests, pushes, rays > 200 steps
     }
     atomicMax(P.scratch.counters + 0, dbg_max);                           // longest ray, inner-node steps
-    if (lane == 0) atomicMax(P.scratch.counters + 8, globaltimer_ns());  // last warp out
+  }
+#endif
+#if defined(RDN_DEBUG_STEPS) || defined(RDN_DEBUG_TIMELINE)
+  if (lane == 0) {
+    const unsigned long long t_out = globaltimer_ns();
+    atomicMax(P.scratch.counters + 8, t_out);               // last warp out
+    atomicAdd(P.scratch.counters + 9, t_out - dbg_t_in);    // sum of the warps' busy time (before the tie drain / exit barrier)
   }
 #endif
   if (DRAIN_TIES) drain_tie_queue(P);
@@ -627,6 +639,9 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
   }
   __syncthreads();
   if (s_last) {
+    // ... and this launch must not COMPLETE before its predecessor: whatever follows in the stream (a copy of the previous
+    // launch's hits, a kernel reading them) is ordered behind this grid only
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (DRAIN_TIES) {
       __threadfence();
       drain_tie_queue(P);
@@ -673,7 +688,7 @@ static int ordered_variant() {
 int ordered_tie_mode() { return ordered_variant() == 9 ? 0 : 3; }
 
 bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, uint32_t world_root, const rdn_ray *d_rays, uint64_t n,
-                          rdn_hit *d_hits, const TraceScratch &scratch, int sm_count, cudaStream_t stream) {
+                          rdn_hit *d_hits, const TraceScratch &scratch, int sm_count, cudaStream_t stream, bool allow_overlap) {
   if (n == 0) return true;
   OrderedParams P;
   P.S = scene; P.L = launch; P.rays = d_rays; P.hits = d_hits; P.n = n; P.scratch = scratch;
@@ -704,7 +719,20 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, uint3
   uint64_t blocks = static_cast<uint64_t>(sm_count) * blocks_per_sm;
   const uint64_t needed = (P.n_fetch + ORDERED_BLOCK - 1) / ORDERED_BLOCK;
   if (blocks > needed) blocks = needed;
-  fn<<<static_cast<unsigned>(blocks), ORDERED_BLOCK, 0, stream>>>(P);
+  // Tail overlap is only requested for grids that fill the GPU: such a grid needs every CTA slot, so launch k+2 cannot start
+  // before launch k has left entirely, and two alternating scratch sets are enough (capi.cu).
+  static const bool pdl_enabled = []() { const char *e = getenv("RDN_PDL"); return !e || atoi(e) != 0; }();
+  const bool full_grid = blocks == static_cast<uint64_t>(sm_count) * blocks_per_sm;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(blocks));
+  cfg.blockDim = dim3(ORDERED_BLOCK);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  if (allow_overlap && pdl_enabled && full_grid && inline_ties) { cfg.attrs = attr; cfg.numAttrs = 1; }
+  cudaLaunchKernelEx(&cfg, fn, P);
   return inline_ties;
 }
 

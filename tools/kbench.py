@@ -66,6 +66,9 @@ n = rays.shape[0]
 d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1, 32).copy()).cuda()
 d_hits = torch.zeros((n, 32), dtype=torch.uint8, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+if os.environ.get("KBENCH_SIDE_STREAM", "0") == "1":  # a created stream instead of the legacy default stream
+    _side = torch.cuda.Stream()
+    torch.cuda.set_stream(_side)
 st = torch.cuda.current_stream().cuda_stream
 for _ in range(3):
     sysm.trace_closest_device(d_rays.data_ptr(), n, d_hits.data_ptr(), ray_flags=flags, grid_width=grid, stream=st)
@@ -79,6 +82,22 @@ for _ in range(iters):
     e1.record(); torch.cuda.synchronize()
     ms.append(e0.elapsed_time(e1))
 ms = np.array(ms)
+# back-to-back launches on one stream (no flush, no events in between): consecutive launches may overlap their tails
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(iters):
+    sysm.trace_closest_device(d_rays.data_ptr(), n, d_hits.data_ptr(), ray_flags=flags, grid_width=grid, stream=st)
+e1.record(); torch.cuda.synchronize()
+b2b_ms = e0.elapsed_time(e1) / iters
+# the same with an event recorded between launches (does a marker between two kernels serialise them?)
+evs = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+evs[0].record()
+for k in range(iters):
+    sysm.trace_closest_device(d_rays.data_ptr(), n, d_hits.data_ptr(), ray_flags=flags, grid_width=grid, stream=st)
+    evs[k + 1].record()
+torch.cuda.synchronize()
+b2b_ev_ms = evs[0].elapsed_time(evs[-1]) / iters
 ok = None
 if check:
     sel = np.arange(0, n, 7)
@@ -87,4 +106,5 @@ if check:
     ok = got.tobytes() == want.tobytes()
 print(f"cfg={cfg} variant={os.environ.get('RDN_ORDERED_VARIANT','default')} skip_tie={'RDN_DEBUG_SKIP_TIE' in os.environ} rays={n} "
       f"mean_ms={ms.mean():.4f} min_ms={ms.min():.4f} Mrays/s(mean)={n/ms.mean()/1e3:.1f} best={n/ms.min()/1e3:.1f} ties={stats['tie_rays']} "
-      f"bit_identical_sample={ok} build_s={t_build:.2f}")
+      f"bit_identical_sample={ok} build_s={t_build:.2f} | back-to-back {n/b2b_ms/1e3:.1f} Mrays/s ({b2b_ms:.4f} ms), with events between {n/b2b_ev_ms/1e3:.1f} "
+      f"pdl={os.environ.get('RDN_PDL','1')} side_stream={os.environ.get('KBENCH_SIDE_STREAM','0')}")
