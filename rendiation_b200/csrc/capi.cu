@@ -47,6 +47,7 @@ struct Scratch {
   uint32_t *tie_queue = nullptr;
   float *tie_best = nullptr;
   uint64_t capacity = 0;       // rays
+  mutable uint32_t ordered_launches = 0;  // ordered kernels issued on this set so far (their completion count lives in epoch_done)
   TraceScratch view() const {
     TraceScratch s;
     char *b = static_cast<char *>(base);
@@ -57,13 +58,14 @@ struct Scratch {
     s.blocks_done = reinterpret_cast<uint32_t *>(b + 20);
     s.tie_cursor = reinterpret_cast<uint32_t *>(b + 24);
     s.tie_total = reinterpret_cast<uint32_t *>(b + 28);
+    s.epoch_done = reinterpret_cast<uint32_t *>(b + 112);
     s.counters = reinterpret_cast<unsigned long long *>(b + 32);
     s.tie_queue = tie_queue;
     s.tie_best = tie_best;
     return s;
   }
 };
-constexpr size_t SCRATCH_BASE_BYTES = 32 + 10 * 8;  // + 6 visit counters (rdn_counters) + 3 debug timestamps + 1 spare
+constexpr size_t SCRATCH_BASE_BYTES = 128;  // 32 B of cursors/flags + 10 u64 counters (6 visit counters, 4 debug) + epoch_done at 112
 
 struct Slot {  // one pipeline lane of the host-buffer path
   cudaStream_t stream = nullptr;
@@ -257,7 +259,8 @@ int enqueue_trace(rdn_rt_scene *s, DeviceCtx &dc, const Scratch &scratch, const 
     {
       ScopedKernelTimer tm(dc, KERNEL_ORDERED, stream);
       ties_done = launch_trace_ordered(dc.dev, launch, resolve_world_root(s, launch.tlas_idx), d_rays, n, d_hits, ts, dc.sm_count, stream,
-                                       allow_overlap && !dc.timing && !count_ties);
+                                       allow_overlap && !dc.timing && !count_ties, scratch.ordered_launches);
+      if (n) scratch.ordered_launches++;
     }
     if (!ties_done) {
       ScopedKernelTimer tm(dc, KERNEL_TIES, stream);
@@ -581,7 +584,7 @@ int rdn_rt_trace_counted(rdn_rt_scene *s, const rdn_launch *launch, const rdn_ra
   for (uint64_t off = 0; off < n; off += chunk) {
     const uint64_t m = std::min(chunk, n - off);
     RDN_CUDA(cudaMemcpyAsync(slot.d_rays, rays + off, m * sizeof(rdn_ray), cudaMemcpyHostToDevice, slot.stream));
-    RDN_CUDA(cudaMemsetAsync(slot.scratch.base, 0, SCRATCH_BASE_BYTES, slot.stream));
+    RDN_CUDA(cudaMemsetAsync(static_cast<char *>(slot.scratch.base) + 32, 0, 10 * 8, slot.stream));  // the visit counters only
     launch_trace_reference(dc.dev, *launch, slot.d_rays, m, slot.d_hits, slot.scratch.view(), true, dc.sm_count, slot.stream);
     RDN_CUDA(cudaGetLastError());
     RDN_CUDA(cudaMemcpyAsync(out_hits + off, slot.d_hits, m * sizeof(rdn_hit), cudaMemcpyDeviceToHost, slot.stream));

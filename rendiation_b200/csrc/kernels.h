@@ -34,6 +34,7 @@ struct TraceScratch {
   uint32_t *stack_overflow;          // safety net: traversal stack overflow (must stay 0)
   uint32_t *tie_cursor;              // next queued tie to resolve (in-kernel drain)
   uint32_t *tie_total;               // ties of completed launches since the host last cleared it (in-kernel drain resets tie_count)
+  uint32_t *epoch_done;              // ordered launches completed on this scratch set (gate of the next launch on the set)
   uint32_t *blocks_done;             // CTAs of the running ordered kernel that have left; the last one re-arms work_counter
   uint32_t *tie_queue;               // ray indices, capacity >= rays of the launch
   float *tie_best;                   // closest distance found by the ordered kernel, per queued ray
@@ -57,7 +58,8 @@ void launch_resolve_ties(const SceneDev &scene, const rdn_launch &launch, const 
 // world_root = TlasRoot::wide_root of tlas_binding[launch.tlas_idx] (resolved by the caller from its host copy).
 int ordered_tie_mode();  // 0: queue + launch_resolve_ties; 1/2: re-walk by the finishing lane; 3: queue drained inside the kernel
 bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, uint32_t world_root, const rdn_ray *d_rays, uint64_t n,
-                          rdn_hit *d_hits, const TraceScratch &scratch, int sm_count, cudaStream_t stream, bool allow_overlap = false);
+                          rdn_hit *d_hits, const TraceScratch &scratch, int sm_count, cudaStream_t stream, bool allow_overlap = false,
+                          uint32_t wait_epoch = 0);  // wait_epoch = ordered launches issued before this one on `scratch`
 
 // Stable stream compaction of u32 (single pass, decoupled look-back); d_status needs compact_status_words(n) u64.
 uint64_t compact_status_words(uint64_t n);

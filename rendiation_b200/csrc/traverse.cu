@@ -293,6 +293,7 @@ struct OrderedParams {
   uint32_t tiles_x;  // 0: linear
   uint32_t width, height;
   uint32_t world_root;  // wide reference of the bound TLAS (REF_EMPTY: every ray misses)
+  uint32_t wait_epoch;  // launches issued before this one on the same scratch set: they must have left before this one touches it
   TraceScratch scratch;
 };
 
@@ -367,6 +368,15 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
   // leave, i.e. while the last long rays of this launch are still being walked (a no-op when launched without the attribute).
   // The next launch reads nothing this one writes (its own rays, the read-only scene, the other scratch set).
   asm volatile("griddepcontrol.launch_dependents;");
+  // Gate: with tails overlapping, the launch after next can reach the device while the launch that last used THIS scratch
+  // set still has a straggler CTA (late CTAs of the launch in between find the ray list dry and leave at once).  Every
+  // earlier launch is fully resident by then (a dependent launch starts only after all CTAs of its predecessor have
+  // started), so waiting here cannot deadlock.
+  if (threadIdx.x == 0) {
+    while (ld_volatile_u32(P.scratch.epoch_done) != P.wait_epoch) __nanosleep(200);
+    __threadfence();
+  }
+  __syncthreads();
 
   // the world pseudo-root (TLAS root box + its reference) is launch-uniform: keep it in registers
   Vec3 root_min = {0, 0, 0}, root_max = {0, 0, 0};
@@ -656,6 +666,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
         *P.scratch.tie_cursor = 0u;
       }
       __threadfence();
+      *reinterpret_cast<volatile uint32_t *>(P.scratch.epoch_done) = P.wait_epoch + 1u;  // the set is free for the next launch on it
     }
   }
 }
@@ -688,7 +699,8 @@ static int ordered_variant() {
 int ordered_tie_mode() { return ordered_variant() == 9 ? 0 : 3; }
 
 bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, uint32_t world_root, const rdn_ray *d_rays, uint64_t n,
-                          rdn_hit *d_hits, const TraceScratch &scratch, int sm_count, cudaStream_t stream, bool allow_overlap) {
+                          rdn_hit *d_hits, const TraceScratch &scratch, int sm_count, cudaStream_t stream, bool allow_overlap,
+                          uint32_t wait_epoch) {
   if (n == 0) return true;
   OrderedParams P;
   P.S = scene; P.L = launch; P.rays = d_rays; P.hits = d_hits; P.n = n; P.scratch = scratch;
@@ -700,6 +712,7 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, uint3
     P.n_fetch = static_cast<uint64_t>(P.tiles_x) * ((P.height + 3u) / 4u) * 32u;
   }
   P.world_root = world_root;
+  P.wait_epoch = wait_epoch;
 
   // RDN_ORDERED_VARIANT: experimentation knob (rounds per vote / refill threshold / tie handling / register cap)
   const int variant = ordered_variant();
@@ -710,6 +723,11 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, uint3
     case 1: fn = k_trace_ordered_rounds<4, 8, 1, true>; break;
     case 2: fn = k_trace_ordered_rounds<3, 8, 4, true>; break;
     case 3: fn = k_trace_ordered_rounds<4, 8, 8, true>; break;
+    case 4: fn = k_trace_ordered_rounds<2, 8, 4, true>; break;
+    case 5: fn = k_trace_ordered_rounds<2, 8, 8, true>; break;
+    case 6: fn = k_trace_ordered_rounds<2, 8, 16, true>; break;
+    case 7: fn = k_trace_ordered_rounds<2, 8, 24, true>; break;
+    case 8: fn = k_trace_ordered_rounds<1, 8, 1, true>; break;
     case 9: fn = k_trace_ordered_rounds<2, 8, 1, false>; inline_ties = false; break;  // queue drained by k_resolve_ties
     default: fn = k_trace_ordered_rounds<2, 8, 1, true>; break;
   }

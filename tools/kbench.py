@@ -82,14 +82,19 @@ for _ in range(iters):
     e1.record(); torch.cuda.synchronize()
     ms.append(e0.elapsed_time(e1))
 ms = np.array(ms)
-# back-to-back launches on one stream (no flush, no events in between): consecutive launches may overlap their tails
+# back-to-back launches on one stream (no flush, no events in between): consecutive launches may overlap their tails.
+# Every launch writes its OWN hit buffer (pre-filled with 0xAB) so that a ray skipped by an overlapped launch cannot hide
+# behind the result of another launch; all buffers are compared with the serialised result below.
+b2b_hits = [torch.full((n, 32), 0xAB, dtype=torch.uint8, device="cuda") for _ in range(iters)]
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 torch.cuda.synchronize()
 e0.record()
-for _ in range(iters):
-    sysm.trace_closest_device(d_rays.data_ptr(), n, d_hits.data_ptr(), ray_flags=flags, grid_width=grid, stream=st)
+for k in range(iters):
+    sysm.trace_closest_device(d_rays.data_ptr(), n, b2b_hits[k].data_ptr(), ray_flags=flags, grid_width=grid, stream=st)
 e1.record(); torch.cuda.synchronize()
 b2b_ms = e0.elapsed_time(e1) / iters
+b2b_ok = all(torch.equal(h, d_hits) for h in b2b_hits)
+del b2b_hits
 # the same with an event recorded between launches (does a marker between two kernels serialise them?)
 evs = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
 evs[0].record()
@@ -106,5 +111,5 @@ if check:
     ok = got.tobytes() == want.tobytes()
 print(f"cfg={cfg} variant={os.environ.get('RDN_ORDERED_VARIANT','default')} skip_tie={'RDN_DEBUG_SKIP_TIE' in os.environ} rays={n} "
       f"mean_ms={ms.mean():.4f} min_ms={ms.min():.4f} Mrays/s(mean)={n/ms.mean()/1e3:.1f} best={n/ms.min()/1e3:.1f} ties={stats['tie_rays']} "
-      f"bit_identical_sample={ok} build_s={t_build:.2f} | back-to-back {n/b2b_ms/1e3:.1f} Mrays/s ({b2b_ms:.4f} ms), with events between {n/b2b_ev_ms/1e3:.1f} "
+      f"bit_identical_sample={ok} build_s={t_build:.2f} | back-to-back {n/b2b_ms/1e3:.1f} Mrays/s ({b2b_ms:.4f} ms, all {iters} results identical to the serialised one: {b2b_ok}), with events between {n/b2b_ev_ms/1e3:.1f} "
       f"pdl={os.environ.get('RDN_PDL','1')} side_stream={os.environ.get('KBENCH_SIDE_STREAM','0')}")
