@@ -355,3 +355,43 @@ def test_in_process_multi_device_scene_shards_host_rays():
                                       stream=torch.cuda.current_stream(di).cuda_stream, device_index=di)
             torch.cuda.synchronize(di)
             assert h.cpu().numpy().view(api.HIT_DTYPE).reshape(-1).tobytes() == want.tobytes(), di
+
+
+def test_back_to_back_launches_overlap_without_losing_rays():
+    """Consecutive ordered launches on one stream overlap their tails (programmatic dependent launch, two alternating scratch
+    sets guarded by an epoch gate).  Every launch writes its own pre-filled buffer; all must equal a synchronised launch, which
+    equals the oracle.  Also alternates two streams (the library orders them through an event) and mixes in a small launch
+    (partial grid: no overlap requested) and a reference-order launch."""
+    import torch
+    sp, _ = helpers.torus_scene(160)
+    W, H = 1280, 800  # 1,024,000 rays: the grid fills the GPU, so overlap is requested
+    rays = S.pinhole_rays(W, H, 0.01, 100.0)
+    n = rays.shape[0]
+    want = sp.o.trace(rays, ray_flags=helpers.CULL_BACK, n_threads=8, want_counters=False)
+    d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1, 32).copy()).cuda()
+    ref = torch.zeros((n, 32), dtype=torch.uint8, device="cuda")
+    s0 = torch.cuda.Stream(); s1 = torch.cuda.Stream()
+    sp.p.trace_closest_device(d_rays.data_ptr(), n, ref.data_ptr(), ray_flags=helpers.CULL_BACK, grid_width=W, stream=s0.cuda_stream)
+    torch.cuda.synchronize()
+    assert ref.cpu().numpy().view(api.HIT_DTYPE).reshape(-1).tobytes() == want.tobytes()
+
+    def burst(streams, count, small_every=0, reforder_every=0):
+        outs = [torch.full((n, 32), 0xAB, dtype=torch.uint8, device="cuda") for _ in range(count)]
+        torch.cuda.synchronize()
+        for k, o in enumerate(outs):
+            st = streams[k % len(streams)]
+            if small_every and k % small_every == small_every - 1:
+                m = 4096 * W // W  # a launch far too small to fill the GPU, in the middle of the burst
+                sp.p.trace_closest_device(d_rays.data_ptr(), m, o.data_ptr(), ray_flags=helpers.CULL_BACK, stream=st.cuda_stream)
+                sp.p.trace_closest_device(d_rays.data_ptr() + m * 32, n - m, o.data_ptr() + m * 32, ray_flags=helpers.CULL_BACK, stream=st.cuda_stream)
+            elif reforder_every and k % reforder_every == reforder_every - 1:
+                sp.p.trace_closest_device(d_rays.data_ptr(), n, o.data_ptr(), ray_flags=helpers.CULL_BACK, stream=st.cuda_stream,
+                                          mode=api.TRACE_REFERENCE_ORDER)
+            else:
+                sp.p.trace_closest_device(d_rays.data_ptr(), n, o.data_ptr(), ray_flags=helpers.CULL_BACK, grid_width=W, stream=st.cuda_stream)
+        torch.cuda.synchronize()
+        return [bool(torch.equal(o, ref)) for o in outs]
+
+    assert all(burst([s0], 24))                                   # one stream: every launch overlaps its predecessor's tail
+    assert all(burst([s0, s1], 16))                               # two streams alternating: ordered through the library's event
+    assert all(burst([s0], 18, small_every=5, reforder_every=7))  # partial grids and the other kernel in between
