@@ -7,17 +7,21 @@
 //   NaiveSahBvhCpu::traverse    .../geometry/naive/traverse_cpu.rs:52-319
 //   TraverseFlags               .../geometry/naive/flag.rs:6-117
 //
-// Two kernels:
-//   k_trace_reference  the reference's stackless threaded pre-order walk, one ray per thread.  Identical to the
-//                      CPU query by construction (same visit order, same live-range pruning, "last accepted of
-//                      equal t wins").  Used for ACCEPT_FIRST_HIT rays, for visit counters, and to resolve ties.
+// Kernels:
+//   k_trace_reference       the reference's stackless threaded pre-order walk, one ray per thread.  Identical to the
+//                           CPU query by construction (same visit order, same live-range pruning, "last accepted of
+//                           equal t wins").  Used for ACCEPT_FIRST_HIT rays and for the reference's visit counters; its
+//                           walk (reference_walk) also resolves near-ties.
 //   k_trace_ordered_rounds  persistent-thread, near-child-first walk over the 64 B two-box nodes with a per-thread
-//                      stack, float4 node/triangle fetches through the read-only path, warp-synchronous rounds and
-//                      warp-level ray refill (ballot + one atomic per warp).  Box decisions use the reference's arithmetic on the
-//                      reference's boxes; the pruning bound is inflated by TIE_EPS and any ray that saw a second
-//                      candidate within TIE_EPS of the closest is queued (warp-aggregated append) and re-walked by
-//                      k_resolve_ties in the reference's order with its range clamped around the closest distance —
-//                      so ids come out exactly as the CPU query's.
+//                           stack, float4 node/triangle fetches through the read-only path, warp-synchronous rounds and
+//                           whole-tile ray refill (ballot + one atomic per warp).  Box decisions use the reference's
+//                           arithmetic on the reference's boxes; the pruning bound is inflated by TIE_EPS and any ray
+//                           that saw a second candidate within TIE_EPS of the closest is queued (warp-aggregated append)
+//                           and re-walked in the reference's order with its range clamped around the closest distance —
+//                           so ids come out exactly as the CPU query's.  The queue is drained inside the kernel by
+//                           warps that ran out of rays (last CTA sweeps the rest); consecutive launches on a stream
+//                           overlap their tails (programmatic dependent launch, two scratch sets, epoch gate).
+//   k_resolve_ties          the separate tie kernel of the first version, kept for A/B runs (RDN_ORDERED_VARIANT=9).
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -720,14 +724,9 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, uint3
   KernelFn fn;
   bool inline_ties = true;
   switch (variant) {
-    case 1: fn = k_trace_ordered_rounds<4, 8, 1, true>; break;
-    case 2: fn = k_trace_ordered_rounds<3, 8, 4, true>; break;
-    case 3: fn = k_trace_ordered_rounds<4, 8, 8, true>; break;
-    case 4: fn = k_trace_ordered_rounds<2, 8, 4, true>; break;
-    case 5: fn = k_trace_ordered_rounds<2, 8, 8, true>; break;
-    case 6: fn = k_trace_ordered_rounds<2, 8, 16, true>; break;
-    case 7: fn = k_trace_ordered_rounds<2, 8, 24, true>; break;
-    case 8: fn = k_trace_ordered_rounds<1, 8, 1, true>; break;
+    case 1: fn = k_trace_ordered_rounds<4, 8, 1, true>; break;   // more node steps per vote
+    case 2: fn = k_trace_ordered_rounds<3, 8, 4, true>; break;   // refill once fewer than 4 lanes are busy
+    case 3: fn = k_trace_ordered_rounds<4, 8, 8, true>; break;   // the first version's policy
     case 9: fn = k_trace_ordered_rounds<2, 8, 1, false>; inline_ties = false; break;  // queue drained by k_resolve_ties
     default: fn = k_trace_ordered_rounds<2, 8, 1, true>; break;
   }
