@@ -108,10 +108,22 @@ typedef enum rdn_trace_mode {
 } rdn_trace_mode;
 
 typedef struct rdn_trace_stats {
-  uint64_t rays, tie_rays;       /* rays re-walked in reference order to resolve a near-tie */
+  uint64_t rays, tie_rays;       /* rays re-walked in reference order: near-ties + rays whose range meets an irregular instance */
   uint32_t kernel_launches;      /* kernels this call launched */
   float kernel_ms;               /* device time of the traversal kernels (CUDA events on the call's stream) */
+  uint64_t whole_range_rewalks;  /* near-tie re-walks that had to be repeated over the ray's whole range (the closest candidate
+                                    lay outside its boxes: an irregular triangle the build-time classification did not flag) */
 } rdn_trace_stats;
+
+/* What the flattener found (rdn_rt_scene_build_stats).  "Irregular" triangles / instances are those whose hits need not
+ * lie inside their bounding boxes — needle triangles, singular / non-affine / ill-conditioned instance transforms, and the
+ * reference's per-geometry blas_box indexing (naive/mod.rs:239,273) — so that NaiveSahBvhCpu::traverse's answer depends on
+ * its visiting order; rays that can reach them are walked in that order (DESIGN.md "Exactness"). */
+typedef struct rdn_build_stats {
+  uint64_t balance_fallbacks, balance_fallbacks_gt10;  /* SAH -> BalanceTree fallbacks (strategy.rs:230-233); ... over > 10 primitives */
+  uint64_t irregular_triangles, irregular_instances;
+  uint64_t reference_routed_tlas;                      /* TLASes whose every ray takes the reference-order kernel */
+} rdn_build_stats;
 
 typedef struct rdn_rt_scene rdn_rt_scene;   /* opaque: NaiveSahBVHSystem (geometry/naive/mod.rs:495-610) */
 
@@ -219,9 +231,13 @@ int rdn_rt_scene_adopt_blob(rdn_rt_scene *scene, int device_index, const void *d
 typedef enum rdn_array_id {
   RDN_ARRAY_TLAS_BINDING = 0, RDN_ARRAY_TLAS_BVH_ROOT, RDN_ARRAY_TLAS_BVH_FOREST, RDN_ARRAY_TLAS_BOUNDING,
   RDN_ARRAY_INSTANCES, RDN_ARRAY_BLAS_META, RDN_ARRAY_GEOMETRY_META, RDN_ARRAY_TRI_BVH_FOREST,
-  RDN_ARRAY_TRIANGLES, RDN_ARRAY_SLOT_INFO, RDN_ARRAY_WIDE_NODES, RDN_ARRAY_PRIM_TO_SLOT, RDN_ARRAY_COUNT
+  RDN_ARRAY_TRIANGLES, RDN_ARRAY_SLOT_INFO, RDN_ARRAY_WIDE_NODES, RDN_ARRAY_PRIM_TO_SLOT, RDN_ARRAY_IRREGULAR_INSTANCES,
+  RDN_ARRAY_IRREGULAR_LEAF_BOXES, RDN_ARRAY_COUNT
 } rdn_array_id;
 int rdn_rt_scene_array(rdn_rt_scene *scene, int array_id, void *out, uint64_t capacity_bytes, uint64_t *out_bytes);
+/* build statistics of the committed scene (commits first); a scene that adopted another rank's blob reports only what the
+ * blob itself records (irregular_instances listed per TLAS, reference_routed_tlas) */
+int rdn_rt_scene_build_stats(rdn_rt_scene *scene, rdn_build_stats *out);
 
 /* ---- space-query surface: FlattenBVH::new (content/space/src/bvh/mod.rs:55-79) and
  *      intersect_nearest_bvh (content/mesh/core/src/feature/bvh.rs:57-86) ---- */

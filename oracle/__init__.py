@@ -40,6 +40,10 @@ STRATEGY_SAH, STRATEGY_BALANCE = 0, 1
 FACE_FRONT, FACE_BACK, FACE_DOUBLE = 0, 1, 2
 
 
+CANDIDATE_DTYPE = np.dtype([("distance", "f4"), ("t_object", "f4"), ("u", "f4"), ("v", "f4"), ("sign", "f4"), ("scaling", "f4"),
+                            ("instance_id", "u4"), ("geometry_id", "u4"), ("primitive_id", "u4"), ("slot", "u4"), ("in_range", "u4"), ("pad", "u4")])
+
+
 class Launch(C.Structure):
     _fields_ = [("ray_flags", C.c_uint32), ("cull_mask", C.c_uint32), ("tlas_idx", C.c_uint32), ("grid_width", C.c_uint32)]
 
@@ -248,6 +252,29 @@ class Scene:
         out["balance_fallbacks"] = int(v.balance_fallbacks)
         out["balance_fallbacks_gt10"] = int(v.balance_fallbacks_gt10)
         return out
+
+    def candidates(self, ray, ray_flags=0, cull_mask=0xFFFFFFFF, tlas_idx=0, cap=4096) -> np.ndarray:
+        """brute force: every (instance, triangle) whose triangle test passes with the ray's original range (no BVH, no pruning)"""
+        ray = _c(np.asarray(ray).reshape(1), RAY_DTYPE)
+        out = np.zeros(cap, CANDIDATE_DTYPE)
+        launch = Launch(ray_flags, cull_mask, tlas_idx, 0)
+        L = lib()
+        L.orc_scene_candidates.restype = C.c_uint64
+        L.orc_scene_candidates.argtypes = [C.c_void_p, C.POINTER(Launch), C.c_void_p, C.c_void_p, C.c_uint64]
+        n = L.orc_scene_candidates(self._h, C.byref(launch), _p(ray), _p(out), cap)
+        return out[:min(int(n), cap)]
+
+    def trace_unpruned(self, rays, ray_flags=0, cull_mask=0xFFFFFFFF, tlas_idx=0, n_threads=1) -> np.ndarray:
+        """NOT the reference: closest candidate of a walk that never shrinks its range (order-free model, oracle_scene.c)"""
+        rays = _c(rays, RAY_DTYPE)
+        hits = np.zeros(rays.shape[0], HIT_DTYPE)
+        launch = Launch(ray_flags, cull_mask, tlas_idx, 0)
+        L = lib()
+        L.orc_scene_trace_unpruned.restype = C.c_int
+        L.orc_scene_trace_unpruned.argtypes = [C.c_void_p, C.POINTER(Launch), C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]
+        if L.orc_scene_trace_unpruned(self._h, C.byref(launch), _p(rays), rays.shape[0], _p(hits), n_threads) != 0:
+            raise RuntimeError("oracle trace failed (scene not built?)")
+        return hits
 
     def trace(self, rays, ray_flags=0, cull_mask=0xFFFFFFFF, tlas_idx=0, n_threads=1, want_counters=True):
         rays = _c(rays, RAY_DTYPE)

@@ -131,6 +131,14 @@ void orc_scene_get_view(const orc_scene *s, orc_scene_view *out);
 int orc_scene_trace(const orc_scene *s, const orc_launch *launch, const orc_ray *rays, uint64_t n_rays,
                     orc_hit *out_hits, orc_counters *counters, int n_threads);
 
+/* test tool, NOT the reference: same trees, no shrinking range, closest candidate kept (order-free model of a pruning traversal) */
+int orc_scene_trace_unpruned(const orc_scene *s, const orc_launch *launch, const orc_ray *rays, uint64_t n_rays,
+                             orc_hit *out_hits, int n_threads);
+
+/* every (instance, triangle) pair of the bound TLAS whose triangle test passes with the ray's ORIGINAL range: no BVH, no pruning */
+typedef struct { float distance, t_object, u, v, sign, scaling; uint32_t instance_id, geometry_id, primitive_id, slot, in_range, pad; } orc_candidate;
+uint64_t orc_scene_candidates(const orc_scene *s, const orc_launch *launch, const orc_ray *ray, orc_candidate *out, uint64_t cap);
+
 /* ---------- parallel-compute restatements (scan / compaction / scatter) ---------- */
 void orc_workgroup_inclusive_scan_u32(const uint32_t *in, uint64_t n, uint32_t workgroup, uint32_t *out);
 void orc_inclusive_scan_u32(const uint32_t *in, uint64_t n, uint32_t *out);

@@ -353,7 +353,10 @@ static inline uint32_t bvh_iter_next(const orc_dev_node *bvh, uint32_t *curr_idx
   return ORC_INVALID_NEXT;
 }
 
-static void traverse_one(const orc_scene *s, const orc_launch *L, const orc_ray *ray, orc_hit *out, orc_counters *c) {
+/* unpruned != 0: NOT the reference — the order-free model used to test the regularity classification (orc_scene_trace_unpruned):
+ * every box / triangle range test uses the ray's ORIGINAL range and the closest accepted candidate is kept, i.e. the result every
+ * traversal that prunes by its own closest hit converges to when hits lie inside their boxes. */
+static void traverse_one(const orc_scene *s, const orc_launch *L, const orc_ray *ray, orc_hit *out, orc_counters *c, int unpruned) {
   out->t = ray->tmax; out->u = 0; out->v = 0;
   out->primitive_id = out->geometry_id = out->instance_id = out->instance_custom_id = 0xFFFFFFFFu;
   out->hit_kind = 0;
@@ -361,6 +364,8 @@ static void traverse_one(const orc_scene *s, const orc_launch *L, const orc_ray 
   const uint32_t flags0 = L->ray_flags;
   const float near = ray->tmin;
   float far = ray->tmax;             /* the shared Rc<Cell<f32>> */
+  float fixed_far = ray->tmax;
+  float *pf = unpruned ? &fixed_far : &far;  /* what the box / triangle range tests see */
   const ov3 ro = ov3_new(ray->ox, ray->oy, ray->oz);
   const ov3 rd = ov3_new(ray->dx, ray->dy, ray->dz);
 
@@ -370,7 +375,7 @@ static void traverse_one(const orc_scene *s, const orc_launch *L, const orc_ray 
   uint32_t tlas_cursor = s->tlas_bvh_root.p[handle];
 
   for (;;) {
-    uint32_t leaf = bvh_iter_next(s->tlas_bvh_forest.p, &tlas_cursor, ro, rd, near, &far, 1.0f, c);
+    uint32_t leaf = bvh_iter_next(s->tlas_bvh_forest.p, &tlas_cursor, ro, rd, near, pf, 1.0f, c);
     if (leaf == ORC_INVALID_NEXT) break;
     const orc_dev_node *node = &s->tlas_bvh_forest.p[leaf];
     for (uint32_t tlas_idx = node->range_x; tlas_idx < node->range_y; tlas_idx++) {
@@ -411,7 +416,7 @@ static void traverse_one(const orc_scene *s, const orc_launch *L, const orc_ray 
 
         uint32_t cursor = geometry.bvh_root_idx;
         for (;;) {
-          uint32_t bl = bvh_iter_next(s->tri_bvh_forest.p, &cursor, bo, bd, near, &far, scaling, c);
+          uint32_t bl = bvh_iter_next(s->tri_bvh_forest.p, &cursor, bo, bd, near, pf, scaling, c);
           if (bl == ORC_INVALID_NEXT) break;
           const orc_dev_node *bn = &s->tri_bvh_forest.p[bl];
           for (uint32_t slot = bn->range_x; slot < bn->range_y; slot++) {
@@ -419,11 +424,12 @@ static void traverse_one(const orc_scene *s, const orc_launch *L, const orc_ray 
             uint32_t i0 = s->indices.p[(uint64_t)tri_idx * 3], i1 = s->indices.p[(uint64_t)tri_idx * 3 + 1], i2 = s->indices.p[(uint64_t)tri_idx * 3 + 2];
             ov3 v0 = s->vertices.p[i0], v1 = s->vertices.p[i1], v2 = s->vertices.p[i2];
             c->tri_visit++;
-            ov4 isect = intersect_ray_triangle(bo, bd, near * scaling, far * scaling, v0, v1, v2, cull_enable, cull_back);
+            ov4 isect = intersect_ray_triangle(bo, bd, near * scaling, *pf * scaling, v0, v1, v2, cull_enable, cull_back);
             if (isect.x != 0.0f) {
               float distance = isect.y / scaling;
               uint32_t primitive_idx = tri_idx - geometry.primitive_start;
               c->tri_hit++;
+              if (unpruned && !(near <= distance && distance <= ray->tmax && distance <= far)) continue;
               /* opaque -> ACCEPT; non-opaque -> any_hit(), fixed to ACCEPT here */
               (void)is_opaque;
               /* RayRange::update_far: assert!(near <= far); assert!(far <= self.far) */
@@ -442,23 +448,89 @@ static void traverse_one(const orc_scene *s, const orc_launch *L, const orc_ray 
   }
 }
 
+/* Brute-force candidate list of one ray (debugging / self-consistency): every instance of the bound TLAS that passes the
+ * mask + original-range box test and every triangle of its BLAS, NO BVH pruning and NO live range: the triangle test runs with
+ * the ray's original range.  The closest hit of the traversal is the minimum-distance entry (first / last of equals per the
+ * reference's order).  Returns the number of candidates (may exceed cap; only cap are written). */
+uint64_t orc_scene_candidates(const orc_scene *s, const orc_launch *L, const orc_ray *ray, orc_candidate *out, uint64_t cap) {
+  uint64_t n = 0;
+  const ov3 ro = ov3_new(ray->ox, ray->oy, ray->oz), rd = ov3_new(ray->dx, ray->dy, ray->dz);
+  if (L->tlas_idx >= s->binding.n) return 0;
+  uint32_t handle = s->binding.p[L->tlas_idx];
+  if (handle >= s->tlas_bvh_root.n) return 0;
+  for (uint32_t tn = s->tlas_bvh_root.p[handle]; tn != ORC_INVALID_NEXT;) {
+    const orc_dev_node *node = &s->tlas_bvh_forest.p[tn];
+    const int leaf = node->hit_next == node->miss_next;
+    tn = node->hit_next;  /* pre-order over ALL nodes */
+    if (!leaf) continue;
+    for (uint32_t tlas_idx = node->range_x; tlas_idx < node->range_y; tlas_idx++) {
+      const orc_tlas_bounding *tb = &s->tlas_bounding.p[tlas_idx];
+      if (!intersect_ray_aabb(ro, rd, ray->tmin, ray->tmax, tb->world_min, tb->world_max)) continue;
+      if ((L->cull_mask & tb->mask) == 0) continue;
+      const orc_dev_instance *td = &s->tlas_data.p[tlas_idx];
+      uint32_t flags = merge_geometry_instance_flag(L->ray_flags, td->flags);
+      ov4 o4 = {ro.x, ro.y, ro.z, 1.0f};
+      o4 = om4_mul_v4(td->transform_inv, o4);
+      ov3 bo = ov3_divs(ov3_new(o4.x, o4.y, o4.z), o4.w);
+      ov3 bd = om3_mul_v3(om4_to_mat3(td->transform_inv), rd);
+      float scaling = ov3_length(bd);
+      bd = ov3_normalize(bd);
+      if (td->blas >= s->blas_meta_info.n || (flags & F_SKIP_TRIANGLES)) continue;
+      const orc_blas_meta *bm = &s->blas_meta_info.p[td->blas];
+      for (uint32_t g = bm->tri_root_x; g < bm->tri_root_y; g++) {
+        orc_geom_meta geometry = s->tri_bvh_root.p[g];
+        int geometry_opaque = (geometry.geometry_flags & G_OPAQUE) != 0;
+        int is_opaque = (geometry_opaque || (flags & F_FORCE_OPAQUE)) && !(flags & F_FORCE_NON_OPAQUE);
+        int pass = (is_opaque && !(flags & F_CULL_OPAQUE)) || (!is_opaque && !(flags & F_CULL_NON_OPAQUE));
+        if (!pass) continue;
+        int flip = (flags & F_TRIANGLE_FLIP_FACING) != 0;
+        int cull_front = (flags & F_CULL_FRONT_FACING_TRIANGLES) != 0, cull_back_f = (flags & F_CULL_BACK_FACING_TRIANGLES) != 0;
+        int cull_enable = cull_front || cull_back_f;
+        int cull_back = (flip && cull_back_f) || (!flip && cull_front);
+        for (uint32_t bn = geometry.bvh_root_idx; bn != ORC_INVALID_NEXT;) {
+          const orc_dev_node *b = &s->tri_bvh_forest.p[bn];
+          const int bleaf = b->hit_next == b->miss_next;
+          bn = b->hit_next;
+          if (!bleaf) continue;
+          for (uint32_t slot = b->range_x; slot < b->range_y; slot++) {
+            uint32_t tri_idx = s->indices_redirect.p[slot];
+            ov3 v0 = s->vertices.p[s->indices.p[(uint64_t)tri_idx * 3]], v1 = s->vertices.p[s->indices.p[(uint64_t)tri_idx * 3 + 1]],
+                v2 = s->vertices.p[s->indices.p[(uint64_t)tri_idx * 3 + 2]];
+            ov4 isect = intersect_ray_triangle(bo, bd, ray->tmin * scaling, ray->tmax * scaling, v0, v1, v2, cull_enable, cull_back);
+            if (isect.x == 0.0f) continue;
+            float distance = isect.y / scaling;
+            if (n < cap) {
+              orc_candidate *c = &out[n];
+              c->distance = distance; c->t_object = isect.y; c->u = isect.z; c->v = isect.w; c->sign = isect.x; c->scaling = scaling;
+              c->instance_id = tlas_idx; c->geometry_id = geometry.geometry_idx; c->primitive_id = tri_idx - geometry.primitive_start;
+              c->slot = slot; c->in_range = (ray->tmin <= distance) && (distance <= ray->tmax); c->pad = 0;
+            }
+            n++;
+          }
+        }
+      }
+    }
+  }
+  return n;
+}
+
 /* multi-thread driver: rays are handed out in chunks from an atomic cursor (hit rays cluster in image space, so static
  * ranges would leave most threads idle) */
 #define ORC_CHUNK 2048u
-typedef struct { const orc_scene *s; const orc_launch *L; const orc_ray *rays; orc_hit *hits; uint64_t n; atomic_ullong *cursor; orc_counters c; } trace_job;
+typedef struct { const orc_scene *s; const orc_launch *L; const orc_ray *rays; orc_hit *hits; uint64_t n; atomic_ullong *cursor; orc_counters c; int unpruned; } trace_job;
 static void *trace_worker(void *p) {
   trace_job *j = (trace_job *)p;
   for (;;) {
     uint64_t begin = atomic_fetch_add(j->cursor, ORC_CHUNK);
     if (begin >= j->n) break;
     uint64_t end = begin + ORC_CHUNK < j->n ? begin + ORC_CHUNK : j->n;
-    for (uint64_t i = begin; i < end; i++) traverse_one(j->s, j->L, &j->rays[i], &j->hits[i], &j->c);
+    for (uint64_t i = begin; i < end; i++) traverse_one(j->s, j->L, &j->rays[i], &j->hits[i], &j->c, j->unpruned);
   }
   return NULL;
 }
 
-int orc_scene_trace(const orc_scene *s, const orc_launch *launch, const orc_ray *rays, uint64_t n_rays,
-                    orc_hit *out_hits, orc_counters *counters, int n_threads) {
+static int scene_trace(const orc_scene *s, const orc_launch *launch, const orc_ray *rays, uint64_t n_rays,
+                       orc_hit *out_hits, orc_counters *counters, int n_threads, int unpruned) {
   if (!s->built) return -1;
   if (n_threads < 1) n_threads = 1;
   trace_job *jobs = (trace_job *)calloc(n_threads, sizeof(trace_job));
@@ -467,6 +539,7 @@ int orc_scene_trace(const orc_scene *s, const orc_launch *launch, const orc_ray 
   atomic_init(&cursor, 0);
   for (int t = 0; t < n_threads; t++) {
     jobs[t].s = s; jobs[t].L = launch; jobs[t].rays = rays; jobs[t].hits = out_hits; jobs[t].n = n_rays; jobs[t].cursor = &cursor;
+    jobs[t].unpruned = unpruned;
   }
   if (n_threads == 1) trace_worker(&jobs[0]);
   else {
@@ -483,6 +556,18 @@ int orc_scene_trace(const orc_scene *s, const orc_launch *launch, const orc_ray 
   }
   free(jobs); free(th);
   return 0;
+}
+
+int orc_scene_trace(const orc_scene *s, const orc_launch *launch, const orc_ray *rays, uint64_t n_rays,
+                    orc_hit *out_hits, orc_counters *counters, int n_threads) {
+  return scene_trace(s, launch, rays, n_rays, out_hits, counters, n_threads, 0);
+}
+
+/* NOT the reference: the closest candidate of a walk over the same trees that never shrinks its range (see traverse_one).  Where
+ * it differs from orc_scene_trace beyond an exact tie, the reference's answer depends on its visiting order. */
+int orc_scene_trace_unpruned(const orc_scene *s, const orc_launch *launch, const orc_ray *rays, uint64_t n_rays,
+                             orc_hit *out_hits, int n_threads) {
+  return scene_trace(s, launch, rays, n_rays, out_hits, NULL, n_threads, 1);
 }
 
 /* ---- Mat4 helpers for KATs / scene builders ---- */

@@ -44,10 +44,12 @@ WIDE_NODE_DTYPE = np.dtype([("c0_min", "f4", (3,)), ("ref0", "u4"), ("c0_max", "
                             ("c1_min", "f4", (3,)), ("pad0", "u4"), ("c1_max", "f4", (3,)), ("pad1", "u4")])
 
 ARRAYS = {  # rdn_array_id -> (name, dtype)
-    0: ("tlas_binding", np.dtype("u4")), 1: ("tlas_root", np.dtype(("u4", (2,)))), 2: ("tlas_bvh_forest", DEV_NODE_DTYPE),
-    3: ("tlas_bounding", TLAS_BOUNDING_DTYPE), 4: ("instances", INSTANCE_RECORD_DTYPE), 5: ("blas_meta", np.dtype(("u4", (2,)))),
+    0: ("tlas_binding", np.dtype("u4")), 1: ("tlas_root", np.dtype(("u4", (4,)))), 2: ("tlas_bvh_forest", DEV_NODE_DTYPE),
+    3: ("tlas_bounding", TLAS_BOUNDING_DTYPE), 4: ("instances", INSTANCE_RECORD_DTYPE), 5: ("blas_meta", np.dtype(("u4", (4,)))),
     6: ("geometry_meta", GEOMETRY_META_DTYPE), 7: ("tri_bvh_forest", DEV_NODE_DTYPE), 8: ("triangles", TRI_RECORD_DTYPE),
     9: ("slot_info", np.dtype(("u4", (2,)))), 10: ("wide_nodes", WIDE_NODE_DTYPE), 11: ("prim_to_slot", np.dtype("u4")),
+    12: ("irregular_instances", np.dtype("u4")),
+    13: ("irregular_leaf_boxes", np.dtype([("bmin", "f4", (3,)), ("pad0", "u4"), ("bmax", "f4", (3,)), ("pad1", "u4")])),
 }
 
 # RayFlagConfigRaw (api/ty.rs:102-114)
@@ -97,7 +99,13 @@ class _Counters(C.Structure):
 
 
 class _TraceStats(C.Structure):
-    _fields_ = [("rays", C.c_uint64), ("tie_rays", C.c_uint64), ("kernel_launches", C.c_uint32), ("kernel_ms", C.c_float)]
+    _fields_ = [("rays", C.c_uint64), ("tie_rays", C.c_uint64), ("kernel_launches", C.c_uint32), ("kernel_ms", C.c_float),
+                ("whole_range_rewalks", C.c_uint64)]
+
+
+class _BuildStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("balance_fallbacks", "balance_fallbacks_gt10", "irregular_triangles", "irregular_instances",
+                                          "reference_routed_tlas")]
 
 
 class _KernelTimes(C.Structure):
@@ -135,7 +143,7 @@ EXPORTED_SYMBOLS = [
     "rdn_rt_tlas_destroy", "rdn_rt_bind_tlas", "rdn_rt_bind_tlas_max_len", "rdn_rt_commit", "rdn_rt_trace_closest",
     "rdn_rt_trace_closest_device", "rdn_rt_trace_counted", "rdn_rt_kernel_timing_begin", "rdn_rt_kernel_timing_end",
     "rdn_rt_gen_pinhole_rays_device", "rdn_rt_gen_pinhole_rays_batch_device", "rdn_rt_gen_camera_rays_device", "rdn_rt_gen_bounce_rays_device", "rdn_rt_compact_u32", "rdn_rt_compact_u32_device",
-    "rdn_rt_scene_blob", "rdn_rt_scene_adopt_blob", "rdn_rt_scene_array", "rdn_bvh_build", "rdn_bvh_destroy", "rdn_bvh_nodes",
+    "rdn_rt_scene_blob", "rdn_rt_scene_adopt_blob", "rdn_rt_scene_array", "rdn_rt_scene_build_stats", "rdn_bvh_build", "rdn_bvh_destroy", "rdn_bvh_nodes",
     "rdn_bvh_sorted_primitive_index", "rdn_bvh_build_for_mesh", "rdn_bvh_query_nearest", "rdn_bvh_upload", "rdn_bvh_query_nearest_device", "rdn_bvh_query_list", "rdn_rt_last_error", "rdn_rt_version",
 ]
 
@@ -180,6 +188,7 @@ def lib() -> C.CDLL:
     L.rdn_rt_scene_blob.argtypes = [vp, i32, P(vp), P(u64)]
     L.rdn_rt_scene_adopt_blob.argtypes = [vp, i32, vp, u64]
     L.rdn_rt_scene_array.argtypes = [vp, i32, vp, u64, P(u64)]
+    L.rdn_rt_scene_build_stats.argtypes = [vp, P(_BuildStats)]
     L.rdn_bvh_build.argtypes = [vp, u64, i32, u32, P(_Option), P(vp)]
     L.rdn_bvh_build_for_mesh.argtypes = [P(_MeshView), i32, u32, P(_Option), P(vp)]
     L.rdn_bvh_destroy.argtypes = [vp]
@@ -307,7 +316,7 @@ class NaiveSahBVHSystem:
                                                    C.byref(st) if want_stats else None))
         if want_stats:
             return {"rays": int(st.rays), "tie_rays": int(st.tie_rays), "kernel_launches": int(st.kernel_launches),
-                    "kernel_ms": float(st.kernel_ms)}
+                    "kernel_ms": float(st.kernel_ms), "whole_range_rewalks": int(st.whole_range_rewalks)}
         return None
 
     def trace_counted(self, rays: np.ndarray, ray_flags=0, cull_mask=0xFFFFFFFF, tlas_idx=0):
@@ -396,6 +405,12 @@ class NaiveSahBVHSystem:
         if nb.value:
             _check(self._L.rdn_rt_scene_array(self._h, array_id, _p(out), nb.value, C.byref(nb)))
         return out
+
+    def build_stats(self) -> dict:
+        """What the flattener found: SAH->BalanceTree fallbacks and the irregular triangles / instances (include/rdn_rt.h)."""
+        st = _BuildStats()
+        _check(self._L.rdn_rt_scene_build_stats(self._h, C.byref(st)))
+        return {n: int(getattr(st, n)) for n, _ in _BuildStats._fields_}
 
     def arrays(self) -> dict:
         return {ARRAYS[i][0]: self.array(i) for i in ARRAYS}

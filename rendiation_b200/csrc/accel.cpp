@@ -1,6 +1,7 @@
 // accel.cpp — BLAS/TLAS assembly and flattening.  Compiled with -ffp-contract=off.
 #include "accel.h"
 
+#include <cmath>
 #include <cstring>
 
 #include "../../include/rdn_rt.h"
@@ -199,6 +200,72 @@ static TriRecord make_tri_record(Vec3 v0, Vec3 v1, Vec3 v2) {
   return t;
 }
 
+// ------------------------------------------------------------------------------------------------ regularity
+// The ordered kernel visits near children first and prunes against its own closest hit, so it agrees with the reference's
+// pre-order walk only where every accepted hit lies inside the boxes that lead to it (up to rounding, which the TIE_EPS
+// slack of the kernel absorbs).  The reference's result is traversal-order dependent where that fails:
+//   * needle triangles: uv*uv - uu*vv cancels to noise, the barycentric test passes for points far outside the triangle
+//     (and its leaf box); the reference then finds or prunes them depending on what it met first;
+//   * instances whose world box does not bound their hits: singular transform (inverse_or_identity gives the identity while
+//     the box uses the singular matrix), non-finite or projective matrices, inverses that do not round-trip, and the
+//     reference's own blas_box indexing (one entry per GEOMETRY, looked up by BLAS handle, mod.rs:239,273), which hands an
+//     instance the box of another BLAS's geometry once an earlier BLAS has more or fewer than one geometry.
+// Such triangles / instances are "irregular".  Rays whose ORIGINAL range meets the world box of an irregular instance — a
+// superset of the rays whose reference walk can enter it — are walked in the reference's order (unclamped) instead.
+// sin^2 of the angle between the edges below which a triangle counts as a needle.  uv*uv - uu*vv carries a relative error of
+// about 2e-7 / sin^2, which is also how far beyond its far edge (in units of its long edge) the barycentric test still accepts:
+// 2 % at this threshold, shrinking fast above it (thin but honest triangles, e.g. next to the poles of a finely tessellated
+// UV sphere at sin^2 ~ 1e-4, stay regular); below it the determinant is mostly noise.
+constexpr double NEEDLE_SIN2 = 1e-5;
+constexpr float ROUND_TRIP_TOLERANCE = 1e-3f;  // |Minv (M c) - c| allowed, relative to the box diagonal
+
+static bool finite3(const float *v) { return std::isfinite(v[0]) && std::isfinite(v[1]) && std::isfinite(v[2]); }
+
+static bool triangle_is_irregular(const TriRecord &t) {
+  // zero normal (exactly degenerate, e.g. the pole triangles of a UV sphere): b = 0, a = -0, t = NaN, which the range asserts
+  // reject in every traversal order — harmless
+  if (t.n[0] == 0.0f && t.n[1] == 0.0f && t.n[2] == 0.0f) return false;
+  if (!finite3(t.n) || !finite3(t.v0) || !finite3(t.e1) || !finite3(t.e2) || !std::isfinite(t.inv_d)) return true;
+  const double area2 = static_cast<double>(t.uu) * t.vv - static_cast<double>(t.uv) * t.uv;  // |e1 x e2|^2
+  return !(area2 >= NEEDLE_SIN2 * static_cast<double>(t.uu) * t.vv);
+}
+
+static bool box_is_empty(const Box3 &b) { return (b.max.x < b.min.x) || (b.max.y < b.min.y) || (b.max.z < b.min.z); }
+static bool box_contains(const Box3 &outer, const Box3 &inner) {
+  return outer.min.x <= inner.min.x && outer.min.y <= inner.min.y && outer.min.z <= inner.min.z && outer.max.x >= inner.max.x &&
+         outer.max.y >= inner.max.y && outer.max.z >= inner.max.z;
+}
+static float box_diagonal(const Box3 &b) { return length(b.max - b.min); }
+
+// `used_box`: the object-space box the reference transforms into the instance's world box; `true_box`: the bound of the
+// triangles the instance really holds
+static bool instance_is_irregular(const Mat4 &m, const Mat4 &inv, const Box3 &used_box, const Box3 &true_box) {
+  if (box_is_empty(true_box)) return false;  // nothing to hit
+  if (box_is_empty(used_box) || !box_contains(used_box, true_box)) return true;
+  const float *mp = &m.a1, *ip = &inv.a1;
+  for (int i = 0; i < 16; ++i)
+    if (!std::isfinite(mp[i]) || !std::isfinite(ip[i])) return true;
+  if (mat4_det(m) == 0.0f) return true;                                                    // inverse_or_identity fell back
+  if (m.a4 != 0.0f || m.b4 != 0.0f || m.c4 != 0.0f || m.d4 != 1.0f) return true;          // the ray transform is affine only
+  const float object_diag = box_diagonal(used_box);
+  Box3 world = box_empty();
+  Vec3 corners[8], images[8];
+  for (int corner = 0; corner < 8; ++corner) {
+    corners[corner] = Vec3{(corner & 4) ? used_box.max.x : used_box.min.x, (corner & 2) ? used_box.max.y : used_box.min.y,
+                           (corner & 1) ? used_box.max.z : used_box.min.z};
+    images[corner] = transform_point(m, corners[corner].x, corners[corner].y, corners[corner].z);
+    expand(world, images[corner]);
+  }
+  const float world_diag = box_diagonal(world);
+  for (int corner = 0; corner < 8; ++corner) {
+    const Vec3 back = transform_point(inv, images[corner].x, images[corner].y, images[corner].z);
+    const Vec3 again = transform_point(m, back.x, back.y, back.z);
+    if (!(length(back - corners[corner]) <= ROUND_TRIP_TOLERANCE * object_diag)) return true;
+    if (!(length(again - images[corner]) <= ROUND_TRIP_TOLERANCE * world_diag)) return true;
+  }
+  return false;
+}
+
 int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScene &out, std::string &err) const {
   out = FlatScene{};
   out.tlas_binding = tlas_binding;
@@ -208,16 +275,22 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
   // deleted BLAS, and build_tlas indexes it by BLAS handle (mod.rs:239,273) — reproduced as is.
   struct OptBox { bool some; Box3 box; };
   std::vector<OptBox> blas_box;
+  std::vector<Box3> blas_true_box;       // per BLAS HANDLE: bound of all its triangle geometries
+  std::vector<uint32_t> blas_irregular;  // per BLAS handle: BlasMeta::irregular_leaf_count
   uint64_t n_indices_total = 0;  // geometry_indices.len()
   const TreeBuildOption blas_option{50, 2};
 
   for (const Blas &blas : blas_data_) {
     if (!blas.alive) {
-      out.blas_meta.push_back(BlasMeta{{0, 0}});
+      out.blas_meta.push_back(BlasMeta{{0, 0}, 0, 0});
       blas_box.push_back(OptBox{false, box_empty()});
+      blas_true_box.push_back(box_empty());
+      blas_irregular.push_back(0);
       continue;
     }
     const uint32_t tri_start = static_cast<uint32_t>(out.geometry_meta.size());
+    Box3 true_box = box_empty();
+    const uint32_t leaf_start = static_cast<uint32_t>(out.irregular_leaf_boxes.size());
     for (size_t g = 0; g < blas.geometries.size(); ++g) {
       const GeometrySource &src = blas.geometries[g];
       Box3 root_box = box_empty();
@@ -242,20 +315,36 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
         out.stats.balance_fallbacks += bvh.stats.balance_fallbacks;
         out.stats.balance_fallbacks_gt10 += bvh.stats.balance_fallbacks_gt10;
         expand(root_box, bvh.nodes[0].bounding);
+        if (n_tri) expand(true_box, bvh.nodes[0].bounding);
         const auto next = compute_bvh_next(bvh.nodes);
 
         // slots of this geometry start at primitive_start (indices_redirect and indices grow in lock step)
         const uint64_t slot_base = out.triangles.size();
         if (slot_base != primitive_start) { err = "internal: slot/primitive offset mismatch"; return RDN_ERR_BUILD; }
         out.prim_to_slot.resize(slot_base + n_tri, 0u);
+        std::vector<uint8_t> slot_irregular(n_tri, 0);
         for (uint64_t k = 0; k < n_tri; ++k) {
           const uint64_t tri = bvh.sorted_primitive_index[k];  // indices_redirect[slot] - raw_primitive_start
           out.prim_to_slot[slot_base + tri] = static_cast<uint32_t>(slot_base + k);
           out.triangles.push_back(make_tri_record(src.positions[vertex_of(tri, 0)], src.positions[vertex_of(tri, 1)],
                                                   src.positions[vertex_of(tri, 2)]));
+          slot_irregular[k] = triangle_is_irregular(out.triangles.back()) ? 1 : 0;
+          out.stats.irregular_triangles += slot_irregular[k];
           out.slot_info.push_back(SlotInfo{static_cast<uint32_t>(tri), static_cast<uint32_t>(g)});
         }
         n_indices_total += n_tri * 3;
+        // the boxes of the leaves that hold an irregular triangle: the reference can test such a triangle only after this box test
+        for (const FlattenBVHNode &node : bvh.nodes) {
+          if (node.has_child) continue;
+          bool any = false;
+          for (uint64_t k = node.primitive_start; k < node.primitive_end && !any; ++k) any = slot_irregular[k] != 0;
+          if (!any) continue;
+          LeafBox lb;
+          std::memset(&lb, 0, sizeof(lb));
+          lb.bmin[0] = node.bounding.min.x; lb.bmin[1] = node.bounding.min.y; lb.bmin[2] = node.bounding.min.z;
+          lb.bmax[0] = node.bounding.max.x; lb.bmax[1] = node.bounding.max.y; lb.bmax[2] = node.bounding.max.z;
+          out.irregular_leaf_boxes.push_back(lb);
+        }
 
         const uint32_t bvh_start = static_cast<uint32_t>(out.tri_bvh_forest.size());
         GeometryMeta gm;
@@ -271,14 +360,21 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
       }
       blas_box.push_back(OptBox{true, root_box});
     }
-    out.blas_meta.push_back(BlasMeta{{tri_start, static_cast<uint32_t>(out.geometry_meta.size())}});
+    uint32_t leaf_count = static_cast<uint32_t>(out.irregular_leaf_boxes.size() - leaf_start);
+    if (leaf_count > IRREGULAR_LEAF_MAX) {
+      out.irregular_leaf_boxes.resize(leaf_start);
+      leaf_count = IRREGULAR_ROUTE_ALL;
+    }
+    out.blas_meta.push_back(BlasMeta{{tri_start, static_cast<uint32_t>(out.geometry_meta.size())}, leaf_start, leaf_count});
+    blas_true_box.push_back(true_box);
+    blas_irregular.push_back(leaf_count);
   }
 
   // ---- build_tlas per TLAS (mod.rs:262-320, 428-448)
   const TreeBuildOption tlas_option{50, 10};
   for (const Tlas &tlas : tlas_data_) {
     if (!tlas.alive) {
-      out.tlas_root.push_back(TlasRoot{INVALID_NEXT, REF_EMPTY});
+      out.tlas_root.push_back(TlasRoot{INVALID_NEXT, REF_EMPTY, 0, 0});
       continue;
     }
     const uint32_t bvh_start = static_cast<uint32_t>(out.tlas_bvh_forest.size());
@@ -299,6 +395,8 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
     out.stats.balance_fallbacks_gt10 += bvh.stats.balance_fallbacks_gt10;
     const auto next = compute_bvh_next(bvh.nodes);
 
+    const uint32_t irregular_start = static_cast<uint32_t>(out.irregular_instances.size());
+    double irregular_area = 0.0;
     for (uint64_t box_idx : bvh.sorted_primitive_index) {
       const InstanceSource &src = tlas.instances[box_idx];
       uint32_t flags = src.flags;
@@ -310,6 +408,16 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
       rec.sbt_offset = src.sbt_offset;
       rec.flags = flags;
       rec.blas = src.blas_handle;
+      const bool known_blas = src.blas_handle < blas_true_box.size();  // else the kernels skip the instance (blas >= n_blas_meta)
+      if (known_blas) {
+        const bool whole = blas_irregular[src.blas_handle] == IRREGULAR_ROUTE_ALL ||
+                           instance_is_irregular(src.transform, inv, blas_box[src.blas_handle].box, blas_true_box[src.blas_handle]);
+        if (whole || blas_irregular[src.blas_handle] != 0) {
+          out.irregular_instances.push_back(static_cast<uint32_t>(out.instances.size()) | (whole ? IRREGULAR_WHOLE_BIT : 0u));
+          out.stats.irregular_instances++;
+          if (whole) irregular_area += static_cast<double>(surface_area(aabbs[box_idx]));
+        }
+      }
       out.instances.push_back(rec);
       TlasBounding tb;
       tb.world_min[0] = aabbs[box_idx].min.x; tb.world_min[1] = aabbs[box_idx].min.y; tb.world_min[2] = aabbs[box_idx].min.z;
@@ -321,6 +429,18 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
     TlasRoot root;
     root.bvh_root_idx = bvh_start;
     root.wide_root = emit_wide_nodes(bvh.nodes, primitive_start, out.wide_nodes, capacity_error);
+    root.irregular_start = irregular_start;
+    root.irregular_count = static_cast<uint32_t>(out.irregular_instances.size() - irregular_start);
+    // a short list is checked per ray by the ordered kernel; a long one, or boxes that cover most of the TLAS anyway
+    // (e.g. its only instance), send the whole TLAS to the reference-order kernel
+    if (root.irregular_count != 0) {
+      const double root_area = bvh.nodes.empty() ? 0.0 : static_cast<double>(surface_area(bvh.nodes[0].bounding));
+      if (root.irregular_count > IRREGULAR_LIST_MAX || !(irregular_area < 0.5 * root_area)) {
+        out.irregular_instances.resize(irregular_start);
+        root.irregular_count = IRREGULAR_ROUTE_ALL;
+        out.stats.reference_routed_tlas++;
+      }
+    }
     out.tlas_root.push_back(root);
     for (size_t i = 0; i < bvh.nodes.size(); ++i)
       out.tlas_bvh_forest.push_back(to_device_node(bvh.nodes[i], next[i].first, next[i].second, bvh_start, primitive_start));
@@ -366,6 +486,8 @@ std::vector<uint8_t> FlatScene::serialize() const {
   place(blob, h, ARR_SLOT_INFO, slot_info);
   place(blob, h, ARR_WIDE_NODES, wide_nodes);
   place(blob, h, ARR_PRIM_TO_SLOT, prim_to_slot);
+  place(blob, h, ARR_IRREGULAR_INSTANCES, irregular_instances);
+  place(blob, h, ARR_IRREGULAR_LEAF_BOXES, irregular_leaf_boxes);
   blob.resize((blob.size() + BLOB_ALIGN - 1) / BLOB_ALIGN * BLOB_ALIGN, 0);
   h.total_bytes = blob.size();
   std::memcpy(blob.data(), &h, sizeof(h));

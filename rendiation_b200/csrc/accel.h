@@ -40,6 +40,8 @@ struct FlatScene {
   std::vector<SlotInfo> slot_info;
   std::vector<WideNode> wide_nodes;
   std::vector<uint32_t> prim_to_slot;
+  std::vector<uint32_t> irregular_instances;
+  std::vector<LeafBox> irregular_leaf_boxes;
   BuildStats stats;
 
   // pack into one contiguous, BLOB_ALIGN-aligned byte image starting with a BlobHeader

@@ -50,6 +50,10 @@ struct BuildStats {
   uint64_t balance_fallbacks = 0;       // SAH -> BalanceTree fallbacks (all primitives in one bucket)
   uint64_t balance_fallbacks_gt10 = 0;  // ... over more than 10 primitives (Rust's select_nth order is unspecified there)
   bool bucket_out_of_range = false;     // the reference would have panicked
+  // regularity classification of the flattener (accel.cpp): what the ordered kernel may not prune around
+  uint64_t irregular_triangles = 0;     // needle / non-finite triangle records (their test can pass far outside their leaf box)
+  uint64_t irregular_instances = 0;     // singular / non-finite / ill-conditioned transforms, or instances of a BLAS with irregular triangles
+  uint64_t reference_routed_tlas = 0;   // TLASes whose rays all take the reference-order kernel
 };
 
 class BVHBuildStrategy {

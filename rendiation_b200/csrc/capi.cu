@@ -161,6 +161,8 @@ void bind_blob(DeviceCtx &dc, const BlobHeader &h) {
   d.slot_info = reinterpret_cast<const SlotInfo *>(b + h.offset[ARR_SLOT_INFO]);
   d.wide_nodes = reinterpret_cast<const WideNode *>(b + h.offset[ARR_WIDE_NODES]);
   d.prim_to_slot = reinterpret_cast<const uint32_t *>(b + h.offset[ARR_PRIM_TO_SLOT]);
+  d.irregular_instances = reinterpret_cast<const uint32_t *>(b + h.offset[ARR_IRREGULAR_INSTANCES]);
+  d.irregular_leaf_boxes = reinterpret_cast<const LeafBox *>(b + h.offset[ARR_IRREGULAR_LEAF_BOXES]);
   d.n_tlas_binding = static_cast<uint32_t>(h.count[ARR_TLAS_BINDING]);
   d.n_tlas_root = static_cast<uint32_t>(h.count[ARR_TLAS_ROOT]);
   d.n_blas_meta = static_cast<uint32_t>(h.count[ARR_BLAS_META]);
@@ -215,11 +217,12 @@ int ensure_committed(rdn_rt_scene *s) {
   return commit_locked(s);
 }
 
-uint32_t resolve_world_root(const rdn_rt_scene *s, uint32_t tlas_idx) {
-  if (tlas_idx >= s->h_tlas_binding.size()) return REF_EMPTY;
+TlasRoot resolve_tlas(const rdn_rt_scene *s, uint32_t tlas_idx) {
+  const TlasRoot none{INVALID_NEXT, REF_EMPTY, 0, 0};
+  if (tlas_idx >= s->h_tlas_binding.size()) return none;
   const uint32_t handle = s->h_tlas_binding[tlas_idx];
-  if (handle >= s->h_tlas_root.size()) return REF_EMPTY;
-  return s->h_tlas_root[handle].wide_root;
+  if (handle >= s->h_tlas_root.size()) return none;
+  return s->h_tlas_root[handle];
 }
 
 // CUDA events around one kernel launch while kernel timing is enabled (recorded on the launching stream)
@@ -250,15 +253,18 @@ int enqueue_trace(rdn_rt_scene *s, DeviceCtx &dc, const Scratch &scratch, const 
   const int tie_mode = ordered_tie_mode();
   if (tie_mode == 0 || (count_ties && tie_mode != 3)) RDN_CUDA(cudaMemsetAsync(static_cast<char *>(scratch.base) + 8, 0, 4, stream));
   if (count_ties && tie_mode == 3) RDN_CUDA(cudaMemsetAsync(static_cast<char *>(scratch.base) + 28, 0, 4, stream));
+  if (count_ties) RDN_CUDA(cudaMemsetAsync(static_cast<char *>(scratch.base) + 12, 0, 4, stream));
   const bool end_search = (launch.ray_flags & RDN_RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH) != 0;
-  if (mode == RDN_TRACE_REFERENCE_ORDER || end_search) {
+  const TlasRoot tlas = resolve_tlas(s, launch.tlas_idx);
+  // a TLAS made mostly of irregular instances (accel.cpp "regularity") has a traversal-order dependent answer: reference order
+  if (mode == RDN_TRACE_REFERENCE_ORDER || end_search || tlas.irregular_count == IRREGULAR_ROUTE_ALL) {
     ScopedKernelTimer tm(dc, KERNEL_REFERENCE, stream);
     launch_trace_reference(dc.dev, launch, d_rays, n, d_hits, ts, false, dc.sm_count, stream);
   } else {
     bool ties_done;
     {
       ScopedKernelTimer tm(dc, KERNEL_ORDERED, stream);
-      ties_done = launch_trace_ordered(dc.dev, launch, resolve_world_root(s, launch.tlas_idx), d_rays, n, d_hits, ts, dc.sm_count, stream,
+      ties_done = launch_trace_ordered(dc.dev, launch, tlas, d_rays, n, d_hits, ts, dc.sm_count, stream,
                                        allow_overlap && !dc.timing && !count_ties, scratch.ordered_launches);
       if (n) scratch.ordered_launches++;
     }
@@ -443,7 +449,7 @@ int rdn_rt_trace_closest_device(rdn_rt_scene *s, int device_index, const rdn_lau
 
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (stats) { RDN_CUDA(cudaEventCreate(&e0)); RDN_CUDA(cudaEventCreate(&e1)); }
-  uint64_t ties = 0;
+  uint64_t ties = 0, fallbacks = 0;
   float ms_total = 0.f;
   for (uint64_t off = 0; off < n; off += chunk) {
     const uint64_t m = std::min(chunk, n - off);
@@ -470,7 +476,7 @@ int rdn_rt_trace_closest_device(rdn_rt_scene *s, int device_index, const rdn_lau
       uint32_t small[6] = {0, 0, 0, 0, 0, 0};  // tie_count | tie_unresolved | stack_overflow | blocks_done | tie_cursor | tie_total
       RDN_CUDA(cudaMemcpy(small, static_cast<char *>(scratch.base) + 8, sizeof(small), cudaMemcpyDeviceToHost));
       ties += ordered_tie_mode() == 3 ? small[5] : small[0];
-      if (small[1]) return fail(RDN_ERR_CUDA, "tie re-walk found no hit (internal invariant broken)");
+      fallbacks += small[1];
       if (small[2]) return fail(RDN_ERR_CAPACITY, "traversal stack overflow");
 #if defined(RDN_DEBUG_STEPS) || defined(RDN_DEBUG_TIMELINE)
       unsigned long long c[10];
@@ -487,7 +493,7 @@ int rdn_rt_trace_closest_device(rdn_rt_scene *s, int device_index, const rdn_lau
     }
   }
   if (stats) {
-    stats->rays = n; stats->tie_rays = ties; stats->kernel_ms = ms_total;
+    stats->rays = n; stats->tie_rays = ties; stats->kernel_ms = ms_total; stats->whole_range_rewalks = fallbacks;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
   }
   return RDN_OK;
@@ -559,7 +565,6 @@ int rdn_rt_trace_closest(rdn_rt_scene *s, const rdn_launch *launch, const rdn_ra
     for (uint64_t k = 0; k < used; ++k) {
       Slot &slot = dc.slots[k];
       RDN_CUDA(cudaStreamSynchronize(slot.stream));
-      if (slot.h_flags[1]) return fail(RDN_ERR_CUDA, "tie re-walk found no hit (internal invariant broken)");
       if (slot.h_flags[2]) return fail(RDN_ERR_CAPACITY, "traversal stack overflow");
     }
   }
@@ -809,7 +814,7 @@ int rdn_rt_scene_adopt_blob(rdn_rt_scene *s, int device_index, const void *d_blo
   dc.blob_bytes = bytes;
   bind_blob(dc, h);
   s->h_tlas_binding.assign(h.count[ARR_TLAS_BINDING], 0);
-  s->h_tlas_root.assign(h.count[ARR_TLAS_ROOT], TlasRoot{INVALID_NEXT, REF_EMPTY});
+  s->h_tlas_root.assign(h.count[ARR_TLAS_ROOT], TlasRoot{INVALID_NEXT, REF_EMPTY, 0, 0});
   if (!s->h_tlas_binding.empty())
     RDN_CUDA(cudaMemcpy(s->h_tlas_binding.data(), dc.dev.tlas_binding, s->h_tlas_binding.size() * 4, cudaMemcpyDeviceToHost));
   if (!s->h_tlas_root.empty())
@@ -839,6 +844,27 @@ int rdn_rt_scene_array(rdn_rt_scene *s, int array_id, void *out, uint64_t capaci
   if (bytes) {
     if (s->devices.empty()) std::memcpy(out, s->host_blob.data() + h.offset[array_id], bytes);
     else RDN_CUDA(cudaMemcpy(out, static_cast<const char *>(s->devices[0].d_blob) + h.offset[array_id], bytes, cudaMemcpyDeviceToHost));
+  }
+  return RDN_OK;
+}
+
+int rdn_rt_scene_build_stats(rdn_rt_scene *s, rdn_build_stats *out) {
+  if (!s || !out) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_scene_build_stats: null argument");
+  int rc = ensure_committed(s);
+  if (rc != RDN_OK) return rc;
+  std::shared_lock<std::shared_mutex> rd(s->lock);
+  std::memset(out, 0, sizeof(*out));
+  if (!s->adopted) {
+    out->balance_fallbacks = s->flat.stats.balance_fallbacks;
+    out->balance_fallbacks_gt10 = s->flat.stats.balance_fallbacks_gt10;
+    out->irregular_triangles = s->flat.stats.irregular_triangles;
+    out->irregular_instances = s->flat.stats.irregular_instances;
+    out->reference_routed_tlas = s->flat.stats.reference_routed_tlas;
+  } else {
+    for (const TlasRoot &t : s->h_tlas_root) {
+      if (t.irregular_count == IRREGULAR_ROUTE_ALL) out->reference_routed_tlas++;
+      else out->irregular_instances += t.irregular_count;
+    }
   }
   return RDN_OK;
 }

@@ -23,6 +23,8 @@ struct SceneDev {
   const SlotInfo *slot_info;
   const WideNode *wide_nodes;
   const uint32_t *prim_to_slot;
+  const uint32_t *irregular_instances;
+  const LeafBox *irregular_leaf_boxes;
   uint32_t n_tlas_binding, n_tlas_root, n_blas_meta, n_instances;
 };
 
@@ -30,7 +32,8 @@ struct SceneDev {
 struct TraceScratch {
   unsigned long long *work_counter;  // next ray fetch index (persistent kernel)
   uint32_t *tie_count;               // rays queued for exact tie resolution
-  uint32_t *tie_unresolved;          // safety net: clamped re-walk found nothing (must stay 0)
+  uint32_t *tie_unresolved;          // clamped re-walks that found nothing and were repeated over the ray's whole range (an irregular
+                                     // candidate the flattener's classification did not catch; not an error, reported in the stats)
   uint32_t *stack_overflow;          // safety net: traversal stack overflow (must stay 0)
   uint32_t *tie_cursor;              // next queued tie to resolve (in-kernel drain)
   uint32_t *tie_total;               // ties of completed launches since the host last cleared it (in-kernel drain resets tie_count)
@@ -55,9 +58,11 @@ void launch_resolve_ties(const SceneDev &scene, const rdn_launch &launch, const 
 // Ordered (near child first) persistent-thread traversal with tie detection.  Near-tie rays are re-walked in the
 // reference's order by the finishing lane itself (returns true), or — RDN_ORDERED_VARIANT=9 — queued in scratch for
 // launch_resolve_ties (returns false).  Needs *work_counter == 0 at launch; its last CTA resets it on the way out.
-// world_root = TlasRoot::wide_root of tlas_binding[launch.tlas_idx] (resolved by the caller from its host copy).
+// `tlas` = the TlasRoot of tlas_binding[launch.tlas_idx] (resolved by the caller from its host copy; wide_root REF_EMPTY: every
+// ray misses).  Rays whose original range meets one of the TLAS's irregular instances are queued for an unclamped
+// reference-order walk instead of being traversed; a TLAS marked IRREGULAR_ROUTE_ALL must not come here at all.
 int ordered_tie_mode();  // 0: queue + launch_resolve_ties; 1/2: re-walk by the finishing lane; 3: queue drained inside the kernel
-bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, uint32_t world_root, const rdn_ray *d_rays, uint64_t n,
+bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const TlasRoot &tlas, const rdn_ray *d_rays, uint64_t n,
                           rdn_hit *d_hits, const TraceScratch &scratch, int sm_count, cudaStream_t stream, bool allow_overlap = false,
                           uint32_t wait_epoch = 0);  // wait_epoch = ordered launches issued before this one on `scratch`
 

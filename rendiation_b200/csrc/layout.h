@@ -42,8 +42,17 @@ struct InstanceRecord {
 static_assert(sizeof(InstanceRecord) == 80, "InstanceRecord");
 
 struct BlasMeta {
-  uint32_t tri_root_range[2];  // into GeometryMeta[]
+  uint32_t tri_root_range[2];     // into GeometryMeta[]
+  uint32_t irregular_leaf_start;  // [start, start + count) in irregular_leaf_boxes: object-space boxes of the BVH leaves that hold an
+  uint32_t irregular_leaf_count;  // irregular triangle; IRREGULAR_ROUTE_ALL: too many — every instance of the BLAS is irregular
 };
+static_assert(sizeof(BlasMeta) == 16, "BlasMeta");
+
+struct LeafBox {  // 32 B
+  float bmin[3]; uint32_t pad0;
+  float bmax[3]; uint32_t pad1;
+};
+static_assert(sizeof(LeafBox) == 32, "LeafBox");
 
 struct GeometryMeta {
   uint32_t bvh_root_idx;    // root in tri_bvh_forest (reference layout)
@@ -56,9 +65,16 @@ struct GeometryMeta {
 static_assert(sizeof(GeometryMeta) == 32, "GeometryMeta");
 
 struct TlasRoot {
-  uint32_t bvh_root_idx;  // root in tlas_bvh_forest or INVALID_NEXT for a deleted TLAS
-  uint32_t wide_root;     // REF_EMPTY when deleted / empty
+  uint32_t bvh_root_idx;     // root in tlas_bvh_forest or INVALID_NEXT for a deleted TLAS
+  uint32_t wide_root;        // REF_EMPTY when deleted / empty
+  uint32_t irregular_start;  // [start, start + count) in irregular_instances: instance slots whose hits need not lie inside
+  uint32_t irregular_count;  // their boxes (see accel.cpp "regularity"); IRREGULAR_ROUTE_ALL: walk every ray in reference order
 };
+static_assert(sizeof(TlasRoot) == 16, "TlasRoot");
+constexpr uint32_t IRREGULAR_ROUTE_ALL = 0xFFFFFFFFu;
+constexpr uint32_t IRREGULAR_LIST_MAX = 8;       // more irregular instances than this in one TLAS: the whole TLAS is walked in reference order
+constexpr uint32_t IRREGULAR_LEAF_MAX = 16;      // more irregular leaves than this in one BLAS: its instances are irregular as a whole
+constexpr uint32_t IRREGULAR_WHOLE_BIT = 1u << 31;  // irregular_instances entry: the whole instance (else only its BLAS's listed leaves)
 
 // 64 B, sector 0 = plane test operands, sector 1 = barycentric operands
 struct TriRecord {
@@ -111,11 +127,13 @@ enum ArrayId : int {
   ARR_SLOT_INFO,          // SlotInfo
   ARR_WIDE_NODES,         // WideNode
   ARR_PRIM_TO_SLOT,       // u32: (primitive_start + original triangle index) -> slot; inverse of the reference's indices_redirect
+  ARR_IRREGULAR_INSTANCES,  // u32: instance slots (| IRREGULAR_WHOLE_BIT), grouped per TLAS (TlasRoot::irregular_start / _count)
+  ARR_IRREGULAR_LEAF_BOXES, // LeafBox, grouped per BLAS (BlasMeta::irregular_leaf_start / _count)
   ARR_COUNT
 };
 
 constexpr uint64_t BLOB_MAGIC = 0x52444E5F424C4F42ull;  // "RDN_BLOB"
-constexpr uint32_t BLOB_VERSION = 2;
+constexpr uint32_t BLOB_VERSION = 3;
 constexpr uint64_t BLOB_ALIGN = 128;
 
 struct BlobHeader {

@@ -263,27 +263,44 @@ __global__ void __launch_bounds__(128) k_trace_reference(const SceneDev S, const
   }
 }
 
-// Exact tie resolution: every ray the ordered kernel queued (a second candidate within TIE_EPS of its closest hit) is
-// re-walked in the reference's order with its range clamped to [best*(1-3eps), best*(1+3eps)].  Subtrees that end before
-// the clamp hold no hit at all and candidates beyond it cannot win, so from the first shared accept on the clamped walk is
-// in the same state as the reference's unclamped one and ends on the reference's answer.  Grid-stride over the
-// device-side queue: no host round trip between the two kernels.
+// Exact re-walk of a ray the ordered kernel queued, in the reference's order.
+//   best is a distance: a near-tie (a second candidate within TIE_EPS of the closest hit).  The walk's range is clamped to
+//     best -/+ 3*TIE_EPS*|best|: subtrees that end before the clamp hold no hit at all and candidates beyond it cannot win, so
+//     from the first shared accept on the clamped walk is in the same state as the reference's unclamped one and ends on the
+//     reference's answer.  Should the clamped walk find nothing (the closest candidate lies outside the boxes that lead to
+//     it: an irregular triangle the flattener's classification missed) the ray is walked again over its whole range.
+//   best is NaN: a ray that may enter an irregular instance; walked over its whole range straight away.
+// Either way the record written is NaiveSahBvhCpu::traverse's.
+__device__ __forceinline__ void rewalk_in_reference_order(const SceneDev &S, const rdn_launch &L, const rdn_ray *rays, rdn_hit *hits,
+                                                          uint64_t ri, float best, uint32_t *fallbacks) {
+  const float4 r0 = __ldg(reinterpret_cast<const float4 *>(rays + ri));
+  const float4 r1 = __ldg(reinterpret_cast<const float4 *>(rays + ri) + 1);
+  WalkResult res;
+  WalkCounters ctr;
+  bool clamped = best == best;
+  float near_walk = r0.w, far_init = r1.w;
+  if (clamped) {
+    const float slack = 3.0f * TIE_EPS * fabsf(best);
+    near_walk = fmaxf(r0.w, best - slack);
+    far_init = fminf(r1.w, best + slack);
+  }
+#pragma unroll 1
+  for (;;) {
+    reference_walk<false>(S, L, xyz(r0), xyz(r1), r0.w, r1.w, near_walk, far_init, res, ctr);
+    if (res.slot != RDN_INVALID_ID || !clamped) break;
+    clamped = false; near_walk = r0.w; far_init = r1.w;
+    atomicAdd(fallbacks, 1u);
+  }
+  store_walk_result(S, hits + ri, res, r1.w);
+}
+
+// The queue drained by a separate kernel (RDN_ORDERED_VARIANT=9, the first version; kept for A/B runs): grid-stride over the
+// device-side queue, no host round trip between the two kernels.
 __global__ void __launch_bounds__(128) k_resolve_ties(const SceneDev S, const rdn_launch L, const rdn_ray *__restrict__ rays,
                                                       rdn_hit *__restrict__ hits, const TraceScratch scratch) {
   const uint32_t count = *scratch.tie_count;
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
-    const uint64_t ri = scratch.tie_queue[k];
-    const float best = scratch.tie_best[k];
-    const float4 r0 = __ldg(reinterpret_cast<const float4 *>(rays + ri));
-    const float4 r1 = __ldg(reinterpret_cast<const float4 *>(rays + ri) + 1);
-    WalkResult res;
-    WalkCounters ctr;
-    const float near_walk = fmaxf(r0.w, best * (1.0f - 3.0f * TIE_EPS));
-    const float far_init = fminf(r1.w, best * (1.0f + 3.0f * TIE_EPS));
-    reference_walk<false>(S, L, xyz(r0), xyz(r1), r0.w, r1.w, near_walk, far_init, res, ctr);
-    if (res.slot != RDN_INVALID_ID) store_walk_result(S, hits + ri, res, r1.w);
-    else atomicAdd(scratch.tie_unresolved, 1u);  // cannot happen: the closest candidate itself lies inside the clamp
-  }
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x)
+    rewalk_in_reference_order(S, L, rays, hits, scratch.tie_queue[k], scratch.tie_best[k], scratch.tie_unresolved);
 }
 
 // ================================================================================================ ordered
@@ -297,27 +314,64 @@ struct OrderedParams {
   uint32_t tiles_x;  // 0: linear
   uint32_t width, height;
   uint32_t world_root;  // wide reference of the bound TLAS (REF_EMPTY: every ray misses)
+  uint32_t irregular_start, irregular_count;  // the bound TLAS's irregular instances (S.irregular_instances), at most IRREGULAR_LIST_MAX
   uint32_t wait_epoch;  // launches issued before this one on the same scratch set: they must have left before this one touches it
   TraceScratch scratch;
 };
 
-// Exact tie resolution inside the ordered kernel: the lane that finished a ray with a second candidate within TIE_EPS of
-// its closest hit re-walks it on the spot in the reference's order, range clamped around the closest distance (same
-// argument as k_resolve_ties).  Near-ties are a handful of rays per frame, so the cost is one lane for a few tens of
-// microseconds — far less than a second kernel launch whose whole duration is this one serial walk.
-__device__ __forceinline__ bool resolve_tie_body(const OrderedParams &P, uint64_t ri, float best) {
-  const float4 r0 = __ldg(reinterpret_cast<const float4 *>(P.rays + ri));
-  const float4 r1 = __ldg(reinterpret_cast<const float4 *>(P.rays + ri) + 1);
-  WalkResult res;
-  WalkCounters ctr;
-  const float near_walk = fmaxf(r0.w, best * (1.0f - 3.0f * TIE_EPS));
-  const float far_init = fminf(r1.w, best * (1.0f + 3.0f * TIE_EPS));
-  reference_walk<false>(P.S, P.L, xyz(r0), xyz(r1), r0.w, r1.w, near_walk, far_init, res, ctr);
-  if (res.slot == RDN_INVALID_ID) return false;
-  store_walk_result(P.S, P.hits + ri, res, r1.w);
-  return true;
-}
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+
+// Hits of an irregular instance (or of the irregular triangles of an otherwise regular BLAS) need not lie inside their boxes,
+// so what the ordered walk would prune the reference may have found.  A ray whose ORIGINAL range meets such an instance (the
+// reference's own instance test, traverse_cpu.rs:80-86) — and, when only some leaves of its BLAS are irregular, the box of
+// one of those leaves in object space — can reach it in the reference's walk; this is a superset of the rays that do, and
+// they are handed to the reference-order walk as they are.  Out of line: regular scenes never call it and it must not
+// cost the traversal loop registers.
+__device__ __noinline__ bool meets_irregular_instance(const SceneDev &S, uint32_t start, uint32_t count, uint32_t cull_mask,
+                                                      const rdn_ray *ray) {
+  const float4 r0 = __ldg(reinterpret_cast<const float4 *>(ray)), r1 = __ldg(reinterpret_cast<const float4 *>(ray) + 1);
+  const Vec3 ro = xyz(r0), rd = xyz(r1), rinv = recip3(rd);
+  const float t_min = r0.w, t_max = r1.w;
+  for (uint32_t k = 0; k < count; ++k) {
+    const uint32_t entry = __ldg(S.irregular_instances + start + k);
+    const uint32_t slot = entry & ~IRREGULAR_WHOLE_BIT;
+    const float4 *tb = reinterpret_cast<const float4 *>(S.tlas_bounding + slot);
+    const float4 b0 = __ldg(tb), b1 = __ldg(tb + 1);
+    float tn;
+    if (!slab_test(ro, rinv, t_min, t_max, xyz(b0), xyz(b1), tn) || (cull_mask & __float_as_uint(b0.w)) == 0) continue;
+    if (entry & IRREGULAR_WHOLE_BIT) return true;
+    const InstanceRecord *rec = S.instances + slot;
+    const uint32_t blas = rec->blas;
+    if (blas >= S.n_blas_meta) continue;
+    const uint32_t l0 = S.blas_meta[blas].irregular_leaf_start, ln = S.blas_meta[blas].irregular_leaf_count;
+    Vec3 bo, bd;
+    float scaling;
+    to_object_space(rec, ro, rd, bo, bd, scaling);
+    const Vec3 inv_bd = recip3(bd);
+    for (uint32_t j = 0; j < ln; ++j) {
+      const float4 *lb = reinterpret_cast<const float4 *>(S.irregular_leaf_boxes + l0 + j);
+      const float4 m0 = __ldg(lb), m1 = __ldg(lb + 1);
+      if (slab_test(bo, inv_bd, t_min * scaling, t_max * scaling, xyz(m0), xyz(m1), tn)) return true;
+    }
+  }
+  return false;
+}
+
+// Warp-aggregated append to the device-side re-walk queue (called by whatever lanes are active): one atomic per warp; the
+// count is bumped first, then the distance is written, then (after a fence when the queue is drained concurrently) the
+// ray index publishes the slot.
+template <bool DRAIN_TIES>
+__device__ __forceinline__ void enqueue_rewalk(const TraceScratch &scratch, uint32_t lane, uint64_t ri, float best) {
+  const uint32_t peers = __activemask();
+  const int pl = __ffs(peers) - 1;
+  uint32_t qbase = 0;
+  if (static_cast<int>(lane) == pl) qbase = atomicAdd(scratch.tie_count, static_cast<uint32_t>(__popc(peers)));
+  qbase = __shfl_sync(peers, qbase, pl);
+  const uint32_t q = qbase + __popc(peers & ((1u << lane) - 1u));
+  scratch.tie_best[q] = best;
+  if (DRAIN_TIES) __threadfence();  // the distance is visible before the index publishes the slot
+  *reinterpret_cast<volatile uint32_t *>(scratch.tie_queue + q) = static_cast<uint32_t>(ri);
+}
 
 // Drain of the device-side tie queue by threads that have left the traversal loop (DRAIN_TIES).  Entries are
 // claimed one at a time with a CAS on the cursor; a claimed slot is awaited until its ray index is published (the
@@ -348,7 +402,7 @@ __device__ __forceinline__ void drain_tie_queue(const OrderedParams &P) {
       __threadfence();
       const float best = __ldcg(P.scratch.tie_best + q);
       P.scratch.tie_queue[q] = RDN_INVALID_ID;
-      if (!resolve_tie_body(P, ri, best)) atomicAdd(P.scratch.tie_unresolved, 1u);  // cannot happen: the closest candidate lies inside the clamp
+      rewalk_in_reference_order(P.S, P.L, P.rays, P.hits, ri, best, P.scratch.tie_unresolved);
     }
     __syncwarp();
   }
@@ -362,7 +416,9 @@ __device__ __forceinline__ void drain_tie_queue(const OrderedParams &P) {
 // (3) vote: when fewer than THRESH lanes still hold a ray (and rays remain) the warp goes back to the refill point.
 // Refill culls rays against the TLAS root box on the spot (the reference's first test), so rays that miss the scene
 // never occupy a traversal lane.
-template <int K, int MINB, int THRESH, bool DRAIN_TIES>  // DRAIN_TIES: near-tie queue drained inside the kernel (else by k_resolve_ties)
+// IRREGULAR: the bound TLAS lists irregular instances (checked at refill); a separate instantiation so that regular scenes pay
+// nothing for the out-of-line test (the call makes ptxas save two dozen registers around the whole refill block).
+template <int K, int MINB, int THRESH, bool DRAIN_TIES, bool IRREGULAR>  // DRAIN_TIES: near-tie queue drained inside the kernel (else by k_resolve_ties)
 __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(const __grid_constant__ OrderedParams P) {
   const SceneDev &S = P.S;
   const uint32_t lane = threadIdx.x & 31u;
@@ -449,7 +505,12 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
           const float4 r1 = __ldg(reinterpret_cast<const float4 *>(P.rays + idx) + 1);
           const Vec3 ro = xyz(r0), rd = xyz(r1), rinv = recip3(rd);
           float tn;
-          if (world_entry != REF_EMPTY && slab_test(ro, rinv, r0.w, r1.w, root_min, root_max, tn)) {
+          const bool enters = world_entry != REF_EMPTY && slab_test(ro, rinv, r0.w, r1.w, root_min, root_max, tn);
+          const bool suspect = IRREGULAR && enters &&
+                               meets_irregular_instance(S, P.irregular_start, P.irregular_count, P.L.cull_mask, P.rays + idx);
+          if (suspect) {
+            enqueue_rewalk<DRAIN_TIES>(P.scratch, lane, idx, __int_as_float(0x7FC00000));  // NaN: walk the whole range
+          } else if (enters) {
             ri = idx; o = ro; d = rd; inv = rinv;
             t_near_world = r0.w; far0 = r1.w;
             scaling = 1.f; near_s = t_near_world; bound = far0; far_s = far0;
@@ -522,7 +583,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
                   second = fminf(second, best);
                   best = distance; best_u = u; best_v = v; best_slot = slot; best_inst = cur_inst;
                   best_back = sign < 0.0f ? 1u : 0u;
-                  bound = fminf(far0, best * (1.0f + TIE_EPS));
+                  bound = fminf(far0, best + TIE_EPS * fabsf(best));
                   far_s = bound * scaling;
                 } else {
                   second = fminf(second, distance);
@@ -600,17 +661,9 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
           store_hit(dst, best, best_u, best_v, si.primitive_id, si.geometry_idx, best_inst,
                     S.instances[best_inst].instance_custom_index,
                     best_back ? RDN_HIT_KIND_BACK_FACING_TRIANGLE : RDN_HIT_KIND_FRONT_FACING_TRIANGLE);
-          if (second <= best * (1.0f + TIE_EPS)) {
+          if (second <= best + TIE_EPS * fabsf(best)) {
             __threadfence();  // the ordered record lands before whoever drains the queue writes the exact one
-            const uint32_t peers = __activemask();
-            const int pl = __ffs(peers) - 1;
-            uint32_t qbase = 0;
-            if (static_cast<int>(lane) == pl) qbase = atomicAdd(P.scratch.tie_count, static_cast<uint32_t>(__popc(peers)));
-            qbase = __shfl_sync(peers, qbase, pl);
-            const uint32_t q = qbase + __popc(peers & ((1u << lane) - 1u));
-            P.scratch.tie_best[q] = best;
-            if (DRAIN_TIES) __threadfence();  // the distance is visible before the index publishes the slot
-            *reinterpret_cast<volatile uint32_t *>(P.scratch.tie_queue + q) = static_cast<uint32_t>(ri);
+            enqueue_rewalk<DRAIN_TIES>(P.scratch, lane, ri, best);
           }
         } else {
           store_hit(dst, far0, 0.f, 0.f, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, 0);
@@ -702,7 +755,7 @@ static int ordered_variant() {
 }
 int ordered_tie_mode() { return ordered_variant() == 9 ? 0 : 3; }
 
-bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, uint32_t world_root, const rdn_ray *d_rays, uint64_t n,
+bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const TlasRoot &tlas, const rdn_ray *d_rays, uint64_t n,
                           rdn_hit *d_hits, const TraceScratch &scratch, int sm_count, cudaStream_t stream, bool allow_overlap,
                           uint32_t wait_epoch) {
   if (n == 0) return true;
@@ -715,7 +768,9 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, uint3
     P.tiles_x = (P.width + 7u) / 8u;
     P.n_fetch = static_cast<uint64_t>(P.tiles_x) * ((P.height + 3u) / 4u) * 32u;
   }
-  P.world_root = world_root;
+  P.world_root = tlas.wide_root;
+  P.irregular_start = tlas.irregular_start;
+  P.irregular_count = tlas.irregular_count == IRREGULAR_ROUTE_ALL ? 0u : tlas.irregular_count;  // (the caller routes those elsewhere)
   P.wait_epoch = wait_epoch;
 
   // RDN_ORDERED_VARIANT: experimentation knob (rounds per vote / refill threshold / tie handling / register cap)
@@ -724,11 +779,14 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, uint3
   KernelFn fn;
   bool inline_ties = true;
   switch (variant) {
-    case 1: fn = k_trace_ordered_rounds<4, 8, 1, true>; break;   // more node steps per vote
-    case 2: fn = k_trace_ordered_rounds<3, 8, 4, true>; break;   // refill once fewer than 4 lanes are busy
-    case 3: fn = k_trace_ordered_rounds<4, 8, 8, true>; break;   // the first version's policy
-    case 9: fn = k_trace_ordered_rounds<2, 8, 1, false>; inline_ties = false; break;  // queue drained by k_resolve_ties
-    default: fn = k_trace_ordered_rounds<2, 8, 1, true>; break;
+    case 1: fn = k_trace_ordered_rounds<4, 8, 1, true, false>; break;   // more node steps per vote
+    case 2: fn = k_trace_ordered_rounds<3, 8, 4, true, false>; break;   // refill once fewer than 4 lanes are busy
+    case 3: fn = k_trace_ordered_rounds<4, 8, 8, true, false>; break;   // the first version's policy
+    case 9: fn = k_trace_ordered_rounds<2, 8, 1, false, false>; inline_ties = false; break;  // queue drained by k_resolve_ties
+    default: fn = k_trace_ordered_rounds<2, 8, 1, true, false>; break;
+  }
+  if (P.irregular_count != 0) {  // (the experimentation variants exist for regular scenes only)
+    fn = inline_ties ? k_trace_ordered_rounds<2, 8, 1, true, true> : k_trace_ordered_rounds<2, 8, 1, false, true>;
   }
   int blocks_per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, ORDERED_BLOCK, 0);

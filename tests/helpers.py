@@ -98,6 +98,22 @@ def reference_fixture(devices=(0,), product=True):
     return sp.build(), handles
 
 
+def canonical_nan(hits: np.ndarray) -> np.ndarray:
+    """Hit records with every NaN replaced by one quiet NaN.  A needle triangle whose determinant cancels to zero yields a hit
+    with finite t and NaN barycentrics (0 * inf) in the reference; which NaN is hardware-defined: x86 SSE generates 0xFFC00000
+    and propagates operand payloads, the GPU always returns 0x7FFFFFFF.  Everything else stays bit for bit."""
+    out = hits.copy()
+    for f in ("t", "u", "v"):
+        bits = out[f].view(np.uint32)
+        bits[np.isnan(out[f])] = 0x7FC00000
+    return out
+
+
+def identical_hits(got: np.ndarray, want: np.ndarray) -> bool:
+    """whole 32-byte records equal, NaNs compared as NaN == NaN (see canonical_nan)"""
+    return canonical_nan(got).tobytes() == canonical_nan(want).tobytes()
+
+
 def compare_hits(got: np.ndarray, want: np.ndarray, rel_tol: float = 1e-6):
     """Parity report per the north star: ids bit-exact, t/u/v within rel_tol, near-ties reported separately."""
     assert got.shape == want.shape
@@ -112,7 +128,7 @@ def compare_hits(got: np.ndarray, want: np.ndarray, rel_tol: float = 1e-6):
         rel = np.abs(tg - tw) / np.maximum(np.abs(tw), 1e-30)
     near_tie = (~ids_equal) & both_hit & (rel < rel_tol)
     hard_mismatch = (~ids_equal) & ~near_tie
-    bits_equal = got.tobytes() == want.tobytes()
+    bits_equal = identical_hits(got, want)
     exact = ids_equal & both_hit
     max_rel_t = float(rel[exact].max()) if exact.any() else 0.0
     max_abs_uv = 0.0
@@ -121,3 +137,67 @@ def compare_hits(got: np.ndarray, want: np.ndarray, rel_tol: float = 1e-6):
     return {"n": int(got.shape[0]), "ids_exact": int(ids_equal.sum()), "near_ties": int(near_tie.sum()),
             "hard_mismatch": int(hard_mismatch.sum()), "bit_identical": bool(bits_equal), "max_rel_t": max_rel_t,
             "max_abs_uv": max_abs_uv, "hits": int((want["instance_id"] != 0xFFFFFFFF).sum())}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# numpy mirror of the ordered kernel's refill test (traverse.cu meets_irregular_instance), over the product's
+# flattened arrays: which rays are handed to the reference-order walk because they can reach something irregular
+IRREGULAR_ROUTE_ALL = 0xFFFFFFFF
+IRREGULAR_WHOLE_BIT = 1 << 31
+
+
+def _slab(o, inv, tmin, tmax, bmin, bmax):
+    """intersect_ray_aabb_cpu, vectorised over rays (f32, fmin/fmax NaN semantics)"""
+    with np.errstate(all="ignore"):
+        t0 = ((bmin - o) * inv).astype(np.float32)
+        t1 = ((bmax - o) * inv).astype(np.float32)
+        near = np.fmax.reduce(np.fmin(t0, t1), axis=1)
+        far = np.fmin.reduce(np.fmax(t0, t1), axis=1)
+        return (near <= far) & (tmin < far) & (near < tmax)
+
+
+def suspect_rays(arrays: dict, rays: np.ndarray, tlas_idx: int, cull_mask: int):
+    """(route_all, mask): route_all = the bound TLAS takes the reference-order kernel as a whole; mask[i] = ray i meets an
+    irregular instance (or an irregular leaf of its BLAS) with its original range."""
+    n = rays.shape[0]
+    binding = arrays["tlas_binding"]
+    if tlas_idx >= binding.size or binding[tlas_idx] >= arrays["tlas_root"].shape[0]:
+        return False, np.zeros(n, bool)
+    _, _, start, count = (int(x) for x in arrays["tlas_root"][binding[tlas_idx]])
+    if count == IRREGULAR_ROUTE_ALL:
+        return True, np.ones(n, bool)
+    f32 = np.float32
+    o = np.stack([rays["ox"], rays["oy"], rays["oz"]], 1).astype(f32)
+    d = np.stack([rays["dx"], rays["dy"], rays["dz"]], 1).astype(f32)
+    tmin, tmax = rays["tmin"].astype(f32), rays["tmax"].astype(f32)
+    with np.errstate(all="ignore"):
+        inv = (f32(1.0) / d).astype(f32)
+    mask = np.zeros(n, bool)
+    for entry in arrays["irregular_instances"][start:start + count]:
+        slot = int(entry) & ~IRREGULAR_WHOLE_BIT
+        tb = arrays["tlas_bounding"][slot]
+        meets = _slab(o, inv, tmin, tmax, tb["world_min"], tb["world_max"]) & bool(cull_mask & int(tb["mask"]))
+        if int(entry) & IRREGULAR_WHOLE_BIT:
+            mask |= meets
+            continue
+        rec = arrays["instances"][slot]
+        blas = int(rec["blas"])
+        if blas >= arrays["blas_meta"].shape[0]:
+            continue
+        l0, ln = int(arrays["blas_meta"][blas][2]), int(arrays["blas_meta"][blas][3])
+        m = rec["transform_inv"].reshape(4, 4)  # m[c] = column c
+        with np.errstate(all="ignore"):
+            p = [((((o[:, 0] * m[0][i]).astype(f32) + (o[:, 1] * m[1][i]).astype(f32)).astype(f32) + (o[:, 2] * m[2][i]).astype(f32)).astype(f32)
+                  + f32(f32(1.0) * m[3][i])).astype(f32) for i in range(4)]
+            bo = np.stack([(p[i] / p[3]).astype(f32) for i in range(3)], 1)
+            d0 = np.stack([(((d[:, 0] * m[0][i]).astype(f32) + (d[:, 1] * m[1][i]).astype(f32)).astype(f32) + (d[:, 2] * m[2][i]).astype(f32)).astype(f32)
+                           for i in range(3)], 1)
+            len2 = (((d0[:, 0] * d0[:, 0]).astype(f32) + (d0[:, 1] * d0[:, 1]).astype(f32)).astype(f32) + (d0[:, 2] * d0[:, 2]).astype(f32)).astype(f32)
+            scaling = np.sqrt(len2).astype(f32)
+            bd = np.where((len2 > 0)[:, None], (d0 * (f32(1.0) / scaling)[:, None]).astype(f32), d0)
+            inv_bd = (f32(1.0) / bd).astype(f32)
+        leaf = np.zeros(n, bool)
+        for lb in arrays["irregular_leaf_boxes"][l0:l0 + ln]:
+            leaf |= _slab(bo, inv_bd, (tmin * scaling).astype(f32), (tmax * scaling).astype(f32), lb["bmin"], lb["bmax"])
+        mask |= meets & leaf
+    return False, mask
