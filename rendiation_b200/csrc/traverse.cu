@@ -315,6 +315,11 @@ struct OrderedParams {
   uint32_t width, height;
   uint32_t world_root;  // wide reference of the bound TLAS (REF_EMPTY: every ray misses)
   uint32_t irregular_start, irregular_count;  // the bound TLAS's irregular instances (S.irregular_instances), at most IRREGULAR_LIST_MAX
+  // SM-local scheduling: the launch is cut into units of 32 fetch slots (one 8x4 pixel tile, or 32 consecutive rays), ordered so
+  // that neighbours in the order are neighbours on screen (16x16-tile macro blocks in raster order, Morton order inside), and
+  // the unit list into n_ranges contiguous ranges, one per SM
+  uint32_t n_units, n_ranges, units_per_range, blocks_x;  // blocks_x == 0: units in raster tile order (or a linear ray list)
+  uint32_t prefetch_unit;  // take the next unit from the home range while the current one is being traversed
   uint32_t wait_epoch;  // launches issued before this one on the same scratch set: they must have left before this one touches it
   TraceScratch scratch;
 };
@@ -409,6 +414,49 @@ __device__ __forceinline__ void drain_tie_queue(const OrderedParams &P) {
 }
 
 
+// SM-local work distribution.  Every SM owns one contiguous range of the (screen-coherent) unit order and its warps take
+// units from the range's cursor, so the 32 warps resident on an SM walk 32 neighbouring tiles at the same time and share the
+// BVH nodes they pull into that SM's L1 — with one global cursor, consecutive tiles go to whichever warp of the whole GPU
+// asks next and an SM's tiles are scattered over a band of the frame.  A warp whose home range is dry takes units from the
+// following ranges (cursors only grow, so a range found dry is never looked at again: at most n_ranges probes per warp per
+// launch).  Returns a warp-uniform unit index or RDN_INVALID_ID when the launch has no unit left.
+__device__ __forceinline__ uint32_t smid() {
+  uint32_t id;
+  asm("mov.u32 %0, %%smid;" : "=r"(id));
+  return id;
+}
+__device__ __forceinline__ uint32_t grab_unit(const OrderedParams &P, uint32_t lane, uint32_t home, uint32_t &probe) {
+  // the 32 lanes look at 32 ranges at a time (one coalesced read of their cursors): a serial probe per range costs an L2 round
+  // trip each, ~50 us per warp once the launch runs dry
+  while (probe < P.n_ranges) {
+    const uint32_t k = probe + lane;
+    uint32_t r = home + k;
+    if (r >= P.n_ranges) r -= P.n_ranges;
+    const uint32_t begin = r * P.units_per_range;
+    uint32_t len = 0;
+    if (k < P.n_ranges && begin < P.n_units) len = P.n_units - begin < P.units_per_range ? P.n_units - begin : P.units_per_range;
+    const bool has = len != 0u && ld_volatile_u32(P.scratch.sm_cursor + r) < len;
+    const uint32_t mask = __ballot_sync(FULL_MASK, has);
+    if (mask == 0u) { probe += 32u; continue; }
+    const uint32_t first = __ffs(mask) - 1u;
+    probe += first;  // the ranges before it are dry for good
+    uint32_t unit = RDN_INVALID_ID;
+    if (lane == first) {
+      const uint32_t t = atomicAdd(P.scratch.sm_cursor + r, 1u);
+      if (t < len) unit = begin + t;
+    }
+    unit = __shfl_sync(FULL_MASK, unit, first);
+    if (unit != RDN_INVALID_ID) return unit;
+    probe += 1u;  // it went dry between the look and the take
+  }
+  return RDN_INVALID_ID;
+}
+__device__ __forceinline__ uint32_t compact_even_bits4(uint32_t x) {  // bits 0,2,4,6 -> 0..3
+  x &= 0x55u;
+  x = (x | (x >> 1)) & 0x33u;
+  return (x | (x >> 2)) & 0x0Fu;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Warp-synchronous rounds: every round the alive lanes (1) descend up to K inner nodes each, (2) re-converge
 // (__syncwarp) and handle their leaf / instance / bookkeeping item TOGETHER — on Volta+ lanes do not re-converge at a
@@ -418,7 +466,9 @@ __device__ __forceinline__ void drain_tie_queue(const OrderedParams &P) {
 // never occupy a traversal lane.
 // IRREGULAR: the bound TLAS lists irregular instances (checked at refill); a separate instantiation so that regular scenes pay
 // nothing for the out-of-line test (the call makes ptxas save two dozen registers around the whole refill block).
-template <int K, int MINB, int THRESH, bool DRAIN_TIES, bool IRREGULAR>  // DRAIN_TIES: near-tie queue drained inside the kernel (else by k_resolve_ties)
+// UNITS: whole units of 32 fetch slots from the range cursors (grab_unit; one range = one global cursor, n_ranges = SM count = every
+// SM its own range) instead of single fetch slots from one 64-bit cursor; needs THRESH == 1 (whole-tile refill).
+template <int K, int MINB, int THRESH, bool DRAIN_TIES, bool IRREGULAR, bool UNITS>  // DRAIN_TIES: near-tie queue drained inside the kernel (else by k_resolve_ties)
 __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(const __grid_constant__ OrderedParams P) {
   const SceneDev &S = P.S;
   const uint32_t lane = threadIdx.x & 31u;
@@ -459,6 +509,10 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
   uint32_t cur = REF_DONE, cur_inst = 0, cur_flags = 0, cull_bits = 0, geom_end = 0;
   bool in_object = false;
   bool warp_exhausted = false;
+  const uint32_t sm_home = UNITS ? smid() % P.n_ranges : 0u;
+  uint32_t sm_probe = 0;  // ranges, counted from the home range, already found dry
+  uint32_t pending_take = RDN_INVALID_ID;  // lane 0: result of a take from the home range issued ahead of need
+  bool have_pending = false;
 #ifdef RDN_DEBUG_STEPS
   // per-thread totals, reduced once per warp at kernel exit so the counters do not perturb the timeline
   unsigned long long dbg_steps = 0, dbg_tris = 0, dbg_pushes = 0, dbg_ray_steps = 0, dbg_max = 0, dbg_rays = 0, dbg_long = 0;
@@ -472,6 +526,75 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
 #define RDN_POP() (sp > 0 ? stack[--sp] : REF_DONE)
 
   for (;;) {
+    if (UNITS) {
+      // ---------------- whole-tile refill from this SM's range: no lane holds a ray here (THRESH == 1)
+#pragma unroll 1
+      while (!warp_exhausted && !__any_sync(FULL_MASK, alive)) {
+        uint32_t unit = RDN_INVALID_ID;
+        if (have_pending) {  // warp-uniform
+          have_pending = false;
+          const uint32_t t = __shfl_sync(FULL_MASK, pending_take, 0);
+          const uint32_t begin = sm_home * P.units_per_range;
+          const uint32_t len = begin < P.n_units ? (P.n_units - begin < P.units_per_range ? P.n_units - begin : P.units_per_range) : 0u;
+          if (t < len) unit = begin + t;
+          else if (sm_probe == 0u) sm_probe = 1u;  // the home range is dry
+        }
+        if (unit == RDN_INVALID_ID) unit = grab_unit(P, lane, sm_home, sm_probe);
+        if (unit == RDN_INVALID_ID) {
+#if defined(RDN_DEBUG_STEPS) || defined(RDN_DEBUG_TIMELINE)
+          if (lane == 0) atomicMin(P.scratch.counters + 7, globaltimer_ns());  // ray list ran dry
+#endif
+          warp_exhausted = true;
+          break;
+        }
+        uint64_t idx;
+        bool valid;
+        if (P.tiles_x && P.blocks_x == 0u) {
+          const uint32_t ty = unit / P.tiles_x, tx = unit - ty * P.tiles_x;
+          const uint32_t x = tx * 8u + (lane & 7u), y = ty * 4u + (lane >> 3);
+          valid = x < P.width && y < P.height;
+          idx = static_cast<uint64_t>(y) * P.width + x;
+        } else if (P.tiles_x) {
+          const uint32_t block = unit >> 8, within = unit & 255u;
+          const uint32_t by = block / P.blocks_x, bx = block - by * P.blocks_x;
+          const uint32_t x = (bx * 16u + compact_even_bits4(within)) * 8u + (lane & 7u);
+          const uint32_t y = (by * 16u + compact_even_bits4(within >> 1)) * 4u + (lane >> 3);
+          valid = x < P.width && y < P.height;
+          idx = static_cast<uint64_t>(y) * P.width + x;
+        } else {
+          idx = static_cast<uint64_t>(unit) * 32u + lane;
+          valid = idx < P.n;
+        }
+      if (valid) {
+        const float4 r0 = __ldg(reinterpret_cast<const float4 *>(P.rays + idx));
+        const float4 r1 = __ldg(reinterpret_cast<const float4 *>(P.rays + idx) + 1);
+        const Vec3 ro = xyz(r0), rd = xyz(r1), rinv = recip3(rd);
+        float tn;
+        const bool enters = world_entry != REF_EMPTY && slab_test(ro, rinv, r0.w, r1.w, root_min, root_max, tn);
+        const bool suspect = IRREGULAR && enters &&
+                             meets_irregular_instance(S, P.irregular_start, P.irregular_count, P.L.cull_mask, P.rays + idx);
+        if (suspect) {
+          enqueue_rewalk<DRAIN_TIES>(P.scratch, lane, idx, __int_as_float(0x7FC00000));  // NaN: walk the whole range
+        } else if (enters) {
+          ri = idx; o = ro; d = rd; inv = rinv;
+          t_near_world = r0.w; far0 = r1.w;
+          scaling = 1.f; near_s = t_near_world; bound = far0; far_s = far0;
+          best = INFINITY; second = INFINITY; best_slot = RDN_INVALID_ID; best_inst = RDN_INVALID_ID;
+          in_object = false; sp = 0;
+          cur = world_entry;
+          alive = true;
+        } else {
+          store_hit(P.hits + idx, r1.w, 0.f, 0.f, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, 0);
+        }
+      }
+        // take the following unit now: the round trip of the atomic overlaps the traversal of this one (the result is
+        // only looked at by the next refill)
+        if (P.prefetch_unit != 0u && sm_probe == 0u) {
+          if (lane == 0) pending_take = atomicAdd(P.scratch.sm_cursor + sm_home, 1u);
+          have_pending = true;
+        }
+      }
+    } else {
     // ---------------- warp-converged refill (a few rounds, so scene-missing rays are retired here)
 #pragma unroll 1
     for (int attempt = 0; attempt < 4; ++attempt) {
@@ -523,6 +646,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
           }
         }
       }
+    }
     }
     const uint32_t amask = __ballot_sync(FULL_MASK, alive);
     if (amask == 0) {
@@ -714,6 +838,11 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
       drain_tie_queue(P);
       __syncthreads();
     }
+    if (UNITS) {
+      for (uint32_t i = threadIdx.x; i < P.n_ranges; i += blockDim.x) P.scratch.sm_cursor[i] = 0u;
+      __threadfence();
+      __syncthreads();
+    }
     if (threadIdx.x == 0) {
       *P.scratch.work_counter = 0ull;
       *P.scratch.blocks_done = 0u;
@@ -768,6 +897,21 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const
     P.tiles_x = (P.width + 7u) / 8u;
     P.n_fetch = static_cast<uint64_t>(P.tiles_x) * ((P.height + 3u) / 4u) * 32u;
   }
+  // unit scheduling experiments: 10 = one cursor, raster tiles, next unit taken ahead; 11 = the same over 16x16-tile Morton blocks;
+  // 12 = a range of the Morton order per SM, with stealing; 13 / 14 = 10 / 12 without taking ahead
+  const int variant_ = ordered_variant();
+  const bool morton = variant_ == 11 || variant_ == 12 || variant_ == 14;
+  const bool sm_local = variant_ == 12 || variant_ == 14;
+  P.prefetch_unit = (variant_ == 13 || variant_ == 14) ? 0u : 1u;
+  if (P.tiles_x && morton) {
+    P.blocks_x = (P.tiles_x + 15u) / 16u;
+    P.n_units = P.blocks_x * ((((P.height + 3u) / 4u) + 15u) / 16u) * 256u;
+  } else {
+    P.blocks_x = 0;
+    P.n_units = P.tiles_x ? P.tiles_x * ((P.height + 3u) / 4u) : static_cast<uint32_t>((n + 31u) / 32u);
+  }
+  P.n_ranges = sm_local ? static_cast<uint32_t>(sm_count < SM_CURSOR_SLOTS ? sm_count : SM_CURSOR_SLOTS) : 1u;
+  P.units_per_range = (P.n_units + P.n_ranges - 1u) / P.n_ranges;
   P.world_root = tlas.wide_root;
   P.irregular_start = tlas.irregular_start;
   P.irregular_count = tlas.irregular_count == IRREGULAR_ROUTE_ALL ? 0u : tlas.irregular_count;  // (the caller routes those elsewhere)
@@ -779,14 +923,17 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const
   KernelFn fn;
   bool inline_ties = true;
   switch (variant) {
-    case 1: fn = k_trace_ordered_rounds<4, 8, 1, true, false>; break;   // more node steps per vote
-    case 2: fn = k_trace_ordered_rounds<3, 8, 4, true, false>; break;   // refill once fewer than 4 lanes are busy
-    case 3: fn = k_trace_ordered_rounds<4, 8, 8, true, false>; break;   // the first version's policy
-    case 9: fn = k_trace_ordered_rounds<2, 8, 1, false, false>; inline_ties = false; break;  // queue drained by k_resolve_ties
-    default: fn = k_trace_ordered_rounds<2, 8, 1, true, false>; break;
+    case 1: fn = k_trace_ordered_rounds<4, 8, 1, true, false, false>; break;   // more node steps per vote
+    case 2: fn = k_trace_ordered_rounds<3, 8, 4, true, false, false>; break;   // global cursor; refill once fewer than 4 lanes are busy
+    case 3: fn = k_trace_ordered_rounds<4, 8, 8, true, false, false>; break;   // the first version's policy
+    // whole-unit scheduling experiments, all measured slower than the default (profiles/kbench_r1_unit_scheduling.log): lanes whose
+    // ray misses the scene stay idle for the rest of the tile instead of being topped up with the next rays
+    case 10: case 11: case 12: case 13: case 14: fn = k_trace_ordered_rounds<2, 8, 1, true, false, true>; break;
+    case 9: fn = k_trace_ordered_rounds<2, 8, 1, false, false, false>; inline_ties = false; break;  // queue drained by k_resolve_ties
+    default: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false>; break;
   }
   if (P.irregular_count != 0) {  // (the experimentation variants exist for regular scenes only)
-    fn = inline_ties ? k_trace_ordered_rounds<2, 8, 1, true, true> : k_trace_ordered_rounds<2, 8, 1, false, true>;
+    fn = inline_ties ? k_trace_ordered_rounds<2, 8, 1, true, true, false> : k_trace_ordered_rounds<2, 8, 1, false, true, false>;
   }
   int blocks_per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, ORDERED_BLOCK, 0);
