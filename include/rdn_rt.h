@@ -123,6 +123,8 @@ typedef struct rdn_build_stats {
   uint64_t balance_fallbacks, balance_fallbacks_gt10;  /* SAH -> BalanceTree fallbacks (strategy.rs:230-233); ... over > 10 primitives */
   uint64_t irregular_triangles, irregular_instances;
   uint64_t reference_routed_tlas;                      /* TLASes whose every ray takes the reference-order kernel */
+  double bvh_build_ms, flatten_ms, upload_ms;          /* wall clock of the last commit: tree builds / flattening / blob + upload */
+  uint64_t build_threads;                              /* worker threads the tree builder used (RDN_BUILD_THREADS caps it) */
 } rdn_build_stats;
 
 typedef struct rdn_rt_scene rdn_rt_scene;   /* opaque: NaiveSahBVHSystem (geometry/naive/mod.rs:495-610) */

@@ -105,7 +105,8 @@ class _TraceStats(C.Structure):
 
 class _BuildStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("balance_fallbacks", "balance_fallbacks_gt10", "irregular_triangles", "irregular_instances",
-                                          "reference_routed_tlas")]
+                                          "reference_routed_tlas")] + \
+               [(n, C.c_double) for n in ("bvh_build_ms", "flatten_ms", "upload_ms")] + [("build_threads", C.c_uint64)]
 
 
 class _KernelTimes(C.Structure):
@@ -410,7 +411,7 @@ class NaiveSahBVHSystem:
         """What the flattener found: SAH->BalanceTree fallbacks and the irregular triangles / instances (include/rdn_rt.h)."""
         st = _BuildStats()
         _check(self._L.rdn_rt_scene_build_stats(self._h, C.byref(st)))
-        return {n: int(getattr(st, n)) for n, _ in _BuildStats._fields_}
+        return {n: (float(getattr(st, n)) if t is C.c_double else int(getattr(st, n))) for n, t in _BuildStats._fields_}
 
     def arrays(self) -> dict:
         return {ARRAYS[i][0]: self.array(i) for i in ARRAYS}

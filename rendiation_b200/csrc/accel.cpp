@@ -1,6 +1,8 @@
 // accel.cpp — BLAS/TLAS assembly and flattening.  Compiled with -ffp-contract=off.
 #include "accel.h"
 
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 
@@ -270,6 +272,16 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
   out = FlatScene{};
   out.tlas_binding = tlas_binding;
   bool capacity_error = false;
+  using Clock = std::chrono::steady_clock;
+  const auto t_begin = Clock::now();
+  double bvh_ms = 0.0;
+  auto timed_build = [&](const Box3 *boxes, uint64_t n, BVHBuildStrategy &strategy, const TreeBuildOption &option) {
+    const auto t0 = Clock::now();
+    FlattenBVH bvh = FlattenBVH::build(boxes, n, strategy, option);
+    bvh_ms += std::chrono::duration<double, std::milli>(Clock::now() - t0).count();
+    if (bvh.stats.build_threads > out.stats.build_threads) out.stats.build_threads = bvh.stats.build_threads;
+    return bvh;
+  };
 
   // ---- build_blas (mod.rs:122-260).  NOTE blas_box gets one entry PER GEOMETRY of a live BLAS but one per
   // deleted BLAS, and build_tlas indexes it by BLAS handle (mod.rs:239,273) — reproduced as is.
@@ -300,17 +312,21 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
         const uint64_t n_tri = n_idx / 3;  // as_chunks::<3>().0 drops the remainder
         auto vertex_of = [&](uint64_t tri, int k) -> uint64_t { return src.has_indices ? src.indices[3 * tri + k] : 3 * tri + k; };
         std::vector<Box3> boxes(n_tri);
-        for (uint64_t t = 0; t < n_tri; ++t) {
-          Box3 b = box_empty();
-          for (int k = 0; k < 3; ++k) {
-            const uint64_t vi = vertex_of(t, k);
-            if (vi >= src.positions.size()) { err = "triangle index out of bounds (the reference panics here)"; return RDN_ERR_BUILD; }
-            expand(b, src.positions[vi]);
+        std::atomic<bool> index_out_of_bounds{false};
+        parallel_for(n_tri, PARALLEL_BUILD_MIN, [&](uint64_t t_begin_, uint64_t t_end_) {
+          for (uint64_t t = t_begin_; t < t_end_; ++t) {
+            Box3 b = box_empty();
+            for (int k = 0; k < 3; ++k) {
+              const uint64_t vi = vertex_of(t, k);
+              if (vi >= src.positions.size()) { index_out_of_bounds = true; return; }
+              expand(b, src.positions[vi]);
+            }
+            boxes[t] = b;
           }
-          boxes[t] = b;
-        }
+        });
+        if (index_out_of_bounds) { err = "triangle index out of bounds (the reference panics here)"; return RDN_ERR_BUILD; }
         SAH sah(4);
-        FlattenBVH bvh = FlattenBVH::build(boxes.data(), n_tri, sah, blas_option);
+        FlattenBVH bvh = timed_build(boxes.data(), n_tri, sah, blas_option);
         if (bvh.stats.bucket_out_of_range) { err = "SAH bucket index out of range (the reference panics here)"; return RDN_ERR_BUILD; }
         out.stats.balance_fallbacks += bvh.stats.balance_fallbacks;
         out.stats.balance_fallbacks_gt10 += bvh.stats.balance_fallbacks_gt10;
@@ -322,16 +338,20 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
         const uint64_t slot_base = out.triangles.size();
         if (slot_base != primitive_start) { err = "internal: slot/primitive offset mismatch"; return RDN_ERR_BUILD; }
         out.prim_to_slot.resize(slot_base + n_tri, 0u);
+        out.triangles.resize(slot_base + n_tri);
+        out.slot_info.resize(slot_base + n_tri);
         std::vector<uint8_t> slot_irregular(n_tri, 0);
-        for (uint64_t k = 0; k < n_tri; ++k) {
-          const uint64_t tri = bvh.sorted_primitive_index[k];  // indices_redirect[slot] - raw_primitive_start
-          out.prim_to_slot[slot_base + tri] = static_cast<uint32_t>(slot_base + k);
-          out.triangles.push_back(make_tri_record(src.positions[vertex_of(tri, 0)], src.positions[vertex_of(tri, 1)],
-                                                  src.positions[vertex_of(tri, 2)]));
-          slot_irregular[k] = triangle_is_irregular(out.triangles.back()) ? 1 : 0;
-          out.stats.irregular_triangles += slot_irregular[k];
-          out.slot_info.push_back(SlotInfo{static_cast<uint32_t>(tri), static_cast<uint32_t>(g)});
-        }
+        parallel_for(n_tri, PARALLEL_BUILD_MIN, [&](uint64_t k_begin, uint64_t k_end) {
+          for (uint64_t k = k_begin; k < k_end; ++k) {
+            const uint64_t tri = bvh.sorted_primitive_index[k];  // indices_redirect[slot] - raw_primitive_start
+            out.prim_to_slot[slot_base + tri] = static_cast<uint32_t>(slot_base + k);
+            out.triangles[slot_base + k] = make_tri_record(src.positions[vertex_of(tri, 0)], src.positions[vertex_of(tri, 1)],
+                                                           src.positions[vertex_of(tri, 2)]);
+            out.slot_info[slot_base + k] = SlotInfo{static_cast<uint32_t>(tri), static_cast<uint32_t>(g)};
+            slot_irregular[k] = triangle_is_irregular(out.triangles[slot_base + k]) ? 1 : 0;
+          }
+        });
+        for (uint64_t k = 0; k < n_tri; ++k) out.stats.irregular_triangles += slot_irregular[k];
         n_indices_total += n_tri * 3;
         // the boxes of the leaves that hold an irregular triangle: the reference can test such a triangle only after this box test
         for (const FlattenBVHNode &node : bvh.nodes) {
@@ -355,8 +375,11 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
         gm.geometry_flags = src.flags;
         gm.wide_root = emit_wide_nodes(bvh.nodes, primitive_start, out.wide_nodes, capacity_error);
         out.geometry_meta.push_back(gm);
-        for (size_t i = 0; i < bvh.nodes.size(); ++i)
-          out.tri_bvh_forest.push_back(to_device_node(bvh.nodes[i], next[i].first, next[i].second, bvh_start, primitive_start));
+        out.tri_bvh_forest.resize(bvh_start + bvh.nodes.size());
+        parallel_for(bvh.nodes.size(), PARALLEL_BUILD_MIN, [&](uint64_t i_begin, uint64_t i_end) {
+          for (uint64_t i = i_begin; i < i_end; ++i)
+            out.tri_bvh_forest[bvh_start + i] = to_device_node(bvh.nodes[i], next[i].first, next[i].second, bvh_start, primitive_start);
+        });
       }
       blas_box.push_back(OptBox{true, root_box});
     }
@@ -389,7 +412,7 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
       aabbs[i] = box_apply_matrix(blas_box[src.blas_handle].box, src.transform);
     }
     SAH sah(4);
-    FlattenBVH bvh = FlattenBVH::build(aabbs.data(), aabbs.size(), sah, tlas_option);
+    FlattenBVH bvh = timed_build(aabbs.data(), aabbs.size(), sah, tlas_option);
     if (bvh.stats.bucket_out_of_range) { err = "SAH bucket index out of range (the reference panics here)"; return RDN_ERR_BUILD; }
     out.stats.balance_fallbacks += bvh.stats.balance_fallbacks;
     out.stats.balance_fallbacks_gt10 += bvh.stats.balance_fallbacks_gt10;
@@ -451,6 +474,8 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
     err = "scene exceeds the 32-bit child-reference encoding (2^27 slots / 0x7F000000 nodes / 2^24 geometries)";
     return RDN_ERR_CAPACITY;
   }
+  out.stats.bvh_build_ms = bvh_ms;
+  out.stats.flatten_ms = std::chrono::duration<double, std::milli>(Clock::now() - t_begin).count() - bvh_ms;
   return RDN_OK;
 }
 

@@ -2,7 +2,10 @@
 #include "bvh_builder.h"
 
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace rdn {
 
@@ -119,48 +122,188 @@ SplitResult SAH::split(const FlattenBVHNode &parent, const std::vector<BuildPrim
   return r;
 }
 
-FlattenBVH FlattenBVH::build(const Box3 *boxes, uint64_t n, BVHBuildStrategy &strategy, const TreeBuildOption &option) {
-  FlattenBVH out;
-  std::vector<BuildPrimitive> primitives(n);
-  out.sorted_primitive_index.resize(n);
-  for (uint64_t i = 0; i < n; ++i) {
-    primitives[i].bounding = boxes[i];
-    primitives[i].center = box_center(boxes[i]);
-    out.sorted_primitive_index[i] = i;
+unsigned build_thread_count() {
+  unsigned n = std::thread::hardware_concurrency();
+  if (n == 0) n = 1;
+  if (const char *e = getenv("RDN_BUILD_THREADS")) {
+    const int cap = atoi(e);
+    if (cap >= 1 && static_cast<unsigned>(cap) < n) n = static_cast<unsigned>(cap);
   }
+  return n;
+}
+
+void parallel_for(uint64_t n, uint64_t min_parallel, const std::function<void(uint64_t, uint64_t)> &fn) {
+  const unsigned threads = build_thread_count();
+  if (threads <= 1 || n < min_parallel) { fn(0, n); return; }
+  const uint64_t chunk = (n + threads - 1) / threads;
+  std::vector<std::thread> pool;
+  for (unsigned t = 1; t < threads; ++t) {
+    const uint64_t begin = std::min<uint64_t>(n, t * chunk), end = std::min<uint64_t>(n, begin + chunk);
+    if (begin < end) pool.emplace_back([&fn, begin, end]() { fn(begin, end); });
+  }
+  fn(0, std::min<uint64_t>(n, chunk));
+  for (auto &th : pool) th.join();
+}
+
+namespace {
+
+// Pre-order construction of the subtree over [start, end) without recursion: descend left, park the right sibling; when a
+// leaf is reached the most recent parked sibling is emitted next, which fixes its parent's left_count.  Node indices are local
+// to `nodes` (the subtree root is node 0); left_count is position independent.
+void build_subtree(const Box3 &box, uint64_t start, uint64_t end, uint64_t depth0, BVHBuildStrategy &strategy, const TreeBuildOption &option,
+                   const std::vector<BuildPrimitive> &primitives, std::vector<uint64_t> &index, std::vector<FlattenBVHNode> &nodes,
+                   BuildStats &stats) {
   auto make_node = [&](const Box3 &b, uint64_t s, uint64_t e) {
     FlattenBVHNode nd;
     std::memset(&nd, 0, sizeof(nd));
-    nd.bounding = b; nd.primitive_start = s; nd.primitive_end = e; nd.self_index = out.nodes.size();
-    out.nodes.push_back(nd);
+    nd.bounding = b; nd.primitive_start = s; nd.primitive_end = e; nd.self_index = nodes.size();
+    nodes.push_back(nd);
   };
-  make_node(bounding_of_range(primitives, out.sorted_primitive_index, 0, n), 0, n);
-
-  // Pre-order construction without recursion: descend left, park the right sibling; when a leaf is
-  // reached the most recent parked sibling is emitted next, which fixes its parent's left_count.
+  make_node(box, start, end);
   struct Parked { uint64_t parent; Box3 box; uint64_t start, end; uint64_t depth; int32_t axis; };
   std::vector<Parked> parked;
-  uint64_t cur = 0, depth = 0;
+  uint64_t cur = 0, depth = depth0;
   for (;;) {
-    const FlattenBVHNode node = out.nodes[cur];
+    const FlattenBVHNode node = nodes[cur];
     if (option.should_continue(node.primitive_end - node.primitive_start, depth)) {
-      const SplitResult s = strategy.split(node, primitives, out.sorted_primitive_index, out.stats);
+      const SplitResult s = strategy.split(node, primitives, index, stats);
       parked.push_back(Parked{cur, s.right_box, s.right_start, s.right_end, depth + 1, s.axis});
       make_node(s.left_box, s.left_start, s.left_end);
-      cur = out.nodes.size() - 1;
+      cur = nodes.size() - 1;
       depth += 1;
       continue;
     }
     if (parked.empty()) break;
     const Parked p = parked.back();
     parked.pop_back();
-    FlattenBVHNode &parent = out.nodes[p.parent];
+    FlattenBVHNode &parent = nodes[p.parent];
     parent.has_child = 1;
     parent.split_axis = p.axis;
-    parent.left_count = out.nodes.size() - (p.parent + 1);
+    parent.left_count = nodes.size() - (p.parent + 1);
     make_node(p.box, p.start, p.end);
-    cur = out.nodes.size() - 1;
+    cur = nodes.size() - 1;
     depth = p.depth;
+  }
+}
+
+void merge_stats(BuildStats &into, const BuildStats &from) {
+  into.balance_fallbacks += from.balance_fallbacks;
+  into.balance_fallbacks_gt10 += from.balance_fallbacks_gt10;
+  into.bucket_out_of_range = into.bucket_out_of_range || from.bucket_out_of_range;
+}
+
+}  // namespace
+
+FlattenBVH FlattenBVH::build(const Box3 *boxes, uint64_t n, BVHBuildStrategy &strategy, const TreeBuildOption &option, unsigned n_threads) {
+  FlattenBVH out;
+  std::vector<BuildPrimitive> primitives(n);
+  out.sorted_primitive_index.resize(n);
+  parallel_for(n, PARALLEL_BUILD_MIN, [&](uint64_t begin, uint64_t end) {
+    for (uint64_t i = begin; i < end; ++i) {
+      primitives[i].bounding = boxes[i];
+      primitives[i].center = box_center(boxes[i]);
+      out.sorted_primitive_index[i] = i;
+    }
+  });
+  const Box3 root_box = bounding_of_range(primitives, out.sorted_primitive_index, 0, n);
+  if (n_threads == 0) n_threads = build_thread_count();
+  if (n_threads <= 1 || n < PARALLEL_BUILD_MIN) {
+    build_subtree(root_box, 0, n, 0, strategy, option, primitives, out.sorted_primitive_index, out.nodes, out.stats);
+    return out;
+  }
+
+  // ---- top of the tree on this thread: split the largest open subtree until there are enough of them
+  struct Top { Box3 box; uint64_t start, end, depth; int left = -1, right = -1; int32_t axis = 0; int task = -1; };
+  std::vector<Top> top;
+  top.push_back(Top{root_box, 0, n, 0});
+  std::vector<int> open{0};
+  const size_t want_open = static_cast<size_t>(n_threads) * 8;
+  const uint64_t min_task = 2048;
+  while (open.size() < want_open) {
+    size_t pick = open.size();
+    uint64_t largest = min_task;
+    for (size_t k = 0; k < open.size(); ++k) {
+      const Top &t = top[open[k]];
+      const uint64_t count = t.end - t.start;
+      if (count > largest && option.should_continue(count, t.depth)) { largest = count; pick = k; }
+    }
+    if (pick == open.size()) break;
+    const int ti = open[pick];
+    FlattenBVHNode node;
+    std::memset(&node, 0, sizeof(node));
+    node.bounding = top[ti].box; node.primitive_start = top[ti].start; node.primitive_end = top[ti].end;
+    const SplitResult s = strategy.split(node, primitives, out.sorted_primitive_index, out.stats);
+    const uint64_t depth = top[ti].depth + 1;
+    top[ti].axis = s.axis;
+    top[ti].left = static_cast<int>(top.size());
+    top.push_back(Top{s.left_box, s.left_start, s.left_end, depth});
+    top[ti].right = static_cast<int>(top.size());
+    top.push_back(Top{s.right_box, s.right_start, s.right_end, depth});
+    open[pick] = top[ti].left;
+    open.push_back(top[ti].right);
+  }
+
+  // ---- the open subtrees on worker threads, largest first
+  struct Task { int top; std::vector<FlattenBVHNode> nodes; BuildStats stats; };
+  std::vector<Task> tasks(open.size());
+  for (size_t k = 0; k < open.size(); ++k) { tasks[k].top = open[k]; top[open[k]].task = static_cast<int>(k); }
+  std::vector<size_t> order(tasks.size());
+  for (size_t k = 0; k < order.size(); ++k) order[k] = k;
+  std::sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+    const uint64_t ca = top[tasks[a].top].end - top[tasks[a].top].start, cb = top[tasks[b].top].end - top[tasks[b].top].start;
+    return ca != cb ? ca > cb : a < b;
+  });
+  std::atomic<size_t> next{0};
+  auto worker = [&]() {
+    std::unique_ptr<BVHBuildStrategy> mine = strategy.clone();
+    for (;;) {
+      const size_t k = next.fetch_add(1);
+      if (k >= order.size()) break;
+      Task &task = tasks[order[k]];
+      const Top &t = top[task.top];
+      build_subtree(t.box, t.start, t.end, t.depth, *mine, option, primitives, out.sorted_primitive_index, task.nodes, task.stats);
+    }
+  };
+  const unsigned workers = static_cast<unsigned>(std::min<size_t>(n_threads, tasks.size()));
+  std::vector<std::thread> pool;
+  for (unsigned w = 1; w < workers; ++w) pool.emplace_back(worker);
+  worker();
+  for (auto &th : pool) th.join();
+  out.stats.build_threads = workers;
+
+  // ---- splice in pre-order
+  uint64_t total = 0;
+  for (const Task &task : tasks) { total += task.nodes.size(); merge_stats(out.stats, task.stats); }
+  out.nodes.reserve(total + top.size());
+  struct Frame { int top; uint64_t node; int stage; };
+  std::vector<Frame> stack{Frame{0, 0, 0}};
+  while (!stack.empty()) {
+    Frame &f = stack.back();
+    const Top &t = top[f.top];
+    if (t.task >= 0) {
+      const uint64_t base = out.nodes.size();
+      for (FlattenBVHNode nd : tasks[t.task].nodes) { nd.self_index += base; out.nodes.push_back(nd); }
+      stack.pop_back();
+      continue;
+    }
+    if (f.stage == 0) {
+      FlattenBVHNode nd;
+      std::memset(&nd, 0, sizeof(nd));
+      nd.bounding = t.box; nd.primitive_start = t.start; nd.primitive_end = t.end; nd.self_index = out.nodes.size();
+      nd.has_child = 1; nd.split_axis = t.axis;
+      f.node = out.nodes.size();
+      out.nodes.push_back(nd);
+      f.stage = 1;
+      const int left = t.left;
+      stack.push_back(Frame{left, 0, 0});
+    } else if (f.stage == 1) {
+      out.nodes[f.node].left_count = out.nodes.size() - (f.node + 1);
+      f.stage = 2;
+      const int right = t.right;
+      stack.push_back(Frame{right, 0, 0});
+    } else {
+      stack.pop_back();
+    }
   }
   return out;
 }

@@ -9,6 +9,8 @@
 // right = self+left_count+1): visit order decides which of two equal-distance hits is reported.
 #pragma once
 #include <cstdint>
+#include <functional>
+#include <memory>
 #include <utility>
 #include <vector>
 
@@ -54,6 +56,10 @@ struct BuildStats {
   uint64_t irregular_triangles = 0;     // needle / non-finite triangle records (their test can pass far outside their leaf box)
   uint64_t irregular_instances = 0;     // singular / non-finite / ill-conditioned transforms, or instances of a BLAS with irregular triangles
   uint64_t reference_routed_tlas = 0;   // TLASes whose rays all take the reference-order kernel
+  // wall-clock of the last build (ms): FlattenBVH::build calls, the rest of build_blas/build_tlas (boxes, triangle records,
+  // wide nodes, threaded layout), blob serialisation + upload
+  double bvh_build_ms = 0, flatten_ms = 0, upload_ms = 0;
+  uint32_t build_threads = 1;           // worker threads FlattenBVH::build used for its largest tree
 };
 
 class BVHBuildStrategy {
@@ -61,12 +67,15 @@ class BVHBuildStrategy {
   virtual ~BVHBuildStrategy() = default;
   virtual SplitResult split(const FlattenBVHNode &parent, const std::vector<BuildPrimitive> &build_source,
                             std::vector<uint64_t> &index_source, BuildStats &stats) = 0;
+  // a strategy object holds scratch (SAH's buckets): every worker thread of the parallel build splits with its own copy
+  virtual std::unique_ptr<BVHBuildStrategy> clone() const = 0;
 };
 
 class BalanceTree : public BVHBuildStrategy {
  public:
   SplitResult split(const FlattenBVHNode &parent, const std::vector<BuildPrimitive> &build_source,
                     std::vector<uint64_t> &index_source, BuildStats &stats) override;
+  std::unique_ptr<BVHBuildStrategy> clone() const override { return std::make_unique<BalanceTree>(); }
 };
 
 class SAH : public BVHBuildStrategy {
@@ -74,6 +83,7 @@ class SAH : public BVHBuildStrategy {
   explicit SAH(uint32_t pre_partition_check_count);
   SplitResult split(const FlattenBVHNode &parent, const std::vector<BuildPrimitive> &build_source,
                     std::vector<uint64_t> &index_source, BuildStats &stats) override;
+  std::unique_ptr<BVHBuildStrategy> clone() const override { return std::make_unique<SAH>(static_cast<uint32_t>(pre_partition_.size())); }
 
  private:
   struct Bucket {
@@ -88,8 +98,19 @@ struct FlattenBVH {
   std::vector<uint64_t> sorted_primitive_index;
   BuildStats stats;
 
-  static FlattenBVH build(const Box3 *boxes, uint64_t n, BVHBuildStrategy &strategy, const TreeBuildOption &option);
+  // The reference builds on one thread (`// todo par`, naive/mod.rs:147).  A split only reads and rewrites its own index
+  // range, so disjoint subtrees are independent: above PARALLEL_BUILD_MIN primitives the top of the tree is split on the
+  // calling thread until there are enough open subtrees, the subtrees are built by worker threads (each with its own clone
+  // of the strategy) and spliced back in pre-order — node for node the tree of the sequential build.
+  // n_threads: 0 = hardware concurrency capped by the RDN_BUILD_THREADS environment variable, 1 = sequential.
+  static FlattenBVH build(const Box3 *boxes, uint64_t n, BVHBuildStrategy &strategy, const TreeBuildOption &option, unsigned n_threads = 0);
 };
+constexpr uint64_t PARALLEL_BUILD_MIN = 1u << 15;
+
+// worker threads for host-side loops: min(hardware concurrency, RDN_BUILD_THREADS), at least 1
+unsigned build_thread_count();
+// fn(begin, end) over [0, n) in contiguous chunks, one per thread (sequential below `min_parallel` items)
+void parallel_for(uint64_t n, uint64_t min_parallel, const std::function<void(uint64_t, uint64_t)> &fn);
 
 constexpr uint32_t INVALID_NEXT = 0xFFFFFFFFu;
 // (hit_next, miss_next) per node for the stackless threaded walk

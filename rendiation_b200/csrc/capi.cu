@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <mutex>
 #include <shared_mutex>
@@ -186,6 +187,7 @@ int commit_locked(rdn_rt_scene *s) {
   FlatScene flat;
   const int rc = s->source.build(s->tlas_binding, flat, err);
   if (rc != RDN_OK) return fail(rc, err);
+  const auto t_upload = std::chrono::steady_clock::now();
   const std::vector<uint8_t> blob = flat.serialize();
   BlobHeader h;
   std::memcpy(&h, blob.data(), sizeof(h));
@@ -202,6 +204,7 @@ int commit_locked(rdn_rt_scene *s) {
     }
     bind_blob(dc, h);
   }
+  flat.stats.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_upload).count();
   s->h_tlas_binding = flat.tlas_binding;
   s->h_tlas_root = flat.tlas_root;
   s->flat = std::move(flat);
@@ -862,6 +865,10 @@ int rdn_rt_scene_build_stats(rdn_rt_scene *s, rdn_build_stats *out) {
     out->irregular_triangles = s->flat.stats.irregular_triangles;
     out->irregular_instances = s->flat.stats.irregular_instances;
     out->reference_routed_tlas = s->flat.stats.reference_routed_tlas;
+    out->bvh_build_ms = s->flat.stats.bvh_build_ms;
+    out->flatten_ms = s->flat.stats.flatten_ms;
+    out->upload_ms = s->flat.stats.upload_ms;
+    out->build_threads = s->flat.stats.build_threads;
   } else {
     for (const TlasRoot &t : s->h_tlas_root) {
       if (t.irregular_count == IRREGULAR_ROUTE_ALL) out->reference_routed_tlas++;

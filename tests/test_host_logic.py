@@ -53,6 +53,22 @@ def test_flatten_bvh_builder_matches_oracle(strategy, opt):
     assert np.array_equal(ob.sorted_primitive_index, pb.sorted_primitive_index)
 
 
+@pytest.mark.parametrize("strategy", ["sah", "balance"])
+def test_parallel_builder_is_the_sequential_tree(strategy, monkeypatch):
+    """above 32,768 primitives the product builds subtrees on worker threads and splices them in pre-order: node for node the
+    oracle's (= the reference's single-threaded) tree, for any thread count"""
+    pos, idx = S.torus_mesh(170, 130)
+    tri = idx.reshape(-1, 3)
+    assert tri.shape[0] > (1 << 15)
+    boxes = np.concatenate([pos[tri].min(1), pos[tri].max(1)], 1)
+    ob = oracle.FlattenBVH(boxes, oracle.STRATEGY_SAH if strategy == "sah" else oracle.STRATEGY_BALANCE, 4, 50, 2)
+    for threads in ("1", "3", "8"):
+        monkeypatch.setenv("RDN_BUILD_THREADS", threads)
+        pb = api.FlattenBVH(boxes, api.SAH(4) if strategy == "sah" else api.BalanceTree(), api.TreeBuildOption(50, 2))
+        assert _eq(ob.nodes, pb.nodes), threads
+        assert np.array_equal(ob.sorted_primitive_index, pb.sorted_primitive_index), threads
+
+
 def test_builder_edge_cases():
     for n in (0, 1, 2, 3):
         boxes = np.tile(np.array([[0, 0, 0, 1, 1, 1]], np.float32), (n, 1))
