@@ -370,6 +370,7 @@ def run_ours(args):
         tie_ms = kernel_times["tie_ms"] / max(kernel_times["tie_launches"], 1)
         achieved = bytes_per_ray * n / (kernel_ms * 1e-3) / 1e9
         compulsory = (64.0 * n + blob_bytes) / (kernel_ms * 1e-3) / 1e9
+        l2_peak = sysm.measure_l2_read_gbs(64 << 20, 50)  # resident-set read microbenchmark, this box, this run
         traffic, traffic_src = None, None
         prof = os.path.join(ROOT, "profiles", "ncu_r1b_k_trace_ordered_c2.json")
         if os.path.exists(prof):  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
@@ -403,6 +404,9 @@ def run_ours(args):
                          "kernel": "k_trace_ordered_rounds", "kernel_ms_avg": kernel_ms, "kernel_launches_timed": kernel_times["ordered_launches"],
                          "kernel_share_of_step": kernel_ms / ms_per_step_serial, "tie_kernel_ms_avg": tie_ms,
                          "achieved_with_launch_overlap": bytes_per_ray * n / (ms_per_step * 1e-3) / 1e9,
+                         "l2": {"peak": l2_peak, "unit": "GB/s", "frac": achieved / l2_peak,
+                                "peak_source": "measured in this run: uint4 reads bypassing L1 over a 64 MiB L2-resident buffer, 50 sweeps "
+                                               "(rdn_rt_measure_l2_read_gbs)"},
                          "tie_rays_per_step": tie_rays,
                          "note": "algorithmic bytes are defined on the REFERENCE's traversal (48 B threaded nodes in pre-order, 52 B "
                                  "triangle chains); the ordered kernel visits fewer nodes and the 171 MB scene is mostly L2-resident, "

@@ -205,11 +205,20 @@ int rdn_rt_gen_camera_rays_device(rdn_rt_scene *scene, int device_index, const r
  *      scrambles (math/statistics/src/distribution_map.rs:10-58, sampling/sobol.rs:40-68)
  *   1  tbn(normal) * sample_hemisphere_cos(hammersley_2d(sample_index, max_sample)), the AO secondary ray
  *      (feature/ao.rs:249-284, shader/library/src/sampling.rs:33-83)
+ *   2  the shadow-test ray of the path tracer's closest-hit stage (feature/path_tracing/ray_hit.rs:20-45) towards a point light
+ *      at `target` (lighting_bridge.rs:86-94): to_light = target - hit_world_position, distance = |to_light|,
+ *      direction = to_light / distance, range [tmin, distance]; trace it with RDN_RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH
+ * flags & RDN_BOUNCE_OFFSET_ORIGIN: the ray starts at offset_ray_hit(hit_world_position, geometric normal)
+ * (scene/rendering/gpu-ray-tracing/src/ray_util.rs:6-40, the integer-offset self-intersection guard of Ray Tracing Gems ch. 6)
+ * as ray_hit.rs:26,82 does; directions are computed from the un-offset position, as there.
  * d_rays_out and d_src_index need n slots; d_src_index[k] = index of the primary ray behind bounce ray k;
  * *d_out_n (device) = number of bounce rays.  Uses the scene's compaction scratch (rdn_rt_compact_u32_device). */
+#define RDN_BOUNCE_OFFSET_ORIGIN 0x1u
 typedef struct rdn_bounce {
   uint32_t mode, index_base, scramble0, scramble1, sample_index, max_sample;
   float tmin, tmax;
+  uint32_t flags;
+  float target[3];
 } rdn_bounce;
 int rdn_rt_gen_bounce_rays_device(rdn_rt_scene *scene, int device_index, const rdn_bounce *params, const rdn_ray *d_rays_in,
                                   const rdn_hit *d_hits, uint64_t n, rdn_ray *d_rays_out, uint32_t *d_src_index,
@@ -279,6 +288,11 @@ int rdn_bvh_query_list(const rdn_flat_bvh *bvh, const rdn_mesh_view *mesh, const
 int rdn_bvh_upload(rdn_flat_bvh *bvh, const rdn_mesh_view *mesh, int device);
 int rdn_bvh_query_nearest_device(const rdn_flat_bvh *bvh, const rdn_ray *d_rays, uint64_t n, uint32_t face_side,
                                  rdn_mesh_hit *d_out, void *cuda_stream);
+
+/* ---- measurement hook (no reference counterpart): read bandwidth, in GB/s, of a buffer of `bytes` that has been made L2
+ *      resident on the scene's device (uint4 loads that bypass L1, `passes` sweeps inside one kernel, CUDA events) — the L2
+ *      denominator of the roofline next to the HBM copy peak.  Synchronous; allocates and frees the buffer. */
+int rdn_rt_measure_l2_read_gbs(rdn_rt_scene *scene, int device_index, uint64_t bytes, int passes, double *out_gbs);
 
 const char *rdn_rt_last_error(void);
 const char *rdn_rt_version(void);

@@ -136,6 +136,28 @@ def geometric_normals(positions, indices, prim, world_to_object, ray_origin, hit
     return g
 
 
+def offset_ray_hit(position, normal):
+    """scene/rendering/gpu-ray-tracing/src/ray_util.rs:6-40 (Ray Tracing Gems ch. 6): per component, the position moved by
+    int(256 * n) units in the last place along the normal, or by n / 65536 when |p| < 1/32"""
+    p = np.asarray(position, f32)
+    n = np.asarray(normal, f32)
+    of_i = np.trunc((n * f32(256.0)).astype(f32)).astype(np.int32)  # into_i32
+    step = np.where(p < 0, -of_i, of_i).astype(np.int32)
+    p_i = (p.view(np.int32) + step).astype(np.int32).view(f32)
+    near = (p + (f32(1.0 / 65536.0) * n).astype(f32)).astype(f32)
+    return np.where(np.abs(p) < f32(1.0 / 32.0), near, p_i).astype(f32)
+
+
+def towards_point(position, target):
+    """PointLight::importance_sampling_light_impl (feature/path_tracing/lighting_bridge.rs:86-94): (direction, distance)"""
+    to_light = (np.asarray(target, f32)[None, :] - np.asarray(position, f32)).astype(f32)
+    acc = (to_light[:, 0] * to_light[:, 0]).astype(f32)
+    acc = (acc + (to_light[:, 1] * to_light[:, 1]).astype(f32)).astype(f32)
+    acc = (acc + (to_light[:, 2] * to_light[:, 2]).astype(f32)).astype(f32)
+    distance = np.sqrt(acc, dtype=f32)
+    return (to_light / distance[:, None]).astype(f32), distance
+
+
 def sample_hemisphere_cos(uv):
     """shader/library/src/sampling.rs:55-62"""
     phi = (f32(2.0 * np.pi) * uv[..., 1]).astype(f32)

@@ -74,6 +74,7 @@ GEOMETRY_FLAG_NO_DUPLICATE_ANYHIT_INVOCATION = 0x2
 HIT_KIND_FRONT_FACING_TRIANGLE = 0xFE
 HIT_KIND_BACK_FACING_TRIANGLE = 0xFF
 INVALID_ID = 0xFFFFFFFF
+BOUNCE_OFFSET_ORIGIN = 0x1
 
 TRACE_AUTO, TRACE_REFERENCE_ORDER = 0, 1
 FACE_FRONT, FACE_BACK, FACE_DOUBLE = 0, 1, 2
@@ -128,7 +129,8 @@ class _Camera(C.Structure):
 
 class _Bounce(C.Structure):
     _fields_ = [("mode", C.c_uint32), ("index_base", C.c_uint32), ("scramble0", C.c_uint32), ("scramble1", C.c_uint32),
-                ("sample_index", C.c_uint32), ("max_sample", C.c_uint32), ("tmin", C.c_float), ("tmax", C.c_float)]
+                ("sample_index", C.c_uint32), ("max_sample", C.c_uint32), ("tmin", C.c_float), ("tmax", C.c_float),
+                ("flags", C.c_uint32), ("target", C.c_float * 3)]
 
 
 class _Option(C.Structure):
@@ -144,7 +146,7 @@ EXPORTED_SYMBOLS = [
     "rdn_rt_tlas_destroy", "rdn_rt_bind_tlas", "rdn_rt_bind_tlas_max_len", "rdn_rt_commit", "rdn_rt_trace_closest",
     "rdn_rt_trace_closest_device", "rdn_rt_trace_counted", "rdn_rt_kernel_timing_begin", "rdn_rt_kernel_timing_end",
     "rdn_rt_gen_pinhole_rays_device", "rdn_rt_gen_pinhole_rays_batch_device", "rdn_rt_gen_camera_rays_device", "rdn_rt_gen_bounce_rays_device", "rdn_rt_compact_u32", "rdn_rt_compact_u32_device",
-    "rdn_rt_scene_blob", "rdn_rt_scene_adopt_blob", "rdn_rt_scene_array", "rdn_rt_scene_build_stats", "rdn_bvh_build", "rdn_bvh_destroy", "rdn_bvh_nodes",
+    "rdn_rt_scene_blob", "rdn_rt_scene_adopt_blob", "rdn_rt_scene_array", "rdn_rt_scene_build_stats", "rdn_rt_measure_l2_read_gbs", "rdn_bvh_build", "rdn_bvh_destroy", "rdn_bvh_nodes",
     "rdn_bvh_sorted_primitive_index", "rdn_bvh_build_for_mesh", "rdn_bvh_query_nearest", "rdn_bvh_upload", "rdn_bvh_query_nearest_device", "rdn_bvh_query_list", "rdn_rt_last_error", "rdn_rt_version",
 ]
 
@@ -190,6 +192,7 @@ def lib() -> C.CDLL:
     L.rdn_rt_scene_adopt_blob.argtypes = [vp, i32, vp, u64]
     L.rdn_rt_scene_array.argtypes = [vp, i32, vp, u64, P(u64)]
     L.rdn_rt_scene_build_stats.argtypes = [vp, P(_BuildStats)]
+    L.rdn_rt_measure_l2_read_gbs.argtypes = [vp, i32, u64, i32, P(C.c_double)]
     L.rdn_bvh_build.argtypes = [vp, u64, i32, u32, P(_Option), P(vp)]
     L.rdn_bvh_build_for_mesh.argtypes = [P(_MeshView), i32, u32, P(_Option), P(vp)]
     L.rdn_bvh_destroy.argtypes = [vp]
@@ -371,9 +374,13 @@ class NaiveSahBVHSystem:
 
     def gen_bounce_rays_device(self, d_rays_in: int, d_hits: int, n: int, d_rays_out: int, d_src_index: int, d_out_n: int, mode: int = 0,
                                index_base: int = 0, scrambles=(0x9E3779B9, 0x85EBCA6B), sample_index: int = 0, max_sample: int = 256,
-                               tmin=0.01, tmax=100.0, stream: int = 0, device_index: int = 0):
-        """One compacted bounce ray per primary hit (mode 0: SURVEY config-3 cosine bounce, mode 1: the AO secondary ray of ao.rs:249-284)."""
-        p = _Bounce(mode, index_base, scrambles[0], scrambles[1], sample_index, max_sample, tmin, tmax)
+                               tmin=0.01, tmax=100.0, stream: int = 0, device_index: int = 0, offset_origin: bool = False,
+                               target=(0.0, 0.0, 0.0)):
+        """One compacted bounce ray per primary hit (mode 0: SURVEY config-3 cosine bounce, mode 1: the AO secondary ray of
+        ao.rs:249-284, mode 2: the path tracer's shadow-test ray towards a point light at ``target``, ray_hit.rs:20-45);
+        ``offset_origin``: start at offset_ray_hit(hit position, geometric normal) (ray_util.rs:6-40)."""
+        p = _Bounce(mode, index_base, scrambles[0], scrambles[1], sample_index, max_sample, tmin, tmax,
+                    BOUNCE_OFFSET_ORIGIN if offset_origin else 0, (C.c_float * 3)(*[float(x) for x in target]))
         _check(self._L.rdn_rt_gen_bounce_rays_device(self._h, device_index, C.byref(p), C.c_void_p(d_rays_in), C.c_void_p(d_hits), n,
                                                      C.c_void_p(d_rays_out), C.c_void_p(d_src_index), C.c_void_p(d_out_n), C.c_void_p(stream)))
 
@@ -406,6 +413,12 @@ class NaiveSahBVHSystem:
         if nb.value:
             _check(self._L.rdn_rt_scene_array(self._h, array_id, _p(out), nb.value, C.byref(nb)))
         return out
+
+    def measure_l2_read_gbs(self, nbytes: int = 64 << 20, passes: int = 50, device_index: int = 0) -> float:
+        """read bandwidth (GB/s) of an L2-resident buffer: the roofline's L2 denominator (measurement hook)"""
+        out = C.c_double()
+        _check(self._L.rdn_rt_measure_l2_read_gbs(self._h, device_index, nbytes, passes, C.byref(out)))
+        return float(out.value)
 
     def build_stats(self) -> dict:
         """What the flattener found: SAH->BalanceTree fallbacks and the irregular triangles / instances (include/rdn_rt.h)."""

@@ -672,7 +672,7 @@ int rdn_rt_gen_bounce_rays_device(rdn_rt_scene *s, int device_index, const rdn_b
   if (!s || !p || !d_out_n || (n && (!d_rays_in || !d_hits || !d_rays_out || !d_src_index)))
     return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_gen_bounce_rays_device: null argument");
   if (device_index < 0 || device_index >= static_cast<int>(s->devices.size())) return fail(RDN_ERR_INVALID_ARGUMENT, "bad device_index");
-  if (p->mode > 1 || (p->mode == 1 && p->max_sample == 0)) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_gen_bounce_rays_device: bad mode");
+  if (p->mode > 2 || (p->mode == 1 && p->max_sample == 0)) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_gen_bounce_rays_device: bad mode");
   if (n > MAX_LAUNCH_RAYS) return fail(RDN_ERR_CAPACITY, "rdn_rt_gen_bounce_rays_device: more than 2^31 rays in one call");
   int rc = ensure_committed(s);
   if (rc != RDN_OK) return rc;
@@ -850,6 +850,15 @@ int rdn_rt_scene_array(rdn_rt_scene *s, int array_id, void *out, uint64_t capaci
     if (s->devices.empty()) std::memcpy(out, s->host_blob.data() + h.offset[array_id], bytes);
     else RDN_CUDA(cudaMemcpy(out, static_cast<const char *>(s->devices[0].d_blob) + h.offset[array_id], bytes, cudaMemcpyDeviceToHost));
   }
+  return RDN_OK;
+}
+
+int rdn_rt_measure_l2_read_gbs(rdn_rt_scene *s, int device_index, uint64_t bytes, int passes, double *out_gbs) {
+  if (!s || !out_gbs || bytes < (1u << 20) || passes < 1) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_measure_l2_read_gbs: bad argument");
+  if (device_index < 0 || device_index >= static_cast<int>(s->devices.size())) return fail(RDN_ERR_INVALID_ARGUMENT, "bad device_index");
+  std::lock_guard<std::mutex> lg(s->launch_lock);
+  RDN_CUDA(cudaSetDevice(s->devices[device_index].device));
+  if (measure_l2_read_gbs(bytes, passes, s->devices[device_index].sm_count, out_gbs) != 0) return fail(RDN_ERR_CUDA, "rdn_rt_measure_l2_read_gbs: CUDA error");
   return RDN_OK;
 }
 

@@ -83,6 +83,9 @@ void launch_mark_hits(const rdn_hit *d_hits, uint64_t n, uint8_t *d_keep, uint32
 void launch_gen_bounce_rays(const SceneDev &scene, const rdn_bounce &p, const rdn_ray *d_rays_in, const rdn_hit *d_hits,
                             const uint32_t *d_src_index, const uint64_t *d_n_src, uint64_t n_max, rdn_ray *d_rays_out, cudaStream_t stream);
 
+// measurement hook (probe.cu): read bandwidth of an L2-resident buffer of `bytes` on the current device, GB/s
+int measure_l2_read_gbs(uint64_t bytes, int passes, int sm_count, double *out_gbs);
+
 // path A: intersect_nearest_bvh over a FlattenBVH (content/mesh/core/src/feature/bvh.rs:57-86); the kernel walks
 // the tree in the reference's order (right child first, no distance pruning) so equal-distance ties resolve identically.
 constexpr int PATHA_MAX_DEPTH = 128;

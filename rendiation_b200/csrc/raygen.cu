@@ -185,6 +185,17 @@ __device__ __forceinline__ Vec3 ao_direction(Vec3 nrm, uint32_t sample_index, ui
               tangent.z * local.x + bi_tangent.z * local.y + nrm.z * local.z};
 }
 
+// offset_ray_hit (scene/rendering/gpu-ray-tracing/src/ray_util.rs:6-40): per component, move the position by
+// int(256 * n) units in the last place away from the surface (towards the normal), or by n / 65536 near the origin
+__device__ __forceinline__ float offset_component(float p, float n) {
+  const int of_i = static_cast<int>(n * 256.0f);  // into_i32: truncation
+  const float p_i = __int_as_float(__float_as_int(p) + (p < 0.0f ? -of_i : of_i));
+  return fabsf(p) < (1.0f / 32.0f) ? p + (1.0f / 65536.0f) * n : p_i;
+}
+__device__ __forceinline__ Vec3 offset_ray_hit(Vec3 p, Vec3 n) {
+  return Vec3{offset_component(p.x, n.x), offset_component(p.y, n.y), offset_component(p.z, n.z)};
+}
+
 __global__ void __launch_bounds__(256) k_gen_bounce_rays(const SceneDev S, const rdn_bounce P, const rdn_ray *__restrict__ rays_in,
                                                          const rdn_hit *__restrict__ hits, const uint32_t *__restrict__ src_index,
                                                          const uint64_t *__restrict__ n_src, rdn_ray *__restrict__ rays_out) {
@@ -216,9 +227,20 @@ __global__ void __launch_bounds__(256) k_gen_bounce_rays(const SceneDev S, const
                             wi[8] * c.x + wi[9] * c.y + wi[10] * c.z});
     if (dot(ro - pos, g) < 0.0f) g = Vec3{-g.x, -g.y, -g.z};
     Vec3 dir;
-    if (P.mode == 0) dir = cosine_sample_hemisphere_in_dir(g, van_der_corput(src + P.index_base, P.scramble0), sobol2(src + P.index_base, P.scramble1));
-    else dir = ao_direction(g, P.sample_index, P.max_sample);
-    store_ray(rays_out + k, pos, P.tmin, dir, P.tmax);
+    float tmax = P.tmax;
+    if (P.mode == 0) {
+      dir = cosine_sample_hemisphere_in_dir(g, van_der_corput(src + P.index_base, P.scramble0), sobol2(src + P.index_base, P.scramble1));
+    } else if (P.mode == 1) {
+      dir = ao_direction(g, P.sample_index, P.max_sample);
+    } else {
+      // PointLight::importance_sampling_light_impl (lighting_bridge.rs:86-94), from the un-offset hit position (ray_hit.rs:20-23)
+      const Vec3 to_light = Vec3{P.target[0], P.target[1], P.target[2]} - pos;
+      const float distance = length(to_light);
+      dir = to_light / distance;
+      tmax = distance;
+    }
+    const Vec3 origin = (P.flags & RDN_BOUNCE_OFFSET_ORIGIN) ? offset_ray_hit(pos, g) : pos;
+    store_ray(rays_out + k, origin, P.tmin, dir, tmax);
   }
 }
 

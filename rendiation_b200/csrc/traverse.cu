@@ -414,6 +414,17 @@ __device__ __forceinline__ void drain_tie_queue(const OrderedParams &P) {
 }
 
 
+template <int PF>
+__device__ __forceinline__ void prefetch_ref(const SceneDev &S, uint32_t ref, bool in_object) {
+  const void *p = nullptr;
+  if (ref < REF_SPECIAL) p = S.wide_nodes + ref;
+  else if ((ref & REF_LEAF_BIT) && in_object) p = S.triangles + (ref & REF_LEAF_START_MASK);
+  if (p) {
+    if (PF == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+    else asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+  }
+}
+
 // SM-local work distribution.  Every SM owns one contiguous range of the (screen-coherent) unit order and its warps take
 // units from the range's cursor, so the 32 warps resident on an SM walk 32 neighbouring tiles at the same time and share the
 // BVH nodes they pull into that SM's L1 — with one global cursor, consecutive tiles go to whichever warp of the whole GPU
@@ -468,7 +479,10 @@ __device__ __forceinline__ uint32_t compact_even_bits4(uint32_t x) {  // bits 0,
 // nothing for the out-of-line test (the call makes ptxas save two dozen registers around the whole refill block).
 // UNITS: whole units of 32 fetch slots from the range cursors (grab_unit; one range = one global cursor, n_ranges = SM count = every
 // SM its own range) instead of single fetch slots from one 64-bit cursor; needs THRESH == 1 (whole-tile refill).
-template <int K, int MINB, int THRESH, bool DRAIN_TIES, bool IRREGULAR, bool UNITS>  // DRAIN_TIES: near-tie queue drained inside the kernel (else by k_resolve_ties)
+// PF: as soon as a node's child references are known, prefetch what they point to (1: into L1, 2: into L2) — the two slab tests
+// that decide which child is entered take a warp several hundred cycles of wall clock (it shares its issue slot with seven
+// others), enough for the line to arrive before the next dependent fetch asks for it; no register is held by a prefetch.
+template <int K, int MINB, int THRESH, bool DRAIN_TIES, bool IRREGULAR, bool UNITS, int PF>  // DRAIN_TIES: near-tie queue drained inside the kernel (else by k_resolve_ties)
 __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(const __grid_constant__ OrderedParams P) {
   const SceneDev &S = P.S;
   const uint32_t lane = threadIdx.x & 31u;
@@ -665,10 +679,14 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
 #endif
           const float4 *np = reinterpret_cast<const float4 *>(S.wide_nodes + cur);
           const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
+          const uint32_t r0 = __float_as_uint(q0.w), r1 = __float_as_uint(q1.w);
+          if (PF != 0) {
+            prefetch_ref<PF>(S, r0, in_object);
+            prefetch_ref<PF>(S, r1, in_object);
+          }
           float n0, n1;
           const bool h0 = slab_test(o, inv, near_s, far_s, xyz(q0), xyz(q1), n0);
           const bool h1 = slab_test(o, inv, near_s, far_s, xyz(q2), xyz(q3), n1);
-          const uint32_t r0 = __float_as_uint(q0.w), r1 = __float_as_uint(q1.w);
           if (h0 && h1) {
             const bool first0 = n0 <= n1;
             RDN_PUSH(first0 ? r1 : r0);
@@ -923,17 +941,19 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const
   KernelFn fn;
   bool inline_ties = true;
   switch (variant) {
-    case 1: fn = k_trace_ordered_rounds<4, 8, 1, true, false, false>; break;   // more node steps per vote
-    case 2: fn = k_trace_ordered_rounds<3, 8, 4, true, false, false>; break;   // global cursor; refill once fewer than 4 lanes are busy
-    case 3: fn = k_trace_ordered_rounds<4, 8, 8, true, false, false>; break;   // the first version's policy
+    case 1: fn = k_trace_ordered_rounds<4, 8, 1, true, false, false, 0>; break;   // more node steps per vote
+    case 2: fn = k_trace_ordered_rounds<3, 8, 4, true, false, false, 0>; break;   // global cursor; refill once fewer than 4 lanes are busy
+    case 3: fn = k_trace_ordered_rounds<4, 8, 8, true, false, false, 0>; break;   // the first version's policy
     // whole-unit scheduling experiments, all measured slower than the default (profiles/kbench_r1_unit_scheduling.log): lanes whose
     // ray misses the scene stay idle for the rest of the tile instead of being topped up with the next rays
-    case 10: case 11: case 12: case 13: case 14: fn = k_trace_ordered_rounds<2, 8, 1, true, false, true>; break;
-    case 9: fn = k_trace_ordered_rounds<2, 8, 1, false, false, false>; inline_ties = false; break;  // queue drained by k_resolve_ties
-    default: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false>; break;
+    case 10: case 11: case 12: case 13: case 14: fn = k_trace_ordered_rounds<2, 8, 1, true, false, true, 0>; break;
+    case 9: fn = k_trace_ordered_rounds<2, 8, 1, false, false, false, 0>; inline_ties = false; break;  // queue drained by k_resolve_ties
+    case 20: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 1>; break;  // children prefetched into L1
+    case 21: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 2>; break;  // ... into L2
+    default: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0>; break;
   }
   if (P.irregular_count != 0) {  // (the experimentation variants exist for regular scenes only)
-    fn = inline_ties ? k_trace_ordered_rounds<2, 8, 1, true, true, false> : k_trace_ordered_rounds<2, 8, 1, false, true, false>;
+    fn = inline_ties ? k_trace_ordered_rounds<2, 8, 1, true, true, false, 0> : k_trace_ordered_rounds<2, 8, 1, false, true, false, 0>;
   }
   int blocks_per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, ORDERED_BLOCK, 0);

@@ -143,6 +143,51 @@ def test_bounce_rays_follow_the_reference_recipe(mode):
     assert np.all(got["tmin"] == f32(0.01)) and np.all(got["tmax"] == f32(100.0))
 
 
+def test_shadow_test_rays_with_offset_origin_are_bit_exact():
+    """mode 2 + RDN_BOUNCE_OFFSET_ORIGIN: the path tracer's shadow-test ray (ray_hit.rs:20-45) — integer origin offset, division by the
+    distance — is plain f32 / integer arithmetic, so the device rays equal the numpy restatement bit for bit; traced with
+    ACCEPT_FIRST_HIT_AND_END_SEARCH they equal the oracle's first-hit walk"""
+    import torch
+    sp, (pos, idx, m) = helpers.torus_scene(96)
+    W, H = 192, 160
+    d_rays, d_hits = _primary_and_hits(sp, W, H)
+    n = W * H
+    st = torch.cuda.current_stream().cuda_stream
+    d_out = _dev_rays(n)
+    d_src = torch.zeros(n, dtype=torch.int32, device="cuda")
+    d_n = torch.zeros(1, dtype=torch.int64, device="cuda")
+    light = (3.0, 8.0, -4.0)
+    sp.p.gen_bounce_rays_device(d_rays.data_ptr(), d_hits.data_ptr(), n, d_out.data_ptr(), d_src.data_ptr(), d_n.data_ptr(), mode=2,
+                                tmin=float(np.finfo(f32).eps), target=light, offset_origin=True, stream=st)
+    k = int(d_n.item())
+    rays = _np_rays(d_rays)
+    hits = d_hits.cpu().numpy().view(api.HIT_DTYPE).reshape(-1)
+    src = np.nonzero(hits["instance_id"] != api.INVALID_ID)[0]
+    assert k == src.size and k > 1000
+    got = _np_rays(d_out)[:k]
+    o, d, t = _orig(rays)[src], _dirs(rays)[src], hits["t"][src]
+    p = (o + (d * t[:, None]).astype(f32)).astype(f32)
+    g = R.geometric_normals(pos, idx, hits["primitive_id"][src].astype(np.int64), oracle.mat4_inverse_or_identity(m), o, p)
+    want_dir, want_dist = R.towards_point(p, light)
+    # the geometric normal goes through a normalisation (rsqrt-free, but sqrt + division): allow the offset to differ by the
+    # truncation of 256 * n at most by one unit in the last place
+    want_o = R.offset_ray_hit(p, g)
+    assert np.all(np.abs(_orig(got).view(np.int32).astype(np.int64) - want_o.view(np.int32).astype(np.int64)) <= 1)
+    assert float(np.mean(_orig(got).view(np.int32) == want_o.view(np.int32))) > 0.999
+    assert np.array_equal(_dirs(got), want_dir) and np.array_equal(got["tmax"], want_dist)
+    assert np.all(got["tmin"] == np.finfo(f32).eps)
+    # shadow test: first accepted hit ends the search (reference-order kernel), bit-identical to the oracle on these rays
+    d_sh = torch.zeros_like(d_out)
+    flags = api.RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH
+    sp.p.trace_closest_device(d_out.data_ptr(), k, d_sh.data_ptr(), ray_flags=flags, stream=st)
+    torch.cuda.synchronize()
+    want = sp.o.trace(got, ray_flags=flags, n_threads=4, want_counters=False)
+    got_h = d_sh.cpu().numpy().view(api.HIT_DTYPE).reshape(-1)[:k]
+    assert got_h.tobytes() == want.tobytes()
+    occluded = int((got_h["instance_id"] != api.INVALID_ID).sum())
+    assert 0 < occluded < k  # part of the torus is in its own shadow, part is lit
+
+
 def test_device_resident_wavefront_matches_the_oracle_on_the_rays_it_generated():
     """primary (device gen) -> closest hit -> compacted cosine bounce (device gen) -> closest hit, no host round trip in between;
     both waves bit-identical to the oracle traversal of the same rays"""

@@ -88,3 +88,34 @@ def test_geometric_normal_faces_the_ray_and_follows_the_instance_transform():
     d = R._normalize(centre)
     g2 = S.geometric_normals(pos, idx, prim, m, d)
     assert np.max(np.abs(g - g2)) < 1e-4
+
+
+def test_offset_ray_hit_known_answers():
+    """ray_util.rs:6-40: integer offset of int(256 n) ulps away from the origin side for |p| >= 1/32, n/65536 below"""
+    p = np.array([[1.0, -2.0, 0.01], [100.0, 0.5, -0.03], [-1e-3, 1 / 32, -(1 / 32)]], f32)
+    n = np.array([[0.0, 1.0, 0.0], [0.6, -0.8, 0.0], [1.0, 0.5, -0.25]], f32)
+    out = R.offset_ray_hit(p, n)
+    # row 0: x: of_i = 0 -> unchanged; y: p<0, of_i=256 -> bits - 256 (towards zero = along +n); z: |p|<1/32 -> p + n/65536 = p
+    assert out[0, 0] == f32(1.0)
+    assert out[0, 1].view(np.int32) == p[0, 1].view(np.int32) - 256 and out[0, 1] > p[0, 1]
+    assert out[0, 2] == p[0, 2]
+    # row 1: int(153.6) = 153 ulps up; int(-204.8) = -204 ulps (truncation, not floor)
+    assert out[1, 0].view(np.int32) == p[1, 0].view(np.int32) + 153
+    assert out[1, 1].view(np.int32) == p[1, 1].view(np.int32) - 204 and out[1, 1] < p[1, 1]
+    assert out[1, 2] == (p[1, 2] + f32(1 / 65536) * n[1, 2]).astype(f32)
+    # row 2: the 1/32 boundary is exclusive on the small side
+    assert out[2, 0] == (p[2, 0] + f32(1 / 65536) * n[2, 0]).astype(f32)
+    assert out[2, 1].view(np.int32) == p[2, 1].view(np.int32) + 128
+    assert out[2, 2].view(np.int32) == p[2, 2].view(np.int32) + 64  # p<0: -of_i = +64 -> larger magnitude = along -z = along n
+    # the offset always moves along the normal's sign, component by component
+    rng = np.random.default_rng(5)
+    P = rng.uniform(-50, 50, (4096, 3)).astype(f32)
+    N = rng.normal(size=(4096, 3)).astype(f32); N /= np.linalg.norm(N, axis=1, keepdims=True)
+    D = R.offset_ray_hit(P, N).astype(np.float64) - P
+    assert np.all(D * N >= 0) and np.all(np.abs(D) <= np.abs(P) * 4e-5 + 2e-5)
+
+
+def test_towards_point():
+    d, dist = R.towards_point(np.array([[1.0, 2.0, 3.0], [0.0, 0.0, 0.0]], f32), (4.0, 6.0, 3.0))
+    assert np.array_equal(dist, np.array([5.0, np.sqrt(f32(61.0))], f32))
+    assert np.array_equal(d[0], np.array([0.6, 0.8, 0.0], f32))
