@@ -155,7 +155,8 @@ int rdn_rt_commit(rdn_rt_scene *scene);
 int rdn_rt_trace_closest(rdn_rt_scene *scene, const rdn_launch *launch, const rdn_ray *rays, uint64_t n,
                          rdn_hit *out_hits);
 /* device-resident buffers on device `device_index` (index into the scene's device list); asynchronous on
- * `cuda_stream` (a cudaStream_t, 0 = default stream) unless `stats` is non-NULL (then it synchronises). */
+ * `cuda_stream` (a cudaStream_t, 0 = default stream) unless `stats` is non-NULL (then it synchronises).
+ * d_rays and d_hits must be 32-byte aligned (any cudaMalloc pointer plus a whole number of records is). */
 int rdn_rt_trace_closest_device(rdn_rt_scene *scene, int device_index, const rdn_launch *launch,
                                 const rdn_ray *d_rays, uint64_t n, rdn_hit *d_hits, void *cuda_stream,
                                 int mode, rdn_trace_stats *stats);

@@ -429,6 +429,8 @@ int rdn_rt_commit(rdn_rt_scene *s) {
 int rdn_rt_trace_closest_device(rdn_rt_scene *s, int device_index, const rdn_launch *launch, const rdn_ray *d_rays, uint64_t n,
                                 rdn_hit *d_hits, void *cuda_stream, int mode, rdn_trace_stats *stats) {
   if (!s || !launch || (n && (!d_rays || !d_hits))) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_trace_closest_device: null argument");
+  if ((reinterpret_cast<uintptr_t>(d_rays) | reinterpret_cast<uintptr_t>(d_hits)) & 31u)
+    return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_trace_closest_device: ray and hit arrays must be 32-byte aligned (one 256-bit access per record)");
   if (device_index < 0 || device_index >= static_cast<int>(s->devices.size())) return fail(RDN_ERR_INVALID_ARGUMENT, "bad device_index (host-only scene?)");
   int rc = ensure_committed(s);
   if (rc != RDN_OK) return rc;

@@ -131,6 +131,31 @@ __device__ __forceinline__ void store_hit(rdn_hit *dst, float t, float u, float 
   p[1] = make_float4(__uint_as_float(geom), __uint_as_float(inst), __uint_as_float(custom), __uint_as_float(kind));
 }
 
+// 32 bytes in one instruction (Blackwell's 256-bit global loads / stores: LDG.E.256 / STG.E.256): a 64 B node or triangle record is
+// two load instructions instead of four, a ray or a hit record one instead of two.  The address must be 32-byte aligned.
+template <bool WIDE>
+__device__ __forceinline__ void load_pair(const void *p, float4 &a, float4 &b) {
+  if (WIDE) {
+    asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+        : "l"(p));
+  } else {
+    a = __ldg(reinterpret_cast<const float4 *>(p));
+    b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+  }
+}
+template <bool WIDE>
+__device__ __forceinline__ void store_hit_as(rdn_hit *dst, float t, float u, float v, uint32_t prim, uint32_t geom, uint32_t inst,
+                                             uint32_t custom, uint32_t kind) {
+  if (WIDE) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "f"(t), "f"(u), "f"(v), "f"(__uint_as_float(prim)),
+                 "f"(__uint_as_float(geom)), "f"(__uint_as_float(inst)), "f"(__uint_as_float(custom)), "f"(__uint_as_float(kind))
+                 : "memory");
+  } else {
+    store_hit(dst, t, u, v, prim, geom, inst, custom, kind);
+  }
+}
+
 // ================================================================================================ reference order
 struct WalkResult {
   float t, u, v;
@@ -482,7 +507,8 @@ __device__ __forceinline__ uint32_t compact_even_bits4(uint32_t x) {  // bits 0,
 // PF: as soon as a node's child references are known, prefetch what they point to (1: into L1, 2: into L2) — the two slab tests
 // that decide which child is entered take a warp several hundred cycles of wall clock (it shares its issue slot with seven
 // others), enough for the line to arrive before the next dependent fetch asks for it; no register is held by a prefetch.
-template <int K, int MINB, int THRESH, bool DRAIN_TIES, bool IRREGULAR, bool UNITS, int PF>  // DRAIN_TIES: near-tie queue drained inside the kernel (else by k_resolve_ties)
+// LD256: 256-bit loads / stores for nodes, triangles, instance boxes, rays and hit records.
+template <int K, int MINB, int THRESH, bool DRAIN_TIES, bool IRREGULAR, bool UNITS, int PF, bool LD256>  // DRAIN_TIES: near-tie queue drained inside the kernel (else by k_resolve_ties)
 __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(const __grid_constant__ OrderedParams P) {
   const SceneDev &S = P.S;
   const uint32_t lane = threadIdx.x & 31u;
@@ -580,8 +606,8 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
           valid = idx < P.n;
         }
       if (valid) {
-        const float4 r0 = __ldg(reinterpret_cast<const float4 *>(P.rays + idx));
-        const float4 r1 = __ldg(reinterpret_cast<const float4 *>(P.rays + idx) + 1);
+        float4 r0, r1;
+        load_pair<LD256>(P.rays + idx, r0, r1);
         const Vec3 ro = xyz(r0), rd = xyz(r1), rinv = recip3(rd);
         float tn;
         const bool enters = world_entry != REF_EMPTY && slab_test(ro, rinv, r0.w, r1.w, root_min, root_max, tn);
@@ -598,7 +624,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
           cur = world_entry;
           alive = true;
         } else {
-          store_hit(P.hits + idx, r1.w, 0.f, 0.f, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, 0);
+          store_hit_as<LD256>(P.hits + idx, r1.w, 0.f, 0.f, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, 0);
         }
       }
         // take the following unit now: the round trip of the atomic overlaps the traversal of this one (the result is
@@ -638,8 +664,8 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
           idx = static_cast<uint64_t>(y) * P.width + x;
         }
         if (valid) {
-          const float4 r0 = __ldg(reinterpret_cast<const float4 *>(P.rays + idx));
-          const float4 r1 = __ldg(reinterpret_cast<const float4 *>(P.rays + idx) + 1);
+          float4 r0, r1;
+          load_pair<LD256>(P.rays + idx, r0, r1);
           const Vec3 ro = xyz(r0), rd = xyz(r1), rinv = recip3(rd);
           float tn;
           const bool enters = world_entry != REF_EMPTY && slab_test(ro, rinv, r0.w, r1.w, root_min, root_max, tn);
@@ -656,7 +682,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
             cur = world_entry;
             alive = true;
           } else {
-            store_hit(P.hits + idx, r1.w, 0.f, 0.f, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, 0);
+            store_hit_as<LD256>(P.hits + idx, r1.w, 0.f, 0.f, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, 0);
           }
         }
       }
@@ -678,7 +704,9 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
           ++dbg_steps; ++dbg_ray_steps;
 #endif
           const float4 *np = reinterpret_cast<const float4 *>(S.wide_nodes + cur);
-          const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
+          float4 q0, q1, q2, q3;
+          load_pair<LD256>(np, q0, q1);
+          load_pair<LD256>(np + 2, q2, q3);
           const uint32_t r0 = __float_as_uint(q0.w), r1 = __float_as_uint(q1.w);
           if (PF != 0) {
             prefetch_ref<PF>(S, r0, in_object);
@@ -713,7 +741,9 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
               for (uint32_t k = 0; k < count; ++k) {
                 const uint32_t slot = start + k;
                 const float4 *tp = reinterpret_cast<const float4 *>(S.triangles + slot);
-                const float4 qn = __ldg(tp), qv0 = __ldg(tp + 1), qe1 = __ldg(tp + 2), qe2 = __ldg(tp + 3);
+                float4 qn, qv0, qe1, qe2;
+                load_pair<LD256>(tp, qn, qv0);
+                load_pair<LD256>(tp + 2, qe1, qe2);
                 float sign, t, u, v;
 #ifdef RDN_DEBUG_STEPS
                 ++dbg_tris;
@@ -736,7 +766,8 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
               // instance leaf (world space): take the first slot, park the rest
               if (count > 1) RDN_PUSH(REF_LEAF_BIT | ((count - 2u) << REF_LEAF_COUNT_SHIFT) | (start + 1u));
               const float4 *tb = reinterpret_cast<const float4 *>(S.tlas_bounding + start);
-              const float4 b0 = __ldg(tb), b1 = __ldg(tb + 1);
+              float4 b0, b1;
+              load_pair<LD256>(tb, b0, b1);
               float tn;
               bool entered = false;
               if (slab_test(o, inv, t_near_world, bound, xyz(b0), xyz(b1), tn) && (P.L.cull_mask & __float_as_uint(b0.w)) != 0) {
@@ -765,8 +796,8 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
             cur = REF_DONE;  // nothing deferred in world space: the ray is finished, no need to restore the world ray
           } else if (cur == REF_EXIT_INSTANCE) {
             // back to world space: the world ray is re-read instead of being held in registers
-            const float4 r0 = __ldg(reinterpret_cast<const float4 *>(P.rays + ri));
-            const float4 r1 = __ldg(reinterpret_cast<const float4 *>(P.rays + ri) + 1);
+            float4 r0, r1;
+            load_pair<LD256>(P.rays + ri, r0, r1);
             o = xyz(r0); d = xyz(r1); inv = recip3(d);
             scaling = 1.f; near_s = t_near_world; far_s = bound;
             in_object = false;
@@ -800,7 +831,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
           // the ordered result is stored first; a near-tie ray is also queued (warp-aggregated append) for the exact
           // reference-order re-walk, which overwrites the record
           const SlotInfo si = S.slot_info[best_slot];
-          store_hit(dst, best, best_u, best_v, si.primitive_id, si.geometry_idx, best_inst,
+          store_hit_as<LD256>(dst, best, best_u, best_v, si.primitive_id, si.geometry_idx, best_inst,
                     S.instances[best_inst].instance_custom_index,
                     best_back ? RDN_HIT_KIND_BACK_FACING_TRIANGLE : RDN_HIT_KIND_FRONT_FACING_TRIANGLE);
           if (second <= best + TIE_EPS * fabsf(best)) {
@@ -808,7 +839,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
             enqueue_rewalk<DRAIN_TIES>(P.scratch, lane, ri, best);
           }
         } else {
-          store_hit(dst, far0, 0.f, 0.f, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, 0);
+          store_hit_as<LD256>(dst, far0, 0.f, 0.f, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, 0);
         }
         alive = false;
       }
@@ -941,19 +972,18 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const
   KernelFn fn;
   bool inline_ties = true;
   switch (variant) {
-    case 1: fn = k_trace_ordered_rounds<4, 8, 1, true, false, false, 0>; break;   // more node steps per vote
-    case 2: fn = k_trace_ordered_rounds<3, 8, 4, true, false, false, 0>; break;   // global cursor; refill once fewer than 4 lanes are busy
-    case 3: fn = k_trace_ordered_rounds<4, 8, 8, true, false, false, 0>; break;   // the first version's policy
+    // (K, THRESH) = (4,1), (3,4), (4,8) were instantiated here during the sweep of profiles/kbench_r1_variant_sweep.log
+    case 30: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, false>; break;  // 128-bit loads / stores
     // whole-unit scheduling experiments, all measured slower than the default (profiles/kbench_r1_unit_scheduling.log): lanes whose
     // ray misses the scene stay idle for the rest of the tile instead of being topped up with the next rays
-    case 10: case 11: case 12: case 13: case 14: fn = k_trace_ordered_rounds<2, 8, 1, true, false, true, 0>; break;
-    case 9: fn = k_trace_ordered_rounds<2, 8, 1, false, false, false, 0>; inline_ties = false; break;  // queue drained by k_resolve_ties
-    case 20: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 1>; break;  // children prefetched into L1
-    case 21: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 2>; break;  // ... into L2
-    default: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0>; break;
+    case 10: case 11: case 12: case 13: case 14: fn = k_trace_ordered_rounds<2, 8, 1, true, false, true, 0, true>; break;
+    case 9: fn = k_trace_ordered_rounds<2, 8, 1, false, false, false, 0, true>; inline_ties = false; break;  // queue drained by k_resolve_ties
+    case 20: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 1, true>; break;  // children prefetched into L1
+    case 21: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 2, true>; break;  // ... into L2
+    default: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, true>; break;
   }
   if (P.irregular_count != 0) {  // (the experimentation variants exist for regular scenes only)
-    fn = inline_ties ? k_trace_ordered_rounds<2, 8, 1, true, true, false, 0> : k_trace_ordered_rounds<2, 8, 1, false, true, false, 0>;
+    fn = inline_ties ? k_trace_ordered_rounds<2, 8, 1, true, true, false, 0, true> : k_trace_ordered_rounds<2, 8, 1, false, true, false, 0, true>;
   }
   int blocks_per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, ORDERED_BLOCK, 0);
