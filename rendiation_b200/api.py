@@ -44,7 +44,7 @@ WIDE_NODE_DTYPE = np.dtype([("c0_min", "f4", (3,)), ("ref0", "u4"), ("c0_max", "
                             ("c1_min", "f4", (3,)), ("pad0", "u4"), ("c1_max", "f4", (3,)), ("pad1", "u4")])
 
 ARRAYS = {  # rdn_array_id -> (name, dtype)
-    0: ("tlas_binding", np.dtype("u4")), 1: ("tlas_root", np.dtype(("u4", (4,)))), 2: ("tlas_bvh_forest", DEV_NODE_DTYPE),
+    0: ("tlas_binding", np.dtype("u4")), 1: ("tlas_root", np.dtype(("u4", (8,)))), 2: ("tlas_bvh_forest", DEV_NODE_DTYPE),
     3: ("tlas_bounding", TLAS_BOUNDING_DTYPE), 4: ("instances", INSTANCE_RECORD_DTYPE), 5: ("blas_meta", np.dtype(("u4", (4,)))),
     6: ("geometry_meta", GEOMETRY_META_DTYPE), 7: ("tri_bvh_forest", DEV_NODE_DTYPE), 8: ("triangles", TRI_RECORD_DTYPE),
     9: ("slot_info", np.dtype(("u4", (2,)))), 10: ("wide_nodes", WIDE_NODE_DTYPE), 11: ("prim_to_slot", np.dtype("u4")),

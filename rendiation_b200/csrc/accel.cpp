@@ -129,12 +129,26 @@ static void set_child(WideNode &w, int which, const Box3 *box, uint32_t ref) {
 uint32_t emit_wide_nodes(const std::vector<FlattenBVHNode> &nodes, uint64_t slot_offset, std::vector<WideNode> &out,
                          bool &capacity_error) {
   if (nodes.empty() || nodes[0].primitive_end == nodes[0].primitive_start) return REF_EMPTY;
-  // wide index of every inner reference node (pre-order), after the pseudo root
+  // Wide index of every inner reference node, after the pseudo root: the top of the tree breadth first (pseudo root + up to
+  // HOT_TOP_NODES - 1 inner nodes form one contiguous block: what every ray touches, and what the kernel's staging variant
+  // copies into shared memory), everything below in the reference's pre-order (a parent next to its left subtree).
   const uint64_t base = out.size();
   std::vector<uint32_t> wide_of(nodes.size(), 0);
   uint64_t n_inner = 0;
-  for (size_t i = 0; i < nodes.size(); ++i)
-    if (nodes[i].has_child) wide_of[i] = static_cast<uint32_t>(base + 1 + n_inner++);
+  {
+    std::vector<uint8_t> in_top(nodes.size(), 0);
+    std::vector<size_t> queue{0};
+    for (size_t head = 0; head < queue.size() && n_inner + 1 < HOT_TOP_NODES; ++head) {
+      const size_t i = queue[head];
+      if (!nodes[i].has_child) continue;
+      in_top[i] = 1;
+      wide_of[i] = static_cast<uint32_t>(base + 1 + n_inner++);
+      queue.push_back(nodes[i].left_child_offset());
+      queue.push_back(nodes[i].right_child_offset());
+    }
+    for (size_t i = 0; i < nodes.size(); ++i)
+      if (nodes[i].has_child && !in_top[i]) wide_of[i] = static_cast<uint32_t>(base + 1 + n_inner++);
+  }
   out.resize(base + 1 + n_inner);
 
   // a leaf reference; leaves longer than REF_LEAF_MAX_COUNT become a chain of nodes that repeat the leaf's box
@@ -289,6 +303,8 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
   std::vector<OptBox> blas_box;
   std::vector<Box3> blas_true_box;       // per BLAS HANDLE: bound of all its triangle geometries
   std::vector<uint32_t> blas_irregular;  // per BLAS handle: BlasMeta::irregular_leaf_count
+  struct HotBlock { uint32_t base = 0, count = 0; uint64_t triangles = 0; };
+  std::vector<HotBlock> blas_hot;        // per BLAS handle: the top block of its largest geometry tree
   uint64_t n_indices_total = 0;  // geometry_indices.len()
   const TreeBuildOption blas_option{50, 2};
 
@@ -298,8 +314,10 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
       blas_box.push_back(OptBox{false, box_empty()});
       blas_true_box.push_back(box_empty());
       blas_irregular.push_back(0);
+      blas_hot.push_back(HotBlock{});
       continue;
     }
+    HotBlock hot;
     const uint32_t tri_start = static_cast<uint32_t>(out.geometry_meta.size());
     Box3 true_box = box_empty();
     const uint32_t leaf_start = static_cast<uint32_t>(out.irregular_leaf_boxes.size());
@@ -374,6 +392,10 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
         gm.primitive_start = primitive_start;
         gm.geometry_flags = src.flags;
         gm.wide_root = emit_wide_nodes(bvh.nodes, primitive_start, out.wide_nodes, capacity_error);
+        if (gm.wide_root != REF_EMPTY && n_tri > hot.triangles) {
+          const uint64_t block = out.wide_nodes.size() - gm.wide_root;
+          hot = HotBlock{gm.wide_root, static_cast<uint32_t>(block < HOT_TOP_NODES ? block : HOT_TOP_NODES), n_tri};
+        }
         out.geometry_meta.push_back(gm);
         out.tri_bvh_forest.resize(bvh_start + bvh.nodes.size());
         parallel_for(bvh.nodes.size(), PARALLEL_BUILD_MIN, [&](uint64_t i_begin, uint64_t i_end) {
@@ -391,15 +413,17 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
     out.blas_meta.push_back(BlasMeta{{tri_start, static_cast<uint32_t>(out.geometry_meta.size())}, leaf_start, leaf_count});
     blas_true_box.push_back(true_box);
     blas_irregular.push_back(leaf_count);
+    blas_hot.push_back(hot);
   }
 
   // ---- build_tlas per TLAS (mod.rs:262-320, 428-448)
   const TreeBuildOption tlas_option{50, 10};
   for (const Tlas &tlas : tlas_data_) {
     if (!tlas.alive) {
-      out.tlas_root.push_back(TlasRoot{INVALID_NEXT, REF_EMPTY, 0, 0});
+      out.tlas_root.push_back(TlasRoot{INVALID_NEXT, REF_EMPTY, 0, 0, 0, 0, 0, 0});
       continue;
     }
+    HotBlock tlas_hot_geometry;
     const uint32_t bvh_start = static_cast<uint32_t>(out.tlas_bvh_forest.size());
     const uint32_t primitive_start = static_cast<uint32_t>(out.instances.size());
     std::vector<Box3> aabbs(tlas.instances.size());
@@ -432,6 +456,7 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
       rec.flags = flags;
       rec.blas = src.blas_handle;
       const bool known_blas = src.blas_handle < blas_true_box.size();  // else the kernels skip the instance (blas >= n_blas_meta)
+      if (known_blas && blas_hot[src.blas_handle].triangles > tlas_hot_geometry.triangles) tlas_hot_geometry = blas_hot[src.blas_handle];
       if (known_blas) {
         const bool whole = blas_irregular[src.blas_handle] == IRREGULAR_ROUTE_ALL ||
                            instance_is_irregular(src.transform, inv, blas_box[src.blas_handle].box, blas_true_box[src.blas_handle]);
@@ -452,6 +477,14 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
     TlasRoot root;
     root.bvh_root_idx = bvh_start;
     root.wide_root = emit_wide_nodes(bvh.nodes, primitive_start, out.wide_nodes, capacity_error);
+    root.pad = 0;
+    root.hot_count = 0;
+    if (root.wide_root != REF_EMPTY) {
+      const uint64_t block = out.wide_nodes.size() - root.wide_root;
+      root.hot_count = static_cast<uint32_t>(block < HOT_TOP_NODES ? block : HOT_TOP_NODES);
+    }
+    root.hot_geometry_base = tlas_hot_geometry.base;
+    root.hot_geometry_count = tlas_hot_geometry.count;
     root.irregular_start = irregular_start;
     root.irregular_count = static_cast<uint32_t>(out.irregular_instances.size() - irregular_start);
     // a short list is checked per ray by the ordered kernel; a long one, or boxes that cover most of the TLAS anyway

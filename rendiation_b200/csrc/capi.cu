@@ -821,7 +821,7 @@ int rdn_rt_scene_adopt_blob(rdn_rt_scene *s, int device_index, const void *d_blo
   dc.blob_bytes = bytes;
   bind_blob(dc, h);
   s->h_tlas_binding.assign(h.count[ARR_TLAS_BINDING], 0);
-  s->h_tlas_root.assign(h.count[ARR_TLAS_ROOT], TlasRoot{INVALID_NEXT, REF_EMPTY, 0, 0});
+  s->h_tlas_root.assign(h.count[ARR_TLAS_ROOT], TlasRoot{INVALID_NEXT, REF_EMPTY, 0, 0, 0, 0, 0, 0});
   if (!s->h_tlas_binding.empty())
     RDN_CUDA(cudaMemcpy(s->h_tlas_binding.data(), dc.dev.tlas_binding, s->h_tlas_binding.size() * 4, cudaMemcpyDeviceToHost));
   if (!s->h_tlas_root.empty())

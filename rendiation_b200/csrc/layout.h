@@ -69,8 +69,11 @@ struct TlasRoot {
   uint32_t wide_root;        // REF_EMPTY when deleted / empty
   uint32_t irregular_start;  // [start, start + count) in irregular_instances: instance slots whose hits need not lie inside
   uint32_t irregular_count;  // their boxes (see accel.cpp "regularity"); IRREGULAR_ROUTE_ALL: walk every ray in reference order
+  uint32_t hot_count;        // wide nodes [wide_root, wide_root + hot_count): the top of the TLAS tree (<= HOT_TOP_NODES)
+  uint32_t hot_geometry_base, hot_geometry_count;  // the same block of the largest geometry tree among the instances' BLASes
+  uint32_t pad;
 };
-static_assert(sizeof(TlasRoot) == 16, "TlasRoot");
+static_assert(sizeof(TlasRoot) == 32, "TlasRoot");
 constexpr uint32_t IRREGULAR_ROUTE_ALL = 0xFFFFFFFFu;
 constexpr uint32_t IRREGULAR_LIST_MAX = 8;       // more irregular instances than this in one TLAS: the whole TLAS is walked in reference order
 constexpr uint32_t IRREGULAR_LEAF_MAX = 16;      // more irregular leaves than this in one BLAS: its instances are irregular as a whole
@@ -113,6 +116,8 @@ constexpr uint32_t REF_DONE = 0x7FFFFFFDu;           // traversal stack exhauste
 constexpr uint32_t REF_EMPTY = 0x7FFFFFFEu;
 constexpr uint32_t REF_EXIT_INSTANCE = 0x7FFFFFFFu;
 constexpr uint32_t REF_GEOM_ITER_MAX = 0x00FFFFFCu;
+// the first HOT_TOP_NODES wide nodes of every tree (pseudo root first) are its top levels in breadth-first order
+constexpr uint32_t HOT_TOP_NODES = 128;
 
 enum ArrayId : int {
   ARR_TLAS_BINDING = 0,   // u32
@@ -133,7 +138,7 @@ enum ArrayId : int {
 };
 
 constexpr uint64_t BLOB_MAGIC = 0x52444E5F424C4F42ull;  // "RDN_BLOB"
-constexpr uint32_t BLOB_VERSION = 3;
+constexpr uint32_t BLOB_VERSION = 4;
 constexpr uint64_t BLOB_ALIGN = 128;
 
 struct BlobHeader {

@@ -345,6 +345,9 @@ struct OrderedParams {
   // the unit list into n_ranges contiguous ranges, one per SM
   uint32_t n_units, n_ranges, units_per_range, blocks_x;  // blocks_x == 0: units in raster tile order (or a linear ray list)
   uint32_t prefetch_unit;  // take the next unit from the home range while the current one is being traversed
+  // HOT: wide nodes [hot_a_base, +hot_a_count) (top of the TLAS tree) and [hot_b_base, +hot_b_count) (top of the largest geometry
+  // tree) are staged in shared memory by two bulk copies (TMA) at CTA start
+  uint32_t hot_a_base, hot_a_count, hot_b_base, hot_b_count;
   uint32_t wait_epoch;  // launches issued before this one on the same scratch set: they must have left before this one touches it
   TraceScratch scratch;
 };
@@ -508,7 +511,10 @@ __device__ __forceinline__ uint32_t compact_even_bits4(uint32_t x) {  // bits 0,
 // that decide which child is entered take a warp several hundred cycles of wall clock (it shares its issue slot with seven
 // others), enough for the line to arrive before the next dependent fetch asks for it; no register is held by a prefetch.
 // LD256: 256-bit loads / stores for nodes, triangles, instance boxes, rays and hit records.
-template <int K, int MINB, int THRESH, bool DRAIN_TIES, bool IRREGULAR, bool UNITS, int PF, bool LD256>  // DRAIN_TIES: near-tie queue drained inside the kernel (else by k_resolve_ties)
+// HOT: the top levels of the TLAS tree and of the largest geometry tree (breadth-first blocks of HOT_TOP_NODES wide nodes, 8 KB
+// each) are copied into shared memory with cp.async.bulk (TMA, completion on an mbarrier) when the CTA starts, and node fetches
+// that fall into either block read shared memory instead of L1.
+template <int K, int MINB, int THRESH, bool DRAIN_TIES, bool IRREGULAR, bool UNITS, int PF, bool LD256, bool HOT>  // DRAIN_TIES: near-tie queue drained inside the kernel (else by k_resolve_ties)
 __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(const __grid_constant__ OrderedParams P) {
   const SceneDev &S = P.S;
   const uint32_t lane = threadIdx.x & 31u;
@@ -527,6 +533,33 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
     __threadfence();
   }
   __syncthreads();
+
+  __shared__ __align__(128) float4 s_hot[HOT ? 2 * HOT_TOP_NODES * 4 : 4];
+  __shared__ __align__(8) unsigned long long s_hot_bar;
+  if (HOT) {
+    const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&s_hot_bar));
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      const uint32_t bytes_a = P.hot_a_count * 64u, bytes_b = P.hot_b_count * 64u;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes_a + bytes_b) : "memory");
+      if (bytes_a)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         static_cast<uint32_t>(__cvta_generic_to_shared(s_hot))),
+                     "l"(S.wide_nodes + P.hot_a_base), "r"(bytes_a), "r"(bar)
+                     : "memory");
+      if (bytes_b)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         static_cast<uint32_t>(__cvta_generic_to_shared(s_hot + HOT_TOP_NODES * 4))),
+                     "l"(S.wide_nodes + P.hot_b_base), "r"(bytes_b), "r"(bar)
+                     : "memory");
+    }
+    __syncthreads();
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
+    }
+  }
 
   // the world pseudo-root (TLAS root box + its reference) is launch-uniform: keep it in registers
   Vec3 root_min = {0, 0, 0}, root_max = {0, 0, 0};
@@ -705,8 +738,20 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
 #endif
           const float4 *np = reinterpret_cast<const float4 *>(S.wide_nodes + cur);
           float4 q0, q1, q2, q3;
-          load_pair<LD256>(np, q0, q1);
-          load_pair<LD256>(np + 2, q2, q3);
+          bool staged = false;
+          if (HOT) {
+            const uint32_t ia = cur - P.hot_a_base, ib = cur - P.hot_b_base;
+            const uint32_t h = ia < P.hot_a_count ? ia : (ib < P.hot_b_count ? HOT_TOP_NODES + ib : 0xFFFFFFFFu);
+            if (h != 0xFFFFFFFFu) {
+              const float4 *sp = s_hot + h * 4u;
+              q0 = sp[0]; q1 = sp[1]; q2 = sp[2]; q3 = sp[3];
+              staged = true;
+            }
+          }
+          if (!staged) {
+            load_pair<LD256>(np, q0, q1);
+            load_pair<LD256>(np + 2, q2, q3);
+          }
           const uint32_t r0 = __float_as_uint(q0.w), r1 = __float_as_uint(q1.w);
           if (PF != 0) {
             prefetch_ref<PF>(S, r0, in_object);
@@ -962,6 +1007,10 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const
   P.n_ranges = sm_local ? static_cast<uint32_t>(sm_count < SM_CURSOR_SLOTS ? sm_count : SM_CURSOR_SLOTS) : 1u;
   P.units_per_range = (P.n_units + P.n_ranges - 1u) / P.n_ranges;
   P.world_root = tlas.wide_root;
+  P.hot_a_base = tlas.wide_root == REF_EMPTY ? 0u : tlas.wide_root;
+  P.hot_a_count = tlas.wide_root == REF_EMPTY ? 0u : tlas.hot_count;
+  P.hot_b_base = tlas.hot_geometry_base;
+  P.hot_b_count = tlas.hot_geometry_count;
   P.irregular_start = tlas.irregular_start;
   P.irregular_count = tlas.irregular_count == IRREGULAR_ROUTE_ALL ? 0u : tlas.irregular_count;  // (the caller routes those elsewhere)
   P.wait_epoch = wait_epoch;
@@ -973,17 +1022,18 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const
   bool inline_ties = true;
   switch (variant) {
     // (K, THRESH) = (4,1), (3,4), (4,8) were instantiated here during the sweep of profiles/kbench_r1_variant_sweep.log
-    case 30: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, false>; break;  // 128-bit loads / stores
+    case 30: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, false, false>; break;  // 128-bit loads / stores
+    case 40: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, true, true>; break;    // top levels staged in shared memory (TMA)
     // whole-unit scheduling experiments, all measured slower than the default (profiles/kbench_r1_unit_scheduling.log): lanes whose
     // ray misses the scene stay idle for the rest of the tile instead of being topped up with the next rays
-    case 10: case 11: case 12: case 13: case 14: fn = k_trace_ordered_rounds<2, 8, 1, true, false, true, 0, true>; break;
-    case 9: fn = k_trace_ordered_rounds<2, 8, 1, false, false, false, 0, true>; inline_ties = false; break;  // queue drained by k_resolve_ties
-    case 20: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 1, true>; break;  // children prefetched into L1
-    case 21: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 2, true>; break;  // ... into L2
-    default: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, true>; break;
+    case 10: case 11: case 12: case 13: case 14: fn = k_trace_ordered_rounds<2, 8, 1, true, false, true, 0, true, false>; break;
+    case 9: fn = k_trace_ordered_rounds<2, 8, 1, false, false, false, 0, true, false>; inline_ties = false; break;  // queue drained by k_resolve_ties
+    case 20: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 1, true, false>; break;  // children prefetched into L1
+    case 21: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 2, true, false>; break;  // ... into L2
+    default: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, true, false>; break;
   }
   if (P.irregular_count != 0) {  // (the experimentation variants exist for regular scenes only)
-    fn = inline_ties ? k_trace_ordered_rounds<2, 8, 1, true, true, false, 0, true> : k_trace_ordered_rounds<2, 8, 1, false, true, false, 0, true>;
+    fn = inline_ties ? k_trace_ordered_rounds<2, 8, 1, true, true, false, 0, true, false> : k_trace_ordered_rounds<2, 8, 1, false, true, false, 0, true, false>;
   }
   int blocks_per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, ORDERED_BLOCK, 0);

@@ -163,7 +163,7 @@ def suspect_rays(arrays: dict, rays: np.ndarray, tlas_idx: int, cull_mask: int):
     binding = arrays["tlas_binding"]
     if tlas_idx >= binding.size or binding[tlas_idx] >= arrays["tlas_root"].shape[0]:
         return False, np.zeros(n, bool)
-    _, _, start, count = (int(x) for x in arrays["tlas_root"][binding[tlas_idx]])
+    _, _, start, count = (int(x) for x in arrays["tlas_root"][binding[tlas_idx]][:4])
     if count == IRREGULAR_ROUTE_ALL:
         return True, np.ones(n, bool)
     f32 = np.float32

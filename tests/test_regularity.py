@@ -57,7 +57,7 @@ def test_needle_triangle_marks_its_leaf_only():
     a = sp.p.arrays()
     assert tuple(a["blas_meta"][b][2:]) == (0, 1) and tuple(a["blas_meta"][far][2:]) == (1, 0)
     assert a["irregular_leaf_boxes"].shape[0] == 1
-    start, count = (int(x) for x in a["tlas_root"][0][2:])
+    start, count = (int(x) for x in a["tlas_root"][0][2:4])
     assert count == 1 and not (int(a["irregular_instances"][start]) & WHOLE)
     assert int(a["instances"][int(a["irregular_instances"][start])]["blas"]) == b
     # only rays through the needle's leaf box are kept for the reference-order walk
@@ -78,7 +78,7 @@ def test_irregular_instances_are_listed_or_the_tlas_is_routed():
     # one singular transform among regular ones: listed as a whole
     sp = _cube_scene(lambda b: [S.make_instance(T(3.0 * i, 0, -10), b) for i in range(-4, 5)] + [S.make_instance(mul(T(0, 5, -10), Sc(1, 0, 1)), b)])
     a = sp.p.arrays()
-    start, count = (int(x) for x in a["tlas_root"][0][2:])
+    start, count = (int(x) for x in a["tlas_root"][0][2:4])
     assert count == 1 and int(a["irregular_instances"][start]) & WHOLE
     assert sp.p.build_stats()["irregular_instances"] == 1
     # the only instance is singular / more than IRREGULAR_LIST_MAX irregular instances: whole TLAS in reference order
@@ -105,7 +105,7 @@ def test_reference_blas_box_indexing_makes_instances_irregular():
                                     [S.make_instance(S.mat4_translate(0, 4, -10), other)]))])
     sp.build()
     a = sp.p.arrays()
-    start, count = (int(x) for x in a["tlas_root"][0][2:])
+    start, count = (int(x) for x in a["tlas_root"][0][2:4])
     listed = [int(e) & ~WHOLE for e in a["irregular_instances"][start:start + count]]
     assert count == 1 and int(a["instances"][listed[0]]["blas"]) == other
 
