@@ -405,6 +405,7 @@ def run_ours(args):
                          "kernel_share_of_step": kernel_ms / ms_per_step_serial, "tie_kernel_ms_avg": tie_ms,
                          "achieved_with_launch_overlap": bytes_per_ray * n / (ms_per_step * 1e-3) / 1e9,
                          "l2": {"peak": l2_peak, "unit": "GB/s", "frac": achieved / l2_peak,
+                                "frac_with_launch_overlap": bytes_per_ray * n / (ms_per_step * 1e-3) / 1e9 / l2_peak,
                                 "peak_source": "measured in this run: uint4 reads bypassing L1 over a 64 MiB L2-resident buffer, 50 sweeps "
                                                "(rdn_rt_measure_l2_read_gbs)"},
                          "tie_rays_per_step": tie_rays,

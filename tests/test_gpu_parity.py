@@ -126,6 +126,49 @@ def test_instanced_scene_ids_exact():
     assert rep["hits"] > 10000 and len(np.unique(want["instance_custom_id"])) > 50
 
 
+def test_c2_c3_full_size():
+    """BASELINE configs 2 and 3 at full size: 1920x1080 primary rays vs the 1,002,528-triangle torus, then one incoherent
+    cosine-weighted bounce ray per hit; whole hit records bit-identical to the oracle on every ray"""
+    sp, (pos, idx, m) = helpers.torus_scene(708)
+    assert idx.size // 3 == 1002528
+    st = sp.p.build_stats()
+    assert st["irregular_triangles"] == 0 and st["irregular_instances"] == 0 and st["balance_fallbacks_gt10"] == 0
+    rays = S.pinhole_rays(1920, 1080, 0.01, 100.0, aspect_correct=True)
+    nt = os.cpu_count() or 4
+    want, ctr = sp.o.trace(rays, ray_flags=0x10, n_threads=nt)
+    got, stats = _device_trace(sp.p, rays, api.TRACE_AUTO, ray_flags=0x10, grid_width=1920)
+    rep = _assert_parity("c2_full", got, want)
+    assert rep["hits"] > 300000 and ctr["ref_abort"] == 0 and stats["whole_range_rewalks"] == 0
+    d = np.stack([rays["dx"], rays["dy"], rays["dz"]], -1)
+    hit = want["instance_id"] != 0xFFFFFFFF
+    normals = np.zeros((rays.shape[0], 3), np.float32)
+    normals[hit] = S.geometric_normals(pos, idx, want["primitive_id"][hit], m, d[hit])
+    brays, _ = S.bounce_rays(rays, want, normals)
+    bwant, bctr = sp.o.trace(brays, ray_flags=0, n_threads=nt)
+    bgot, bstats = _device_trace(sp.p, brays, api.TRACE_AUTO, ray_flags=0)
+    brep = _assert_parity("c3_full", bgot, bwant)
+    assert brep["n"] == int(hit.sum()) and brep["hits"] > 10000 and bctr["ref_abort"] == 0 and bstats["whole_range_rewalks"] == 0
+
+
+def test_c4_instanced_full_size():
+    """BASELINE config 4 at full size: 10,000 transform-instanced copies of a 100,352-triangle sphere, 1920x1080 primary rays;
+    (instance_id, instance_custom_id, primitive_id) and everything else bit-identical, near-ties included"""
+    pos, idx = S.uv_sphere_mesh(224, 224)
+    assert idx.size // 3 == 100352
+    sp = helpers.ScenePair()
+    b = sp.blas([(pos, idx.reshape(-1), 1)])
+    sp.bind([sp.tlas(S.instance_grid(100, 100, b, 3.5, -200.0))])
+    sp.build()
+    st = sp.p.build_stats()
+    assert st["irregular_triangles"] == 0 and st["irregular_instances"] == 0 and st["reference_routed_tlas"] == 0
+    rays = S.pinhole_rays(1920, 1080, 0.0, 1000.0, aspect_correct=True)
+    want, ctr = sp.o.trace(rays, ray_flags=0x10, n_threads=os.cpu_count() or 4)
+    got, stats = _device_trace(sp.p, rays, api.TRACE_AUTO, ray_flags=0x10, grid_width=1920)
+    rep = _assert_parity("c4_full", got, want)
+    assert rep["hits"] > 500000 and len(np.unique(want["instance_custom_id"])) > 5000
+    assert stats["tie_rays"] > 0 and stats["whole_range_rewalks"] == 0  # touching spheres of neighbouring instances: real near-ties
+
+
 def test_flags_masks_multi_geometry_and_edge_cases():
     cube = (S.CUBE_POSITION, S.CUBE_INDEX, 1)
     non_opaque = (S.CUBE_POSITION + np.array([2.0, 0, 0], np.float32), S.CUBE_INDEX, 0)
