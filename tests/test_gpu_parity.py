@@ -165,7 +165,7 @@ def test_c4_instanced_full_size():
     want, ctr = sp.o.trace(rays, ray_flags=0x10, n_threads=os.cpu_count() or 4)
     got, stats = _device_trace(sp.p, rays, api.TRACE_AUTO, ray_flags=0x10, grid_width=1920)
     rep = _assert_parity("c4_full", got, want)
-    assert rep["hits"] > 500000 and len(np.unique(want["instance_custom_id"])) > 5000
+    assert rep["hits"] > 400000 and len(np.unique(want["instance_custom_id"])) > 5000
     assert stats["tie_rays"] > 0 and stats["whole_range_rewalks"] == 0  # touching spheres of neighbouring instances: real near-ties
 
 
