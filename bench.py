@@ -197,6 +197,7 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's own banner ("NCCL version ...") must not land on stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- scene: build + flatten on rank 0, one NCCL broadcast of the blob, every other rank adopts it

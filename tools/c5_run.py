@@ -42,6 +42,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's own banner ("NCCL version ...") must not land on stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     pos, idx = S.torus_mesh(SEG, SEG, 1.0, 0.35)
