@@ -256,12 +256,18 @@ int enqueue_trace(rdn_rt_scene *s, DeviceCtx &dc, const Scratch &scratch, const 
   // work_counter is zero here: zeroed at allocation and re-armed by the last CTA of every ordered launch.  tie_count and
   // the two error flags accumulate until read (the stats path clears tie_count first).
   const int tie_mode = ordered_tie_mode();
-  if (tie_mode == 0 || (count_ties && tie_mode != 3)) RDN_CUDA(cudaMemsetAsync(static_cast<char *>(scratch.base) + 8, 0, 4, stream));
-  if (count_ties && tie_mode == 3) RDN_CUDA(cudaMemsetAsync(static_cast<char *>(scratch.base) + 28, 0, 4, stream));
-  if (count_ties) RDN_CUDA(cudaMemsetAsync(static_cast<char *>(scratch.base) + 12, 0, 4, stream));
   const bool end_search = (launch.ray_flags & RDN_RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH) != 0;
+  // launches whose queue is walked by k_resolve_ties start from an empty queue and leave one (in-kernel drains re-arm it themselves)
+  const bool separate_resolve = tie_mode == 0;
+  if (separate_resolve) RDN_CUDA(cudaMemsetAsync(static_cast<char *>(scratch.base) + 8, 0, 4, stream));
+  if (count_ties) RDN_CUDA(cudaMemsetAsync(static_cast<char *>(scratch.base) + 28, 0, 4, stream));  // tie_total: re-walked rays of this launch
+  if (count_ties) RDN_CUDA(cudaMemsetAsync(static_cast<char *>(scratch.base) + 12, 0, 4, stream));
   const TlasRoot tlas = resolve_tlas(s, launch.tlas_idx);
   // a TLAS made mostly of irregular instances (accel.cpp "regularity") has a traversal-order dependent answer: reference order
+  // ACCEPT_FIRST_HIT_AND_END_SEARCH (shadow / AO rays): the answer is the first candidate the reference's pre-order walk accepts,
+  // order dependent by definition.  (Measured alternative, profiles/kbench_r1_anyhit.log: the ordered kernel stopping at its first
+  // candidate to separate misses, the reference-order walk only for the occluded rays — slower than walking everything in
+  // reference order, whose early exit is what makes these rays cheap.)
   if (mode == RDN_TRACE_REFERENCE_ORDER || end_search || tlas.irregular_count == IRREGULAR_ROUTE_ALL) {
     ScopedKernelTimer tm(dc, KERNEL_REFERENCE, stream);
     launch_trace_reference(dc.dev, launch, d_rays, n, d_hits, ts, false, dc.sm_count, stream);
@@ -277,6 +283,7 @@ int enqueue_trace(rdn_rt_scene *s, DeviceCtx &dc, const Scratch &scratch, const 
       ScopedKernelTimer tm(dc, KERNEL_TIES, stream);
       launch_resolve_ties(dc.dev, launch, d_rays, d_hits, ts, dc.sm_count, stream);
       if (launches) *launches += 1;
+      RDN_CUDA(cudaMemsetAsync(static_cast<char *>(scratch.base) + 8, 0, 4, stream));  // the next launch on this set may drain in-kernel
     }
   }
   if (launches) *launches += 1;
@@ -482,7 +489,7 @@ int rdn_rt_trace_closest_device(rdn_rt_scene *s, int device_index, const rdn_lau
       ms_total += ms;
       uint32_t small[6] = {0, 0, 0, 0, 0, 0};  // tie_count | tie_unresolved | stack_overflow | blocks_done | tie_cursor | tie_total
       RDN_CUDA(cudaMemcpy(small, static_cast<char *>(scratch.base) + 8, sizeof(small), cudaMemcpyDeviceToHost));
-      ties += ordered_tie_mode() == 3 ? small[5] : small[0];
+      ties += small[5];
       fallbacks += small[1];
       if (small[2]) return fail(RDN_ERR_CAPACITY, "traversal stack overflow");
 #if defined(RDN_DEBUG_STEPS) || defined(RDN_DEBUG_TIMELINE)

@@ -199,8 +199,8 @@ __device__ __forceinline__ void reference_walk(const SceneDev &S, const rdn_laun
     const uint2 irange = *reinterpret_cast<const uint2 *>(S.tlas_bvh_forest[leaf_node].content_range);
 
     for (uint32_t tlas_idx = irange.x; tlas_idx < irange.y && !end_search; ++tlas_idx) {
-      const float4 *tb = reinterpret_cast<const float4 *>(S.tlas_bounding + tlas_idx);
-      const float4 b0 = __ldg(tb), b1 = __ldg(tb + 1);
+      float4 b0, b1;
+      load_pair<true>(S.tlas_bounding + tlas_idx, b0, b1);
       // ORIGINAL ray.range for the instance box (traverse_cpu.rs:80-86)
       if (!slab_test(ro, inv_rd, near, far0, xyz(b0), xyz(b1), tn)) continue;
       if ((L.cull_mask & __float_as_uint(b0.w)) == 0) continue;
@@ -234,7 +234,9 @@ __device__ __forceinline__ void reference_walk(const SceneDev &S, const rdn_laun
           const uint2 trange = *reinterpret_cast<const uint2 *>(S.tri_bvh_forest[leaf].content_range);
           for (uint32_t slot = trange.x; slot < trange.y; ++slot) {
             const float4 *tp = reinterpret_cast<const float4 *>(S.triangles + slot);
-            const float4 qn = __ldg(tp), qv0 = __ldg(tp + 1), qe1 = __ldg(tp + 2), qe2 = __ldg(tp + 3);
+            float4 qn, qv0, qe1, qe2;
+            load_pair<true>(tp, qn, qv0);
+            load_pair<true>(tp + 2, qe1, qe2);
             if (COUNT) ctr.tri_visit++;
             float sign, t, u, v;
             if (!triangle_test(qn, qv0, qe1, qe2, bo, bd, near_walk * scaling, far * scaling, cull_bits, sign, t, u, v)) continue;
@@ -265,10 +267,20 @@ __device__ __forceinline__ void store_walk_result(const SceneDev &S, rdn_hit *ds
 
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_trace_reference(const SceneDev S, const rdn_launch L, const rdn_ray *__restrict__ rays,
-                                                         uint64_t n, rdn_hit *__restrict__ hits, const TraceScratch scratch) {
+                                                         uint64_t n, rdn_hit *__restrict__ hits, const TraceScratch scratch,
+                                                         uint32_t tiles_x, uint32_t width, uint32_t height, uint64_t n_fetch) {
   WalkCounters ctr;
-  for (uint64_t ri = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; ri < n;
-       ri += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+  for (uint64_t f = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; f < n_fetch;
+       f += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    // a warp walks an 8x4 pixel tile of a grid launch (neighbours on screen walk the same nodes), else 32 consecutive rays
+    uint64_t ri = f;
+    if (tiles_x) {
+      const uint32_t tile = static_cast<uint32_t>(f >> 5), in_tile = static_cast<uint32_t>(f) & 31u;
+      const uint32_t ty = tile / tiles_x, tx = tile - ty * tiles_x;
+      const uint32_t x = tx * 8u + (in_tile & 7u), y = ty * 4u + (in_tile >> 3);
+      if (x >= width || y >= height) continue;
+      ri = static_cast<uint64_t>(y) * width + x;
+    }
     const float4 r0 = __ldg(reinterpret_cast<const float4 *>(rays + ri));
     const float4 r1 = __ldg(reinterpret_cast<const float4 *>(rays + ri) + 1);
     WalkResult res;
@@ -323,9 +335,13 @@ __device__ __forceinline__ void rewalk_in_reference_order(const SceneDev &S, con
 // device-side queue, no host round trip between the two kernels.
 __global__ void __launch_bounds__(128) k_resolve_ties(const SceneDev S, const rdn_launch L, const rdn_ray *__restrict__ rays,
                                                       rdn_hit *__restrict__ hits, const TraceScratch scratch) {
-  const uint32_t count = *scratch.tie_count;
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x)
-    rewalk_in_reference_order(S, L, rays, hits, scratch.tie_queue[k], scratch.tie_best[k], scratch.tie_unresolved);
+  const uint32_t count = *scratch.tie_count;  // (reset by the memset the launcher puts behind this kernel)
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(scratch.tie_total, count);
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+    const uint32_t ri = scratch.tie_queue[k];
+    scratch.tie_queue[k] = RDN_INVALID_ID;  // unpublished again: launches that drain the queue in-kernel wait on this value
+    rewalk_in_reference_order(S, L, rays, hits, ri, scratch.tie_best[k], scratch.tie_unresolved);
+  }
 }
 
 // ================================================================================================ ordered
@@ -957,19 +973,28 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
 void launch_trace_reference(const SceneDev &scene, const rdn_launch &launch, const rdn_ray *d_rays, uint64_t n, rdn_hit *d_hits,
                             const TraceScratch &scratch, bool count_visits, int sm_count, cudaStream_t stream) {
   if (n == 0) return;
+  uint32_t tiles_x = 0, width = 0, height = 0;
+  uint64_t n_fetch = n;
+  static const bool tiles_enabled = []() { const char *e = getenv("RDN_REF_TILES"); return !e || atoi(e) != 0; }();
+  if (tiles_enabled && launch.grid_width != 0 && n % launch.grid_width == 0) {
+    width = launch.grid_width;
+    height = static_cast<uint32_t>(n / launch.grid_width);
+    tiles_x = (width + 7u) / 8u;
+    n_fetch = static_cast<uint64_t>(tiles_x) * ((height + 3u) / 4u) * 32u;
+  }
   const int block = 128;
-  uint64_t blocks = (n + block - 1) / block;
+  uint64_t blocks = (n_fetch + block - 1) / block;
   const uint64_t cap = static_cast<uint64_t>(sm_count) * 1024;
   if (blocks > cap) blocks = cap;
   if (count_visits)
-    k_trace_reference<true><<<static_cast<unsigned>(blocks), block, 0, stream>>>(scene, launch, d_rays, n, d_hits, scratch);
+    k_trace_reference<true><<<static_cast<unsigned>(blocks), block, 0, stream>>>(scene, launch, d_rays, n, d_hits, scratch, tiles_x, width, height, n_fetch);
   else
-    k_trace_reference<false><<<static_cast<unsigned>(blocks), block, 0, stream>>>(scene, launch, d_rays, n, d_hits, scratch);
+    k_trace_reference<false><<<static_cast<unsigned>(blocks), block, 0, stream>>>(scene, launch, d_rays, n, d_hits, scratch, tiles_x, width, height, n_fetch);
 }
 
 void launch_resolve_ties(const SceneDev &scene, const rdn_launch &launch, const rdn_ray *d_rays, rdn_hit *d_hits,
                          const TraceScratch &scratch, int sm_count, cudaStream_t stream) {
-  k_resolve_ties<<<static_cast<unsigned>(sm_count), 128, 0, stream>>>(scene, launch, d_rays, d_hits, scratch);
+  k_resolve_ties<<<static_cast<unsigned>(sm_count) * 16u, 128, 0, stream>>>(scene, launch, d_rays, d_hits, scratch);
 }
 
 static int ordered_variant() {

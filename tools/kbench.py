@@ -54,6 +54,8 @@ if cfg == "c3":  # incoherent cosine-weighted bounce rays off the primary hits, 
     normals[hit] = S.geometric_normals(pos, idx, ph["primitive_id"][hit], m, d[hit])
     rays, _ = S.bounce_rays(rays, ph, normals)
     flags, grid = 0, 0
+if os.environ.get("KBENCH_FLAGS"):  # e.g. 0x14: ACCEPT_FIRST_HIT_AND_END_SEARCH | CULL_BACK (shadow / AO rays)
+    flags = int(os.environ["KBENCH_FLAGS"], 0)
 rows = os.environ.get("KBENCH_ROWS")
 if rows:
     r0, r1 = (int(x) for x in rows.split(":"))
@@ -109,7 +111,7 @@ if check:
     want = osc.trace(rays[sel], ray_flags=flags, n_threads=nt, want_counters=False)
     got = d_hits.cpu().numpy().view(api.HIT_DTYPE).reshape(-1)[sel]
     ok = got.tobytes() == want.tobytes()
-print(f"cfg={cfg} variant={os.environ.get('RDN_ORDERED_VARIANT','default')} skip_tie={'RDN_DEBUG_SKIP_TIE' in os.environ} rays={n} "
+print(f"cfg={cfg} flags={flags:#x} variant={os.environ.get('RDN_ORDERED_VARIANT','default')} skip_tie={'RDN_DEBUG_SKIP_TIE' in os.environ} rays={n} "
       f"mean_ms={ms.mean():.4f} min_ms={ms.min():.4f} Mrays/s(mean)={n/ms.mean()/1e3:.1f} best={n/ms.min()/1e3:.1f} ties={stats['tie_rays']} "
       f"bit_identical_sample={ok} build_s={t_build:.2f} | back-to-back {n/b2b_ms/1e3:.1f} Mrays/s ({b2b_ms:.4f} ms, all {iters} results identical to the serialised one: {b2b_ok}), with events between {n/b2b_ev_ms/1e3:.1f} "
       f"pdl={os.environ.get('RDN_PDL','1')} side_stream={os.environ.get('KBENCH_SIDE_STREAM','0')}")
