@@ -3,6 +3,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -70,24 +72,69 @@ SplitResult SAH::split(const FlattenBVHNode &parent, const std::vector<BuildPrim
   const uint64_t begin = parent.primitive_start, end = parent.primitive_end;
   const size_t n_part = pre_partition_.size();
   for (auto &p : pre_partition_) { p.primitive_bucket.clear(); p.bounding = box_empty(); }
+  std::vector<uint64_t> &counts = counts_;  // member scratch: a split per inner node must not allocate
+  counts.assign(n_part, 0);
 
   // step 1: bucket every primitive by its centre along the longest axis of the NODE box
   const int axis = longest_axis(parent.bounding);
   const float range_start = component(parent.bounding.min, axis);
   const float range_end = component(parent.bounding.max, axis);
   const float step = (range_end - range_start) / static_cast<float>(n_part);
-  for (uint64_t i = begin; i < end; ++i) {
-    const uint64_t prim = index[i];
+  auto bucket_of = [&](uint64_t prim, bool &out_of_range) -> size_t {
     const float axis_value = component(src[prim].center, axis);
     uint64_t which = saturating_usize(floorf((axis_value - range_start) / step));
     if (which == n_part) which -= 1;
-    if (which >= n_part) { stats.bucket_out_of_range = true; which = n_part - 1; }
-    expand(pre_partition_[which].bounding, src[prim].bounding);
-    pre_partition_[which].primitive_bucket.push_back(prim);
+    if (which >= n_part) { out_of_range = true; which = n_part - 1; }
+    return static_cast<size_t>(which);
+  };
+
+  // Large ranges (the top levels of a big tree, split on the calling thread before the subtrees fan out) are bucketed and
+  // rewritten by all threads: chunk t counts its primitives per bucket, the rewrite offsets are the prefix sums over
+  // (bucket, chunk), so the result is the sequential bucket-by-bucket stable order; box unions are exact in any order.
+  // (thread count only looked up for ranges that qualify: hardware_concurrency() is a system call and there is a split per inner node)
+  const unsigned threads = (parallel_split_ && end - begin >= PARALLEL_SPLIT_MIN && n_part <= 255) ? build_thread_count() : 1u;
+  const bool parallel = threads > 1;
+  std::vector<uint8_t> which_of;
+  std::vector<std::vector<uint64_t>> chunk_counts;
+  uint64_t chunk = 0;
+  if (parallel) {
+    const uint64_t n = end - begin;
+    chunk = (n + threads - 1) / threads;
+    which_of.resize(n);
+    chunk_counts.assign(threads, std::vector<uint64_t>(n_part, 0));
+    std::vector<std::vector<Box3>> chunk_boxes(threads, std::vector<Box3>(n_part, box_empty()));
+    std::atomic<bool> out_of_range{false};
+    parallel_for(n, 0, [&](uint64_t b0, uint64_t b1) {
+      const size_t t = static_cast<size_t>(b0 / chunk);
+      bool oor = false;
+      std::vector<uint64_t> my_counts(n_part, 0);  // thread-private while counting: the shared rows sit in one cache line
+      std::vector<Box3> my_boxes(n_part, box_empty());
+      for (uint64_t i = b0; i < b1; ++i) {
+        const uint64_t prim = index[begin + i];
+        const size_t w = bucket_of(prim, oor);
+        which_of[i] = static_cast<uint8_t>(w);
+        my_counts[w]++;
+        expand(my_boxes[w], src[prim].bounding);
+      }
+      chunk_counts[t] = my_counts;
+      chunk_boxes[t] = my_boxes;
+      if (oor) out_of_range = true;
+    });
+    if (out_of_range) stats.bucket_out_of_range = true;
+    for (size_t t = 0; t < threads; ++t)
+      for (size_t k = 0; k < n_part; ++k) { counts[k] += chunk_counts[t][k]; expand(pre_partition_[k].bounding, chunk_boxes[t][k]); }
+  } else {
+    for (uint64_t i = begin; i < end; ++i) {
+      const uint64_t prim = index[i];
+      const size_t which = bucket_of(prim, stats.bucket_out_of_range);
+      expand(pre_partition_[which].bounding, src[prim].bounding);
+      pre_partition_[which].primitive_bucket.push_back(prim);
+      counts[which]++;
+    }
   }
 
   size_t empty_buckets = 0;
-  for (const auto &p : pre_partition_) empty_buckets += p.primitive_bucket.empty();
+  for (size_t k = 0; k < n_part; ++k) empty_buckets += counts[k] == 0;
   if (empty_buckets == n_part - 1) {
     stats.balance_fallbacks++;
     if (end - begin > 10) stats.balance_fallbacks_gt10++;
@@ -99,7 +146,7 @@ SplitResult SAH::split(const FlattenBVHNode &parent, const std::vector<BuildPrim
   struct Group { Box3 box; uint64_t count; };
   auto group_of = [&](size_t from, size_t to) {
     Group g{box_empty(), 0};
-    for (size_t k = from; k < to; ++k) { expand(g.box, pre_partition_[k].bounding); g.count += pre_partition_[k].primitive_bucket.size(); }
+    for (size_t k = from; k < to; ++k) { expand(g.box, pre_partition_[k].bounding); g.count += counts[k]; }
     return g;
   };
   Group best_left = group_of(0, 1), best_right = group_of(1, n_part);
@@ -111,9 +158,22 @@ SplitResult SAH::split(const FlattenBVHNode &parent, const std::vector<BuildPrim
   }
 
   // step 3: rewrite the index range bucket by bucket (stable)
-  uint64_t ptr = begin;
-  for (const auto &p : pre_partition_)
-    for (uint64_t prim : p.primitive_bucket) index[ptr++] = prim;
+  if (parallel) {
+    const uint64_t n = end - begin;
+    std::vector<uint64_t> old(index.begin() + begin, index.begin() + end);
+    std::vector<std::vector<uint64_t>> offset(threads, std::vector<uint64_t>(n_part, 0));
+    uint64_t ptr = begin;
+    for (size_t k = 0; k < n_part; ++k)
+      for (size_t t = 0; t < threads; ++t) { offset[t][k] = ptr; ptr += chunk_counts[t][k]; }
+    parallel_for(n, 0, [&](uint64_t b0, uint64_t b1) {
+      std::vector<uint64_t> off = offset[static_cast<size_t>(b0 / chunk)];  // private copy (see above)
+      for (uint64_t i = b0; i < b1; ++i) index[off[which_of[i]]++] = old[i];
+    });
+  } else {
+    uint64_t ptr = begin;
+    for (const auto &p : pre_partition_)
+      for (uint64_t prim : p.primitive_bucket) index[ptr++] = prim;
+  }
 
   SplitResult r;
   r.axis = axis;
@@ -195,6 +255,7 @@ void merge_stats(BuildStats &into, const BuildStats &from) {
 }  // namespace
 
 FlattenBVH FlattenBVH::build(const Box3 *boxes, uint64_t n, BVHBuildStrategy &strategy, const TreeBuildOption &option, unsigned n_threads) {
+  const auto t_begin = std::chrono::steady_clock::now();
   FlattenBVH out;
   std::vector<BuildPrimitive> primitives(n);
   out.sorted_primitive_index.resize(n);
@@ -243,6 +304,8 @@ FlattenBVH FlattenBVH::build(const Box3 *boxes, uint64_t n, BVHBuildStrategy &st
     open.push_back(top[ti].right);
   }
 
+  const bool timing = getenv("RDN_BUILD_TIMING") != nullptr;
+  const auto t_top = std::chrono::steady_clock::now();
   // ---- the open subtrees on worker threads, largest first
   struct Task { int top; std::vector<FlattenBVHNode> nodes; BuildStats stats; };
   std::vector<Task> tasks(open.size());
@@ -270,6 +333,7 @@ FlattenBVH FlattenBVH::build(const Box3 *boxes, uint64_t n, BVHBuildStrategy &st
   worker();
   for (auto &th : pool) th.join();
   out.stats.build_threads = workers;
+  const auto t_workers = std::chrono::steady_clock::now();
 
   // ---- splice in pre-order
   uint64_t total = 0;
@@ -304,6 +368,12 @@ FlattenBVH FlattenBVH::build(const Box3 *boxes, uint64_t n, BVHBuildStrategy &st
     } else {
       stack.pop_back();
     }
+  }
+  if (timing) {
+    const auto t_end = std::chrono::steady_clock::now();
+    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    fprintf(stderr, "[rdn build] %llu primitives: setup+top %.1f ms (%zu open subtrees), workers %.1f ms on %u threads, splice %.1f ms\n",
+            static_cast<unsigned long long>(n), ms(t_begin, t_top), tasks.size(), ms(t_top, t_workers), workers, ms(t_workers, t_end));
   }
   return out;
 }

@@ -83,14 +83,21 @@ class SAH : public BVHBuildStrategy {
   explicit SAH(uint32_t pre_partition_check_count);
   SplitResult split(const FlattenBVHNode &parent, const std::vector<BuildPrimitive> &build_source,
                     std::vector<uint64_t> &index_source, BuildStats &stats) override;
-  std::unique_ptr<BVHBuildStrategy> clone() const override { return std::make_unique<SAH>(static_cast<uint32_t>(pre_partition_.size())); }
+  // (a worker's copy splits on its own thread only: the workers already occupy the cores)
+  std::unique_ptr<BVHBuildStrategy> clone() const override {
+    auto copy = std::make_unique<SAH>(static_cast<uint32_t>(pre_partition_.size()));
+    copy->parallel_split_ = false;
+    return copy;
+  }
 
  private:
+  bool parallel_split_ = true;
   struct Bucket {
     Box3 bounding;
     std::vector<uint64_t> primitive_bucket;
   };
   std::vector<Bucket> pre_partition_;
+  std::vector<uint64_t> counts_;
 };
 
 struct FlattenBVH {
@@ -106,6 +113,7 @@ struct FlattenBVH {
   static FlattenBVH build(const Box3 *boxes, uint64_t n, BVHBuildStrategy &strategy, const TreeBuildOption &option, unsigned n_threads = 0);
 };
 constexpr uint64_t PARALLEL_BUILD_MIN = 1u << 15;
+constexpr uint64_t PARALLEL_SPLIT_MIN = 1u << 14;  // a single SAH split over at least this many primitives uses all threads too
 
 // worker threads for host-side loops: min(hardware concurrency, RDN_BUILD_THREADS), at least 1
 unsigned build_thread_count();
