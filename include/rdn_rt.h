@@ -290,6 +290,32 @@ int rdn_bvh_upload(rdn_flat_bvh *bvh, const rdn_mesh_view *mesh, int device);
 int rdn_bvh_query_nearest_device(const rdn_flat_bvh *bvh, const rdn_ray *d_rays, uint64_t n, uint32_t face_side,
                                  rdn_mesh_hit *d_out, void *cuda_stream);
 
+/* ---- mesh picking: AbstractMeshIntersectionExt::ray_intersect_nearest / ray_intersect_all
+ *      (content/mesh/core/src/feature/intersection.rs:3-37) over an attribute mesh of any MeshPrimitiveTopology
+ *      (content/mesh/core/src/primitive.rs:108-148; primitive k reads `stride` consecutive (indexed) vertices from step*k,
+ *      container/attributes/access.rs:142-150,199-243) with MeshBufferIntersectConfig (container/attributes/picking.rs:4-27):
+ *      points and line segments hit within `tolerance_local` (math/geometry/src/dimension3/intersection.rs:79-121, Ray3::
+ *      distance_sq_to_segment ray3.rs:48-145), triangles by the GTE test with `triangle_face`.  The reference tests every
+ *      primitive on one CPU thread per pick (scene/geometry-query/src/model.rs:245-255); here the primitives of a ray are spread
+ *      over the GPU.  Ray directions are unit vectors (Ray3 holds a NormalizedVector); tmin / tmax of rdn_ray are ignored. ---- */
+typedef enum rdn_topology {
+  RDN_TOPOLOGY_POINT_LIST = 0, RDN_TOPOLOGY_LINE_LIST = 1, RDN_TOPOLOGY_LINE_STRIP = 2, RDN_TOPOLOGY_TRIANGLE_LIST = 3,
+  RDN_TOPOLOGY_TRIANGLE_STRIP = 4
+} rdn_topology;
+typedef struct rdn_pick_config { float tolerance_local; uint32_t triangle_face; } rdn_pick_config;   /* MeshBufferIntersectConfig */
+typedef struct rdn_pick_mesh rdn_pick_mesh;   /* a mesh resident on one CUDA device */
+/* copies positions (and indices, when mesh->indices != NULL) to `device`; vertex indices are checked here (the reference's
+ * index_get returns None and the primitive is skipped; an out-of-range index is an error instead) */
+int rdn_pick_mesh_create(const rdn_mesh_view *mesh, uint32_t topology, int device, rdn_pick_mesh **out);
+void rdn_pick_mesh_destroy(rdn_pick_mesh *mesh);
+int rdn_pick_mesh_primitive_count(const rdn_pick_mesh *mesh, uint64_t *out_count);
+/* ray_intersect_nearest for a batch of pick rays (host buffers): strict `<` refresh in primitive order, i.e. the smallest
+ * primitive index among equally near hits */
+int rdn_pick_mesh_nearest(rdn_pick_mesh *mesh, const rdn_pick_config *config, const rdn_ray *rays, uint64_t n, rdn_mesh_hit *out);
+/* ray_intersect_all for one ray: every hit in primitive order; *out_total = number of hits, min(total, capacity) written */
+int rdn_pick_mesh_all(rdn_pick_mesh *mesh, const rdn_pick_config *config, const rdn_ray *ray, rdn_mesh_hit *out, uint64_t capacity,
+                      uint64_t *out_total);
+
 /* ---- measurement hook (no reference counterpart): read bandwidth, in GB/s, of a buffer of `bytes` that has been made L2
  *      resident on the scene's device (uint4 loads that bypass L1, `passes` sweeps inside one kernel, CUDA events) — the L2
  *      denominator of the roofline next to the HBM copy peak.  Synchronous; allocates and frees the buffer. */

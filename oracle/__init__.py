@@ -292,6 +292,48 @@ class Scene:
             self._h = None
 
 
+TOPOLOGY_POINT_LIST, TOPOLOGY_LINE_LIST, TOPOLOGY_LINE_STRIP, TOPOLOGY_TRIANGLE_LIST, TOPOLOGY_TRIANGLE_STRIP = range(5)
+
+
+def _pick_args(positions, indices):
+    pos = _c(positions, np.float32).reshape(-1, 3)
+    idx = None if indices is None else _c(indices, np.uint32).reshape(-1)
+    return pos, idx, (None if idx is None else _p(idx)), (0 if idx is None else idx.size)
+
+
+def pick_nearest(positions, indices, topology, rays, tolerance=0.0, face_side=FACE_DOUBLE, n_threads=1) -> np.ndarray:
+    """ray_intersect_nearest over every primitive (content/mesh/core/src/feature/intersection.rs:11-17), oracle_pick.c"""
+    pos, idx, ip, ni = _pick_args(positions, indices)
+    rays = _c(rays, RAY_DTYPE)
+    out = np.zeros(rays.shape[0], MESH_HIT_DTYPE)
+    L = lib()
+    L.orc_pick_nearest.restype = None
+    L.orc_pick_nearest.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]
+    L.orc_pick_nearest(_p(pos), pos.shape[0], ip, ni, topology, tolerance, face_side, _p(rays), rays.shape[0], _p(out), n_threads)
+    return out
+
+
+def pick_all(positions, indices, topology, ray, tolerance=0.0, face_side=FACE_DOUBLE) -> np.ndarray:
+    """ray_intersect_all of one ray: every hit in primitive order (feature/intersection.rs:6-10)"""
+    pos, idx, ip, ni = _pick_args(positions, indices)
+    ray = _c(np.asarray(ray).reshape(1), RAY_DTYPE)
+    L = lib()
+    L.orc_pick_all.restype = C.c_uint64
+    L.orc_pick_all.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64]
+    n = int(L.orc_pick_all(_p(pos), pos.shape[0], ip, ni, topology, tolerance, face_side, _p(ray), None, 0))
+    out = np.zeros(n, MESH_HIT_DTYPE)
+    if n:
+        L.orc_pick_all(_p(pos), pos.shape[0], ip, ni, topology, tolerance, face_side, _p(ray), _p(out), n)
+    return out
+
+
+def pick_primitive_count(n_positions, n_indices, has_indices, topology) -> int:
+    L = lib()
+    L.orc_pick_primitive_count.restype = C.c_uint64
+    L.orc_pick_primitive_count.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int]
+    return int(L.orc_pick_primitive_count(n_positions, n_indices, 1 if has_indices else 0, topology))
+
+
 def workgroup_inclusive_scan(x, workgroup: int) -> np.ndarray:
     x = _c(x, np.uint32); out = np.zeros_like(x)
     lib().orc_workgroup_inclusive_scan_u32(_p(x), x.size, workgroup, _p(out))

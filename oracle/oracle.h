@@ -139,6 +139,16 @@ int orc_scene_trace_unpruned(const orc_scene *s, const orc_launch *launch, const
 typedef struct { float distance, t_object, u, v, sign, scaling; uint32_t instance_id, geometry_id, primitive_id, slot, in_range, pad; } orc_candidate;
 uint64_t orc_scene_candidates(const orc_scene *s, const orc_launch *launch, const orc_ray *ray, orc_candidate *out, uint64_t cap);
 
+/* ---------- brute-force mesh picking (oracle_pick.c): points / lines with tolerance, triangles ---------- */
+enum { ORC_TOPOLOGY_POINT_LIST = 0, ORC_TOPOLOGY_LINE_LIST = 1, ORC_TOPOLOGY_LINE_STRIP = 2, ORC_TOPOLOGY_TRIANGLE_LIST = 3, ORC_TOPOLOGY_TRIANGLE_STRIP = 4 };
+int orc_ray_segment(const float *ray_od6, ov3 v0, ov3 v1, float tolerance, float *out_pos3_dist);
+int orc_ray_point(const float *ray_od6, ov3 point, float tolerance, float *out_pos3_dist);
+uint64_t orc_pick_primitive_count(uint64_t n_positions, uint64_t n_indices, int has_indices, int topology);
+void orc_pick_nearest(const float *positions, uint64_t n_positions, const uint32_t *indices, uint64_t n_indices, int topology,
+                      float tolerance, int face_side, const orc_ray *rays, uint64_t n_rays, orc_mesh_hit *out, int n_threads);
+uint64_t orc_pick_all(const float *positions, uint64_t n_positions, const uint32_t *indices, uint64_t n_indices, int topology,
+                      float tolerance, int face_side, const orc_ray *ray, orc_mesh_hit *out, uint64_t capacity);
+
 /* ---------- parallel-compute restatements (scan / compaction / scatter) ---------- */
 void orc_workgroup_inclusive_scan_u32(const uint32_t *in, uint64_t n, uint32_t workgroup, uint32_t *out);
 void orc_inclusive_scan_u32(const uint32_t *in, uint64_t n, uint32_t *out);

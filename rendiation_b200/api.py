@@ -137,6 +137,10 @@ class _Option(C.Structure):
     _fields_ = [("max_tree_depth", C.c_uint64), ("bin_size", C.c_uint64)]
 
 
+class _PickConfig(C.Structure):
+    _fields_ = [("tolerance_local", C.c_float), ("triangle_face", C.c_uint32)]
+
+
 class _MeshView(C.Structure):
     _fields_ = [("positions", C.c_void_p), ("n_positions", C.c_uint64), ("indices", C.c_void_p), ("n_indices", C.c_uint64)]
 
@@ -146,7 +150,8 @@ EXPORTED_SYMBOLS = [
     "rdn_rt_tlas_destroy", "rdn_rt_bind_tlas", "rdn_rt_bind_tlas_max_len", "rdn_rt_commit", "rdn_rt_trace_closest",
     "rdn_rt_trace_closest_device", "rdn_rt_trace_counted", "rdn_rt_kernel_timing_begin", "rdn_rt_kernel_timing_end",
     "rdn_rt_gen_pinhole_rays_device", "rdn_rt_gen_pinhole_rays_batch_device", "rdn_rt_gen_camera_rays_device", "rdn_rt_gen_bounce_rays_device", "rdn_rt_compact_u32", "rdn_rt_compact_u32_device",
-    "rdn_rt_scene_blob", "rdn_rt_scene_adopt_blob", "rdn_rt_scene_array", "rdn_rt_scene_build_stats", "rdn_rt_measure_l2_read_gbs", "rdn_bvh_build", "rdn_bvh_destroy", "rdn_bvh_nodes",
+    "rdn_rt_scene_blob", "rdn_rt_scene_adopt_blob", "rdn_rt_scene_array", "rdn_rt_scene_build_stats", "rdn_rt_measure_l2_read_gbs", "rdn_pick_mesh_create", "rdn_pick_mesh_destroy",
+    "rdn_pick_mesh_primitive_count", "rdn_pick_mesh_nearest", "rdn_pick_mesh_all", "rdn_bvh_build", "rdn_bvh_destroy", "rdn_bvh_nodes",
     "rdn_bvh_sorted_primitive_index", "rdn_bvh_build_for_mesh", "rdn_bvh_query_nearest", "rdn_bvh_upload", "rdn_bvh_query_nearest_device", "rdn_bvh_query_list", "rdn_rt_last_error", "rdn_rt_version",
 ]
 
@@ -193,6 +198,12 @@ def lib() -> C.CDLL:
     L.rdn_rt_scene_array.argtypes = [vp, i32, vp, u64, P(u64)]
     L.rdn_rt_scene_build_stats.argtypes = [vp, P(_BuildStats)]
     L.rdn_rt_measure_l2_read_gbs.argtypes = [vp, i32, u64, i32, P(C.c_double)]
+    L.rdn_pick_mesh_create.argtypes = [P(_MeshView), u32, i32, P(vp)]
+    L.rdn_pick_mesh_destroy.argtypes = [vp]
+    L.rdn_pick_mesh_destroy.restype = None
+    L.rdn_pick_mesh_primitive_count.argtypes = [vp, P(u64)]
+    L.rdn_pick_mesh_nearest.argtypes = [vp, P(_PickConfig), vp, u64, vp]
+    L.rdn_pick_mesh_all.argtypes = [vp, P(_PickConfig), vp, vp, u64, P(u64)]
     L.rdn_bvh_build.argtypes = [vp, u64, i32, u32, P(_Option), P(vp)]
     L.rdn_bvh_build_for_mesh.argtypes = [P(_MeshView), i32, u32, P(_Option), P(vp)]
     L.rdn_bvh_destroy.argtypes = [vp]
@@ -457,6 +468,53 @@ class SAH:
 
 class BalanceTree:
     """content/space/src/bvh/strategy.rs:65."""
+
+
+# MeshPrimitiveTopology (content/mesh/core/src/primitive.rs:108-128)
+TOPOLOGY_POINT_LIST, TOPOLOGY_LINE_LIST, TOPOLOGY_LINE_STRIP, TOPOLOGY_TRIANGLE_LIST, TOPOLOGY_TRIANGLE_STRIP = range(5)
+
+
+class PickMesh:
+    """A device-resident attribute mesh for brute-force picking: ``ray_intersect_nearest`` / ``ray_intersect_all``
+    (content/mesh/core/src/feature/intersection.rs:3-37) with ``MeshBufferIntersectConfig`` (container/attributes/picking.rs:4-27)."""
+
+    def __init__(self, positions, indices=None, topology: int = TOPOLOGY_TRIANGLE_LIST, device: int = 0):
+        self._L = lib()
+        self._pos = _c(positions, np.float32).reshape(-1, 3)
+        self._idx = None if indices is None else _c(indices, np.uint32).reshape(-1)
+        view = _MeshView(self._pos.ctypes.data, self._pos.shape[0], None if self._idx is None else self._idx.ctypes.data,
+                         0 if self._idx is None else self._idx.size)
+        h = C.c_void_p()
+        _check(self._L.rdn_pick_mesh_create(C.byref(view), topology, device, C.byref(h)))
+        self._h = h
+
+    @property
+    def primitive_count(self) -> int:
+        n = C.c_uint64()
+        _check(self._L.rdn_pick_mesh_primitive_count(self._h, C.byref(n)))
+        return int(n.value)
+
+    def ray_intersect_nearest(self, rays, tolerance_local: float = 0.0, triangle_face: int = FACE_DOUBLE) -> np.ndarray:
+        rays = _c(rays, RAY_DTYPE)
+        out = np.zeros(rays.shape[0], MESH_HIT_DTYPE)
+        cfg = _PickConfig(tolerance_local, triangle_face)
+        _check(self._L.rdn_pick_mesh_nearest(self._h, C.byref(cfg), _p(rays), rays.shape[0], _p(out)))
+        return out
+
+    def ray_intersect_all(self, ray, tolerance_local: float = 0.0, triangle_face: int = FACE_DOUBLE) -> np.ndarray:
+        ray = _c(np.asarray(ray).reshape(1), RAY_DTYPE)
+        cfg = _PickConfig(tolerance_local, triangle_face)
+        total = C.c_uint64()
+        _check(self._L.rdn_pick_mesh_all(self._h, C.byref(cfg), _p(ray), None, 0, C.byref(total)))
+        out = np.zeros(int(total.value), MESH_HIT_DTYPE)
+        if total.value:
+            _check(self._L.rdn_pick_mesh_all(self._h, C.byref(cfg), _p(ray), _p(out), out.shape[0], C.byref(total)))
+        return out
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            self._L.rdn_pick_mesh_destroy(self._h)
+            self._h = None
 
 
 class FlattenBVH:

@@ -862,6 +862,156 @@ int rdn_rt_scene_array(rdn_rt_scene *s, int array_id, void *out, uint64_t capaci
   return RDN_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ mesh picking (f2)
+struct rdn_pick_mesh {
+  int device = -1;
+  int sm_count = 148;
+  PickMeshDev dev{};
+  float *d_positions = nullptr;
+  uint32_t *d_indices = nullptr;
+  // per-call scratch, grown on demand
+  rdn_ray *d_rays = nullptr;
+  rdn_mesh_hit *d_hits = nullptr;
+  unsigned long long *d_best_key = nullptr;
+  uint32_t *d_first_hit = nullptr;
+  uint64_t ray_cap = 0;
+  uint8_t *d_keep = nullptr;
+  uint32_t *d_iota = nullptr, *d_index = nullptr;
+  rdn_mesh_hit *d_records = nullptr, *d_gathered = nullptr;
+  uint64_t *d_n_kept = nullptr;
+  unsigned long long *d_compact_status = nullptr;
+  uint64_t gathered_cap = 0;
+  std::mutex lock;
+};
+
+static void free_pick_mesh(rdn_pick_mesh *m) {
+  void *ptrs[] = {m->d_positions, m->d_indices, m->d_rays, m->d_hits, m->d_best_key, m->d_first_hit, m->d_keep, m->d_iota, m->d_index,
+                  m->d_records, m->d_gathered, m->d_n_kept, m->d_compact_status};
+  if (m->device >= 0) cudaSetDevice(m->device);
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+}
+
+int rdn_pick_mesh_create(const rdn_mesh_view *mesh, uint32_t topology, int device, rdn_pick_mesh **out) {
+  if (!mesh || !out || (!mesh->positions && mesh->n_positions) || topology > RDN_TOPOLOGY_TRIANGLE_STRIP)
+    return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_pick_mesh_create: bad argument");
+  const bool indexed = mesh->indices != nullptr;
+  if (indexed)
+    for (uint64_t k = 0; k < mesh->n_indices; ++k)
+      if (mesh->indices[k] >= mesh->n_positions) return fail(RDN_ERR_BUILD, "rdn_pick_mesh_create: vertex index out of bounds");
+  static const uint64_t stride_of[5] = {1, 2, 2, 3, 3}, step_of[5] = {1, 2, 1, 3, 1};
+  const uint64_t count = indexed ? mesh->n_indices : mesh->n_positions;
+  const uint64_t n_prims = count + step_of[topology] < stride_of[topology] ? 0 : (count + step_of[topology] - stride_of[topology]) / step_of[topology];
+  if (n_prims >= 0xFFFFFFFFull) return fail(RDN_ERR_CAPACITY, "rdn_pick_mesh_create: more than 2^32 - 1 primitives");
+  int available = 0;
+  RDN_CUDA(cudaGetDeviceCount(&available));
+  if (device < 0 || device >= available) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_pick_mesh_create: no such CUDA device (there is no CPU fallback)");
+  auto *m = new rdn_pick_mesh();
+  m->device = device;
+  auto bail = [&](cudaError_t e, const char *what) { free_pick_mesh(m); delete m; return fail(RDN_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e)); };
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return bail(e, "cudaSetDevice");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) m->sm_count = prop.multiProcessorCount;
+  e = cudaMalloc(&m->d_positions, std::max<uint64_t>(mesh->n_positions, 1) * 3 * sizeof(float));
+  if (e != cudaSuccess) return bail(e, "cudaMalloc");
+  e = cudaMemcpy(m->d_positions, mesh->positions, mesh->n_positions * 3 * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return bail(e, "cudaMemcpy");
+  if (indexed) {
+    e = cudaMalloc(&m->d_indices, std::max<uint64_t>(mesh->n_indices, 1) * sizeof(uint32_t));
+    if (e != cudaSuccess) return bail(e, "cudaMalloc");
+    e = cudaMemcpy(m->d_indices, mesh->indices, mesh->n_indices * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return bail(e, "cudaMemcpy");
+  }
+  m->dev = PickMeshDev{m->d_positions, m->d_indices, n_prims, topology};
+  *out = m;
+  return RDN_OK;
+}
+
+void rdn_pick_mesh_destroy(rdn_pick_mesh *m) {
+  if (!m) return;
+  free_pick_mesh(m);
+  delete m;
+}
+
+int rdn_pick_mesh_primitive_count(const rdn_pick_mesh *m, uint64_t *out_count) {
+  if (!m || !out_count) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_pick_mesh_primitive_count: null argument");
+  *out_count = m->dev.n_prims;
+  return RDN_OK;
+}
+
+int rdn_pick_mesh_nearest(rdn_pick_mesh *m, const rdn_pick_config *config, const rdn_ray *rays, uint64_t n, rdn_mesh_hit *out) {
+  if (!m || !config || (n && (!rays || !out))) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_pick_mesh_nearest: null argument");
+  if (config->triangle_face > RDN_FACE_DOUBLE) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_pick_mesh_nearest: bad triangle_face");
+  if (n == 0) return RDN_OK;
+  std::lock_guard<std::mutex> lg(m->lock);
+  RDN_CUDA(cudaSetDevice(m->device));
+  if (m->ray_cap < n) {
+    for (void *p : {static_cast<void *>(m->d_rays), static_cast<void *>(m->d_hits), static_cast<void *>(m->d_best_key), static_cast<void *>(m->d_first_hit)})
+      if (p) cudaFree(p);
+    m->d_rays = nullptr; m->d_hits = nullptr; m->d_best_key = nullptr; m->d_first_hit = nullptr; m->ray_cap = 0;
+    RDN_CUDA(cudaMalloc(&m->d_rays, n * sizeof(rdn_ray)));
+    RDN_CUDA(cudaMalloc(&m->d_hits, n * sizeof(rdn_mesh_hit)));
+    RDN_CUDA(cudaMalloc(&m->d_best_key, n * sizeof(unsigned long long)));
+    RDN_CUDA(cudaMalloc(&m->d_first_hit, n * sizeof(uint32_t)));
+    RDN_CUDA(cudaMemset(m->d_best_key, 0xFF, n * sizeof(unsigned long long)));
+    RDN_CUDA(cudaMemset(m->d_first_hit, 0xFF, n * sizeof(uint32_t)));
+    m->ray_cap = n;
+  }
+  RDN_CUDA(cudaMemcpy(m->d_rays, rays, n * sizeof(rdn_ray), cudaMemcpyHostToDevice));
+  launch_pick_nearest(m->dev, m->d_rays, n, config->tolerance_local, config->triangle_face, m->d_best_key, m->d_first_hit, m->d_hits, m->sm_count, nullptr);
+  RDN_CUDA(cudaGetLastError());
+  RDN_CUDA(cudaMemcpy(out, m->d_hits, n * sizeof(rdn_mesh_hit), cudaMemcpyDeviceToHost));
+  return RDN_OK;
+}
+
+int rdn_pick_mesh_all(rdn_pick_mesh *m, const rdn_pick_config *config, const rdn_ray *ray, rdn_mesh_hit *out, uint64_t capacity, uint64_t *out_total) {
+  if (!m || !config || !ray || !out_total || (capacity && !out)) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_pick_mesh_all: null argument");
+  if (config->triangle_face > RDN_FACE_DOUBLE) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_pick_mesh_all: bad triangle_face");
+  *out_total = 0;
+  const uint64_t np = m->dev.n_prims;
+  if (np == 0) return RDN_OK;
+  std::lock_guard<std::mutex> lg(m->lock);
+  RDN_CUDA(cudaSetDevice(m->device));
+  if (!m->d_keep) {
+    RDN_CUDA(cudaMalloc(&m->d_keep, np));
+    RDN_CUDA(cudaMalloc(&m->d_iota, np * sizeof(uint32_t)));
+    RDN_CUDA(cudaMalloc(&m->d_index, np * sizeof(uint32_t)));
+    RDN_CUDA(cudaMalloc(&m->d_records, np * sizeof(rdn_mesh_hit)));
+    RDN_CUDA(cudaMalloc(&m->d_n_kept, sizeof(uint64_t)));
+    RDN_CUDA(cudaMalloc(&m->d_compact_status, compact_status_words(np) * sizeof(unsigned long long)));
+  }
+  if (m->ray_cap < 1) {
+    RDN_CUDA(cudaMalloc(&m->d_rays, sizeof(rdn_ray)));
+    RDN_CUDA(cudaMalloc(&m->d_hits, sizeof(rdn_mesh_hit)));
+    RDN_CUDA(cudaMalloc(&m->d_best_key, sizeof(unsigned long long)));
+    RDN_CUDA(cudaMalloc(&m->d_first_hit, sizeof(uint32_t)));
+    RDN_CUDA(cudaMemset(m->d_best_key, 0xFF, sizeof(unsigned long long)));
+    RDN_CUDA(cudaMemset(m->d_first_hit, 0xFF, sizeof(uint32_t)));
+    m->ray_cap = 1;
+  }
+  RDN_CUDA(cudaMemcpy(m->d_rays, ray, sizeof(rdn_ray), cudaMemcpyHostToDevice));
+  launch_pick_all_mark(m->dev, m->d_rays, config->tolerance_local, config->triangle_face, m->d_keep, m->d_iota, m->d_records, m->sm_count, nullptr);
+  launch_compact_u32(m->d_iota, m->d_keep, np, m->d_index, m->d_n_kept, m->d_compact_status, nullptr);
+  RDN_CUDA(cudaGetLastError());
+  uint64_t total = 0;
+  RDN_CUDA(cudaMemcpy(&total, m->d_n_kept, sizeof(total), cudaMemcpyDeviceToHost));
+  *out_total = total;
+  const uint64_t take = std::min(total, capacity);
+  if (take) {
+    if (m->gathered_cap < take) {
+      if (m->d_gathered) cudaFree(m->d_gathered);
+      m->d_gathered = nullptr; m->gathered_cap = 0;
+      RDN_CUDA(cudaMalloc(&m->d_gathered, take * sizeof(rdn_mesh_hit)));
+      m->gathered_cap = take;
+    }
+    launch_pick_all_gather(m->d_index, m->d_n_kept, take, m->d_records, m->d_gathered, m->sm_count, nullptr);
+    RDN_CUDA(cudaGetLastError());
+    RDN_CUDA(cudaMemcpy(out, m->d_gathered, take * sizeof(rdn_mesh_hit), cudaMemcpyDeviceToHost));
+  }
+  return RDN_OK;
+}
+
 int rdn_rt_measure_l2_read_gbs(rdn_rt_scene *s, int device_index, uint64_t bytes, int passes, double *out_gbs) {
   if (!s || !out_gbs || bytes < (1u << 20) || passes < 1) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_measure_l2_read_gbs: bad argument");
   if (device_index < 0 || device_index >= static_cast<int>(s->devices.size())) return fail(RDN_ERR_INVALID_ARGUMENT, "bad device_index");

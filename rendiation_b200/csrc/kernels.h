@@ -83,6 +83,21 @@ void launch_mark_hits(const rdn_hit *d_hits, uint64_t n, uint8_t *d_keep, uint32
 void launch_gen_bounce_rays(const SceneDev &scene, const rdn_bounce &p, const rdn_ray *d_rays_in, const rdn_hit *d_hits,
                             const uint32_t *d_src_index, const uint64_t *d_n_src, uint64_t n_max, rdn_ray *d_rays_out, cudaStream_t stream);
 
+// brute-force mesh picking (pick.cu)
+struct PickMeshDev {
+  const float *positions;   // 3 floats per vertex
+  const uint32_t *indices;  // nullptr: non-indexed
+  uint64_t n_prims;         // (count + step - stride) / step, access.rs:142-150
+  uint32_t topology;        // rdn_topology
+};
+// d_best_key / d_first_hit: one slot per ray, 0xFF-filled before the first call (the finish kernel re-arms them)
+void launch_pick_nearest(const PickMeshDev &mesh, const rdn_ray *d_rays, uint64_t n_rays, float tolerance, uint32_t face_side,
+                         unsigned long long *d_best_key, uint32_t *d_first_hit, rdn_mesh_hit *d_out, int sm_count, cudaStream_t stream);
+void launch_pick_all_mark(const PickMeshDev &mesh, const rdn_ray *d_ray, float tolerance, uint32_t face_side, uint8_t *d_keep, uint32_t *d_iota,
+                          rdn_mesh_hit *d_records, int sm_count, cudaStream_t stream);
+void launch_pick_all_gather(const uint32_t *d_index, const uint64_t *d_n_kept, uint64_t capacity, const rdn_mesh_hit *d_records, rdn_mesh_hit *d_out,
+                            int sm_count, cudaStream_t stream);
+
 // measurement hook (probe.cu): read bandwidth of an L2-resident buffer of `bytes` on the current device, GB/s
 int measure_l2_read_gbs(uint64_t bytes, int passes, int sm_count, double *out_gbs);
 
