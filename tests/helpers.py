@@ -103,9 +103,10 @@ def canonical_nan(hits: np.ndarray) -> np.ndarray:
     with finite t and NaN barycentrics (0 * inf) in the reference; which NaN is hardware-defined: x86 SSE generates 0xFFC00000
     and propagates operand payloads, the GPU always returns 0x7FFFFFFF.  Everything else stays bit for bit."""
     out = hits.copy()
-    for f in ("t", "u", "v"):
-        bits = out[f].view(np.uint32)
-        bits[np.isnan(out[f])] = 0x7FC00000
+    for f in out.dtype.names:
+        if out.dtype[f] == np.float32:   # (t, u, v) of rdn_hit, (px, py, pz, distance) of rdn_mesh_hit
+            bits = out[f].view(np.uint32)
+            bits[np.isnan(out[f])] = 0x7FC00000
     return out
 
 
