@@ -225,6 +225,16 @@ int rdn_rt_gen_bounce_rays_device(rdn_rt_scene *scene, int device_index, const r
                                   const rdn_hit *d_hits, uint64_t n, rdn_ray *d_rays_out, uint32_t *d_src_index,
                                   uint64_t *d_out_n, void *cuda_stream);
 
+/* One sample of the AO frame's accumulation (scene/rendering/gpu-ray-tracing/src/feature/ao.rs:187-232): payload(pixel) = 1 where the
+ * primary ray misses (miss shader) or its AO test ray misses, 0 where the AO test ray hits (secondary closest-hit shader);
+ * ao_buffer = (ao_buffer * sample_count + payload) / (sample_count + 1) while sample_count < max_sample (256 in the reference),
+ * else unchanged.  d_secondary_hits / d_src_index / d_n_secondary: the hits of the compacted AO rays generated by
+ * rdn_rt_gen_bounce_rays_device(mode 1) and traced with ACCEPT_FIRST_HIT_AND_END_SEARCH, and that call's d_src_index / d_out_n.
+ * d_ao_buffer: n_pixels floats (the .x the reference stores in its Rgba32Float texture).  Asynchronous on cuda_stream. */
+int rdn_rt_ao_accumulate_device(rdn_rt_scene *scene, int device_index, const rdn_hit *d_secondary_hits, const uint32_t *d_src_index,
+                                const uint64_t *d_n_secondary, uint64_t n_pixels, uint32_t sample_count, uint32_t max_sample,
+                                float *d_ao_buffer, void *cuda_stream);
+
 /* ---- wavefront active-list compaction: use_stream_compaction
  *      (shader/parallel-compute/src/stream_compaction.rs:3-45) as used by use_compact_alive_tasks
  *      (shader/task-graph/src/runtime/task_group.rs:220-278).  Stable; out has n slots, zero past *out_n. ---- */

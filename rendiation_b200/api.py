@@ -149,7 +149,7 @@ EXPORTED_SYMBOLS = [
     "rdn_rt_scene_create", "rdn_rt_scene_destroy", "rdn_rt_blas_create", "rdn_rt_blas_destroy", "rdn_rt_tlas_create",
     "rdn_rt_tlas_destroy", "rdn_rt_bind_tlas", "rdn_rt_bind_tlas_max_len", "rdn_rt_commit", "rdn_rt_trace_closest",
     "rdn_rt_trace_closest_device", "rdn_rt_trace_counted", "rdn_rt_kernel_timing_begin", "rdn_rt_kernel_timing_end",
-    "rdn_rt_gen_pinhole_rays_device", "rdn_rt_gen_pinhole_rays_batch_device", "rdn_rt_gen_camera_rays_device", "rdn_rt_gen_bounce_rays_device", "rdn_rt_compact_u32", "rdn_rt_compact_u32_device",
+    "rdn_rt_gen_pinhole_rays_device", "rdn_rt_gen_pinhole_rays_batch_device", "rdn_rt_gen_camera_rays_device", "rdn_rt_gen_bounce_rays_device", "rdn_rt_ao_accumulate_device", "rdn_rt_compact_u32", "rdn_rt_compact_u32_device",
     "rdn_rt_scene_blob", "rdn_rt_scene_adopt_blob", "rdn_rt_scene_array", "rdn_rt_scene_build_stats", "rdn_rt_measure_l2_read_gbs", "rdn_pick_mesh_create", "rdn_pick_mesh_destroy",
     "rdn_pick_mesh_primitive_count", "rdn_pick_mesh_nearest", "rdn_pick_mesh_all", "rdn_bvh_build", "rdn_bvh_destroy", "rdn_bvh_nodes",
     "rdn_bvh_sorted_primitive_index", "rdn_bvh_build_for_mesh", "rdn_bvh_query_nearest", "rdn_bvh_upload", "rdn_bvh_query_nearest_device", "rdn_bvh_query_list", "rdn_rt_last_error", "rdn_rt_version",
@@ -191,6 +191,7 @@ def lib() -> C.CDLL:
     L.rdn_rt_gen_pinhole_rays_batch_device.argtypes = [vp, i32, P(_Pinhole), u32, vp, vp]
     L.rdn_rt_gen_camera_rays_device.argtypes = [vp, i32, P(_Camera), vp, vp]
     L.rdn_rt_gen_bounce_rays_device.argtypes = [vp, i32, P(_Bounce), vp, vp, u64, vp, vp, vp, vp]
+    L.rdn_rt_ao_accumulate_device.argtypes = [vp, i32, vp, vp, vp, u64, u32, u32, vp, vp]
     L.rdn_rt_compact_u32.argtypes = [vp, vp, vp, u64, vp, P(u64)]
     L.rdn_rt_compact_u32_device.argtypes = [vp, i32, vp, vp, u64, vp, vp, vp]
     L.rdn_rt_scene_blob.argtypes = [vp, i32, P(vp), P(u64)]
@@ -394,6 +395,13 @@ class NaiveSahBVHSystem:
                     BOUNCE_OFFSET_ORIGIN if offset_origin else 0, (C.c_float * 3)(*[float(x) for x in target]))
         _check(self._L.rdn_rt_gen_bounce_rays_device(self._h, device_index, C.byref(p), C.c_void_p(d_rays_in), C.c_void_p(d_hits), n,
                                                      C.c_void_p(d_rays_out), C.c_void_p(d_src_index), C.c_void_p(d_out_n), C.c_void_p(stream)))
+
+    def ao_accumulate_device(self, d_secondary_hits: int, d_src_index: int, d_n_secondary: int, n_pixels: int, sample_count: int,
+                             d_ao_buffer: int, max_sample: int = 256, stream: int = 0, device_index: int = 0):
+        """One sample of the AO frame's running mean (feature/ao.rs:187-232); see include/rdn_rt.h."""
+        _check(self._L.rdn_rt_ao_accumulate_device(self._h, device_index, C.c_void_p(d_secondary_hits), C.c_void_p(d_src_index),
+                                                   C.c_void_p(d_n_secondary), n_pixels, sample_count, max_sample, C.c_void_p(d_ao_buffer),
+                                                   C.c_void_p(stream)))
 
     # --- wavefront queue compaction ---
     def compact_u32(self, values, keep):

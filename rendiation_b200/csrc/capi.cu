@@ -100,6 +100,8 @@ struct DeviceCtx {
   bool ext_pending = false;
   unsigned long long *d_compact_status = nullptr;
   uint64_t compact_status_cap = 0;
+  float *d_ao_payload = nullptr;   // AO accumulation: per-pixel payload, 1.0f between samples
+  uint64_t ao_payload_cap = 0;
   uint8_t *d_keep = nullptr;       // bounce step: keep flags + identity indices feeding the compaction
   uint32_t *d_iota = nullptr;
   uint64_t bounce_cap = 0;
@@ -357,6 +359,7 @@ void rdn_rt_scene_destroy(rdn_rt_scene *s) {
     for (TimedLaunch &t : dc.timed) { cudaEventDestroy(t.begin); cudaEventDestroy(t.end); }
     if (dc.ext_done) cudaEventDestroy(dc.ext_done);
     if (dc.d_compact_status) cudaFree(dc.d_compact_status);
+    if (dc.d_ao_payload) cudaFree(dc.d_ao_payload);
     if (dc.d_keep) cudaFree(dc.d_keep);
     if (dc.d_iota) cudaFree(dc.d_iota);
   }
@@ -859,6 +862,28 @@ int rdn_rt_scene_array(rdn_rt_scene *s, int array_id, void *out, uint64_t capaci
     if (s->devices.empty()) std::memcpy(out, s->host_blob.data() + h.offset[array_id], bytes);
     else RDN_CUDA(cudaMemcpy(out, static_cast<const char *>(s->devices[0].d_blob) + h.offset[array_id], bytes, cudaMemcpyDeviceToHost));
   }
+  return RDN_OK;
+}
+
+int rdn_rt_ao_accumulate_device(rdn_rt_scene *s, int device_index, const rdn_hit *d_secondary_hits, const uint32_t *d_src_index,
+                                const uint64_t *d_n_secondary, uint64_t n_pixels, uint32_t sample_count, uint32_t max_sample,
+                                float *d_ao_buffer, void *cuda_stream) {
+  if (!s || !d_n_secondary || (n_pixels && (!d_secondary_hits || !d_src_index || !d_ao_buffer)))
+    return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_ao_accumulate_device: null argument");
+  if (device_index < 0 || device_index >= static_cast<int>(s->devices.size())) return fail(RDN_ERR_INVALID_ARGUMENT, "bad device_index");
+  std::lock_guard<std::mutex> lg(s->launch_lock);
+  DeviceCtx &dc = s->devices[device_index];
+  RDN_CUDA(cudaSetDevice(dc.device));
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  if (dc.ao_payload_cap < n_pixels) {
+    if (dc.d_ao_payload) cudaFree(dc.d_ao_payload);
+    dc.d_ao_payload = nullptr; dc.ao_payload_cap = 0;
+    RDN_CUDA(cudaMalloc(&dc.d_ao_payload, std::max<uint64_t>(n_pixels, 1) * sizeof(float)));
+    dc.ao_payload_cap = n_pixels;
+    launch_fill_f32(dc.d_ao_payload, n_pixels, 1.0f, stream);
+  }
+  launch_ao_accumulate(d_secondary_hits, d_src_index, d_n_secondary, n_pixels, sample_count, max_sample, dc.d_ao_payload, d_ao_buffer, stream);
+  RDN_CUDA(cudaGetLastError());
   return RDN_OK;
 }
 

@@ -79,6 +79,10 @@ void launch_gen_pinhole_rays_batch(const rdn_pinhole *d_params, const uint64_t *
                                    rdn_ray *d_rays, cudaStream_t stream);  // n_params <= 65535 per call
 void launch_gen_camera_rays(const rdn_camera &p, rdn_ray *d_rays, cudaStream_t stream);
 void launch_mark_hits(const rdn_hit *d_hits, uint64_t n, uint8_t *d_keep, uint32_t *d_iota, cudaStream_t stream);
+// AO frame accumulation (feature/ao.rs:187-232); d_payload: n_pixels floats, 1.0f before the first sample (the kernel re-arms it)
+void launch_fill_f32(float *d_dst, uint64_t n, float v, cudaStream_t stream);
+void launch_ao_accumulate(const rdn_hit *d_secondary_hits, const uint32_t *d_src_index, const uint64_t *d_n_secondary, uint64_t n_pixels,
+                          uint32_t sample_count, uint32_t max_sample, float *d_payload, float *d_ao_buffer, cudaStream_t stream);
 // d_src_index[0 .. *d_n_src) = indices of the source rays (stable compaction of the hits); n_max bounds the grid
 void launch_gen_bounce_rays(const SceneDev &scene, const rdn_bounce &p, const rdn_ray *d_rays_in, const rdn_hit *d_hits,
                             const uint32_t *d_src_index, const uint64_t *d_n_src, uint64_t n_max, rdn_ray *d_rays_out, cudaStream_t stream);

@@ -8,6 +8,7 @@
 //                        (shader_uv_space_to_render_space, shader/library/src/lib.rs:18-28); the sampler is
 //                        PCGRandomSampler seeded by xxhash32(pixel.x, pixel.y, sample_index) (sampler.rs:11-72)
 //   k_mark_hits          keep flag per ray (hit <=> instance_id != INVALID) feeding the wavefront compaction (compact.cu)
+//   k_ao_scatter / k_ao_accumulate   the AO frame's payload and running mean (feature/ao.rs:187-232)
 //   k_gen_bounce_rays    one ray per surviving hit: origin = hit_world_position (api/ctx.rs:209-211: origin + dir * t),
 //                        geometric normal = normalize(normal_mat * (pa-pb) x (pa-pc)) turned towards the ray origin
 //                        (bindless_mesh_bridge.rs:103-114), direction either
@@ -115,6 +116,30 @@ __global__ void __launch_bounds__(256) k_mark_hits(const rdn_hit *__restrict__ h
     keep[k] = hits[k].instance_id != RDN_INVALID_ID ? 1 : 0;
     iota[k] = static_cast<uint32_t>(k);
   }
+}
+
+// ---- the AO frame's accumulation (feature/ao.rs:187-232): payload = 1 where the primary ray misses (miss shader) or its AO test
+// ray misses, 0 where the AO test ray hits anything (secondary closest-hit shader); the running mean over the samples so far
+// is updated in place, frozen once max_sample samples are in.  One thread per pixel; the AO ray of pixel p (if any) is the
+// k-th compacted bounce ray with src_index[k] == p, found through a scatter pass.
+__global__ void __launch_bounds__(256) k_ao_scatter(const rdn_hit *__restrict__ secondary_hits, const uint32_t *__restrict__ src_index,
+                                                    const uint64_t *__restrict__ n_secondary, float *__restrict__ payload) {
+  const uint64_t n = *n_secondary;
+  for (uint64_t k = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; k < n; k += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+    payload[src_index[k]] = secondary_hits[k].instance_id != RDN_INVALID_ID ? 0.0f : 1.0f;
+}
+__global__ void __launch_bounds__(256) k_ao_accumulate(float *__restrict__ payload_then_unused, uint64_t n, uint32_t sample_count, uint32_t max_sample,
+                                                       float *__restrict__ ao_buffer) {
+  const float previous_sample_count = static_cast<float>(sample_count);
+  const float all_sample_count = previous_sample_count + 1.0f;
+  for (uint64_t p = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; p < n; p += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const float payload = payload_then_unused[p];
+    payload_then_unused[p] = 1.0f;  // re-armed: "miss" is the default of the next sample
+    if (sample_count < max_sample) ao_buffer[p] = (ao_buffer[p] * previous_sample_count + payload) / all_sample_count;
+  }
+}
+__global__ void __launch_bounds__(256) k_fill_f32(float *__restrict__ dst, uint64_t n, float v) {
+  for (uint64_t p = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; p < n; p += static_cast<uint64_t>(gridDim.x) * blockDim.x) dst[p] = v;
 }
 
 // ---- low-discrepancy points with fixed scrambles (sampling/sobol.rs:40-68)
@@ -268,6 +293,15 @@ void launch_gen_camera_rays(const rdn_camera &p, rdn_ray *d_rays, cudaStream_t s
 }
 void launch_mark_hits(const rdn_hit *d_hits, uint64_t n, uint8_t *d_keep, uint32_t *d_iota, cudaStream_t stream) {
   if (n) k_mark_hits<<<grid_for(n, 256), 256, 0, stream>>>(d_hits, n, d_keep, d_iota);
+}
+void launch_fill_f32(float *d_dst, uint64_t n, float v, cudaStream_t stream) {
+  if (n) k_fill_f32<<<grid_for(n, 256), 256, 0, stream>>>(d_dst, n, v);
+}
+void launch_ao_accumulate(const rdn_hit *d_secondary_hits, const uint32_t *d_src_index, const uint64_t *d_n_secondary, uint64_t n_pixels,
+                          uint32_t sample_count, uint32_t max_sample, float *d_payload, float *d_ao_buffer, cudaStream_t stream) {
+  if (n_pixels == 0) return;
+  k_ao_scatter<<<grid_for(n_pixels, 256), 256, 0, stream>>>(d_secondary_hits, d_src_index, d_n_secondary, d_payload);
+  k_ao_accumulate<<<grid_for(n_pixels, 256), 256, 0, stream>>>(d_payload, n_pixels, sample_count, max_sample, d_ao_buffer);
 }
 void launch_gen_bounce_rays(const SceneDev &scene, const rdn_bounce &p, const rdn_ray *d_rays_in, const rdn_hit *d_hits,
                             const uint32_t *d_src_index, const uint64_t *d_n_src, uint64_t n_max, rdn_ray *d_rays_out, cudaStream_t stream) {

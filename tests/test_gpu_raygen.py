@@ -188,6 +188,49 @@ def test_shadow_test_rays_with_offset_origin_are_bit_exact():
     assert 0 < occluded < k  # part of the torus is in its own shadow, part is lit
 
 
+def test_ao_frame_accumulates_like_the_reference_ray_gen_shader():
+    """feature/ao.rs:150-330 as a device-resident pipeline, three samples: camera primary rays (CULL_BACK) -> compacted AO test rays
+    (mode 1, sample index = sample count, range 0.01..100, ACCEPT_FIRST_HIT_AND_END_SEARCH) -> payload (miss 1 / occluded 0) ->
+    running mean in the AO buffer.  Each wave's hits are checked against the oracle on the rays the device generated, the buffer
+    against the same f32 recurrence in numpy."""
+    import torch
+    sp, _ = helpers.torus_scene(96)
+    W, H = 160, 120
+    n = W * H
+    st = torch.cuda.current_stream().cuda_stream
+    d_rays, d_hits, d_ao, d_aoh = _dev_rays(n), torch.zeros((n, 32), dtype=torch.uint8, device="cuda"), _dev_rays(n), torch.zeros((n, 32), dtype=torch.uint8, device="cuda")
+    d_src = torch.zeros(n, dtype=torch.int32, device="cuda")
+    d_n = torch.zeros(1, dtype=torch.int64, device="cuda")
+    d_buf = torch.zeros(n, dtype=torch.float32, device="cuda")
+    want_buf = np.zeros(n, f32)
+    first_hit = api.RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH
+    for sample in range(3):
+        sp.p.gen_pinhole_rays_device(d_rays.data_ptr(), W, H, tmin=0.0, tmax=1e30, stream=st)  # (camera model is tested separately)
+        sp.p.trace_closest_device(d_rays.data_ptr(), n, d_hits.data_ptr(), ray_flags=helpers.CULL_BACK, grid_width=W, stream=st)
+        sp.p.gen_bounce_rays_device(d_rays.data_ptr(), d_hits.data_ptr(), n, d_ao.data_ptr(), d_src.data_ptr(), d_n.data_ptr(), mode=1,
+                                    sample_index=sample, max_sample=256, tmin=0.01, tmax=100.0, stream=st)
+        k = int(d_n.item())
+        sp.p.trace_closest_device(d_ao.data_ptr(), k, d_aoh.data_ptr(), ray_flags=first_hit, stream=st)
+        sp.p.ao_accumulate_device(d_aoh.data_ptr(), d_src.data_ptr(), d_n.data_ptr(), n, sample, d_buf.data_ptr(), stream=st)
+        torch.cuda.synchronize()
+        prim = d_hits.cpu().numpy().view(api.HIT_DTYPE).reshape(-1)
+        ao_rays = _np_rays(d_ao)[:k]
+        sec = d_aoh.cpu().numpy().view(api.HIT_DTYPE).reshape(-1)[:k]
+        assert sec.tobytes() == sp.o.trace(ao_rays, ray_flags=first_hit, n_threads=4, want_counters=False).tobytes()
+        src = d_src.cpu().numpy().view(np.uint32)[:k]
+        assert np.array_equal(src, np.nonzero(prim["instance_id"] != api.INVALID_ID)[0])
+        payload = np.ones(n, f32)
+        payload[src] = np.where(sec["instance_id"] != api.INVALID_ID, f32(0.0), f32(1.0))
+        want_buf = ((want_buf * f32(sample)).astype(f32) + payload).astype(f32) / f32(sample + 1)
+        assert np.array_equal(d_buf.cpu().numpy(), want_buf.astype(f32)), sample
+    assert 0.0 < float(want_buf[prim["instance_id"] != api.INVALID_ID].mean()) < 1.0   # the torus occludes part of its own hemisphere
+    assert np.all(want_buf[prim["instance_id"] == api.INVALID_ID] == 1.0)
+    # frozen once max_sample samples are in
+    sp.p.ao_accumulate_device(d_aoh.data_ptr(), d_src.data_ptr(), d_n.data_ptr(), n, 256, d_buf.data_ptr(), stream=st)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_buf.cpu().numpy(), want_buf.astype(f32))
+
+
 def test_device_resident_wavefront_matches_the_oracle_on_the_rays_it_generated():
     """primary (device gen) -> closest hit -> compacted cosine bounce (device gen) -> closest hit, no host round trip in between;
     both waves bit-identical to the oracle traversal of the same rays"""
