@@ -259,12 +259,13 @@ int enqueue_trace(rdn_rt_scene *s, DeviceCtx &dc, const Scratch &scratch, const 
   // the two error flags accumulate until read (the stats path clears tie_count first).
   const int tie_mode = ordered_tie_mode();
   const bool end_search = (launch.ray_flags & RDN_RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH) != 0;
-  // launches whose queue is walked by k_resolve_ties start from an empty queue and leave one (in-kernel drains re-arm it themselves)
-  const bool separate_resolve = tie_mode == 0;
+  const TlasRoot tlas = resolve_tlas(s, launch.tlas_idx);
+  // launches whose queue is walked by k_resolve_ties (the separate-kernel variant, and every TLAS that lists irregular instances)
+  // start from an empty queue and leave one (in-kernel drains re-arm it themselves)
+  const bool separate_resolve = tie_mode == 0 || (tlas.irregular_count != 0 && tlas.irregular_count != IRREGULAR_ROUTE_ALL);
   if (separate_resolve) RDN_CUDA(cudaMemsetAsync(static_cast<char *>(scratch.base) + 8, 0, 4, stream));
   if (count_ties) RDN_CUDA(cudaMemsetAsync(static_cast<char *>(scratch.base) + 28, 0, 4, stream));  // tie_total: re-walked rays of this launch
   if (count_ties) RDN_CUDA(cudaMemsetAsync(static_cast<char *>(scratch.base) + 12, 0, 4, stream));
-  const TlasRoot tlas = resolve_tlas(s, launch.tlas_idx);
   // a TLAS made mostly of irregular instances (accel.cpp "regularity") has a traversal-order dependent answer: reference order
   // ACCEPT_FIRST_HIT_AND_END_SEARCH (shadow / AO rays): the answer is the first candidate the reference's pre-order walk accepts,
   // order dependent by definition.  (Measured alternative, profiles/kbench_r1_anyhit.log: the ordered kernel stopping at its first

@@ -1058,7 +1058,11 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const
     default: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, true, false>; break;
   }
   if (P.irregular_count != 0) {  // (the experimentation variants exist for regular scenes only)
-    fn = inline_ties ? k_trace_ordered_rounds<2, 8, 1, true, true, false, 0, true, false> : k_trace_ordered_rounds<2, 8, 1, false, true, false, 0, true, false>;
+    // Rays handed over at refill can be a large part of the launch, and the in-kernel drain claims entries through one CAS
+    // cursor (fine for a handful of ties, 55 ms for 400 K entries): the queue of an irregular launch is walked by
+    // k_resolve_ties, one thread per entry, right behind this kernel.
+    inline_ties = false;
+    fn = k_trace_ordered_rounds<2, 8, 1, false, true, false, 0, true, false>;
   }
   int blocks_per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, ORDERED_BLOCK, 0);

@@ -19,7 +19,7 @@ T, Sc, Rx, mul = S.mat4_translate, S.mat4_scale, S.mat4_rotate_x, S.mat4_mul
 sysm = api.NaiveSahBVHSystem()
 osc = oracle.Scene()
 flags = 0x10
-if cfg in ("c2", "c3"):
+if cfg in ("c2", "c3", "c2i"):
     pos, idx = S.torus_mesh(708, 708, 1.0, 0.35)
     m = mul(mul(T(0, 0, -10), Sc(5, 5, 5)), Rx(-0.5))
     inst_o = inst_p = None
@@ -37,12 +37,25 @@ elif cfg == "c4":
     W, H = 1920, 1080
     rays = S.pinhole_rays(W, H, 0.0, 1000.0, aspect_correct=True)
     insts = lambda b: S.instance_grid(100, 100, b, 3.5, -200.0)
+extra = None
+if cfg == "c2i":  # config 2 plus a few cubes, one of them under a singular transform (an irregular instance: rays whose range meets
+    # its box are handed to the reference-order walk); it covers a corner of the frame
+    def extra(cube):
+        return np.concatenate([S.make_instance(mul(T(-7.0, 3.5, -12.0), Sc(2.0, 0.0, 2.0)), cube),
+                               S.make_instance(mul(T(7.0, 3.5, -12.0), Sc(1.5, 1.5, 1.5)), cube),
+                               S.make_instance(mul(T(7.0, -3.5, -12.0), Sc(1.5, 1.5, 1.5)), cube)])
 t0 = time.time()
 b = sysm.create_bottom_level_acceleration_structure([api.BottomLevelAccelerationStructureBuildSource(pos, idx.reshape(-1))])
+if extra is not None:
+    cube = sysm.create_bottom_level_acceleration_structure([api.BottomLevelAccelerationStructureBuildSource(S.CUBE_POSITION, S.CUBE_INDEX)])
+    _insts = insts
+    insts = lambda bb: np.concatenate([_insts(bb), extra(1)])
 t = sysm.create_top_level_acceleration_structure(insts(b.id))
 sysm.bind_tlas([t]); sysm.commit()
 t_build = time.time() - t0
 ob = osc.create_blas([(pos, idx.reshape(-1), 1)])
+if extra is not None:
+    osc.create_blas([(S.CUBE_POSITION, S.CUBE_INDEX, 1)])
 osc.bind_tlas([osc.create_tlas(insts(ob))]); assert osc.build() == 0
 nt = os.cpu_count() or 4
 grid = W
@@ -112,6 +125,6 @@ if check:
     got = d_hits.cpu().numpy().view(api.HIT_DTYPE).reshape(-1)[sel]
     ok = got.tobytes() == want.tobytes()
 print(f"cfg={cfg} flags={flags:#x} variant={os.environ.get('RDN_ORDERED_VARIANT','default')} skip_tie={'RDN_DEBUG_SKIP_TIE' in os.environ} rays={n} "
-      f"mean_ms={ms.mean():.4f} min_ms={ms.min():.4f} Mrays/s(mean)={n/ms.mean()/1e3:.1f} best={n/ms.min()/1e3:.1f} ties={stats['tie_rays']} "
+      f"irregular={sysm.build_stats()['irregular_instances']}/{sysm.build_stats()['reference_routed_tlas']} mean_ms={ms.mean():.4f} min_ms={ms.min():.4f} Mrays/s(mean)={n/ms.mean()/1e3:.1f} best={n/ms.min()/1e3:.1f} ties={stats['tie_rays']} "
       f"bit_identical_sample={ok} build_s={t_build:.2f} | back-to-back {n/b2b_ms/1e3:.1f} Mrays/s ({b2b_ms:.4f} ms, all {iters} results identical to the serialised one: {b2b_ok}), with events between {n/b2b_ev_ms/1e3:.1f} "
       f"pdl={os.environ.get('RDN_PDL','1')} side_stream={os.environ.get('KBENCH_SIDE_STREAM','0')}")
