@@ -198,7 +198,9 @@ def suspect_rays(arrays: dict, rays: np.ndarray, tlas_idx: int, cull_mask: int):
             bd = np.where((len2 > 0)[:, None], (d0 * (f32(1.0) / scaling)[:, None]).astype(f32), d0)
             inv_bd = (f32(1.0) / bd).astype(f32)
         leaf = np.zeros(n, bool)
+        with np.errstate(all="ignore"):
+            smin, smax = (tmin * scaling).astype(f32), (tmax * scaling).astype(f32)
         for lb in arrays["irregular_leaf_boxes"][l0:l0 + ln]:
-            leaf |= _slab(bo, inv_bd, (tmin * scaling).astype(f32), (tmax * scaling).astype(f32), lb["bmin"], lb["bmax"])
+            leaf |= _slab(bo, inv_bd, smin, smax, lb["bmin"], lb["bmax"])
         mask |= meets & leaf
     return False, mask

@@ -141,6 +141,16 @@ def _rays(rng, n):
     tmax = rng.choice([1e30, 100.0, 2.0, 0.75], n).astype(f32)
     rays = S.make_rays(o, d, 0.0, 1.0)
     rays["tmin"], rays["tmax"] = tmin, tmax
+    # a sprinkling of rays no renderer should produce, which must still come out as the reference computes them: NaN / infinite
+    # components, a zero direction, an empty or inverted range, a negative near
+    w = rng.integers(0, n, 64)
+    rays["ox"][w[0:6]] = np.nan; rays["dy"][w[6:12]] = np.nan; rays["oz"][w[12:16]] = np.inf; rays["dx"][w[16:20]] = -np.inf
+    for f in ("dx", "dy", "dz"):
+        rays[f][w[20:28]] = 0.0
+    rays["tmin"][w[28:36]] = 5.0; rays["tmax"][w[28:36]] = 1.0
+    rays["tmin"][w[36:44]] = 0.5; rays["tmax"][w[36:44]] = 0.5
+    rays["tmin"][w[44:52]] = -3.0
+    rays["tmax"][w[52:58]] = np.inf; rays["tmin"][w[58:64]] = np.nan
     return rays
 
 
