@@ -193,6 +193,8 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product has no CPU fallback)")
+    from rendiation_b200 import multi_gpu
+    numa_cpus = multi_gpu.bind_process_to_gpu_numa_node(local_rank) if world > 1 else 0  # pinned e2e buffers local to the GPU's socket
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -341,7 +343,7 @@ def run_ours(args):
 
     if rank == 0:
         # ---- roofline + cpu baseline + parity spot check (oracle = checker / baseline only)
-        cores = os.cpu_count() or 1
+        cores = len(os.sched_getaffinity(0)) or 1  # (the CPUs this rank may run on: see host_affinity)
         osc = build_oracle_scene()
         bytes_per_ray, visits, n_sample = algorithmic_bytes_per_ray(osc, rays_np, cores)
         # bounded CPU sample: the N_FRAMES full frames of this rank, twice (~14 core-seconds of traversal work)
@@ -393,7 +395,8 @@ def run_ours(args):
                                          "CUDA events, which serialises them (RDN_PDL=0 gives the same)",
                        "value_serialized": value_serial, "ms_per_step_serialized": ms_per_step_serial,
                        "parallelism": f"rays sharded by frame x{world}, BVH replicated ({blob_bytes / 1e6:.0f} MB blob, "
-                                      f"NCCL broadcast {t_repl_ms:.2f} ms)", "build_s": round(t_build, 3)},
+                                      f"NCCL broadcast {t_repl_ms:.2f} ms)", "build_s": round(t_build, 3),
+                       "host_affinity": (f"each rank bound to the {numa_cpus} CPUs NVML reports local to its GPU" if numa_cpus else "unchanged")},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 32 * n,
                     "steps": e2e_steps, "matches_device_path": same},
             "gpu_launches": launches_per_step * args.steps,

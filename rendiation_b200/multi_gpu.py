@@ -159,3 +159,26 @@ def gather_launch_hits(shard: TileShard, shard_hits: np.ndarray, dst: int = 0, g
     for r, part in enumerate(parts):
         TileShard(shard.width, shard.height, world, r, tile=shard.tile).scatter_hits(part, full)
     return full
+
+
+def bind_process_to_gpu_numa_node(device_index: int) -> int:
+    """One process per GPU: run this process (and, by first touch, place its pinned host buffers) on the CPUs NVML reports as
+    local to the GPU, so that host<->device copies of the ranks on the second socket do not cross the inter-socket link.
+    Returns the number of CPUs bound to, 0 when NVML / the affinity call is unavailable (nothing changed).  Call before
+    allocating pinned memory."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return 0
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
