@@ -8,20 +8,25 @@
 //   TraverseFlags               .../geometry/naive/flag.rs:6-117
 //
 // Kernels:
-//   k_trace_reference       the reference's stackless threaded pre-order walk, one ray per thread.  Identical to the
-//                           CPU query by construction (same visit order, same live-range pruning, "last accepted of
-//                           equal t wins").  Used for ACCEPT_FIRST_HIT rays and for the reference's visit counters; its
-//                           walk (reference_walk) also resolves near-ties.
-//   k_trace_ordered_rounds  persistent-thread, near-child-first walk over the 64 B two-box nodes with a per-thread
-//                           stack, float4 node/triangle fetches through the read-only path, warp-synchronous rounds and
-//                           whole-tile ray refill (ballot + one atomic per warp).  Box decisions use the reference's
-//                           arithmetic on the reference's boxes; the pruning bound is inflated by TIE_EPS and any ray
-//                           that saw a second candidate within TIE_EPS of the closest is queued (warp-aggregated append)
-//                           and re-walked in the reference's order with its range clamped around the closest distance —
-//                           so ids come out exactly as the CPU query's.  The queue is drained inside the kernel by
-//                           warps that ran out of rays (last CTA sweeps the rest); consecutive launches on a stream
-//                           overlap their tails (programmatic dependent launch, two scratch sets, epoch gate).
-//   k_resolve_ties          the separate tie kernel of the first version, kept for A/B runs (RDN_ORDERED_VARIANT=9).
+//   k_trace_reference       the reference's stackless threaded pre-order walk, one ray per thread (a warp = an 8x4 pixel tile on
+//                           grid launches).  Identical to the CPU query by construction (same visit order, same live-range
+//                           pruning, "last accepted of equal t wins").  Used for ACCEPT_FIRST_HIT rays, for TLASes the
+//                           flattener routes as irregular, and for the reference's visit counters; its walk
+//                           (reference_walk) also serves every re-walk below.
+//   k_trace_ordered_rounds  persistent-thread, near-child-first walk over the 64 B two-box nodes with a per-thread stack,
+//                           256-bit node / triangle fetches through the read-only path, warp-synchronous rounds and whole-tile
+//                           ray refill (ballot + one atomic per warp).  Box decisions use the reference's arithmetic on the
+//                           reference's boxes; the pruning bound is inflated by TIE_EPS and any ray that saw a second
+//                           candidate within TIE_EPS of the closest is queued (warp-aggregated append) and re-walked in the
+//                           reference's order with its range clamped around the closest distance — so ids come out exactly
+//                           as the CPU query's.  Rays that can reach an irregular instance (accel.cpp "regularity") are
+//                           queued at refill instead of being traversed and re-walked over their whole range.  The queue is
+//                           drained inside the kernel by warps that ran out of rays (last CTA sweeps the rest); consecutive
+//                           launches on a stream overlap their tails (programmatic dependent launch, two scratch sets,
+//                           epoch gate).  Template switches select measured-and-rejected experiments kept for A/B runs
+//                           (RDN_ORDERED_VARIANT, see launch_trace_ordered and DESIGN.md §5).
+//   k_resolve_ties          the queue walked by a separate kernel, one thread per entry: launches of a TLAS that lists
+//                           irregular instances (their queue can be long), and RDN_ORDERED_VARIANT=9.
 #include <cuda_runtime.h>
 
 #include <cstdlib>
