@@ -531,7 +531,16 @@ std::vector<uint8_t> FlatScene::serialize() const {
   h.magic = BLOB_MAGIC;
   h.version = BLOB_VERSION;
   h.header_bytes = sizeof(BlobHeader);
-  std::vector<uint8_t> blob(sizeof(BlobHeader), 0);
+  auto padded = [](uint64_t count, uint64_t elem) { return ((count ? count : 1) * elem + BLOB_ALIGN - 1) / BLOB_ALIGN * BLOB_ALIGN + BLOB_ALIGN; };
+  std::vector<uint8_t> blob;
+  blob.reserve(sizeof(BlobHeader) + BLOB_ALIGN + padded(tlas_binding.size(), 4) + padded(tlas_root.size(), sizeof(TlasRoot)) +
+               padded(tlas_bvh_forest.size(), sizeof(DeviceBVHNode)) + padded(tlas_bounding.size(), sizeof(TlasBounding)) +
+               padded(instances.size(), sizeof(InstanceRecord)) + padded(blas_meta.size(), sizeof(BlasMeta)) +
+               padded(geometry_meta.size(), sizeof(GeometryMeta)) + padded(tri_bvh_forest.size(), sizeof(DeviceBVHNode)) +
+               padded(triangles.size(), sizeof(TriRecord)) + padded(slot_info.size(), sizeof(SlotInfo)) +
+               padded(wide_nodes.size(), sizeof(WideNode)) + padded(prim_to_slot.size(), 4) + padded(irregular_instances.size(), 4) +
+               padded(irregular_leaf_boxes.size(), sizeof(LeafBox)));  // one allocation: every place() below only appends
+  blob.resize(sizeof(BlobHeader), 0);
   place(blob, h, ARR_TLAS_BINDING, tlas_binding);
   place(blob, h, ARR_TLAS_ROOT, tlas_root);
   place(blob, h, ARR_TLAS_BVH_FOREST, tlas_bvh_forest);

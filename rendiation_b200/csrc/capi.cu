@@ -190,7 +190,7 @@ int commit_locked(rdn_rt_scene *s) {
   const int rc = s->source.build(s->tlas_binding, flat, err);
   if (rc != RDN_OK) return fail(rc, err);
   const auto t_upload = std::chrono::steady_clock::now();
-  const std::vector<uint8_t> blob = flat.serialize();
+  std::vector<uint8_t> blob = flat.serialize();
   BlobHeader h;
   std::memcpy(&h, blob.data(), sizeof(h));
   for (size_t i = 0; i < s->devices.size(); ++i) {
@@ -210,7 +210,7 @@ int commit_locked(rdn_rt_scene *s) {
   s->h_tlas_binding = flat.tlas_binding;
   s->h_tlas_root = flat.tlas_root;
   s->flat = std::move(flat);
-  if (s->devices.empty()) s->host_blob = blob;
+  if (s->devices.empty()) s->host_blob = std::move(blob);
   s->dirty = false;
   return RDN_OK;
 }
