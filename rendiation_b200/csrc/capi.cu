@@ -465,7 +465,11 @@ int rdn_rt_trace_closest_device(rdn_rt_scene *s, int device_index, const rdn_lau
   if (rc == RDN_OK) rc = ensure_scratch(dc.ext_scratch[1], chunk);
   if (rc != RDN_OK) return rc;
 
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  struct EventPair {  // destroyed on every return path
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+  } events;
+  cudaEvent_t &e0 = events.a, &e1 = events.b;
   if (stats) { RDN_CUDA(cudaEventCreate(&e0)); RDN_CUDA(cudaEventCreate(&e1)); }
   uint64_t ties = 0, fallbacks = 0;
   float ms_total = 0.f;
@@ -512,7 +516,6 @@ int rdn_rt_trace_closest_device(rdn_rt_scene *s, int device_index, const rdn_lau
   }
   if (stats) {
     stats->rays = n; stats->tie_rays = ties; stats->kernel_ms = ms_total; stats->whole_range_rewalks = fallbacks;
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
   }
   return RDN_OK;
 }

@@ -134,3 +134,42 @@ def test_rays_kept_by_the_ordered_kernel_have_order_free_results(seed, profile):
             kept_total += int(kept.sum())
     if profile != "hostile":
         assert kept_total > 0
+
+
+def _slivers(rng, n, lo, hi, length=0.4):
+    """triangles whose edges at v0 enclose an angle with sin^2 log-uniform in [lo, hi]"""
+    c = rng.uniform(-1, 1, (n, 3))
+    e1 = rng.normal(size=(n, 3)); e1 /= np.linalg.norm(e1, axis=1, keepdims=True)
+    perp = np.cross(e1, rng.normal(size=(n, 3))); perp /= np.linalg.norm(perp, axis=1, keepdims=True)
+    theta = np.arcsin(np.sqrt(np.exp(rng.uniform(np.log(lo), np.log(hi), n))))
+    e2 = (np.cos(theta)[:, None] * e1 + np.sin(theta)[:, None] * perp) * rng.uniform(0.5, 1.0, (n, 1))
+    return np.stack([c, c + length * e1, c + length * e2], 1).astype(f32).reshape(-1, 3)
+
+
+@pytest.mark.parametrize("band", [(2e-5, 1e-4), (1e-4, 1e-2), (1e-12, 1e-9)])
+def test_needle_threshold_has_margin(band):
+    """Where does the reference's answer start to depend on its visiting order?  Thousands of slivers per band, 150 K rays through them:
+    none above the flattener's threshold (sin^2 = 1e-5; in a sweep the first order-dependent rays appear below 1e-6), plenty far
+    below it — and there every triangle is flagged, so every ray is handed over."""
+    rng = np.random.default_rng(11)
+    pos = _slivers(rng, 12000, *band)
+    sp = helpers.ScenePair(devices=(), product=True)
+    b = sp.blas([(pos, None, 1)])
+    sp.bind([sp.tlas(S.make_instance(S.mat4_identity(), b))])
+    sp.build()
+    n = 150000
+    o = rng.uniform(-1.2, 1.2, (n, 3)).astype(f32)
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = S.make_rays(o, d.astype(f32), 0.0, 100.0)
+    ref = sp.o.trace(rays, n_threads=8, want_counters=False)
+    free = sp.o.trace_unpruned(rays, n_threads=8)
+    differs = (ref["t"].view(np.uint32) != free["t"].view(np.uint32)) | ((ref["instance_id"] == 0xFFFFFFFF) != (free["instance_id"] == 0xFFFFFFFF))
+    route_all, suspect = helpers.suspect_rays(sp.p.arrays(), rays, 0, 0xFFFFFFFF)
+    st = sp.p.build_stats()
+    assert int((ref["instance_id"] != 0xFFFFFFFF).sum()) > 5000
+    if band[0] >= 2e-5:
+        assert st["irregular_triangles"] == 0 and not route_all and not suspect.any()
+        assert not differs.any(), int(differs.sum())
+    else:
+        assert st["irregular_triangles"] == 12000 and route_all
+        assert int(differs.sum()) > 100
