@@ -43,7 +43,33 @@ def main():
     hits_a = bvh.query_nearest(wpos, idx, rays, oracle.FACE_DOUBLE)
     np.savez_compressed(os.path.join(HERE, "c1_sphere_96.npz"), rays=rays, hits_b=hits_b, hits_a=hits_a,
                         ctr=np.array([ctr[c] for c in ("bvh_visit", "bvh_hit", "tri_visit", "tri_hit", "inst_visit", "ref_abort")], np.uint64))
+    # 3. the file the reference's own test writes: test_cpu_triangle (geometry/naive/test.rs:234-299) traces a 256x256 pinhole
+    # grid over tlas 0 of the fixture with CULL_BACK_FACING and dumps `primitive_idx % 12 + 1` (0 = miss) as trace_cpu.pbm, and
+    # prints the four visit counters.  A maintainer with the Rust toolchain can run that test and byte-compare the two files:
+    # the one place where this oracle can be pinned against the real reference.
+    sp, handles = helpers.reference_fixture(product=False)
+    text, counters = trace_cpu_pbm(sp.o)
+    open(os.path.join(HERE, "trace_cpu.pbm"), "w").write(text)
+    import json
+    json.dump(counters, open(os.path.join(HERE, "trace_cpu_counters.json"), "w"), indent=1)
     print("golden written")
+
+
+def trace_cpu_pbm(scene, trace=None):
+    """test_cpu_triangle's output: (the text of trace_cpu.pbm, its counter printout).  `trace(rays, ray_flags, tlas_idx)` defaults
+    to the oracle scene's own traversal; the GPU tests pass the product's."""
+    W = H = 256
+    PRIMITIVE_IDX_MAX = 12
+    rays = S.pinhole_rays(W, H, 0.0, 100.0)
+    if trace is None:
+        hits, ctr = scene.trace(rays, ray_flags=0x10, tlas_idx=0)
+    else:
+        hits, ctr = trace(rays, 0x10, 0)
+    ids = np.where(hits["instance_id"] != 0xFFFFFFFF, hits["primitive_id"] % PRIMITIVE_IDX_MAX + 1, 0).reshape(H, W)
+    text = f"P2\n{W} {H}\n{PRIMITIVE_IDX_MAX}\n" + "".join(" ".join(str(int(v)) for v in row) + "\n" for row in ids)
+    counters = {"tri visit count": int(ctr["tri_visit"]), "tri hit count": int(ctr["tri_hit"]), "bvh visit count": int(ctr["bvh_visit"]),
+                "bvh hit count": int(ctr["bvh_hit"])}
+    return text, counters
 
 
 if __name__ == "__main__":

@@ -62,6 +62,27 @@ def test_reference_fixture_goldens(k):
         assert [ctr[c] for c in CTR] == g[f"ctr_tlas{k}_{name}"].tolist(), (name, ctr)
 
 
+def test_reference_test_output_file_from_the_gpu():
+    """the file and the counter printout of the reference's test_cpu_triangle (tests/golden/trace_cpu.pbm, made by the oracle; a
+    maintainer can byte-compare it with the Rust test's) come out of the CUDA path unchanged: ids from the ordered kernel, the four
+    visit counters from the reference-order kernel"""
+    import json
+    import sys
+    sys.path.insert(0, GOLD)
+    import make_golden
+    sp, _ = helpers.reference_fixture()
+
+    def trace(rays, flags, tlas_idx):
+        hits = sp.p.trace_closest_batch(rays, ray_flags=flags, tlas_idx=tlas_idx, grid_width=256)
+        counted, ctr = sp.p.trace_counted(rays, ray_flags=flags, tlas_idx=tlas_idx)
+        assert counted.tobytes() == hits.tobytes()
+        return hits, ctr
+
+    text, counters = make_golden.trace_cpu_pbm(None, trace)
+    assert text == open(os.path.join(GOLD, "trace_cpu.pbm")).read()
+    assert counters == json.load(open(os.path.join(GOLD, "trace_cpu_counters.json")))
+
+
 def test_c1_golden_path_b_and_a():
     g = np.load(os.path.join(GOLD, "c1_sphere_96.npz"))
     sp, (pos, idx, m) = helpers.sphere_c1()

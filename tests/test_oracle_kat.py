@@ -4,6 +4,7 @@ Traversal results are "parity unpinned" upstream (no assertions in the reference
 reference does pin is replayed here.
 """
 import os
+import sys
 
 import numpy as np
 
@@ -238,3 +239,18 @@ def test_list_query_contains_the_nearest_and_every_brute_force_hit():
     # a torus is closed: a ray from outside crosses an even number of faces (2 or 4) unless it grazes an edge
     n_per_ray = np.diff(off.astype(np.int64))
     assert set(np.unique(n_per_ray)) <= {0, 1, 2, 3, 4, 5, 6} and np.count_nonzero(n_per_ray % 2) < 0.05 * rays.shape[0]
+
+
+def test_oracle_reproduces_the_reference_tests_own_output_file():
+    """tests/golden/trace_cpu.pbm is what the reference's test_cpu_triangle (geometry/naive/test.rs:234-299) writes, as produced by
+    this oracle: a maintainer can run that Rust test and byte-compare.  Here: the oracle still produces the committed file."""
+    import json
+    sys.path.insert(0, GOLD)
+    import make_golden
+    sp, _ = helpers.reference_fixture(product=False)
+    text, counters = make_golden.trace_cpu_pbm(sp.o)
+    assert text == open(os.path.join(GOLD, "trace_cpu.pbm")).read()
+    assert counters == json.load(open(os.path.join(GOLD, "trace_cpu_counters.json")))
+    rows = text.splitlines()
+    assert rows[:3] == ["P2", "256 256", "12"] and len(rows) == 259 and all(len(r.split()) == 256 for r in rows[3:])
+    assert 0 < sum(v != "0" for r in rows[3:] for v in r.split()) < 256 * 256
