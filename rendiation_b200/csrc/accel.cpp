@@ -4,6 +4,8 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/rdn_rt.h"
@@ -289,6 +291,9 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
   using Clock = std::chrono::steady_clock;
   const auto t_begin = Clock::now();
   double bvh_ms = 0.0;
+  const bool timing = getenv("RDN_BUILD_TIMING") != nullptr;
+  double ms_boxes = 0, ms_records = 0, ms_wide = 0, ms_threaded = 0, ms_leaves = 0;
+  auto since = [](Clock::time_point t0) { return std::chrono::duration<double, std::milli>(Clock::now() - t0).count(); };
   auto timed_build = [&](const Box3 *boxes, uint64_t n, BVHBuildStrategy &strategy, const TreeBuildOption &option) {
     const auto t0 = Clock::now();
     FlattenBVH bvh = FlattenBVH::build(boxes, n, strategy, option);
@@ -329,6 +334,7 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
         const uint64_t n_idx = src.has_indices ? src.indices.size() : src.positions.size();
         const uint64_t n_tri = n_idx / 3;  // as_chunks::<3>().0 drops the remainder
         auto vertex_of = [&](uint64_t tri, int k) -> uint64_t { return src.has_indices ? src.indices[3 * tri + k] : 3 * tri + k; };
+        auto t_phase = Clock::now();
         std::vector<Box3> boxes(n_tri);
         std::atomic<bool> index_out_of_bounds{false};
         parallel_for(n_tri, PARALLEL_BUILD_MIN, [&](uint64_t t_begin_, uint64_t t_end_) {
@@ -343,6 +349,7 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
           }
         });
         if (index_out_of_bounds) { err = "triangle index out of bounds (the reference panics here)"; return RDN_ERR_BUILD; }
+        ms_boxes += since(t_phase);
         SAH sah(4);
         FlattenBVH bvh = timed_build(boxes.data(), n_tri, sah, blas_option);
         if (bvh.stats.bucket_out_of_range) { err = "SAH bucket index out of range (the reference panics here)"; return RDN_ERR_BUILD; }
@@ -350,7 +357,10 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
         out.stats.balance_fallbacks_gt10 += bvh.stats.balance_fallbacks_gt10;
         expand(root_box, bvh.nodes[0].bounding);
         if (n_tri) expand(true_box, bvh.nodes[0].bounding);
+        t_phase = Clock::now();
         const auto next = compute_bvh_next(bvh.nodes);
+        ms_threaded += since(t_phase);
+        t_phase = Clock::now();
 
         // slots of this geometry start at primitive_start (indices_redirect and indices grow in lock step)
         const uint64_t slot_base = out.triangles.size();
@@ -370,6 +380,8 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
           }
         });
         for (uint64_t k = 0; k < n_tri; ++k) out.stats.irregular_triangles += slot_irregular[k];
+        ms_records += since(t_phase);
+        t_phase = Clock::now();
         n_indices_total += n_tri * 3;
         // the boxes of the leaves that hold an irregular triangle: the reference can test such a triangle only after this box test
         for (const FlattenBVHNode &node : bvh.nodes) {
@@ -384,6 +396,8 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
           out.irregular_leaf_boxes.push_back(lb);
         }
 
+        ms_leaves += since(t_phase);
+        t_phase = Clock::now();
         const uint32_t bvh_start = static_cast<uint32_t>(out.tri_bvh_forest.size());
         GeometryMeta gm;
         std::memset(&gm, 0, sizeof(gm));
@@ -397,11 +411,14 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
           hot = HotBlock{gm.wide_root, static_cast<uint32_t>(block < HOT_TOP_NODES ? block : HOT_TOP_NODES), n_tri};
         }
         out.geometry_meta.push_back(gm);
+        ms_wide += since(t_phase);
+        t_phase = Clock::now();
         out.tri_bvh_forest.resize(bvh_start + bvh.nodes.size());
         parallel_for(bvh.nodes.size(), PARALLEL_BUILD_MIN, [&](uint64_t i_begin, uint64_t i_end) {
           for (uint64_t i = i_begin; i < i_end; ++i)
             out.tri_bvh_forest[bvh_start + i] = to_device_node(bvh.nodes[i], next[i].first, next[i].second, bvh_start, primitive_start);
         });
+        ms_threaded += since(t_phase);
       }
       blas_box.push_back(OptBox{true, root_box});
     }
@@ -507,6 +524,9 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
     err = "scene exceeds the 32-bit child-reference encoding (2^27 slots / 0x7F000000 nodes / 2^24 geometries)";
     return RDN_ERR_CAPACITY;
   }
+  if (timing)
+    fprintf(stderr, "[rdn flatten] BLAS geometries: boxes %.1f ms, triangle records %.1f ms, irregular-leaf scan %.1f ms, wide nodes %.1f ms, "
+                    "threaded nodes %.1f ms\n", ms_boxes, ms_records, ms_leaves, ms_wide, ms_threaded);
   out.stats.bvh_build_ms = bvh_ms;
   out.stats.flatten_ms = std::chrono::duration<double, std::milli>(Clock::now() - t_begin).count() - bvh_ms;
   return RDN_OK;
