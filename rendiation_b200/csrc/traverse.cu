@@ -535,7 +535,10 @@ __device__ __forceinline__ uint32_t compact_even_bits4(uint32_t x) {  // bits 0,
 // HOT: the top levels of the TLAS tree and of the largest geometry tree (breadth-first blocks of HOT_TOP_NODES wide nodes, 8 KB
 // each) are copied into shared memory with cp.async.bulk (TMA, completion on an mbarrier) when the CTA starts, and node fetches
 // that fall into either block read shared memory instead of L1.
-template <int K, int MINB, int THRESH, bool DRAIN_TIES, bool IRREGULAR, bool UNITS, int PF, bool LD256, bool HOT>  // DRAIN_TIES: near-tie queue drained inside the kernel (else by k_resolve_ties)
+// SPEC: speculative traversal with one postponed leaf per lane (Aila & Laine): a lane that reaches a triangle leaf parks it and
+// keeps descending (against the bound it had), so that more lanes hold a leaf when the warp runs the triangle code — profiled at
+// ~5 of 32 lanes for a quarter of all issued instructions.  The parked leaf is tested before the lane leaves the instance.
+template <int K, int MINB, int THRESH, bool DRAIN_TIES, bool IRREGULAR, bool UNITS, int PF, bool LD256, bool HOT, bool SPEC>  // DRAIN_TIES: near-tie queue drained inside the kernel (else by k_resolve_ties)
 __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(const __grid_constant__ OrderedParams P) {
   const SceneDev &S = P.S;
   const uint32_t lane = threadIdx.x & 31u;
@@ -602,6 +605,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
   uint32_t best_slot = RDN_INVALID_ID, best_inst = RDN_INVALID_ID, best_back = 0;
   uint32_t cur = REF_DONE, cur_inst = 0, cur_flags = 0, cull_bits = 0, geom_end = 0;
   bool in_object = false;
+  uint32_t pending = REF_DONE;  // SPEC: the postponed triangle leaf (REF_DONE = none)
   bool warp_exhausted = false;
   const uint32_t sm_home = UNITS ? smid() % P.n_ranges : 0u;
   uint32_t sm_probe = 0;  // ranges, counted from the home range, already found dry
@@ -616,7 +620,10 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
   if (lane == 0) atomicMin(P.scratch.counters + 6, dbg_t_in);  // first warp in
 #endif
 
-#define RDN_PUSH(v) do { if (sp < STACK_MAX) stack[sp++] = (v); else atomicAdd(P.scratch.stack_overflow, 1u); } while (0)
+  // a full stack drops the entry and raises a sticky flag, reported once when the ray ends: no atomic (and so no branch around one)
+  // inside the traversal loop
+  bool stack_overflowed = false;
+#define RDN_PUSH(v) do { if (sp < STACK_MAX) stack[sp++] = (v); else stack_overflowed = true; } while (0)
 #define RDN_POP() (sp > 0 ? stack[--sp] : REF_DONE)
 
   for (;;) {
@@ -753,7 +760,9 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
       for (;;) {
         // ---------------- phase 1: up to K inner nodes (both child boxes in one 64 B fetch)
 #pragma unroll 1
-        for (int k = 0; k < K && cur < REF_SPECIAL; ++k) {
+        for (int k = 0; k < K; ++k) {
+          if (SPEC && pending == REF_DONE && in_object && (cur & REF_LEAF_BIT)) { pending = cur; cur = RDN_POP(); }
+          if (!(cur < REF_SPECIAL)) break;
 #ifdef RDN_DEBUG_STEPS
           ++dbg_steps; ++dbg_ray_steps;
 #endif
@@ -781,29 +790,30 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
           float n0, n1;
           const bool h0 = slab_test(o, inv, near_s, far_s, xyz(q0), xyz(q1), n0);
           const bool h1 = slab_test(o, inv, near_s, far_s, xyz(q2), xyz(q3), n1);
-          if (h0 && h1) {
-            const bool first0 = n0 <= n1;
-            RDN_PUSH(first0 ? r1 : r0);
+          // near child first, the other one deferred; written as selects so that the step stays one basic block
+          const bool both = h0 && h1;
+          const bool take0 = both ? n0 <= n1 : h0;
+          if (both) {
+            RDN_PUSH(take0 ? r1 : r0);
 #ifdef RDN_DEBUG_STEPS
             ++dbg_pushes;
 #endif
-            cur = first0 ? r0 : r1;
-          } else if (h0) {
-            cur = r0;
-          } else if (h1) {
-            cur = r1;
-          } else {
-            cur = RDN_POP();
           }
+          cur = take0 ? r0 : r1;
+          if (!(h0 || h1)) cur = RDN_POP();
         }
+        if (SPEC && pending == REF_DONE && in_object && (cur & REF_LEAF_BIT)) { pending = cur; cur = RDN_POP(); }
         __syncwarp(amask);
 
         // ---------------- phase 2: one leaf / instance / bookkeeping item, all lanes that have one at the same time
-        if (cur >= REF_SPECIAL && cur != REF_DONE) {
-          if (cur & REF_LEAF_BIT) {
-            const uint32_t start = cur & REF_LEAF_START_MASK;
-            const uint32_t count = ((cur >> REF_LEAF_COUNT_SHIFT) & 15u) + 1u;
-            if (in_object) {
+        uint32_t leaf_item = REF_DONE;
+        if (SPEC) { leaf_item = pending; pending = REF_DONE; }
+        else if (in_object && (cur & REF_LEAF_BIT)) leaf_item = cur;
+        if (leaf_item != REF_DONE) {
+          {
+            const uint32_t start = leaf_item & REF_LEAF_START_MASK;
+            const uint32_t count = ((leaf_item >> REF_LEAF_COUNT_SHIFT) & 15u) + 1u;
+            {
               for (uint32_t k = 0; k < count; ++k) {
                 const uint32_t slot = start + k;
                 const float4 *tp = reinterpret_cast<const float4 *>(S.triangles + slot);
@@ -827,7 +837,15 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
                   second = fminf(second, distance);
                 }
               }
-              cur = RDN_POP();
+              if (!SPEC) cur = RDN_POP();
+            }
+          }
+        } else if (cur >= REF_SPECIAL && cur != REF_DONE) {
+          if (cur & REF_LEAF_BIT) {
+            const uint32_t start = cur & REF_LEAF_START_MASK;
+            const uint32_t count = ((cur >> REF_LEAF_COUNT_SHIFT) & 15u) + 1u;
+            if (in_object) {
+              // (SPEC only: a second leaf while one is parked; it is parked in the next round)
             } else {
               // instance leaf (world space): take the first slot, park the rest
               if (count > 1) RDN_PUSH(REF_LEAF_BIT | ((count - 2u) << REF_LEAF_COUNT_SHIFT) | (start + 1u));
@@ -881,17 +899,18 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
         }
 
         // ---------------- vote (also the re-convergence point of phase 2)
-        const int active = __popc(__ballot_sync(amask, cur != REF_DONE));
+        const int active = __popc(__ballot_sync(amask, cur != REF_DONE || (SPEC && pending != REF_DONE)));
         if (active == 0 || (active < THRESH && !warp_exhausted)) break;
       }
 
-      if (cur == REF_DONE) {
+      if (cur == REF_DONE && (!SPEC || pending == REF_DONE)) {
 #ifdef RDN_DEBUG_STEPS
         dbg_max = dbg_ray_steps > dbg_max ? dbg_ray_steps : dbg_max;
         dbg_long += dbg_ray_steps > 200 ? 1 : 0;
         ++dbg_rays;
         dbg_ray_steps = 0;
 #endif
+        if (stack_overflowed) { atomicAdd(P.scratch.stack_overflow, 1u); stack_overflowed = false; }
         rdn_hit *dst = P.hits + ri;
         if (best_slot != RDN_INVALID_ID) {
           // the ordered result is stored first; a near-tie ray is also queued (warp-aggregated append) for the exact
@@ -1052,22 +1071,23 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const
   bool inline_ties = true;
   switch (variant) {
     // (K, THRESH) = (4,1), (3,4), (4,8) were instantiated here during the sweep of profiles/kbench_r1_variant_sweep.log
-    case 30: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, false, false>; break;  // 128-bit loads / stores
-    case 40: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, true, true>; break;    // top levels staged in shared memory (TMA)
+    case 30: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, false, false, false>; break;  // 128-bit loads / stores
+    case 40: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, true, true, false>; break;    // top levels staged in shared memory (TMA)
+    case 50: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, true, false, true>; break;    // speculative traversal, one postponed leaf per lane
     // whole-unit scheduling experiments, all measured slower than the default (profiles/kbench_r1_unit_scheduling.log): lanes whose
     // ray misses the scene stay idle for the rest of the tile instead of being topped up with the next rays
-    case 10: case 11: case 12: case 13: case 14: fn = k_trace_ordered_rounds<2, 8, 1, true, false, true, 0, true, false>; break;
-    case 9: fn = k_trace_ordered_rounds<2, 8, 1, false, false, false, 0, true, false>; inline_ties = false; break;  // queue drained by k_resolve_ties
-    case 20: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 1, true, false>; break;  // children prefetched into L1
-    case 21: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 2, true, false>; break;  // ... into L2
-    default: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, true, false>; break;
+    case 10: case 11: case 12: case 13: case 14: fn = k_trace_ordered_rounds<2, 8, 1, true, false, true, 0, true, false, false>; break;
+    case 9: fn = k_trace_ordered_rounds<2, 8, 1, false, false, false, 0, true, false, false>; inline_ties = false; break;  // queue drained by k_resolve_ties
+    case 20: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 1, true, false, false>; break;  // children prefetched into L1
+    case 21: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 2, true, false, false>; break;  // ... into L2
+    default: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, true, false, false>; break;
   }
   if (P.irregular_count != 0) {  // (the experimentation variants exist for regular scenes only)
     // Rays handed over at refill can be a large part of the launch, and the in-kernel drain claims entries through one CAS
     // cursor (fine for a handful of ties, 55 ms for 400 K entries): the queue of an irregular launch is walked by
     // k_resolve_ties, one thread per entry, right behind this kernel.
     inline_ties = false;
-    fn = k_trace_ordered_rounds<2, 8, 1, false, true, false, 0, true, false>;
+    fn = k_trace_ordered_rounds<2, 8, 1, false, true, false, 0, true, false, false>;
   }
   int blocks_per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, ORDERED_BLOCK, 0);
