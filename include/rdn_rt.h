@@ -278,6 +278,12 @@ typedef struct rdn_mesh_hit { float px, py, pz, distance; uint32_t primitive_ind
 
 int rdn_bvh_build(const float *boxes_min_max6, uint64_t n, int strategy, uint32_t sah_buckets,
                   const rdn_tree_build_option *option, rdn_flat_bvh **out);
+/* the same tree, built on CUDA device `device` (SAH with up to 4 buckets: level-synchronous passes, see csrc/build_device.cu);
+ * what the device build does not cover (more buckets, a degenerate range of more than 64 primitives) is built by the host
+ * builder instead — rdn_bvh_built_on_device tells which it was */
+int rdn_bvh_build_device(const float *boxes_min_max6, uint64_t n, uint32_t sah_buckets, const rdn_tree_build_option *option,
+                         int device, rdn_flat_bvh **out);
+int rdn_bvh_built_on_device(const rdn_flat_bvh *bvh);
 void rdn_bvh_destroy(rdn_flat_bvh *bvh);
 int rdn_bvh_nodes(const rdn_flat_bvh *bvh, const rdn_flat_bvh_node **out_nodes, uint64_t *out_n);
 int rdn_bvh_sorted_primitive_index(const rdn_flat_bvh *bvh, const uint64_t **out_index, uint64_t *out_n);

@@ -151,7 +151,7 @@ EXPORTED_SYMBOLS = [
     "rdn_rt_trace_closest_device", "rdn_rt_trace_counted", "rdn_rt_kernel_timing_begin", "rdn_rt_kernel_timing_end",
     "rdn_rt_gen_pinhole_rays_device", "rdn_rt_gen_pinhole_rays_batch_device", "rdn_rt_gen_camera_rays_device", "rdn_rt_gen_bounce_rays_device", "rdn_rt_ao_accumulate_device", "rdn_rt_compact_u32", "rdn_rt_compact_u32_device",
     "rdn_rt_scene_blob", "rdn_rt_scene_adopt_blob", "rdn_rt_scene_array", "rdn_rt_scene_build_stats", "rdn_rt_measure_l2_read_gbs", "rdn_pick_mesh_create", "rdn_pick_mesh_destroy",
-    "rdn_pick_mesh_primitive_count", "rdn_pick_mesh_nearest", "rdn_pick_mesh_all", "rdn_bvh_build", "rdn_bvh_destroy", "rdn_bvh_nodes",
+    "rdn_pick_mesh_primitive_count", "rdn_pick_mesh_nearest", "rdn_pick_mesh_all", "rdn_bvh_build", "rdn_bvh_build_device", "rdn_bvh_built_on_device", "rdn_bvh_destroy", "rdn_bvh_nodes",
     "rdn_bvh_sorted_primitive_index", "rdn_bvh_build_for_mesh", "rdn_bvh_query_nearest", "rdn_bvh_upload", "rdn_bvh_query_nearest_device", "rdn_bvh_query_list", "rdn_rt_last_error", "rdn_rt_version",
 ]
 
@@ -206,6 +206,8 @@ def lib() -> C.CDLL:
     L.rdn_pick_mesh_nearest.argtypes = [vp, P(_PickConfig), vp, u64, vp]
     L.rdn_pick_mesh_all.argtypes = [vp, P(_PickConfig), vp, vp, u64, P(u64)]
     L.rdn_bvh_build.argtypes = [vp, u64, i32, u32, P(_Option), P(vp)]
+    L.rdn_bvh_build_device.argtypes = [vp, u64, u32, P(_Option), i32, P(vp)]
+    L.rdn_bvh_built_on_device.argtypes = [vp]
     L.rdn_bvh_build_for_mesh.argtypes = [P(_MeshView), i32, u32, P(_Option), P(vp)]
     L.rdn_bvh_destroy.argtypes = [vp]
     L.rdn_bvh_destroy.restype = None
@@ -528,7 +530,9 @@ class PickMesh:
 class FlattenBVH:
     """content/space/src/bvh/mod.rs:26-79: ``FlattenBVH::new(boxes, &mut strategy, &option)``; boxes = [n,6] (min,max)."""
 
-    def __init__(self, boxes=None, strategy=None, option: TreeBuildOption | None = None, _handle=None):
+    def __init__(self, boxes=None, strategy=None, option: TreeBuildOption | None = None, _handle=None, device: int | None = None):
+        """``device``: build on that CUDA device (SAH only; same tree — what the device build does not cover falls to the host builder,
+        see ``built_on_device``)"""
         self._L = lib()
         if _handle is not None:
             self._h = _handle
@@ -538,12 +542,18 @@ class FlattenBVH:
         option = option or TreeBuildOption()
         opt = _Option(option.max_tree_depth, option.bin_size)
         h = C.c_void_p()
-        if isinstance(strategy, SAH):
+        if device is not None and isinstance(strategy, SAH):
+            rc = self._L.rdn_bvh_build_device(_p(boxes), boxes.shape[0], strategy.pre_partition_check_count, C.byref(opt), device, C.byref(h))
+        elif isinstance(strategy, SAH):
             rc = self._L.rdn_bvh_build(_p(boxes), boxes.shape[0], 0, strategy.pre_partition_check_count, C.byref(opt), C.byref(h))
         else:
             rc = self._L.rdn_bvh_build(_p(boxes), boxes.shape[0], 1, 0, C.byref(opt), C.byref(h))
         _check(rc)
         self._h = h
+
+    @property
+    def built_on_device(self) -> bool:
+        return bool(self._L.rdn_bvh_built_on_device(self._h))
 
     @property
     def nodes(self) -> np.ndarray:

@@ -1081,6 +1081,7 @@ struct rdn_flat_bvh {
   uint64_t depth = 0;
   // device-resident copy made by rdn_bvh_upload: nodes + triangles pre-gathered in sorted_primitive_index order
   int device = -1;
+  bool built_on_device = false;
   PathANode *d_nodes = nullptr;
   PathATri *d_tris = nullptr;
   std::mutex lock;
@@ -1126,6 +1127,31 @@ int rdn_bvh_build(const float *boxes6, uint64_t n, int strategy, uint32_t sah_bu
   static_assert(sizeof(Box3) == 24, "Box3 layout");
   return build_bvh_common(reinterpret_cast<const Box3 *>(boxes6), n, strategy, sah_buckets, option, out);
 }
+
+int rdn_bvh_build_device(const float *boxes6, uint64_t n, uint32_t sah_buckets, const rdn_tree_build_option *option, int device,
+                         rdn_flat_bvh **out) {
+  if (!out || (n && !boxes6)) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_bvh_build_device: null argument");
+  int available = 0;
+  RDN_CUDA(cudaGetDeviceCount(&available));
+  if (device < 0 || device >= available) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_bvh_build_device: no such CUDA device");
+  TreeBuildOption opt;
+  if (option) { opt.max_tree_depth = option->max_tree_depth; opt.bin_size = option->bin_size; }
+  auto *r = new rdn_flat_bvh();
+  std::string err;
+  const int rc = build_bvh_sah_device(reinterpret_cast<const Box3 *>(boxes6), n, sah_buckets ? sah_buckets : 4, opt, device, r->bvh, err);
+  if (rc == 0) {
+    r->built_on_device = true;
+    r->depth = tree_depth(r->bvh.nodes);
+    *out = r;
+    return RDN_OK;
+  }
+  delete r;
+  if (rc == -1) return fail(RDN_ERR_CUDA, "rdn_bvh_build_device: " + err);
+  if (rc == -2) return fail(RDN_ERR_BUILD, "SAH bucket index out of range (the reference panics here)");
+  return build_bvh_common(reinterpret_cast<const Box3 *>(boxes6), n, RDN_BVH_SAH, sah_buckets, option, out);  // not covered on the device
+}
+
+int rdn_bvh_built_on_device(const rdn_flat_bvh *b) { return b && b->built_on_device ? 1 : 0; }
 
 int rdn_bvh_build_for_mesh(const rdn_mesh_view *mesh, int strategy, uint32_t sah_buckets, const rdn_tree_build_option *option, rdn_flat_bvh **out) {
   if (!out || !mesh || !mesh->positions || !mesh->indices) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_bvh_build_for_mesh: null argument");

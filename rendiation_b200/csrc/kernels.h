@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <string>
 
 #include "../../include/rdn_rt.h"
 #include "layout.h"
@@ -101,6 +102,14 @@ void launch_pick_all_mark(const PickMeshDev &mesh, const rdn_ray *d_ray, float t
                           rdn_mesh_hit *d_records, int sm_count, cudaStream_t stream);
 void launch_pick_all_gather(const uint32_t *d_index, const uint64_t *d_n_kept, uint64_t capacity, const rdn_mesh_hit *d_records, rdn_mesh_hit *d_out,
                             int sm_count, cudaStream_t stream);
+
+// binned-SAH build on the device (build_device.cu): 0 = built (node for node the host builder's tree),
+// 1 = not supported there (buckets > 4, a long degenerate range, ...: use the host builder), < 0 = error
+struct FlattenBVH;
+struct TreeBuildOption;
+struct Box3;
+int build_bvh_sah_device(const Box3 *boxes, uint64_t n, uint32_t n_buckets, const TreeBuildOption &option, int device, FlattenBVH &out,
+                         std::string &err);
 
 // measurement hook (probe.cu): read bandwidth of an L2-resident buffer of `bytes` on the current device, GB/s
 int measure_l2_read_gbs(uint64_t bytes, int passes, int sm_count, double *out_gbs);

@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
 
   __shared__ __align__(128) float4 s_hot[HOT ? 2 * HOT_TOP_NODES * 4 : 4];
   __shared__ __align__(8) unsigned long long s_hot_bar;
-  if (HOT) {
+  if constexpr (HOT) {
     const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&s_hot_bar));
     if (threadIdx.x == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
