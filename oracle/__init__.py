@@ -276,6 +276,20 @@ class Scene:
             raise RuntimeError("oracle trace failed (scene not built?)")
         return hits
 
+    def trace_ordered_model(self, rays, ray_flags=0, cull_mask=0xFFFFFFFF, tlas_idx=0):
+        """NOT the reference: scalar model of the CUDA kernel's ordered traversal + tie re-walk (oracle_scene.c); returns
+        (hits, rays resolved by the clamped re-walk, rays resolved by the whole-range walk)"""
+        rays = _c(rays, RAY_DTYPE)
+        hits = np.zeros(rays.shape[0], HIT_DTYPE)
+        launch = Launch(ray_flags, cull_mask, tlas_idx, 0)
+        stats = np.zeros(2, np.uint64)
+        L = lib()
+        L.orc_scene_trace_ordered_model.restype = C.c_int
+        L.orc_scene_trace_ordered_model.argtypes = [C.c_void_p, C.POINTER(Launch), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        if L.orc_scene_trace_ordered_model(self._h, C.byref(launch), _p(rays), rays.shape[0], _p(hits), _p(stats)) != 0:
+            raise RuntimeError("oracle trace failed (scene not built?)")
+        return hits, int(stats[0]), int(stats[1])
+
     def trace(self, rays, ray_flags=0, cull_mask=0xFFFFFFFF, tlas_idx=0, n_threads=1, want_counters=True):
         rays = _c(rays, RAY_DTYPE)
         hits = np.zeros(rays.shape[0], HIT_DTYPE)

@@ -135,6 +135,10 @@ int orc_scene_trace(const orc_scene *s, const orc_launch *launch, const orc_ray 
 int orc_scene_trace_unpruned(const orc_scene *s, const orc_launch *launch, const orc_ray *rays, uint64_t n_rays,
                              orc_hit *out_hits, int n_threads);
 
+/* test tool, NOT the reference: scalar model of the ordered traversal + tie re-walk of csrc/traverse.cu (algorithm-level fuzzing) */
+int orc_scene_trace_ordered_model(const orc_scene *s, const orc_launch *launch, const orc_ray *rays, uint64_t n_rays, orc_hit *out_hits,
+                                  uint64_t *out_stats);
+
 /* every (instance, triangle) pair of the bound TLAS whose triangle test passes with the ray's ORIGINAL range: no BVH, no pruning */
 typedef struct { float distance, t_object, u, v, sign, scaling; uint32_t instance_id, geometry_id, primitive_id, slot, in_range, pad; } orc_candidate;
 uint64_t orc_scene_candidates(const orc_scene *s, const orc_launch *launch, const orc_ray *ray, orc_candidate *out, uint64_t cap);

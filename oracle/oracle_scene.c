@@ -356,14 +356,23 @@ static inline uint32_t bvh_iter_next(const orc_dev_node *bvh, uint32_t *curr_idx
 /* unpruned != 0: NOT the reference — the order-free model used to test the regularity classification (orc_scene_trace_unpruned):
  * every box / triangle range test uses the ray's ORIGINAL range and the closest accepted candidate is kept, i.e. the result every
  * traversal that prunes by its own closest hit converges to when hits lie inside their boxes. */
+static void traverse_clamped(const orc_scene *s, const orc_launch *L, const orc_ray *ray, orc_hit *out, orc_counters *c, int unpruned,
+                             float near_walk, float far_init);
 static void traverse_one(const orc_scene *s, const orc_launch *L, const orc_ray *ray, orc_hit *out, orc_counters *c, int unpruned) {
+  traverse_clamped(s, L, ray, out, c, unpruned, ray->tmin, ray->tmax);
+}
+/* near_walk / far_init: the range the box and triangle range tests start from.  The reference's walk has near_walk = tmin and
+ * far_init = tmax; the tie re-walk of the ordered traversal (orc_scene_trace_ordered_model, csrc/traverse.cu) clamps them around the
+ * closest distance while the update_far asserts keep using the ray's own near. */
+static void traverse_clamped(const orc_scene *s, const orc_launch *L, const orc_ray *ray, orc_hit *out, orc_counters *c, int unpruned,
+                             float near_walk, float far_init) {
   out->t = ray->tmax; out->u = 0; out->v = 0;
   out->primitive_id = out->geometry_id = out->instance_id = out->instance_custom_id = 0xFFFFFFFFu;
   out->hit_kind = 0;
 
   const uint32_t flags0 = L->ray_flags;
   const float near = ray->tmin;
-  float far = ray->tmax;             /* the shared Rc<Cell<f32>> */
+  float far = far_init;              /* the shared Rc<Cell<f32>> */
   float fixed_far = ray->tmax;
   float *pf = unpruned ? &fixed_far : &far;  /* what the box / triangle range tests see */
   const ov3 ro = ov3_new(ray->ox, ray->oy, ray->oz);
@@ -375,7 +384,7 @@ static void traverse_one(const orc_scene *s, const orc_launch *L, const orc_ray 
   uint32_t tlas_cursor = s->tlas_bvh_root.p[handle];
 
   for (;;) {
-    uint32_t leaf = bvh_iter_next(s->tlas_bvh_forest.p, &tlas_cursor, ro, rd, near, pf, 1.0f, c);
+    uint32_t leaf = bvh_iter_next(s->tlas_bvh_forest.p, &tlas_cursor, ro, rd, near_walk, pf, 1.0f, c);
     if (leaf == ORC_INVALID_NEXT) break;
     const orc_dev_node *node = &s->tlas_bvh_forest.p[leaf];
     for (uint32_t tlas_idx = node->range_x; tlas_idx < node->range_y; tlas_idx++) {
@@ -416,7 +425,7 @@ static void traverse_one(const orc_scene *s, const orc_launch *L, const orc_ray 
 
         uint32_t cursor = geometry.bvh_root_idx;
         for (;;) {
-          uint32_t bl = bvh_iter_next(s->tri_bvh_forest.p, &cursor, bo, bd, near, pf, scaling, c);
+          uint32_t bl = bvh_iter_next(s->tri_bvh_forest.p, &cursor, bo, bd, near_walk, pf, scaling, c);
           if (bl == ORC_INVALID_NEXT) break;
           const orc_dev_node *bn = &s->tri_bvh_forest.p[bl];
           for (uint32_t slot = bn->range_x; slot < bn->range_y; slot++) {
@@ -424,7 +433,7 @@ static void traverse_one(const orc_scene *s, const orc_launch *L, const orc_ray 
             uint32_t i0 = s->indices.p[(uint64_t)tri_idx * 3], i1 = s->indices.p[(uint64_t)tri_idx * 3 + 1], i2 = s->indices.p[(uint64_t)tri_idx * 3 + 2];
             ov3 v0 = s->vertices.p[i0], v1 = s->vertices.p[i1], v2 = s->vertices.p[i2];
             c->tri_visit++;
-            ov4 isect = intersect_ray_triangle(bo, bd, near * scaling, *pf * scaling, v0, v1, v2, cull_enable, cull_back);
+            ov4 isect = intersect_ray_triangle(bo, bd, near_walk * scaling, *pf * scaling, v0, v1, v2, cull_enable, cull_back);
             if (isect.x != 0.0f) {
               float distance = isect.y / scaling;
               uint32_t primitive_idx = tri_idx - geometry.primitive_start;
@@ -512,6 +521,175 @@ uint64_t orc_scene_candidates(const orc_scene *s, const orc_launch *L, const orc
     }
   }
   return n;
+}
+
+
+/* ---------------------------------------------------------------------------------------------------------------------------
+ * NOT the reference: a scalar model of the ORDERED traversal the CUDA kernel performs (csrc/traverse.cu k_trace_ordered_rounds) —
+ * near child first with a stack, pruning against bound = min(tmax, best + TIE_EPS |best|), the kernel's acceptance rule, near-tie
+ * detection through the second-smallest candidate distance, re-walk in the reference's order clamped to best -/+ 3 TIE_EPS |best|,
+ * whole-range walk when the clamped one finds nothing.  Test tool: lets the CPU suite fuzz the ALGORITHM (does it end on the
+ * reference's record?) over far more rays and scenes than GPU time allows.  Rays the product classifies as able to reach irregular
+ * content are the caller's business (the kernel hands them to the reference-order walk). */
+#define ORC_TIE_EPS 1e-5f
+typedef struct { float best, second, u, v, sign; uint32_t slot_tri, inst, geom, prim; int found; float bound; } ordered_state;
+
+static inline int slab_entry(ov3 o, ov3 inv_d, float t_min, float t_max, ov3 bmin, ov3 bmax, float *t_near_max) {
+  ov3 t0 = ov3_mul(ov3_sub(bmin, o), inv_d);
+  ov3 t1 = ov3_mul(ov3_sub(bmax, o), inv_d);
+  ov3 t_near = ov3_min(t0, t1);
+  ov3 t_far = ov3_max(t0, t1);
+  *t_near_max = ov3_max_channel(t_near);
+  float t_far_min = ov3_min_channel(t_far);
+  return *t_near_max <= t_far_min && t_min < t_far_min && *t_near_max < t_max;
+}
+
+/* near-first walk of one threaded tree; leaf_fn(ctx, leaf node) may shrink *far_s */
+typedef void (*ordered_leaf_fn)(void *ctx, const orc_dev_node *leaf);
+static void ordered_walk_tree(const orc_dev_node *forest, uint32_t root, ov3 o, ov3 d, float near_s, const float *far_s, ordered_leaf_fn fn, void *ctx) {
+  if (root == ORC_INVALID_NEXT) return;
+  ov3 inv = ov3_div(ov3_new(1.0f, 1.0f, 1.0f), d);
+  float tn;
+  if (!slab_entry(o, inv, near_s, *far_s, forest[root].aabb_min, forest[root].aabb_max, &tn)) return;  /* the pseudo root */
+  uint32_t stack[256];
+  int sp = 0;
+  uint32_t cur = root;
+  for (;;) {
+    const orc_dev_node *node = &forest[cur];
+    if (node->hit_next == node->miss_next) {
+      fn(ctx, node);
+    } else {
+      uint32_t l = cur + 1, r = forest[l].miss_next;
+      float n0, n1;
+      int h0 = slab_entry(o, inv, near_s, *far_s, forest[l].aabb_min, forest[l].aabb_max, &n0);
+      int h1 = slab_entry(o, inv, near_s, *far_s, forest[r].aabb_min, forest[r].aabb_max, &n1);
+      if (h0 && h1) {
+        int first0 = n0 <= n1;
+        if (sp < 256) stack[sp++] = first0 ? r : l;
+        cur = first0 ? l : r;
+        continue;
+      } else if (h0) { cur = l; continue; }
+      else if (h1) { cur = r; continue; }
+    }
+    if (sp == 0) return;
+    cur = stack[--sp];
+  }
+}
+
+typedef struct {
+  const orc_scene *s; const orc_launch *L; const orc_ray *ray; ordered_state *st;
+  ov3 ro, rd;            /* world ray */
+  ov3 bo, bd; float scaling, far_s; uint32_t flags, tlas_idx; orc_geom_meta geometry; int cull_enable, cull_back;  /* current instance / geometry */
+  float far_world;       /* = bound, as the world-level range end */
+} ordered_ctx;
+
+static void ordered_triangle_leaf(void *p, const orc_dev_node *leaf) {
+  ordered_ctx *x = (ordered_ctx *)p;
+  const orc_scene *s = x->s;
+  ordered_state *st = x->st;
+  const float near = x->ray->tmin, far0 = x->ray->tmax;
+  for (uint32_t slot = leaf->range_x; slot < leaf->range_y; slot++) {
+    uint32_t tri_idx = s->indices_redirect.p[slot];
+    ov3 v0 = s->vertices.p[s->indices.p[(uint64_t)tri_idx * 3]], v1 = s->vertices.p[s->indices.p[(uint64_t)tri_idx * 3 + 1]],
+        v2 = s->vertices.p[s->indices.p[(uint64_t)tri_idx * 3 + 2]];
+    ov4 isect = intersect_ray_triangle(x->bo, x->bd, near * x->scaling, x->far_s, v0, v1, v2, x->cull_enable, x->cull_back);
+    if (isect.x == 0.0f) continue;
+    float distance = isect.y / x->scaling;
+    if (!(near <= distance) || !(distance <= far0)) continue;
+    if (!st->found || distance < st->best) {
+      if (st->found) st->second = fminf(st->second, st->best);
+      st->found = 1;
+      st->best = distance; st->u = isect.z; st->v = isect.w; st->sign = isect.x;
+      st->inst = x->tlas_idx; st->geom = x->geometry.geometry_idx; st->prim = tri_idx - x->geometry.primitive_start;
+      st->bound = fminf(far0, st->best + ORC_TIE_EPS * fabsf(st->best));
+      x->far_s = st->bound * x->scaling;
+      x->far_world = st->bound;
+    } else {
+      st->second = fminf(st->second, distance);
+    }
+  }
+}
+
+static void ordered_instance_leaf(void *p, const orc_dev_node *leaf) {
+  ordered_ctx *x = (ordered_ctx *)p;
+  const orc_scene *s = x->s;
+  const orc_launch *L = x->L;
+  ov3 inv = ov3_div(ov3_new(1.0f, 1.0f, 1.0f), x->rd);
+  for (uint32_t tlas_idx = leaf->range_x; tlas_idx < leaf->range_y; tlas_idx++) {
+    const orc_tlas_bounding *tb = &s->tlas_bounding.p[tlas_idx];
+    float tn;
+    if (!slab_entry(x->ro, inv, x->ray->tmin, x->st->bound, tb->world_min, tb->world_max, &tn)) continue;  /* the kernel prunes with its bound */
+    if ((L->cull_mask & tb->mask) == 0) continue;
+    const orc_dev_instance *td = &s->tlas_data.p[tlas_idx];
+    uint32_t flags = merge_geometry_instance_flag(L->ray_flags, td->flags);
+    if ((flags & F_SKIP_TRIANGLES) || td->blas >= s->blas_meta_info.n) continue;
+    const orc_blas_meta *bm = &s->blas_meta_info.p[td->blas];
+    ov4 o4 = {x->ro.x, x->ro.y, x->ro.z, 1.0f};
+    o4 = om4_mul_v4(td->transform_inv, o4);
+    x->bo = ov3_divs(ov3_new(o4.x, o4.y, o4.z), o4.w);
+    ov3 bd0 = om3_mul_v3(om4_to_mat3(td->transform_inv), x->rd);
+    x->scaling = ov3_length(bd0);
+    x->bd = ov3_normalize(bd0);
+    x->far_s = x->st->bound * x->scaling;
+    x->flags = flags; x->tlas_idx = tlas_idx;
+    int flip = (flags & F_TRIANGLE_FLIP_FACING) != 0;
+    int cull_front = (flags & F_CULL_FRONT_FACING_TRIANGLES) != 0, cull_back_f = (flags & F_CULL_BACK_FACING_TRIANGLES) != 0;
+    x->cull_enable = cull_front || cull_back_f;
+    x->cull_back = (flip && cull_back_f) || (!flip && cull_front);
+    for (uint32_t g = bm->tri_root_x; g < bm->tri_root_y; g++) {
+      x->geometry = s->tri_bvh_root.p[g];
+      int geometry_opaque = (x->geometry.geometry_flags & G_OPAQUE) != 0;
+      int is_opaque = (geometry_opaque || (flags & F_FORCE_OPAQUE)) && !(flags & F_FORCE_NON_OPAQUE);
+      int pass = (is_opaque && !(flags & F_CULL_OPAQUE)) || (!is_opaque && !(flags & F_CULL_NON_OPAQUE));
+      if (!pass) continue;
+      ordered_walk_tree(s->tri_bvh_forest.p, x->geometry.bvh_root_idx, x->bo, x->bd, x->ray->tmin * x->scaling, &x->far_s, ordered_triangle_leaf, x);
+    }
+  }
+}
+
+/* returns 0 = the ordered result stands, 1 = near-tie resolved by the clamped re-walk, 2 = ... by the whole-range walk */
+static int traverse_ordered_model(const orc_scene *s, const orc_launch *L, const orc_ray *ray, orc_hit *out) {
+  orc_counters c; memset(&c, 0, sizeof(c));
+  if (L->ray_flags & F_ACCEPT_FIRST_HIT_AND_END_SEARCH) { traverse_one(s, L, ray, out, &c, 0); return 0; }  /* reference-order kernel */
+  out->t = ray->tmax; out->u = 0; out->v = 0;
+  out->primitive_id = out->geometry_id = out->instance_id = out->instance_custom_id = 0xFFFFFFFFu;
+  out->hit_kind = 0;
+  if (L->tlas_idx >= s->binding.n) return 0;
+  uint32_t handle = s->binding.p[L->tlas_idx];
+  if (handle >= s->tlas_bvh_root.n) return 0;
+  ordered_state st; memset(&st, 0, sizeof(st));
+  st.best = INFINITY; st.second = INFINITY; st.bound = ray->tmax;
+  ordered_ctx x; memset(&x, 0, sizeof(x));
+  x.s = s; x.L = L; x.ray = ray; x.st = &st;
+  x.ro = ov3_new(ray->ox, ray->oy, ray->oz); x.rd = ov3_new(ray->dx, ray->dy, ray->dz);
+  x.far_world = ray->tmax;
+  ordered_walk_tree(s->tlas_bvh_forest.p, s->tlas_bvh_root.p[handle], x.ro, x.rd, ray->tmin, &x.far_world, ordered_instance_leaf, &x);
+  if (!st.found) return 0;
+  if (st.second <= st.best + ORC_TIE_EPS * fabsf(st.best)) {
+    const float slack = 3.0f * ORC_TIE_EPS * fabsf(st.best);
+    traverse_clamped(s, L, ray, out, &c, 0, fmaxf(ray->tmin, st.best - slack), fminf(ray->tmax, st.best + slack));
+    if (out->instance_id != 0xFFFFFFFFu) return 1;
+    traverse_one(s, L, ray, out, &c, 0);
+    return 2;
+  }
+  out->t = st.best; out->u = st.u; out->v = st.v;
+  out->primitive_id = st.prim; out->geometry_id = st.geom; out->instance_id = st.inst;
+  out->instance_custom_id = s->tlas_data.p[st.inst].instance_custom_index;
+  out->hit_kind = st.sign < 0.0f ? HIT_KIND_BACK : HIT_KIND_FRONT;
+  return 0;
+}
+
+/* single-threaded batch; out_stats[0] = rays resolved by the clamped re-walk, [1] = by the whole-range walk */
+int orc_scene_trace_ordered_model(const orc_scene *s, const orc_launch *launch, const orc_ray *rays, uint64_t n_rays, orc_hit *out_hits,
+                                  uint64_t *out_stats) {
+  if (!s->built) return -1;
+  uint64_t ties = 0, whole = 0;
+  for (uint64_t i = 0; i < n_rays; i++) {
+    int r = traverse_ordered_model(s, launch, &rays[i], &out_hits[i]);
+    ties += r == 1; whole += r == 2;
+  }
+  if (out_stats) { out_stats[0] = ties; out_stats[1] = whole; }
+  return 0;
 }
 
 /* multi-thread driver: rays are handed out in chunks from an atomic cursor (hit rays cluster in image space, so static

@@ -173,3 +173,28 @@ def test_needle_threshold_has_margin(band):
     else:
         assert st["irregular_triangles"] == 12000 and route_all
         assert int(differs.sum()) > 100
+
+
+@pytest.mark.parametrize("profile", ["regular", "mixed", "hostile"])
+@pytest.mark.parametrize("seed", range(8))
+def test_ordered_traversal_algorithm_ends_on_the_reference_record(seed, profile):
+    """A scalar model of the kernel's ordered traversal (near child first, pruning against the inflated bound, near-tie detection,
+    clamped re-walk, whole-range fallback; oracle_scene.c orc_scene_trace_ordered_model) must produce the reference's whole hit record
+    on every ray the kernel keeps for itself — the exactness argument of DESIGN.md §3, fuzzed on the CPU at a volume GPU time does
+    not allow.  (Rays the flattener's classification hands over are walked in reference order by construction.)"""
+    sp, n_tlas, rng = fuzz._scene(2000 + seed, devices=(), profile=profile)
+    rays = fuzz._rays(rng, 20000)
+    arrays = sp.p.arrays()
+    checked = 0
+    for tlas_idx in range(n_tlas):
+        for flags, mask in ((0, 0xFFFFFFFF), (api.RAY_FLAG_CULL_BACK_FACING_TRIANGLES, 0xFFFFFFFF), (api.RAY_FLAG_FORCE_NON_OPAQUE | api.RAY_FLAG_CULL_FRONT_FACING_TRIANGLES, 0xF3)):
+            route_all, suspect = helpers.suspect_rays(arrays, rays, tlas_idx, mask)
+            if route_all:
+                continue
+            kept = ~suspect
+            ref = sp.o.trace(rays[kept], ray_flags=flags, cull_mask=mask, tlas_idx=tlas_idx, n_threads=4, want_counters=False)
+            got, ties, whole = sp.o.trace_ordered_model(rays[kept], ray_flags=flags, cull_mask=mask, tlas_idx=tlas_idx)
+            assert helpers.identical_hits(got, ref), (seed, profile, tlas_idx, hex(flags), int((helpers.canonical_nan(got) != helpers.canonical_nan(ref)).sum()))
+            checked += int(kept.sum())
+    if profile != "hostile":
+        assert checked > 0
