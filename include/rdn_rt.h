@@ -254,7 +254,7 @@ typedef enum rdn_array_id {
   RDN_ARRAY_TLAS_BINDING = 0, RDN_ARRAY_TLAS_BVH_ROOT, RDN_ARRAY_TLAS_BVH_FOREST, RDN_ARRAY_TLAS_BOUNDING,
   RDN_ARRAY_INSTANCES, RDN_ARRAY_BLAS_META, RDN_ARRAY_GEOMETRY_META, RDN_ARRAY_TRI_BVH_FOREST,
   RDN_ARRAY_TRIANGLES, RDN_ARRAY_SLOT_INFO, RDN_ARRAY_WIDE_NODES, RDN_ARRAY_PRIM_TO_SLOT, RDN_ARRAY_IRREGULAR_INSTANCES,
-  RDN_ARRAY_IRREGULAR_LEAF_BOXES, RDN_ARRAY_COUNT
+  RDN_ARRAY_IRREGULAR_LEAF_BOXES, RDN_ARRAY_WIDE4_NODES, RDN_ARRAY_COUNT
 } rdn_array_id;
 int rdn_rt_scene_array(rdn_rt_scene *scene, int array_id, void *out, uint64_t capacity_bytes, uint64_t *out_bytes);
 /* build statistics of the committed scene (commits first); a scene that adopted another rank's blob reports only what the

@@ -37,7 +37,7 @@ TLAS_BOUNDING_DTYPE = np.dtype([("world_min", "f4", (3,)), ("mask", "u4"), ("wor
 INSTANCE_RECORD_DTYPE = np.dtype([("transform_inv", "f4", (16,)), ("instance_custom_index", "u4"), ("sbt_offset", "u4"),
                                   ("flags", "u4"), ("blas", "u4")])
 GEOMETRY_META_DTYPE = np.dtype([("bvh_root_idx", "u4"), ("geometry_idx", "u4"), ("primitive_start", "u4"), ("geometry_flags", "u4"),
-                                ("wide_root", "u4"), ("pad", "u4", (3,))])
+                                ("wide_root", "u4"), ("wide4_root", "u4"), ("pad", "u4", (2,))])
 TRI_RECORD_DTYPE = np.dtype([("n", "f4", (3,)), ("inv_d", "f4"), ("v0", "f4", (3,)), ("uu", "f4"),
                              ("e1", "f4", (3,)), ("uv", "f4"), ("e2", "f4", (3,)), ("vv", "f4")])
 WIDE_NODE_DTYPE = np.dtype([("c0_min", "f4", (3,)), ("ref0", "u4"), ("c0_max", "f4", (3,)), ("ref1", "u4"),
@@ -49,6 +49,7 @@ ARRAYS = {  # rdn_array_id -> (name, dtype)
     6: ("geometry_meta", GEOMETRY_META_DTYPE), 7: ("tri_bvh_forest", DEV_NODE_DTYPE), 8: ("triangles", TRI_RECORD_DTYPE),
     9: ("slot_info", np.dtype(("u4", (2,)))), 10: ("wide_nodes", WIDE_NODE_DTYPE), 11: ("prim_to_slot", np.dtype("u4")),
     12: ("irregular_instances", np.dtype("u4")),
+    14: ("wide4_nodes", np.dtype([("child", [("bmin", "f4", (3,)), ("ref", "u4"), ("bmax", "f4", (3,)), ("pad", "u4")], (4,))])),
     13: ("irregular_leaf_boxes", np.dtype([("bmin", "f4", (3,)), ("pad0", "u4"), ("bmax", "f4", (3,)), ("pad1", "u4")])),
 }
 

@@ -1,6 +1,7 @@
 // accel.cpp — BLAS/TLAS assembly and flattening.  Compiled with -ffp-contract=off.
 #include "accel.h"
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -195,6 +196,89 @@ uint32_t emit_wide_nodes(const std::vector<FlattenBVHNode> &nodes, uint64_t slot
     const uint32_t lr = child_ref(l), rr = child_ref(r);
     set_child(w, 0, &nodes[l].bounding, lr);
     set_child(w, 1, &nodes[r].bounding, rr);
+    out[wide_of[i]] = w;
+  }
+  if (out.size() >= REF_SPECIAL) capacity_error = true;
+  return static_cast<uint32_t>(base);
+}
+
+uint32_t emit_wide4_nodes(const std::vector<FlattenBVHNode> &nodes, uint64_t slot_offset, std::vector<Wide4Node> &out,
+                          bool &capacity_error) {
+  if (nodes.empty() || nodes[0].primitive_end == nodes[0].primitive_start) return REF_EMPTY;
+  const uint64_t base = out.size();
+  auto set = [](Wide4Node &w, int k, const Box3 *box, uint32_t ref) {
+    const float nan = NAN;
+    Wide4Node::Child &c = w.child[k];
+    c.bmin[0] = box ? box->min.x : nan; c.bmin[1] = box ? box->min.y : nan; c.bmin[2] = box ? box->min.z : nan;
+    c.bmax[0] = box ? box->max.x : nan; c.bmax[1] = box ? box->max.y : nan; c.bmax[2] = box ? box->max.z : nan;
+    c.ref = ref; c.pad = 0;
+  };
+  auto blank = [&](Wide4Node &w) { for (int k = 0; k < 4; ++k) set(w, k, nullptr, REF_EMPTY); };
+  // which inner nodes own a 4-wide node: the root, and every inner grandchild (or inner child of a leaf-sibling... no: an inner
+  // CHILD is always absorbed into its parent's node; only its children surface) — found by a walk from the root
+  std::vector<uint32_t> wide_of(nodes.size(), 0);
+  std::vector<size_t> owners;
+  {
+    std::vector<size_t> stack;
+    if (nodes[0].has_child) stack.push_back(0);
+    while (!stack.empty()) {
+      const size_t i = stack.back();
+      stack.pop_back();
+      owners.push_back(i);
+      for (size_t c : {static_cast<size_t>(nodes[i].left_child_offset()), static_cast<size_t>(nodes[i].right_child_offset())}) {
+        if (!nodes[c].has_child) continue;
+        for (size_t g : {static_cast<size_t>(nodes[c].left_child_offset()), static_cast<size_t>(nodes[c].right_child_offset())})
+          if (nodes[g].has_child) stack.push_back(g);
+      }
+    }
+    std::sort(owners.begin(), owners.end());  // pre-order of the reference tree
+    for (size_t k = 0; k < owners.size(); ++k) wide_of[owners[k]] = static_cast<uint32_t>(base + 1 + k);
+  }
+  out.resize(base + 1 + owners.size());
+  auto leaf_ref = [&](const FlattenBVHNode &leaf) -> uint32_t {
+    uint64_t start = slot_offset + leaf.primitive_start;
+    uint64_t count = leaf.primitive_end - leaf.primitive_start;
+    if (count == 0) return REF_EMPTY;
+    if (start + count > REF_LEAF_START_MASK) { capacity_error = true; return REF_EMPTY; }
+    auto enc = [](uint64_t s, uint64_t c) { return REF_LEAF_BIT | (static_cast<uint32_t>(c - 1) << REF_LEAF_COUNT_SHIFT) | static_cast<uint32_t>(s); };
+    if (count <= REF_LEAF_MAX_COUNT) return enc(start, count);
+    // chain of nodes that repeat the leaf's box: up to three 16-slot groups per node, the rest behind the fourth reference
+    const uint32_t head = static_cast<uint32_t>(out.size());
+    while (count > 0) {
+      Wide4Node w;
+      blank(w);
+      int k = 0;
+      for (; k < 3 && count > 0; ++k) {
+        const uint64_t take = std::min<uint64_t>(count, REF_LEAF_MAX_COUNT);
+        set(w, k, &leaf.bounding, enc(start, take));
+        start += take; count -= take;
+      }
+      if (count > 0) {
+        if (count <= REF_LEAF_MAX_COUNT) { set(w, 3, &leaf.bounding, enc(start, count)); start += count; count = 0; }
+        else set(w, 3, &leaf.bounding, static_cast<uint32_t>(out.size() + 1));
+      }
+      out.push_back(w);
+    }
+    return head;
+  };
+  auto ref_of = [&](size_t idx) -> uint32_t { return nodes[idx].has_child ? wide_of[idx] : leaf_ref(nodes[idx]); };
+  {
+    Wide4Node w;
+    blank(w);
+    set(w, 0, &nodes[0].bounding, ref_of(0));  // pseudo root: the root's own box is tested first, as the reference does
+    out[base] = w;
+  }
+  for (size_t i : owners) {
+    Wide4Node w;
+    blank(w);
+    int k = 0;
+    for (size_t c : {static_cast<size_t>(nodes[i].left_child_offset()), static_cast<size_t>(nodes[i].right_child_offset())}) {
+      if (!nodes[c].has_child) { const uint32_t r = ref_of(c); set(w, k++, &nodes[c].bounding, r); continue; }
+      for (size_t g : {static_cast<size_t>(nodes[c].left_child_offset()), static_cast<size_t>(nodes[c].right_child_offset())}) {
+        const uint32_t r = ref_of(g);
+        set(w, k++, &nodes[g].bounding, r);
+      }
+    }
     out[wide_of[i]] = w;
   }
   if (out.size() >= REF_SPECIAL) capacity_error = true;
@@ -406,6 +490,7 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
         gm.primitive_start = primitive_start;
         gm.geometry_flags = src.flags;
         gm.wide_root = emit_wide_nodes(bvh.nodes, primitive_start, out.wide_nodes, capacity_error);
+        gm.wide4_root = emit_wide4_nodes(bvh.nodes, primitive_start, out.wide4_nodes, capacity_error);
         if (gm.wide_root != REF_EMPTY && n_tri > hot.triangles) {
           const uint64_t block = out.wide_nodes.size() - gm.wide_root;
           hot = HotBlock{gm.wide_root, static_cast<uint32_t>(block < HOT_TOP_NODES ? block : HOT_TOP_NODES), n_tri};
@@ -437,7 +522,7 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
   const TreeBuildOption tlas_option{50, 10};
   for (const Tlas &tlas : tlas_data_) {
     if (!tlas.alive) {
-      out.tlas_root.push_back(TlasRoot{INVALID_NEXT, REF_EMPTY, 0, 0, 0, 0, 0, 0});
+      out.tlas_root.push_back(TlasRoot{INVALID_NEXT, REF_EMPTY, 0, 0, 0, 0, 0, REF_EMPTY});
       continue;
     }
     HotBlock tlas_hot_geometry;
@@ -494,7 +579,7 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
     TlasRoot root;
     root.bvh_root_idx = bvh_start;
     root.wide_root = emit_wide_nodes(bvh.nodes, primitive_start, out.wide_nodes, capacity_error);
-    root.pad = 0;
+    root.wide4_root = emit_wide4_nodes(bvh.nodes, primitive_start, out.wide4_nodes, capacity_error);
     root.hot_count = 0;
     if (root.wide_root != REF_EMPTY) {
       const uint64_t block = out.wide_nodes.size() - root.wide_root;
@@ -559,7 +644,7 @@ std::vector<uint8_t> FlatScene::serialize() const {
                padded(geometry_meta.size(), sizeof(GeometryMeta)) + padded(tri_bvh_forest.size(), sizeof(DeviceBVHNode)) +
                padded(triangles.size(), sizeof(TriRecord)) + padded(slot_info.size(), sizeof(SlotInfo)) +
                padded(wide_nodes.size(), sizeof(WideNode)) + padded(prim_to_slot.size(), 4) + padded(irregular_instances.size(), 4) +
-               padded(irregular_leaf_boxes.size(), sizeof(LeafBox)));  // one allocation: every place() below only appends
+               padded(irregular_leaf_boxes.size(), sizeof(LeafBox)) + padded(wide4_nodes.size(), sizeof(Wide4Node)));  // one allocation: every place() below only appends
   blob.resize(sizeof(BlobHeader), 0);
   place(blob, h, ARR_TLAS_BINDING, tlas_binding);
   place(blob, h, ARR_TLAS_ROOT, tlas_root);
@@ -575,6 +660,7 @@ std::vector<uint8_t> FlatScene::serialize() const {
   place(blob, h, ARR_PRIM_TO_SLOT, prim_to_slot);
   place(blob, h, ARR_IRREGULAR_INSTANCES, irregular_instances);
   place(blob, h, ARR_IRREGULAR_LEAF_BOXES, irregular_leaf_boxes);
+  place(blob, h, ARR_WIDE4_NODES, wide4_nodes);
   blob.resize((blob.size() + BLOB_ALIGN - 1) / BLOB_ALIGN * BLOB_ALIGN, 0);
   h.total_bytes = blob.size();
   std::memcpy(blob.data(), &h, sizeof(h));

@@ -42,6 +42,7 @@ struct FlatScene {
   std::vector<uint32_t> prim_to_slot;
   std::vector<uint32_t> irregular_instances;
   std::vector<LeafBox> irregular_leaf_boxes;
+  std::vector<Wide4Node> wide4_nodes;
   BuildStats stats;
 
   // pack into one contiguous, BLOB_ALIGN-aligned byte image starting with a BlobHeader
@@ -75,5 +76,8 @@ Box3 box_apply_matrix(const Box3 &b, const Mat4 &m);
 // sets `capacity_error`.
 uint32_t emit_wide_nodes(const std::vector<FlattenBVHNode> &nodes, uint64_t slot_offset, std::vector<WideNode> &out,
                          bool &capacity_error);
+// the same for the 4-wide view: one node per inner reference node at even depth below the root (its inner children are absorbed)
+uint32_t emit_wide4_nodes(const std::vector<FlattenBVHNode> &nodes, uint64_t slot_offset, std::vector<Wide4Node> &out,
+                          bool &capacity_error);
 
 }  // namespace rdn

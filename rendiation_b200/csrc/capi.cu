@@ -168,6 +168,7 @@ void bind_blob(DeviceCtx &dc, const BlobHeader &h) {
   d.prim_to_slot = reinterpret_cast<const uint32_t *>(b + h.offset[ARR_PRIM_TO_SLOT]);
   d.irregular_instances = reinterpret_cast<const uint32_t *>(b + h.offset[ARR_IRREGULAR_INSTANCES]);
   d.irregular_leaf_boxes = reinterpret_cast<const LeafBox *>(b + h.offset[ARR_IRREGULAR_LEAF_BOXES]);
+  d.wide4_nodes = reinterpret_cast<const Wide4Node *>(b + h.offset[ARR_WIDE4_NODES]);
   d.n_tlas_binding = static_cast<uint32_t>(h.count[ARR_TLAS_BINDING]);
   d.n_tlas_root = static_cast<uint32_t>(h.count[ARR_TLAS_ROOT]);
   d.n_blas_meta = static_cast<uint32_t>(h.count[ARR_BLAS_META]);
@@ -835,7 +836,7 @@ int rdn_rt_scene_adopt_blob(rdn_rt_scene *s, int device_index, const void *d_blo
   dc.blob_bytes = bytes;
   bind_blob(dc, h);
   s->h_tlas_binding.assign(h.count[ARR_TLAS_BINDING], 0);
-  s->h_tlas_root.assign(h.count[ARR_TLAS_ROOT], TlasRoot{INVALID_NEXT, REF_EMPTY, 0, 0, 0, 0, 0, 0});
+  s->h_tlas_root.assign(h.count[ARR_TLAS_ROOT], TlasRoot{INVALID_NEXT, REF_EMPTY, 0, 0, 0, 0, 0, REF_EMPTY});
   if (!s->h_tlas_binding.empty())
     RDN_CUDA(cudaMemcpy(s->h_tlas_binding.data(), dc.dev.tlas_binding, s->h_tlas_binding.size() * 4, cudaMemcpyDeviceToHost));
   if (!s->h_tlas_root.empty())

@@ -26,6 +26,7 @@ struct SceneDev {
   const uint32_t *prim_to_slot;
   const uint32_t *irregular_instances;
   const LeafBox *irregular_leaf_boxes;
+  const Wide4Node *wide4_nodes;
   uint32_t n_tlas_binding, n_tlas_root, n_blas_meta, n_instances;
 };
 

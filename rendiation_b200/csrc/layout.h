@@ -60,7 +60,8 @@ struct GeometryMeta {
   uint32_t primitive_start;
   uint32_t geometry_flags;
   uint32_t wide_root;       // child reference of the pseudo-root in wide_nodes, or REF_EMPTY
-  uint32_t pad[3];
+  uint32_t wide4_root;      // ... in wide4_nodes
+  uint32_t pad[2];
 };
 static_assert(sizeof(GeometryMeta) == 32, "GeometryMeta");
 
@@ -71,7 +72,7 @@ struct TlasRoot {
   uint32_t irregular_count;  // their boxes (see accel.cpp "regularity"); IRREGULAR_ROUTE_ALL: walk every ray in reference order
   uint32_t hot_count;        // wide nodes [wide_root, wide_root + hot_count): the top of the TLAS tree (<= HOT_TOP_NODES)
   uint32_t hot_geometry_base, hot_geometry_count;  // the same block of the largest geometry tree among the instances' BLASes
-  uint32_t pad;
+  uint32_t wide4_root;       // pseudo root of the TLAS tree in wide4_nodes (REF_EMPTY when deleted / empty)
 };
 static_assert(sizeof(TlasRoot) == 32, "TlasRoot");
 constexpr uint32_t IRREGULAR_ROUTE_ALL = 0xFFFFFFFFu;
@@ -101,6 +102,13 @@ struct WideNode {
   float c1_max[3]; uint32_t pad1;
 };
 static_assert(sizeof(WideNode) == 64, "WideNode");
+
+// 128 B: up to four children — the grandchildren of an inner reference node, a child that is a leaf kept as it is — child k in
+// floats [8k, 8k+8): {min.xyz, ref} {max.xyz, 0}; an unused slot has a NaN box and REF_EMPTY.  Inner references index wide4_nodes.
+struct Wide4Node {
+  struct Child { float bmin[3]; uint32_t ref; float bmax[3]; uint32_t pad; } child[4];
+};
+static_assert(sizeof(Wide4Node) == 128, "Wide4Node");
 
 // ---- child reference encoding (u32) ----
 //   inner  : index into wide_nodes (< REF_SPECIAL)
@@ -134,11 +142,12 @@ enum ArrayId : int {
   ARR_PRIM_TO_SLOT,       // u32: (primitive_start + original triangle index) -> slot; inverse of the reference's indices_redirect
   ARR_IRREGULAR_INSTANCES,  // u32: instance slots (| IRREGULAR_WHOLE_BIT), grouped per TLAS (TlasRoot::irregular_start / _count)
   ARR_IRREGULAR_LEAF_BOXES, // LeafBox, grouped per BLAS (BlasMeta::irregular_leaf_start / _count)
+  ARR_WIDE4_NODES,          // Wide4Node: the 4-wide view of the same trees (experiment: RDN_ORDERED_VARIANT=60)
   ARR_COUNT
 };
 
 constexpr uint64_t BLOB_MAGIC = 0x52444E5F424C4F42ull;  // "RDN_BLOB"
-constexpr uint32_t BLOB_VERSION = 4;
+constexpr uint32_t BLOB_VERSION = 5;
 constexpr uint64_t BLOB_ALIGN = 128;
 
 struct BlobHeader {

@@ -538,7 +538,10 @@ __device__ __forceinline__ uint32_t compact_even_bits4(uint32_t x) {  // bits 0,
 // SPEC: speculative traversal with one postponed leaf per lane (Aila & Laine): a lane that reaches a triangle leaf parks it and
 // keeps descending (against the bound it had), so that more lanes hold a leaf when the warp runs the triangle code — profiled at
 // ~5 of 32 lanes for a quarter of all issued instructions.  The parked leaf is tested before the lane leaves the instance.
-template <int K, int MINB, int THRESH, bool DRAIN_TIES, bool IRREGULAR, bool UNITS, int PF, bool LD256, bool HOT, bool SPEC>  // DRAIN_TIES: near-tie queue drained inside the kernel (else by k_resolve_ties)
+// WIDE4: the walk runs over the 128 B four-box nodes (layout.h Wide4Node: the grandchildren of a reference node, exact boxes): half
+// the steps for the same box tests (nested boxes make the skipped test of the absorbed child redundant), the hit children entered
+// nearest first and the others deferred farthest first.
+template <int K, int MINB, int THRESH, bool DRAIN_TIES, bool IRREGULAR, bool UNITS, int PF, bool LD256, bool HOT, bool SPEC, bool WIDE4>  // DRAIN_TIES: near-tie queue drained inside the kernel (else by k_resolve_ties)
 __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(const __grid_constant__ OrderedParams P) {
   const SceneDev &S = P.S;
   const uint32_t lane = threadIdx.x & 31u;
@@ -589,7 +592,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
   Vec3 root_min = {0, 0, 0}, root_max = {0, 0, 0};
   uint32_t world_entry = REF_EMPTY;
   if (P.world_root != REF_EMPTY) {
-    const float4 *np = reinterpret_cast<const float4 *>(S.wide_nodes + P.world_root);
+    const float4 *np = WIDE4 ? reinterpret_cast<const float4 *>(S.wide4_nodes + P.world_root) : reinterpret_cast<const float4 *>(S.wide_nodes + P.world_root);
     const float4 q0 = __ldg(np), q1 = __ldg(np + 1);
     root_min = xyz(q0); root_max = xyz(q1);
     world_entry = __float_as_uint(q0.w);
@@ -766,6 +769,30 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
 #ifdef RDN_DEBUG_STEPS
           ++dbg_steps; ++dbg_ray_steps;
 #endif
+          if (WIDE4) {
+            const float4 *np4 = reinterpret_cast<const float4 *>(S.wide4_nodes + cur);
+            float key[4];
+            uint32_t ref[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              float4 a, b;
+              load_pair<true>(np4 + 2 * c, a, b);
+              float n;
+              const bool h = slab_test(o, inv, near_s, far_s, xyz(a), xyz(b), n);
+              key[c] = h ? n : INFINITY;  // (an unused slot is a NaN box: never hit)
+              ref[c] = h ? __float_as_uint(a.w) : REF_EMPTY;
+            }
+            // sort the four (entry distance, reference) pairs, nearest first (5 compare-exchanges)
+#define RDN_CSWAP(i, j) do { const bool sw = key[j] < key[i]; const float tk = sw ? key[j] : key[i]; const uint32_t tr = sw ? ref[j] : ref[i]; \
+                             key[j] = sw ? key[i] : key[j]; ref[j] = sw ? ref[i] : ref[j]; key[i] = tk; ref[i] = tr; } while (0)
+            RDN_CSWAP(0, 1); RDN_CSWAP(2, 3); RDN_CSWAP(0, 2); RDN_CSWAP(1, 3); RDN_CSWAP(1, 2);
+#undef RDN_CSWAP
+            if (ref[3] != REF_EMPTY) RDN_PUSH(ref[3]);
+            if (ref[2] != REF_EMPTY) RDN_PUSH(ref[2]);
+            if (ref[1] != REF_EMPTY) RDN_PUSH(ref[1]);
+            cur = ref[0] != REF_EMPTY ? ref[0] : RDN_POP();
+            continue;
+          }
           const float4 *np = reinterpret_cast<const float4 *>(S.wide_nodes + cur);
           float4 q0, q1, q2, q3;
           bool staged = false;
@@ -893,7 +920,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
             const uint32_t g = cur & 0x00FFFFFFu;
             if (g + 1u < geom_end) RDN_PUSH(REF_SPECIAL | (g + 1u));
             const uint4 gm0 = __ldg(reinterpret_cast<const uint4 *>(S.geometry_meta + g));
-            const uint32_t wide_root = __ldg(&S.geometry_meta[g].wide_root);
+            const uint32_t wide_root = WIDE4 ? __ldg(&S.geometry_meta[g].wide4_root) : __ldg(&S.geometry_meta[g].wide_root);
             cur = (cull_geometry_pass(cur_flags, gm0.w) && wide_root != REF_EMPTY) ? wide_root : RDN_POP();
           }
         }
@@ -1055,7 +1082,8 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const
   }
   P.n_ranges = sm_local ? static_cast<uint32_t>(sm_count < SM_CURSOR_SLOTS ? sm_count : SM_CURSOR_SLOTS) : 1u;
   P.units_per_range = (P.n_units + P.n_ranges - 1u) / P.n_ranges;
-  P.world_root = tlas.wide_root;
+  const bool irregular_tlas = tlas.irregular_count != 0 && tlas.irregular_count != IRREGULAR_ROUTE_ALL;
+  P.world_root = ((variant_ == 60 || variant_ == 61) && !irregular_tlas) ? tlas.wide4_root : tlas.wide_root;  // (irregular launches: default kernel)
   P.hot_a_base = tlas.wide_root == REF_EMPTY ? 0u : tlas.wide_root;
   P.hot_a_count = tlas.wide_root == REF_EMPTY ? 0u : tlas.hot_count;
   P.hot_b_base = tlas.hot_geometry_base;
@@ -1071,23 +1099,25 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const
   bool inline_ties = true;
   switch (variant) {
     // (K, THRESH) = (4,1), (3,4), (4,8) were instantiated here during the sweep of profiles/kbench_r1_variant_sweep.log
-    case 30: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, false, false, false>; break;  // 128-bit loads / stores
-    case 40: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, true, true, false>; break;    // top levels staged in shared memory (TMA)
-    case 50: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, true, false, true>; break;    // speculative traversal, one postponed leaf per lane
+    case 30: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, false, false, false, false>; break;  // 128-bit loads / stores
+    case 40: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, true, true, false, false>; break;    // top levels staged in shared memory (TMA)
+    case 50: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, true, false, true, false>; break;    // speculative traversal, one postponed leaf per lane
+    case 60: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, true, false, false, true>; break;    // four-box nodes, K = 2 steps per round
+    case 61: fn = k_trace_ordered_rounds<1, 8, 1, true, false, false, 0, true, false, false, true>; break;    // ... one step per round
     // whole-unit scheduling experiments, all measured slower than the default (profiles/kbench_r1_unit_scheduling.log): lanes whose
     // ray misses the scene stay idle for the rest of the tile instead of being topped up with the next rays
-    case 10: case 11: case 12: case 13: case 14: fn = k_trace_ordered_rounds<2, 8, 1, true, false, true, 0, true, false, false>; break;
-    case 9: fn = k_trace_ordered_rounds<2, 8, 1, false, false, false, 0, true, false, false>; inline_ties = false; break;  // queue drained by k_resolve_ties
-    case 20: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 1, true, false, false>; break;  // children prefetched into L1
-    case 21: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 2, true, false, false>; break;  // ... into L2
-    default: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, true, false, false>; break;
+    case 10: case 11: case 12: case 13: case 14: fn = k_trace_ordered_rounds<2, 8, 1, true, false, true, 0, true, false, false, false>; break;
+    case 9: fn = k_trace_ordered_rounds<2, 8, 1, false, false, false, 0, true, false, false, false>; inline_ties = false; break;  // queue drained by k_resolve_ties
+    case 20: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 1, true, false, false, false>; break;  // children prefetched into L1
+    case 21: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 2, true, false, false, false>; break;  // ... into L2
+    default: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, true, false, false, false>; break;
   }
   if (P.irregular_count != 0) {  // (the experimentation variants exist for regular scenes only)
     // Rays handed over at refill can be a large part of the launch, and the in-kernel drain claims entries through one CAS
     // cursor (fine for a handful of ties, 55 ms for 400 K entries): the queue of an irregular launch is walked by
     // k_resolve_ties, one thread per entry, right behind this kernel.
     inline_ties = false;
-    fn = k_trace_ordered_rounds<2, 8, 1, false, true, false, 0, true, false, false>;
+    fn = k_trace_ordered_rounds<2, 8, 1, false, true, false, 0, true, false, false, false>;
   }
   int blocks_per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, ORDERED_BLOCK, 0);

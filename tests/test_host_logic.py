@@ -154,6 +154,55 @@ def test_wide_nodes_cover_the_reference_tree():
     assert sorted(seen_slots) == list(range(len(pa["triangles"])))
 
 
+@pytest.mark.parametrize("builder", [helpers.sphere_c1, helpers.reference_fixture])
+def test_wide4_nodes_cover_the_reference_tree(builder):
+    """the 4-wide view: every node holds the exact boxes of the reference nodes it stands for (grandchildren of an inner node, a
+    leaf child kept as it is), unused slots are NaN / REF_EMPTY, and the leaves decode to every slot exactly once"""
+    ov, pa, sp = _flat_pair(builder)
+    w4, LEAF, EMPTY = pa["wide4_nodes"], 0x80000000, 0x7FFFFFFE
+
+    def check_tree(forest, root_node, w4_root, slot_lo, slot_hi):
+        is_leaf = lambda k: forest[k]["hit_next"] == forest[k]["miss_next"]
+        kids_of = lambda k: (k + 1, int(forest[k + 1]["miss_next"]))
+        seen = []
+
+        def leaf(ref, k):
+            assert ref & LEAF
+            start, cnt = ref & ((1 << 27) - 1), ((ref >> 27) & 15) + 1
+            assert start == forest[k]["range"][0] and start + cnt == forest[k]["range"][1]
+            seen.extend(range(start, start + cnt))
+
+        def visit(ref, k):  # ref stands for reference node k
+            if is_leaf(k):
+                return leaf(ref, k)
+            node = w4[ref]["child"]
+            want = []
+            for c in kids_of(k):
+                want += [c] if is_leaf(c) else list(kids_of(c))
+            for j, g in enumerate(want):
+                assert np.array_equal(node[j]["bmin"], forest[g]["aabb_min"]) and np.array_equal(node[j]["bmax"], forest[g]["aabb_max"])
+                visit(int(node[j]["ref"]), g)
+            for j in range(len(want), 4):
+                assert node[j]["ref"] == EMPTY and np.isnan(node[j]["bmin"]).all()
+
+        root = w4[w4_root]["child"]
+        assert np.array_equal(root[0]["bmin"], forest[root_node]["aabb_min"]) and all(root[j]["ref"] == EMPTY for j in (1, 2, 3))
+        visit(int(root[0]["ref"]), root_node)
+        assert sorted(seen) == list(range(slot_lo, slot_hi))
+
+    import sys
+    sys.setrecursionlimit(20000)
+    tri_forest, slot = pa["tri_bvh_forest"], 0
+    for g in pa["geometry_meta"]:
+        n_slots = int(tri_forest[g["bvh_root_idx"]]["range"][1] - tri_forest[g["bvh_root_idx"]]["range"][0])
+        check_tree(tri_forest, int(g["bvh_root_idx"]), int(g["wide4_root"]), slot, slot + n_slots)
+        slot += n_slots
+    tlas_forest = pa["tlas_bvh_forest"]
+    for t in pa["tlas_root"]:
+        r = int(t[0])
+        check_tree(tlas_forest, r, int(t[7]), int(tlas_forest[r]["range"][0]), int(tlas_forest[r]["range"][1]))
+
+
 def test_errors_are_status_codes_not_aborts():
     s = api.NaiveSahBVHSystem(devices=())
     b = s.create_bottom_level_acceleration_structure([api.BottomLevelAccelerationStructureBuildSource(S.CUBE_POSITION, S.CUBE_INDEX)])
