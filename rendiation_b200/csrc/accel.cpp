@@ -376,6 +376,9 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
   const auto t_begin = Clock::now();
   double bvh_ms = 0.0;
   const bool timing = getenv("RDN_BUILD_TIMING") != nullptr;
+  // the four-box view is only emitted for the kernel experiment that walks it (RDN_ORDERED_VARIANT=60/61): +45 % blob otherwise unused
+  const char *variant_env = getenv("RDN_ORDERED_VARIANT");
+  const bool want_wide4 = variant_env && (atoi(variant_env) == 60 || atoi(variant_env) == 61);
   double ms_boxes = 0, ms_records = 0, ms_wide = 0, ms_threaded = 0, ms_leaves = 0;
   auto since = [](Clock::time_point t0) { return std::chrono::duration<double, std::milli>(Clock::now() - t0).count(); };
   auto timed_build = [&](const Box3 *boxes, uint64_t n, BVHBuildStrategy &strategy, const TreeBuildOption &option) {
@@ -490,7 +493,7 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
         gm.primitive_start = primitive_start;
         gm.geometry_flags = src.flags;
         gm.wide_root = emit_wide_nodes(bvh.nodes, primitive_start, out.wide_nodes, capacity_error);
-        gm.wide4_root = emit_wide4_nodes(bvh.nodes, primitive_start, out.wide4_nodes, capacity_error);
+        gm.wide4_root = want_wide4 ? emit_wide4_nodes(bvh.nodes, primitive_start, out.wide4_nodes, capacity_error) : REF_EMPTY;
         if (gm.wide_root != REF_EMPTY && n_tri > hot.triangles) {
           const uint64_t block = out.wide_nodes.size() - gm.wide_root;
           hot = HotBlock{gm.wide_root, static_cast<uint32_t>(block < HOT_TOP_NODES ? block : HOT_TOP_NODES), n_tri};
@@ -579,7 +582,7 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
     TlasRoot root;
     root.bvh_root_idx = bvh_start;
     root.wide_root = emit_wide_nodes(bvh.nodes, primitive_start, out.wide_nodes, capacity_error);
-    root.wide4_root = emit_wide4_nodes(bvh.nodes, primitive_start, out.wide4_nodes, capacity_error);
+    root.wide4_root = want_wide4 ? emit_wide4_nodes(bvh.nodes, primitive_start, out.wide4_nodes, capacity_error) : REF_EMPTY;
     root.hot_count = 0;
     if (root.wide_root != REF_EMPTY) {
       const uint64_t block = out.wide_nodes.size() - root.wide_root;

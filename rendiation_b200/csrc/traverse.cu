@@ -1083,7 +1083,9 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const
   P.n_ranges = sm_local ? static_cast<uint32_t>(sm_count < SM_CURSOR_SLOTS ? sm_count : SM_CURSOR_SLOTS) : 1u;
   P.units_per_range = (P.n_units + P.n_ranges - 1u) / P.n_ranges;
   const bool irregular_tlas = tlas.irregular_count != 0 && tlas.irregular_count != IRREGULAR_ROUTE_ALL;
-  P.world_root = ((variant_ == 60 || variant_ == 61) && !irregular_tlas) ? tlas.wide4_root : tlas.wide_root;  // (irregular launches: default kernel)
+  // the four-box walk needs the four-box view (emitted only when the scene was built under the same variant) and a regular TLAS
+  const bool use_wide4 = (variant_ == 60 || variant_ == 61) && !irregular_tlas && tlas.wide4_root != REF_EMPTY;
+  P.world_root = use_wide4 ? tlas.wide4_root : tlas.wide_root;
   P.hot_a_base = tlas.wide_root == REF_EMPTY ? 0u : tlas.wide_root;
   P.hot_a_count = tlas.wide_root == REF_EMPTY ? 0u : tlas.hot_count;
   P.hot_b_base = tlas.hot_geometry_base;
@@ -1112,6 +1114,7 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const
     case 21: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 2, true, false, false, false>; break;  // ... into L2
     default: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, true, false, false, false>; break;
   }
+  if ((variant == 60 || variant == 61) && !use_wide4) fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, true, false, false, false>;
   if (P.irregular_count != 0) {  // (the experimentation variants exist for regular scenes only)
     // Rays handed over at refill can be a large part of the launch, and the in-kernel drain claims entries through one CAS
     // cursor (fine for a handful of ties, 55 ms for 400 K entries): the queue of an irregular launch is walked by

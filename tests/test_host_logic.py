@@ -158,7 +158,11 @@ def test_wide_nodes_cover_the_reference_tree():
 def test_wide4_nodes_cover_the_reference_tree(builder):
     """the 4-wide view: every node holds the exact boxes of the reference nodes it stands for (grandchildren of an inner node, a
     leaf child kept as it is), unused slots are NaN / REF_EMPTY, and the leaves decode to every slot exactly once"""
-    ov, pa, sp = _flat_pair(builder)
+    os.environ["RDN_ORDERED_VARIANT"] = "60"  # the view is only emitted for the experiment that walks it
+    try:
+        ov, pa, sp = _flat_pair(builder)
+    finally:
+        del os.environ["RDN_ORDERED_VARIANT"]
     w4, LEAF, EMPTY = pa["wide4_nodes"], 0x80000000, 0x7FFFFFFE
 
     def check_tree(forest, root_node, w4_root, slot_lo, slot_hi):
