@@ -122,19 +122,47 @@ def test_flattened_scene_matches_oracle_reference_fixture():
     assert np.array_equal(pa["triangles"]["e1"], v1 - v0) and np.array_equal(pa["triangles"]["e2"], v2 - v0)
 
 
-def test_wide_nodes_cover_the_reference_tree():
+def _exponential_scene(devices=(), product=True):
+    """200 triangles whose size and position halve from one to the next: the SAH split peels a few off per level, depth 50 is
+    reached with a hundred left, and that leaf (more than 16 slots) becomes a chain of wide nodes"""
+    x = 2.0 ** (60 - np.arange(200)).astype(np.float64)
+    tri = np.zeros((200, 3, 3))
+    tri[:, 0] = np.stack([x, 0 * x, 0 * x - 5], 1)
+    tri[:, 1] = np.stack([x * 1.05, 0 * x, 0 * x - 5], 1)
+    tri[:, 2] = np.stack([x, x * 0.05, 0 * x - 5], 1)
+    sp = helpers.ScenePair(devices, product)
+    b = sp.blas([(tri.reshape(-1, 3).astype(np.float32), None, 1)])
+    sp.bind([sp.tlas(S.make_instance(S.mat4_identity(), b))])
+    return sp.build()
+
+
+@pytest.mark.parametrize("builder", [helpers.sphere_c1, _exponential_scene])
+def test_wide_nodes_cover_the_reference_tree(builder):
     """every inner reference node appears once with its children's exact boxes; leaves decode to the same slot ranges"""
-    ov, pa, sp = _flat_pair(helpers.sphere_c1)
+    ov, pa, sp = _flat_pair(builder)
     wide, forest, gm = pa["wide_nodes"], pa["tri_bvh_forest"], pa["geometry_meta"][0]
     LEAF = 0x80000000
     seen_slots = []
 
-    def walk(ref, ref_node):
-        rn = forest[ref_node]
+    def chain_slots(ref, rn):
+        """slots behind a reference that stands for reference leaf rn: one leaf reference, or (leaves of more than 16 slots) a
+        chain of nodes that repeat the leaf's box"""
         if ref & LEAF:
             start, cnt = ref & ((1 << 27) - 1), ((ref >> 27) & 15) + 1
-            assert rn["hit_next"] == rn["miss_next"] and start == rn["range"][0] and start + cnt == rn["range"][1]
-            seen_slots.extend(range(start, start + cnt))
+            return list(range(start, start + cnt))
+        w = wide[ref]
+        out = []
+        for cmin, cmax, r in ((w["c0_min"], w["c0_max"], w["ref0"]), (w["c1_min"], w["c1_max"], w["ref1"])):
+            assert np.array_equal(cmin, rn["aabb_min"]) and np.array_equal(cmax, rn["aabb_max"])
+            out += chain_slots(int(r), rn)
+        return out
+
+    def walk(ref, ref_node):
+        rn = forest[ref_node]
+        if rn["hit_next"] == rn["miss_next"]:
+            slots = chain_slots(ref, rn)
+            assert slots == list(range(rn["range"][0], rn["range"][1]))
+            seen_slots.extend(slots)
             return
         w = wide[ref]
         left, right = ref_node + 1, None
@@ -154,7 +182,7 @@ def test_wide_nodes_cover_the_reference_tree():
     assert sorted(seen_slots) == list(range(len(pa["triangles"])))
 
 
-@pytest.mark.parametrize("builder", [helpers.sphere_c1, helpers.reference_fixture])
+@pytest.mark.parametrize("builder", [helpers.sphere_c1, helpers.reference_fixture, _exponential_scene])
 def test_wide4_nodes_cover_the_reference_tree(builder):
     """the 4-wide view: every node holds the exact boxes of the reference nodes it stands for (grandchildren of an inner node, a
     leaf child kept as it is), unused slots are NaN / REF_EMPTY, and the leaves decode to every slot exactly once"""
@@ -170,11 +198,22 @@ def test_wide4_nodes_cover_the_reference_tree(builder):
         kids_of = lambda k: (k + 1, int(forest[k + 1]["miss_next"]))
         seen = []
 
+        def chain_slots(ref, k):
+            if ref & LEAF:
+                start, cnt = ref & ((1 << 27) - 1), ((ref >> 27) & 15) + 1
+                return list(range(start, start + cnt))
+            out = []
+            for c in w4[ref]["child"]:
+                if c["ref"] == EMPTY:
+                    continue
+                assert np.array_equal(c["bmin"], forest[k]["aabb_min"]) and np.array_equal(c["bmax"], forest[k]["aabb_max"])
+                out += chain_slots(int(c["ref"]), k)
+            return out
+
         def leaf(ref, k):
-            assert ref & LEAF
-            start, cnt = ref & ((1 << 27) - 1), ((ref >> 27) & 15) + 1
-            assert start == forest[k]["range"][0] and start + cnt == forest[k]["range"][1]
-            seen.extend(range(start, start + cnt))
+            slots = chain_slots(ref, k)
+            assert slots == list(range(forest[k]["range"][0], forest[k]["range"][1]))
+            seen.extend(slots)
 
         def visit(ref, k):  # ref stands for reference node k
             if is_leaf(k):
