@@ -69,6 +69,23 @@ def test_parallel_builder_is_the_sequential_tree(strategy, monkeypatch):
         assert np.array_equal(ob.sorted_primitive_index, pb.sorted_primitive_index), threads
 
 
+def test_flattened_scene_does_not_depend_on_the_thread_count(monkeypatch):
+    """the multi-threaded build / flatten is deterministic: every array of the blob is byte-identical for 1, 3 and all threads"""
+    pos, idx = S.torus_mesh(200, 130)   # 52,000 triangles: above the parallel thresholds
+    blobs = []
+    for threads in ("1", "3", None):
+        if threads is None:
+            monkeypatch.delenv("RDN_BUILD_THREADS", raising=False)
+        else:
+            monkeypatch.setenv("RDN_BUILD_THREADS", threads)
+        sp = helpers.single_mesh_scene(pos, idx, S.mat4_translate(0, 0, -10), devices=(), product=True)
+        blobs.append({k: v.tobytes() for k, v in sp.p.arrays().items()})
+    for other in blobs[1:]:
+        assert other.keys() == blobs[0].keys()
+        for k in other:
+            assert other[k] == blobs[0][k], k
+
+
 def test_builder_edge_cases():
     for n in (0, 1, 2, 3):
         boxes = np.tile(np.array([[0, 0, 0, 1, 1, 1]], np.float32), (n, 1))
