@@ -375,11 +375,11 @@ def run_ours(args):
         compulsory = (64.0 * n + blob_bytes) / (kernel_ms * 1e-3) / 1e9
         l2_peak = sysm.measure_l2_read_gbs(64 << 20, 50)  # resident-set read microbenchmark, this box, this run
         traffic, traffic_src = None, None
-        prof = os.path.join(ROOT, "profiles", "ncu_r1e_k_trace_ordered_c2.json")
+        prof = os.path.join(ROOT, "profiles", "ncu_r1f_k_trace_ordered_c2.json")
         if os.path.exists(prof):  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
             pl = json.load(open(prof))["launches"]
             traffic = float(np.mean([x["dram_traffic_bytes"] for x in pl]))
-            traffic_src = "profiles/ncu_r1e_k_trace_ordered_c2.json (ncu --set full, cold-cache replay of one launch)"
+            traffic_src = "profiles/ncu_r1f_k_trace_ordered_c2.json (ncu --set full, cold-cache replay of one launch)"
         out = {
             "metric": "closest-hit Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
