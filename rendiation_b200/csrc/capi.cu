@@ -61,14 +61,13 @@ struct Scratch {
     s.tie_total = reinterpret_cast<uint32_t *>(b + 28);
     s.epoch_done = reinterpret_cast<uint32_t *>(b + 112);
     s.counters = reinterpret_cast<unsigned long long *>(b + 32);
-    s.sm_cursor = reinterpret_cast<uint32_t *>(b + 128);
     s.tie_queue = tie_queue;
     s.tie_best = tie_best;
     return s;
   }
 };
-// 32 B of cursors/flags + 10 u64 counters (6 visit counters, 4 debug) + epoch_done at 112 + the per-SM unit cursors
-constexpr size_t SCRATCH_BASE_BYTES = 128 + SM_CURSOR_SLOTS * sizeof(uint32_t);
+// 32 B of cursors/flags + 10 u64 counters (6 visit counters, 4 debug) + epoch_done at 112
+constexpr size_t SCRATCH_BASE_BYTES = 128;
 
 struct Slot {  // one pipeline lane of the host-buffer path
   cudaStream_t stream = nullptr;

@@ -44,9 +44,7 @@ struct TraceScratch {
   uint32_t *tie_queue;               // ray indices, capacity >= rays of the launch
   float *tie_best;                   // closest distance found by the ordered kernel, per queued ray
   unsigned long long *counters;      // 6 x u64 (rdn_counters)
-  uint32_t *sm_cursor;               // SM_CURSOR_SLOTS per-SM unit cursors of the running ordered kernel (its last CTA zeroes them again)
 };
-constexpr int SM_CURSOR_SLOTS = 256;
 
 // relative slack of the ordered kernel's pruning bound and near-tie detection (see DESIGN.md "Exactness")
 constexpr float TIE_EPS = 1e-5f;

@@ -68,11 +68,13 @@ __device__ __forceinline__ uint32_t cull_triangle_bits(uint32_t f) {
   return (enable ? 1u : 0u) | (back ? 2u : 0u);
 }
 
+#if defined(RDN_DEBUG_STEPS) || defined(RDN_DEBUG_TIMELINE)
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+#endif
 __device__ __forceinline__ Vec3 xyz(const float4 &q) { return Vec3{q.x, q.y, q.z}; }
 __device__ __forceinline__ Vec3 recip3(Vec3 d) { return Vec3{1.0f / d.x, 1.0f / d.y, 1.0f / d.z}; }
 
@@ -361,11 +363,6 @@ struct OrderedParams {
   uint32_t width, height;
   uint32_t world_root;  // wide reference of the bound TLAS (REF_EMPTY: every ray misses)
   uint32_t irregular_start, irregular_count;  // the bound TLAS's irregular instances (S.irregular_instances), at most IRREGULAR_LIST_MAX
-  // SM-local scheduling: the launch is cut into units of 32 fetch slots (one 8x4 pixel tile, or 32 consecutive rays), ordered so
-  // that neighbours in the order are neighbours on screen (16x16-tile macro blocks in raster order, Morton order inside), and
-  // the unit list into n_ranges contiguous ranges, one per SM
-  uint32_t n_units, n_ranges, units_per_range, blocks_x;  // blocks_x == 0: units in raster tile order (or a linear ray list)
-  uint32_t prefetch_unit;  // take the next unit from the home range while the current one is being traversed
   // HOT: wide nodes [hot_a_base, +hot_a_count) (top of the TLAS tree) and [hot_b_base, +hot_b_count) (top of the largest geometry
   // tree) are staged in shared memory by two bulk copies (TMA) at CTA start
   uint32_t hot_a_base, hot_a_count, hot_b_base, hot_b_count;
@@ -463,85 +460,26 @@ __device__ __forceinline__ void drain_tie_queue(const OrderedParams &P) {
 }
 
 
-template <int PF>
-__device__ __forceinline__ void prefetch_ref(const SceneDev &S, uint32_t ref, bool in_object) {
-  const void *p = nullptr;
-  if (ref < REF_SPECIAL) p = S.wide_nodes + ref;
-  else if ((ref & REF_LEAF_BIT) && in_object) p = S.triangles + (ref & REF_LEAF_START_MASK);
-  if (p) {
-    if (PF == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-    else asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-  }
-}
-
-// SM-local work distribution.  Every SM owns one contiguous range of the (screen-coherent) unit order and its warps take
-// units from the range's cursor, so the 32 warps resident on an SM walk 32 neighbouring tiles at the same time and share the
-// BVH nodes they pull into that SM's L1 — with one global cursor, consecutive tiles go to whichever warp of the whole GPU
-// asks next and an SM's tiles are scattered over a band of the frame.  A warp whose home range is dry takes units from the
-// following ranges (cursors only grow, so a range found dry is never looked at again: at most n_ranges probes per warp per
-// launch).  Returns a warp-uniform unit index or RDN_INVALID_ID when the launch has no unit left.
-__device__ __forceinline__ uint32_t smid() {
-  uint32_t id;
-  asm("mov.u32 %0, %%smid;" : "=r"(id));
-  return id;
-}
-__device__ __forceinline__ uint32_t grab_unit(const OrderedParams &P, uint32_t lane, uint32_t home, uint32_t &probe) {
-  // the 32 lanes look at 32 ranges at a time (one coalesced read of their cursors): a serial probe per range costs an L2 round
-  // trip each, ~50 us per warp once the launch runs dry
-  while (probe < P.n_ranges) {
-    const uint32_t k = probe + lane;
-    uint32_t r = home + k;
-    if (r >= P.n_ranges) r -= P.n_ranges;
-    const uint32_t begin = r * P.units_per_range;
-    uint32_t len = 0;
-    if (k < P.n_ranges && begin < P.n_units) len = P.n_units - begin < P.units_per_range ? P.n_units - begin : P.units_per_range;
-    const bool has = len != 0u && ld_volatile_u32(P.scratch.sm_cursor + r) < len;
-    const uint32_t mask = __ballot_sync(FULL_MASK, has);
-    if (mask == 0u) { probe += 32u; continue; }
-    const uint32_t first = __ffs(mask) - 1u;
-    probe += first;  // the ranges before it are dry for good
-    uint32_t unit = RDN_INVALID_ID;
-    if (lane == first) {
-      const uint32_t t = atomicAdd(P.scratch.sm_cursor + r, 1u);
-      if (t < len) unit = begin + t;
-    }
-    unit = __shfl_sync(FULL_MASK, unit, first);
-    if (unit != RDN_INVALID_ID) return unit;
-    probe += 1u;  // it went dry between the look and the take
-  }
-  return RDN_INVALID_ID;
-}
-__device__ __forceinline__ uint32_t compact_even_bits4(uint32_t x) {  // bits 0,2,4,6 -> 0..3
-  x &= 0x55u;
-  x = (x | (x >> 1)) & 0x33u;
-  return (x | (x >> 2)) & 0x0Fu;
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // Warp-synchronous rounds: every round the alive lanes (1) descend up to K inner nodes each, (2) re-converge
 // (__syncwarp) and handle their leaf / instance / bookkeeping item TOGETHER — on Volta+ lanes do not re-converge at a
 // loop exit by themselves, and a triangle test executed by 3 lanes costs the warp as much as one executed by 32 —
-// (3) vote: when fewer than THRESH lanes still hold a ray (and rays remain) the warp goes back to the refill point.
+// (3) vote: when no lane holds a ray any more the warp goes back to the refill point (whole-tile refill).
 // Refill culls rays against the TLAS root box on the spot (the reference's first test), so rays that miss the scene
 // never occupy a traversal lane.
-// IRREGULAR: the bound TLAS lists irregular instances (checked at refill); a separate instantiation so that regular scenes pay
-// nothing for the out-of-line test (the call makes ptxas save two dozen registers around the whole refill block).
-// UNITS: whole units of 32 fetch slots from the range cursors (grab_unit; one range = one global cursor, n_ranges = SM count = every
-// SM its own range) instead of single fetch slots from one 64-bit cursor; needs THRESH == 1 (whole-tile refill).
-// PF: as soon as a node's child references are known, prefetch what they point to (1: into L1, 2: into L2) — the two slab tests
-// that decide which child is entered take a warp several hundred cycles of wall clock (it shares its issue slot with seven
-// others), enough for the line to arrive before the next dependent fetch asks for it; no register is held by a prefetch.
-// LD256: 256-bit loads / stores for nodes, triangles, instance boxes, rays and hit records.
-// HOT: the top levels of the TLAS tree and of the largest geometry tree (breadth-first blocks of HOT_TOP_NODES wide nodes, 8 KB
-// each) are copied into shared memory with cp.async.bulk (TMA, completion on an mbarrier) when the CTA starts, and node fetches
-// that fall into either block read shared memory instead of L1.
-// SPEC: speculative traversal with one postponed leaf per lane (Aila & Laine): a lane that reaches a triangle leaf parks it and
-// keeps descending (against the bound it had), so that more lanes hold a leaf when the warp runs the triangle code — profiled at
-// ~5 of 32 lanes for a quarter of all issued instructions.  The parked leaf is tested before the lane leaves the instance.
-// WIDE4: the walk runs over the 128 B four-box nodes (layout.h Wide4Node: the grandchildren of a reference node, exact boxes): half
-// the steps for the same box tests (nested boxes make the skipped test of the absorbed child redundant), the hit children entered
-// nearest first and the others deferred farthest first.
-template <int K, int MINB, int THRESH, bool DRAIN_TIES, bool IRREGULAR, bool UNITS, int PF, bool LD256, bool HOT, bool SPEC, bool WIDE4>  // DRAIN_TIES: near-tie queue drained inside the kernel (else by k_resolve_ties)
+// Template switches.  DRAIN_TIES: near-tie queue drained inside the kernel (else by k_resolve_ties).  IRREGULAR: the bound TLAS
+// lists irregular instances (checked at refill); a separate instantiation so that regular scenes pay nothing for the out-of-line
+// test (the call makes ptxas save two dozen registers around the whole refill block).  LD256: 256-bit loads / stores for nodes,
+// triangles, instance boxes, rays and hit records.  HOT: the top levels of the TLAS tree and of the largest geometry tree
+// (breadth-first blocks of HOT_TOP_NODES wide nodes, 8 KB each) are copied into shared memory with cp.async.bulk (TMA,
+// completion on an mbarrier) when the CTA starts, and node fetches that fall into either block read shared memory instead of L1
+// (measured 9-13 % slower: experiment).  WIDE4: the walk runs over the 128 B four-box nodes (layout.h Wide4Node: the
+// grandchildren of a reference node, exact boxes): half the steps for the same box tests (nested boxes make the skipped test of
+// the absorbed child redundant), the hit children entered nearest first and the others deferred farthest first (measured
+// neutral: experiment).  Experiments that were measured, rejected and removed — whole-unit / per-SM work distribution, child
+// prefetch, speculative traversal with a postponed leaf, any-hit pre-classification — are described in DESIGN.md §5 with their
+// logs under profiles/.
+template <int K, int MINB, bool DRAIN_TIES, bool IRREGULAR, bool LD256, bool HOT, bool WIDE4>
 __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(const __grid_constant__ OrderedParams P) {
   const SceneDev &S = P.S;
   const uint32_t lane = threadIdx.x & 31u;
@@ -608,12 +546,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
   uint32_t best_slot = RDN_INVALID_ID, best_inst = RDN_INVALID_ID, best_back = 0;
   uint32_t cur = REF_DONE, cur_inst = 0, cur_flags = 0, cull_bits = 0, geom_end = 0;
   bool in_object = false;
-  uint32_t pending = REF_DONE;  // SPEC: the postponed triangle leaf (REF_DONE = none)
   bool warp_exhausted = false;
-  const uint32_t sm_home = UNITS ? smid() % P.n_ranges : 0u;
-  uint32_t sm_probe = 0;  // ranges, counted from the home range, already found dry
-  uint32_t pending_take = RDN_INVALID_ID;  // lane 0: result of a take from the home range issued ahead of need
-  bool have_pending = false;
 #ifdef RDN_DEBUG_STEPS
   // per-thread totals, reduced once per warp at kernel exit so the counters do not perturb the timeline
   unsigned long long dbg_steps = 0, dbg_tris = 0, dbg_pushes = 0, dbg_ray_steps = 0, dbg_max = 0, dbg_rays = 0, dbg_long = 0;
@@ -630,75 +563,6 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
 #define RDN_POP() (sp > 0 ? stack[--sp] : REF_DONE)
 
   for (;;) {
-    if (UNITS) {
-      // ---------------- whole-tile refill from this SM's range: no lane holds a ray here (THRESH == 1)
-#pragma unroll 1
-      while (!warp_exhausted && !__any_sync(FULL_MASK, alive)) {
-        uint32_t unit = RDN_INVALID_ID;
-        if (have_pending) {  // warp-uniform
-          have_pending = false;
-          const uint32_t t = __shfl_sync(FULL_MASK, pending_take, 0);
-          const uint32_t begin = sm_home * P.units_per_range;
-          const uint32_t len = begin < P.n_units ? (P.n_units - begin < P.units_per_range ? P.n_units - begin : P.units_per_range) : 0u;
-          if (t < len) unit = begin + t;
-          else if (sm_probe == 0u) sm_probe = 1u;  // the home range is dry
-        }
-        if (unit == RDN_INVALID_ID) unit = grab_unit(P, lane, sm_home, sm_probe);
-        if (unit == RDN_INVALID_ID) {
-#if defined(RDN_DEBUG_STEPS) || defined(RDN_DEBUG_TIMELINE)
-          if (lane == 0) atomicMin(P.scratch.counters + 7, globaltimer_ns());  // ray list ran dry
-#endif
-          warp_exhausted = true;
-          break;
-        }
-        uint64_t idx;
-        bool valid;
-        if (P.tiles_x && P.blocks_x == 0u) {
-          const uint32_t ty = unit / P.tiles_x, tx = unit - ty * P.tiles_x;
-          const uint32_t x = tx * 8u + (lane & 7u), y = ty * 4u + (lane >> 3);
-          valid = x < P.width && y < P.height;
-          idx = static_cast<uint64_t>(y) * P.width + x;
-        } else if (P.tiles_x) {
-          const uint32_t block = unit >> 8, within = unit & 255u;
-          const uint32_t by = block / P.blocks_x, bx = block - by * P.blocks_x;
-          const uint32_t x = (bx * 16u + compact_even_bits4(within)) * 8u + (lane & 7u);
-          const uint32_t y = (by * 16u + compact_even_bits4(within >> 1)) * 4u + (lane >> 3);
-          valid = x < P.width && y < P.height;
-          idx = static_cast<uint64_t>(y) * P.width + x;
-        } else {
-          idx = static_cast<uint64_t>(unit) * 32u + lane;
-          valid = idx < P.n;
-        }
-      if (valid) {
-        float4 r0, r1;
-        load_pair<LD256>(P.rays + idx, r0, r1);
-        const Vec3 ro = xyz(r0), rd = xyz(r1), rinv = recip3(rd);
-        float tn;
-        const bool enters = world_entry != REF_EMPTY && slab_test(ro, rinv, r0.w, r1.w, root_min, root_max, tn);
-        const bool suspect = IRREGULAR && enters &&
-                             meets_irregular_instance(S, P.irregular_start, P.irregular_count, P.L.cull_mask, P.rays + idx);
-        if (suspect) {
-          enqueue_rewalk<DRAIN_TIES>(P.scratch, lane, idx, __int_as_float(0x7FC00000));  // NaN: walk the whole range
-        } else if (enters) {
-          ri = idx; o = ro; d = rd; inv = rinv;
-          t_near_world = r0.w; far0 = r1.w;
-          scaling = 1.f; near_s = t_near_world; bound = far0; far_s = far0;
-          best = INFINITY; second = INFINITY; best_slot = RDN_INVALID_ID; best_inst = RDN_INVALID_ID;
-          in_object = false; sp = 0;
-          cur = world_entry;
-          alive = true;
-        } else {
-          store_hit_as<LD256>(P.hits + idx, r1.w, 0.f, 0.f, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, 0);
-        }
-      }
-        // take the following unit now: the round trip of the atomic overlaps the traversal of this one (the result is
-        // only looked at by the next refill)
-        if (P.prefetch_unit != 0u && sm_probe == 0u) {
-          if (lane == 0) pending_take = atomicAdd(P.scratch.sm_cursor + sm_home, 1u);
-          have_pending = true;
-        }
-      }
-    } else {
     // ---------------- warp-converged refill (a few rounds, so scene-missing rays are retired here)
 #pragma unroll 1
     for (int attempt = 0; attempt < 4; ++attempt) {
@@ -751,7 +615,6 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
         }
       }
     }
-    }
     const uint32_t amask = __ballot_sync(FULL_MASK, alive);
     if (amask == 0) {
       if (warp_exhausted) break;
@@ -764,7 +627,6 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
         // ---------------- phase 1: up to K inner nodes (both child boxes in one 64 B fetch)
 #pragma unroll 1
         for (int k = 0; k < K; ++k) {
-          if (SPEC && pending == REF_DONE && in_object && (cur & REF_LEAF_BIT)) { pending = cur; cur = RDN_POP(); }
           if (!(cur < REF_SPECIAL)) break;
 #ifdef RDN_DEBUG_STEPS
           ++dbg_steps; ++dbg_ray_steps;
@@ -810,10 +672,6 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
             load_pair<LD256>(np + 2, q2, q3);
           }
           const uint32_t r0 = __float_as_uint(q0.w), r1 = __float_as_uint(q1.w);
-          if (PF != 0) {
-            prefetch_ref<PF>(S, r0, in_object);
-            prefetch_ref<PF>(S, r1, in_object);
-          }
           float n0, n1;
           const bool h0 = slab_test(o, inv, near_s, far_s, xyz(q0), xyz(q1), n0);
           const bool h1 = slab_test(o, inv, near_s, far_s, xyz(q2), xyz(q3), n1);
@@ -829,13 +687,11 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
           cur = take0 ? r0 : r1;
           if (!(h0 || h1)) cur = RDN_POP();
         }
-        if (SPEC && pending == REF_DONE && in_object && (cur & REF_LEAF_BIT)) { pending = cur; cur = RDN_POP(); }
         __syncwarp(amask);
 
         // ---------------- phase 2: one leaf / instance / bookkeeping item, all lanes that have one at the same time
         uint32_t leaf_item = REF_DONE;
-        if (SPEC) { leaf_item = pending; pending = REF_DONE; }
-        else if (in_object && (cur & REF_LEAF_BIT)) leaf_item = cur;
+        if (in_object && (cur & REF_LEAF_BIT)) leaf_item = cur;
         if (leaf_item != REF_DONE) {
           {
             const uint32_t start = leaf_item & REF_LEAF_START_MASK;
@@ -864,7 +720,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
                   second = fminf(second, distance);
                 }
               }
-              if (!SPEC) cur = RDN_POP();
+              cur = RDN_POP();
             }
           }
         } else if (cur >= REF_SPECIAL && cur != REF_DONE) {
@@ -872,7 +728,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
             const uint32_t start = cur & REF_LEAF_START_MASK;
             const uint32_t count = ((cur >> REF_LEAF_COUNT_SHIFT) & 15u) + 1u;
             if (in_object) {
-              // (SPEC only: a second leaf while one is parked; it is parked in the next round)
+              // (not reached: triangle leaves are handled above)
             } else {
               // instance leaf (world space): take the first slot, park the rest
               if (count > 1) RDN_PUSH(REF_LEAF_BIT | ((count - 2u) << REF_LEAF_COUNT_SHIFT) | (start + 1u));
@@ -926,11 +782,11 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
         }
 
         // ---------------- vote (also the re-convergence point of phase 2)
-        const int active = __popc(__ballot_sync(amask, cur != REF_DONE || (SPEC && pending != REF_DONE)));
-        if (active == 0 || (active < THRESH && !warp_exhausted)) break;
+        const int active = __popc(__ballot_sync(amask, cur != REF_DONE));
+        if (active == 0) break;
       }
 
-      if (cur == REF_DONE && (!SPEC || pending == REF_DONE)) {
+      if (cur == REF_DONE) {
 #ifdef RDN_DEBUG_STEPS
         dbg_max = dbg_ray_steps > dbg_max ? dbg_ray_steps : dbg_max;
         dbg_long += dbg_ray_steps > 200 ? 1 : 0;
@@ -999,11 +855,6 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
       drain_tie_queue(P);
       __syncthreads();
     }
-    if (UNITS) {
-      for (uint32_t i = threadIdx.x; i < P.n_ranges; i += blockDim.x) P.scratch.sm_cursor[i] = 0u;
-      __threadfence();
-      __syncthreads();
-    }
     if (threadIdx.x == 0) {
       *P.scratch.work_counter = 0ull;
       *P.scratch.blocks_done = 0u;
@@ -1067,21 +918,7 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const
     P.tiles_x = (P.width + 7u) / 8u;
     P.n_fetch = static_cast<uint64_t>(P.tiles_x) * ((P.height + 3u) / 4u) * 32u;
   }
-  // unit scheduling experiments: 10 = one cursor, raster tiles, next unit taken ahead; 11 = the same over 16x16-tile Morton blocks;
-  // 12 = a range of the Morton order per SM, with stealing; 13 / 14 = 10 / 12 without taking ahead
   const int variant_ = ordered_variant();
-  const bool morton = variant_ == 11 || variant_ == 12 || variant_ == 14;
-  const bool sm_local = variant_ == 12 || variant_ == 14;
-  P.prefetch_unit = (variant_ == 13 || variant_ == 14) ? 0u : 1u;
-  if (P.tiles_x && morton) {
-    P.blocks_x = (P.tiles_x + 15u) / 16u;
-    P.n_units = P.blocks_x * ((((P.height + 3u) / 4u) + 15u) / 16u) * 256u;
-  } else {
-    P.blocks_x = 0;
-    P.n_units = P.tiles_x ? P.tiles_x * ((P.height + 3u) / 4u) : static_cast<uint32_t>((n + 31u) / 32u);
-  }
-  P.n_ranges = sm_local ? static_cast<uint32_t>(sm_count < SM_CURSOR_SLOTS ? sm_count : SM_CURSOR_SLOTS) : 1u;
-  P.units_per_range = (P.n_units + P.n_ranges - 1u) / P.n_ranges;
   const bool irregular_tlas = tlas.irregular_count != 0 && tlas.irregular_count != IRREGULAR_ROUTE_ALL;
   // the four-box walk needs the four-box view (emitted only when the scene was built under the same variant) and a regular TLAS
   const bool use_wide4 = (variant_ == 60 || variant_ == 61) && !irregular_tlas && tlas.wide4_root != REF_EMPTY;
@@ -1099,28 +936,22 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const
   using KernelFn = void (*)(const OrderedParams);
   KernelFn fn;
   bool inline_ties = true;
+  // template arguments: <K, MINB, DRAIN_TIES, IRREGULAR, LD256, HOT, WIDE4>
   switch (variant) {
-    // (K, THRESH) = (4,1), (3,4), (4,8) were instantiated here during the sweep of profiles/kbench_r1_variant_sweep.log
-    case 30: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, false, false, false, false>; break;  // 128-bit loads / stores
-    case 40: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, true, true, false, false>; break;    // top levels staged in shared memory (TMA)
-    case 50: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, true, false, true, false>; break;    // speculative traversal, one postponed leaf per lane
-    case 60: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, true, false, false, true>; break;    // four-box nodes, K = 2 steps per round
-    case 61: fn = k_trace_ordered_rounds<1, 8, 1, true, false, false, 0, true, false, false, true>; break;    // ... one step per round
-    // whole-unit scheduling experiments, all measured slower than the default (profiles/kbench_r1_unit_scheduling.log): lanes whose
-    // ray misses the scene stay idle for the rest of the tile instead of being topped up with the next rays
-    case 10: case 11: case 12: case 13: case 14: fn = k_trace_ordered_rounds<2, 8, 1, true, false, true, 0, true, false, false, false>; break;
-    case 9: fn = k_trace_ordered_rounds<2, 8, 1, false, false, false, 0, true, false, false, false>; inline_ties = false; break;  // queue drained by k_resolve_ties
-    case 20: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 1, true, false, false, false>; break;  // children prefetched into L1
-    case 21: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 2, true, false, false, false>; break;  // ... into L2
-    default: fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, true, false, false, false>; break;
+    case 9: fn = k_trace_ordered_rounds<2, 8, false, false, true, false, false>; inline_ties = false; break;  // queue drained by k_resolve_ties
+    case 30: fn = k_trace_ordered_rounds<2, 8, true, false, false, false, false>; break;  // 128-bit loads / stores
+    case 40: fn = k_trace_ordered_rounds<2, 8, true, false, true, true, false>; break;    // top levels staged in shared memory (TMA)
+    case 60: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, true>; break;    // four-box nodes, K = 2 steps per round
+    case 61: fn = k_trace_ordered_rounds<1, 8, true, false, true, false, true>; break;    // ... one step per round
+    default: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false>; break;
   }
-  if ((variant == 60 || variant == 61) && !use_wide4) fn = k_trace_ordered_rounds<2, 8, 1, true, false, false, 0, true, false, false, false>;
+  if ((variant == 60 || variant == 61) && !use_wide4) fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false>;
   if (P.irregular_count != 0) {  // (the experimentation variants exist for regular scenes only)
     // Rays handed over at refill can be a large part of the launch, and the in-kernel drain claims entries through one CAS
     // cursor (fine for a handful of ties, 55 ms for 400 K entries): the queue of an irregular launch is walked by
     // k_resolve_ties, one thread per entry, right behind this kernel.
     inline_ties = false;
-    fn = k_trace_ordered_rounds<2, 8, 1, false, true, false, 0, true, false, false, false>;
+    fn = k_trace_ordered_rounds<2, 8, false, true, true, false, false>;
   }
   int blocks_per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, ORDERED_BLOCK, 0);
