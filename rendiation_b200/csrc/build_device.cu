@@ -16,8 +16,10 @@
 // FALLBACK_MAX primitives (many identical centres) are left to the host builder.  f32 arithmetic in the reference's order, -fmad=false.
 #include <cuda_runtime.h>
 
+#ifndef RDN_SIMT_EMU  // (the CPU emulation build of the test-suite, tests/simt/, scans with a plain loop: CUB needs nvcc)
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
+#endif
 
 #include <cmath>
 #include <string>
@@ -63,6 +65,19 @@ struct OneHot {
   }
 };
 struct Control { uint32_t node_count, next_count, unsupported, out_of_range; };
+
+// exclusive prefix sums of the one-hot bucket indicators (d_temp == nullptr: only the scratch size is returned)
+cudaError_t scan_one_hot(void *d_temp, size_t &temp_bytes, const uint8_t *d_which, Counts4 *d_scan, uint32_t n) {
+#ifndef RDN_SIMT_EMU
+  cub::TransformInputIterator<Counts4, OneHot, const uint8_t *> it(d_which, OneHot());
+  return cub::DeviceScan::ExclusiveScan(d_temp, temp_bytes, it, d_scan, Counts4Add(), Counts4{}, static_cast<int>(n));
+#else
+  if (!d_temp) { temp_bytes = 16; return cudaSuccess; }
+  Counts4 run{};
+  for (uint32_t i = 0; i < n; ++i) { d_scan[i] = run; run = Counts4Add()(run, OneHot()(d_which[i])); }
+  return cudaSuccess;
+#endif
+}
 
 __device__ __forceinline__ uint32_t float_key(float f) {
   const uint32_t u = __float_as_uint(f);
@@ -303,11 +318,8 @@ int build_bvh_sah_device(const Box3 *boxes, uint64_t n64, uint32_t n_buckets, co
   BD_CUDA(cudaMalloc(&d_nodes, node_cap * sizeof(DevNode)));
   BD_CUDA(cudaMalloc(&d_slots, static_cast<size_t>(n) * sizeof(Slot)));
   BD_CUDA(cudaMalloc(&d_ctl, sizeof(Control)));
-  {
-    cub::TransformInputIterator<Counts4, OneHot, const uint8_t *> it(d_which, OneHot());
-    BD_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, temp_bytes, it, d_scan, Counts4Add(), Counts4{}, static_cast<int>(n)));
-    BD_CUDA(cudaMalloc(&d_temp, temp_bytes ? temp_bytes : 16));
-  }
+  BD_CUDA(scan_one_hot(nullptr, temp_bytes, d_which, d_scan, n));
+  BD_CUDA(cudaMalloc(&d_temp, temp_bytes ? temp_bytes : 16));
   BD_CUDA(cudaMemcpy(d_boxes, boxes, static_cast<size_t>(n) * sizeof(Box3), cudaMemcpyHostToDevice));
   BD_CUDA(cudaMemcpy(d_nodes, &root, sizeof(root), cudaMemcpyHostToDevice));
   k_fill_u32<<<blocks_n, threads>>>(d_index[0], n, 0, true);
@@ -324,10 +336,7 @@ int build_bvh_sah_device(const Box3 *boxes, uint64_t n64, uint32_t n_buckets, co
     const uint32_t blocks_a = (n_active + threads - 1) / threads;
     k_slot_begin<<<blocks_a, threads>>>(d_active[cur], n_active, d_nodes, d_slots, n_buckets);
     k_bucket<<<blocks_n, threads>>>(d_boxes, d_index[cur], d_index[cur ^ 1], d_owner[cur], d_owner[cur ^ 1], n, d_slots, n_buckets, d_which, d_ctl);
-    {
-      cub::TransformInputIterator<Counts4, OneHot, const uint8_t *> it(d_which, OneHot());
-      BD_CUDA(cub::DeviceScan::ExclusiveScan(d_temp, temp_bytes, it, d_scan, Counts4Add(), Counts4{}, static_cast<int>(n)));
-    }
+    BD_CUDA(scan_one_hot(d_temp, temp_bytes, d_which, d_scan, n));
     k_split<<<blocks_a, threads>>>(d_slots, n_active, d_nodes, n_buckets, max_depth, bin_size, d_active[cur ^ 1], d_ctl);
     k_scatter<<<blocks_n, threads>>>(d_index[cur], d_index[cur ^ 1], d_owner[cur], d_owner[cur ^ 1], n, d_slots, d_nodes, d_which, d_scan);
     k_fallback<<<blocks_a, threads>>>(d_boxes, d_index[cur ^ 1], d_slots, n_active, d_nodes);

@@ -118,7 +118,10 @@ static_assert(sizeof(Wide4Node) == 128, "Wide4Node");
 constexpr uint32_t REF_LEAF_BIT = 0x80000000u;
 constexpr uint32_t REF_LEAF_COUNT_SHIFT = 27;
 constexpr uint32_t REF_LEAF_START_MASK = (1u << 27) - 1u;
-constexpr uint32_t REF_LEAF_MAX_COUNT = 16;
+#ifndef RDN_REF_LEAF_MAX_COUNT
+#define RDN_REF_LEAF_MAX_COUNT 16  // (the emulated test build of tests/simt lowers it so that ordinary scenes walk leaf chains)
+#endif
+constexpr uint32_t REF_LEAF_MAX_COUNT = RDN_REF_LEAF_MAX_COUNT;
 constexpr uint32_t REF_SPECIAL = 0x7F000000u;
 constexpr uint32_t REF_DONE = 0x7FFFFFFDu;           // traversal stack exhausted (kernel-internal)
 constexpr uint32_t REF_EMPTY = 0x7FFFFFFEu;

@@ -140,12 +140,30 @@ __device__ __forceinline__ void store_hit(rdn_hit *dst, float t, float u, float 
 
 // 32 bytes in one instruction (Blackwell's 256-bit global loads / stores: LDG.E.256 / STG.E.256): a 64 B node or triangle record is
 // two load instructions instead of four, a ray or a hit record one instead of two.  The address must be 32-byte aligned.
+// (RDN_SIMT_EMU: the CPU emulation build of the test-suite, tests/simt/ — PTX-only operations get plain C++ stand-ins there)
+#ifndef RDN_SIMT_EMU
+__device__ __forceinline__ void ld_global_nc_256(const void *p, float4 &a, float4 &b) {
+  asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+      : "l"(p));
+}
+__device__ __forceinline__ void st_global_256(void *p, float4 a, float4 b) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x),
+               "f"(b.y), "f"(b.z), "f"(b.w)
+               : "memory");
+}
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#else
+inline void ld_global_nc_256(const void *p, float4 &a, float4 &b) { a = static_cast<const float4 *>(p)[0]; b = static_cast<const float4 *>(p)[1]; }
+inline void st_global_256(void *p, float4 a, float4 b) { static_cast<float4 *>(p)[0] = a; static_cast<float4 *>(p)[1] = b; }
+inline void pdl_launch_dependents() {}
+inline void pdl_wait() {}
+#endif
 template <bool WIDE>
 __device__ __forceinline__ void load_pair(const void *p, float4 &a, float4 &b) {
   if (WIDE) {
-    asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
-        : "l"(p));
+    ld_global_nc_256(p, a, b);
   } else {
     a = __ldg(reinterpret_cast<const float4 *>(p));
     b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
@@ -155,9 +173,8 @@ template <bool WIDE>
 __device__ __forceinline__ void store_hit_as(rdn_hit *dst, float t, float u, float v, uint32_t prim, uint32_t geom, uint32_t inst,
                                              uint32_t custom, uint32_t kind) {
   if (WIDE) {
-    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "f"(t), "f"(u), "f"(v), "f"(__uint_as_float(prim)),
-                 "f"(__uint_as_float(geom)), "f"(__uint_as_float(inst)), "f"(__uint_as_float(custom)), "f"(__uint_as_float(kind))
-                 : "memory");
+    st_global_256(dst, make_float4(t, u, v, __uint_as_float(prim)),
+                  make_float4(__uint_as_float(geom), __uint_as_float(inst), __uint_as_float(custom), __uint_as_float(kind)));
   } else {
     store_hit(dst, t, u, v, prim, geom, inst, custom, kind);
   }
@@ -488,7 +505,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
   // Programmatic dependent launch: the NEXT ordered launch on this stream may start filling SM slots as soon as CTAs of this one
   // leave, i.e. while the last long rays of this launch are still being walked (a no-op when launched without the attribute).
   // The next launch reads nothing this one writes (its own rays, the read-only scene, the other scratch set).
-  asm volatile("griddepcontrol.launch_dependents;");
+  pdl_launch_dependents();
   // Gate: with tails overlapping, the launch after next can reach the device while the launch that last used THIS scratch
   // set still has a straggler CTA (late CTAs of the launch in between find the ray list dry and leave at once).  Every
   // earlier launch is fully resident by then (a dependent launch starts only after all CTAs of its predecessor have
@@ -501,6 +518,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
 
   __shared__ __align__(128) float4 s_hot[HOT ? 2 * HOT_TOP_NODES * 4 : 4];
   __shared__ __align__(8) unsigned long long s_hot_bar;
+#ifndef RDN_SIMT_EMU
   if constexpr (HOT) {
     const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&s_hot_bar));
     if (threadIdx.x == 0) {
@@ -525,6 +543,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
       asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
     }
   }
+#endif
 
   // the world pseudo-root (TLAS root box + its reference) is launch-uniform: keep it in registers
   Vec3 root_min = {0, 0, 0}, root_max = {0, 0, 0};
@@ -849,7 +868,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
   if (s_last) {
     // ... and this launch must not COMPLETE before its predecessor: whatever follows in the stream (a copy of the previous
     // launch's hits, a kernel reading them) is ordered behind this grid only
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    pdl_wait();
     if (DRAIN_TIES) {
       __threadfence();
       drain_tie_queue(P);
@@ -940,7 +959,9 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const
   switch (variant) {
     case 9: fn = k_trace_ordered_rounds<2, 8, false, false, true, false, false>; inline_ties = false; break;  // queue drained by k_resolve_ties
     case 30: fn = k_trace_ordered_rounds<2, 8, true, false, false, false, false>; break;  // 128-bit loads / stores
+#ifndef RDN_SIMT_EMU
     case 40: fn = k_trace_ordered_rounds<2, 8, true, false, true, true, false>; break;    // top levels staged in shared memory (TMA)
+#endif
     case 60: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, true>; break;    // four-box nodes, K = 2 steps per round
     case 61: fn = k_trace_ordered_rounds<1, 8, true, false, true, false, true>; break;    // ... one step per round
     default: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false>; break;

@@ -1,0 +1,174 @@
+// simt_engine.cpp — TEST INFRASTRUCTURE (see simt_emu.h): the fiber scheduler behind ::simt::launch.
+#include <sys/mman.h>
+
+#include <mutex>
+#include <thread>
+
+#include "simt_emu.h"
+
+namespace simt {
+
+thread_local Fiber *g_cur = nullptr;
+
+namespace {
+constexpr size_t FIBER_STACK = 256 * 1024;
+
+// fiber stacks of one OS thread, reused from CTA to CTA
+struct StackPool {
+  std::vector<char *> stacks;
+  char *get(size_t i) {
+    while (stacks.size() <= i) {
+      void *p = mmap(nullptr, FIBER_STACK, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_STACK, -1, 0);
+      if (p == MAP_FAILED) { std::perror("simt: mmap"); std::abort(); }
+      stacks.push_back(static_cast<char *>(p));
+    }
+    return stacks[i];
+  }
+  ~StackPool() { for (char *s : stacks) munmap(s, FIBER_STACK); }
+};
+thread_local StackPool t_stacks;
+
+unsigned worker_count() {
+  static const unsigned n = []() {
+    const char *e = std::getenv("RDN_SIMT_THREADS");
+    unsigned v = e ? static_cast<unsigned>(std::atoi(e)) : std::thread::hardware_concurrency();
+    if (v < 1) v = 1;
+    if (v > 16) v = 16;
+    return v;
+  }();
+  return n;
+}
+
+void on_fiber_exit(Fiber *f) {
+  Cta *cta = f->cta;
+  Warp &w = *f->warp;
+  f->done = true;
+  w.exited |= 1u << f->lane;
+  cta->n_done++;
+  cta->progress++;
+  // lanes that have left count as arrived (what the hardware does for exited threads)
+  for (auto &kv : w.colls)
+    if (kv.second.arrived) complete_if_ready(w, kv.second, kv.first);
+  const uint32_t n_threads = static_cast<uint32_t>(cta->fibers.size());
+  if (cta->sync_arrived && cta->sync_arrived + cta->n_done >= n_threads) {
+    cta->sync_arrived = 0;
+    cta->sync_gen++;
+  }
+}
+
+void trampoline() {
+  Fiber *f = g_cur;
+  (*f->cta->body)();
+  on_fiber_exit(f);
+  swapcontext(&f->ctx, &f->cta->sched);  // never resumed
+}
+
+void run_cta(Cta &cta) {
+  const uint32_t n_threads = cta.bdim.x * cta.bdim.y * cta.bdim.z;
+  cta.fibers.assign(n_threads, Fiber{});
+  cta.warps.assign((n_threads + 31u) / 32u, Warp{});
+  for (uint32_t t = 0; t < n_threads; ++t) {
+    Fiber &f = cta.fibers[t];
+    f.tid = uint3{t % cta.bdim.x, (t / cta.bdim.x) % cta.bdim.y, t / (cta.bdim.x * cta.bdim.y)};
+    f.lane = t & 31u;
+    f.warp = &cta.warps[t >> 5];
+    f.warp->exists |= 1u << f.lane;
+    f.cta = &cta;
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = t_stacks.get(t);
+    f.ctx.uc_stack.ss_size = FIBER_STACK;
+    f.ctx.uc_link = nullptr;
+    makecontext(&f.ctx, trampoline, 0);
+  }
+  uint64_t idle_passes = 0;
+  while (cta.n_done < n_threads) {
+    const uint64_t before = cta.progress;
+    bool ran = false;
+    for (uint32_t t = 0; t < n_threads; ++t) {
+      Fiber &f = cta.fibers[t];
+      if (f.done) continue;
+      if (f.wait_gen && *f.wait_gen == f.wait_val) continue;  // still blocked
+      ran = true;
+      g_cur = &f;
+      swapcontext(&cta.sched, &f.ctx);
+    }
+    g_cur = nullptr;
+    if (!ran && cta.progress == before) {
+      if (++idle_passes > 2) {
+        std::fprintf(stderr, "simt: deadlock in CTA (%u,%u): every live thread waits in a collective that cannot complete\n",
+                     cta.bid.x, cta.bid.y);
+        for (uint32_t wi = 0; wi < cta.warps.size(); ++wi)
+          for (auto &kv : cta.warps[wi].colls)
+            if (kv.second.arrived)
+              std::fprintf(stderr, "  warp %u mask %08x arrived %08x exited %08x\n", wi, kv.first, kv.second.arrived, cta.warps[wi].exited);
+        std::abort();
+      }
+    } else {
+      idle_passes = 0;
+    }
+  }
+}
+}  // namespace
+
+void complete_if_ready(Warp &w, Coll &c, uint32_t mask) {
+  const uint32_t need = mask & ~w.exited;
+  if ((c.arrived & need) != need) return;
+  std::memcpy(c.out, c.in, sizeof(c.in));
+  c.out_mask = c.arrived & mask;
+  c.out_pred = c.pred & c.out_mask;
+  c.arrived = 0;
+  c.pred = 0;
+  c.gen++;
+  if (g_cur) g_cur->cta->progress++;
+}
+
+void yield() {
+  Fiber *f = g_cur;
+  swapcontext(&f->ctx, &f->cta->sched);
+}
+
+void syncthreads() {
+  Fiber *f = g_cur;
+  Cta *cta = f->cta;
+  const uint32_t n_threads = static_cast<uint32_t>(cta->fibers.size());
+  const uint64_t my_gen = cta->sync_gen;
+  cta->sync_arrived++;
+  if (cta->sync_arrived + cta->n_done >= n_threads) {
+    cta->sync_arrived = 0;
+    cta->sync_gen++;
+    cta->progress++;
+    return;
+  }
+  while (cta->sync_gen == my_gen) {
+    f->wait_gen = &cta->sync_gen;
+    f->wait_val = my_gen;
+    yield();
+  }
+  f->wait_gen = nullptr;
+}
+
+void launch(dim3 grid, dim3 block, const std::function<void()> &body) {
+  const uint64_t n_ctas = static_cast<uint64_t>(grid.x) * grid.y * grid.z;
+  if (n_ctas == 0 || block.x * block.y * block.z == 0) return;
+  std::atomic<uint64_t> next{0};
+  auto worker = [&]() {
+    for (;;) {
+      const uint64_t i = next.fetch_add(1);
+      if (i >= n_ctas) break;
+      Cta cta;
+      cta.bid = uint3{static_cast<unsigned>(i % grid.x), static_cast<unsigned>((i / grid.x) % grid.y),
+                      static_cast<unsigned>(i / (static_cast<uint64_t>(grid.x) * grid.y))};
+      cta.bdim = block;
+      cta.gdim = grid;
+      cta.body = &body;
+      run_cta(cta);
+    }
+  };
+  const unsigned n_workers = static_cast<unsigned>(std::min<uint64_t>(worker_count(), n_ctas));
+  // always on fresh threads: thread_local __shared__ storage and the fiber stacks belong to the worker
+  std::vector<std::thread> pool;
+  for (unsigned w = 0; w < n_workers; ++w) pool.emplace_back(worker);
+  for (auto &t : pool) t.join();
+}
+
+}  // namespace simt

@@ -1,0 +1,71 @@
+"""The CUDA kernels executed on the CPU, thread for thread (tests/simt): the `-m gpu` test-suite run against
+``tests/simt/_build/librdn_rt_emu.so`` — the same .cu sources compiled by g++ with a SIMT emulation header (one fiber per
+CUDA thread, warp collectives, atomics, a host-memory stand-in for the CUDA runtime) behind the same C-ABI.
+
+This checks kernel LOGIC without a GPU (traversal order, tie queue, refill votes, scans, the device builder's level loop); it
+is test infrastructure, not a fallback: the package cannot load that library, only tests/conftest.py does under RDN_SIMT_EMU=1.
+The GPU run of the same tests stays the parity gate.
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+pytestmark = pytest.mark.skipif(os.environ.get("RDN_SIMT_EMU") == "1", reason="already inside the emulated run")
+
+# not meaningful or too slow on the emulator: stream overlap (58 launches of a million rays), a copy made with cuda-python,
+# and the full-size BASELINE configurations (they pass — about a minute — and are run with RDN_SIMT_FULL=1)
+SKIP_ALWAYS = ["back_to_back", "blob_adoption"]
+SKIP_BIG = ["c2_c3_full_size", "c4_instanced_full_size", "million_triangles"]
+
+
+def _run_emulated(selection, k_expr, env_extra=None, timeout=1500):
+    env = dict(os.environ, RDN_SIMT_EMU="1", **(env_extra or {}))
+    cmd = [sys.executable, "-m", "pytest", *selection, "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "-k", k_expr]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+    tail = (r.stdout + r.stderr)[-4000:]
+    assert r.returncode == 0, tail
+    summary = [line for line in r.stdout.splitlines() if " passed" in line]
+    assert summary, tail
+    return summary[-1]
+
+
+def _not(names):
+    return " and ".join(f"not {n}" for n in names)
+
+
+def test_gpu_suite_passes_on_the_emulated_kernels():
+    skip = SKIP_ALWAYS + ([] if os.environ.get("RDN_SIMT_FULL") == "1" else SKIP_BIG)
+    summary = _run_emulated(["tests"], _not(skip))
+    passed = int(summary.split(" passed")[0].split()[-1])
+    assert passed >= 60, summary
+
+
+def test_leaf_chains_walked_by_the_ordered_kernel():
+    """Leaves of more than REF_LEAF_MAX_COUNT slots are stored as chains of wide nodes; with the real limit of 16 only
+    geometry at the builder's depth limit produces one (and such geometry is irregular, so its rays take the reference-order
+    walk).  Built with the limit lowered to 1, every two-triangle leaf and every multi-instance TLAS leaf is a chain, and
+    the parity and fuzz tests must still hold bit for bit."""
+    summary = _run_emulated(["tests/test_gpu_parity.py", "tests/test_gpu_fuzz.py"], _not(SKIP_ALWAYS + SKIP_BIG + ["hostile"]),
+                            {"RDN_SIMT_DEFINES": "RDN_REF_LEAF_MAX_COUNT=1"})
+    assert int(summary.split(" passed")[0].split()[-1]) >= 30, summary
+
+
+def test_two_emulated_devices_shard_a_host_batch():
+    summary = _run_emulated(["tests/test_gpu_parity.py"], "multi_device", {"RDN_SIMT_DEVICES": "2"})
+    assert "1 passed" in summary, summary
+
+
+def test_launch_rewriter():
+    sys.path.insert(0, os.path.join(ROOT, "tests", "simt"))
+    import build_emu
+    text, n = build_emu.rewrite_launches(
+        "  k_a<true><<<static_cast<unsigned>(blocks), block, 0, stream>>>(scene, f(a, b), n);\n"
+        "  if (n) k_b<<<dim3(gx, gy), 256>>>(p,\n      q);\n")
+    assert n == 2 and "<<<" not in text
+    assert "::simt::launch(dim3(static_cast<unsigned>(blocks)), dim3(block), [&]() { k_a<true>(scene, f(a, b), n); });" in text
+    assert "::simt::launch(dim3(dim3(gx, gy)), dim3(256), [&]() { k_b(p, q); });" in text
+    assert text.count("\n") == 3  # line numbers preserved
