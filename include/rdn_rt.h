@@ -164,6 +164,44 @@ int rdn_rt_trace_closest_device(rdn_rt_scene *scene, int device_index, const rdn
 int rdn_rt_trace_counted(rdn_rt_scene *scene, const rdn_launch *launch, const rdn_ray *rays, uint64_t n,
                          rdn_hit *out_hits, rdn_counters *out_counters);
 
+/* ---- f4 (first slice): shader binding table and the dispatch that follows a trace.
+ *      Replaces ShaderBindingTableProvider (shader/ray-tracing/src/api/backend.rs:90-101), GPURayTracingDeviceProvider::create_sbt
+ *      (api/backend.rs:74-79; wavefront_compute/mod.rs:78-93, sbt.rs:13-50,164-230) and the closest-hit / miss shader selection of
+ *      TraceTaskImpl::device_poll (wavefront_compute/trace_task.rs:206-268, api/ctx.rs:53-55, sbt.rs:252-273).
+ *      A shader is named by its ShaderHandle value (u32); RDN_SBT_NO_SHADER = the reference's None / u32::MAX.
+ *      The table holds max_geometry_count_in_blas * max_tlas_offset * ray_type_count hit groups (all empty at creation),
+ *      ray_type_count miss shaders and one ray generation shader; hit group (geometry_idx, tlas_offset, ray_ty_idx) sits at
+ *      ray_ty_idx + geometry_idx * ray_type_count + tlas_offset, as in the reference. */
+#define RDN_SBT_NO_SHADER 0xFFFFFFFFu
+#define RDN_TASK_NONE 0xFFFFFFFFu        /* nothing is spawned for this ray */
+#define RDN_TASK_MISS_BIT 0x80000000u    /* task code = miss shader | RDN_TASK_MISS_BIT, or the closest-hit shader */
+typedef struct rdn_sbt rdn_sbt;
+typedef struct rdn_sbt_ray_config {      /* the launch-uniform part of ShaderRayTraceCallStoragePayload that dispatch reads */
+  uint32_t ray_flags;                    /* RDN_RAY_FLAG_SKIP_CLOSEST_HIT_SHADER: hits spawn nothing */
+  uint32_t sbt_ray_offset, sbt_ray_stride;   /* RaySBTConfig { offset, stride } */
+  uint32_t miss_index;
+} rdn_sbt_ray_config;
+int rdn_sbt_create(rdn_rt_scene *scene, uint32_t max_geometry_count_in_blas, uint32_t max_tlas_offset, uint32_t ray_type_count, rdn_sbt **out);
+void rdn_sbt_destroy(rdn_sbt *sbt);
+int rdn_sbt_config_ray_generation(rdn_sbt *sbt, uint32_t shader);
+int rdn_sbt_config_hit_group(rdn_sbt *sbt, uint32_t geometry_idx, uint32_t tlas_offset, uint32_t ray_ty_idx, uint32_t closest_hit,
+                             uint32_t any_hit, uint32_t intersection);
+int rdn_sbt_config_missing(rdn_sbt *sbt, uint32_t ray_ty_idx, uint32_t shader);
+int rdn_sbt_ray_generation(const rdn_sbt *sbt, uint32_t *out_shader);
+/* d_task[i] = task code of ray i from its hit record (device arrays of scene device `device_index`, asynchronous on `cuda_stream`).
+ * A hit group index beyond the table selects nothing (the reference reads out of bounds there). */
+int rdn_rt_sbt_dispatch_device(rdn_rt_scene *scene, int device_index, rdn_sbt *sbt, const rdn_sbt_ray_config *config, const rdn_hit *d_hits,
+                               uint64_t n, uint32_t *d_task, void *cuda_stream);
+/* The per-shader task lists: ray indices grouped by task code, ray order kept inside a group.  Groups: closest-hit shaders
+ * 0 .. n_closest_shaders-1, then miss shaders 0 .. n_miss_shaders-1; group g is d_queue[d_offsets[g] .. d_offsets[g+1]).
+ * d_queue: n u32, d_offsets: n_closest_shaders + n_miss_shaders + 1 u64.  Rays with RDN_TASK_NONE (or a shader beyond the
+ * counts) are in no group. */
+int rdn_rt_sbt_group_device(rdn_rt_scene *scene, int device_index, rdn_sbt *sbt, const uint32_t *d_task, uint64_t n, uint32_t n_closest_shaders,
+                            uint32_t n_miss_shaders, uint32_t *d_queue, uint64_t *d_offsets, void *cuda_stream);
+/* both steps on host buffers (synchronous; device 0 of the scene); task / queue may be NULL when not wanted */
+int rdn_rt_sbt_dispatch(rdn_rt_scene *scene, rdn_sbt *sbt, const rdn_sbt_ray_config *config, const rdn_hit *hits, uint64_t n,
+                        uint32_t n_closest_shaders, uint32_t n_miss_shaders, uint32_t *task, uint32_t *queue, uint64_t *offsets);
+
 /* ---- measurement hook (no reference counterpart): between _begin and _end every traversal kernel launched on the
  *      device is bracketed by CUDA events on its launching stream; _end waits for them and returns the summed device
  *      time per kernel (k_trace_ordered_rounds / k_resolve_ties / k_trace_reference). ---- */

@@ -142,6 +142,10 @@ class _PickConfig(C.Structure):
     _fields_ = [("tolerance_local", C.c_float), ("triangle_face", C.c_uint32)]
 
 
+class _SbtRayConfig(C.Structure):
+    _fields_ = [("ray_flags", C.c_uint32), ("sbt_ray_offset", C.c_uint32), ("sbt_ray_stride", C.c_uint32), ("miss_index", C.c_uint32)]
+
+
 class _MeshView(C.Structure):
     _fields_ = [("positions", C.c_void_p), ("n_positions", C.c_uint64), ("indices", C.c_void_p), ("n_indices", C.c_uint64)]
 
@@ -154,6 +158,8 @@ EXPORTED_SYMBOLS = [
     "rdn_rt_scene_blob", "rdn_rt_scene_adopt_blob", "rdn_rt_scene_array", "rdn_rt_scene_build_stats", "rdn_rt_measure_l2_read_gbs", "rdn_pick_mesh_create", "rdn_pick_mesh_destroy",
     "rdn_pick_mesh_primitive_count", "rdn_pick_mesh_nearest", "rdn_pick_mesh_all", "rdn_bvh_build", "rdn_bvh_build_device", "rdn_bvh_built_on_device", "rdn_bvh_destroy", "rdn_bvh_nodes",
     "rdn_bvh_sorted_primitive_index", "rdn_bvh_build_for_mesh", "rdn_bvh_query_nearest", "rdn_bvh_upload", "rdn_bvh_query_nearest_device", "rdn_bvh_query_list", "rdn_rt_last_error", "rdn_rt_version",
+    "rdn_sbt_create", "rdn_sbt_destroy", "rdn_sbt_config_ray_generation", "rdn_sbt_config_hit_group", "rdn_sbt_config_missing", "rdn_sbt_ray_generation",
+    "rdn_rt_sbt_dispatch_device", "rdn_rt_sbt_group_device", "rdn_rt_sbt_dispatch",
 ]
 
 _lib = None
@@ -218,6 +224,16 @@ def lib() -> C.CDLL:
     L.rdn_bvh_upload.argtypes = [vp, P(_MeshView), i32]
     L.rdn_bvh_query_list.argtypes = [vp, P(_MeshView), vp, u64, u32, i32, vp, vp, u64, P(u64)]
     L.rdn_bvh_query_nearest_device.argtypes = [vp, vp, u64, u32, vp, vp]
+    L.rdn_sbt_create.argtypes = [vp, u32, u32, u32, P(vp)]
+    L.rdn_sbt_destroy.argtypes = [vp]
+    L.rdn_sbt_destroy.restype = None
+    L.rdn_sbt_config_ray_generation.argtypes = [vp, u32]
+    L.rdn_sbt_config_hit_group.argtypes = [vp, u32, u32, u32, u32, u32, u32]
+    L.rdn_sbt_config_missing.argtypes = [vp, u32, u32]
+    L.rdn_sbt_ray_generation.argtypes = [vp, P(u32)]
+    L.rdn_rt_sbt_dispatch_device.argtypes = [vp, i32, vp, P(_SbtRayConfig), vp, u64, vp, vp]
+    L.rdn_rt_sbt_group_device.argtypes = [vp, i32, vp, vp, u64, u32, u32, vp, vp, vp]
+    L.rdn_rt_sbt_dispatch.argtypes = [vp, vp, P(_SbtRayConfig), vp, u64, u32, u32, vp, vp, vp]
     _lib = L
     return L
 
@@ -451,9 +467,94 @@ class NaiveSahBVHSystem:
     def arrays(self) -> dict:
         return {ARRAYS[i][0]: self.array(i) for i in ARRAYS}
 
+    def create_sbt(self, max_geometry_count_in_blas: int, max_tlas_offset: int, ray_type_count: int) -> "ShaderBindingTable":
+        """``GPURayTracingDeviceProvider::create_sbt`` (api/backend.rs:74-79)"""
+        return ShaderBindingTable(self, max_geometry_count_in_blas, max_tlas_offset, ray_type_count)
+
     def close(self):
         if getattr(self, "_h", None):
             self._L.rdn_rt_scene_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------------ shader binding table
+SBT_NO_SHADER = 0xFFFFFFFF
+TASK_NONE = 0xFFFFFFFF
+TASK_MISS_BIT = 0x80000000
+RAY_FLAG_SKIP_CLOSEST_HIT_SHADER = 0x08
+
+
+class HitGroupShaderRecord:
+    """``HitGroupShaderRecord`` (shader/ray-tracing/src/api/backend.rs:83-88); ``None`` = no shader."""
+
+    def __init__(self, closest_hit=None, any_hit=None, intersection=None):
+        self.closest_hit, self.any_hit, self.intersection = closest_hit, any_hit, intersection
+
+
+class ShaderBindingTable:
+    """``ShaderBindingTableProvider`` (api/backend.rs:90-101) as created by ``GPURayTracingDeviceProvider::create_sbt``
+    (api/backend.rs:74-79), plus the dispatch the wavefront executor performs with it after traversal
+    (wavefront_compute/trace_task.rs:206-268): a task code per ray and the per-shader task lists."""
+
+    def __init__(self, system: "NaiveSahBVHSystem", max_geometry_count_in_blas: int, max_tlas_offset: int, ray_type_count: int):
+        self._L = lib()
+        self._sys = system
+        h = C.c_void_p()
+        _check(self._L.rdn_sbt_create(system._h, max_geometry_count_in_blas, max_tlas_offset, ray_type_count, C.byref(h)))
+        self._h = h
+
+    @staticmethod
+    def _handle(s) -> int:
+        return SBT_NO_SHADER if s is None else int(s)
+
+    def config_ray_generation(self, s: int):
+        _check(self._L.rdn_sbt_config_ray_generation(self._h, int(s)))
+
+    def config_hit_group(self, geometry_idx: int, tlas_offset: int, ray_ty_idx: int, hit_group: HitGroupShaderRecord):
+        _check(self._L.rdn_sbt_config_hit_group(self._h, geometry_idx, tlas_offset, ray_ty_idx, self._handle(hit_group.closest_hit),
+                                                self._handle(hit_group.any_hit), self._handle(hit_group.intersection)))
+
+    def config_missing(self, ray_ty_idx: int, s: int):
+        _check(self._L.rdn_sbt_config_missing(self._h, ray_ty_idx, int(s)))
+
+    @property
+    def ray_generation(self) -> int:
+        v = C.c_uint32()
+        _check(self._L.rdn_sbt_ray_generation(self._h, C.byref(v)))
+        return int(v.value)
+
+    def dispatch(self, hits: np.ndarray, n_closest_shaders: int, n_miss_shaders: int, ray_flags: int = 0, sbt_ray_offset: int = 0,
+                 sbt_ray_stride: int = 1, miss_index: int = 0):
+        """host buffers: returns (task code per ray, ray indices grouped by shader, group offsets)"""
+        hits = _c(hits, HIT_DTYPE)
+        n = hits.shape[0]
+        task = np.zeros(n, np.uint32)
+        queue = np.zeros(max(n, 1), np.uint32)
+        offsets = np.zeros(n_closest_shaders + n_miss_shaders + 1, np.uint64)
+        cfg = _SbtRayConfig(ray_flags, sbt_ray_offset, sbt_ray_stride, miss_index)
+        _check(self._L.rdn_rt_sbt_dispatch(self._sys._h, self._h, C.byref(cfg), _p(hits), n, n_closest_shaders, n_miss_shaders, _p(task),
+                                           _p(queue), _p(offsets)))
+        return task, queue[:int(offsets[-1])], offsets
+
+    def dispatch_device(self, d_hits: int, n: int, d_task: int, ray_flags: int = 0, sbt_ray_offset: int = 0, sbt_ray_stride: int = 1,
+                        miss_index: int = 0, stream: int = 0, device_index: int = 0):
+        cfg = _SbtRayConfig(ray_flags, sbt_ray_offset, sbt_ray_stride, miss_index)
+        _check(self._L.rdn_rt_sbt_dispatch_device(self._sys._h, device_index, self._h, C.byref(cfg), d_hits, n, d_task, stream))
+
+    def group_device(self, d_task: int, n: int, n_closest_shaders: int, n_miss_shaders: int, d_queue: int, d_offsets: int, stream: int = 0,
+                     device_index: int = 0):
+        _check(self._L.rdn_rt_sbt_group_device(self._sys._h, device_index, self._h, d_task, n, n_closest_shaders, n_miss_shaders, d_queue,
+                                               d_offsets, stream))
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            self._L.rdn_sbt_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -1041,6 +1041,187 @@ int rdn_pick_mesh_all(rdn_pick_mesh *m, const rdn_pick_config *config, const rdn
   return RDN_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// f4: shader binding table + dispatch (sbt.cu)
+struct rdn_sbt {
+  rdn_rt_scene *scene = nullptr;
+  uint32_t ray_stride = 0, max_geometry = 0, max_tlas_offset = 0;
+  std::mutex lock;
+  std::vector<SbtHitGroup> hit_groups;   // ray_ty_idx + geometry_idx * ray_stride + tlas_offset (sbt.rs:20-38)
+  std::vector<uint32_t> miss;            // ray_type_count entries
+  uint32_t ray_gen = RDN_SBT_NO_SHADER;
+  struct PerDevice {
+    SbtHitGroup *d_hit_groups = nullptr;
+    uint32_t *d_miss = nullptr;
+    bool stale = true;
+    uint8_t *d_keep = nullptr;           // grouping scratch, `cap` rays
+    uint32_t *d_iota = nullptr, *d_segment = nullptr;
+    uint64_t *d_count = nullptr;
+    unsigned long long *d_status = nullptr;
+    uint64_t cap = 0;
+  };
+  std::vector<PerDevice> per_device;
+};
+
+namespace {
+int sbt_upload(rdn_sbt *t, int device_index) {
+  rdn_sbt::PerDevice &pd = t->per_device[device_index];
+  if (!pd.stale) return RDN_OK;
+  if (!pd.d_hit_groups) RDN_CUDA(cudaMalloc(&pd.d_hit_groups, std::max<size_t>(t->hit_groups.size(), 1) * sizeof(SbtHitGroup)));
+  if (!pd.d_miss) RDN_CUDA(cudaMalloc(&pd.d_miss, std::max<size_t>(t->miss.size(), 1) * sizeof(uint32_t)));
+  // (synchronous copies: a table is configured once per pipeline, not per launch)
+  RDN_CUDA(cudaMemcpy(pd.d_hit_groups, t->hit_groups.data(), t->hit_groups.size() * sizeof(SbtHitGroup), cudaMemcpyHostToDevice));
+  RDN_CUDA(cudaMemcpy(pd.d_miss, t->miss.data(), t->miss.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  pd.stale = false;
+  return RDN_OK;
+}
+void sbt_touch(rdn_sbt *t) { for (auto &pd : t->per_device) pd.stale = true; }
+}  // namespace
+
+int rdn_sbt_create(rdn_rt_scene *scene, uint32_t max_geometry_count_in_blas, uint32_t max_tlas_offset, uint32_t ray_type_count, rdn_sbt **out) {
+  if (!scene || !out) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_sbt_create: null argument");
+  const uint64_t groups = static_cast<uint64_t>(max_geometry_count_in_blas) * max_tlas_offset * ray_type_count;
+  if (groups > (1ull << 28)) return fail(RDN_ERR_CAPACITY, "rdn_sbt_create: more than 2^28 hit groups");
+  rdn_sbt *t = new rdn_sbt;
+  t->scene = scene;
+  t->ray_stride = ray_type_count;
+  t->max_geometry = max_geometry_count_in_blas;
+  t->max_tlas_offset = max_tlas_offset;
+  t->hit_groups.assign(groups, SbtHitGroup{RDN_SBT_NO_SHADER, RDN_SBT_NO_SHADER, RDN_SBT_NO_SHADER});
+  t->miss.assign(ray_type_count, RDN_SBT_NO_SHADER);
+  t->per_device.resize(scene->devices.size());
+  *out = t;
+  return RDN_OK;
+}
+
+void rdn_sbt_destroy(rdn_sbt *t) {
+  if (!t) return;
+  for (size_t i = 0; i < t->per_device.size(); ++i) {
+    rdn_sbt::PerDevice &pd = t->per_device[i];
+    if (i < t->scene->devices.size()) cudaSetDevice(t->scene->devices[i].device);
+    cudaFree(pd.d_hit_groups); cudaFree(pd.d_miss); cudaFree(pd.d_keep); cudaFree(pd.d_iota); cudaFree(pd.d_segment);
+    cudaFree(pd.d_count); cudaFree(pd.d_status);
+  }
+  delete t;
+}
+
+int rdn_sbt_config_ray_generation(rdn_sbt *t, uint32_t shader) {
+  if (!t) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_sbt_config_ray_generation: null table");
+  std::lock_guard<std::mutex> lg(t->lock);
+  t->ray_gen = shader;
+  return RDN_OK;
+}
+
+int rdn_sbt_ray_generation(const rdn_sbt *t, uint32_t *out_shader) {
+  if (!t || !out_shader) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_sbt_ray_generation: null argument");
+  *out_shader = t->ray_gen;
+  return RDN_OK;
+}
+
+int rdn_sbt_config_hit_group(rdn_sbt *t, uint32_t geometry_idx, uint32_t tlas_offset, uint32_t ray_ty_idx, uint32_t closest_hit,
+                             uint32_t any_hit, uint32_t intersection) {
+  if (!t) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_sbt_config_hit_group: null table");
+  std::lock_guard<std::mutex> lg(t->lock);
+  // the reference's set_value(...).unwrap() panics outside the allocated range
+  const uint64_t idx = static_cast<uint64_t>(ray_ty_idx) + static_cast<uint64_t>(geometry_idx) * t->ray_stride + tlas_offset;
+  if (idx >= t->hit_groups.size()) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_sbt_config_hit_group: record outside the table");
+  if ((closest_hit != RDN_SBT_NO_SHADER && (closest_hit & RDN_TASK_MISS_BIT)))
+    return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_sbt_config_hit_group: shader handles are below 2^31");
+  t->hit_groups[idx] = SbtHitGroup{closest_hit, any_hit, intersection};
+  sbt_touch(t);
+  return RDN_OK;
+}
+
+int rdn_sbt_config_missing(rdn_sbt *t, uint32_t ray_ty_idx, uint32_t shader) {
+  if (!t) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_sbt_config_missing: null table");
+  std::lock_guard<std::mutex> lg(t->lock);
+  if (ray_ty_idx >= t->miss.size()) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_sbt_config_missing: ray type outside the table");
+  if (shader != RDN_SBT_NO_SHADER && (shader & RDN_TASK_MISS_BIT)) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_sbt_config_missing: shader handles are below 2^31");
+  t->miss[ray_ty_idx] = shader;
+  sbt_touch(t);
+  return RDN_OK;
+}
+
+int rdn_rt_sbt_dispatch_device(rdn_rt_scene *s, int device_index, rdn_sbt *t, const rdn_sbt_ray_config *config, const rdn_hit *d_hits,
+                               uint64_t n, uint32_t *d_task, void *cuda_stream) {
+  if (!s || !t || !config || (n && (!d_hits || !d_task))) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_sbt_dispatch_device: null argument");
+  if (t->scene != s) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_sbt_dispatch_device: the table belongs to another scene");
+  if (device_index < 0 || device_index >= static_cast<int>(s->devices.size())) return fail(RDN_ERR_INVALID_ARGUMENT, "bad device_index");
+  if (reinterpret_cast<uintptr_t>(d_hits) & 15u) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_sbt_dispatch_device: hit array must be 16-byte aligned");
+  int rc = ensure_committed(s);
+  if (rc != RDN_OK) return rc;
+  std::shared_lock<std::shared_mutex> rd(s->lock);
+  std::lock_guard<std::mutex> lg(t->lock);
+  DeviceCtx &dc = s->devices[device_index];
+  RDN_CUDA(cudaSetDevice(dc.device));
+  rc = sbt_upload(t, device_index);
+  if (rc != RDN_OK) return rc;
+  const rdn_sbt::PerDevice &pd = t->per_device[device_index];
+  launch_sbt_dispatch(dc.dev, pd.d_hit_groups, static_cast<uint32_t>(t->hit_groups.size()), pd.d_miss, static_cast<uint32_t>(t->miss.size()),
+                      *config, d_hits, n, d_task, static_cast<cudaStream_t>(cuda_stream));
+  RDN_CUDA(cudaGetLastError());
+  return RDN_OK;
+}
+
+int rdn_rt_sbt_group_device(rdn_rt_scene *s, int device_index, rdn_sbt *t, const uint32_t *d_task, uint64_t n, uint32_t n_closest_shaders,
+                            uint32_t n_miss_shaders, uint32_t *d_queue, uint64_t *d_offsets, void *cuda_stream) {
+  if (!s || !t || !d_offsets || (n && (!d_task || !d_queue))) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_sbt_group_device: null argument");
+  if (t->scene != s) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_sbt_group_device: the table belongs to another scene");
+  if (device_index < 0 || device_index >= static_cast<int>(s->devices.size())) return fail(RDN_ERR_INVALID_ARGUMENT, "bad device_index");
+  if (n > MAX_LAUNCH_RAYS) return fail(RDN_ERR_CAPACITY, "rdn_rt_sbt_group_device: more than 2^31 rays in one call");
+  if (static_cast<uint64_t>(n_closest_shaders) + n_miss_shaders > 4096) return fail(RDN_ERR_CAPACITY, "rdn_rt_sbt_group_device: more than 4096 shaders");
+  std::lock_guard<std::mutex> lg(t->lock);
+  DeviceCtx &dc = s->devices[device_index];
+  RDN_CUDA(cudaSetDevice(dc.device));
+  rdn_sbt::PerDevice &pd = t->per_device[device_index];
+  if (pd.cap < n || !pd.d_count) {
+    cudaFree(pd.d_keep); cudaFree(pd.d_iota); cudaFree(pd.d_segment); cudaFree(pd.d_count); cudaFree(pd.d_status);
+    pd.d_keep = nullptr; pd.d_iota = nullptr; pd.d_segment = nullptr; pd.d_count = nullptr; pd.d_status = nullptr; pd.cap = 0;
+    const uint64_t m = std::max<uint64_t>(n, 1);
+    RDN_CUDA(cudaMalloc(&pd.d_keep, m));
+    RDN_CUDA(cudaMalloc(&pd.d_iota, m * sizeof(uint32_t)));
+    RDN_CUDA(cudaMalloc(&pd.d_segment, m * sizeof(uint32_t)));
+    RDN_CUDA(cudaMalloc(&pd.d_count, sizeof(uint64_t)));
+    RDN_CUDA(cudaMalloc(&pd.d_status, compact_status_words(m) * sizeof(unsigned long long)));
+    pd.cap = m;
+  }
+  launch_sbt_group(d_task, n, n_closest_shaders, n_miss_shaders, pd.d_keep, pd.d_iota, pd.d_segment, pd.d_count, pd.d_status, d_queue, d_offsets,
+                   static_cast<cudaStream_t>(cuda_stream));
+  RDN_CUDA(cudaGetLastError());
+  return RDN_OK;
+}
+
+int rdn_rt_sbt_dispatch(rdn_rt_scene *s, rdn_sbt *t, const rdn_sbt_ray_config *config, const rdn_hit *hits, uint64_t n,
+                        uint32_t n_closest_shaders, uint32_t n_miss_shaders, uint32_t *task, uint32_t *queue, uint64_t *offsets) {
+  if (!s || !t || !config || (n && !hits) || (queue && !offsets)) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_sbt_dispatch: null argument");
+  if (s->devices.empty()) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_sbt_dispatch: host-only scene has no CUDA device (there is no CPU fallback)");
+  RDN_CUDA(cudaSetDevice(s->devices[0].device));
+  const uint64_t m = std::max<uint64_t>(n, 1);
+  const size_t n_groups = static_cast<size_t>(n_closest_shaders) + n_miss_shaders;
+  rdn_hit *d_hits = nullptr;
+  uint32_t *d_task = nullptr, *d_queue = nullptr;
+  uint64_t *d_offsets = nullptr;
+  int rc = RDN_OK;
+  auto release = [&]() { cudaFree(d_hits); cudaFree(d_task); cudaFree(d_queue); cudaFree(d_offsets); };
+  if (cudaMalloc(&d_hits, m * sizeof(rdn_hit)) != cudaSuccess || cudaMalloc(&d_task, m * 4) != cudaSuccess ||
+      cudaMalloc(&d_queue, m * 4) != cudaSuccess || cudaMalloc(&d_offsets, (n_groups + 1) * 8) != cudaSuccess) {
+    release();
+    return fail(RDN_ERR_CUDA, "rdn_rt_sbt_dispatch: out of device memory");
+  }
+  if (cudaMemcpy(d_hits, hits, n * sizeof(rdn_hit), cudaMemcpyHostToDevice) != cudaSuccess) rc = fail(RDN_ERR_CUDA, "rdn_rt_sbt_dispatch: copy failed");
+  if (rc == RDN_OK) rc = rdn_rt_sbt_dispatch_device(s, 0, t, config, d_hits, n, d_task, nullptr);
+  if (rc == RDN_OK && offsets) rc = rdn_rt_sbt_group_device(s, 0, t, d_task, n, n_closest_shaders, n_miss_shaders, d_queue, d_offsets, nullptr);
+  if (rc == RDN_OK && cudaDeviceSynchronize() != cudaSuccess) rc = fail(RDN_ERR_CUDA, "rdn_rt_sbt_dispatch: kernel failed");
+  if (rc == RDN_OK && task && cudaMemcpy(task, d_task, n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(RDN_ERR_CUDA, "rdn_rt_sbt_dispatch: copy failed");
+  if (rc == RDN_OK && offsets) {
+    if (cudaMemcpy(offsets, d_offsets, (n_groups + 1) * 8, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(RDN_ERR_CUDA, "rdn_rt_sbt_dispatch: copy failed");
+    if (rc == RDN_OK && queue && cudaMemcpy(queue, d_queue, offsets[n_groups] * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+      rc = fail(RDN_ERR_CUDA, "rdn_rt_sbt_dispatch: copy failed");
+  }
+  release();
+  return rc;
+}
+
 int rdn_rt_measure_l2_read_gbs(rdn_rt_scene *s, int device_index, uint64_t bytes, int passes, double *out_gbs) {
   if (!s || !out_gbs || bytes < (1u << 20) || passes < 1) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_measure_l2_read_gbs: bad argument");
   if (device_index < 0 || device_index >= static_cast<int>(s->devices.size())) return fail(RDN_ERR_INVALID_ARGUMENT, "bad device_index");

@@ -110,6 +110,17 @@ struct Box3;
 int build_bvh_sah_device(const Box3 *boxes, uint64_t n, uint32_t n_buckets, const TreeBuildOption &option, int device, FlattenBVH &out,
                          std::string &err);
 
+// shader binding table dispatch (sbt.cu)
+struct SbtHitGroup {  // DeviceHitGroupShaderRecord, sbt.rs:62-69
+  uint32_t closest_hit, any_hit, intersection;
+};
+void launch_sbt_dispatch(const SceneDev &scene, const SbtHitGroup *d_hit_groups, uint32_t n_hit_groups, const uint32_t *d_miss, uint32_t n_miss,
+                         const rdn_sbt_ray_config &cfg, const rdn_hit *d_hits, uint64_t n, uint32_t *d_task, cudaStream_t stream);
+// d_keep: n bytes, d_iota / d_segment: n u32, d_count: one u64, d_status: compact_status_words(n) u64
+void launch_sbt_group(const uint32_t *d_task, uint64_t n, uint32_t n_closest, uint32_t n_miss, uint8_t *d_keep, uint32_t *d_iota,
+                      uint32_t *d_segment, uint64_t *d_count, unsigned long long *d_status, uint32_t *d_queue, uint64_t *d_offsets,
+                      cudaStream_t stream);
+
 // measurement hook (probe.cu): read bandwidth of an L2-resident buffer of `bytes` on the current device, GB/s
 int measure_l2_read_gbs(uint64_t bytes, int passes, int sm_count, double *out_gbs);
 

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "rdn_rt.h")).read()
-    declared = set(re.findall(r"\b(rdn_(?:rt|bvh|pick)_[a-z0-9_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(rdn_(?:rt|bvh|pick|sbt)_[a-z0-9_]+)\s*\(", header))
     assert declared == set(api.EXPORTED_SYMBOLS), declared ^ set(api.EXPORTED_SYMBOLS)
     L = ctypes.CDLL(api.LIB_PATH)
     for sym in declared:
