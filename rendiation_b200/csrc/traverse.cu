@@ -78,6 +78,20 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 __device__ __forceinline__ Vec3 xyz(const float4 &q) { return Vec3{q.x, q.y, q.z}; }
 __device__ __forceinline__ Vec3 recip3(Vec3 d) { return Vec3{1.0f / d.x, 1.0f / d.y, 1.0f / d.z}; }
 
+// Region markers of the ordered kernel for the SIMT issue model of the emulated build (tests/simt, tools/issue_model.py): how often
+// a warp issues each region, to be multiplied by the region's SASS instruction count.  They compile to nothing in the product.
+#if defined(RDN_SIMT_EMU)
+#define RDN_COST(region) ::simt::cost_mark(region)
+#else
+#define RDN_COST(region) ((void)0)
+#endif
+enum CostRegion {
+  COST_PROLOGUE = 0, COST_REFILL, COST_RAY_LOAD, COST_OUTER, COST_ROUND, COST_NODE, COST_PHASE2, COST_LEAF, COST_TRI, COST_LEAF_END,
+  COST_INSTANCE, COST_INSTANCE_ENTER, COST_EXIT_INSTANCE, COST_EMPTY, COST_GEOMETRY, COST_VOTE, COST_FINISH, COST_TIE, COST_EPILOGUE,
+  COST_TRI_RANGE, COST_TRI_U, COST_TRI_V, COST_TRI_HIT,  // inside a triangle iteration: past the facing test, past the range test, past u, accepted
+  COST_REGION_COUNT
+};
+
 // intersect_ray_aabb_cpu with inv_d = 1/d hoisted (same value every call)
 __device__ __forceinline__ bool slab_test(Vec3 o, Vec3 inv_d, float t_min, float t_max, Vec3 bmin, Vec3 bmax, float &t_near_max) {
   const Vec3 t0 = (bmin - o) * inv_d;
@@ -100,10 +114,12 @@ __device__ __forceinline__ bool triangle_test(const float4 qn, const float4 qv0,
     const bool cull_back = (cull_bits & 2u) != 0;
     if (!(cull_back != (b < 0.0f))) return false;
   }
+  RDN_COST(COST_TRI_RANGE);
   const Vec3 w0 = origin - v0;
   const float a = -dot(normal, w0);
   t = a / b;
   if (t < range_x || t > range_y) return false;
+  RDN_COST(COST_TRI_U);
   const Vec3 p = origin + direction * t;
   const float uu = qv0.w, uv = qe1.w, vv = qe2.w, inverse_d = qn.w;
   const Vec3 w = p - v0;
@@ -111,6 +127,7 @@ __device__ __forceinline__ bool triangle_test(const float4 qn, const float4 qv0,
   const float wv = dot(w, e2);
   u = (uv * wv - vv * wu) * inverse_d;
   if (u < 0.0f || u > 1.0f) return false;
+  RDN_COST(COST_TRI_V);
   v = (uv * wu - uu * wv) * inverse_d;
   if (v < 0.0f || (u + v) > 1.0f) return false;
   return true;
@@ -498,6 +515,7 @@ __device__ __forceinline__ void drain_tie_queue(const OrderedParams &P) {
 // logs under profiles/.
 template <int K, int MINB, bool DRAIN_TIES, bool IRREGULAR, bool LD256, bool HOT, bool WIDE4>
 __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(const __grid_constant__ OrderedParams P) {
+  RDN_COST(COST_PROLOGUE);
   const SceneDev &S = P.S;
   const uint32_t lane = threadIdx.x & 31u;
   uint32_t stack[STACK_MAX];
@@ -585,6 +603,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
     // ---------------- warp-converged refill (a few rounds, so scene-missing rays are retired here)
 #pragma unroll 1
     for (int attempt = 0; attempt < 4; ++attempt) {
+      RDN_COST(COST_REFILL);
       const uint32_t want = __ballot_sync(FULL_MASK, !alive);
       if (!want || warp_exhausted) break;
       const int cnt = __popc(want);
@@ -611,6 +630,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
           idx = static_cast<uint64_t>(y) * P.width + x;
         }
         if (valid) {
+          RDN_COST(COST_RAY_LOAD);
           float4 r0, r1;
           load_pair<LD256>(P.rays + idx, r0, r1);
           const Vec3 ro = xyz(r0), rd = xyz(r1), rinv = recip3(rd);
@@ -634,6 +654,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
         }
       }
     }
+    RDN_COST(COST_OUTER);
     const uint32_t amask = __ballot_sync(FULL_MASK, alive);
     if (amask == 0) {
       if (warp_exhausted) break;
@@ -643,10 +664,12 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
     if (alive) {
 #pragma unroll 1
       for (;;) {
+        RDN_COST(COST_ROUND);
         // ---------------- phase 1: up to K inner nodes (both child boxes in one 64 B fetch)
 #pragma unroll 1
         for (int k = 0; k < K; ++k) {
           if (!(cur < REF_SPECIAL)) break;
+          RDN_COST(COST_NODE);
 #ifdef RDN_DEBUG_STEPS
           ++dbg_steps; ++dbg_ray_steps;
 #endif
@@ -706,6 +729,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
           cur = take0 ? r0 : r1;
           if (!(h0 || h1)) cur = RDN_POP();
         }
+        RDN_COST(COST_PHASE2);
         __syncwarp(amask);
 
         // ---------------- phase 2: one leaf / instance / bookkeeping item, all lanes that have one at the same time
@@ -713,10 +737,12 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
         if (in_object && (cur & REF_LEAF_BIT)) leaf_item = cur;
         if (leaf_item != REF_DONE) {
           {
+            RDN_COST(COST_LEAF);
             const uint32_t start = leaf_item & REF_LEAF_START_MASK;
             const uint32_t count = ((leaf_item >> REF_LEAF_COUNT_SHIFT) & 15u) + 1u;
             {
               for (uint32_t k = 0; k < count; ++k) {
+                RDN_COST(COST_TRI);
                 const uint32_t slot = start + k;
                 const float4 *tp = reinterpret_cast<const float4 *>(S.triangles + slot);
                 float4 qn, qv0, qe1, qe2;
@@ -727,6 +753,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
                 ++dbg_tris;
 #endif
                 if (!triangle_test(qn, qv0, qe1, qe2, o, d, near_s, far_s, cull_bits, sign, t, u, v)) continue;
+                RDN_COST(COST_TRI_HIT);
                 const float distance = t / scaling;
                 if (!(t_near_world <= distance) || !(distance <= far0)) continue;  // the reference's update_far asserts
                 if (distance < best) {
@@ -739,6 +766,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
                   second = fminf(second, distance);
                 }
               }
+              RDN_COST(COST_LEAF_END);
               cur = RDN_POP();
             }
           }
@@ -750,6 +778,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
               // (not reached: triangle leaves are handled above)
             } else {
               // instance leaf (world space): take the first slot, park the rest
+              RDN_COST(COST_INSTANCE);
               if (count > 1) RDN_PUSH(REF_LEAF_BIT | ((count - 2u) << REF_LEAF_COUNT_SHIFT) | (start + 1u));
               const float4 *tb = reinterpret_cast<const float4 *>(S.tlas_bounding + start);
               float4 b0, b1;
@@ -763,6 +792,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
                 if (!(flags & TF_SKIP_TRIANGLES) && tail.w < S.n_blas_meta) {
                   const uint2 groots = __ldg(reinterpret_cast<const uint2 *>(S.blas_meta[tail.w].tri_root_range));
                   if (groots.x < groots.y) {
+                    RDN_COST(COST_INSTANCE_ENTER);
                     Vec3 bo, bd;
                     float s;
                     to_object_space(rec, o, d, bo, bd, s);
@@ -782,6 +812,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
             cur = REF_DONE;  // nothing deferred in world space: the ray is finished, no need to restore the world ray
           } else if (cur == REF_EXIT_INSTANCE) {
             // back to world space: the world ray is re-read instead of being held in registers
+            RDN_COST(COST_EXIT_INSTANCE);
             float4 r0, r1;
             load_pair<LD256>(P.rays + ri, r0, r1);
             o = xyz(r0); d = xyz(r1); inv = recip3(d);
@@ -789,9 +820,11 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
             in_object = false;
             cur = RDN_POP();
           } else if (cur == REF_EMPTY) {
+            RDN_COST(COST_EMPTY);
             cur = RDN_POP();
           } else {
             // geometry iterator of the current instance's BLAS
+            RDN_COST(COST_GEOMETRY);
             const uint32_t g = cur & 0x00FFFFFFu;
             if (g + 1u < geom_end) RDN_PUSH(REF_SPECIAL | (g + 1u));
             const uint4 gm0 = __ldg(reinterpret_cast<const uint4 *>(S.geometry_meta + g));
@@ -801,11 +834,13 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
         }
 
         // ---------------- vote (also the re-convergence point of phase 2)
+        RDN_COST(COST_VOTE);
         const int active = __popc(__ballot_sync(amask, cur != REF_DONE));
         if (active == 0) break;
       }
 
       if (cur == REF_DONE) {
+        RDN_COST(COST_FINISH);
 #ifdef RDN_DEBUG_STEPS
         dbg_max = dbg_ray_steps > dbg_max ? dbg_ray_steps : dbg_max;
         dbg_long += dbg_ray_steps > 200 ? 1 : 0;
@@ -822,6 +857,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
                     S.instances[best_inst].instance_custom_index,
                     best_back ? RDN_HIT_KIND_BACK_FACING_TRIANGLE : RDN_HIT_KIND_FRONT_FACING_TRIANGLE);
           if (second <= best + TIE_EPS * fabsf(best)) {
+            RDN_COST(COST_TIE);
             __threadfence();  // the ordered record lands before whoever drains the queue writes the exact one
             enqueue_rewalk<DRAIN_TIES>(P.scratch, lane, ri, best);
           }
@@ -855,6 +891,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
     atomicAdd(P.scratch.counters + 9, t_out - dbg_t_in);    // sum of the warps' busy time (before the tie drain / exit barrier)
   }
 #endif
+  RDN_COST(COST_EPILOGUE);
   if (DRAIN_TIES) drain_tie_queue(P);
   // the last CTA to leave sweeps the ties appended after everyone else looked, then re-arms the counters for the next
   // launch on this scratch (no memset node between launches)

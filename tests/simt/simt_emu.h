@@ -52,7 +52,9 @@ struct Warp {
   uint32_t exists = 0, exited = 0;
   std::unordered_map<uint32_t, Coll> colls;  // node based: references stay valid
 };
+constexpr int COST_REGIONS = 32;
 struct Fiber {
+  uint32_t cost[COST_REGIONS] = {};  // RDN_SIMT_COST: passes through each marked region since the lane's last collective
   ucontext_t ctx;
   uint3 tid;
   uint32_t lane = 0;
@@ -118,7 +120,15 @@ inline T from_bits(uint64_t b) {
 
 void syncthreads();
 
+// RDN_SIMT_COST: a SIMT issue model.  Kernels mark code regions (RDN_COST(region) in the sources); when a collective
+// completes, every region costs the warp max-over-its-lanes passes since their previous collective (lanes that run the same
+// region run it in lockstep, different regions serialise) — the number of times the warp ISSUES that region.  Multiplied by the
+// region's static SASS instruction count (tools/sass_regions.py) this predicts the kernel's warp-level instruction count.
+inline void cost_mark(int region) { g_cur->cost[region]++; }
+
 }  // namespace simt
+extern "C" void simt_cost_reset();
+extern "C" void simt_cost_read(uint64_t *warp_issues, uint64_t *lane_passes, int n);
 
 // ---- built-in variables (objects, not macros: cudaLaunchConfig_t has members called gridDim / blockDim)
 namespace simt {

@@ -10,6 +10,26 @@ namespace simt {
 
 thread_local Fiber *g_cur = nullptr;
 
+static std::atomic<uint64_t> g_cost_warp[COST_REGIONS], g_cost_lane[COST_REGIONS];
+// the lanes in `lanes` of warp `w` have met in a collective (or one lane leaves): charge the regions they passed since
+static const bool g_cost_enabled = []() { const char *e = std::getenv("RDN_SIMT_COST"); return e && std::atoi(e) != 0; }();
+static void cost_flush(Cta *cta, Warp &w, uint32_t lanes) {
+  if (!g_cost_enabled) return;
+  Fiber *base = &cta->fibers[static_cast<size_t>(&w - cta->warps.data()) * 32u];
+  for (int r = 0; r < COST_REGIONS; ++r) {
+    uint32_t mx = 0;
+    uint64_t sum = 0;
+    for (uint32_t l = 0; l < 32; ++l)
+      if ((lanes >> l) & 1u) {
+        uint32_t &c = base[l].cost[r];
+        mx = c > mx ? c : mx;
+        sum += c;
+        c = 0;
+      }
+    if (mx) { g_cost_warp[r] += mx; g_cost_lane[r] += sum; }
+  }
+}
+
 namespace {
 constexpr size_t FIBER_STACK = 256 * 1024;
 
@@ -43,6 +63,7 @@ void on_fiber_exit(Fiber *f) {
   Cta *cta = f->cta;
   Warp &w = *f->warp;
   f->done = true;
+  cost_flush(cta, w, 1u << f->lane);
   w.exited |= 1u << f->lane;
   cta->n_done++;
   cta->progress++;
@@ -116,6 +137,7 @@ void complete_if_ready(Warp &w, Coll &c, uint32_t mask) {
   std::memcpy(c.out, c.in, sizeof(c.in));
   c.out_mask = c.arrived & mask;
   c.out_pred = c.pred & c.out_mask;
+  if (g_cur) cost_flush(g_cur->cta, w, c.out_mask);
   c.arrived = 0;
   c.pred = 0;
   c.gen++;
@@ -172,3 +194,10 @@ void launch(dim3 grid, dim3 block, const std::function<void()> &body) {
 }
 
 }  // namespace simt
+
+extern "C" void simt_cost_reset() {
+  for (int r = 0; r < simt::COST_REGIONS; ++r) { simt::g_cost_warp[r] = 0; simt::g_cost_lane[r] = 0; }
+}
+extern "C" void simt_cost_read(uint64_t *warp_issues, uint64_t *lane_passes, int n) {
+  for (int r = 0; r < n && r < simt::COST_REGIONS; ++r) { warp_issues[r] = simt::g_cost_warp[r]; lane_passes[r] = simt::g_cost_lane[r]; }
+}

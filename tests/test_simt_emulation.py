@@ -69,3 +69,21 @@ def test_launch_rewriter():
     assert "::simt::launch(dim3(static_cast<unsigned>(blocks)), dim3(block), [&]() { k_a<true>(scene, f(a, b), n); });" in text
     assert "::simt::launch(dim3(dim3(gx, gy)), dim3(256), [&]() { k_b(p, q); });" in text
     assert text.count("\n") == 3  # line numbers preserved
+
+
+def test_issue_model_attributes_every_sass_instruction():
+    """tools/issue_model.py, static half: every instruction of the default instantiation lands in a region, and the node step and
+    the triangle iteration have plausible sizes (a change of the markers or of nvdisasm's output format shows up here)."""
+    import shutil
+    if not (shutil.which("nvdisasm") and shutil.which("cuobjdump")):
+        pytest.skip("CUDA binary utilities not on PATH")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import issue_model
+    names = issue_model.region_names()
+    static, total = issue_model.static_counts("ILi2ELi8ELb1ELb0ELb1ELb0ELb0EE", names)
+    by = dict(zip(names, static))
+    tri_family = ("COST_TRI", "COST_TRI_RANGE", "COST_TRI_U", "COST_TRI_V", "COST_TRI_HIT")
+    copies = 3  # (the division below undoes the per-copy scaling only approximately: allow slack)
+    assert abs(sum(static) + sum(by[n] for n in tri_family) * (copies - 1) - total) < 0.02 * total, (sum(static), total)
+    assert 60 <= by["COST_NODE"] <= 110, by["COST_NODE"]
+    assert 80 <= sum(by[n] for n in tri_family) <= 160, [by[n] for n in tri_family]
