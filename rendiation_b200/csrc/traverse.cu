@@ -603,9 +603,9 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
     // ---------------- warp-converged refill (a few rounds, so scene-missing rays are retired here)
 #pragma unroll 1
     for (int attempt = 0; attempt < 4; ++attempt) {
-      RDN_COST(COST_REFILL);
       const uint32_t want = __ballot_sync(FULL_MASK, !alive);
       if (!want || warp_exhausted) break;
+      RDN_COST(COST_REFILL);
       const int cnt = __popc(want);
       const int leader = __ffs(want) - 1;
       unsigned long long base = 0;

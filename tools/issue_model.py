@@ -61,6 +61,9 @@ def region_lines(names: list[str]):
     return kernel, callee, (t0 + 1, t1 + 1)
 
 
+DUMP: dict[int, list[str]] = {}   # region -> its SASS lines (filled by static_counts; printed with --dump REGION)
+
+
 def static_counts(template_args: str, names: list[str]) -> tuple[list[float], int]:
     """SASS instructions per region PER PASS of its marker, for the instantiation whose mangled name contains `template_args`.
     An instruction belongs to the kernel-body line it was inlined into (last entry of its inline chain) and to the region whose
@@ -112,6 +115,7 @@ def static_counts(template_args: str, names: list[str]) -> tuple[list[float], in
             if mi.group(1).startswith("LDG"):
                 tri_loads += 1
         counts[region] += 1
+        DUMP.setdefault(region, []).append(f"{outer:5d} {line.strip()}")
     copies = max(1, round(tri_loads / 2))
     for r in tri_family:
         counts[r] /= copies
@@ -171,6 +175,10 @@ def main():
     template_args = "ILi2ELi8ELb1ELb0ELb1ELb0ELb0EE"  # the default instantiation <2, 8, true, false, true, false, false>
     names = region_names()
     static, total_static = static_counts(template_args, names)
+    if "--dump" in sys.argv:
+        want = "COST_" + sys.argv[sys.argv.index("--dump") + 1].upper()
+        print("\n".join(DUMP.get(names.index(want), [])))
+        return
     warp, lane, n_rays, dt, same = dynamic_counts(cfg, names)
     rows = []
     model_total = 0
