@@ -53,9 +53,22 @@ struct Warp {
   std::unordered_map<uint32_t, Coll> colls;  // node based: references stay valid
 };
 constexpr int COST_REGIONS = 32;
+// Context switch: on x86-64 a hand-written one (callee-saved registers and the stack pointer; glibc's swapcontext makes a
+// sigprocmask system call per switch, which was half of the emulation's run time), elsewhere ucontext.
+#if defined(__x86_64__) && !defined(SIMT_USE_UCONTEXT)
+#define SIMT_FAST_SWITCH 1
+struct Context {
+  void *sp = nullptr;
+};
+#else
+#define SIMT_FAST_SWITCH 0
+struct Context {
+  ucontext_t uc;
+};
+#endif
 struct Fiber {
   uint32_t cost[COST_REGIONS] = {};  // RDN_SIMT_COST: passes through each marked region since the lane's last collective
-  ucontext_t ctx;
+  Context ctx;
   uint3 tid;
   uint32_t lane = 0;
   Warp *warp = nullptr;
@@ -72,7 +85,7 @@ struct Cta {
   uint32_t sync_arrived = 0, n_done = 0;
   uint64_t sync_gen = 0;
   uint64_t progress = 0;
-  ucontext_t sched;
+  Context sched;
   const std::function<void()> *body = nullptr;
 };
 

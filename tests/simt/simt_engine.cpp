@@ -30,6 +30,36 @@ static void cost_flush(Cta *cta, Warp &w, uint32_t lanes) {
   }
 }
 
+#if SIMT_FAST_SWITCH
+extern "C" void simt_switch(void **save_sp, void *load_sp);
+asm(R"(
+    .text
+    .globl simt_switch
+    .hidden simt_switch
+    .type simt_switch,@function
+simt_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+    .size simt_switch,.-simt_switch
+)");
+static inline void switch_context(Context &from, Context &to) { simt_switch(&from.sp, to.sp); }
+#else
+static inline void switch_context(Context &from, Context &to) { swapcontext(&from.uc, &to.uc); }
+#endif
+
 namespace {
 constexpr size_t FIBER_STACK = 256 * 1024;
 
@@ -81,7 +111,26 @@ void trampoline() {
   Fiber *f = g_cur;
   (*f->cta->body)();
   on_fiber_exit(f);
-  swapcontext(&f->ctx, &f->cta->sched);  // never resumed
+  switch_context(f->ctx, f->cta->sched);  // never resumed
+  std::abort();
+}
+
+void prepare_fiber(Fiber &f, char *stack) {
+#if SIMT_FAST_SWITCH
+  // the frame simt_switch pops: r15 r14 r13 r12 rbx rbp, then `ret` into trampoline with the stack as after a call
+  uintptr_t top = (reinterpret_cast<uintptr_t>(stack) + FIBER_STACK) & ~static_cast<uintptr_t>(15);
+  void **frame = reinterpret_cast<void **>(top - 32 - 8 * 6);  // six registers below the return slot, which sits on a 16-byte boundary
+  for (int i = 0; i < 6; ++i) frame[i] = nullptr;
+  frame[6] = reinterpret_cast<void *>(&trampoline);
+  frame[7] = nullptr;  // the return address trampoline would see (it never returns)
+  f.ctx.sp = frame;
+#else
+  getcontext(&f.ctx.uc);
+  f.ctx.uc.uc_stack.ss_sp = stack;
+  f.ctx.uc.uc_stack.ss_size = FIBER_STACK;
+  f.ctx.uc.uc_link = nullptr;
+  makecontext(&f.ctx.uc, trampoline, 0);
+#endif
 }
 
 void run_cta(Cta &cta) {
@@ -95,11 +144,7 @@ void run_cta(Cta &cta) {
     f.warp = &cta.warps[t >> 5];
     f.warp->exists |= 1u << f.lane;
     f.cta = &cta;
-    getcontext(&f.ctx);
-    f.ctx.uc_stack.ss_sp = t_stacks.get(t);
-    f.ctx.uc_stack.ss_size = FIBER_STACK;
-    f.ctx.uc_link = nullptr;
-    makecontext(&f.ctx, trampoline, 0);
+    prepare_fiber(f, t_stacks.get(t));
   }
   uint64_t idle_passes = 0;
   while (cta.n_done < n_threads) {
@@ -111,7 +156,7 @@ void run_cta(Cta &cta) {
       if (f.wait_gen && *f.wait_gen == f.wait_val) continue;  // still blocked
       ran = true;
       g_cur = &f;
-      swapcontext(&cta.sched, &f.ctx);
+      switch_context(cta.sched, f.ctx);
     }
     g_cur = nullptr;
     if (!ran && cta.progress == before) {
@@ -146,7 +191,7 @@ void complete_if_ready(Warp &w, Coll &c, uint32_t mask) {
 
 void yield() {
   Fiber *f = g_cur;
-  swapcontext(&f->ctx, &f->cta->sched);
+  switch_context(f->ctx, f->cta->sched);
 }
 
 void syncthreads() {
