@@ -172,7 +172,13 @@ def dynamic_counts(cfg: str, names: list[str]):
 
 def main():
     cfg = next((a for a in sys.argv[1:] if a in CONFIGS), "c2s")
-    template_args = "ILi2ELi8ELb1ELb0ELb1ELb0ELb0EE"  # the default instantiation <2, 8, true, false, true, false, false>
+    # mangled template arguments <K, MINB, DRAIN_TIES, IRREGULAR, LD256, HOT, WIDE4> of the instantiation RDN_ORDERED_VARIANT selects
+    variants = {0: "ILi2ELi8ELb1ELb0ELb1ELb0ELb0EE", 9: "ILi2ELi8ELb0ELb0ELb1ELb0ELb0EE", 30: "ILi2ELi8ELb1ELb0ELb0ELb0ELb0EE",
+                60: "ILi2ELi8ELb1ELb0ELb1ELb0ELb1EE", 61: "ILi1ELi8ELb1ELb0ELb1ELb0ELb1EE"}
+    variant = int(sys.argv[sys.argv.index("--variant") + 1]) if "--variant" in sys.argv else 0
+    template_args = variants[variant]
+    if variant:
+        os.environ["RDN_ORDERED_VARIANT"] = str(variant)  # read by the library at its first launch (and by the flattener: wide4 view)
     names = region_names()
     static, total_static = static_counts(template_args, names)
     if "--dump" in sys.argv:
@@ -191,7 +197,7 @@ def main():
                      "lanes_per_issue": round(lane[i] / warp[i], 2) if warp[i] else None, "warp_instructions": issued})
     for r in rows:
         r["share"] = round(r["warp_instructions"] / model_total, 4) if model_total else 0
-    out = {"config": cfg, "rays": n_rays, "emulation_seconds": round(dt, 1), "result_identical_to_oracle": same,
+    out = {"config": cfg, "variant": variant, "rays": n_rays, "emulation_seconds": round(dt, 1), "result_identical_to_oracle": same,
            "sass_instructions_in_kernel": total_static, "model_warp_instructions": model_total,
            "model_warp_instructions_per_ray": round(model_total / n_rays, 2),
            "model_active_lanes": round(lane_total / model_total, 2) if model_total else None, "regions": rows}
