@@ -87,3 +87,11 @@ def test_issue_model_attributes_every_sass_instruction():
     assert abs(sum(static) + sum(by[n] for n in tri_family) * (copies - 1) - total) < 0.02 * total, (sum(static), total)
     assert 60 <= by["COST_NODE"] <= 110, by["COST_NODE"]
     assert 80 <= sum(by[n] for n in tri_family) <= 160, [by[n] for n in tri_family]
+
+
+def test_two_gloo_ranks_trace_their_tiles_on_emulated_kernels():
+    """the N > 1 launch path end to end on CPU: tile sharding, per-tile 2-D launches through the C ABI, gather on rank 0"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "simt", "two_rank_emulated.py")], cwd=ROOT, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    assert "identical to the oracle" in r.stdout, r.stdout[-1000:]
