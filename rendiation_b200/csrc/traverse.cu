@@ -404,7 +404,12 @@ struct OrderedParams {
   TraceScratch scratch;
 };
 
-__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
+#ifdef RDN_SIMT_EMU
+  ::simt::preempt();  // (a spin on another thread's store must let that thread run: cooperative scheduling in the emulated build)
+#endif
+  return *reinterpret_cast<const volatile uint32_t *>(p);
+}
 
 // Hits of an irregular instance (or of the irregular triangles of an otherwise regular BLAS) need not lie inside their boxes,
 // so what the ordered walk would prune the reference may have found.  A ray whose ORIGINAL range meets such an instance (the

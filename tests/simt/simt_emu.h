@@ -139,6 +139,12 @@ void syncthreads();
 // region's static SASS instruction count (tools/sass_regions.py) this predicts the kernel's warp-level instruction count.
 inline void cost_mark(int region) { g_cur->cost[region]++; }
 
+// RDN_SIMT_SEED=n (n != 0): randomised scheduling.  The CTA scheduler visits its threads in a random order each pass and a thread
+// may be preempted at every atomic, fence, volatile / .cg load and __nanosleep, so lanes of a warp and warps of a CTA interleave
+// differently from run to run of different seeds — results that depend on the interleaving (a missing fence or barrier whose
+// effect the round-robin order happens to hide) show up as parity failures.  Independent thread scheduling in miniature.
+void preempt();
+
 }  // namespace simt
 extern "C" void simt_cost_reset();
 extern "C" void simt_cost_read(uint64_t *warp_issues, uint64_t *lane_passes, int n);
@@ -195,12 +201,13 @@ inline T __shfl_up_sync(unsigned mask, T v, unsigned delta, int width = 32) {
 }
 inline unsigned __activemask() { return 1u << ::simt::g_cur->lane; }
 inline void __syncthreads() { ::simt::syncthreads(); }
-inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
-inline void __nanosleep(unsigned) { __builtin_ia32_pause(); }
+inline void __threadfence() { ::simt::preempt(); __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __nanosleep(unsigned) { ::simt::preempt(); __builtin_ia32_pause(); }
 
 // ---- atomics on global memory
 template <class T, class U>
 inline T atomicAdd(T *p, U v) {
+  ::simt::preempt();
   if constexpr (std::is_floating_point<T>::value) {
     T old = *reinterpret_cast<volatile T *>(p);
     for (;;) {
@@ -215,18 +222,21 @@ inline T atomicAdd(T *p, U v) {
 }
 template <class T, class U>
 inline T atomicMin(T *p, U v) {
+  ::simt::preempt();
   T old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
   while (static_cast<T>(v) < old && !__atomic_compare_exchange_n(p, &old, static_cast<T>(v), false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
   return old;
 }
 template <class T, class U>
 inline T atomicMax(T *p, U v) {
+  ::simt::preempt();
   T old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
   while (static_cast<T>(v) > old && !__atomic_compare_exchange_n(p, &old, static_cast<T>(v), false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
   return old;
 }
 template <class T, class U, class V>
 inline T atomicCAS(T *p, U compare, V value) {
+  ::simt::preempt();
   T expected = static_cast<T>(compare);
   __atomic_compare_exchange_n(p, &expected, static_cast<T>(value), false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
   return expected;
@@ -237,6 +247,7 @@ template <class T>
 inline T __ldg(const T *p) { return *p; }
 template <class T>
 inline T __ldcg(const T *p) {
+  ::simt::preempt();
   __atomic_thread_fence(__ATOMIC_ACQUIRE);
   T v;
   std::memcpy(&v, const_cast<const T *>(p), sizeof(T));

@@ -10,6 +10,13 @@ namespace simt {
 
 thread_local Fiber *g_cur = nullptr;
 
+static const uint64_t g_seed = []() { const char *e = std::getenv("RDN_SIMT_SEED"); return e ? std::strtoull(e, nullptr, 10) : 0ull; }();
+static thread_local uint64_t t_rng = 0;
+static inline uint64_t rng_next() {  // xorshift64*
+  t_rng ^= t_rng >> 12; t_rng ^= t_rng << 25; t_rng ^= t_rng >> 27;
+  return t_rng * 0x2545F4914F6CDD1Dull;
+}
+
 static std::atomic<uint64_t> g_cost_warp[COST_REGIONS], g_cost_lane[COST_REGIONS];
 // the lanes in `lanes` of warp `w` have met in a collective (or one lane leaves): charge the regions they passed since
 static const bool g_cost_enabled = []() { const char *e = std::getenv("RDN_SIMT_COST"); return e && std::atoi(e) != 0; }();
@@ -147,10 +154,16 @@ void run_cta(Cta &cta) {
     prepare_fiber(f, t_stacks.get(t));
   }
   uint64_t idle_passes = 0;
+  if (g_seed) t_rng = (g_seed * 0x9E3779B97F4A7C15ull) ^ (0xD1B54A32D192ED03ull * (1 + cta.bid.x + 65536ull * cta.bid.y)) | 1ull;
   while (cta.n_done < n_threads) {
     const uint64_t before = cta.progress;
     bool ran = false;
-    for (uint32_t t = 0; t < n_threads; ++t) {
+    // randomised scheduling: a random rotation and a random odd stride (a permutation when the thread count is a power of two;
+    // otherwise some threads are skipped in this pass and come up in a later one)
+    const uint32_t rot = g_seed ? static_cast<uint32_t>(rng_next() % n_threads) : 0u;
+    const uint32_t stride = g_seed ? static_cast<uint32_t>(rng_next() | 1u) : 1u;
+    for (uint32_t k = 0; k < n_threads; ++k) {
+      const uint32_t t = g_seed ? static_cast<uint32_t>((rot + static_cast<uint64_t>(k) * stride) % n_threads) : k;
       Fiber &f = cta.fibers[t];
       if (f.done) continue;
       if (f.wait_gen && *f.wait_gen == f.wait_val) continue;  // still blocked
@@ -192,6 +205,14 @@ void complete_if_ready(Warp &w, Coll &c, uint32_t mask) {
 void yield() {
   Fiber *f = g_cur;
   switch_context(f->ctx, f->cta->sched);
+}
+
+void preempt() {
+  if (!g_seed || !g_cur) return;
+  if ((rng_next() & 3u) != 0) return;
+  g_cur->wait_gen = nullptr;  // still runnable: picked up again in a later pass
+  g_cur->cta->progress++;
+  yield();
 }
 
 void syncthreads() {

@@ -95,3 +95,40 @@ def test_two_gloo_ranks_trace_their_tiles_on_emulated_kernels():
                        text=True, timeout=900)
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
     assert "identical to the oracle" in r.stdout, r.stdout[-1000:]
+
+
+def _selftest(seed=None):
+    code = ("import ctypes, sys; sys.path.insert(0, %r); import build_emu; L = ctypes.CDLL(build_emu.build()); "
+            "L.simt_selftest_race.restype = ctypes.c_uint; print(L.simt_selftest_collectives(), L.simt_selftest_race())"
+            % os.path.join(ROOT, "tests", "simt"))
+    env = dict(os.environ)
+    env.pop("RDN_SIMT_SEED", None)
+    if seed is not None:
+        env["RDN_SIMT_SEED"] = str(seed)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    collectives, race = r.stdout.split()[-2:]
+    return int(collectives), int(race)
+
+
+def test_emulator_primitives_and_randomised_scheduling():
+    """known answers for votes / shuffles / diverged masks / barriers / exited lanes, and the randomised scheduler really
+    interleaves: a deliberately racy read-modify-write keeps all 64 increments under round-robin scheduling (every thread runs
+    to completion) and loses some under RDN_SIMT_SEED"""
+    ok, race = _selftest()
+    assert ok == 0 and race == 64, (ok, race)
+    lost = []
+    for seed in (1, 2, 3):
+        ok, race = _selftest(seed)
+        assert ok == 0, (seed, ok)
+        lost.append(64 - race)
+    assert any(l > 0 for l in lost), lost
+
+
+def test_parity_holds_under_randomised_scheduling():
+    """the tie queue, the refill votes, the compaction's look-back and the fuzz scenes under a randomised interleaving of the
+    lanes and warps (RDN_SIMT_SEED): the records must not depend on who runs when"""
+    sel = "fixture or ties or flags or degenerate or instanced_scene or compaction or (fuzz and regular) or (fuzz and mixed)"
+    for seed in (11, 12):
+        summary = _run_emulated(["tests/test_gpu_parity.py", "tests/test_gpu_fuzz.py"], sel, {"RDN_SIMT_SEED": str(seed)})
+        assert int(summary.split(" passed")[0].split()[-1]) >= 30, summary
