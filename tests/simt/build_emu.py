@@ -80,7 +80,11 @@ def _stale(target: str, deps: list[str]) -> bool:
 def build(force: bool = False, defines: tuple[str, ...] = ()) -> str:
     """defines: extra -D macros (e.g. ("RDN_REF_LEAF_MAX_COUNT=1",)); each set of defines gets its own build directory"""
     defines = tuple(defines) or tuple(d for d in os.environ.get("RDN_SIMT_DEFINES", "").split() if d)
-    tag = "_".join(re.sub(r"\W+", "-", d) for d in defines)
+    # RDN_SIMT_CXXFLAGS: extra compiler / linker flags, e.g. "-fsanitize=address -fno-omit-frame-pointer" (then run python with
+    # LD_PRELOAD=$(g++ -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0): every access of
+    # the kernels to "device" memory is then checked against the bounds of its cudaMalloc — a memcheck without a GPU
+    extra = tuple(os.environ.get("RDN_SIMT_CXXFLAGS", "").split())
+    tag = "_".join(re.sub(r"\W+", "-", d) for d in defines + extra)
     OUT = os.path.join(HERE, "_build", tag) if tag else os.path.join(HERE, "_build")
     LIB = os.path.join(OUT, "librdn_rt_emu.so")
     os.makedirs(OUT, exist_ok=True)
@@ -104,7 +108,7 @@ def build(force: bool = False, defines: tuple[str, ...] = ()) -> str:
             with open(gen, "w") as f:
                 f.write(f'#line 1 "{sp}"\n' + text)
             sp = gen
-        jobs.append(["g++", *CXXFLAGS, *[f"-D{d}" for d in defines], "-c", sp, "-o", op])
+        jobs.append(["g++", *CXXFLAGS, *extra, *[f"-D{d}" for d in defines], "-c", sp, "-o", op])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -116,7 +120,7 @@ def build(force: bool = False, defines: tuple[str, ...] = ()) -> str:
         with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
             list(ex.map(run, jobs))
     if jobs or force or _stale(LIB, objs):
-        run(["g++", "-shared", "-o", LIB, *objs, "-Wl,--no-undefined", "-Wl,-Bsymbolic", "-lpthread"])  # -Bsymbolic: our cuda* stand-ins, not a libcudart torch loaded
+        run(["g++", "-shared", *extra, "-o", LIB, *objs, *([] if any("sanitize" in f for f in extra) else ["-Wl,--no-undefined"]), "-Wl,-Bsymbolic", "-lpthread"])  # -Bsymbolic: our cuda* stand-ins, not a libcudart torch loaded
     return LIB
 
 
