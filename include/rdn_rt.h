@@ -125,6 +125,7 @@ typedef struct rdn_build_stats {
   uint64_t reference_routed_tlas;                      /* TLASes whose every ray takes the reference-order kernel */
   double bvh_build_ms, flatten_ms, upload_ms;          /* wall clock of the last commit: tree builds / flattening / blob + upload */
   uint64_t build_threads;                              /* worker threads the tree builder used (RDN_BUILD_THREADS caps it) */
+  uint64_t device_built_trees;                         /* geometry trees built by the device SAH builder (RDN_COMMIT_DEVICE_BUILD=1) */
 } rdn_build_stats;
 
 typedef struct rdn_rt_scene rdn_rt_scene;   /* opaque: NaiveSahBVHSystem (geometry/naive/mod.rs:495-610) */

@@ -13,6 +13,10 @@
 
 namespace rdn {
 
+// build_device.cu: 0 = built, 1 = not supported on the device, < 0 = error
+int build_bvh_sah_device(const Box3 *boxes, uint64_t n, uint32_t n_buckets, const TreeBuildOption &option, int device, FlattenBVH &out,
+                         std::string &err);
+
 // ------------------------------------------------------------------------------------------------ matrices
 // three-term cofactor row: x*(p*q - r*s) + y*(...) + z*(...), the shape of every entry of mat4.rs:82-100
 static inline float cof3(float x, float p0, float q0, float r0, float s0, float y, float p1, float q1, float r1, float s1,
@@ -383,7 +387,16 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
   auto since = [](Clock::time_point t0) { return std::chrono::duration<double, std::milli>(Clock::now() - t0).count(); };
   auto timed_build = [&](const Box3 *boxes, uint64_t n, BVHBuildStrategy &strategy, const TreeBuildOption &option) {
     const auto t0 = Clock::now();
-    FlattenBVH bvh = FlattenBVH::build(boxes, n, strategy, option);
+    FlattenBVH bvh;
+    bool on_device = false;
+    if (build_device >= 0 && n >= device_build_min) {
+      if (const SAH *sah = dynamic_cast<const SAH *>(&strategy)) {
+        std::string device_err;
+        on_device = build_bvh_sah_device(boxes, n, sah->bucket_count(), option, build_device, bvh, device_err) == 0;
+        if (on_device) out.stats.device_built_trees++;
+      }
+    }
+    if (!on_device) bvh = FlattenBVH::build(boxes, n, strategy, option);  // (also reports the reference's build errors)
     bvh_ms += std::chrono::duration<double, std::milli>(Clock::now() - t0).count();
     if (bvh.stats.build_threads > out.stats.build_threads) out.stats.build_threads = bvh.stats.build_threads;
     return bvh;

@@ -59,6 +59,12 @@ class NaiveSahBvhSource {
   // NaiveSahBvhSource::build: returns 0 or a negative rdn_status; `err` gets a message on failure
   int build(const std::vector<uint32_t> &tlas_binding, FlatScene &out, std::string &err) const;
 
+  // Opt-in (RDN_COMMIT_DEVICE_BUILD=1, set by the C ABI for scenes that own a CUDA device): geometry trees of at least
+  // `device_build_min` triangles are built by the device SAH builder (build_device.cu: the reference's tree node for node) and by
+  // the host builder when the device declines (more than four buckets, a long degenerate range).  -1: host builder only.
+  int build_device = -1;
+  uint64_t device_build_min = 1u << 16;
+
  private:
   struct Blas { bool alive = false; std::vector<GeometrySource> geometries; };
   struct Tlas { bool alive = false; std::vector<InstanceSource> instances; };

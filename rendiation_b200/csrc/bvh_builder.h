@@ -60,6 +60,7 @@ struct BuildStats {
   // wide nodes, threaded layout), blob serialisation + upload
   double bvh_build_ms = 0, flatten_ms = 0, upload_ms = 0;
   uint32_t build_threads = 1;           // worker threads FlattenBVH::build used for its largest tree
+  uint64_t device_built_trees = 0;      // geometry trees that came from the device SAH builder (build_device.cu)
 };
 
 class BVHBuildStrategy {
@@ -81,6 +82,7 @@ class BalanceTree : public BVHBuildStrategy {
 class SAH : public BVHBuildStrategy {
  public:
   explicit SAH(uint32_t pre_partition_check_count);
+  uint32_t bucket_count() const { return static_cast<uint32_t>(pre_partition_.size()); }
   SplitResult split(const FlattenBVHNode &parent, const std::vector<BuildPrimitive> &build_source,
                     std::vector<uint64_t> &index_source, BuildStats &stats) override;
   // (a worker's copy splits on its own thread only: the workers already occupy the cores)

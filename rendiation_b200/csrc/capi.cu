@@ -187,6 +187,10 @@ int commit_locked(rdn_rt_scene *s) {
   if (s->adopted && ((!s->devices.empty() && s->devices[0].d_blob) || (s->devices.empty() && !s->host_blob.empty()))) { s->dirty = false; return RDN_OK; }
   std::string err;
   FlatScene flat;
+  const char *device_build_env = getenv("RDN_COMMIT_DEVICE_BUILD");  // (read at every commit: a test flips it between scenes)
+  const bool device_build = device_build_env && atoi(device_build_env) != 0;
+  s->source.build_device = (device_build && !s->devices.empty()) ? s->devices[0].device : -1;
+  if (const char *e = getenv("RDN_COMMIT_DEVICE_BUILD_MIN")) s->source.device_build_min = strtoull(e, nullptr, 10);
   const int rc = s->source.build(s->tlas_binding, flat, err);
   if (rc != RDN_OK) return fail(rc, err);
   const auto t_upload = std::chrono::steady_clock::now();
@@ -1247,6 +1251,7 @@ int rdn_rt_scene_build_stats(rdn_rt_scene *s, rdn_build_stats *out) {
     out->flatten_ms = s->flat.stats.flatten_ms;
     out->upload_ms = s->flat.stats.upload_ms;
     out->build_threads = s->flat.stats.build_threads;
+    out->device_built_trees = s->flat.stats.device_built_trees;
   } else {
     for (const TlasRoot &t : s->h_tlas_root) {
       if (t.irregular_count == IRREGULAR_ROUTE_ALL) out->reference_routed_tlas++;

@@ -51,3 +51,36 @@ def test_device_build_of_a_million_triangles_and_its_fallbacks():
     same_centres = api.FlattenBVH(many, api.SAH(4), api.TreeBuildOption(50, 2), device=0)
     assert not same_centres.built_on_device
     _same_tree(same_centres, oracle.FlattenBVH(many, oracle.STRATEGY_SAH, 4, 50, 2))
+
+
+def test_commit_with_the_device_builder_flattens_the_same_scene(monkeypatch):
+    """RDN_COMMIT_DEVICE_BUILD=1: geometry trees above the size threshold come from the device SAH builder; the flattened scene
+    (every array of the blob) and the traced records are those of the host-built scene"""
+    from rendiation_b200 import scenes as S
+    import helpers
+
+    def build():
+        sp = helpers.ScenePair(product=True)
+        tpos, tidx = S.torus_mesh(96, 64, 1.0, 0.35)           # 12,288 triangles: device
+        spos, sidx = S.uv_sphere_mesh(12, 8)                   # small: stays on the host
+        a = sp.blas([(tpos, tidx.reshape(-1), 1)])
+        b = sp.blas([(spos, sidx.reshape(-1), 1)])
+        T = S.mat4_translate
+        sp.bind([sp.tlas(np.concatenate([S.make_instance(S.mat4_mul(T(0, 0, -8), S.mat4_rotate_x(-0.6)), a),
+                                         S.make_instance(T(2.5, 1.5, -7), b, custom_index=3)]))])
+        return sp.build()
+
+    host = build()
+    assert host.p.build_stats()["device_built_trees"] == 0
+    monkeypatch.setenv("RDN_COMMIT_DEVICE_BUILD", "1")
+    monkeypatch.setenv("RDN_COMMIT_DEVICE_BUILD_MIN", "4096")
+    dev = build()
+    assert dev.p.build_stats()["device_built_trees"] == 1
+    ha, da = host.p.arrays(), dev.p.arrays()
+    assert ha.keys() == da.keys()
+    for name in ha:
+        assert ha[name].tobytes() == da[name].tobytes(), name
+    rays = S.pinhole_rays(96, 64, 0.01, 100.0)
+    got = dev.p.trace_closest_batch(rays, ray_flags=0x10, grid_width=96)
+    want, _ = dev.o.trace(rays, ray_flags=0x10, n_threads=4)
+    assert got.tobytes() == want.tobytes() and int((got["instance_id"] != 0xFFFFFFFF).sum()) > 100
