@@ -1006,6 +1006,8 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const
 #endif
     case 60: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, true>; break;    // four-box nodes, K = 2 steps per round
     case 61: fn = k_trace_ordered_rounds<1, 8, true, false, true, false, true>; break;    // ... one step per round
+    case 70: fn = k_trace_ordered_rounds<3, 8, true, false, true, false, false>; break;   // three node steps per round (issue model: tools/issue_model.py)
+    case 71: fn = k_trace_ordered_rounds<1, 8, true, false, true, false, false>; break;   // one node step per round
     default: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false>; break;
   }
   if ((variant == 60 || variant == 61) && !use_wide4) fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false>;
