@@ -10,8 +10,9 @@
 // Execution model: a CTA runs on one OS thread as blockDim cooperatively scheduled fibers (ucontext); CTAs of a grid are dealt
 // to a few OS threads.  A fiber runs until it reaches a warp collective (__ballot_sync, __shfl*_sync, __syncwarp, ...) or
 // __syncthreads and is resumed when every lane named by the mask (that has not exited) has arrived.  Collectives on different
-// masks may be pending in a warp at the same time (diverged lanes).  __activemask() returns the calling lane alone — a legal
-// answer on hardware with independent thread scheduling.  __shared__ variables are thread_local statics (one CTA per OS thread
+// masks may be pending in a warp at the same time (diverged lanes).  __activemask() returns the lanes that reach the call site
+// in the same scheduler pass (a legal answer on hardware with independent thread scheduling, and one that exercises
+// warp-aggregated code with real groups).  __shared__ variables are thread_local statics (one CTA per OS thread
 // at a time).  Global-memory atomics are host atomics, so CTAs on different OS threads interact as CTAs on different SMs do.
 // Arithmetic: compiled with -ffp-contract=off, SSE f32 — bit-identical to the -fmad=false device code except NaN payloads.
 #pragma once
@@ -48,9 +49,15 @@ struct Coll {  // one pending collective per (warp, mask)
   uint64_t out[32];
   uint32_t out_pred = 0, out_mask = 0;
 };
+struct ActiveGather {  // lanes that reached one __activemask() call site during the same scheduler pass
+  uint32_t mask = 0;
+  uint64_t pass = ~0ull;
+  bool closed = true;
+};
 struct Warp {
   uint32_t exists = 0, exited = 0;
   std::unordered_map<uint32_t, Coll> colls;  // node based: references stay valid
+  std::unordered_map<const void *, ActiveGather> gathers;
 };
 constexpr int COST_REGIONS = 32;
 // Context switch: on x86-64 a hand-written one (callee-saved registers and the stack pointer; glibc's swapcontext makes a
@@ -76,6 +83,7 @@ struct Fiber {
   bool done = false;
   const volatile uint64_t *wait_gen = nullptr;  // blocked while *wait_gen == wait_val
   uint64_t wait_val = 0;
+  uint32_t active_result = 0;                   // __activemask(): filled when the lane's gather closes
 };
 struct Cta {
   uint3 bid;
@@ -85,6 +93,7 @@ struct Cta {
   uint32_t sync_arrived = 0, n_done = 0;
   uint64_t sync_gen = 0;
   uint64_t progress = 0;
+  uint64_t pass_id = 0;                         // scheduler passes over the CTA's threads so far
   Context sched;
   const std::function<void()> *body = nullptr;
 };
@@ -199,7 +208,15 @@ inline T __shfl_up_sync(unsigned mask, T v, unsigned delta, int width = 32) {
   const ::simt::Coll &c = ::simt::collective(mask, ::simt::to_bits(v), false);
   return (delta <= lane && ((c.out_mask >> (lane - delta)) & 1u)) ? ::simt::from_bits<T>(c.out[lane - delta]) : v;
 }
-inline unsigned __activemask() { return 1u << ::simt::g_cur->lane; }
+// __activemask(): the lanes of the warp that reach the same call site within one scheduler pass form a converged group (all of
+// them then continue from that site, so a __shfl_sync over the returned mask completes).  Under RDN_SIMT_SEED the groups vary.
+namespace simt { unsigned activemask_at(const void *site); }
+__attribute__((noinline)) inline unsigned __activemask() { return ::simt::activemask_at(__builtin_return_address(0)); }
+inline unsigned __fns(unsigned mask, unsigned base, int offset) {  // offset-th set bit at or above `base` (offset >= 1), else 0xFFFFFFFF
+  for (unsigned b = base; b < 32; ++b)
+    if (((mask >> b) & 1u) && --offset == 0) return b;
+  return 0xFFFFFFFFu;
+}
 inline void __syncthreads() { ::simt::syncthreads(); }
 inline void __threadfence() { ::simt::preempt(); __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __nanosleep(unsigned) { ::simt::preempt(); __builtin_ia32_pause(); }

@@ -158,6 +158,7 @@ void run_cta(Cta &cta) {
   while (cta.n_done < n_threads) {
     const uint64_t before = cta.progress;
     bool ran = false;
+    cta.pass_id++;
     // randomised scheduling: a random rotation and a random odd stride (a permutation when the thread count is a power of two;
     // otherwise some threads are skipped in this pass and come up in a later one)
     const uint32_t rot = g_seed ? static_cast<uint32_t>(rng_next() % n_threads) : 0u;
@@ -205,6 +206,29 @@ void complete_if_ready(Warp &w, Coll &c, uint32_t mask) {
 void yield() {
   Fiber *f = g_cur;
   switch_context(f->ctx, f->cta->sched);
+}
+
+static void close_gather(Cta *cta, Warp &w, ActiveGather &g) {
+  Fiber *base = &cta->fibers[static_cast<size_t>(&w - cta->warps.data()) * 32u];
+  for (uint32_t l = 0; l < 32; ++l)
+    if ((g.mask >> l) & 1u) base[l].active_result = g.mask;
+  g.closed = true;
+}
+
+unsigned activemask_at(const void *site) {
+  Fiber *f = g_cur;
+  Cta *cta = f->cta;
+  Warp &w = *f->warp;
+  ActiveGather &g = w.gathers[site];
+  if (!g.closed && g.pass != cta->pass_id) close_gather(cta, w, g);  // a group of an earlier pass that nobody has resumed from yet
+  if (g.closed) { g.mask = 0; g.pass = cta->pass_id; g.closed = false; }
+  g.mask |= 1u << f->lane;
+  f->active_result = 0;
+  f->wait_gen = nullptr;  // runnable: resumed in a later pass, when everyone who arrives in this one has
+  cta->progress++;
+  yield();
+  if (f->active_result == 0) close_gather(cta, w, w.gathers[site]);
+  return f->active_result;
 }
 
 void preempt() {

@@ -68,3 +68,38 @@ extern "C" unsigned simt_selftest_race() {
   ::simt::launch(dim3(1), dim3(64), [&]() { k_race(&word); });
   return word;
 }
+
+namespace {
+// warp-aggregated append (the pattern of traverse.cu's enqueue_rewalk): every participating lane must get a distinct slot
+void k_aggregate(unsigned *count, unsigned *slots, unsigned *groups_seen) {
+  const unsigned lane = threadIdx.x & 31u;
+  if ((lane % 3u) == 0u) return;  // a third of the lanes do not take part
+  const unsigned peers = __activemask();
+  const int leader = __ffs(peers) - 1;
+  unsigned base = 0;
+  if (static_cast<int>(lane) == leader) base = atomicAdd(count, static_cast<unsigned>(__popc(peers)));
+  base = __shfl_sync(peers, base, leader);
+  const unsigned q = base + __popc(peers & ((1u << lane) - 1u));
+  slots[q] = threadIdx.x + 1u;
+  if (__popc(peers) > 1) atomicAdd(groups_seen, 1u);
+}
+}  // namespace
+
+// returns the number of lanes that found themselves in a group of more than one, or -1 when two lanes got the same slot
+extern "C" int simt_selftest_aggregate() {
+  unsigned count = 0, groups = 0;
+  unsigned slots[128] = {};
+  ::simt::launch(dim3(1), dim3(128), [&]() { k_aggregate(&count, slots, &groups); });
+  unsigned expected = 0;
+  for (unsigned t = 0; t < 128; ++t) expected += (t & 31u) % 3u != 0u;
+  if (count != expected) return -1;
+  unsigned long long seen_lo = 0, seen_hi = 0;
+  for (unsigned q = 0; q < count; ++q) {
+    if (slots[q] == 0 || slots[q] > 128) return -1;
+    unsigned long long &word = slots[q] <= 64 ? seen_lo : seen_hi;
+    const unsigned long long bit = 1ull << ((slots[q] - 1u) & 63u);
+    if (word & bit) return -1;
+    word |= bit;
+  }
+  return static_cast<int>(groups);
+}

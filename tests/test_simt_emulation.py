@@ -99,7 +99,7 @@ def test_two_gloo_ranks_trace_their_tiles_on_emulated_kernels():
 
 def _selftest(seed=None):
     code = ("import ctypes, sys; sys.path.insert(0, %r); import build_emu; L = ctypes.CDLL(build_emu.build()); "
-            "L.simt_selftest_race.restype = ctypes.c_uint; print(L.simt_selftest_collectives(), L.simt_selftest_race())"
+            "L.simt_selftest_race.restype = ctypes.c_uint; print(L.simt_selftest_collectives(), L.simt_selftest_race(), L.simt_selftest_aggregate())"
             % os.path.join(ROOT, "tests", "simt"))
     env = dict(os.environ)
     env.pop("RDN_SIMT_SEED", None)
@@ -107,20 +107,21 @@ def _selftest(seed=None):
         env["RDN_SIMT_SEED"] = str(seed)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
-    collectives, race = r.stdout.split()[-2:]
-    return int(collectives), int(race)
+    collectives, race, aggregate = r.stdout.split()[-3:]
+    return int(collectives), int(race), int(aggregate)
 
 
 def test_emulator_primitives_and_randomised_scheduling():
     """known answers for votes / shuffles / diverged masks / barriers / exited lanes, and the randomised scheduler really
     interleaves: a deliberately racy read-modify-write keeps all 64 increments under round-robin scheduling (every thread runs
     to completion) and loses some under RDN_SIMT_SEED"""
-    ok, race = _selftest()
+    ok, race, aggregate = _selftest()
     assert ok == 0 and race == 64, (ok, race)
+    assert aggregate > 32, aggregate   # __activemask() groups the lanes that arrive together: the aggregated append ran with real groups
     lost = []
     for seed in (1, 2, 3):
-        ok, race = _selftest(seed)
-        assert ok == 0, (seed, ok)
+        ok, race, aggregate = _selftest(seed)
+        assert ok == 0 and aggregate >= 0, (seed, ok, aggregate)
         lost.append(64 - race)
     assert any(l > 0 for l in lost), lost
 
