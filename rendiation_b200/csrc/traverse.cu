@@ -39,7 +39,10 @@ namespace rdn {
 namespace {
 
 constexpr uint32_t FULL_MASK = 0xFFFFFFFFu;
-constexpr int STACK_MAX = 120;       // TLAS depth 50 + BLAS depth 50 (TreeBuildOption of naive/mod.rs:173-176,280-283) + bookkeeping
+#ifndef RDN_STACK_MAX
+#define RDN_STACK_MAX 120  // (the emulated test build of tests/simt lowers it to reach the overflow report)
+#endif
+constexpr int STACK_MAX = RDN_STACK_MAX;  // TLAS depth 50 + BLAS depth 50 (TreeBuildOption of naive/mod.rs:173-176,280-283) + bookkeeping
 constexpr int ORDERED_BLOCK = 128;
 
 // TraverseFlags bits (flag.rs:6-25)

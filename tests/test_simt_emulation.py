@@ -133,3 +133,10 @@ def test_parity_holds_under_randomised_scheduling():
     for seed in (11, 12):
         summary = _run_emulated(["tests/test_gpu_parity.py", "tests/test_gpu_fuzz.py"], sel, {"RDN_SIMT_SEED": str(seed)})
         assert int(summary.split(" passed")[0].split()[-1]) >= 30, summary
+
+
+def test_traversal_stack_overflow_is_reported_not_swallowed():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "simt", "stack_overflow_case.py")], cwd=ROOT, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    assert "stack overflow is reported" in r.stdout
