@@ -1065,6 +1065,7 @@ struct rdn_sbt {
     uint64_t cap = 0;
   };
   std::vector<PerDevice> per_device;
+  std::vector<int> device_ids;           // CUDA device of each entry (kept here: the table may outlive the scene object)
 };
 
 namespace {
@@ -1094,6 +1095,7 @@ int rdn_sbt_create(rdn_rt_scene *scene, uint32_t max_geometry_count_in_blas, uin
   t->hit_groups.assign(groups, SbtHitGroup{RDN_SBT_NO_SHADER, RDN_SBT_NO_SHADER, RDN_SBT_NO_SHADER});
   t->miss.assign(ray_type_count, RDN_SBT_NO_SHADER);
   t->per_device.resize(scene->devices.size());
+  for (const DeviceCtx &dc : scene->devices) t->device_ids.push_back(dc.device);
   *out = t;
   return RDN_OK;
 }
@@ -1102,7 +1104,7 @@ void rdn_sbt_destroy(rdn_sbt *t) {
   if (!t) return;
   for (size_t i = 0; i < t->per_device.size(); ++i) {
     rdn_sbt::PerDevice &pd = t->per_device[i];
-    if (i < t->scene->devices.size()) cudaSetDevice(t->scene->devices[i].device);
+    cudaSetDevice(t->device_ids[i]);
     cudaFree(pd.d_hit_groups); cudaFree(pd.d_miss); cudaFree(pd.d_keep); cudaFree(pd.d_iota); cudaFree(pd.d_segment);
     cudaFree(pd.d_count); cudaFree(pd.d_status);
   }
