@@ -1,6 +1,6 @@
 """Issue-slot model of k_trace_ordered_rounds from the CPU emulation of the kernel (tests/simt) — no GPU needed.
 
-    python tools/issue_model.py [c1|c2|c2s|c3s|c4s] [--variant N]
+    python tools/issue_model.py [c1|c2|c2s|c2t|c4] [--variant N] [--dump REGION] [--json]
 
 static  : SASS instructions per marked source region of the kernel instantiation (nvdisasm line info of csrc/_obj/traverse.o,
           each instruction attributed to the kernel-body line it was inlined into, regions = the RDN_COST markers)
@@ -128,6 +128,7 @@ CONFIGS = {
     "c2": ("torus", 708, 1920, 1080, 0x10, 0.01),     # BASELINE config 2 (a few minutes on the emulator)
     "c2s": ("torus", 708, 960, 540, 0x10, 0.01),      # config 2's scene, a quarter of the pixels
     "c2t": ("torus", 256, 640, 360, 0x10, 0.01),
+    "c4": ("instances", 224, 1920, 1080, 0x10, 0.0),  # BASELINE config 4: 10,000 instances of a 100,352-triangle sphere
 }
 
 
@@ -142,6 +143,13 @@ def dynamic_counts(cfg: str, names: list[str]):
     if kind == "sphere":
         sp, _ = helpers.sphere_c1(seg=seg)
         rays = S.pinhole_rays(w, h, tmin, 100.0)
+    elif kind == "instances":
+        pos, idx = S.uv_sphere_mesh(seg, seg)
+        sp = helpers.ScenePair()
+        b = sp.blas([(pos, idx.reshape(-1), 1)])
+        sp.bind([sp.tlas(S.instance_grid(100, 100, b, 3.5, -200.0))])
+        sp.build()
+        rays = S.pinhole_rays(w, h, tmin, 1000.0, aspect_correct=True)
     else:
         sp, _ = helpers.torus_scene(seg)
         rays = S.pinhole_rays(w, h, tmin, 100.0, aspect_correct=True)
