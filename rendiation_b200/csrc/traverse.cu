@@ -506,7 +506,7 @@ __device__ __forceinline__ void drain_tie_queue(const OrderedParams &P) {
 // Warp-synchronous rounds: every round the alive lanes (1) descend up to K inner nodes each, (2) re-converge
 // (__syncwarp) and handle their leaf / instance / bookkeeping item TOGETHER — on Volta+ lanes do not re-converge at a
 // loop exit by themselves, and a triangle test executed by 3 lanes costs the warp as much as one executed by 32 —
-// (3) vote: when no lane holds a ray any more the warp goes back to the refill point (whole-tile refill).
+// (3) vote: when no lane holds a ray any more (fewer than THRESH lanes, for the top-up experiment) the warp goes back to the refill point.
 // Refill culls rays against the TLAS root box on the spot (the reference's first test), so rays that miss the scene
 // never occupy a traversal lane.
 // Template switches.  DRAIN_TIES: near-tie queue drained inside the kernel (else by k_resolve_ties).  IRREGULAR: the bound TLAS
@@ -521,7 +521,7 @@ __device__ __forceinline__ void drain_tie_queue(const OrderedParams &P) {
 // neutral: experiment).  Experiments that were measured, rejected and removed — whole-unit / per-SM work distribution, child
 // prefetch, speculative traversal with a postponed leaf, any-hit pre-classification — are described in DESIGN.md §5 with their
 // logs under profiles/.
-template <int K, int MINB, bool DRAIN_TIES, bool IRREGULAR, bool LD256, bool HOT, bool WIDE4>
+template <int K, int MINB, bool DRAIN_TIES, bool IRREGULAR, bool LD256, bool HOT, bool WIDE4, int THRESH = 1>
 __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(const __grid_constant__ OrderedParams P) {
   RDN_COST(COST_PROLOGUE);
   const SceneDev &S = P.S;
@@ -844,7 +844,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
         // ---------------- vote (also the re-convergence point of phase 2)
         RDN_COST(COST_VOTE);
         const int active = __popc(__ballot_sync(amask, cur != REF_DONE));
-        if (active == 0) break;
+        if (active == 0 || (THRESH > 1 && active < THRESH && !warp_exhausted)) break;  // THRESH > 1: top the tile up once it has thinned out
       }
 
       if (cur == REF_DONE) {
@@ -1009,6 +1009,11 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const
 #endif
     case 60: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, true>; break;    // four-box nodes, K = 2 steps per round
     case 61: fn = k_trace_ordered_rounds<1, 8, true, false, true, false, true>; break;    // ... one step per round
+    // topping a thinned-out tile up with the next rays of the launch (lost on config 2's dense tiles in the first sweep; the issue model
+    // says instanced scenes idle at 12 of 32 lanes without it)
+    case 80: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false, 8>; break;
+    case 81: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false, 16>; break;
+    case 82: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false, 24>; break;
     case 70: fn = k_trace_ordered_rounds<3, 8, true, false, true, false, false>; break;   // three node steps per round (issue model: tools/issue_model.py)
     case 71: fn = k_trace_ordered_rounds<1, 8, true, false, true, false, false>; break;   // one node step per round
     default: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false>; break;
