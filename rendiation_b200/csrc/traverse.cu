@@ -91,7 +91,7 @@ __device__ __forceinline__ Vec3 recip3(Vec3 d) { return Vec3{1.0f / d.x, 1.0f / 
 enum CostRegion {
   COST_PROLOGUE = 0, COST_REFILL, COST_RAY_LOAD, COST_OUTER, COST_ROUND, COST_NODE, COST_PHASE2, COST_LEAF, COST_TRI, COST_LEAF_END,
   COST_INSTANCE, COST_INSTANCE_ENTER, COST_EXIT_INSTANCE, COST_EMPTY, COST_GEOMETRY, COST_VOTE, COST_FINISH, COST_TIE, COST_EPILOGUE,
-  COST_TRI_RANGE, COST_TRI_U, COST_TRI_V, COST_TRI_HIT,  // inside a triangle iteration: past the facing test, past the range test, past u, accepted
+  COST_TRI_RANGE, COST_TRI_U, COST_TRI_V, COST_TRI_HIT, COST_INSTANCE_SKIP,  // inside a triangle iteration: past the facing test, past the range test, past u, accepted
   COST_REGION_COUNT
 };
 
@@ -521,7 +521,7 @@ __device__ __forceinline__ void drain_tie_queue(const OrderedParams &P) {
 // neutral: experiment).  Experiments that were measured, rejected and removed — whole-unit / per-SM work distribution, child
 // prefetch, speculative traversal with a postponed leaf, any-hit pre-classification — are described in DESIGN.md §5 with their
 // logs under profiles/.
-template <int K, int MINB, bool DRAIN_TIES, bool IRREGULAR, bool LD256, bool HOT, bool WIDE4, int THRESH = 1>
+template <int K, int MINB, bool DRAIN_TIES, bool IRREGULAR, bool LD256, bool HOT, bool WIDE4, int THRESH = 1, bool INST_LOOP = false>
 __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(const __grid_constant__ OrderedParams P) {
   RDN_COST(COST_PROLOGUE);
   const SceneDev &S = P.S;
@@ -786,15 +786,28 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
               // (not reached: triangle leaves are handled above)
             } else {
               // instance leaf (world space): take the first slot, park the rest
+              uint32_t istart = start, icount = count;
+              if constexpr (INST_LOOP) {
+                // skip the leading instances whose box the ray misses here, one slab test each, instead of one round each (a TLAS
+                // leaf holds up to ten instances; the same tests in the same order against the same bound)
+                while (icount > 1) {
+                  RDN_COST(COST_INSTANCE_SKIP);
+                  float4 s0, s1;
+                  load_pair<LD256>(S.tlas_bounding + istart, s0, s1);
+                  float sn;
+                  if (slab_test(o, inv, t_near_world, bound, xyz(s0), xyz(s1), sn) && (P.L.cull_mask & __float_as_uint(s0.w)) != 0) break;
+                  ++istart; --icount;
+                }
+              }
               RDN_COST(COST_INSTANCE);
-              if (count > 1) RDN_PUSH(REF_LEAF_BIT | ((count - 2u) << REF_LEAF_COUNT_SHIFT) | (start + 1u));
-              const float4 *tb = reinterpret_cast<const float4 *>(S.tlas_bounding + start);
+              if (icount > 1) RDN_PUSH(REF_LEAF_BIT | ((icount - 2u) << REF_LEAF_COUNT_SHIFT) | (istart + 1u));
+              const float4 *tb = reinterpret_cast<const float4 *>(S.tlas_bounding + istart);
               float4 b0, b1;
               load_pair<LD256>(tb, b0, b1);
               float tn;
               bool entered = false;
               if (slab_test(o, inv, t_near_world, bound, xyz(b0), xyz(b1), tn) && (P.L.cull_mask & __float_as_uint(b0.w)) != 0) {
-                const InstanceRecord *rec = S.instances + start;
+                const InstanceRecord *rec = S.instances + istart;
                 const uint4 tail = __ldg(reinterpret_cast<const uint4 *>(&rec->instance_custom_index));
                 const uint32_t flags = merge_geometry_instance_flag(P.L.ray_flags, tail.z);
                 if (!(flags & TF_SKIP_TRIANGLES) && tail.w < S.n_blas_meta) {
@@ -806,7 +819,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
                     to_object_space(rec, o, d, bo, bd, s);
                     o = bo; d = bd; inv = recip3(bd);
                     scaling = s; near_s = t_near_world * s; far_s = bound * s;
-                    cur_inst = start; cur_flags = flags; cull_bits = cull_triangle_bits(flags); geom_end = groots.y;
+                    cur_inst = istart; cur_flags = flags; cull_bits = cull_triangle_bits(flags); geom_end = groots.y;
                     in_object = true;
                     RDN_PUSH(REF_EXIT_INSTANCE);
                     cur = REF_SPECIAL | groots.x;
@@ -1014,6 +1027,9 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const
     case 80: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false, 8>; break;
     case 81: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false, 16>; break;
     case 82: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false, 24>; break;
+    // missed instances of a TLAS leaf skipped in a loop instead of one per round (issue model: instanced scenes)
+    case 90: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false, 1, true>; break;
+    case 91: fn = k_trace_ordered_rounds<3, 8, true, false, true, false, false, 1, true>; break;   // ... with three node steps per round
     case 70: fn = k_trace_ordered_rounds<3, 8, true, false, true, false, false>; break;   // three node steps per round (issue model: tools/issue_model.py)
     case 71: fn = k_trace_ordered_rounds<1, 8, true, false, true, false, false>; break;   // one node step per round
     default: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false>; break;

@@ -181,10 +181,11 @@ def dynamic_counts(cfg: str, names: list[str]):
 def main():
     cfg = next((a for a in sys.argv[1:] if a in CONFIGS), "c2s")
     # mangled template arguments <K, MINB, DRAIN_TIES, IRREGULAR, LD256, HOT, WIDE4> of the instantiation RDN_ORDERED_VARIANT selects
-    variants = {0: "ILi2ELi8ELb1ELb0ELb1ELb0ELb0ELi1EE", 9: "ILi2ELi8ELb0ELb0ELb1ELb0ELb0ELi1EE", 30: "ILi2ELi8ELb1ELb0ELb0ELb0ELb0ELi1EE",
-                60: "ILi2ELi8ELb1ELb0ELb1ELb0ELb1ELi1EE", 61: "ILi1ELi8ELb1ELb0ELb1ELb0ELb1ELi1EE",
-                70: "ILi3ELi8ELb1ELb0ELb1ELb0ELb0ELi1EE", 71: "ILi1ELi8ELb1ELb0ELb1ELb0ELb0ELi1EE",
-                80: "ILi2ELi8ELb1ELb0ELb1ELb0ELb0ELi8EE", 81: "ILi2ELi8ELb1ELb0ELb1ELb0ELb0ELi16EE", 82: "ILi2ELi8ELb1ELb0ELb1ELb0ELb0ELi24EE"}
+    variants = {0: "ILi2ELi8ELb1ELb0ELb1ELb0ELb0ELi1ELb0EE", 9: "ILi2ELi8ELb0ELb0ELb1ELb0ELb0ELi1ELb0EE", 30: "ILi2ELi8ELb1ELb0ELb0ELb0ELb0ELi1ELb0EE",
+                60: "ILi2ELi8ELb1ELb0ELb1ELb0ELb1ELi1ELb0EE", 61: "ILi1ELi8ELb1ELb0ELb1ELb0ELb1ELi1ELb0EE",
+                70: "ILi3ELi8ELb1ELb0ELb1ELb0ELb0ELi1ELb0EE", 71: "ILi1ELi8ELb1ELb0ELb1ELb0ELb0ELi1ELb0EE",
+                80: "ILi2ELi8ELb1ELb0ELb1ELb0ELb0ELi8ELb0EE", 81: "ILi2ELi8ELb1ELb0ELb1ELb0ELb0ELi16ELb0EE", 82: "ILi2ELi8ELb1ELb0ELb1ELb0ELb0ELi24ELb0EE",
+                90: "ILi2ELi8ELb1ELb0ELb1ELb0ELb0ELi1ELb1EE", 91: "ILi3ELi8ELb1ELb0ELb1ELb0ELb0ELi1ELb1EE"}
     variant = int(sys.argv[sys.argv.index("--variant") + 1]) if "--variant" in sys.argv else 0
     template_args = variants[variant]
     if variant:
