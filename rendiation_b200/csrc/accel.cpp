@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 
 #include "../../include/rdn_rt.h"
 
@@ -134,7 +135,7 @@ static void set_child(WideNode &w, int which, const Box3 *box, uint32_t ref) {
 }
 
 uint32_t emit_wide_nodes(const std::vector<FlattenBVHNode> &nodes, uint64_t slot_offset, std::vector<WideNode> &out,
-                         bool &capacity_error) {
+                         bool &capacity_error, const TlasBounding *item_bounds) {
   if (nodes.empty() || nodes[0].primitive_end == nodes[0].primitive_start) return REF_EMPTY;
   // Wide index of every inner reference node, after the pseudo root: the top of the tree breadth first (pseudo root + up to
   // HOT_TOP_NODES - 1 inner nodes form one contiguous block: what every ray touches, and what the kernel's staging variant
@@ -165,6 +166,32 @@ uint32_t emit_wide_nodes(const std::vector<FlattenBVHNode> &nodes, uint64_t slot
     if (count == 0) return REF_EMPTY;
     if (start + count > REF_LEAF_START_MASK) { capacity_error = true; return REF_EMPTY; }
     auto enc = [](uint64_t s, uint64_t c) { return REF_LEAF_BIT | (static_cast<uint32_t>(c - 1) << REF_LEAF_COUNT_SHIFT) | static_cast<uint32_t>(s); };
+    if (item_bounds && count > 1) {
+      // a binary tree over contiguous halves of the leaf's slots, single slots at the bottom
+      auto union_of = [&](uint64_t s, uint64_t c) {
+        Box3 b = box_empty();
+        for (uint64_t k = 0; k < c; ++k) {
+          const TlasBounding &t = item_bounds[s - slot_offset + k];
+          expand(b, Box3{Vec3{t.world_min[0], t.world_min[1], t.world_min[2]}, Vec3{t.world_max[0], t.world_max[1], t.world_max[2]}});
+        }
+        return b;
+      };
+      std::function<uint32_t(uint64_t, uint64_t)> subtree = [&](uint64_t s, uint64_t c) -> uint32_t {
+        if (c == 1) return enc(s, 1);
+        const uint64_t cl = (c + 1) / 2;
+        const size_t idx = out.size();
+        out.push_back(WideNode{});
+        const Box3 bl = union_of(s, cl), br = union_of(s + cl, c - cl);
+        const uint32_t rl = subtree(s, cl), rr = subtree(s + cl, c - cl);
+        WideNode w;
+        std::memset(&w, 0, sizeof(w));
+        set_child(w, 0, &bl, rl);
+        set_child(w, 1, &br, rr);
+        out[idx] = w;
+        return static_cast<uint32_t>(idx);
+      };
+      return subtree(start, count);
+    }
     if (count <= REF_LEAF_MAX_COUNT) return enc(start, count);
     // chain: node k = {first 16 slots, rest}
     uint32_t head = static_cast<uint32_t>(out.size());
@@ -383,6 +410,10 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
   // the four-box view is only emitted for the kernel experiment that walks it (RDN_ORDERED_VARIANT=60/61): +45 % blob otherwise unused
   const char *variant_env = getenv("RDN_ORDERED_VARIANT");
   const bool want_wide4 = variant_env && (atoi(variant_env) == 60 || atoi(variant_env) == 61);
+  // TLAS leaves of several instances (the reference bins up to ten) become small subtrees of the wide view: a data-only change of
+  // what the ordered kernel walks (issue model, config 4: -19 % warp instructions).  RDN_FINE_TLAS=0 restores the multi-slot leaves.
+  const char *fine_env = getenv("RDN_FINE_TLAS");
+  const bool fine_tlas = !fine_env || atoi(fine_env) != 0;
   double ms_boxes = 0, ms_records = 0, ms_wide = 0, ms_threaded = 0, ms_leaves = 0;
   auto since = [](Clock::time_point t0) { return std::chrono::duration<double, std::milli>(Clock::now() - t0).count(); };
   auto timed_build = [&](const Box3 *boxes, uint64_t n, BVHBuildStrategy &strategy, const TreeBuildOption &option) {
@@ -594,7 +625,8 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
     }
     TlasRoot root;
     root.bvh_root_idx = bvh_start;
-    root.wide_root = emit_wide_nodes(bvh.nodes, primitive_start, out.wide_nodes, capacity_error);
+    root.wide_root = emit_wide_nodes(bvh.nodes, primitive_start, out.wide_nodes, capacity_error,
+                                     fine_tlas ? out.tlas_bounding.data() + primitive_start : nullptr);
     root.wide4_root = want_wide4 ? emit_wide4_nodes(bvh.nodes, primitive_start, out.wide4_nodes, capacity_error) : REF_EMPTY;
     root.hot_count = 0;
     if (root.wide_root != REF_EMPTY) {

@@ -80,8 +80,13 @@ Box3 box_apply_matrix(const Box3 &b, const Mat4 &m);
 // Emit the wide (two-boxes-per-node) view of one reference tree into `out`; leaf references address
 // `slot_offset + primitive_range`.  Returns the pseudo-root reference (REF_EMPTY for an empty tree) or
 // sets `capacity_error`.
+// `item_bounds` (optional; TLAS only): the exact box of every slot of this tree, slot order.  A leaf of more than one slot is then
+// emitted as a small binary tree over contiguous halves of its slots (boxes = unions of the slots' boxes, leaves = single slots)
+// instead of one multi-slot leaf reference: the ordered kernel finds the instances a ray can enter with node steps rather than
+// one instance-box test per slot.  Visibility is unchanged — nested boxes keep the slab test monotone, and entering an instance
+// still takes the reference's test of its own box.
 uint32_t emit_wide_nodes(const std::vector<FlattenBVHNode> &nodes, uint64_t slot_offset, std::vector<WideNode> &out,
-                         bool &capacity_error);
+                         bool &capacity_error, const TlasBounding *item_bounds = nullptr);
 // the same for the 4-wide view: one node per inner reference node at even depth below the root (its inner children are absorbed)
 uint32_t emit_wide4_nodes(const std::vector<FlattenBVHNode> &nodes, uint64_t slot_offset, std::vector<Wide4Node> &out,
                           bool &capacity_error);

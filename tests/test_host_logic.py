@@ -302,3 +302,40 @@ def test_no_cpu_fallback():
             if f.endswith((".py", ".cu", ".cpp", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in txt and "oracle/" not in txt and "liboracle" not in txt, f
+
+
+def test_tlas_wide_view_reaches_every_instance_through_single_slot_leaves():
+    """TLAS leaves of several instances are emitted as subtrees over contiguous halves of their slots: every instance slot of
+    every TLAS is reachable exactly once, as a one-slot leaf, and every box on the way down contains the exact instance boxes
+    below it (nested boxes keep the slab test monotone)"""
+    sp, handles = helpers.reference_fixture(devices=(), product=True)
+    pa = sp.p.arrays()
+    wide, roots, tb = pa["wide_nodes"], pa["tlas_root"], pa["tlas_bounding"]
+    LEAF, SPECIAL = 0x80000000, 0x7F000000
+    total = 0
+    for r in roots:
+        wide_root = int(r[1])
+        if wide_root == 0x7FFFFFFE:
+            continue
+        seen = []
+
+        def walk(ref, bmin, bmax):
+            if ref & LEAF:
+                start, cnt = ref & ((1 << 27) - 1), ((ref >> 27) & 15) + 1
+                assert cnt == 1, "a multi-slot instance leaf survived"
+                seen.append(start)
+                assert (tb[start]["world_min"] >= bmin).all() and (tb[start]["world_max"] <= bmax).all()
+                return
+            assert ref < SPECIAL
+            w = wide[ref]
+            for cmin, cmax, child in ((w["c0_min"], w["c0_max"], int(w["ref0"])), (w["c1_min"], w["c1_max"], int(w["ref1"]))):
+                if child == 0x7FFFFFFE:
+                    continue
+                assert (cmin >= bmin).all() and (cmax <= bmax).all()
+                walk(child, cmin, cmax)
+
+        root = wide[wide_root]
+        walk(int(root["ref0"]), root["c0_min"], root["c0_max"])
+        assert len(seen) == len(set(seen)) and seen, seen
+        total += len(seen)
+    assert total == len(tb)
