@@ -823,6 +823,15 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
                     in_object = true;
                     RDN_PUSH(REF_EXIT_INSTANCE);
                     cur = REF_SPECIAL | groots.x;
+                    if constexpr (INST_LOOP) {
+                      // a BLAS of one geometry (the usual case): go straight to its tree instead of spending a round on the
+                      // geometry iterator
+                      if (groots.y - groots.x == 1u) {
+                        const uint4 gm0 = __ldg(reinterpret_cast<const uint4 *>(S.geometry_meta + groots.x));
+                        const uint32_t wide_root = WIDE4 ? __ldg(&S.geometry_meta[groots.x].wide4_root) : __ldg(&S.geometry_meta[groots.x].wide_root);
+                        cur = (cull_geometry_pass(flags, gm0.w) && wide_root != REF_EMPTY) ? wide_root : RDN_POP();
+                      }
+                    }
                     entered = true;
                   }
                 }
