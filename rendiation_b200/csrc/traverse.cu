@@ -520,7 +520,9 @@ __device__ __forceinline__ void drain_tie_queue(const OrderedParams &P) {
 // the absorbed child redundant), the hit children entered nearest first and the others deferred farthest first (measured
 // neutral: experiment).  Experiments that were measured, rejected and removed — whole-unit / per-SM work distribution, child
 // prefetch, speculative traversal with a postponed leaf, any-hit pre-classification — are described in DESIGN.md §5 with their
-// logs under profiles/.
+// logs under profiles/.  THRESH (top a tile up below that many live lanes) and INST_LOOP (missed instances of a TLAS leaf skipped
+// in a loop; a one-geometry BLAS entered without a geometry-iterator round) are candidates ranked by the issue model
+// (tools/issue_model.py), bit-identical on the emulated kernels and not yet timed on a GPU.
 template <int K, int MINB, bool DRAIN_TIES, bool IRREGULAR, bool LD256, bool HOT, bool WIDE4, int THRESH = 1, bool INST_LOOP = false>
 __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(const __grid_constant__ OrderedParams P) {
   RDN_COST(COST_PROLOGUE);
@@ -1017,7 +1019,7 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const
   P.irregular_count = tlas.irregular_count == IRREGULAR_ROUTE_ALL ? 0u : tlas.irregular_count;  // (the caller routes those elsewhere)
   P.wait_epoch = wait_epoch;
 
-  // RDN_ORDERED_VARIANT: experimentation knob (rounds per vote / refill threshold / tie handling / register cap)
+  // RDN_ORDERED_VARIANT: experimentation knob (node steps per round / refill threshold / tie handling / instance path)
   const int variant = ordered_variant();
   using KernelFn = void (*)(const OrderedParams);
   KernelFn fn;
