@@ -1045,6 +1045,11 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const
     case 71: fn = k_trace_ordered_rounds<1, 8, true, false, true, false, false>; break;   // one node step per round
     default: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false>; break;
   }
+  // RDN_LIST_TOPUP=1 (candidate, not yet timed on a GPU): launches that are ray LISTS (no grid width: bounce / shadow waves) top a
+  // thinned-out tile up below 8 live lanes — the issue model has config 3 at -25 % warp instructions with it (no screen coherence
+  // to lose), while grid launches keep the whole-tile refill that won on the GPU
+  static const bool list_topup = []() { const char *e = getenv("RDN_LIST_TOPUP"); return e && atoi(e) != 0; }();
+  if (variant == 0 && list_topup && P.tiles_x == 0) fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false, 8>;
   if ((variant == 60 || variant == 61) && !use_wide4) fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false>;
   if (P.irregular_count != 0) {  // (the experimentation variants exist for regular scenes only)
     // Rays handed over at refill can be a large part of the launch, and the in-kernel drain claims entries through one CAS

@@ -128,6 +128,7 @@ CONFIGS = {
     "c2": ("torus", 708, 1920, 1080, 0x10, 0.01),     # BASELINE config 2 (a few minutes on the emulator)
     "c2s": ("torus", 708, 960, 540, 0x10, 0.01),      # config 2's scene, a quarter of the pixels
     "c2t": ("torus", 256, 640, 360, 0x10, 0.01),
+    "c3": ("torus_bounce", 708, 1920, 1080, 0x00, 0.01),  # BASELINE config 3: one cosine-weighted bounce ray per primary hit of config 2
     "c4": ("instances", 224, 1920, 1080, 0x10, 0.0),  # BASELINE config 4: 10,000 instances of a 100,352-triangle sphere
 }
 
@@ -150,6 +151,16 @@ def dynamic_counts(cfg: str, names: list[str]):
         sp.bind([sp.tlas(S.instance_grid(100, 100, b, 3.5, -200.0))])
         sp.build()
         rays = S.pinhole_rays(w, h, tmin, 1000.0, aspect_correct=True)
+    elif kind == "torus_bounce":
+        sp, (pos, idx, m) = helpers.torus_scene(seg)
+        primary = S.pinhole_rays(w, h, tmin, 100.0, aspect_correct=True)
+        first, _ = sp.o.trace(primary, ray_flags=0x10, n_threads=os.cpu_count() or 4)
+        d = np.stack([primary["dx"], primary["dy"], primary["dz"]], -1)
+        hit = first["instance_id"] != 0xFFFFFFFF
+        normals = np.zeros((primary.shape[0], 3), np.float32)
+        normals[hit] = S.geometric_normals(pos, idx, first["primitive_id"][hit], m, d[hit])
+        rays, _ = S.bounce_rays(primary, first, normals)
+        w = 0  # a ray list, not a grid
     else:
         sp, _ = helpers.torus_scene(seg)
         rays = S.pinhole_rays(w, h, tmin, 100.0, aspect_correct=True)
