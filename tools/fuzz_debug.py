@@ -1,16 +1,21 @@
 """Debug harness for tests/test_gpu_fuzz.py: per profile / seed / trial, which kernel disagrees with the oracle, on what kind of ray.
-Usage: python tools/fuzz_debug.py [profile ...] (default: all three), seeds 0..7"""
+Usage: python tools/fuzz_debug.py [profile ...] (default: all three), seeds 0..7; FUZZ_SEED_BASE / FUZZ_SEEDS select others.
+FUZZ_EMU=1 runs the campaign on the CPU emulation of the kernels (tests/simt) instead of a GPU."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-import helpers, test_gpu_fuzz as F
 from rendiation_b200 import api
+if os.environ.get("FUZZ_EMU") == "1":
+    sys.path.insert(0, os.path.join(ROOT, "tests", "simt"))
+    import build_emu
+    api.LIB_PATH = build_emu.build()
+import helpers, test_gpu_fuzz as F
 
 profiles = sys.argv[1:] or ["regular", "mixed", "hostile"]
 total_bad = 0
 for profile in profiles:
-    for seed in range(8):
+    for seed in range(int(os.environ.get("FUZZ_SEED_BASE", "0")), int(os.environ.get("FUZZ_SEED_BASE", "0")) + int(os.environ.get("FUZZ_SEEDS", "8"))):
         sp, n_tlas, rng = F._scene(1000 + seed, profile=profile)
         rays = F._rays(rng, 12000)
         st = sp.p.build_stats()
