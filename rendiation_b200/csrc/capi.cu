@@ -67,7 +67,7 @@ struct Scratch {
   }
 };
 // 32 B of cursors/flags + 10 u64 counters (6 visit counters, 4 debug) + epoch_done at 112
-constexpr size_t SCRATCH_BASE_BYTES = 128;
+constexpr size_t SCRATCH_BASE_BYTES = 1024;  // (bytes 128.. : tile histogram of the RDN_DEBUG_TIMELINE build, counters[16..])
 
 struct Slot {  // one pipeline lane of the host-buffer path
   cudaStream_t stream = nullptr;
@@ -488,6 +488,7 @@ int rdn_rt_trace_closest_device(rdn_rt_scene *s, int device_index, const rdn_lau
       RDN_CUDA(cudaMemsetAsync(static_cast<char *>(scratch.base) + 32, 0, 6 * 8, stream));
       RDN_CUDA(cudaMemsetAsync(static_cast<char *>(scratch.base) + 32 + 6 * 8, 0xFF, 2 * 8, stream));
       RDN_CUDA(cudaMemsetAsync(static_cast<char *>(scratch.base) + 32 + 8 * 8, 0, 16, stream));
+      RDN_CUDA(cudaMemsetAsync(static_cast<char *>(scratch.base) + 128, 0, SCRATCH_BASE_BYTES - 128, stream));
     }
 #endif
     if (stats) RDN_CUDA(cudaEventRecord(e0, stream));
@@ -515,6 +516,14 @@ int rdn_rt_trace_closest_device(rdn_rt_scene *s, int device_index, const rdn_lau
               c[0], c[1], c[2], c[3], c[4], c[5], double(c[1]) / r, double(c[3]) / r, double(c[4]) / r,
               (double(c[7]) - double(c[6])) * 1e-3, span_us, (double(c[8]) - double(c[7])) * 1e-3, double(c[9]) * 1e-3 / warps,
               100.0 * double(c[9]) * 1e-3 / warps / (span_us > 0 ? span_us : 1));
+      {  // tile passes by duration (8 us buckets): count, mean rounds; the longest pass
+        unsigned long long h[100];
+        RDN_CUDA(cudaMemcpy(h, static_cast<char *>(scratch.base) + 128, sizeof(h), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[dbg tiles] passes by duration (8 us buckets) count/mean_rounds/mean_busy_lanes_at_round_start:");
+        for (int b = 0; b < 32; ++b)
+          if (h[b]) fprintf(stderr, " [%d-%d us] %llu/%.1f/%.1f", b * 8, b * 8 + 8, h[b], double(h[32 + b]) / double(h[b]), double(h[66 + b]) / double(h[32 + b] ? h[32 + b] : 1));
+        fprintf(stderr, " | longest pass %.1f us, %llu rounds\n", double(h[64] >> 20) * 1e-3, h[64] & 0xFFFFFull);
+      }
 #endif
     }
   }

@@ -29,6 +29,7 @@
 //                           irregular instances (their queue can be long), and RDN_ORDERED_VARIANT=9.
 #include <cuda_runtime.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "kernels.h"
@@ -92,6 +93,7 @@ enum CostRegion {
   COST_PROLOGUE = 0, COST_REFILL, COST_RAY_LOAD, COST_OUTER, COST_ROUND, COST_NODE, COST_PHASE2, COST_LEAF, COST_TRI, COST_LEAF_END,
   COST_INSTANCE, COST_INSTANCE_ENTER, COST_EXIT_INSTANCE, COST_EMPTY, COST_GEOMETRY, COST_VOTE, COST_FINISH, COST_TIE, COST_EPILOGUE,
   COST_TRI_RANGE, COST_TRI_U, COST_TRI_V, COST_TRI_HIT, COST_INSTANCE_SKIP,  // inside a triangle iteration: past the facing test, past the range test, past u, accepted
+  COST_SHARE, COST_MERGE,  // SHARE: deferred subtrees handed to idle lanes, partial results merged back
   COST_REGION_COUNT
 };
 
@@ -397,12 +399,16 @@ struct OrderedParams {
   uint64_t n;        // rays
   uint64_t n_fetch;  // fetch indices (= n, or 32 * tiles when walking 8x4 pixel tiles)
   uint32_t tiles_x;  // 0: linear
+  uint32_t tiles_y;  // 0: rows of tiles in raster order, else from the middle row outwards
   uint32_t width, height;
   uint32_t world_root;  // wide reference of the bound TLAS (REF_EMPTY: every ray misses)
   uint32_t irregular_start, irregular_count;  // the bound TLAS's irregular instances (S.irregular_instances), at most IRREGULAR_LIST_MAX
   // HOT: wide nodes [hot_a_base, +hot_a_count) (top of the TLAS tree) and [hot_b_base, +hot_b_count) (top of the largest geometry
   // tree) are staged in shared memory by two bulk copies (TMA) at CTA start
   uint32_t hot_a_base, hot_a_count, hot_b_base, hot_b_count;
+  // SHARE: deferred subtrees are handed to idle lanes once no more than share_busy lanes are busy, by lanes that have at least
+  // share_min of them
+  int share_busy, share_min;
   uint32_t wait_epoch;  // launches issued before this one on the same scratch set: they must have left before this one touches it
   TraceScratch scratch;
 };
@@ -523,13 +529,24 @@ __device__ __forceinline__ void drain_tie_queue(const OrderedParams &P) {
 // logs under profiles/.  THRESH (top a tile up below that many live lanes) and INST_LOOP (missed instances of a TLAS leaf skipped
 // in a loop; a one-geometry BLAS entered without a geometry-iterator round) are candidates ranked by the issue model
 // (tools/issue_model.py), bit-identical on the emulated kernels and not yet timed on a GPU.
-template <int K, int MINB, bool DRAIN_TIES, bool IRREGULAR, bool LD256, bool HOT, bool WIDE4, int THRESH = 1, bool INST_LOOP = false>
+template <int K, int MINB, bool DRAIN_TIES, bool IRREGULAR, bool LD256, bool HOT, bool WIDE4, int THRESH = 1, bool INST_LOOP = false, int SHARE = 0, int SSTACK = 0>
 __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(const __grid_constant__ OrderedParams P) {
   RDN_COST(COST_PROLOGUE);
   const SceneDev &S = P.S;
   const uint32_t lane = threadIdx.x & 31u;
-  uint32_t stack[STACK_MAX];
+  // The traversal stack: its first SSTACK entries per thread in shared memory (entry i of thread t at [i * blockDim + t]: the lanes
+  // of a warp hit 32 different banks whatever their depths), what goes deeper in local memory.  Rays defer about two subtrees on
+  // average and rarely more than a dozen at once, so the local part is touched by the occasional grazing ray only.
+  __shared__ uint32_t s_stack[SSTACK > 0 ? SSTACK * ORDERED_BLOCK : 1];
+  uint32_t stack[STACK_MAX - SSTACK];
+#define RDN_ST_GET(i) ((SSTACK > 0 && (i) < SSTACK) ? s_stack[(i) * ORDERED_BLOCK + threadIdx.x] : stack[(i) - SSTACK])
+#define RDN_ST_SET(i, v) do { if (SSTACK > 0 && (i) < SSTACK) s_stack[(i) * ORDERED_BLOCK + threadIdx.x] = (v); else stack[(i) - SSTACK] = (v); } while (0)
   int sp = 0;
+  // SHARE (lanes of a warp share the work of its long rays, see the vote): entries [lo, sp) of the stack are the deferred subtrees
+  // of the space the lane is in (world, or the instance it entered) and may be handed to idle lanes, lowest = largest first;
+  // `home` is the lane that owns the ray this lane works on; `helpers` (owner only) the lanes still out with pieces of its ray
+  int lo = 0;
+  uint32_t home = lane, helpers = 0;
   // Programmatic dependent launch: the NEXT ordered launch on this stream may start filling SM slots as soon as CTAs of this one
   // leave, i.e. while the last long rays of this launch are still being walked (a no-op when launched without the attribute).
   // The next launch reads nothing this one writes (its own rays, the read-only scene, the other scratch set).
@@ -606,8 +623,37 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
   // a full stack drops the entry and raises a sticky flag, reported once when the ray ends: no atomic (and so no branch around one)
   // inside the traversal loop
   bool stack_overflowed = false;
-#define RDN_PUSH(v) do { if (sp < STACK_MAX) stack[sp++] = (v); else stack_overflowed = true; } while (0)
-#define RDN_POP() (sp > 0 ? stack[--sp] : REF_DONE)
+#define RDN_PUSH(v) do { if (sp < STACK_MAX) { RDN_ST_SET(sp, (v)); ++sp; } else stack_overflowed = true; } while (0)
+#define RDN_POP() (sp > 0 ? (--sp, RDN_ST_GET(sp)) : REF_DONE)
+
+  // a finished ray: the record of its closest candidate (or the miss record), near-ties queued for the reference-order re-walk
+  auto finish_ray = [&]() {
+    RDN_COST(COST_FINISH);
+#ifdef RDN_DEBUG_STEPS
+    dbg_max = dbg_ray_steps > dbg_max ? dbg_ray_steps : dbg_max;
+    dbg_long += dbg_ray_steps > 200 ? 1 : 0;
+    ++dbg_rays;
+    dbg_ray_steps = 0;
+#endif
+    if (stack_overflowed) { atomicAdd(P.scratch.stack_overflow, 1u); stack_overflowed = false; }
+    rdn_hit *dst = P.hits + ri;
+    if (best_slot != RDN_INVALID_ID) {
+      // the ordered result is stored first; a near-tie ray is also queued (warp-aggregated append) for the exact
+      // reference-order re-walk, which overwrites the record
+      const SlotInfo si = S.slot_info[best_slot];
+      store_hit_as<LD256>(dst, best, best_u, best_v, si.primitive_id, si.geometry_idx, best_inst,
+                S.instances[best_inst].instance_custom_index,
+                best_back ? RDN_HIT_KIND_BACK_FACING_TRIANGLE : RDN_HIT_KIND_FRONT_FACING_TRIANGLE);
+      if (second <= best + TIE_EPS * fabsf(best)) {
+        RDN_COST(COST_TIE);
+        __threadfence();  // the ordered record lands before whoever drains the queue writes the exact one
+        enqueue_rewalk<DRAIN_TIES>(P.scratch, lane, ri, best);
+      }
+    } else {
+      store_hit_as<LD256>(dst, far0, 0.f, 0.f, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, 0);
+    }
+    alive = false;
+  };
 
   for (;;) {
     // ---------------- warp-converged refill (a few rounds, so scene-missing rays are retired here)
@@ -634,7 +680,12 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
         if (valid && P.tiles_x) {
           const uint32_t tile = static_cast<uint32_t>(f >> 5);  // launches hold < 2^31 rays: 32-bit tile arithmetic
           const uint32_t in_tile = static_cast<uint32_t>(f) & 31u;
-          const uint32_t ty = tile / P.tiles_x, tx = tile - ty * P.tiles_x;
+          uint32_t ty = tile / P.tiles_x;
+          const uint32_t tx = tile - ty * P.tiles_x;
+          // rows of tiles are taken from the middle of the grid outwards: what a launch starts LAST decides its tail (a pass over a
+          // tile of long rays takes ten times the mean), and the rows at the top and bottom edge of a frame are the likeliest to hold
+          // nothing but short rays
+          if (P.tiles_y) { const uint32_t half = (ty + 1u) >> 1; ty = (ty & 1u) ? ((P.tiles_y - 1u) >> 1) + half : ((P.tiles_y - 1u) >> 1) - half; }
           const uint32_t x = tx * 8u + (in_tile & 7u), y = ty * 4u + (in_tile >> 3);
           valid = x < P.width && y < P.height;
           idx = static_cast<uint64_t>(y) * P.width + x;
@@ -656,6 +707,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
             scaling = 1.f; near_s = t_near_world; bound = far0; far_s = far0;
             best = INFINITY; second = INFINITY; best_slot = RDN_INVALID_ID; best_inst = RDN_INVALID_ID;
             in_object = false; sp = 0;
+            if constexpr (SHARE > 0) { lo = 0; home = lane; helpers = 0; }
             cur = world_entry;
             alive = true;
           } else {
@@ -670,11 +722,21 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
       if (warp_exhausted) break;
       continue;
     }
+#ifdef RDN_DEBUG_TIMELINE
+    const unsigned long long dbg_pass_t0 = globaltimer_ns();
+    unsigned long long dbg_pass_rounds = 0, dbg_pass_busy = 0;
+#endif
 
-    if (alive) {
+    // (SHARE: every lane takes part in the rounds — a lane without a ray idles at cur == REF_DONE until it is handed a subtree)
+    const uint32_t rmask = SHARE > 0 ? FULL_MASK : amask;
+    if (SHARE > 0 || alive) {
 #pragma unroll 1
       for (;;) {
         RDN_COST(COST_ROUND);
+#ifdef RDN_DEBUG_TIMELINE
+        ++dbg_pass_rounds;
+        dbg_pass_busy += __popc(__ballot_sync(rmask, cur != REF_DONE));
+#endif
         // ---------------- phase 1: up to K inner nodes (both child boxes in one 64 B fetch)
 #pragma unroll 1
         for (int k = 0; k < K; ++k) {
@@ -740,7 +802,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
           if (!(h0 || h1)) cur = RDN_POP();
         }
         RDN_COST(COST_PHASE2);
-        __syncwarp(amask);
+        __syncwarp(rmask);
 
         // ---------------- phase 2: one leaf / instance / bookkeeping item, all lanes that have one at the same time
         uint32_t leaf_item = REF_DONE;
@@ -770,7 +832,8 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
                   second = fminf(second, best);
                   best = distance; best_u = u; best_v = v; best_slot = slot; best_inst = cur_inst;
                   best_back = sign < 0.0f ? 1u : 0u;
-                  bound = fminf(far0, best + TIE_EPS * fabsf(best));
+                  // (SHARE: a helper's bound came from the ray's owner and may already be tighter than its own closest candidate)
+                  bound = fminf(SHARE > 0 ? bound : far0, best + TIE_EPS * fabsf(best));
                   far_s = bound * scaling;
                 } else {
                   second = fminf(second, distance);
@@ -814,7 +877,10 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
                 const uint32_t flags = merge_geometry_instance_flag(P.L.ray_flags, tail.z);
                 if (!(flags & TF_SKIP_TRIANGLES) && tail.w < S.n_blas_meta) {
                   const uint2 groots = __ldg(reinterpret_cast<const uint2 *>(S.blas_meta[tail.w].tri_root_range));
-                  if (groots.x < groots.y) {
+                  // (SHARE: the frame of an instance is two entries — the world segment's `lo`, then the exit marker — pushed together or not at all)
+                  const bool room = SHARE == 0 || sp + 2 <= STACK_MAX;
+                  if (!room) stack_overflowed = true;
+                  if (groots.x < groots.y && room) {
                     RDN_COST(COST_INSTANCE_ENTER);
                     Vec3 bo, bd;
                     float s;
@@ -823,7 +889,13 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
                     scaling = s; near_s = t_near_world * s; far_s = bound * s;
                     cur_inst = istart; cur_flags = flags; cull_bits = cull_triangle_bits(flags); geom_end = groots.y;
                     in_object = true;
-                    RDN_PUSH(REF_EXIT_INSTANCE);
+                    if constexpr (SHARE > 0) {
+                      RDN_ST_SET(sp, static_cast<uint32_t>(lo)); ++sp;
+                      RDN_ST_SET(sp, REF_EXIT_INSTANCE); ++sp;
+                      lo = sp;
+                    } else {
+                      RDN_PUSH(REF_EXIT_INSTANCE);
+                    }
                     cur = REF_SPECIAL | groots.x;
                     if constexpr (INST_LOOP) {
                       // a BLAS of one geometry (the usual case): go straight to its tree instead of spending a round on the
@@ -840,20 +912,26 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
               }
               if (!entered) cur = RDN_POP();
             }
-          } else if (cur == REF_EXIT_INSTANCE && sp == 0) {
+          } else if (SHARE == 0 && cur == REF_EXIT_INSTANCE && sp == 0) {
             cur = REF_DONE;  // nothing deferred in world space: the ray is finished, no need to restore the world ray
           } else if (cur == REF_EXIT_INSTANCE) {
             // back to world space: the world ray is re-read instead of being held in registers
             RDN_COST(COST_EXIT_INSTANCE);
-            float4 r0, r1;
-            load_pair<LD256>(P.rays + ri, r0, r1);
-            o = xyz(r0); d = xyz(r1); inv = recip3(d);
-            scaling = 1.f; near_s = t_near_world; far_s = bound;
-            in_object = false;
-            cur = RDN_POP();
+            if constexpr (SHARE > 0) { --sp; lo = static_cast<int>(RDN_ST_GET(sp)); }  // (what lies below `lo` was handed to other lanes)
+            if (SHARE > 0 && sp <= lo) {
+              cur = REF_DONE;
+            } else {
+              float4 r0, r1;
+              load_pair<LD256>(P.rays + ri, r0, r1);
+              o = xyz(r0); d = xyz(r1); inv = recip3(d);
+              scaling = 1.f; near_s = t_near_world; far_s = bound;
+              in_object = false;
+              cur = RDN_POP();
+            }
           } else if (cur == REF_EMPTY) {
             RDN_COST(COST_EMPTY);
-            cur = RDN_POP();
+            // (SHARE: entries handed to other lanes are left behind as REF_EMPTY, a run of them at the bottom of a segment)
+            do { cur = RDN_POP(); } while (SHARE > 0 && cur == REF_EMPTY);
           } else {
             // geometry iterator of the current instance's BLAS
             RDN_COST(COST_GEOMETRY);
@@ -867,42 +945,133 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
 
         // ---------------- vote (also the re-convergence point of phase 2)
         RDN_COST(COST_VOTE);
-        const int active = __popc(__ballot_sync(amask, cur != REF_DONE));
-        if (active == 0 || (THRESH > 1 && active < THRESH && !warp_exhausted)) break;  // THRESH > 1: top the tile up once it has thinned out
-      }
-
-      if (cur == REF_DONE) {
-        RDN_COST(COST_FINISH);
-#ifdef RDN_DEBUG_STEPS
-        dbg_max = dbg_ray_steps > dbg_max ? dbg_ray_steps : dbg_max;
-        dbg_long += dbg_ray_steps > 200 ? 1 : 0;
-        ++dbg_rays;
-        dbg_ray_steps = 0;
-#endif
-        if (stack_overflowed) { atomicAdd(P.scratch.stack_overflow, 1u); stack_overflowed = false; }
-        rdn_hit *dst = P.hits + ri;
-        if (best_slot != RDN_INVALID_ID) {
-          // the ordered result is stored first; a near-tie ray is also queued (warp-aggregated append) for the exact
-          // reference-order re-walk, which overwrites the record
-          const SlotInfo si = S.slot_info[best_slot];
-          store_hit_as<LD256>(dst, best, best_u, best_v, si.primitive_id, si.geometry_idx, best_inst,
-                    S.instances[best_inst].instance_custom_index,
-                    best_back ? RDN_HIT_KIND_BACK_FACING_TRIANGLE : RDN_HIT_KIND_FRONT_FACING_TRIANGLE);
-          if (second <= best + TIE_EPS * fabsf(best)) {
-            RDN_COST(COST_TIE);
-            __threadfence();  // the ordered record lands before whoever drains the queue writes the exact one
-            enqueue_rewalk<DRAIN_TIES>(P.scratch, lane, ri, best);
+        if constexpr (SHARE > 0) {
+          // Lanes of a warp share the work of its long rays.  The rays of a tile end at very different depths (a ray grazing the
+          // surface takes ten times the node steps of its neighbours) and the finished lanes would idle until the last one ends.
+          // Instead, a lane without work is handed deferred subtrees of a busy lane's ray — the LOWEST entries of the busy
+          // lane's stack segment, i.e. the largest subtrees — together with a copy of the ray as the busy lane holds it (world
+          // or object space).  The helper walks its piece like any ray, prunes against the owner's bound (refreshed every round)
+          // and, once out of work, merges what it found into the owner's registers: closest of the two, and the second-closest
+          // of everything seen (so a near-tie between candidates found by different lanes is still detected and re-walked in
+          // the reference's order — the result stays the reference's, whoever walked what).  Everything below is warp-uniform.
+          // Nothing is shared while more than SHARE lanes are busy, and a tile whose busy lanes have nothing deferred pays two
+          // votes per round.  Finished rays are stored together at the end of the tile, or when their lanes are wanted as helpers.
+          const uint32_t busy = __ballot_sync(FULL_MASK, cur != REF_DONE);
+          // (recomputed every round instead of kept: a loop-carried flag ends up spilled, and a local load per round costs a stall)
+          if (__ballot_sync(FULL_MASK, home != lane) != 0) {
+            {  // the owner's bound, so that pieces stop as soon as the owner (who walks the near side) has a closer candidate
+              const float hb = __shfl_sync(FULL_MASK, bound, home);
+              if (hb < bound) { bound = hb; far_s = bound * scaling; }
+            }
+            // helpers that ran out of work hand their partial result to the owner of the ray
+            uint32_t fin = __ballot_sync(FULL_MASK, home != lane && cur == REF_DONE);
+            while (fin) {
+              RDN_COST(COST_MERGE);
+              const int T = __ffs(fin) - 1;
+              fin &= fin - 1u;
+              const uint32_t h = __shfl_sync(FULL_MASK, home, T);
+              const float tb = __shfl_sync(FULL_MASK, best, T);
+              const float ts = __shfl_sync(FULL_MASK, second, T);
+              if (tb != INFINITY) {  // (uniform) the helper found a candidate
+                const float tu = __shfl_sync(FULL_MASK, best_u, T), tv = __shfl_sync(FULL_MASK, best_v, T);
+                const uint32_t tslot = __shfl_sync(FULL_MASK, best_slot, T), tinst = __shfl_sync(FULL_MASK, best_inst, T);
+                const uint32_t tback = __shfl_sync(FULL_MASK, best_back, T);
+                if (lane == h) {
+                  if (tb < best) {
+                    second = fminf(fminf(second, ts), best);
+                    best = tb; best_u = tu; best_v = tv; best_slot = tslot; best_inst = tinst; best_back = tback;
+                    bound = fminf(bound, best + TIE_EPS * fabsf(best));
+                    far_s = bound * scaling;
+                  } else {
+                    second = fminf(second, tb);  // (tb <= ts)
+                  }
+                }
+              }
+              if (lane == h) helpers &= ~(1u << T);
+              if (static_cast<int>(lane) == T) {
+                home = lane;
+                if (stack_overflowed) { atomicAdd(P.scratch.stack_overflow, 1u); stack_overflowed = false; }
+              }
+            }
+          }
+          if (busy == 0) break;  // (every helper has merged: the rays of the tile are stored behind the loop)
+          if (__popc(busy) <= P.share_busy) {
+            const int avail = cur != REF_DONE ? sp - lo : 0;
+            const uint32_t donors = __ballot_sync(FULL_MASK, avail >= P.share_min);
+            if (donors != 0) {
+              // lanes whose own ray is complete become helpers
+              if (alive && cur == REF_DONE && helpers == 0) finish_ray();
+              const uint32_t idle = __ballot_sync(FULL_MASK, cur == REF_DONE && !alive);
+              if (idle != 0) {
+                RDN_COST(COST_SHARE);
+                const int D = __ffs(donors) - 1;
+                const int n_avail = __shfl_sync(FULL_MASK, avail, D), n_idle = __popc(idle);
+                const int m = n_avail < n_idle ? n_avail : n_idle;
+                const int rank = __popc(idle & ((1u << lane) - 1u));
+                const bool take = ((idle >> lane) & 1u) != 0 && rank < m;
+                const int d_lo = __shfl_sync(FULL_MASK, lo, D);
+                uint32_t piece = REF_EMPTY;
+#pragma unroll 1
+                for (int j = 0; j < m; ++j) {
+                  uint32_t e = 0;
+                  if (static_cast<int>(lane) == D) { e = RDN_ST_GET(d_lo + j); RDN_ST_SET(d_lo + j, REF_EMPTY); }
+                  e = __shfl_sync(FULL_MASK, e, D);
+                  if (take && rank == j) piece = e;
+                }
+                if (static_cast<int>(lane) == D) lo += m;
+                // the ray as the donor holds it
+#define RDN_TAKE(x) do { const auto t__ = __shfl_sync(FULL_MASK, x, D); if (take) x = t__; } while (0)
+                RDN_TAKE(o.x); RDN_TAKE(o.y); RDN_TAKE(o.z); RDN_TAKE(d.x); RDN_TAKE(d.y); RDN_TAKE(d.z);
+                RDN_TAKE(inv.x); RDN_TAKE(inv.y); RDN_TAKE(inv.z);
+                RDN_TAKE(scaling); RDN_TAKE(bound); RDN_TAKE(t_near_world); RDN_TAKE(far0);
+                RDN_TAKE(cur_inst); RDN_TAKE(cur_flags); RDN_TAKE(cull_bits); RDN_TAKE(geom_end); RDN_TAKE(home);
+#undef RDN_TAKE
+                const uint32_t d_ri = __shfl_sync(FULL_MASK, static_cast<uint32_t>(ri), D);  // (launches hold < 2^31 rays)
+                const bool d_in_object = __shfl_sync(FULL_MASK, in_object ? 1 : 0, D) != 0;
+                if (take) {
+                  ri = d_ri;
+                  near_s = t_near_world * scaling; far_s = bound * scaling;
+                  best = INFINITY; second = INFINITY; best_slot = RDN_INVALID_ID; best_inst = RDN_INVALID_ID;
+                  in_object = d_in_object;
+                  sp = 0;
+                  if (d_in_object) { RDN_ST_SET(0, 0u); RDN_ST_SET(1, REF_EXIT_INSTANCE); sp = 2; }  // the frame of the donor's instance
+                  lo = sp;
+                  cur = piece;
+                }
+                const uint32_t takers = __ballot_sync(FULL_MASK, take);
+                const uint32_t d_home = __shfl_sync(FULL_MASK, home, D);
+                if (lane == d_home) helpers |= takers;
+              }
+            }
           }
         } else {
-          store_hit_as<LD256>(dst, far0, 0.f, 0.f, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, RDN_INVALID_ID, 0);
+          const int active = __popc(__ballot_sync(amask, cur != REF_DONE));
+          if (active == 0 || (THRESH > 1 && active < THRESH && !warp_exhausted)) break;  // THRESH > 1: top the tile up once it has thinned out
         }
-        alive = false;
+      }
+
+      if (SHARE > 0 ? alive : cur == REF_DONE) finish_ray();
+    }
+#ifdef RDN_DEBUG_TIMELINE
+    {  // one pass over a tile: duration histogram (8 us buckets), rounds per bucket, the longest pass, passes ending after the list ran dry
+      const unsigned long long now = globaltimer_ns(), dt = now - dbg_pass_t0;
+      unsigned long long rounds = dbg_pass_rounds;
+      for (int off = 16; off > 0; off >>= 1) { const unsigned long long r = __shfl_xor_sync(FULL_MASK, rounds, off); rounds = r > rounds ? r : rounds; }
+      if (lane == 0) {
+        const unsigned b = dt / 8000ull < 31ull ? static_cast<unsigned>(dt / 8000ull) : 31u;
+        atomicAdd(P.scratch.counters + 12 + b, 1ull);
+        atomicAdd(P.scratch.counters + 12 + 32 + b, rounds);
+        atomicMax(P.scratch.counters + 12 + 64, (dt << 20) | (rounds & 0xFFFFFull));
+        atomicAdd(P.scratch.counters + 12 + 66 + b, dbg_pass_busy);  // (lane 0 takes part in every ballot: its sum is the warp's)
       }
     }
+#endif
     __syncwarp();
   }
 #undef RDN_PUSH
 #undef RDN_POP
+#undef RDN_ST_GET
+#undef RDN_ST_SET
 #ifdef RDN_DEBUG_STEPS
   {
     unsigned long long vals[5] = {dbg_steps, dbg_rays, dbg_tris, dbg_pushes, dbg_long};
@@ -999,11 +1168,13 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const
   if (n == 0) return true;
   OrderedParams P;
   P.S = scene; P.L = launch; P.rays = d_rays; P.hits = d_hits; P.n = n; P.scratch = scratch;
-  P.tiles_x = 0; P.width = 0; P.height = 0; P.n_fetch = n;
+  P.tiles_x = 0; P.tiles_y = 0; P.width = 0; P.height = 0; P.n_fetch = n;
   if (launch.grid_width != 0 && n % launch.grid_width == 0) {
+    static const bool centre_out = []() { const char *e = getenv("RDN_TILE_ORDER"); return !e || atoi(e) != 0; }();
     P.width = launch.grid_width;
     P.height = static_cast<uint32_t>(n / launch.grid_width);
     P.tiles_x = (P.width + 7u) / 8u;
+    P.tiles_y = centre_out ? (P.height + 3u) / 4u : 0u;
     P.n_fetch = static_cast<uint64_t>(P.tiles_x) * ((P.height + 3u) / 4u) * 32u;
   }
   const int variant_ = ordered_variant();
@@ -1018,6 +1189,10 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const
   P.irregular_start = tlas.irregular_start;
   P.irregular_count = tlas.irregular_count == IRREGULAR_ROUTE_ALL ? 0u : tlas.irregular_count;  // (the caller routes those elsewhere)
   P.wait_epoch = wait_epoch;
+  {
+    static const struct ShareKnobs { int busy = 16, min = 2; ShareKnobs() { if (const char *e = getenv("RDN_SHARE")) sscanf(e, "%d,%d", &busy, &min); } } knobs;
+    P.share_busy = knobs.busy; P.share_min = knobs.min;
+  }
 
   // RDN_ORDERED_VARIANT: experimentation knob (node steps per round / refill threshold / tie handling / instance path)
   const int variant = ordered_variant();
@@ -1043,20 +1218,25 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const
     case 91: fn = k_trace_ordered_rounds<3, 8, true, false, true, false, false, 1, true>; break;   // ... with three node steps per round
     case 70: fn = k_trace_ordered_rounds<3, 8, true, false, true, false, false>; break;   // three node steps per round (issue model: tools/issue_model.py)
     case 71: fn = k_trace_ordered_rounds<1, 8, true, false, true, false, false>; break;   // one node step per round
-    default: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false>; break;
+    // idle lanes take deferred subtrees of the warp's busy lanes once no more than SHARE lanes are busy
+    case 110: fn = k_trace_ordered_rounds<3, 8, true, false, true, false, false, 1, true, 1>; break;  // RDN_SHARE=busy,min
+    // the first entries of the traversal stack in shared memory
+    case 120: fn = k_trace_ordered_rounds<3, 8, true, false, true, false, false, 1, true, 0, 8>; break;
+    case 121: fn = k_trace_ordered_rounds<3, 8, true, false, true, false, false, 1, true, 0, 12>; break;
+    case 122: fn = k_trace_ordered_rounds<3, 8, true, false, true, false, false, 1, true, 0, 16>; break;
+    case 123: fn = k_trace_ordered_rounds<3, 8, true, false, true, false, false, 1, true, 0, 24>; break;
+    case 124: fn = k_trace_ordered_rounds<3, 8, true, false, true, false, false, 1, true, 0, 32>; break;
+    case 130: fn = k_trace_ordered_rounds<3, 8, true, false, true, false, false, 1, true, 1, 16>; break;  // ... with sharing
+    case 2: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false>; break;     // two node steps per round, one round per missed instance (the round-1 default)
+    default: fn = k_trace_ordered_rounds<3, 8, true, false, true, false, false, 1, true>; break;
   }
-  // RDN_LIST_TOPUP=1 (candidate, not yet timed on a GPU): launches that are ray LISTS (no grid width: bounce / shadow waves) top a
-  // thinned-out tile up below 8 live lanes — the issue model has config 3 at -25 % warp instructions with it (no screen coherence
-  // to lose), while grid launches keep the whole-tile refill that won on the GPU
-  static const bool list_topup = []() { const char *e = getenv("RDN_LIST_TOPUP"); return e && atoi(e) != 0; }();
-  if (variant == 0 && list_topup && P.tiles_x == 0) fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false, 8>;
-  if ((variant == 60 || variant == 61) && !use_wide4) fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false>;
+  if ((variant == 60 || variant == 61) && !use_wide4) fn = k_trace_ordered_rounds<3, 8, true, false, true, false, false, 1, true>;
   if (P.irregular_count != 0) {  // (the experimentation variants exist for regular scenes only)
     // Rays handed over at refill can be a large part of the launch, and the in-kernel drain claims entries through one CAS
     // cursor (fine for a handful of ties, 55 ms for 400 K entries): the queue of an irregular launch is walked by
     // k_resolve_ties, one thread per entry, right behind this kernel.
     inline_ties = false;
-    fn = k_trace_ordered_rounds<2, 8, false, true, true, false, false>;
+    fn = k_trace_ordered_rounds<3, 8, false, true, true, false, false, 1, true>;
   }
   int blocks_per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, ORDERED_BLOCK, 0);

@@ -192,11 +192,12 @@ def dynamic_counts(cfg: str, names: list[str]):
 def main():
     cfg = next((a for a in sys.argv[1:] if a in CONFIGS), "c2s")
     # mangled template arguments <K, MINB, DRAIN_TIES, IRREGULAR, LD256, HOT, WIDE4> of the instantiation RDN_ORDERED_VARIANT selects
-    variants = {0: "ILi2ELi8ELb1ELb0ELb1ELb0ELb0ELi1ELb0EE", 9: "ILi2ELi8ELb0ELb0ELb1ELb0ELb0ELi1ELb0EE", 30: "ILi2ELi8ELb1ELb0ELb0ELb0ELb0ELi1ELb0EE",
-                60: "ILi2ELi8ELb1ELb0ELb1ELb0ELb1ELi1ELb0EE", 61: "ILi1ELi8ELb1ELb0ELb1ELb0ELb1ELi1ELb0EE",
-                70: "ILi3ELi8ELb1ELb0ELb1ELb0ELb0ELi1ELb0EE", 71: "ILi1ELi8ELb1ELb0ELb1ELb0ELb0ELi1ELb0EE",
-                80: "ILi2ELi8ELb1ELb0ELb1ELb0ELb0ELi8ELb0EE", 81: "ILi2ELi8ELb1ELb0ELb1ELb0ELb0ELi16ELb0EE", 82: "ILi2ELi8ELb1ELb0ELb1ELb0ELb0ELi24ELb0EE",
-                90: "ILi2ELi8ELb1ELb0ELb1ELb0ELb0ELi1ELb1EE", 91: "ILi3ELi8ELb1ELb0ELb1ELb0ELb0ELi1ELb1EE"}
+    def mangled(k, drain=True, ld256=True, wide4=False, thresh=1, inst_loop=False, share=0, sstack=0):
+        bl = lambda v: "Lb1E" if v else "Lb0E"
+        return f"ILi{k}ELi8E{bl(drain)}Lb0E{bl(ld256)}Lb0E{bl(wide4)}Li{thresh}E{bl(inst_loop)}Li{share}ELi{sstack}EE"
+    variants = {0: mangled(3, inst_loop=True), 2: mangled(2), 9: mangled(2, drain=False), 30: mangled(2, ld256=False), 60: mangled(2, wide4=True), 61: mangled(1, wide4=True),
+                70: mangled(3), 71: mangled(1), 80: mangled(2, thresh=8), 81: mangled(2, thresh=16), 82: mangled(2, thresh=24),
+                90: mangled(2, inst_loop=True), 91: mangled(3, inst_loop=True), 110: mangled(3, inst_loop=True, share=1), 122: mangled(3, inst_loop=True, sstack=16), 130: mangled(3, inst_loop=True, share=1, sstack=16)}
     variant = int(sys.argv[sys.argv.index("--variant") + 1]) if "--variant" in sys.argv else 0
     template_args = variants[variant]
     if variant:
