@@ -239,8 +239,10 @@ def run_ours(args):
     def step_device(k=0, stats=False, out=None):
         j = k % N_FRAMES
         dst = out if out is not None else d_hits[k % n_hit_bufs]
+        # (overlap_previous: consecutive steps are independent frames with their own ray and hit buffers and nothing else goes
+        # into the stream between them — the contract of RDN_TRACE_OVERLAP_PREVIOUS)
         return sysm.trace_closest_device(d_rays[j].data_ptr(), n, dst.data_ptr(), ray_flags=RAY_FLAGS, grid_width=W,
-                                         stream=stream, want_stats=stats)
+                                         stream=stream, want_stats=stats, overlap_previous=True)
 
     def reset_hit_buffers():
         for h in d_hits:

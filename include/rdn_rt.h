@@ -103,8 +103,16 @@ typedef struct rdn_counters { uint64_t bvh_visit, bvh_hit, tri_visit, tri_hit, i
 
 /* traversal order selection for rdn_rt_trace_closest_device */
 typedef enum rdn_trace_mode {
-  RDN_TRACE_AUTO = 0,            /* ordered traversal + exact tie resolution (default) */
-  RDN_TRACE_REFERENCE_ORDER = 1  /* the reference's threaded pre-order walk, one ray per thread */
+  RDN_TRACE_AUTO = 0,             /* ordered traversal + exact tie resolution (default) */
+  RDN_TRACE_REFERENCE_ORDER = 1,  /* the reference's threaded pre-order walk, one ray per thread */
+  /* OR-ed into the order selection: this launch may start while the last long rays of the PREVIOUS rdn_rt_trace_closest_device
+   * call on the same stream are still being walked (programmatic dependent launch; +45 % on back-to-back frames).
+   * The caller promises that (1) nothing else was put into that stream since that call — a kernel of the caller's own that
+   * produces this launch's rays would not be waited for — and (2) this launch's d_rays / d_hits do not alias the previous launch's
+   * d_hits, nor its d_hits the previous d_rays (stragglers of the previous launch still read and write them).  The library checks
+   * what it can see (same stream, no other entry point of this library in between, the four address ranges) and launches in plain
+   * stream order when the check fails or the flag is absent. */
+  RDN_TRACE_OVERLAP_PREVIOUS = 0x100
 } rdn_trace_mode;
 
 typedef struct rdn_trace_stats {
@@ -161,6 +169,20 @@ int rdn_rt_trace_closest(rdn_rt_scene *scene, const rdn_launch *launch, const rd
 int rdn_rt_trace_closest_device(rdn_rt_scene *scene, int device_index, const rdn_launch *launch,
                                 const rdn_ray *d_rays, uint64_t n, rdn_hit *d_hits, void *cuda_stream,
                                 int mode, rdn_trace_stats *stats);
+/* The same for a wave whose size a previous kernel left ON THE DEVICE (the output count of a compaction / bounce step): the
+ * launch covers rays [0, min(*d_n, n_max)), *d_n is read by the kernel when it runs, and nothing comes back to the host — the
+ * reference reads the size of every wave back after its compaction (task-graph/src/runtime/task_group.rs:259-277).  d_rays and
+ * d_hits hold n_max records (<= 2^31); records at and beyond *d_n are left untouched.  Ray lists only (launch->grid_width is ignored). */
+int rdn_rt_trace_closest_device_n(rdn_rt_scene *scene, int device_index, const rdn_launch *launch, const rdn_ray *d_rays,
+                                  const uint64_t *d_n, uint64_t n_max, rdn_hit *d_hits, void *cuda_stream, int mode);
+/* Safety-net flags of the asynchronous device path.  A launch that overflowed the 120-entry traversal stack (deeper than the
+ * builder's depth limits allow) or gave up waiting for its predecessor wrote unreliable records; the synchronous paths
+ * (host buffers, `stats`) return the error themselves, the asynchronous one is polled: rdn_rt_poll_errors waits for
+ * `cuda_stream`, returns the flags raised on `device_index` since the last poll in *out_flags (may be NULL) and clears them;
+ * return value RDN_OK, RDN_ERR_CAPACITY (stack overflow) or RDN_ERR_CUDA (gate timeout). */
+#define RDN_ERROR_FLAG_STACK_OVERFLOW 1u
+#define RDN_ERROR_FLAG_GATE_TIMEOUT 2u
+int rdn_rt_poll_errors(rdn_rt_scene *scene, int device_index, void *cuda_stream, uint32_t *out_flags);
 /* reference-order walk with the reference's visit counters (host buffers; for parity / bytes model) */
 int rdn_rt_trace_counted(rdn_rt_scene *scene, const rdn_launch *launch, const rdn_ray *rays, uint64_t n,
                          rdn_hit *out_hits, rdn_counters *out_counters);

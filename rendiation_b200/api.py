@@ -78,6 +78,8 @@ INVALID_ID = 0xFFFFFFFF
 BOUNCE_OFFSET_ORIGIN = 0x1
 
 TRACE_AUTO, TRACE_REFERENCE_ORDER = 0, 1
+TRACE_OVERLAP_PREVIOUS = 0x100  # may start while the previous device trace on the stream still walks its last rays (rdn_rt.h)
+ERROR_FLAG_STACK_OVERFLOW, ERROR_FLAG_GATE_TIMEOUT = 1, 2
 FACE_FRONT, FACE_BACK, FACE_DOUBLE = 0, 1, 2
 
 
@@ -153,7 +155,7 @@ class _MeshView(C.Structure):
 EXPORTED_SYMBOLS = [
     "rdn_rt_scene_create", "rdn_rt_scene_destroy", "rdn_rt_blas_create", "rdn_rt_blas_destroy", "rdn_rt_tlas_create",
     "rdn_rt_tlas_destroy", "rdn_rt_bind_tlas", "rdn_rt_bind_tlas_max_len", "rdn_rt_commit", "rdn_rt_trace_closest",
-    "rdn_rt_trace_closest_device", "rdn_rt_trace_counted", "rdn_rt_kernel_timing_begin", "rdn_rt_kernel_timing_end",
+    "rdn_rt_trace_closest_device", "rdn_rt_trace_closest_device_n", "rdn_rt_poll_errors", "rdn_rt_trace_counted", "rdn_rt_kernel_timing_begin", "rdn_rt_kernel_timing_end",
     "rdn_rt_gen_pinhole_rays_device", "rdn_rt_gen_pinhole_rays_batch_device", "rdn_rt_gen_camera_rays_device", "rdn_rt_gen_bounce_rays_device", "rdn_rt_ao_accumulate_device", "rdn_rt_compact_u32", "rdn_rt_compact_u32_device",
     "rdn_rt_scene_blob", "rdn_rt_scene_adopt_blob", "rdn_rt_scene_array", "rdn_rt_scene_build_stats", "rdn_rt_measure_l2_read_gbs", "rdn_pick_mesh_create", "rdn_pick_mesh_destroy",
     "rdn_pick_mesh_primitive_count", "rdn_pick_mesh_nearest", "rdn_pick_mesh_all", "rdn_bvh_build", "rdn_bvh_build_device", "rdn_bvh_built_on_device", "rdn_bvh_destroy", "rdn_bvh_nodes",
@@ -191,6 +193,8 @@ def lib() -> C.CDLL:
     L.rdn_rt_commit.argtypes = [vp]
     L.rdn_rt_trace_closest.argtypes = [vp, P(_Launch), vp, u64, vp]
     L.rdn_rt_trace_closest_device.argtypes = [vp, i32, P(_Launch), vp, u64, vp, vp, i32, P(_TraceStats)]
+    L.rdn_rt_poll_errors.argtypes = [vp, i32, vp, P(u32)]
+    L.rdn_rt_trace_closest_device_n.argtypes = [vp, i32, P(_Launch), vp, vp, u64, vp, vp, i32]
     L.rdn_rt_trace_counted.argtypes = [vp, P(_Launch), vp, u64, vp, P(_Counters)]
     L.rdn_rt_kernel_timing_begin.argtypes = [vp, i32]
     L.rdn_rt_kernel_timing_end.argtypes = [vp, i32, P(_KernelTimes)]
@@ -342,9 +346,13 @@ class NaiveSahBVHSystem:
         _check(self._L.rdn_rt_trace_closest(self._h, C.byref(launch), C.c_void_p(rays_ptr), n, C.c_void_p(hits_ptr)))
 
     def trace_closest_device(self, d_rays_ptr: int, n: int, d_hits_ptr: int, ray_flags=0, cull_mask=0xFFFFFFFF, tlas_idx=0,
-                             grid_width=0, stream: int = 0, mode: int = TRACE_AUTO, device_index: int = 0, want_stats: bool = False):
-        """Device-resident rays/hits; asynchronous on ``stream`` unless ``want_stats``."""
+                             grid_width=0, stream: int = 0, mode: int = TRACE_AUTO, device_index: int = 0, want_stats: bool = False,
+                             overlap_previous: bool = False):
+        """Device-resident rays/hits; asynchronous on ``stream`` unless ``want_stats``.  ``overlap_previous``: the caller's promise
+        behind RDN_TRACE_OVERLAP_PREVIOUS (nothing else enqueued on the stream since the previous trace, buffers disjoint)."""
         launch = _Launch(ray_flags, cull_mask, tlas_idx, grid_width)
+        if overlap_previous:
+            mode |= TRACE_OVERLAP_PREVIOUS
         st = _TraceStats()
         _check(self._L.rdn_rt_trace_closest_device(self._h, device_index, C.byref(launch), C.c_void_p(d_rays_ptr), n,
                                                    C.c_void_p(d_hits_ptr), C.c_void_p(stream), mode,
@@ -353,6 +361,20 @@ class NaiveSahBVHSystem:
             return {"rays": int(st.rays), "tie_rays": int(st.tie_rays), "kernel_launches": int(st.kernel_launches),
                     "kernel_ms": float(st.kernel_ms), "whole_range_rewalks": int(st.whole_range_rewalks)}
         return None
+
+    def trace_closest_device_n(self, d_rays_ptr: int, d_n_ptr: int, n_max: int, d_hits_ptr: int, ray_flags=0, cull_mask=0xFFFFFFFF, tlas_idx=0,
+                               stream: int = 0, mode: int = TRACE_AUTO, device_index: int = 0):
+        """A wave whose size lives on the device (``d_n_ptr``: one u64, e.g. the count a bounce step left there); nothing
+        comes back to the host."""
+        launch = _Launch(ray_flags, cull_mask, tlas_idx, 0)
+        _check(self._L.rdn_rt_trace_closest_device_n(self._h, device_index, C.byref(launch), C.c_void_p(d_rays_ptr), C.c_void_p(d_n_ptr), n_max,
+                                                     C.c_void_p(d_hits_ptr), C.c_void_p(stream), mode))
+
+    def poll_errors(self, stream: int = 0, device_index: int = 0) -> int:
+        """Wait for ``stream`` and return (and clear) the safety-net flags of the asynchronous device path; raises on any."""
+        flags = C.c_uint32(0)
+        _check(self._L.rdn_rt_poll_errors(self._h, device_index, C.c_void_p(stream), C.byref(flags)))
+        return int(flags.value)
 
     def trace_counted(self, rays: np.ndarray, ray_flags=0, cull_mask=0xFFFFFFFF, tlas_idx=0):
         """Reference-order walk returning hits and the reference's visit counters."""
@@ -392,6 +414,23 @@ class NaiveSahBVHSystem:
             arr[k] = _Pinhole(width, height, x0, y0, w, h, (C.c_float * 3)(*origin), tmin, tmax, aspect, jx, jy)
             total += w * h
         _check(self._L.rdn_rt_gen_pinhole_rays_batch_device(self._h, device_index, arr, len(rects), C.c_void_p(d_rays), C.c_void_p(stream)))
+        return total
+
+    @staticmethod
+    def pinhole_batch(width: int, height: int, rects, jitters, origin=(0.0, 0.0, 0.0), tmin=0.0, tmax=100.0, aspect=1.0):
+        """The descriptor array of :meth:`gen_pinhole_rays_batch_device`, built once for a frame layout that is launched many
+        times; returns ``(array, count, total_rays)`` for :meth:`gen_pinhole_rays_prebuilt_device`."""
+        arr = (_Pinhole * max(len(rects), 1))()
+        total = 0
+        org = (C.c_float * 3)(*origin)
+        for k, ((x0, y0, w, h), (jx, jy)) in enumerate(zip(rects, jitters)):
+            arr[k] = _Pinhole(width, height, x0, y0, w, h, org, tmin, tmax, aspect, jx, jy)
+            total += w * h
+        return arr, len(rects), total
+
+    def gen_pinhole_rays_prebuilt_device(self, batch, d_rays: int, stream: int = 0, device_index: int = 0) -> int:
+        arr, count, total = batch
+        _check(self._L.rdn_rt_gen_pinhole_rays_batch_device(self._h, device_index, arr, count, C.c_void_p(d_rays), C.c_void_p(stream)))
         return total
 
     def gen_camera_rays_device(self, d_rays: int, view_projection_inv, world_position, width: int, height: int, sample_index: int = 0,

@@ -60,6 +60,7 @@ struct Scratch {
     s.tie_cursor = reinterpret_cast<uint32_t *>(b + 24);
     s.tie_total = reinterpret_cast<uint32_t *>(b + 28);
     s.epoch_done = reinterpret_cast<uint32_t *>(b + 112);
+    s.gate_timeout = reinterpret_cast<uint32_t *>(b + 116);
     s.counters = reinterpret_cast<unsigned long long *>(b + 32);
     s.tie_queue = tie_queue;
     s.tie_best = tie_best;
@@ -97,6 +98,10 @@ struct DeviceCtx {
   cudaEvent_t ext_done = nullptr; // orders device-resident traces issued on DIFFERENT streams (they share the scratch sets)
   cudaStream_t ext_last_stream = nullptr;
   bool ext_pending = false;
+  // the previous device-resident trace, as far as tail overlap is concerned: valid while nothing else of this library went into
+  // that stream since, and only if it was ONE ordered launch that resolves its ties itself
+  struct { bool valid = false; uintptr_t rays_lo = 0, rays_hi = 0, hits_lo = 0, hits_hi = 0; } ext_prev;
+  bool last_enqueue_overlappable = false;  // set by enqueue_trace
   unsigned long long *d_compact_status = nullptr;
   uint64_t compact_status_cap = 0;
   float *d_ao_payload = nullptr;   // AO accumulation: per-pixel payload, 1.0f between samples
@@ -127,9 +132,11 @@ struct rdn_rt_scene {
 namespace {
 
 int ensure_scratch(Scratch &s, uint64_t n) {
+  bool fresh = false;
   if (!s.base) {
     RDN_CUDA(cudaMalloc(&s.base, SCRATCH_BASE_BYTES));
     RDN_CUDA(cudaMemset(s.base, 0, SCRATCH_BASE_BYTES));
+    fresh = true;
   }
   if (s.capacity < n) {
     if (s.tie_queue) cudaFree(s.tie_queue);
@@ -139,7 +146,11 @@ int ensure_scratch(Scratch &s, uint64_t n) {
     RDN_CUDA(cudaMalloc(&s.tie_best, std::max<uint64_t>(n, 1) * sizeof(float)));
     RDN_CUDA(cudaMemset(s.tie_queue, 0xFF, std::max<uint64_t>(n, 1) * sizeof(uint32_t)));  // RDN_INVALID_ID = slot not published
     s.capacity = n;
+    fresh = true;
   }
+  // the memsets above run on the legacy default stream, asynchronously to the host; the consumers are non-blocking slot streams and
+  // caller streams, which do not synchronise with it: make the initial state visible before anything is launched on it
+  if (fresh) RDN_CUDA(cudaDeviceSynchronize());
   return RDN_OK;
 }
 
@@ -255,9 +266,25 @@ struct ScopedKernelTimer {
   }
 };
 
+// The two safety-net words of a scratch set — traversal stack overflow, a launch that gave up waiting at its gate — read and
+// cleared (the device is idle on this set when this is called), so that one bad launch is reported once and not for ever after.
+int take_error_flags(const Scratch &scratch, uint32_t *out_flags = nullptr) {
+  uint32_t overflow = 0, gate = 0;
+  RDN_CUDA(cudaMemcpy(&overflow, static_cast<char *>(scratch.base) + 16, 4, cudaMemcpyDeviceToHost));
+  RDN_CUDA(cudaMemcpy(&gate, static_cast<char *>(scratch.base) + 116, 4, cudaMemcpyDeviceToHost));
+  if (overflow) RDN_CUDA(cudaMemset(static_cast<char *>(scratch.base) + 16, 0, 4));
+  if (gate) RDN_CUDA(cudaMemset(static_cast<char *>(scratch.base) + 116, 0, 4));
+  if (overflow || gate) RDN_CUDA(cudaDeviceSynchronize());
+  if (out_flags) *out_flags |= (overflow ? RDN_ERROR_FLAG_STACK_OVERFLOW : 0u) | (gate ? RDN_ERROR_FLAG_GATE_TIMEOUT : 0u);
+  if (overflow) return fail(RDN_ERR_CAPACITY, "traversal stack overflow (hit records of that launch are not reliable)");
+  if (gate) return fail(RDN_ERR_CUDA, "an ordered launch gave up waiting for the previous launch on its scratch set");
+  return RDN_OK;
+}
+
 // enqueue the kernels of one trace on `stream`; returns the number of kernels launched
 int enqueue_trace(rdn_rt_scene *s, DeviceCtx &dc, const Scratch &scratch, const rdn_launch &launch, const rdn_ray *d_rays, uint64_t n,
-                  rdn_hit *d_hits, int mode, cudaStream_t stream, uint32_t *launches, bool count_ties = false, bool allow_overlap = false) {
+                  rdn_hit *d_hits, int mode, cudaStream_t stream, uint32_t *launches, bool count_ties = false, bool allow_overlap = false,
+                  const unsigned long long *d_n = nullptr) {
   const TraceScratch ts = scratch.view();
   // work_counter is zero here: zeroed at allocation and re-armed by the last CTA of every ordered launch.  tie_count and
   // the two error flags accumulate until read (the stats path clears tie_count first).
@@ -275,16 +302,20 @@ int enqueue_trace(rdn_rt_scene *s, DeviceCtx &dc, const Scratch &scratch, const 
   // order dependent by definition.  (Measured alternative, profiles/kbench_r1_anyhit.log: the ordered kernel stopping at its first
   // candidate to separate misses, the reference-order walk only for the occluded rays — slower than walking everything in
   // reference order, whose early exit is what makes these rays cheap.)
+  dc.last_enqueue_overlappable = false;
   if (mode == RDN_TRACE_REFERENCE_ORDER || end_search || tlas.irregular_count == IRREGULAR_ROUTE_ALL) {
     ScopedKernelTimer tm(dc, KERNEL_REFERENCE, stream);
-    launch_trace_reference(dc.dev, launch, d_rays, n, d_hits, ts, false, dc.sm_count, stream);
+    launch_trace_reference(dc.dev, launch, d_rays, n, d_hits, ts, false, dc.sm_count, stream, d_n);
   } else {
-    bool ties_done;
+    bool ties_done = true;
     {
       ScopedKernelTimer tm(dc, KERNEL_ORDERED, stream);
-      ties_done = launch_trace_ordered(dc.dev, launch, tlas, d_rays, n, d_hits, ts, dc.sm_count, stream,
-                                       allow_overlap && !dc.timing && !count_ties, scratch.ordered_launches);
+      // (a launch that failed never advances the set's epoch: the host-side count moves only when the kernel is in the stream,
+      // or the next launch on the set would wait at its gate for an epoch that never comes)
+      RDN_CUDA(launch_trace_ordered(dc.dev, launch, tlas, d_rays, n, d_hits, ts, dc.sm_count, stream,
+                                    allow_overlap && !dc.timing && !count_ties, scratch.ordered_launches, &ties_done, d_n));
       if (n) scratch.ordered_launches++;
+      dc.last_enqueue_overlappable = ties_done && n != 0;
     }
     if (!ties_done) {
       ScopedKernelTimer tm(dc, KERNEL_TIES, stream);
@@ -441,9 +472,10 @@ int rdn_rt_commit(rdn_rt_scene *s) {
   return commit_locked(s);
 }
 
-int rdn_rt_trace_closest_device(rdn_rt_scene *s, int device_index, const rdn_launch *launch, const rdn_ray *d_rays, uint64_t n,
-                                rdn_hit *d_hits, void *cuda_stream, int mode, rdn_trace_stats *stats) {
+static int trace_device_impl(rdn_rt_scene *s, int device_index, const rdn_launch *launch, const rdn_ray *d_rays, uint64_t n,
+                             rdn_hit *d_hits, void *cuda_stream, int mode, rdn_trace_stats *stats, const unsigned long long *d_n) {
   if (!s || !launch || (n && (!d_rays || !d_hits))) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_trace_closest_device: null argument");
+  if (d_n && n > MAX_LAUNCH_RAYS) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_trace_closest_device_n: n_max above 2^31 rays");
   if ((reinterpret_cast<uintptr_t>(d_rays) | reinterpret_cast<uintptr_t>(d_hits)) & 31u)
     return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_trace_closest_device: ray and hit arrays must be 32-byte aligned (one 256-bit access per record)");
   if (device_index < 0 || device_index >= static_cast<int>(s->devices.size())) return fail(RDN_ERR_INVALID_ARGUMENT, "bad device_index (host-only scene?)");
@@ -455,6 +487,20 @@ int rdn_rt_trace_closest_device(rdn_rt_scene *s, int device_index, const rdn_lau
   RDN_CUDA(cudaSetDevice(dc.device));
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   if (stats) std::memset(stats, 0, sizeof(*stats));
+  // Tail overlap with the previous launch (programmatic dependent launch) is the caller's request AND the library's own check:
+  // the previous thing this library put into the same stream was a single ordered launch, and this launch neither reads what that
+  // one writes nor writes what it reads or writes.  (What the caller itself enqueued in between the library cannot see: that is
+  // the contract of RDN_TRACE_OVERLAP_PREVIOUS, include/rdn_rt.h.)
+  const bool want_overlap = (mode & RDN_TRACE_OVERLAP_PREVIOUS) != 0;
+  mode &= ~RDN_TRACE_OVERLAP_PREVIOUS;
+  const uintptr_t rays_lo = reinterpret_cast<uintptr_t>(d_rays), rays_hi = rays_lo + n * sizeof(rdn_ray);
+  const uintptr_t hits_lo = reinterpret_cast<uintptr_t>(d_hits), hits_hi = hits_lo + n * sizeof(rdn_hit);
+  auto overlaps = [](uintptr_t a0, uintptr_t a1, uintptr_t b0, uintptr_t b1) { return a0 < b1 && b0 < a1; };
+  const bool overlap_ok = want_overlap && !stats && dc.ext_prev.valid && dc.ext_last_stream == stream &&
+                          !overlaps(rays_lo, rays_hi, dc.ext_prev.hits_lo, dc.ext_prev.hits_hi) &&
+                          !overlaps(hits_lo, hits_hi, dc.ext_prev.hits_lo, dc.ext_prev.hits_hi) &&
+                          !overlaps(hits_lo, hits_hi, dc.ext_prev.rays_lo, dc.ext_prev.rays_hi);
+  dc.ext_prev.valid = false;
   // The scratch sets are shared by every caller stream: a call on another stream than the previous one first waits for that
   // stream's work (event recorded there now).  Calls on the same stream need nothing — and get nothing between their kernels.
   if (!dc.ext_done) RDN_CUDA(cudaEventCreateWithFlags(&dc.ext_done, cudaEventDisableTiming));
@@ -492,8 +538,13 @@ int rdn_rt_trace_closest_device(rdn_rt_scene *s, int device_index, const rdn_lau
     }
 #endif
     if (stats) RDN_CUDA(cudaEventRecord(e0, stream));
-    rc = enqueue_trace(s, dc, scratch, l, d_rays + off, m, d_hits + off, mode, stream, stats ? &stats->kernel_launches : nullptr, stats != nullptr, true);
+    rc = enqueue_trace(s, dc, scratch, l, d_rays + off, m, d_hits + off, mode, stream, stats ? &stats->kernel_launches : nullptr, stats != nullptr,
+                       overlap_ok && off == 0, d_n);
     if (rc != RDN_OK) return rc;
+    if (!stats && m == n && dc.last_enqueue_overlappable) {
+      dc.ext_prev.valid = true;
+      dc.ext_prev.rays_lo = rays_lo; dc.ext_prev.rays_hi = rays_hi; dc.ext_prev.hits_lo = hits_lo; dc.ext_prev.hits_hi = hits_hi;
+    }
     if (stats) {
       RDN_CUDA(cudaEventRecord(e1, stream));
       RDN_CUDA(cudaEventSynchronize(e1));
@@ -504,7 +555,8 @@ int rdn_rt_trace_closest_device(rdn_rt_scene *s, int device_index, const rdn_lau
       RDN_CUDA(cudaMemcpy(small, static_cast<char *>(scratch.base) + 8, sizeof(small), cudaMemcpyDeviceToHost));
       ties += small[5];
       fallbacks += small[1];
-      if (small[2]) return fail(RDN_ERR_CAPACITY, "traversal stack overflow");
+      rc = take_error_flags(scratch);  // (reported once: the flags are cleared)
+      if (rc != RDN_OK) return rc;
 #if defined(RDN_DEBUG_STEPS) || defined(RDN_DEBUG_TIMELINE)
       unsigned long long c[10];
       RDN_CUDA(cudaMemcpy(c, static_cast<char *>(scratch.base) + 32, sizeof(c), cudaMemcpyDeviceToHost));
@@ -531,6 +583,18 @@ int rdn_rt_trace_closest_device(rdn_rt_scene *s, int device_index, const rdn_lau
     stats->rays = n; stats->tie_rays = ties; stats->kernel_ms = ms_total; stats->whole_range_rewalks = fallbacks;
   }
   return RDN_OK;
+}
+
+int rdn_rt_trace_closest_device(rdn_rt_scene *s, int device_index, const rdn_launch *launch, const rdn_ray *d_rays, uint64_t n,
+                                rdn_hit *d_hits, void *cuda_stream, int mode, rdn_trace_stats *stats) {
+  return trace_device_impl(s, device_index, launch, d_rays, n, d_hits, cuda_stream, mode, stats, nullptr);
+}
+
+int rdn_rt_trace_closest_device_n(rdn_rt_scene *s, int device_index, const rdn_launch *launch, const rdn_ray *d_rays, const uint64_t *d_n,
+                                  uint64_t n_max, rdn_hit *d_hits, void *cuda_stream, int mode) {
+  if (!d_n) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_trace_closest_device_n: null count");
+  static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "u64");
+  return trace_device_impl(s, device_index, launch, d_rays, n_max, d_hits, cuda_stream, mode, nullptr, reinterpret_cast<const unsigned long long *>(d_n));
 }
 
 int rdn_rt_trace_closest(rdn_rt_scene *s, const rdn_launch *launch, const rdn_ray *rays, uint64_t n, rdn_hit *out_hits) {
@@ -592,6 +656,7 @@ int rdn_rt_trace_closest(rdn_rt_scene *s, const rdn_launch *launch, const rdn_ra
       RDN_CUDA(cudaMemcpyAsync(slot.h_flags, static_cast<char *>(slot.scratch.base) + 8, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, slot.stream));
     }
   }
+  int host_rc = RDN_OK;
   for (size_t di = 0; di < n_dev; ++di) {
     DeviceCtx &dc = s->devices[di];
     RDN_CUDA(cudaSetDevice(dc.device));
@@ -599,10 +664,28 @@ int rdn_rt_trace_closest(rdn_rt_scene *s, const rdn_launch *launch, const rdn_ra
     for (uint64_t k = 0; k < used; ++k) {
       Slot &slot = dc.slots[k];
       RDN_CUDA(cudaStreamSynchronize(slot.stream));
-      if (slot.h_flags[2]) return fail(RDN_ERR_CAPACITY, "traversal stack overflow");
+      if (slot.h_flags[2]) { take_error_flags(slot.scratch); host_rc = RDN_ERR_CAPACITY; }
     }
   }
-  return RDN_OK;
+  return host_rc;
+}
+
+int rdn_rt_poll_errors(rdn_rt_scene *s, int device_index, void *cuda_stream, uint32_t *out_flags) {
+  if (!s) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_poll_errors: null scene");
+  if (device_index < 0 || device_index >= static_cast<int>(s->devices.size())) return fail(RDN_ERR_INVALID_ARGUMENT, "bad device_index (host-only scene?)");
+  if (out_flags) *out_flags = 0;
+  std::shared_lock<std::shared_mutex> rd(s->lock);
+  std::lock_guard<std::mutex> lg(s->launch_lock);
+  DeviceCtx &dc = s->devices[device_index];
+  RDN_CUDA(cudaSetDevice(dc.device));
+  RDN_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream)));
+  int rc = RDN_OK;
+  for (Scratch &scratch : dc.ext_scratch) {
+    if (!scratch.base) continue;
+    const int r = take_error_flags(scratch, out_flags);
+    if (r != RDN_OK && rc == RDN_OK) rc = r;
+  }
+  return rc;
 }
 
 int rdn_rt_trace_counted(rdn_rt_scene *s, const rdn_launch *launch, const rdn_ray *rays, uint64_t n, rdn_hit *out_hits,
@@ -645,6 +728,7 @@ int rdn_rt_gen_pinhole_rays_device(rdn_rt_scene *s, int device_index, const rdn_
   if (p->width == 0 || p->height == 0 || p->rect_x + static_cast<uint64_t>(p->rect_w) > p->width || p->rect_y + static_cast<uint64_t>(p->rect_h) > p->height)
     return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_gen_pinhole_rays_device: rectangle outside the launch");
   RDN_CUDA(cudaSetDevice(s->devices[device_index].device));
+  s->devices[device_index].ext_prev.valid = false;  // (something of ours now sits between two traces on that stream)
   launch_gen_pinhole_rays(*p, d_rays, static_cast<cudaStream_t>(cuda_stream));
   RDN_CUDA(cudaGetLastError());
   return RDN_OK;
@@ -667,6 +751,7 @@ int rdn_rt_gen_pinhole_rays_batch_device(rdn_rt_scene *s, int device_index, cons
     biggest = std::max(biggest, m);
   }
   RDN_CUDA(cudaSetDevice(s->devices[device_index].device));
+  s->devices[device_index].ext_prev.valid = false;  // (something of ours now sits between two traces on that stream)
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   // descriptors travel through a stream-ordered allocation, so calls on different streams never share them
   rdn_pinhole *d_params = nullptr;
@@ -691,6 +776,7 @@ int rdn_rt_gen_camera_rays_device(rdn_rt_scene *s, int device_index, const rdn_c
   if (p->width == 0 || p->height == 0 || p->rect_x + static_cast<uint64_t>(p->rect_w) > p->width || p->rect_y + static_cast<uint64_t>(p->rect_h) > p->height)
     return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_gen_camera_rays_device: rectangle outside the launch");
   RDN_CUDA(cudaSetDevice(s->devices[device_index].device));
+  s->devices[device_index].ext_prev.valid = false;  // (something of ours now sits between two traces on that stream)
   launch_gen_camera_rays(*p, d_rays, static_cast<cudaStream_t>(cuda_stream));
   RDN_CUDA(cudaGetLastError());
   return RDN_OK;
@@ -711,6 +797,7 @@ int rdn_rt_gen_bounce_rays_device(rdn_rt_scene *s, int device_index, const rdn_b
     std::lock_guard<std::mutex> lg(s->launch_lock);
     DeviceCtx &dc = s->devices[device_index];
     RDN_CUDA(cudaSetDevice(dc.device));
+  s->devices[device_index].ext_prev.valid = false;  // (something of ours now sits between two traces on that stream)
     if (dc.bounce_cap < n) {
       if (dc.d_keep) cudaFree(dc.d_keep);
       if (dc.d_iota) cudaFree(dc.d_iota);
@@ -767,6 +854,7 @@ int rdn_rt_compact_u32_device(rdn_rt_scene *s, int device_index, const uint32_t 
   std::lock_guard<std::mutex> lg(s->launch_lock);
   DeviceCtx &dc = s->devices[device_index];
   RDN_CUDA(cudaSetDevice(dc.device));
+  s->devices[device_index].ext_prev.valid = false;  // (something of ours now sits between two traces on that stream)
   const uint64_t words = compact_status_words(n);
   if (dc.compact_status_cap < words) {
     if (dc.d_compact_status) cudaFree(dc.d_compact_status);
@@ -891,6 +979,7 @@ int rdn_rt_ao_accumulate_device(rdn_rt_scene *s, int device_index, const rdn_hit
   std::lock_guard<std::mutex> lg(s->launch_lock);
   DeviceCtx &dc = s->devices[device_index];
   RDN_CUDA(cudaSetDevice(dc.device));
+  s->devices[device_index].ext_prev.valid = false;  // (something of ours now sits between two traces on that stream)
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   if (dc.ao_payload_cap < n_pixels) {
     if (dc.d_ao_payload) cudaFree(dc.d_ao_payload);
@@ -1169,6 +1258,7 @@ int rdn_rt_sbt_dispatch_device(rdn_rt_scene *s, int device_index, rdn_sbt *t, co
   std::lock_guard<std::mutex> lg(t->lock);
   DeviceCtx &dc = s->devices[device_index];
   RDN_CUDA(cudaSetDevice(dc.device));
+  s->devices[device_index].ext_prev.valid = false;  // (something of ours now sits between two traces on that stream)
   rc = sbt_upload(t, device_index);
   if (rc != RDN_OK) return rc;
   const rdn_sbt::PerDevice &pd = t->per_device[device_index];
@@ -1188,6 +1278,7 @@ int rdn_rt_sbt_group_device(rdn_rt_scene *s, int device_index, rdn_sbt *t, const
   std::lock_guard<std::mutex> lg(t->lock);
   DeviceCtx &dc = s->devices[device_index];
   RDN_CUDA(cudaSetDevice(dc.device));
+  s->devices[device_index].ext_prev.valid = false;  // (something of ours now sits between two traces on that stream)
   rdn_sbt::PerDevice &pd = t->per_device[device_index];
   if (pd.cap < n || !pd.d_count) {
     cudaFree(pd.d_keep); cudaFree(pd.d_iota); cudaFree(pd.d_segment); cudaFree(pd.d_count); cudaFree(pd.d_status);
@@ -1477,6 +1568,11 @@ int rdn_bvh_query_list(const rdn_flat_bvh *b, const rdn_mesh_view *mesh, const r
   if (!b || !mesh || !mesh->positions || !mesh->indices || !out_offsets || !out_total || (n && !rays))
     return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_bvh_query_list: null argument");
   if (face_side > RDN_FACE_DOUBLE) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_bvh_query_list: bad face_side");
+  if (b->bvh.nodes.empty()) {  // an empty tree has no hits (and its device arrays hold nothing to walk): all offsets zero
+    for (uint64_t i = 0; i <= n; ++i) out_offsets[i] = 0;
+    *out_total = 0;
+    return RDN_OK;
+  }
   int rc = rdn_bvh_upload(const_cast<rdn_flat_bvh *>(b), mesh, device);
   if (rc != RDN_OK) return rc;
   rdn_ray *d_rays = nullptr; uint32_t *d_counts = nullptr; uint64_t *d_offsets = nullptr; rdn_mesh_hit *d_out = nullptr;

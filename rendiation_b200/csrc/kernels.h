@@ -40,6 +40,7 @@ struct TraceScratch {
   uint32_t *tie_cursor;              // next queued tie to resolve (in-kernel drain)
   uint32_t *tie_total;               // ties of completed launches since the host last cleared it (in-kernel drain resets tie_count)
   uint32_t *epoch_done;              // ordered launches completed on this scratch set (gate of the next launch on the set)
+  uint32_t *gate_timeout;            // safety net: launches that gave up waiting at that gate (must stay 0)
   uint32_t *blocks_done;             // CTAs of the running ordered kernel that have left; the last one re-arms work_counter
   uint32_t *tie_queue;               // ray indices, capacity >= rays of the launch
   float *tie_best;                   // closest distance found by the ordered kernel, per queued ray
@@ -50,23 +51,26 @@ struct TraceScratch {
 constexpr float TIE_EPS = 1e-5f;
 
 // The reference's threaded pre-order walk, one ray per thread (NaiveSahBvhCpu::traverse on the device).
+// d_n (optional): the ray count lives on the device (what a compaction left there), n is its upper bound; ray lists only.
 void launch_trace_reference(const SceneDev &scene, const rdn_launch &launch, const rdn_ray *d_rays, uint64_t n, rdn_hit *d_hits,
-                            const TraceScratch &scratch, bool count_visits, int sm_count, cudaStream_t stream);
+                            const TraceScratch &scratch, bool count_visits, int sm_count, cudaStream_t stream,
+                            const unsigned long long *d_n = nullptr);
 
 // Re-walk of the rays queued by the ordered kernel (grid-stride over the device-side queue, no host sync in between).
 void launch_resolve_ties(const SceneDev &scene, const rdn_launch &launch, const rdn_ray *d_rays, rdn_hit *d_hits,
                          const TraceScratch &scratch, int sm_count, cudaStream_t stream);
 
 // Ordered (near child first) persistent-thread traversal with tie detection.  Near-tie rays are re-walked in the
-// reference's order by the finishing lane itself (returns true), or — RDN_ORDERED_VARIANT=9 — queued in scratch for
-// launch_resolve_ties (returns false).  Needs *work_counter == 0 at launch; its last CTA resets it on the way out.
+// reference's order inside the kernel (*ties_resolved_in_kernel = true), or — RDN_ORDERED_VARIANT=9, irregular TLASes — queued in
+// scratch for launch_resolve_ties (false).  Returns the launch's status.  Needs *work_counter == 0 at launch; its last CTA resets it on the way out.
 // `tlas` = the TlasRoot of tlas_binding[launch.tlas_idx] (resolved by the caller from its host copy; wide_root REF_EMPTY: every
 // ray misses).  Rays whose original range meets one of the TLAS's irregular instances are queued for an unclamped
 // reference-order walk instead of being traversed; a TLAS marked IRREGULAR_ROUTE_ALL must not come here at all.
 int ordered_tie_mode();  // 0: queue + launch_resolve_ties; 1/2: re-walk by the finishing lane; 3: queue drained inside the kernel
-bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const TlasRoot &tlas, const rdn_ray *d_rays, uint64_t n,
-                          rdn_hit *d_hits, const TraceScratch &scratch, int sm_count, cudaStream_t stream, bool allow_overlap = false,
-                          uint32_t wait_epoch = 0);  // wait_epoch = ordered launches issued before this one on `scratch`
+cudaError_t launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const TlasRoot &tlas, const rdn_ray *d_rays, uint64_t n,
+                                 rdn_hit *d_hits, const TraceScratch &scratch, int sm_count, cudaStream_t stream, bool allow_overlap,
+                                 uint32_t wait_epoch,  // = ordered launches issued before this one on `scratch`
+                                 bool *ties_resolved_in_kernel, const unsigned long long *d_n = nullptr);
 
 // Stable stream compaction of u32 (single pass, decoupled look-back); d_status needs compact_status_words(n) u64.
 uint64_t compact_status_words(uint64_t n);

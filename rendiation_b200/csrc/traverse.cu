@@ -314,8 +314,10 @@ __device__ __forceinline__ void store_walk_result(const SceneDev &S, rdn_hit *ds
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_trace_reference(const SceneDev S, const rdn_launch L, const rdn_ray *__restrict__ rays,
                                                          uint64_t n, rdn_hit *__restrict__ hits, const TraceScratch scratch,
-                                                         uint32_t tiles_x, uint32_t width, uint32_t height, uint64_t n_fetch) {
+                                                         uint32_t tiles_x, uint32_t width, uint32_t height, uint64_t n_fetch_max,
+                                                         const unsigned long long *n_ptr) {
   WalkCounters ctr;
+  const uint64_t n_fetch = n_ptr ? (__ldg(n_ptr) < n_fetch_max ? __ldg(n_ptr) : n_fetch_max) : n_fetch_max;  // device-side wave size
   for (uint64_t f = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; f < n_fetch;
        f += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
     // a warp walks an 8x4 pixel tile of a grid launch (neighbours on screen walk the same nodes), else 32 consecutive rays
@@ -398,8 +400,8 @@ struct OrderedParams {
   rdn_hit *hits;
   uint64_t n;        // rays
   uint64_t n_fetch;  // fetch indices (= n, or 32 * tiles when walking 8x4 pixel tiles)
+  const unsigned long long *n_ptr;  // optional (ray lists): the ray count lives on the device (a compaction's output), n is its upper bound
   uint32_t tiles_x;  // 0: linear
-  uint32_t tiles_y;  // 0: rows of tiles in raster order, else from the middle row outwards
   uint32_t width, height;
   uint32_t world_root;  // wide reference of the bound TLAS (REF_EMPTY: every ray misses)
   uint32_t irregular_start, irregular_count;  // the bound TLAS's irregular instances (S.irregular_instances), at most IRREGULAR_LIST_MAX
@@ -512,35 +514,33 @@ __device__ __forceinline__ void drain_tie_queue(const OrderedParams &P) {
 // Warp-synchronous rounds: every round the alive lanes (1) descend up to K inner nodes each, (2) re-converge
 // (__syncwarp) and handle their leaf / instance / bookkeeping item TOGETHER — on Volta+ lanes do not re-converge at a
 // loop exit by themselves, and a triangle test executed by 3 lanes costs the warp as much as one executed by 32 —
-// (3) vote: when no lane holds a ray any more (fewer than THRESH lanes, for the top-up experiment) the warp goes back to the refill point.
+// (3) vote: when no lane holds a ray any more the warp goes back to the refill point.
 // Refill culls rays against the TLAS root box on the spot (the reference's first test), so rays that miss the scene
 // never occupy a traversal lane.
-// Template switches.  DRAIN_TIES: near-tie queue drained inside the kernel (else by k_resolve_ties).  IRREGULAR: the bound TLAS
-// lists irregular instances (checked at refill); a separate instantiation so that regular scenes pay nothing for the out-of-line
-// test (the call makes ptxas save two dozen registers around the whole refill block).  LD256: 256-bit loads / stores for nodes,
-// triangles, instance boxes, rays and hit records.  HOT: the top levels of the TLAS tree and of the largest geometry tree
-// (breadth-first blocks of HOT_TOP_NODES wide nodes, 8 KB each) are copied into shared memory with cp.async.bulk (TMA,
-// completion on an mbarrier) when the CTA starts, and node fetches that fall into either block read shared memory instead of L1
-// (measured 9-13 % slower: experiment).  WIDE4: the walk runs over the 128 B four-box nodes (layout.h Wide4Node: the
-// grandchildren of a reference node, exact boxes): half the steps for the same box tests (nested boxes make the skipped test of
-// the absorbed child redundant), the hit children entered nearest first and the others deferred farthest first (measured
-// neutral: experiment).  Experiments that were measured, rejected and removed — whole-unit / per-SM work distribution, child
-// prefetch, speculative traversal with a postponed leaf, any-hit pre-classification — are described in DESIGN.md §5 with their
-// logs under profiles/.  THRESH (top a tile up below that many live lanes) and INST_LOOP (missed instances of a TLAS leaf skipped
-// in a loop; a one-geometry BLAS entered without a geometry-iterator round) are candidates ranked by the issue model
-// (tools/issue_model.py), bit-identical on the emulated kernels and not yet timed on a GPU.
-template <int K, int MINB, bool DRAIN_TIES, bool IRREGULAR, bool LD256, bool HOT, bool WIDE4, int THRESH = 1, bool INST_LOOP = false, int SHARE = 0, int SSTACK = 0>
+// Template switches.  K: node steps per round (3; 2 was the round-1 default).  DRAIN_TIES: near-tie queue drained inside the
+// kernel (else by k_resolve_ties).  IRREGULAR: the bound TLAS lists irregular instances (checked at refill); a separate
+// instantiation so that regular scenes pay nothing for the out-of-line test (the call makes ptxas save two dozen registers around
+// the whole refill block).  LD256: 256-bit loads / stores for nodes, triangles, instance boxes, rays and hit records.  INST_LOOP:
+// the instances of a TLAS leaf whose box the ray misses are skipped in a loop instead of costing a round each, and a BLAS of one
+// geometry is entered without a geometry-iterator round (+2..4 % with K = 3, profiles/kbench_r2a_*.log).  SHARE: the lanes of a
+// warp share the work of its long rays (see the vote) — used for launches that are ray LISTS (bounce / shadow waves), whose
+// duration is the latency of their longest rays: +14 % on config 3; it costs 5-7 % on grids, which keep the plain loop
+// (profiles/kbench_r2h_*.log).
+// Experiments kept for A/B runs.  HOT: the top levels of the TLAS tree and of the largest geometry tree (breadth-first blocks of
+// HOT_TOP_NODES wide nodes, 8 KB each) are copied into shared memory with cp.async.bulk (TMA, completion on an mbarrier) when the
+// CTA starts, and node fetches that fall into either block read shared memory instead of L1 (measured 9-13 % slower).  WIDE4: the
+// walk runs over the 128 B four-box nodes (layout.h Wide4Node: the grandchildren of a reference node, exact boxes): half the steps
+// for the same box tests, the hit children entered nearest first and the others deferred farthest first (measured neutral).
+// Measured, rejected and removed (logs under profiles/): whole-unit / per-SM work distribution, child prefetch,
+// speculative traversal with a postponed leaf, any-hit pre-classification, topping a thinned-out tile up with new rays, the first
+// 8-32 stack entries per thread in shared memory (3-10 % slower than the L1-cached local stack), rows of tiles taken from the
+// middle of the frame outwards (+2..5 % on configs 1 / 2, -11 % on config 4).
+template <int K, int MINB, bool DRAIN_TIES, bool IRREGULAR, bool LD256, bool HOT, bool WIDE4, bool INST_LOOP = false, bool SHARE = false>
 __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(const __grid_constant__ OrderedParams P) {
   RDN_COST(COST_PROLOGUE);
   const SceneDev &S = P.S;
   const uint32_t lane = threadIdx.x & 31u;
-  // The traversal stack: its first SSTACK entries per thread in shared memory (entry i of thread t at [i * blockDim + t]: the lanes
-  // of a warp hit 32 different banks whatever their depths), what goes deeper in local memory.  Rays defer about two subtrees on
-  // average and rarely more than a dozen at once, so the local part is touched by the occasional grazing ray only.
-  __shared__ uint32_t s_stack[SSTACK > 0 ? SSTACK * ORDERED_BLOCK : 1];
-  uint32_t stack[STACK_MAX - SSTACK];
-#define RDN_ST_GET(i) ((SSTACK > 0 && (i) < SSTACK) ? s_stack[(i) * ORDERED_BLOCK + threadIdx.x] : stack[(i) - SSTACK])
-#define RDN_ST_SET(i, v) do { if (SSTACK > 0 && (i) < SSTACK) s_stack[(i) * ORDERED_BLOCK + threadIdx.x] = (v); else stack[(i) - SSTACK] = (v); } while (0)
+  uint32_t stack[STACK_MAX];
   int sp = 0;
   // SHARE (lanes of a warp share the work of its long rays, see the vote): entries [lo, sp) of the stack are the deferred subtrees
   // of the space the lane is in (world, or the instance it entered) and may be handed to idle lanes, lowest = largest first;
@@ -556,7 +556,13 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
   // earlier launch is fully resident by then (a dependent launch starts only after all CTAs of its predecessor have
   // started), so waiting here cannot deadlock.
   if (threadIdx.x == 0) {
-    while (ld_volatile_u32(P.scratch.epoch_done) != P.wait_epoch) __nanosleep(200);
+    // (bounded: about ten seconds.  A launch that gives up says so in gate_timeout and goes on — its results may be wrong, which the
+    // host reports as an error, but the device does not hang)
+    uint32_t spins = 0;
+    while (ld_volatile_u32(P.scratch.epoch_done) != P.wait_epoch) {
+      __nanosleep(200);
+      if (++spins > 40000000u) { atomicAdd(P.scratch.gate_timeout, 1u); break; }
+    }
     __threadfence();
   }
   __syncthreads();
@@ -623,8 +629,8 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
   // a full stack drops the entry and raises a sticky flag, reported once when the ray ends: no atomic (and so no branch around one)
   // inside the traversal loop
   bool stack_overflowed = false;
-#define RDN_PUSH(v) do { if (sp < STACK_MAX) { RDN_ST_SET(sp, (v)); ++sp; } else stack_overflowed = true; } while (0)
-#define RDN_POP() (sp > 0 ? (--sp, RDN_ST_GET(sp)) : REF_DONE)
+#define RDN_PUSH(v) do { if (sp < STACK_MAX) stack[sp++] = (v); else stack_overflowed = true; } while (0)
+#define RDN_POP() (sp > 0 ? stack[--sp] : REF_DONE)
 
   // a finished ray: the record of its closest candidate (or the miss record), near-ties queued for the reference-order re-walk
   auto finish_ray = [&]() {
@@ -667,7 +673,9 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
       unsigned long long base = 0;
       if (static_cast<int>(lane) == leader) base = atomicAdd(P.scratch.work_counter, static_cast<unsigned long long>(cnt));
       base = __shfl_sync(FULL_MASK, base, leader);
-      if (base + cnt >= P.n_fetch) {
+      // (a wave whose size a previous kernel left on the device: read at every refill rather than kept in registers)
+      const uint64_t n_fetch = P.n_ptr ? (__ldg(P.n_ptr) < P.n_fetch ? __ldg(P.n_ptr) : P.n_fetch) : P.n_fetch;
+      if (base + cnt >= n_fetch) {
 #if defined(RDN_DEBUG_STEPS) || defined(RDN_DEBUG_TIMELINE)
         if (!warp_exhausted && static_cast<int>(lane) == leader) atomicMin(P.scratch.counters + 7, globaltimer_ns());  // ray list ran dry
 #endif
@@ -675,17 +683,12 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
       }
       if (!alive) {
         const uint64_t f = base + __popc(want & ((1u << lane) - 1u));
-        bool valid = f < P.n_fetch;
+        bool valid = f < n_fetch;
         uint64_t idx = f;
         if (valid && P.tiles_x) {
           const uint32_t tile = static_cast<uint32_t>(f >> 5);  // launches hold < 2^31 rays: 32-bit tile arithmetic
           const uint32_t in_tile = static_cast<uint32_t>(f) & 31u;
-          uint32_t ty = tile / P.tiles_x;
-          const uint32_t tx = tile - ty * P.tiles_x;
-          // rows of tiles are taken from the middle of the grid outwards: what a launch starts LAST decides its tail (a pass over a
-          // tile of long rays takes ten times the mean), and the rows at the top and bottom edge of a frame are the likeliest to hold
-          // nothing but short rays
-          if (P.tiles_y) { const uint32_t half = (ty + 1u) >> 1; ty = (ty & 1u) ? ((P.tiles_y - 1u) >> 1) + half : ((P.tiles_y - 1u) >> 1) - half; }
+          const uint32_t ty = tile / P.tiles_x, tx = tile - ty * P.tiles_x;
           const uint32_t x = tx * 8u + (in_tile & 7u), y = ty * 4u + (in_tile >> 3);
           valid = x < P.width && y < P.height;
           idx = static_cast<uint64_t>(y) * P.width + x;
@@ -707,7 +710,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
             scaling = 1.f; near_s = t_near_world; bound = far0; far_s = far0;
             best = INFINITY; second = INFINITY; best_slot = RDN_INVALID_ID; best_inst = RDN_INVALID_ID;
             in_object = false; sp = 0;
-            if constexpr (SHARE > 0) { lo = 0; home = lane; helpers = 0; }
+            if constexpr (SHARE) { lo = 0; home = lane; helpers = 0; }
             cur = world_entry;
             alive = true;
           } else {
@@ -728,8 +731,8 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
 #endif
 
     // (SHARE: every lane takes part in the rounds — a lane without a ray idles at cur == REF_DONE until it is handed a subtree)
-    const uint32_t rmask = SHARE > 0 ? FULL_MASK : amask;
-    if (SHARE > 0 || alive) {
+    const uint32_t rmask = SHARE ? FULL_MASK : amask;
+    if (SHARE || alive) {
 #pragma unroll 1
       for (;;) {
         RDN_COST(COST_ROUND);
@@ -833,7 +836,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
                   best = distance; best_u = u; best_v = v; best_slot = slot; best_inst = cur_inst;
                   best_back = sign < 0.0f ? 1u : 0u;
                   // (SHARE: a helper's bound came from the ray's owner and may already be tighter than its own closest candidate)
-                  bound = fminf(SHARE > 0 ? bound : far0, best + TIE_EPS * fabsf(best));
+                  bound = fminf(SHARE ? bound : far0, best + TIE_EPS * fabsf(best));
                   far_s = bound * scaling;
                 } else {
                   second = fminf(second, distance);
@@ -878,7 +881,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
                 if (!(flags & TF_SKIP_TRIANGLES) && tail.w < S.n_blas_meta) {
                   const uint2 groots = __ldg(reinterpret_cast<const uint2 *>(S.blas_meta[tail.w].tri_root_range));
                   // (SHARE: the frame of an instance is two entries — the world segment's `lo`, then the exit marker — pushed together or not at all)
-                  const bool room = SHARE == 0 || sp + 2 <= STACK_MAX;
+                  const bool room = !SHARE || sp + 2 <= STACK_MAX;
                   if (!room) stack_overflowed = true;
                   if (groots.x < groots.y && room) {
                     RDN_COST(COST_INSTANCE_ENTER);
@@ -889,9 +892,9 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
                     scaling = s; near_s = t_near_world * s; far_s = bound * s;
                     cur_inst = istart; cur_flags = flags; cull_bits = cull_triangle_bits(flags); geom_end = groots.y;
                     in_object = true;
-                    if constexpr (SHARE > 0) {
-                      RDN_ST_SET(sp, static_cast<uint32_t>(lo)); ++sp;
-                      RDN_ST_SET(sp, REF_EXIT_INSTANCE); ++sp;
+                    if constexpr (SHARE) {
+                      stack[sp++] = static_cast<uint32_t>(lo);
+                      stack[sp++] = REF_EXIT_INSTANCE;
                       lo = sp;
                     } else {
                       RDN_PUSH(REF_EXIT_INSTANCE);
@@ -912,13 +915,13 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
               }
               if (!entered) cur = RDN_POP();
             }
-          } else if (SHARE == 0 && cur == REF_EXIT_INSTANCE && sp == 0) {
+          } else if (!SHARE && cur == REF_EXIT_INSTANCE && sp == 0) {
             cur = REF_DONE;  // nothing deferred in world space: the ray is finished, no need to restore the world ray
           } else if (cur == REF_EXIT_INSTANCE) {
             // back to world space: the world ray is re-read instead of being held in registers
             RDN_COST(COST_EXIT_INSTANCE);
-            if constexpr (SHARE > 0) { --sp; lo = static_cast<int>(RDN_ST_GET(sp)); }  // (what lies below `lo` was handed to other lanes)
-            if (SHARE > 0 && sp <= lo) {
+            if constexpr (SHARE) lo = static_cast<int>(stack[--sp]);  // (what lies below `lo` was handed to other lanes)
+            if (SHARE && sp <= lo) {
               cur = REF_DONE;
             } else {
               float4 r0, r1;
@@ -931,7 +934,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
           } else if (cur == REF_EMPTY) {
             RDN_COST(COST_EMPTY);
             // (SHARE: entries handed to other lanes are left behind as REF_EMPTY, a run of them at the bottom of a segment)
-            do { cur = RDN_POP(); } while (SHARE > 0 && cur == REF_EMPTY);
+            do { cur = RDN_POP(); } while (SHARE && cur == REF_EMPTY);
           } else {
             // geometry iterator of the current instance's BLAS
             RDN_COST(COST_GEOMETRY);
@@ -945,7 +948,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
 
         // ---------------- vote (also the re-convergence point of phase 2)
         RDN_COST(COST_VOTE);
-        if constexpr (SHARE > 0) {
+        if constexpr (SHARE) {
           // Lanes of a warp share the work of its long rays.  The rays of a tile end at very different depths (a ray grazing the
           // surface takes ten times the node steps of its neighbours) and the finished lanes would idle until the last one ends.
           // Instead, a lane without work is handed deferred subtrees of a busy lane's ray — the LOWEST entries of the busy
@@ -1014,7 +1017,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
 #pragma unroll 1
                 for (int j = 0; j < m; ++j) {
                   uint32_t e = 0;
-                  if (static_cast<int>(lane) == D) { e = RDN_ST_GET(d_lo + j); RDN_ST_SET(d_lo + j, REF_EMPTY); }
+                  if (static_cast<int>(lane) == D) { e = stack[d_lo + j]; stack[d_lo + j] = REF_EMPTY; }
                   e = __shfl_sync(FULL_MASK, e, D);
                   if (take && rank == j) piece = e;
                 }
@@ -1034,7 +1037,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
                   best = INFINITY; second = INFINITY; best_slot = RDN_INVALID_ID; best_inst = RDN_INVALID_ID;
                   in_object = d_in_object;
                   sp = 0;
-                  if (d_in_object) { RDN_ST_SET(0, 0u); RDN_ST_SET(1, REF_EXIT_INSTANCE); sp = 2; }  // the frame of the donor's instance
+                  if (d_in_object) { stack[0] = 0u; stack[1] = REF_EXIT_INSTANCE; sp = 2; }  // the frame of the donor's instance
                   lo = sp;
                   cur = piece;
                 }
@@ -1046,11 +1049,11 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
           }
         } else {
           const int active = __popc(__ballot_sync(amask, cur != REF_DONE));
-          if (active == 0 || (THRESH > 1 && active < THRESH && !warp_exhausted)) break;  // THRESH > 1: top the tile up once it has thinned out
+          if (active == 0) break;
         }
       }
 
-      if (SHARE > 0 ? alive : cur == REF_DONE) finish_ray();
+      if (SHARE ? alive : cur == REF_DONE) finish_ray();
     }
 #ifdef RDN_DEBUG_TIMELINE
     {  // one pass over a tile: duration histogram (8 us buckets), rounds per bucket, the longest pass, passes ending after the list ran dry
@@ -1070,8 +1073,6 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
   }
 #undef RDN_PUSH
 #undef RDN_POP
-#undef RDN_ST_GET
-#undef RDN_ST_SET
 #ifdef RDN_DEBUG_STEPS
   {
     unsigned long long vals[5] = {dbg_steps, dbg_rays, dbg_tris, dbg_pushes, dbg_long};
@@ -1130,12 +1131,12 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
 
 // ------------------------------------------------------------------------------------------------ launchers
 void launch_trace_reference(const SceneDev &scene, const rdn_launch &launch, const rdn_ray *d_rays, uint64_t n, rdn_hit *d_hits,
-                            const TraceScratch &scratch, bool count_visits, int sm_count, cudaStream_t stream) {
+                            const TraceScratch &scratch, bool count_visits, int sm_count, cudaStream_t stream, const unsigned long long *d_n) {
   if (n == 0) return;
   uint32_t tiles_x = 0, width = 0, height = 0;
   uint64_t n_fetch = n;
   static const bool tiles_enabled = []() { const char *e = getenv("RDN_REF_TILES"); return !e || atoi(e) != 0; }();
-  if (tiles_enabled && launch.grid_width != 0 && n % launch.grid_width == 0) {
+  if (tiles_enabled && !d_n && launch.grid_width != 0 && n % launch.grid_width == 0) {
     width = launch.grid_width;
     height = static_cast<uint32_t>(n / launch.grid_width);
     tiles_x = (width + 7u) / 8u;
@@ -1146,9 +1147,9 @@ void launch_trace_reference(const SceneDev &scene, const rdn_launch &launch, con
   const uint64_t cap = static_cast<uint64_t>(sm_count) * 1024;
   if (blocks > cap) blocks = cap;
   if (count_visits)
-    k_trace_reference<true><<<static_cast<unsigned>(blocks), block, 0, stream>>>(scene, launch, d_rays, n, d_hits, scratch, tiles_x, width, height, n_fetch);
+    k_trace_reference<true><<<static_cast<unsigned>(blocks), block, 0, stream>>>(scene, launch, d_rays, n, d_hits, scratch, tiles_x, width, height, n_fetch, d_n);
   else
-    k_trace_reference<false><<<static_cast<unsigned>(blocks), block, 0, stream>>>(scene, launch, d_rays, n, d_hits, scratch, tiles_x, width, height, n_fetch);
+    k_trace_reference<false><<<static_cast<unsigned>(blocks), block, 0, stream>>>(scene, launch, d_rays, n, d_hits, scratch, tiles_x, width, height, n_fetch, d_n);
 }
 
 void launch_resolve_ties(const SceneDev &scene, const rdn_launch &launch, const rdn_ray *d_rays, rdn_hit *d_hits,
@@ -1162,19 +1163,18 @@ static int ordered_variant() {
 }
 int ordered_tie_mode() { return ordered_variant() == 9 ? 0 : 3; }
 
-bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const TlasRoot &tlas, const rdn_ray *d_rays, uint64_t n,
-                          rdn_hit *d_hits, const TraceScratch &scratch, int sm_count, cudaStream_t stream, bool allow_overlap,
-                          uint32_t wait_epoch) {
-  if (n == 0) return true;
+cudaError_t launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const TlasRoot &tlas, const rdn_ray *d_rays, uint64_t n,
+                                 rdn_hit *d_hits, const TraceScratch &scratch, int sm_count, cudaStream_t stream, bool allow_overlap,
+                                 uint32_t wait_epoch, bool *ties_resolved_in_kernel, const unsigned long long *d_n) {
+  *ties_resolved_in_kernel = true;
+  if (n == 0) return cudaSuccess;
   OrderedParams P;
   P.S = scene; P.L = launch; P.rays = d_rays; P.hits = d_hits; P.n = n; P.scratch = scratch;
-  P.tiles_x = 0; P.tiles_y = 0; P.width = 0; P.height = 0; P.n_fetch = n;
-  if (launch.grid_width != 0 && n % launch.grid_width == 0) {
-    static const bool centre_out = []() { const char *e = getenv("RDN_TILE_ORDER"); return !e || atoi(e) != 0; }();
+  P.tiles_x = 0; P.width = 0; P.height = 0; P.n_fetch = n; P.n_ptr = d_n;
+  if (!d_n && launch.grid_width != 0 && n % launch.grid_width == 0) {
     P.width = launch.grid_width;
     P.height = static_cast<uint32_t>(n / launch.grid_width);
     P.tiles_x = (P.width + 7u) / 8u;
-    P.tiles_y = centre_out ? (P.height + 3u) / 4u : 0u;
     P.n_fetch = static_cast<uint64_t>(P.tiles_x) * ((P.height + 3u) / 4u) * 32u;
   }
   const int variant_ = ordered_variant();
@@ -1189,54 +1189,39 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const
   P.irregular_start = tlas.irregular_start;
   P.irregular_count = tlas.irregular_count == IRREGULAR_ROUTE_ALL ? 0u : tlas.irregular_count;  // (the caller routes those elsewhere)
   P.wait_epoch = wait_epoch;
-  {
-    static const struct ShareKnobs { int busy = 16, min = 2; ShareKnobs() { if (const char *e = getenv("RDN_SHARE")) sscanf(e, "%d,%d", &busy, &min); } } knobs;
+  {  // (RDN_SHARE=busy,min: experimentation knob)
+    static const struct ShareKnobs { int busy = 4, min = 1; ShareKnobs() { if (const char *e = getenv("RDN_SHARE")) sscanf(e, "%d,%d", &busy, &min); } } knobs;
     P.share_busy = knobs.busy; P.share_min = knobs.min;
   }
 
-  // RDN_ORDERED_VARIANT: experimentation knob (node steps per round / refill threshold / tie handling / instance path)
+  // RDN_ORDERED_VARIANT: experimentation knob
   const int variant = ordered_variant();
   using KernelFn = void (*)(const OrderedParams);
   KernelFn fn;
   bool inline_ties = true;
-  // template arguments: <K, MINB, DRAIN_TIES, IRREGULAR, LD256, HOT, WIDE4>
+  // template arguments: <K, MINB, DRAIN_TIES, IRREGULAR, LD256, HOT, WIDE4, INST_LOOP, SHARE>
+  const KernelFn plain = k_trace_ordered_rounds<3, 8, true, false, true, false, false, true, false>;
+  const KernelFn sharing = k_trace_ordered_rounds<3, 8, true, false, true, false, false, true, true>;
   switch (variant) {
-    case 9: fn = k_trace_ordered_rounds<2, 8, false, false, true, false, false>; inline_ties = false; break;  // queue drained by k_resolve_ties
-    case 30: fn = k_trace_ordered_rounds<2, 8, true, false, false, false, false>; break;  // 128-bit loads / stores
+    case 2: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false>; break;     // the round-1 default: K = 2, one round per missed instance
+    case 9: fn = k_trace_ordered_rounds<3, 8, false, false, true, false, false, true>; inline_ties = false; break;  // queue drained by k_resolve_ties
+    case 30: fn = k_trace_ordered_rounds<3, 8, true, false, false, false, false, true>; break;  // 128-bit loads / stores
 #ifndef RDN_SIMT_EMU
-    case 40: fn = k_trace_ordered_rounds<2, 8, true, false, true, true, false>; break;    // top levels staged in shared memory (TMA)
+    case 40: fn = k_trace_ordered_rounds<3, 8, true, false, true, true, false, true>; break;    // top levels staged in shared memory (TMA)
 #endif
     case 60: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, true>; break;    // four-box nodes, K = 2 steps per round
     case 61: fn = k_trace_ordered_rounds<1, 8, true, false, true, false, true>; break;    // ... one step per round
-    // topping a thinned-out tile up with the next rays of the launch (lost on config 2's dense tiles in the first sweep; the issue model
-    // says instanced scenes idle at 12 of 32 lanes without it)
-    case 80: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false, 8>; break;
-    case 81: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false, 16>; break;
-    case 82: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false, 24>; break;
-    // missed instances of a TLAS leaf skipped in a loop instead of one per round (issue model: instanced scenes)
-    case 90: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false, 1, true>; break;
-    case 91: fn = k_trace_ordered_rounds<3, 8, true, false, true, false, false, 1, true>; break;   // ... with three node steps per round
-    case 70: fn = k_trace_ordered_rounds<3, 8, true, false, true, false, false>; break;   // three node steps per round (issue model: tools/issue_model.py)
-    case 71: fn = k_trace_ordered_rounds<1, 8, true, false, true, false, false>; break;   // one node step per round
-    // idle lanes take deferred subtrees of the warp's busy lanes once no more than SHARE lanes are busy
-    case 110: fn = k_trace_ordered_rounds<3, 8, true, false, true, false, false, 1, true, 1>; break;  // RDN_SHARE=busy,min
-    // the first entries of the traversal stack in shared memory
-    case 120: fn = k_trace_ordered_rounds<3, 8, true, false, true, false, false, 1, true, 0, 8>; break;
-    case 121: fn = k_trace_ordered_rounds<3, 8, true, false, true, false, false, 1, true, 0, 12>; break;
-    case 122: fn = k_trace_ordered_rounds<3, 8, true, false, true, false, false, 1, true, 0, 16>; break;
-    case 123: fn = k_trace_ordered_rounds<3, 8, true, false, true, false, false, 1, true, 0, 24>; break;
-    case 124: fn = k_trace_ordered_rounds<3, 8, true, false, true, false, false, 1, true, 0, 32>; break;
-    case 130: fn = k_trace_ordered_rounds<3, 8, true, false, true, false, false, 1, true, 1, 16>; break;  // ... with sharing
-    case 2: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false>; break;     // two node steps per round, one round per missed instance (the round-1 default)
-    default: fn = k_trace_ordered_rounds<3, 8, true, false, true, false, false, 1, true>; break;
+    case 100: fn = plain; break;     // never share
+    case 110: fn = sharing; break;   // always share
+    default: fn = P.tiles_x == 0 ? sharing : plain; break;  // ray lists share, grids do not
   }
-  if ((variant == 60 || variant == 61) && !use_wide4) fn = k_trace_ordered_rounds<3, 8, true, false, true, false, false, 1, true>;
+  if ((variant == 60 || variant == 61) && !use_wide4) fn = plain;
   if (P.irregular_count != 0) {  // (the experimentation variants exist for regular scenes only)
     // Rays handed over at refill can be a large part of the launch, and the in-kernel drain claims entries through one CAS
     // cursor (fine for a handful of ties, 55 ms for 400 K entries): the queue of an irregular launch is walked by
     // k_resolve_ties, one thread per entry, right behind this kernel.
     inline_ties = false;
-    fn = k_trace_ordered_rounds<3, 8, false, true, true, false, false, 1, true>;
+    fn = k_trace_ordered_rounds<3, 8, false, true, true, false, false, true>;
   }
   int blocks_per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, ORDERED_BLOCK, 0);
@@ -1257,8 +1242,8 @@ bool launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   if (allow_overlap && pdl_enabled && full_grid && inline_ties) { cfg.attrs = attr; cfg.numAttrs = 1; }
-  cudaLaunchKernelEx(&cfg, fn, P);
-  return inline_ties;
+  *ties_resolved_in_kernel = inline_ties;
+  return cudaLaunchKernelEx(&cfg, fn, P);
 }
 
 }  // namespace rdn

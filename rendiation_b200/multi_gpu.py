@@ -23,14 +23,16 @@ TILE = 512  # the reference's launch tile (wavefront_compute/mod.rs:134)
 Tile = Tuple[int, int, int, int]  # x0, y0, w, h
 
 
-def launch_tiles(width: int, height: int, tile: int = TILE) -> List[Tile]:
-    """Row-major list of tiles covering a ``width x height`` launch exactly (edge tiles are narrower; nothing dropped)."""
-    if width < 0 or height < 0 or tile <= 0:
+def launch_tiles(width: int, height: int, tile: int = TILE, tile_h: int | None = None) -> List[Tile]:
+    """Row-major list of tiles (``tile`` wide, ``tile_h`` high — square by default) covering a ``width x height`` launch exactly
+    (edge tiles are narrower; nothing dropped)."""
+    tile_h = tile if tile_h is None else tile_h
+    if width < 0 or height < 0 or tile <= 0 or tile_h <= 0:
         raise ValueError("launch_tiles: bad extent")
     out = []
-    for y0 in range(0, height, tile):
+    for y0 in range(0, height, tile_h):
         for x0 in range(0, width, tile):
-            out.append((x0, y0, min(tile, width - x0), min(tile, height - y0)))
+            out.append((x0, y0, min(tile, width - x0), min(tile_h, height - y0)))
     return out
 
 
@@ -52,9 +54,9 @@ class TileShard:
     put its hits back.  Rays of a tile are stored contiguously in the tile's row-major order, so each tile is traced
     as its own small 2-D launch (``grid_width`` = tile width keeps the kernel's 8 x 4 pixel-tile walk)."""
 
-    def __init__(self, width: int, height: int, world: int, rank: int, tile: int = TILE):
-        self.width, self.height, self.world, self.rank, self.tile = width, height, world, rank, tile
-        self.tiles_all = launch_tiles(width, height, tile)
+    def __init__(self, width: int, height: int, world: int, rank: int, tile: int = TILE, tile_h: int | None = None):
+        self.width, self.height, self.world, self.rank, self.tile, self.tile_h = width, height, world, rank, tile, tile_h
+        self.tiles_all = launch_tiles(width, height, tile, tile_h)
         self.tile_ids = shard_tiles(len(self.tiles_all), world, rank)
         self.tiles = [self.tiles_all[i] for i in self.tile_ids]
         counts = [w * h for (_, _, w, h) in self.tiles]
@@ -86,6 +88,64 @@ def trace_shard(system, shard: TileShard, shard_rays: np.ndarray, **launch_kw) -
     for off, cnt, gw in shard.launches():
         system.trace_closest_batch(shard_rays[off:off + cnt], grid_width=gw, out=hits[off:off + cnt], **launch_kw)
     return hits
+
+
+# ----------------------------------------------------------------------------------------------- one frame, sharded
+class ShardedFrame:
+    """One rank's share of a multi-sample frame — BASELINE configs[4]: ``width x height x spp`` jittered pinhole rays plus one
+    cosine bounce per hit — kept on the device from the camera parameters to the last hit record.
+
+    Sharding: the frame is cut into SMALL tiles (64 x 32 pixels by default) dealt round-robin, so every rank gets an even
+    sample of cheap (background) and expensive (silhouette) image regions; the 512 x 512 launch tiles of the reference
+    (wavefront_compute/mod.rs:134) left 40 unequal tiles for 8 GPUs.  Small tiles cost nothing here because all tiles and all
+    samples of a rank are ONE wave: its rays form a virtual image, tile width wide, with the tiles and sample planes stacked
+    vertically (tile heights are multiples of 4 and widths multiples of 8, so the kernel's 8 x 4 pixel blocks never straddle two
+    tiles), generated by one batched launch and traced by one launch; the bounce wave is sized on the device
+    (rdn_rt_trace_closest_device_n), so a frame is six kernels and no host round trip.
+    """
+
+    def __init__(self, system, width: int, height: int, spp: int, world: int, rank: int, device, tile_w: int = 64, tile_h: int = 32,
+                 tmin: float = 0.01, tmax: float = 100.0, primary_flags: int = 0x10, bounce_flags: int = 0):
+        import torch
+
+        from . import scenes as S
+        if tile_w % 8 or tile_h % 4:
+            raise ValueError("ShardedFrame: tile width must be a multiple of 8 and tile height a multiple of 4")
+        self.system, self.spp, self.device = system, spp, device
+        self.primary_flags, self.bounce_flags, self.tmin, self.tmax = primary_flags, bounce_flags, tmin, tmax
+        self.shard = TileShard(width, height, world, rank, tile=tile_w, tile_h=tile_h)
+        aspect = float(np.float32(width / height))
+        jitters = [S.sample_2d(np.full(1, s, np.uint32))[0] if s else np.array([0.5, 0.5], np.float32) for s in range(spp)]
+        # tiles of one width form one wave (only the last column of a frame can be narrower: at most two waves per rank)
+        by_width = {}
+        for t in self.shard.tiles:
+            by_width.setdefault(t[2], []).append(t)
+        self.waves = []
+        for gw, tiles in by_width.items():
+            rects = [t for s in range(spp) for t in tiles]
+            jits = [(float(jitters[s][0]), float(jitters[s][1])) for s in range(spp) for _ in tiles]
+            batch = system.pinhole_batch(width, height, rects, jits, tmin=tmin, tmax=tmax, aspect=aspect)
+            n = batch[2]
+            buf = lambda: torch.empty((max(n, 1), 32), dtype=torch.uint8, device=device)
+            self.waves.append(dict(gw=gw, n=n, tiles=tiles, batch=batch, rays=buf(), hits=buf(), brays=buf(), bhits=buf(),
+                                   src=torch.empty(max(n, 1), dtype=torch.int32, device=device), cnt=torch.zeros(1, dtype=torch.int64, device=device)))
+        self.n_primary = sum(w["n"] for w in self.waves)
+
+    def enqueue(self, stream: int) -> None:
+        """all kernels of one frame on ``stream``; returns without waiting"""
+        p = self.system
+        for w in self.waves:
+            if w["n"] == 0:
+                continue
+            p.gen_pinhole_rays_prebuilt_device(w["batch"], w["rays"].data_ptr(), stream=stream)
+            p.trace_closest_device(w["rays"].data_ptr(), w["n"], w["hits"].data_ptr(), ray_flags=self.primary_flags, grid_width=w["gw"], stream=stream)
+            p.gen_bounce_rays_device(w["rays"].data_ptr(), w["hits"].data_ptr(), w["n"], w["brays"].data_ptr(), w["src"].data_ptr(),
+                                     w["cnt"].data_ptr(), mode=0, index_base=0, tmin=self.tmin, tmax=self.tmax, stream=stream)
+            p.trace_closest_device_n(w["brays"].data_ptr(), w["cnt"].data_ptr(), w["n"], w["bhits"].data_ptr(), ray_flags=self.bounce_flags, stream=stream)
+
+    def n_bounce(self) -> int:
+        """bounce rays of the last frame (reads the device-side counts: call after the stream has been waited for)"""
+        return int(sum(int(w["cnt"].item()) for w in self.waves if w["n"]))
 
 
 # ----------------------------------------------------------------------------------------------- replication

@@ -439,23 +439,29 @@ def test_back_to_back_launches_overlap_without_losing_rays():
     torch.cuda.synchronize()
     assert ref.cpu().numpy().view(api.HIT_DTYPE).reshape(-1).tobytes() == want.tobytes()
 
-    def burst(streams, count, small_every=0, reforder_every=0):
+    def burst(streams, count, small_every=0, reforder_every=0, same_buffer=False):
         outs = [torch.full((n, 32), 0xAB, dtype=torch.uint8, device="cuda") for _ in range(count)]
         torch.cuda.synchronize()
+        if same_buffer:  # every launch writes the SAME hit buffer: the library must refuse the overlap (stragglers of launch k
+            outs = [outs[0]] * count  # would overwrite records of launch k + 1) and the result is still right
         for k, o in enumerate(outs):
             st = streams[k % len(streams)]
             if small_every and k % small_every == small_every - 1:
                 m = 4096 * W // W  # a launch far too small to fill the GPU, in the middle of the burst
-                sp.p.trace_closest_device(d_rays.data_ptr(), m, o.data_ptr(), ray_flags=helpers.CULL_BACK, stream=st.cuda_stream)
-                sp.p.trace_closest_device(d_rays.data_ptr() + m * 32, n - m, o.data_ptr() + m * 32, ray_flags=helpers.CULL_BACK, stream=st.cuda_stream)
+                sp.p.trace_closest_device(d_rays.data_ptr(), m, o.data_ptr(), ray_flags=helpers.CULL_BACK, stream=st.cuda_stream, overlap_previous=True)
+                sp.p.trace_closest_device(d_rays.data_ptr() + m * 32, n - m, o.data_ptr() + m * 32, ray_flags=helpers.CULL_BACK, stream=st.cuda_stream,
+                                          overlap_previous=True)
             elif reforder_every and k % reforder_every == reforder_every - 1:
                 sp.p.trace_closest_device(d_rays.data_ptr(), n, o.data_ptr(), ray_flags=helpers.CULL_BACK, stream=st.cuda_stream,
-                                          mode=api.TRACE_REFERENCE_ORDER)
+                                          mode=api.TRACE_REFERENCE_ORDER, overlap_previous=True)
             else:
-                sp.p.trace_closest_device(d_rays.data_ptr(), n, o.data_ptr(), ray_flags=helpers.CULL_BACK, grid_width=W, stream=st.cuda_stream)
+                sp.p.trace_closest_device(d_rays.data_ptr(), n, o.data_ptr(), ray_flags=helpers.CULL_BACK, grid_width=W, stream=st.cuda_stream,
+                                          overlap_previous=True)
         torch.cuda.synchronize()
+        assert sp.p.poll_errors(stream=streams[0].cuda_stream) == 0
         return [bool(torch.equal(o, ref)) for o in outs]
 
     assert all(burst([s0], 24))                                   # one stream: every launch overlaps its predecessor's tail
     assert all(burst([s0, s1], 16))                               # two streams alternating: ordered through the library's event
     assert all(burst([s0], 18, small_every=5, reforder_every=7))  # partial grids and the other kernel in between
+    assert all(burst([s0], 12, same_buffer=True))                 # aliased hit buffers: overlap refused by the library

@@ -256,3 +256,30 @@ def test_device_resident_wavefront_matches_the_oracle_on_the_rays_it_generated()
     assert got1.tobytes() == want1.tobytes()
     assert got2.tobytes() == want2.tobytes()
     assert int((got2["instance_id"] != api.INVALID_ID).sum()) > 100  # the torus re-hits itself
+
+
+@pytest.mark.parametrize("first_hit", [False, True])
+def test_wave_sized_on_the_device_needs_no_host_read(first_hit):
+    """rdn_rt_trace_closest_device_n: the bounce wave is launched over the upper bound with its size left on the device by the
+    bounce step — no read-back between the waves (both kernels: the ordered one and, for ACCEPT_FIRST_HIT rays, the
+    reference-order one).  Records beyond the device-side count stay untouched."""
+    import torch
+    sp, _ = helpers.torus_scene(128)
+    W, H = 320, 200
+    n = W * H
+    d_rays, d_hits = _primary_and_hits(sp, W, H)
+    st = torch.cuda.current_stream().cuda_stream
+    d_b = _dev_rays(n)
+    d_bh = torch.full((n, 32), 0xAB, dtype=torch.uint8, device="cuda")
+    d_src = torch.zeros(n, dtype=torch.int32, device="cuda")
+    d_n = torch.zeros(1, dtype=torch.int64, device="cuda")
+    flags = 0x04 if first_hit else 0
+    sp.p.gen_bounce_rays_device(d_rays.data_ptr(), d_hits.data_ptr(), n, d_b.data_ptr(), d_src.data_ptr(), d_n.data_ptr(), mode=0, stream=st)
+    sp.p.trace_closest_device_n(d_b.data_ptr(), d_n.data_ptr(), n, d_bh.data_ptr(), ray_flags=flags, stream=st)
+    assert sp.p.poll_errors(stream=st) == 0
+    k = int(d_n.item())
+    assert 0 < k < n
+    want = sp.o.trace(_np_rays(d_b)[:k], ray_flags=flags, n_threads=4, want_counters=False)
+    got = d_bh.cpu().numpy()
+    assert got[:k].view(api.HIT_DTYPE).reshape(-1).tobytes() == want.tobytes()
+    assert np.all(got[k:] == 0xAB)

@@ -80,7 +80,7 @@ def test_issue_model_attributes_every_sass_instruction():
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import issue_model
     names = issue_model.region_names()
-    static, total = issue_model.static_counts("ILi2ELi8ELb1ELb0ELb1ELb0ELb0ELi1ELb0EE", names)
+    static, total = issue_model.static_counts(issue_model.mangled(3, inst_loop=True), names)
     by = dict(zip(names, static))
     tri_family = ("COST_TRI", "COST_TRI_RANGE", "COST_TRI_U", "COST_TRI_V", "COST_TRI_HIT")
     copies = 3  # (the division below undoes the per-copy scaling only approximately: allow slack)

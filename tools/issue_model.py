@@ -189,15 +189,17 @@ def dynamic_counts(cfg: str, names: list[str]):
     return list(warp), list(lane), rays.shape[0], dt, bool(same)
 
 
+def mangled(k, drain=True, ld256=True, wide4=False, inst_loop=False, share=False):
+    """mangled template arguments <K, MINB, DRAIN_TIES, IRREGULAR, LD256, HOT, WIDE4, INST_LOOP, SHARE> of an instantiation"""
+    bl = lambda v: "Lb1E" if v else "Lb0E"
+    return f"ILi{k}ELi8E{bl(drain)}Lb0E{bl(ld256)}Lb0E{bl(wide4)}{bl(inst_loop)}{bl(share)}E"
+
+
 def main():
     cfg = next((a for a in sys.argv[1:] if a in CONFIGS), "c2s")
-    # mangled template arguments <K, MINB, DRAIN_TIES, IRREGULAR, LD256, HOT, WIDE4> of the instantiation RDN_ORDERED_VARIANT selects
-    def mangled(k, drain=True, ld256=True, wide4=False, thresh=1, inst_loop=False, share=0, sstack=0):
-        bl = lambda v: "Lb1E" if v else "Lb0E"
-        return f"ILi{k}ELi8E{bl(drain)}Lb0E{bl(ld256)}Lb0E{bl(wide4)}Li{thresh}E{bl(inst_loop)}Li{share}ELi{sstack}EE"
-    variants = {0: mangled(3, inst_loop=True), 2: mangled(2), 9: mangled(2, drain=False), 30: mangled(2, ld256=False), 60: mangled(2, wide4=True), 61: mangled(1, wide4=True),
-                70: mangled(3), 71: mangled(1), 80: mangled(2, thresh=8), 81: mangled(2, thresh=16), 82: mangled(2, thresh=24),
-                90: mangled(2, inst_loop=True), 91: mangled(3, inst_loop=True), 110: mangled(3, inst_loop=True, share=1), 122: mangled(3, inst_loop=True, sstack=16), 130: mangled(3, inst_loop=True, share=1, sstack=16)}
+    # the instantiation RDN_ORDERED_VARIANT selects (grids; ray lists take the sharing instantiation by default)
+    variants = {0: mangled(3, inst_loop=True), 2: mangled(2), 9: mangled(3, drain=False, inst_loop=True), 30: mangled(3, ld256=False, inst_loop=True),
+                60: mangled(2, wide4=True), 61: mangled(1, wide4=True), 100: mangled(3, inst_loop=True), 110: mangled(3, inst_loop=True, share=True)}
     variant = int(sys.argv[sys.argv.index("--variant") + 1]) if "--variant" in sys.argv else 0
     template_args = variants[variant]
     if variant:

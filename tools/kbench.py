@@ -105,7 +105,7 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 torch.cuda.synchronize()
 e0.record()
 for k in range(iters):
-    sysm.trace_closest_device(d_rays.data_ptr(), n, b2b_hits[k].data_ptr(), ray_flags=flags, grid_width=grid, stream=st)
+    sysm.trace_closest_device(d_rays.data_ptr(), n, b2b_hits[k].data_ptr(), ray_flags=flags, grid_width=grid, stream=st, overlap_previous=True)
 e1.record(); torch.cuda.synchronize()
 b2b_ms = e0.elapsed_time(e1) / iters
 b2b_ok = all(torch.equal(h, d_hits) for h in b2b_hits)
