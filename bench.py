@@ -13,10 +13,18 @@ For N > 1 the flattened BVH is built on rank 0, replicated with one NCCL broadca
 value   = whole-job Mrays/s with rays/hits resident in HBM, device-timed (CUDA events), max over ranks.  Successive steps
           trace N_FRAMES different frames (ray + hit buffers 4 x 133 MB, scene 171 MB: inputs far larger than the 126 MB
           L2, no artificial flush — the BVH staying L2-warm between frames is the steady state of a renderer);
-          config.value_l2_flushed is the same loop with a 256 MiB flush between steps.
-e2e     = same metric through the host-buffer C-ABI call (pinned host rays -> H2D -> traversal -> D2H hits).
-roofline= algorithmic bytes (64 + 48*V_node + 52*V_tri + 176*V_inst per ray, V counted by the oracle
-          under the reference traversal order) / ordered-kernel time, against the measured HBM copy peak.
+          details.value_l2_flushed is the same loop with a 256 MiB flush between steps, details.value_serialized the same
+          loop without tail overlap between launches.
+e2e     = same metric through the host-buffer C-ABI call (pinned host rays -> H2D -> traversal -> D2H hits); e2e_pageable =
+          the same call on plain pageable buffers (what a Rust Vec is), which the library page-locks and keeps registered.
+roofline= the kernel is bound by instruction issue at ~20 of 32 active lanes; the memory level that serves it is L2.  `frac` =
+          reference-defined algorithmic bytes (64 + 48*V_node + 52*V_tri + 176*V_inst per ray, V counted by
+          the oracle under the reference traversal order) / serialised kernel time / the L2 read peak measured in this run;
+          the bytes the kernel ACTUALLY moves (lts__t_bytes, dram__bytes of the committed ncu capture of the shipped
+          instantiation) are reported against the L2 and HBM peaks beside it.
+c5      = (every N) BASELINE configs[4], strong scaling: ONE 3840x2160 x 16 spp primary + 1 bounce frame cut into 64x32-pixel
+          tiles dealt round-robin to the ranks, device-resident from the camera to the hit records (--config c5 makes it the
+          headline of the line instead).
 """
 from __future__ import annotations
 
@@ -39,6 +47,33 @@ RAY_FLAGS = 0x10  # RAY_FLAG_CULL_BACK_FACING_TRIANGLES
 TMIN, TMAX = 0.01, 100.0
 N_FRAMES = 4  # distinct ray/hit buffers cycled by successive steps
 WORKLOAD = "1920x1080 primary rays vs 1,002,528-triangle generated torus mesh (BASELINE configs[1])"
+C5_W, C5_H, C5_SPP = 3840, 2160, 16
+C5_WORKLOAD = "3840x2160 x 16 spp primary + 1 cosine bounce rays vs the 1,002,528-triangle torus, ray tiles sharded across the GPUs, BVH replicated (BASELINE configs[4])"
+# the instantiation launch_trace_ordered selects for grid launches (rendiation_b200/csrc/traverse.cu, `plain`), as ncu prints it:
+# the committed capture whose numbers the roofline quotes must be of this kernel (tests/test_bench_contract.py holds the two together)
+SHIPPED_ORDERED_KERNEL = "k_trace_ordered_rounds<3, 8, 1, 0, 1, 0, 0, 1, 0>"
+
+
+def base_config(workload=WORKLOAD, rays=W * H):
+    """the workload description both arms print (identical keys and values: the driver compares them)"""
+    return {"workload": workload, "rays_per_gpu_per_step": int(rays), "triangles": int(SEG * SEG * 2), "ray_flags": RAY_FLAGS}
+
+
+def shipped_kernel_capture():
+    """(path, launch) of the newest committed ncu --set full summary of the shipped ordered kernel on configs[1], or (None, None)"""
+    import glob
+    import re
+    want = re.sub(r"[()\s]|int|bool", "", SHIPPED_ORDERED_KERNEL)
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_r*_k_trace_ordered_c2.json"))):
+        try:
+            launches = json.load(open(path)).get("launches", [])
+        except (OSError, ValueError):
+            continue
+        for x in launches:
+            if want in re.sub(r"[()\s]|int|bool", "", x.get("kernel", "")) and "dram_traffic_bytes" in x:
+                best = (path, x)  # (sorted by name: later rounds / sessions win)
+    return best if best else (None, None)
 
 
 def scene_inputs():
@@ -165,6 +200,8 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     osc = build_oracle_scene()
+    if args.config == "c5":
+        return run_reference_c5(args, osc, cores)
     rays = frame_rays(0)
     for _ in range(args.warmup):
         osc.trace(rays, ray_flags=RAY_FLAGS, n_threads=cores, want_counters=False)
@@ -177,23 +214,150 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": "closest-hit Mrays/s", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "rays_per_step": int(rays.shape[0]), "host_threads": cores},
+        "dtype": "f32", "data": "synthetic", "config": base_config(), "details": {"host_threads": cores},
         "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
 
 
-def run_ours(args):
+def c5_sample_rays(osc, cores, tile=512):
+    """a bounded sample of configs[4] for the CPU: the central 512 x 512 pixel tile of the 3840 x 2160 frame at one sample per pixel
+    (pixel centres) and the cosine bounce off its hits — (primary rays, bounce rays)"""
+    from rendiation_b200 import scenes as S
+    pos, idx, m = scene_inputs()
+    x0, y0 = (C5_W - tile) // 2, (C5_H - tile) // 2
+    full_row = np.arange(C5_W, dtype=np.float32)
+    aspect = np.float32(C5_W / C5_H)
+    i = np.arange(x0, x0 + tile, dtype=np.float32)[None, :].repeat(tile, 0).reshape(-1)
+    j = np.arange(y0, y0 + tile, dtype=np.float32)[:, None].repeat(tile, 1).reshape(-1)
+    f32 = np.float32
+    x = ((i + f32(0.5)) / f32(C5_W) * f32(2) - f32(1)) * aspect
+    y = f32(1) - (j + f32(0.5)) / f32(C5_H) * f32(2)
+    d = np.stack([x, y, np.full_like(x, -1)], -1).astype(np.float32)
+    d = d * (f32(1) / np.sqrt((d * d).sum(-1, dtype=np.float32)))[:, None]
+    rays = np.zeros(tile * tile, S.RAY_DTYPE)
+    rays["tmin"], rays["tmax"] = TMIN, TMAX
+    rays["dx"], rays["dy"], rays["dz"] = d[:, 0], d[:, 1], d[:, 2]
+    del full_row
+    ph = osc.trace(rays, ray_flags=RAY_FLAGS, n_threads=cores, want_counters=False)
+    hit = ph["instance_id"] != 0xFFFFFFFF
+    normals = np.zeros((rays.shape[0], 3), np.float32)
+    normals[hit] = S.geometric_normals(pos, idx, ph["primitive_id"][hit], m, d[hit])
+    bounce, _ = S.bounce_rays(rays, ph, normals)
+    return rays, bounce
+
+
+def run_reference_c5(args, osc, cores):
+    """--impl reference --config c5: the CPU traversal on a bounded sample of configs[4] per step (one 512 x 512 tile, primary + bounce)"""
+    rays, bounce = c5_sample_rays(osc, cores)
+    n = rays.shape[0] + bounce.shape[0]
+
+    def step():
+        osc.trace(rays, ray_flags=RAY_FLAGS, n_threads=cores, want_counters=False)
+        osc.trace(bounce, ray_flags=0, n_threads=cores, want_counters=False)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = n * args.steps / dt / 1e6
+    sample = (f"the central 512x512 tile at 1 spp + its bounce rays ({n} rays) per step, {args.steps} steps, {dt:.2f} s wall on {cores} threads")
+    print(json.dumps({
+        "impl": "reference", "metric": "closest-hit Mrays/s", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": base_config(C5_WORKLOAD, C5_W * C5_H * C5_SPP // max(args.gpus, 1)), "details": {"host_threads": cores},
+        "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+def measure_c5(sysm, world, rank, dev, steps, warmup=1, want_e2e=True):
+    """BASELINE configs[4] on the ranks of this job: one frame per step, strong scaling.  Device time = CUDA events around the K
+    frames on the launching stream, max over ranks; rays = primary + bounce of all ranks.  e2e adds, inside the timed region, the
+    device->host copy of both waves' hit records into pinned memory (the input of this workload is a camera: a few hundred bytes)."""
     import torch
     import torch.distributed as dist
 
-    from rendiation_b200 import api, scenes as S
+    from rendiation_b200 import multi_gpu
+    frame = multi_gpu.ShardedFrame(sysm, C5_W, C5_H, C5_SPP, world, rank, dev, tmin=TMIN, tmax=TMAX, primary_flags=RAY_FLAGS, bounce_flags=0)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce(x, op):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    for _ in range(max(warmup, 1)):
+        frame.enqueue(stream)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        frame.enqueue(stream)
+    e1.record()
+    barrier()
+    sysm.poll_errors(stream=stream)
+    ms = reduce(e0.elapsed_time(e1), dist.ReduceOp.MAX if world > 1 else None) / steps
+    ms_min = -reduce(-e0.elapsed_time(e1), dist.ReduceOp.MAX if world > 1 else None) / steps
+    n_bounce_local = frame.n_bounce()
+    n_primary = reduce(frame.n_primary, dist.ReduceOp.SUM if world > 1 else None)
+    n_bounce = reduce(n_bounce_local, dist.ReduceOp.SUM if world > 1 else None)
+    rays = n_primary + n_bounce
+    out = {"workload": C5_WORKLOAD, "scaling": "strong", "value": rays / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_frame": ms,
+           "ms_per_frame_fastest_rank": ms_min, "steps": steps, "primary_rays": int(n_primary), "bounce_rays": int(n_bounce),
+           "tiles": "%dx%d pixels, %d tiles dealt round-robin, one wave per rank (all tiles x %d spp)" % (frame.shard.tile, frame.shard.tile_h, len(frame.shard.tiles_all), C5_SPP),
+           "kernels_per_frame": 6 * len([w for w in frame.waves if w["n"]]),
+           "includes": "device ray generation, traversal, hit compaction, bounce generation, bounce traversal sized on the device: no host round trip"}
+    if want_e2e:
+        bytes_local = 0
+        pins = []
+        for w in frame.waves:
+            if w["n"]:
+                pins.append((torch.empty((w["n"], 32), dtype=torch.uint8).pin_memory(), torch.empty((w["n"], 32), dtype=torch.uint8).pin_memory(), w))
+        e2e_steps = max(1, min(steps, 2))
+
+        def e2e_frame():
+            nb = 0
+            frame.enqueue(stream)
+            for h1, h2, w in pins:
+                h1.copy_(w["hits"], non_blocking=True)
+                k = int(w["cnt"].item())  # (the result size is part of the result: this read is the frame's own synchronisation point)
+                h2[:k].copy_(w["bhits"][:k], non_blocking=True)
+                nb += 32 * (w["n"] + k)
+            torch.cuda.synchronize()
+            return nb
+
+        e2e_frame()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            bytes_local = e2e_frame()
+        dt = reduce(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
+        out["e2e"] = {"value": rays * e2e_steps / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 512, "d2h_bytes_per_step": int(bytes_local),
+                      "steps": e2e_steps, "note": "camera parameters in, both waves' hit records out to pinned host memory (bytes are this rank's)"}
+    del frame
+    torch.cuda.empty_cache()
+    return out
+
+
+def setup_job():
+    """one process per GPU: device, process group, the scene built on rank 0 and replicated with one NCCL broadcast"""
+    import torch
+    import torch.distributed as dist
+
+    from rendiation_b200 import api, multi_gpu, scenes as S
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product has no CPU fallback)")
-    from rendiation_b200 import multi_gpu
     numa_cpus = multi_gpu.bind_process_to_gpu_numa_node(local_rank) if world > 1 else 0  # pinned e2e buffers local to the GPU's socket
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -215,8 +379,52 @@ def run_ours(args):
         t_build = time.perf_counter() - t0
     t_repl_ms = 0.0
     if world > 1:  # the one collective of the path: BVH replication (NCCL broadcast over NVLink), then the other ranks adopt the blob
-        from rendiation_b200 import multi_gpu
         t_repl_ms = multi_gpu.replicate_scene(sysm, src=0, device=dev)
+    return world, rank, local_rank, dev, sysm, t_build, t_repl_ms, numa_cpus
+
+
+def run_c5(args):
+    """--config c5: BASELINE configs[4] is the line — one 3840x2160x16spp + bounce frame per step, tiles sharded over the ranks"""
+    import torch
+    import torch.distributed as dist
+
+    world, rank, local_rank, dev, sysm, t_build, t_repl_ms, _ = setup_job()
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
+    with ClockSampler(local_rank) as clocks:
+        c5 = measure_c5(sysm, world, rank, dev, steps=args.steps, warmup=max(args.warmup, 3))
+    if rank == 0:
+        import oracle  # noqa: F401  (checker / baseline only)
+        cores = len(os.sched_getaffinity(0)) or 1
+        osc = build_oracle_scene()
+        rays, bounce = c5_sample_rays(osc, cores)
+        t0 = time.perf_counter()
+        osc.trace(rays, ray_flags=RAY_FLAGS, n_threads=cores, want_counters=False)
+        osc.trace(bounce, ray_flags=0, n_threads=cores, want_counters=False)
+        t_cpu = time.perf_counter() - t0
+        n_cpu = rays.shape[0] + bounce.shape[0]
+        print(json.dumps({
+            "metric": "closest-hit Mrays/s", "value": c5["value"], "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": c5["ms_per_frame"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": base_config(C5_WORKLOAD, C5_W * C5_H * C5_SPP // world),
+            "details": {k: v for k, v in c5.items() if k not in ("e2e", "value", "unit")} | {"build_s": round(t_build, 3), "blob_broadcast_ms": t_repl_ms,
+                        "l2": "inputs larger than L2 (each rank streams %.1f GB of rays and hits per frame)" % (4 * 32 * C5_W * C5_H * C5_SPP / world / 1e9)},
+            "e2e": c5.get("e2e"), "gpu_launches": c5["kernels_per_frame"] * args.steps,
+            "roofline": None,
+            "cpu_baseline": {"value": n_cpu / t_cpu / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                             "sample": f"the central 512x512 tile at 1 spp + its bounce rays ({n_cpu} rays), {t_cpu:.2f} s wall on {cores} threads"},
+            "clocks": clocks.summary()}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from rendiation_b200 import api
+
+    world, rank, local_rank, dev, sysm, t_build, t_repl_ms, numa_cpus = setup_job()
     blob_bytes = sysm.blob()[1]
 
     # ---- rays: this rank's frames (tile shard of the job), resident in HBM; steps cycle through N_FRAMES buffers
@@ -336,12 +544,44 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = world * n * e2e_steps / float(t_e2e.item()) / 1e6
+    # the same call on host arrays that are NOT torch-pinned (plain numpy arrays — what a Rust Vec<Ray> is): first as they are
+    # (pageable: the driver stages the copies), then page-locked by their owner through rdn_rt_host_register, which is what the
+    # Rust wrapper does for buffers that live longer than a frame
+    p_rays = np.ascontiguousarray(rays_np).copy()
+    p_hits = np.zeros(n, api.HIT_DTYPE)
+
+    def step_pageable():
+        sysm.trace_closest_host_ptr(p_rays.ctypes.data, n, p_hits.ctypes.data, ray_flags=RAY_FLAGS, grid_width=W)
+
+    def timed_host_steps():
+        step_pageable()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_pageable()
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return world * n * e2e_steps / float(t.item()) / 1e6
+
+    e2e_unpinned_value = timed_host_steps()
+    t0 = time.perf_counter()
+    with api.HostRegistration(p_rays), api.HostRegistration(p_hits):
+        t_register = time.perf_counter() - t0
+        e2e_pageable_value = timed_host_steps()
+    same_pageable = p_hits.tobytes() == h_hits.numpy().tobytes()
     # device-resident and host-path results must be the same bits; every rank's timed loop must have matched its yardstick
     same = bool(torch.equal(h_hits.to(dev), d_ref[0]))
     ok_all = torch.tensor([1.0 if timed_loop_ok else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
     timed_loop_ok_all_ranks = bool(ok_all.item() > 0.5)
+
+    # ---- BASELINE configs[4] on the same ranks (strong scaling of one frame), after the headline loops
+    del d_hits, d_rays, flush
+    torch.cuda.empty_cache()
+    c5 = measure_c5(sysm, world, rank, dev, steps=args.c5_steps) if args.c5_steps > 0 else None
 
     if rank == 0:
         # ---- roofline + cpu baseline + parity spot check (oracle = checker / baseline only)
@@ -376,54 +616,66 @@ def run_ours(args):
         achieved = bytes_per_ray * n / (kernel_ms * 1e-3) / 1e9
         compulsory = (64.0 * n + blob_bytes) / (kernel_ms * 1e-3) / 1e9
         l2_peak = sysm.measure_l2_read_gbs(64 << 20, 50)  # resident-set read microbenchmark, this box, this run
-        traffic, traffic_src = None, None
-        prof = os.path.join(ROOT, "profiles", "ncu_r1f_k_trace_ordered_c2.json")
-        if os.path.exists(prof):  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-            pl = json.load(open(prof))["launches"]
-            traffic = float(np.mean([x["dram_traffic_bytes"] for x in pl]))
-            traffic_src = "profiles/ncu_r1f_k_trace_ordered_c2.json (ncu --set full, cold-cache replay of one launch)"
+        cap_path, cap = shipped_kernel_capture()
+        traffic = traffic_l2 = None
+        traffic_src = "no committed ncu capture of " + SHIPPED_ORDERED_KERNEL
+        if cap:  # per launch, from the committed ncu --set full capture of the shipped instantiation (cold-cache replay of one launch)
+            traffic, traffic_l2 = float(cap["dram_traffic_bytes"]), float(cap["l2_traffic_bytes"])
+            traffic_src = os.path.relpath(cap_path, ROOT) + " (" + cap["kernel"].split("::")[-1].split("(")[0] + ")"
+        per_s = 1.0 / (kernel_ms * 1e-3) / 1e9
         out = {
             "metric": "closest-hit Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rays_per_gpu_per_step": n, "triangles": int(SEG * SEG * 2), "ray_flags": RAY_FLAGS,
-                       "l2": "inputs larger than L2: steps cycle %d frames of rays+hits (%.0f MB) over a %.0f MB scene, no flush; "
-                             "value_l2_flushed = same loop with a 256 MiB write between steps" %
-                             (N_FRAMES, N_FRAMES * 64 * n / 1e6, blob_bytes / 1e6),
-                       "value_l2_flushed": value_flushed, "ms_per_step_l2_flushed": ms_per_step_flushed,
-                       "launch_overlap": "the K steps are issued back to back on one stream; each ordered launch lets the next one start "
-                                         "filling SM slots while its own last long rays finish (programmatic dependent launch, distinct "
-                                         "ray/hit buffers per step).  value_serialized = the same K steps with every kernel bracketed by "
-                                         "CUDA events, which serialises them (RDN_PDL=0 gives the same)",
-                       "value_serialized": value_serial, "ms_per_step_serialized": ms_per_step_serial,
-                       "parallelism": f"rays sharded by frame x{world}, BVH replicated ({blob_bytes / 1e6:.0f} MB blob, "
-                                      f"NCCL broadcast {t_repl_ms:.2f} ms)", "build_s": round(t_build, 3),
-                       "host_affinity": (f"each rank bound to the {numa_cpus} CPUs NVML reports local to its GPU" if numa_cpus else "unchanged")},
+            "config": base_config(),
+            "details": {"l2": "inputs larger than L2: steps cycle %d frames of rays+hits (%.0f MB) over a %.0f MB scene, no flush; "
+                              "value_l2_flushed = same loop with a 256 MiB write between steps" %
+                              (N_FRAMES, N_FRAMES * 64 * n / 1e6, blob_bytes / 1e6),
+                        "value_l2_flushed": value_flushed, "ms_per_step_l2_flushed": ms_per_step_flushed,
+                        "launch_overlap": "the K steps are issued back to back on one stream with RDN_TRACE_OVERLAP_PREVIOUS: each ordered "
+                                          "launch lets the next one start filling SM slots while its own last long rays finish (programmatic "
+                                          "dependent launch, distinct ray/hit buffers per step).  value_serialized = the same K steps with every "
+                                          "kernel bracketed by CUDA events, which serialises them (RDN_PDL=0 gives the same)",
+                        "value_serialized": value_serial, "ms_per_step_serialized": ms_per_step_serial,
+                        "parallelism": f"rays sharded by frame x{world}, BVH replicated ({blob_bytes / 1e6:.0f} MB blob, "
+                                       f"NCCL broadcast {t_repl_ms:.2f} ms)", "build_s": round(t_build, 3), "build_stats": sysm.build_stats(),
+                        "host_affinity": (f"each rank bound to the {numa_cpus} CPUs NVML reports local to its GPU" if numa_cpus else "unchanged")},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 32 * n,
                     "steps": e2e_steps, "matches_device_path": same},
+            "e2e_pageable": {"value": e2e_pageable_value, "unit": "Mrays/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 32 * n,
+                             "steps": e2e_steps, "matches_device_path": same_pageable, "register_ms": t_register * 1e3,
+                             "value_unregistered": e2e_unpinned_value,
+                             "note": "host arrays owned by the caller (numpy, not torch-pinned) and page-locked by it once with "
+                                     "rdn_rt_host_register (register_ms, outside the timed steps) — what the Rust wrapper does for a long-lived "
+                                     "Vec; value_unregistered = the same arrays left pageable (the driver stages the copies)"},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "traffic_source": traffic_src,
-                         "peak_source": peak_src, "algorithmic_bytes_per_ray": bytes_per_ray,
-                         "algorithmic_bytes_per_launch": bytes_per_ray * n, "visits_per_ray": visits,
-                         "bytes_model_sample_rays": n_sample, "compulsory_hbm_gbs": compulsory,
-                         "kernel": "k_trace_ordered_rounds", "kernel_ms_avg": kernel_ms, "kernel_launches_timed": kernel_times["ordered_launches"],
-                         "kernel_share_of_step": kernel_ms / ms_per_step_serial, "tie_kernel_ms_avg": tie_ms,
-                         "achieved_with_launch_overlap": bytes_per_ray * n / (ms_per_step * 1e-3) / 1e9,
-                         "l2": {"peak": l2_peak, "unit": "GB/s", "frac": achieved / l2_peak,
-                                "frac_with_launch_overlap": bytes_per_ray * n / (ms_per_step * 1e-3) / 1e9 / l2_peak,
-                                "peak_source": "measured in this run: uint4 reads bypassing L1 over a 64 MiB L2-resident buffer, 50 sweeps "
-                                               "(rdn_rt_measure_l2_read_gbs)"},
-                         "tie_rays_per_step": tie_rays,
-                         "note": "algorithmic bytes are defined on the REFERENCE's traversal (48 B threaded nodes in pre-order, 52 B "
-                                 "triangle chains); the ordered kernel visits fewer nodes and the 171 MB scene is mostly L2-resident, "
-                                 "so frac can exceed 1 of the HBM copy peak; traffic = DRAM bytes actually moved per launch"},
+            "roofline": {"bound": "l2", "binding": "instruction issue at ~20 of 32 active lanes (see profiles/ncu_*: issue slots ~50 % busy over the "
+                                                   "launch incl. its tail, DRAM < 10 % and L2 < 15 % of peak); L2 is the memory level that serves the kernel",
+                         "achieved": achieved, "peak": l2_peak, "unit": "GB/s", "frac": achieved / l2_peak,
+                         "peak_source": "measured in this run: uint4 reads bypassing L1 over a 64 MiB L2-resident buffer, 50 sweeps "
+                                        "(rdn_rt_measure_l2_read_gbs); MEASURED_PEAKS.json holds no L2 figure",
+                         "frac_with_launch_overlap": bytes_per_ray * n / (ms_per_step * 1e-3) / 1e9 / l2_peak,
+                         "traffic": traffic, "traffic_l2": traffic_l2, "traffic_source": traffic_src,
+                         "actual": None if traffic is None else {
+                             "l2_gbs": traffic_l2 * per_s, "l2_frac": traffic_l2 * per_s / l2_peak,
+                             "hbm_gbs": traffic * per_s, "hbm_frac": traffic * per_s / peak,
+                             "note": "bytes the kernel actually moves per launch (ncu lts__t_sectors x 32, dram__bytes_read + _write) over the "
+                                     "serialised kernel time measured here"},
+                         "hbm": {"peak": peak, "peak_source": peak_src, "frac_of_reference_bytes": achieved / peak,
+                                 "compulsory_gbs": compulsory},
+                         "algorithmic_bytes_per_ray": bytes_per_ray, "algorithmic_bytes_per_launch": bytes_per_ray * n,
+                         "visits_per_ray": visits, "bytes_model_sample_rays": n_sample,
+                         "kernel": SHIPPED_ORDERED_KERNEL, "kernel_ms_avg": kernel_ms, "kernel_launches_timed": kernel_times["ordered_launches"],
+                         "kernel_share_of_step": kernel_ms / ms_per_step_serial, "tie_kernel_ms_avg": tie_ms, "tie_rays_per_step": tie_rays,
+                         "note": "algorithmic bytes are defined on the REFERENCE's traversal (48 B threaded nodes in pre-order, 52 B triangle "
+                                 "chains); the ordered kernel visits about half the nodes through 64 B two-box nodes and most of its fetches "
+                                 "hit L1 / L2, so the reference-defined figure is several times what moves"},
             "cpu_baseline": {"value": cpu_rays / t_cpu / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
                              "sample": f"{cpu_reps} x {N_FRAMES} full frames ({cpu_rays} rays), {t_cpu:.2f} s wall on {cores} threads "
                                        f"= {t_cpu * cores:.1f} core-seconds",
                              "single_thread_mrays": one.shape[0] / t_cpu1 / 1e6, "parity_bit_identical_full_frames": parity_bits,
                              "timed_loop_results_identical_to_synchronised_launches_all_ranks": timed_loop_ok_all_ranks},
-            "clocks": clocks.summary(), "wall_s_timed_region": t_wall,
+            "clocks": clocks.summary(), "wall_s_timed_region": t_wall, "c5": c5,
         }
         print(json.dumps(out))
     if world > 1:
@@ -437,9 +689,14 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=["c2", "c5"], help="c2: BASELINE configs[1] per GPU (the headline, weak scaling; "
+                    "configs[4] rides along as the line's `c5` object).  c5: BASELINE configs[4] is the line (strong scaling of one frame)")
+    ap.add_argument("--c5-steps", type=int, default=3, help="frames of configs[4] timed after the headline loops (0: skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "c5":
+        run_c5(args)
     else:
         run_ours(args)
 

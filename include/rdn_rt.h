@@ -163,6 +163,15 @@ int rdn_rt_commit(rdn_rt_scene *scene);
 /* host buffers: H2D, traversal, D2H pipelined inside the call; sharded over the scene's devices */
 int rdn_rt_trace_closest(rdn_rt_scene *scene, const rdn_launch *launch, const rdn_ray *rays, uint64_t n,
                          rdn_hit *out_hits);
+/* Page-locked host memory for the call above (and every other host-buffer entry point).  Copies from pageable memory are staged by
+ * the driver and run at about a third of the PCIe rate without overlapping the kernels; the call takes any host pointer, but ray
+ * and hit buffers that live for more than a frame should be page-locked: allocated with rdn_rt_host_alloc (freed with
+ * rdn_rt_host_free), or — memory the caller owns, e.g. a Vec — registered with rdn_rt_host_register for as long as it lives and
+ * unregistered before it is freed.  The library never registers caller memory by itself: it cannot see the free. */
+int rdn_rt_host_alloc(uint64_t bytes, void **out);
+void rdn_rt_host_free(void *ptr);
+int rdn_rt_host_register(void *ptr, uint64_t bytes);
+int rdn_rt_host_unregister(void *ptr);
 /* device-resident buffers on device `device_index` (index into the scene's device list); asynchronous on
  * `cuda_stream` (a cudaStream_t, 0 = default stream) unless `stats` is non-NULL (then it synchronises).
  * d_rays and d_hits must be 32-byte aligned (any cudaMalloc pointer plus a whole number of records is). */

@@ -155,7 +155,8 @@ class _MeshView(C.Structure):
 EXPORTED_SYMBOLS = [
     "rdn_rt_scene_create", "rdn_rt_scene_destroy", "rdn_rt_blas_create", "rdn_rt_blas_destroy", "rdn_rt_tlas_create",
     "rdn_rt_tlas_destroy", "rdn_rt_bind_tlas", "rdn_rt_bind_tlas_max_len", "rdn_rt_commit", "rdn_rt_trace_closest",
-    "rdn_rt_trace_closest_device", "rdn_rt_trace_closest_device_n", "rdn_rt_poll_errors", "rdn_rt_trace_counted", "rdn_rt_kernel_timing_begin", "rdn_rt_kernel_timing_end",
+    "rdn_rt_trace_closest_device", "rdn_rt_trace_closest_device_n", "rdn_rt_poll_errors", "rdn_rt_host_alloc", "rdn_rt_host_free",
+    "rdn_rt_host_register", "rdn_rt_host_unregister", "rdn_rt_trace_counted", "rdn_rt_kernel_timing_begin", "rdn_rt_kernel_timing_end",
     "rdn_rt_gen_pinhole_rays_device", "rdn_rt_gen_pinhole_rays_batch_device", "rdn_rt_gen_camera_rays_device", "rdn_rt_gen_bounce_rays_device", "rdn_rt_ao_accumulate_device", "rdn_rt_compact_u32", "rdn_rt_compact_u32_device",
     "rdn_rt_scene_blob", "rdn_rt_scene_adopt_blob", "rdn_rt_scene_array", "rdn_rt_scene_build_stats", "rdn_rt_measure_l2_read_gbs", "rdn_pick_mesh_create", "rdn_pick_mesh_destroy",
     "rdn_pick_mesh_primitive_count", "rdn_pick_mesh_nearest", "rdn_pick_mesh_all", "rdn_bvh_build", "rdn_bvh_build_device", "rdn_bvh_built_on_device", "rdn_bvh_destroy", "rdn_bvh_nodes",
@@ -194,6 +195,11 @@ def lib() -> C.CDLL:
     L.rdn_rt_trace_closest.argtypes = [vp, P(_Launch), vp, u64, vp]
     L.rdn_rt_trace_closest_device.argtypes = [vp, i32, P(_Launch), vp, u64, vp, vp, i32, P(_TraceStats)]
     L.rdn_rt_poll_errors.argtypes = [vp, i32, vp, P(u32)]
+    L.rdn_rt_host_alloc.argtypes = [u64, P(vp)]
+    L.rdn_rt_host_free.argtypes = [vp]
+    L.rdn_rt_host_free.restype = None
+    L.rdn_rt_host_register.argtypes = [vp, u64]
+    L.rdn_rt_host_unregister.argtypes = [vp]
     L.rdn_rt_trace_closest_device_n.argtypes = [vp, i32, P(_Launch), vp, vp, u64, vp, vp, i32]
     L.rdn_rt_trace_counted.argtypes = [vp, P(_Launch), vp, u64, vp, P(_Counters)]
     L.rdn_rt_kernel_timing_begin.argtypes = [vp, i32]
@@ -273,6 +279,30 @@ class BottomLevelAccelerationStructureBuildSource:
     indices: np.ndarray | None = None
     flags: int = GEOMETRY_FLAG_OPAQUE
     aabbs: bool = False
+
+
+class HostRegistration:
+    """Page-locks a numpy array for as long as the object lives (rdn_rt_host_register / _unregister): what a Rust caller does with a
+    long-lived Vec<Ray> so that the host-buffer trace runs at PCIe speed."""
+
+    def __init__(self, array: np.ndarray):
+        self.array = array  # keeps the memory alive while it is registered
+        self._ptr = array.ctypes.data
+        _check(lib().rdn_rt_host_register(C.c_void_p(self._ptr), array.nbytes))
+
+    def close(self):
+        if self._ptr:
+            lib().rdn_rt_host_unregister(C.c_void_p(self._ptr))
+            self._ptr = 0
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        self.close()
 
 
 class NaiveSahBVHSystem:

@@ -670,6 +670,31 @@ int rdn_rt_trace_closest(rdn_rt_scene *s, const rdn_launch *launch, const rdn_ra
   return host_rc;
 }
 
+// Page-locked host memory for the host-buffer entry points.  Transfers from pageable memory (a plain Vec, a numpy array) are staged by
+// the driver: they neither overlap with the kernels nor reach PCIe speed.  The library does NOT page-lock caller memory behind the
+// caller's back: a registration outlives a free() it cannot see, and the stale entry then fails every later copy that touches a new
+// allocation at the same addresses (tried: a cache keyed by pointer and size broke an unrelated cudaMemcpy two tests later).  The
+// owner of the memory decides: allocate it here, or register what it owns for as long as it lives.
+int rdn_rt_host_alloc(uint64_t bytes, void **out) {
+  if (!out) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_host_alloc: null argument");
+  *out = nullptr;
+  RDN_CUDA(cudaHostAlloc(out, std::max<uint64_t>(bytes, 1), cudaHostAllocPortable));
+  return RDN_OK;
+}
+void rdn_rt_host_free(void *ptr) {
+  if (ptr) cudaFreeHost(ptr);
+}
+int rdn_rt_host_register(void *ptr, uint64_t bytes) {
+  if (!ptr || !bytes) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_host_register: null argument");
+  RDN_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+  return RDN_OK;
+}
+int rdn_rt_host_unregister(void *ptr) {
+  if (!ptr) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_host_unregister: null argument");
+  RDN_CUDA(cudaHostUnregister(ptr));
+  return RDN_OK;
+}
+
 int rdn_rt_poll_errors(rdn_rt_scene *s, int device_index, void *cuda_stream, uint32_t *out_flags) {
   if (!s) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_poll_errors: null scene");
   if (device_index < 0 || device_index >= static_cast<int>(s->devices.size())) return fail(RDN_ERR_INVALID_ARGUMENT, "bad device_index (host-only scene?)");

@@ -30,6 +30,8 @@ cudaError_t cudaFree(void *p) { std::free(p); return cudaSuccess; }
 cudaError_t cudaMallocHost(void **p, size_t n) { return cudaMalloc(p, n); }
 cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { return cudaMalloc(p, n); }
 cudaError_t cudaFreeHost(void *p) { return cudaFree(p); }
+cudaError_t cudaHostRegister(void *, size_t, unsigned) { return cudaSuccess; }  // (everything is host memory here)
+cudaError_t cudaHostUnregister(void *) { return cudaSuccess; }
 cudaError_t cudaMallocAsync(void **p, size_t n, cudaStream_t) { return cudaMalloc(p, n); }
 cudaError_t cudaFreeAsync(void *p, cudaStream_t) { return cudaFree(p); }
 cudaError_t cudaMemcpy(void *dst, const void *src, size_t n, cudaMemcpyKind) { if (n) std::memmove(dst, src, n); return cudaSuccess; }

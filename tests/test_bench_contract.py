@@ -32,3 +32,34 @@ def test_our_arm_needs_a_cuda_device():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
                        timeout=300, cwd=ROOT)
     assert r.returncode != 0 and "no CPU fallback" in (r.stdout + r.stderr)
+
+
+def test_both_arms_describe_the_workload_with_the_same_config():
+    """the driver compares the `config` objects of the two arms: they come from one function"""
+    sys.path.insert(0, ROOT)
+    import bench
+    c = bench.base_config()
+    assert set(c) == {"workload", "rays_per_gpu_per_step", "triangles", "ray_flags"} and c["rays_per_gpu_per_step"] == 1920 * 1080
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count('"config": base_config()') == 2  # reference arm and our arm, configs[1]
+
+
+def test_the_kernel_named_in_the_roofline_is_the_one_the_launcher_selects_for_grids():
+    """bench.py quotes ncu numbers of SHIPPED_ORDERED_KERNEL; it must be the instantiation launch_trace_ordered picks for grid launches"""
+    import re
+    sys.path.insert(0, ROOT)
+    import bench
+    src = open(os.path.join(ROOT, "rendiation_b200", "csrc", "traverse.cu")).read()
+    m = re.search(r"const KernelFn plain = k_trace_ordered_rounds<([^>]*)>;", src)
+    assert m, "launcher changed: update this test and bench.SHIPPED_ORDERED_KERNEL"
+    args = [a.strip() for a in m.group(1).split(",")]
+    as_ncu = ", ".join({"true": "1", "false": "0"}.get(a, a) for a in args)
+    assert bench.SHIPPED_ORDERED_KERNEL == f"k_trace_ordered_rounds<{as_ncu}>", (bench.SHIPPED_ORDERED_KERNEL, as_ncu)
+
+
+def test_reference_arm_of_config_5_runs_a_bounded_sample():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "c5", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.strip()][-1])
+    assert d["impl"] == "reference" and "configs[4]" in d["config"]["workload"] and d["scaling"] == "strong" and d["value"] > 0

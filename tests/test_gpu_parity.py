@@ -465,3 +465,28 @@ def test_back_to_back_launches_overlap_without_losing_rays():
     assert all(burst([s0, s1], 16))                               # two streams alternating: ordered through the library's event
     assert all(burst([s0], 18, small_every=5, reforder_every=7))  # partial grids and the other kernel in between
     assert all(burst([s0], 12, same_buffer=True))                 # aliased hit buffers: overlap refused by the library
+
+
+@pytest.mark.gpu
+def test_host_buffers_page_locked_by_their_owner():
+    """rdn_rt_host_register / rdn_rt_host_alloc: the host-buffer trace on memory the caller page-locked (a registered numpy array,
+    a library-allocated buffer) returns the records of the plain pageable call; registrations end with their owner."""
+    import ctypes as C
+    sp, _ = helpers.torus_scene(96)
+    rays = S.pinhole_rays(512, 384, 0.01, 100.0)
+    want = sp.p.trace_closest_batch(rays, ray_flags=helpers.CULL_BACK, grid_width=512)
+    hits = np.zeros(rays.shape[0], api.HIT_DTYPE)
+    with api.HostRegistration(rays), api.HostRegistration(hits):
+        sp.p.trace_closest_host_ptr(rays.ctypes.data, rays.shape[0], hits.ctypes.data, ray_flags=helpers.CULL_BACK, grid_width=512)
+    assert hits.tobytes() == want.tobytes()
+    L = api.lib()
+    p_rays, p_hits = C.c_void_p(), C.c_void_p()
+    assert L.rdn_rt_host_alloc(rays.nbytes, C.byref(p_rays)) == 0 and L.rdn_rt_host_alloc(hits.nbytes, C.byref(p_hits)) == 0
+    C.memmove(p_rays, rays.ctypes.data, rays.nbytes)
+    sp.p.trace_closest_host_ptr(p_rays.value, rays.shape[0], p_hits.value, ray_flags=helpers.CULL_BACK, grid_width=512)
+    assert C.string_at(p_hits, hits.nbytes) == want.tobytes()
+    L.rdn_rt_host_free(p_rays); L.rdn_rt_host_free(p_hits)
+    # the arrays are ordinary memory again: a fresh allocation may land on the same addresses and must still copy
+    del rays, hits
+    again = sp.p.trace_closest_batch(S.pinhole_rays(512, 384, 0.01, 100.0), ray_flags=helpers.CULL_BACK, grid_width=512)
+    assert again.tobytes() == want.tobytes()
