@@ -319,7 +319,7 @@ def measure_c5(sysm, world, rank, dev, steps, warmup=1, want_e2e=True):
         pins = []
         for w in frame.waves:
             if w["n"]:
-                pins.append((torch.empty((w["n"], 32), dtype=torch.uint8).pin_memory(), torch.empty((w["n"], 32), dtype=torch.uint8).pin_memory(), w))
+                pins.append((torch.empty((w["n"], 32), dtype=torch.uint8, pin_memory=True), torch.empty((w["n"], 32), dtype=torch.uint8, pin_memory=True), w))
         e2e_steps = max(1, min(steps, 2))
 
         def e2e_frame():
