@@ -22,8 +22,14 @@ namespace rdn {
 namespace {
 
 constexpr uint32_t FULL_MASK = 0xFFFFFFFFu;
-constexpr int CB = 256;        // threads per CTA
-constexpr int ITEMS = 8;       // consecutive items per thread
+#ifndef RDN_COMPACT_CB
+#define RDN_COMPACT_CB 256
+#endif
+#ifndef RDN_COMPACT_MINB
+#define RDN_COMPACT_MINB 1
+#endif
+constexpr int CB = RDN_COMPACT_CB;        // threads per CTA
+constexpr int ITEMS = 16;      // consecutive items per thread: 64 B of values + 16 B of flags per thread in flight before the look-back
 constexpr int TILE = CB * ITEMS;
 constexpr unsigned long long ST_AGGREGATE = 1ull << 62, ST_PREFIX = 2ull << 62, ST_FLAG_MASK = 3ull << 62;
 
@@ -35,32 +41,49 @@ __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long l
 }
 
 // status[0] = dynamic tile counter, status[1 + tile] = (flag << 62) | value
-template <bool VEC_KEEP>
-__global__ void __launch_bounds__(CB) k_compact_u32(const uint32_t *__restrict__ in, const uint8_t *__restrict__ keep, uint64_t n,
+// One pass.  Per tile of 4096 elements: (1) every thread loads its 16 flags and 16 values — all loads of the tile are in flight
+// before anything waits; (2) warp shuffle scan + block scan of the kept counts; (3) the kept values are packed into shared memory
+// in order (local offsets only), which overlaps with (4) warp 0's decoupled look-back for the tile's global offset; (5) the tile's
+// kept values leave shared memory as one contiguous, coalesced run.  FAST: 16-byte aligned inputs (vector loads).
+template <bool FAST>
+__global__ void __launch_bounds__(CB, RDN_COMPACT_MINB) k_compact_u32(const uint32_t *__restrict__ in, const uint8_t *__restrict__ keep, uint64_t n,
                                                     uint32_t *__restrict__ out, uint64_t *__restrict__ out_n,
                                                     unsigned long long *__restrict__ status, uint64_t n_tiles) {
   __shared__ unsigned long long s_tile, s_prefix;
   __shared__ uint32_t s_warp_total[CB / 32];
+  __shared__ uint32_t s_vals[TILE];
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
+#ifdef RDN_COMPACT_STATIC_TILES
+  const uint64_t tile = blockIdx.x;
+#else
   if (tid == 0) s_tile = atomicAdd(status, 1ull);  // tiles are claimed in launch order: look-back never waits on an unscheduled CTA
   __syncthreads();
   const uint64_t tile = s_tile;
+#endif
   const uint64_t idx0 = tile * TILE + static_cast<uint64_t>(tid) * ITEMS;
 
-  // ---- 8 keep flags -> bit mask
+  // ---- 16 keep flags -> bit mask, 16 values -> registers
   uint32_t mask = 0;
-  if (VEC_KEEP && idx0 + ITEMS <= n) {
-    const uint2 k8 = __ldg(reinterpret_cast<const uint2 *>(keep + idx0));
+  uint32_t vals[ITEMS];
+  if (FAST && idx0 + ITEMS <= n) {
+    const uint4 k16 = __ldg(reinterpret_cast<const uint4 *>(keep + idx0));
+    const uint4 *vp = reinterpret_cast<const uint4 *>(in + idx0);
+    const uint4 v0 = __ldg(vp), v1 = __ldg(vp + 1), v2 = __ldg(vp + 2), v3 = __ldg(vp + 3);
+    const uint32_t kw[4] = {k16.x, k16.y, k16.z, k16.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      mask |= (((k8.x >> (8 * j)) & 0xFFu) != 0 ? 1u : 0u) << j;
-      mask |= (((k8.y >> (8 * j)) & 0xFFu) != 0 ? 1u : 0u) << (4 + j);
-    }
+    for (int w = 0; w < 4; ++w)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mask |= (((kw[w] >> (8 * j)) & 0xFFu) != 0 ? 1u : 0u) << (4 * w + j);
+    vals[0] = v0.x; vals[1] = v0.y; vals[2] = v0.z; vals[3] = v0.w; vals[4] = v1.x; vals[5] = v1.y; vals[6] = v1.z; vals[7] = v1.w;
+    vals[8] = v2.x; vals[9] = v2.y; vals[10] = v2.z; vals[11] = v2.w; vals[12] = v3.x; vals[13] = v3.y; vals[14] = v3.z; vals[15] = v3.w;
   } else {
 #pragma unroll
-    for (int j = 0; j < ITEMS; ++j)
-      if (idx0 + j < n && keep[idx0 + j] != 0) mask |= 1u << j;
+    for (int j = 0; j < ITEMS; ++j) {
+      const bool inside = idx0 + j < n;
+      vals[j] = inside ? in[idx0 + j] : 0u;
+      if (inside && keep[idx0 + j] != 0) mask |= 1u << j;
+    }
   }
   const uint32_t count = __popc(mask);
 
@@ -79,6 +102,14 @@ __global__ void __launch_bounds__(CB) k_compact_u32(const uint32_t *__restrict__
     const uint32_t t = s_warp_total[w];
     if (w < static_cast<int>(warp)) warp_offset += t;
     block_total += t;
+  }
+
+  // ---- the tile's kept values, packed in order (block-local offsets; overlaps with the look-back below for warps 1..7)
+  {
+    uint32_t local = warp_offset + (incl - count);
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j)
+      if (mask & (1u << j)) s_vals[local++] = vals[j];
   }
 
   // ---- decoupled look-back by warp 0: 32 predecessors per probe
@@ -113,22 +144,9 @@ __global__ void __launch_bounds__(CB) k_compact_u32(const uint32_t *__restrict__
   }
   __syncthreads();
 
-  // ---- scatter (order preserving)
-  uint64_t dst = s_prefix + warp_offset + (incl - count);
-  if (mask) {
-    if (idx0 + ITEMS <= n && (reinterpret_cast<uintptr_t>(in + idx0) & 15u) == 0) {
-      const uint4 a = __ldg(reinterpret_cast<const uint4 *>(in + idx0));
-      const uint4 b = __ldg(reinterpret_cast<const uint4 *>(in + idx0) + 1);
-      const uint32_t vals[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int j = 0; j < ITEMS; ++j)
-        if (mask & (1u << j)) out[dst++] = vals[j];
-    } else {
-#pragma unroll
-      for (int j = 0; j < ITEMS; ++j)
-        if (mask & (1u << j)) out[dst++] = in[idx0 + j];
-    }
-  }
+  // ---- one contiguous run per tile (order preserving)
+  const uint64_t base = s_prefix;
+  for (uint32_t i = tid; i < block_total; i += CB) out[base + i] = s_vals[i];
 }
 
 __global__ void k_zero_tail_u32(uint32_t *__restrict__ out, const uint64_t *__restrict__ out_n, uint64_t n) {
@@ -287,7 +305,7 @@ void launch_compact_u32(const uint32_t *d_in, const uint8_t *d_keep, uint64_t n,
     cudaMemsetAsync(d_out_n, 0, sizeof(uint64_t), stream);
     return;
   }
-  const bool vec_keep = (reinterpret_cast<uintptr_t>(d_keep) & 7u) == 0;
+  const bool vec_keep = ((reinterpret_cast<uintptr_t>(d_keep) | reinterpret_cast<uintptr_t>(d_in)) & 15u) == 0;
   if (vec_keep)
     k_compact_u32<true><<<static_cast<unsigned>(n_tiles), CB, 0, stream>>>(d_in, d_keep, n, d_out, d_out_n, d_status, n_tiles);
   else

@@ -1157,9 +1157,9 @@ void launch_resolve_ties(const SceneDev &scene, const rdn_launch &launch, const 
   k_resolve_ties<<<static_cast<unsigned>(sm_count) * 16u, 128, 0, stream>>>(scene, launch, d_rays, d_hits, scratch);
 }
 
-static int ordered_variant() {
-  static const int variant = []() { const char *e = getenv("RDN_ORDERED_VARIANT"); return e ? atoi(e) : 0; }();
-  return variant;
+static int ordered_variant() {  // (read at every launch: the parity tests walk the variants inside one process)
+  const char *e = getenv("RDN_ORDERED_VARIANT");
+  return e ? atoi(e) : 0;
 }
 int ordered_tie_mode() { return ordered_variant() == 9 ? 0 : 3; }
 
@@ -1190,8 +1190,8 @@ cudaError_t launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch
   P.irregular_count = tlas.irregular_count == IRREGULAR_ROUTE_ALL ? 0u : tlas.irregular_count;  // (the caller routes those elsewhere)
   P.wait_epoch = wait_epoch;
   {  // (RDN_SHARE=busy,min: experimentation knob)
-    static const struct ShareKnobs { int busy = 4, min = 1; ShareKnobs() { if (const char *e = getenv("RDN_SHARE")) sscanf(e, "%d,%d", &busy, &min); } } knobs;
-    P.share_busy = knobs.busy; P.share_min = knobs.min;
+    P.share_busy = 4; P.share_min = 1;
+    if (const char *e = getenv("RDN_SHARE")) sscanf(e, "%d,%d", &P.share_busy, &P.share_min);
   }
 
   // RDN_ORDERED_VARIANT: experimentation knob

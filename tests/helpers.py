@@ -16,6 +16,7 @@ class ScenePair:
         self.o = oracle.Scene()
         self.p = api.NaiveSahBVHSystem(devices=devices) if product else None
         self.blas_sources = []
+        self.tlas_sources = []
 
     def blas(self, geometries):
         """geometries: list of (positions, indices|None, flags[, is_aabb])"""
@@ -28,6 +29,7 @@ class ScenePair:
         return ho
 
     def tlas(self, instances):
+        self.tlas_sources.append(instances)
         ho = self.o.create_tlas(instances)
         if self.p is not None:
             hp = self.p.create_top_level_acceleration_structure(instances)

@@ -490,3 +490,44 @@ def test_host_buffers_page_locked_by_their_owner():
     del rays, hits
     again = sp.p.trace_closest_batch(S.pinhole_rays(512, 384, 0.01, 100.0), ray_flags=helpers.CULL_BACK, grid_width=512)
     assert again.tobytes() == want.tobytes()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", [0, 2, 9, 30, 40, 60, 61, 100, 110])
+def test_every_instantiation_of_the_ordered_kernel_is_bit_identical(variant, monkeypatch):
+    """Every instantiation RDN_ORDERED_VARIANT can select — the shipped ones (0: grids plain, ray lists sharing work between lanes;
+    100 / 110 force either for both launch kinds) and the experiments kept for A/B runs (2 the round-1 kernel, 9 the separate tie
+    kernel, 30 128-bit loads, 40 the top of the trees staged in shared memory by TMA, 60 / 61 the four-box nodes) — gives the
+    oracle's records on a grid launch, on the incoherent bounce list off its hits, and on an instanced scene with several
+    instances per TLAS leaf.  (The variant is read at every launch; the flattener reads it for the four-box view.)"""
+    if variant == 40 and os.environ.get("RDN_SIMT_EMU") == "1":
+        pytest.skip("the TMA staging has no CPU stand-in")
+    monkeypatch.setenv("RDN_ORDERED_VARIANT", str(variant))
+    nt = os.cpu_count() or 4
+    sp, (pos, idx, m) = helpers.torus_scene(192)
+    W, H = 640, 400
+    rays = S.pinhole_rays(W, H, 0.01, 100.0, aspect_correct=True)
+    want = sp.o.trace(rays, ray_flags=0x10, n_threads=nt, want_counters=False)
+    got, stats = _device_trace(sp.p, rays, api.TRACE_AUTO, ray_flags=0x10, grid_width=W)
+    _assert_parity(f"variant{variant}_grid", got, want)
+    d = np.stack([rays["dx"], rays["dy"], rays["dz"]], -1)
+    hit = want["instance_id"] != 0xFFFFFFFF
+    normals = np.zeros((rays.shape[0], 3), np.float32)
+    normals[hit] = S.geometric_normals(pos, idx, want["primitive_id"][hit], m, d[hit])
+    brays, _ = S.bounce_rays(rays, want, normals)
+    bwant = sp.o.trace(brays, ray_flags=0, n_threads=nt, want_counters=False)
+    bgot, _ = _device_trace(sp.p, brays, api.TRACE_AUTO, ray_flags=0)
+    _assert_parity(f"variant{variant}_list", bgot, bwant)
+    # instanced: 20 x 20 spheres, up to ten instances per TLAS leaf in the reference's tree
+    spos, sidx = S.uv_sphere_mesh(48, 48)
+    si = helpers.ScenePair((0,), True)
+    b = si.blas([(spos, sidx.reshape(-1), 1)])
+    si.bind([si.tlas(S.instance_grid(20, 20, b, 3.5, -60.0))])
+    si.build()
+    irays = S.pinhole_rays(480, 320, 0.0, 1000.0, aspect_correct=True)
+    iwant = si.o.trace(irays, ray_flags=0x10, n_threads=nt, want_counters=False)
+    igot, _ = _device_trace(si.p, irays, api.TRACE_AUTO, ray_flags=0x10, grid_width=480)
+    rep = _assert_parity(f"variant{variant}_instanced", igot, iwant)
+    assert rep["hits"] > 10000
+    ilist, _ = _device_trace(si.p, irays, api.TRACE_AUTO, ray_flags=0x10)  # the same rays as a list (no grid hint)
+    _assert_parity(f"variant{variant}_instanced_list", ilist, iwant)
