@@ -63,10 +63,22 @@ typedef enum rdn_status {
  * (wavefront_compute/ctx.rs:15-29).  32 B = 2 x float4. */
 typedef struct rdn_ray { float ox, oy, oz, tmin, dx, dy, dz, tmax; } rdn_ray;
 
-/* Launch-uniform part of ShaderRayTraceCallStoragePayload (ctx.rs:15-29): tlas_idx, ray_flags, cull_mask.
+/* Launch-uniform part of ShaderRayTraceCallStoragePayload (ctx.rs:15-29): tlas_idx, ray_flags, cull_mask, the SBT ray
+ * configuration and miss index.
  * grid_width: optional hint — rays form a row-major 2D launch of this width (launch_size.x); 0 = plain list.
- * The result is identical either way; the hint only lets the kernel walk rays in 8x4 pixel tiles. */
-typedef struct rdn_launch { uint32_t ray_flags, cull_mask, tlas_idx, grid_width; } rdn_launch;
+ * The result is identical either way; the hint only lets the kernel walk rays in 8x4 pixel tiles.
+ * any_hit: what the any-hit stage of the pipeline decides for candidate hits of NON-OPAQUE geometry (traverse_cpu.rs:164-192):
+ * RDN_ANYHIT_NONE = every candidate is accepted (the reference without an any-hit shader), k + 1 = program k of
+ * rdn_rt_set_any_hit_programs for all non-opaque geometry, RDN_ANYHIT_FROM_SBT = the any_hit handle of the candidate's hit group
+ * in the table bound with rdn_rt_bind_sbt (hit group = sbt_ray_offset + sbt_ray_stride * geometry_id + the instance's record
+ * offset, api/ctx.rs:53-55; trace_task.rs:189-203), RDN_SBT_NO_SHADER there = accepted.
+ * A zero-filled tail (any_hit, sbt_ray_offset, sbt_ray_stride, miss_index) is the plain closest-hit query. */
+typedef struct rdn_launch {
+  uint32_t ray_flags, cull_mask, tlas_idx, grid_width;
+  uint32_t any_hit, sbt_ray_offset, sbt_ray_stride, miss_index;
+} rdn_launch;
+#define RDN_ANYHIT_NONE 0u
+#define RDN_ANYHIT_FROM_SBT 0xFFFFFFFFu
 
 /* Closest-hit record = the fields of RayClosestHitCtx a consumer reads (api/ctx.rs:13-55;
  * storage forms wavefront_compute/ctx.rs:34-57): hit_distance (world), bary_coord (u,v) with
@@ -192,6 +204,23 @@ int rdn_rt_trace_closest_device_n(rdn_rt_scene *scene, int device_index, const r
 #define RDN_ERROR_FLAG_STACK_OVERFLOW 1u
 #define RDN_ERROR_FLAG_GATE_TIMEOUT 2u
 int rdn_rt_poll_errors(rdn_rt_scene *scene, int device_index, void *cuda_stream, uint32_t *out_flags);
+/* ---- any-hit (row a19 / f4): RayAnyHitBehavior bits (api/ty.rs:134-136) and the any-hit shaders of a pipeline as DATA.
+ *      The reference's any-hit shader is arbitrary EDSL code run inside the traversal for every candidate of non-opaque geometry;
+ *      a precompiled kernel cannot take device code through a C ABI, so a shader is one of a few stateless programs over the fields
+ *      of the reference's `Hit` (geometry_idx, primitive_idx, distance — traverse_cpu.rs:43-49): `behavior` where its predicate
+ *      holds, `otherwise` where not.  ACCEPT_HIT commits the candidate (the range shrinks, the result is replaced), END_SEARCH
+ *      stops the whole traversal — with or without ACCEPT_HIT, exactly as traverse_cpu.rs:177-192.  Launches whose programs can
+ *      return END_SEARCH have an order-dependent answer and take the reference-order kernel, like ACCEPT_FIRST_HIT rays. */
+#define RDN_ANYHIT_BEHAVIOR_ACCEPT_HIT 1u
+#define RDN_ANYHIT_BEHAVIOR_END_SEARCH 2u
+typedef enum rdn_anyhit_kind {
+  RDN_ANYHIT_CONSTANT = 0,        /* always `behavior` (the reference's tests: TEST_ANYHIT_BEHAVIOR, naive/test.rs:7) */
+  RDN_ANYHIT_PRIMITIVE_MASK = 1,  /* (primitive_idx & mask) == value: a cut-out pattern over the triangles */
+  RDN_ANYHIT_MIN_DISTANCE = 2     /* distance >= distance: candidates nearer than that are seen through */
+} rdn_anyhit_kind;
+typedef struct rdn_anyhit_program { uint32_t kind, behavior, otherwise, mask, value; float distance; uint32_t pad0, pad1; } rdn_anyhit_program;
+/* the programs an SBT's any_hit handles (and rdn_launch.any_hit) name by index; copied; n = 0 removes them */
+int rdn_rt_set_any_hit_programs(rdn_rt_scene *scene, const rdn_anyhit_program *programs, uint32_t n);
 /* reference-order walk with the reference's visit counters (host buffers; for parity / bytes model) */
 int rdn_rt_trace_counted(rdn_rt_scene *scene, const rdn_launch *launch, const rdn_ray *rays, uint64_t n,
                          rdn_hit *out_hits, rdn_counters *out_counters);
@@ -213,6 +242,8 @@ typedef struct rdn_sbt_ray_config {      /* the launch-uniform part of ShaderRay
   uint32_t sbt_ray_offset, sbt_ray_stride;   /* RaySBTConfig { offset, stride } */
   uint32_t miss_index;
 } rdn_sbt_ray_config;
+/* the executor's current_sbt (wavefront_compute/mod.rs:147-151): the table RDN_ANYHIT_FROM_SBT launches and rdn_rt_trace_ray read; NULL unbinds */
+int rdn_rt_bind_sbt(rdn_rt_scene *scene, rdn_sbt *sbt);
 int rdn_sbt_create(rdn_rt_scene *scene, uint32_t max_geometry_count_in_blas, uint32_t max_tlas_offset, uint32_t ray_type_count, rdn_sbt **out);
 void rdn_sbt_destroy(rdn_sbt *sbt);
 int rdn_sbt_config_ray_generation(rdn_sbt *sbt, uint32_t shader);

@@ -44,6 +44,17 @@ CANDIDATE_DTYPE = np.dtype([("distance", "f4"), ("t_object", "f4"), ("u", "f4"),
                             ("instance_id", "u4"), ("geometry_id", "u4"), ("primitive_id", "u4"), ("slot", "u4"), ("in_range", "u4"), ("pad", "u4")])
 
 
+ANYHIT_PROGRAM_DTYPE = np.dtype([("kind", "u4"), ("behavior", "u4"), ("otherwise", "u4"), ("mask", "u4"), ("value", "u4"), ("distance", "f4"),
+                                 ("pad0", "u4"), ("pad1", "u4")])
+ANYHIT_CONSTANT, ANYHIT_PRIMITIVE_MASK, ANYHIT_MIN_DISTANCE = 0, 1, 2
+ANYHIT_ACCEPT, ANYHIT_END_SEARCH = 1, 2
+
+
+class _AnyHitSetup(C.Structure):
+    _fields_ = [("mode", C.c_uint32), ("uniform_program", C.c_uint32), ("programs", C.c_void_p), ("n_programs", C.c_uint32),
+                ("hit_group_any", C.c_void_p), ("n_hit_groups", C.c_uint32), ("sbt_ray_offset", C.c_uint32), ("sbt_ray_stride", C.c_uint32)]
+
+
 class Launch(C.Structure):
     _fields_ = [("ray_flags", C.c_uint32), ("cull_mask", C.c_uint32), ("tlas_idx", C.c_uint32), ("grid_width", C.c_uint32)]
 
@@ -263,6 +274,24 @@ class Scene:
         L.orc_scene_candidates.argtypes = [C.c_void_p, C.POINTER(Launch), C.c_void_p, C.c_void_p, C.c_uint64]
         n = L.orc_scene_candidates(self._h, C.byref(launch), _p(ray), _p(out), cap)
         return out[:min(int(n), cap)]
+
+    def set_any_hit(self, programs=None, uniform_program=None, hit_group_any=None, sbt_ray_offset=0, sbt_ray_stride=1):
+        """Any-hit shaders as data (oracle_scene.c "any-hit") for the traces that follow.  ``programs``: list of
+        (kind, behavior, otherwise, mask, value, distance); ``uniform_program``: index used for all non-opaque geometry, or
+        ``hit_group_any``: the any_hit handle of every SBT hit group (selection as in trace_task.rs:189-203).  No arguments: off."""
+        L = lib()
+        L.orc_scene_set_any_hit.restype = C.c_int
+        L.orc_scene_set_any_hit.argtypes = [C.c_void_p, C.c_void_p]
+        if programs is None:
+            L.orc_scene_set_any_hit(self._h, None)
+            return
+        prog = np.zeros(len(programs), ANYHIT_PROGRAM_DTYPE)
+        for k, p in enumerate(programs):
+            prog[k] = tuple(p) + (0, 0)
+        groups = np.zeros(0, np.uint32) if hit_group_any is None else _c(hit_group_any, np.uint32)
+        setup = _AnyHitSetup(2 if hit_group_any is not None else 1, 0 if uniform_program is None else uniform_program, _p(prog), len(programs),
+                             _p(groups) if groups.size else None, groups.size, sbt_ray_offset, sbt_ray_stride)
+        L.orc_scene_set_any_hit(self._h, C.byref(setup))
 
     def trace_unpruned(self, rays, ray_flags=0, cull_mask=0xFFFFFFFF, tlas_idx=0, n_threads=1) -> np.ndarray:
         """NOT the reference: closest candidate of a walk that never shrinks its range (order-free model, oracle_scene.c)"""

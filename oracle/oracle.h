@@ -35,6 +35,17 @@ typedef struct { uint32_t ray_flags, cull_mask, tlas_idx, grid_width; } orc_laun
 typedef struct { float t, u, v; uint32_t primitive_id, geometry_id, instance_id, instance_custom_id, hit_kind; } orc_hit; /* 32 B */
 typedef struct { float px, py, pz, distance; uint32_t primitive_index, hit; uint32_t pad0, pad1; } orc_mesh_hit;        /* path A */
 
+/* any-hit shaders as data (oracle_scene.c "any-hit"): kind 0 constant, 1 (primitive_idx & mask) == value, 2 distance >= distance;
+ * `behavior` when the predicate holds, `otherwise` when not (ANYHIT_BEHAVIOR_ACCEPT_HIT = 1, _END_SEARCH = 2, api/ty.rs:134-136) */
+typedef struct { uint32_t kind, behavior, otherwise, mask, value; float distance; uint32_t pad0, pad1; } orc_anyhit_program;   /* 32 B */
+typedef struct {
+  uint32_t mode;              /* 0: every candidate accepted, 1: uniform_program for all non-opaque geometry, 2: through the hit groups */
+  uint32_t uniform_program;
+  const orc_anyhit_program *programs; uint32_t n_programs;
+  const uint32_t *hit_group_any; uint32_t n_hit_groups;   /* any_hit handle of each SBT hit group (0xFFFFFFFF: none) */
+  uint32_t sbt_ray_offset, sbt_ray_stride;
+} orc_anyhit_setup;
+
 /* the reference's four traversal counters (traverse_cpu.rs:37-41) + instances entered + would-abort events */
 typedef struct { uint64_t bvh_visit, bvh_hit, tri_visit, tri_hit, inst_visit, ref_abort; } orc_counters;
 
@@ -128,6 +139,8 @@ void orc_scene_get_view(const orc_scene *s, orc_scene_view *out);
 
 /* NaiveSahBvhCpu::traverse for a batch (any_hit == always ACCEPT, as TEST_ANYHIT_BEHAVIOR, naive/test.rs:7);
  * counters may be NULL; n_threads <= 1 runs on the calling thread */
+/* the any-hit setup used by the traces that follow (NULL: every candidate accepted); copied */
+int orc_scene_set_any_hit(orc_scene *s, const orc_anyhit_setup *setup);
 int orc_scene_trace(const orc_scene *s, const orc_launch *launch, const orc_ray *rays, uint64_t n_rays,
                     orc_hit *out_hits, orc_counters *counters, int n_threads);
 

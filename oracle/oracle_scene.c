@@ -66,6 +66,10 @@ struct orc_scene {
   VEC(ov3) vertices;
   uint64_t balance_fallbacks, balance_fallbacks_gt10;
   int built;
+  /* any-hit shaders of the bound pipeline, as data (orc_scene_set_any_hit) */
+  orc_anyhit_setup anyhit;
+  orc_anyhit_program *anyhit_programs;
+  uint32_t *anyhit_groups;
 };
 
 orc_scene *orc_scene_new(void) { return (orc_scene *)calloc(1, sizeof(orc_scene)); }
@@ -356,6 +360,7 @@ static inline uint32_t bvh_iter_next(const orc_dev_node *bvh, uint32_t *curr_idx
 /* unpruned != 0: NOT the reference — the order-free model used to test the regularity classification (orc_scene_trace_unpruned):
  * every box / triangle range test uses the ray's ORIGINAL range and the closest accepted candidate is kept, i.e. the result every
  * traversal that prunes by its own closest hit converges to when hits lie inside their boxes. */
+static uint32_t any_hit_eval(const orc_scene *s, uint32_t geometry_idx, uint32_t primitive_idx, float distance, uint32_t instance_sbt_offset);
 static void traverse_clamped(const orc_scene *s, const orc_launch *L, const orc_ray *ray, orc_hit *out, orc_counters *c, int unpruned,
                              float near_walk, float far_init);
 static void traverse_one(const orc_scene *s, const orc_launch *L, const orc_ray *ray, orc_hit *out, orc_counters *c, int unpruned) {
@@ -439,22 +444,67 @@ static void traverse_clamped(const orc_scene *s, const orc_launch *L, const orc_
               uint32_t primitive_idx = tri_idx - geometry.primitive_start;
               c->tri_hit++;
               if (unpruned && !(near <= distance && distance <= ray->tmax && distance <= far)) continue;
-              /* opaque -> ACCEPT; non-opaque -> any_hit(), fixed to ACCEPT here */
-              (void)is_opaque;
-              /* RayRange::update_far: assert!(near <= far); assert!(far <= self.far) */
-              if (!(near <= distance) || !(distance <= far)) { c->ref_abort++; continue; }
-              far = distance;
-              out->t = distance; out->u = isect.z; out->v = isect.w;
-              out->primitive_id = primitive_idx; out->geometry_id = geometry.geometry_idx;
-              out->instance_id = tlas_idx; out->instance_custom_id = td->instance_custom_index;
-              out->hit_kind = isect.x < 0.0f ? HIT_KIND_BACK : HIT_KIND_FRONT;
-              if (flags & F_ACCEPT_FIRST_HIT_AND_END_SEARCH) return;
+              /* opaque -> ACCEPT; non-opaque -> any_hit() */
+              uint32_t behavior = is_opaque ? 1u : any_hit_eval(s, geometry.geometry_idx, primitive_idx, distance, td->sbt_offset);
+              if (behavior & 1u) {
+                /* RayRange::update_far: assert!(near <= far); assert!(far <= self.far) */
+                if (!(near <= distance) || !(distance <= far)) { c->ref_abort++; continue; }
+                far = distance;
+                out->t = distance; out->u = isect.z; out->v = isect.w;
+                out->primitive_id = primitive_idx; out->geometry_id = geometry.geometry_idx;
+                out->instance_id = tlas_idx; out->instance_custom_id = td->instance_custom_index;
+                out->hit_kind = isect.x < 0.0f ? HIT_KIND_BACK : HIT_KIND_FRONT;
+                if (flags & F_ACCEPT_FIRST_HIT_AND_END_SEARCH) behavior |= 2u;
+              }
+              if (behavior & 2u) return;
             }
           }
         }
       }
     }
   }
+}
+
+/* ---------- any-hit (traverse_cpu.rs:164-192) ----------
+ * The reference calls the pipeline's any-hit shader for every candidate of NON-OPAQUE geometry: TraceTaskImpl::device_poll selects
+ * it through the shader binding table — hit_group = sbt_ray_config.offset + stride * geometry_id + instance_sbt_offset
+ * (api/ctx.rs:53-55), shader = sbt.get_any_handle(current_sbt, hit_group), no shader = ANYHIT_BEHAVIOR_ACCEPT_HIT
+ * (trace_task.rs:189-203) — and honours the bits it returns: ACCEPT_HIT commits the candidate (range shrinks, result replaced),
+ * END_SEARCH stops the whole traversal.  A shader is arbitrary code there; here it is one of a few stateless programs over the
+ * fields of the reference's `Hit` (geometry_idx, primitive_idx, distance). */
+static uint32_t any_hit_eval(const orc_scene *s, uint32_t geometry_idx, uint32_t primitive_idx, float distance, uint32_t instance_sbt_offset) {
+  const orc_anyhit_setup *a = &s->anyhit;
+  uint32_t program = 0xFFFFFFFFu;
+  if (a->mode == 1) {
+    program = a->uniform_program;
+  } else if (a->mode == 2) {
+    uint32_t group = a->sbt_ray_offset + a->sbt_ray_stride * geometry_idx + instance_sbt_offset;
+    if (group < a->n_hit_groups) program = s->anyhit_groups[group];
+  }
+  if (program >= a->n_programs) return 1u; /* no shader: ACCEPT_HIT */
+  const orc_anyhit_program *p = &s->anyhit_programs[program];
+  int holds = 1;
+  if (p->kind == 1) holds = (primitive_idx & p->mask) == p->value;
+  else if (p->kind == 2) holds = distance >= p->distance;
+  return holds ? p->behavior : p->otherwise;
+}
+
+int orc_scene_set_any_hit(orc_scene *s, const orc_anyhit_setup *setup) {
+  free(s->anyhit_programs); free(s->anyhit_groups);
+  s->anyhit_programs = NULL; s->anyhit_groups = NULL;
+  memset(&s->anyhit, 0, sizeof(s->anyhit));
+  if (!setup) return 0;
+  s->anyhit = *setup;
+  if (setup->n_programs) {
+    s->anyhit_programs = (orc_anyhit_program *)malloc(sizeof(orc_anyhit_program) * setup->n_programs);
+    memcpy(s->anyhit_programs, setup->programs, sizeof(orc_anyhit_program) * setup->n_programs);
+  }
+  if (setup->n_hit_groups) {
+    s->anyhit_groups = (uint32_t *)malloc(sizeof(uint32_t) * setup->n_hit_groups);
+    memcpy(s->anyhit_groups, setup->hit_group_any, sizeof(uint32_t) * setup->n_hit_groups);
+  }
+  s->anyhit.programs = s->anyhit_programs; s->anyhit.hit_group_any = s->anyhit_groups;
+  return 0;
 }
 
 /* Brute-force candidate list of one ray (debugging / self-consistency): every instance of the bound TLAS that passes the

@@ -90,7 +90,20 @@ class RdnError(RuntimeError):
 
 
 class _Launch(C.Structure):
-    _fields_ = [("ray_flags", C.c_uint32), ("cull_mask", C.c_uint32), ("tlas_idx", C.c_uint32), ("grid_width", C.c_uint32)]
+    _fields_ = [("ray_flags", C.c_uint32), ("cull_mask", C.c_uint32), ("tlas_idx", C.c_uint32), ("grid_width", C.c_uint32),
+                ("any_hit", C.c_uint32), ("sbt_ray_offset", C.c_uint32), ("sbt_ray_stride", C.c_uint32), ("miss_index", C.c_uint32)]
+
+
+ANYHIT_NONE, ANYHIT_FROM_SBT = 0, 0xFFFFFFFF
+ANYHIT_CONSTANT, ANYHIT_PRIMITIVE_MASK, ANYHIT_MIN_DISTANCE = 0, 1, 2
+ANYHIT_BEHAVIOR_ACCEPT_HIT, ANYHIT_BEHAVIOR_END_SEARCH = 1, 2
+ANYHIT_PROGRAM_DTYPE = np.dtype([("kind", "u4"), ("behavior", "u4"), ("otherwise", "u4"), ("mask", "u4"), ("value", "u4"), ("distance", "f4"),
+                                 ("pad0", "u4"), ("pad1", "u4")])
+
+
+def _launch(ray_flags, cull_mask, tlas_idx, grid_width, any_hit=ANYHIT_NONE, sbt_ray=(0, 0), miss_index=0):
+    """rdn_launch; ``any_hit``: ANYHIT_NONE, ANYHIT_FROM_SBT, or a program index + 1 (see rdn_rt.h)"""
+    return _Launch(ray_flags, cull_mask, tlas_idx, grid_width, any_hit, sbt_ray[0], sbt_ray[1], miss_index)
 
 
 class _Geometry(C.Structure):
@@ -156,7 +169,7 @@ EXPORTED_SYMBOLS = [
     "rdn_rt_scene_create", "rdn_rt_scene_destroy", "rdn_rt_blas_create", "rdn_rt_blas_destroy", "rdn_rt_tlas_create",
     "rdn_rt_tlas_destroy", "rdn_rt_bind_tlas", "rdn_rt_bind_tlas_max_len", "rdn_rt_commit", "rdn_rt_trace_closest",
     "rdn_rt_trace_closest_device", "rdn_rt_trace_closest_device_n", "rdn_rt_poll_errors", "rdn_rt_host_alloc", "rdn_rt_host_free",
-    "rdn_rt_host_register", "rdn_rt_host_unregister", "rdn_rt_trace_counted", "rdn_rt_kernel_timing_begin", "rdn_rt_kernel_timing_end",
+    "rdn_rt_host_register", "rdn_rt_host_unregister", "rdn_rt_set_any_hit_programs", "rdn_rt_bind_sbt", "rdn_rt_trace_counted", "rdn_rt_kernel_timing_begin", "rdn_rt_kernel_timing_end",
     "rdn_rt_gen_pinhole_rays_device", "rdn_rt_gen_pinhole_rays_batch_device", "rdn_rt_gen_camera_rays_device", "rdn_rt_gen_bounce_rays_device", "rdn_rt_ao_accumulate_device", "rdn_rt_compact_u32", "rdn_rt_compact_u32_device",
     "rdn_rt_scene_blob", "rdn_rt_scene_adopt_blob", "rdn_rt_scene_array", "rdn_rt_scene_build_stats", "rdn_rt_measure_l2_read_gbs", "rdn_pick_mesh_create", "rdn_pick_mesh_destroy",
     "rdn_pick_mesh_primitive_count", "rdn_pick_mesh_nearest", "rdn_pick_mesh_all", "rdn_bvh_build", "rdn_bvh_build_device", "rdn_bvh_built_on_device", "rdn_bvh_destroy", "rdn_bvh_nodes",
@@ -195,6 +208,8 @@ def lib() -> C.CDLL:
     L.rdn_rt_trace_closest.argtypes = [vp, P(_Launch), vp, u64, vp]
     L.rdn_rt_trace_closest_device.argtypes = [vp, i32, P(_Launch), vp, u64, vp, vp, i32, P(_TraceStats)]
     L.rdn_rt_poll_errors.argtypes = [vp, i32, vp, P(u32)]
+    L.rdn_rt_set_any_hit_programs.argtypes = [vp, vp, u32]
+    L.rdn_rt_bind_sbt.argtypes = [vp, vp]
     L.rdn_rt_host_alloc.argtypes = [u64, P(vp)]
     L.rdn_rt_host_free.argtypes = [vp]
     L.rdn_rt_host_free.restype = None
@@ -362,25 +377,25 @@ class NaiveSahBVHSystem:
 
     # --- traversal ---
     def trace_closest_batch(self, rays: np.ndarray, ray_flags: int = 0, cull_mask: int = 0xFFFFFFFF, tlas_idx: int = 0,
-                            grid_width: int = 0, out: np.ndarray | None = None) -> np.ndarray:
+                            grid_width: int = 0, out: np.ndarray | None = None, **launch_kw) -> np.ndarray:
         """Host buffers in, host buffers out (H2D + traversal + D2H inside the call)."""
         rays = _c(rays, RAY_DTYPE)
         hits = np.empty(rays.shape[0], HIT_DTYPE) if out is None else out
-        launch = _Launch(ray_flags, cull_mask, tlas_idx, grid_width)
+        launch = _launch(ray_flags, cull_mask, tlas_idx, grid_width, **launch_kw)
         _check(self._L.rdn_rt_trace_closest(self._h, C.byref(launch), _p(rays), rays.shape[0], _p(hits)))
         return hits
 
-    def trace_closest_host_ptr(self, rays_ptr: int, n: int, hits_ptr: int, ray_flags=0, cull_mask=0xFFFFFFFF, tlas_idx=0, grid_width=0):
+    def trace_closest_host_ptr(self, rays_ptr: int, n: int, hits_ptr: int, ray_flags=0, cull_mask=0xFFFFFFFF, tlas_idx=0, grid_width=0, **launch_kw):
         """Same as :meth:`trace_closest_batch` on raw host pointers (e.g. pinned torch tensors)."""
-        launch = _Launch(ray_flags, cull_mask, tlas_idx, grid_width)
+        launch = _launch(ray_flags, cull_mask, tlas_idx, grid_width, **launch_kw)
         _check(self._L.rdn_rt_trace_closest(self._h, C.byref(launch), C.c_void_p(rays_ptr), n, C.c_void_p(hits_ptr)))
 
     def trace_closest_device(self, d_rays_ptr: int, n: int, d_hits_ptr: int, ray_flags=0, cull_mask=0xFFFFFFFF, tlas_idx=0,
                              grid_width=0, stream: int = 0, mode: int = TRACE_AUTO, device_index: int = 0, want_stats: bool = False,
-                             overlap_previous: bool = False):
+                             overlap_previous: bool = False, **launch_kw):
         """Device-resident rays/hits; asynchronous on ``stream`` unless ``want_stats``.  ``overlap_previous``: the caller's promise
         behind RDN_TRACE_OVERLAP_PREVIOUS (nothing else enqueued on the stream since the previous trace, buffers disjoint)."""
-        launch = _Launch(ray_flags, cull_mask, tlas_idx, grid_width)
+        launch = _launch(ray_flags, cull_mask, tlas_idx, grid_width, **launch_kw)
         if overlap_previous:
             mode |= TRACE_OVERLAP_PREVIOUS
         st = _TraceStats()
@@ -393,12 +408,23 @@ class NaiveSahBVHSystem:
         return None
 
     def trace_closest_device_n(self, d_rays_ptr: int, d_n_ptr: int, n_max: int, d_hits_ptr: int, ray_flags=0, cull_mask=0xFFFFFFFF, tlas_idx=0,
-                               stream: int = 0, mode: int = TRACE_AUTO, device_index: int = 0):
+                               stream: int = 0, mode: int = TRACE_AUTO, device_index: int = 0, **launch_kw):
         """A wave whose size lives on the device (``d_n_ptr``: one u64, e.g. the count a bounce step left there); nothing
         comes back to the host."""
-        launch = _Launch(ray_flags, cull_mask, tlas_idx, 0)
+        launch = _launch(ray_flags, cull_mask, tlas_idx, 0, **launch_kw)
         _check(self._L.rdn_rt_trace_closest_device_n(self._h, device_index, C.byref(launch), C.c_void_p(d_rays_ptr), C.c_void_p(d_n_ptr), n_max,
                                                      C.c_void_p(d_hits_ptr), C.c_void_p(stream), mode))
+
+    def set_any_hit_programs(self, programs):
+        """The any-hit shaders of the pipeline as data: list of (kind, behavior, otherwise, mask, value, distance) — see rdn_rt.h."""
+        arr = np.zeros(len(programs), ANYHIT_PROGRAM_DTYPE)
+        for k, p in enumerate(programs):
+            arr[k] = tuple(p) + (0, 0)
+        _check(self._L.rdn_rt_set_any_hit_programs(self._h, _p(arr) if len(programs) else None, len(programs)))
+
+    def bind_sbt(self, sbt):
+        """the executor's current table (read by ANYHIT_FROM_SBT launches and trace_ray); None unbinds"""
+        _check(self._L.rdn_rt_bind_sbt(self._h, sbt._h if sbt is not None else None))
 
     def poll_errors(self, stream: int = 0, device_index: int = 0) -> int:
         """Wait for ``stream`` and return (and clear) the safety-net flags of the asynchronous device path; raises on any."""
@@ -406,11 +432,11 @@ class NaiveSahBVHSystem:
         _check(self._L.rdn_rt_poll_errors(self._h, device_index, C.c_void_p(stream), C.byref(flags)))
         return int(flags.value)
 
-    def trace_counted(self, rays: np.ndarray, ray_flags=0, cull_mask=0xFFFFFFFF, tlas_idx=0):
+    def trace_counted(self, rays: np.ndarray, ray_flags=0, cull_mask=0xFFFFFFFF, tlas_idx=0, **launch_kw):
         """Reference-order walk returning hits and the reference's visit counters."""
         rays = _c(rays, RAY_DTYPE)
         hits = np.empty(rays.shape[0], HIT_DTYPE)
-        launch = _Launch(ray_flags, cull_mask, tlas_idx, 0)
+        launch = _launch(ray_flags, cull_mask, tlas_idx, 0, **launch_kw)
         ctr = _Counters()
         _check(self._L.rdn_rt_trace_counted(self._h, C.byref(launch), _p(rays), rays.shape[0], _p(hits), C.byref(ctr)))
         return hits, {n: int(getattr(ctr, n)) for n, _ in _Counters._fields_}

@@ -109,6 +109,9 @@ struct DeviceCtx {
   uint8_t *d_keep = nullptr;       // bounce step: keep flags + identity indices feeding the compaction
   uint32_t *d_iota = nullptr;
   uint64_t bounce_cap = 0;
+  rdn_anyhit_program *d_anyhit = nullptr;  // device copy of the scene's any-hit programs
+  uint32_t n_anyhit = 0;
+  bool anyhit_stale = true;
   bool timing = false;                 // rdn_rt_kernel_timing_begin .. _end: events around every traversal kernel
   std::vector<TimedLaunch> timed;
 };
@@ -127,7 +130,46 @@ struct rdn_rt_scene {
   std::vector<uint32_t> h_tlas_binding;  // host copies used to resolve the wide root of a launch
   std::vector<TlasRoot> h_tlas_root;
   std::vector<DeviceCtx> devices;
+  // any-hit stage: the programs of the pipeline (rdn_rt_set_any_hit_programs) and the executor's current table (rdn_rt_bind_sbt)
+  std::vector<rdn_anyhit_program> anyhit_programs;
+  struct rdn_sbt *bound_sbt = nullptr;
 };
+
+struct rdn_sbt {
+  rdn_rt_scene *scene = nullptr;
+  uint32_t ray_stride = 0, max_geometry = 0, max_tlas_offset = 0;
+  std::mutex lock;
+  std::vector<SbtHitGroup> hit_groups;   // ray_ty_idx + geometry_idx * ray_stride + tlas_offset (sbt.rs:20-38)
+  std::vector<uint32_t> miss;            // ray_type_count entries
+  uint32_t ray_gen = RDN_SBT_NO_SHADER;
+  struct PerDevice {
+    SbtHitGroup *d_hit_groups = nullptr;
+    uint32_t *d_miss = nullptr;
+    bool stale = true;
+    uint8_t *d_keep = nullptr;           // grouping scratch, `cap` rays
+    uint32_t *d_iota = nullptr, *d_segment = nullptr;
+    uint64_t *d_count = nullptr;
+    unsigned long long *d_status = nullptr;
+    uint64_t cap = 0;
+  };
+  std::vector<PerDevice> per_device;
+  std::vector<int> device_ids;           // CUDA device of each entry (kept here: the table may outlive the scene object)
+};
+
+namespace {
+int sbt_upload(rdn_sbt *t, int device_index) {
+  rdn_sbt::PerDevice &pd = t->per_device[device_index];
+  if (!pd.stale) return RDN_OK;
+  if (!pd.d_hit_groups) RDN_CUDA(cudaMalloc(&pd.d_hit_groups, std::max<size_t>(t->hit_groups.size(), 1) * sizeof(SbtHitGroup)));
+  if (!pd.d_miss) RDN_CUDA(cudaMalloc(&pd.d_miss, std::max<size_t>(t->miss.size(), 1) * sizeof(uint32_t)));
+  // (synchronous copies: a table is configured once per pipeline, not per launch)
+  RDN_CUDA(cudaMemcpy(pd.d_hit_groups, t->hit_groups.data(), t->hit_groups.size() * sizeof(SbtHitGroup), cudaMemcpyHostToDevice));
+  RDN_CUDA(cudaMemcpy(pd.d_miss, t->miss.data(), t->miss.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  pd.stale = false;
+  return RDN_OK;
+}
+void sbt_touch(rdn_sbt *t) { for (auto &pd : t->per_device) pd.stale = true; }
+}  // namespace
 
 namespace {
 
@@ -281,6 +323,37 @@ int take_error_flags(const Scratch &scratch, uint32_t *out_flags = nullptr) {
   return RDN_OK;
 }
 
+// The any-hit stage of a launch: device copies of the scene's programs and, for RDN_ANYHIT_FROM_SBT, of the bound table's hit groups,
+// wired into the SceneDev the kernels get; *can_end_search = the stage may stop a traversal (the answer is then order dependent).
+int prepare_any_hit(rdn_rt_scene *s, DeviceCtx &dc, const rdn_launch &launch, SceneDev &dev, bool &can_end_search) {
+  can_end_search = false;
+  if (launch.any_hit == RDN_ANYHIT_NONE) return RDN_OK;
+  if (dc.anyhit_stale) {
+    if (dc.d_anyhit) { cudaFree(dc.d_anyhit); dc.d_anyhit = nullptr; }
+    dc.n_anyhit = static_cast<uint32_t>(s->anyhit_programs.size());
+    if (dc.n_anyhit) {
+      RDN_CUDA(cudaMalloc(&dc.d_anyhit, dc.n_anyhit * sizeof(rdn_anyhit_program)));
+      RDN_CUDA(cudaMemcpy(dc.d_anyhit, s->anyhit_programs.data(), dc.n_anyhit * sizeof(rdn_anyhit_program), cudaMemcpyHostToDevice));
+    }
+    dc.anyhit_stale = false;
+  }
+  dev.anyhit_programs = dc.d_anyhit; dev.n_anyhit_programs = dc.n_anyhit;
+  if (launch.any_hit == RDN_ANYHIT_FROM_SBT) {
+    rdn_sbt *t = s->bound_sbt;
+    if (!t) return fail(RDN_ERR_INVALID_ARGUMENT, "RDN_ANYHIT_FROM_SBT without a bound table (rdn_rt_bind_sbt)");
+    const int di = static_cast<int>(&dc - s->devices.data());
+    std::lock_guard<std::mutex> tl(t->lock);
+    const int rc = sbt_upload(t, di);
+    if (rc != RDN_OK) return rc;
+    dev.sbt_hit_groups = t->per_device[di].d_hit_groups;
+    dev.n_sbt_hit_groups = static_cast<uint32_t>(t->hit_groups.size());
+    can_end_search = any_hit_can_end_search(launch, s->anyhit_programs.data(), dc.n_anyhit, t->hit_groups.data(), dev.n_sbt_hit_groups);
+  } else {
+    can_end_search = any_hit_can_end_search(launch, s->anyhit_programs.data(), dc.n_anyhit, nullptr, 0);
+  }
+  return RDN_OK;
+}
+
 // enqueue the kernels of one trace on `stream`; returns the number of kernels launched
 int enqueue_trace(rdn_rt_scene *s, DeviceCtx &dc, const Scratch &scratch, const rdn_launch &launch, const rdn_ray *d_rays, uint64_t n,
                   rdn_hit *d_hits, int mode, cudaStream_t stream, uint32_t *launches, bool count_ties = false, bool allow_overlap = false,
@@ -303,23 +376,32 @@ int enqueue_trace(rdn_rt_scene *s, DeviceCtx &dc, const Scratch &scratch, const 
   // candidate to separate misses, the reference-order walk only for the occluded rays — slower than walking everything in
   // reference order, whose early exit is what makes these rays cheap.)
   dc.last_enqueue_overlappable = false;
-  if (mode == RDN_TRACE_REFERENCE_ORDER || end_search || tlas.irregular_count == IRREGULAR_ROUTE_ALL) {
+  // any-hit stage: device copies of the programs and of the bound table's hit groups; a stage that can stop a traversal
+  // (END_SEARCH) makes the answer order dependent, and so does one on a TLAS with irregular instances: reference order
+  SceneDev dev = dc.dev;
+  bool any_hit_reference_order = false;
+  {
+    const int rc = prepare_any_hit(s, dc, launch, dev, any_hit_reference_order);
+    if (rc != RDN_OK) return rc;
+    if (launch.any_hit != RDN_ANYHIT_NONE && tlas.irregular_count != 0) any_hit_reference_order = true;
+  }
+  if (mode == RDN_TRACE_REFERENCE_ORDER || end_search || tlas.irregular_count == IRREGULAR_ROUTE_ALL || any_hit_reference_order) {
     ScopedKernelTimer tm(dc, KERNEL_REFERENCE, stream);
-    launch_trace_reference(dc.dev, launch, d_rays, n, d_hits, ts, false, dc.sm_count, stream, d_n);
+    launch_trace_reference(dev, launch, d_rays, n, d_hits, ts, false, dc.sm_count, stream, d_n);
   } else {
     bool ties_done = true;
     {
       ScopedKernelTimer tm(dc, KERNEL_ORDERED, stream);
       // (a launch that failed never advances the set's epoch: the host-side count moves only when the kernel is in the stream,
       // or the next launch on the set would wait at its gate for an epoch that never comes)
-      RDN_CUDA(launch_trace_ordered(dc.dev, launch, tlas, d_rays, n, d_hits, ts, dc.sm_count, stream,
+      RDN_CUDA(launch_trace_ordered(dev, launch, tlas, d_rays, n, d_hits, ts, dc.sm_count, stream,
                                     allow_overlap && !dc.timing && !count_ties, scratch.ordered_launches, &ties_done, d_n));
       if (n) scratch.ordered_launches++;
       dc.last_enqueue_overlappable = ties_done && n != 0;
     }
     if (!ties_done) {
       ScopedKernelTimer tm(dc, KERNEL_TIES, stream);
-      launch_resolve_ties(dc.dev, launch, d_rays, d_hits, ts, dc.sm_count, stream);
+      launch_resolve_ties(dev, launch, d_rays, d_hits, ts, dc.sm_count, stream);
       if (launches) *launches += 1;
       RDN_CUDA(cudaMemsetAsync(static_cast<char *>(scratch.base) + 8, 0, 4, stream));  // the next launch on this set may drain in-kernel
     }
@@ -379,6 +461,7 @@ int rdn_rt_scene_create(int n_devices, const int *device_ids, rdn_rt_scene **out
 
 void rdn_rt_scene_destroy(rdn_rt_scene *s) {
   if (!s) return;
+  if (s->bound_sbt) s->bound_sbt->scene = nullptr;  // (a table may outlive its scene; it must not point back at it then)
   for (DeviceCtx &dc : s->devices) {
     cudaSetDevice(dc.device);
     cudaDeviceSynchronize();
@@ -395,6 +478,7 @@ void rdn_rt_scene_destroy(rdn_rt_scene *s) {
     for (TimedLaunch &t : dc.timed) { cudaEventDestroy(t.begin); cudaEventDestroy(t.end); }
     if (dc.ext_done) cudaEventDestroy(dc.ext_done);
     if (dc.d_compact_status) cudaFree(dc.d_compact_status);
+    if (dc.d_anyhit) cudaFree(dc.d_anyhit);
     if (dc.d_ao_payload) cudaFree(dc.d_ao_payload);
     if (dc.d_keep) cudaFree(dc.d_keep);
     if (dc.d_iota) cudaFree(dc.d_iota);
@@ -695,6 +779,25 @@ int rdn_rt_host_unregister(void *ptr) {
   return RDN_OK;
 }
 
+int rdn_rt_set_any_hit_programs(rdn_rt_scene *s, const rdn_anyhit_program *programs, uint32_t n) {
+  if (!s || (n && !programs)) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_set_any_hit_programs: null argument");
+  for (uint32_t k = 0; k < n; ++k)
+    if (programs[k].kind > RDN_ANYHIT_MIN_DISTANCE) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_set_any_hit_programs: unknown program kind");
+  std::unique_lock<std::shared_mutex> wr(s->lock);
+  std::lock_guard<std::mutex> lg(s->launch_lock);
+  s->anyhit_programs.assign(programs, programs + n);
+  for (DeviceCtx &dc : s->devices) dc.anyhit_stale = true;
+  return RDN_OK;
+}
+
+int rdn_rt_bind_sbt(rdn_rt_scene *s, rdn_sbt *sbt) {
+  if (!s) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_bind_sbt: null scene");
+  if (sbt && sbt->scene != s) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_bind_sbt: the table belongs to another scene");
+  std::unique_lock<std::shared_mutex> wr(s->lock);
+  s->bound_sbt = sbt;
+  return RDN_OK;
+}
+
 int rdn_rt_poll_errors(rdn_rt_scene *s, int device_index, void *cuda_stream, uint32_t *out_flags) {
   if (!s) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_poll_errors: null scene");
   if (device_index < 0 || device_index >= static_cast<int>(s->devices.size())) return fail(RDN_ERR_INVALID_ARGUMENT, "bad device_index (host-only scene?)");
@@ -732,7 +835,11 @@ int rdn_rt_trace_counted(rdn_rt_scene *s, const rdn_launch *launch, const rdn_ra
     const uint64_t m = std::min(chunk, n - off);
     RDN_CUDA(cudaMemcpyAsync(slot.d_rays, rays + off, m * sizeof(rdn_ray), cudaMemcpyHostToDevice, slot.stream));
     RDN_CUDA(cudaMemsetAsync(static_cast<char *>(slot.scratch.base) + 32, 0, 10 * 8, slot.stream));  // the visit counters only
-    launch_trace_reference(dc.dev, *launch, slot.d_rays, m, slot.d_hits, slot.scratch.view(), true, dc.sm_count, slot.stream);
+    SceneDev dev = dc.dev;
+    bool unused = false;
+    rc = prepare_any_hit(s, dc, *launch, dev, unused);
+    if (rc != RDN_OK) return rc;
+    launch_trace_reference(dev, *launch, slot.d_rays, m, slot.d_hits, slot.scratch.view(), true, dc.sm_count, slot.stream);
     RDN_CUDA(cudaGetLastError());
     RDN_CUDA(cudaMemcpyAsync(out_hits + off, slot.d_hits, m * sizeof(rdn_hit), cudaMemcpyDeviceToHost, slot.stream));
     unsigned long long c[6];
@@ -1170,42 +1277,6 @@ int rdn_pick_mesh_all(rdn_pick_mesh *m, const rdn_pick_config *config, const rdn
 
 // ---------------------------------------------------------------------------------------------------------------
 // f4: shader binding table + dispatch (sbt.cu)
-struct rdn_sbt {
-  rdn_rt_scene *scene = nullptr;
-  uint32_t ray_stride = 0, max_geometry = 0, max_tlas_offset = 0;
-  std::mutex lock;
-  std::vector<SbtHitGroup> hit_groups;   // ray_ty_idx + geometry_idx * ray_stride + tlas_offset (sbt.rs:20-38)
-  std::vector<uint32_t> miss;            // ray_type_count entries
-  uint32_t ray_gen = RDN_SBT_NO_SHADER;
-  struct PerDevice {
-    SbtHitGroup *d_hit_groups = nullptr;
-    uint32_t *d_miss = nullptr;
-    bool stale = true;
-    uint8_t *d_keep = nullptr;           // grouping scratch, `cap` rays
-    uint32_t *d_iota = nullptr, *d_segment = nullptr;
-    uint64_t *d_count = nullptr;
-    unsigned long long *d_status = nullptr;
-    uint64_t cap = 0;
-  };
-  std::vector<PerDevice> per_device;
-  std::vector<int> device_ids;           // CUDA device of each entry (kept here: the table may outlive the scene object)
-};
-
-namespace {
-int sbt_upload(rdn_sbt *t, int device_index) {
-  rdn_sbt::PerDevice &pd = t->per_device[device_index];
-  if (!pd.stale) return RDN_OK;
-  if (!pd.d_hit_groups) RDN_CUDA(cudaMalloc(&pd.d_hit_groups, std::max<size_t>(t->hit_groups.size(), 1) * sizeof(SbtHitGroup)));
-  if (!pd.d_miss) RDN_CUDA(cudaMalloc(&pd.d_miss, std::max<size_t>(t->miss.size(), 1) * sizeof(uint32_t)));
-  // (synchronous copies: a table is configured once per pipeline, not per launch)
-  RDN_CUDA(cudaMemcpy(pd.d_hit_groups, t->hit_groups.data(), t->hit_groups.size() * sizeof(SbtHitGroup), cudaMemcpyHostToDevice));
-  RDN_CUDA(cudaMemcpy(pd.d_miss, t->miss.data(), t->miss.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-  pd.stale = false;
-  return RDN_OK;
-}
-void sbt_touch(rdn_sbt *t) { for (auto &pd : t->per_device) pd.stale = true; }
-}  // namespace
-
 int rdn_sbt_create(rdn_rt_scene *scene, uint32_t max_geometry_count_in_blas, uint32_t max_tlas_offset, uint32_t ray_type_count, rdn_sbt **out) {
   if (!scene || !out) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_sbt_create: null argument");
   const uint64_t groups = static_cast<uint64_t>(max_geometry_count_in_blas) * max_tlas_offset * ray_type_count;
@@ -1225,6 +1296,7 @@ int rdn_sbt_create(rdn_rt_scene *scene, uint32_t max_geometry_count_in_blas, uin
 
 void rdn_sbt_destroy(rdn_sbt *t) {
   if (!t) return;
+  if (t->scene && t->scene->bound_sbt == t) t->scene->bound_sbt = nullptr;
   for (size_t i = 0; i < t->per_device.size(); ++i) {
     rdn_sbt::PerDevice &pd = t->per_device[i];
     cudaSetDevice(t->device_ids[i]);

@@ -10,6 +10,10 @@
 
 namespace rdn {
 
+struct SbtHitGroup {  // DeviceHitGroupShaderRecord, sbt.rs:62-69
+  uint32_t closest_hit, any_hit, intersection;
+};
+
 // device pointers into one blob
 struct SceneDev {
   const uint32_t *tlas_binding;
@@ -28,6 +32,11 @@ struct SceneDev {
   const LeafBox *irregular_leaf_boxes;
   const Wide4Node *wide4_nodes;
   uint32_t n_tlas_binding, n_tlas_root, n_blas_meta, n_instances;
+  // any-hit stage of the launch (filled per launch by capi.cu when rdn_launch.any_hit != RDN_ANYHIT_NONE): the scene's programs and,
+  // for RDN_ANYHIT_FROM_SBT, the hit groups of the bound table
+  const rdn_anyhit_program *anyhit_programs;
+  const struct SbtHitGroup *sbt_hit_groups;
+  uint32_t n_anyhit_programs, n_sbt_hit_groups;
 };
 
 // per-device scratch owned by the scene
@@ -71,6 +80,10 @@ cudaError_t launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch
                                  rdn_hit *d_hits, const TraceScratch &scratch, int sm_count, cudaStream_t stream, bool allow_overlap,
                                  uint32_t wait_epoch,  // = ordered launches issued before this one on `scratch`
                                  bool *ties_resolved_in_kernel, const unsigned long long *d_n = nullptr);
+// can the any-hit stage of this launch stop a traversal (END_SEARCH)?  Then the answer depends on the visiting order and the launch
+// takes the reference-order kernel.  (host copy of the programs / hit groups)
+bool any_hit_can_end_search(const rdn_launch &launch, const rdn_anyhit_program *programs, uint32_t n_programs, const SbtHitGroup *groups,
+                            uint32_t n_groups);
 
 // Stable stream compaction of u32 (single pass, decoupled look-back); d_status needs compact_status_words(n) u64.
 uint64_t compact_status_words(uint64_t n);
@@ -115,9 +128,7 @@ int build_bvh_sah_device(const Box3 *boxes, uint64_t n, uint32_t n_buckets, cons
                          std::string &err);
 
 // shader binding table dispatch (sbt.cu)
-struct SbtHitGroup {  // DeviceHitGroupShaderRecord, sbt.rs:62-69
-  uint32_t closest_hit, any_hit, intersection;
-};
+
 void launch_sbt_dispatch(const SceneDev &scene, const SbtHitGroup *d_hit_groups, uint32_t n_hit_groups, const uint32_t *d_miss, uint32_t n_miss,
                          const rdn_sbt_ray_config &cfg, const rdn_hit *d_hits, uint64_t n, uint32_t *d_task, cudaStream_t stream);
 // d_keep: n bytes, d_iota / d_segment: n u32, d_count: one u64, d_status: compact_status_words(n) u64

@@ -72,6 +72,30 @@ __device__ __forceinline__ uint32_t cull_triangle_bits(uint32_t f) {
   return (enable ? 1u : 0u) | (back ? 2u : 0u);
 }
 
+// is the geometry non-opaque for this ray (cull_geometry's is_opaque, flag.rs:62-78)?  Its candidates go through the any-hit stage.
+__device__ __forceinline__ bool geometry_non_opaque(uint32_t f, uint32_t geometry_flags) {
+  const bool geometry_opaque = (geometry_flags & RDN_GEOMETRY_FLAG_OPAQUE) != 0;
+  return !((geometry_opaque || (f & TF_FORCE_OPAQUE)) && !(f & TF_FORCE_NON_OPAQUE));
+}
+// The any-hit stage for one candidate of non-opaque geometry (traverse_cpu.rs:164-176; shader selection trace_task.rs:189-203):
+// RayAnyHitBehavior bits.  Out of line on purpose: opaque scenes never get here.
+__device__ __noinline__ uint32_t any_hit_behavior(const SceneDev &S, const rdn_launch &L, uint32_t slot, uint32_t inst, float distance) {
+  uint32_t program = RDN_SBT_NO_SHADER;
+  const SlotInfo si = S.slot_info[slot];
+  if (L.any_hit == RDN_ANYHIT_FROM_SBT) {
+    const uint32_t group = L.sbt_ray_offset + L.sbt_ray_stride * si.geometry_idx + __ldg(&S.instances[inst].sbt_offset);
+    if (group < S.n_sbt_hit_groups) program = __ldg(&S.sbt_hit_groups[group].any_hit);
+  } else {
+    program = L.any_hit - 1u;
+  }
+  if (program >= S.n_anyhit_programs) return RDN_ANYHIT_BEHAVIOR_ACCEPT_HIT;  // no shader: the candidate is accepted
+  const rdn_anyhit_program p = S.anyhit_programs[program];
+  bool holds = true;
+  if (p.kind == RDN_ANYHIT_PRIMITIVE_MASK) holds = (si.primitive_id & p.mask) == p.value;
+  else if (p.kind == RDN_ANYHIT_MIN_DISTANCE) holds = distance >= p.distance;
+  return holds ? p.behavior : p.otherwise;
+}
+
 #if defined(RDN_DEBUG_STEPS) || defined(RDN_DEBUG_TIMELINE)
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
@@ -266,6 +290,7 @@ __device__ __forceinline__ void reference_walk(const SceneDev &S, const rdn_laun
       for (uint32_t g = g0; g < g1 && !end_search; ++g) {
         const GeometryMeta gm = S.geometry_meta[g];
         if (!cull_geometry_pass(flags, gm.geometry_flags)) continue;
+        const bool ask_any_hit = L.any_hit != RDN_ANYHIT_NONE && geometry_non_opaque(flags, gm.geometry_flags);
         uint32_t cursor = gm.bvh_root_idx;
         while (cursor != 0xFFFFFFFFu && !end_search) {
           const float4 *bp = reinterpret_cast<const float4 *>(S.tri_bvh_forest + cursor);
@@ -288,13 +313,18 @@ __device__ __forceinline__ void reference_walk(const SceneDev &S, const rdn_laun
             if (!triangle_test(qn, qv0, qe1, qe2, bo, bd, near_walk * scaling, far * scaling, cull_bits, sign, t, u, v)) continue;
             const float distance = t / scaling;
             if (COUNT) ctr.tri_hit++;
-            // RayRange::update_far asserts: the reference aborts; the candidate is rejected here
-            if (!(near <= distance) || !(distance <= far)) { if (COUNT) ctr.abort++; continue; }
-            far = distance;
-            res.t = distance; res.u = u; res.v = v;
-            res.slot = slot; res.inst = tlas_idx;
-            res.kind = sign < 0.0f ? RDN_HIT_KIND_BACK_FACING_TRIANGLE : RDN_HIT_KIND_FRONT_FACING_TRIANGLE;
-            if (flags & TF_END_SEARCH) { end_search = true; break; }
+            uint32_t behavior = RDN_ANYHIT_BEHAVIOR_ACCEPT_HIT;  // opaque -> commit; non-opaque -> the any-hit stage
+            if (ask_any_hit) behavior = any_hit_behavior(S, L, slot, tlas_idx, distance);
+            if (behavior & RDN_ANYHIT_BEHAVIOR_ACCEPT_HIT) {
+              // RayRange::update_far asserts: the reference aborts; the candidate is rejected here
+              if (!(near <= distance) || !(distance <= far)) { if (COUNT) ctr.abort++; continue; }
+              far = distance;
+              res.t = distance; res.u = u; res.v = v;
+              res.slot = slot; res.inst = tlas_idx;
+              res.kind = sign < 0.0f ? RDN_HIT_KIND_BACK_FACING_TRIANGLE : RDN_HIT_KIND_FRONT_FACING_TRIANGLE;
+              if (flags & TF_END_SEARCH) behavior |= RDN_ANYHIT_BEHAVIOR_END_SEARCH;
+            }
+            if (behavior & RDN_ANYHIT_BEHAVIOR_END_SEARCH) { end_search = true; break; }
           }
         }
       }
@@ -535,7 +565,7 @@ __device__ __forceinline__ void drain_tie_queue(const OrderedParams &P) {
 // speculative traversal with a postponed leaf, any-hit pre-classification, topping a thinned-out tile up with new rays, the first
 // 8-32 stack entries per thread in shared memory (3-10 % slower than the L1-cached local stack), rows of tiles taken from the
 // middle of the frame outwards (+2..5 % on configs 1 / 2, -11 % on config 4).
-template <int K, int MINB, bool DRAIN_TIES, bool IRREGULAR, bool LD256, bool HOT, bool WIDE4, bool INST_LOOP = false, bool SHARE = false>
+template <int K, int MINB, bool DRAIN_TIES, bool IRREGULAR, bool LD256, bool HOT, bool WIDE4, bool INST_LOOP = false, bool SHARE = false, bool ANYHIT = false>
 __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(const __grid_constant__ OrderedParams P) {
   RDN_COST(COST_PROLOGUE);
   const SceneDev &S = P.S;
@@ -830,6 +860,10 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
                 if (!triangle_test(qn, qv0, qe1, qe2, o, d, near_s, far_s, cull_bits, sign, t, u, v)) continue;
                 RDN_COST(COST_TRI_HIT);
                 const float distance = t / scaling;
+                // any-hit stage (stateless programs without END_SEARCH only: the candidates a ray accepts do not depend on the order)
+                if constexpr (ANYHIT) {
+                  if ((cull_bits & 4u) && !(any_hit_behavior(S, P.L, slot, cur_inst, distance) & RDN_ANYHIT_BEHAVIOR_ACCEPT_HIT)) continue;
+                }
                 if (!(t_near_world <= distance) || !(distance <= far0)) continue;  // the reference's update_far asserts
                 if (distance < best) {
                   second = fminf(second, best);
@@ -907,6 +941,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
                         const uint4 gm0 = __ldg(reinterpret_cast<const uint4 *>(S.geometry_meta + groots.x));
                         const uint32_t wide_root = WIDE4 ? __ldg(&S.geometry_meta[groots.x].wide4_root) : __ldg(&S.geometry_meta[groots.x].wide_root);
                         cur = (cull_geometry_pass(flags, gm0.w) && wide_root != REF_EMPTY) ? wide_root : RDN_POP();
+                        if constexpr (ANYHIT) cull_bits = (cull_bits & 3u) | (geometry_non_opaque(flags, gm0.w) ? 4u : 0u);
                       }
                     }
                     entered = true;
@@ -943,6 +978,9 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
             const uint4 gm0 = __ldg(reinterpret_cast<const uint4 *>(S.geometry_meta + g));
             const uint32_t wide_root = WIDE4 ? __ldg(&S.geometry_meta[g].wide4_root) : __ldg(&S.geometry_meta[g].wide_root);
             cur = (cull_geometry_pass(cur_flags, gm0.w) && wide_root != REF_EMPTY) ? wide_root : RDN_POP();
+            // (bit 2 of cull_bits: candidates of this geometry go through the any-hit stage; every deferred subtree of a geometry is
+            // walked before the iterator moves on, so the bit is that of the geometry being walked)
+            if constexpr (ANYHIT) cull_bits = (cull_bits & 3u) | (geometry_non_opaque(cur_flags, gm0.w) ? 4u : 0u);
           }
         }
 
@@ -1163,6 +1201,16 @@ static int ordered_variant() {  // (read at every launch: the parity tests walk 
 }
 int ordered_tie_mode() { return ordered_variant() == 9 ? 0 : 3; }
 
+bool any_hit_can_end_search(const rdn_launch &launch, const rdn_anyhit_program *programs, uint32_t n_programs, const SbtHitGroup *groups,
+                            uint32_t n_groups) {
+  if (launch.any_hit == RDN_ANYHIT_NONE) return false;
+  auto ends = [&](uint32_t k) { return k < n_programs && ((programs[k].behavior | programs[k].otherwise) & RDN_ANYHIT_BEHAVIOR_END_SEARCH) != 0; };
+  if (launch.any_hit != RDN_ANYHIT_FROM_SBT) return ends(launch.any_hit - 1u);
+  for (uint32_t g = 0; g < n_groups; ++g)
+    if (ends(groups[g].any_hit)) return true;
+  return false;
+}
+
 cudaError_t launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const TlasRoot &tlas, const rdn_ray *d_rays, uint64_t n,
                                  rdn_hit *d_hits, const TraceScratch &scratch, int sm_count, cudaStream_t stream, bool allow_overlap,
                                  uint32_t wait_epoch, bool *ties_resolved_in_kernel, const unsigned long long *d_n) {
@@ -1200,9 +1248,12 @@ cudaError_t launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch
   KernelFn fn;
   bool inline_ties = true;
   // template arguments: <K, MINB, DRAIN_TIES, IRREGULAR, LD256, HOT, WIDE4, INST_LOOP, SHARE>
-  const KernelFn plain = k_trace_ordered_rounds<3, 8, true, false, true, false, false, true, false>;
-  const KernelFn sharing = k_trace_ordered_rounds<3, 8, true, false, true, false, false, true, true>;
-  switch (variant) {
+  const bool any_hit = launch.any_hit != RDN_ANYHIT_NONE;  // (launches whose any-hit stage can END_SEARCH never get here)
+  const KernelFn plain = any_hit ? k_trace_ordered_rounds<3, 8, true, false, true, false, false, true, false, true>
+                                 : k_trace_ordered_rounds<3, 8, true, false, true, false, false, true, false>;
+  const KernelFn sharing = any_hit ? k_trace_ordered_rounds<3, 8, true, false, true, false, false, true, true, true>
+                                   : k_trace_ordered_rounds<3, 8, true, false, true, false, false, true, true>;
+  switch (any_hit ? 0 : variant) {  // (the A/B instantiations exist without the any-hit stage only)
     case 2: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false>; break;     // the round-1 default: K = 2, one round per missed instance
     case 9: fn = k_trace_ordered_rounds<3, 8, false, false, true, false, false, true>; inline_ties = false; break;  // queue drained by k_resolve_ties
     case 30: fn = k_trace_ordered_rounds<3, 8, true, false, false, false, false, true>; break;  // 128-bit loads / stores

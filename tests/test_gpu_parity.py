@@ -531,3 +531,67 @@ def test_every_instantiation_of_the_ordered_kernel_is_bit_identical(variant, mon
     assert rep["hits"] > 10000
     ilist, _ = _device_trace(si.p, irays, api.TRACE_AUTO, ray_flags=0x10)  # the same rays as a list (no grid hint)
     _assert_parity(f"variant{variant}_instanced_list", ilist, iwant)
+
+
+def _non_opaque_scene():
+    """a non-opaque torus (geometry flags 0) in front of an opaque sphere, two instances with different SBT record offsets"""
+    tpos, tidx = S.torus_mesh(96, 48, 1.0, 0.35)
+    spos, sidx = S.uv_sphere_mesh(48, 48)
+    sp = helpers.ScenePair((0,), True)
+    torus = sp.blas([(tpos, tidx.reshape(-1), 0)])                      # non-opaque: candidates go through the any-hit stage
+    both = sp.blas([(spos, sidx.reshape(-1), 1), (tpos, tidx.reshape(-1), 0)])   # geometry 0 opaque, geometry 1 not
+    T, Sc, Rx, mul = S.mat4_translate, S.mat4_scale, S.mat4_rotate_x, S.mat4_mul
+    inst = np.concatenate([S.make_instance(mul(mul(T(-2.5, 0, -9), Sc(3, 3, 3)), Rx(-0.6)), torus, custom_index=11, sbt_offset=0),
+                           S.make_instance(mul(T(3.0, 0, -11), Sc(2.2, 2.2, 2.2)), both, custom_index=22, sbt_offset=2)])
+    sp.bind([sp.tlas(inst)])
+    sp.build()
+    return sp
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["ignore_odd_primitives", "see_through_near", "accept_and_end_search", "end_search_without_accept", "from_sbt"])
+def test_any_hit_stage_decides_over_candidates_of_non_opaque_geometry(case):
+    """traverse_cpu.rs:164-192: candidates of non-opaque geometry are put to the any-hit stage; ACCEPT_HIT commits, END_SEARCH stops the
+    traversal.  Stateless programs without END_SEARCH run in the ordered kernel, the others in reference order; whole records equal
+    the oracle's either way, for grid launches, ray lists and the host-buffer call."""
+    sp = _non_opaque_scene()
+    A, E = api.ANYHIT_BEHAVIOR_ACCEPT_HIT, api.ANYHIT_BEHAVIOR_END_SEARCH
+    programs = [(api.ANYHIT_PRIMITIVE_MASK, A, 0, 1, 0, 0.0),      # 0: odd primitives are holes
+                (api.ANYHIT_MIN_DISTANCE, A, 0, 0, 0, 8.5),        # 1: nothing nearer than 8.5 is seen
+                (api.ANYHIT_CONSTANT, A | E, 0, 0, 0, 0.0),        # 2: first candidate wins (= ACCEPT_FIRST_HIT_AND_END_SEARCH)
+                (api.ANYHIT_PRIMITIVE_MASK, A, E, 3, 0, 0.0)]      # 3: every fourth primitive is a surface, any other one ends the search unseen
+    sp.p.set_any_hit_programs(programs)
+    kw = {}
+    if case == "from_sbt":
+        sbt = sp.p.create_sbt(2, 4, 1)
+        sbt.config_hit_group(0, 0, 0, api.HitGroupShaderRecord(closest_hit=0, any_hit=0))   # instance 0 (record offset 0), geometry 0: program 0
+        sbt.config_hit_group(1, 2, 0, api.HitGroupShaderRecord(closest_hit=0, any_hit=1))   # instance 1 (record offset 2), geometry 1 -> group 0 + 1 * 1 + 2 = 3: program 1
+        sp.p.bind_sbt(sbt)
+        groups = np.full(2 * 4 * 1, 0xFFFFFFFF, np.uint32)
+        groups[0], groups[3] = 0, 1
+        sp.o.set_any_hit(programs, hit_group_any=groups, sbt_ray_offset=0, sbt_ray_stride=1)
+        kw = dict(any_hit=api.ANYHIT_FROM_SBT, sbt_ray=(0, 1))
+    else:
+        k = ["ignore_odd_primitives", "see_through_near", "accept_and_end_search", "end_search_without_accept"].index(case)
+        sp.o.set_any_hit(programs, uniform_program=k)
+        kw = dict(any_hit=k + 1)
+    W, H = 320, 200
+    rays = S.pinhole_rays(W, H, 0.0, 100.0, aspect_correct=True)
+    staged = sp.o.trace(rays, ray_flags=0, n_threads=4, want_counters=False)
+    for flags in (0x00, 0x10):
+        want, wctr = sp.o.trace(rays, ray_flags=flags, n_threads=4)
+        got, _ = _device_trace(sp.p, rays, api.TRACE_AUTO, ray_flags=flags, grid_width=W, **kw)
+        _assert_parity(f"anyhit_{case}_{flags:#x}_grid", got, want)
+        got, _ = _device_trace(sp.p, rays, api.TRACE_AUTO, ray_flags=flags, **kw)
+        _assert_parity(f"anyhit_{case}_{flags:#x}_list", got, want)
+        got = sp.p.trace_closest_batch(rays, ray_flags=flags, grid_width=W, **kw)
+        _assert_parity(f"anyhit_{case}_{flags:#x}_host", got, want)
+        got, gctr = sp.p.trace_counted(rays, ray_flags=flags, **kw)
+        assert got.tobytes() == want.tobytes() and gctr == wctr
+    # the stage changes answers (otherwise the test proves nothing), and FORCE_OPAQUE switches it off
+    forced, _ = _device_trace(sp.p, rays, api.TRACE_AUTO, ray_flags=0x01, grid_width=W, **kw)
+    _assert_parity(f"anyhit_{case}_force_opaque", forced, sp.o.trace(rays, ray_flags=0x01, n_threads=4, want_counters=False))
+    sp.o.set_any_hit()
+    base = sp.o.trace(rays, ray_flags=0, n_threads=4, want_counters=False)
+    assert base.tobytes() != staged.tobytes()
+    assert forced.tobytes() == sp.o.trace(rays, ray_flags=0x01, n_threads=4, want_counters=False).tobytes()  # (FORCE_OPAQUE: no stage)

@@ -254,3 +254,43 @@ def test_oracle_reproduces_the_reference_tests_own_output_file():
     rows = text.splitlines()
     assert rows[:3] == ["P2", "256 256", "12"] and len(rows) == 259 and all(len(r.split()) == 256 for r in rows[3:])
     assert 0 < sum(v != "0" for r in rows[3:] for v in r.split()) < 256 * 256
+
+
+def test_any_hit_stage_known_answers():
+    """traverse_cpu.rs:164-192 restated (oracle_scene.c "any-hit"): only candidates of NON-OPAQUE geometry are put to the stage;
+    ACCEPT_HIT commits, END_SEARCH stops; a constant ACCEPT | END_SEARCH program is ACCEPT_FIRST_HIT_AND_END_SEARCH; a program that
+    accepts nothing makes non-opaque geometry invisible while opaque geometry is untouched."""
+    import oracle
+    from rendiation_b200 import scenes as S
+    pos, idx = S.uv_sphere_mesh(24, 24)
+    A, E = oracle.ANYHIT_ACCEPT, oracle.ANYHIT_END_SEARCH
+    rays = S.pinhole_rays(48, 48, 0.0, 100.0)
+
+    def scene(flags):
+        o = oracle.Scene()
+        b = o.create_blas([(pos, idx.reshape(-1), flags)])
+        o.bind_tlas([o.create_tlas(S.make_instance(S.mat4_mul(S.mat4_translate(0, 0, -10), S.mat4_scale(5, 5, 5)), b))])
+        assert o.build() == 0
+        return o
+
+    non_opaque, opaque = scene(0), scene(1)
+    plain = non_opaque.trace(rays, ray_flags=0, want_counters=False)
+    first = non_opaque.trace(rays, ray_flags=0x04, want_counters=False)
+    assert plain.tobytes() == opaque.trace(rays, ray_flags=0, want_counters=False).tobytes()
+    for o in (non_opaque, opaque):
+        o.set_any_hit([(oracle.ANYHIT_CONSTANT, 0, 0, 0, 0, 0.0), (oracle.ANYHIT_CONSTANT, A | E, 0, 0, 0, 0.0), (oracle.ANYHIT_CONSTANT, E, 0, 0, 0, 0.0)], uniform_program=0)
+    assert (non_opaque.trace(rays, ray_flags=0, want_counters=False)["instance_id"] == 0xFFFFFFFF).all()      # nothing accepted: invisible
+    assert opaque.trace(rays, ray_flags=0, want_counters=False).tobytes() == plain.tobytes()                   # opaque: never asked
+    assert non_opaque.trace(rays, ray_flags=0x01, want_counters=False).tobytes() == plain.tobytes()            # FORCE_OPAQUE: never asked
+    assert (opaque.trace(rays, ray_flags=0x02, want_counters=False)["instance_id"] == 0xFFFFFFFF).all()        # FORCE_NON_OPAQUE: asked
+    non_opaque.set_any_hit([(oracle.ANYHIT_CONSTANT, A | E, 0, 0, 0, 0.0)], uniform_program=0)
+    assert non_opaque.trace(rays, ray_flags=0, want_counters=False).tobytes() == first.tobytes()
+    non_opaque.set_any_hit([(oracle.ANYHIT_CONSTANT, E, 0, 0, 0, 0.0)], uniform_program=0)                     # END_SEARCH without ACCEPT
+    assert (non_opaque.trace(rays, ray_flags=0, want_counters=False)["instance_id"] == 0xFFFFFFFF).all()
+    non_opaque.set_any_hit([(oracle.ANYHIT_MIN_DISTANCE, A, 0, 0, 0, 10.0)], uniform_program=0)                # the near half is seen through
+    far_only = non_opaque.trace(rays, ray_flags=0, want_counters=False)
+    hit = far_only["instance_id"] != 0xFFFFFFFF
+    assert hit.sum() > 100 and (far_only["t"][hit] >= 10.0).all()
+    assert (far_only["hit_kind"][hit] != plain["hit_kind"][hit]).all()   # the far side of the sphere faces the other way
+    non_opaque.set_any_hit()
+    assert non_opaque.trace(rays, ray_flags=0, want_counters=False).tobytes() == plain.tobytes()
