@@ -336,6 +336,71 @@ int rdn_rt_ao_accumulate_device(rdn_rt_scene *scene, int device_index, const rdn
                                 const uint64_t *d_n_secondary, uint64_t n_pixels, uint32_t sample_count, uint32_t max_sample,
                                 float *d_ao_buffer, void *cuda_stream);
 
+/* ---- a20 / f4: the wavefront executor in ONE call.
+ *      Replaces RayTracingEncoderProvider::trace_ray (shader/ray-tracing/src/api/backend.rs:48-55) as implemented by
+ *      GPUWaveFrontComputeRaytracingEncoder::trace_ray (wavefront_compute/mod.rs:111-196): ray generation over the launch grid, then
+ *      `execution_round_hint` rounds of { trace the wave (TraceTaskImpl::device_poll, trace_task.rs:152-360) -> pick the closest-hit or
+ *      miss shader of every ray through the shader binding table (trace_task.rs:206-268) -> run each shader over its tasks -> the rays
+ *      those tasks ask for, compacted in order, are the next wave (use_compact_alive_tasks, task-graph/src/runtime/task_group.rs:220-278) },
+ *      all on the device: no size comes back to the host between rounds (the reference reads every task group's size back after each
+ *      compaction to record its indirect dispatch).
+ *      A shader stage is a callback that ENQUEUES the caller's kernels on the given stream (it must not synchronise); it sees its task
+ *      list as device memory (rdn_wave).  A task that wants a ray traced in the next round writes it to d_next_rays[slot] and sets
+ *      d_spawn[slot] = 1, slot = d_tasks[k] (round 0: slot = launch index) — one ray per task, the launch index is inherited.
+ *      What of shader/task-graph is NOT reproduced, and what stands in for it: a task's states (task_pool.rs:85-107) collapse to
+ *      membership — WAKEN = the ray is in the wave, FINISHED = its slot spawned nothing; the SLEEP / GO_TO_SLEEP states exist in the
+ *      reference so that a parent task can wait for the payload of its child and copy it back (trace_task.rs:271-357) — here payloads
+ *      live in caller memory indexed by launch index and stages update them in place, so nothing waits and nothing is copied back.
+ *      Ray flags, cull mask, TLAS, SBT ray configuration and miss index are uniform per wave (round_launch[r], the last entry
+ *      repeating) instead of per trace call. */
+typedef struct rdn_wave {
+  uint32_t round;                  /* 0 = ray generation; r >= 1: the stages after the r-th traversal */
+  uint32_t shader;                 /* the ShaderHandle value this call runs (index into closest_hit / miss; the table's ray-gen shader) */
+  const uint32_t *d_tasks;         /* this shader's tasks: indices into the traced wave, in wave order; NULL in round 0 (task k = launch index k) */
+  const uint64_t *d_task_count;    /* how many, ON THE DEVICE */
+  uint64_t max_tasks;              /* upper bound of *d_task_count: size grids by it */
+  const rdn_ray *d_rays;           /* the wave that was traced (NULL in round 0) ... */
+  const rdn_hit *d_hits;           /* ... and its hit records */
+  const uint32_t *d_launch_index;  /* launch index (x + y * width) of every ray of the wave (NULL in round 0: identity) */
+  uint32_t width, height;
+  void *d_payload;                 /* rdn_trace_ray_desc.d_payload: caller memory, by convention indexed by launch index */
+  rdn_ray *d_next_rays;            /* out: slot i = the ray task i of the wave wants traced next */
+  uint8_t *d_spawn;                /* out: 1 where d_next_rays[slot] was written (zeroed by the library before the stages of a round) */
+} rdn_wave;
+typedef int (*rdn_stage_fn)(void *user, const rdn_wave *wave, void *cuda_stream);   /* returns 0, or a negative status that aborts the call */
+typedef struct rdn_wave_counts {   /* one row per round, read back once when the call ends (rdn_trace_ray_desc.counts) */
+  uint64_t wave;                   /* rays traced in this round (round 0: rays the ray generation spawned... see rdn_rt_trace_ray) */
+  uint64_t closest_tasks, miss_tasks, no_task;   /* wave == closest_tasks + miss_tasks + no_task: every ray ends in exactly one list or none */
+  uint64_t spawned;                /* rays the round's stages asked for = the next round's wave */
+} rdn_wave_counts;
+typedef struct rdn_trace_ray_desc {
+  uint32_t width, height;                      /* launch size (z = 1, as the reference asserts, mod.rs:152) */
+  uint32_t execution_round_hint;               /* GPURaytracingPipelineAndBindingSource::execution_round_hint: traversal rounds */
+  uint32_t n_round_launch;
+  const rdn_launch *round_launch;              /* the launch-uniform trace parameters of round r = round_launch[min(r - 1, n - 1)]; grid_width is ignored */
+  rdn_stage_fn ray_generation; void *ray_generation_user;
+  uint32_t n_closest_hit, n_miss;              /* shader handles 0 .. n - 1 of each kind (what the SBT's records name) */
+  const rdn_stage_fn *closest_hit; void *const *closest_hit_user;   /* NULL entries = an empty stage */
+  const rdn_stage_fn *miss; void *const *miss_user;
+  void *d_payload;
+  rdn_wave_counts *counts; uint32_t n_counts;  /* optional: rows 0 .. min(n_counts, rounds + 1) - 1; asking for them synchronises the stream at the end */
+} rdn_trace_ray_desc;
+/* `sbt`: the table whose hit groups / miss shaders pick the stages (also read by RDN_ANYHIT_FROM_SBT rounds).  Asynchronous on
+ * `cuda_stream` unless desc->counts is set.  Rays whose shader handle is >= n_closest_hit / n_miss count as no_task. */
+int rdn_rt_trace_ray(rdn_rt_scene *scene, int device_index, rdn_sbt *sbt, const rdn_trace_ray_desc *desc, void *cuda_stream);
+/* What stages are usually made of, callable from inside a stage callback (asynchronous on the stream):
+ *   spawn_all      d_spawn[k] = 1 for every task of a ray-generation stage that filled d_next_rays (e.g. with rdn_rt_gen_*_rays_device)
+ *   bounce         the closest-hit -> next-ray step (rdn_rt_gen_bounce_rays_device's recipes, same `params`) for the stage's tasks,
+ *                  low-discrepancy indices taken from the launch index
+ *   store_f32      d_dst[launch index of the task] = value  (a payload write: "occluded" / "sky")
+ *   ao_resolve     the AO ray-gen shader's accumulation over a payload buffer (feature/ao.rs:187-232); re-arms the payload to 1 */
+int rdn_rt_stage_spawn_all(rdn_rt_scene *scene, int device_index, const rdn_wave *wave, void *cuda_stream);
+int rdn_rt_stage_bounce(rdn_rt_scene *scene, int device_index, const rdn_bounce *params, const rdn_wave *wave, void *cuda_stream);
+int rdn_rt_stage_store_f32(rdn_rt_scene *scene, int device_index, const rdn_wave *wave, float value, float *d_dst, void *cuda_stream);
+int rdn_rt_ao_resolve_device(rdn_rt_scene *scene, int device_index, float *d_payload, uint64_t n_pixels, uint32_t sample_count,
+                             uint32_t max_sample, float *d_ao_buffer, void *cuda_stream);
+
+
 /* ---- wavefront active-list compaction: use_stream_compaction
  *      (shader/parallel-compute/src/stream_compaction.rs:3-45) as used by use_compact_alive_tasks
  *      (shader/task-graph/src/runtime/task_group.rs:220-278).  Stable; out has n slots, zero past *out_n. ---- */

@@ -149,6 +149,28 @@ class _Bounce(C.Structure):
                 ("flags", C.c_uint32), ("target", C.c_float * 3)]
 
 
+class Wave(C.Structure):
+    """rdn_wave: what a shader stage of :meth:`NaiveSahBVHSystem.trace_ray` sees (device pointers as integers)"""
+    _fields_ = [("round", C.c_uint32), ("shader", C.c_uint32), ("d_tasks", C.c_void_p), ("d_task_count", C.c_void_p), ("max_tasks", C.c_uint64),
+                ("d_rays", C.c_void_p), ("d_hits", C.c_void_p), ("d_launch_index", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32),
+                ("d_payload", C.c_void_p), ("d_next_rays", C.c_void_p), ("d_spawn", C.c_void_p)]
+
+
+STAGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(Wave), C.c_void_p)
+
+
+class _WaveCounts(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("wave", "closest_tasks", "miss_tasks", "no_task", "spawned")]
+
+
+class _TraceRayDesc(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("execution_round_hint", C.c_uint32), ("n_round_launch", C.c_uint32),
+                ("round_launch", C.POINTER(_Launch)), ("ray_generation", STAGE_FN), ("ray_generation_user", C.c_void_p),
+                ("n_closest_hit", C.c_uint32), ("n_miss", C.c_uint32), ("closest_hit", C.POINTER(STAGE_FN)), ("closest_hit_user", C.POINTER(C.c_void_p)),
+                ("miss", C.POINTER(STAGE_FN)), ("miss_user", C.POINTER(C.c_void_p)), ("d_payload", C.c_void_p),
+                ("counts", C.POINTER(_WaveCounts)), ("n_counts", C.c_uint32)]
+
+
 class _Option(C.Structure):
     _fields_ = [("max_tree_depth", C.c_uint64), ("bin_size", C.c_uint64)]
 
@@ -169,7 +191,8 @@ EXPORTED_SYMBOLS = [
     "rdn_rt_scene_create", "rdn_rt_scene_destroy", "rdn_rt_blas_create", "rdn_rt_blas_destroy", "rdn_rt_tlas_create",
     "rdn_rt_tlas_destroy", "rdn_rt_bind_tlas", "rdn_rt_bind_tlas_max_len", "rdn_rt_commit", "rdn_rt_trace_closest",
     "rdn_rt_trace_closest_device", "rdn_rt_trace_closest_device_n", "rdn_rt_poll_errors", "rdn_rt_host_alloc", "rdn_rt_host_free",
-    "rdn_rt_host_register", "rdn_rt_host_unregister", "rdn_rt_set_any_hit_programs", "rdn_rt_bind_sbt", "rdn_rt_trace_counted", "rdn_rt_kernel_timing_begin", "rdn_rt_kernel_timing_end",
+    "rdn_rt_host_register", "rdn_rt_host_unregister", "rdn_rt_set_any_hit_programs", "rdn_rt_bind_sbt", "rdn_rt_trace_ray",
+    "rdn_rt_stage_spawn_all", "rdn_rt_stage_bounce", "rdn_rt_stage_store_f32", "rdn_rt_ao_resolve_device", "rdn_rt_trace_counted", "rdn_rt_kernel_timing_begin", "rdn_rt_kernel_timing_end",
     "rdn_rt_gen_pinhole_rays_device", "rdn_rt_gen_pinhole_rays_batch_device", "rdn_rt_gen_camera_rays_device", "rdn_rt_gen_bounce_rays_device", "rdn_rt_ao_accumulate_device", "rdn_rt_compact_u32", "rdn_rt_compact_u32_device",
     "rdn_rt_scene_blob", "rdn_rt_scene_adopt_blob", "rdn_rt_scene_array", "rdn_rt_scene_build_stats", "rdn_rt_measure_l2_read_gbs", "rdn_pick_mesh_create", "rdn_pick_mesh_destroy",
     "rdn_pick_mesh_primitive_count", "rdn_pick_mesh_nearest", "rdn_pick_mesh_all", "rdn_bvh_build", "rdn_bvh_build_device", "rdn_bvh_built_on_device", "rdn_bvh_destroy", "rdn_bvh_nodes",
@@ -210,6 +233,11 @@ def lib() -> C.CDLL:
     L.rdn_rt_poll_errors.argtypes = [vp, i32, vp, P(u32)]
     L.rdn_rt_set_any_hit_programs.argtypes = [vp, vp, u32]
     L.rdn_rt_bind_sbt.argtypes = [vp, vp]
+    L.rdn_rt_trace_ray.argtypes = [vp, i32, vp, P(_TraceRayDesc), vp]
+    L.rdn_rt_stage_spawn_all.argtypes = [vp, i32, P(Wave), vp]
+    L.rdn_rt_stage_bounce.argtypes = [vp, i32, P(_Bounce), P(Wave), vp]
+    L.rdn_rt_stage_store_f32.argtypes = [vp, i32, P(Wave), C.c_float, vp, vp]
+    L.rdn_rt_ao_resolve_device.argtypes = [vp, i32, vp, u64, u32, u32, vp, vp]
     L.rdn_rt_host_alloc.argtypes = [u64, P(vp)]
     L.rdn_rt_host_free.argtypes = [vp]
     L.rdn_rt_host_free.restype = None
@@ -516,6 +544,60 @@ class NaiveSahBVHSystem:
         _check(self._L.rdn_rt_ao_accumulate_device(self._h, device_index, C.c_void_p(d_secondary_hits), C.c_void_p(d_src_index),
                                                    C.c_void_p(d_n_secondary), n_pixels, sample_count, max_sample, C.c_void_p(d_ao_buffer),
                                                    C.c_void_p(stream)))
+
+    # --- the wavefront executor in one call (rdn_rt_trace_ray) ---
+    def trace_ray(self, sbt, width: int, height: int, ray_generation, closest_hit=(), miss=(), rounds: int = 1, round_launch=(), d_payload: int = 0,
+                  stream: int = 0, device_index: int = 0, want_counts: bool = False):
+        """``RayTracingEncoderProvider::trace_ray``: ray generation over ``width x height``, then ``rounds`` rounds of trace -> SBT
+        dispatch -> stages -> next wave, all on the device.  ``ray_generation`` / ``closest_hit[k]`` / ``miss[k]`` are Python callables
+        ``f(wave: Wave, stream: int)`` that ENQUEUE work (e.g. the ``stage_*`` helpers below) and must not synchronise; ``None`` = empty
+        stage.  ``round_launch``: one dict of :func:`_launch` keyword arguments (``ray_flags``, ``cull_mask``, ``tlas_idx``, ``any_hit``,
+        ``sbt_ray``, ``miss_index``) per round, the last one repeating.  Returns the per-round counts when ``want_counts``."""
+        errors = []
+
+        def wrap(f):
+            if f is None:
+                return STAGE_FN()
+            def call(_user, wave_ptr, st):
+                try:
+                    f(wave_ptr.contents, int(st or 0))
+                    return 0
+                except Exception as e:  # noqa: BLE001  (an exception must not cross the C boundary)
+                    errors.append(e)
+                    return -1
+            return STAGE_FN(call)
+
+        launches = [dict(rl) for rl in (round_launch or [{}])]
+        L = (_Launch * len(launches))(*[_launch(rl.pop("ray_flags", 0), rl.pop("cull_mask", 0xFFFFFFFF), rl.pop("tlas_idx", 0), 0, **rl) for rl in launches])
+        gen = wrap(ray_generation)
+        ch = (STAGE_FN * max(len(closest_hit), 1))(*[wrap(f) for f in closest_hit])
+        ms = (STAGE_FN * max(len(miss), 1))(*[wrap(f) for f in miss])
+        counts = (_WaveCounts * (rounds + 1))()
+        d = _TraceRayDesc(width, height, rounds, len(launches), L, gen, None, len(closest_hit), len(miss), ch, None, ms, None, d_payload,
+                          counts if want_counts else None, rounds + 1 if want_counts else 0)
+        rc = self._L.rdn_rt_trace_ray(self._h, device_index, sbt._h, C.byref(d), C.c_void_p(stream))
+        if errors:
+            raise errors[0]
+        _check(rc)
+        if want_counts:
+            return [{n: int(getattr(c, n)) for n, _ in _WaveCounts._fields_} for c in counts]
+        return None
+
+    def stage_spawn_all(self, wave: Wave, stream: int = 0, device_index: int = 0):
+        _check(self._L.rdn_rt_stage_spawn_all(self._h, device_index, C.byref(wave), C.c_void_p(stream)))
+
+    def stage_bounce(self, wave: Wave, mode: int = 0, index_base: int = 0, scrambles=(0x9E3779B9, 0x85EBCA6B), sample_index: int = 0, max_sample: int = 256,
+                     tmin=0.01, tmax=100.0, stream: int = 0, device_index: int = 0, offset_origin: bool = False, target=(0.0, 0.0, 0.0)):
+        p = _Bounce(mode, index_base, scrambles[0], scrambles[1], sample_index, max_sample, tmin, tmax,
+                    BOUNCE_OFFSET_ORIGIN if offset_origin else 0, (C.c_float * 3)(*[float(x) for x in target]))
+        _check(self._L.rdn_rt_stage_bounce(self._h, device_index, C.byref(p), C.byref(wave), C.c_void_p(stream)))
+
+    def stage_store_f32(self, wave: Wave, value: float, d_dst: int, stream: int = 0, device_index: int = 0):
+        _check(self._L.rdn_rt_stage_store_f32(self._h, device_index, C.byref(wave), value, C.c_void_p(d_dst), C.c_void_p(stream)))
+
+    def ao_resolve_device(self, d_payload: int, n_pixels: int, sample_count: int, d_ao_buffer: int, max_sample: int = 256, stream: int = 0, device_index: int = 0):
+        _check(self._L.rdn_rt_ao_resolve_device(self._h, device_index, C.c_void_p(d_payload), n_pixels, sample_count, max_sample, C.c_void_p(d_ao_buffer),
+                                                C.c_void_p(stream)))
 
     # --- wavefront queue compaction ---
     def compact_u32(self, values, keep):

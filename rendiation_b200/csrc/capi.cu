@@ -109,6 +109,20 @@ struct DeviceCtx {
   uint8_t *d_keep = nullptr;       // bounce step: keep flags + identity indices feeding the compaction
   uint32_t *d_iota = nullptr;
   uint64_t bounce_cap = 0;
+  // wavefront executor (rdn_rt_trace_ray): buffers of one launch grid, kept between calls
+  struct WaveScratch {
+    uint64_t cap = 0;        // rays
+    uint32_t buckets = 0;    // task lists (closest-hit + miss shaders)
+    uint32_t rows = 0;       // rounds + 1
+    rdn_ray *rays[2] = {nullptr, nullptr}, *next = nullptr;
+    uint32_t *launch[2] = {nullptr, nullptr}, *iota = nullptr, *idx = nullptr, *task = nullptr, *segments = nullptr;
+    rdn_hit *hits = nullptr;
+    uint8_t *spawn = nullptr, *keep = nullptr;
+    uint64_t *counters = nullptr;          // [0] the grid size, [1] [2] wave sizes (alternating), [3 ..] task-list sizes
+    uint64_t *rows_dev = nullptr;          // per round: wave, spawned, task-list sizes
+    const uint64_t **ptrs = nullptr;       // device array of counter addresses for one row
+    unsigned long long *status = nullptr;
+  } wave;
   rdn_anyhit_program *d_anyhit = nullptr;  // device copy of the scene's any-hit programs
   uint32_t n_anyhit = 0;
   bool anyhit_stale = true;
@@ -121,6 +135,7 @@ struct DeviceCtx {
 struct rdn_rt_scene {
   std::shared_mutex lock;
   std::mutex launch_lock;          // serialises use of the per-device scratch / slots
+  std::mutex wave_lock;            // serialises rdn_rt_trace_ray calls (their wave buffers)
   NaiveSahBvhSource source;
   std::vector<uint32_t> tlas_binding;
   bool dirty = true;               // invalidate(): cpu_data = gpu_data = None
@@ -308,6 +323,40 @@ struct ScopedKernelTimer {
   }
 };
 
+void free_wave_scratch(DeviceCtx &dc) {
+  auto &w = dc.wave;
+  void *all[] = {w.rays[0], w.rays[1], w.next, w.launch[0], w.launch[1], w.iota, w.idx, w.task, w.segments, w.hits, w.spawn, w.keep, w.counters,
+                 w.rows_dev, const_cast<uint64_t **>(w.ptrs), w.status};
+  for (void *p : all) if (p) cudaFree(p);
+  w = DeviceCtx::WaveScratch{};
+}
+
+int ensure_wave_scratch(DeviceCtx &dc, uint64_t n, uint32_t buckets, uint32_t rows) {
+  auto &w = dc.wave;
+  if (w.cap >= n && w.buckets >= buckets && w.rows >= rows) return RDN_OK;
+  const uint64_t cap = std::max<uint64_t>(std::max(w.cap, n), 1);
+  const uint32_t nb = std::max(std::max(w.buckets, buckets), 1u), nr = std::max(std::max(w.rows, rows), 1u);
+  free_wave_scratch(dc);
+  for (int k = 0; k < 2; ++k) {
+    RDN_CUDA(cudaMalloc(&w.rays[k], cap * sizeof(rdn_ray)));
+    RDN_CUDA(cudaMalloc(&w.launch[k], cap * sizeof(uint32_t)));
+  }
+  RDN_CUDA(cudaMalloc(&w.next, cap * sizeof(rdn_ray)));
+  RDN_CUDA(cudaMalloc(&w.hits, cap * sizeof(rdn_hit)));
+  RDN_CUDA(cudaMalloc(&w.iota, cap * sizeof(uint32_t)));
+  RDN_CUDA(cudaMalloc(&w.idx, cap * sizeof(uint32_t)));
+  RDN_CUDA(cudaMalloc(&w.task, cap * sizeof(uint32_t)));
+  RDN_CUDA(cudaMalloc(&w.segments, cap * nb * sizeof(uint32_t)));
+  RDN_CUDA(cudaMalloc(&w.spawn, cap));
+  RDN_CUDA(cudaMalloc(&w.keep, cap));
+  RDN_CUDA(cudaMalloc(&w.counters, (3 + nb) * sizeof(uint64_t)));
+  RDN_CUDA(cudaMalloc(&w.rows_dev, static_cast<size_t>(nr) * (2 + nb) * sizeof(uint64_t)));
+  RDN_CUDA(cudaMalloc(&w.ptrs, (2 + nb) * sizeof(uint64_t *)));
+  RDN_CUDA(cudaMalloc(&w.status, compact_status_words(cap) * sizeof(unsigned long long)));
+  w.cap = cap; w.buckets = nb; w.rows = nr;
+  return RDN_OK;
+}
+
 // The two safety-net words of a scratch set — traversal stack overflow, a launch that gave up waiting at its gate — read and
 // cleared (the device is idle on this set when this is called), so that one bad launch is reported once and not for ever after.
 int take_error_flags(const Scratch &scratch, uint32_t *out_flags = nullptr) {
@@ -479,6 +528,7 @@ void rdn_rt_scene_destroy(rdn_rt_scene *s) {
     if (dc.ext_done) cudaEventDestroy(dc.ext_done);
     if (dc.d_compact_status) cudaFree(dc.d_compact_status);
     if (dc.d_anyhit) cudaFree(dc.d_anyhit);
+    free_wave_scratch(dc);
     if (dc.d_ao_payload) cudaFree(dc.d_ao_payload);
     if (dc.d_keep) cudaFree(dc.d_keep);
     if (dc.d_iota) cudaFree(dc.d_iota);
@@ -1390,6 +1440,173 @@ int rdn_rt_sbt_group_device(rdn_rt_scene *s, int device_index, rdn_sbt *t, const
   }
   launch_sbt_group(d_task, n, n_closest_shaders, n_miss_shaders, pd.d_keep, pd.d_iota, pd.d_segment, pd.d_count, pd.d_status, d_queue, d_offsets,
                    static_cast<cudaStream_t>(cuda_stream));
+  RDN_CUDA(cudaGetLastError());
+  return RDN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// a20 / f4: the wavefront executor in one call (include/rdn_rt.h "a20 / f4"; device glue in wavefront.cu)
+static int trace_device_impl(rdn_rt_scene *s, int device_index, const rdn_launch *launch, const rdn_ray *d_rays, uint64_t n,
+                             rdn_hit *d_hits, void *cuda_stream, int mode, rdn_trace_stats *stats, const unsigned long long *d_n);
+
+int rdn_rt_trace_ray(rdn_rt_scene *s, int device_index, rdn_sbt *t, const rdn_trace_ray_desc *d, void *cuda_stream) {
+  if (!s || !t || !d || !d->ray_generation || !d->round_launch || d->n_round_launch == 0)
+    return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_trace_ray: null argument");
+  if (t->scene != s) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_trace_ray: the table belongs to another scene");
+  if (device_index < 0 || device_index >= static_cast<int>(s->devices.size())) return fail(RDN_ERR_INVALID_ARGUMENT, "bad device_index (host-only scene?)");
+  if ((d->n_closest_hit && !d->closest_hit) || (d->n_miss && !d->miss) || d->n_closest_hit + static_cast<uint64_t>(d->n_miss) > 64)
+    return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_trace_ray: bad shader lists (at most 64 closest-hit + miss shaders)");
+  const uint64_t n0 = static_cast<uint64_t>(d->width) * d->height;
+  if (n0 == 0) return RDN_OK;
+  if (n0 > MAX_LAUNCH_RAYS) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_trace_ray: more than 2^31 launch indices");
+  int rc = ensure_committed(s);
+  if (rc != RDN_OK) return rc;
+  std::lock_guard<std::mutex> wl(s->wave_lock);
+  DeviceCtx &dc = s->devices[device_index];
+  RDN_CUDA(cudaSetDevice(dc.device));
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  const uint32_t rounds = d->execution_round_hint, buckets = d->n_closest_hit + d->n_miss;
+  rc = ensure_wave_scratch(dc, n0, buckets, rounds + 1);
+  if (rc != RDN_OK) return rc;
+  auto &w = dc.wave;
+  {
+    std::lock_guard<std::mutex> tl(t->lock);
+    rc = sbt_upload(t, device_index);
+    if (rc != RDN_OK) return rc;
+  }
+  rdn_sbt *previous_sbt;
+  {  // the executor's current table for the duration of the call (RDN_ANYHIT_FROM_SBT rounds read it)
+    std::unique_lock<std::shared_mutex> wr(s->lock);
+    previous_sbt = s->bound_sbt;
+    s->bound_sbt = t;
+  }
+  struct Restore { rdn_rt_scene *s; rdn_sbt *prev; ~Restore() { std::unique_lock<std::shared_mutex> wr(s->lock); s->bound_sbt = prev; } } restore{s, previous_sbt};
+  const rdn_sbt::PerDevice &pd = t->per_device[device_index];
+  const uint32_t row_width = 2 + w.buckets;
+  uint64_t *grid_size = w.counters, *wave_size[2] = {w.counters + 1, w.counters + 2}, *list_size = w.counters + 3;
+  launch_store_u64(grid_size, n0, stream);
+
+  rdn_wave wave{};
+  wave.width = d->width; wave.height = d->height; wave.d_payload = d->d_payload;
+  wave.d_next_rays = w.next; wave.d_spawn = w.spawn; wave.max_tasks = n0;
+  auto record_row = [&](uint32_t round, const uint64_t *wave_n, const uint64_t *spawned, bool with_lists) -> int {
+    std::vector<const uint64_t *> ptrs(row_width);
+    ptrs[0] = wave_n; ptrs[1] = spawned;
+    for (uint32_t b = 0; b < w.buckets; ++b) ptrs[2 + b] = (with_lists && b < buckets) ? list_size + b : nullptr;
+    // (nullptr entries: the row keeps the zero it was cleared to)
+    std::vector<const uint64_t *> live;
+    std::vector<uint32_t> col;
+    for (uint32_t c = 0; c < row_width; ++c) if (ptrs[c]) { live.push_back(ptrs[c]); col.push_back(c); }
+    for (size_t k = 0; k < live.size(); ++k)
+      RDN_CUDA(cudaMemcpyAsync(w.rows_dev + static_cast<size_t>(round) * row_width + col[k], live[k], sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
+    return RDN_OK;
+  };
+  RDN_CUDA(cudaMemsetAsync(w.rows_dev, 0, static_cast<size_t>(rounds + 1) * row_width * sizeof(uint64_t), stream));
+
+  // ---- round 0: ray generation over the launch grid
+  RDN_CUDA(cudaMemsetAsync(w.spawn, 0, n0, stream));
+  wave.round = 0; wave.shader = t->ray_gen; wave.d_tasks = nullptr; wave.d_task_count = grid_size;
+  wave.d_rays = nullptr; wave.d_hits = nullptr; wave.d_launch_index = nullptr;
+  rc = d->ray_generation(d->ray_generation_user, &wave, cuda_stream);
+  if (rc != 0) return fail(rc < 0 ? rc : RDN_ERR_INVALID_ARGUMENT, "rdn_rt_trace_ray: the ray generation stage failed");
+  int cur = 0;
+  launch_wave_clip_spawn(w.spawn, grid_size, n0, w.iota, stream);
+  launch_compact_u32(w.iota, w.spawn, n0, w.idx, wave_size[cur], w.status, stream);
+  launch_wave_gather(w.next, nullptr, w.idx, wave_size[cur], n0, w.rays[cur], w.launch[cur], stream);
+  rc = record_row(0, grid_size, wave_size[cur], false);
+  if (rc != RDN_OK) return rc;
+
+  // ---- rounds: trace, pick the stage of every ray, run the stages over their task lists, compact what they spawned
+  for (uint32_t r = 1; r <= rounds; ++r) {
+    rdn_launch L = d->round_launch[std::min(r - 1, d->n_round_launch - 1)];
+    L.grid_width = 0;
+    rc = trace_device_impl(s, device_index, &L, w.rays[cur], n0, w.hits, cuda_stream, RDN_TRACE_AUTO, nullptr,
+                           reinterpret_cast<const unsigned long long *>(wave_size[cur]));
+    if (rc != RDN_OK) return rc;
+    dc.ext_prev.valid = false;
+    rdn_sbt_ray_config cfg{};
+    cfg.ray_flags = L.ray_flags; cfg.sbt_ray_offset = L.sbt_ray_offset; cfg.sbt_ray_stride = L.sbt_ray_stride; cfg.miss_index = L.miss_index;
+    launch_sbt_dispatch_n(dc.dev, pd.d_hit_groups, static_cast<uint32_t>(t->hit_groups.size()), pd.d_miss, static_cast<uint32_t>(t->miss.size()), cfg,
+                          w.hits, wave_size[cur], n0, w.task, stream);
+    for (uint32_t b = 0; b < buckets; ++b) {
+      const uint32_t code = b < d->n_closest_hit ? b : ((b - d->n_closest_hit) | RDN_TASK_MISS_BIT);
+      launch_wave_mark(w.task, wave_size[cur], n0, code, w.keep, w.iota, stream);
+      launch_compact_u32(w.iota, w.keep, n0, w.segments + static_cast<size_t>(b) * w.cap, list_size + b, w.status, stream);
+    }
+    RDN_CUDA(cudaMemsetAsync(w.spawn, 0, n0, stream));
+    wave.round = r; wave.d_rays = w.rays[cur]; wave.d_hits = w.hits; wave.d_launch_index = w.launch[cur];
+    for (uint32_t b = 0; b < buckets; ++b) {
+      const bool closest = b < d->n_closest_hit;
+      const uint32_t k = closest ? b : b - d->n_closest_hit;
+      const rdn_stage_fn fn = closest ? d->closest_hit[k] : d->miss[k];
+      if (!fn) continue;
+      wave.shader = k; wave.d_tasks = w.segments + static_cast<size_t>(b) * w.cap; wave.d_task_count = list_size + b;
+      void *user = closest ? (d->closest_hit_user ? d->closest_hit_user[k] : nullptr) : (d->miss_user ? d->miss_user[k] : nullptr);
+      rc = fn(user, &wave, cuda_stream);
+      if (rc != 0) return fail(rc < 0 ? rc : RDN_ERR_INVALID_ARGUMENT, "rdn_rt_trace_ray: a shader stage failed");
+    }
+    RDN_CUDA(cudaSetDevice(dc.device));  // (a stage may have switched devices)
+    const int nxt = cur ^ 1;
+    launch_wave_clip_spawn(w.spawn, wave_size[cur], n0, w.iota, stream);
+    launch_compact_u32(w.iota, w.spawn, n0, w.idx, wave_size[nxt], w.status, stream);
+    launch_wave_gather(w.next, w.launch[cur], w.idx, wave_size[nxt], n0, w.rays[nxt], w.launch[nxt], stream);
+    rc = record_row(r, wave_size[cur], wave_size[nxt], true);
+    if (rc != RDN_OK) return rc;
+    cur = nxt;
+  }
+  RDN_CUDA(cudaGetLastError());
+  if (d->counts && d->n_counts) {
+    std::vector<uint64_t> rows(static_cast<size_t>(rounds + 1) * row_width);
+    RDN_CUDA(cudaMemcpyAsync(rows.data(), w.rows_dev, rows.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+    RDN_CUDA(cudaStreamSynchronize(stream));
+    for (uint32_t r = 0; r <= rounds && r < d->n_counts; ++r) {
+      const uint64_t *row = rows.data() + static_cast<size_t>(r) * row_width;
+      rdn_wave_counts &c = d->counts[r];
+      c.wave = row[0]; c.spawned = row[1]; c.closest_tasks = 0; c.miss_tasks = 0;
+      for (uint32_t b = 0; b < buckets; ++b) (b < d->n_closest_hit ? c.closest_tasks : c.miss_tasks) += row[2 + b];
+      c.no_task = r == 0 ? 0 : c.wave - c.closest_tasks - c.miss_tasks;
+    }
+  }
+  return RDN_OK;
+}
+
+static int stage_device(rdn_rt_scene *s, int device_index, const rdn_wave *wave, const char *what) {
+  if (!s || !wave) return fail(RDN_ERR_INVALID_ARGUMENT, std::string(what) + ": null argument");
+  if (device_index < 0 || device_index >= static_cast<int>(s->devices.size())) return fail(RDN_ERR_INVALID_ARGUMENT, "bad device_index");
+  RDN_CUDA(cudaSetDevice(s->devices[device_index].device));
+  return RDN_OK;
+}
+int rdn_rt_stage_spawn_all(rdn_rt_scene *s, int device_index, const rdn_wave *wave, void *cuda_stream) {
+  const int rc = stage_device(s, device_index, wave, "rdn_rt_stage_spawn_all");
+  if (rc != RDN_OK) return rc;
+  launch_stage_spawn_all(wave->d_spawn, wave->d_task_count, wave->max_tasks, static_cast<cudaStream_t>(cuda_stream));
+  RDN_CUDA(cudaGetLastError());
+  return RDN_OK;
+}
+int rdn_rt_stage_bounce(rdn_rt_scene *s, int device_index, const rdn_bounce *p, const rdn_wave *wave, void *cuda_stream) {
+  const int rc = stage_device(s, device_index, wave, "rdn_rt_stage_bounce");
+  if (rc != RDN_OK) return rc;
+  if (!p || !wave->d_rays || !wave->d_hits || !wave->d_tasks) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_stage_bounce: needs a traced wave (round >= 1)");
+  if (p->mode > 2) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_stage_bounce: unknown mode");
+  launch_stage_bounce_rays(s->devices[device_index].dev, *p, wave->d_rays, wave->d_hits, wave->d_tasks, wave->d_task_count, wave->max_tasks,
+                           wave->d_launch_index, wave->d_next_rays, wave->d_spawn, static_cast<cudaStream_t>(cuda_stream));
+  RDN_CUDA(cudaGetLastError());
+  return RDN_OK;
+}
+int rdn_rt_stage_store_f32(rdn_rt_scene *s, int device_index, const rdn_wave *wave, float value, float *d_dst, void *cuda_stream) {
+  const int rc = stage_device(s, device_index, wave, "rdn_rt_stage_store_f32");
+  if (rc != RDN_OK) return rc;
+  if (!d_dst) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_stage_store_f32: null destination");
+  launch_stage_store_f32(wave->d_tasks, wave->d_task_count, wave->max_tasks, wave->d_launch_index, value, d_dst, static_cast<cudaStream_t>(cuda_stream));
+  RDN_CUDA(cudaGetLastError());
+  return RDN_OK;
+}
+int rdn_rt_ao_resolve_device(rdn_rt_scene *s, int device_index, float *d_payload, uint64_t n_pixels, uint32_t sample_count, uint32_t max_sample,
+                             float *d_ao_buffer, void *cuda_stream) {
+  if (!s || !d_payload || !d_ao_buffer) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_ao_resolve_device: null argument");
+  if (device_index < 0 || device_index >= static_cast<int>(s->devices.size())) return fail(RDN_ERR_INVALID_ARGUMENT, "bad device_index");
+  RDN_CUDA(cudaSetDevice(s->devices[device_index].device));
+  launch_ao_resolve(d_payload, n_pixels, sample_count, max_sample, d_ao_buffer, static_cast<cudaStream_t>(cuda_stream));
   RDN_CUDA(cudaGetLastError());
   return RDN_OK;
 }

@@ -136,6 +136,28 @@ void launch_sbt_group(const uint32_t *d_task, uint64_t n, uint32_t n_closest, ui
                       uint32_t *d_segment, uint64_t *d_count, unsigned long long *d_status, uint32_t *d_queue, uint64_t *d_offsets,
                       cudaStream_t stream);
 
+// one-call wavefront executor (wavefront.cu): glue kernels between the rounds of rdn_rt_trace_ray
+void launch_wave_gather(const rdn_ray *d_next_rays, const uint32_t *d_launch_in, const uint32_t *d_idx, const uint64_t *d_count, uint64_t n_max,
+                        rdn_ray *d_rays_out, uint32_t *d_launch_out, cudaStream_t stream);
+void launch_wave_mark(const uint32_t *d_task, const uint64_t *d_wave_size, uint64_t n_max, uint32_t code, uint8_t *d_keep, uint32_t *d_iota,
+                      cudaStream_t stream);
+void launch_wave_clip_spawn(uint8_t *d_spawn, const uint64_t *d_wave_size, uint64_t n_max, uint32_t *d_iota, cudaStream_t stream);
+void launch_wave_record(const uint64_t *const *d_counters, uint32_t n, uint64_t *d_row, cudaStream_t stream);
+void launch_store_u64(uint64_t *d_dst, uint64_t v, cudaStream_t stream);
+void launch_stage_spawn_all(uint8_t *d_spawn, const uint64_t *d_count, uint64_t n_max, cudaStream_t stream);
+void launch_stage_store_f32(const uint32_t *d_tasks, const uint64_t *d_count, uint64_t n_max, const uint32_t *d_launch_index, float value,
+                            float *d_dst, cudaStream_t stream);
+// the closest-hit -> next ray step as a stage: source rays are the tasks of `d_tasks`, ray k goes to slot d_tasks[k] of d_rays_out
+// with d_spawn[slot] = 1; sample indices come from the launch index when d_launch_index is given
+void launch_stage_bounce_rays(const SceneDev &scene, const rdn_bounce &p, const rdn_ray *d_rays_in, const rdn_hit *d_hits, const uint32_t *d_tasks,
+                              const uint64_t *d_count, uint64_t n_max, const uint32_t *d_launch_index, rdn_ray *d_rays_out, uint8_t *d_spawn,
+                              cudaStream_t stream);
+// device-sized variant of launch_sbt_dispatch: rays [0, *d_n) of an upper bound n_max
+void launch_sbt_dispatch_n(const SceneDev &scene, const SbtHitGroup *d_hit_groups, uint32_t n_hit_groups, const uint32_t *d_miss, uint32_t n_miss,
+                           const rdn_sbt_ray_config &cfg, const rdn_hit *d_hits, const uint64_t *d_n, uint64_t n_max, uint32_t *d_task,
+                           cudaStream_t stream);
+void launch_ao_resolve(float *d_payload, uint64_t n_pixels, uint32_t sample_count, uint32_t max_sample, float *d_ao_buffer, cudaStream_t stream);
+
 // measurement hook (probe.cu): read bandwidth of an L2-resident buffer of `bytes` on the current device, GB/s
 int measure_l2_read_gbs(uint64_t bytes, int passes, int sm_count, double *out_gbs);
 

@@ -221,9 +221,13 @@ __device__ __forceinline__ Vec3 offset_ray_hit(Vec3 p, Vec3 n) {
   return Vec3{offset_component(p.x, n.x), offset_component(p.y, n.y), offset_component(p.z, n.z)};
 }
 
+// SCATTER (a stage of rdn_rt_trace_ray): ray k is written to slot src of rays_out and announced in spawn[src]; its low-discrepancy
+// index is the launch index of the source ray.  Otherwise (the compacting bounce step): ray k goes to rays_out[k].
+template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_gen_bounce_rays(const SceneDev S, const rdn_bounce P, const rdn_ray *__restrict__ rays_in,
                                                          const rdn_hit *__restrict__ hits, const uint32_t *__restrict__ src_index,
-                                                         const uint64_t *__restrict__ n_src, rdn_ray *__restrict__ rays_out) {
+                                                         const uint64_t *__restrict__ n_src, rdn_ray *__restrict__ rays_out,
+                                                         const uint32_t *__restrict__ launch_index, uint8_t *__restrict__ spawn) {
   const uint64_t n = *n_src;
   for (uint64_t k = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; k < n; k += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
     const uint32_t src = src_index[k];
@@ -254,7 +258,8 @@ __global__ void __launch_bounds__(256) k_gen_bounce_rays(const SceneDev S, const
     Vec3 dir;
     float tmax = P.tmax;
     if (P.mode == 0) {
-      dir = cosine_sample_hemisphere_in_dir(g, van_der_corput(src + P.index_base, P.scramble0), sobol2(src + P.index_base, P.scramble1));
+      const uint32_t sample = (SCATTER && launch_index ? launch_index[src] : src) + P.index_base;
+      dir = cosine_sample_hemisphere_in_dir(g, van_der_corput(sample, P.scramble0), sobol2(sample, P.scramble1));
     } else if (P.mode == 1) {
       dir = ao_direction(g, P.sample_index, P.max_sample);
     } else {
@@ -265,7 +270,8 @@ __global__ void __launch_bounds__(256) k_gen_bounce_rays(const SceneDev S, const
       tmax = distance;
     }
     const Vec3 origin = (P.flags & RDN_BOUNCE_OFFSET_ORIGIN) ? offset_ray_hit(pos, g) : pos;
-    store_ray(rays_out + k, origin, P.tmin, dir, tmax);
+    store_ray(rays_out + (SCATTER ? src : k), origin, P.tmin, dir, tmax);
+    if (SCATTER) spawn[src] = 1;
   }
 }
 
@@ -305,7 +311,15 @@ void launch_ao_accumulate(const rdn_hit *d_secondary_hits, const uint32_t *d_src
 }
 void launch_gen_bounce_rays(const SceneDev &scene, const rdn_bounce &p, const rdn_ray *d_rays_in, const rdn_hit *d_hits,
                             const uint32_t *d_src_index, const uint64_t *d_n_src, uint64_t n_max, rdn_ray *d_rays_out, cudaStream_t stream) {
-  if (n_max) k_gen_bounce_rays<<<grid_for(n_max, 256), 256, 0, stream>>>(scene, p, d_rays_in, d_hits, d_src_index, d_n_src, d_rays_out);
+  if (n_max) k_gen_bounce_rays<false><<<grid_for(n_max, 256), 256, 0, stream>>>(scene, p, d_rays_in, d_hits, d_src_index, d_n_src, d_rays_out, nullptr, nullptr);
+}
+void launch_stage_bounce_rays(const SceneDev &scene, const rdn_bounce &p, const rdn_ray *d_rays_in, const rdn_hit *d_hits, const uint32_t *d_tasks,
+                              const uint64_t *d_count, uint64_t n_max, const uint32_t *d_launch_index, rdn_ray *d_rays_out, uint8_t *d_spawn,
+                              cudaStream_t stream) {
+  if (n_max) k_gen_bounce_rays<true><<<grid_for(n_max, 256), 256, 0, stream>>>(scene, p, d_rays_in, d_hits, d_tasks, d_count, d_rays_out, d_launch_index, d_spawn);
+}
+void launch_ao_resolve(float *d_payload, uint64_t n_pixels, uint32_t sample_count, uint32_t max_sample, float *d_ao_buffer, cudaStream_t stream) {
+  if (n_pixels) k_ao_accumulate<<<grid_for(n_pixels, 256), 256, 0, stream>>>(d_payload, n_pixels, sample_count, max_sample, d_ao_buffer);
 }
 
 }  // namespace rdn

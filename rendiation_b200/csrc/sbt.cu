@@ -25,7 +25,9 @@ namespace {
 __global__ void __launch_bounds__(256) k_sbt_dispatch(const InstanceRecord *__restrict__ instances, uint32_t n_instances,
                                                       const SbtHitGroup *__restrict__ hit_groups, uint32_t n_hit_groups,
                                                       const uint32_t *__restrict__ miss_shaders, uint32_t n_miss, rdn_sbt_ray_config cfg,
-                                                      const rdn_hit *__restrict__ hits, uint64_t n, uint32_t *__restrict__ task) {
+                                                      const rdn_hit *__restrict__ hits, uint64_t n_max, uint32_t *__restrict__ task,
+                                                      const uint64_t *__restrict__ n_ptr) {
+  const uint64_t n = n_ptr ? (*n_ptr < n_max ? *n_ptr : n_max) : n_max;  // (a wave sized on the device)
   for (uint64_t k = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; k < n; k += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
     const uint4 ids = __ldg(reinterpret_cast<const uint4 *>(hits + k) + 1);  // geometry_id, instance_id, instance_custom_id, hit_kind
     uint32_t code = RDN_TASK_NONE;
@@ -72,7 +74,12 @@ unsigned grid_for(uint64_t n) {
 
 void launch_sbt_dispatch(const SceneDev &scene, const SbtHitGroup *d_hit_groups, uint32_t n_hit_groups, const uint32_t *d_miss, uint32_t n_miss,
                          const rdn_sbt_ray_config &cfg, const rdn_hit *d_hits, uint64_t n, uint32_t *d_task, cudaStream_t stream) {
-  if (n) k_sbt_dispatch<<<grid_for(n), 256, 0, stream>>>(scene.instances, scene.n_instances, d_hit_groups, n_hit_groups, d_miss, n_miss, cfg, d_hits, n, d_task);
+  if (n) k_sbt_dispatch<<<grid_for(n), 256, 0, stream>>>(scene.instances, scene.n_instances, d_hit_groups, n_hit_groups, d_miss, n_miss, cfg, d_hits, n, d_task, nullptr);
+}
+void launch_sbt_dispatch_n(const SceneDev &scene, const SbtHitGroup *d_hit_groups, uint32_t n_hit_groups, const uint32_t *d_miss, uint32_t n_miss,
+                           const rdn_sbt_ray_config &cfg, const rdn_hit *d_hits, const uint64_t *d_n, uint64_t n_max, uint32_t *d_task,
+                           cudaStream_t stream) {
+  if (n_max) k_sbt_dispatch<<<grid_for(n_max), 256, 0, stream>>>(scene.instances, scene.n_instances, d_hit_groups, n_hit_groups, d_miss, n_miss, cfg, d_hits, n_max, d_task, d_n);
 }
 
 void launch_sbt_group(const uint32_t *d_task, uint64_t n, uint32_t n_closest, uint32_t n_miss, uint8_t *d_keep, uint32_t *d_iota,

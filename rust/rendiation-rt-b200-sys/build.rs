@@ -8,7 +8,7 @@ use std::env;
 use std::path::PathBuf;
 
 const SOURCES: &[&str] = &[
-    "bvh_builder.cpp", "accel.cpp", "traverse.cu", "compact.cu", "raygen.cu", "probe.cu", "pick.cu", "build_device.cu", "sbt.cu", "capi.cu",
+    "bvh_builder.cpp", "accel.cpp", "traverse.cu", "compact.cu", "raygen.cu", "probe.cu", "pick.cu", "build_device.cu", "sbt.cu", "wavefront.cu", "capi.cu",
 ];
 
 fn main() {

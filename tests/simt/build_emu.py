@@ -26,7 +26,7 @@ OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "librdn_rt_emu.so")
 CUDA_INCLUDE = os.environ.get("CUDA_INCLUDE", "/usr/local/cuda/include")
 
-SOURCES = ["bvh_builder.cpp", "accel.cpp", "traverse.cu", "compact.cu", "raygen.cu", "probe.cu", "pick.cu", "build_device.cu", "sbt.cu", "capi.cu"]
+SOURCES = ["bvh_builder.cpp", "accel.cpp", "traverse.cu", "compact.cu", "raygen.cu", "probe.cu", "pick.cu", "build_device.cu", "sbt.cu", "wavefront.cu", "capi.cu"]
 EMU_SOURCES = ["simt_engine.cpp", "simt_cudart.cpp", "simt_selftest.cpp"]
 CXXFLAGS = ["-std=c++17", "-O2", "-g", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-DRDN_SIMT_EMU", "-Wno-attributes",
             "-Wno-unknown-pragmas", "-I", INCLUDE, "-I", CSRC, "-I", HERE, "-isystem", CUDA_INCLUDE, "-include",
