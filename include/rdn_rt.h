@@ -146,6 +146,8 @@ typedef struct rdn_build_stats {
   double bvh_build_ms, flatten_ms, upload_ms;          /* wall clock of the last commit: tree builds / flattening / blob + upload */
   uint64_t build_threads;                              /* worker threads the tree builder used (RDN_BUILD_THREADS caps it) */
   uint64_t device_built_trees;                         /* geometry trees built by the device SAH builder (RDN_COMMIT_DEVICE_BUILD=1) */
+  uint64_t tlas_only_commits;                          /* commits so far that kept every BLAS array and patched the TLAS part of the device
+                                                          blobs in place (rdn_rt_tlas_update) */
 } rdn_build_stats;
 
 typedef struct rdn_rt_scene rdn_rt_scene;   /* opaque: NaiveSahBVHSystem (geometry/naive/mod.rs:495-610) */
@@ -163,6 +165,12 @@ int rdn_rt_blas_destroy(rdn_rt_scene *scene, uint32_t handle); /* delete_bottom_
 int rdn_rt_tlas_create(rdn_rt_scene *scene, const rdn_instance *instances, uint32_t n, uint32_t *out_handle);
                                                             /* create_top_level_acceleration_structure */
 int rdn_rt_tlas_destroy(rdn_rt_scene *scene, uint32_t handle); /* delete_top_level_acceleration_structure */
+/* Replace the instances of a live TLAS (moving objects: same handle, new transforms).  No reference counterpart — its build is
+ * "todo incremental change" (naive/mod.rs:121) and any mutation invalidates everything (:546-549).  The next commit after TLAS-only
+ * mutations (this call, TLAS create / destroy, bind_tlas) rebuilds the TLAS trees alone — the reference's build_tlas on the new
+ * instances, same result as a from-scratch build — keeps every BLAS array, and, when no array changes its length, patches the
+ * device blobs in place instead of uploading the scene again. */
+int rdn_rt_tlas_update(rdn_rt_scene *scene, uint32_t handle, const rdn_instance *instances, uint32_t n);
 int rdn_rt_bind_tlas(rdn_rt_scene *scene, const uint32_t *handles, uint32_t n);   /* bind_tlas */
 uint32_t rdn_rt_bind_tlas_max_len(const rdn_rt_scene *scene);                     /* bind_tlas_max_len */
 

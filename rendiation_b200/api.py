@@ -123,7 +123,7 @@ class _TraceStats(C.Structure):
 class _BuildStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("balance_fallbacks", "balance_fallbacks_gt10", "irregular_triangles", "irregular_instances",
                                           "reference_routed_tlas")] + \
-               [(n, C.c_double) for n in ("bvh_build_ms", "flatten_ms", "upload_ms")] + [("build_threads", C.c_uint64), ("device_built_trees", C.c_uint64)]
+               [(n, C.c_double) for n in ("bvh_build_ms", "flatten_ms", "upload_ms")] + [("build_threads", C.c_uint64), ("device_built_trees", C.c_uint64), ("tlas_only_commits", C.c_uint64)]
 
 
 class _KernelTimes(C.Structure):
@@ -189,7 +189,7 @@ class _MeshView(C.Structure):
 
 EXPORTED_SYMBOLS = [
     "rdn_rt_scene_create", "rdn_rt_scene_destroy", "rdn_rt_blas_create", "rdn_rt_blas_destroy", "rdn_rt_tlas_create",
-    "rdn_rt_tlas_destroy", "rdn_rt_bind_tlas", "rdn_rt_bind_tlas_max_len", "rdn_rt_commit", "rdn_rt_trace_closest",
+    "rdn_rt_tlas_destroy", "rdn_rt_tlas_update", "rdn_rt_bind_tlas", "rdn_rt_bind_tlas_max_len", "rdn_rt_commit", "rdn_rt_trace_closest",
     "rdn_rt_trace_closest_device", "rdn_rt_trace_closest_device_n", "rdn_rt_poll_errors", "rdn_rt_host_alloc", "rdn_rt_host_free",
     "rdn_rt_host_register", "rdn_rt_host_unregister", "rdn_rt_set_any_hit_programs", "rdn_rt_bind_sbt", "rdn_rt_trace_ray",
     "rdn_rt_stage_spawn_all", "rdn_rt_stage_bounce", "rdn_rt_stage_store_f32", "rdn_rt_ao_resolve_device", "rdn_rt_trace_counted", "rdn_rt_kernel_timing_begin", "rdn_rt_kernel_timing_end",
@@ -224,6 +224,7 @@ def lib() -> C.CDLL:
     L.rdn_rt_blas_destroy.argtypes = [vp, u32]
     L.rdn_rt_tlas_create.argtypes = [vp, vp, u32, P(u32)]
     L.rdn_rt_tlas_destroy.argtypes = [vp, u32]
+    L.rdn_rt_tlas_update.argtypes = [vp, u32, vp, u32]
     L.rdn_rt_bind_tlas.argtypes = [vp, vp, u32]
     L.rdn_rt_bind_tlas_max_len.argtypes = [vp]
     L.rdn_rt_bind_tlas_max_len.restype = u32
@@ -388,6 +389,11 @@ class NaiveSahBVHSystem:
         out = C.c_uint32()
         _check(self._L.rdn_rt_tlas_create(self._h, _p(inst), inst.shape[0], C.byref(out)))
         return TlasHandle(out.value)
+
+    def update_top_level_acceleration_structure(self, handle: TlasHandle, source: np.ndarray):
+        """rdn_rt_tlas_update: replace the instances of a live TLAS; the next commit rebuilds the TLAS part only."""
+        inst = _c(source, INSTANCE_DTYPE)
+        _check(self._L.rdn_rt_tlas_update(self._h, handle.id if isinstance(handle, TlasHandle) else int(handle), _p(inst), inst.shape[0]))
 
     def delete_top_level_acceleration_structure(self, handle: TlasHandle):
         _check(self._L.rdn_rt_tlas_destroy(self._h, handle.id))

@@ -92,6 +92,7 @@ Box3 box_apply_matrix(const Box3 &b, const Mat4 &m) {
 
 // ------------------------------------------------------------------------------------------------ sources
 uint32_t NaiveSahBvhSource::create_blas(std::vector<GeometrySource> source) {
+  ++blas_epoch_;
   blas_data_.push_back(Blas{true, std::move(source)});
   return static_cast<uint32_t>(blas_data_.size() - 1);
 }
@@ -101,7 +102,13 @@ uint32_t NaiveSahBvhSource::create_tlas(std::vector<InstanceSource> source) {
 }
 bool NaiveSahBvhSource::delete_blas(uint32_t h) {
   if (h >= blas_data_.size()) return false;
+  ++blas_epoch_;
   blas_data_[h] = Blas{};
+  return true;
+}
+bool NaiveSahBvhSource::update_tlas(uint32_t h, std::vector<InstanceSource> source) {
+  if (h >= tlas_data_.size() || !tlas_data_[h].alive) return false;
+  tlas_data_[h].instances = std::move(source);
   return true;
 }
 bool NaiveSahBvhSource::delete_tlas(uint32_t h) {
@@ -399,9 +406,9 @@ static bool instance_is_irregular(const Mat4 &m, const Mat4 &inv, const Box3 &us
   return false;
 }
 
-int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScene &out, std::string &err) const {
+int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScene &out, std::string &err, FlatScene *previous, bool *reused) const {
   out = FlatScene{};
-  out.tlas_binding = tlas_binding;
+  if (reused) *reused = false;
   bool capacity_error = false;
   using Clock = std::chrono::steady_clock;
   const auto t_begin = Clock::now();
@@ -414,6 +421,18 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
   // what the ordered kernel walks (issue model, config 4: -19 % warp instructions).  RDN_FINE_TLAS=0 restores the multi-slot leaves.
   const char *fine_env = getenv("RDN_FINE_TLAS");
   const bool fine_tlas = !fine_env || atoi(fine_env) != 0;
+  // TLAS-only rebuild: the BLAS arrays of the previous flattened scene are still right when no BLAS was created or deleted since
+  const bool reuse_blas = previous && cache_.blas_epoch == blas_epoch_ && cache_.want_wide4 == want_wide4 && cache_.fine_tlas == fine_tlas &&
+                          previous->wide_nodes.size() >= cache_.wide_nodes_n && previous->blas_meta.size() == blas_data_.size();
+  if (reuse_blas) {
+    out = std::move(*previous);
+    out.tlas_root.clear(); out.tlas_bvh_forest.clear(); out.tlas_bounding.clear(); out.instances.clear(); out.irregular_instances.clear();
+    out.wide_nodes.resize(cache_.wide_nodes_n);
+    out.wide4_nodes.resize(cache_.wide4_nodes_n);
+    out.stats = cache_.stats;
+    if (reused) *reused = true;
+  }
+  out.tlas_binding = tlas_binding;
   double ms_boxes = 0, ms_records = 0, ms_wide = 0, ms_threaded = 0, ms_leaves = 0;
   auto since = [](Clock::time_point t0) { return std::chrono::duration<double, std::milli>(Clock::now() - t0).count(); };
   auto timed_build = [&](const Box3 *boxes, uint64_t n, BVHBuildStrategy &strategy, const TreeBuildOption &option) {
@@ -435,136 +454,146 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
 
   // ---- build_blas (mod.rs:122-260).  NOTE blas_box gets one entry PER GEOMETRY of a live BLAS but one per
   // deleted BLAS, and build_tlas indexes it by BLAS handle (mod.rs:239,273) — reproduced as is.
-  struct OptBox { bool some; Box3 box; };
   std::vector<OptBox> blas_box;
   std::vector<Box3> blas_true_box;       // per BLAS HANDLE: bound of all its triangle geometries
   std::vector<uint32_t> blas_irregular;  // per BLAS handle: BlasMeta::irregular_leaf_count
-  struct HotBlock { uint32_t base = 0, count = 0; uint64_t triangles = 0; };
   std::vector<HotBlock> blas_hot;        // per BLAS handle: the top block of its largest geometry tree
   uint64_t n_indices_total = 0;  // geometry_indices.len()
   const TreeBuildOption blas_option{50, 2};
 
-  for (const Blas &blas : blas_data_) {
-    if (!blas.alive) {
-      out.blas_meta.push_back(BlasMeta{{0, 0}, 0, 0});
-      blas_box.push_back(OptBox{false, box_empty()});
-      blas_true_box.push_back(box_empty());
-      blas_irregular.push_back(0);
-      blas_hot.push_back(HotBlock{});
-      continue;
-    }
-    HotBlock hot;
-    const uint32_t tri_start = static_cast<uint32_t>(out.geometry_meta.size());
-    Box3 true_box = box_empty();
-    const uint32_t leaf_start = static_cast<uint32_t>(out.irregular_leaf_boxes.size());
-    for (size_t g = 0; g < blas.geometries.size(); ++g) {
-      const GeometrySource &src = blas.geometries[g];
-      Box3 root_box = box_empty();
-      if (!src.is_aabbs) {
-        const uint32_t primitive_start = static_cast<uint32_t>(n_indices_total / 3);
-        const uint64_t n_idx = src.has_indices ? src.indices.size() : src.positions.size();
-        const uint64_t n_tri = n_idx / 3;  // as_chunks::<3>().0 drops the remainder
-        auto vertex_of = [&](uint64_t tri, int k) -> uint64_t { return src.has_indices ? src.indices[3 * tri + k] : 3 * tri + k; };
-        auto t_phase = Clock::now();
-        std::vector<Box3> boxes(n_tri);
-        std::atomic<bool> index_out_of_bounds{false};
-        parallel_for(n_tri, PARALLEL_BUILD_MIN, [&](uint64_t t_begin_, uint64_t t_end_) {
-          for (uint64_t t = t_begin_; t < t_end_; ++t) {
-            Box3 b = box_empty();
-            for (int k = 0; k < 3; ++k) {
-              const uint64_t vi = vertex_of(t, k);
-              if (vi >= src.positions.size()) { index_out_of_bounds = true; return; }
-              expand(b, src.positions[vi]);
-            }
-            boxes[t] = b;
-          }
-        });
-        if (index_out_of_bounds) { err = "triangle index out of bounds (the reference panics here)"; return RDN_ERR_BUILD; }
-        ms_boxes += since(t_phase);
-        SAH sah(4);
-        FlattenBVH bvh = timed_build(boxes.data(), n_tri, sah, blas_option);
-        if (bvh.stats.bucket_out_of_range) { err = "SAH bucket index out of range (the reference panics here)"; return RDN_ERR_BUILD; }
-        out.stats.balance_fallbacks += bvh.stats.balance_fallbacks;
-        out.stats.balance_fallbacks_gt10 += bvh.stats.balance_fallbacks_gt10;
-        expand(root_box, bvh.nodes[0].bounding);
-        if (n_tri) expand(true_box, bvh.nodes[0].bounding);
-        t_phase = Clock::now();
-        const auto next = compute_bvh_next(bvh.nodes);
-        ms_threaded += since(t_phase);
-        t_phase = Clock::now();
-
-        // slots of this geometry start at primitive_start (indices_redirect and indices grow in lock step)
-        const uint64_t slot_base = out.triangles.size();
-        if (slot_base != primitive_start) { err = "internal: slot/primitive offset mismatch"; return RDN_ERR_BUILD; }
-        out.prim_to_slot.resize(slot_base + n_tri, 0u);
-        out.triangles.resize(slot_base + n_tri);
-        out.slot_info.resize(slot_base + n_tri);
-        std::vector<uint8_t> slot_irregular(n_tri, 0);
-        parallel_for(n_tri, PARALLEL_BUILD_MIN, [&](uint64_t k_begin, uint64_t k_end) {
-          for (uint64_t k = k_begin; k < k_end; ++k) {
-            const uint64_t tri = bvh.sorted_primitive_index[k];  // indices_redirect[slot] - raw_primitive_start
-            out.prim_to_slot[slot_base + tri] = static_cast<uint32_t>(slot_base + k);
-            out.triangles[slot_base + k] = make_tri_record(src.positions[vertex_of(tri, 0)], src.positions[vertex_of(tri, 1)],
-                                                           src.positions[vertex_of(tri, 2)]);
-            out.slot_info[slot_base + k] = SlotInfo{static_cast<uint32_t>(tri), static_cast<uint32_t>(g)};
-            slot_irregular[k] = triangle_is_irregular(out.triangles[slot_base + k]) ? 1 : 0;
-          }
-        });
-        for (uint64_t k = 0; k < n_tri; ++k) out.stats.irregular_triangles += slot_irregular[k];
-        ms_records += since(t_phase);
-        t_phase = Clock::now();
-        n_indices_total += n_tri * 3;
-        // the boxes of the leaves that hold an irregular triangle: the reference can test such a triangle only after this box test
-        for (const FlattenBVHNode &node : bvh.nodes) {
-          if (node.has_child) continue;
-          bool any = false;
-          for (uint64_t k = node.primitive_start; k < node.primitive_end && !any; ++k) any = slot_irregular[k] != 0;
-          if (!any) continue;
-          LeafBox lb;
-          std::memset(&lb, 0, sizeof(lb));
-          lb.bmin[0] = node.bounding.min.x; lb.bmin[1] = node.bounding.min.y; lb.bmin[2] = node.bounding.min.z;
-          lb.bmax[0] = node.bounding.max.x; lb.bmax[1] = node.bounding.max.y; lb.bmax[2] = node.bounding.max.z;
-          out.irregular_leaf_boxes.push_back(lb);
-        }
-
-        ms_leaves += since(t_phase);
-        t_phase = Clock::now();
-        const uint32_t bvh_start = static_cast<uint32_t>(out.tri_bvh_forest.size());
-        GeometryMeta gm;
-        std::memset(&gm, 0, sizeof(gm));
-        gm.bvh_root_idx = bvh_start;
-        gm.geometry_idx = static_cast<uint32_t>(g);
-        gm.primitive_start = primitive_start;
-        gm.geometry_flags = src.flags;
-        gm.wide_root = emit_wide_nodes(bvh.nodes, primitive_start, out.wide_nodes, capacity_error);
-        gm.wide4_root = want_wide4 ? emit_wide4_nodes(bvh.nodes, primitive_start, out.wide4_nodes, capacity_error) : REF_EMPTY;
-        if (gm.wide_root != REF_EMPTY && n_tri > hot.triangles) {
-          const uint64_t block = out.wide_nodes.size() - gm.wide_root;
-          hot = HotBlock{gm.wide_root, static_cast<uint32_t>(block < HOT_TOP_NODES ? block : HOT_TOP_NODES), n_tri};
-        }
-        out.geometry_meta.push_back(gm);
-        ms_wide += since(t_phase);
-        t_phase = Clock::now();
-        out.tri_bvh_forest.resize(bvh_start + bvh.nodes.size());
-        parallel_for(bvh.nodes.size(), PARALLEL_BUILD_MIN, [&](uint64_t i_begin, uint64_t i_end) {
-          for (uint64_t i = i_begin; i < i_end; ++i)
-            out.tri_bvh_forest[bvh_start + i] = to_device_node(bvh.nodes[i], next[i].first, next[i].second, bvh_start, primitive_start);
-        });
-        ms_threaded += since(t_phase);
+  if (reuse_blas) {
+    blas_box = cache_.blas_box; blas_true_box = cache_.blas_true_box; blas_irregular = cache_.blas_irregular; blas_hot = cache_.blas_hot;
+  } else {
+    for (const Blas &blas : blas_data_) {
+      if (!blas.alive) {
+        out.blas_meta.push_back(BlasMeta{{0, 0}, 0, 0});
+        blas_box.push_back(OptBox{false, box_empty()});
+        blas_true_box.push_back(box_empty());
+        blas_irregular.push_back(0);
+        blas_hot.push_back(HotBlock{});
+        continue;
       }
-      blas_box.push_back(OptBox{true, root_box});
+      HotBlock hot;
+      const uint32_t tri_start = static_cast<uint32_t>(out.geometry_meta.size());
+      Box3 true_box = box_empty();
+      const uint32_t leaf_start = static_cast<uint32_t>(out.irregular_leaf_boxes.size());
+      for (size_t g = 0; g < blas.geometries.size(); ++g) {
+        const GeometrySource &src = blas.geometries[g];
+        Box3 root_box = box_empty();
+        if (!src.is_aabbs) {
+          const uint32_t primitive_start = static_cast<uint32_t>(n_indices_total / 3);
+          const uint64_t n_idx = src.has_indices ? src.indices.size() : src.positions.size();
+          const uint64_t n_tri = n_idx / 3;  // as_chunks::<3>().0 drops the remainder
+          auto vertex_of = [&](uint64_t tri, int k) -> uint64_t { return src.has_indices ? src.indices[3 * tri + k] : 3 * tri + k; };
+          auto t_phase = Clock::now();
+          std::vector<Box3> boxes(n_tri);
+          std::atomic<bool> index_out_of_bounds{false};
+          parallel_for(n_tri, PARALLEL_BUILD_MIN, [&](uint64_t t_begin_, uint64_t t_end_) {
+            for (uint64_t t = t_begin_; t < t_end_; ++t) {
+              Box3 b = box_empty();
+              for (int k = 0; k < 3; ++k) {
+                const uint64_t vi = vertex_of(t, k);
+                if (vi >= src.positions.size()) { index_out_of_bounds = true; return; }
+                expand(b, src.positions[vi]);
+              }
+              boxes[t] = b;
+            }
+          });
+          if (index_out_of_bounds) { err = "triangle index out of bounds (the reference panics here)"; return RDN_ERR_BUILD; }
+          ms_boxes += since(t_phase);
+          SAH sah(4);
+          FlattenBVH bvh = timed_build(boxes.data(), n_tri, sah, blas_option);
+          if (bvh.stats.bucket_out_of_range) { err = "SAH bucket index out of range (the reference panics here)"; return RDN_ERR_BUILD; }
+          out.stats.balance_fallbacks += bvh.stats.balance_fallbacks;
+          out.stats.balance_fallbacks_gt10 += bvh.stats.balance_fallbacks_gt10;
+          expand(root_box, bvh.nodes[0].bounding);
+          if (n_tri) expand(true_box, bvh.nodes[0].bounding);
+          t_phase = Clock::now();
+          const auto next = compute_bvh_next(bvh.nodes);
+          ms_threaded += since(t_phase);
+          t_phase = Clock::now();
+
+          // slots of this geometry start at primitive_start (indices_redirect and indices grow in lock step)
+          const uint64_t slot_base = out.triangles.size();
+          if (slot_base != primitive_start) { err = "internal: slot/primitive offset mismatch"; return RDN_ERR_BUILD; }
+          out.prim_to_slot.resize(slot_base + n_tri, 0u);
+          out.triangles.resize(slot_base + n_tri);
+          out.slot_info.resize(slot_base + n_tri);
+          std::vector<uint8_t> slot_irregular(n_tri, 0);
+          parallel_for(n_tri, PARALLEL_BUILD_MIN, [&](uint64_t k_begin, uint64_t k_end) {
+            for (uint64_t k = k_begin; k < k_end; ++k) {
+              const uint64_t tri = bvh.sorted_primitive_index[k];  // indices_redirect[slot] - raw_primitive_start
+              out.prim_to_slot[slot_base + tri] = static_cast<uint32_t>(slot_base + k);
+              out.triangles[slot_base + k] = make_tri_record(src.positions[vertex_of(tri, 0)], src.positions[vertex_of(tri, 1)],
+                                                             src.positions[vertex_of(tri, 2)]);
+              out.slot_info[slot_base + k] = SlotInfo{static_cast<uint32_t>(tri), static_cast<uint32_t>(g)};
+              slot_irregular[k] = triangle_is_irregular(out.triangles[slot_base + k]) ? 1 : 0;
+            }
+          });
+          for (uint64_t k = 0; k < n_tri; ++k) out.stats.irregular_triangles += slot_irregular[k];
+          ms_records += since(t_phase);
+          t_phase = Clock::now();
+          n_indices_total += n_tri * 3;
+          // the boxes of the leaves that hold an irregular triangle: the reference can test such a triangle only after this box test
+          for (const FlattenBVHNode &node : bvh.nodes) {
+            if (node.has_child) continue;
+            bool any = false;
+            for (uint64_t k = node.primitive_start; k < node.primitive_end && !any; ++k) any = slot_irregular[k] != 0;
+            if (!any) continue;
+            LeafBox lb;
+            std::memset(&lb, 0, sizeof(lb));
+            lb.bmin[0] = node.bounding.min.x; lb.bmin[1] = node.bounding.min.y; lb.bmin[2] = node.bounding.min.z;
+            lb.bmax[0] = node.bounding.max.x; lb.bmax[1] = node.bounding.max.y; lb.bmax[2] = node.bounding.max.z;
+            out.irregular_leaf_boxes.push_back(lb);
+          }
+
+          ms_leaves += since(t_phase);
+          t_phase = Clock::now();
+          const uint32_t bvh_start = static_cast<uint32_t>(out.tri_bvh_forest.size());
+          GeometryMeta gm;
+          std::memset(&gm, 0, sizeof(gm));
+          gm.bvh_root_idx = bvh_start;
+          gm.geometry_idx = static_cast<uint32_t>(g);
+          gm.primitive_start = primitive_start;
+          gm.geometry_flags = src.flags;
+          gm.wide_root = emit_wide_nodes(bvh.nodes, primitive_start, out.wide_nodes, capacity_error);
+          gm.wide4_root = want_wide4 ? emit_wide4_nodes(bvh.nodes, primitive_start, out.wide4_nodes, capacity_error) : REF_EMPTY;
+          if (gm.wide_root != REF_EMPTY && n_tri > hot.triangles) {
+            const uint64_t block = out.wide_nodes.size() - gm.wide_root;
+            hot = HotBlock{gm.wide_root, static_cast<uint32_t>(block < HOT_TOP_NODES ? block : HOT_TOP_NODES), n_tri};
+          }
+          out.geometry_meta.push_back(gm);
+          ms_wide += since(t_phase);
+          t_phase = Clock::now();
+          out.tri_bvh_forest.resize(bvh_start + bvh.nodes.size());
+          parallel_for(bvh.nodes.size(), PARALLEL_BUILD_MIN, [&](uint64_t i_begin, uint64_t i_end) {
+            for (uint64_t i = i_begin; i < i_end; ++i)
+              out.tri_bvh_forest[bvh_start + i] = to_device_node(bvh.nodes[i], next[i].first, next[i].second, bvh_start, primitive_start);
+          });
+          ms_threaded += since(t_phase);
+        }
+        blas_box.push_back(OptBox{true, root_box});
+      }
+      uint32_t leaf_count = static_cast<uint32_t>(out.irregular_leaf_boxes.size() - leaf_start);
+      if (leaf_count > IRREGULAR_LEAF_MAX) {
+        out.irregular_leaf_boxes.resize(leaf_start);
+        leaf_count = IRREGULAR_ROUTE_ALL;
+      }
+      out.blas_meta.push_back(BlasMeta{{tri_start, static_cast<uint32_t>(out.geometry_meta.size())}, leaf_start, leaf_count});
+      blas_true_box.push_back(true_box);
+      blas_irregular.push_back(leaf_count);
+      blas_hot.push_back(hot);
     }
-    uint32_t leaf_count = static_cast<uint32_t>(out.irregular_leaf_boxes.size() - leaf_start);
-    if (leaf_count > IRREGULAR_LEAF_MAX) {
-      out.irregular_leaf_boxes.resize(leaf_start);
-      leaf_count = IRREGULAR_ROUTE_ALL;
-    }
-    out.blas_meta.push_back(BlasMeta{{tri_start, static_cast<uint32_t>(out.geometry_meta.size())}, leaf_start, leaf_count});
-    blas_true_box.push_back(true_box);
-    blas_irregular.push_back(leaf_count);
-    blas_hot.push_back(hot);
+    cache_.blas_epoch = 0;  // (filled below once the BLAS part is known to be complete)
   }
 
+  if (!reuse_blas) {
+    cache_.blas_box = blas_box; cache_.blas_true_box = blas_true_box; cache_.blas_irregular = blas_irregular; cache_.blas_hot = blas_hot;
+    cache_.wide_nodes_n = out.wide_nodes.size(); cache_.wide4_nodes_n = out.wide4_nodes.size();
+    cache_.want_wide4 = want_wide4; cache_.fine_tlas = fine_tlas;
+    cache_.stats = out.stats;
+    cache_.blas_epoch = blas_epoch_;
+  }
   // ---- build_tlas per TLAS (mod.rs:262-320, 428-448)
   const TreeBuildOption tlas_option{50, 10};
   for (const Tlas &tlas : tlas_data_) {

@@ -56,8 +56,17 @@ class NaiveSahBvhSource {
   bool delete_blas(uint32_t handle);
   bool delete_tlas(uint32_t handle);
 
-  // NaiveSahBvhSource::build: returns 0 or a negative rdn_status; `err` gets a message on failure
-  int build(const std::vector<uint32_t> &tlas_binding, FlatScene &out, std::string &err) const;
+  // the reference has no such call (mod.rs:121 `todo incremental change`): replace the instances of a live TLAS in place.  When only
+  // TLASes changed since the last build, the next build keeps every BLAS array of the previous FlatScene and redoes build_tlas alone.
+  bool update_tlas(uint32_t handle, std::vector<InstanceSource> source);
+
+  // NaiveSahBvhSource::build: returns 0 or a negative rdn_status; `err` gets a message on failure.
+  // `previous`: the FlatScene of the previous successful build, consumed when it can be reused (same BLAS set, same flattener
+  // switches): `out` then starts from it and only the TLAS part is rebuilt; *reused says whether that happened.
+  int build(const std::vector<uint32_t> &tlas_binding, FlatScene &out, std::string &err, FlatScene *previous = nullptr, bool *reused = nullptr) const;
+  // first wide node / four-box node of the TLAS part (what a reusing build rewrote from there on)
+  uint64_t tlas_part_wide_start() const { return cache_.wide_nodes_n; }
+  uint64_t tlas_part_wide4_start() const { return cache_.wide4_nodes_n; }
 
   // Opt-in (RDN_COMMIT_DEVICE_BUILD=1, set by the C ABI for scenes that own a CUDA device): geometry trees of at least
   // `device_build_min` triangles are built by the device SAH builder (build_device.cu: the reference's tree node for node) and by
@@ -70,6 +79,21 @@ class NaiveSahBvhSource {
   struct Tlas { bool alive = false; std::vector<InstanceSource> instances; };
   std::vector<Blas> blas_data_;
   std::vector<Tlas> tlas_data_;
+  uint64_t blas_epoch_ = 1;   // bumped by every BLAS mutation
+  // what build_blas leaves behind for build_tlas (per BLAS handle), kept between builds
+  struct OptBox { bool some; Box3 box; };
+  struct HotBlock { uint32_t base = 0, count = 0; uint64_t triangles = 0; };
+  struct BlasPartCache {
+    uint64_t blas_epoch = 0;  // 0: nothing cached
+    bool want_wide4 = false, fine_tlas = true;
+    std::vector<OptBox> blas_box;
+    std::vector<Box3> blas_true_box;
+    std::vector<uint32_t> blas_irregular;
+    std::vector<HotBlock> blas_hot;
+    uint64_t wide_nodes_n = 0, wide4_nodes_n = 0;
+    BuildStats stats;
+  };
+  mutable BlasPartCache cache_;
 };
 
 // Mat4 helpers (math/algebra/src/mat/mat4.rs:40-104, mat3.rs:37-42) used by the TLAS assembly

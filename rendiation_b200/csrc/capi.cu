@@ -142,6 +142,8 @@ struct rdn_rt_scene {
   bool adopted = false;            // blob came from another rank; local sources are not authoritative
   FlatScene flat;                  // host copy (empty when adopted)
   std::vector<uint8_t> host_blob;  // kept only by host-only scenes (n_devices == 0)
+  BlobHeader blob_header{};        // layout of the blob the devices hold (valid when flat is)
+  uint64_t tlas_only_commits = 0;  // commits that kept every BLAS array and patched the TLAS arrays of the device blobs in place
   std::vector<uint32_t> h_tlas_binding;  // host copies used to resolve the wide root of a launch
   std::vector<TlasRoot> h_tlas_root;
   std::vector<DeviceCtx> devices;
@@ -259,9 +261,49 @@ int commit_locked(rdn_rt_scene *s) {
   const bool device_build = device_build_env && atoi(device_build_env) != 0;
   s->source.build_device = (device_build && !s->devices.empty()) ? s->devices[0].device : -1;
   if (const char *e = getenv("RDN_COMMIT_DEVICE_BUILD_MIN")) s->source.device_build_min = strtoull(e, nullptr, 10);
-  const int rc = s->source.build(s->tlas_binding, flat, err);
-  if (rc != RDN_OK) return fail(rc, err);
+  // A commit after TLAS-only changes (rdn_rt_tlas_update, TLAS create / delete, bind) keeps the BLAS arrays of the previous flattened
+  // scene and redoes build_tlas alone; when no array changed its length the device blobs are patched in place — a few hundred
+  // kilobytes instead of the whole scene.  (The reference rebuilds and re-uploads everything on any change, naive/mod.rs:121,546-549.)
+  bool reused = false;
+  const bool have_previous = !s->adopted && !s->flat.blas_meta.empty();
+  const int rc = s->source.build(s->tlas_binding, flat, err, have_previous ? &s->flat : nullptr, &reused);
+  if (rc != RDN_OK) { s->flat = FlatScene{}; return fail(rc, err); }
   const auto t_upload = std::chrono::steady_clock::now();
+  if (reused && !s->devices.empty()) {
+    const BlobHeader &h = s->blob_header;
+    const uint64_t wide0 = s->source.tlas_part_wide_start(), wide4_0 = s->source.tlas_part_wide4_start();
+    auto same = [&](int id, uint64_t count) { return h.count[id] == count; };
+    const bool same_layout = h.magic == BLOB_MAGIC && same(ARR_TLAS_BINDING, flat.tlas_binding.size()) && same(ARR_TLAS_ROOT, flat.tlas_root.size()) &&
+                             same(ARR_TLAS_BVH_FOREST, flat.tlas_bvh_forest.size()) && same(ARR_TLAS_BOUNDING, flat.tlas_bounding.size()) &&
+                             same(ARR_INSTANCES, flat.instances.size()) && same(ARR_WIDE_NODES, flat.wide_nodes.size()) &&
+                             same(ARR_IRREGULAR_INSTANCES, flat.irregular_instances.size()) && same(ARR_WIDE4_NODES, flat.wide4_nodes.size());
+    if (same_layout) {
+      for (DeviceCtx &dc : s->devices) {
+        RDN_CUDA(cudaSetDevice(dc.device));
+        RDN_CUDA(cudaDeviceSynchronize());  // nothing may still be walking the arrays that change
+        char *base = static_cast<char *>(dc.d_blob);
+        auto patch = [&](int id, const void *src, uint64_t first, uint64_t count, uint64_t elem) -> cudaError_t {
+          if (count == 0) return cudaSuccess;
+          return cudaMemcpy(base + h.offset[id] + first * elem, static_cast<const char *>(src) + first * elem, count * elem, cudaMemcpyHostToDevice);
+        };
+        RDN_CUDA(patch(ARR_TLAS_BINDING, flat.tlas_binding.data(), 0, flat.tlas_binding.size(), 4));
+        RDN_CUDA(patch(ARR_TLAS_ROOT, flat.tlas_root.data(), 0, flat.tlas_root.size(), sizeof(TlasRoot)));
+        RDN_CUDA(patch(ARR_TLAS_BVH_FOREST, flat.tlas_bvh_forest.data(), 0, flat.tlas_bvh_forest.size(), sizeof(DeviceBVHNode)));
+        RDN_CUDA(patch(ARR_TLAS_BOUNDING, flat.tlas_bounding.data(), 0, flat.tlas_bounding.size(), sizeof(TlasBounding)));
+        RDN_CUDA(patch(ARR_INSTANCES, flat.instances.data(), 0, flat.instances.size(), sizeof(InstanceRecord)));
+        RDN_CUDA(patch(ARR_WIDE_NODES, flat.wide_nodes.data(), wide0, flat.wide_nodes.size() - wide0, sizeof(WideNode)));
+        RDN_CUDA(patch(ARR_IRREGULAR_INSTANCES, flat.irregular_instances.data(), 0, flat.irregular_instances.size(), 4));
+        RDN_CUDA(patch(ARR_WIDE4_NODES, flat.wide4_nodes.data(), wide4_0, flat.wide4_nodes.size() - wide4_0, sizeof(Wide4Node)));
+      }
+      flat.stats.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_upload).count();
+      s->h_tlas_binding = flat.tlas_binding;
+      s->h_tlas_root = flat.tlas_root;
+      s->flat = std::move(flat);
+      s->tlas_only_commits++;
+      s->dirty = false;
+      return RDN_OK;
+    }
+  }
   std::vector<uint8_t> blob = flat.serialize();
   BlobHeader h;
   std::memcpy(&h, blob.data(), sizeof(h));
@@ -282,6 +324,7 @@ int commit_locked(rdn_rt_scene *s) {
   s->h_tlas_binding = flat.tlas_binding;
   s->h_tlas_root = flat.tlas_root;
   s->flat = std::move(flat);
+  s->blob_header = h;
   if (s->devices.empty()) s->host_blob = std::move(blob);
   s->dirty = false;
   return RDN_OK;
@@ -577,6 +620,24 @@ int rdn_rt_tlas_create(rdn_rt_scene *s, const rdn_instance *inst, uint32_t n, ui
   std::unique_lock<std::shared_mutex> wr(s->lock);
   s->dirty = true; s->adopted = false;
   *out_handle = s->source.create_tlas(std::move(src));
+  return RDN_OK;
+}
+
+int rdn_rt_tlas_update(rdn_rt_scene *s, uint32_t handle, const rdn_instance *inst, uint32_t n) {
+  if (!s || (n && !inst)) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_tlas_update: null argument");
+  std::vector<InstanceSource> src(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    std::memcpy(&src[i].transform, inst[i].transform, sizeof(Mat4));
+    src[i].instance_custom_index = inst[i].instance_custom_index;
+    src[i].mask = inst[i].mask;
+    src[i].sbt_offset = inst[i].instance_shader_binding_table_record_offset;
+    src[i].flags = inst[i].flags;
+    src[i].blas_handle = inst[i].blas_handle;
+  }
+  std::unique_lock<std::shared_mutex> wr(s->lock);
+  if (s->adopted) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_tlas_update: this scene adopted another rank's blob and has no sources");
+  if (!s->source.update_tlas(handle, std::move(src))) return fail(RDN_ERR_INVALID_HANDLE, "rdn_rt_tlas_update: unknown or deleted TLAS");
+  s->dirty = true;
   return RDN_OK;
 }
 
@@ -1668,6 +1729,7 @@ int rdn_rt_scene_build_stats(rdn_rt_scene *s, rdn_build_stats *out) {
     out->upload_ms = s->flat.stats.upload_ms;
     out->build_threads = s->flat.stats.build_threads;
     out->device_built_trees = s->flat.stats.device_built_trees;
+    out->tlas_only_commits = s->tlas_only_commits;
   } else {
     for (const TlasRoot &t : s->h_tlas_root) {
       if (t.irregular_count == IRREGULAR_ROUTE_ALL) out->reference_routed_tlas++;

@@ -595,3 +595,56 @@ def test_any_hit_stage_decides_over_candidates_of_non_opaque_geometry(case):
     base = sp.o.trace(rays, ray_flags=0, n_threads=4, want_counters=False)
     assert base.tobytes() != staged.tobytes()
     assert forced.tobytes() == sp.o.trace(rays, ray_flags=0x01, n_threads=4, want_counters=False).tobytes()  # (FORCE_OPAQUE: no stage)
+
+
+@pytest.mark.gpu
+def test_tlas_only_update_patches_the_resident_scene_in_place():
+    """rdn_rt_tlas_update: moving instances (same TLAS handle, new transforms) rebuilds the TLAS part alone and patches the device blob
+    in place; the traced records equal a scene built from scratch with the new transforms (the oracle), the BLAS arrays are not
+    touched, and a later BLAS mutation goes back to a full build."""
+    import time
+    spos, sidx = S.uv_sphere_mesh(48, 48)
+    sp = helpers.ScenePair((0,), True)
+    b = sp.blas([(spos, sidx.reshape(-1), 1)])
+    inst0 = S.instance_grid(30, 30, b, 3.5, -80.0)
+    t = sp.tlas(inst0)
+    sp.bind([t]); sp.build()
+    rays = S.pinhole_rays(480, 320, 0.0, 1000.0, aspect_correct=True)
+    before, _ = _device_trace(sp.p, rays, api.TRACE_AUTO, ray_flags=0x10, grid_width=480)
+    _assert_parity("tlas_update_before", before, sp.o.trace(rays, ray_flags=0x10, n_threads=4, want_counters=False))
+    tri_before = sp.p.array(8).tobytes()   # RDN_ARRAY_TRIANGLES
+    assert sp.p.build_stats()["tlas_only_commits"] == 0
+    # every instance moves: a different grid spacing and depth, same count
+    inst1 = S.instance_grid(30, 30, b, 4.25, -95.0)
+    t0 = time.perf_counter()
+    sp.p.update_top_level_acceleration_structure(api.TlasHandle(t), inst1)
+    sp.p.commit()
+    dt_ms = (time.perf_counter() - t0) * 1e3
+    st = sp.p.build_stats()
+    assert st["tlas_only_commits"] == 1, st
+    fresh = oracle.Scene()
+    fb = fresh.create_blas([(spos, sidx.reshape(-1), 1)])
+    fresh.bind_tlas([fresh.create_tlas(inst1)]); assert fresh.build() == 0
+    after, _ = _device_trace(sp.p, rays, api.TRACE_AUTO, ray_flags=0x10, grid_width=480)
+    want = fresh.trace(rays, ray_flags=0x10, n_threads=4, want_counters=False)
+    _assert_parity("tlas_update_after", after, want)
+    assert after.tobytes() != before.tobytes()
+    got_ref, _ = _device_trace(sp.p, rays, api.TRACE_REFERENCE_ORDER, ray_flags=0x10)
+    _assert_parity("tlas_update_after_reference_order", got_ref, want)
+    assert sp.p.array(8).tobytes() == tri_before
+    with open(os.path.join(os.path.dirname(__file__), "..", "gpurun_out", "parity.jsonl"), "a") as f:
+        f.write(json.dumps({"test": "tlas_only_update", "instances": int(inst1.shape[0]), "update_and_commit_ms": dt_ms}) + "\\n")
+    # a different instance COUNT cannot be patched in place: still TLAS-only on the host, full upload
+    sp.p.update_top_level_acceleration_structure(api.TlasHandle(t), inst1[:500])
+    fresh2 = oracle.Scene(); fb2 = fresh2.create_blas([(spos, sidx.reshape(-1), 1)])
+    fresh2.bind_tlas([fresh2.create_tlas(inst1[:500])]); assert fresh2.build() == 0
+    got2, _ = _device_trace(sp.p, rays, api.TRACE_AUTO, ray_flags=0x10, grid_width=480)
+    _assert_parity("tlas_update_fewer_instances", got2, fresh2.trace(rays, ray_flags=0x10, n_threads=4, want_counters=False))
+    assert sp.p.build_stats()["tlas_only_commits"] == 1
+    # a new BLAS: everything is rebuilt
+    b2 = sp.p.create_bottom_level_acceleration_structure([api.BottomLevelAccelerationStructureBuildSource(spos * 0.5, sidx.reshape(-1))])
+    sp.p.update_top_level_acceleration_structure(api.TlasHandle(t), S.instance_grid(10, 10, b2.id, 4.0, -60.0))
+    fresh3 = oracle.Scene(); fresh3.create_blas([(spos, sidx.reshape(-1), 1)]); fb3 = fresh3.create_blas([(spos * 0.5, sidx.reshape(-1), 1)])
+    fresh3.bind_tlas([fresh3.create_tlas(S.instance_grid(10, 10, fb3, 4.0, -60.0))]); assert fresh3.build() == 0
+    got3, _ = _device_trace(sp.p, rays, api.TRACE_AUTO, ray_flags=0x10, grid_width=480)
+    _assert_parity("tlas_update_after_new_blas", got3, fresh3.trace(rays, ray_flags=0x10, n_threads=4, want_counters=False))
