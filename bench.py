@@ -346,6 +346,93 @@ def measure_c5(sysm, world, rank, dev, steps, warmup=1, want_e2e=True):
     return out
 
 
+def measure_other_configs(sysm_c2, dev, iters=12):
+    """BASELINE configs[0], [2] and [3] on this GPU (N = 1 only), device-resident like `value`: Mrays/s of back-to-back launches with
+    tail overlap, of serialised launches (L2 flushed before each), the shipped kernel of each, and a 1-in-7 sample of the records
+    compared with the oracle.  configs[2]'s rays are the cosine bounce off configs[1]'s hits, generated on the device."""
+    import torch
+
+    import oracle
+    from rendiation_b200 import api, scenes as S
+    stream = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    cores = len(os.sched_getaffinity(0)) or 1
+    out = {}
+
+    def run(name, sysm, osc, d_rays, n, flags, grid, note):
+        hits = [torch.full((n, 32), 0xAB, dtype=torch.uint8, device=dev) for _ in range(iters)]
+        ref = torch.zeros((n, 32), dtype=torch.uint8, device=dev)
+        for _ in range(3):
+            sysm.trace_closest_device(d_rays.data_ptr(), n, ref.data_ptr(), ray_flags=flags, grid_width=grid, stream=stream)
+        st = sysm.trace_closest_device(d_rays.data_ptr(), n, ref.data_ptr(), ray_flags=flags, grid_width=grid, stream=stream, want_stats=True)
+        ms = []
+        for k in range(iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); sysm.trace_closest_device(d_rays.data_ptr(), n, hits[k].data_ptr(), ray_flags=flags, grid_width=grid, stream=stream); e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        for h in hits:
+            h.fill_(0xAB)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(iters):
+            sysm.trace_closest_device(d_rays.data_ptr(), n, hits[k].data_ptr(), ray_flags=flags, grid_width=grid, stream=stream, overlap_previous=True)
+        e1.record()
+        torch.cuda.synchronize()
+        b2b = e0.elapsed_time(e1) / iters
+        same = all(bool(torch.equal(h, ref)) for h in hits)
+        rays_np = d_rays.cpu().numpy().view(S.RAY_DTYPE).reshape(-1)
+        sel = np.arange(0, n, 7)
+        want = osc.trace(rays_np[sel], ray_flags=flags, n_threads=cores, want_counters=False)
+        got = ref.cpu().numpy().view(api.HIT_DTYPE).reshape(-1)[sel]
+        out[name] = {"workload": note, "rays": int(n), "value_serialized": n / float(np.mean(ms)) / 1e3, "ms_serialized": float(np.mean(ms)),
+                     "value": n / b2b / 1e3, "ms": b2b, "unit": "Mrays/s", "tie_rays": st["tie_rays"],
+                     "sample_bit_identical_to_oracle": bool(got.tobytes() == want.tobytes()), "overlapped_launches_identical": same}
+
+    # configs[0]: 1024 x 1024 primary rays vs the 64 x 64-segment sphere (path B)
+    pos, idx = S.uv_sphere_mesh(64, 64)
+    m = S.mat4_mul(S.mat4_translate(0, 0, -10), S.mat4_scale(5, 5, 5))
+    s1 = api.NaiveSahBVHSystem(devices=(dev.index,))
+    b = s1.create_bottom_level_acceleration_structure([api.BottomLevelAccelerationStructureBuildSource(pos, idx.reshape(-1))])
+    s1.bind_tlas([s1.create_top_level_acceleration_structure(S.make_instance(m, b.id))]); s1.commit()
+    o1 = oracle.Scene(); ob = o1.create_blas([(pos, idx.reshape(-1), 1)]); o1.bind_tlas([o1.create_tlas(S.make_instance(m, ob))]); assert o1.build() == 0
+    r1 = torch.from_numpy(S.pinhole_rays(1024, 1024, 0.0, 100.0).view(np.uint8).reshape(-1, 32).copy()).to(dev)
+    run("c1", s1, o1, r1, 1024 * 1024, RAY_FLAGS, 1024, "1,048,576 coherent primary rays vs the 64x64-segment sphere (8,192 triangles), BASELINE configs[0], path B")
+    del s1, r1
+    # configs[2]: one incoherent cosine bounce ray per primary hit of configs[1]
+    o2 = build_oracle_scene()
+    n = W * H
+    d_rays = torch.from_numpy(frame_rays(0).view(np.uint8).reshape(-1, 32).copy()).to(dev)
+    d_hits = torch.zeros((n, 32), dtype=torch.uint8, device=dev)
+    d_b = torch.zeros((n, 32), dtype=torch.uint8, device=dev)
+    d_src = torch.zeros(n, dtype=torch.int32, device=dev); d_n = torch.zeros(1, dtype=torch.int64, device=dev)
+    sysm_c2.trace_closest_device(d_rays.data_ptr(), n, d_hits.data_ptr(), ray_flags=RAY_FLAGS, grid_width=W, stream=stream)
+    sysm_c2.gen_bounce_rays_device(d_rays.data_ptr(), d_hits.data_ptr(), n, d_b.data_ptr(), d_src.data_ptr(), d_n.data_ptr(), mode=0, tmin=TMIN, tmax=TMAX, stream=stream)
+    k = int(d_n.item())
+    run("c3", sysm_c2, o2, d_b[:k].contiguous(), k, 0, 0, "incoherent cosine-weighted bounce rays off the hits of configs[1] (no culling), BASELINE configs[2]")
+    del d_rays, d_hits, d_b
+    # configs[3]: 10,000 instances of a 100,352-triangle sphere
+    pos, idx = S.uv_sphere_mesh(224, 224)
+    s4 = api.NaiveSahBVHSystem(devices=(dev.index,))
+    t0 = time.perf_counter()
+    b = s4.create_bottom_level_acceleration_structure([api.BottomLevelAccelerationStructureBuildSource(pos, idx.reshape(-1))])
+    inst = S.instance_grid(100, 100, b.id, 3.5, -200.0)
+    t4 = s4.create_top_level_acceleration_structure(inst)
+    s4.bind_tlas([t4]); s4.commit()
+    commit_ms = (time.perf_counter() - t0) * 1e3
+    o4 = oracle.Scene(); ob = o4.create_blas([(pos, idx.reshape(-1), 1)]); o4.bind_tlas([o4.create_tlas(S.instance_grid(100, 100, ob, 3.5, -200.0))]); assert o4.build() == 0
+    r4 = torch.from_numpy(S.pinhole_rays(W, H, 0.0, 1000.0, aspect_correct=True).view(np.uint8).reshape(-1, 32).copy()).to(dev)
+    run("c4", s4, o4, r4, n, RAY_FLAGS, W, "1920x1080 primary rays vs 10,000 transform-instanced copies of a 100,352-triangle sphere, BASELINE configs[3]")
+    t0 = time.perf_counter()
+    s4.update_top_level_acceleration_structure(t4, S.instance_grid(100, 100, b.id, 3.51, -201.0))
+    s4.commit()
+    out["c4"]["commit_ms"] = commit_ms
+    out["c4"]["tlas_only_update_ms"] = (time.perf_counter() - t0) * 1e3
+    return out
+
+
 def setup_job():
     """one process per GPU: device, process group, the scene built on rank 0 and replicated with one NCCL broadcast"""
     import torch
@@ -582,6 +669,7 @@ def run_ours(args):
     del d_hits, d_rays, flush
     torch.cuda.empty_cache()
     c5 = measure_c5(sysm, world, rank, dev, steps=args.c5_steps) if args.c5_steps > 0 else None
+    other = measure_other_configs(sysm, dev) if (world == 1 and args.other_configs) else None
 
     if rank == 0:
         # ---- roofline + cpu baseline + parity spot check (oracle = checker / baseline only)
@@ -675,7 +763,7 @@ def run_ours(args):
                                        f"= {t_cpu * cores:.1f} core-seconds",
                              "single_thread_mrays": one.shape[0] / t_cpu1 / 1e6, "parity_bit_identical_full_frames": parity_bits,
                              "timed_loop_results_identical_to_synchronised_launches_all_ranks": timed_loop_ok_all_ranks},
-            "clocks": clocks.summary(), "wall_s_timed_region": t_wall, "c5": c5,
+            "clocks": clocks.summary(), "wall_s_timed_region": t_wall, "c5": c5, "other_configs": other,
         }
         print(json.dumps(out))
     if world > 1:
@@ -691,6 +779,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=["c2", "c5"], help="c2: BASELINE configs[1] per GPU (the headline, weak scaling; "
                     "configs[4] rides along as the line's `c5` object).  c5: BASELINE configs[4] is the line (strong scaling of one frame)")
+    ap.add_argument("--other-configs", type=int, default=1, help="1: also time BASELINE configs[0], [2], [3] on this GPU after the headline (N = 1 only)")
     ap.add_argument("--c5-steps", type=int, default=3, help="frames of configs[4] timed after the headline loops (0: skip)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -611,8 +611,11 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
         err = "instance references a deleted or unknown BLAS (the reference panics here)";
         return RDN_ERR_INVALID_HANDLE;
       }
-      aabbs[i] = box_apply_matrix(blas_box[src.blas_handle].box, src.transform);
     }
+    constexpr uint64_t PARALLEL_TLAS_MIN = 2048;  // (a TLAS-only commit of ten thousand moving instances should take a millisecond or two)
+    parallel_for(tlas.instances.size(), PARALLEL_TLAS_MIN, [&](uint64_t i0, uint64_t i1) {
+      for (uint64_t i = i0; i < i1; ++i) aabbs[i] = box_apply_matrix(blas_box[tlas.instances[i].blas_handle].box, tlas.instances[i].transform);
+    });
     SAH sah(4);
     FlattenBVH bvh = timed_build(aabbs.data(), aabbs.size(), sah, tlas_option);
     if (bvh.stats.bucket_out_of_range) { err = "SAH bucket index out of range (the reference panics here)"; return RDN_ERR_BUILD; }
@@ -620,37 +623,51 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
     out.stats.balance_fallbacks_gt10 += bvh.stats.balance_fallbacks_gt10;
     const auto next = compute_bvh_next(bvh.nodes);
 
+    // instance records and boxes in BVH order: independent per slot, written in place; what depends on the order (the irregular
+    // list, the hot geometry) is gathered afterwards
     const uint32_t irregular_start = static_cast<uint32_t>(out.irregular_instances.size());
-    double irregular_area = 0.0;
-    for (uint64_t box_idx : bvh.sorted_primitive_index) {
-      const InstanceSource &src = tlas.instances[box_idx];
-      uint32_t flags = src.flags;
-      if (mat4_upper3_det(src.transform) < 0.0f) flags ^= RDN_GEOMETRY_INSTANCE_TRIANGLE_FLIP_FACING;
-      InstanceRecord rec;
-      const Mat4 inv = mat4_inverse_or_identity(src.transform);
-      std::memcpy(rec.transform_inv, &inv, sizeof(inv));
-      rec.instance_custom_index = src.instance_custom_index;
-      rec.sbt_offset = src.sbt_offset;
-      rec.flags = flags;
-      rec.blas = src.blas_handle;
-      const bool known_blas = src.blas_handle < blas_true_box.size();  // else the kernels skip the instance (blas >= n_blas_meta)
-      if (known_blas && blas_hot[src.blas_handle].triangles > tlas_hot_geometry.triangles) tlas_hot_geometry = blas_hot[src.blas_handle];
-      if (known_blas) {
-        const bool whole = blas_irregular[src.blas_handle] == IRREGULAR_ROUTE_ALL ||
-                           instance_is_irregular(src.transform, inv, blas_box[src.blas_handle].box, blas_true_box[src.blas_handle]);
-        if (whole || blas_irregular[src.blas_handle] != 0) {
-          out.irregular_instances.push_back(static_cast<uint32_t>(out.instances.size()) | (whole ? IRREGULAR_WHOLE_BIT : 0u));
-          out.stats.irregular_instances++;
-          if (whole) irregular_area += static_cast<double>(surface_area(aabbs[box_idx]));
+    const size_t n_slots = bvh.sorted_primitive_index.size();
+    out.instances.resize(primitive_start + n_slots);
+    out.tlas_bounding.resize(primitive_start + n_slots);
+    std::vector<uint8_t> slot_irregular(n_slots, 0);  // 1: only the listed leaves of its BLAS, 2: the whole instance
+    parallel_for(n_slots, PARALLEL_TLAS_MIN, [&](uint64_t k0, uint64_t k1) {
+      for (uint64_t k = k0; k < k1; ++k) {
+        const uint64_t box_idx = bvh.sorted_primitive_index[k];
+        const InstanceSource &src = tlas.instances[box_idx];
+        uint32_t flags = src.flags;
+        if (mat4_upper3_det(src.transform) < 0.0f) flags ^= RDN_GEOMETRY_INSTANCE_TRIANGLE_FLIP_FACING;
+        InstanceRecord rec;
+        const Mat4 inv = mat4_inverse_or_identity(src.transform);
+        std::memcpy(rec.transform_inv, &inv, sizeof(inv));
+        rec.instance_custom_index = src.instance_custom_index;
+        rec.sbt_offset = src.sbt_offset;
+        rec.flags = flags;
+        rec.blas = src.blas_handle;
+        if (src.blas_handle < blas_true_box.size()) {  // else the kernels skip the instance (blas >= n_blas_meta)
+          const bool whole = blas_irregular[src.blas_handle] == IRREGULAR_ROUTE_ALL ||
+                             instance_is_irregular(src.transform, inv, blas_box[src.blas_handle].box, blas_true_box[src.blas_handle]);
+          slot_irregular[k] = whole ? 2 : (blas_irregular[src.blas_handle] != 0 ? 1 : 0);
         }
+        out.instances[primitive_start + k] = rec;
+        TlasBounding tb;
+        tb.world_min[0] = aabbs[box_idx].min.x; tb.world_min[1] = aabbs[box_idx].min.y; tb.world_min[2] = aabbs[box_idx].min.z;
+        tb.world_max[0] = aabbs[box_idx].max.x; tb.world_max[1] = aabbs[box_idx].max.y; tb.world_max[2] = aabbs[box_idx].max.z;
+        tb.mask = src.mask;
+        tb.flags = flags;
+        out.tlas_bounding[primitive_start + k] = tb;
       }
-      out.instances.push_back(rec);
-      TlasBounding tb;
-      tb.world_min[0] = aabbs[box_idx].min.x; tb.world_min[1] = aabbs[box_idx].min.y; tb.world_min[2] = aabbs[box_idx].min.z;
-      tb.world_max[0] = aabbs[box_idx].max.x; tb.world_max[1] = aabbs[box_idx].max.y; tb.world_max[2] = aabbs[box_idx].max.z;
-      tb.mask = src.mask;
-      tb.flags = flags;
-      out.tlas_bounding.push_back(tb);
+    });
+    double irregular_area = 0.0;
+    for (size_t k = 0; k < n_slots; ++k) {
+      const uint64_t box_idx = bvh.sorted_primitive_index[k];
+      const uint32_t blas_handle = tlas.instances[box_idx].blas_handle;
+      if (blas_handle < blas_true_box.size() && blas_hot[blas_handle].triangles > tlas_hot_geometry.triangles) tlas_hot_geometry = blas_hot[blas_handle];
+      if (slot_irregular[k]) {
+        const bool whole = slot_irregular[k] == 2;
+        out.irregular_instances.push_back(static_cast<uint32_t>(primitive_start + k) | (whole ? IRREGULAR_WHOLE_BIT : 0u));
+        out.stats.irregular_instances++;
+        if (whole) irregular_area += static_cast<double>(surface_area(aabbs[box_idx]));
+      }
     }
     TlasRoot root;
     root.bvh_root_idx = bvh_start;

@@ -13,6 +13,6 @@ for c in c1 c2 c3 c4; do
       -o $OUT/prof_ordered_$c python tools/kbench.py $c 3 > $OUT/ncu_full_$c.log 2>&1
 done
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
-    python bench.py --steps 2 --warmup 1 --c5-steps 0 > $OUT/bench_under_ncu.log 2>&1
+    python bench.py --steps 2 --warmup 1 --c5-steps 0 --other-configs 0 > $OUT/bench_under_ncu.log 2>&1
 fi
 tail -3 $OUT/pytest_gpu.log; cat $OUT/ab.log; cat $OUT/bench.json; tail -3 $OUT/bench.err; cat $OUT/bench_c5.json
