@@ -44,7 +44,16 @@ constexpr uint32_t FULL_MASK = 0xFFFFFFFFu;
 #define RDN_STACK_MAX 120  // (the emulated test build of tests/simt lowers it to reach the overflow report)
 #endif
 constexpr int STACK_MAX = RDN_STACK_MAX;  // TLAS depth 50 + BLAS depth 50 (TreeBuildOption of naive/mod.rs:173-176,280-283) + bookkeeping
-constexpr int ORDERED_BLOCK = 128;
+#ifndef RDN_ORDERED_BLOCK
+#define RDN_ORDERED_BLOCK 128
+#endif
+#ifndef RDN_ORDERED_MINB
+#define RDN_ORDERED_MINB 8
+#endif
+#ifndef RDN_ORDERED_K
+#define RDN_ORDERED_K 3
+#endif
+constexpr int ORDERED_BLOCK = RDN_ORDERED_BLOCK;
 
 // TraverseFlags bits (flag.rs:6-25)
 constexpr uint32_t TF_FORCE_OPAQUE = 0x01, TF_FORCE_NON_OPAQUE = 0x02, TF_END_SEARCH = 0x04, TF_CULL_BACK = 0x10,
@@ -438,9 +447,9 @@ struct OrderedParams {
   // HOT: wide nodes [hot_a_base, +hot_a_count) (top of the TLAS tree) and [hot_b_base, +hot_b_count) (top of the largest geometry
   // tree) are staged in shared memory by two bulk copies (TMA) at CTA start
   uint32_t hot_a_base, hot_a_count, hot_b_base, hot_b_count;
-  // SHARE: deferred subtrees are handed to idle lanes once no more than share_busy lanes are busy, by lanes that have at least
-  // share_min of them
-  int share_busy, share_min;
+  // SHARE: deferred subtrees are handed to idle lanes once a pass over a tile is share_after rounds old and no more than share_busy
+  // lanes are busy, by lanes that have at least share_min of them
+  int share_busy, share_min, share_after;
   uint32_t wait_epoch;  // launches issued before this one on the same scratch set: they must have left before this one touches it
   TraceScratch scratch;
 };
@@ -554,8 +563,9 @@ __device__ __forceinline__ void drain_tie_queue(const OrderedParams &P) {
 // the instances of a TLAS leaf whose box the ray misses are skipped in a loop instead of costing a round each, and a BLAS of one
 // geometry is entered without a geometry-iterator round (+2..4 % with K = 3, profiles/kbench_r2a_*.log).  SHARE: the lanes of a
 // warp share the work of its long rays (see the vote) — used for launches that are ray LISTS (bounce / shadow waves), whose
-// duration is the latency of their longest rays: +14 % on config 3; it costs 5-7 % on grids, which keep the plain loop
-// (profiles/kbench_r2h_*.log).
+// duration is the latency of their longest rays: +24 % on config 3 (passes older than 30 rounds, at most 16 busy lanes, donors with
+// two or more deferred subtrees); the instantiation itself costs 6 % before anything is shared, which grids never win back, so
+// they keep the plain loop (profiles/kbench_r2h_*.log, kbench_r2u_*.log, kbench_r2v_*.log).
 // Experiments kept for A/B runs.  HOT: the top levels of the TLAS tree and of the largest geometry tree (breadth-first blocks of
 // HOT_TOP_NODES wide nodes, 8 KB each) are copied into shared memory with cp.async.bulk (TMA, completion on an mbarrier) when the
 // CTA starts, and node fetches that fall into either block read shared memory instead of L1 (measured 9-13 % slower).  WIDE4: the
@@ -575,8 +585,9 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
   // SHARE (lanes of a warp share the work of its long rays, see the vote): entries [lo, sp) of the stack are the deferred subtrees
   // of the space the lane is in (world, or the instance it entered) and may be handed to idle lanes, lowest = largest first;
   // `home` is the lane that owns the ray this lane works on; `helpers` (owner only) the lanes still out with pieces of its ray
-  int lo = 0;
-  uint32_t home = lane, helpers = 0;
+  int lo = 0;  // bits 0-7: the floor of the segment the lane is in; bits 8-15: the world segment's floor while the lane is inside an instance
+  uint32_t home = lane, helpers = 0;  // home: bits 0-4 the owner's lane, bits 5.. the age of the pass over the tile in rounds (a separate
+                                      // loop counter ends up spilled, and a local access per round stalls the round)
   // Programmatic dependent launch: the NEXT ordered launch on this stream may start filling SM slots as soon as CTAs of this one
   // leave, i.e. while the last long rays of this launch are still being walked (a no-op when launched without the attribute).
   // The next launch reads nothing this one writes (its own rays, the read-only scene, the other scratch set).
@@ -762,10 +773,12 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
 
     // (SHARE: every lane takes part in the rounds — a lane without a ray idles at cur == REF_DONE until it is handed a subtree)
     const uint32_t rmask = SHARE ? FULL_MASK : amask;
+    if constexpr (SHARE) home &= 31u;  // a new pass over a tile: age 0
     if (SHARE || alive) {
 #pragma unroll 1
       for (;;) {
         RDN_COST(COST_ROUND);
+        if constexpr (SHARE) home += 32u;
 #ifdef RDN_DEBUG_TIMELINE
         ++dbg_pass_rounds;
         dbg_pass_busy += __popc(__ballot_sync(rmask, cur != REF_DONE));
@@ -914,8 +927,8 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
                 const uint32_t flags = merge_geometry_instance_flag(P.L.ray_flags, tail.z);
                 if (!(flags & TF_SKIP_TRIANGLES) && tail.w < S.n_blas_meta) {
                   const uint2 groots = __ldg(reinterpret_cast<const uint2 *>(S.blas_meta[tail.w].tri_root_range));
-                  // (SHARE: the frame of an instance is two entries — the world segment's `lo`, then the exit marker — pushed together or not at all)
-                  const bool room = !SHARE || sp + 2 <= STACK_MAX;
+                  // (SHARE: the exit marker must not be dropped by a full stack — the segment floors count from it)
+                  const bool room = !SHARE || sp + 1 <= STACK_MAX;
                   if (!room) stack_overflowed = true;
                   if (groots.x < groots.y && room) {
                     RDN_COST(COST_INSTANCE_ENTER);
@@ -927,9 +940,8 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
                     cur_inst = istart; cur_flags = flags; cull_bits = cull_triangle_bits(flags); geom_end = groots.y;
                     in_object = true;
                     if constexpr (SHARE) {
-                      stack[sp++] = static_cast<uint32_t>(lo);
                       stack[sp++] = REF_EXIT_INSTANCE;
-                      lo = sp;
+                      lo = ((lo & 0xFF) << 8) | sp;  // the world segment's floor is kept beside the new one: no memory traffic
                     } else {
                       RDN_PUSH(REF_EXIT_INSTANCE);
                     }
@@ -955,7 +967,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
           } else if (cur == REF_EXIT_INSTANCE) {
             // back to world space: the world ray is re-read instead of being held in registers
             RDN_COST(COST_EXIT_INSTANCE);
-            if constexpr (SHARE) lo = static_cast<int>(stack[--sp]);  // (what lies below `lo` was handed to other lanes)
+            if constexpr (SHARE) lo >>= 8;  // back to the world segment's floor (what lies below it was handed to other lanes)
             if (SHARE && sp <= lo) {
               cur = REF_DONE;
             } else {
@@ -999,18 +1011,18 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
           // votes per round.  Finished rays are stored together at the end of the tile, or when their lanes are wanted as helpers.
           const uint32_t busy = __ballot_sync(FULL_MASK, cur != REF_DONE);
           // (recomputed every round instead of kept: a loop-carried flag ends up spilled, and a local load per round costs a stall)
-          if (__ballot_sync(FULL_MASK, home != lane) != 0) {
+          if (__ballot_sync(FULL_MASK, (home & 31u) != lane) != 0) {
             {  // the owner's bound, so that pieces stop as soon as the owner (who walks the near side) has a closer candidate
-              const float hb = __shfl_sync(FULL_MASK, bound, home);
+              const float hb = __shfl_sync(FULL_MASK, bound, home & 31u);
               if (hb < bound) { bound = hb; far_s = bound * scaling; }
             }
             // helpers that ran out of work hand their partial result to the owner of the ray
-            uint32_t fin = __ballot_sync(FULL_MASK, home != lane && cur == REF_DONE);
+            uint32_t fin = __ballot_sync(FULL_MASK, (home & 31u) != lane && cur == REF_DONE);
             while (fin) {
               RDN_COST(COST_MERGE);
               const int T = __ffs(fin) - 1;
               fin &= fin - 1u;
-              const uint32_t h = __shfl_sync(FULL_MASK, home, T);
+              const uint32_t h = __shfl_sync(FULL_MASK, home, T) & 31u;
               const float tb = __shfl_sync(FULL_MASK, best, T);
               const float ts = __shfl_sync(FULL_MASK, second, T);
               if (tb != INFINITY) {  // (uniform) the helper found a candidate
@@ -1030,14 +1042,14 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
               }
               if (lane == h) helpers &= ~(1u << T);
               if (static_cast<int>(lane) == T) {
-                home = lane;
+                home = (home & ~31u) | lane;
                 if (stack_overflowed) { atomicAdd(P.scratch.stack_overflow, 1u); stack_overflowed = false; }
               }
             }
           }
           if (busy == 0) break;  // (every helper has merged: the rays of the tile are stored behind the loop)
-          if (__popc(busy) <= P.share_busy) {
-            const int avail = cur != REF_DONE ? sp - lo : 0;
+          if (__popc(busy) <= P.share_busy && static_cast<int>(home >> 5) >= P.share_after) {
+            const int avail = cur != REF_DONE ? sp - (lo & 0xFF) : 0;
             const uint32_t donors = __ballot_sync(FULL_MASK, avail >= P.share_min);
             if (donors != 0) {
               // lanes whose own ray is complete become helpers
@@ -1050,7 +1062,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
                 const int m = n_avail < n_idle ? n_avail : n_idle;
                 const int rank = __popc(idle & ((1u << lane) - 1u));
                 const bool take = ((idle >> lane) & 1u) != 0 && rank < m;
-                const int d_lo = __shfl_sync(FULL_MASK, lo, D);
+                const int d_lo = __shfl_sync(FULL_MASK, lo, D) & 0xFF;
                 uint32_t piece = REF_EMPTY;
 #pragma unroll 1
                 for (int j = 0; j < m; ++j) {
@@ -1075,12 +1087,12 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
                   best = INFINITY; second = INFINITY; best_slot = RDN_INVALID_ID; best_inst = RDN_INVALID_ID;
                   in_object = d_in_object;
                   sp = 0;
-                  if (d_in_object) { stack[0] = 0u; stack[1] = REF_EXIT_INSTANCE; sp = 2; }  // the frame of the donor's instance
+                  if (d_in_object) { stack[0] = REF_EXIT_INSTANCE; sp = 1; }  // the frame of the donor's instance (world floor 0)
                   lo = sp;
                   cur = piece;
                 }
                 const uint32_t takers = __ballot_sync(FULL_MASK, take);
-                const uint32_t d_home = __shfl_sync(FULL_MASK, home, D);
+                const uint32_t d_home = __shfl_sync(FULL_MASK, home, D) & 31u;
                 if (lane == d_home) helpers |= takers;
               }
             }
@@ -1238,8 +1250,8 @@ cudaError_t launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch
   P.irregular_count = tlas.irregular_count == IRREGULAR_ROUTE_ALL ? 0u : tlas.irregular_count;  // (the caller routes those elsewhere)
   P.wait_epoch = wait_epoch;
   {  // (RDN_SHARE=busy,min: experimentation knob)
-    P.share_busy = 4; P.share_min = 1;
-    if (const char *e = getenv("RDN_SHARE")) sscanf(e, "%d,%d", &P.share_busy, &P.share_min);
+    P.share_busy = 16; P.share_min = 2; P.share_after = 30;  // (sweeps: profiles/kbench_r2u_*.log, kbench_r2v_*.log)
+    if (const char *e = getenv("RDN_SHARE")) sscanf(e, "%d,%d,%d", &P.share_busy, &P.share_min, &P.share_after);
   }
 
   // RDN_ORDERED_VARIANT: experimentation knob
@@ -1249,10 +1261,10 @@ cudaError_t launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch
   bool inline_ties = true;
   // template arguments: <K, MINB, DRAIN_TIES, IRREGULAR, LD256, HOT, WIDE4, INST_LOOP, SHARE>
   const bool any_hit = launch.any_hit != RDN_ANYHIT_NONE;  // (launches whose any-hit stage can END_SEARCH never get here)
-  const KernelFn plain = any_hit ? k_trace_ordered_rounds<3, 8, true, false, true, false, false, true, false, true>
-                                 : k_trace_ordered_rounds<3, 8, true, false, true, false, false, true, false>;
-  const KernelFn sharing = any_hit ? k_trace_ordered_rounds<3, 8, true, false, true, false, false, true, true, true>
-                                   : k_trace_ordered_rounds<3, 8, true, false, true, false, false, true, true>;
+  const KernelFn plain = any_hit ? k_trace_ordered_rounds<RDN_ORDERED_K, RDN_ORDERED_MINB, true, false, true, false, false, true, false, true>
+                                 : k_trace_ordered_rounds<RDN_ORDERED_K, RDN_ORDERED_MINB, true, false, true, false, false, true, false>;
+  const KernelFn sharing = any_hit ? k_trace_ordered_rounds<RDN_ORDERED_K, RDN_ORDERED_MINB, true, false, true, false, false, true, true, true>
+                                   : k_trace_ordered_rounds<RDN_ORDERED_K, RDN_ORDERED_MINB, true, false, true, false, false, true, true>;
   switch (any_hit ? 0 : variant) {  // (the A/B instantiations exist without the any-hit stage only)
     case 2: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false>; break;     // the round-1 default: K = 2, one round per missed instance
     case 9: fn = k_trace_ordered_rounds<3, 8, false, false, true, false, false, true>; inline_ties = false; break;  // queue drained by k_resolve_ties

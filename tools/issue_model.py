@@ -189,10 +189,10 @@ def dynamic_counts(cfg: str, names: list[str]):
     return list(warp), list(lane), rays.shape[0], dt, bool(same)
 
 
-def mangled(k, drain=True, ld256=True, wide4=False, inst_loop=False, share=False):
-    """mangled template arguments <K, MINB, DRAIN_TIES, IRREGULAR, LD256, HOT, WIDE4, INST_LOOP, SHARE> of an instantiation"""
+def mangled(k, drain=True, ld256=True, wide4=False, inst_loop=False, share=False, anyhit=False):
+    """mangled template arguments <K, MINB, DRAIN_TIES, IRREGULAR, LD256, HOT, WIDE4, INST_LOOP, SHARE, ANYHIT> of an instantiation"""
     bl = lambda v: "Lb1E" if v else "Lb0E"
-    return f"ILi{k}ELi8E{bl(drain)}Lb0E{bl(ld256)}Lb0E{bl(wide4)}{bl(inst_loop)}{bl(share)}E"
+    return f"ILi{k}ELi8E{bl(drain)}Lb0E{bl(ld256)}Lb0E{bl(wide4)}{bl(inst_loop)}{bl(share)}{bl(anyhit)}E"
 
 
 def main():
