@@ -51,7 +51,7 @@ C5_W, C5_H, C5_SPP = 3840, 2160, 16
 C5_WORKLOAD = "3840x2160 x 16 spp primary + 1 cosine bounce rays vs the 1,002,528-triangle torus, ray tiles sharded across the GPUs, BVH replicated (BASELINE configs[4])"
 # the instantiation launch_trace_ordered selects for grid launches (rendiation_b200/csrc/traverse.cu, `plain`), as ncu prints it:
 # the committed capture whose numbers the roofline quotes must be of this kernel (tests/test_bench_contract.py holds the two together)
-SHIPPED_ORDERED_KERNEL = "k_trace_ordered_rounds<3, 8, 1, 0, 1, 0, 0, 1, 0>"
+SHIPPED_ORDERED_KERNEL = "k_trace_ordered_rounds<3, 8, 1, 0, 1, 0, 0, 1, 0, 0>"
 
 
 def base_config(workload=WORKLOAD, rays=W * H):
@@ -385,10 +385,17 @@ def measure_other_configs(sysm_c2, dev, iters=12):
         same = all(bool(torch.equal(h, ref)) for h in hits)
         rays_np = d_rays.cpu().numpy().view(S.RAY_DTYPE).reshape(-1)
         sel = np.arange(0, n, 7)
+        t0 = time.perf_counter()
         want = osc.trace(rays_np[sel], ray_flags=flags, n_threads=cores, want_counters=False)
+        t_cpu = time.perf_counter() - t0
+        one = rays_np[::97]
+        t0 = time.perf_counter()
+        osc.trace(one, ray_flags=flags, n_threads=1, want_counters=False)
+        t_cpu1 = time.perf_counter() - t0
         got = ref.cpu().numpy().view(api.HIT_DTYPE).reshape(-1)[sel]
         out[name] = {"workload": note, "rays": int(n), "value_serialized": n / float(np.mean(ms)) / 1e3, "ms_serialized": float(np.mean(ms)),
                      "value": n / b2b / 1e3, "ms": b2b, "unit": "Mrays/s", "tie_rays": st["tie_rays"],
+                     "cpu_mrays": sel.size / t_cpu / 1e6, "cpu_cores": cores, "cpu_single_thread_mrays": one.shape[0] / t_cpu1 / 1e6,
                      "sample_bit_identical_to_oracle": bool(got.tobytes() == want.tobytes()), "overlapped_launches_identical": same}
 
     # configs[0]: 1024 x 1024 primary rays vs the 64 x 64-segment sphere (path B)
