@@ -164,58 +164,76 @@ uint32_t emit_wide_nodes(const std::vector<FlattenBVHNode> &nodes, uint64_t slot
     for (size_t i = 0; i < nodes.size(); ++i)
       if (nodes[i].has_child && !in_top[i]) wide_of[i] = static_cast<uint32_t>(base + 1 + n_inner++);
   }
-  out.resize(base + 1 + n_inner);
+  // Leaves that need nodes of their own — a fine TLAS leaf becomes a small subtree, a leaf longer than REF_LEAF_MAX_COUNT a chain —
+  // get them behind the inner nodes, in the order the leaves are met (root, then every inner node's left and right child): the
+  // ranges are laid out first so that the nodes can be written by all threads.
+  auto own_nodes = [&](const FlattenBVHNode &leaf) -> uint64_t {
+    uint64_t count = leaf.primitive_end - leaf.primitive_start;
+    if (count == 0 || slot_offset + leaf.primitive_start + count > REF_LEAF_START_MASK) return 0;
+    if (item_bounds && count > 1) return count - 1;
+    uint64_t chain = 0;
+    while (count > REF_LEAF_MAX_COUNT) { ++chain; count -= REF_LEAF_MAX_COUNT; }
+    return chain;
+  };
+  std::vector<uint64_t> own_base(nodes.size(), 0);
+  uint64_t own_total = 0;
+  auto lay_out = [&](size_t idx) { if (!nodes[idx].has_child) { own_base[idx] = base + 1 + n_inner + own_total; own_total += own_nodes(nodes[idx]); } };
+  lay_out(0);
+  for (size_t i = 0; i < nodes.size(); ++i)
+    if (nodes[i].has_child) { lay_out(nodes[i].left_child_offset()); lay_out(nodes[i].right_child_offset()); }
+  out.resize(base + 1 + n_inner + own_total);
+  std::atomic<bool> over_capacity{false};
 
-  // a leaf reference; leaves longer than REF_LEAF_MAX_COUNT become a chain of nodes that repeat the leaf's box
-  auto leaf_ref = [&](const FlattenBVHNode &leaf) -> uint32_t {
+  // a leaf reference
+  auto leaf_ref = [&](size_t leaf_idx) -> uint32_t {
+    const FlattenBVHNode &leaf = nodes[leaf_idx];
     uint64_t start = slot_offset + leaf.primitive_start;
     uint64_t count = leaf.primitive_end - leaf.primitive_start;
     if (count == 0) return REF_EMPTY;
-    if (start + count > REF_LEAF_START_MASK) { capacity_error = true; return REF_EMPTY; }
+    if (start + count > REF_LEAF_START_MASK) { over_capacity = true; return REF_EMPTY; }
     auto enc = [](uint64_t s, uint64_t c) { return REF_LEAF_BIT | (static_cast<uint32_t>(c - 1) << REF_LEAF_COUNT_SHIFT) | static_cast<uint32_t>(s); };
+    uint64_t cursor = own_base[leaf_idx];  // next node of this leaf's own range
     if (item_bounds && count > 1) {
-      // a binary tree over contiguous halves of the leaf's slots, single slots at the bottom
-      auto union_of = [&](uint64_t s, uint64_t c) {
-        Box3 b = box_empty();
-        for (uint64_t k = 0; k < c; ++k) {
-          const TlasBounding &t = item_bounds[s - slot_offset + k];
-          expand(b, Box3{Vec3{t.world_min[0], t.world_min[1], t.world_min[2]}, Vec3{t.world_max[0], t.world_max[1], t.world_max[2]}});
-        }
-        return b;
+      // a binary tree over contiguous halves of the leaf's slots, single slots at the bottom; a node's boxes are the unions of
+      // its halves' boxes (min / max are exact: the same boxes as the unions over the slots), handed up with the reference
+      struct Built { uint32_t ref; Box3 box; };
+      auto slot_box = [&](uint64_t s) {
+        const TlasBounding &t = item_bounds[s - slot_offset];
+        return Box3{Vec3{t.world_min[0], t.world_min[1], t.world_min[2]}, Vec3{t.world_max[0], t.world_max[1], t.world_max[2]}};
       };
-      std::function<uint32_t(uint64_t, uint64_t)> subtree = [&](uint64_t s, uint64_t c) -> uint32_t {
-        if (c == 1) return enc(s, 1);
+      auto subtree_impl = [&](auto &&self, uint64_t s, uint64_t c) -> Built {
+        if (c == 1) return Built{enc(s, 1), slot_box(s)};
         const uint64_t cl = (c + 1) / 2;
-        const size_t idx = out.size();
-        out.push_back(WideNode{});
-        const Box3 bl = union_of(s, cl), br = union_of(s + cl, c - cl);
-        const uint32_t rl = subtree(s, cl), rr = subtree(s + cl, c - cl);
+        const uint64_t idx = cursor++;
+        const Built l = self(self, s, cl), r = self(self, s + cl, c - cl);
         WideNode w;
         std::memset(&w, 0, sizeof(w));
-        set_child(w, 0, &bl, rl);
-        set_child(w, 1, &br, rr);
+        set_child(w, 0, &l.box, l.ref);
+        set_child(w, 1, &r.box, r.ref);
         out[idx] = w;
-        return static_cast<uint32_t>(idx);
+        Box3 b = l.box;
+        expand(b, r.box);  // (a NaN operand loses: the box of an instance nothing can hit does not swallow its neighbours')
+        return Built{static_cast<uint32_t>(idx), b};
       };
-      return subtree(start, count);
+      return subtree_impl(subtree_impl, start, count).ref;
     }
     if (count <= REF_LEAF_MAX_COUNT) return enc(start, count);
     // chain: node k = {first 16 slots, rest}
-    uint32_t head = static_cast<uint32_t>(out.size());
+    const uint32_t head = static_cast<uint32_t>(cursor);
     while (count > REF_LEAF_MAX_COUNT) {
       WideNode w;
       std::memset(&w, 0, sizeof(w));
       const uint64_t rest = count - REF_LEAF_MAX_COUNT;
-      const uint32_t next = rest > REF_LEAF_MAX_COUNT ? static_cast<uint32_t>(out.size() + 1) : enc(start + REF_LEAF_MAX_COUNT, rest);
+      const uint32_t next = rest > REF_LEAF_MAX_COUNT ? static_cast<uint32_t>(cursor + 1) : enc(start + REF_LEAF_MAX_COUNT, rest);
       set_child(w, 0, &leaf.bounding, enc(start, REF_LEAF_MAX_COUNT));
       set_child(w, 1, &leaf.bounding, next);
-      out.push_back(w);
+      out[cursor++] = w;
       start += REF_LEAF_MAX_COUNT;
       count = rest;
     }
     return head;
   };
-  auto child_ref = [&](size_t idx) -> uint32_t { return nodes[idx].has_child ? wide_of[idx] : leaf_ref(nodes[idx]); };
+  auto child_ref = [&](size_t idx) -> uint32_t { return nodes[idx].has_child ? wide_of[idx] : leaf_ref(idx); };
 
   // pseudo root: the reference tests the root's own box before anything else
   {
@@ -226,16 +244,19 @@ uint32_t emit_wide_nodes(const std::vector<FlattenBVHNode> &nodes, uint64_t slot
     set_child(w, 1, nullptr, REF_EMPTY);
     out[base] = w;
   }
-  for (size_t i = 0; i < nodes.size(); ++i) {
-    if (!nodes[i].has_child) continue;
-    const size_t l = nodes[i].left_child_offset(), r = nodes[i].right_child_offset();
-    WideNode w;
-    std::memset(&w, 0, sizeof(w));
-    const uint32_t lr = child_ref(l), rr = child_ref(r);
-    set_child(w, 0, &nodes[l].bounding, lr);
-    set_child(w, 1, &nodes[r].bounding, rr);
-    out[wide_of[i]] = w;
-  }
+  parallel_for(nodes.size(), 1024, [&](uint64_t i0, uint64_t i1) {
+    for (size_t i = i0; i < i1; ++i) {
+      if (!nodes[i].has_child) continue;
+      const size_t l = nodes[i].left_child_offset(), r = nodes[i].right_child_offset();
+      WideNode w;
+      std::memset(&w, 0, sizeof(w));
+      const uint32_t lr = child_ref(l), rr = child_ref(r);
+      set_child(w, 0, &nodes[l].bounding, lr);
+      set_child(w, 1, &nodes[r].bounding, rr);
+      out[wide_of[i]] = w;
+    }
+  });
+  if (over_capacity) capacity_error = true;
   if (out.size() >= REF_SPECIAL) capacity_error = true;
   return static_cast<uint32_t>(base);
 }
@@ -613,11 +634,16 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
       }
     }
     constexpr uint64_t PARALLEL_TLAS_MIN = 2048;  // (a TLAS-only commit of ten thousand moving instances should take a millisecond or two)
+    auto t_stage = Clock::now();
+    double ms_t_boxes = 0, ms_t_tree = 0, ms_t_records = 0, ms_t_lists = 0, ms_t_wide = 0, ms_t_forest = 0;
+    auto lap = [&](double &into) { into += since(t_stage); t_stage = Clock::now(); };
     parallel_for(tlas.instances.size(), PARALLEL_TLAS_MIN, [&](uint64_t i0, uint64_t i1) {
       for (uint64_t i = i0; i < i1; ++i) aabbs[i] = box_apply_matrix(blas_box[tlas.instances[i].blas_handle].box, tlas.instances[i].transform);
     });
+    lap(ms_t_boxes);
     SAH sah(4);
     FlattenBVH bvh = timed_build(aabbs.data(), aabbs.size(), sah, tlas_option);
+    lap(ms_t_tree);
     if (bvh.stats.bucket_out_of_range) { err = "SAH bucket index out of range (the reference panics here)"; return RDN_ERR_BUILD; }
     out.stats.balance_fallbacks += bvh.stats.balance_fallbacks;
     out.stats.balance_fallbacks_gt10 += bvh.stats.balance_fallbacks_gt10;
@@ -657,6 +683,7 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
         out.tlas_bounding[primitive_start + k] = tb;
       }
     });
+    lap(ms_t_records);
     double irregular_area = 0.0;
     for (size_t k = 0; k < n_slots; ++k) {
       const uint64_t box_idx = bvh.sorted_primitive_index[k];
@@ -669,6 +696,7 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
         if (whole) irregular_area += static_cast<double>(surface_area(aabbs[box_idx]));
       }
     }
+    lap(ms_t_lists);
     TlasRoot root;
     root.bvh_root_idx = bvh_start;
     root.wide_root = emit_wide_nodes(bvh.nodes, primitive_start, out.wide_nodes, capacity_error,
@@ -694,8 +722,13 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
       }
     }
     out.tlas_root.push_back(root);
+    lap(ms_t_wide);
     for (size_t i = 0; i < bvh.nodes.size(); ++i)
       out.tlas_bvh_forest.push_back(to_device_node(bvh.nodes[i], next[i].first, next[i].second, bvh_start, primitive_start));
+    lap(ms_t_forest);
+    if (timing)
+      fprintf(stderr, "[rdn flatten] TLAS of %zu instances: boxes %.2f ms, tree %.2f ms (+ next links), records %.2f ms, lists %.2f ms, wide nodes %.2f ms, "
+                      "threaded nodes %.2f ms\n", tlas.instances.size(), ms_t_boxes, ms_t_tree, ms_t_records, ms_t_lists, ms_t_wide, ms_t_forest);
   }
 
   if (out.geometry_meta.size() > REF_GEOM_ITER_MAX) capacity_error = true;

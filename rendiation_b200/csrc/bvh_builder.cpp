@@ -7,7 +7,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
+
+#include <unistd.h>
 
 namespace rdn {
 
@@ -82,7 +86,9 @@ SplitResult SAH::split(const FlattenBVHNode &parent, const std::vector<BuildPrim
   const float step = (range_end - range_start) / static_cast<float>(n_part);
   auto bucket_of = [&](uint64_t prim, bool &out_of_range) -> size_t {
     const float axis_value = component(src[prim].center, axis);
-    uint64_t which = saturating_usize(floorf((axis_value - range_start) / step));
+    // (the reference floors before the cast; the saturating cast truncates towards zero and sends everything negative to 0, so the
+    // floor changes nothing and the libm call is left out)
+    uint64_t which = saturating_usize((axis_value - range_start) / step);
     if (which == n_part) which -= 1;
     if (which >= n_part) { out_of_range = true; which = n_part - 1; }
     return static_cast<size_t>(which);
@@ -94,21 +100,24 @@ SplitResult SAH::split(const FlattenBVHNode &parent, const std::vector<BuildPrim
   // (thread count only looked up for ranges that qualify: hardware_concurrency() is a system call and there is a split per inner node)
   const unsigned threads = (parallel_split_ && end - begin >= PARALLEL_SPLIT_MIN && n_part <= 255) ? build_thread_count() : 1u;
   const bool parallel = threads > 1;
-  std::vector<uint8_t> which_of;
-  std::vector<std::vector<uint64_t>> chunk_counts;
+  // (member scratch: a split per inner node must not allocate)
+  std::vector<uint8_t> &which_of = which_of_;
+  std::vector<uint64_t> &chunk_counts = chunk_counts_;  // [thread][bucket]
+  std::vector<Box3> &chunk_boxes = chunk_boxes_;
+  const uint64_t n = end - begin;
   uint64_t chunk = 0;
   if (parallel) {
-    const uint64_t n = end - begin;
     chunk = (n + threads - 1) / threads;
     which_of.resize(n);
-    chunk_counts.assign(threads, std::vector<uint64_t>(n_part, 0));
-    std::vector<std::vector<Box3>> chunk_boxes(threads, std::vector<Box3>(n_part, box_empty()));
+    chunk_counts.assign(static_cast<size_t>(threads) * n_part, 0);
+    chunk_boxes.assign(static_cast<size_t>(threads) * n_part, box_empty());
     std::atomic<bool> out_of_range{false};
     parallel_for(n, 0, [&](uint64_t b0, uint64_t b1) {
       const size_t t = static_cast<size_t>(b0 / chunk);
       bool oor = false;
-      std::vector<uint64_t> my_counts(n_part, 0);  // thread-private while counting: the shared rows sit in one cache line
-      std::vector<Box3> my_boxes(n_part, box_empty());
+      uint64_t my_counts[256] = {0};  // thread-private while counting: the shared rows sit in one cache line
+      Box3 my_boxes[256];
+      for (size_t k = 0; k < n_part; ++k) my_boxes[k] = box_empty();
       for (uint64_t i = b0; i < b1; ++i) {
         const uint64_t prim = index[begin + i];
         const size_t w = bucket_of(prim, oor);
@@ -116,13 +125,22 @@ SplitResult SAH::split(const FlattenBVHNode &parent, const std::vector<BuildPrim
         my_counts[w]++;
         expand(my_boxes[w], src[prim].bounding);
       }
-      chunk_counts[t] = my_counts;
-      chunk_boxes[t] = my_boxes;
+      for (size_t k = 0; k < n_part; ++k) { chunk_counts[t * n_part + k] = my_counts[k]; chunk_boxes[t * n_part + k] = my_boxes[k]; }
       if (oor) out_of_range = true;
     });
     if (out_of_range) stats.bucket_out_of_range = true;
     for (size_t t = 0; t < threads; ++t)
-      for (size_t k = 0; k < n_part; ++k) { counts[k] += chunk_counts[t][k]; expand(pre_partition_[k].bounding, chunk_boxes[t][k]); }
+      for (size_t k = 0; k < n_part; ++k) { counts[k] += chunk_counts[t * n_part + k]; expand(pre_partition_[k].bounding, chunk_boxes[t * n_part + k]); }
+  } else if (n_part <= 255) {
+    // one pass that notes the bucket of every primitive; the range is rewritten by a counting scatter below
+    which_of.resize(n);
+    for (uint64_t i = 0; i < n; ++i) {
+      const uint64_t prim = index[begin + i];
+      const size_t which = bucket_of(prim, stats.bucket_out_of_range);
+      which_of[i] = static_cast<uint8_t>(which);
+      expand(pre_partition_[which].bounding, src[prim].bounding);
+      counts[which]++;
+    }
   } else {
     for (uint64_t i = begin; i < end; ++i) {
       const uint64_t prim = index[i];
@@ -159,16 +177,26 @@ SplitResult SAH::split(const FlattenBVHNode &parent, const std::vector<BuildPrim
 
   // step 3: rewrite the index range bucket by bucket (stable)
   if (parallel) {
-    const uint64_t n = end - begin;
-    std::vector<uint64_t> old(index.begin() + begin, index.begin() + end);
-    std::vector<std::vector<uint64_t>> offset(threads, std::vector<uint64_t>(n_part, 0));
+    std::vector<uint64_t> &old = old_;
+    old.assign(index.begin() + begin, index.begin() + end);
+    std::vector<uint64_t> &offset = offset_;  // [thread][bucket]
+    offset.assign(static_cast<size_t>(threads) * n_part, 0);
     uint64_t ptr = begin;
     for (size_t k = 0; k < n_part; ++k)
-      for (size_t t = 0; t < threads; ++t) { offset[t][k] = ptr; ptr += chunk_counts[t][k]; }
+      for (size_t t = 0; t < threads; ++t) { offset[t * n_part + k] = ptr; ptr += chunk_counts[t * n_part + k]; }
     parallel_for(n, 0, [&](uint64_t b0, uint64_t b1) {
-      std::vector<uint64_t> off = offset[static_cast<size_t>(b0 / chunk)];  // private copy (see above)
+      uint64_t off[256];  // private copy (see above)
+      const size_t t = static_cast<size_t>(b0 / chunk);
+      for (size_t k = 0; k < n_part; ++k) off[k] = offset[t * n_part + k];
       for (uint64_t i = b0; i < b1; ++i) index[off[which_of[i]]++] = old[i];
     });
+  } else if (n_part <= 255) {
+    std::vector<uint64_t> &old = old_;
+    old.assign(index.begin() + begin, index.begin() + end);
+    uint64_t off[256];
+    uint64_t ptr = begin;
+    for (size_t k = 0; k < n_part; ++k) { off[k] = ptr; ptr += counts[k]; }
+    for (uint64_t i = 0; i < n; ++i) index[off[which_of[i]]++] = old[i];
   } else {
     uint64_t ptr = begin;
     for (const auto &p : pre_partition_)
@@ -192,17 +220,161 @@ unsigned build_thread_count() {
   return n;
 }
 
+// ------------------------------------------------------------------------------------------------ worker pool
+// A commit of a few thousand moving instances is a handful of parallel sections of some tens of microseconds each; starting and
+// joining sixteen threads costs more than that per section.  The sections run on a process-wide pool instead.  A section is a
+// list of chunks claimed one at a time through one atomic word (no lock on the way in: sixteen threads queueing on a mutex cost
+// more than the section) by the calling thread and by whatever workers are awake: the
+// caller never waits for a worker to wake up, only for the chunks that were claimed to finish — workers that were asleep (they
+// spin for a moment after a section, then sleep on a condition variable) join when they get there, or find nothing left.
+// Sections of different callers (concurrent commits of different scenes) run on the same workers one after another; a section
+// requested from inside a worker runs on the caller alone.  After a fork() the child gets a fresh pool.
+namespace {
+
+inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+  __builtin_ia32_pause();
+#elif defined(__aarch64__)
+  asm volatile("yield" ::: "memory");
+#endif
+}
+
+thread_local bool t_pool_worker = false;
+
+class WorkerPool {
+ public:
+  explicit WorkerPool(unsigned workers) {
+    for (unsigned i = 0; i < workers; ++i) threads_.emplace_back([this]() { worker_main(); });
+  }
+  ~WorkerPool() {
+    stop_.store(true);
+    { std::lock_guard<std::mutex> g(sleep_mutex_); sleep_cv_.notify_all(); }
+    for (auto &t : threads_) t.join();
+  }
+
+  // a hint that sections are about to follow: sleeping workers go back to spinning (waking one takes longer than a short section)
+  void wake() {
+    wake_epoch_.fetch_add(1);
+    if (sleepers_.load() != 0) { std::lock_guard<std::mutex> g(sleep_mutex_); sleep_cv_.notify_all(); }
+  }
+
+  void run(unsigned n, const std::function<void(unsigned)> &fn) {
+    std::lock_guard<std::mutex> one_section(run_mutex_);
+    const uint64_t g = (ticket_.load(std::memory_order_relaxed) >> 32) + 1;
+    fn_.store(&fn, std::memory_order_relaxed);
+    n_.store(n, std::memory_order_relaxed);
+    done_.store(0, std::memory_order_relaxed);
+    ticket_.store(g << 32);                   // publishes the section (sequentially consistent with the sleepers' count, see worker_main)
+    if (sleepers_.load() != 0) { std::lock_guard<std::mutex> lk(sleep_mutex_); sleep_cv_.notify_all(); }
+    work(g);
+    for (unsigned spins = 0; done_.load(std::memory_order_acquire) != n; ++spins) {
+      if (spins < 4096) cpu_relax(); else std::this_thread::yield();
+    }
+  }
+
+ private:
+  // Claims chunks of section g until none is left.  The ticket holds (section, next chunk): a claim is a compare-exchange on it, so a
+  // worker that read the section's description late — the caller may have moved on to the next section meanwhile — fails the
+  // exchange and throws what it read away; a chunk that was claimed is always run (the caller waits for done_ before `fn` dies).
+  void work(uint64_t g) {
+    for (;;) {
+      uint64_t t = ticket_.load(std::memory_order_acquire);
+      if ((t >> 32) != g) return;
+      const std::function<void(unsigned)> *fn = fn_.load(std::memory_order_relaxed);
+      const unsigned n = n_.load(std::memory_order_relaxed);
+      const unsigned c = static_cast<unsigned>(t & 0xFFFFFFFFu);
+      if (c >= n) {
+        if (ticket_.load(std::memory_order_acquire) == t) return;  // (n belongs to this section: nothing left)
+        continue;
+      }
+      if (!ticket_.compare_exchange_weak(t, t + 1, std::memory_order_acq_rel)) continue;
+      (*fn)(c);
+      done_.fetch_add(1, std::memory_order_release);
+    }
+  }
+
+  void worker_main() {
+    t_pool_worker = true;
+    uint64_t seen = 0;
+    for (;;) {
+      auto t_idle = std::chrono::steady_clock::now();
+      for (unsigned spins = 0; (ticket_.load(std::memory_order_acquire) >> 32) == seen && !stop_.load(std::memory_order_relaxed); ++spins) {
+        if ((spins & 255u) != 255u || std::chrono::steady_clock::now() - t_idle < std::chrono::microseconds(300)) { cpu_relax(); continue; }
+        std::unique_lock<std::mutex> lk(sleep_mutex_);
+        const uint64_t woken = wake_epoch_.load();
+        sleepers_.fetch_add(1);
+        sleep_cv_.wait(lk, [&]() { return (ticket_.load() >> 32) != seen || wake_epoch_.load() != woken || stop_.load(); });
+        sleepers_.fetch_sub(1);
+        t_idle = std::chrono::steady_clock::now();  // (woken by a hint: spin for another while)
+      }
+      if (stop_.load()) return;
+      seen = ticket_.load(std::memory_order_acquire) >> 32;
+      work(seen);
+    }
+  }
+
+  std::vector<std::thread> threads_;
+  std::mutex run_mutex_, sleep_mutex_;
+  std::condition_variable sleep_cv_;
+  std::atomic<uint64_t> ticket_{0};   // (section number << 32) | next chunk of it
+  std::atomic<const std::function<void(unsigned)> *> fn_{nullptr};
+  std::atomic<unsigned> n_{0}, done_{0};
+  std::atomic<uint64_t> wake_epoch_{0};
+  std::atomic<unsigned> sleepers_{0};
+  std::atomic<bool> stop_{false};
+};
+
+struct PoolHolder {
+  std::mutex mutex;
+  WorkerPool *pool = nullptr;
+  pid_t pid = 0;
+  ~PoolHolder() { if (pool && pid == getpid()) delete pool; }  // (a forked child must not join threads it never had)
+};
+PoolHolder g_pool;
+
+WorkerPool *the_pool() {
+  if (t_pool_worker) return nullptr;
+  static const bool disabled = []() { const char *e = getenv("RDN_BUILD_POOL"); return e && atoi(e) == 0; }();
+  if (disabled) return nullptr;
+  std::lock_guard<std::mutex> g(g_pool.mutex);
+  const pid_t me = getpid();
+  if (!g_pool.pool || g_pool.pid != me) {  // first use, or first use in a forked child (the parent's pool object is leaked there)
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw <= 1) return nullptr;
+    g_pool.pool = new WorkerPool(hw - 1);
+    g_pool.pid = me;
+  }
+  return g_pool.pool;
+}
+
+bool run_on_pool(unsigned n, const std::function<void(unsigned)> &fn) {
+  WorkerPool *pool = the_pool();
+  if (!pool) return false;
+  pool->run(n, fn);
+  return true;
+}
+
+}  // namespace
+
+void warm_worker_pool() {
+  if (WorkerPool *pool = the_pool()) pool->wake();
+}
+
+void run_parallel(unsigned n, const std::function<void(unsigned)> &fn) {
+  if (n <= 1) { if (n == 1) fn(0); return; }
+  if (run_on_pool(n, fn)) return;
+  for (unsigned t = 0; t < n; ++t) fn(t);  // (inside a worker, a single-core host, RDN_BUILD_POOL=0: the caller alone)
+}
+
 void parallel_for(uint64_t n, uint64_t min_parallel, const std::function<void(uint64_t, uint64_t)> &fn) {
   const unsigned threads = build_thread_count();
   if (threads <= 1 || n < min_parallel) { fn(0, n); return; }
   const uint64_t chunk = (n + threads - 1) / threads;
-  std::vector<std::thread> pool;
-  for (unsigned t = 1; t < threads; ++t) {
+  const unsigned used = static_cast<unsigned>((n + chunk - 1) / chunk);  // chunks that hold anything
+  run_parallel(used, [&](unsigned t) {
     const uint64_t begin = std::min<uint64_t>(n, t * chunk), end = std::min<uint64_t>(n, begin + chunk);
-    if (begin < end) pool.emplace_back([&fn, begin, end]() { fn(begin, end); });
-  }
-  fn(0, std::min<uint64_t>(n, chunk));
-  for (auto &th : pool) th.join();
+    if (begin < end) fn(begin, end);
+  });
 }
 
 namespace {
@@ -273,35 +445,66 @@ FlattenBVH FlattenBVH::build(const Box3 *boxes, uint64_t n, BVHBuildStrategy &st
     return out;
   }
 
+  const auto t_setup = std::chrono::steady_clock::now();
   // ---- top of the tree on this thread: split the largest open subtree until there are enough of them
   struct Top { Box3 box; uint64_t start, end, depth; int left = -1, right = -1; int32_t axis = 0; int task = -1; };
   std::vector<Top> top;
   top.push_back(Top{root_box, 0, n, 0});
   std::vector<int> open{0};
   const size_t want_open = static_cast<size_t>(n_threads) * 8;
-  const uint64_t min_task = 2048;
+  // (subtrees below this size are not split further on the calling thread; RDN_BUILD_MIN_TASK: measurement knob)
+  static const uint64_t min_task = []() { const char *e = getenv("RDN_BUILD_MIN_TASK"); return e && atoll(e) > 0 ? static_cast<uint64_t>(atoll(e)) : 512ull; }();
+  // Rounds: every open subtree that is still worth splitting is split once per round.  Several small ones are split side by side,
+  // one thread each with its own copy of the strategy (disjoint index ranges); a few large ones one after another, each by all
+  // threads (SAH::split).  Which subtrees end up as tasks does not change the tree: a split depends on its own range only.
   while (open.size() < want_open) {
-    size_t pick = open.size();
-    uint64_t largest = min_task;
+    std::vector<size_t> cand;
     for (size_t k = 0; k < open.size(); ++k) {
       const Top &t = top[open[k]];
       const uint64_t count = t.end - t.start;
-      if (count > largest && option.should_continue(count, t.depth)) { largest = count; pick = k; }
+      if (count > min_task && option.should_continue(count, t.depth)) cand.push_back(k);
     }
-    if (pick == open.size()) break;
-    const int ti = open[pick];
-    FlattenBVHNode node;
-    std::memset(&node, 0, sizeof(node));
-    node.bounding = top[ti].box; node.primitive_start = top[ti].start; node.primitive_end = top[ti].end;
-    const SplitResult s = strategy.split(node, primitives, out.sorted_primitive_index, out.stats);
-    const uint64_t depth = top[ti].depth + 1;
-    top[ti].axis = s.axis;
-    top[ti].left = static_cast<int>(top.size());
-    top.push_back(Top{s.left_box, s.left_start, s.left_end, depth});
-    top[ti].right = static_cast<int>(top.size());
-    top.push_back(Top{s.right_box, s.right_start, s.right_end, depth});
-    open[pick] = top[ti].left;
-    open.push_back(top[ti].right);
+    if (cand.empty()) break;
+    std::sort(cand.begin(), cand.end(), [&](size_t a, size_t b) {
+      const uint64_t ca = top[open[a]].end - top[open[a]].start, cb = top[open[b]].end - top[open[b]].start;
+      return ca != cb ? ca > cb : a < b;
+    });
+    if (cand.size() > want_open - open.size()) cand.resize(want_open - open.size());
+    const uint64_t largest = top[open[cand[0]]].end - top[open[cand[0]]].start;
+    std::vector<SplitResult> results(cand.size());
+    std::vector<BuildStats> split_stats(cand.size());
+    auto split_one = [&](BVHBuildStrategy &with, size_t k) {
+      const Top &t = top[open[cand[k]]];
+      FlattenBVHNode node;
+      std::memset(&node, 0, sizeof(node));
+      node.bounding = t.box; node.primitive_start = t.start; node.primitive_end = t.end;
+      const auto t_split = std::chrono::steady_clock::now();
+      results[k] = with.split(node, primitives, out.sorted_primitive_index, split_stats[k]);
+      if (getenv("RDN_BUILD_TIMING_SPLITS"))
+        fprintf(stderr, "[rdn build] top split of %llu primitives: %.1f us\n", static_cast<unsigned long long>(t.end - t.start),
+                std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_split).count());
+    };
+    if (cand.size() > 1 && (cand.size() * 4 >= n_threads || largest < 8192)) {
+      run_parallel(static_cast<unsigned>(cand.size()), [&](unsigned k) {
+        std::unique_ptr<BVHBuildStrategy> mine = strategy.clone();
+        split_one(*mine, k);
+      });
+    } else {
+      for (size_t k = 0; k < cand.size(); ++k) split_one(strategy, k);
+    }
+    for (size_t k = 0; k < cand.size(); ++k) {
+      merge_stats(out.stats, split_stats[k]);
+      const int ti = open[cand[k]];
+      const SplitResult &s = results[k];
+      const uint64_t depth = top[ti].depth + 1;
+      top[ti].axis = s.axis;
+      top[ti].left = static_cast<int>(top.size());
+      top.push_back(Top{s.left_box, s.left_start, s.left_end, depth});
+      top[ti].right = static_cast<int>(top.size());
+      top.push_back(Top{s.right_box, s.right_start, s.right_end, depth});
+      open[cand[k]] = top[ti].left;
+      open.push_back(top[ti].right);
+    }
   }
 
   const bool timing = getenv("RDN_BUILD_TIMING") != nullptr;
@@ -328,10 +531,7 @@ FlattenBVH FlattenBVH::build(const Box3 *boxes, uint64_t n, BVHBuildStrategy &st
     }
   };
   const unsigned workers = static_cast<unsigned>(std::min<size_t>(n_threads, tasks.size()));
-  std::vector<std::thread> pool;
-  for (unsigned w = 1; w < workers; ++w) pool.emplace_back(worker);
-  worker();
-  for (auto &th : pool) th.join();
+  run_parallel(workers, [&](unsigned) { worker(); });
   out.stats.build_threads = workers;
   const auto t_workers = std::chrono::steady_clock::now();
 
@@ -372,8 +572,8 @@ FlattenBVH FlattenBVH::build(const Box3 *boxes, uint64_t n, BVHBuildStrategy &st
   if (timing) {
     const auto t_end = std::chrono::steady_clock::now();
     auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-    fprintf(stderr, "[rdn build] %llu primitives: setup+top %.1f ms (%zu open subtrees), workers %.1f ms on %u threads, splice %.1f ms\n",
-            static_cast<unsigned long long>(n), ms(t_begin, t_top), tasks.size(), ms(t_top, t_workers), workers, ms(t_workers, t_end));
+    fprintf(stderr, "[rdn build] %llu primitives: setup %.2f ms, top %.2f ms (%zu open subtrees), workers %.2f ms on %u threads, splice %.2f ms\n",
+            static_cast<unsigned long long>(n), ms(t_begin, t_setup), ms(t_setup, t_top), tasks.size(), ms(t_top, t_workers), workers, ms(t_workers, t_end));
   }
   return out;
 }

@@ -100,6 +100,11 @@ class SAH : public BVHBuildStrategy {
   };
   std::vector<Bucket> pre_partition_;
   std::vector<uint64_t> counts_;
+  // scratch of one split (a split per inner node must not allocate): bucket of every primitive of the range, the range before the
+  // rewrite, per-thread bucket counts / boxes / rewrite offsets of the all-threads split
+  std::vector<uint8_t> which_of_;
+  std::vector<uint64_t> old_, chunk_counts_, offset_;
+  std::vector<Box3> chunk_boxes_;
 };
 
 struct FlattenBVH {
@@ -114,13 +119,17 @@ struct FlattenBVH {
   // n_threads: 0 = hardware concurrency capped by the RDN_BUILD_THREADS environment variable, 1 = sequential.
   static FlattenBVH build(const Box3 *boxes, uint64_t n, BVHBuildStrategy &strategy, const TreeBuildOption &option, unsigned n_threads = 0);
 };
-constexpr uint64_t PARALLEL_BUILD_MIN = 1u << 15;
-constexpr uint64_t PARALLEL_SPLIT_MIN = 1u << 14;  // a single SAH split over at least this many primitives uses all threads too
+constexpr uint64_t PARALLEL_BUILD_MIN = 1u << 12;
+constexpr uint64_t PARALLEL_SPLIT_MIN = 1u << 11;  // a single SAH split over at least this many primitives uses all threads too
 
 // worker threads for host-side loops: min(hardware concurrency, RDN_BUILD_THREADS), at least 1
 unsigned build_thread_count();
 // fn(begin, end) over [0, n) in contiguous chunks, one per thread (sequential below `min_parallel` items)
 void parallel_for(uint64_t n, uint64_t min_parallel, const std::function<void(uint64_t, uint64_t)> &fn);
+// fn(0) on the calling thread and fn(1) .. fn(n - 1) on the process-wide worker pool (bvh_builder.cpp; own threads when the pool is taken)
+void run_parallel(unsigned n, const std::function<void(unsigned)> &fn);
+// hint that parallel sections are about to follow (a commit): sleeping pool workers start spinning again
+void warm_worker_pool();
 
 constexpr uint32_t INVALID_NEXT = 0xFFFFFFFFu;
 // (hit_next, miss_next) per node for the stackless threaded walk

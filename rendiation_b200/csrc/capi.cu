@@ -144,6 +144,8 @@ struct rdn_rt_scene {
   std::vector<uint8_t> host_blob;  // kept only by host-only scenes (n_devices == 0)
   BlobHeader blob_header{};        // layout of the blob the devices hold (valid when flat is)
   uint64_t tlas_only_commits = 0;  // commits that kept every BLAS array and patched the TLAS arrays of the device blobs in place
+  void *patch_staging = nullptr;   // page-locked staging buffer of those patches
+  uint64_t patch_staging_cap = 0;
   std::vector<uint32_t> h_tlas_binding;  // host copies used to resolve the wide root of a launch
   std::vector<TlasRoot> h_tlas_root;
   std::vector<DeviceCtx> devices;
@@ -278,22 +280,43 @@ int commit_locked(rdn_rt_scene *s) {
                              same(ARR_INSTANCES, flat.instances.size()) && same(ARR_WIDE_NODES, flat.wide_nodes.size()) &&
                              same(ARR_IRREGULAR_INSTANCES, flat.irregular_instances.size()) && same(ARR_WIDE4_NODES, flat.wide4_nodes.size());
     if (same_layout) {
+      // the changed ranges are gathered into one page-locked staging buffer (pageable sources would be staged by the driver one
+      // copy at a time, each with its own synchronisation) and go out as asynchronous copies behind one another
+      struct Range { int id; const char *src; uint64_t first_byte, bytes, staged_at; };
+      std::vector<Range> ranges;
+      uint64_t staged_bytes = 0;
+      auto add = [&](int id, const void *src, uint64_t first, uint64_t count, uint64_t elem) {
+        if (count == 0) return;
+        ranges.push_back(Range{id, static_cast<const char *>(src) + first * elem, first * elem, count * elem, staged_bytes});
+        staged_bytes += (count * elem + 255) / 256 * 256;
+      };
+      add(ARR_TLAS_BINDING, flat.tlas_binding.data(), 0, flat.tlas_binding.size(), 4);
+      add(ARR_TLAS_ROOT, flat.tlas_root.data(), 0, flat.tlas_root.size(), sizeof(TlasRoot));
+      add(ARR_TLAS_BVH_FOREST, flat.tlas_bvh_forest.data(), 0, flat.tlas_bvh_forest.size(), sizeof(DeviceBVHNode));
+      add(ARR_TLAS_BOUNDING, flat.tlas_bounding.data(), 0, flat.tlas_bounding.size(), sizeof(TlasBounding));
+      add(ARR_INSTANCES, flat.instances.data(), 0, flat.instances.size(), sizeof(InstanceRecord));
+      add(ARR_WIDE_NODES, flat.wide_nodes.data(), wide0, flat.wide_nodes.size() - wide0, sizeof(WideNode));
+      add(ARR_IRREGULAR_INSTANCES, flat.irregular_instances.data(), 0, flat.irregular_instances.size(), 4);
+      add(ARR_WIDE4_NODES, flat.wide4_nodes.data(), wide4_0, flat.wide4_nodes.size() - wide4_0, sizeof(Wide4Node));
+      RDN_CUDA(cudaSetDevice(s->devices[0].device));
+      if (s->patch_staging_cap < staged_bytes) {
+        if (s->patch_staging) cudaFreeHost(s->patch_staging);
+        s->patch_staging = nullptr; s->patch_staging_cap = 0;
+        RDN_CUDA(cudaHostAlloc(&s->patch_staging, staged_bytes + staged_bytes / 4, cudaHostAllocPortable));
+        s->patch_staging_cap = staged_bytes + staged_bytes / 4;
+      }
+      char *staging = static_cast<char *>(s->patch_staging);
+      run_parallel(static_cast<unsigned>(ranges.size()), [&](unsigned k) { std::memcpy(staging + ranges[k].staged_at, ranges[k].src, ranges[k].bytes); });
       for (DeviceCtx &dc : s->devices) {
         RDN_CUDA(cudaSetDevice(dc.device));
         RDN_CUDA(cudaDeviceSynchronize());  // nothing may still be walking the arrays that change
         char *base = static_cast<char *>(dc.d_blob);
-        auto patch = [&](int id, const void *src, uint64_t first, uint64_t count, uint64_t elem) -> cudaError_t {
-          if (count == 0) return cudaSuccess;
-          return cudaMemcpy(base + h.offset[id] + first * elem, static_cast<const char *>(src) + first * elem, count * elem, cudaMemcpyHostToDevice);
-        };
-        RDN_CUDA(patch(ARR_TLAS_BINDING, flat.tlas_binding.data(), 0, flat.tlas_binding.size(), 4));
-        RDN_CUDA(patch(ARR_TLAS_ROOT, flat.tlas_root.data(), 0, flat.tlas_root.size(), sizeof(TlasRoot)));
-        RDN_CUDA(patch(ARR_TLAS_BVH_FOREST, flat.tlas_bvh_forest.data(), 0, flat.tlas_bvh_forest.size(), sizeof(DeviceBVHNode)));
-        RDN_CUDA(patch(ARR_TLAS_BOUNDING, flat.tlas_bounding.data(), 0, flat.tlas_bounding.size(), sizeof(TlasBounding)));
-        RDN_CUDA(patch(ARR_INSTANCES, flat.instances.data(), 0, flat.instances.size(), sizeof(InstanceRecord)));
-        RDN_CUDA(patch(ARR_WIDE_NODES, flat.wide_nodes.data(), wide0, flat.wide_nodes.size() - wide0, sizeof(WideNode)));
-        RDN_CUDA(patch(ARR_IRREGULAR_INSTANCES, flat.irregular_instances.data(), 0, flat.irregular_instances.size(), 4));
-        RDN_CUDA(patch(ARR_WIDE4_NODES, flat.wide4_nodes.data(), wide4_0, flat.wide4_nodes.size() - wide4_0, sizeof(Wide4Node)));
+        for (const Range &r : ranges)
+          RDN_CUDA(cudaMemcpyAsync(base + h.offset[r.id] + r.first_byte, staging + r.staged_at, r.bytes, cudaMemcpyHostToDevice, cudaStreamPerThread));
+      }
+      for (DeviceCtx &dc : s->devices) {
+        RDN_CUDA(cudaSetDevice(dc.device));
+        RDN_CUDA(cudaStreamSynchronize(cudaStreamPerThread));
       }
       flat.stats.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_upload).count();
       s->h_tlas_binding = flat.tlas_binding;
@@ -336,6 +359,7 @@ int ensure_committed(rdn_rt_scene *s) {
     if (!s->dirty) return RDN_OK;
   }
   std::unique_lock<std::shared_mutex> wr(s->lock);
+  if (s->dirty) warm_worker_pool();
   return commit_locked(s);
 }
 
@@ -576,6 +600,7 @@ void rdn_rt_scene_destroy(rdn_rt_scene *s) {
     if (dc.d_keep) cudaFree(dc.d_keep);
     if (dc.d_iota) cudaFree(dc.d_iota);
   }
+  if (s->patch_staging) cudaFreeHost(s->patch_staging);
   delete s;
 }
 
@@ -625,6 +650,7 @@ int rdn_rt_tlas_create(rdn_rt_scene *s, const rdn_instance *inst, uint32_t n, ui
 
 int rdn_rt_tlas_update(rdn_rt_scene *s, uint32_t handle, const rdn_instance *inst, uint32_t n) {
   if (!s || (n && !inst)) return fail(RDN_ERR_INVALID_ARGUMENT, "rdn_rt_tlas_update: null argument");
+  warm_worker_pool();  // (the commit that follows is a handful of short parallel sections)
   std::vector<InstanceSource> src(n);
   for (uint32_t i = 0; i < n; ++i) {
     std::memcpy(&src[i].transform, inst[i].transform, sizeof(Mat4));
@@ -664,6 +690,7 @@ uint32_t rdn_rt_bind_tlas_max_len(const rdn_rt_scene *) { return 0xFFFFFFFFu; } 
 int rdn_rt_commit(rdn_rt_scene *s) {
   if (!s) return fail(RDN_ERR_INVALID_ARGUMENT, "null scene");
   std::unique_lock<std::shared_mutex> wr(s->lock);
+  if (s->dirty) warm_worker_pool();
   return commit_locked(s);
 }
 

@@ -32,8 +32,24 @@ RDN_HD float dot(Vec3 a, Vec3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 RDN_HD Vec3 cross(Vec3 a, Vec3 b) {
   return Vec3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
-RDN_HD Vec3 vmin(Vec3 a, Vec3 b) { return Vec3{fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)}; }
-RDN_HD Vec3 vmax(Vec3 a, Vec3 b) { return Vec3{fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)}; }
+// fminf / fmaxf (a NaN operand loses).  Host compilers keep them as calls into libm unless given -ffinite-math-only — a third of the
+// host builder's time went there — so the host spells the same selection out (glibc's own: x if x <= y, y if y < x, else the non-NaN).
+RDN_HD float min_f32(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return fminf(a, b);
+#else
+  return a <= b ? a : (b < a ? b : (b != b ? a : b));
+#endif
+}
+RDN_HD float max_f32(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return fmaxf(a, b);
+#else
+  return a >= b ? a : (b > a ? b : (b != b ? a : b));
+#endif
+}
+RDN_HD Vec3 vmin(Vec3 a, Vec3 b) { return Vec3{min_f32(a.x, b.x), min_f32(a.y, b.y), min_f32(a.z, b.z)}; }
+RDN_HD Vec3 vmax(Vec3 a, Vec3 b) { return Vec3{max_f32(a.x, b.x), max_f32(a.y, b.y), max_f32(a.z, b.z)}; }
 RDN_HD float length(Vec3 a) { return sqrtf(dot(a, a)); }
 // InnerProductSpace::normalize: unchanged when the squared length is not > 0
 RDN_HD Vec3 normalize(Vec3 a) {

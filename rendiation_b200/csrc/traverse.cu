@@ -432,6 +432,8 @@ __global__ void __launch_bounds__(128) k_resolve_ties(const SceneDev S, const rd
 }
 
 // ================================================================================================ ordered
+enum { SHARE_NEVER = 0, SHARE_ALWAYS = 1, SHARE_LATE = 2 };  // template argument SHARE of k_trace_ordered_rounds
+
 struct OrderedParams {
   SceneDev S;
   rdn_launch L;
@@ -575,7 +577,7 @@ __device__ __forceinline__ void drain_tie_queue(const OrderedParams &P) {
 // speculative traversal with a postponed leaf, any-hit pre-classification, topping a thinned-out tile up with new rays, the first
 // 8-32 stack entries per thread in shared memory (3-10 % slower than the L1-cached local stack), rows of tiles taken from the
 // middle of the frame outwards (+2..5 % on configs 1 / 2, -11 % on config 4).
-template <int K, int MINB, bool DRAIN_TIES, bool IRREGULAR, bool LD256, bool HOT, bool WIDE4, bool INST_LOOP = false, bool SHARE = false, bool ANYHIT = false>
+template <int K, int MINB, bool DRAIN_TIES, bool IRREGULAR, bool LD256, bool HOT, bool WIDE4, bool INST_LOOP = false, int SHARE = 0, bool ANYHIT = false>
 __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(const __grid_constant__ OrderedParams P) {
   RDN_COST(COST_PROLOGUE);
   const SceneDev &S = P.S;
@@ -610,6 +612,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
 
   __shared__ __align__(128) float4 s_hot[HOT ? 2 * HOT_TOP_NODES * 4 : 4];
   __shared__ __align__(8) unsigned long long s_hot_bar;
+  __shared__ int s_age[SHARE == SHARE_LATE ? ORDERED_BLOCK : 1];  // SHARE_LATE: the age of the pass over the tile in rounds, one word per thread
 #ifndef RDN_SIMT_EMU
   if constexpr (HOT) {
     const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&s_hot_bar));
@@ -751,7 +754,7 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
             scaling = 1.f; near_s = t_near_world; bound = far0; far_s = far0;
             best = INFINITY; second = INFINITY; best_slot = RDN_INVALID_ID; best_inst = RDN_INVALID_ID;
             in_object = false; sp = 0;
-            if constexpr (SHARE) { lo = 0; home = lane; helpers = 0; }
+            if constexpr (SHARE == SHARE_ALWAYS) { lo = 0; home = lane; helpers = 0; }
             cur = world_entry;
             alive = true;
           } else {
@@ -771,339 +774,45 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
     unsigned long long dbg_pass_rounds = 0, dbg_pass_busy = 0;
 #endif
 
-    // (SHARE: every lane takes part in the rounds — a lane without a ray idles at cur == REF_DONE until it is handed a subtree)
-    const uint32_t rmask = SHARE ? FULL_MASK : amask;
-    if constexpr (SHARE) home &= 31u;  // a new pass over a tile: age 0
-    if (SHARE || alive) {
-#pragma unroll 1
-      for (;;) {
-        RDN_COST(COST_ROUND);
-        if constexpr (SHARE) home += 32u;
-#ifdef RDN_DEBUG_TIMELINE
-        ++dbg_pass_rounds;
-        dbg_pass_busy += __popc(__ballot_sync(rmask, cur != REF_DONE));
-#endif
-        // ---------------- phase 1: up to K inner nodes (both child boxes in one 64 B fetch)
-#pragma unroll 1
-        for (int k = 0; k < K; ++k) {
-          if (!(cur < REF_SPECIAL)) break;
-          RDN_COST(COST_NODE);
-#ifdef RDN_DEBUG_STEPS
-          ++dbg_steps; ++dbg_ray_steps;
-#endif
-          if (WIDE4) {
-            const float4 *np4 = reinterpret_cast<const float4 *>(S.wide4_nodes + cur);
-            float key[4];
-            uint32_t ref[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              float4 a, b;
-              load_pair<true>(np4 + 2 * c, a, b);
-              float n;
-              const bool h = slab_test(o, inv, near_s, far_s, xyz(a), xyz(b), n);
-              key[c] = h ? n : INFINITY;  // (an unused slot is a NaN box: never hit)
-              ref[c] = h ? __float_as_uint(a.w) : REF_EMPTY;
-            }
-            // sort the four (entry distance, reference) pairs, nearest first (5 compare-exchanges)
-#define RDN_CSWAP(i, j) do { const bool sw = key[j] < key[i]; const float tk = sw ? key[j] : key[i]; const uint32_t tr = sw ? ref[j] : ref[i]; \
-                             key[j] = sw ? key[i] : key[j]; ref[j] = sw ? ref[i] : ref[j]; key[i] = tk; ref[i] = tr; } while (0)
-            RDN_CSWAP(0, 1); RDN_CSWAP(2, 3); RDN_CSWAP(0, 2); RDN_CSWAP(1, 3); RDN_CSWAP(1, 2);
-#undef RDN_CSWAP
-            if (ref[3] != REF_EMPTY) RDN_PUSH(ref[3]);
-            if (ref[2] != REF_EMPTY) RDN_PUSH(ref[2]);
-            if (ref[1] != REF_EMPTY) RDN_PUSH(ref[1]);
-            cur = ref[0] != REF_EMPTY ? ref[0] : RDN_POP();
-            continue;
-          }
-          const float4 *np = reinterpret_cast<const float4 *>(S.wide_nodes + cur);
-          float4 q0, q1, q2, q3;
-          bool staged = false;
-          if (HOT) {
-            const uint32_t ia = cur - P.hot_a_base, ib = cur - P.hot_b_base;
-            const uint32_t h = ia < P.hot_a_count ? ia : (ib < P.hot_b_count ? HOT_TOP_NODES + ib : 0xFFFFFFFFu);
-            if (h != 0xFFFFFFFFu) {
-              const float4 *sp = s_hot + h * 4u;
-              q0 = sp[0]; q1 = sp[1]; q2 = sp[2]; q3 = sp[3];
-              staged = true;
-            }
-          }
-          if (!staged) {
-            load_pair<LD256>(np, q0, q1);
-            load_pair<LD256>(np + 2, q2, q3);
-          }
-          const uint32_t r0 = __float_as_uint(q0.w), r1 = __float_as_uint(q1.w);
-          float n0, n1;
-          const bool h0 = slab_test(o, inv, near_s, far_s, xyz(q0), xyz(q1), n0);
-          const bool h1 = slab_test(o, inv, near_s, far_s, xyz(q2), xyz(q3), n1);
-          // near child first, the other one deferred; written as selects so that the step stays one basic block
-          const bool both = h0 && h1;
-          const bool take0 = both ? n0 <= n1 : h0;
-          if (both) {
-            RDN_PUSH(take0 ? r1 : r0);
-#ifdef RDN_DEBUG_STEPS
-            ++dbg_pushes;
-#endif
-          }
-          cur = take0 ? r0 : r1;
-          if (!(h0 || h1)) cur = RDN_POP();
-        }
-        RDN_COST(COST_PHASE2);
-        __syncwarp(rmask);
-
-        // ---------------- phase 2: one leaf / instance / bookkeeping item, all lanes that have one at the same time
-        uint32_t leaf_item = REF_DONE;
-        if (in_object && (cur & REF_LEAF_BIT)) leaf_item = cur;
-        if (leaf_item != REF_DONE) {
-          {
-            RDN_COST(COST_LEAF);
-            const uint32_t start = leaf_item & REF_LEAF_START_MASK;
-            const uint32_t count = ((leaf_item >> REF_LEAF_COUNT_SHIFT) & 15u) + 1u;
-            {
-              for (uint32_t k = 0; k < count; ++k) {
-                RDN_COST(COST_TRI);
-                const uint32_t slot = start + k;
-                const float4 *tp = reinterpret_cast<const float4 *>(S.triangles + slot);
-                float4 qn, qv0, qe1, qe2;
-                load_pair<LD256>(tp, qn, qv0);
-                load_pair<LD256>(tp + 2, qe1, qe2);
-                float sign, t, u, v;
-#ifdef RDN_DEBUG_STEPS
-                ++dbg_tris;
-#endif
-                if (!triangle_test(qn, qv0, qe1, qe2, o, d, near_s, far_s, cull_bits, sign, t, u, v)) continue;
-                RDN_COST(COST_TRI_HIT);
-                const float distance = t / scaling;
-                // any-hit stage (stateless programs without END_SEARCH only: the candidates a ray accepts do not depend on the order)
-                if constexpr (ANYHIT) {
-                  if ((cull_bits & 4u) && !(any_hit_behavior(S, P.L, slot, cur_inst, distance) & RDN_ANYHIT_BEHAVIOR_ACCEPT_HIT)) continue;
-                }
-                if (!(t_near_world <= distance) || !(distance <= far0)) continue;  // the reference's update_far asserts
-                if (distance < best) {
-                  second = fminf(second, best);
-                  best = distance; best_u = u; best_v = v; best_slot = slot; best_inst = cur_inst;
-                  best_back = sign < 0.0f ? 1u : 0u;
-                  // (SHARE: a helper's bound came from the ray's owner and may already be tighter than its own closest candidate)
-                  bound = fminf(SHARE ? bound : far0, best + TIE_EPS * fabsf(best));
-                  far_s = bound * scaling;
-                } else {
-                  second = fminf(second, distance);
-                }
-              }
-              RDN_COST(COST_LEAF_END);
-              cur = RDN_POP();
-            }
-          }
-        } else if (cur >= REF_SPECIAL && cur != REF_DONE) {
-          if (cur & REF_LEAF_BIT) {
-            const uint32_t start = cur & REF_LEAF_START_MASK;
-            const uint32_t count = ((cur >> REF_LEAF_COUNT_SHIFT) & 15u) + 1u;
-            if (in_object) {
-              // (not reached: triangle leaves are handled above)
-            } else {
-              // instance leaf (world space): take the first slot, park the rest
-              uint32_t istart = start, icount = count;
-              if constexpr (INST_LOOP) {
-                // skip the leading instances whose box the ray misses here, one slab test each, instead of one round each (a TLAS
-                // leaf holds up to ten instances; the same tests in the same order against the same bound)
-                while (icount > 1) {
-                  RDN_COST(COST_INSTANCE_SKIP);
-                  float4 s0, s1;
-                  load_pair<LD256>(S.tlas_bounding + istart, s0, s1);
-                  float sn;
-                  if (slab_test(o, inv, t_near_world, bound, xyz(s0), xyz(s1), sn) && (P.L.cull_mask & __float_as_uint(s0.w)) != 0) break;
-                  ++istart; --icount;
-                }
-              }
-              RDN_COST(COST_INSTANCE);
-              if (icount > 1) RDN_PUSH(REF_LEAF_BIT | ((icount - 2u) << REF_LEAF_COUNT_SHIFT) | (istart + 1u));
-              const float4 *tb = reinterpret_cast<const float4 *>(S.tlas_bounding + istart);
-              float4 b0, b1;
-              load_pair<LD256>(tb, b0, b1);
-              float tn;
-              bool entered = false;
-              if (slab_test(o, inv, t_near_world, bound, xyz(b0), xyz(b1), tn) && (P.L.cull_mask & __float_as_uint(b0.w)) != 0) {
-                const InstanceRecord *rec = S.instances + istart;
-                const uint4 tail = __ldg(reinterpret_cast<const uint4 *>(&rec->instance_custom_index));
-                const uint32_t flags = merge_geometry_instance_flag(P.L.ray_flags, tail.z);
-                if (!(flags & TF_SKIP_TRIANGLES) && tail.w < S.n_blas_meta) {
-                  const uint2 groots = __ldg(reinterpret_cast<const uint2 *>(S.blas_meta[tail.w].tri_root_range));
-                  // (SHARE: the exit marker must not be dropped by a full stack — the segment floors count from it)
-                  const bool room = !SHARE || sp + 1 <= STACK_MAX;
-                  if (!room) stack_overflowed = true;
-                  if (groots.x < groots.y && room) {
-                    RDN_COST(COST_INSTANCE_ENTER);
-                    Vec3 bo, bd;
-                    float s;
-                    to_object_space(rec, o, d, bo, bd, s);
-                    o = bo; d = bd; inv = recip3(bd);
-                    scaling = s; near_s = t_near_world * s; far_s = bound * s;
-                    cur_inst = istart; cur_flags = flags; cull_bits = cull_triangle_bits(flags); geom_end = groots.y;
-                    in_object = true;
-                    if constexpr (SHARE) {
-                      stack[sp++] = REF_EXIT_INSTANCE;
-                      lo = ((lo & 0xFF) << 8) | sp;  // the world segment's floor is kept beside the new one: no memory traffic
-                    } else {
-                      RDN_PUSH(REF_EXIT_INSTANCE);
-                    }
-                    cur = REF_SPECIAL | groots.x;
-                    if constexpr (INST_LOOP) {
-                      // a BLAS of one geometry (the usual case): go straight to its tree instead of spending a round on the
-                      // geometry iterator
-                      if (groots.y - groots.x == 1u) {
-                        const uint4 gm0 = __ldg(reinterpret_cast<const uint4 *>(S.geometry_meta + groots.x));
-                        const uint32_t wide_root = WIDE4 ? __ldg(&S.geometry_meta[groots.x].wide4_root) : __ldg(&S.geometry_meta[groots.x].wide_root);
-                        cur = (cull_geometry_pass(flags, gm0.w) && wide_root != REF_EMPTY) ? wide_root : RDN_POP();
-                        if constexpr (ANYHIT) cull_bits = (cull_bits & 3u) | (geometry_non_opaque(flags, gm0.w) ? 4u : 0u);
-                      }
-                    }
-                    entered = true;
-                  }
-                }
-              }
-              if (!entered) cur = RDN_POP();
-            }
-          } else if (!SHARE && cur == REF_EXIT_INSTANCE && sp == 0) {
-            cur = REF_DONE;  // nothing deferred in world space: the ray is finished, no need to restore the world ray
-          } else if (cur == REF_EXIT_INSTANCE) {
-            // back to world space: the world ray is re-read instead of being held in registers
-            RDN_COST(COST_EXIT_INSTANCE);
-            if constexpr (SHARE) lo >>= 8;  // back to the world segment's floor (what lies below it was handed to other lanes)
-            if (SHARE && sp <= lo) {
-              cur = REF_DONE;
-            } else {
-              float4 r0, r1;
-              load_pair<LD256>(P.rays + ri, r0, r1);
-              o = xyz(r0); d = xyz(r1); inv = recip3(d);
-              scaling = 1.f; near_s = t_near_world; far_s = bound;
-              in_object = false;
-              cur = RDN_POP();
-            }
-          } else if (cur == REF_EMPTY) {
-            RDN_COST(COST_EMPTY);
-            // (SHARE: entries handed to other lanes are left behind as REF_EMPTY, a run of them at the bottom of a segment)
-            do { cur = RDN_POP(); } while (SHARE && cur == REF_EMPTY);
-          } else {
-            // geometry iterator of the current instance's BLAS
-            RDN_COST(COST_GEOMETRY);
-            const uint32_t g = cur & 0x00FFFFFFu;
-            if (g + 1u < geom_end) RDN_PUSH(REF_SPECIAL | (g + 1u));
-            const uint4 gm0 = __ldg(reinterpret_cast<const uint4 *>(S.geometry_meta + g));
-            const uint32_t wide_root = WIDE4 ? __ldg(&S.geometry_meta[g].wide4_root) : __ldg(&S.geometry_meta[g].wide_root);
-            cur = (cull_geometry_pass(cur_flags, gm0.w) && wide_root != REF_EMPTY) ? wide_root : RDN_POP();
-            // (bit 2 of cull_bits: candidates of this geometry go through the any-hit stage; every deferred subtree of a geometry is
-            // walked before the iterator moves on, so the bit is that of the geometry being walked)
-            if constexpr (ANYHIT) cull_bits = (cull_bits & 3u) | (geometry_non_opaque(cur_flags, gm0.w) ? 4u : 0u);
-          }
-        }
-
-        // ---------------- vote (also the re-convergence point of phase 2)
-        RDN_COST(COST_VOTE);
-        if constexpr (SHARE) {
-          // Lanes of a warp share the work of its long rays.  The rays of a tile end at very different depths (a ray grazing the
-          // surface takes ten times the node steps of its neighbours) and the finished lanes would idle until the last one ends.
-          // Instead, a lane without work is handed deferred subtrees of a busy lane's ray — the LOWEST entries of the busy
-          // lane's stack segment, i.e. the largest subtrees — together with a copy of the ray as the busy lane holds it (world
-          // or object space).  The helper walks its piece like any ray, prunes against the owner's bound (refreshed every round)
-          // and, once out of work, merges what it found into the owner's registers: closest of the two, and the second-closest
-          // of everything seen (so a near-tie between candidates found by different lanes is still detected and re-walked in
-          // the reference's order — the result stays the reference's, whoever walked what).  Everything below is warp-uniform.
-          // Nothing is shared while more than SHARE lanes are busy, and a tile whose busy lanes have nothing deferred pays two
-          // votes per round.  Finished rays are stored together at the end of the tile, or when their lanes are wanted as helpers.
-          const uint32_t busy = __ballot_sync(FULL_MASK, cur != REF_DONE);
-          // (recomputed every round instead of kept: a loop-carried flag ends up spilled, and a local load per round costs a stall)
-          if (__ballot_sync(FULL_MASK, (home & 31u) != lane) != 0) {
-            {  // the owner's bound, so that pieces stop as soon as the owner (who walks the near side) has a closer candidate
-              const float hb = __shfl_sync(FULL_MASK, bound, home & 31u);
-              if (hb < bound) { bound = hb; far_s = bound * scaling; }
-            }
-            // helpers that ran out of work hand their partial result to the owner of the ray
-            uint32_t fin = __ballot_sync(FULL_MASK, (home & 31u) != lane && cur == REF_DONE);
-            while (fin) {
-              RDN_COST(COST_MERGE);
-              const int T = __ffs(fin) - 1;
-              fin &= fin - 1u;
-              const uint32_t h = __shfl_sync(FULL_MASK, home, T) & 31u;
-              const float tb = __shfl_sync(FULL_MASK, best, T);
-              const float ts = __shfl_sync(FULL_MASK, second, T);
-              if (tb != INFINITY) {  // (uniform) the helper found a candidate
-                const float tu = __shfl_sync(FULL_MASK, best_u, T), tv = __shfl_sync(FULL_MASK, best_v, T);
-                const uint32_t tslot = __shfl_sync(FULL_MASK, best_slot, T), tinst = __shfl_sync(FULL_MASK, best_inst, T);
-                const uint32_t tback = __shfl_sync(FULL_MASK, best_back, T);
-                if (lane == h) {
-                  if (tb < best) {
-                    second = fminf(fminf(second, ts), best);
-                    best = tb; best_u = tu; best_v = tv; best_slot = tslot; best_inst = tinst; best_back = tback;
-                    bound = fminf(bound, best + TIE_EPS * fabsf(best));
-                    far_s = bound * scaling;
-                  } else {
-                    second = fminf(second, tb);  // (tb <= ts)
-                  }
-                }
-              }
-              if (lane == h) helpers &= ~(1u << T);
-              if (static_cast<int>(lane) == T) {
-                home = (home & ~31u) | lane;
-                if (stack_overflowed) { atomicAdd(P.scratch.stack_overflow, 1u); stack_overflowed = false; }
-              }
-            }
-          }
-          if (busy == 0) break;  // (every helper has merged: the rays of the tile are stored behind the loop)
-          if (__popc(busy) <= P.share_busy && static_cast<int>(home >> 5) >= P.share_after) {
-            const int avail = cur != REF_DONE ? sp - (lo & 0xFF) : 0;
-            const uint32_t donors = __ballot_sync(FULL_MASK, avail >= P.share_min);
-            if (donors != 0) {
-              // lanes whose own ray is complete become helpers
-              if (alive && cur == REF_DONE && helpers == 0) finish_ray();
-              const uint32_t idle = __ballot_sync(FULL_MASK, cur == REF_DONE && !alive);
-              if (idle != 0) {
-                RDN_COST(COST_SHARE);
-                const int D = __ffs(donors) - 1;
-                const int n_avail = __shfl_sync(FULL_MASK, avail, D), n_idle = __popc(idle);
-                const int m = n_avail < n_idle ? n_avail : n_idle;
-                const int rank = __popc(idle & ((1u << lane) - 1u));
-                const bool take = ((idle >> lane) & 1u) != 0 && rank < m;
-                const int d_lo = __shfl_sync(FULL_MASK, lo, D) & 0xFF;
-                uint32_t piece = REF_EMPTY;
-#pragma unroll 1
-                for (int j = 0; j < m; ++j) {
-                  uint32_t e = 0;
-                  if (static_cast<int>(lane) == D) { e = stack[d_lo + j]; stack[d_lo + j] = REF_EMPTY; }
-                  e = __shfl_sync(FULL_MASK, e, D);
-                  if (take && rank == j) piece = e;
-                }
-                if (static_cast<int>(lane) == D) lo += m;
-                // the ray as the donor holds it
-#define RDN_TAKE(x) do { const auto t__ = __shfl_sync(FULL_MASK, x, D); if (take) x = t__; } while (0)
-                RDN_TAKE(o.x); RDN_TAKE(o.y); RDN_TAKE(o.z); RDN_TAKE(d.x); RDN_TAKE(d.y); RDN_TAKE(d.z);
-                RDN_TAKE(inv.x); RDN_TAKE(inv.y); RDN_TAKE(inv.z);
-                RDN_TAKE(scaling); RDN_TAKE(bound); RDN_TAKE(t_near_world); RDN_TAKE(far0);
-                RDN_TAKE(cur_inst); RDN_TAKE(cur_flags); RDN_TAKE(cull_bits); RDN_TAKE(geom_end); RDN_TAKE(home);
-#undef RDN_TAKE
-                const uint32_t d_ri = __shfl_sync(FULL_MASK, static_cast<uint32_t>(ri), D);  // (launches hold < 2^31 rays)
-                const bool d_in_object = __shfl_sync(FULL_MASK, in_object ? 1 : 0, D) != 0;
-                if (take) {
-                  ri = d_ri;
-                  near_s = t_near_world * scaling; far_s = bound * scaling;
-                  best = INFINITY; second = INFINITY; best_slot = RDN_INVALID_ID; best_inst = RDN_INVALID_ID;
-                  in_object = d_in_object;
-                  sp = 0;
-                  if (d_in_object) { stack[0] = REF_EXIT_INSTANCE; sp = 1; }  // the frame of the donor's instance (world floor 0)
-                  lo = sp;
-                  cur = piece;
-                }
-                const uint32_t takers = __ballot_sync(FULL_MASK, take);
-                const uint32_t d_home = __shfl_sync(FULL_MASK, home, D) & 31u;
-                if (lane == d_home) helpers |= takers;
-              }
-            }
-          }
-        } else {
-          const int active = __popc(__ballot_sync(amask, cur != REF_DONE));
-          if (active == 0) break;
-        }
+    if constexpr (SHARE == SHARE_LATE) {
+      // Two loops: the plain one for the first share_after rounds of a pass (what almost every tile needs), then — for the few passes
+      // that have grown old with a handful of long rays left — the loop in which idle lanes take over deferred subtrees.  The plain
+      // loop pays one shared-memory word per round for it instead of the 6 % the sharing loop costs before anything is shared.
+      bool late = false;
+      s_age[threadIdx.x] = 0;
+      if (alive) {
+        constexpr bool SH = false, LATE_FIRST = true;
+        const uint32_t rmask = amask;
+#include "ordered_rounds.inc"
+        if (!late && cur == REF_DONE) finish_ray();
       }
-
-      if (SHARE ? alive : cur == REF_DONE) finish_ray();
+      if (__ballot_sync(FULL_MASK, late) != 0) {
+        // every lane joins: the busy ones find the floor of the stack segment they are in (inside an instance: what lies above the
+        // exit marker; the marker already popped, or dropped by a full stack: nothing to hand out), the others are idle helpers
+        home = lane | (1023u << 5);
+        helpers = 0;
+        lo = 0;
+        if (alive && cur != REF_DONE && in_object) {
+          int k = sp;
+          while (k > 0 && stack[k - 1] != REF_EXIT_INSTANCE) --k;
+          lo = k > 0 ? k : sp + 1;
+        }
+        if (!alive) { cur = REF_DONE; sp = 0; }
+        constexpr bool SH = true, LATE_FIRST = false;
+        const uint32_t rmask = FULL_MASK;
+#include "ordered_rounds.inc"
+        if (alive) finish_ray();
+      }
+    } else {
+      // (SHARE_ALWAYS: every lane takes part in the rounds — a lane without a ray idles at cur == REF_DONE until it is handed a subtree)
+      constexpr bool SH = SHARE == SHARE_ALWAYS, LATE_FIRST = false;
+      [[maybe_unused]] bool late = false;
+      const uint32_t rmask = SH ? FULL_MASK : amask;
+      if constexpr (SH) home &= 31u;  // a new pass over a tile: age 0
+      if (SH || alive) {
+#include "ordered_rounds.inc"
+        if (SH ? alive : cur == REF_DONE) finish_ray();
+      }
     }
 #ifdef RDN_DEBUG_TIMELINE
     {  // one pass over a tile: duration histogram (8 us buckets), rounds per bucket, the longest pass, passes ending after the list ran dry
@@ -1261,10 +970,12 @@ cudaError_t launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch
   bool inline_ties = true;
   // template arguments: <K, MINB, DRAIN_TIES, IRREGULAR, LD256, HOT, WIDE4, INST_LOOP, SHARE>
   const bool any_hit = launch.any_hit != RDN_ANYHIT_NONE;  // (launches whose any-hit stage can END_SEARCH never get here)
-  const KernelFn plain = any_hit ? k_trace_ordered_rounds<RDN_ORDERED_K, RDN_ORDERED_MINB, true, false, true, false, false, true, false, true>
-                                 : k_trace_ordered_rounds<RDN_ORDERED_K, RDN_ORDERED_MINB, true, false, true, false, false, true, false>;
-  const KernelFn sharing = any_hit ? k_trace_ordered_rounds<RDN_ORDERED_K, RDN_ORDERED_MINB, true, false, true, false, false, true, true, true>
-                                   : k_trace_ordered_rounds<RDN_ORDERED_K, RDN_ORDERED_MINB, true, false, true, false, false, true, true>;
+  const KernelFn plain = any_hit ? k_trace_ordered_rounds<RDN_ORDERED_K, RDN_ORDERED_MINB, true, false, true, false, false, true, SHARE_NEVER, true>
+                                 : k_trace_ordered_rounds<RDN_ORDERED_K, RDN_ORDERED_MINB, true, false, true, false, false, true, SHARE_NEVER>;
+  const KernelFn sharing = any_hit ? k_trace_ordered_rounds<RDN_ORDERED_K, RDN_ORDERED_MINB, true, false, true, false, false, true, SHARE_ALWAYS, true>
+                                   : k_trace_ordered_rounds<RDN_ORDERED_K, RDN_ORDERED_MINB, true, false, true, false, false, true, SHARE_ALWAYS>;
+  const KernelFn late = any_hit ? k_trace_ordered_rounds<RDN_ORDERED_K, RDN_ORDERED_MINB, true, false, true, false, false, true, SHARE_LATE, true>
+                                : k_trace_ordered_rounds<RDN_ORDERED_K, RDN_ORDERED_MINB, true, false, true, false, false, true, SHARE_LATE>;
   switch (any_hit ? 0 : variant) {  // (the A/B instantiations exist without the any-hit stage only)
     case 2: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false>; break;     // the round-1 default: K = 2, one round per missed instance
     case 9: fn = k_trace_ordered_rounds<3, 8, false, false, true, false, false, true>; inline_ties = false; break;  // queue drained by k_resolve_ties
@@ -1275,8 +986,9 @@ cudaError_t launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch
     case 60: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, true>; break;    // four-box nodes, K = 2 steps per round
     case 61: fn = k_trace_ordered_rounds<1, 8, true, false, true, false, true>; break;    // ... one step per round
     case 100: fn = plain; break;     // never share
-    case 110: fn = sharing; break;   // always share
-    default: fn = P.tiles_x == 0 ? sharing : plain; break;  // ray lists share, grids do not
+    case 110: fn = sharing; break;   // the sharing loop from the first round
+    case 120: fn = late; break;      // the plain loop, then the sharing loop for passes that have grown old
+    default: fn = P.tiles_x == 0 ? late : plain; break;  // ray lists share (from the 30th round of a pass on), grids do not
   }
   if ((variant == 60 || variant == 61) && !use_wide4) fn = plain;
   if (P.irregular_count != 0) {  // (the experimentation variants exist for regular scenes only)
@@ -1284,7 +996,7 @@ cudaError_t launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch
     // cursor (fine for a handful of ties, 55 ms for 400 K entries): the queue of an irregular launch is walked by
     // k_resolve_ties, one thread per entry, right behind this kernel.
     inline_ties = false;
-    fn = k_trace_ordered_rounds<3, 8, false, true, true, false, false, true>;
+    fn = k_trace_ordered_rounds<3, 8, false, true, true, false, false, true, SHARE_NEVER>;
   }
   int blocks_per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, ORDERED_BLOCK, 0);

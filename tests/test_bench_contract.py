@@ -57,7 +57,7 @@ def test_the_kernel_named_in_the_roofline_is_the_one_the_launcher_selects_for_gr
     args = [macros.get(a.strip(), a.strip()) for a in m.group(1).split(",")]
     n_params = len(re.search(r"template <(int K, int MINB,[^>]*)>\n__global__", src).group(1).split(","))
     args += ["false"] * (n_params - len(args))   # defaulted trailing parameters
-    as_ncu = ", ".join({"true": "1", "false": "0"}.get(a, a) for a in args)
+    as_ncu = ", ".join({"true": "1", "false": "0", "SHARE_NEVER": "0", "SHARE_ALWAYS": "1", "SHARE_LATE": "2"}.get(a, a) for a in args)
     assert bench.SHIPPED_ORDERED_KERNEL == f"k_trace_ordered_rounds<{as_ncu}>", (bench.SHIPPED_ORDERED_KERNEL, as_ncu)
 
 

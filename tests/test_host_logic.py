@@ -3,6 +3,8 @@ builder/flattener reproduce the oracle's (= the reference's) trees and arrays, a
 import ctypes
 import os
 import re
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -339,3 +341,86 @@ def test_tlas_wide_view_reaches_every_instance_through_single_slot_leaves():
         assert len(seen) == len(set(seen)) and seen, seen
         total += len(seen)
     assert total == len(tb)
+
+
+# ---- worker pool of the host builder / flattener (bvh_builder.cpp) -----------------------------------------------------------------
+def _instanced_host_scene(n_side=70, spacing=3.5):
+    pos, idx = S.uv_sphere_mesh(24, 24)
+    s = api.NaiveSahBVHSystem(devices=())
+    b = s.create_bottom_level_acceleration_structure([api.BottomLevelAccelerationStructureBuildSource(pos, idx.reshape(-1))])
+    t = s.create_top_level_acceleration_structure(S.instance_grid(n_side, n_side, b.id, spacing, -200.0))
+    s.bind_tlas([t])
+    s.commit()
+    return s, b, t
+
+
+def _arrays(s):
+    return [s.array(aid).tobytes() for aid in range(len(api.ARRAYS))]
+
+
+def test_pool_sections_give_the_sequential_arrays():
+    """4,900 instances: the TLAS build takes the parallel path (top splits by all threads, subtrees on the pool); the flattened arrays
+    must be those of a one-thread build, and a TLAS-only update must give what a fresh scene with the moved instances gives"""
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import hashlib, test_host_logic as T\n"
+            "s, b, t = T._instanced_host_scene()\n"
+            "print(hashlib.sha256(b''.join(T._arrays(s))).hexdigest())\n") % (ROOT, os.path.join(ROOT, "tests"))
+    digests = set()
+    for env in ({"RDN_BUILD_THREADS": "1"}, {"RDN_BUILD_POOL": "0"}, {}, {"RDN_BUILD_THREADS": "3"}):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, **env), timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests.add(r.stdout.strip().splitlines()[-1])
+    assert len(digests) == 1, digests
+    s, b, t = _instanced_host_scene()
+    moved = S.instance_grid(70, 70, b.id, 3.6, -190.0)
+    s.update_top_level_acceleration_structure(t, moved)
+    s.commit()
+    fresh = api.NaiveSahBVHSystem(devices=())
+    pos, idx = S.uv_sphere_mesh(24, 24)
+    fb = fresh.create_bottom_level_acceleration_structure([api.BottomLevelAccelerationStructureBuildSource(pos, idx.reshape(-1))])
+    fresh.bind_tlas([fresh.create_top_level_acceleration_structure(S.instance_grid(70, 70, fb.id, 3.6, -190.0))])
+    fresh.commit()
+    assert _arrays(s) == _arrays(fresh)
+
+
+def test_concurrent_commits_share_the_pool():
+    """commits of different scenes from different host threads: their parallel sections queue on the one pool"""
+    import threading
+    want = _arrays(_instanced_host_scene()[0])
+    got, errors = [None] * 4, []
+
+    def work(k):
+        try:
+            for _ in range(3):
+                got[k] = _arrays(_instanced_host_scene()[0])
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    [th.start() for th in threads]
+    [th.join(300) for th in threads]
+    assert not errors and all(g == want for g in got)
+
+
+def test_a_forked_child_gets_its_own_pool():
+    """the pool's threads do not exist in a forked child: the first section there must start a fresh pool, not wait for ghosts"""
+    want = _arrays(_instanced_host_scene()[0])  # (the parent's pool is running now)
+    r, w = os.pipe()
+    pid = os.fork()
+    if pid == 0:
+        code = 1
+        try:
+            os.close(r)
+            ok = _arrays(_instanced_host_scene()[0]) == want
+            os.write(w, b"ok" if ok else b"differs")
+            code = 0
+        finally:
+            os._exit(code)
+    os.close(w)
+    import select
+    ready, _, _ = select.select([r], [], [], 120)
+    msg = os.read(r, 16) if ready else b"timeout"
+    os.close(r)
+    if not ready:
+        os.kill(pid, 9)
+    os.waitpid(pid, 0)
+    assert msg == b"ok", msg

@@ -192,7 +192,7 @@ def dynamic_counts(cfg: str, names: list[str]):
 def mangled(k, drain=True, ld256=True, wide4=False, inst_loop=False, share=False, anyhit=False):
     """mangled template arguments <K, MINB, DRAIN_TIES, IRREGULAR, LD256, HOT, WIDE4, INST_LOOP, SHARE, ANYHIT> of an instantiation"""
     bl = lambda v: "Lb1E" if v else "Lb0E"
-    return f"ILi{k}ELi8E{bl(drain)}Lb0E{bl(ld256)}Lb0E{bl(wide4)}{bl(inst_loop)}{bl(share)}{bl(anyhit)}E"
+    return f"ILi{k}ELi8E{bl(drain)}Lb0E{bl(ld256)}Lb0E{bl(wide4)}{bl(inst_loop)}Li{int(share)}E{bl(anyhit)}E"  # share: 0 never, 1 always, 2 late
 
 
 def main():
