@@ -16,7 +16,9 @@ value   = whole-job Mrays/s with rays/hits resident in HBM, device-timed (CUDA e
           details.value_l2_flushed is the same loop with a 256 MiB flush between steps, details.value_serialized the same
           loop without tail overlap between launches.
 e2e     = same metric through the host-buffer C-ABI call (pinned host rays -> H2D -> traversal -> D2H hits); e2e_pageable =
-          the same call on plain pageable buffers (what a Rust Vec is), which the library page-locks and keeps registered.
+          the same call on caller-owned arrays (what a Rust Vec is): `value` page-locked once by their owner (rdn_rt_host_register),
+          `value_unregistered` left ordinary pageable memory, which the library stages chunk by chunk through its own page-locked
+          buffers with several host threads.
 roofline= the kernel is bound by instruction issue at ~20 of 32 active lanes; the memory level that serves it is L2.  `frac` =
           reference-defined algorithmic bytes (64 + 48*V_node + 52*V_tri + 176*V_inst per ray, V counted by
           the oracle under the reference traversal order) / serialised kernel time / the L2 read peak measured in this run;
@@ -639,8 +641,9 @@ def run_ours(args):
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = world * n * e2e_steps / float(t_e2e.item()) / 1e6
     # the same call on host arrays that are NOT torch-pinned (plain numpy arrays — what a Rust Vec<Ray> is): first as they are
-    # (pageable: the driver stages the copies), then page-locked by their owner through rdn_rt_host_register, which is what the
-    # Rust wrapper does for buffers that live longer than a frame
+    # (pageable: the library stages every chunk through page-locked buffers of its own, copied by several host threads), then
+    # page-locked by their owner through rdn_rt_host_register, which is what the Rust wrapper does for buffers that live longer
+    # than a frame
     p_rays = np.ascontiguousarray(rays_np).copy()
     p_hits = np.zeros(n, api.HIT_DTYPE)
 
@@ -742,7 +745,9 @@ def run_ours(args):
                              "value_unregistered": e2e_unpinned_value,
                              "note": "host arrays owned by the caller (numpy, not torch-pinned) and page-locked by it once with "
                                      "rdn_rt_host_register (register_ms, outside the timed steps) — what the Rust wrapper does for a long-lived "
-                                     "Vec; value_unregistered = the same arrays left pageable (the driver stages the copies)"},
+                                     "Vec; value_unregistered = the same arrays left pageable: the library stages each chunk through page-locked buffers of "
+                                     "its own, filled and emptied by up to 16 host threads while earlier chunks are on the link (224 Mrays/s when the "
+                                     "driver staged the copies, profiles/bench_r2w.json)"},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "l2", "binding": "instruction issue at ~20 of 32 active lanes (see profiles/ncu_*: issue slots ~50 % busy over the "
                                                    "launch incl. its tail, DRAM < 10 % and L2 < 15 % of peak); L2 is the memory level that serves the kernel",

@@ -5,11 +5,16 @@
 // (get_or_build_gpu_data, mod.rs:521-536).  Errors are status codes + a thread-local message, never an abort.
 #include <cuda_runtime.h>
 
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+#endif
+
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <chrono>
 #include <cstring>
+#include <deque>
 #include <mutex>
 #include <shared_mutex>
 #include <string>
@@ -77,6 +82,12 @@ struct Slot {  // one pipeline lane of the host-buffer path
   uint64_t capacity = 0;
   Scratch scratch;
   uint32_t *h_flags = nullptr;  // pinned: tie_count | tie_unresolved | stack_overflow read back after the last chunk
+  // page-locked staging of one chunk for callers whose buffers are ordinary (pageable) memory, and the event behind the chunk
+  rdn_ray *h_rays = nullptr;
+  rdn_hit *h_hits = nullptr;
+  uint64_t staging_capacity = 0;
+  cudaEvent_t chunk_done = nullptr;
+  bool chunk_in_flight = false;
 };
 
 enum KernelKind : int { KERNEL_ORDERED = 0, KERNEL_TIES = 1, KERNEL_REFERENCE = 2, KERNEL_KIND_COUNT = 3 };
@@ -527,6 +538,72 @@ int enqueue_trace(rdn_rt_scene *s, DeviceCtx &dc, const Scratch &scratch, const 
   return RDN_OK;
 }
 
+int ensure_slot_staging(Slot &slot, uint64_t rays) {
+  if (!slot.chunk_done) RDN_CUDA(cudaEventCreateWithFlags(&slot.chunk_done, cudaEventDisableTiming));
+  if (slot.staging_capacity < rays) {
+    if (slot.h_rays) cudaFreeHost(slot.h_rays);
+    if (slot.h_hits) cudaFreeHost(slot.h_hits);
+    slot.h_rays = nullptr; slot.h_hits = nullptr; slot.staging_capacity = 0;
+    RDN_CUDA(cudaHostAlloc(&slot.h_rays, rays * sizeof(rdn_ray), cudaHostAllocPortable));
+    RDN_CUDA(cudaHostAlloc(&slot.h_hits, rays * sizeof(rdn_hit), cudaHostAllocPortable));
+    slot.staging_capacity = rays;
+  }
+  return RDN_OK;
+}
+
+// is this host pointer ordinary pageable memory (neither allocated nor registered through CUDA)?
+bool is_pageable(const void *p) {
+  cudaPointerAttributes attr{};
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return true; }
+  return attr.type == cudaMemoryTypeUnregistered;
+}
+
+// One thread's share of a staging copy.  Non-temporal stores where the ISA has them: the destination is not read again by this
+// core (the DMA engine reads the staging buffer, the caller's result array is far larger than the caches), and an ordinary store
+// would first fetch every destination line it is about to overwrite — a third of the copy's memory traffic.
+void copy_streaming(char *dst, const char *src, uint64_t bytes) {
+#if defined(__x86_64__) || defined(_M_X64)
+  const uint64_t head = std::min<uint64_t>(bytes, (16u - (reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u);
+  if (head) { std::memcpy(dst, src, head); dst += head; src += head; bytes -= head; }
+  const uint64_t lines = bytes / 64;
+  for (uint64_t i = 0; i < lines; ++i) {
+    const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src)), b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + 16));
+    const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + 32)), d = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + 48));
+    _mm_stream_si128(reinterpret_cast<__m128i *>(dst), a);
+    _mm_stream_si128(reinterpret_cast<__m128i *>(dst + 16), b);
+    _mm_stream_si128(reinterpret_cast<__m128i *>(dst + 32), c);
+    _mm_stream_si128(reinterpret_cast<__m128i *>(dst + 48), d);
+    src += 64; dst += 64;
+  }
+  _mm_sfence();
+  if (bytes % 64) std::memcpy(dst, src, bytes % 64);
+#else
+  std::memcpy(dst, src, bytes);
+#endif
+}
+
+// a staging copy by several threads of the worker pool (one thread moves 5-10 GB/s, a PCIe 5 x16 link wants 50)
+void parallel_copy(void *dst, const void *src, uint64_t bytes) {
+  static const unsigned max_threads = []() {
+    const char *e = getenv("RDN_STAGE_THREADS");
+    const int v = e ? atoi(e) : 0;
+    return static_cast<unsigned>(v > 0 ? v : 16);
+  }();
+  static const bool streaming = []() { const char *e = getenv("RDN_STAGE_STREAMING"); return !e || atoi(e) != 0; }();
+  constexpr uint64_t PIECE = 256u << 10;
+  const unsigned pieces = static_cast<unsigned>(std::min<uint64_t>(std::min<unsigned>(max_threads, build_thread_count()), (bytes + PIECE - 1) / PIECE));
+  auto one = [&](uint64_t b, uint64_t e) {
+    if (streaming) copy_streaming(static_cast<char *>(dst) + b, static_cast<const char *>(src) + b, e - b);
+    else std::memcpy(static_cast<char *>(dst) + b, static_cast<const char *>(src) + b, e - b);
+  };
+  if (pieces <= 1) { one(0, bytes); return; }
+  const uint64_t each = ((bytes + pieces - 1) / pieces + 63) / 64 * 64;
+  run_parallel(pieces, [&](unsigned k) {
+    const uint64_t b = std::min<uint64_t>(bytes, k * each), e = std::min<uint64_t>(bytes, b + each);
+    if (b < e) one(b, e);
+  });
+}
+
 int ensure_slot(Slot &slot, uint64_t rays) {
   if (!slot.stream) RDN_CUDA(cudaStreamCreateWithFlags(&slot.stream, cudaStreamNonBlocking));
   if (slot.capacity < rays) {
@@ -587,6 +664,9 @@ void rdn_rt_scene_destroy(rdn_rt_scene *s) {
       if (slot.d_hits) cudaFree(slot.d_hits);
       free_scratch(slot.scratch);
       if (slot.h_flags) cudaFreeHost(slot.h_flags);
+      if (slot.h_rays) cudaFreeHost(slot.h_rays);
+      if (slot.h_hits) cudaFreeHost(slot.h_hits);
+      if (slot.chunk_done) cudaEventDestroy(slot.chunk_done);
       if (slot.stream) cudaStreamDestroy(slot.stream);
     }
     free_scratch(dc.ext_scratch[0]);
@@ -844,6 +924,11 @@ int rdn_rt_trace_closest(rdn_rt_scene *s, const rdn_launch *launch, const rdn_ra
   const uint64_t n_chunks = (n + chunk - 1) / chunk;
   const size_t n_dev = s->devices.size();
 
+  // Ordinary (pageable) caller memory — what the reference's own callers hand over — is not copied from directly: the driver would
+  // stage it through its own small buffer, synchronously, at a fifth of the link's rate.  Each chunk goes through page-locked
+  // staging buffers of its slot instead, filled / emptied by several host threads while earlier chunks are on the link and in the
+  // kernels.  Buffers from rdn_rt_host_alloc / rdn_rt_host_register are copied from directly.
+  const bool stage_in = is_pageable(rays), stage_out = is_pageable(out_hits);
   // tiles (chunks) are dealt round-robin to devices; each device pipelines its chunks over N_SLOTS streams:
   // H2D(k+1) || kernels(k) || D2H(k-1)
   for (size_t di = 0; di < n_dev; ++di) {
@@ -852,22 +937,53 @@ int rdn_rt_trace_closest(rdn_rt_scene *s, const rdn_launch *launch, const rdn_ra
     for (Slot &slot : dc.slots) {
       rc = ensure_slot(slot, std::min<uint64_t>(chunk, n));
       if (rc != RDN_OK) return rc;
+      if (stage_in || stage_out) {
+        rc = ensure_slot_staging(slot, std::min<uint64_t>(chunk, n));
+        if (rc != RDN_OK) return rc;
+      }
+      slot.chunk_in_flight = false;
     }
   }
+  struct Pending { Slot *slot; int device; uint64_t off, m; };
+  std::deque<Pending> pending;  // staged chunks in issue order: results still to be copied out of the slot's staging buffer
+  auto retire_front = [&]() -> cudaError_t {
+    const Pending p = pending.front();
+    pending.pop_front();
+    cudaError_t e = cudaSetDevice(p.device);
+    if (e == cudaSuccess) e = cudaEventSynchronize(p.slot->chunk_done);
+    if (e != cudaSuccess) return e;
+    if (stage_out) parallel_copy(out_hits + p.off, p.slot->h_hits, p.m * sizeof(rdn_hit));
+    p.slot->chunk_in_flight = false;
+    return cudaSuccess;
+  };
   std::vector<uint64_t> per_dev_seq(n_dev, 0);
   for (uint64_t c = 0; c < n_chunks; ++c) {
     const size_t di = c % n_dev;
     DeviceCtx &dc = s->devices[di];
-    RDN_CUDA(cudaSetDevice(dc.device));
     Slot &slot = dc.slots[per_dev_seq[di]++ % N_SLOTS];
     const uint64_t off = c * chunk, m = std::min(chunk, n - off);
     rdn_launch l = *launch;
     l.grid_width = grid ? gw : 0;
-    RDN_CUDA(cudaMemcpyAsync(slot.d_rays, rays + off, m * sizeof(rdn_ray), cudaMemcpyHostToDevice, slot.stream));
+    const rdn_ray *src = rays + off;
+    rdn_hit *dst = out_hits + off;
+    if (stage_in || stage_out) {
+      // the slot's previous chunk must have left its staging buffers (chunks retire in issue order)
+      while (slot.chunk_in_flight) RDN_CUDA(retire_front());
+      if (stage_in) { parallel_copy(slot.h_rays, src, m * sizeof(rdn_ray)); src = slot.h_rays; }
+      if (stage_out) dst = slot.h_hits;
+    }
+    RDN_CUDA(cudaSetDevice(dc.device));
+    RDN_CUDA(cudaMemcpyAsync(slot.d_rays, src, m * sizeof(rdn_ray), cudaMemcpyHostToDevice, slot.stream));
     rc = enqueue_trace(s, dc, slot.scratch, l, slot.d_rays, m, slot.d_hits, RDN_TRACE_AUTO, slot.stream, nullptr);
     if (rc != RDN_OK) return rc;
-    RDN_CUDA(cudaMemcpyAsync(out_hits + off, slot.d_hits, m * sizeof(rdn_hit), cudaMemcpyDeviceToHost, slot.stream));
+    RDN_CUDA(cudaMemcpyAsync(dst, slot.d_hits, m * sizeof(rdn_hit), cudaMemcpyDeviceToHost, slot.stream));
+    if (stage_in || stage_out) {
+      RDN_CUDA(cudaEventRecord(slot.chunk_done, slot.stream));
+      slot.chunk_in_flight = true;
+      pending.push_back(Pending{&slot, dc.device, off, m});
+    }
   }
+  while (!pending.empty()) RDN_CUDA(retire_front());
   // error flags of every used slot come back through pinned memory behind the slot's last chunk: one wait per stream
   for (size_t di = 0; di < n_dev; ++di) {
     DeviceCtx &dc = s->devices[di];

@@ -32,6 +32,8 @@ cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { return cudaMalloc(p, n
 cudaError_t cudaFreeHost(void *p) { return cudaFree(p); }
 cudaError_t cudaHostRegister(void *, size_t, unsigned) { return cudaSuccess; }  // (everything is host memory here)
 cudaError_t cudaHostUnregister(void *) { return cudaSuccess; }
+// (every caller buffer counts as pageable: the host-buffer path always runs its staging pipeline here)
+cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *) { std::memset(a, 0, sizeof(*a)); a->type = cudaMemoryTypeUnregistered; return cudaSuccess; }
 cudaError_t cudaMallocAsync(void **p, size_t n, cudaStream_t) { return cudaMalloc(p, n); }
 cudaError_t cudaFreeAsync(void *p, cudaStream_t) { return cudaFree(p); }
 cudaError_t cudaMemcpy(void *dst, const void *src, size_t n, cudaMemcpyKind) { if (n) std::memmove(dst, src, n); return cudaSuccess; }

@@ -468,6 +468,33 @@ def test_back_to_back_launches_overlap_without_losing_rays():
 
 
 @pytest.mark.gpu
+def test_pageable_buffers_go_through_the_staging_pipeline():
+    """Ordinary caller memory (what the reference's API hands over) is staged chunk by chunk through page-locked buffers by several
+    host threads: several chunks, buffers at odd addresses (the streaming copy aligns its stores itself), a page-locked array on
+    one side only — always the oracle's records."""
+    sp, _ = helpers.torus_scene(128)
+    W, H = 1024, 640   # 655,360 rays: three chunks of the default size
+    rays = S.pinhole_rays(W, H, 0.01, 100.0, aspect_correct=True)
+    n = rays.shape[0]
+    want = sp.o.trace(rays, ray_flags=helpers.CULL_BACK, n_threads=os.cpu_count() or 4, want_counters=False)
+    for ray_shift, hit_shift in ((0, 0), (4, 12), (20, 8)):
+        raw_rays = np.zeros(n * 32 + 64, np.uint8)
+        raw_rays[ray_shift:ray_shift + n * 32] = rays.view(np.uint8).reshape(-1)
+        raw_hits = np.full(n * 32 + 64, 0xAB, np.uint8)
+        sp.p.trace_closest_host_ptr(raw_rays.ctypes.data + ray_shift, n, raw_hits.ctypes.data + hit_shift, ray_flags=helpers.CULL_BACK, grid_width=W)
+        assert raw_hits[hit_shift:hit_shift + n * 32].tobytes() == want.tobytes(), (ray_shift, hit_shift)
+        assert (raw_hits[:hit_shift] == 0xAB).all() and (raw_hits[hit_shift + n * 32:] == 0xAB).all()  # nothing written outside
+    hits = np.zeros(n, api.HIT_DTYPE)
+    with api.HostRegistration(hits):   # rays staged, hits copied straight into the page-locked array
+        sp.p.trace_closest_host_ptr(rays.ctypes.data, n, hits.ctypes.data, ray_flags=helpers.CULL_BACK, grid_width=W)
+    assert hits.tobytes() == want.tobytes()
+    hits[:] = 0
+    with api.HostRegistration(rays):   # ... and the other way round
+        sp.p.trace_closest_host_ptr(rays.ctypes.data, n, hits.ctypes.data, ray_flags=helpers.CULL_BACK, grid_width=W)
+    assert hits.tobytes() == want.tobytes()
+
+
+@pytest.mark.gpu
 def test_host_buffers_page_locked_by_their_owner():
     """rdn_rt_host_register / rdn_rt_host_alloc: the host-buffer trace on memory the caller page-locked (a registered numpy array,
     a library-allocated buffer) returns the records of the plain pageable call; registrations end with their owner."""

@@ -1,5 +1,6 @@
-"""Host-buffer path (rdn_rt_trace_closest: pinned rays in, hits out, chunked over 4 streams) on BASELINE configs[1].
-Usage: [RDN_HOST_RAMP=0|1] [RDN_HOST_CHUNK_RAYS=n] python tools/e2e_bench.py [iters]"""
+"""Host-buffer path (rdn_rt_trace_closest: rays in, hits out, chunked over 4 streams) on BASELINE configs[1], with page-locked caller
+buffers and with ordinary (pageable) ones, which go through the library's staging pipeline.
+Usage: [RDN_HOST_CHUNK_RAYS=n] [RDN_STAGE_THREADS=t] python tools/e2e_bench.py [iters]"""
 import os, sys, time
 import numpy as np
 import torch
@@ -28,5 +29,19 @@ for _ in range(iters):
     ts.append(time.perf_counter() - t0)
 ts = np.array(ts)
 same = bool(torch.equal(h_hits.cuda(), d_hits))
-print(f"ramp={os.environ.get('RDN_HOST_RAMP','1')} chunk={os.environ.get('RDN_HOST_CHUNK_RAYS','default')} mean_ms={ts.mean()*1e3:.4f} min_ms={ts.min()*1e3:.4f} "
+print(f"pinned   chunk={os.environ.get('RDN_HOST_CHUNK_RAYS','default')} mean_ms={ts.mean()*1e3:.4f} min_ms={ts.min()*1e3:.4f} "
       f"Mrays/s(mean)={n/ts.mean()/1e6:.1f} best={n/ts.min()/1e6:.1f} same_as_device_path={same}")
+# ordinary memory, as a caller of the reference's API would hand over
+p_rays = rays.view(np.uint8).reshape(-1, 32).copy()
+p_hits = np.zeros((n, 32), np.uint8)
+for _ in range(3):
+    sysm.trace_closest_host_ptr(p_rays.ctypes.data, n, p_hits.ctypes.data, ray_flags=0x10, grid_width=W)
+ts = []
+for _ in range(iters):
+    t0 = time.perf_counter()
+    sysm.trace_closest_host_ptr(p_rays.ctypes.data, n, p_hits.ctypes.data, ray_flags=0x10, grid_width=W)
+    ts.append(time.perf_counter() - t0)
+ts = np.array(ts)
+same = bool(np.array_equal(p_hits, d_hits.cpu().numpy()))
+print(f"pageable chunk={os.environ.get('RDN_HOST_CHUNK_RAYS','default')} threads={os.environ.get('RDN_STAGE_THREADS','default')} mean_ms={ts.mean()*1e3:.4f} "
+      f"min_ms={ts.min()*1e3:.4f} Mrays/s(mean)={n/ts.mean()/1e6:.1f} best={n/ts.min()/1e6:.1f} same_as_device_path={same}")
