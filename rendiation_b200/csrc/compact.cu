@@ -42,6 +42,63 @@ __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long l
   *reinterpret_cast<volatile unsigned long long *>(p) = v;
 }
 
+// A warp's 512 consecutive elements as four rows of 128: lane l holds elements [128 r + 4 l, + 4) of row r, so that every load
+// instruction of the warp reads one contiguous run (512 B of values, 128 B of flags) — sixteen consecutive elements per thread
+// would make each instruction touch thirty-two separate 64 B segments.  mask bit 4 r + c: element c of row r is kept.
+template <bool FAST>
+__device__ __forceinline__ void load_rows(const uint32_t *__restrict__ in, const uint8_t *__restrict__ keep, uint64_t n, uint64_t warp_base,
+                                          uint32_t lane, uint32_t (&vals)[ITEMS], uint32_t &mask) {
+  static_assert(ITEMS == 16, "four rows of four elements per lane");
+  mask = 0;
+  if (FAST && warp_base + 512 <= n) {
+    uint4 v[4];
+    uint32_t f[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const uint64_t idx = warp_base + 128u * r + 4u * lane;
+      v[r] = __ldg(reinterpret_cast<const uint4 *>(in + idx));
+      f[r] = __ldg(reinterpret_cast<const uint32_t *>(keep + idx));
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      vals[4 * r] = v[r].x; vals[4 * r + 1] = v[r].y; vals[4 * r + 2] = v[r].z; vals[4 * r + 3] = v[r].w;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) mask |= (((f[r] >> (8 * c)) & 0xFFu) != 0 ? 1u : 0u) << (4 * r + c);
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint64_t idx = warp_base + 128u * r + 4u * lane + c;
+        const bool inside = idx < n;
+        vals[4 * r + c] = inside ? in[idx] : 0u;
+        if (inside && keep[idx] != 0) mask |= 1u << (4 * r + c);
+      }
+  }
+}
+
+// Ranks of a warp's kept elements in element order.  The four per-row counts of a lane travel through ONE shuffle scan, a byte each
+// (a row of 128 elements cannot overflow its byte).  Returns the warp's total; first[r] = rank of the lane's first kept element of
+// row r within the warp.
+__device__ __forceinline__ uint32_t rank_rows(uint32_t mask, uint32_t lane, uint32_t (&first)[4]) {
+  const uint32_t packed = __popc(mask & 0xFu) | (__popc(mask & 0xF0u) << 8) | (__popc(mask & 0xF00u) << 16) | (__popc(mask & 0xF000u) << 24);
+  uint32_t incl = packed;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t up = __shfl_up_sync(FULL_MASK, incl, off);
+    if (lane >= static_cast<uint32_t>(off)) incl += up;
+  }
+  const uint32_t total = __shfl_sync(FULL_MASK, incl, 31);
+  const uint32_t excl = incl - packed;
+  const uint32_t t0 = total & 0xFFu, t1 = (total >> 8) & 0xFFu, t2 = (total >> 16) & 0xFFu, t3 = total >> 24;
+  first[0] = excl & 0xFFu;
+  first[1] = t0 + ((excl >> 8) & 0xFFu);
+  first[2] = t0 + t1 + ((excl >> 16) & 0xFFu);
+  first[3] = t0 + t1 + t2 + (excl >> 24);
+  return t0 + t1 + t2 + t3;
+}
+
 // status[0] = dynamic tile counter, status[1 + tile] = (flag << 62) | value
 // One pass.  Per tile of 4096 elements: (1) every thread loads its 16 flags and 16 values — all loads of the tile are in flight
 // before anything waits; (2) warp shuffle scan + block scan of the kept counts; (3) the kept values are packed into shared memory
@@ -63,40 +120,13 @@ __global__ void __launch_bounds__(CB, RDN_COMPACT_MINB) k_compact_u32(const uint
   __syncthreads();
   const uint64_t tile = s_tile;
 #endif
-  const uint64_t idx0 = tile * TILE + static_cast<uint64_t>(tid) * ITEMS;
-
-  // ---- 16 keep flags -> bit mask, 16 values -> registers
-  uint32_t mask = 0;
+  // ---- the warp's 512 elements: 16 values and 16 keep flags per thread, every load in flight before anything waits
+  uint32_t mask;
   uint32_t vals[ITEMS];
-  if (FAST && idx0 + ITEMS <= n) {
-    const uint4 k16 = __ldg(reinterpret_cast<const uint4 *>(keep + idx0));
-    const uint4 *vp = reinterpret_cast<const uint4 *>(in + idx0);
-    const uint4 v0 = __ldg(vp), v1 = __ldg(vp + 1), v2 = __ldg(vp + 2), v3 = __ldg(vp + 3);
-    const uint32_t kw[4] = {k16.x, k16.y, k16.z, k16.w};
-#pragma unroll
-    for (int w = 0; w < 4; ++w)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) mask |= (((kw[w] >> (8 * j)) & 0xFFu) != 0 ? 1u : 0u) << (4 * w + j);
-    vals[0] = v0.x; vals[1] = v0.y; vals[2] = v0.z; vals[3] = v0.w; vals[4] = v1.x; vals[5] = v1.y; vals[6] = v1.z; vals[7] = v1.w;
-    vals[8] = v2.x; vals[9] = v2.y; vals[10] = v2.z; vals[11] = v2.w; vals[12] = v3.x; vals[13] = v3.y; vals[14] = v3.z; vals[15] = v3.w;
-  } else {
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-      const bool inside = idx0 + j < n;
-      vals[j] = inside ? in[idx0 + j] : 0u;
-      if (inside && keep[idx0 + j] != 0) mask |= 1u << j;
-    }
-  }
-  const uint32_t count = __popc(mask);
-
-  // ---- warp-aggregated inclusive scan of the per-thread counts
-  uint32_t incl = count;
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const uint32_t up = __shfl_up_sync(FULL_MASK, incl, off);
-    if (lane >= static_cast<uint32_t>(off)) incl += up;
-  }
-  if (lane == 31) s_warp_total[warp] = incl;
+  load_rows<FAST>(in, keep, n, tile * TILE + 512ull * warp, lane, vals, mask);
+  uint32_t first[4];
+  const uint32_t warp_total = rank_rows(mask, lane, first);
+  if (lane == 31) s_warp_total[warp] = warp_total;
   __syncthreads();
   uint32_t warp_offset = 0, block_total = 0;
 #pragma unroll
@@ -107,11 +137,12 @@ __global__ void __launch_bounds__(CB, RDN_COMPACT_MINB) k_compact_u32(const uint
   }
 
   // ---- the tile's kept values, packed in order (block-local offsets; overlaps with the look-back below for warps 1..7)
-  {
-    uint32_t local = warp_offset + (incl - count);
 #pragma unroll
-    for (int j = 0; j < ITEMS; ++j)
-      if (mask & (1u << j)) s_vals[local++] = vals[j];
+  for (int r = 0; r < 4; ++r) {
+    uint32_t local = warp_offset + first[r];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (mask & (1u << (4 * r + c))) s_vals[local++] = vals[4 * r + c];
   }
 
   // ---- decoupled look-back by warp 0: 32 predecessors per probe
@@ -154,52 +185,62 @@ __global__ void __launch_bounds__(CB, RDN_COMPACT_MINB) k_compact_u32(const uint
 // ---- large inputs: three streaming passes instead of one pass with a look-back chain.  The single-pass kernel is bound by the
 // latency of that chain (every tile waits for the running prefix of the tiles before it: 2.9 TB/s at best on 132 M elements);
 // counting first costs one more read of the flags (10 B per element instead of 9) and no tile ever waits for another.
-__global__ void __launch_bounds__(CB) k_compact_count(const uint8_t *__restrict__ keep, uint64_t n, unsigned long long *__restrict__ counts) {
-  __shared__ uint32_t s_warp_total[CB / 32];
+constexpr int COUNT_TILES = 2;  // tiles per CTA of the counting pass: 32 B of flags per thread in flight
+constexpr int GROUP = 64;       // tiles per group: the scan runs over group sums, a tile adds up the counts of its group before it
+__global__ void __launch_bounds__(CB) k_compact_count(const uint8_t *__restrict__ keep, uint64_t n, unsigned long long *__restrict__ counts,
+                                                      unsigned long long *__restrict__ groups, uint64_t n_tiles) {
+  __shared__ uint32_t s_warp_total[COUNT_TILES][CB / 32];
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  const uint64_t idx0 = static_cast<uint64_t>(blockIdx.x) * TILE + static_cast<uint64_t>(tid) * ITEMS;
-  uint32_t count = 0;
-  if (idx0 + ITEMS <= n && (reinterpret_cast<uintptr_t>(keep) & 15u) == 0) {
-    const uint4 k16 = __ldg(reinterpret_cast<const uint4 *>(keep + idx0));
-    const uint32_t kw[4] = {k16.x, k16.y, k16.z, k16.w};
+  const uint64_t tile0 = static_cast<uint64_t>(blockIdx.x) * COUNT_TILES;
+  const bool aligned = (reinterpret_cast<uintptr_t>(keep) & 15u) == 0;
+  uint4 k16[COUNT_TILES];
+  bool fast[COUNT_TILES];
 #pragma unroll
-    for (int w = 0; w < 4; ++w)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) count += ((kw[w] >> (8 * j)) & 0xFFu) != 0 ? 1u : 0u;
-  } else {
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j)
-      if (idx0 + j < n && keep[idx0 + j] != 0) ++count;
+  for (int t = 0; t < COUNT_TILES; ++t) {
+    const uint64_t idx0 = (tile0 + t) * TILE + static_cast<uint64_t>(tid) * ITEMS;
+    fast[t] = aligned && idx0 + ITEMS <= n;
+    k16[t] = fast[t] ? __ldg(reinterpret_cast<const uint4 *>(keep + idx0)) : make_uint4(0, 0, 0, 0);
   }
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) count += __shfl_down_sync(FULL_MASK, count, off);
-  if (lane == 0) s_warp_total[warp] = count;
+  for (int t = 0; t < COUNT_TILES; ++t) {
+    const uint64_t idx0 = (tile0 + t) * TILE + static_cast<uint64_t>(tid) * ITEMS;
+    uint32_t count = 0;
+    if (fast[t]) {
+      const uint32_t kw[4] = {k16[t].x, k16[t].y, k16[t].z, k16[t].w};
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) count += ((kw[w] >> (8 * j)) & 0xFFu) != 0 ? 1u : 0u;
+    } else {
+#pragma unroll
+      for (int j = 0; j < ITEMS; ++j)
+        if (idx0 + j < n && keep[idx0 + j] != 0) ++count;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) count += __shfl_down_sync(FULL_MASK, count, off);
+    if (lane == 0) s_warp_total[t][warp] = count;
+  }
   __syncthreads();
-  if (tid == 0) {
+  if (tid < COUNT_TILES && tile0 + tid < n_tiles) {
     uint32_t total = 0;
 #pragma unroll
-    for (int w = 0; w < CB / 32; ++w) total += s_warp_total[w];
-    counts[blockIdx.x] = total;
+    for (int w = 0; w < CB / 32; ++w) total += s_warp_total[tid][w];
+    counts[tile0 + tid] = total;
+    atomicAdd(groups + (tile0 + tid) / GROUP, static_cast<unsigned long long>(total));
   }
 }
 
-// exclusive scan of the per-tile counts in place (one CTA: 32 K tiles for 132 M elements), total -> *out_n
-__global__ void __launch_bounds__(1024) k_compact_scan_tiles(unsigned long long *__restrict__ counts, uint64_t n_tiles, uint64_t *__restrict__ out_n) {
+// exclusive scan of the group sums in place (one CTA, one value per thread and round: 507 groups for 132 M elements), total -> *out_n
+__global__ void __launch_bounds__(1024) k_compact_scan_groups(unsigned long long *__restrict__ groups, uint64_t n_groups, uint64_t *__restrict__ out_n) {
   __shared__ unsigned long long s_warp[32];
   __shared__ unsigned long long s_carry;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  constexpr int PER = 8;
   if (tid == 0) s_carry = 0ull;
   __syncthreads();
-  for (uint64_t base = 0; base < n_tiles; base += 1024ull * PER) {
-    unsigned long long v[PER], sum = 0;
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-      const uint64_t i = base + static_cast<uint64_t>(tid) * PER + j;
-      v[j] = i < n_tiles ? counts[i] : 0ull;
-      sum += v[j];
-    }
-    unsigned long long incl = sum;
+  for (uint64_t base = 0; base < n_groups; base += 1024) {
+    const uint64_t i = base + tid;
+    const unsigned long long v = i < n_groups ? groups[i] : 0ull;
+    unsigned long long incl = v;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
       const unsigned long long up = __shfl_up_sync(FULL_MASK, incl, off);
@@ -207,61 +248,55 @@ __global__ void __launch_bounds__(1024) k_compact_scan_tiles(unsigned long long 
     }
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    unsigned long long warp_offset = 0;
-    for (uint32_t w = 0; w < warp; ++w) warp_offset += s_warp[w];
-    unsigned long long run = s_carry + warp_offset + (incl - sum);
+    unsigned long long w = lane < warp ? s_warp[lane] : 0ull;  // (32 warps: one value per lane)
 #pragma unroll
-    for (int j = 0; j < PER; ++j) {
-      const uint64_t i = base + static_cast<uint64_t>(tid) * PER + j;
-      if (i < n_tiles) counts[i] = run;
-      run += v[j];
-    }
+    for (int off = 16; off > 0; off >>= 1) w += __shfl_xor_sync(FULL_MASK, w, off);
+    const unsigned long long carry = s_carry;
+    if (i < n_groups) groups[i] = carry + w + (incl - v);
     __syncthreads();
-    if (tid == 1023) s_carry = run;
+    if (tid == 1023) s_carry = carry + w + incl;
     __syncthreads();
   }
   if (tid == 0) *out_n = s_carry;
 }
 
-// the tile's kept values to out[offsets[tile] ...): the body of k_compact_u32 without the look-back
+// the tile's kept values to out[offsets[tile] ...): the body of k_compact_u32 without the look-back.  The tile also writes its share
+// of the zeros behind the kept values — as many as it dropped, at total + (elements dropped by the tiles before it) — so the tail
+// needs no kernel of its own.
 template <bool FAST>
 __global__ void __launch_bounds__(CB, RDN_COMPACT_MINB) k_compact_scatter(const uint32_t *__restrict__ in, const uint8_t *__restrict__ keep, uint64_t n,
-                                                                          uint32_t *__restrict__ out, const unsigned long long *__restrict__ offsets) {
+                                                                          uint32_t *__restrict__ out, const unsigned long long *__restrict__ counts,
+                                                                          const unsigned long long *__restrict__ group_prefix,
+                                                                          const uint64_t *__restrict__ total_kept) {
   __shared__ uint32_t s_warp_total[CB / 32];
   __shared__ uint32_t s_vals[TILE];
+  __shared__ unsigned long long s_base;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint64_t tile = blockIdx.x;
-  const uint64_t idx0 = tile * TILE + static_cast<uint64_t>(tid) * ITEMS;
-  uint32_t mask = 0;
+  // the tile's offset: the prefix of its group + the counts of the tiles of the group before it (the last warp adds them up while
+  // the values are on their way)
+  unsigned long long before = 0;
+  if (warp == CB / 32 - 1) {
+    const uint64_t g0 = tile / GROUP * GROUP;
+    static_assert(GROUP == 64, "two counts per lane");
+    if (g0 + lane < tile) before += counts[g0 + lane];
+    if (g0 + 32 + lane < tile) before += counts[g0 + 32 + lane];
+    if (lane == 0) before += group_prefix[tile / GROUP];
+  }
+  uint32_t mask;
   uint32_t vals[ITEMS];
-  if (FAST && idx0 + ITEMS <= n) {
-    const uint4 k16 = __ldg(reinterpret_cast<const uint4 *>(keep + idx0));
-    const uint4 *vp = reinterpret_cast<const uint4 *>(in + idx0);
-    const uint4 v0 = __ldg(vp), v1 = __ldg(vp + 1), v2 = __ldg(vp + 2), v3 = __ldg(vp + 3);
-    const uint32_t kw[4] = {k16.x, k16.y, k16.z, k16.w};
+  load_rows<FAST>(in, keep, n, tile * TILE + 512ull * warp, lane, vals, mask);
+  const uint64_t total = *total_kept;
+  if (warp == CB / 32 - 1) {
 #pragma unroll
-    for (int w = 0; w < 4; ++w)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) mask |= (((kw[w] >> (8 * j)) & 0xFFu) != 0 ? 1u : 0u) << (4 * w + j);
-    vals[0] = v0.x; vals[1] = v0.y; vals[2] = v0.z; vals[3] = v0.w; vals[4] = v1.x; vals[5] = v1.y; vals[6] = v1.z; vals[7] = v1.w;
-    vals[8] = v2.x; vals[9] = v2.y; vals[10] = v2.z; vals[11] = v2.w; vals[12] = v3.x; vals[13] = v3.y; vals[14] = v3.z; vals[15] = v3.w;
-  } else {
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-      const bool inside = idx0 + j < n;
-      vals[j] = inside ? in[idx0 + j] : 0u;
-      if (inside && keep[idx0 + j] != 0) mask |= 1u << j;
-    }
+    for (int off = 16; off > 0; off >>= 1) before += __shfl_xor_sync(FULL_MASK, before, off);
+    if (lane == 0) s_base = before;
   }
-  const uint32_t count = __popc(mask);
-  uint32_t incl = count;
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const uint32_t up = __shfl_up_sync(FULL_MASK, incl, off);
-    if (lane >= static_cast<uint32_t>(off)) incl += up;
-  }
-  if (lane == 31) s_warp_total[warp] = incl;
+  uint32_t first[4];
+  const uint32_t warp_total = rank_rows(mask, lane, first);
+  if (lane == 31) s_warp_total[warp] = warp_total;
   __syncthreads();
+  const uint64_t base = s_base;
   uint32_t warp_offset = 0, block_total = 0;
 #pragma unroll
   for (int w = 0; w < CB / 32; ++w) {
@@ -269,13 +304,19 @@ __global__ void __launch_bounds__(CB, RDN_COMPACT_MINB) k_compact_scatter(const 
     if (w < static_cast<int>(warp)) warp_offset += t;
     block_total += t;
   }
-  uint32_t local = warp_offset + (incl - count);
 #pragma unroll
-  for (int j = 0; j < ITEMS; ++j)
-    if (mask & (1u << j)) s_vals[local++] = vals[j];
+  for (int r = 0; r < 4; ++r) {
+    uint32_t local = warp_offset + first[r];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (mask & (1u << (4 * r + c))) s_vals[local++] = vals[4 * r + c];
+  }
   __syncthreads();
-  const uint64_t base = offsets[tile];
   for (uint32_t i = tid; i < block_total; i += CB) out[base + i] = s_vals[i];
+  const uint64_t tile_first = tile * TILE;
+  const uint32_t tile_elems = static_cast<uint32_t>(n - tile_first < TILE ? n - tile_first : TILE);
+  const uint64_t zero_at = total + (tile_first - base);
+  for (uint32_t i = tid; i < tile_elems - block_total; i += CB) out[zero_at + i] = 0u;
 }
 
 __global__ void k_zero_tail_u32(uint32_t *__restrict__ out, const uint64_t *__restrict__ out_n, uint64_t n) {
@@ -424,7 +465,10 @@ __global__ void __launch_bounds__(128) k_patha_list(const PathANode *__restrict_
 
 }  // namespace
 
-uint64_t compact_status_words(uint64_t n) { return 2 + (n + TILE - 1) / TILE; }
+uint64_t compact_status_words(uint64_t n) {  // tile counter, one word per tile, one per group of tiles
+  const uint64_t n_tiles = (n + TILE - 1) / TILE;
+  return 2 + n_tiles + (n_tiles + GROUP - 1) / GROUP + 1;
+}
 
 void launch_compact_u32(const uint32_t *d_in, const uint8_t *d_keep, uint64_t n, uint32_t *d_out, uint64_t *d_out_n,
                         unsigned long long *d_status, cudaStream_t stream) {
@@ -437,15 +481,15 @@ void launch_compact_u32(const uint32_t *d_in, const uint8_t *d_keep, uint64_t n,
   const bool vec_keep = ((reinterpret_cast<uintptr_t>(d_keep) | reinterpret_cast<uintptr_t>(d_in)) & 15u) == 0;
   const unsigned zb = static_cast<unsigned>(n_tiles < 1184 ? n_tiles : 1184);
   static const uint64_t streaming_min = []() { const char *e = getenv("RDN_COMPACT_STREAMING_MIN"); return e ? strtoull(e, nullptr, 10) : (1ull << 22); }();
-  if (n >= streaming_min) {  // count -> scan of the tile counts -> scatter: no tile waits for another (the memset above is not needed here)
-    unsigned long long *counts = d_status + 1;
-    k_compact_count<<<static_cast<unsigned>(n_tiles), CB, 0, stream>>>(d_keep, n, counts);
-    k_compact_scan_tiles<<<1, 1024, 0, stream>>>(counts, n_tiles, d_out_n);
+  if (n >= streaming_min) {  // count -> scan of the tile counts -> scatter: no tile waits for another 
+    unsigned long long *counts = d_status + 1, *groups = counts + n_tiles;   // (the group sums start at zero: the memset above)
+    const uint64_t n_groups = (n_tiles + GROUP - 1) / GROUP;
+    k_compact_count<<<static_cast<unsigned>((n_tiles + COUNT_TILES - 1) / COUNT_TILES), CB, 0, stream>>>(d_keep, n, counts, groups, n_tiles);
+    k_compact_scan_groups<<<1, 1024, 0, stream>>>(groups, n_groups, d_out_n);
     if (vec_keep)
-      k_compact_scatter<true><<<static_cast<unsigned>(n_tiles), CB, 0, stream>>>(d_in, d_keep, n, d_out, counts);
+      k_compact_scatter<true><<<static_cast<unsigned>(n_tiles), CB, 0, stream>>>(d_in, d_keep, n, d_out, counts, groups, d_out_n);
     else
-      k_compact_scatter<false><<<static_cast<unsigned>(n_tiles), CB, 0, stream>>>(d_in, d_keep, n, d_out, counts);
-    k_zero_tail_u32<<<zb, 256, 0, stream>>>(d_out, d_out_n, n);
+      k_compact_scatter<false><<<static_cast<unsigned>(n_tiles), CB, 0, stream>>>(d_in, d_keep, n, d_out, counts, groups, d_out_n);
     return;
   }
   if (vec_keep)

@@ -208,6 +208,14 @@ inline T __shfl_up_sync(unsigned mask, T v, unsigned delta, int width = 32) {
   const ::simt::Coll &c = ::simt::collective(mask, ::simt::to_bits(v), false);
   return (delta <= lane && ((c.out_mask >> (lane - delta)) & 1u)) ? ::simt::from_bits<T>(c.out[lane - delta]) : v;
 }
+template <class T>
+inline T __shfl_xor_sync(unsigned mask, T v, int lane_mask, int width = 32) {
+  (void)width;
+  const unsigned lane = ::simt::g_cur->lane;
+  const ::simt::Coll &c = ::simt::collective(mask, ::simt::to_bits(v), false);
+  const unsigned src = (lane ^ static_cast<unsigned>(lane_mask)) & 31u;
+  return ((c.out_mask >> src) & 1u) ? ::simt::from_bits<T>(c.out[src]) : v;
+}
 // __activemask(): the lanes of the warp that reach the same call site within one scheduler pass form a converged group (all of
 // them then continue from that site, so a __shfl_sync over the returned mask completes).  Under RDN_SIMT_SEED the groups vary.
 namespace simt { unsigned activemask_at(const void *site); }

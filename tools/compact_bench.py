@@ -41,6 +41,6 @@ for n in (2_073_600, 132_710_400):
             ms.append(e0.elapsed_time(e1))
         ms = float(np.median(ms))
         nbytes = 9.0 * n + 8.0 * (n / 2048)
-        print(json.dumps({"kernel": "k_compact_u32 (+ k_zero_tail_u32)", "n": n, "keep_fraction": frac, "kept": k, "ms_median": ms, "iters": iters,
+        print(json.dumps({"kernel": ("k_compact_count + k_compact_scan_groups + k_compact_scatter" if n >= (1 << 22) else "k_compact_u32 + k_zero_tail_u32"), "n": n, "keep_fraction": frac, "kept": k, "ms_median": ms, "iters": iters,
                           "algorithmic_bytes": nbytes, "gbs": nbytes / ms / 1e6, "hbm_peak_gbs": peak, "frac_of_hbm_peak": nbytes / ms / 1e6 / peak,
                           "elements_per_s": n / ms * 1e3, "matches_numpy": ok}))
