@@ -113,6 +113,12 @@ struct DeviceCtx {
   // that stream since, and only if it was ONE ordered launch that resolves its ties itself
   struct { bool valid = false; uintptr_t rays_lo = 0, rays_hi = 0, hits_lo = 0, hits_hi = 0; } ext_prev;
   bool last_enqueue_overlappable = false;  // set by enqueue_trace
+  // tile history of grid launches (device-resident traces): how long each 8x4 tile took in the last launch over a grid of this size,
+  // and the order built from it for the next one (traverse.cu k_build_tile_order)
+  uint32_t *d_tile_cost = nullptr, *d_tile_lists = nullptr;  // lists: two sets of TILE_CLASSES lists (one read by launches, one being built)
+  TileMeta *d_tile_meta = nullptr;                           // [2]
+  uint64_t tile_cap = 0;
+  struct { uint32_t width = 0, height = 0; int current = 0; bool built = false; } tile_hist;
   unsigned long long *d_compact_status = nullptr;
   uint64_t compact_status_cap = 0;
   float *d_ao_payload = nullptr;   // AO accumulation: per-pixel payload, 1.0f between samples
@@ -484,7 +490,7 @@ int prepare_any_hit(rdn_rt_scene *s, DeviceCtx &dc, const rdn_launch &launch, Sc
 // enqueue the kernels of one trace on `stream`; returns the number of kernels launched
 int enqueue_trace(rdn_rt_scene *s, DeviceCtx &dc, const Scratch &scratch, const rdn_launch &launch, const rdn_ray *d_rays, uint64_t n,
                   rdn_hit *d_hits, int mode, cudaStream_t stream, uint32_t *launches, bool count_ties = false, bool allow_overlap = false,
-                  const unsigned long long *d_n = nullptr) {
+                  const unsigned long long *d_n = nullptr, bool tile_history = false) {
   const TraceScratch ts = scratch.view();
   // work_counter is zero here: zeroed at allocation and re-armed by the last CTA of every ordered launch.  tie_count and
   // the two error flags accumulate until read (the stats path clears tie_count first).
@@ -521,10 +527,55 @@ int enqueue_trace(rdn_rt_scene *s, DeviceCtx &dc, const Scratch &scratch, const 
       ScopedKernelTimer tm(dc, KERNEL_ORDERED, stream);
       // (a launch that failed never advances the set's epoch: the host-side count moves only when the kernel is in the stream,
       // or the next launch on the set would wait at its gate for an epoch that never comes)
-      RDN_CUDA(launch_trace_ordered(dev, launch, tlas, d_rays, n, d_hits, ts, dc.sm_count, stream,
-                                    allow_overlap && !dc.timing && !count_ties, scratch.ordered_launches, &ties_done, d_n));
+      // Tile history (device-resident grid launches): the launch takes its tiles by how long they took in an earlier launch over a
+      // grid of the same size — longest first, see k_build_tile_lists — and notes its own pass durations for the next.  Frames of
+      // an animation, the samples of a pixel, the bench's repeated frame: what was long stays long.  A launch that may overlap its
+      // predecessor's tail only reads the lists (a kernel behind every launch would separate the launches again).  The first two
+      // launches over a grid run in grid order: the classes are measured by the mean of the launch before.  RDN_TILE_HISTORY=0
+      // switches all of it off.
+      static const bool history_enabled = []() { const char *e = getenv("RDN_TILE_HISTORY"); return !e || atoi(e) != 0; }();
+      constexpr int TILE_LISTS = 8;  // (= TILE_CLASSES of traverse.cu: sizeof(TileMeta::count))
+      static_assert(sizeof(TileMeta::count) / sizeof(uint32_t) == TILE_LISTS, "one list per class");
+      TileHistory hist{};
+      const bool overlap = allow_overlap && !dc.timing && !count_ties;
+      const bool with_history = tile_history && history_enabled && !d_n && launch.grid_width != 0 && n % launch.grid_width == 0 && n >= (1u << 16);
+      if (with_history) {
+        const uint32_t w = launch.grid_width, h = static_cast<uint32_t>(n / launch.grid_width);
+        const uint32_t n_tiles = ((w + 7u) / 8u) * ((h + 3u) / 4u);
+        if (dc.tile_cap < n_tiles) {
+          if (dc.d_tile_cost) cudaFree(dc.d_tile_cost);
+          if (dc.d_tile_lists) cudaFree(dc.d_tile_lists);
+          dc.d_tile_cost = dc.d_tile_lists = nullptr; dc.tile_cap = 0; dc.tile_hist.width = 0;
+          RDN_CUDA(cudaMalloc(&dc.d_tile_cost, n_tiles * sizeof(uint32_t)));
+          RDN_CUDA(cudaMalloc(&dc.d_tile_lists, 2ull * TILE_LISTS * n_tiles * sizeof(uint32_t)));
+          if (!dc.d_tile_meta) RDN_CUDA(cudaMalloc(&dc.d_tile_meta, 2 * sizeof(TileMeta)));
+          dc.tile_cap = n_tiles;
+        }
+        if (dc.tile_hist.width != w || dc.tile_hist.height != h) {  // another grid: start over
+          RDN_CUDA(cudaMemsetAsync(dc.d_tile_cost, 0, n_tiles * sizeof(uint32_t), stream));
+          RDN_CUDA(cudaMemsetAsync(dc.d_tile_meta, 0, 2 * sizeof(TileMeta), stream));
+          dc.tile_hist.width = w; dc.tile_hist.height = h; dc.tile_hist.current = 0; dc.tile_hist.built = false;
+        }
+        const int cur = dc.tile_hist.current;
+        hist.n_tiles = n_tiles;
+        if (dc.tile_hist.built) { hist.lists = dc.d_tile_lists + static_cast<uint64_t>(cur) * TILE_LISTS * n_tiles; hist.meta = dc.d_tile_meta + cur; }
+        if (!overlap) { hist.cost = dc.d_tile_cost; hist.meta_clear = dc.d_tile_meta + (cur ^ 1); }
+      }
+      RDN_CUDA(launch_trace_ordered(dev, launch, tlas, d_rays, n, d_hits, ts, dc.sm_count, stream, overlap, scratch.ordered_launches, &ties_done, d_n,
+                                    with_history ? &hist : nullptr));
       if (n) scratch.ordered_launches++;
       dc.last_enqueue_overlappable = ties_done && n != 0;
+      if (with_history && hist.used && hist.cost) {
+        // the lists for the launches to come, into the set nobody reads (its description was zeroed by the launch's last CTA)
+        const int cur = dc.tile_hist.current;
+        launch_build_tile_lists(dc.d_tile_cost, dc.d_tile_lists + static_cast<uint64_t>(cur ^ 1) * TILE_LISTS * hist.n_tiles, dc.d_tile_meta + (cur ^ 1),
+                                dc.d_tile_meta + cur, hist.n_tiles, stream);
+        dc.tile_hist.current = cur ^ 1;
+        dc.tile_hist.built = true;
+        if (launches) *launches += 1;
+      } else if (with_history && !hist.used) {
+        dc.tile_hist.built = false;  // (another instantiation took the launch — any-hit stage, an A/B variant —: the lists are stale)
+      }
     }
     if (!ties_done) {
       ScopedKernelTimer tm(dc, KERNEL_TIES, stream);
@@ -674,6 +725,9 @@ void rdn_rt_scene_destroy(rdn_rt_scene *s) {
     for (TimedLaunch &t : dc.timed) { cudaEventDestroy(t.begin); cudaEventDestroy(t.end); }
     if (dc.ext_done) cudaEventDestroy(dc.ext_done);
     if (dc.d_compact_status) cudaFree(dc.d_compact_status);
+    if (dc.d_tile_cost) cudaFree(dc.d_tile_cost);
+    if (dc.d_tile_lists) cudaFree(dc.d_tile_lists);
+    if (dc.d_tile_meta) cudaFree(dc.d_tile_meta);
     if (dc.d_anyhit) cudaFree(dc.d_anyhit);
     free_wave_scratch(dc);
     if (dc.d_ao_payload) cudaFree(dc.d_ao_payload);
@@ -841,7 +895,7 @@ static int trace_device_impl(rdn_rt_scene *s, int device_index, const rdn_launch
 #endif
     if (stats) RDN_CUDA(cudaEventRecord(e0, stream));
     rc = enqueue_trace(s, dc, scratch, l, d_rays + off, m, d_hits + off, mode, stream, stats ? &stats->kernel_launches : nullptr, stats != nullptr,
-                       overlap_ok && off == 0, d_n);
+                       overlap_ok && off == 0, d_n, /*tile_history=*/m == n);
     if (rc != RDN_OK) return rc;
     if (!stats && m == n && dc.last_enqueue_overlappable) {
       dc.ext_prev.valid = true;

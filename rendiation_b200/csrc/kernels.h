@@ -79,7 +79,21 @@ int ordered_tie_mode();  // 0: queue + launch_resolve_ties; 1/2: re-walk by the 
 cudaError_t launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const TlasRoot &tlas, const rdn_ray *d_rays, uint64_t n,
                                  rdn_hit *d_hits, const TraceScratch &scratch, int sm_count, cudaStream_t stream, bool allow_overlap,
                                  uint32_t wait_epoch,  // = ordered launches issued before this one on `scratch`
-                                 bool *ties_resolved_in_kernel, const unsigned long long *d_n = nullptr);
+                                 bool *ties_resolved_in_kernel, const unsigned long long *d_n = nullptr, struct TileHistory *history = nullptr);
+// Tile history of a grid (traverse.cu k_build_tile_lists): TILE_CLASSES lists of tile indices, capacity n_tiles each, and their lengths.
+struct TileMeta {
+  uint32_t count[8];
+  unsigned long long sum, ran;  // durations of the passes the lists were built from (what the next build measures its classes by)
+};
+struct TileHistory {
+  const uint32_t *lists;   // what the launch reads (null: grid order) ...
+  const TileMeta *meta;
+  uint32_t *cost;          // ... where it notes its pass durations (null: nowhere) ...
+  TileMeta *meta_clear;    // ... and the description it zeroes for the build behind it (null: none follows)
+  uint32_t n_tiles;        // ceil(width / 8) * ceil(height / 4)
+  bool used;               // out: the launch took the instantiation that does all this (plain grids only)
+};
+void launch_build_tile_lists(uint32_t *d_cost, uint32_t *d_lists, TileMeta *d_meta, const TileMeta *d_previous, uint32_t n_tiles, cudaStream_t stream);
 // can the any-hit stage of this launch stop a traversal (END_SEARCH)?  Then the answer depends on the visiting order and the launch
 // takes the reference-order kernel.  (host copy of the programs / hit groups)
 bool any_hit_can_end_search(const rdn_launch &launch, const rdn_anyhit_program *programs, uint32_t n_programs, const SbtHitGroup *groups,

@@ -29,6 +29,7 @@
 //                           irregular instances (their queue can be long), and RDN_ORDERED_VARIANT=9.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 
@@ -432,6 +433,7 @@ __global__ void __launch_bounds__(128) k_resolve_ties(const SceneDev S, const rd
 }
 
 // ================================================================================================ ordered
+constexpr int TILE_CLASSES = 8;
 enum { SHARE_NEVER = 0, SHARE_ALWAYS = 1, SHARE_LATE = 2 };  // template argument SHARE of k_trace_ordered_rounds
 
 struct OrderedParams {
@@ -453,8 +455,26 @@ struct OrderedParams {
   // lanes are busy, by lanes that have at least share_min of them
   int share_busy, share_min, share_after;
   uint32_t wait_epoch;  // launches issued before this one on the same scratch set: they must have left before this one touches it
+  // HISTORY (grids; see k_build_tile_lists): tile_lists / tile_meta = the tiles of the grid by how long they took in an earlier
+  // launch over it (TILE_CLASSES lists of capacity n_tiles each, longest class last) and the lists' lengths, or null: grid order;
+  // tile_cost = where this launch notes the duration of its passes, or null; tile_meta_clear = the description the order kernel
+  // behind this launch will fill, zeroed by the last CTA on its way out
+  const uint32_t *tile_lists;
+  const TileMeta *tile_meta;
+  uint32_t *tile_cost;
+  TileMeta *tile_meta_clear;
+  uint32_t n_tiles;
   TraceScratch scratch;
 };
+
+// the SM's cycle counter (durations of passes over tiles; the emulated build counts host nanoseconds instead)
+__device__ __forceinline__ uint32_t pass_clock() {
+#ifdef RDN_SIMT_EMU
+  return static_cast<uint32_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count());
+#else
+  return static_cast<uint32_t>(clock());
+#endif
+}
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
 #ifdef RDN_SIMT_EMU
@@ -577,7 +597,7 @@ __device__ __forceinline__ void drain_tie_queue(const OrderedParams &P) {
 // speculative traversal with a postponed leaf, any-hit pre-classification, topping a thinned-out tile up with new rays, the first
 // 8-32 stack entries per thread in shared memory (3-10 % slower than the L1-cached local stack), rows of tiles taken from the
 // middle of the frame outwards (+2..5 % on configs 1 / 2, -11 % on config 4).
-template <int K, int MINB, bool DRAIN_TIES, bool IRREGULAR, bool LD256, bool HOT, bool WIDE4, bool INST_LOOP = false, int SHARE = 0, bool ANYHIT = false>
+template <int K, int MINB, bool DRAIN_TIES, bool IRREGULAR, bool LD256, bool HOT, bool WIDE4, bool INST_LOOP = false, int SHARE = 0, bool ANYHIT = false, bool HISTORY = false>
 __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(const __grid_constant__ OrderedParams P) {
   RDN_COST(COST_PROLOGUE);
   const SceneDev &S = P.S;
@@ -610,6 +630,12 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
   }
   __syncthreads();
 
+  __shared__ uint32_t s_tile_count[TILE_CLASSES];
+  if constexpr (HISTORY) {
+    // (written by an order kernel that completed before this launch was allowed to start: launches that record are not overlapped)
+    if (P.tile_lists && threadIdx.x < TILE_CLASSES) s_tile_count[threadIdx.x] = P.tile_meta->count[threadIdx.x];
+    __syncthreads();
+  }
   __shared__ __align__(128) float4 s_hot[HOT ? 2 * HOT_TOP_NODES * 4 : 4];
   __shared__ __align__(8) unsigned long long s_hot_bar;
   __shared__ int s_age[SHARE == SHARE_LATE ? ORDERED_BLOCK : 1];  // SHARE_LATE: the age of the pass over the tile in rounds, one word per thread
@@ -730,7 +756,19 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
         bool valid = f < n_fetch;
         uint64_t idx = f;
         if (valid && P.tiles_x) {
-          const uint32_t tile = static_cast<uint32_t>(f >> 5);  // launches hold < 2^31 rays: 32-bit tile arithmetic
+          uint32_t tile = static_cast<uint32_t>(f >> 5);  // launches hold < 2^31 rays: 32-bit tile arithmetic
+          if constexpr (HISTORY) {
+            if (P.tile_lists) {  // slot -> (class, position): the longest class is taken first
+              int q = TILE_CLASSES - 1;
+#pragma unroll
+              for (; q > 0; --q) {
+                const uint32_t len = s_tile_count[q];
+                if (tile < len) break;
+                tile -= len;
+              }
+              tile = __ldg(P.tile_lists + static_cast<uint64_t>(q) * P.n_tiles + tile);
+            }
+          }
           const uint32_t in_tile = static_cast<uint32_t>(f) & 31u;
           const uint32_t ty = tile / P.tiles_x, tx = tile - ty * P.tiles_x;
           const uint32_t x = tx * 8u + (in_tile & 7u), y = ty * 4u + (in_tile >> 3);
@@ -774,6 +812,8 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
     unsigned long long dbg_pass_rounds = 0, dbg_pass_busy = 0;
 #endif
 
+    [[maybe_unused]] uint32_t pass_t0 = 0;
+    if constexpr (HISTORY) pass_t0 = pass_clock();
     if constexpr (SHARE == SHARE_LATE) {
       // Two loops: the plain one for the first share_after rounds of a pass (what almost every tile needs), then — for the few passes
       // that have grown old with a handful of long rays left — the loop in which idle lanes take over deferred subtrees.  The plain
@@ -812,6 +852,15 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
       if (SH || alive) {
 #include "ordered_rounds.inc"
         if (SH ? alive : cur == REF_DONE) finish_ray();
+      }
+    }
+    if constexpr (HISTORY) {
+      // how long the pass took, noted at the tile of its first ray (a pass is one tile, or the ends of two): what the next launch
+      // over this grid sorts its tiles by
+      if (P.tile_cost && static_cast<int>(lane) == __ffs(amask) - 1) {
+        const uint32_t dt = pass_clock() - pass_t0;
+        const uint32_t y = static_cast<uint32_t>(ri / P.width), x = static_cast<uint32_t>(ri - static_cast<uint64_t>(y) * P.width);
+        atomicMax(P.tile_cost + ((y >> 2) * P.tiles_x + (x >> 3)), dt);
       }
     }
 #ifdef RDN_DEBUG_TIMELINE
@@ -872,6 +921,9 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
       drain_tie_queue(P);
       __syncthreads();
     }
+    if constexpr (HISTORY) {
+      if (P.tile_meta_clear && threadIdx.x < sizeof(TileMeta) / 4) reinterpret_cast<uint32_t *>(P.tile_meta_clear)[threadIdx.x] = 0u;
+    }
     if (threadIdx.x == 0) {
       *P.scratch.work_counter = 0ull;
       *P.scratch.blocks_done = 0u;
@@ -886,7 +938,92 @@ __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(co
   }
 }
 
+// Tiles of a grid by how long they took.  A launch ends when its last long pass ends, and a pass over a tile that straddles a
+// silhouette takes as long as the rest of the launch: such tiles have to start first.  Behind a launch that noted its pass durations
+// (tile_cost), this kernel files every tile under one of up to TILE_CLASSES classes — longest pass more than 4x / 3x / 2x / 1.5x the
+// mean pass of the launch before, or none of that (nine tiles in ten) — and the next launch over the grid takes the classes longest
+// first.  One thread per tile, 1024 consecutive tiles per CTA: ranks inside the CTA by ballot, one atomic per CTA and class for its
+// range in the class's list, so every list is in grid order up to the order in which the CTAs arrive, and neighbouring warps of the
+// next launch still walk neighbouring tiles.  Also sums up the durations for the kernel behind the next launch, and clears them.
+struct TileThresholds { uint32_t quarters[TILE_CLASSES - 1]; };  // class boundaries in quarters of the mean, ascending (unused: 0xFFFFFFFF)
+__device__ __forceinline__ int tile_class(uint32_t cost, unsigned long long mean, const TileThresholds &th) {
+  const unsigned long long c = 4ull * cost;
+  int k = 0;
+#pragma unroll
+  for (int q = 0; q < TILE_CLASSES - 1; ++q) k += c > th.quarters[q] * mean ? 1 : 0;
+  return k;
+}
+__global__ void __launch_bounds__(1024) k_build_tile_lists(uint32_t *__restrict__ cost, uint32_t *__restrict__ lists, TileMeta *__restrict__ meta,
+                                                           const TileMeta *__restrict__ previous, uint32_t n_tiles, const TileThresholds th) {
+  __shared__ uint32_t s_warp[TILE_CLASSES][32];
+  __shared__ uint32_t s_base[TILE_CLASSES];
+  __shared__ unsigned long long s_sum[32];
+  __shared__ uint32_t s_ran[32];
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t t = blockIdx.x * 1024u + tid;
+  const bool inside = t < n_tiles;
+  const uint32_t c = inside ? cost[t] : 0u;
+  // (no launch before, or none of its tiles ran a pass: everything is class 0)
+  const unsigned long long mean = previous->ran ? previous->sum / previous->ran : 0xFFFFFFFFull;
+  const int k = inside ? tile_class(c, mean, th) : -1;
+  uint32_t rank = 0;
+#pragma unroll
+  for (int q = 0; q < TILE_CLASSES; ++q) {
+    const uint32_t b = __ballot_sync(FULL_MASK, k == q);
+    if (k == q) rank = __popc(b & ((1u << lane) - 1u));
+    if (lane == 0) s_warp[q][warp] = __popc(b);
+  }
+  unsigned long long sum = c;
+  uint32_t ran = c != 0 ? 1u : 0u;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) { sum += __shfl_xor_sync(FULL_MASK, sum, off); ran += __shfl_xor_sync(FULL_MASK, ran, off); }
+  if (lane == 0) { s_sum[warp] = sum; s_ran[warp] = ran; }
+  __syncthreads();
+  if (warp < TILE_CLASSES) {  // warp q: the CTA's total of class q -> its range in the list (one atomic), the warps' offsets in place
+    const uint32_t mine = s_warp[warp][lane];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t up = __shfl_up_sync(FULL_MASK, incl, off);
+      if (lane >= static_cast<uint32_t>(off)) incl += up;
+    }
+    s_warp[warp][lane] = incl - mine;
+    if (lane == 31) s_base[warp] = incl ? atomicAdd(&meta->count[warp], incl) : 0u;
+  } else if (warp == TILE_CLASSES) {
+    unsigned long long a = s_sum[lane];
+    uint32_t r = s_ran[lane];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { a += __shfl_xor_sync(FULL_MASK, a, off); r += __shfl_xor_sync(FULL_MASK, r, off); }
+    if (lane == 0 && r) { atomicAdd(&meta->sum, a); atomicAdd(&meta->ran, static_cast<unsigned long long>(r)); }
+  }
+  __syncthreads();
+  if (inside) {
+    lists[static_cast<uint64_t>(k) * n_tiles + s_base[k] + s_warp[k][warp] + rank] = t;
+    cost[t] = 0u;
+  }
+}
+
 }  // namespace
+
+void launch_build_tile_lists(uint32_t *d_cost, uint32_t *d_lists, TileMeta *d_meta, const TileMeta *d_previous, uint32_t n_tiles, cudaStream_t stream) {
+  // longest pass more than 1.5x / 2x / 3x / 4x the mean pass (RDN_TILE_THRESHOLDS: quarters of the mean, ascending — measurement knob)
+  static const TileThresholds th = []() {
+    TileThresholds t;
+    for (uint32_t &q : t.quarters) q = 0xFFFFFFFFu;
+    const uint32_t standard[4] = {6, 8, 12, 16};
+    for (int i = 0; i < 4; ++i) t.quarters[i] = standard[i];
+    if (const char *e = getenv("RDN_TILE_THRESHOLDS")) {
+      for (uint32_t &q : t.quarters) q = 0xFFFFFFFFu;
+      int i = 0;
+      for (const char *p = e; *p && i < TILE_CLASSES - 1; ++i) {
+        t.quarters[i] = static_cast<uint32_t>(strtoul(p, const_cast<char **>(&p), 10));
+        while (*p == ',' || *p == ' ') ++p;
+      }
+    }
+    return t;
+  }();
+  if (n_tiles) k_build_tile_lists<<<(n_tiles + 1023u) / 1024u, 1024, 0, stream>>>(d_cost, d_lists, d_meta, d_previous, n_tiles, th);
+}
 
 // ------------------------------------------------------------------------------------------------ launchers
 void launch_trace_reference(const SceneDev &scene, const rdn_launch &launch, const rdn_ray *d_rays, uint64_t n, rdn_hit *d_hits,
@@ -934,11 +1071,14 @@ bool any_hit_can_end_search(const rdn_launch &launch, const rdn_anyhit_program *
 
 cudaError_t launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch, const TlasRoot &tlas, const rdn_ray *d_rays, uint64_t n,
                                  rdn_hit *d_hits, const TraceScratch &scratch, int sm_count, cudaStream_t stream, bool allow_overlap,
-                                 uint32_t wait_epoch, bool *ties_resolved_in_kernel, const unsigned long long *d_n) {
+                                 uint32_t wait_epoch, bool *ties_resolved_in_kernel, const unsigned long long *d_n,
+                                 TileHistory *history) {
   *ties_resolved_in_kernel = true;
   if (n == 0) return cudaSuccess;
   OrderedParams P;
   P.S = scene; P.L = launch; P.rays = d_rays; P.hits = d_hits; P.n = n; P.scratch = scratch;
+  P.tile_lists = nullptr; P.tile_meta = nullptr; P.tile_cost = nullptr; P.tile_meta_clear = nullptr; P.n_tiles = 0;
+  if (history) history->used = false;
   P.tiles_x = 0; P.width = 0; P.height = 0; P.n_fetch = n; P.n_ptr = d_n;
   if (!d_n && launch.grid_width != 0 && n % launch.grid_width == 0) {
     P.width = launch.grid_width;
@@ -989,6 +1129,13 @@ cudaError_t launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch
     case 110: fn = sharing; break;   // the sharing loop from the first round
     case 120: fn = late; break;      // the plain loop, then the sharing loop for passes that have grown old
     default: fn = P.tiles_x == 0 ? late : plain; break;  // ray lists share (from the 30th round of a pass on), grids do not
+  }
+  if (history && fn == plain && !any_hit && P.tiles_x != 0 && P.irregular_count == 0 &&
+      history->n_tiles == P.tiles_x * ((P.height + 3u) / 4u)) {  // a grid with a tile history (capi.cu)
+    fn = k_trace_ordered_rounds<RDN_ORDERED_K, RDN_ORDERED_MINB, true, false, true, false, false, true, SHARE_NEVER, false, true>;
+    P.tile_lists = history->lists; P.tile_meta = history->meta; P.tile_cost = history->cost; P.tile_meta_clear = history->meta_clear;
+    P.n_tiles = history->n_tiles;
+    history->used = true;
   }
   if ((variant == 60 || variant == 61) && !use_wide4) fn = plain;
   if (P.irregular_count != 0) {  // (the experimentation variants exist for regular scenes only)

@@ -45,14 +45,14 @@ def test_both_arms_describe_the_workload_with_the_same_config():
 
 
 def test_the_kernel_named_in_the_roofline_is_the_one_the_launcher_selects_for_grids():
-    """bench.py quotes ncu numbers of SHIPPED_ORDERED_KERNEL; it must be the instantiation launch_trace_ordered picks for grid launches
-    without an any-hit stage (template arguments as ncu prints them: every parameter, booleans as 0 / 1)"""
+    """bench.py quotes ncu numbers of SHIPPED_ORDERED_KERNEL; it must be the instantiation launch_trace_ordered picks for device-resident
+    grid launches without an any-hit stage — the one that keeps a tile history (template arguments as ncu prints them: every
+    parameter, booleans as 0 / 1)"""
     import re
     sys.path.insert(0, ROOT)
     import bench
     src = open(os.path.join(ROOT, "rendiation_b200", "csrc", "traverse.cu")).read()
-    m = re.search(r"const KernelFn plain = any_hit \? k_trace_ordered_rounds<[^>]*>\s*: k_trace_ordered_rounds<([^>]*)>;", src)
-    assert m, "launcher changed: update this test and bench.SHIPPED_ORDERED_KERNEL"
+    m = re.search(r"// a grid with a tile history \(capi\.cu\)\n\s*fn = k_trace_ordered_rounds<([^>]*)>;", src)
     macros = {name: re.search(r"#define %s (\d+)" % name, src).group(1) for name in ("RDN_ORDERED_K", "RDN_ORDERED_MINB")}
     args = [macros.get(a.strip(), a.strip()) for a in m.group(1).split(",")]
     n_params = len(re.search(r"template <(int K, int MINB,[^>]*)>\n__global__", src).group(1).split(","))

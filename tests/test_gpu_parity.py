@@ -468,6 +468,32 @@ def test_back_to_back_launches_overlap_without_losing_rays():
 
 
 @pytest.mark.gpu
+def test_tile_history_reorders_the_launch_not_the_results():
+    """Device-resident grid launches take their tiles in the order built from the previous launch over a grid of the same size (long
+    passes first).  Whatever the order — first launch (grid order), repeated frames, a moved camera over the same grid, another grid
+    size in between, a grid whose tile count is no multiple of anything, history switched off — every launch gives the oracle's
+    records, and every ray is traced exactly once (the hit buffers start out as 0xAB)."""
+    import torch
+    sp, _ = helpers.torus_scene(160)
+    nt = os.cpu_count() or 4
+    st = torch.cuda.current_stream().cuda_stream
+
+    def frame(W, H, tmin, shift):
+        rays = S.pinhole_rays(W, H, tmin, 100.0, aspect_correct=True)
+        rays["ox"] += np.float32(shift)
+        return rays
+    cases = [(640, 408, 0.0), (640, 408, 0.0), (640, 408, 0.35), (641, 403, 0.0), (640, 408, -0.2), (1021, 517, 0.0), (1021, 517, 0.1), (640, 408, 0.0)]
+    for k, (W, H, shift) in enumerate(cases):
+        rays = frame(W, H, 0.01, shift)
+        want = sp.o.trace(rays, ray_flags=helpers.CULL_BACK, n_threads=nt, want_counters=False)
+        r = torch.from_numpy(rays.view(np.uint8).reshape(-1, 32).copy()).cuda()
+        h = torch.full((rays.shape[0], 32), 0xAB, dtype=torch.uint8, device="cuda")
+        sp.p.trace_closest_device(r.data_ptr(), rays.shape[0], h.data_ptr(), ray_flags=helpers.CULL_BACK, grid_width=W, stream=st)
+        torch.cuda.synchronize()
+        _assert_parity(f"tile_history_launch{k}", h.cpu().numpy().view(api.HIT_DTYPE).reshape(-1), want)
+
+
+@pytest.mark.gpu
 def test_pageable_buffers_go_through_the_staging_pipeline():
     """Ordinary caller memory (what the reference's API hands over) is staged chunk by chunk through page-locked buffers by several
     host threads: several chunks, buffers at odd addresses (the streaming copy aligns its stores itself), a page-locked array on

@@ -29,6 +29,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "tests", "simt"))
 SRC = os.path.join(ROOT, "rendiation_b200", "csrc", "traverse.cu")
+INC = os.path.join(ROOT, "rendiation_b200", "csrc", "ordered_rounds.inc")
+INC_AT = 0  # line of traverse.cu whose #include the loop's instructions are attributed to (set by region_lines)
 OBJ = os.path.join(ROOT, "rendiation_b200", "csrc", "_obj", "traverse.o")
 
 
@@ -55,6 +57,15 @@ def region_lines(names: list[str]):
 
     k0 = next(i for i, l in enumerate(lines) if "k_trace_ordered_rounds(const __grid_constant__" in l)
     kernel = collect(k0, lambda l, i: l.startswith("}  // namespace"))
+    # the round loop lives in ordered_rounds.inc, included once per loop of the kernel: its lines get positions right behind the
+    # include line of the plain instantiations (the last one), include_line + line / 1e5
+    global INC_AT
+    INC_AT = max(i + 1 for i in range(k0, len(lines)) if lines[i].strip() == '#include "ordered_rounds.inc"')
+    for i, l in enumerate(open(INC).read().split("\n")):
+        m = re.search(r"RDN_COST\((COST_[A-Z0-9_]+)\)", l)
+        if m:
+            kernel.append((INC_AT + (i + 1) * 1e-5, names.index(m.group(1))))
+    kernel.sort()
     t0 = next(i for i, l in enumerate(lines) if "bool triangle_test(" in l)
     t1 = next(i for i in range(t0, len(lines)) if lines[i] == "}")
     callee = collect(t0, lambda l, i: i >= t1)
@@ -91,10 +102,11 @@ def static_counts(template_args: str, names: list[str]) -> tuple[list[float], in
         if m:
             if not chain_open:
                 chain, chain_open = [], True
-            if m.group(1).endswith("traverse.cu"):
-                chain.append(int(m.group(2)))
-            if m.group(4) and m.group(3).endswith("traverse.cu"):
-                chain.append(int(m.group(4)))
+            for f, l in ((m.group(1), m.group(2)), (m.group(3), m.group(4))):
+                if f and f.endswith("traverse.cu"):
+                    chain.append(int(l))
+                elif f and f.endswith("ordered_rounds.inc"):
+                    chain.append(INC_AT + int(l) * 1e-5)
             continue
         mi = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
         if not mi:
@@ -115,7 +127,7 @@ def static_counts(template_args: str, names: list[str]) -> tuple[list[float], in
             if mi.group(1).startswith("LDG"):
                 tri_loads += 1
         counts[region] += 1
-        DUMP.setdefault(region, []).append(f"{outer:5d} {line.strip()}")
+        DUMP.setdefault(region, []).append(f"{outer:10.5f} {line.strip()}")
     copies = max(1, round(tri_loads / 2))
     for r in tri_family:
         counts[r] /= copies
@@ -189,10 +201,10 @@ def dynamic_counts(cfg: str, names: list[str]):
     return list(warp), list(lane), rays.shape[0], dt, bool(same)
 
 
-def mangled(k, drain=True, ld256=True, wide4=False, inst_loop=False, share=False, anyhit=False):
-    """mangled template arguments <K, MINB, DRAIN_TIES, IRREGULAR, LD256, HOT, WIDE4, INST_LOOP, SHARE, ANYHIT> of an instantiation"""
+def mangled(k, drain=True, ld256=True, wide4=False, inst_loop=False, share=False, anyhit=False, history=False):
+    """mangled template arguments <K, MINB, DRAIN_TIES, IRREGULAR, LD256, HOT, WIDE4, INST_LOOP, SHARE, ANYHIT, HISTORY> of an instantiation"""
     bl = lambda v: "Lb1E" if v else "Lb0E"
-    return f"ILi{k}ELi8E{bl(drain)}Lb0E{bl(ld256)}Lb0E{bl(wide4)}{bl(inst_loop)}Li{int(share)}E{bl(anyhit)}E"  # share: 0 never, 1 always, 2 late
+    return f"ILi{k}ELi8E{bl(drain)}Lb0E{bl(ld256)}Lb0E{bl(wide4)}{bl(inst_loop)}Li{int(share)}E{bl(anyhit)}{bl(history)}E"  # share: 0 never, 1 always, 2 late
 
 
 def main():
