@@ -434,11 +434,18 @@ def measure_other_configs(sysm_c2, dev, iters=12):
     o4 = oracle.Scene(); ob = o4.create_blas([(pos, idx.reshape(-1), 1)]); o4.bind_tlas([o4.create_tlas(S.instance_grid(100, 100, ob, 3.5, -200.0))]); assert o4.build() == 0
     r4 = torch.from_numpy(S.pinhole_rays(W, H, 0.0, 1000.0, aspect_correct=True).view(np.uint8).reshape(-1, 32).copy()).to(dev)
     run("c4", s4, o4, r4, n, RAY_FLAGS, W, "1920x1080 primary rays vs 10,000 transform-instanced copies of a 100,352-triangle sphere, BASELINE configs[3]")
-    t0 = time.perf_counter()
-    s4.update_top_level_acceleration_structure(t4, moved)
-    s4.commit()
+    # every instance moves: rdn_rt_tlas_update + commit (the TLAS part alone is rebuilt, the device blob patched in place); the first
+    # update also allocates the page-locked staging buffer of the patches, so the figure is the median of five
+    updates = []
+    for k in range(5):
+        nxt = moved if k % 2 == 0 else inst
+        t0 = time.perf_counter()
+        s4.update_top_level_acceleration_structure(t4, nxt)
+        s4.commit()
+        updates.append((time.perf_counter() - t0) * 1e3)
     out["c4"]["commit_ms"] = commit_ms
-    out["c4"]["tlas_only_update_ms"] = (time.perf_counter() - t0) * 1e3
+    out["c4"]["tlas_only_update_ms"] = sorted(updates)[2]
+    out["c4"]["tlas_only_update_ms_first"] = updates[0]
     return out
 
 
