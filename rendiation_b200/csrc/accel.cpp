@@ -141,7 +141,7 @@ static void set_child(WideNode &w, int which, const Box3 *box, uint32_t ref) {
   (which == 0 ? w.ref0 : w.ref1) = ref;
 }
 
-uint32_t emit_wide_nodes(const std::vector<FlattenBVHNode> &nodes, uint64_t slot_offset, std::vector<WideNode> &out,
+uint32_t emit_wide_nodes(const BigVector<FlattenBVHNode> &nodes, uint64_t slot_offset, BigVector<WideNode> &out,
                          bool &capacity_error, const TlasBounding *item_bounds) {
   if (nodes.empty() || nodes[0].primitive_end == nodes[0].primitive_start) return REF_EMPTY;
   // Wide index of every inner reference node, after the pseudo root: the top of the tree breadth first (pseudo root + up to
@@ -261,7 +261,7 @@ uint32_t emit_wide_nodes(const std::vector<FlattenBVHNode> &nodes, uint64_t slot
   return static_cast<uint32_t>(base);
 }
 
-uint32_t emit_wide4_nodes(const std::vector<FlattenBVHNode> &nodes, uint64_t slot_offset, std::vector<Wide4Node> &out,
+uint32_t emit_wide4_nodes(const BigVector<FlattenBVHNode> &nodes, uint64_t slot_offset, BigVector<Wide4Node> &out,
                           bool &capacity_error) {
   if (nodes.empty() || nodes[0].primitive_end == nodes[0].primitive_start) return REF_EMPTY;
   const uint64_t base = out.size();
@@ -745,52 +745,53 @@ int NaiveSahBvhSource::build(const std::vector<uint32_t> &tlas_binding, FlatScen
 }
 
 // ------------------------------------------------------------------------------------------------ blob
-template <typename T>
-static void place(std::vector<uint8_t> &blob, BlobHeader &h, int id, const std::vector<T> &v) {
-  uint64_t off = (blob.size() + BLOB_ALIGN - 1) / BLOB_ALIGN * BLOB_ALIGN;
+template <typename V>
+static void place(uint64_t &cursor, BlobHeader &h, std::vector<FlatScene::ArrayRef> &arrays, int id, const V &v) {
+  using T = typename V::value_type;
+  const uint64_t off = (cursor + BLOB_ALIGN - 1) / BLOB_ALIGN * BLOB_ALIGN;
   // every array keeps at least one zeroed element so kernels never see a null base (create_gpu_buffer, mod.rs:386-400)
   const uint64_t bytes = (v.empty() ? 1 : v.size()) * sizeof(T);
-  blob.resize(off + bytes, 0);
-  if (!v.empty()) std::memcpy(blob.data() + off, v.data(), v.size() * sizeof(T));
+  cursor = off + bytes;
   h.offset[id] = off;
   h.count[id] = v.size();
   h.elem_size[id] = sizeof(T);
+  arrays.push_back(FlatScene::ArrayRef{id, v.data(), v.size() * sizeof(T)});
 }
 
-std::vector<uint8_t> FlatScene::serialize() const {
+BlobHeader FlatScene::layout(std::vector<ArrayRef> &arrays) const {
   BlobHeader h;
   std::memset(&h, 0, sizeof(h));
   h.magic = BLOB_MAGIC;
   h.version = BLOB_VERSION;
   h.header_bytes = sizeof(BlobHeader);
-  auto padded = [](uint64_t count, uint64_t elem) { return ((count ? count : 1) * elem + BLOB_ALIGN - 1) / BLOB_ALIGN * BLOB_ALIGN + BLOB_ALIGN; };
-  std::vector<uint8_t> blob;
-  blob.reserve(sizeof(BlobHeader) + BLOB_ALIGN + padded(tlas_binding.size(), 4) + padded(tlas_root.size(), sizeof(TlasRoot)) +
-               padded(tlas_bvh_forest.size(), sizeof(DeviceBVHNode)) + padded(tlas_bounding.size(), sizeof(TlasBounding)) +
-               padded(instances.size(), sizeof(InstanceRecord)) + padded(blas_meta.size(), sizeof(BlasMeta)) +
-               padded(geometry_meta.size(), sizeof(GeometryMeta)) + padded(tri_bvh_forest.size(), sizeof(DeviceBVHNode)) +
-               padded(triangles.size(), sizeof(TriRecord)) + padded(slot_info.size(), sizeof(SlotInfo)) +
-               padded(wide_nodes.size(), sizeof(WideNode)) + padded(prim_to_slot.size(), 4) + padded(irregular_instances.size(), 4) +
-               padded(irregular_leaf_boxes.size(), sizeof(LeafBox)) + padded(wide4_nodes.size(), sizeof(Wide4Node)));  // one allocation: every place() below only appends
-  blob.resize(sizeof(BlobHeader), 0);
-  place(blob, h, ARR_TLAS_BINDING, tlas_binding);
-  place(blob, h, ARR_TLAS_ROOT, tlas_root);
-  place(blob, h, ARR_TLAS_BVH_FOREST, tlas_bvh_forest);
-  place(blob, h, ARR_TLAS_BOUNDING, tlas_bounding);
-  place(blob, h, ARR_INSTANCES, instances);
-  place(blob, h, ARR_BLAS_META, blas_meta);
-  place(blob, h, ARR_GEOMETRY_META, geometry_meta);
-  place(blob, h, ARR_TRI_BVH_FOREST, tri_bvh_forest);
-  place(blob, h, ARR_TRIANGLES, triangles);
-  place(blob, h, ARR_SLOT_INFO, slot_info);
-  place(blob, h, ARR_WIDE_NODES, wide_nodes);
-  place(blob, h, ARR_PRIM_TO_SLOT, prim_to_slot);
-  place(blob, h, ARR_IRREGULAR_INSTANCES, irregular_instances);
-  place(blob, h, ARR_IRREGULAR_LEAF_BOXES, irregular_leaf_boxes);
-  place(blob, h, ARR_WIDE4_NODES, wide4_nodes);
-  blob.resize((blob.size() + BLOB_ALIGN - 1) / BLOB_ALIGN * BLOB_ALIGN, 0);
-  h.total_bytes = blob.size();
+  arrays.clear();
+  uint64_t cursor = sizeof(BlobHeader);
+  place(cursor, h, arrays, ARR_TLAS_BINDING, tlas_binding);
+  place(cursor, h, arrays, ARR_TLAS_ROOT, tlas_root);
+  place(cursor, h, arrays, ARR_TLAS_BVH_FOREST, tlas_bvh_forest);
+  place(cursor, h, arrays, ARR_TLAS_BOUNDING, tlas_bounding);
+  place(cursor, h, arrays, ARR_INSTANCES, instances);
+  place(cursor, h, arrays, ARR_BLAS_META, blas_meta);
+  place(cursor, h, arrays, ARR_GEOMETRY_META, geometry_meta);
+  place(cursor, h, arrays, ARR_TRI_BVH_FOREST, tri_bvh_forest);
+  place(cursor, h, arrays, ARR_TRIANGLES, triangles);
+  place(cursor, h, arrays, ARR_SLOT_INFO, slot_info);
+  place(cursor, h, arrays, ARR_WIDE_NODES, wide_nodes);
+  place(cursor, h, arrays, ARR_PRIM_TO_SLOT, prim_to_slot);
+  place(cursor, h, arrays, ARR_IRREGULAR_INSTANCES, irregular_instances);
+  place(cursor, h, arrays, ARR_IRREGULAR_LEAF_BOXES, irregular_leaf_boxes);
+  place(cursor, h, arrays, ARR_WIDE4_NODES, wide4_nodes);
+  h.total_bytes = (cursor + BLOB_ALIGN - 1) / BLOB_ALIGN * BLOB_ALIGN;
+  return h;
+}
+
+std::vector<uint8_t> FlatScene::serialize() const {
+  std::vector<ArrayRef> arrays;
+  const BlobHeader h = layout(arrays);
+  std::vector<uint8_t> blob(h.total_bytes, 0);
   std::memcpy(blob.data(), &h, sizeof(h));
+  for (const ArrayRef &a : arrays)
+    if (a.bytes) std::memcpy(blob.data() + h.offset[a.id], a.data, a.bytes);
   return blob;
 }
 

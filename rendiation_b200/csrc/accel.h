@@ -35,18 +35,21 @@ struct FlatScene {
   std::vector<InstanceRecord> instances;
   std::vector<BlasMeta> blas_meta;
   std::vector<GeometryMeta> geometry_meta;
-  std::vector<DeviceBVHNode> tri_bvh_forest;
-  std::vector<TriRecord> triangles;
-  std::vector<SlotInfo> slot_info;
-  std::vector<WideNode> wide_nodes;
+  BigVector<DeviceBVHNode> tri_bvh_forest;
+  BigVector<TriRecord> triangles;
+  BigVector<SlotInfo> slot_info;
+  BigVector<WideNode> wide_nodes;
   std::vector<uint32_t> prim_to_slot;
   std::vector<uint32_t> irregular_instances;
   std::vector<LeafBox> irregular_leaf_boxes;
-  std::vector<Wide4Node> wide4_nodes;
+  BigVector<Wide4Node> wide4_nodes;
   BuildStats stats;
 
   // pack into one contiguous, BLOB_ALIGN-aligned byte image starting with a BlobHeader
   std::vector<uint8_t> serialize() const;
+  // the same image without building it: where every array goes (header filled in, total_bytes included) and where it comes from
+  struct ArrayRef { int id; const void *data; uint64_t bytes; };
+  BlobHeader layout(std::vector<ArrayRef> &arrays) const;
 };
 
 class NaiveSahBvhSource {
@@ -109,10 +112,10 @@ Box3 box_apply_matrix(const Box3 &b, const Mat4 &m);
 // instead of one multi-slot leaf reference: the ordered kernel finds the instances a ray can enter with node steps rather than
 // one instance-box test per slot.  Visibility is unchanged — nested boxes keep the slab test monotone, and entering an instance
 // still takes the reference's test of its own box.
-uint32_t emit_wide_nodes(const std::vector<FlattenBVHNode> &nodes, uint64_t slot_offset, std::vector<WideNode> &out,
+uint32_t emit_wide_nodes(const BigVector<FlattenBVHNode> &nodes, uint64_t slot_offset, BigVector<WideNode> &out,
                          bool &capacity_error, const TlasBounding *item_bounds = nullptr);
 // the same for the 4-wide view: one node per inner reference node at even depth below the root (its inner children are absorbed)
-uint32_t emit_wide4_nodes(const std::vector<FlattenBVHNode> &nodes, uint64_t slot_offset, std::vector<Wide4Node> &out,
+uint32_t emit_wide4_nodes(const BigVector<FlattenBVHNode> &nodes, uint64_t slot_offset, BigVector<Wide4Node> &out,
                           bool &capacity_error);
 
 }  // namespace rdn

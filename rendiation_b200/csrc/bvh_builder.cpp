@@ -35,15 +35,15 @@ Vec3 box_center(const Box3 &b) { return (b.min + b.max) * 0.5f; }
 
 static inline float component(const Vec3 &v, int axis) { return axis == 0 ? v.x : (axis == 1 ? v.y : v.z); }
 
-static Box3 bounding_of_range(const std::vector<BuildPrimitive> &src, const std::vector<uint64_t> &index, uint64_t begin,
+static Box3 bounding_of_range(const BigVector<BuildPrimitive> &src, const BigVector<uint64_t> &index, uint64_t begin,
                               uint64_t end) {
   Box3 r = box_empty();
   for (uint64_t i = begin; i < end; ++i) expand(r, src[index[i]].bounding);
   return r;
 }
 
-SplitResult BalanceTree::split(const FlattenBVHNode &parent, const std::vector<BuildPrimitive> &src,
-                               std::vector<uint64_t> &index, BuildStats &) {
+SplitResult BalanceTree::split(const FlattenBVHNode &parent, const BigVector<BuildPrimitive> &src,
+                               BigVector<uint64_t> &index, BuildStats &) {
   SplitResult r;
   r.axis = longest_axis(parent.bounding);
   const uint64_t begin = parent.primitive_start, end = parent.primitive_end;
@@ -71,7 +71,7 @@ static inline uint64_t saturating_usize(float v) {
   return static_cast<uint64_t>(v);
 }
 
-SplitResult SAH::split(const FlattenBVHNode &parent, const std::vector<BuildPrimitive> &src, std::vector<uint64_t> &index,
+SplitResult SAH::split(const FlattenBVHNode &parent, const BigVector<BuildPrimitive> &src, BigVector<uint64_t> &index,
                        BuildStats &stats) {
   const uint64_t begin = parent.primitive_start, end = parent.primitive_end;
   const size_t n_part = pre_partition_.size();
@@ -383,7 +383,7 @@ namespace {
 // leaf is reached the most recent parked sibling is emitted next, which fixes its parent's left_count.  Node indices are local
 // to `nodes` (the subtree root is node 0); left_count is position independent.
 void build_subtree(const Box3 &box, uint64_t start, uint64_t end, uint64_t depth0, BVHBuildStrategy &strategy, const TreeBuildOption &option,
-                   const std::vector<BuildPrimitive> &primitives, std::vector<uint64_t> &index, std::vector<FlattenBVHNode> &nodes,
+                   const BigVector<BuildPrimitive> &primitives, BigVector<uint64_t> &index, BigVector<FlattenBVHNode> &nodes,
                    BuildStats &stats) {
   auto make_node = [&](const Box3 &b, uint64_t s, uint64_t e) {
     FlattenBVHNode nd;
@@ -429,7 +429,7 @@ void merge_stats(BuildStats &into, const BuildStats &from) {
 FlattenBVH FlattenBVH::build(const Box3 *boxes, uint64_t n, BVHBuildStrategy &strategy, const TreeBuildOption &option, unsigned n_threads) {
   const auto t_begin = std::chrono::steady_clock::now();
   FlattenBVH out;
-  std::vector<BuildPrimitive> primitives(n);
+  BigVector<BuildPrimitive> primitives(n);
   out.sorted_primitive_index.resize(n);
   parallel_for(n, PARALLEL_BUILD_MIN, [&](uint64_t begin, uint64_t end) {
     for (uint64_t i = begin; i < end; ++i) {
@@ -484,7 +484,7 @@ FlattenBVH FlattenBVH::build(const Box3 *boxes, uint64_t n, BVHBuildStrategy &st
         fprintf(stderr, "[rdn build] top split of %llu primitives: %.1f us\n", static_cast<unsigned long long>(t.end - t.start),
                 std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_split).count());
     };
-    if (cand.size() > 1 && (cand.size() * 4 >= n_threads || largest < 8192)) {
+    if (cand.size() > 1 && (cand.size() >= n_threads || largest < 8192)) {  // (enough of them to occupy every thread, or small)
       run_parallel(static_cast<unsigned>(cand.size()), [&](unsigned k) {
         std::unique_ptr<BVHBuildStrategy> mine = strategy.clone();
         split_one(*mine, k);
@@ -510,7 +510,7 @@ FlattenBVH FlattenBVH::build(const Box3 *boxes, uint64_t n, BVHBuildStrategy &st
   const bool timing = getenv("RDN_BUILD_TIMING") != nullptr;
   const auto t_top = std::chrono::steady_clock::now();
   // ---- the open subtrees on worker threads, largest first
-  struct Task { int top; std::vector<FlattenBVHNode> nodes; BuildStats stats; };
+  struct Task { int top; BigVector<FlattenBVHNode> nodes; BuildStats stats; };
   std::vector<Task> tasks(open.size());
   for (size_t k = 0; k < open.size(); ++k) { tasks[k].top = open[k]; top[open[k]].task = static_cast<int>(k); }
   std::vector<size_t> order(tasks.size());
@@ -535,39 +535,54 @@ FlattenBVH FlattenBVH::build(const Box3 *boxes, uint64_t n, BVHBuildStrategy &st
   out.stats.build_threads = workers;
   const auto t_workers = std::chrono::steady_clock::now();
 
-  // ---- splice in pre-order
+  // ---- splice in pre-order: the top nodes and every task's position are laid out by one walk over the (small) top of the tree,
+  // then the tasks' nodes are copied to their places by all threads
   uint64_t total = 0;
   for (const Task &task : tasks) { total += task.nodes.size(); merge_stats(out.stats, task.stats); }
-  out.nodes.reserve(total + top.size());
-  struct Frame { int top; uint64_t node; int stage; };
-  std::vector<Frame> stack{Frame{0, 0, 0}};
-  while (!stack.empty()) {
-    Frame &f = stack.back();
-    const Top &t = top[f.top];
-    if (t.task >= 0) {
-      const uint64_t base = out.nodes.size();
-      for (FlattenBVHNode nd : tasks[t.task].nodes) { nd.self_index += base; out.nodes.push_back(nd); }
-      stack.pop_back();
-      continue;
+  out.nodes.resize(total + top.size() - tasks.size());
+  std::vector<uint64_t> task_base(tasks.size(), 0);
+  {
+    uint64_t cursor = 0;
+    struct Frame { int top; uint64_t node; int stage; };
+    std::vector<Frame> stack{Frame{0, 0, 0}};
+    while (!stack.empty()) {
+      Frame &f = stack.back();
+      const Top &t = top[f.top];
+      if (t.task >= 0) {
+        task_base[t.task] = cursor;
+        cursor += tasks[t.task].nodes.size();
+        stack.pop_back();
+        continue;
+      }
+      if (f.stage == 0) {
+        FlattenBVHNode nd;
+        std::memset(&nd, 0, sizeof(nd));
+        nd.bounding = t.box; nd.primitive_start = t.start; nd.primitive_end = t.end; nd.self_index = cursor;
+        nd.has_child = 1; nd.split_axis = t.axis;
+        f.node = cursor;
+        out.nodes[cursor++] = nd;
+        f.stage = 1;
+        const int left = t.left;
+        stack.push_back(Frame{left, 0, 0});
+      } else if (f.stage == 1) {
+        out.nodes[f.node].left_count = cursor - (f.node + 1);
+        f.stage = 2;
+        const int right = t.right;
+        stack.push_back(Frame{right, 0, 0});
+      } else {
+        stack.pop_back();
+      }
     }
-    if (f.stage == 0) {
-      FlattenBVHNode nd;
-      std::memset(&nd, 0, sizeof(nd));
-      nd.bounding = t.box; nd.primitive_start = t.start; nd.primitive_end = t.end; nd.self_index = out.nodes.size();
-      nd.has_child = 1; nd.split_axis = t.axis;
-      f.node = out.nodes.size();
-      out.nodes.push_back(nd);
-      f.stage = 1;
-      const int left = t.left;
-      stack.push_back(Frame{left, 0, 0});
-    } else if (f.stage == 1) {
-      out.nodes[f.node].left_count = out.nodes.size() - (f.node + 1);
-      f.stage = 2;
-      const int right = t.right;
-      stack.push_back(Frame{right, 0, 0});
-    } else {
-      stack.pop_back();
-    }
+  }
+  {
+    std::atomic<size_t> next_copy{0};
+    run_parallel(workers, [&](unsigned) {
+      for (size_t k; (k = next_copy.fetch_add(1)) < tasks.size();) {
+        const uint64_t base = task_base[k];
+        const BigVector<FlattenBVHNode> &from = tasks[k].nodes;
+        for (size_t i = 0; i < from.size(); ++i) { FlattenBVHNode nd = from[i]; nd.self_index += base; out.nodes[base + i] = nd; }
+      }
+    });
   }
   if (timing) {
     const auto t_end = std::chrono::steady_clock::now();
@@ -578,7 +593,7 @@ FlattenBVH FlattenBVH::build(const Box3 *boxes, uint64_t n, BVHBuildStrategy &st
   return out;
 }
 
-std::vector<std::pair<uint32_t, uint32_t>> compute_bvh_next(const std::vector<FlattenBVHNode> &nodes) {
+std::vector<std::pair<uint32_t, uint32_t>> compute_bvh_next(const BigVector<FlattenBVHNode> &nodes) {
   std::vector<std::pair<uint32_t, uint32_t>> result;
   result.reserve(nodes.size());
   std::vector<uint32_t> pending_right;

@@ -14,6 +14,7 @@
 #include <utility>
 #include <vector>
 
+#include "big_vector.h"
 #include "rdn_math.h"
 
 namespace rdn {
@@ -66,16 +67,16 @@ struct BuildStats {
 class BVHBuildStrategy {
  public:
   virtual ~BVHBuildStrategy() = default;
-  virtual SplitResult split(const FlattenBVHNode &parent, const std::vector<BuildPrimitive> &build_source,
-                            std::vector<uint64_t> &index_source, BuildStats &stats) = 0;
+  virtual SplitResult split(const FlattenBVHNode &parent, const BigVector<BuildPrimitive> &build_source,
+                            BigVector<uint64_t> &index_source, BuildStats &stats) = 0;
   // a strategy object holds scratch (SAH's buckets): every worker thread of the parallel build splits with its own copy
   virtual std::unique_ptr<BVHBuildStrategy> clone() const = 0;
 };
 
 class BalanceTree : public BVHBuildStrategy {
  public:
-  SplitResult split(const FlattenBVHNode &parent, const std::vector<BuildPrimitive> &build_source,
-                    std::vector<uint64_t> &index_source, BuildStats &stats) override;
+  SplitResult split(const FlattenBVHNode &parent, const BigVector<BuildPrimitive> &build_source,
+                    BigVector<uint64_t> &index_source, BuildStats &stats) override;
   std::unique_ptr<BVHBuildStrategy> clone() const override { return std::make_unique<BalanceTree>(); }
 };
 
@@ -83,8 +84,8 @@ class SAH : public BVHBuildStrategy {
  public:
   explicit SAH(uint32_t pre_partition_check_count);
   uint32_t bucket_count() const { return static_cast<uint32_t>(pre_partition_.size()); }
-  SplitResult split(const FlattenBVHNode &parent, const std::vector<BuildPrimitive> &build_source,
-                    std::vector<uint64_t> &index_source, BuildStats &stats) override;
+  SplitResult split(const FlattenBVHNode &parent, const BigVector<BuildPrimitive> &build_source,
+                    BigVector<uint64_t> &index_source, BuildStats &stats) override;
   // (a worker's copy splits on its own thread only: the workers already occupy the cores)
   std::unique_ptr<BVHBuildStrategy> clone() const override {
     auto copy = std::make_unique<SAH>(static_cast<uint32_t>(pre_partition_.size()));
@@ -108,8 +109,8 @@ class SAH : public BVHBuildStrategy {
 };
 
 struct FlattenBVH {
-  std::vector<FlattenBVHNode> nodes;
-  std::vector<uint64_t> sorted_primitive_index;
+  BigVector<FlattenBVHNode> nodes;
+  BigVector<uint64_t> sorted_primitive_index;
   BuildStats stats;
 
   // The reference builds on one thread (`// todo par`, naive/mod.rs:147).  A split only reads and rewrites its own index
@@ -133,7 +134,7 @@ void warm_worker_pool();
 
 constexpr uint32_t INVALID_NEXT = 0xFFFFFFFFu;
 // (hit_next, miss_next) per node for the stackless threaded walk
-std::vector<std::pair<uint32_t, uint32_t>> compute_bvh_next(const std::vector<FlattenBVHNode> &nodes);
+std::vector<std::pair<uint32_t, uint32_t>> compute_bvh_next(const BigVector<FlattenBVHNode> &nodes);
 
 // box3.rs helpers the builder and the TLAS assembly need
 int longest_axis(const Box3 &b);
