@@ -12,6 +12,9 @@
 #include <thread>
 
 #include <unistd.h>
+#if defined(__linux__)
+#include <sched.h>
+#endif
 
 namespace rdn {
 
@@ -210,9 +213,27 @@ SplitResult SAH::split(const FlattenBVHNode &parent, const BigVector<BuildPrimit
   return r;
 }
 
+// CPUs this process may reasonably use: those its affinity mask allows, and — one process per GPU under torchrun, several of them
+// bound to the same socket — no more than its share of the machine (LOCAL_WORLD_SIZE).  Eight ranks that each start a thread per
+// CPU of the box run slower than eight ranks with eight threads each (the pageable host-buffer path at 8 GPUs: 604 against 914
+// Mrays/s for the driver's own staging, profiles/bench_r3m_n8.json).  RDN_POOL_THREADS overrides.
+unsigned usable_cpu_count() {
+  unsigned hw = std::thread::hardware_concurrency();
+  if (hw == 0) hw = 1;
+  unsigned allowed = hw;
+#if defined(__linux__)
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) allowed = static_cast<unsigned>(CPU_COUNT(&set));
+#endif
+  unsigned ranks = 1;
+  if (const char *e = getenv("LOCAL_WORLD_SIZE")) { const int v = atoi(e); if (v > 1) ranks = static_cast<unsigned>(v); }
+  unsigned n = std::min(allowed, (hw + ranks - 1) / ranks);
+  if (const char *e = getenv("RDN_POOL_THREADS")) { const int v = atoi(e); if (v >= 1) n = static_cast<unsigned>(v); }
+  return n ? n : 1u;
+}
+
 unsigned build_thread_count() {
-  unsigned n = std::thread::hardware_concurrency();
-  if (n == 0) n = 1;
+  unsigned n = usable_cpu_count();
   if (const char *e = getenv("RDN_BUILD_THREADS")) {
     const int cap = atoi(e);
     if (cap >= 1 && static_cast<unsigned>(cap) < n) n = static_cast<unsigned>(cap);
@@ -339,9 +360,9 @@ WorkerPool *the_pool() {
   std::lock_guard<std::mutex> g(g_pool.mutex);
   const pid_t me = getpid();
   if (!g_pool.pool || g_pool.pid != me) {  // first use, or first use in a forked child (the parent's pool object is leaked there)
-    unsigned hw = std::thread::hardware_concurrency();
-    if (hw <= 1) return nullptr;
-    g_pool.pool = new WorkerPool(hw - 1);
+    const unsigned cpus = usable_cpu_count();
+    if (cpus <= 1) return nullptr;
+    g_pool.pool = new WorkerPool(cpus - 1);
     g_pool.pid = me;
   }
   return g_pool.pool;

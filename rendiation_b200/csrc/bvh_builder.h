@@ -123,7 +123,9 @@ struct FlattenBVH {
 constexpr uint64_t PARALLEL_BUILD_MIN = 1u << 12;
 constexpr uint64_t PARALLEL_SPLIT_MIN = 1u << 11;  // a single SAH split over at least this many primitives uses all threads too
 
-// worker threads for host-side loops: min(hardware concurrency, RDN_BUILD_THREADS), at least 1
+// CPUs this process may use: its affinity mask, capped by its share of the machine under torchrun (LOCAL_WORLD_SIZE); RDN_POOL_THREADS overrides
+unsigned usable_cpu_count();
+// worker threads for host-side loops: min(usable_cpu_count(), RDN_BUILD_THREADS), at least 1
 unsigned build_thread_count();
 // fn(begin, end) over [0, n) in contiguous chunks, one per thread (sequential below `min_parallel` items)
 void parallel_for(uint64_t n, uint64_t min_parallel, const std::function<void(uint64_t, uint64_t)> &fn);
