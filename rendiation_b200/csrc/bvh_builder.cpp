@@ -281,6 +281,10 @@ class WorkerPool {
 
   void run(unsigned n, const std::function<void(unsigned)> &fn) {
     std::lock_guard<std::mutex> one_section(run_mutex_);
+    struct InSection {  // (a section opened from inside a chunk the caller itself runs stays on the caller: see the_pool)
+      InSection() { t_pool_worker = true; }
+      ~InSection() { t_pool_worker = false; }
+    } in_section;
     const uint64_t g = (ticket_.load(std::memory_order_relaxed) >> 32) + 1;
     fn_.store(&fn, std::memory_order_relaxed);
     n_.store(n, std::memory_order_relaxed);

@@ -23,8 +23,11 @@
 //                           queued at refill instead of being traversed and re-walked over their whole range.  The queue is
 //                           drained inside the kernel by warps that ran out of rays (last CTA sweeps the rest); consecutive
 //                           launches on a stream overlap their tails (programmatic dependent launch, two scratch sets,
-//                           epoch gate).  Template switches select measured-and-rejected experiments kept for A/B runs
-//                           (RDN_ORDERED_VARIANT, see launch_trace_ordered and DESIGN.md §5).
+//                           epoch gate).  The round loop itself is ordered_rounds.inc.  Template switches select the shipped
+//                           forms (tile history for grids, late work sharing for lists, any-hit stage) and the
+//                           measured-and-rejected experiments kept for A/B runs (RDN_ORDERED_VARIANT, see
+//                           launch_trace_ordered and DESIGN.md §5).
+//   k_build_tile_lists      behind a grid launch that noted its pass durations: the tiles filed by class for the next launch.
 //   k_resolve_ties          the queue walked by a separate kernel, one thread per entry: launches of a TLAS that lists
 //                           irregular instances (their queue can be long), and RDN_ORDERED_VARIANT=9.
 #include <cuda_runtime.h>
@@ -584,10 +587,15 @@ __device__ __forceinline__ void drain_tie_queue(const OrderedParams &P) {
 // the whole refill block).  LD256: 256-bit loads / stores for nodes, triangles, instance boxes, rays and hit records.  INST_LOOP:
 // the instances of a TLAS leaf whose box the ray misses are skipped in a loop instead of costing a round each, and a BLAS of one
 // geometry is entered without a geometry-iterator round (+2..4 % with K = 3, profiles/kbench_r2a_*.log).  SHARE: the lanes of a
-// warp share the work of its long rays (see the vote) — used for launches that are ray LISTS (bounce / shadow waves), whose
-// duration is the latency of their longest rays: +24 % on config 3 (passes older than 30 rounds, at most 16 busy lanes, donors with
-// two or more deferred subtrees); the instantiation itself costs 6 % before anything is shared, which grids never win back, so
-// they keep the plain loop (profiles/kbench_r2h_*.log, kbench_r2u_*.log, kbench_r2v_*.log).
+// warp share the work of its long rays (see the vote in ordered_rounds.inc) — used for launches that are ray LISTS (bounce / shadow
+// waves), whose duration is the latency of their longest rays: +24 % on config 3 (passes older than 30 rounds, at most 16 busy
+// lanes, donors with two or more deferred subtrees).  SHARE_ALWAYS runs the sharing loop from the first round; SHARE_LATE (the
+// lists' default) runs the plain loop and hands a pass that has grown old over to the sharing loop.  Either way the kernel is 5-6 %
+// slower than the plain one before anything is shared, which grids never win back: they keep the plain loop
+// (profiles/kbench_r2h_*.log, kbench_r2u_*.log, kbench_r2v_*.log, kbench_r2x_late_sharing.log).  ANYHIT: candidates of non-opaque
+// geometry go through the any-hit stage.  HISTORY (device-resident grids): the tiles are taken in the order of the lists
+// k_build_tile_lists made from the pass durations an earlier launch over the grid noted — long tiles first — and the launch notes its
+// own (+7..9 % on serialised launches of configs 1 / 2, profiles/kbench_r3h_tile_history.log).
 // Experiments kept for A/B runs.  HOT: the top levels of the TLAS tree and of the largest geometry tree (breadth-first blocks of
 // HOT_TOP_NODES wide nodes, 8 KB each) are copied into shared memory with cp.async.bulk (TMA, completion on an mbarrier) when the
 // CTA starts, and node fetches that fall into either block read shared memory instead of L1 (measured 9-13 % slower).  WIDE4: the
