@@ -66,7 +66,8 @@ typedef struct rdn_ray { float ox, oy, oz, tmin, dx, dy, dz, tmax; } rdn_ray;
 /* Launch-uniform part of ShaderRayTraceCallStoragePayload (ctx.rs:15-29): tlas_idx, ray_flags, cull_mask, the SBT ray
  * configuration and miss index.
  * grid_width: optional hint — rays form a row-major 2D launch of this width (launch_size.x); 0 = plain list.
- * The result is identical either way; the hint only lets the kernel walk rays in 8x4 pixel tiles.
+ * The result is identical either way; the hint lets the kernel walk rays in 8x4 pixel tiles and, for device-resident launches,
+ * start the tiles that took longest in the previous launch over a grid of the same size first.
  * any_hit: what the any-hit stage of the pipeline decides for candidate hits of NON-OPAQUE geometry (traverse_cpu.rs:164-192):
  * RDN_ANYHIT_NONE = every candidate is accepted (the reference without an any-hit shader), k + 1 = program k of
  * rdn_rt_set_any_hit_programs for all non-opaque geometry, RDN_ANYHIT_FROM_SBT = the any_hit handle of the candidate's hit group
@@ -183,8 +184,9 @@ int rdn_rt_commit(rdn_rt_scene *scene);
 /* host buffers: H2D, traversal, D2H pipelined inside the call; sharded over the scene's devices */
 int rdn_rt_trace_closest(rdn_rt_scene *scene, const rdn_launch *launch, const rdn_ray *rays, uint64_t n,
                          rdn_hit *out_hits);
-/* Page-locked host memory for the call above (and every other host-buffer entry point).  Copies from pageable memory are staged by
- * the driver and run at about a third of the PCIe rate without overlapping the kernels; the call takes any host pointer, but ray
+/* Page-locked host memory for the call above (and every other host-buffer entry point).  The call takes any host pointer: ordinary
+ * (pageable) memory is staged chunk by chunk through page-locked buffers of the library by several host threads (about two thirds
+ * of the page-locked rate, bound by the host's memory bandwidth; left to the driver it was a fifth), but ray
  * and hit buffers that live for more than a frame should be page-locked: allocated with rdn_rt_host_alloc (freed with
  * rdn_rt_host_free), or — memory the caller owns, e.g. a Vec — registered with rdn_rt_host_register for as long as it lives and
  * unregistered before it is freed.  The library never registers caller memory by itself: it cannot see the free. */
