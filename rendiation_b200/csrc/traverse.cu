@@ -590,7 +590,7 @@ __device__ __forceinline__ void drain_tie_queue(const OrderedParams &P) {
 // warp share the work of its long rays (see the vote in ordered_rounds.inc) — used for launches that are ray LISTS (bounce / shadow
 // waves), whose duration is the latency of their longest rays: +24 % on config 3 (passes older than 30 rounds, at most 16 busy
 // lanes, donors with two or more deferred subtrees).  SHARE_ALWAYS runs the sharing loop from the first round; SHARE_LATE (the
-// lists' default) runs the plain loop and hands a pass that has grown old over to the sharing loop.  Either way the kernel is 5-6 %
+// default of lists under 2 M rays) runs the plain loop and hands a pass that has grown old over to the sharing loop.  Either way the kernel is 5-6 %
 // slower than the plain one before anything is shared, which grids never win back: they keep the plain loop
 // (profiles/kbench_r2h_*.log, kbench_r2u_*.log, kbench_r2v_*.log, kbench_r2x_late_sharing.log).  ANYHIT: candidates of non-opaque
 // geometry go through the any-hit stage.  HISTORY (device-resident grids): the tiles are taken in the order of the lists
@@ -1136,7 +1136,9 @@ cudaError_t launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch
     case 100: fn = plain; break;     // never share
     case 110: fn = sharing; break;   // the sharing loop from the first round
     case 120: fn = late; break;      // the plain loop, then the sharing loop for passes that have grown old
-    default: fn = P.tiles_x == 0 ? late : plain; break;  // ray lists share (from the 30th round of a pass on), grids do not
+    // ray lists share (from the 30th round of a pass on) while they are short enough for their longest rays to decide the launch:
+    // +25 % at 0.4 M rays, +7 % at 0.8 M, even at 2 M, -4.5 % at 4 M, -7 % at 8 M (profiles/kbench_r3p_list_sizes.log); grids do not
+    default: fn = (P.tiles_x == 0 && n < (1ull << 21)) ? late : plain; break;
   }
   if (history && fn == plain && !any_hit && P.tiles_x != 0 && P.irregular_count == 0 &&
       history->n_tiles == P.tiles_x * ((P.height + 3u) / 4u)) {  // a grid with a tile history (capi.cu)
