@@ -437,6 +437,7 @@ __global__ void __launch_bounds__(128) k_resolve_ties(const SceneDev S, const rd
 
 // ================================================================================================ ordered
 constexpr int TILE_CLASSES = 8;
+constexpr uint64_t LONG_LIST_RAYS = 2000000;  // ray lists from here on: throughput, not the longest ray, decides the launch (launch_trace_ordered)
 enum { SHARE_NEVER = 0, SHARE_ALWAYS = 1, SHARE_LATE = 2 };  // template argument SHARE of k_trace_ordered_rounds
 
 struct OrderedParams {
@@ -457,6 +458,8 @@ struct OrderedParams {
   // SHARE: deferred subtrees are handed to idle lanes once a pass over a tile is share_after rounds old and no more than share_busy
   // lanes are busy, by lanes that have at least share_min of them
   int share_busy, share_min, share_after;
+  // TOPUP (long ray lists): a warp with no more than topup_lanes busy lanes goes back to the refill point and fills the others
+  int topup_lanes;
   uint32_t wait_epoch;  // launches issued before this one on the same scratch set: they must have left before this one touches it
   // HISTORY (grids; see k_build_tile_lists): tile_lists / tile_meta = the tiles of the grid by how long they took in an earlier
   // launch over it (TILE_CLASSES lists of capacity n_tiles each, longest class last) and the lists' lengths, or null: grid order;
@@ -605,7 +608,7 @@ __device__ __forceinline__ void drain_tie_queue(const OrderedParams &P) {
 // speculative traversal with a postponed leaf, any-hit pre-classification, topping a thinned-out tile up with new rays, the first
 // 8-32 stack entries per thread in shared memory (3-10 % slower than the L1-cached local stack), rows of tiles taken from the
 // middle of the frame outwards (+2..5 % on configs 1 / 2, -11 % on config 4).
-template <int K, int MINB, bool DRAIN_TIES, bool IRREGULAR, bool LD256, bool HOT, bool WIDE4, bool INST_LOOP = false, int SHARE = 0, bool ANYHIT = false, bool HISTORY = false>
+template <int K, int MINB, bool DRAIN_TIES, bool IRREGULAR, bool LD256, bool HOT, bool WIDE4, bool INST_LOOP = false, int SHARE = 0, bool ANYHIT = false, bool HISTORY = false, bool TOPUP = false>
 __global__ void __launch_bounds__(ORDERED_BLOCK, MINB) k_trace_ordered_rounds(const __grid_constant__ OrderedParams P) {
   RDN_COST(COST_PROLOGUE);
   const SceneDev &S = P.S;
@@ -1109,6 +1112,8 @@ cudaError_t launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch
   {  // (RDN_SHARE=busy,min: experimentation knob)
     P.share_busy = 16; P.share_min = 2; P.share_after = 30;  // (sweeps: profiles/kbench_r2u_*.log, kbench_r2v_*.log)
     if (const char *e = getenv("RDN_SHARE")) sscanf(e, "%d,%d,%d", &P.share_busy, &P.share_min, &P.share_after);
+    P.topup_lanes = 4;
+    if (const char *e = getenv("RDN_TOPUP")) P.topup_lanes = atoi(e);
   }
 
   // RDN_ORDERED_VARIANT: experimentation knob
@@ -1124,6 +1129,7 @@ cudaError_t launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch
                                    : k_trace_ordered_rounds<RDN_ORDERED_K, RDN_ORDERED_MINB, true, false, true, false, false, true, SHARE_ALWAYS>;
   const KernelFn late = any_hit ? k_trace_ordered_rounds<RDN_ORDERED_K, RDN_ORDERED_MINB, true, false, true, false, false, true, SHARE_LATE, true>
                                 : k_trace_ordered_rounds<RDN_ORDERED_K, RDN_ORDERED_MINB, true, false, true, false, false, true, SHARE_LATE>;
+  const KernelFn topup = any_hit ? late : k_trace_ordered_rounds<RDN_ORDERED_K, RDN_ORDERED_MINB, true, false, true, false, false, true, SHARE_NEVER, false, false, true>;
   switch (any_hit ? 0 : variant) {  // (the A/B instantiations exist without the any-hit stage only)
     case 2: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false>; break;     // the round-1 default: K = 2, one round per missed instance
     case 9: fn = k_trace_ordered_rounds<3, 8, false, false, true, false, false, true>; inline_ties = false; break;  // queue drained by k_resolve_ties
@@ -1136,9 +1142,13 @@ cudaError_t launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch
     case 100: fn = plain; break;     // never share
     case 110: fn = sharing; break;   // the sharing loop from the first round
     case 120: fn = late; break;      // the plain loop, then the sharing loop for passes that have grown old
+    case 130: fn = topup; break;     // the plain loop, thinned-out warps topped up with new rays (whatever the launch: grids lose their tiles)
     // ray lists share (from the 30th round of a pass on) while they are short enough for their longest rays to decide the launch:
     // +25 % at 0.4 M rays, +7 % at 0.8 M, even at 2 M, -4.5 % at 4 M, -7 % at 8 M (profiles/kbench_r3p_list_sizes.log); grids do not
-    default: fn = (P.tiles_x == 0 && n < (1ull << 21)) ? late : plain; break;
+    // ... and lists long enough for throughput to decide top their thinned-out warps up with new rays (no tile to keep together):
+    // +13 % at 8 M rays and +5 % on the configs[4] frame with a threshold of 4 busy lanes; 8 lanes: +16 % on the first but -11 % on
+    // the second, whose bounce wave is full of short rays (profiles/kbench_r3q_list_topup.log)
+    default: fn = P.tiles_x != 0 ? plain : (n < LONG_LIST_RAYS ? late : topup); break;
   }
   if (history && fn == plain && !any_hit && P.tiles_x != 0 && P.irregular_count == 0 &&
       history->n_tiles == P.tiles_x * ((P.height + 3u) / 4u)) {  // a grid with a tile history (capi.cu)

@@ -160,6 +160,9 @@ def test_c2_c3_full_size():
     got, stats = _device_trace(sp.p, rays, api.TRACE_AUTO, ray_flags=0x10, grid_width=1920)
     rep = _assert_parity("c2_full", got, want)
     assert rep["hits"] > 300000 and ctr["ref_abort"] == 0 and stats["whole_range_rewalks"] == 0
+    # the same frame as a LIST of more than two million rays: the launch takes the loop that tops thinned-out warps up with new rays
+    lgot, _ = _device_trace(sp.p, rays, api.TRACE_AUTO, ray_flags=0x10)
+    _assert_parity("c2_full_as_list", lgot, want)
     d = np.stack([rays["dx"], rays["dy"], rays["dz"]], -1)
     hit = want["instance_id"] != 0xFFFFFFFF
     normals = np.zeros((rays.shape[0], 3), np.float32)
@@ -546,7 +549,7 @@ def test_host_buffers_page_locked_by_their_owner():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant", [0, 2, 9, 30, 40, 60, 61, 100, 110, 120])
+@pytest.mark.parametrize("variant", [0, 2, 9, 30, 40, 60, 61, 100, 110, 120, 130])
 def test_every_instantiation_of_the_ordered_kernel_is_bit_identical(variant, monkeypatch):
     """Every instantiation RDN_ORDERED_VARIANT can select — the shipped ones (0: grids plain, ray lists sharing work between lanes;
     100 / 110 force either for both launch kinds) and the experiments kept for A/B runs (2 the round-1 kernel, 9 the separate tie
