@@ -1130,6 +1130,9 @@ cudaError_t launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch
   const KernelFn late = any_hit ? k_trace_ordered_rounds<RDN_ORDERED_K, RDN_ORDERED_MINB, true, false, true, false, false, true, SHARE_LATE, true>
                                 : k_trace_ordered_rounds<RDN_ORDERED_K, RDN_ORDERED_MINB, true, false, true, false, false, true, SHARE_LATE>;
   const KernelFn topup = any_hit ? late : k_trace_ordered_rounds<RDN_ORDERED_K, RDN_ORDERED_MINB, true, false, true, false, false, true, SHARE_NEVER, false, false, true>;
+  static const uint32_t topup_grid_instances = []() { const char *e = getenv("RDN_TOPUP_GRID_INSTANCES"); return e ? static_cast<uint32_t>(strtoul(e, nullptr, 10)) : 256u; }();
+  const bool grid_topup = topup_grid_instances != 0 && scene.n_instances >= topup_grid_instances;
+  if (P.tiles_x != 0 && grid_topup && !getenv("RDN_TOPUP")) P.topup_lanes = 8;
   switch (any_hit ? 0 : variant) {  // (the A/B instantiations exist without the any-hit stage only)
     case 2: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false>; break;     // the round-1 default: K = 2, one round per missed instance
     case 9: fn = k_trace_ordered_rounds<3, 8, false, false, true, false, false, true>; inline_ties = false; break;  // queue drained by k_resolve_ties
@@ -1148,7 +1151,11 @@ cudaError_t launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch
     // ... and lists long enough for throughput to decide top their thinned-out warps up with new rays (no tile to keep together):
     // +13 % at 8 M rays and +5 % on the configs[4] frame with a threshold of 4 busy lanes; 8 lanes: +16 % on the first but -11 % on
     // the second, whose bounce wave is full of short rays (profiles/kbench_r3q_list_topup.log)
-    default: fn = P.tiles_x != 0 ? plain : (n < LONG_LIST_RAYS ? late : topup); break;
+    // ... and so do grids over scenes of many instances, whose tiles fall apart anyway (rays of a tile enter different instances and
+    // end at very different times: 11 of 32 lanes busy on config 4): 3,050 -> 3,480-3,510 Mrays/s serialised, 3,800 -> 4,550-4,580
+    // back to back with a threshold of 4-8 lanes; the single-instance configs[1] loses 9.5 % to it (profiles/kbench_r3r_grid_topup.log).
+    // The instance count is a stand-in for "tiles diverge", RDN_TOPUP_GRID_INSTANCES moves it (0: never).
+    default: fn = P.tiles_x != 0 ? (grid_topup ? topup : plain) : (n < LONG_LIST_RAYS ? late : topup); break;
   }
   if (history && fn == plain && !any_hit && P.tiles_x != 0 && P.irregular_count == 0 &&
       history->n_tiles == P.tiles_x * ((P.height + 3u) / 4u)) {  // a grid with a tile history (capi.cu)
