@@ -53,7 +53,7 @@ C5_W, C5_H, C5_SPP = 3840, 2160, 16
 C5_WORKLOAD = "3840x2160 x 16 spp primary + 1 cosine bounce rays vs the 1,002,528-triangle torus, ray tiles sharded across the GPUs, BVH replicated (BASELINE configs[4])"
 # the instantiation launch_trace_ordered selects for grid launches (rendiation_b200/csrc/traverse.cu, `plain`), as ncu prints it:
 # the committed capture whose numbers the roofline quotes must be of this kernel (tests/test_bench_contract.py holds the two together)
-SHIPPED_ORDERED_KERNEL = "k_trace_ordered_rounds<3, 8, 1, 0, 1, 0, 0, 1, 0, 0, 1>"  # (the last argument: the instantiation that keeps a tile history)
+SHIPPED_ORDERED_KERNEL = "k_trace_ordered_rounds<3, 8, 1, 0, 1, 0, 0, 1, 0, 0, 1, 0>"  # (the last two arguments: tile history, no top-up)
 
 
 def base_config(workload=WORKLOAD, rays=W * H):

@@ -201,10 +201,10 @@ def dynamic_counts(cfg: str, names: list[str]):
     return list(warp), list(lane), rays.shape[0], dt, bool(same)
 
 
-def mangled(k, drain=True, ld256=True, wide4=False, inst_loop=False, share=False, anyhit=False, history=False):
-    """mangled template arguments <K, MINB, DRAIN_TIES, IRREGULAR, LD256, HOT, WIDE4, INST_LOOP, SHARE, ANYHIT, HISTORY> of an instantiation"""
+def mangled(k, drain=True, ld256=True, wide4=False, inst_loop=False, share=False, anyhit=False, history=False, topup=False):
+    """mangled template arguments <K, MINB, DRAIN_TIES, IRREGULAR, LD256, HOT, WIDE4, INST_LOOP, SHARE, ANYHIT, HISTORY, TOPUP> of an instantiation"""
     bl = lambda v: "Lb1E" if v else "Lb0E"
-    return f"ILi{k}ELi8E{bl(drain)}Lb0E{bl(ld256)}Lb0E{bl(wide4)}{bl(inst_loop)}Li{int(share)}E{bl(anyhit)}{bl(history)}E"  # share: 0 never, 1 always, 2 late
+    return f"ILi{k}ELi8E{bl(drain)}Lb0E{bl(ld256)}Lb0E{bl(wide4)}{bl(inst_loop)}Li{int(share)}E{bl(anyhit)}{bl(history)}{bl(topup)}E"  # share: 0 never, 1 always, 2 late
 
 
 def main():

@@ -1,6 +1,6 @@
 """Where a captured launch of k_trace_ordered_rounds spends its issue slots, by source region — no GPU needed.
 
-    python tools/ncu_region_profile.py <report.ncu-rep> [--history] [--share N] [--anyhit] [--json out.json]
+    python tools/ncu_region_profile.py <report.ncu-rep> [--history] [--topup] [--share N] [--anyhit] [--json out.json]
 
 Joins the SASS page of an `ncu --set full --import-source on` capture (instructions executed, thread instructions executed and
 stall samples per SASS instruction) with the region of every instruction of the same instantiation in csrc/_obj/traverse.o
@@ -69,7 +69,7 @@ def main():
     rep = sys.argv[1]
     share = int(sys.argv[sys.argv.index("--share") + 1]) if "--share" in sys.argv else 0
     names = issue_model.region_names()
-    regions = instruction_regions(issue_model.mangled(3, inst_loop=True, share=share, anyhit="--anyhit" in sys.argv, history="--history" in sys.argv), names)
+    regions = instruction_regions(issue_model.mangled(3, inst_loop=True, share=share, anyhit="--anyhit" in sys.argv, history="--history" in sys.argv, topup="--topup" in sys.argv), names)
     page = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True, check=True).stdout
     lines = page.split("\n")
     start = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
