@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(128) k_resolve_ties(const SceneDev S, const rd
 
 // ================================================================================================ ordered
 constexpr int TILE_CLASSES = 8;
-constexpr uint64_t LONG_LIST_RAYS = 2000000;  // ray lists from here on: throughput, not the longest ray, decides the launch (launch_trace_ordered)
+constexpr uint64_t MID_LIST_RAYS = 600000, LONG_LIST_RAYS = 2000000;  // ray lists from here on: throughput, not the longest ray, decides the launch (launch_trace_ordered)
 enum { SHARE_NEVER = 0, SHARE_ALWAYS = 1, SHARE_LATE = 2 };  // template argument SHARE of k_trace_ordered_rounds
 
 struct OrderedParams {
@@ -1133,6 +1133,9 @@ cudaError_t launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch
   static const uint32_t topup_grid_instances = []() { const char *e = getenv("RDN_TOPUP_GRID_INSTANCES"); return e ? static_cast<uint32_t>(strtoul(e, nullptr, 10)) : 256u; }();
   const bool grid_topup = topup_grid_instances != 0 && scene.n_instances >= topup_grid_instances;
   if (P.tiles_x != 0 && grid_topup && !getenv("RDN_TOPUP")) P.topup_lanes = 8;
+  const KernelFn late_topup = any_hit ? late : k_trace_ordered_rounds<RDN_ORDERED_K, RDN_ORDERED_MINB, true, false, true, false, false, true, SHARE_LATE, false, false, true>;
+  const bool mid_list = P.tiles_x == 0 && n >= MID_LIST_RAYS && n < LONG_LIST_RAYS;
+  if (mid_list && !getenv("RDN_TOPUP")) P.topup_lanes = 8;
   switch (any_hit ? 0 : variant) {  // (the A/B instantiations exist without the any-hit stage only)
     case 2: fn = k_trace_ordered_rounds<2, 8, true, false, true, false, false>; break;     // the round-1 default: K = 2, one round per missed instance
     case 9: fn = k_trace_ordered_rounds<3, 8, false, false, true, false, false, true>; inline_ties = false; break;  // queue drained by k_resolve_ties
@@ -1145,6 +1148,7 @@ cudaError_t launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch
     case 100: fn = plain; break;     // never share
     case 110: fn = sharing; break;   // the sharing loop from the first round
     case 120: fn = late; break;      // the plain loop, then the sharing loop for passes that have grown old
+    case 140: fn = late_topup; break;  // top-up while the list lasts, then late sharing
     case 130: fn = topup; break;     // the plain loop, thinned-out warps topped up with new rays (whatever the launch: grids lose their tiles)
     // ray lists share (from the 30th round of a pass on) while they are short enough for their longest rays to decide the launch:
     // +25 % at 0.4 M rays, +7 % at 0.8 M, even at 2 M, -4.5 % at 4 M, -7 % at 8 M (profiles/kbench_r3p_list_sizes.log); grids do not
@@ -1155,7 +1159,9 @@ cudaError_t launch_trace_ordered(const SceneDev &scene, const rdn_launch &launch
     // end at very different times: 11 of 32 lanes busy on config 4): 3,050 -> 3,480-3,510 Mrays/s serialised, 3,800 -> 4,550-4,580
     // back to back with a threshold of 4-8 lanes; the single-instance configs[1] loses 9.5 % to it (profiles/kbench_r3r_grid_topup.log).
     // The instance count is a stand-in for "tiles diverge", RDN_TOPUP_GRID_INSTANCES moves it (0: never).
-    default: fn = P.tiles_x != 0 ? (grid_topup ? topup : plain) : (n < LONG_LIST_RAYS ? late : topup); break;
+    // Lists in between do both — top up while the list lasts, share work once it has run dry: 0.8 M rays +4 %, 2 M +13-15 % over
+    // sharing alone (0.4 M: -7 %, which is where the lower bound comes from; profiles/kbench_r3v_mid_lists.log)
+    default: fn = P.tiles_x != 0 ? (grid_topup ? topup : plain) : (n < MID_LIST_RAYS ? late : (n < LONG_LIST_RAYS ? late_topup : topup)); break;
   }
   if (history && fn == plain && !any_hit && P.tiles_x != 0 && P.irregular_count == 0 &&
       history->n_tiles == P.tiles_x * ((P.height + 3u) / 4u)) {  // a grid with a tile history (capi.cu)

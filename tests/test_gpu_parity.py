@@ -549,7 +549,7 @@ def test_host_buffers_page_locked_by_their_owner():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant", [0, 2, 9, 30, 40, 60, 61, 100, 110, 120, 130])
+@pytest.mark.parametrize("variant", [0, 2, 9, 30, 40, 60, 61, 100, 110, 120, 130, 140])
 def test_every_instantiation_of_the_ordered_kernel_is_bit_identical(variant, monkeypatch):
     """Every instantiation RDN_ORDERED_VARIANT can select — the shipped ones (0: grids plain, ray lists sharing work between lanes;
     100 / 110 force either for both launch kinds) and the experiments kept for A/B runs (2 the round-1 kernel, 9 the separate tie
