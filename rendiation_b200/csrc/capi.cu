@@ -570,7 +570,10 @@ int enqueue_trace(rdn_rt_scene *s, DeviceCtx &dc, const Scratch &scratch, const 
       static_assert(sizeof(TileMeta::count) / sizeof(uint32_t) == TILE_LISTS, "one list per class");
       TileHistory hist{};
       const bool overlap = allow_overlap && !dc.timing && !count_ties;
-      const bool with_history = tile_history && history_enabled && !d_n && launch.grid_width != 0 && n % launch.grid_width == 0 && n >= (1u << 16);
+      // (launches of 64 Ki to 32 Mi rays: below, a launch is a handful of tiles per warp; above, its tail no longer matters and the
+      // lists — 64 B per tile — would run into hundreds of megabytes)
+      const bool with_history = tile_history && history_enabled && !d_n && launch.grid_width != 0 && n % launch.grid_width == 0 && n >= (1u << 16) &&
+                                n <= (1u << 25);
       if (with_history) {
         const uint32_t w = launch.grid_width, h = static_cast<uint32_t>(n / launch.grid_width);
         const uint32_t n_tiles = ((w + 7u) / 8u) * ((h + 3u) / 4u);
