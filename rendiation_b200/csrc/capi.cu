@@ -118,7 +118,7 @@ struct DeviceCtx {
   uint32_t *d_tile_cost = nullptr, *d_tile_lists = nullptr;  // lists: two sets of TILE_CLASSES lists (one read by launches, one being built)
   TileMeta *d_tile_meta = nullptr;                           // [2]
   uint64_t tile_cap = 0;
-  struct { uint32_t width = 0, height = 0; int current = 0; bool built = false; } tile_hist;
+  struct { uint32_t width = 0, height = 0; int current = 0; bool built = false; uint32_t builds = 0, since_build = 0; } tile_hist;
   unsigned long long *d_compact_status = nullptr;
   uint64_t compact_status_cap = 0;
   float *d_ao_payload = nullptr;   // AO accumulation: per-pixel payload, 1.0f between samples
@@ -590,11 +590,15 @@ int enqueue_trace(rdn_rt_scene *s, DeviceCtx &dc, const Scratch &scratch, const 
           RDN_CUDA(cudaMemsetAsync(dc.d_tile_cost, 0, n_tiles * sizeof(uint32_t), stream));
           RDN_CUDA(cudaMemsetAsync(dc.d_tile_meta, 0, 2 * sizeof(TileMeta), stream));
           dc.tile_hist.width = w; dc.tile_hist.height = h; dc.tile_hist.current = 0; dc.tile_hist.built = false;
+          dc.tile_hist.builds = 0; dc.tile_hist.since_build = 0;
         }
         const int cur = dc.tile_hist.current;
         hist.n_tiles = n_tiles;
         if (dc.tile_hist.built) { hist.lists = dc.d_tile_lists + static_cast<uint64_t>(cur) * TILE_LISTS * n_tiles; hist.meta = dc.d_tile_meta + cur; }
-        if (!overlap) { hist.cost = dc.d_tile_cost; hist.meta_clear = dc.d_tile_meta + (cur ^ 1); }
+        // (the lists are rebuilt behind the first three launches over a grid — the classes need the mean of the launch before — and
+        // behind every fourth from then on: what is long changes slowly, and the kernel behind the launch is 2 % of a 2 M-ray launch)
+        const bool due = dc.tile_hist.builds < 3 || dc.tile_hist.since_build >= 3;
+        if (!overlap && due) { hist.cost = dc.d_tile_cost; hist.meta_clear = dc.d_tile_meta + (cur ^ 1); }
       }
       RDN_CUDA(launch_trace_ordered(dev, launch, tlas, d_rays, n, d_hits, ts, dc.sm_count, stream, overlap, scratch.ordered_launches, &ties_done, d_n,
                                     with_history ? &hist : nullptr));
@@ -607,7 +611,11 @@ int enqueue_trace(rdn_rt_scene *s, DeviceCtx &dc, const Scratch &scratch, const 
                                 dc.d_tile_meta + cur, hist.n_tiles, stream);
         dc.tile_hist.current = cur ^ 1;
         dc.tile_hist.built = true;
+        dc.tile_hist.builds++;
+        dc.tile_hist.since_build = 0;
         if (launches) *launches += 1;
+      } else if (with_history && hist.used) {
+        dc.tile_hist.since_build++;
       } else if (with_history && !hist.used) {
         dc.tile_hist.built = false;  // (another instantiation took the launch — any-hit stage, an A/B variant —: the lists are stale)
       }
