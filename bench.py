@@ -611,7 +611,9 @@ def run_ours(args):
     # ---- timed region: exactly K steps back to back on one stream, CUDA events on that stream at both ends
     with ClockSampler(local_rank) as clocks:
         t_wall0 = time.perf_counter()
+        launched_before = sysm.build_stats()["kernels_enqueued"]
         total_ms_local, _ = timed_loop()
+        launched_in_timed_region = sysm.build_stats()["kernels_enqueued"] - launched_before   # counted by the library, this rank
         t_wall = time.perf_counter() - t_wall0
         timed_loop_ok = hit_buffers_match_reference()  # what the overlapped launches of the timed region wrote
         serial_ms_local, kernel_times = timed_loop(per_kernel=True)   # same K steps, each kernel bracketed by events (no overlap)
@@ -755,7 +757,7 @@ def run_ours(args):
                                      "Vec; value_unregistered = the same arrays left pageable: the library stages each chunk through page-locked buffers of "
                                      "its own, filled and emptied by up to 16 host threads while earlier chunks are on the link (224 Mrays/s when the "
                                      "driver staged the copies, profiles/bench_r2w.json)"},
-            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches": int(launched_in_timed_region),
             "roofline": {"bound": "l2", "binding": "instruction issue at ~20 of 32 active lanes (see profiles/ncu_*: issue slots ~50 % busy over the "
                                                    "launch incl. its tail, DRAM < 10 % and L2 < 15 % of peak); L2 is the memory level that serves the kernel",
                          "achieved": achieved, "peak": l2_peak, "unit": "GB/s", "frac": achieved / l2_peak,

@@ -149,6 +149,9 @@ typedef struct rdn_build_stats {
   uint64_t device_built_trees;                         /* geometry trees built by the device SAH builder (RDN_COMMIT_DEVICE_BUILD=1) */
   uint64_t tlas_only_commits;                          /* commits so far that kept every BLAS array and patched the TLAS part of the device
                                                           blobs in place (rdn_rt_tlas_update) */
+  uint64_t kernels_enqueued;                           /* traversal-path kernels this scene has put into streams so far (ordered /
+                                                          reference-order / tie / tile-list kernels): a caller that wants to know what a
+                                                          loop launched reads it before and after */
 } rdn_build_stats;
 
 typedef struct rdn_rt_scene rdn_rt_scene;   /* opaque: NaiveSahBVHSystem (geometry/naive/mod.rs:495-610) */

@@ -123,7 +123,7 @@ class _TraceStats(C.Structure):
 class _BuildStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("balance_fallbacks", "balance_fallbacks_gt10", "irregular_triangles", "irregular_instances",
                                           "reference_routed_tlas")] + \
-               [(n, C.c_double) for n in ("bvh_build_ms", "flatten_ms", "upload_ms")] + [("build_threads", C.c_uint64), ("device_built_trees", C.c_uint64), ("tlas_only_commits", C.c_uint64)]
+               [(n, C.c_double) for n in ("bvh_build_ms", "flatten_ms", "upload_ms")] + [("build_threads", C.c_uint64), ("device_built_trees", C.c_uint64), ("tlas_only_commits", C.c_uint64), ("kernels_enqueued", C.c_uint64)]
 
 
 class _KernelTimes(C.Structure):

@@ -10,6 +10,7 @@
 #endif
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <chrono>
@@ -161,6 +162,7 @@ struct rdn_rt_scene {
   std::vector<uint8_t> host_blob;  // kept only by host-only scenes (n_devices == 0)
   BlobHeader blob_header{};        // layout of the blob the devices hold (valid when flat is)
   uint64_t tlas_only_commits = 0;  // commits that kept every BLAS array and patched the TLAS arrays of the device blobs in place
+  std::atomic<uint64_t> kernels_enqueued{0};  // traversal-path kernels put into streams so far (rdn_build_stats)
   void *patch_staging = nullptr;   // page-locked staging buffer of those patches
   uint64_t patch_staging_cap = 0;
   std::vector<uint32_t> h_tlas_binding;  // host copies used to resolve the wide root of a launch
@@ -613,6 +615,7 @@ int enqueue_trace(rdn_rt_scene *s, DeviceCtx &dc, const Scratch &scratch, const 
         dc.tile_hist.built = true;
         dc.tile_hist.builds++;
         dc.tile_hist.since_build = 0;
+        s->kernels_enqueued++;
         if (launches) *launches += 1;
       } else if (with_history && hist.used) {
         dc.tile_hist.since_build++;
@@ -623,10 +626,12 @@ int enqueue_trace(rdn_rt_scene *s, DeviceCtx &dc, const Scratch &scratch, const 
     if (!ties_done) {
       ScopedKernelTimer tm(dc, KERNEL_TIES, stream);
       launch_resolve_ties(dev, launch, d_rays, d_hits, ts, dc.sm_count, stream);
+      s->kernels_enqueued++;
       if (launches) *launches += 1;
       RDN_CUDA(cudaMemsetAsync(static_cast<char *>(scratch.base) + 8, 0, 4, stream));  // the next launch on this set may drain in-kernel
     }
   }
+  if (n) s->kernels_enqueued++;
   if (launches) *launches += 1;
   RDN_CUDA(cudaGetLastError());
   return RDN_OK;
@@ -1970,6 +1975,7 @@ int rdn_rt_scene_build_stats(rdn_rt_scene *s, rdn_build_stats *out) {
     out->build_threads = s->flat.stats.build_threads;
     out->device_built_trees = s->flat.stats.device_built_trees;
     out->tlas_only_commits = s->tlas_only_commits;
+    out->kernels_enqueued = s->kernels_enqueued.load();
   } else {
     for (const TlasRoot &t : s->h_tlas_root) {
       if (t.irregular_count == IRREGULAR_ROUTE_ALL) out->reference_routed_tlas++;
