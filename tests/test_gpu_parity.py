@@ -147,16 +147,26 @@ def test_instanced_scene_ids_exact():
     assert rep["hits"] > 10000 and len(np.unique(want["instance_custom_id"])) > 50
 
 
-def test_c2_c3_full_size():
+_FULL_SIZE = {}   # scene and oracle results of the full-size test, shared by its variants
+
+
+@pytest.mark.parametrize("variant", [0, 100, 110, 120, 130, 140])
+def test_c2_c3_full_size(variant, monkeypatch):
     """BASELINE configs 2 and 3 at full size: 1920x1080 primary rays vs the 1,002,528-triangle torus, then one incoherent
-    cosine-weighted bounce ray per hit; whole hit records bit-identical to the oracle on every ray"""
-    sp, (pos, idx, m) = helpers.torus_scene(708)
+    cosine-weighted bounce ray per hit; whole hit records bit-identical to the oracle on every ray — with the shipped choice of
+    loops (0: tile history on the grid, top-up on the two-million-ray list, late work sharing on the bounce list) and with every
+    loop forced on every launch (100 plain, 110 / 120 work sharing, 130 top-up, 140 top-up then sharing)"""
+    monkeypatch.setenv("RDN_ORDERED_VARIANT", str(variant))
+    if not _FULL_SIZE:
+        sp, (pos, idx, m) = helpers.torus_scene(708)
+        rays = S.pinhole_rays(1920, 1080, 0.01, 100.0, aspect_correct=True)
+        _FULL_SIZE.update(sp=sp, pos=pos, idx=idx, m=m, rays=rays, primary=sp.o.trace(rays, ray_flags=0x10, n_threads=os.cpu_count() or 4))
+    sp, pos, idx, m, rays = (_FULL_SIZE[k] for k in ("sp", "pos", "idx", "m", "rays"))
     assert idx.size // 3 == 1002528
     st = sp.p.build_stats()
     assert st["irregular_triangles"] == 0 and st["irregular_instances"] == 0 and st["balance_fallbacks_gt10"] == 0
-    rays = S.pinhole_rays(1920, 1080, 0.01, 100.0, aspect_correct=True)
     nt = os.cpu_count() or 4
-    want, ctr = sp.o.trace(rays, ray_flags=0x10, n_threads=nt)
+    want, ctr = _FULL_SIZE["primary"]
     got, stats = _device_trace(sp.p, rays, api.TRACE_AUTO, ray_flags=0x10, grid_width=1920)
     rep = _assert_parity("c2_full", got, want)
     assert rep["hits"] > 300000 and ctr["ref_abort"] == 0 and stats["whole_range_rewalks"] == 0
@@ -168,7 +178,9 @@ def test_c2_c3_full_size():
     normals = np.zeros((rays.shape[0], 3), np.float32)
     normals[hit] = S.geometric_normals(pos, idx, want["primitive_id"][hit], m, d[hit])
     brays, _ = S.bounce_rays(rays, want, normals)
-    bwant, bctr = sp.o.trace(brays, ray_flags=0, n_threads=nt)
+    if "bounce" not in _FULL_SIZE:
+        _FULL_SIZE["bounce"] = sp.o.trace(brays, ray_flags=0, n_threads=nt)
+    bwant, bctr = _FULL_SIZE["bounce"]
     bgot, bstats = _device_trace(sp.p, brays, api.TRACE_AUTO, ray_flags=0)
     brep = _assert_parity("c3_full", bgot, bwant)
     assert brep["n"] == int(hit.sum()) and brep["hits"] > 10000 and bctr["ref_abort"] == 0 and bstats["whole_range_rewalks"] == 0
