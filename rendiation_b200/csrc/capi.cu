@@ -1975,13 +1975,13 @@ int rdn_rt_scene_build_stats(rdn_rt_scene *s, rdn_build_stats *out) {
     out->build_threads = s->flat.stats.build_threads;
     out->device_built_trees = s->flat.stats.device_built_trees;
     out->tlas_only_commits = s->tlas_only_commits;
-    out->kernels_enqueued = s->kernels_enqueued.load();
   } else {
     for (const TlasRoot &t : s->h_tlas_root) {
       if (t.irregular_count == IRREGULAR_ROUTE_ALL) out->reference_routed_tlas++;
       else out->irregular_instances += t.irregular_count;
     }
   }
+  out->kernels_enqueued = s->kernels_enqueued.load();
   return RDN_OK;
 }
 
